@@ -1,0 +1,9 @@
+"""colorid_b200 — B200-native BIGSI hot path (build / search / read_id) of hcdenbakker/colorid.
+
+The product is the CUDA shared library `libcolorid_b200.so` behind the C ABI declared in
+include/colorid_b200.h; this package only loads it (ctypes) and offers numpy-facing wrappers
+for tests and benchmarks.  There is no CPU fallback.
+"""
+from . import lib  # noqa: F401
+from .api import Context, Index, pack_seqs, group_offsets  # noqa: F401
+from .lib import CID_SEQ_FASTA, CID_SEQ_FASTQ, CidError  # noqa: F401

@@ -1,0 +1,202 @@
+"""Thin numpy-facing wrappers over the C ABI (include/colorid_b200.h).
+
+These exist for the tests and bench.py; the product is the shared library.  Naming follows the
+reference's domain: accessions, colours, queries, reads, rows.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import lib as L
+
+
+def _p(a, t=L.vp):
+    if a is None:
+        return None
+    return a.ctypes.data_as(t)
+
+
+def pack_seqs(seqs):
+    """list of bytes -> (uint8 bases, uint64 seq_offs[n+1])."""
+    offs = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    if seqs:
+        offs[1:] = np.cumsum([len(s) for s in seqs], dtype=np.uint64)
+    bases = np.frombuffer(b"".join(seqs), dtype=np.uint8).copy() if seqs else np.zeros(0, np.uint8)
+    if bases.size == 0:
+        bases = np.zeros(1, np.uint8)
+    return bases, offs
+
+
+def group_offsets(groups):
+    o = np.zeros(len(groups) + 1, dtype=np.uint64)
+    if groups:
+        o[1:] = np.cumsum([len(g) for g in groups], dtype=np.uint64)
+    return o
+
+
+class Context:
+    def __init__(self, device=0):
+        self.lib = L.load()
+        h = L.vp()
+        L.check(self.lib.cid_ctx_create(device, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cid_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    @property
+    def launches(self):
+        return self.lib.cid_ctx_launch_count(self.h)
+
+
+class Index:
+    """Device-resident BIGSI index (bigsi.rs:19-27 BigsyMapNew)."""
+
+    def __init__(self, ctx, bloom_size, num_hash, k, n_colours):
+        self.ctx, self.lib = ctx, ctx.lib
+        self.S, self.H, self.k, self.N = bloom_size, num_hash, k, n_colours
+        h = L.vp()
+        L.check(self.lib.cid_index_create(ctx.h, bloom_size, num_hash, k, n_colours, C.byref(h)))
+        self.h = h
+        self.W = self.lib.cid_index_row_words(h)
+        self.n_ref = np.zeros(n_colours, dtype=np.uint64)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cid_index_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    # ---- build (build.rs:33-130) ----
+    def build_accession(self, colour, seqs, mode=L.CID_SEQ_FASTA, cutoff=-1):
+        bases, offs = pack_seqs(list(seqs))
+        n_ref, used = C.c_uint64(0), C.c_int64(0)
+        L.check(self.lib.cid_build_accession(self.h, colour, _p(bases), _p(offs, L.u64p), len(seqs), mode, cutoff,
+                                             C.byref(n_ref), C.byref(used)))
+        self.n_ref[colour] = n_ref.value
+        return n_ref.value, used.value
+
+    def build_accession_dev(self, colour, d_bases_ptr, d_offs_ptr, nseq, nbases, mode=L.CID_SEQ_FASTA, cutoff=-1):
+        n_ref, used = C.c_uint64(0), C.c_int64(0)
+        L.check(self.lib.cid_build_accession_dev(self.h, colour, d_bases_ptr, d_offs_ptr, nseq, nbases, mode, cutoff,
+                                                 C.byref(n_ref), C.byref(used)))
+        self.n_ref[colour] = n_ref.value
+        return n_ref.value, used.value
+
+    def finalize(self):
+        L.check(self.lib.cid_build_finalize(self.h))
+
+    # ---- index I/O (bigsi.rs:51-69) ----
+    def upload_rows(self, row_ids, words):
+        row_ids = np.ascontiguousarray(row_ids, dtype=np.uint64)
+        words = np.ascontiguousarray(words, dtype=np.uint32)
+        L.check(self.lib.cid_index_upload_rows(self.h, _p(row_ids, L.u64p), _p(words, L.u32p), len(row_ids)))
+
+    def nonzero_rows(self):
+        n = C.c_uint64(0)
+        L.check(self.lib.cid_index_count_nonzero_rows(self.h, C.byref(n)))
+        return n.value
+
+    def download_nonzero_rows(self):
+        n = self.nonzero_rows()
+        ids = np.zeros(max(n, 1), dtype=np.uint64)
+        words = np.zeros((max(n, 1), self.W), dtype=np.uint32)
+        got = C.c_uint64(0)
+        L.check(self.lib.cid_index_download_nonzero_rows(self.h, _p(ids, L.u64p), _p(words, L.u32p), n, C.byref(got)))
+        return ids[:n], words[:n]
+
+    def download_dense(self):
+        words = np.zeros((self.S, self.W), dtype=np.uint32)
+        L.check(self.lib.cid_index_download_dense(self.h, _p(words, L.u32p)))
+        return words
+
+    def device_ptrs(self):
+        rows, bm, nw = L.vp(), L.vp(), C.c_uint64(0)
+        L.check(self.lib.cid_index_device_ptrs(self.h, C.byref(rows), C.byref(bm), C.byref(nw)))
+        return rows.value, bm.value, nw.value
+
+    def set_rownz_global(self, flag=True):
+        L.check(self.lib.cid_index_set_rownz_global(self.h, int(flag)))
+
+    # ---- search (batch_search_pe.rs:9-179) ----
+    def query_counts(self, queries, seq_mode=L.CID_SEQ_FASTA, gene_search=False, filt=-1, want_uniq=True):
+        flat = [s for q in queries for s in q]
+        bases, offs = pack_seqs(flat)
+        qoffs = group_offsets(queries)
+        nq = len(queries)
+        counts = np.zeros((nq, self.N), dtype=np.uint32)
+        num_kmers = np.zeros(nq, dtype=np.uint64)
+        un = np.zeros((nq, self.N), dtype=np.uint64) if want_uniq else None
+        us = np.zeros((nq, self.N), dtype=np.uint64) if want_uniq else None
+        um = np.zeros((nq, self.N), dtype=np.uint64) if want_uniq else None
+        used = np.zeros(max(nq, 1), dtype=np.int64)
+        L.check(self.lib.cid_query_counts(self.h, _p(bases), _p(offs, L.u64p), len(flat), _p(qoffs, L.u64p), nq, seq_mode,
+                                          int(gene_search), filt, _p(counts, L.u32p), _p(num_kmers, L.u64p),
+                                          _p(un, L.u64p), _p(us, L.u64p), _p(um, L.u64p), _p(used, L.i64p)))
+        return dict(counts=counts, num_kmers=num_kmers, uniq_n=un, uniq_sum=us, uniq_mode=um, cutoff=used[:nq])
+
+    # ---- perfect search (perfect_search.rs:6-60) ----
+    def query_perfect(self, queries):
+        flat = [s for q in queries for s in q]
+        bases, offs = pack_seqs(flat)
+        qoffs = group_offsets(queries)
+        nq = len(queries)
+        and_rows = np.zeros((nq, self.W), dtype=np.uint32)
+        status = np.zeros(max(nq, 1), dtype=np.uint8)
+        n_kmers = np.zeros(max(nq, 1), dtype=np.uint64)
+        L.check(self.lib.cid_query_perfect(self.h, _p(bases), _p(offs, L.u64p), len(flat), _p(qoffs, L.u64p), nq,
+                                           _p(and_rows, L.u32p), _p(status, L.u8p), _p(n_kmers, L.u64p)))
+        return dict(and_rows=and_rows, status=status[:nq], n_kmers=n_kmers[:nq])
+
+    # ---- read_id (read_id_mt_pe.rs:282-363) ----
+    def _params(self, d, start_sample, qual_offset, group_width, reserve_before_find, rep_cap):
+        return L.ReadIdParams(d, start_sample, qual_offset, group_width, int(reserve_before_find),
+                              rep_cap if rep_cap else self.N + 1)
+
+    def read_id_batch(self, reads, quals=None, d=1, start_sample=3, qual_offset=0, group_width=16,
+                      reserve_before_find=True, rep_cap=None):
+        flat = [s for r in reads for s in r]
+        bases, offs = pack_seqs(flat)
+        roffs = group_offsets(reads)
+        qarr = None
+        if quals is not None:
+            qarr, _ = pack_seqs([s for r in quals for s in r])
+        nr = len(reads)
+        p = self._params(d, start_sample, qual_offset, group_width, reserve_before_find, rep_cap)
+        cap = p.rep_cap
+        n_set = np.zeros(max(nr, 1), np.uint32)
+        flags = np.zeros(max(nr, 1), np.uint32)
+        rep_n = np.zeros(max(nr, 1), np.uint32)
+        rep_c = np.zeros((max(nr, 1), cap), np.uint32)
+        rep_v = np.zeros((max(nr, 1), cap), np.uint32)
+        L.check(self.lib.cid_read_id_batch(self.h, _p(bases), _p(qarr), _p(offs, L.u64p), len(flat), _p(roffs, L.u64p), nr,
+                                           C.byref(p), _p(n_set, L.u32p), _p(flags, L.u32p), _p(rep_n, L.u32p),
+                                           _p(rep_c, L.u32p), _p(rep_v, L.u32p)))
+        return dict(n_set=n_set[:nr], flags=flags[:nr], rep_n=rep_n[:nr], rep_colour=rep_c[:nr], rep_count=rep_v[:nr])
+
+    def read_kmer_order(self, reads, d=1, group_width=16, reserve_before_find=True, order_cap=512):
+        flat = [s for r in reads for s in r]
+        bases, offs = pack_seqs(flat)
+        roffs = group_offsets(reads)
+        nr = len(reads)
+        p = self._params(d, 3, 0, group_width, reserve_before_find, None)
+        on = np.zeros(max(nr, 1), np.uint32)
+        osq = np.zeros((max(nr, 1), order_cap), np.uint8)
+        opos = np.zeros((max(nr, 1), order_cap), np.uint16)
+        L.check(self.lib.cid_read_kmer_order(self.h, _p(bases), _p(offs, L.u64p), len(flat), _p(roffs, L.u64p), nr,
+                                             C.byref(p), order_cap, _p(on, L.u32p), _p(osq, L.u8p), _p(opos, L.u16p)))
+        return on[:nr], osq[:nr], opos[:nr]
+
+    def hash_kmers(self, kmers):
+        """kmers: list of k-byte ASCII strings -> row ids [n, H]."""
+        arr = np.frombuffer(b"".join(kmers), dtype=np.uint8).copy()
+        out = np.zeros((len(kmers), self.H), dtype=np.uint64)
+        L.check(self.lib.cid_hash_kmers(self.h, _p(arr), len(kmers), _p(out, L.u64p)))
+        return out

@@ -1,0 +1,727 @@
+// C ABI of libcolorid_b200 (see include/colorid_b200.h): context, index lifecycle and the
+// host-pointer / device-pointer entry points that drive the kernels.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <map>
+#include <vector>
+
+#include "cid_device.cuh"
+#include "cid_internal.h"
+
+namespace cid {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int DevBuf::ensure(size_t bytes) {
+    if (bytes <= cap && p) return CID_OK;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    size_t want = std::max<size_t>(bytes, 256);
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { p = nullptr; set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); cudaGetLastError(); return CID_E_NOMEM; }
+    cap = want;
+    return CID_OK;
+}
+void DevBuf::release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+int PinBuf::ensure(size_t bytes) {
+    if (bytes <= cap && p) return CID_OK;
+    if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+    size_t want = std::max<size_t>(bytes, 256);
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e != cudaSuccess) { p = nullptr; set_error("cudaMallocHost(%zu) failed: %s", want, cudaGetErrorString(e)); cudaGetLastError(); return CID_E_NOMEM; }
+    cap = want;
+    return CID_OK;
+}
+void PinBuf::release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+
+int check_err_flags(cid_ctx* ctx, cudaStream_t st) {
+    CID_CUDA(cudaMemcpyAsync(ctx->h_err, ctx->d_err, 4, cudaMemcpyDeviceToHost, st));
+    CID_CUDA(cudaStreamSynchronize(st));
+    uint32_t f = ctx->h_err[0];
+    if (!f) return CID_OK;
+    CID_CUDA(cudaMemsetAsync(ctx->d_err, 0, 16, st));
+    if (f & ERRF_LOWER_RAW) {
+        set_error("lower-case bases inside k-mers of a raw-case input (FASTQ / read_id) are not supported on the device yet");
+        return CID_E_UNSUPPORTED;
+    }
+    if (f & ERRF_READ_TOO_LONG) { set_error("a read exceeds the declared maximum read length"); return CID_E_CAPACITY; }
+    set_error("internal capacity exceeded (flags 0x%x)", f);
+    return CID_E_CAPACITY;
+}
+
+// kmer.rs:866-942 auto_cutoff on a dense histogram h[c] = number of distinct k-mers seen c times.
+// Returns CID_E_REF_PANIC where the Rust code would index out of range / underflow.
+static int auto_cutoff_dense(const std::vector<uint64_t>& h, uint64_t max_cov, int64_t* out) {
+    uint64_t distinct = 0, weighted = 0;
+    for (uint64_t c = 1; c <= max_cov; c++) { distinct += h[c]; weighted += c * h[c]; }
+    const double total_mean = (double)weighted / (double)distinct;
+    if (total_mean < 1.5) { *out = 0; return CID_OK; }
+    // coverages[c-1] = h[c] for c in 1..max_cov (the maximum itself is excluded, kmer.rs:887)
+    const size_t ncov = max_cov >= 1 ? (size_t)(max_cov - 1) : 0;
+    if (ncov < 3) { set_error("auto_cutoff: degenerate k-mer histogram (reference panics)"); return CID_E_REF_PANIC; }
+    auto cov = [&](size_t i) { return (double)h[i + 1]; };
+    size_t nd1 = ncov - 2;                       // d1[j] = cov[j+1]/cov[j+2]
+    size_t pos1 = 0, pos2 = 0;
+    for (size_t j = 0; j < nd1; j++) if (cov(j + 1) / cov(j + 2) < 1.0) { pos1 = j + 1; break; }
+    for (size_t j = 0; j + 1 < nd1; j++) {
+        double a = cov(j + 1) / cov(j + 2), b = cov(j + 2) / cov(j + 3);
+        if (a / b < 1.0) { pos2 = j + 1; break; }
+    }
+    uint64_t bigsum = 0, num = 0;
+    for (size_t i = 0; i + 1 < ncov; i++) { bigsum += i * h[i + 2]; num += h[i + 2]; }
+    const double mean = (double)bigsum / (double)num;
+    if (pos1 > 0 && (double)pos1 < mean * 0.75) *out = (int64_t)pos1;
+    else if (pos2 > 0) *out = (int64_t)pos2;
+    else {
+        double half = std::ceil(mean / 2.0);
+        uint64_t hv = std::isnan(half) ? 0 : (uint64_t)half;
+        *out = (int64_t)std::max<uint64_t>(1, hv);
+    }
+    return CID_OK;
+}
+
+__global__ void table_clear_kernel(Slot* t, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        Slot s; s.key = CID_EMPTY_KEY; s.count = 0; s.pad = 0;
+        t[i] = s;
+    }
+}
+static int table_clear(cid_ctx* ctx, cudaStream_t st, void* d_table, uint64_t nslots) {
+    unsigned grid = (unsigned)std::min<uint64_t>((nslots + 255) / 256, (uint64_t)ctx->sm_count * 32);
+    if (grid == 0) grid = 1;
+    table_clear_kernel<<<grid, 256, 0, st>>>((Slot*)d_table, nslots);
+    ctx->launches++;
+    CID_CUDA(cudaGetLastError());
+    return CID_OK;
+}
+
+enum { HIST_BINS = 65536, HIST_OVERFLOW_CAP = 1 << 20 };
+
+// Histogram of one region -> auto_cutoff (host arithmetic on a few KB).
+static int region_auto_cutoff(cid_ctx* ctx, cudaStream_t st, const Slot* d_region, uint64_t nslots, int64_t* cutoff) {
+    CID_TRY(ctx->scratch[8].ensure((size_t)HIST_BINS * 4 + 16));
+    CID_TRY(ctx->scratch[9].ensure((size_t)HIST_OVERFLOW_CAP * 4));
+    uint32_t* d_hist = ctx->scratch[8].as<uint32_t>();
+    uint32_t* d_ovn = d_hist + HIST_BINS;
+    CID_CUDA(cudaMemsetAsync(d_hist, 0, (size_t)HIST_BINS * 4 + 16, st));
+    CID_TRY(launch_region_histogram(ctx, st, d_region, nslots, d_hist, HIST_BINS, ctx->scratch[9].as<uint32_t>(),
+                                    HIST_OVERFLOW_CAP, d_ovn));
+    std::vector<uint32_t> hh(HIST_BINS + 4);
+    CID_CUDA(cudaMemcpyAsync(hh.data(), d_hist, (size_t)HIST_BINS * 4 + 16, cudaMemcpyDeviceToHost, st));
+    CID_CUDA(cudaStreamSynchronize(st));
+    uint32_t novf = hh[HIST_BINS];
+    if (novf > HIST_OVERFLOW_CAP) { set_error("auto_cutoff: too many k-mers with count >= %d", HIST_BINS); return CID_E_CAPACITY; }
+    std::vector<uint32_t> ovf(novf);
+    if (novf) {
+        CID_CUDA(cudaMemcpy(ovf.data(), ctx->scratch[9].p, (size_t)novf * 4, cudaMemcpyDeviceToHost));
+    }
+    uint64_t max_cov = 0;
+    for (uint32_t c = 1; c < HIST_BINS; c++) if (hh[c]) max_cov = c;
+    for (uint32_t v : ovf) max_cov = std::max<uint64_t>(max_cov, v);
+    if (max_cov > (1u << 28)) { set_error("auto_cutoff: k-mer multiplicity above 2^28"); return CID_E_CAPACITY; }
+    std::vector<uint64_t> h(max_cov + 2, 0);
+    for (uint64_t c = 1; c < std::min<uint64_t>(HIST_BINS, max_cov + 1); c++) h[c] = hh[c];
+    for (uint32_t v : ovf) h[v] += 1;
+    return auto_cutoff_dense(h, max_cov, cutoff);
+}
+
+static int ensure_bitsets(cid_index* idx) {
+    if (idx->bitsets) return CID_OK;
+    idx->bs_words = ((idx->S + 31) / 32 + 31) / 32 * 32;
+    size_t bytes = (size_t)idx->N * idx->bs_words * 4;
+    cudaError_t e = cudaMalloc((void**)&idx->bitsets, std::max<size_t>(bytes, 256));
+    if (e != cudaSuccess) { idx->bitsets = nullptr; set_error("cudaMalloc(bitsets %zu B) failed: %s", bytes, cudaGetErrorString(e)); cudaGetLastError(); return CID_E_NOMEM; }
+    CID_CUDA(cudaMemsetAsync(idx->bitsets, 0, bytes, idx->ctx->stream));
+    return CID_OK;
+}
+
+// One group worth of count table on scratch[0]; off/mask on scratch[1].
+static int single_region(cid_ctx* ctx, cudaStream_t st, uint64_t nbases, uint32_t k, uint64_t* nslots_out,
+                         uint64_t** d_off, uint64_t** d_mask) {
+    uint64_t npos = nbases >= k ? nbases - k + 1 : 0;
+    uint64_t slots = next_pow2(std::max<uint64_t>(64, 2 * npos));
+    CID_TRY(ctx->scratch[0].ensure(slots * sizeof(Slot)));
+    CID_TRY(ctx->scratch[1].ensure(64));
+    uint64_t hv[2] = {0, slots - 1};
+    CID_CUDA(cudaMemcpyAsync(ctx->scratch[1].p, hv, 16, cudaMemcpyHostToDevice, st));
+    CID_TRY(table_clear(ctx, st, ctx->scratch[0].p, slots));
+    *nslots_out = slots;
+    *d_off = ctx->scratch[1].as<uint64_t>();
+    *d_mask = ctx->scratch[1].as<uint64_t>() + 1;
+    return CID_OK;
+}
+
+}  // namespace cid
+
+using namespace cid;
+
+extern "C" {
+
+int cid_version(void) { return 100; }
+const char* cid_last_error(void) { return g_err; }
+
+int cid_ctx_create(int device, cid_ctx** out) {
+    if (!out) { set_error("cid_ctx_create: null out"); return CID_E_INVALID; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_error("no usable CUDA device (%s); colorid_b200 has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "0 devices");
+        cudaGetLastError();
+        return CID_E_CUDA;
+    }
+    if (device < 0 || device >= ndev) { set_error("device %d out of range (%d devices)", device, ndev); return CID_E_INVALID; }
+    CID_CUDA(cudaSetDevice(device));
+    cid_ctx* c = new cid_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    CID_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    CID_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CID_CUDA(cudaMalloc((void**)&c->d_err, 16));
+    CID_CUDA(cudaMemset(c->d_err, 0, 16));
+    CID_CUDA(cudaMallocHost((void**)&c->h_err, 16));
+    *out = c;
+    return CID_OK;
+}
+void cid_ctx_destroy(cid_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (auto& b : c->scratch) b.release();
+    for (auto& b : c->pinned) b.release();
+    if (c->d_err) cudaFree(c->d_err);
+    if (c->h_err) cudaFreeHost(c->h_err);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+int cid_ctx_device(const cid_ctx* c) { return c ? c->device : -1; }
+uint64_t cid_ctx_launch_count(const cid_ctx* c) { return c ? c->launches : 0; }
+
+// ------------------------------------------------------------------ index
+int cid_index_create(cid_ctx* ctx, uint64_t bloom_size, uint32_t num_hash, uint32_t k_size, uint32_t n_colors,
+                     cid_index** out) {
+    if (!ctx || !out) { set_error("cid_index_create: null argument"); return CID_E_INVALID; }
+    if (k_size < 1 || k_size > 31) { set_error("k-mer size %u not supported on the device (1..31)", k_size); return CID_E_UNSUPPORTED; }
+    if (num_hash < 1 || num_hash > MAX_HASH) { set_error("num_hash %u not supported (1..%d)", num_hash, MAX_HASH); return CID_E_UNSUPPORTED; }
+    if (bloom_size < 1 || bloom_size >= (1ull << 32)) { set_error("bloom_size %llu not supported (1..2^32-1)", (unsigned long long)bloom_size); return CID_E_UNSUPPORTED; }
+    if (n_colors < 1) { set_error("n_colors must be >= 1"); return CID_E_INVALID; }
+    CID_CUDA(cudaSetDevice(ctx->device));
+    cid_index* ix = new cid_index();
+    ix->ctx = ctx; ix->S = bloom_size; ix->H = num_hash; ix->k = k_size; ix->N = n_colors;
+    ix->W = (n_colors + 31) / 32;
+    ix->Wp = padded_row_words(ix->W);
+    size_t bytes = (size_t)ix->S * ix->Wp * 4;
+    cudaError_t e = cudaMalloc((void**)&ix->rows, std::max<size_t>(bytes, 256));
+    if (e != cudaSuccess) { set_error("cudaMalloc(matrix %zu B) failed: %s", bytes, cudaGetErrorString(e)); cudaGetLastError(); delete ix; return CID_E_NOMEM; }
+    ix->rownz_words = (ix->S + 31) / 32;
+    e = cudaMalloc((void**)&ix->rownz, ix->rownz_words * 4 + 256);
+    if (e != cudaSuccess) { set_error("cudaMalloc(rownz) failed"); cudaGetLastError(); cudaFree(ix->rows); delete ix; return CID_E_NOMEM; }
+    CID_CUDA(cudaMemsetAsync(ix->rows, 0, bytes, ctx->stream));
+    CID_CUDA(cudaMemsetAsync(ix->rownz, 0, ix->rownz_words * 4, ctx->stream));
+    CID_CUDA(cudaStreamSynchronize(ctx->stream));
+    ix->rownz_valid = true;
+    *out = ix;
+    return CID_OK;
+}
+void cid_index_destroy(cid_index* ix) {
+    if (!ix) return;
+    cudaSetDevice(ix->ctx->device);
+    if (ix->rows) cudaFree(ix->rows);
+    if (ix->rownz) cudaFree(ix->rownz);
+    if (ix->bitsets) cudaFree(ix->bitsets);
+    delete ix;
+}
+uint32_t cid_index_row_words(const cid_index* ix) { return ix ? ix->W : 0; }
+uint32_t cid_index_row_stride(const cid_index* ix) { return ix ? ix->Wp : 0; }
+
+int cid_index_refresh_rownz(cid_index* ix) {
+    cid_ctx* ctx = ix->ctx;
+    CID_CUDA(cudaSetDevice(ctx->device));
+    CID_TRY(launch_rownz(ctx, ctx->stream, ix));
+    CID_CUDA(cudaStreamSynchronize(ctx->stream));
+    ix->rownz_valid = true;
+    return CID_OK;
+}
+int cid_index_set_rownz_global(cid_index* ix, int is_global) { ix->rownz_global = is_global != 0; return CID_OK; }
+
+int cid_index_upload_rows(cid_index* ix, const uint64_t* row_ids, const uint32_t* words, uint64_t nrows) {
+    cid_ctx* ctx = ix->ctx;
+    CID_CUDA(cudaSetDevice(ctx->device));
+    // scatter on the host into a dense staging image in chunks of rows, then copy (rows are W words each)
+    for (uint64_t i = 0; i < nrows; i++) {
+        if (row_ids[i] >= ix->S) { set_error("row id %llu >= bloom_size", (unsigned long long)row_ids[i]); return CID_E_INVALID; }
+    }
+    // cudaMemcpy2D cannot scatter; group consecutive ids into runs
+    uint64_t i = 0;
+    while (i < nrows) {
+        uint64_t j = i + 1;
+        while (j < nrows && row_ids[j] == row_ids[j - 1] + 1) j++;
+        CID_CUDA(cudaMemcpy2DAsync(ix->rows + row_ids[i] * ix->Wp, (size_t)ix->Wp * 4, words + i * ix->W, (size_t)ix->W * 4,
+                                   (size_t)ix->W * 4, j - i, cudaMemcpyHostToDevice, ctx->stream));
+        i = j;
+    }
+    CID_CUDA(cudaStreamSynchronize(ctx->stream));
+    return cid_index_refresh_rownz(ix);
+}
+
+int cid_index_download_dense(cid_index* ix, uint32_t* words) {
+    cid_ctx* ctx = ix->ctx;
+    CID_CUDA(cudaSetDevice(ctx->device));
+    CID_CUDA(cudaMemcpy2DAsync(words, (size_t)ix->W * 4, ix->rows, (size_t)ix->Wp * 4, (size_t)ix->W * 4, ix->S,
+                               cudaMemcpyDeviceToHost, ctx->stream));
+    CID_CUDA(cudaStreamSynchronize(ctx->stream));
+    return CID_OK;
+}
+
+int cid_index_count_nonzero_rows(cid_index* ix, uint64_t* nrows) {
+    cid_ctx* ctx = ix->ctx;
+    CID_CUDA(cudaSetDevice(ctx->device));
+    std::vector<uint32_t> bm(ix->rownz_words);
+    CID_CUDA(cudaMemcpy(bm.data(), ix->rownz, ix->rownz_words * 4, cudaMemcpyDeviceToHost));
+    uint64_t n = 0;
+    for (uint64_t w = 0; w < ix->rownz_words; w++) n += __builtin_popcount(bm[w]);
+    *nrows = n;
+    return CID_OK;
+}
+
+int cid_index_download_nonzero_rows(cid_index* ix, uint64_t* row_ids, uint32_t* words, uint64_t cap, uint64_t* nrows) {
+    cid_ctx* ctx = ix->ctx;
+    CID_CUDA(cudaSetDevice(ctx->device));
+    std::vector<uint32_t> bm(ix->rownz_words);
+    CID_CUDA(cudaMemcpy(bm.data(), ix->rownz, ix->rownz_words * 4, cudaMemcpyDeviceToHost));
+    // stream the dense matrix through a pinned window and keep the non-zero rows
+    const uint64_t win_rows = std::max<uint64_t>(1, (64ull << 20) / ((size_t)ix->Wp * 4));
+    CID_TRY(ctx->pinned[0].ensure(win_rows * ix->Wp * 4));
+    uint32_t* win = ctx->pinned[0].as<uint32_t>();
+    uint64_t n = 0;
+    for (uint64_t r0 = 0; r0 < ix->S; r0 += win_rows) {
+        uint64_t nr = std::min(win_rows, ix->S - r0);
+        CID_CUDA(cudaMemcpyAsync(win, ix->rows + r0 * ix->Wp, nr * ix->Wp * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CID_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (uint64_t r = r0; r < r0 + nr; r++) {
+            if (!((bm[r >> 5] >> (r & 31)) & 1u)) continue;
+            if (n < cap) {
+                row_ids[n] = r;
+                memcpy(words + n * ix->W, win + (r - r0) * ix->Wp, (size_t)ix->W * 4);
+            }
+            n++;
+        }
+    }
+    *nrows = n;
+    if (n > cap) { set_error("download_nonzero_rows: %llu rows, capacity %llu", (unsigned long long)n, (unsigned long long)cap); return CID_E_CAPACITY; }
+    return CID_OK;
+}
+
+int cid_index_device_ptrs(cid_index* ix, void** rows, void** rownz_bitmap, uint64_t* rownz_words) {
+    if (rows) *rows = ix->rows;
+    if (rownz_bitmap) *rownz_bitmap = ix->rownz;
+    if (rownz_words) *rownz_words = ix->rownz_words;
+    return CID_OK;
+}
+
+// ------------------------------------------------------------------ build
+int cid_build_accession_dev(cid_index* ix, uint32_t colour, const char* d_bases, const uint64_t* d_seq_offs,
+                            uint64_t nseq, uint64_t nbases, int seq_mode, int64_t cutoff, uint64_t* n_ref_kmers,
+                            int64_t* cutoff_used) {
+    cid_ctx* ctx = ix->ctx;
+    cudaStream_t st = ctx->stream;
+    if (colour >= ix->N) { set_error("colour %u >= n_colors %u", colour, ix->N); return CID_E_INVALID; }
+    if (seq_mode != CID_SEQ_FASTA && seq_mode != CID_SEQ_FASTQ) { set_error("bad seq_mode"); return CID_E_INVALID; }
+    if (cutoff < -1) { set_error("cutoff must be >= -1"); return CID_E_INVALID; }
+    CID_CUDA(cudaSetDevice(ctx->device));
+    CID_TRY(ensure_bitsets(ix));
+    uint64_t nslots; uint64_t *d_off, *d_mask;
+    CID_TRY(single_region(ctx, st, nbases, ix->k, &nslots, &d_off, &d_mask));
+    CID_TRY(launch_kmerize_insert(ctx, st, (const uint8_t*)d_bases, d_seq_offs, nseq, 0, nbases, nullptr, d_off, d_mask,
+                                  ctx->scratch[0].p, ix->k, seq_mode));
+    CID_TRY(check_err_flags(ctx, st));
+    int64_t used = cutoff;       // FASTA with -1: keep everything (count > -1)
+    if (seq_mode == CID_SEQ_FASTQ && cutoff == -1)
+        CID_TRY(region_auto_cutoff(ctx, st, ctx->scratch[0].as<Slot>(), nslots, &used));
+    uint32_t* bitset = ix->bitsets + (uint64_t)colour * ix->bs_words;
+    CID_CUDA(cudaMemsetAsync(bitset, 0, ix->bs_words * 4, st));
+    CID_TRY(ctx->scratch[2].ensure(16));
+    unsigned long long* d_nref = ctx->scratch[2].as<unsigned long long>();
+    CID_CUDA(cudaMemsetAsync(d_nref, 0, 8, st));
+    CID_TRY(launch_region_to_bloom(ctx, st, ctx->scratch[0].p, nslots, used, ix->k, ix->H, ix->S, bitset, d_nref));
+    unsigned long long nref = 0;
+    CID_CUDA(cudaMemcpyAsync(&nref, d_nref, 8, cudaMemcpyDeviceToHost, st));
+    CID_CUDA(cudaStreamSynchronize(st));
+    if (n_ref_kmers) *n_ref_kmers = nref;
+    if (cutoff_used) *cutoff_used = used;
+    return CID_OK;
+}
+
+int cid_build_accession(cid_index* ix, uint32_t colour, const char* bases, const uint64_t* seq_offs, uint64_t nseq,
+                        int seq_mode, int64_t cutoff, uint64_t* n_ref_kmers, int64_t* cutoff_used) {
+    cid_ctx* ctx = ix->ctx;
+    if (!seq_offs) { set_error("null seq_offs"); return CID_E_INVALID; }
+    CID_CUDA(cudaSetDevice(ctx->device));
+    const uint64_t nbases = seq_offs[nseq];
+    CID_TRY(ctx->scratch[4].ensure(nbases + 64));
+    CID_TRY(ctx->scratch[5].ensure((nseq + 1) * 8));
+    if (nbases) CID_CUDA(cudaMemcpyAsync(ctx->scratch[4].p, bases, nbases, cudaMemcpyHostToDevice, ctx->stream));
+    CID_CUDA(cudaMemcpyAsync(ctx->scratch[5].p, seq_offs, (nseq + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    return cid_build_accession_dev(ix, colour, ctx->scratch[4].as<char>(), ctx->scratch[5].as<uint64_t>(), nseq, nbases,
+                                   seq_mode, cutoff, n_ref_kmers, cutoff_used);
+}
+
+int cid_build_finalize(cid_index* ix) {
+    cid_ctx* ctx = ix->ctx;
+    CID_CUDA(cudaSetDevice(ctx->device));
+    if (!ix->bitsets) return cid_index_refresh_rownz(ix);
+    CID_TRY(launch_transpose(ctx, ctx->stream, ix));
+    CID_TRY(launch_rownz(ctx, ctx->stream, ix));
+    CID_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ix->bitsets);
+    ix->bitsets = nullptr;
+    ix->rownz_valid = true;
+    return CID_OK;
+}
+
+// ------------------------------------------------------------------ search
+// Shared front end: table regions for a batch of queries, k-mer counting, work units.
+struct QueryPlan {
+    GroupRegions gr;
+    QueryUnits qu;
+    uint32_t* d_unit_group; uint64_t* d_unit_slot0; uint32_t* d_unit_nslots;
+    Slot* d_table;
+};
+static int query_front(cid_index* ix, cudaStream_t st, const uint8_t* d_bases, const uint64_t* d_seq_offs,
+                       const uint64_t* h_seq_offs, const uint64_t* h_query_offs, uint64_t q0, uint64_t q1, int seq_mode,
+                       QueryPlan& qp) {
+    cid_ctx* ctx = ix->ctx;
+    const uint64_t nq = q1 - q0;
+    const uint64_t s_lo = h_query_offs[q0], s_hi = h_query_offs[q1];
+    const uint64_t nseq = s_hi - s_lo;
+    plan_regions(h_seq_offs, h_query_offs + q0, nq, ix->k, qp.gr);
+    plan_units(qp.gr, QUERY_CHUNK, qp.qu);
+    // sequence -> group
+    std::vector<uint32_t> seq_group(nseq);
+    for (uint64_t q = q0; q < q1; q++)
+        for (uint64_t s = h_query_offs[q]; s < h_query_offs[q + 1]; s++) seq_group[s - s_lo] = (uint32_t)(q - q0);
+    const uint64_t nunits = qp.qu.group.size();
+    CID_TRY(ctx->scratch[0].ensure(qp.gr.total_slots * sizeof(Slot)));
+    CID_TRY(ctx->scratch[1].ensure(nq * 16 + 64));
+    CID_TRY(ctx->scratch[3].ensure(nseq * 4 + 64));
+    CID_TRY(ctx->scratch[6].ensure(nunits * 16 + 64));
+    uint64_t* d_off = ctx->scratch[1].as<uint64_t>();
+    uint64_t* d_mask = d_off + nq;
+    CID_CUDA(cudaMemcpyAsync(d_off, qp.gr.off.data(), nq * 8, cudaMemcpyHostToDevice, st));
+    CID_CUDA(cudaMemcpyAsync(d_mask, qp.gr.mask.data(), nq * 8, cudaMemcpyHostToDevice, st));
+    if (nseq) CID_CUDA(cudaMemcpyAsync(ctx->scratch[3].p, seq_group.data(), nseq * 4, cudaMemcpyHostToDevice, st));
+    qp.d_unit_slot0 = ctx->scratch[6].as<uint64_t>();
+    qp.d_unit_group = (uint32_t*)(qp.d_unit_slot0 + nunits);
+    qp.d_unit_nslots = qp.d_unit_group + nunits;
+    if (nunits) {
+        CID_CUDA(cudaMemcpyAsync(qp.d_unit_slot0, qp.qu.slot0.data(), nunits * 8, cudaMemcpyHostToDevice, st));
+        CID_CUDA(cudaMemcpyAsync(qp.d_unit_group, qp.qu.group.data(), nunits * 4, cudaMemcpyHostToDevice, st));
+        CID_CUDA(cudaMemcpyAsync(qp.d_unit_nslots, qp.qu.nslots.data(), nunits * 4, cudaMemcpyHostToDevice, st));
+    }
+    qp.d_table = ctx->scratch[0].as<Slot>();
+    CID_TRY(table_clear(ctx, st, qp.d_table, qp.gr.total_slots));
+    // the batch's sequences are [s_lo, s_hi): bases [h_seq_offs[s_lo], h_seq_offs[s_hi])
+    const uint64_t b_lo = h_seq_offs[s_lo], b_hi = h_seq_offs[s_hi];
+    // kmerize works on absolute base offsets: pass the offsets slice and the base range it covers
+    CID_TRY(launch_kmerize_insert(ctx, st, d_bases, d_seq_offs + s_lo, nseq, b_lo, b_hi,
+                                        ctx->scratch[3].as<uint32_t>(), d_off, d_mask, qp.d_table, ix->k, seq_mode));
+    // pageable host vectors above must stay alive until the copies complete
+    CID_CUDA(cudaStreamSynchronize(st));
+    return CID_OK;
+}
+
+// Splits [0,nq) into batches whose count tables fit `max_slots`.
+static std::vector<uint64_t> query_batches(const uint64_t* h_seq_offs, const uint64_t* h_query_offs, uint64_t nq,
+                                           uint32_t k, uint64_t max_slots) {
+    std::vector<uint64_t> cuts{0};
+    uint64_t acc = 0;
+    for (uint64_t q = 0; q < nq; q++) {
+        uint64_t nb = h_seq_offs[h_query_offs[q + 1]] - h_seq_offs[h_query_offs[q]];
+        uint64_t npos = nb >= k ? nb - k + 1 : 0;
+        uint64_t slots = next_pow2(std::max<uint64_t>(64, 2 * npos));
+        if (acc && acc + slots > max_slots) { cuts.push_back(q); acc = 0; }
+        acc += slots;
+    }
+    cuts.push_back(nq);
+    return cuts;
+}
+static const uint64_t kMaxBatchSlots = 1ull << 28;   // 4 GiB of count table per pass
+
+int cid_query_counts(cid_index* ix, const char* bases, const uint64_t* seq_offs, uint64_t nseq,
+                     const uint64_t* query_offs, uint64_t nq, int seq_mode, int gene_search, int64_t filter,
+                     uint32_t* counts, uint64_t* num_kmers, uint64_t* uniq_n, uint64_t* uniq_sum, uint64_t* uniq_mode,
+                     int64_t* cutoff_used) {
+    cid_ctx* ctx = ix->ctx;
+    cudaStream_t st = ctx->stream;
+    if (!seq_offs || !query_offs || !counts || !num_kmers) { set_error("cid_query_counts: null argument"); return CID_E_INVALID; }
+    if (seq_mode != CID_SEQ_FASTA && seq_mode != CID_SEQ_FASTQ) { set_error("bad seq_mode"); return CID_E_INVALID; }
+    CID_CUDA(cudaSetDevice(ctx->device));
+    const uint64_t nbases = seq_offs[nseq];
+    CID_TRY(ctx->scratch[4].ensure(nbases + 64));
+    CID_TRY(ctx->scratch[5].ensure((nseq + 1) * 8));
+    if (nbases) CID_CUDA(cudaMemcpyAsync(ctx->scratch[4].p, bases, nbases, cudaMemcpyHostToDevice, st));
+    CID_CUDA(cudaMemcpyAsync(ctx->scratch[5].p, seq_offs, (nseq + 1) * 8, cudaMemcpyHostToDevice, st));
+    const uint8_t* d_bases = ctx->scratch[4].as<uint8_t>();
+    const uint64_t* d_seq_offs = ctx->scratch[5].as<uint64_t>();
+    const bool want_uniq = uniq_n || uniq_sum || uniq_mode;
+    const uint32_t N = ix->N;
+    if (uniq_n) memset(uniq_n, 0, nq * N * 8);
+    if (uniq_sum) memset(uniq_sum, 0, nq * N * 8);
+    if (uniq_mode) memset(uniq_mode, 0, nq * N * 8);
+
+    std::vector<uint64_t> cuts = query_batches(seq_offs, query_offs, nq, ix->k, kMaxBatchSlots);
+    for (size_t b = 0; b + 1 < cuts.size(); b++) {
+        const uint64_t q0 = cuts[b], q1 = cuts[b + 1], bq = q1 - q0;
+        QueryPlan qp;
+        CID_TRY(query_front(ix, st, d_bases, d_seq_offs, seq_offs, query_offs, q0, q1, seq_mode, qp));
+        CID_TRY(check_err_flags(ctx, st));
+        // per-query filter (batch_search_pe.rs:34-39 / :112-120)
+        std::vector<int64_t> filt(bq);
+        for (uint64_t q = 0; q < bq; q++) {
+            if (seq_mode == CID_SEQ_FASTA && gene_search) filt[q] = 0;
+            else if (filter < 0) CID_TRY(region_auto_cutoff(ctx, st, qp.d_table + qp.gr.off[q], qp.gr.mask[q] + 1, &filt[q]));
+            else filt[q] = filter;
+            if (cutoff_used) cutoff_used[q0 + q] = filt[q];
+        }
+        const uint64_t npos_total = qp.gr.total_slots / 2;
+        const uint32_t uniq_cap = want_uniq ? (uint32_t)std::min<uint64_t>(npos_total + 1, 0xFFFFFFF0u / 3) : 0;
+        CID_TRY(ctx->scratch[7].ensure(bq * 8));
+        CID_TRY(ctx->scratch[10].ensure(bq * N * 4));
+        CID_TRY(ctx->scratch[11].ensure(bq * 8));
+        CID_TRY(ctx->scratch[12].ensure((size_t)uniq_cap * 12 + 16));
+        CID_TRY(ctx->scratch[13].ensure(16));
+        CID_CUDA(cudaMemcpyAsync(ctx->scratch[7].p, filt.data(), bq * 8, cudaMemcpyHostToDevice, st));
+        CID_CUDA(cudaMemsetAsync(ctx->scratch[10].p, 0, bq * N * 4, st));
+        CID_CUDA(cudaMemsetAsync(ctx->scratch[11].p, 0, bq * 8, st));
+        CID_CUDA(cudaMemsetAsync(ctx->scratch[13].p, 0, 16, st));
+        CID_TRY(launch_query_counts(ctx, st, ix, qp.d_table, qp.d_unit_group, qp.d_unit_slot0, qp.d_unit_nslots,
+                                    qp.qu.group.size(), ctx->scratch[7].as<int64_t>(), ctx->scratch[10].as<uint32_t>(),
+                                    ctx->scratch[11].as<unsigned long long>(), want_uniq, ctx->scratch[12].as<uint32_t>(),
+                                    uniq_cap, ctx->scratch[13].as<uint32_t>()));
+        CID_CUDA(cudaMemcpyAsync(counts + q0 * N, ctx->scratch[10].p, bq * N * 4, cudaMemcpyDeviceToHost, st));
+        CID_CUDA(cudaMemcpyAsync(num_kmers + q0, ctx->scratch[11].p, bq * 8, cudaMemcpyDeviceToHost, st));
+        uint32_t nu = 0;
+        CID_CUDA(cudaMemcpyAsync(&nu, ctx->scratch[13].p, 4, cudaMemcpyDeviceToHost, st));
+        CID_CUDA(cudaStreamSynchronize(st));
+        if (want_uniq) {
+            if (nu > uniq_cap) { set_error("unique-hit list overflow"); return CID_E_CAPACITY; }
+            std::vector<uint32_t> ul((size_t)nu * 3);
+            if (nu) CID_CUDA(cudaMemcpy(ul.data(), ctx->scratch[12].p, (size_t)nu * 12, cudaMemcpyDeviceToHost));
+            // reports.rs:20-26: mean = sum/len, modus = mode(values), specific = len.  Mode ties are
+            // broken towards the smallest value (the reference's tie-break is hash-order dependent).
+            std::map<std::pair<uint64_t, uint32_t>, std::map<uint32_t, uint64_t>> freq;
+            for (uint32_t i = 0; i < nu; i++) freq[{q0 + ul[3 * i], ul[3 * i + 1]}][ul[3 * i + 2]] += 1;
+            for (auto& kv : freq) {
+                uint64_t n = 0, s = 0, mode = 0, best = 0;
+                for (auto& fv : kv.second) { n += fv.second; s += (uint64_t)fv.first * fv.second; if (fv.second > best) { best = fv.second; mode = fv.first; } }
+                size_t at = kv.first.first * N + kv.first.second;
+                if (uniq_n) uniq_n[at] = n;
+                if (uniq_sum) uniq_sum[at] = s;
+                if (uniq_mode) uniq_mode[at] = mode;
+            }
+        }
+    }
+    return CID_OK;
+}
+
+int cid_query_counts_dev(cid_index* ix, const char* d_bases, const uint64_t* d_seq_offs, uint64_t nseq,
+                         uint64_t nbases, const uint64_t* d_query_offs, const uint64_t* h_query_offs,
+                         const uint64_t* h_seq_offs, uint64_t nq, int seq_mode, uint32_t* d_counts,
+                         uint64_t* d_num_kmers, void* stream) {
+    (void)nseq; (void)nbases; (void)d_query_offs;
+    cid_ctx* ctx = ix->ctx;
+    cudaStream_t st = (cudaStream_t)stream;
+    CID_CUDA(cudaSetDevice(ctx->device));
+    const uint32_t N = ix->N;
+    CID_CUDA(cudaMemsetAsync(d_counts, 0, nq * N * 4, st));
+    CID_CUDA(cudaMemsetAsync(d_num_kmers, 0, nq * 8, st));
+    std::vector<uint64_t> cuts = query_batches(h_seq_offs, h_query_offs, nq, ix->k, kMaxBatchSlots);
+    for (size_t b = 0; b + 1 < cuts.size(); b++) {
+        const uint64_t q0 = cuts[b], q1 = cuts[b + 1];
+        QueryPlan qp;
+        CID_TRY(query_front(ix, st, (const uint8_t*)d_bases, d_seq_offs, h_seq_offs, h_query_offs, q0, q1, seq_mode, qp));
+        CID_TRY(launch_query_counts(ctx, st, ix, qp.d_table, qp.d_unit_group, qp.d_unit_slot0, qp.d_unit_nslots,
+                                    qp.qu.group.size(), nullptr, d_counts + q0 * N,
+                                    (unsigned long long*)d_num_kmers + q0, false, nullptr, 0, nullptr));
+    }
+    return CID_OK;
+}
+
+int cid_query_perfect(cid_index* ix, const char* bases, const uint64_t* seq_offs, uint64_t nseq,
+                      const uint64_t* query_offs, uint64_t nq, uint32_t* and_rows, uint8_t* status, uint64_t* n_kmers) {
+    cid_ctx* ctx = ix->ctx;
+    cudaStream_t st = ctx->stream;
+    if (!seq_offs || !query_offs || !and_rows || !status || !n_kmers) { set_error("cid_query_perfect: null argument"); return CID_E_INVALID; }
+    CID_CUDA(cudaSetDevice(ctx->device));
+    const uint64_t nbases = seq_offs[nseq];
+    CID_TRY(ctx->scratch[4].ensure(nbases + 64));
+    CID_TRY(ctx->scratch[5].ensure((nseq + 1) * 8));
+    if (nbases) CID_CUDA(cudaMemcpyAsync(ctx->scratch[4].p, bases, nbases, cudaMemcpyHostToDevice, st));
+    CID_CUDA(cudaMemcpyAsync(ctx->scratch[5].p, seq_offs, (nseq + 1) * 8, cudaMemcpyHostToDevice, st));
+    const uint32_t W = ix->W;
+    std::vector<uint64_t> cuts = query_batches(seq_offs, query_offs, nq, ix->k, kMaxBatchSlots);
+    for (size_t b = 0; b + 1 < cuts.size(); b++) {
+        const uint64_t q0 = cuts[b], q1 = cuts[b + 1], bq = q1 - q0;
+        QueryPlan qp;
+        CID_TRY(query_front(ix, st, ctx->scratch[4].as<uint8_t>(), ctx->scratch[5].as<uint64_t>(), seq_offs, query_offs,
+                            q0, q1, CID_SEQ_FASTA, qp));
+        CID_TRY(check_err_flags(ctx, st));
+        CID_TRY(ctx->scratch[10].ensure(bq * W * 4));
+        CID_TRY(ctx->scratch[11].ensure(bq * 8));
+        CID_TRY(ctx->scratch[13].ensure(bq * 4));
+        CID_CUDA(cudaMemsetAsync(ctx->scratch[10].p, 0xFF, bq * W * 4, st));
+        CID_CUDA(cudaMemsetAsync(ctx->scratch[11].p, 0, bq * 8, st));
+        CID_CUDA(cudaMemsetAsync(ctx->scratch[13].p, 0, bq * 4, st));
+        CID_TRY(launch_query_perfect(ctx, st, ix, qp.d_table, qp.d_unit_group, qp.d_unit_slot0, qp.d_unit_nslots,
+                                     qp.qu.group.size(), ctx->scratch[10].as<uint32_t>(), ctx->scratch[13].as<uint32_t>(),
+                                     ctx->scratch[11].as<unsigned long long>()));
+        std::vector<uint32_t> missing(bq);
+        CID_CUDA(cudaMemcpyAsync(and_rows + q0 * W, ctx->scratch[10].p, bq * W * 4, cudaMemcpyDeviceToHost, st));
+        CID_CUDA(cudaMemcpyAsync(n_kmers + q0, ctx->scratch[11].p, bq * 8, cudaMemcpyDeviceToHost, st));
+        CID_CUDA(cudaMemcpyAsync(missing.data(), ctx->scratch[13].p, bq * 4, cudaMemcpyDeviceToHost, st));
+        CID_CUDA(cudaStreamSynchronize(st));
+        for (uint64_t q = 0; q < bq; q++) {
+            uint8_t s = n_kmers[q0 + q] == 0 ? 2 : (missing[q] ? 1 : 0);
+            status[q0 + q] = s;
+            if (s != 0) memset(and_rows + (q0 + q) * W, 0, (size_t)W * 4);
+        }
+    }
+    return CID_OK;
+}
+
+// ------------------------------------------------------------------ read_id
+static void default_params(cid_readid_params& p, const cid_readid_params* in, uint32_t N) {
+    if (in) p = *in;
+    else { p.downsample = 1; p.start_sample = 3; p.qual_offset = 0; p.group_width = 16; p.reserve_before_find = 1; p.rep_cap = 0; }
+    if (p.downsample == 0) p.downsample = 1;
+    if (p.group_width == 0) p.group_width = 16;
+    if (p.rep_cap == 0) p.rep_cap = N + 1;
+}
+
+int cid_read_id_batch_dev(cid_index* ix, const char* d_bases, const char* d_quals, const uint64_t* d_seq_offs,
+                          uint64_t nseq, uint64_t nbases, const uint64_t* d_read_offs, uint64_t nreads,
+                          uint32_t h_max_read_bases, uint32_t h_max_kmers, const cid_readid_params* p,
+                          uint32_t* d_n_set, uint32_t* d_flags, uint32_t* d_rep_n, uint32_t* d_rep_colour,
+                          uint32_t* d_rep_count, void* stream) {
+    CID_CUDA(cudaSetDevice(ix->ctx->device));
+    cid_readid_params pp;
+    default_params(pp, p, ix->N);
+    return readid_run(ix, (cudaStream_t)stream, (const uint8_t*)d_bases, (const uint8_t*)d_quals, d_seq_offs, nseq, nbases,
+                      d_read_offs, nreads, h_max_read_bases, h_max_kmers, pp, d_n_set, d_flags, d_rep_n, d_rep_colour,
+                      d_rep_count, 0, nullptr, nullptr, nullptr);
+}
+
+// host scan of the read geometry: longest read and most k-mer start positions
+static void read_geometry(const uint64_t* seq_offs, const uint64_t* read_offs, uint64_t nreads, uint32_t k, uint32_t d,
+                          uint32_t* max_bases, uint32_t* max_kmers) {
+    uint64_t mb = 0, mk = 0;
+    for (uint64_t r = 0; r < nreads; r++) {
+        uint64_t b = seq_offs[read_offs[r + 1]] - seq_offs[read_offs[r]], kk = 0;
+        for (uint64_t s = read_offs[r]; s < read_offs[r + 1]; s++) {
+            uint64_t l = seq_offs[s + 1] - seq_offs[s];
+            if (l >= k) kk += (l - k) / d + 1;
+        }
+        mb = std::max(mb, b); mk = std::max(mk, kk);
+    }
+    *max_bases = (uint32_t)std::min<uint64_t>(mb, 0xFFFFFFFFu);
+    *max_kmers = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(mk, 1), 0xFFFFFFFFu);
+}
+
+static int read_id_host(cid_index* ix, const char* bases, const char* quals, const uint64_t* seq_offs, uint64_t nseq,
+                        const uint64_t* read_offs, uint64_t nreads, const cid_readid_params* p, uint32_t* n_set,
+                        uint32_t* flags, uint32_t* rep_n, uint32_t* rep_colour, uint32_t* rep_count, uint32_t order_cap,
+                        uint32_t* order_n, uint8_t* order_seq, uint16_t* order_pos) {
+    cid_ctx* ctx = ix->ctx;
+    cudaStream_t st = ctx->stream;
+    if (!seq_offs || !read_offs) { set_error("read_id: null argument"); return CID_E_INVALID; }
+    CID_CUDA(cudaSetDevice(ctx->device));
+    cid_readid_params pp;
+    default_params(pp, p, ix->N);
+    if (nreads == 0) return CID_OK;
+    const uint64_t nbases = seq_offs[nseq];
+    uint32_t max_bases, max_kmers;
+    read_geometry(seq_offs, read_offs, nreads, ix->k, pp.downsample, &max_bases, &max_kmers);
+    const bool use_q = quals && pp.qual_offset;
+    CID_TRY(ctx->scratch[4].ensure(nbases + 64));
+    CID_TRY(ctx->scratch[5].ensure((nseq + 1) * 8));
+    CID_TRY(ctx->scratch[14].ensure((nreads + 1) * 8));
+    if (use_q) CID_TRY(ctx->scratch[15].ensure(nbases + 64));
+    if (nbases) CID_CUDA(cudaMemcpyAsync(ctx->scratch[4].p, bases, nbases, cudaMemcpyHostToDevice, st));
+    if (use_q && nbases) CID_CUDA(cudaMemcpyAsync(ctx->scratch[15].p, quals, nbases, cudaMemcpyHostToDevice, st));
+    CID_CUDA(cudaMemcpyAsync(ctx->scratch[5].p, seq_offs, (nseq + 1) * 8, cudaMemcpyHostToDevice, st));
+    CID_CUDA(cudaMemcpyAsync(ctx->scratch[14].p, read_offs, (nreads + 1) * 8, cudaMemcpyHostToDevice, st));
+    const bool want_rep = rep_n != nullptr;
+    CID_TRY(ctx->scratch[19].ensure(nreads * 4));
+    CID_TRY(ctx->scratch[20].ensure(nreads * 4));
+    uint32_t* d_n_set = ctx->scratch[19].as<uint32_t>();
+    uint32_t* d_flags = ctx->scratch[20].as<uint32_t>();
+    uint32_t *d_rep_n = nullptr, *d_rc = nullptr, *d_rv = nullptr;
+    if (want_rep) {
+        CID_TRY(ctx->scratch[21].ensure(nreads * 4));
+        CID_TRY(ctx->scratch[22].ensure(nreads * (size_t)pp.rep_cap * 8));
+        d_rep_n = ctx->scratch[21].as<uint32_t>();
+        d_rc = ctx->scratch[22].as<uint32_t>();
+        d_rv = d_rc + nreads * (size_t)pp.rep_cap;
+    }
+    uint32_t* d_on = nullptr; uint8_t* d_os = nullptr; uint16_t* d_op = nullptr;
+    if (order_n) {
+        CID_TRY(ctx->scratch[23].ensure(nreads * 4 + nreads * (size_t)order_cap * 3 + 64));
+        d_on = ctx->scratch[23].as<uint32_t>();
+        d_op = (uint16_t*)(d_on + nreads);
+        d_os = (uint8_t*)(d_op + nreads * (size_t)order_cap);
+    }
+    CID_TRY(readid_run(ix, st, ctx->scratch[4].as<uint8_t>(), use_q ? ctx->scratch[15].as<uint8_t>() : nullptr,
+                       ctx->scratch[5].as<uint64_t>(), nseq, nbases, ctx->scratch[14].as<uint64_t>(), nreads, max_bases,
+                       max_kmers, pp, d_n_set, d_flags, d_rep_n, d_rc, d_rv, order_cap, d_on, d_os, d_op));
+    if (n_set) CID_CUDA(cudaMemcpyAsync(n_set, d_n_set, nreads * 4, cudaMemcpyDeviceToHost, st));
+    if (flags) CID_CUDA(cudaMemcpyAsync(flags, d_flags, nreads * 4, cudaMemcpyDeviceToHost, st));
+    if (want_rep) {
+        CID_CUDA(cudaMemcpyAsync(rep_n, d_rep_n, nreads * 4, cudaMemcpyDeviceToHost, st));
+        CID_CUDA(cudaMemcpyAsync(rep_colour, d_rc, nreads * (size_t)pp.rep_cap * 4, cudaMemcpyDeviceToHost, st));
+        CID_CUDA(cudaMemcpyAsync(rep_count, d_rv, nreads * (size_t)pp.rep_cap * 4, cudaMemcpyDeviceToHost, st));
+    }
+    if (order_n) {
+        CID_CUDA(cudaMemcpyAsync(order_n, d_on, nreads * 4, cudaMemcpyDeviceToHost, st));
+        CID_CUDA(cudaMemcpyAsync(order_pos, d_op, nreads * (size_t)order_cap * 2, cudaMemcpyDeviceToHost, st));
+        CID_CUDA(cudaMemcpyAsync(order_seq, d_os, nreads * (size_t)order_cap, cudaMemcpyDeviceToHost, st));
+    }
+    return check_err_flags(ctx, st);
+}
+
+int cid_read_id_batch(cid_index* ix, const char* bases, const char* quals, const uint64_t* seq_offs, uint64_t nseq,
+                      const uint64_t* read_offs, uint64_t nreads, const cid_readid_params* p, uint32_t* n_set,
+                      uint32_t* flags, uint32_t* rep_n, uint32_t* rep_colour, uint32_t* rep_count) {
+    if (!rep_n || !rep_colour || !rep_count) { set_error("read_id: null report buffers"); return CID_E_INVALID; }
+    return read_id_host(ix, bases, quals, seq_offs, nseq, read_offs, nreads, p, n_set, flags, rep_n, rep_colour, rep_count,
+                        0, nullptr, nullptr, nullptr);
+}
+
+int cid_read_kmer_order(cid_index* ix, const char* bases, const uint64_t* seq_offs, uint64_t nseq,
+                        const uint64_t* read_offs, uint64_t nreads, const cid_readid_params* p, uint32_t order_cap,
+                        uint32_t* order_n, uint8_t* order_seq, uint16_t* order_pos) {
+    if (!order_n || !order_seq || !order_pos || order_cap == 0) { set_error("read_kmer_order: null argument"); return CID_E_INVALID; }
+    return read_id_host(ix, bases, nullptr, seq_offs, nseq, read_offs, nreads, p, nullptr, nullptr, nullptr, nullptr, nullptr,
+                        order_cap, order_n, order_seq, order_pos);
+}
+
+int cid_hash_kmers(cid_index* ix, const char* kmers, uint64_t n, uint64_t* row_ids) {
+    cid_ctx* ctx = ix->ctx;
+    cudaStream_t st = ctx->stream;
+    CID_CUDA(cudaSetDevice(ctx->device));
+    if (n == 0) return CID_OK;
+    CID_TRY(ctx->scratch[4].ensure(n * ix->k + 64));
+    CID_TRY(ctx->scratch[10].ensure(n * ix->H * 8));
+    CID_CUDA(cudaMemcpyAsync(ctx->scratch[4].p, kmers, n * ix->k, cudaMemcpyHostToDevice, st));
+    CID_TRY(launch_hash_kmers(ctx, st, ix, ctx->scratch[4].as<uint8_t>(), n, ctx->scratch[10].as<uint64_t>()));
+    CID_CUDA(cudaMemcpyAsync(row_ids, ctx->scratch[10].p, n * ix->H * 8, cudaMemcpyDeviceToHost, st));
+    CID_CUDA(cudaStreamSynchronize(st));
+    return CID_OK;
+}
+
+}  // extern "C"

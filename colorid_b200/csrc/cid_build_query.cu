@@ -1,0 +1,551 @@
+// CUDA kernels (sm_100a) for the build and search halves of the BIGSI hot path.
+//
+//   kmerize_insert   kmer.rs:87-125 / 461-510 / 581-655  canonical k-mer count map (device hash table)
+//   region_histogram kmer.rs:866-884                     count histogram feeding auto_cutoff
+//   region_to_bloom  build.rs:62-67 + simple_bloom.rs:19-26  clean_map + Bloom insert (atomicOr)
+//   transpose_bitsets build.rs:116-128                   per-colour bitsets -> row-major signature matrix
+//   query_counts     batch_search_pe.rs:45-84            row gather, AND, per-accession hit counts
+//   query_perfect    perfect_search.rs:26-46             AND of all rows of all k-mers
+//
+// All of these are HBM/L2-bound integer work; no tensor cores are involved.
+#include <algorithm>
+#include <cstring>
+
+#include "cid_device.cuh"
+#include "cid_internal.h"
+
+namespace cid {
+
+// ================================================================= kmerize_insert
+// One CTA = one tile of KT consecutive k-mer start positions of the concatenated batch (plus a
+// k-1 halo), so reads (150 bp) and contigs (Mbp) are handled by the same code.
+constexpr int KT = 1024;              // start positions per tile
+constexpr int KT_CAP = KT + 64;       // bytes staged per tile (halo <= 31, rounded to 32)
+constexpr int KT_THREADS = 256;
+constexpr int KT_MAXSTARTS = KT_CAP + 8;
+
+__global__ void __launch_bounds__(KT_THREADS)
+kmerize_insert_kernel(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ seq_offs, uint64_t nseq,
+                      uint64_t base_lo, uint64_t nbases, const uint32_t* __restrict__ seq_group, const uint64_t* __restrict__ region_off,
+                      const uint64_t* __restrict__ region_mask, Slot* __restrict__ table, uint32_t k, int seq_mode,
+                      uint32_t* __restrict__ err) {
+    __shared__ __align__(16) uint8_t smem[tile_smem_bytes(KT_CAP)];
+    __shared__ uint32_t s_starts[KT_MAXSTARTS];
+    __shared__ uint64_t s_s0;
+    __shared__ uint32_t s_nstarts;
+
+    const int tid = threadIdx.x;
+    const uint64_t tile_start = base_lo + (uint64_t)blockIdx.x * KT;   // [base_lo, nbases) is the slice of `bases` covered by seq_offs[0..nseq]
+    if (tile_start >= nbases) return;
+    const int tile_len = (int)min((uint64_t)(KT + k - 1), nbases - tile_start);
+
+    Tile t = tile_carve(smem, KT_CAP);
+    t.len = tile_len;
+    for (int i = tid; i < KT_CAP / 32 + 2; i += KT_THREADS) t.start[i] = 0;
+    // stage raw bytes
+    const uint8_t* src = bases + tile_start;
+    if ((((uintptr_t)src) & 3) == 0) {
+        const uint32_t* s4 = (const uint32_t*)src;
+        uint32_t* d4 = (uint32_t*)t.ascii;
+        int n4 = tile_len >> 2;
+        for (int i = tid; i < n4; i += KT_THREADS) d4[i] = __ldg(s4 + i);
+        for (int i = (n4 << 2) + tid; i < tile_len; i += KT_THREADS) t.ascii[i] = __ldg(src + i);
+    } else {
+        for (int i = tid; i < tile_len; i += KT_THREADS) t.ascii[i] = __ldg(src + i);
+    }
+    // sequence owning the first base: largest s with seq_offs[s] <= tile_start
+    if (tid == 0) {
+        uint64_t lo = 0, hi = nseq;   // invariant: seq_offs[lo] <= tile_start < seq_offs[hi]
+        while (hi - lo > 1) {
+            uint64_t mid = (lo + hi) >> 1;
+            if (__ldg(seq_offs + mid) <= tile_start) lo = mid; else hi = mid;
+        }
+        s_s0 = lo;
+        s_nstarts = 0;
+    }
+    __syncthreads();
+    const uint64_t s0 = s_s0;
+    // sequence starts strictly inside the tile, in order (list index j <-> sequence s0+1+j)
+    for (uint64_t base = 0;; base += KT_THREADS) {
+        uint64_t s = s0 + 1 + base + tid;
+        bool in = false;
+        if (s < nseq) {
+            uint64_t o = __ldg(seq_offs + s);
+            if (o < tile_start + (uint64_t)tile_len) {
+                in = true;
+                uint32_t rel = (uint32_t)(o - tile_start);
+                if (base + tid < KT_MAXSTARTS) s_starts[base + tid] = rel; else atomicOr(err, ERRF_STARTS_OVERFLOW);
+                atomicOr(&t.start[rel >> 5], 1u << (rel & 31));
+                atomicAdd(&s_nstarts, 1u);
+            }
+        }
+        if (!__syncthreads_or(in)) break;
+    }
+    tile_pack(t, KT_CAP, tid, KT_THREADS);
+    __syncthreads();
+    const uint32_t nstarts = min(s_nstarts, (uint32_t)KT_MAXSTARTS);
+
+    for (int p = tid; p < KT; p += KT_THREADS) {
+        uint64_t key; bool fwd, low;
+        if (!tile_kmer(t, p, k, key, fwd, low)) continue;
+        if (low && seq_mode != CID_SEQ_FASTA) { atomicOr(err, ERRF_LOWER_RAW); continue; }
+        // owner sequence = s0 + #starts <= p
+        uint32_t lo = 0, hi = nstarts;
+        while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (s_starts[mid] <= (uint32_t)p) lo = mid + 1; else hi = mid; }
+        uint64_t owner = s0 + lo;
+        uint32_t g = seq_group ? __ldg(seq_group + owner) : 0u;
+        table_insert(table + __ldg(region_off + g), __ldg(region_mask + g), key);
+    }
+}
+
+int launch_kmerize_insert(cid_ctx* ctx, cudaStream_t st, const uint8_t* d_bases, const uint64_t* d_seq_offs,
+                          uint64_t nseq, uint64_t base_lo, uint64_t base_hi, const uint32_t* d_seq_group,
+                          const uint64_t* d_region_off, const uint64_t* d_region_mask, void* d_table, uint32_t k,
+                          int seq_mode) {
+    if (base_hi <= base_lo || nseq == 0) return CID_OK;
+    uint64_t ntiles = (base_hi - base_lo + KT - 1) / KT;
+    kmerize_insert_kernel<<<(unsigned)ntiles, KT_THREADS, 0, st>>>(d_bases, d_seq_offs, nseq, base_lo, base_hi, d_seq_group,
+                                                                  d_region_off, d_region_mask, (Slot*)d_table, k,
+                                                                  seq_mode, ctx->d_err);
+    ctx->launches++;
+    CID_CUDA(cudaGetLastError());
+    return CID_OK;
+}
+
+void plan_regions(const uint64_t* h_seq_offs, const uint64_t* h_group_offs, uint64_t ngroups, uint32_t k,
+                  GroupRegions& gr) {
+    gr.ngroups = ngroups;
+    gr.off.resize(ngroups);
+    gr.mask.resize(ngroups);
+    uint64_t total = 0;
+    for (uint64_t g = 0; g < ngroups; g++) {
+        uint64_t nb = h_seq_offs[h_group_offs[g + 1]] - h_seq_offs[h_group_offs[g]];
+        uint64_t npos = nb >= k ? nb - k + 1 : 0;          // upper bound on k-mer occurrences
+        uint64_t slots = next_pow2(std::max<uint64_t>(64, 2 * npos));
+        gr.off[g] = total;
+        gr.mask[g] = slots - 1;
+        total += slots;
+    }
+    gr.total_slots = total;
+}
+
+// ================================================================= region_histogram
+constexpr int HIST_SMEM_BINS = 1024;
+__global__ void __launch_bounds__(256)
+region_histogram_kernel(const Slot* __restrict__ region, uint64_t nslots, uint32_t* __restrict__ hist,
+                        uint32_t hist_bins, uint32_t* __restrict__ overflow, uint32_t overflow_cap,
+                        uint32_t* __restrict__ overflow_n) {
+    __shared__ uint32_t sh[HIST_SMEM_BINS];
+    for (int i = threadIdx.x; i < HIST_SMEM_BINS; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nslots; s += (uint64_t)gridDim.x * blockDim.x) {
+        Slot v = region[s];
+        if (v.key == CID_EMPTY_KEY) continue;
+        uint32_t c = v.count;
+        if (c < HIST_SMEM_BINS) atomicAdd(&sh[c], 1u);
+        else if (c < hist_bins) atomicAdd(&hist[c], 1u);
+        else {
+            uint32_t i = atomicAdd(overflow_n, 1u);
+            if (i < overflow_cap) overflow[i] = c;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < HIST_SMEM_BINS; i += blockDim.x) if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+int launch_region_histogram(cid_ctx* ctx, cudaStream_t st, const void* d_region, uint64_t nslots, uint32_t* d_hist,
+                            uint32_t hist_bins, uint32_t* d_overflow, uint32_t overflow_cap, uint32_t* d_overflow_n) {
+    unsigned grid = (unsigned)std::min<uint64_t>((nslots + 255) / 256, (uint64_t)ctx->sm_count * 16);
+    if (grid == 0) grid = 1;
+    region_histogram_kernel<<<grid, 256, 0, st>>>((const Slot*)d_region, nslots, d_hist, hist_bins, d_overflow,
+                                                  overflow_cap, d_overflow_n);
+    ctx->launches++;
+    CID_CUDA(cudaGetLastError());
+    return CID_OK;
+}
+
+// ================================================================= region_to_bloom
+// clean_map (count > cutoff, kmer.rs:826-837), n_ref_kmers (build.rs:62), BloomFilter::insert.
+__global__ void __launch_bounds__(256)
+region_to_bloom_kernel(const Slot* __restrict__ region, uint64_t nslots, long long cutoff, uint32_t k, uint32_t H,
+                       ModS mods, uint32_t* __restrict__ bitset, unsigned long long* __restrict__ nref) {
+    __shared__ uint32_t lut[256];
+    lut4_init(lut, threadIdx.x, blockDim.x);
+    __syncthreads();
+    uint32_t mine = 0;
+    for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nslots; s += (uint64_t)gridDim.x * blockDim.x) {
+        Slot v = region[s];
+        if (v.key == CID_EMPTY_KEY || (long long)v.count <= cutoff) continue;
+        mine++;
+        HashIn in = hashin_from_key(lut, v.key, k);
+        for (uint32_t i = 0; i < H; i++) {
+            uint64_t bit = mod_s(xxh3_kmer(in, k, i), mods);
+            atomicOr(&bitset[bit >> 5], 1u << (bit & 31));
+        }
+    }
+    // block reduction of the survivor count
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(nref, (unsigned long long)mine);
+}
+int launch_region_to_bloom(cid_ctx* ctx, cudaStream_t st, const void* d_region, uint64_t nslots, int64_t cutoff,
+                           uint32_t k, uint32_t H, uint64_t S, uint32_t* d_bitset, unsigned long long* d_nref) {
+    unsigned grid = (unsigned)std::min<uint64_t>((nslots + 255) / 256, (uint64_t)ctx->sm_count * 16);
+    if (grid == 0) grid = 1;
+    region_to_bloom_kernel<<<grid, 256, 0, st>>>((const Slot*)d_region, nslots, (long long)cutoff, k, H, make_mods(S),
+                                                 d_bitset, d_nref);
+    ctx->launches++;
+    CID_CUDA(cudaGetLastError());
+    return CID_OK;
+}
+
+// ================================================================= transpose_bitsets
+// bitsets[colour][word j] (bit r of word j = Bloom bit 32j+r) -> rows[32j+r][colour/32] bit colour%32.
+// One CTA: 1024 rows x up to 8 word-columns (256 colours): each warp reads 128 B of one colour's
+// bitset (coalesced), 32x32 bit blocks are transposed with ballots, and every row receives up to
+// 32 contiguous bytes.
+constexpr int TR_ROWS = 1024;
+constexpr int TR_WCOLS = 8;
+__global__ void __launch_bounds__(256)
+transpose_bitsets_kernel(const uint32_t* __restrict__ bitsets, uint64_t bs_words, uint32_t N, uint64_t S,
+                         uint32_t* __restrict__ rows, uint32_t Wp, uint32_t W) {
+    __shared__ uint32_t sm[TR_WCOLS][32][33];   // [wcol][colour in group][word in tile]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t word0 = (uint64_t)blockIdx.x * (TR_ROWS / 32);       // first bitset word of this row tile
+    const uint32_t wc0 = blockIdx.y * TR_WCOLS;
+    const uint32_t nwc = min((uint32_t)TR_WCOLS, W - wc0);
+    // load: (wcol, colour) pairs strided over warps
+    for (uint32_t pair = warp; pair < nwc * 32; pair += 8) {
+        uint32_t wc = pair >> 5, c = pair & 31;
+        uint32_t colour = (wc0 + wc) * 32 + c;
+        uint32_t v = 0;
+        if (colour < N && word0 + lane < bs_words) v = __ldg(bitsets + (uint64_t)colour * bs_words + word0 + lane);
+        sm[wc][c][lane] = v;
+    }
+    __syncthreads();
+    // transpose: warp handles (wcol, word j) blocks; lane = colour
+    for (uint32_t blk = warp; blk < nwc * 32; blk += 8) {
+        uint32_t wc = blk >> 5, j = blk & 31;
+        uint32_t x = sm[wc][lane][j];
+        uint32_t mine = 0;
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+            uint32_t b = __ballot_sync(0xffffffffu, (x >> r) & 1u);
+            if (lane == r) mine = b;
+        }
+        uint64_t row = (word0 + j) * 32 + lane;
+        if (row < S) rows[row * Wp + wc0 + wc] = mine;
+    }
+}
+int launch_transpose(cid_ctx* ctx, cudaStream_t st, const cid_index* idx) {
+    dim3 grid((unsigned)((idx->S + TR_ROWS - 1) / TR_ROWS), (idx->W + TR_WCOLS - 1) / TR_WCOLS);
+    transpose_bitsets_kernel<<<grid, 256, 0, st>>>(idx->bitsets, idx->bs_words, idx->N, idx->S, idx->rows, idx->Wp,
+                                                   idx->W);
+    ctx->launches++;
+    CID_CUDA(cudaGetLastError());
+    return CID_OK;
+}
+
+// ================================================================= rownz bitmap
+__global__ void __launch_bounds__(256)
+rownz_kernel(const uint32_t* __restrict__ rows, uint64_t S, uint32_t Wp, uint32_t* __restrict__ rownz) {
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t any = 0;
+    if (r < S) {
+        const uint32_t* p = rows + r * Wp;
+        for (uint32_t w = 0; w < Wp; w++) any |= __ldg(p + w);
+    }
+    uint32_t b = __ballot_sync(0xffffffffu, any != 0);
+    if ((threadIdx.x & 31) == 0 && (r >> 5) < (S + 31) / 32) rownz[r >> 5] = b;
+}
+int launch_rownz(cid_ctx* ctx, cudaStream_t st, const cid_index* idx) {
+    uint64_t nthreads = (idx->S + 31) / 32 * 32;
+    rownz_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(idx->rows, idx->S, idx->Wp, idx->rownz);
+    ctx->launches++;
+    CID_CUDA(cudaGetLastError());
+    return CID_OK;
+}
+
+// ================================================================= query work list
+void plan_units(const GroupRegions& gr, uint32_t chunk, QueryUnits& qu) {
+    qu.group.clear(); qu.slot0.clear(); qu.nslots.clear();
+    for (uint64_t g = 0; g < gr.ngroups; g++) {
+        uint64_t slots = gr.mask[g] + 1;
+        for (uint64_t s = 0; s < slots; s += chunk) {
+            qu.group.push_back((uint32_t)g);
+            qu.slot0.push_back(gr.off[g] + s);
+            qu.nslots.push_back((uint32_t)std::min<uint64_t>(chunk, slots - s));
+        }
+    }
+}
+
+// Shared front half of the gather kernels: compact the surviving (key,count) of a slot chunk into
+// shared memory, then hash every survivor to its H row indices.
+struct UnitSmem {
+    uint32_t* lut;        // [256]
+    uint64_t* keys;       // [QUERY_CHUNK]
+    uint32_t* mult;       // [QUERY_CHUNK]
+    uint32_t* rowid;      // [QUERY_CHUNK * H]
+    uint32_t* cnt;        // [32 * 32] per-colour counters of one column block
+    uint32_t* n;          // [4] list length, missing flag
+};
+__host__ __device__ inline size_t unit_smem_bytes(uint32_t H) {
+    return 256 * 4 + (size_t)QUERY_CHUNK * 8 + (size_t)QUERY_CHUNK * 4 + (size_t)QUERY_CHUNK * H * 4 + 1024 * 4 + 16;
+}
+__device__ __forceinline__ UnitSmem unit_carve(uint8_t* base, uint32_t H) {
+    UnitSmem u;
+    u.keys = (uint64_t*)base;
+    u.mult = (uint32_t*)(u.keys + QUERY_CHUNK);
+    u.rowid = u.mult + QUERY_CHUNK;
+    u.cnt = u.rowid + (size_t)QUERY_CHUNK * H;
+    u.lut = u.cnt + 1024;
+    u.n = u.lut + 256;
+    return u;
+}
+__device__ __forceinline__ uint32_t unit_collect_and_hash(const UnitSmem& u, const Slot* __restrict__ table,
+                                                          uint64_t slot0, uint32_t nslots, long long filter, uint32_t k,
+                                                          uint32_t H, const ModS& mods) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    lut4_init(u.lut, tid, nt);
+    if (tid == 0) { u.n[0] = 0; u.n[1] = 0; }
+    __syncthreads();
+    for (uint32_t s = tid; s < nslots; s += nt) {
+        Slot v = table[slot0 + s];
+        if (v.key != CID_EMPTY_KEY && (long long)v.count > filter) {
+            uint32_t i = atomicAdd(&u.n[0], 1u);
+            u.keys[i] = v.key;
+            u.mult[i] = v.count;
+        }
+    }
+    __syncthreads();
+    const uint32_t n = u.n[0];
+    for (uint32_t i = tid; i < n; i += nt) {
+        HashIn in = hashin_from_key(u.lut, u.keys[i], k);
+        for (uint32_t h = 0; h < H; h++) u.rowid[i * H + h] = (uint32_t)mod_s(xxh3_kmer(in, k, h), mods);
+    }
+    __syncthreads();
+    return n;
+}
+
+// ================================================================= query_counts  (the row-gather kernel)
+// For every surviving k-mer: AND of its H rows, +1 for every set accession (batch_search_pe.rs:60-74).
+// A lane owns one 32-accession word column; hits are accumulated in bit-sliced (carry-save)
+// counters so the per-k-mer cost is a handful of logic ops instead of one atomic per set bit.
+constexpr int QC_PLANES = 11;   // a lane sees at most QUERY_CHUNK (=1024) k-mers per unit
+
+template <bool UNIQ>
+__global__ void __launch_bounds__(256)
+query_counts_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t W, uint32_t N, uint32_t k, uint32_t H,
+                    ModS mods, const Slot* __restrict__ table, const uint32_t* __restrict__ unit_group,
+                    const uint64_t* __restrict__ unit_slot0, const uint32_t* __restrict__ unit_nslots,
+                    const long long* __restrict__ filter, uint32_t* __restrict__ counts,
+                    unsigned long long* __restrict__ num_kmers, uint32_t* __restrict__ uniq_list, uint32_t uniq_cap,
+                    uint32_t* __restrict__ uniq_n) {
+    extern __shared__ __align__(16) uint8_t dsm[];
+    UnitSmem u = unit_carve(dsm, H);
+    const uint32_t g = unit_group[blockIdx.x];
+    const uint32_t n = unit_collect_and_hash(u, table, unit_slot0[blockIdx.x], unit_nslots[blockIdx.x],
+                                             filter ? filter[g] : 0ll, k, H, mods);
+    if (n == 0) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) atomicAdd(&num_kmers[g], (unsigned long long)n);
+
+    const uint32_t lpk = Wp >= 32 ? 32 : Wp;          // lanes per k-mer (Wp is 1,2,4,..: power of two below 32)
+    const uint32_t kpw = 32 / lpk;                    // k-mers per warp pass
+    const uint32_t sub = lane / lpk, colw = lane % lpk;
+    const uint32_t ncb = (Wp + 31) / 32;              // 32-word column blocks
+    for (uint32_t cb = 0; cb < ncb; cb++) {
+        for (int i = tid; i < 1024; i += 256) u.cnt[i] = 0;
+        __syncthreads();
+        const uint32_t col = cb * 32 + colw;
+        const bool colok = col < Wp;
+        uint32_t pl[QC_PLANES];
+#pragma unroll
+        for (int p = 0; p < QC_PLANES; p++) pl[p] = 0;
+        for (uint32_t i0 = warp * kpw; i0 < n; i0 += 8 * kpw) {
+            uint32_t i = i0 + sub;
+            uint32_t x = 0;
+            if (i < n && colok) {
+                x = 0xFFFFFFFFu;
+                for (uint32_t h = 0; h < H; h++) x &= __ldg(rows + (uint64_t)u.rowid[i * H + h] * Wp + col);
+            }
+            if (UNIQ) {
+                // exactly one accession hit over the whole row (batch_search_pe.rs:75-82)
+                uint32_t pc = __popc(x);
+                for (uint32_t o = lpk >> 1; o > 0; o >>= 1) pc += __shfl_xor_sync(0xffffffffu, pc, o);
+                if (ncb == 1 && pc == 1 && x != 0) {
+                    uint32_t e = atomicAdd(uniq_n, 1u);
+                    if (e < uniq_cap) {
+                        uniq_list[3 * (uint64_t)e] = g;
+                        uniq_list[3 * (uint64_t)e + 1] = col * 32 + (__ffs(x) - 1);
+                        uniq_list[3 * (uint64_t)e + 2] = u.mult[i];
+                    }
+                }
+            }
+            // carry-save add of x into the bit planes
+            uint32_t carry = x;
+#pragma unroll
+            for (int p = 0; p < QC_PLANES; p++) {
+                uint32_t t2 = pl[p] & carry;
+                pl[p] ^= carry;
+                carry = t2;
+                if (carry == 0) break;
+            }
+        }
+        // flush planes -> shared counters (lanes with the same column in different sub-groups/warps collide)
+        if (colok) {
+#pragma unroll 4
+            for (int b = 0; b < 32; b++) {
+                uint32_t v = 0;
+#pragma unroll
+                for (int p = 0; p < QC_PLANES; p++) v |= ((pl[p] >> b) & 1u) << p;
+                if (v) atomicAdd(&u.cnt[colw * 32 + b], v);
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < 1024; i += 256) {
+            uint32_t c = cb * 1024 + i;
+            uint32_t v = u.cnt[i];
+            if (v && c < N) atomicAdd(&counts[(uint64_t)g * N + c], v);
+        }
+        __syncthreads();
+    }
+}
+
+// Wide-row unique-hit pass (Wp > 32): one warp per k-mer sums popcounts over the whole row.
+__global__ void __launch_bounds__(256)
+query_uniq_wide_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t k, uint32_t H, ModS mods,
+                       const Slot* __restrict__ table, const uint32_t* __restrict__ unit_group,
+                       const uint64_t* __restrict__ unit_slot0, const uint32_t* __restrict__ unit_nslots,
+                       const long long* __restrict__ filter, uint32_t* __restrict__ uniq_list, uint32_t uniq_cap,
+                       uint32_t* __restrict__ uniq_n) {
+    extern __shared__ __align__(16) uint8_t dsm[];
+    UnitSmem u = unit_carve(dsm, H);
+    const uint32_t g = unit_group[blockIdx.x];
+    const uint32_t n = unit_collect_and_hash(u, table, unit_slot0[blockIdx.x], unit_nslots[blockIdx.x],
+                                             filter ? filter[g] : 0ll, k, H, mods);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (uint32_t i = warp; i < n; i += 8) {
+        uint32_t pc = 0, where = 0;
+        for (uint32_t col = lane; col < Wp; col += 32) {
+            uint32_t x = 0xFFFFFFFFu;
+            for (uint32_t h = 0; h < H; h++) x &= __ldg(rows + (uint64_t)u.rowid[i * H + h] * Wp + col);
+            if (x) { pc += __popc(x); where = col * 32 + (__ffs(x) - 1); }
+        }
+        uint32_t tot = pc;
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        if (tot == 1 && pc == 1) {
+            uint32_t e = atomicAdd(uniq_n, 1u);
+            if (e < uniq_cap) {
+                uniq_list[3 * (uint64_t)e] = g;
+                uniq_list[3 * (uint64_t)e + 1] = where;
+                uniq_list[3 * (uint64_t)e + 2] = u.mult[i];
+            }
+        }
+    }
+}
+
+int launch_query_counts(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, const void* d_table,
+                        const uint32_t* d_unit_group, const uint64_t* d_unit_slot0, const uint32_t* d_unit_nslots,
+                        uint64_t nunits, const int64_t* d_filter, uint32_t* d_counts, unsigned long long* d_num_kmers,
+                        bool want_uniq, uint32_t* d_uniq_list, uint32_t uniq_cap, uint32_t* d_uniq_n) {
+    if (nunits == 0) return CID_OK;
+    size_t smem = unit_smem_bytes(idx->H);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CID_CUDA(cudaFuncSetAttribute(query_counts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CID_CUDA(cudaFuncSetAttribute(query_counts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CID_CUDA(cudaFuncSetAttribute(query_uniq_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr_set = true;
+    }
+    ModS mods = make_mods(idx->S);
+    const bool inline_uniq = want_uniq && idx->Wp <= 32;
+    if (inline_uniq)
+        query_counts_kernel<true><<<(unsigned)nunits, 256, smem, st>>>(
+            idx->rows, idx->Wp, idx->W, idx->N, idx->k, idx->H, mods, (const Slot*)d_table, d_unit_group, d_unit_slot0,
+            d_unit_nslots, (const long long*)d_filter, d_counts, d_num_kmers, d_uniq_list, uniq_cap, d_uniq_n);
+    else
+        query_counts_kernel<false><<<(unsigned)nunits, 256, smem, st>>>(
+            idx->rows, idx->Wp, idx->W, idx->N, idx->k, idx->H, mods, (const Slot*)d_table, d_unit_group, d_unit_slot0,
+            d_unit_nslots, (const long long*)d_filter, d_counts, d_num_kmers, d_uniq_list, uniq_cap, d_uniq_n);
+    ctx->launches++;
+    CID_CUDA(cudaGetLastError());
+    if (want_uniq && !inline_uniq) {
+        query_uniq_wide_kernel<<<(unsigned)nunits, 256, smem, st>>>(
+            idx->rows, idx->Wp, idx->k, idx->H, mods, (const Slot*)d_table, d_unit_group, d_unit_slot0, d_unit_nslots,
+            (const long long*)d_filter, d_uniq_list, uniq_cap, d_uniq_n);
+        ctx->launches++;
+        CID_CUDA(cudaGetLastError());
+    }
+    return CID_OK;
+}
+
+// ================================================================= query_perfect
+__global__ void __launch_bounds__(256)
+query_perfect_kernel(const uint32_t* __restrict__ rows, const uint32_t* __restrict__ rownz, uint32_t Wp, uint32_t W,
+                     uint32_t k, uint32_t H, ModS mods, const Slot* __restrict__ table,
+                     const uint32_t* __restrict__ unit_group, const uint64_t* __restrict__ unit_slot0,
+                     const uint32_t* __restrict__ unit_nslots, uint32_t* __restrict__ and_rows,
+                     uint32_t* __restrict__ missing, unsigned long long* __restrict__ num_kmers) {
+    extern __shared__ __align__(16) uint8_t dsm[];
+    UnitSmem u = unit_carve(dsm, H);
+    const uint32_t g = unit_group[blockIdx.x];
+    const uint32_t n = unit_collect_and_hash(u, table, unit_slot0[blockIdx.x], unit_nslots[blockIdx.x], 0ll, k, H, mods);
+    if (n == 0) return;
+    const int tid = threadIdx.x;
+    if (tid == 0) atomicAdd(&num_kmers[g], (unsigned long long)n);
+    // any absent row -> "No perfect hits!" (perfect_search.rs:32-33,38-39)
+    bool miss = false;
+    for (uint32_t i = tid; i < n * H; i += 256) {
+        uint32_t r = u.rowid[i];
+        if (!((__ldg(rownz + (r >> 5)) >> (r & 31)) & 1u)) miss = true;
+    }
+    if (miss) atomicOr(&missing[g], 1u);
+    // AND of every row, column by column: thread owns (column, k-mer residue)
+    for (uint32_t col = tid % 32; col < W; col += 32) {
+        uint32_t acc = 0xFFFFFFFFu;
+        for (uint32_t i = tid / 32; i < n; i += 8)
+            for (uint32_t h = 0; h < H; h++) acc &= __ldg(rows + (uint64_t)u.rowid[i * H + h] * Wp + col);
+        if (acc != 0xFFFFFFFFu) atomicAnd(&and_rows[(uint64_t)g * W + col], acc);
+    }
+}
+int launch_query_perfect(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, const void* d_table,
+                         const uint32_t* d_unit_group, const uint64_t* d_unit_slot0, const uint32_t* d_unit_nslots,
+                         uint64_t nunits, uint32_t* d_and_rows, uint32_t* d_missing, unsigned long long* d_num_kmers) {
+    if (nunits == 0) return CID_OK;
+    size_t smem = unit_smem_bytes(idx->H);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CID_CUDA(cudaFuncSetAttribute(query_perfect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr_set = true;
+    }
+    query_perfect_kernel<<<(unsigned)nunits, 256, smem, st>>>(idx->rows, idx->rownz, idx->Wp, idx->W, idx->k, idx->H,
+                                                             make_mods(idx->S), (const Slot*)d_table, d_unit_group,
+                                                             d_unit_slot0, d_unit_nslots, d_and_rows, d_missing,
+                                                             d_num_kmers);
+    ctx->launches++;
+    CID_CUDA(cudaGetLastError());
+    return CID_OK;
+}
+
+// ================================================================= hash parity hook
+__global__ void hash_kmers_kernel(const uint8_t* __restrict__ kmers, uint64_t n, uint32_t k, uint32_t H, ModS mods,
+                                  uint64_t* __restrict__ out) {
+    __shared__ uint32_t lut[256];
+    lut4_init(lut, threadIdx.x, blockDim.x);
+    __syncthreads();
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t key = 0;
+    for (uint32_t j = 0; j < k; j++) key = (key << 2) | base_code(kmers[i * k + j]);
+    HashIn in = hashin_from_key(lut, key, k);
+    for (uint32_t h = 0; h < H; h++) out[i * H + h] = mod_s(xxh3_kmer(in, k, h), mods);
+}
+int launch_hash_kmers(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, const uint8_t* d_kmers, uint64_t n,
+                      uint64_t* d_rows) {
+    if (n == 0) return CID_OK;
+    hash_kmers_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_kmers, n, idx->k, idx->H, make_mods(idx->S), d_rows);
+    ctx->launches++;
+    CID_CUDA(cudaGetLastError());
+    return CID_OK;
+}
+
+}  // namespace cid

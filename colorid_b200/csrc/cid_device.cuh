@@ -1,0 +1,266 @@
+// Device-side building blocks shared by every kernel of the BIGSI hot path (sm_100a).
+//
+//  * XXH3-64 (seeded) of a canonical k-mer's ASCII bytes and `% bloom_size` — the reference's
+//    hash/seed scheme, simple_bloom.rs:19-26: bit = xxh3::hash64_with_seed(kmer, i) % len.
+//  * A shared-memory "tile" of bases (ASCII + 2-bit codes + validity/case/boundary bitmasks) from
+//    which every k-mer window of kmer.rs is extracted: has_no_n (seq.rs:66-70), canonical choice
+//    `fwd < revcomp ? fwd : revcomp` on raw bytes (kmer.rs:104), upper-casing (kmer.rs:106).
+//  * FNV-1a low bits for the hashbrown iteration-order emulation used by read_id.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace cid {
+
+// ------------------------------------------------------------------ XXH3-64 with seed, len <= 32
+// Secret words (little-endian u64 at byte offsets 0..64 of the default XXH3 secret).
+#define CID_SEC0 0xbe4ba423396cfeb8ULL
+#define CID_SEC8 0x1cad21f72c81017cULL
+#define CID_SEC16 0xdb979083e96dd4deULL
+#define CID_SEC24 0x1f67b3b7a4a44072ULL
+#define CID_SEC32 0x78e5c0cc4ee679cbULL
+#define CID_SEC40 0x2172ffcc7dd05a82ULL
+#define CID_SEC48 0x8e2443f7744608b8ULL
+#define CID_P64_1 0x9E3779B185EBCA87ULL
+#define CID_P64_2 0xC2B2AE3D27D4EB4FULL
+#define CID_P64_3 0x165667B19E3779F9ULL
+#define CID_PMX1 0x165667919E3779F9ULL
+#define CID_PMX2 0x9FB21C651E98DF25ULL
+
+__device__ __forceinline__ uint64_t mul128_fold64(uint64_t a, uint64_t b) { return (a * b) ^ __umul64hi(a, b); }
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+__device__ __forceinline__ uint64_t bswap64(uint64_t x) {
+    uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    return ((uint64_t)__byte_perm(lo, 0, 0x0123) << 32) | __byte_perm(hi, 0, 0x0123);
+}
+
+// The bytes of a k-mer that XXH3 actually reads, as little-endian words:
+//   k >= 17: w0=in[0:8] w1=in[8:16] w2=in[k-16:k-8] w3=in[k-8:k]
+//   9..16 : w0=in[0:8] w1=in[k-8:k]
+//   4..8  : w0=in[0:4] w1=in[k-4:k]           (32-bit values)
+//   1..3  : w0=in[0]   w1=in[k>>1] w2=in[k-1]
+struct HashIn { uint64_t w0, w1, w2, w3; };
+
+__device__ __forceinline__ uint64_t xxh3_kmer(const HashIn& in, uint32_t k, uint64_t seed) {
+    if (k >= 17) {
+        uint64_t acc = (uint64_t)k * CID_P64_1;
+        acc += mul128_fold64(in.w0 ^ (CID_SEC0 + seed), in.w1 ^ (CID_SEC8 - seed));
+        acc += mul128_fold64(in.w2 ^ (CID_SEC16 + seed), in.w3 ^ (CID_SEC24 - seed));
+        acc ^= acc >> 37; acc *= CID_PMX1; acc ^= acc >> 32;
+        return acc;
+    } else if (k >= 9) {
+        uint64_t lo = in.w0 ^ ((CID_SEC24 ^ CID_SEC32) + seed);
+        uint64_t hi = in.w1 ^ ((CID_SEC40 ^ CID_SEC48) - seed);
+        uint64_t acc = (uint64_t)k + bswap64(lo) + hi + mul128_fold64(lo, hi);
+        acc ^= acc >> 37; acc *= CID_PMX1; acc ^= acc >> 32;
+        return acc;
+    } else if (k >= 4) {
+        uint32_t s32 = (uint32_t)seed;
+        seed ^= (uint64_t)__byte_perm(s32, 0, 0x0123) << 32;
+        uint64_t h = (in.w1 + (in.w0 << 32)) ^ ((CID_SEC8 ^ CID_SEC16) - seed);
+        h ^= rotl64(h, 49) ^ rotl64(h, 24);
+        h *= CID_PMX2;
+        h ^= (h >> 35) + k;
+        h *= CID_PMX2;
+        return h ^ (h >> 28);
+    } else {
+        uint32_t combined = ((uint32_t)in.w0 << 16) | ((uint32_t)in.w1 << 24) | (uint32_t)in.w2 | (k << 8);
+        uint64_t h = (uint64_t)combined ^ ((uint64_t)(0x396cfeb8u ^ 0xbe4ba423u) + seed);
+        h ^= h >> 33; h *= CID_P64_2; h ^= h >> 29; h *= CID_P64_3; h ^= h >> 32;
+        return h;
+    }
+}
+
+// h % S for run-time S (2 <= S < 2^63) with M = floor(2^64 / S): q = mulhi(h, M) is floor(h/S) or
+// one less, so a single conditional subtract makes it exact.
+struct ModS { uint64_t S, M; };
+__host__ __device__ __forceinline__ ModS make_mods(uint64_t S) {
+    ModS m; m.S = S;
+    m.M = S <= 1 ? 0 : (uint64_t)((((unsigned __int128)1) << 64) / S);
+    return m;
+}
+__device__ __forceinline__ uint64_t mod_s(uint64_t h, const ModS& m) {
+    if (m.S <= 1) return 0;
+    uint64_t q = __umul64hi(h, m.M);
+    uint64_t r = h - q * m.S;
+    return r >= m.S ? r - m.S : r;
+}
+
+// ------------------------------------------------------------------ 2-bit codes <-> ASCII
+// code = A0 C1 G2 T3 (byte order == numeric order for upper case)
+__device__ __forceinline__ uint32_t base_code(uint32_t c) { return ((c >> 1) ^ (c >> 2)) & 3u; }
+__device__ __forceinline__ bool base_is_acgt(uint32_t c) {
+    uint32_t u = c & 0xDFu;
+    return u == 'A' || u == 'C' || u == 'G' || u == 'T';
+}
+__device__ __forceinline__ uint32_t code_ascii(uint32_t code) { return 'A' + ((0x13060200u >> (code * 8)) & 0xFFu); }
+
+// 256-entry table: 4 bases (first base in bits 7:6) -> 4 upper-case ASCII bytes (first base in byte 0).
+__device__ __forceinline__ void lut4_init(uint32_t* lut, int tid, int nthreads) {
+    for (int i = tid; i < 256; i += nthreads)
+        lut[i] = code_ascii((i >> 6) & 3) | (code_ascii((i >> 4) & 3) << 8) | (code_ascii((i >> 2) & 3) << 16) |
+                 (code_ascii(i & 3) << 24);
+}
+__device__ __forceinline__ uint64_t ascii8(const uint32_t* lut, uint32_t c16) {
+    return (uint64_t)lut[(c16 >> 8) & 0xFF] | ((uint64_t)lut[c16 & 0xFF] << 32);
+}
+// key: k bases, first base in the top of the low 2k bits.  Upper-case ASCII as XXH3 reads it.
+__device__ __forceinline__ HashIn hashin_from_key(const uint32_t* lut, uint64_t key, uint32_t k) {
+    HashIn in;
+    uint64_t kk = key << (64 - 2 * k);   // left-aligned: first base in bits 63:62
+    if (k >= 17) {
+        in.w0 = ascii8(lut, (uint32_t)(kk >> 48));
+        in.w1 = ascii8(lut, (uint32_t)(kk >> 32) & 0xFFFF);
+        in.w2 = ascii8(lut, (uint32_t)(key >> 16) & 0xFFFF);
+        in.w3 = ascii8(lut, (uint32_t)key & 0xFFFF);
+    } else if (k >= 9) {
+        in.w0 = ascii8(lut, (uint32_t)(kk >> 48));
+        in.w1 = ascii8(lut, (uint32_t)key & 0xFFFF);
+        in.w2 = in.w3 = 0;
+    } else if (k >= 4) {
+        in.w0 = lut[(uint32_t)(kk >> 56)];
+        in.w1 = lut[(uint32_t)key & 0xFF];
+        in.w2 = in.w3 = 0;
+    } else {
+        in.w0 = code_ascii((uint32_t)(kk >> 62));
+        in.w1 = code_ascii((uint32_t)(key >> (2 * (k - 1 - (k >> 1)))) & 3);
+        in.w2 = code_ascii((uint32_t)key & 3);
+        in.w3 = 0;
+    }
+    return in;
+}
+
+// Low 32 bits of FNV-1a-64 over the k upper-case ASCII bytes of `key` followed by 0xFF
+// (`impl Hash for str`).  The low 32 bits of h*0x100000001b3 depend only on the low 32 bits of h.
+__device__ __forceinline__ uint32_t fnv1a_low32_key(uint64_t key, uint32_t k) {
+    uint32_t h = 0x84222325u;   // low 32 bits of 0xcbf29ce484222325
+    uint64_t kk = key << (64 - 2 * k);
+    for (uint32_t j = 0; j < k; j++) {
+        h = (h ^ code_ascii((uint32_t)(kk >> 62))) * 0x1b3u;
+        kk <<= 2;
+    }
+    return (h ^ 0xFFu) * 0x1b3u;
+}
+
+// Reverse complement of a packed k-mer.
+__device__ __forceinline__ uint64_t revcomp_key(uint64_t v, uint32_t k) {
+    uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+    uint64_t r = ((uint64_t)__brev(lo) << 32) | __brev(hi);          // bit-reverse 64
+    r = ((r >> 1) & 0x5555555555555555ULL) | ((r & 0x5555555555555555ULL) << 1);  // restore bit order inside each base
+    r >>= (64 - 2 * k);
+    return r ^ (k == 32 ? ~0ULL : ((1ULL << (2 * k)) - 1));
+}
+
+// ------------------------------------------------------------------ shared-memory tile of bases
+// Layout (all arrays zero-padded so that window reads never leave the allocation):
+//   ascii [cap]           raw bytes (after optional quality masking)
+//   codes [cap/16 + 3]    16 bases per u32, first base in bits 31:30
+//   bad   [cap/32 + 2]    bit j (LSB-first) = base j is not one of ACGTacgt (or beyond len)
+//   lower [cap/32 + 2]    bit j = base j is a lower-case acgt
+//   start [cap/32 + 2]    bit j = a sequence starts at base j (windows may not cross it)
+struct Tile {
+    uint8_t* ascii;
+    uint32_t* codes;
+    uint32_t* bad;
+    uint32_t* lower;
+    uint32_t* start;
+    int len;
+};
+__host__ __device__ constexpr size_t tile_smem_bytes(int cap) {   // cap multiple of 32
+    return (size_t)cap + 4 * (size_t)(cap / 16 + 3) + 3 * 4 * (size_t)(cap / 32 + 2);
+}
+__device__ __forceinline__ Tile tile_carve(uint8_t* smem, int cap) {
+    Tile t;
+    t.ascii = smem;
+    t.codes = (uint32_t*)(smem + cap);
+    t.bad = t.codes + (cap / 16 + 3);
+    t.lower = t.bad + (cap / 32 + 2);
+    t.start = t.lower + (cap / 32 + 2);
+    t.len = 0;
+    return t;
+}
+// Build codes/bad/lower from ascii[0..len) (ascii already in smem; caller syncs before and after).
+__device__ __forceinline__ void tile_pack(Tile& t, int cap, int tid, int nthreads) {
+    const int nwords32 = cap / 32 + 2;
+    for (int w = tid; w < nwords32; w += nthreads) {
+        uint32_t bad = 0, low = 0, c0 = 0, c1 = 0;
+        int base = w * 32;
+        for (int j = 0; j < 32; j++) {
+            int p = base + j;
+            uint32_t c = (p < t.len) ? t.ascii[p] : 0u;
+            bool ok = base_is_acgt(c);
+            bad |= (ok ? 0u : 1u) << j;
+            low |= ((ok && (c & 0x20u)) ? 1u : 0u) << j;
+            uint32_t code = ok ? base_code(c) : 0u;
+            if (j < 16) c0 |= code << (30 - 2 * j); else c1 |= code << (30 - 2 * (j - 16));
+        }
+        t.bad[w] = bad;
+        t.lower[w] = low;
+        if (2 * w < cap / 16 + 3) t.codes[2 * w] = c0;
+        if (2 * w + 1 < cap / 16 + 3) t.codes[2 * w + 1] = c1;
+    }
+}
+__device__ __forceinline__ uint32_t mask_window(const uint32_t* m, int i, uint32_t k) {   // k <= 32
+    uint32_t lo = m[i >> 5], hi = m[(i >> 5) + 1];
+    uint32_t v = __funnelshift_r(lo, hi, i & 31);
+    return k == 32 ? v : (v & ((1u << k) - 1));
+}
+__device__ __forceinline__ uint64_t codes_window(const uint32_t* c, int i, uint32_t k) {
+    int w = i >> 4, s = 2 * (i & 15);
+    uint32_t w0 = c[w], w1 = c[w + 1], w2 = c[w + 2];
+    uint32_t hi = __funnelshift_l(w1, w0, s), lo = __funnelshift_l(w2, w1, s);
+    return (((uint64_t)hi << 32) | lo) >> (64 - 2 * k);
+}
+
+// Case-preserving complement of a valid base (kmer.rs:847-863 switch_base on acgtACGT).
+__device__ __forceinline__ uint32_t comp_base(uint32_t c) {
+    uint32_t u = c & 0xDFu, cs = c & 0x20u;
+    uint32_t r = (u == 'A') ? 'T' : (u == 'C') ? 'G' : (u == 'G') ? 'C' : 'A';
+    return r | cs;
+}
+
+// One k-mer window of the tile.  Returns false when the window is not a k-mer of the reference
+// (contains a non-ACGT byte: seq.rs has_no_n; or crosses a sequence boundary).
+//   key      : packed codes of the chosen strand (after upper-casing)
+//   took_fwd : kmer.rs:104 `l[i..i+k] < l_r[..]` on RAW bytes; ties (palindromes) take the rc branch
+//   has_lower: the window contains lower-case bases (raw-case modes cannot represent the key)
+__device__ __forceinline__ bool tile_kmer(const Tile& t, int i, uint32_t k, uint64_t& key, bool& took_fwd, bool& has_lower) {
+    if (i + (int)k > t.len) return false;
+    if (mask_window(t.bad, i, k) != 0u) return false;
+    if ((mask_window(t.start, i, k) & ~1u) != 0u) return false;
+    uint64_t f = codes_window(t.codes, i, k);
+    uint64_t r = revcomp_key(f, k);
+    uint32_t low = mask_window(t.lower, i, k);
+    has_lower = low != 0u;
+    if (!has_lower) {
+        took_fwd = f < r;
+    } else {
+        // exact raw-byte comparison of fwd against its case-preserving reverse complement
+        took_fwd = false;
+        for (uint32_t j = 0; j < k; j++) {
+            uint32_t a = t.ascii[i + j], b = comp_base(t.ascii[i + k - 1 - j]);
+            if (a != b) { took_fwd = a < b; break; }
+        }
+    }
+    key = took_fwd ? f : r;
+    return true;
+}
+
+// ------------------------------------------------------------------ count table (open addressing)
+struct __align__(16) Slot { unsigned long long key; uint32_t count; uint32_t pad; };
+#define CID_EMPTY_KEY 0xFFFFFFFFFFFFFFFFULL
+
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {   // murmur3 finalizer: slot choice only
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return x;
+}
+__device__ __forceinline__ void table_insert(Slot* region, uint64_t mask, uint64_t key) {
+    uint64_t h = mix64(key) & mask;
+    for (;;) {
+        unsigned long long prev = atomicCAS(&region[h].key, CID_EMPTY_KEY, (unsigned long long)key);
+        if (prev == CID_EMPTY_KEY || prev == key) { atomicAdd(&region[h].count, 1u); return; }
+        h = (h + 1) & mask;
+    }
+}
+
+}  // namespace cid

@@ -1,0 +1,145 @@
+// Internal host-side structures of libcolorid_b200 (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/colorid_b200.h"
+
+namespace cid {
+
+void set_error(const char* fmt, ...);
+
+#define CID_CUDA(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            cid::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return CID_E_CUDA;                                                                 \
+        }                                                                                      \
+    } while (0)
+
+#define CID_TRY(expr)            \
+    do {                         \
+        int _rc = (expr);        \
+        if (_rc != CID_OK) return _rc; \
+    } while (0)
+
+// Growable device buffer (never shrinks); owned by a ctx.
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes);
+    void release();
+    template <class T> T* as() const { return (T*)p; }
+};
+// Growable pinned host buffer.
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes);
+    void release();
+    template <class T> T* as() const { return (T*)p; }
+};
+
+enum { SCRATCH_SLOTS = 24 };
+
+}  // namespace cid
+
+struct cid_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;   // library-owned stream for the host-pointer entry points
+    uint64_t launches = 0;
+    cid::DevBuf scratch[cid::SCRATCH_SLOTS];
+    cid::PinBuf pinned[8];
+    uint32_t* d_err = nullptr;       // device error/flag words (zeroed before each call)
+    uint32_t* h_err = nullptr;       // pinned mirror
+};
+
+struct cid_index {
+    cid_ctx* ctx = nullptr;
+    uint64_t S = 0;
+    uint32_t H = 0, k = 0, N = 0;
+    uint32_t W = 0;      // ceil(N/32)
+    uint32_t Wp = 0;     // device row stride in words
+    uint32_t* rows = nullptr;      // [S][Wp]
+    uint32_t* rownz = nullptr;     // bitmap, bit r = row r has any bit set
+    uint64_t rownz_words = 0;
+    uint32_t* bitsets = nullptr;   // build mode: [N][bs_words] per-colour Bloom bitsets
+    uint64_t bs_words = 0;         // words per bitset (multiple of 32)
+    bool rownz_valid = false;
+    bool rownz_global = false;     // column-sharded: rownz was OR-ed across ranks; never derive presence from local words
+};
+
+namespace cid {
+
+// error flag bits written by kernels into ctx->d_err[0]
+enum {
+    ERRF_LOWER_RAW = 1u << 0,      // lower-case base inside a valid window in a raw-case mode
+    ERRF_STARTS_OVERFLOW = 1u << 1,
+    ERRF_LIST_OVERFLOW = 1u << 2,
+    ERRF_READ_TOO_LONG = 1u << 3,
+};
+
+int check_err_flags(cid_ctx* ctx, cudaStream_t st);   // syncs the stream
+
+inline uint32_t padded_row_words(uint32_t W) {
+    if (W <= 1) return 1;
+    if (W <= 2) return 2;
+    return (W + 3) & ~3u;   // 16-byte aligned rows
+}
+inline uint64_t next_pow2(uint64_t x) { uint64_t p = 1; while (p < x) p <<= 1; return p; }
+
+// ---- launchers implemented in the .cu files (all asynchronous on `st`) ------------------------
+struct GroupRegions {           // count-table regions, one per group (query / accession)
+    uint64_t ngroups = 0;
+    uint64_t total_slots = 0;
+    std::vector<uint64_t> off, mask;   // host copies
+};
+
+// Size regions from per-group base counts; fills host vectors.
+void plan_regions(const uint64_t* h_seq_offs, const uint64_t* h_group_offs, uint64_t ngroups, uint32_t k,
+                  GroupRegions& gr);
+
+int launch_kmerize_insert(cid_ctx* ctx, cudaStream_t st, const uint8_t* d_bases, const uint64_t* d_seq_offs,
+                          uint64_t nseq, uint64_t base_lo, uint64_t base_hi, const uint32_t* d_seq_group,
+                          const uint64_t* d_region_off, const uint64_t* d_region_mask, void* d_table, uint32_t k,
+                          int seq_mode);
+int launch_region_histogram(cid_ctx* ctx, cudaStream_t st, const void* d_region, uint64_t nslots, uint32_t* d_hist,
+                            uint32_t hist_bins, uint32_t* d_overflow, uint32_t overflow_cap, uint32_t* d_overflow_n);
+int launch_region_to_bloom(cid_ctx* ctx, cudaStream_t st, const void* d_region, uint64_t nslots, int64_t cutoff,
+                           uint32_t k, uint32_t H, uint64_t S, uint32_t* d_bitset, unsigned long long* d_nref);
+int launch_transpose(cid_ctx* ctx, cudaStream_t st, const cid_index* idx);
+int launch_rownz(cid_ctx* ctx, cudaStream_t st, const cid_index* idx);
+
+struct QueryUnits {            // work list for the gather kernels: (group, first slot, nslots)
+    std::vector<uint32_t> group;
+    std::vector<uint64_t> slot0;
+    std::vector<uint32_t> nslots;
+};
+void plan_units(const GroupRegions& gr, uint32_t chunk, QueryUnits& qu);
+enum { QUERY_CHUNK = 1024, MAX_HASH = 8 };
+
+int launch_query_counts(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, const void* d_table,
+                        const uint32_t* d_unit_group, const uint64_t* d_unit_slot0, const uint32_t* d_unit_nslots,
+                        uint64_t nunits, const int64_t* d_filter, uint32_t* d_counts, unsigned long long* d_num_kmers,
+                        bool want_uniq, uint32_t* d_uniq_list, uint32_t uniq_cap, uint32_t* d_uniq_n);
+int launch_query_perfect(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, const void* d_table,
+                         const uint32_t* d_unit_group, const uint64_t* d_unit_slot0, const uint32_t* d_unit_nslots,
+                         uint64_t nunits, uint32_t* d_and_rows, uint32_t* d_missing, unsigned long long* d_num_kmers);
+
+int launch_hash_kmers(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, const uint8_t* d_kmers, uint64_t n,
+                      uint64_t* d_rows);
+
+// read_id pipeline on device buffers; scratch comes from ctx.
+int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const uint8_t* d_quals,
+               const uint64_t* d_seq_offs, uint64_t nseq, uint64_t nbases, const uint64_t* d_read_offs,
+               uint64_t nreads, uint32_t max_read_bases, uint32_t max_kmers, const cid_readid_params& p,
+               uint32_t* d_n_set, uint32_t* d_flags, uint32_t* d_rep_n, uint32_t* d_rep_colour, uint32_t* d_rep_count,
+               uint32_t order_cap, uint32_t* d_order_n, uint8_t* d_order_seq, uint16_t* d_order_pos);
+
+}  // namespace cid

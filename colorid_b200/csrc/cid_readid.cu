@@ -1,0 +1,554 @@
+// CUDA kernels (sm_100a) for read_id: read_id_mt_pe.rs:282-363 parallel_vec with m == 0.
+//
+// Per read (1 or 2 mates) the reference builds an FnvHashSet<String> of canonical k-mers
+// (kmer.rs:221-243), iterates it IN HASH-TABLE ORDER and votes (search_index :104-165 /
+// search_index_classic :66-102), breaking at the first k-mer with an absent row.  The result
+// therefore depends on hashbrown's bucket layout, which is reproduced here in three kernels:
+//
+//   readid_kmerize  (warp per read)    canonical k-mers, per-read dedup, FNV-1a low bits,
+//                                      emitted as the sequence of HashSet::insert calls
+//   readid_order    (thread per read)  hashbrown growth/probe emulation in shared memory ->
+//                                      k-mers in iteration order
+//   readid_vote     (warp per read)    XXH3 x num_hash, row gather, AND, first-miss cut-off,
+//                                      candidate set from the first `start_sample` k-mers, counts
+#include <algorithm>
+
+#include "cid_device.cuh"
+#include "cid_internal.h"
+
+namespace cid {
+
+constexpr int RA_WARPS = 4;
+constexpr int MAX_MATES = 8;
+
+// entry layout (u32): [15:0] fnv low16 | [25:16] tile position | [26] took_fwd | [27] fresh
+#define ENT_TP(e) (((e) >> 16) & 0x3FFu)
+#define ENT_FWD(e) (((e) >> 26) & 1u)
+#define ENT_FRESH(e) (((e) >> 27) & 1u)
+
+struct ReadGeom { uint64_t b0; int len; int nm; };
+
+// Loads one read (all mates, contiguous in `bases`) into a warp-private tile, applying
+// seq.rs:36-56 qual_mask when quals != nullptr.  Returns false if the read does not fit.
+__device__ __forceinline__ bool warp_load_read(Tile& t, int cap, const uint8_t* __restrict__ bases,
+                                               const uint8_t* __restrict__ quals, uint32_t maxq,
+                                               const uint64_t* __restrict__ seq_offs, uint64_t s_begin, uint64_t s_end,
+                                               uint32_t* moffs, int lane, ReadGeom& g) {
+    g.b0 = __ldg(seq_offs + s_begin);
+    uint64_t b1 = __ldg(seq_offs + s_end);
+    g.nm = (int)(s_end - s_begin);
+    g.len = (int)min(b1 - g.b0, (uint64_t)0x7fffffff);
+    if (b1 - g.b0 > (uint64_t)cap - 32 || g.nm > MAX_MATES) return false;
+    t.len = g.len;
+    for (int i = lane; i < cap / 32 + 2; i += 32) t.start[i] = 0;
+    __syncwarp();
+    if (lane <= g.nm && lane < MAX_MATES + 1) {
+        uint32_t o = (uint32_t)(__ldg(seq_offs + s_begin + lane) - g.b0);
+        moffs[lane] = o;
+        if (lane > 0 && lane < g.nm) atomicOr(&t.start[o >> 5], 1u << (o & 31));
+    }
+    const uint8_t* src = bases + g.b0;
+    for (int i = lane; i < g.len; i += 32) {
+        uint8_t c = __ldg(src + i);
+        if (quals && (uint32_t)__ldg(quals + g.b0 + i) < maxq) c = 'N';
+        t.ascii[i] = c;
+    }
+    __syncwarp();
+    tile_pack(t, cap, lane, 32);
+    __syncwarp();
+    return true;
+}
+
+// ================================================================= readid_kmerize
+__global__ void __launch_bounds__(RA_WARPS * 32)
+readid_kmerize_kernel(const uint8_t* __restrict__ bases, const uint8_t* __restrict__ quals, uint32_t maxq,
+                      const uint64_t* __restrict__ seq_offs, const uint64_t* __restrict__ read_offs, uint64_t r0,
+                      uint64_t nreads, uint32_t k, uint32_t d, int cap, uint32_t maxocc, uint32_t tsize,
+                      uint32_t* __restrict__ entries, uint32_t* __restrict__ nocc, uint32_t* __restrict__ flags,
+                      uint32_t* __restrict__ err) {
+    extern __shared__ __align__(16) uint8_t dsm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t per_warp = ((tile_smem_bytes(cap) + 7) & ~(size_t)7) + (size_t)tsize * 8 + (size_t)tsize * 4 +
+                            (size_t)cap * 4 + (MAX_MATES + 1) * 4 + 4;
+    uint8_t* base = dsm + (size_t)warp * ((per_warp + 15) & ~(size_t)15);
+    Tile t = tile_carve(base, cap);
+    unsigned long long* tkeys = (unsigned long long*)(base + ((tile_smem_bytes(cap) + 7) & ~(size_t)7));
+    uint32_t* tmin = (uint32_t*)(tkeys + tsize);
+    uint32_t* pinfo = tmin + tsize;
+    uint32_t* moffs = pinfo + cap;
+    const uint32_t tmask = tsize - 1;
+
+    for (uint64_t rl = (uint64_t)blockIdx.x * RA_WARPS + warp; rl < nreads; rl += (uint64_t)gridDim.x * RA_WARPS) {
+        const uint64_t r = r0 + rl;
+        const uint64_t s_begin = __ldg(read_offs + r), s_end = __ldg(read_offs + r + 1);
+        uint32_t fl = 0, emitted = 0;
+        ReadGeom g;
+        __syncwarp();
+        bool ok = s_end > s_begin;
+        if (ok) {
+            // read_id_mt_pe.rs:305 `r.1[0].len() < k` -> too_short
+            uint64_t l0 = __ldg(seq_offs + s_begin + 1) - __ldg(seq_offs + s_begin);
+            if (l0 < k) ok = false;
+        }
+        if (!ok) fl |= 1u;
+        if (ok && !warp_load_read(t, cap, bases, quals, maxq, seq_offs, s_begin, s_end, moffs, lane, g)) {
+            if (lane == 0) atomicOr(err, ERRF_READ_TOO_LONG);
+            fl |= 8u; ok = false;
+        }
+        if (ok) {
+            // kmer.rs:229 `0..l.len()-k+1` wraps for a later mate shorter than k-1 -> slice panic
+            for (int m = 1; m < g.nm; m++) if (moffs[m + 1] - moffs[m] + 1 < k) { fl |= 2u; ok = false; }
+        }
+        if (ok) {
+            for (uint32_t i = lane; i < tsize; i += 32) { tkeys[i] = CID_EMPTY_KEY; tmin[i] = 0xFFFFFFFFu; }
+            __syncwarp();
+            // pass 1: every position -> (valid, dedup slot, strand)
+            for (int tp0 = 0; tp0 < g.len; tp0 += 32) {
+                int tp = tp0 + lane;
+                uint32_t info = 0;
+                if (tp < g.len) {
+                    int m = 0;
+                    for (int j = 1; j < g.nm; j++) if ((int)moffs[j] <= tp) m = j;
+                    uint32_t i = (uint32_t)tp - moffs[m];
+                    uint64_t key; bool fwd, low;
+                    if ((d == 1 || i % d == 0) && tile_kmer(t, tp, k, key, fwd, low)) {
+                        if (low) atomicOr(err, ERRF_LOWER_RAW);
+                        uint32_t s = (uint32_t)mix64(key) & tmask;
+                        for (;;) {
+                            unsigned long long prev = atomicCAS(&tkeys[s], CID_EMPTY_KEY, (unsigned long long)key);
+                            if (prev == CID_EMPTY_KEY || prev == key) break;
+                            s = (s + 1) & tmask;
+                        }
+                        atomicMin(&tmin[s], (uint32_t)tp);
+                        info = 0x80000000u | (fwd ? 0x40000000u : 0u) | s;
+                    }
+                }
+                if (tp < cap) pinfo[tp] = info;
+            }
+            __syncwarp();
+            // pass 2: emit the insert-call sequence in sequence order (kmer.rs:225-240)
+            uint32_t* out = entries + rl * (uint64_t)maxocc;
+            for (int tp0 = 0; tp0 < g.len; tp0 += 32) {
+                int tp = tp0 + lane;
+                uint32_t info = tp < g.len ? pinfo[tp] : 0u;
+                bool valid = info >> 31;
+                uint32_t ent = 0;
+                if (valid) {
+                    uint32_t s = info & 0xFFFFFu;
+                    bool fresh = tmin[s] == (uint32_t)tp;
+                    uint32_t f = fresh ? (fnv1a_low32_key(tkeys[s], k) & 0xFFFFu) : 0u;
+                    ent = f | ((uint32_t)tp << 16) | (((info >> 30) & 1u) << 26) | ((fresh ? 1u : 0u) << 27);
+                }
+                uint32_t bal = __ballot_sync(0xffffffffu, valid);
+                uint32_t rank = __popc(bal & ((1u << lane) - 1));
+                if (valid && emitted + rank < maxocc) out[emitted + rank] = ent;
+                emitted += __popc(bal);
+            }
+            if (emitted > maxocc) { if (lane == 0) atomicOr(err, ERRF_LIST_OVERFLOW); emitted = maxocc; }
+        }
+        if (lane == 0) { nocc[rl] = emitted; flags[r] = fl; }
+    }
+}
+
+// ================================================================= readid_order
+// hashbrown RawTable emulation: buckets 4,8,16,..; capacity b-1 (b<8) or
+// b/8*7; a HashSet::insert with growth_left == 0 resizes (before the duplicate check when
+// `rbf`, i.e. hashbrown >= 0.14); resize re-inserts the old table in ascending bucket order;
+// insert slot = first EMPTY in the `gw`-wide group at hash&mask, else triangular probing.
+template <typename E>
+__device__ __forceinline__ uint32_t hb_probe(const E* T, uint32_t nb, uint32_t pos, uint32_t gw, E empty) {
+    const uint32_t mask = nb - 1;
+    pos &= mask;
+    if (nb < gw) {
+        for (uint32_t b = 0; b < nb; b++) { uint32_t s = (pos + b) & mask; if (T[s] == empty) return s; }
+        return 0;   // unreachable: load factor < 1
+    }
+    uint32_t stride = 0;
+    for (;;) {
+        for (uint32_t b = 0; b < gw; b++) { uint32_t s = (pos + b) & mask; if (T[s] == empty) return s; }
+        stride += gw;
+        pos = (pos + stride) & mask;
+    }
+}
+__device__ __forceinline__ uint32_t hb_cap(uint32_t nb) { return nb == 0 ? 0 : (nb < 8 ? nb - 1 : nb / 8 * 7); }
+
+template <typename E>
+__global__ void __launch_bounds__(64)
+readid_order_kernel(const uint32_t* __restrict__ entries, const uint32_t* __restrict__ nocc, uint64_t nreads,
+                    uint32_t maxocc, uint32_t TB, uint32_t gw, uint32_t rbf, uint16_t* __restrict__ order,
+                    uint32_t* __restrict__ n_set_out, uint64_t r0) {
+    extern __shared__ __align__(16) uint8_t dsm[];
+    const E EMPTY = (E)~(E)0;
+    const uint64_t rl = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (rl >= nreads) return;
+    E* X = (E*)dsm + (size_t)threadIdx.x * (TB + TB / 2);
+    E* Y = X + TB;
+    const uint32_t* row = entries + rl * (uint64_t)maxocc;
+    const uint32_t n = nocc[rl];
+    uint32_t nb = 0, items = 0, growth = 0;
+    E* cur = X;
+    // table of size s lives in X when log2(TB/s) is even, else in Y
+    auto buf_for = [&](uint32_t s) -> E* { return ((__ffs(TB) - __ffs(s)) & 1) ? Y : X; };
+    for (uint32_t j = 0; j < n; j++) {
+        const uint32_t e = __ldg(row + j);
+        const bool fresh = ENT_FRESH(e);
+        if (growth == 0 && (rbf || fresh)) {
+            // reserve_rehash -> resize(capacity_to_buckets(max(items+1, cap+1)))
+            uint32_t newb = nb == 0 ? 4 : nb * 2;
+            E* nt = buf_for(newb);
+            for (uint32_t s = 0; s < newb; s++) nt[s] = EMPTY;
+            for (uint32_t s = 0; s < nb; s++) {
+                E v = cur[s];
+                if (v != EMPTY) nt[hb_probe<E>(nt, newb, __ldg(row + v) & 0xFFFFu, gw, EMPTY)] = v;
+            }
+            cur = nt; nb = newb;
+            growth = hb_cap(nb) - items;
+        }
+        if (fresh) {
+            cur[hb_probe<E>(cur, nb, e & 0xFFFFu, gw, EMPTY)] = (E)j;
+            items++; growth--;
+        }
+    }
+    uint16_t* out = order + rl * (uint64_t)maxocc;
+    uint32_t c = 0;
+    for (uint32_t s = 0; s < nb; s++) {
+        E v = cur[s];
+        if (v != EMPTY) out[c++] = (uint16_t)((__ldg(row + v) >> 16) & 0x7FFu);
+    }
+    n_set_out[r0 + rl] = c;
+}
+
+// ================================================================= readid_vote (rows of <= 64 accessions)
+template <int WP>
+__global__ void __launch_bounds__(RA_WARPS * 32)
+readid_vote_narrow_kernel(const uint8_t* __restrict__ bases, const uint8_t* __restrict__ quals, uint32_t maxq,
+                          const uint64_t* __restrict__ seq_offs, const uint64_t* __restrict__ read_offs, uint64_t r0,
+                          uint64_t nreads, uint32_t k, uint32_t H, ModS mods, const uint32_t* __restrict__ rows,
+                          const uint32_t* __restrict__ rownz, uint32_t N, int cap, uint32_t maxocc,
+                          const uint16_t* __restrict__ order, const uint32_t* __restrict__ n_set,
+                          uint32_t start_sample, uint32_t rep_cap, uint32_t* __restrict__ flags,
+                          uint32_t* __restrict__ rep_n, uint32_t* __restrict__ rep_colour,
+                          uint32_t* __restrict__ rep_count) {
+    extern __shared__ __align__(16) uint8_t dsm[];
+    __shared__ uint32_t lut[256];
+    lut4_init(lut, threadIdx.x, blockDim.x);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t per_warp = ((tile_smem_bytes(cap) + 15) & ~(size_t)15) + 64 + (MAX_MATES + 1) * 4 + 12;
+    uint8_t* base = dsm + (size_t)warp * ((per_warp + 15) & ~(size_t)15);
+    Tile t = tile_carve(base, cap);
+    uint8_t* ord = base + ((tile_smem_bytes(cap) + 15) & ~(size_t)15);
+    uint32_t* moffs = (uint32_t*)(ord + 64);
+    const bool classic = start_sample == 0;
+
+    for (uint64_t rl = (uint64_t)blockIdx.x * RA_WARPS + warp; rl < nreads; rl += (uint64_t)gridDim.x * RA_WARPS) {
+        const uint64_t r = r0 + rl;
+        const uint32_t n = n_set[r];
+        __syncwarp();
+        if (n == 0) { if (lane == 0) rep_n[r] = 0; continue; }
+        ReadGeom g;
+        warp_load_read(t, cap, bases, quals, maxq, seq_offs, __ldg(read_offs + r), __ldg(read_offs + r + 1), moffs, lane, g);
+        const uint16_t* ordrow = order + rl * (uint64_t)maxocc;
+        uint32_t cand0 = 0, cand1 = 0, cnt0 = 0, cnt1 = 0, nrep = 0;
+        bool miss = false;
+        for (uint32_t c0 = 0; c0 < n && !miss; c0 += 32) {
+            const uint32_t idx = c0 + lane;
+            const bool active = idx < n;
+            uint32_t x0 = 0, x1 = 0;
+            bool m = false;
+            if (active) {
+                uint32_t e = __ldg(ordrow + idx);
+                uint32_t tp = e & 0x3FFu;
+                uint64_t f = codes_window(t.codes, (int)tp, k);
+                uint64_t key = ((e >> 10) & 1u) ? f : revcomp_key(f, k);
+                HashIn in = hashin_from_key(lut, key, k);
+                x0 = 0xFFFFFFFFu; x1 = WP == 2 ? 0xFFFFFFFFu : 0u;
+                for (uint32_t h = 0; h < H; h++) {
+                    uint64_t rid = mod_s(xxh3_kmer(in, k, h), mods);
+                    uint32_t a, b = 0;
+                    if (WP == 2) { uint2 v = __ldg((const uint2*)(rows + rid * 2)); a = v.x; b = v.y; }
+                    else a = __ldg(rows + rid);
+                    bool present = rownz ? ((__ldg(rownz + (rid >> 5)) >> (rid & 31)) & 1u) : ((a | b) != 0u);
+                    if (!present) m = true;     // read_id_mt_pe.rs:121-123 `None => break`
+                    x0 &= a; x1 &= b;
+                }
+            }
+            const uint32_t missmask = __ballot_sync(0xffffffffu, active && m);
+            const uint32_t p_local = missmask ? (uint32_t)(__ffs(missmask) - 1) : 32u;
+            const bool valid = active && (uint32_t)lane < p_local;
+            // candidate colours (and report insertion order) from the first start_sample k-mers
+            uint32_t lim = classic ? 32u : (start_sample > c0 ? min(32u, start_sample - c0) : 0u);
+            lim = min(lim, min(p_local, n - c0));
+            for (uint32_t jj = 0; jj < lim; jj++) {
+                uint32_t y0 = __shfl_sync(0xffffffffu, x0, jj), y1 = __shfl_sync(0xffffffffu, x1, jj);
+                uint32_t nw0 = y0 & ~cand0, nw1 = y1 & ~cand1;
+                while (nw0) { uint32_t b = __ffs(nw0) - 1; nw0 &= nw0 - 1; if (lane == 0 && nrep < 64) ord[nrep] = (uint8_t)b; nrep++; }
+                while (nw1) { uint32_t b = __ffs(nw1) - 1; nw1 &= nw1 - 1; if (lane == 0 && nrep < 64) ord[nrep] = (uint8_t)(32 + b); nrep++; }
+                cand0 |= y0; cand1 |= y1;
+            }
+            // per-colour counts over the k-mers before the first miss (colours outside cand never count)
+            const uint32_t z0 = valid ? (x0 & cand0) : 0u, z1 = valid ? (x1 & cand1) : 0u;
+            for (uint32_t cm = cand0; cm; cm &= cm - 1) {
+                uint32_t b = __ffs(cm) - 1;
+                uint32_t v = __popc(__ballot_sync(0xffffffffu, (z0 >> b) & 1u));
+                if ((uint32_t)lane == b) cnt0 += v;
+            }
+            if (WP == 2)
+                for (uint32_t cm = cand1; cm; cm &= cm - 1) {
+                    uint32_t b = __ffs(cm) - 1;
+                    uint32_t v = __popc(__ballot_sync(0xffffffffu, (z1 >> b) & 1u));
+                    if ((uint32_t)lane == b) cnt1 += v;
+                }
+            if (missmask) miss = true;
+        }
+        __syncwarp();
+        // report in final_report insertion order; the "no hit" key N goes last (inserted at the break)
+        const uint32_t total = nrep + (miss ? 1u : 0u);
+        uint32_t* rc = rep_colour + r * (uint64_t)rep_cap;
+        uint32_t* rv = rep_count + r * (uint64_t)rep_cap;
+        for (uint32_t i0 = 0; i0 < nrep; i0 += 32) {
+            uint32_t i = i0 + lane;
+            uint32_t colour = i < nrep ? ord[i] : 0u;
+            uint32_t v0 = __shfl_sync(0xffffffffu, cnt0, colour & 31), v1 = __shfl_sync(0xffffffffu, cnt1, colour & 31);
+            if (i < nrep && i < rep_cap) { rc[i] = colour; rv[i] = colour < 32 ? v0 : v1; }
+        }
+        if (lane == 0) {
+            if (miss && nrep < rep_cap) { rc[nrep] = N; rv[nrep] = 1; }
+            rep_n[r] = min(total, rep_cap);
+            if (total > rep_cap) flags[r] |= 4u;
+        }
+    }
+}
+
+// ================================================================= readid_vote (any row width)
+// One k-mer at a time per warp: lanes cover the row's words (coalesced), counts live in
+// bit-sliced registers per lane; used when a row has more than 64 accessions.
+constexpr int RV_MAXWPL = 4;       // words per lane: rows up to 128 words (4,096 accessions per shard)
+constexpr int RV_PLANES = 11;      // counts up to 2047 k-mers per read
+__global__ void __launch_bounds__(RA_WARPS * 32)
+readid_vote_wide_kernel(const uint8_t* __restrict__ bases, const uint8_t* __restrict__ quals, uint32_t maxq,
+                        const uint64_t* __restrict__ seq_offs, const uint64_t* __restrict__ read_offs, uint64_t r0,
+                        uint64_t nreads, uint32_t k, uint32_t H, ModS mods, const uint32_t* __restrict__ rows,
+                        const uint32_t* __restrict__ rownz, uint32_t N, uint32_t Wp, int cap, uint32_t maxocc,
+                        const uint16_t* __restrict__ order, const uint32_t* __restrict__ n_set, uint32_t start_sample,
+                        uint32_t rep_cap, uint32_t* __restrict__ flags, uint32_t* __restrict__ rep_n,
+                        uint32_t* __restrict__ rep_colour, uint32_t* __restrict__ rep_count) {
+    extern __shared__ __align__(16) uint8_t dsm[];
+    __shared__ uint32_t lut[256];
+    lut4_init(lut, threadIdx.x, blockDim.x);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t per_warp = ((tile_smem_bytes(cap) + 15) & ~(size_t)15) + (MAX_MATES + 1) * 4 + 12;
+    uint8_t* base = dsm + (size_t)warp * ((per_warp + 15) & ~(size_t)15);
+    Tile t = tile_carve(base, cap);
+    uint32_t* moffs = (uint32_t*)(base + ((tile_smem_bytes(cap) + 15) & ~(size_t)15));
+    const bool classic = start_sample == 0;
+    const uint32_t wpl = (Wp + 31) / 32;
+
+    for (uint64_t rl = (uint64_t)blockIdx.x * RA_WARPS + warp; rl < nreads; rl += (uint64_t)gridDim.x * RA_WARPS) {
+        const uint64_t r = r0 + rl;
+        const uint32_t n = n_set[r];
+        __syncwarp();
+        if (n == 0) { if (lane == 0) rep_n[r] = 0; continue; }
+        ReadGeom g;
+        warp_load_read(t, cap, bases, quals, maxq, seq_offs, __ldg(read_offs + r), __ldg(read_offs + r + 1), moffs, lane, g);
+        const uint16_t* ordrow = order + rl * (uint64_t)maxocc;
+        uint32_t* rc = rep_colour + r * (uint64_t)rep_cap;
+        uint32_t* rv = rep_count + r * (uint64_t)rep_cap;
+        uint32_t cand[RV_MAXWPL], pl[RV_MAXWPL][RV_PLANES];
+#pragma unroll
+        for (int w = 0; w < RV_MAXWPL; w++) { cand[w] = 0; for (int p = 0; p < RV_PLANES; p++) pl[w][p] = 0; }
+        uint32_t nrep = 0;
+        bool miss = false;
+        for (uint32_t j = 0; j < n; j++) {
+            uint32_t e = __ldg(ordrow + j);
+            uint64_t f = codes_window(t.codes, (int)(e & 0x3FFu), k);
+            uint64_t key = ((e >> 10) & 1u) ? f : revcomp_key(f, k);
+            HashIn in = hashin_from_key(lut, key, k);
+            uint64_t rid[MAX_HASH];
+            bool present = true;
+            for (uint32_t h = 0; h < H; h++) {
+                rid[h] = mod_s(xxh3_kmer(in, k, h), mods);
+                if (!((__ldg(rownz + (rid[h] >> 5)) >> (rid[h] & 31)) & 1u)) present = false;
+            }
+            if (!present) { miss = true; break; }
+            const bool seeding = classic || j < start_sample;
+#pragma unroll
+            for (int w = 0; w < RV_MAXWPL; w++) {
+                if ((uint32_t)w >= wpl) break;
+                uint32_t col = w * 32 + lane;
+                uint32_t x = 0;
+                if (col < Wp) {
+                    x = 0xFFFFFFFFu;
+                    for (uint32_t h = 0; h < H; h++) x &= __ldg(rows + rid[h] * Wp + col);
+                }
+                if (seeding) {
+                    // new colours in ascending order across the whole row: lanes take turns per word
+                    uint32_t nw = x & ~cand[w];
+                    for (int l = 0; l < 32; l++) {
+                        uint32_t y = __shfl_sync(0xffffffffu, nw, l);
+                        while (y) {
+                            uint32_t b = __ffs(y) - 1; y &= y - 1;
+                            if (lane == 0 && nrep < rep_cap) rc[nrep] = (w * 32 + l) * 32 + b;
+                            nrep++;
+                        }
+                    }
+                    cand[w] |= x;
+                }
+                uint32_t carry = x & cand[w];
+#pragma unroll
+                for (int p = 0; p < RV_PLANES; p++) {
+                    uint32_t t2 = pl[w][p] & carry;
+                    pl[w][p] ^= carry;
+                    carry = t2;
+                }
+            }
+        }
+        __syncwarp();
+        // counts for the reported colours
+        const uint32_t kept = min(nrep, rep_cap);
+        for (uint32_t i = 0; i < kept; i++) {
+            uint32_t colour = rc[i];             // written by lane 0 above
+            colour = __shfl_sync(0xffffffffu, colour, 0);
+            uint32_t word = colour >> 5, b = colour & 31, w = word >> 5, owner = word & 31;
+            uint32_t v = 0;
+#pragma unroll
+            for (int ww = 0; ww < RV_MAXWPL; ww++)
+                if ((uint32_t)ww == w)
+                    for (int p = 0; p < RV_PLANES; p++) v |= ((pl[ww][p] >> b) & 1u) << p;
+            v = __shfl_sync(0xffffffffu, v, owner);
+            if (lane == 0) rv[i] = v;
+        }
+        if (lane == 0) {
+            uint32_t total = nrep + (miss ? 1u : 0u);
+            if (miss && nrep < rep_cap) { rc[nrep] = N; rv[nrep] = 1; }
+            rep_n[r] = min(total, rep_cap);
+            if (total > rep_cap) flags[r] |= 4u;
+        }
+    }
+}
+
+// ================================================================= order export (parity hook)
+__global__ void order_export_kernel(const uint16_t* __restrict__ order, const uint32_t* __restrict__ n_set,
+                                    const uint64_t* __restrict__ seq_offs, const uint64_t* __restrict__ read_offs,
+                                    uint64_t r0, uint64_t nreads, uint32_t maxocc, uint32_t order_cap,
+                                    uint32_t* __restrict__ order_n, uint8_t* __restrict__ order_seq,
+                                    uint16_t* __restrict__ order_pos) {
+    uint64_t rl = blockIdx.x;
+    if (rl >= nreads) return;
+    uint64_t r = r0 + rl;
+    uint32_t n = min(n_set[r], order_cap);
+    uint64_t s_begin = read_offs[r], s_end = read_offs[r + 1];
+    uint64_t b0 = seq_offs[s_begin];
+    if (threadIdx.x == 0) order_n[r] = n;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        uint32_t tp = order[rl * (uint64_t)maxocc + i] & 0x3FFu;
+        uint32_t m = 0;
+        for (uint64_t s = s_begin + 1; s < s_end; s++) if (seq_offs[s] - b0 <= tp) m = (uint32_t)(s - s_begin);
+        order_seq[r * (uint64_t)order_cap + i] = (uint8_t)m;
+        order_pos[r * (uint64_t)order_cap + i] = (uint16_t)(tp - (seq_offs[s_begin + m] - b0));
+    }
+}
+
+// ================================================================= host orchestration
+static uint32_t cap_to_buckets(uint32_t cap) {
+    if (cap < 8) return cap < 4 ? 4 : 8;
+    uint32_t adj = cap * 8 / 7, b = 1;
+    while (b < adj) b <<= 1;
+    return b;
+}
+
+int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const uint8_t* d_quals,
+               const uint64_t* d_seq_offs, uint64_t nseq, uint64_t nbases, const uint64_t* d_read_offs,
+               uint64_t nreads, uint32_t max_read_bases, uint32_t max_kmers, const cid_readid_params& p,
+               uint32_t* d_n_set, uint32_t* d_flags, uint32_t* d_rep_n, uint32_t* d_rep_colour, uint32_t* d_rep_count,
+               uint32_t order_cap, uint32_t* d_order_n, uint8_t* d_order_seq, uint16_t* d_order_pos) {
+    (void)nseq; (void)nbases;
+    cid_ctx* ctx = idx->ctx;
+    if (nreads == 0) return CID_OK;
+    if (max_read_bases > 1000) { set_error("read_id: reads longer than 1000 bases (all mates) are not supported yet"); return CID_E_UNSUPPORTED; }
+    if (p.downsample == 0 || (p.group_width != 16 && p.group_width != 8)) { set_error("read_id: bad params"); return CID_E_INVALID; }
+    if (idx->Wp > 32 * RV_MAXWPL) { set_error("read_id: more than %d accessions per shard not supported", 32 * 32 * RV_MAXWPL); return CID_E_UNSUPPORTED; }
+    const int cap = (int)((max_read_bases + 31) / 32 * 32 + 32);
+    uint32_t bound = max_kmers ? max_kmers : (max_read_bases >= idx->k ? max_read_bases - idx->k + 1 : 1);
+    if (bound < 1) bound = 1;
+    const uint32_t maxocc = (bound + 3) & ~3u;
+    const uint32_t tsize = (uint32_t)next_pow2(2ull * bound);
+    const uint32_t TB = cap_to_buckets(bound + 1);
+    const bool small = maxocc <= 255;
+    const uint32_t maxq = d_quals && p.qual_offset ? p.qual_offset + 33 : 0;
+    const uint8_t* quals = maxq ? d_quals : nullptr;
+
+    const uint64_t sub = std::min<uint64_t>(nreads, 1u << 20);
+    CID_TRY(ctx->scratch[16].ensure(sub * maxocc * 4));
+    CID_TRY(ctx->scratch[17].ensure(sub * maxocc * 2));
+    CID_TRY(ctx->scratch[18].ensure(sub * 4));
+    uint32_t* d_entries = ctx->scratch[16].as<uint32_t>();
+    uint16_t* d_order = ctx->scratch[17].as<uint16_t>();
+    uint32_t* d_nocc = ctx->scratch[18].as<uint32_t>();
+
+    // shared memory budgets
+    size_t a_warp = ((tile_smem_bytes(cap) + 7) & ~(size_t)7) + (size_t)tsize * 12 + (size_t)cap * 4 + (MAX_MATES + 1) * 4 + 4;
+    size_t a_smem = RA_WARPS * ((a_warp + 15) & ~(size_t)15);
+    size_t b_smem = (size_t)64 * (TB + TB / 2) * (small ? 1 : 2);
+    size_t cn_warp = ((tile_smem_bytes(cap) + 15) & ~(size_t)15) + 64 + (MAX_MATES + 1) * 4 + 12;
+    size_t cn_smem = RA_WARPS * ((cn_warp + 15) & ~(size_t)15);
+    size_t cw_warp = ((tile_smem_bytes(cap) + 15) & ~(size_t)15) + (MAX_MATES + 1) * 4 + 12;
+    size_t cw_smem = RA_WARPS * ((cw_warp + 15) & ~(size_t)15);
+    if (a_smem > 200 * 1024 || b_smem > 200 * 1024) { set_error("read_id: read too long for the shared-memory plan"); return CID_E_UNSUPPORTED; }
+    CID_CUDA(cudaFuncSetAttribute(readid_kmerize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a_smem));
+    CID_CUDA(cudaFuncSetAttribute(readid_order_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b_smem));
+    CID_CUDA(cudaFuncSetAttribute(readid_order_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b_smem));
+
+    const ModS mods = make_mods(idx->S);
+    for (uint64_t r0 = 0; r0 < nreads; r0 += sub) {
+        const uint64_t nr = std::min(sub, nreads - r0);
+        unsigned gridA = (unsigned)std::min<uint64_t>((nr + RA_WARPS - 1) / RA_WARPS, (uint64_t)ctx->sm_count * 32);
+        readid_kmerize_kernel<<<gridA, RA_WARPS * 32, a_smem, st>>>(d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr,
+                                                                   idx->k, p.downsample, cap, maxocc, tsize, d_entries,
+                                                                   d_nocc, d_flags, ctx->d_err);
+        ctx->launches++;
+        CID_CUDA(cudaGetLastError());
+        unsigned gridB = (unsigned)((nr + 63) / 64);
+        if (small)
+            readid_order_kernel<uint8_t><<<gridB, 64, b_smem, st>>>(d_entries, d_nocc, nr, maxocc, TB, p.group_width,
+                                                                   p.reserve_before_find, d_order, d_n_set, r0);
+        else
+            readid_order_kernel<uint16_t><<<gridB, 64, b_smem, st>>>(d_entries, d_nocc, nr, maxocc, TB, p.group_width,
+                                                                    p.reserve_before_find, d_order, d_n_set, r0);
+        ctx->launches++;
+        CID_CUDA(cudaGetLastError());
+        if (d_order_n) {
+            order_export_kernel<<<(unsigned)nr, 64, 0, st>>>(d_order, d_n_set, d_seq_offs, d_read_offs, r0, nr, maxocc,
+                                                            order_cap, d_order_n, d_order_seq, d_order_pos);
+            ctx->launches++;
+            CID_CUDA(cudaGetLastError());
+        }
+        if (d_rep_n) {
+            const uint32_t* rownz = idx->rownz;
+            if (idx->Wp <= 2) {
+                if (!idx->rownz_global) rownz = nullptr;   // presence == any word set, already in registers
+                if (idx->Wp == 1)
+                    readid_vote_narrow_kernel<1><<<gridA, RA_WARPS * 32, cn_smem, st>>>(
+                        d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr, idx->k, idx->H, mods, idx->rows, rownz,
+                        idx->N, cap, maxocc, d_order, d_n_set, p.start_sample, p.rep_cap, d_flags, d_rep_n, d_rep_colour,
+                        d_rep_count);
+                else
+                    readid_vote_narrow_kernel<2><<<gridA, RA_WARPS * 32, cn_smem, st>>>(
+                        d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr, idx->k, idx->H, mods, idx->rows, rownz,
+                        idx->N, cap, maxocc, d_order, d_n_set, p.start_sample, p.rep_cap, d_flags, d_rep_n, d_rep_colour,
+                        d_rep_count);
+            } else {
+                readid_vote_wide_kernel<<<gridA, RA_WARPS * 32, cw_smem, st>>>(
+                    d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr, idx->k, idx->H, mods, idx->rows, rownz, idx->N,
+                    idx->Wp, cap, maxocc, d_order, d_n_set, p.start_sample, p.rep_cap, d_flags, d_rep_n, d_rep_colour,
+                    d_rep_count);
+            }
+            ctx->launches++;
+            CID_CUDA(cudaGetLastError());
+        }
+    }
+    return CID_OK;
+}
+
+}  // namespace cid

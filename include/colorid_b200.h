@@ -1,0 +1,159 @@
+/* colorid_b200 — C ABI of the B200-native BIGSI hot path (build / search / read_id).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  The reference
+ * (hcdenbakker/colorid, Rust) has no FFI layer of its own; each entry point below names the
+ * reference `pub fn` whose inner loop it replaces (file:line relative to the reference root),
+ * i.e. what a Rust `extern "C"` block in the reference would bind.
+ *
+ * Conventions
+ *  - Every function returns 0 on success or a negative CID_E_* code; cid_last_error() gives text.
+ *  - Sequences are passed as one byte array `bases` plus `seq_offs[nseq+1]` (byte offsets).
+ *    Grouping arrays (`query_offs`, `read_offs`, …) index into the sequence list.
+ *  - `*_dev` variants take DEVICE pointers and a CUDA stream (as void*) and never synchronise
+ *    the host; the plain variants take HOST pointers, copy in/out and return when results are
+ *    in host memory.
+ *  - A cid_ctx is single-owner (not thread-safe).  The library owns all device memory behind
+ *    the handles; the caller owns every buffer it passes in.
+ *  - There is NO CPU fallback: with no usable CUDA device every call fails with CID_E_CUDA.
+ */
+#ifndef COLORID_B200_H
+#define COLORID_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cid_ctx cid_ctx;
+typedef struct cid_index cid_index;
+
+enum {
+    CID_OK = 0,
+    CID_E_INVALID = -1,      /* bad argument (k out of range, null pointer, …) */
+    CID_E_CUDA = -2,         /* CUDA runtime error / no device */
+    CID_E_NOMEM = -3,        /* device or host allocation failed */
+    CID_E_UNSUPPORTED = -4,  /* input the device path does not cover yet (see message) */
+    CID_E_REF_PANIC = -5,    /* the reference would panic on this input (e.g. auto_cutoff underflow) */
+    CID_E_CAPACITY = -6      /* an internal table/output capacity was exceeded */
+};
+
+/* k-mer extraction semantics (kmer.rs) */
+enum {
+    CID_SEQ_FASTA = 0, /* kmerize_vector  kmer.rs:87-125 : has_no_n, compare raw case, then uppercase */
+    CID_SEQ_FASTQ = 1  /* kmers_from_fq_qual / kmers_fq_pe_qual kmer.rs:461-510,581-655 : has_no_n, raw case */
+};
+
+int cid_version(void);
+const char* cid_last_error(void);
+
+/* ---- context ---------------------------------------------------------------------------- */
+int cid_ctx_create(int device, cid_ctx** out);
+void cid_ctx_destroy(cid_ctx* ctx);
+int cid_ctx_device(const cid_ctx* ctx);
+/* Counters of kernels launched by this library since ctx creation (for bench `gpu_launches`). */
+uint64_t cid_ctx_launch_count(const cid_ctx* ctx);
+
+/* ---- index: bigsi.rs:19-27 BigsyMapNew {bloom_size, num_hash, k_size, colors, map, n_ref_kmers}
+ * Device layout: dense row-major matrix rows[bloom_size][row_words] of u32, bit c of a row =
+ * (word[c/32] >> (c%32)) & 1 (bit-vec_serde/src/lib.rs:465-500).  An absent row of the reference's
+ * sparse map is an all-zero row here (build.rs:123-127 never stores an all-zero row). */
+int cid_index_create(cid_ctx* ctx, uint64_t bloom_size, uint32_t num_hash, uint32_t k_size, uint32_t n_colors,
+                     cid_index** out);
+void cid_index_destroy(cid_index* idx);
+uint32_t cid_index_row_words(const cid_index* idx);    /* ceil(n_colors/32) */
+uint32_t cid_index_row_stride(const cid_index* idx);   /* padded words per row on the device */
+/* Rows from a .bxi `map` (bigsi.rs:25): row_ids[n], words[n*row_words]. Replaces read_bigsi's heap map. */
+int cid_index_upload_rows(cid_index* idx, const uint64_t* row_ids, const uint32_t* words, uint64_t nrows);
+int cid_index_count_nonzero_rows(cid_index* idx, uint64_t* nrows);
+/* Non-zero rows in ascending row order for save_bigsi (bigsi.rs:51-57). */
+int cid_index_download_nonzero_rows(cid_index* idx, uint64_t* row_ids, uint32_t* words, uint64_t cap, uint64_t* nrows);
+int cid_index_download_dense(cid_index* idx, uint32_t* words /* bloom_size*row_words */);
+/* Device pointers for multi-GPU glue (column-sharded mode ORs the row-present bitmap across ranks). */
+int cid_index_device_ptrs(cid_index* idx, void** rows, void** rownz_bitmap, uint64_t* rownz_words);
+int cid_index_refresh_rownz(cid_index* idx);   /* recompute the row-present bitmap from the matrix */
+/* Column-sharded mode: declare that the bitmap now holds the OR over all shards. */
+int cid_index_set_rownz_global(cid_index* idx, int is_global);
+
+/* ---- build: build.rs:33-130 build_single / :132-256 build_multi ---------------------------
+ * Phase 1 for one accession: canonical k-mer count map -> (auto_cutoff | cutoff) -> clean_map ->
+ * n_ref_kmers -> Bloom insert (simple_bloom.rs:19-26) into this colour's bitset.
+ * cutoff == -1: FASTA -> no filter (build.rs:86-87); FASTQ -> auto_cutoff (build.rs:56-58). */
+int cid_build_accession(cid_index* idx, uint32_t colour, const char* bases, const uint64_t* seq_offs, uint64_t nseq,
+                        int seq_mode, int64_t cutoff, uint64_t* n_ref_kmers, int64_t* cutoff_used);
+int cid_build_accession_dev(cid_index* idx, uint32_t colour, const char* d_bases, const uint64_t* d_seq_offs,
+                            uint64_t nseq, uint64_t nbases, int seq_mode, int64_t cutoff, uint64_t* n_ref_kmers,
+                            int64_t* cutoff_used);
+/* Phase 2: transposition of the per-colour bitsets into the row-major matrix (build.rs:116-128). */
+int cid_build_finalize(cid_index* idx);
+
+/* ---- search: batch_search_pe.rs:9-179 batch_search (default and -g) -----------------------
+ * One query = sequences [query_offs[q], query_offs[q+1]) (one file in the reference).
+ * filter < 0 -> auto_cutoff per query (ignored for FASTA with gene_search: clean_map(0), :112-113).
+ * Outputs (host): counts[nq*n_colors], num_kmers[nq]; optional (may be NULL) unique-hit
+ * summaries for generate_report (reports.rs:8-48): uniq_n, uniq_sum, uniq_mode [nq*n_colors];
+ * cutoff_used[nq]. */
+int cid_query_counts(cid_index* idx, const char* bases, const uint64_t* seq_offs, uint64_t nseq,
+                     const uint64_t* query_offs, uint64_t nq, int seq_mode, int gene_search, int64_t filter,
+                     uint32_t* counts, uint64_t* num_kmers, uint64_t* uniq_n, uint64_t* uniq_sum, uint64_t* uniq_mode,
+                     int64_t* cutoff_used);
+/* Device-resident variant for gene search (filter fixed at 0, no unique-hit summaries):
+ * d_counts[nq*n_colors] u32 and d_num_kmers[nq] u64 are device buffers. */
+int cid_query_counts_dev(cid_index* idx, const char* d_bases, const uint64_t* d_seq_offs, uint64_t nseq,
+                         uint64_t nbases, const uint64_t* d_query_offs, const uint64_t* h_query_offs,
+                         const uint64_t* h_seq_offs, uint64_t nq, int seq_mode, uint32_t* d_counts,
+                         uint64_t* d_num_kmers, void* stream);
+
+/* ---- perfect search: perfect_search.rs:6-60 batch_search ----------------------------------
+ * AND of all num_hash rows of all distinct k-mers of the query (kmerize_vector semantics).
+ * and_rows[nq*row_words]; status[q]: 0 = AND valid, 1 = "No perfect hits!" (a row is absent),
+ * 2 = no k-mers in query; n_kmers[q] = distinct canonical k-mers. */
+int cid_query_perfect(cid_index* idx, const char* bases, const uint64_t* seq_offs, uint64_t nseq,
+                      const uint64_t* query_offs, uint64_t nq, uint32_t* and_rows, uint8_t* status,
+                      uint64_t* n_kmers);
+
+/* ---- read_id: read_id_mt_pe.rs:282-363 parallel_vec (m == 0) -------------------------------
+ * One read = sequences [read_offs[r], read_offs[r+1]) (1 or 2 mates).  If `quals` is non-NULL it
+ * has the same layout as `bases` and seq.rs:36-56 qual_mask(seq, qual, qual_offset) is applied on
+ * the device; otherwise `bases` must already be masked.
+ * The device computes, per read: the distinct canonical k-mer set (kmer.rs:221-243), its
+ * FnvHashSet iteration order, and search_index / search_index_classic (read_id_mt_pe.rs:66-165).
+ * Per read r the report is written in final_report INSERTION order:
+ *   rep_n[r] entries at rep_colour/rep_count[r*rep_cap ..]; colour == n_colors is the "no hit" key.
+ * flags[r]: bit0 = too_short (mate 1 shorter than k), bit1 = reference would panic (a later mate
+ * shorter than k-1), bit2 = report truncated at rep_cap. */
+typedef struct cid_readid_params {
+    uint32_t downsample;        /* -d, kmer.rs:229 step_by(d) */
+    uint32_t start_sample;      /* -B bitvector_sample; 0 = search_index_classic */
+    uint32_t qual_offset;       /* -Q (only used when quals != NULL) */
+    uint32_t group_width;       /* hashbrown SIMD group width to emulate: 16 (x86_64) or 8 */
+    uint32_t reserve_before_find; /* 1 = hashbrown >= 0.14 insert rule (default), 0 = older rule */
+    uint32_t rep_cap;           /* report entries kept per read */
+} cid_readid_params;
+
+int cid_read_id_batch(cid_index* idx, const char* bases, const char* quals, const uint64_t* seq_offs, uint64_t nseq,
+                      const uint64_t* read_offs, uint64_t nreads, const cid_readid_params* p, uint32_t* n_set,
+                      uint32_t* flags, uint32_t* rep_n, uint32_t* rep_colour, uint32_t* rep_count);
+/* Device-resident variant; all pointers are device memory.  h_max_read_bases = longest read (sum
+ * of mates, bases) sizes the shared-memory tile; h_max_kmers = largest number of k-mer start
+ * positions of any read (0 = derive a bound from h_max_read_bases). */
+int cid_read_id_batch_dev(cid_index* idx, const char* d_bases, const char* d_quals, const uint64_t* d_seq_offs,
+                          uint64_t nseq, uint64_t nbases, const uint64_t* d_read_offs, uint64_t nreads,
+                          uint32_t h_max_read_bases, uint32_t h_max_kmers, const cid_readid_params* p,
+                          uint32_t* d_n_set, uint32_t* d_flags, uint32_t* d_rep_n, uint32_t* d_rep_colour,
+                          uint32_t* d_rep_count, void* stream);
+/* Debug/parity hook: the emulated FnvHashSet<String> iteration order of each read's k-mer set as
+ * (mate index, position of first occurrence).  order_n[r] entries at [r*order_cap ..]. */
+int cid_read_kmer_order(cid_index* idx, const char* bases, const uint64_t* seq_offs, uint64_t nseq,
+                        const uint64_t* read_offs, uint64_t nreads, const cid_readid_params* p, uint32_t order_cap,
+                        uint32_t* order_n, uint8_t* order_seq, uint16_t* order_pos);
+
+/* Row indices of canonical k-mers given as ASCII (k bytes each): out[n*num_hash] =
+ * xxh3_64(kmer, seed=i) % bloom_size  (simple_bloom.rs:21-24).  Parity hook for the hash. */
+int cid_hash_kmers(cid_index* idx, const char* kmers, uint64_t n, uint64_t* row_ids);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COLORID_B200_H */

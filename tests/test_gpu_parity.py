@@ -1,0 +1,230 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle, bit-exact."""
+import numpy as np
+import pytest
+
+import colorid_b200 as cb
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _rng(seed):
+    return np.random.default_rng(0xC0101D00 + seed)
+
+
+def build_both(oracle, ctx, accessions, S, H, k, mode, cutoff=-1):
+    N = len(accessions)
+    oix = oracle.Index(S, H, k, N)
+    gix = cb.Index(ctx, S, H, k, N)
+    for c, acc in enumerate(accessions):
+        o_n, o_used = oix.build_accession(c, acc, mode, cutoff)
+        g_n, g_used = gix.build_accession(c, acc, mode, cutoff)
+        assert (g_n, g_used) == (o_n, o_used), f"accession {c}: n_ref/cutoff differ"
+    oix.finalize(threads=4)
+    gix.finalize()
+    return oix, gix
+
+
+@pytest.mark.parametrize("k", [4, 8, 9, 16, 17, 21, 27, 31])
+def test_hash_rows_match_oracle(oracle, ctx, k):
+    rng = _rng(k)
+    H = 4
+    gix2 = cb.Index(ctx, 999_983, H, k, 1)   # small matrix; only bloom_size/num_hash/k matter here
+    kmers = [synth.rand_seq(rng, k) for _ in range(2000)]
+    got = gix2.hash_kmers(kmers)
+    exp = np.array([[oracle.xxh3_64(km, s) % 999_983 for s in range(H)] for km in kmers], dtype=np.uint64)
+    assert np.array_equal(got, exp)
+
+
+@pytest.mark.parametrize("k,S,H,N", [(27, 750_000, 4, 4), (31, 300_007, 4, 46), (21, 200_003, 2, 70), (15, 65_536, 3, 33)])
+def test_build_fasta_matrix_bit_exact(oracle, ctx, k, S, H, N):
+    rng = _rng(N)
+    genomes = synth.clade_genomes(rng, N, 6000, n_clades=4, div=0.02)
+    accs = []
+    for i, g in enumerate(genomes):
+        contigs = [g[:2500], g[2500:2510], g[2510:]]          # a contig shorter than k is skipped
+        if i % 5 == 0:
+            contigs[0] = synth.sprinkle(rng, contigs[0], b"NRYn", 0.01)   # has_no_n
+        if i % 7 == 0:
+            contigs[2] = contigs[2].lower()                   # raw-case compare, then upper-case
+        if i % 11 == 0:
+            contigs[2] = synth.sprinkle(rng, contigs[2], b"acgt", 0.3)    # mixed case
+        accs.append(contigs)
+    oix, gix = build_both(oracle, ctx, accs, S, H, k, cb.CID_SEQ_FASTA)
+    assert np.array_equal(gix.download_dense(), oix.words())
+    assert gix.nonzero_rows() == oix.nonzero_rows()
+    ids, words = gix.download_nonzero_rows()
+    dense = oix.words()
+    nz = np.flatnonzero(dense.any(axis=1))
+    assert np.array_equal(ids, nz.astype(np.uint64)) and np.array_equal(words, dense[nz])
+
+
+def test_build_fastq_autocutoff(oracle, ctx):
+    rng = _rng(7)
+    k, S, H = 21, 400_009, 2
+    genomes = synth.clade_genomes(rng, 3, 5000, n_clades=3, div=0.05)
+    accs = []
+    for g in genomes:
+        reads = synth.reads_from(rng, [g], 1200, read_len=100, insert=200, err=0.01, frac_random=0.0, n_rate=0.002)
+        accs.append([m for r in reads for m in r])
+    for cutoff in (-1, 0, 2):
+        oix, gix = build_both(oracle, ctx, accs, S, H, k, cb.CID_SEQ_FASTQ, cutoff)
+        assert np.array_equal(gix.download_dense(), oix.words())
+
+
+def _index_pair(oracle, ctx, rng, N, k, S, H, glen=8000):
+    genomes = synth.clade_genomes(rng, N, glen, n_clades=max(2, N // 8), div=0.01)
+    oix, gix = build_both(oracle, ctx, [[g] for g in genomes], S, H, k, cb.CID_SEQ_FASTA)
+    return genomes, oix, gix
+
+
+@pytest.mark.parametrize("N,k,S,H", [(4, 27, 750_000, 4), (46, 31, 500_009, 4), (100, 21, 300_007, 2), (1100, 21, 60_013, 2)])
+def test_search_counts_and_unique_hits(oracle, ctx, N, k, S, H):
+    rng = _rng(100 + N)
+    genomes, oix, gix = _index_pair(oracle, ctx, rng, N, k, S, H, glen=3000 if N > 200 else 8000)
+    queries = []
+    for i in range(40):
+        g = genomes[int(rng.integers(0, N))]
+        s = int(rng.integers(0, len(g) - 2500))
+        q = g[s:s + int(rng.integers(k, 2400))]
+        if i % 3 == 1:
+            q = synth.mutate(rng, q, 0.02)
+        if i % 3 == 2:
+            q = synth.rand_seq(rng, 1500)
+        queries.append([q] if i % 4 else [q[:len(q) // 2], q[len(q) // 2:], b"ACGT"])
+    queries.append([b"ACG"])               # shorter than k: zero k-mers
+    queries.append([genomes[0]])           # a whole genome (several work units)
+    for gene in (True, False):
+        o = oix.query_counts(queries, oracle.MODE_FASTA, gene, 0)
+        g = gix.query_counts(queries, cb.CID_SEQ_FASTA, gene, 0)
+        assert np.array_equal(g["num_kmers"], o["num_kmers"])
+        assert np.array_equal(g["counts"], o["counts"])
+        assert np.array_equal(g["uniq_n"], o["uniq_n"])
+        assert np.array_equal(g["uniq_sum"], o["uniq_sum"])
+        assert np.array_equal(g["uniq_mode"], o["uniq_mode"])
+
+
+def test_search_fastq_query_with_filters(oracle, ctx):
+    rng = _rng(300)
+    genomes, oix, gix = _index_pair(oracle, ctx, rng, 12, 27, 400_009, 4)
+    reads = synth.reads_from(rng, genomes[:2], 1500, read_len=120, insert=250, err=0.01, frac_random=0.05, n_rate=0.001)
+    q = [[m for r in reads for m in r]]
+    for filt in (-1, 0, 1, 3):
+        o = oix.query_counts(q, oracle.MODE_FASTQ, False, filt)
+        g = gix.query_counts(q, cb.CID_SEQ_FASTQ, False, filt)
+        assert np.array_equal(g["cutoff"], o["cutoff"])
+        assert np.array_equal(g["num_kmers"], o["num_kmers"])
+        assert np.array_equal(g["counts"], o["counts"])
+        assert np.array_equal(g["uniq_n"], o["uniq_n"]) and np.array_equal(g["uniq_sum"], o["uniq_sum"])
+        assert np.array_equal(g["uniq_mode"], o["uniq_mode"])
+
+
+@pytest.mark.parametrize("N,k,S,H", [(4, 27, 750_000, 4), (70, 21, 300_007, 2), (1100, 21, 60_013, 2)])
+def test_perfect_search(oracle, ctx, N, k, S, H):
+    rng = _rng(400 + N)
+    genomes, oix, gix = _index_pair(oracle, ctx, rng, N, k, S, H, glen=3000 if N > 200 else 8000)
+    queries = []
+    for i in range(30):
+        g = genomes[int(rng.integers(0, N))]
+        s = int(rng.integers(0, len(g) - 1500))
+        q = g[s:s + int(rng.integers(k, 1400))]
+        if i % 3 == 2:
+            q = synth.mutate(rng, q, 0.01)
+        queries.append([q])
+    queries.append([b"AC"])
+    queries.append([synth.rand_seq(rng, 500)])
+    o = oix.query_perfect(queries)
+    g = gix.query_perfect(queries)
+    assert np.array_equal(g["status"], o["status"])
+    assert np.array_equal(g["n_kmers"], o["n_kmers"])
+    assert np.array_equal(g["and_rows"], o["and_rows"])
+    assert (o["status"] == 0).sum() >= 10
+
+
+def _readid_compare(oracle, oix, gix, reads, **kw):
+    okw = dict(kw)
+    o = oix.read_id_batch(reads, order_cap=600, **okw)
+    on, osq, opos = gix.read_kmer_order(reads, d=kw.get("d", 1), group_width=kw.get("group_width", 16),
+                                        reserve_before_find=kw.get("reserve_before_find", True), order_cap=600)
+    ok_reads = o["kind"] != oracle.CLS_PANIC
+    assert np.array_equal(on[ok_reads], o["order_n"][ok_reads])
+    for r in np.flatnonzero(ok_reads):
+        n = on[r]
+        assert np.array_equal(osq[r, :n], o["order_seq"][r, :n]), f"read {r}: k-mer order (mate) differs"
+        assert np.array_equal(opos[r, :n], o["order_pos"][r, :n]), f"read {r}: k-mer order (pos) differs"
+    g = gix.read_id_batch(reads, d=kw.get("d", 1), start_sample=kw.get("start_sample", 3),
+                          group_width=kw.get("group_width", 16), reserve_before_find=kw.get("reserve_before_find", True))
+    assert np.array_equal(g["n_set"][ok_reads], o["n_set"][ok_reads])
+    too_short = (g["flags"] & 1) != 0
+    assert np.array_equal(too_short, o["kind"] == oracle.CLS_TOO_SHORT)
+    assert np.array_equal((g["flags"] & 2) != 0, o["kind"] == oracle.CLS_PANIC)
+    # the device reports final_report in insertion order; the oracle in FnvHashMap iteration order:
+    # compare as sets here, ordering of ties is checked in test_host_vote
+    for r in np.flatnonzero(ok_reads):
+        gd = dict(zip(g["rep_colour"][r, :g["rep_n"][r]].tolist(), g["rep_count"][r, :g["rep_n"][r]].tolist()))
+        od = dict(zip(o["rep_colour"][r, :o["rep_n"][r]].tolist(), o["rep_count"][r, :o["rep_n"][r]].tolist()))
+        assert gd == od, f"read {r}: report differs {gd} vs {od}"
+        # insertion order -> emulated map iteration order must reproduce the oracle's sequence
+        keys = g["rep_colour"][r, :g["rep_n"][r]].astype(np.uint64)
+        order = oracle.hashmap_usize_order(keys, kw.get("group_width", 16))
+        assert keys[order].tolist() == o["rep_colour"][r, :o["rep_n"][r]].tolist()
+    return o, g
+
+
+@pytest.mark.parametrize("N,k,S,H", [(4, 27, 750_000, 4), (46, 31, 2_000_003, 4), (40, 21, 100_003, 2)])
+def test_read_id_narrow_rows(oracle, ctx, N, k, S, H):
+    rng = _rng(500 + N)
+    genomes, oix, gix = _index_pair(oracle, ctx, rng, N, k, S, H)
+    reads = synth.reads_from(rng, genomes, 300, read_len=150, insert=320, err=0.004, frac_random=0.25, n_rate=0.002)
+    reads += synth.reads_from(rng, genomes, 60, read_len=150, insert=200, err=0.0, frac_random=0.0)   # overlapping mates
+    reads += synth.reads_from(rng, genomes, 40, read_len=100, insert=300, err=0.0, frac_random=0.0, paired=False)
+    reads.append([b"ACGT", genomes[0][:150]])                         # mate 1 shorter than k -> too_short
+    reads.append([genomes[0][:150], genomes[0][200:200 + k - 1]])     # mate 2 of length k-1: no k-mers, no panic
+    reads.append([genomes[0][:150], b"ACGTAC"])                       # mate 2 shorter than k-1: reference panics
+    reads.append([b"N" * 150, b"N" * 150])                            # no valid k-mers: empty report
+    reads.append([genomes[1][:150], genomes[1][:150]])                # identical mates: every k-mer duplicated
+    for kw in (dict(), dict(start_sample=0), dict(start_sample=1), dict(d=3), dict(reserve_before_find=False),
+               dict(group_width=8)):
+        _readid_compare(oracle, oix, gix, reads, **kw)
+
+
+def test_read_id_wide_rows(oracle, ctx):
+    rng = _rng(900)
+    genomes, oix, gix = _index_pair(oracle, ctx, rng, 150, 21, 300_007, 2, glen=4000)
+    reads = synth.reads_from(rng, genomes, 200, read_len=150, insert=320, err=0.003, frac_random=0.2)
+    for kw in (dict(), dict(start_sample=0)):
+        _readid_compare(oracle, oix, gix, reads, **kw)
+
+
+def test_read_id_quality_mask_on_device(oracle, ctx):
+    rng = _rng(950)
+    genomes, oix, gix = _index_pair(oracle, ctx, rng, 6, 27, 750_000, 4)
+    reads = synth.reads_from(rng, genomes, 120, read_len=150, insert=320, err=0.002, frac_random=0.1)
+    quals = [[bytes(rng.choice(np.frombuffer(b"#+5?I", dtype=np.uint8), size=len(m), p=[.03, .03, .04, .3, .6]).tolist())
+              for m in r] for r in reads]
+    masked = [[oracle.qual_mask(m, q, 15) for m, q in zip(r, qr)] for r, qr in zip(reads, quals)]
+    o = oix.read_id_batch(masked)
+    g = gix.read_id_batch(reads, quals=quals, qual_offset=15)
+    assert np.array_equal(g["n_set"], o["n_set"])
+    for r in range(len(reads)):
+        gd = dict(zip(g["rep_colour"][r, :g["rep_n"][r]].tolist(), g["rep_count"][r, :g["rep_n"][r]].tolist()))
+        od = dict(zip(o["rep_colour"][r, :o["rep_n"][r]].tolist(), o["rep_count"][r, :o["rep_n"][r]].tolist()))
+        assert gd == od
+
+
+def test_upload_rows_roundtrip(oracle, ctx):
+    rng = _rng(77)
+    genomes, oix, gix = _index_pair(oracle, ctx, rng, 40, 21, 100_003, 2)
+    ids, words = gix.download_nonzero_rows()
+    g2 = cb.Index(ctx, 100_003, 2, 21, 40)
+    g2.upload_rows(ids, words)
+    assert np.array_equal(g2.download_dense(), oix.words())
+    q = [[genomes[3][100:900]]]
+    assert np.array_equal(g2.query_counts(q, gene_search=True, filt=0)["counts"], oix.query_counts(q, 0, True, 0)["counts"])
+
+
+def test_lowercase_fastq_is_refused_loudly(ctx):
+    gix = cb.Index(ctx, 10_007, 2, 11, 2)
+    with pytest.raises(cb.CidError) as e:
+        gix.build_accession(0, [b"acgtacgtacgtacgtacgtacgtacgt"], cb.CID_SEQ_FASTQ, 0)
+    assert e.value.code == cb.lib.CID_E_UNSUPPORTED
