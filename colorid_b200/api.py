@@ -53,6 +53,47 @@ class Context:
     def launches(self):
         return self.lib.cid_ctx_launch_count(self.h)
 
+    def profile(self, enable=True):
+        L.check(self.lib.cid_ctx_profile(self.h, int(enable)))
+
+    def profile_read(self):
+        """{kernel name: (total ms, launches)} accumulated since profile(True)."""
+        out = {}
+        k = 0
+        while True:
+            name, ms, n = C.c_char_p(), C.c_double(0), C.c_uint64(0)
+            if self.lib.cid_ctx_profile_read(self.h, k, C.byref(name), C.byref(ms), C.byref(n)) != 0:
+                break
+            if n.value:
+                out[name.value.decode()] = (ms.value, n.value)
+            k += 1
+        return out
+
+
+CLS_NAMES = ["too_short", "no_hits", "no_significant_hits", "accept", "reject_multi", "ref_panic"]
+
+
+def classify_reads(index_params, n_ref, rep, fp_correct=1e-3, group_width=16, threads=0, top_cap=8):
+    """kmer_poll_plus over a batch (host threads). index_params = (bloom_size, num_hash, n_colours);
+    rep = dict from Index.read_id_batch."""
+    lib = L.load()
+    S, H, N = index_params
+    nr = len(rep["n_set"])
+    n_ref = np.ascontiguousarray(n_ref, dtype=np.uint64)
+    kind = np.zeros(max(nr, 1), np.int32)
+    hits = np.zeros(max(nr, 1), np.uint32)
+    n_top = np.zeros(max(nr, 1), np.uint32)
+    top = np.zeros((max(nr, 1), top_cap), np.uint32)
+    rc = np.ascontiguousarray(rep["rep_colour"])
+    rv = np.ascontiguousarray(rep["rep_count"])
+    L.check(lib.cid_classify_reads(S, H, N, _p(n_ref, L.u64p), fp_correct, group_width, nr,
+                                   _p(np.ascontiguousarray(rep["n_set"]), L.u32p),
+                                   _p(np.ascontiguousarray(rep["flags"]), L.u32p),
+                                   _p(np.ascontiguousarray(rep["rep_n"]), L.u32p), _p(rc, L.u32p), _p(rv, L.u32p),
+                                   rc.shape[1] if rc.ndim == 2 else 1, threads, _p(kind, C.POINTER(C.c_int32)),
+                                   _p(hits, L.u32p), _p(n_top, L.u32p), _p(top, L.u32p), top_cap))
+    return dict(kind=kind[:nr], hits=hits[:nr], n_top=n_top[:nr], top=top[:nr])
+
 
 class Index:
     """Device-resident BIGSI index (bigsi.rs:19-27 BigsyMapNew)."""

@@ -41,6 +41,31 @@ int PinBuf::ensure(size_t bytes) {
 }
 void PinBuf::release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 
+static const char* kKernelNames[KID_COUNT] = {"kmerize_insert", "region_histogram", "region_to_bloom", "transpose_bitsets",
+                                              "rownz", "query_counts", "query_uniq_wide", "query_perfect",
+                                              "readid_kmerize", "readid_order", "readid_vote", "table_clear", "other"};
+static cudaEvent_t prof_event(cid_ctx* c) {
+    if (!c->prof_pool.empty()) { cudaEvent_t e = c->prof_pool.back(); c->prof_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+ProfScope::ProfScope(cid_ctx* c, cudaStream_t s, int kernel) : ctx(c), st(s), idx(-1) {
+    if (!c->prof_on) return;
+    cid_ctx::ProfRec r; r.kernel = kernel; r.a = prof_event(c); r.b = prof_event(c);
+    cudaEventRecord(r.a, s);
+    c->prof_recs.push_back(r);
+    idx = (int)c->prof_recs.size() - 1;
+}
+ProfScope::~ProfScope() { if (idx >= 0) cudaEventRecord(ctx->prof_recs[idx].b, st); }
+static void prof_collect(cid_ctx* c) {
+    for (auto& r : c->prof_recs) {
+        cudaEventSynchronize(r.b);
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { c->prof_ms[r.kernel] += ms; c->prof_n[r.kernel]++; }
+        c->prof_pool.push_back(r.a); c->prof_pool.push_back(r.b);
+    }
+    c->prof_recs.clear();
+}
+
 int check_err_flags(cid_ctx* ctx, cudaStream_t st) {
     CID_CUDA(cudaMemcpyAsync(ctx->h_err, ctx->d_err, 4, cudaMemcpyDeviceToHost, st));
     CID_CUDA(cudaStreamSynchronize(st));
@@ -96,6 +121,7 @@ __global__ void table_clear_kernel(Slot* t, uint64_t n) {
 static int table_clear(cid_ctx* ctx, cudaStream_t st, void* d_table, uint64_t nslots) {
     unsigned grid = (unsigned)std::min<uint64_t>((nslots + 255) / 256, (uint64_t)ctx->sm_count * 32);
     if (grid == 0) grid = 1;
+    ProfScope ps(ctx, st, KID_TABLE_CLEAR);
     table_clear_kernel<<<grid, 256, 0, st>>>((Slot*)d_table, nslots);
     ctx->launches++;
     CID_CUDA(cudaGetLastError());
@@ -193,6 +219,8 @@ int cid_ctx_create(int device, cid_ctx** out) {
 void cid_ctx_destroy(cid_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    prof_collect(c);
+    for (auto e : c->prof_pool) cudaEventDestroy(e);
     for (auto& b : c->scratch) b.release();
     for (auto& b : c->pinned) b.release();
     if (c->d_err) cudaFree(c->d_err);
@@ -201,6 +229,20 @@ void cid_ctx_destroy(cid_ctx* c) {
     delete c;
 }
 int cid_ctx_device(const cid_ctx* c) { return c ? c->device : -1; }
+int cid_ctx_profile(cid_ctx* c, int enable) {
+    prof_collect(c);
+    c->prof_on = enable != 0;
+    for (int i = 0; i < KID_COUNT; i++) { c->prof_ms[i] = 0; c->prof_n[i] = 0; }
+    return CID_OK;
+}
+int cid_ctx_profile_read(cid_ctx* c, int kernel, const char** name, double* total_ms, uint64_t* launches) {
+    if (kernel < 0 || kernel >= KID_COUNT) return CID_E_INVALID;
+    prof_collect(c);
+    if (name) *name = kKernelNames[kernel];
+    if (total_ms) *total_ms = c->prof_ms[kernel];
+    if (launches) *launches = c->prof_n[kernel];
+    return CID_OK;
+}
 uint64_t cid_ctx_launch_count(const cid_ctx* c) { return c ? c->launches : 0; }
 
 // ------------------------------------------------------------------ index

@@ -104,6 +104,7 @@ int launch_kmerize_insert(cid_ctx* ctx, cudaStream_t st, const uint8_t* d_bases,
                           int seq_mode) {
     if (base_hi <= base_lo || nseq == 0) return CID_OK;
     uint64_t ntiles = (base_hi - base_lo + KT - 1) / KT;
+    ProfScope ps(ctx, st, KID_KMERIZE_INSERT);
     kmerize_insert_kernel<<<(unsigned)ntiles, KT_THREADS, 0, st>>>(d_bases, d_seq_offs, nseq, base_lo, base_hi, d_seq_group,
                                                                   d_region_off, d_region_mask, (Slot*)d_table, k,
                                                                   seq_mode, ctx->d_err);
@@ -156,6 +157,7 @@ int launch_region_histogram(cid_ctx* ctx, cudaStream_t st, const void* d_region,
                             uint32_t hist_bins, uint32_t* d_overflow, uint32_t overflow_cap, uint32_t* d_overflow_n) {
     unsigned grid = (unsigned)std::min<uint64_t>((nslots + 255) / 256, (uint64_t)ctx->sm_count * 16);
     if (grid == 0) grid = 1;
+    ProfScope ps(ctx, st, KID_HISTOGRAM);
     region_histogram_kernel<<<grid, 256, 0, st>>>((const Slot*)d_region, nslots, d_hist, hist_bins, d_overflow,
                                                   overflow_cap, d_overflow_n);
     ctx->launches++;
@@ -190,6 +192,7 @@ int launch_region_to_bloom(cid_ctx* ctx, cudaStream_t st, const void* d_region, 
                            uint32_t k, uint32_t H, uint64_t S, uint32_t* d_bitset, unsigned long long* d_nref) {
     unsigned grid = (unsigned)std::min<uint64_t>((nslots + 255) / 256, (uint64_t)ctx->sm_count * 16);
     if (grid == 0) grid = 1;
+    ProfScope ps(ctx, st, KID_TO_BLOOM);
     region_to_bloom_kernel<<<grid, 256, 0, st>>>((const Slot*)d_region, nslots, (long long)cutoff, k, H, make_mods(S),
                                                  d_bitset, d_nref);
     ctx->launches++;
@@ -237,6 +240,7 @@ transpose_bitsets_kernel(const uint32_t* __restrict__ bitsets, uint64_t bs_words
 }
 int launch_transpose(cid_ctx* ctx, cudaStream_t st, const cid_index* idx) {
     dim3 grid((unsigned)((idx->S + TR_ROWS - 1) / TR_ROWS), (idx->W + TR_WCOLS - 1) / TR_WCOLS);
+    ProfScope ps(ctx, st, KID_TRANSPOSE);
     transpose_bitsets_kernel<<<grid, 256, 0, st>>>(idx->bitsets, idx->bs_words, idx->N, idx->S, idx->rows, idx->Wp,
                                                    idx->W);
     ctx->launches++;
@@ -258,6 +262,7 @@ rownz_kernel(const uint32_t* __restrict__ rows, uint64_t S, uint32_t Wp, uint32_
 }
 int launch_rownz(cid_ctx* ctx, cudaStream_t st, const cid_index* idx) {
     uint64_t nthreads = (idx->S + 31) / 32 * 32;
+    ProfScope ps(ctx, st, KID_ROWNZ);
     rownz_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(idx->rows, idx->S, idx->Wp, idx->rownz);
     ctx->launches++;
     CID_CUDA(cudaGetLastError());
@@ -458,6 +463,8 @@ int launch_query_counts(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, con
     }
     ModS mods = make_mods(idx->S);
     const bool inline_uniq = want_uniq && idx->Wp <= 32;
+    {
+    ProfScope ps(ctx, st, KID_QUERY_COUNTS);
     if (inline_uniq)
         query_counts_kernel<true><<<(unsigned)nunits, 256, smem, st>>>(
             idx->rows, idx->Wp, idx->W, idx->N, idx->k, idx->H, mods, (const Slot*)d_table, d_unit_group, d_unit_slot0,
@@ -466,9 +473,11 @@ int launch_query_counts(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, con
         query_counts_kernel<false><<<(unsigned)nunits, 256, smem, st>>>(
             idx->rows, idx->Wp, idx->W, idx->N, idx->k, idx->H, mods, (const Slot*)d_table, d_unit_group, d_unit_slot0,
             d_unit_nslots, (const long long*)d_filter, d_counts, d_num_kmers, d_uniq_list, uniq_cap, d_uniq_n);
+    }
     ctx->launches++;
     CID_CUDA(cudaGetLastError());
     if (want_uniq && !inline_uniq) {
+        ProfScope ps(ctx, st, KID_QUERY_UNIQ_WIDE);
         query_uniq_wide_kernel<<<(unsigned)nunits, 256, smem, st>>>(
             idx->rows, idx->Wp, idx->k, idx->H, mods, (const Slot*)d_table, d_unit_group, d_unit_slot0, d_unit_nslots,
             (const long long*)d_filter, d_uniq_list, uniq_cap, d_uniq_n);
@@ -517,6 +526,7 @@ int launch_query_perfect(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, co
         CID_CUDA(cudaFuncSetAttribute(query_perfect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         attr_set = true;
     }
+    ProfScope ps(ctx, st, KID_QUERY_PERFECT);
     query_perfect_kernel<<<(unsigned)nunits, 256, smem, st>>>(idx->rows, idx->rownz, idx->Wp, idx->W, idx->k, idx->H,
                                                              make_mods(idx->S), (const Slot*)d_table, d_unit_group,
                                                              d_unit_slot0, d_unit_nslots, d_and_rows, d_missing,
@@ -542,6 +552,7 @@ __global__ void hash_kmers_kernel(const uint8_t* __restrict__ kmers, uint64_t n,
 int launch_hash_kmers(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, const uint8_t* d_kmers, uint64_t n,
                       uint64_t* d_rows) {
     if (n == 0) return CID_OK;
+    ProfScope ps(ctx, st, KID_OTHER);
     hash_kmers_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_kmers, n, idx->k, idx->H, make_mods(idx->S), d_rows);
     ctx->launches++;
     CID_CUDA(cudaGetLastError());

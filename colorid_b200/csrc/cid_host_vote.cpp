@@ -1,0 +1,186 @@
+// Host side of read_id's vote: read_id_mt_pe.rs:187-251 kmer_poll_plus, :168-181 not_fp_signicant,
+// :695-698 false_prob, :18-38 false_prob_map.  The device hands over each read's final_report in
+// INSERTION order; ties between equally scored accessions are reported in the iteration order of
+// the reference's FnvHashMap<usize,usize> (hashbrown), which is reproduced here from that order.
+//
+// Floating point: f64, same operation order as the Rust source; `probability::Binomial::mass`
+// (third-party, not vendored in the reference) is restated as Loader's saddle-point algorithm.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "cid_internal.h"
+
+namespace cid {
+
+// ---- probability::Binomial::mass ----------------------------------------------------------------
+static double stirling_err(double n) {
+    static const double table[16] = {
+        0.0, 0.081061466795327258219670264, 0.041340695955409294093822081, 0.0276779256849983391487892927,
+        0.020790672103765093111522771, 0.0166446911898211921631948653, 0.013876128823070747998745727,
+        0.0118967099458917700950557241, 0.010411265261972096497478567, 0.0092554621827127329177286366,
+        0.008330563433362871256469318, 0.0075736754879518407949720242, 0.006942840107209529865664152,
+        0.0064089941880042070684396310, 0.005951370112758847735624416, 0.0055547335519628013710386899};
+    if (n < 16.0) return table[(int)n];
+    const double n2 = n * n;
+    const double s0 = 1.0 / 12.0, s1 = 1.0 / 360.0, s2 = 1.0 / 1260.0, s3 = 1.0 / 1680.0, s4 = 1.0 / 1188.0;
+    if (n > 500.0) return (s0 - s1 / n2) / n;
+    if (n > 80.0) return (s0 - (s1 - s2 / n2) / n2) / n;
+    if (n > 35.0) return (s0 - (s1 - (s2 - s3 / n2) / n2) / n2) / n;
+    return (s0 - (s1 - (s2 - (s3 - s4 / n2) / n2) / n2) / n2) / n;
+}
+static double deviance_term(double x, double np) {
+    if (std::fabs(x - np) < 0.1 * (x + np)) {
+        double v = (x - np) / (x + np);
+        double s = (x - np) * (x - np) / (x + np);
+        double ej = 2.0 * x * v;
+        for (int j = 1;; j++) {
+            ej *= v * v;
+            double s1 = s + ej / (double)(2 * j + 1);
+            if (s1 == s) return s1;
+            s = s1;
+        }
+    }
+    return x * std::log(x / np) + np - x;
+}
+double binomial_pmf(uint64_t n_, double p, uint64_t x_) {
+    if (p == 0.0) return x_ == 0 ? 1.0 : 0.0;
+    if (p == 1.0) return x_ == n_ ? 1.0 : 0.0;
+    const double q = 1.0 - p, n = (double)n_;
+    if (x_ == 0) return std::exp(n * std::log(q));
+    if (x_ == n_) return std::exp(n * std::log(p));
+    const double x = (double)x_, rest = n - x;
+    const double lc = stirling_err(n) - stirling_err(x) - stirling_err(rest) - deviance_term(x, n * p) - deviance_term(rest, n * q);
+    return std::exp(lc) * std::sqrt(n / (2.0 * M_PI * x * rest));
+}
+
+// read_id_mt_pe.rs:695-698
+double bloom_false_prob(double m, double k, double n) {
+    return std::pow(1.0 - std::pow(M_E, -((k * (n + 0.5)) / (m - 1.0))), k);
+}
+
+// ---- FnvHashMap<usize,usize> iteration order from the insertion sequence --------------------------
+// fnv: h = 0xcbf29ce484222325; for each of the 8 LE bytes: h ^= b; h *= 0x100000001b3.
+static inline uint64_t fnv_usize(uint64_t v) {
+    uint64_t h = 0xcbf29ce484222325ULL;
+    for (int i = 0; i < 8; i++) { h ^= (v >> (8 * i)) & 0xFF; h *= 0x100000001b3ULL; }
+    return h;
+}
+// entry().or_insert(): the table grows only when a NEW key arrives with no growth left.
+// Returns the positions (into keys[]) in ascending bucket order.
+static void usize_map_order(const uint32_t* keys, uint32_t n, uint32_t gw, std::vector<int32_t>& tab,
+                            std::vector<int32_t>& tmp, std::vector<uint32_t>& order) {
+    uint32_t nb = 0, items = 0, growth = 0;
+    auto cap_of = [](uint32_t b) { return b == 0 ? 0u : (b < 8 ? b - 1 : b / 8 * 7); };
+    auto probe = [&](const std::vector<int32_t>& t, uint32_t buckets, uint64_t hash) -> uint32_t {
+        const uint32_t mask = buckets - 1;
+        uint32_t pos = (uint32_t)hash & mask;
+        if (buckets < gw) {
+            for (uint32_t b = 0; b < buckets; b++) { uint32_t s = (pos + b) & mask; if (t[s] < 0) return s; }
+            return 0;
+        }
+        for (uint32_t stride = 0;;) {
+            for (uint32_t b = 0; b < gw; b++) { uint32_t s = (pos + b) & mask; if (t[s] < 0) return s; }
+            stride += gw;
+            pos = (pos + stride) & mask;
+        }
+    };
+    for (uint32_t i = 0; i < n; i++) {
+        if (growth == 0) {
+            uint32_t nn = nb == 0 ? 4 : nb * 2;
+            tmp.assign(nn, -1);
+            for (uint32_t s = 0; s < nb; s++) if (tab[s] >= 0) tmp[probe(tmp, nn, fnv_usize(keys[tab[s]]))] = tab[s];
+            tab.swap(tmp);
+            nb = nn;
+            growth = cap_of(nb) - items;
+        }
+        tab[probe(tab, nb, fnv_usize(keys[i]))] = (int32_t)i;
+        items++; growth--;
+    }
+    order.clear();
+    for (uint32_t s = 0; s < nb; s++) if (tab[s] >= 0) order.push_back((uint32_t)tab[s]);
+}
+
+}  // namespace cid
+
+using namespace cid;
+
+extern "C" {
+
+double cid_false_prob(double bloom_size, double num_hash, double n_ref_kmers) {
+    return bloom_false_prob(bloom_size, num_hash, n_ref_kmers);
+}
+double cid_binomial_mass(uint64_t n, double p, uint64_t x) { return binomial_pmf(n, p, x); }
+
+int cid_classify_reads(uint64_t bloom_size, uint32_t num_hash, uint32_t n_colors, const uint64_t* n_ref_by_colour,
+                       double fp_correct, uint32_t group_width, uint64_t nreads, const uint32_t* n_set,
+                       const uint32_t* flags, const uint32_t* rep_n, const uint32_t* rep_colour,
+                       const uint32_t* rep_count, uint32_t rep_cap, int threads, int32_t* kind, uint32_t* hits,
+                       uint32_t* n_top, uint32_t* top, uint32_t top_cap) {
+    if (!n_ref_by_colour || !n_set || !flags || !rep_n || !rep_colour || !rep_count || !kind || !hits || !n_top) {
+        set_error("cid_classify_reads: null argument");
+        return CID_E_INVALID;
+    }
+    if (group_width != 8 && group_width != 16) group_width = 16;
+    std::vector<double> fp(n_colors);      // false_prob_map, read_id_mt_pe.rs:18-38
+    for (uint32_t c = 0; c < n_colors; c++)
+        fp[c] = bloom_false_prob((double)bloom_size, (double)num_hash, (double)n_ref_by_colour[c]);
+    if (threads < 1) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    std::atomic<uint64_t> next(0);
+    auto work = [&]() {
+        std::vector<int32_t> tab, tmp;
+        std::vector<uint32_t> order;
+        std::vector<std::pair<uint32_t, uint32_t>> cv, sig;
+        for (;;) {
+            uint64_t r0 = next.fetch_add(4096);
+            if (r0 >= nreads) break;
+            uint64_t r1 = std::min(nreads, r0 + 4096);
+            for (uint64_t r = r0; r < r1; r++) {
+                hits[r] = 0; n_top[r] = 0;
+                if (flags[r] & 1u) { kind[r] = CID_CLS_TOO_SHORT; continue; }          // :305-313
+                if (flags[r] & 2u) { kind[r] = CID_CLS_REF_PANIC; continue; }
+                const uint32_t n = rep_n[r];
+                if (n == 0) { kind[r] = CID_CLS_NO_HITS; continue; }                   // report.is_empty(), :332-340
+                const uint32_t* keys = rep_colour + r * (uint64_t)rep_cap;
+                const uint32_t* vals = rep_count + r * (uint64_t)rep_cap;
+                cv.clear();
+                if (n == 1) cv.push_back({keys[0], vals[0]});
+                else {
+                    usize_map_order(keys, n, group_width, tab, tmp, order);
+                    for (uint32_t i : order) cv.push_back({keys[i], vals[i]});
+                    std::stable_sort(cv.begin(), cv.end(), [](const std::pair<uint32_t, uint32_t>& a,
+                                                              const std::pair<uint32_t, uint32_t>& b) { return a.second > b.second; });
+                }
+                if (cv[0].first == n_colors && cv.size() == 1) { kind[r] = CID_CLS_NO_HITS; continue; }   // :197-205
+                const uint64_t observations = n_set[r];
+                sig.clear();
+                for (auto& t : cv) {
+                    if (t.first == n_colors) continue;
+                    const double p_false = fp[t.first];
+                    const double critical = (double)observations * p_false;
+                    const double th = (double)t.second;
+                    bool drop = th < critical;
+                    if (!drop && th > critical) drop = binomial_pmf(observations, p_false, t.second) >= fp_correct;
+                    if (!drop) sig.push_back(t);
+                }
+                if (sig.empty()) { kind[r] = CID_CLS_NO_SIGNIFICANT; continue; }
+                uint32_t nt = 0;
+                for (auto& h : sig) if (h.second == sig[0].second) { if (top && nt < top_cap) top[r * (uint64_t)top_cap + nt] = h.first; nt++; }
+                hits[r] = sig[0].second;
+                n_top[r] = nt;
+                kind[r] = nt == 1 ? CID_CLS_ACCEPT : CID_CLS_REJECT_MULTI;
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < threads; t++) th.emplace_back(work);
+    work();
+    for (auto& x : th) x.join();
+    return CID_OK;
+}
+
+}  // extern "C"

@@ -58,6 +58,13 @@ struct cid_ctx {
     cid::PinBuf pinned[8];
     uint32_t* d_err = nullptr;       // device error/flag words (zeroed before each call)
     uint32_t* h_err = nullptr;       // pinned mirror
+    // optional per-kernel timing (CUDA events on the launching stream)
+    bool prof_on = false;
+    struct ProfRec { int kernel; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[16] = {0};
+    uint64_t prof_n[16] = {0};
 };
 
 struct cid_index {
@@ -86,6 +93,15 @@ enum {
 };
 
 int check_err_flags(cid_ctx* ctx, cudaStream_t st);   // syncs the stream
+
+// kernel ids for the profiling hooks (names in cid_api.cu: kKernelNames)
+enum { KID_KMERIZE_INSERT = 0, KID_HISTOGRAM, KID_TO_BLOOM, KID_TRANSPOSE, KID_ROWNZ, KID_QUERY_COUNTS, KID_QUERY_UNIQ_WIDE,
+       KID_QUERY_PERFECT, KID_READID_KMERIZE, KID_READID_ORDER, KID_READID_VOTE, KID_TABLE_CLEAR, KID_OTHER, KID_COUNT };
+struct ProfScope {     // records an event pair around a launch when profiling is enabled
+    cid_ctx* ctx; cudaStream_t st; int idx;
+    ProfScope(cid_ctx* c, cudaStream_t s, int kernel);
+    ~ProfScope();
+};
 
 inline uint32_t padded_row_words(uint32_t W) {
     if (W <= 1) return 1;

@@ -172,8 +172,11 @@ __device__ __forceinline__ uint32_t hb_probe(const E* T, uint32_t nb, uint32_t p
 }
 __device__ __forceinline__ uint32_t hb_cap(uint32_t nb) { return nb == 0 ? 0 : (nb < 8 ? nb - 1 : nb / 8 * 7); }
 
+// Per thread in shared memory: the two ping-pong tables (TB + TB/2 entries of E = index of the
+// insert call) and the low hash bits of every call (hp: 8 bits, h9: bit 8), so the dependent
+// probe chain never leaves the SM; the only global traffic is the sequential scan of the entries.
 template <typename E>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(32)
 readid_order_kernel(const uint32_t* __restrict__ entries, const uint32_t* __restrict__ nocc, uint64_t nreads,
                     uint32_t maxocc, uint32_t TB, uint32_t gw, uint32_t rbf, uint16_t* __restrict__ order,
                     uint32_t* __restrict__ n_set_out, uint64_t r0) {
@@ -181,32 +184,53 @@ readid_order_kernel(const uint32_t* __restrict__ entries, const uint32_t* __rest
     const E EMPTY = (E)~(E)0;
     const uint64_t rl = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (rl >= nreads) return;
-    E* X = (E*)dsm + (size_t)threadIdx.x * (TB + TB / 2);
+    // u8 tables (TB <= 512): 9 hash bits as hp (8) + h9 (1); u16 tables: 16 hash bits in hp16
+    constexpr bool kSmall = sizeof(E) == 1;
+    const uint32_t hwords = kSmall ? (maxocc + 31) / 32 : 0;
+    const size_t per_thread = ((size_t)(TB + TB / 2) * sizeof(E) + (size_t)maxocc * sizeof(E) + hwords * 4 + 3) & ~(size_t)3;
+    uint8_t* mine = dsm + (size_t)threadIdx.x * per_thread;
+    E* X = (E*)mine;
     E* Y = X + TB;
+    E* hp = Y + TB / 2;
+    uint32_t* h9 = (uint32_t*)(mine + per_thread - hwords * 4);
     const uint32_t* row = entries + rl * (uint64_t)maxocc;
     const uint32_t n = nocc[rl];
+    for (uint32_t w = 0; w < hwords; w++) h9[w] = 0;
     uint32_t nb = 0, items = 0, growth = 0;
     E* cur = X;
     // table of size s lives in X when log2(TB/s) is even, else in Y
     auto buf_for = [&](uint32_t s) -> E* { return ((__ffs(TB) - __ffs(s)) & 1) ? Y : X; };
-    for (uint32_t j = 0; j < n; j++) {
-        const uint32_t e = __ldg(row + j);
-        const bool fresh = ENT_FRESH(e);
-        if (growth == 0 && (rbf || fresh)) {
-            // reserve_rehash -> resize(capacity_to_buckets(max(items+1, cap+1)))
-            uint32_t newb = nb == 0 ? 4 : nb * 2;
-            E* nt = buf_for(newb);
-            for (uint32_t s = 0; s < newb; s++) nt[s] = EMPTY;
-            for (uint32_t s = 0; s < nb; s++) {
-                E v = cur[s];
-                if (v != EMPTY) nt[hb_probe<E>(nt, newb, __ldg(row + v) & 0xFFFFu, gw, EMPTY)] = v;
+    auto hash_of = [&](uint32_t j) -> uint32_t {
+        if (kSmall) return (uint32_t)hp[j] | (((h9[j >> 5] >> (j & 31)) & 1u) << 8);
+        return (uint32_t)hp[j];
+    };
+    for (uint32_t j0 = 0; j0 < n; j0 += 4) {
+        const uint4 e4 = __ldg((const uint4*)(row + j0));
+        const uint32_t ev[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t j = j0 + q;
+            if (j >= n) break;
+            const uint32_t e = ev[q];
+            const bool fresh = ENT_FRESH(e);
+            if (growth == 0 && (rbf || fresh)) {
+                // reserve_rehash -> resize(capacity_to_buckets(max(items+1, cap+1)))
+                uint32_t newb = nb == 0 ? 4 : nb * 2;
+                E* nt = buf_for(newb);
+                for (uint32_t s = 0; s < newb; s++) nt[s] = EMPTY;
+                for (uint32_t s = 0; s < nb; s++) {
+                    E v = cur[s];
+                    if (v != EMPTY) nt[hb_probe<E>(nt, newb, hash_of(v), gw, EMPTY)] = v;
+                }
+                cur = nt; nb = newb;
+                growth = hb_cap(nb) - items;
             }
-            cur = nt; nb = newb;
-            growth = hb_cap(nb) - items;
-        }
-        if (fresh) {
-            cur[hb_probe<E>(cur, nb, e & 0xFFFFu, gw, EMPTY)] = (E)j;
-            items++; growth--;
+            if (fresh) {
+                hp[j] = (E)e;
+                if (kSmall) h9[j >> 5] |= ((e >> 8) & 1u) << (j & 31);
+                cur[hb_probe<E>(cur, nb, e & 0xFFFFu, gw, EMPTY)] = (E)j;
+                items++; growth--;
+            }
         }
     }
     uint16_t* out = order + rl * (uint64_t)maxocc;
@@ -249,7 +273,7 @@ readid_vote_narrow_kernel(const uint8_t* __restrict__ bases, const uint8_t* __re
         ReadGeom g;
         warp_load_read(t, cap, bases, quals, maxq, seq_offs, __ldg(read_offs + r), __ldg(read_offs + r + 1), moffs, lane, g);
         const uint16_t* ordrow = order + rl * (uint64_t)maxocc;
-        uint32_t cand0 = 0, cand1 = 0, cnt0 = 0, cnt1 = 0, nrep = 0;
+        uint32_t cand0 = 0, cand1 = 0, cnt0 = 0, cnt1 = 0, nrep = 0, nproc = 0;
         bool miss = false;
         for (uint32_t c0 = 0; c0 < n && !miss; c0 += 32) {
             const uint32_t idx = c0 + lane;
@@ -299,6 +323,7 @@ readid_vote_narrow_kernel(const uint8_t* __restrict__ bases, const uint8_t* __re
                     uint32_t v = __popc(__ballot_sync(0xffffffffu, (z1 >> b) & 1u));
                     if ((uint32_t)lane == b) cnt1 += v;
                 }
+            nproc += missmask ? p_local + 1 : min(32u, n - c0);
             if (missmask) miss = true;
         }
         __syncwarp();
@@ -315,7 +340,8 @@ readid_vote_narrow_kernel(const uint8_t* __restrict__ bases, const uint8_t* __re
         if (lane == 0) {
             if (miss && nrep < rep_cap) { rc[nrep] = N; rv[nrep] = 1; }
             rep_n[r] = min(total, rep_cap);
-            if (total > rep_cap) flags[r] |= 4u;
+            // bits 8..23: k-mers whose rows were needed (up to and including the first miss)
+            flags[r] |= (total > rep_cap ? 4u : 0u) | (min(nproc, 0xFFFFu) << 8);
         }
     }
 }
@@ -358,7 +384,7 @@ readid_vote_wide_kernel(const uint8_t* __restrict__ bases, const uint8_t* __rest
         uint32_t cand[RV_MAXWPL], pl[RV_MAXWPL][RV_PLANES];
 #pragma unroll
         for (int w = 0; w < RV_MAXWPL; w++) { cand[w] = 0; for (int p = 0; p < RV_PLANES; p++) pl[w][p] = 0; }
-        uint32_t nrep = 0;
+        uint32_t nrep = 0, nproc = 0;
         bool miss = false;
         for (uint32_t j = 0; j < n; j++) {
             uint32_t e = __ldg(ordrow + j);
@@ -371,6 +397,7 @@ readid_vote_wide_kernel(const uint8_t* __restrict__ bases, const uint8_t* __rest
                 rid[h] = mod_s(xxh3_kmer(in, k, h), mods);
                 if (!((__ldg(rownz + (rid[h] >> 5)) >> (rid[h] & 31)) & 1u)) present = false;
             }
+            nproc++;
             if (!present) { miss = true; break; }
             const bool seeding = classic || j < start_sample;
 #pragma unroll
@@ -423,7 +450,7 @@ readid_vote_wide_kernel(const uint8_t* __restrict__ bases, const uint8_t* __rest
             uint32_t total = nrep + (miss ? 1u : 0u);
             if (miss && nrep < rep_cap) { rc[nrep] = N; rv[nrep] = 1; }
             rep_n[r] = min(total, rep_cap);
-            if (total > rep_cap) flags[r] |= 4u;
+            flags[r] |= (total > rep_cap ? 4u : 0u) | (min(nproc, 0xFFFFu) << 8);
         }
     }
 }
@@ -466,6 +493,7 @@ int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const ui
     (void)nseq; (void)nbases;
     cid_ctx* ctx = idx->ctx;
     if (nreads == 0) return CID_OK;
+    if (idx->k == 0) return CID_E_INVALID;
     if (max_read_bases > 1000) { set_error("read_id: reads longer than 1000 bases (all mates) are not supported yet"); return CID_E_UNSUPPORTED; }
     if (p.downsample == 0 || (p.group_width != 16 && p.group_width != 8)) { set_error("read_id: bad params"); return CID_E_INVALID; }
     if (idx->Wp > 32 * RV_MAXWPL) { set_error("read_id: more than %d accessions per shard not supported", 32 * 32 * RV_MAXWPL); return CID_E_UNSUPPORTED; }
@@ -490,7 +518,9 @@ int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const ui
     // shared memory budgets
     size_t a_warp = ((tile_smem_bytes(cap) + 7) & ~(size_t)7) + (size_t)tsize * 12 + (size_t)cap * 4 + (MAX_MATES + 1) * 4 + 4;
     size_t a_smem = RA_WARPS * ((a_warp + 15) & ~(size_t)15);
-    size_t b_smem = (size_t)64 * (TB + TB / 2) * (small ? 1 : 2);
+    const size_t b_thread = small ? (((size_t)(TB + TB / 2) + maxocc + ((maxocc + 31) / 32) * 4 + 3) & ~(size_t)3)
+                                  : (((size_t)(TB + TB / 2) * 2 + (size_t)maxocc * 2 + 3) & ~(size_t)3);
+    size_t b_smem = 32 * b_thread;
     size_t cn_warp = ((tile_smem_bytes(cap) + 15) & ~(size_t)15) + 64 + (MAX_MATES + 1) * 4 + 12;
     size_t cn_smem = RA_WARPS * ((cn_warp + 15) & ~(size_t)15);
     size_t cw_warp = ((tile_smem_bytes(cap) + 15) & ~(size_t)15) + (MAX_MATES + 1) * 4 + 12;
@@ -504,18 +534,24 @@ int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const ui
     for (uint64_t r0 = 0; r0 < nreads; r0 += sub) {
         const uint64_t nr = std::min(sub, nreads - r0);
         unsigned gridA = (unsigned)std::min<uint64_t>((nr + RA_WARPS - 1) / RA_WARPS, (uint64_t)ctx->sm_count * 32);
+        {
+        ProfScope ps(ctx, st, KID_READID_KMERIZE);
         readid_kmerize_kernel<<<gridA, RA_WARPS * 32, a_smem, st>>>(d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr,
                                                                    idx->k, p.downsample, cap, maxocc, tsize, d_entries,
                                                                    d_nocc, d_flags, ctx->d_err);
+        }
         ctx->launches++;
         CID_CUDA(cudaGetLastError());
-        unsigned gridB = (unsigned)((nr + 63) / 64);
+        unsigned gridB = (unsigned)((nr + 31) / 32);
+        {
+        ProfScope ps(ctx, st, KID_READID_ORDER);
         if (small)
-            readid_order_kernel<uint8_t><<<gridB, 64, b_smem, st>>>(d_entries, d_nocc, nr, maxocc, TB, p.group_width,
+            readid_order_kernel<uint8_t><<<gridB, 32, b_smem, st>>>(d_entries, d_nocc, nr, maxocc, TB, p.group_width,
                                                                    p.reserve_before_find, d_order, d_n_set, r0);
         else
-            readid_order_kernel<uint16_t><<<gridB, 64, b_smem, st>>>(d_entries, d_nocc, nr, maxocc, TB, p.group_width,
+            readid_order_kernel<uint16_t><<<gridB, 32, b_smem, st>>>(d_entries, d_nocc, nr, maxocc, TB, p.group_width,
                                                                     p.reserve_before_find, d_order, d_n_set, r0);
+        }
         ctx->launches++;
         CID_CUDA(cudaGetLastError());
         if (d_order_n) {
@@ -525,6 +561,7 @@ int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const ui
             CID_CUDA(cudaGetLastError());
         }
         if (d_rep_n) {
+            ProfScope ps(ctx, st, KID_READID_VOTE);
             const uint32_t* rownz = idx->rownz;
             if (idx->Wp <= 2) {
                 if (!idx->rownz_global) rownz = nullptr;   // presence == any word set, already in registers

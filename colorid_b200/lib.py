@@ -58,6 +58,13 @@ SIGNATURES = {
     "cid_read_kmer_order": (C.c_int, [vp, vp, u64p, C.c_uint64, u64p, C.c_uint64, C.POINTER(ReadIdParams), C.c_uint32,
                                       u32p, u8p, u16p]),
     "cid_hash_kmers": (C.c_int, [vp, vp, C.c_uint64, u64p]),
+    "cid_ctx_profile": (C.c_int, [vp, C.c_int]),
+    "cid_ctx_profile_read": (C.c_int, [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double), u64p]),
+    "cid_classify_reads": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, u64p, C.c_double, C.c_uint32, C.c_uint64, u32p,
+                                     u32p, u32p, u32p, u32p, C.c_uint32, C.c_int, C.POINTER(C.c_int32), u32p, u32p, u32p,
+                                     C.c_uint32]),
+    "cid_false_prob": (C.c_double, [C.c_double, C.c_double, C.c_double]),
+    "cid_binomial_mass": (C.c_double, [C.c_uint64, C.c_double, C.c_uint64]),
 }
 
 _LIB = None

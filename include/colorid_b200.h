@@ -54,6 +54,12 @@ void cid_ctx_destroy(cid_ctx* ctx);
 int cid_ctx_device(const cid_ctx* ctx);
 /* Counters of kernels launched by this library since ctx creation (for bench `gpu_launches`). */
 uint64_t cid_ctx_launch_count(const cid_ctx* ctx);
+/* Per-kernel device timing with CUDA events on the launching stream (for bench.py's roofline).
+ * cid_ctx_profile(ctx, 1) resets the accumulators and enables timing, (ctx, 0) disables it;
+ * cid_ctx_profile_read returns name / total ms / launch count of kernel id 0..N-1
+ * (CID_E_INVALID past the last id). */
+int cid_ctx_profile(cid_ctx* ctx, int enable);
+int cid_ctx_profile_read(cid_ctx* ctx, int kernel, const char** name, double* total_ms, uint64_t* launches);
 
 /* ---- index: bigsi.rs:19-27 BigsyMapNew {bloom_size, num_hash, k_size, colors, map, n_ref_kmers}
  * Device layout: dense row-major matrix rows[bloom_size][row_words] of u32, bit c of a row =
@@ -122,7 +128,8 @@ int cid_query_perfect(cid_index* idx, const char* bases, const uint64_t* seq_off
  * Per read r the report is written in final_report INSERTION order:
  *   rep_n[r] entries at rep_colour/rep_count[r*rep_cap ..]; colour == n_colors is the "no hit" key.
  * flags[r]: bit0 = too_short (mate 1 shorter than k), bit1 = reference would panic (a later mate
- * shorter than k-1), bit2 = report truncated at rep_cap. */
+ * shorter than k-1), bit2 = report truncated at rep_cap, bits 8..23 = number of k-mers whose rows
+ * were gathered (up to and including the first miss; the algorithmic traffic of SURVEY §8d). */
 typedef struct cid_readid_params {
     uint32_t downsample;        /* -d, kmer.rs:229 step_by(d) */
     uint32_t start_sample;      /* -B bitvector_sample; 0 = search_index_classic */
@@ -148,6 +155,28 @@ int cid_read_id_batch_dev(cid_index* idx, const char* d_bases, const char* d_qua
 int cid_read_kmer_order(cid_index* idx, const char* bases, const uint64_t* seq_offs, uint64_t nseq,
                         const uint64_t* read_offs, uint64_t nreads, const cid_readid_params* p, uint32_t order_cap,
                         uint32_t* order_n, uint8_t* order_seq, uint16_t* order_pos);
+
+/* ---- read_id vote, host side: read_id_mt_pe.rs:187-251 kmer_poll_plus (+ :168-181, :695-698, :18-38)
+ * Takes the per-read reports produced by cid_read_id_batch (insertion order) and classifies every
+ * read with `threads` host threads (<=0: all cores).  kind[r] is one of CID_CLS_*; hits[r] and
+ * n_set[r] are fields 3 and 4 of PREFIX_reads.txt; top[r*top_cap ..] lists the n_top[r] best
+ * accessions in the order the reference joins them with ','. */
+enum {
+    CID_CLS_TOO_SHORT = 0,       /* "too_short", 0, 0, "accept", 0 */
+    CID_CLS_NO_HITS = 1,         /* "no_hits", 0, n_set, "accept", 0 */
+    CID_CLS_NO_SIGNIFICANT = 2,  /* "no_significant_hits", 0, n_set, "reject", 0 */
+    CID_CLS_ACCEPT = 3,          /* name, hits, n_set, "accept", 1 */
+    CID_CLS_REJECT_MULTI = 4,    /* "a,b,..", hits, n_set, "reject", n_top */
+    CID_CLS_REF_PANIC = 5        /* the reference panics on this read (a later mate shorter than k-1) */
+};
+int cid_classify_reads(uint64_t bloom_size, uint32_t num_hash, uint32_t n_colors, const uint64_t* n_ref_by_colour,
+                       double fp_correct, uint32_t group_width, uint64_t nreads, const uint32_t* n_set,
+                       const uint32_t* flags, const uint32_t* rep_n, const uint32_t* rep_colour,
+                       const uint32_t* rep_count, uint32_t rep_cap, int threads, int32_t* kind, uint32_t* hits,
+                       uint32_t* n_top, uint32_t* top, uint32_t top_cap);
+/* read_id_mt_pe.rs:695-698 false_prob and the Binomial pmf used by :168-181 (parity hooks). */
+double cid_false_prob(double bloom_size, double num_hash, double n_ref_kmers);
+double cid_binomial_mass(uint64_t n, double p, uint64_t x);
 
 /* Row indices of canonical k-mers given as ASCII (k bytes each): out[n*num_hash] =
  * xxh3_64(kmer, seed=i) % bloom_size  (simple_bloom.rs:21-24).  Parity hook for the hash. */
