@@ -142,6 +142,26 @@ __device__ __forceinline__ uint32_t fnv1a_low32_key(uint64_t key, uint32_t k) {
     return (h ^ 0xFFu) * 0x1b3u;
 }
 
+// Same, 4 bases per shared-memory LUT lookup (3 ops per byte instead of 7).
+__device__ __forceinline__ uint32_t fnv1a_low32_key_lut(const uint32_t* lut, uint64_t key, uint32_t k) {
+    uint32_t h = 0x84222325u;
+    uint64_t kk = key << (64 - 2 * k);
+    uint32_t j = 0;
+    for (; j + 4 <= k; j += 4) {
+        uint32_t w = lut[(uint32_t)(kk >> 56)];
+        kk <<= 8;
+        h = (h ^ (w & 0xFFu)) * 0x1b3u;
+        h = (h ^ ((w >> 8) & 0xFFu)) * 0x1b3u;
+        h = (h ^ ((w >> 16) & 0xFFu)) * 0x1b3u;
+        h = (h ^ (w >> 24)) * 0x1b3u;
+    }
+    if (j < k) {
+        uint32_t w = lut[(uint32_t)(kk >> 56)];
+        for (; j < k; j++) { h = (h ^ (w & 0xFFu)) * 0x1b3u; w >>= 8; }
+    }
+    return (h ^ 0xFFu) * 0x1b3u;
+}
+
 // Reverse complement of a packed k-mer.
 __device__ __forceinline__ uint64_t revcomp_key(uint64_t v, uint32_t k) {
     uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
@@ -179,25 +199,56 @@ __device__ __forceinline__ Tile tile_carve(uint8_t* smem, int cap) {
     t.len = 0;
     return t;
 }
+// 4 bases (one little-endian u32, first base in byte 0) -> 8 code bits (first base in bits 7:6),
+// and 4-bit LSB-first masks of "not ACGTacgt" / "lower-case acgt".
+__device__ __forceinline__ void pack4(uint32_t w, uint32_t& pk, uint32_t& bad4, uint32_t& low4) {
+    const uint32_t u = w & 0xDFDFDFDFu;                                   // fold case
+    const uint32_t t = ((u >> 1) ^ (u >> 2)) & 0x03030303u;               // A0 C1 G2 T3 per byte
+    const uint32_t c0 = t & 0x01010101u, c1 = (t >> 1) & 0x01010101u, cc = c0 & c1;
+    // the upper-case letter that code stands for: 'A' + {0,2,6,19}
+    const uint32_t expect = 0x41414141u + (c0 << 1) + (c1 << 2) + (c1 << 1) + (cc << 3) + (cc << 1) + cc;
+    const uint32_t x = u ^ expect;
+    const uint32_t nz = (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;   // byte != 0 (exact per byte)
+    const uint32_t badf = nz >> 7;                                                // 0/1 per byte
+    const uint32_t lowf = (w >> 5) & 0x01010101u & ~badf;
+    bad4 = (badf * 0x01020408u) >> 24;
+    low4 = (lowf * 0x01020408u) >> 24;
+    pk = ((t << 6) | (t >> 4) | (t >> 14) | (t >> 24)) & 0xFFu;
+}
 // Build codes/bad/lower from ascii[0..len) (ascii already in smem; caller syncs before and after).
+// Every thread packs 16 bases per step with SIMD-in-register byte arithmetic; nthreads must be a
+// multiple of 32 (mask words are assembled from lane pairs).
 __device__ __forceinline__ void tile_pack(Tile& t, int cap, int tid, int nthreads) {
-    const int nwords32 = cap / 32 + 2;
-    for (int w = tid; w < nwords32; w += nthreads) {
-        uint32_t bad = 0, low = 0, c0 = 0, c1 = 0;
-        int base = w * 32;
-        for (int j = 0; j < 32; j++) {
-            int p = base + j;
-            uint32_t c = (p < t.len) ? t.ascii[p] : 0u;
-            bool ok = base_is_acgt(c);
-            bad |= (ok ? 0u : 1u) << j;
-            low |= ((ok && (c & 0x20u)) ? 1u : 0u) << j;
-            uint32_t code = ok ? base_code(c) : 0u;
-            if (j < 16) c0 |= code << (30 - 2 * j); else c1 |= code << (30 - 2 * (j - 16));
+    const int ngroups = (cap / 16 + 3 + 1) & ~1;            // 16-base groups incl. padding, even
+    const uint32_t* a4 = (const uint32_t*)t.ascii;
+    for (int g0 = 0; g0 < ngroups; g0 += nthreads) {
+        const int g = g0 + tid;
+        uint32_t codes = 0, bad16 = 0xFFFFu, low16 = 0;
+        const int nvalid = t.len - g * 16;                   // bases of this group inside the tile
+        if (g < ngroups && nvalid > 0) {
+            uint32_t pk, b4, l4;
+            bad16 = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                pack4(a4[g * 4 + q], pk, b4, l4);
+                codes |= pk << (24 - 8 * q);
+                bad16 |= b4 << (4 * q);
+                low16 |= l4 << (4 * q);
+            }
+            if (nvalid < 16) {
+                const uint32_t keep = (1u << nvalid) - 1;
+                bad16 |= ~keep & 0xFFFFu;
+                low16 &= keep;
+            }
         }
-        t.bad[w] = bad;
-        t.lower[w] = low;
-        if (2 * w < cap / 16 + 3) t.codes[2 * w] = c0;
-        if (2 * w + 1 < cap / 16 + 3) t.codes[2 * w + 1] = c1;
+        const uint32_t pb = __shfl_down_sync(0xffffffffu, bad16, 1), pl = __shfl_down_sync(0xffffffffu, low16, 1);
+        if (g < ngroups) {
+            if (g < cap / 16 + 3) t.codes[g] = codes;
+            if (!(g & 1) && (g >> 1) < cap / 32 + 2) {
+                t.bad[g >> 1] = bad16 | (pb << 16);
+                t.lower[g >> 1] = low16 | (pl << 16);
+            }
+        }
     }
 }
 __device__ __forceinline__ uint32_t mask_window(const uint32_t* m, int i, uint32_t k) {   // k <= 32

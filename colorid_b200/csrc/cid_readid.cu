@@ -19,6 +19,7 @@
 namespace cid {
 
 constexpr int RA_WARPS = 4;
+constexpr uint32_t FINE_STEPS = 2;   // fine-grained (lane per hash row) steps at the start of each read's vote
 constexpr int MAX_MATES = 8;
 
 // entry layout (u32): [15:0] fnv low16 | [25:16] tile position | [26] took_fwd | [27] fresh
@@ -67,6 +68,9 @@ readid_kmerize_kernel(const uint8_t* __restrict__ bases, const uint8_t* __restri
                       uint32_t* __restrict__ entries, uint32_t* __restrict__ nocc, uint32_t* __restrict__ flags,
                       uint32_t* __restrict__ err) {
     extern __shared__ __align__(16) uint8_t dsm[];
+    __shared__ uint32_t lut[256];
+    lut4_init(lut, threadIdx.x, blockDim.x);
+    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t per_warp = ((tile_smem_bytes(cap) + 7) & ~(size_t)7) + (size_t)tsize * 8 + (size_t)tsize * 4 +
                             (size_t)cap * 4 + (MAX_MATES + 1) * 4 + 4;
@@ -136,7 +140,7 @@ readid_kmerize_kernel(const uint8_t* __restrict__ bases, const uint8_t* __restri
                 if (valid) {
                     uint32_t s = info & 0xFFFFFu;
                     bool fresh = tmin[s] == (uint32_t)tp;
-                    uint32_t f = fresh ? (fnv1a_low32_key(tkeys[s], k) & 0xFFFFu) : 0u;
+                    uint32_t f = fresh ? (fnv1a_low32_key_lut(lut, tkeys[s], k) & 0xFFFFu) : 0u;
                     ent = f | ((uint32_t)tp << 16) | (((info >> 30) & 1u) << 26) | ((fresh ? 1u : 0u) << 27);
                 }
                 uint32_t bal = __ballot_sync(0xffffffffu, valid);
@@ -155,17 +159,28 @@ readid_kmerize_kernel(const uint8_t* __restrict__ bases, const uint8_t* __restri
 // b/8*7; a HashSet::insert with growth_left == 0 resizes (before the duplicate check when
 // `rbf`, i.e. hashbrown >= 0.14); resize re-inserts the old table in ascending bucket order;
 // insert slot = first EMPTY in the `gw`-wide group at hash&mask, else triangular probing.
-template <typename E>
-__device__ __forceinline__ uint32_t hb_probe(const E* T, uint32_t nb, uint32_t pos, uint32_t gw, E empty) {
+// Occupancy bitmaps (bit s = bucket s is full) make the insert-slot search a constant-time
+// funnel-shift + ffs instead of a byte-by-byte scan whose length (and the warp's, which pays the
+// maximum over its 32 reads) explodes as the load factor approaches 7/8.
+__device__ __forceinline__ uint32_t hb_window(const uint32_t* bm, uint32_t nb, uint32_t pos) {
+    // 32 occupancy bits starting at bucket `pos`, cyclic in the nb-bucket table
+    if (nb >= 32) {
+        const uint32_t nw = nb >> 5, w = pos >> 5;
+        return __funnelshift_r(bm[w], bm[(w + 1) & (nw - 1)], pos & 31);
+    }
+    uint32_t x = bm[0];
+    x *= nb == 4 ? 0x11111111u : nb == 8 ? 0x01010101u : 0x00010001u;     // replicate the nb-bit pattern
+    return __funnelshift_r(x, x, pos);
+}
+__device__ __forceinline__ uint32_t hb_probe(const uint32_t* bm, uint32_t nb, uint32_t pos, uint32_t gw) {
     const uint32_t mask = nb - 1;
     pos &= mask;
-    if (nb < gw) {
-        for (uint32_t b = 0; b < nb; b++) { uint32_t s = (pos + b) & mask; if (T[s] == empty) return s; }
-        return 0;   // unreachable: load factor < 1
-    }
+    const uint32_t width = nb < gw ? nb : gw;       // small tables: cyclic linear probe over all buckets
+    const uint32_t wmask = (1u << width) - 1;
     uint32_t stride = 0;
     for (;;) {
-        for (uint32_t b = 0; b < gw; b++) { uint32_t s = (pos + b) & mask; if (T[s] == empty) return s; }
+        const uint32_t free_ = ~hb_window(bm, nb, pos) & wmask;
+        if (free_) return (pos + (uint32_t)__ffs(free_) - 1) & mask;
         stride += gw;
         pos = (pos + stride) & mask;
     }
@@ -173,72 +188,92 @@ __device__ __forceinline__ uint32_t hb_probe(const E* T, uint32_t nb, uint32_t p
 __device__ __forceinline__ uint32_t hb_cap(uint32_t nb) { return nb == 0 ? 0 : (nb < 8 ? nb - 1 : nb / 8 * 7); }
 
 // Per thread in shared memory: the two ping-pong tables (TB + TB/2 entries of E = index of the
-// insert call) and the low hash bits of every call (hp: 8 bits, h9: bit 8), so the dependent
-// probe chain never leaves the SM; the only global traffic is the sequential scan of the entries.
+// insert call), their occupancy bitmaps and the low hash bits of every call, so the dependent
+// probe chain never leaves the SM.  Control flow is a two-state machine (REHASH one old bucket |
+// consume one insert call) so that the 32 reads of a warp stay converged even though they
+// resize at different times.
 template <typename E>
 __global__ void __launch_bounds__(32)
 readid_order_kernel(const uint32_t* __restrict__ entries, const uint32_t* __restrict__ nocc, uint64_t nreads,
                     uint32_t maxocc, uint32_t TB, uint32_t gw, uint32_t rbf, uint16_t* __restrict__ order,
                     uint32_t* __restrict__ n_set_out, uint64_t r0) {
     extern __shared__ __align__(16) uint8_t dsm[];
-    const E EMPTY = (E)~(E)0;
     const uint64_t rl = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (rl >= nreads) return;
-    // u8 tables (TB <= 512): 9 hash bits as hp (8) + h9 (1); u16 tables: 16 hash bits in hp16
+    const bool live = rl < nreads;
+    // u8 tables (TB <= 512): 9 hash bits as hp (8) + h9 (1); u16 tables: 16 hash bits in hp
     constexpr bool kSmall = sizeof(E) == 1;
     const uint32_t hwords = kSmall ? (maxocc + 31) / 32 : 0;
-    const size_t per_thread = ((size_t)(TB + TB / 2) * sizeof(E) + (size_t)maxocc * sizeof(E) + hwords * 4 + 3) & ~(size_t)3;
+    const uint32_t bwX = TB >= 32 ? TB / 32 : 1, bwY = TB >= 64 ? TB / 64 : 1;
+    const size_t tab_bytes = ((size_t)(TB + TB / 2) * sizeof(E) + (size_t)maxocc * sizeof(E) + 3) & ~(size_t)3;
+    const size_t per_thread = tab_bytes + (size_t)(hwords + bwX + bwY) * 4;
     uint8_t* mine = dsm + (size_t)threadIdx.x * per_thread;
     E* X = (E*)mine;
     E* Y = X + TB;
     E* hp = Y + TB / 2;
-    uint32_t* h9 = (uint32_t*)(mine + per_thread - hwords * 4);
-    const uint32_t* row = entries + rl * (uint64_t)maxocc;
-    const uint32_t n = nocc[rl];
-    for (uint32_t w = 0; w < hwords; w++) h9[w] = 0;
+    uint32_t* h9 = (uint32_t*)(mine + tab_bytes);
+    uint32_t* bmX = h9 + hwords;
+    uint32_t* bmY = bmX + bwX;
+    for (uint32_t i = 0; i < hwords + bwX + bwY; i++) h9[i] = 0;
+    const uint32_t* row = entries + (live ? rl : 0) * (uint64_t)maxocc;
+    const uint32_t n = live ? nocc[rl] : 0;
     uint32_t nb = 0, items = 0, growth = 0;
-    E* cur = X;
-    // table of size s lives in X when log2(TB/s) is even, else in Y
-    auto buf_for = [&](uint32_t s) -> E* { return ((__ffs(TB) - __ffs(s)) & 1) ? Y : X; };
+    uint32_t nb_old = 0, s = 0;          // rehash scan state: active while s < nb_old
+    E* cur = X; uint32_t* bcur = bmX;
+    E* old = X; uint32_t* bold = bmX;
+    // a table of size sz lives in X when log2(TB/sz) is even, else in Y
+    auto in_y = [&](uint32_t sz) -> bool { return ((__ffs(TB) - __ffs(sz)) & 1) != 0; };
     auto hash_of = [&](uint32_t j) -> uint32_t {
         if (kSmall) return (uint32_t)hp[j] | (((h9[j >> 5] >> (j & 31)) & 1u) << 8);
         return (uint32_t)hp[j];
     };
-    for (uint32_t j0 = 0; j0 < n; j0 += 4) {
-        const uint4 e4 = __ldg((const uint4*)(row + j0));
-        const uint32_t ev[4] = {e4.x, e4.y, e4.z, e4.w};
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const uint32_t j = j0 + q;
-            if (j >= n) break;
-            const uint32_t e = ev[q];
+    uint32_t j = 0;
+    uint4 buf = n ? __ldg((const uint4*)row) : make_uint4(0, 0, 0, 0);          // entries j&~3 .. +3
+    uint4 nxt = n > 4 ? __ldg((const uint4*)(row + 4)) : make_uint4(0, 0, 0, 0);  // prefetched next group
+    while (j < n || s < nb_old) {
+        if (s < nb_old) {
+            // REHASH: move the next full old bucket (resize re-inserts in ascending bucket order)
+            const uint32_t w = bold[s >> 5] >> (s & 31);
+            if (w == 0) { s = (s | 31) + 1; continue; }
+            s += __ffs(w) - 1;
+            const E v = old[s];
+            const uint32_t slot = hb_probe(bcur, nb, hash_of(v), gw);
+            cur[slot] = v;
+            bcur[slot >> 5] |= 1u << (slot & 31);
+            s++;
+        } else {
+            const uint32_t q = j & 3;
+            const uint32_t e = q == 0 ? buf.x : q == 1 ? buf.y : q == 2 ? buf.z : buf.w;
             const bool fresh = ENT_FRESH(e);
             if (growth == 0 && (rbf || fresh)) {
-                // reserve_rehash -> resize(capacity_to_buckets(max(items+1, cap+1)))
-                uint32_t newb = nb == 0 ? 4 : nb * 2;
-                E* nt = buf_for(newb);
-                for (uint32_t s = 0; s < newb; s++) nt[s] = EMPTY;
-                for (uint32_t s = 0; s < nb; s++) {
-                    E v = cur[s];
-                    if (v != EMPTY) nt[hb_probe<E>(nt, newb, hash_of(v), gw, EMPTY)] = v;
-                }
-                cur = nt; nb = newb;
+                // reserve_rehash -> resize(capacity_to_buckets(max(items+1, cap+1))): buckets double
+                old = cur; bold = bcur; nb_old = nb; s = 0;
+                nb = nb == 0 ? 4 : nb * 2;
+                const bool y = in_y(nb);
+                cur = y ? Y : X; bcur = y ? bmY : bmX;
+                for (uint32_t i = 0; i < (nb >= 32 ? nb / 32 : 1u); i++) bcur[i] = 0;
                 growth = hb_cap(nb) - items;
+                continue;                       // the same insert call is retried after the rehash
             }
             if (fresh) {
                 hp[j] = (E)e;
                 if (kSmall) h9[j >> 5] |= ((e >> 8) & 1u) << (j & 31);
-                cur[hb_probe<E>(cur, nb, e & 0xFFFFu, gw, EMPTY)] = (E)j;
+                const uint32_t slot = hb_probe(bcur, nb, e & 0xFFFFu, gw);
+                cur[slot] = (E)j;
+                bcur[slot >> 5] |= 1u << (slot & 31);
                 items++; growth--;
+            }
+            j++;
+            if ((j & 3) == 0) {
+                buf = nxt;
+                if (j + 4 < n) nxt = __ldg((const uint4*)(row + j + 4));
             }
         }
     }
+    if (!live) return;
     uint16_t* out = order + rl * (uint64_t)maxocc;
     uint32_t c = 0;
-    for (uint32_t s = 0; s < nb; s++) {
-        E v = cur[s];
-        if (v != EMPTY) out[c++] = (uint16_t)((__ldg(row + v) >> 16) & 0x7FFu);
-    }
+    for (uint32_t t = 0; t < nb; t++)
+        if ((bcur[t >> 5] >> (t & 31)) & 1u) out[c++] = (uint16_t)((__ldg(row + cur[t]) >> 16) & 0x7FFu);
     n_set_out[r0 + rl] = c;
 }
 
@@ -275,17 +310,59 @@ readid_vote_narrow_kernel(const uint8_t* __restrict__ bases, const uint8_t* __re
         const uint16_t* ordrow = order + rl * (uint64_t)maxocc;
         uint32_t cand0 = 0, cand1 = 0, cnt0 = 0, cnt1 = 0, nrep = 0, nproc = 0;
         bool miss = false;
-        for (uint32_t c0 = 0; c0 < n && !miss; c0 += 32) {
+        // The first FINE_STEPS steps take only 32/H k-mers with one lane per (k-mer, hash row): most
+        // reads with a sequencing error or off-target origin hit an absent row within a few k-mers,
+        // and every gather is a 64-byte DRAM fetch for an 8-byte row, so gathers past the first
+        // miss are pure waste.  Later steps take 32 k-mers, one lane each.
+        const bool can_fine = (H == 1 || H == 2 || H == 4 || H == 8);
+        uint32_t fine_left = can_fine ? FINE_STEPS : 0;
+        for (uint32_t c0 = 0; c0 < n && !miss;) {
+            const bool fine = fine_left > 0;
+            const uint32_t csize = fine ? 32u / H : 32u;
+            if (fine) fine_left--;
             const uint32_t idx = c0 + lane;
-            const bool active = idx < n;
+            const bool active = idx < n && (uint32_t)lane < csize;
             uint32_t x0 = 0, x1 = 0;
             bool m = false;
+            HashIn in;
+            in.w0 = in.w1 = in.w2 = in.w3 = 0;
             if (active) {
                 uint32_t e = __ldg(ordrow + idx);
                 uint32_t tp = e & 0x3FFu;
                 uint64_t f = codes_window(t.codes, (int)tp, k);
                 uint64_t key = ((e >> 10) & 1u) ? f : revcomp_key(f, k);
-                HashIn in = hashin_from_key(lut, key, k);
+                in = hashin_from_key(lut, key, k);
+            }
+            if (fine) {
+                // lane L serves k-mer L/H, hash L%H
+                const int src = lane / (int)H;
+                const uint32_t h = (uint32_t)lane % H;
+                HashIn mine;
+                mine.w0 = __shfl_sync(0xffffffffu, in.w0, src);
+                mine.w1 = __shfl_sync(0xffffffffu, in.w1, src);
+                mine.w2 = __shfl_sync(0xffffffffu, in.w2, src);
+                mine.w3 = __shfl_sync(0xffffffffu, in.w3, src);
+                const bool act2 = c0 + (uint32_t)src < n;
+                uint32_t a = 0xFFFFFFFFu, b = WP == 2 ? 0xFFFFFFFFu : 0u;
+                bool mm = false;
+                if (act2) {
+                    uint64_t rid = mod_s(xxh3_kmer(mine, k, h), mods);
+                    if (WP == 2) { uint2 v = __ldg((const uint2*)(rows + rid * 2)); a = v.x; b = v.y; }
+                    else { a = __ldg(rows + rid); b = 0; }
+                    mm = rownz ? !((__ldg(rownz + (rid >> 5)) >> (rid & 31)) & 1u) : ((a | b) == 0u);
+                }
+                // AND / OR across the H lanes of a k-mer
+                for (uint32_t o = 1; o < H; o <<= 1) {
+                    a &= __shfl_xor_sync(0xffffffffu, a, o);
+                    b &= __shfl_xor_sync(0xffffffffu, b, o);
+                    mm = __shfl_xor_sync(0xffffffffu, (int)mm, o) || mm;
+                }
+                // compact: lane j takes k-mer j's result from lane j*H
+                const int from = (lane * (int)H) & 31;
+                uint32_t ca = __shfl_sync(0xffffffffu, a, from), cb2 = __shfl_sync(0xffffffffu, b, from);
+                int cm = __shfl_sync(0xffffffffu, (int)mm, from);
+                if (active) { x0 = ca; x1 = cb2; m = cm != 0; }
+            } else if (active) {
                 x0 = 0xFFFFFFFFu; x1 = WP == 2 ? 0xFFFFFFFFu : 0u;
                 for (uint32_t h = 0; h < H; h++) {
                     uint64_t rid = mod_s(xxh3_kmer(in, k, h), mods);
@@ -298,10 +375,10 @@ readid_vote_narrow_kernel(const uint8_t* __restrict__ bases, const uint8_t* __re
                 }
             }
             const uint32_t missmask = __ballot_sync(0xffffffffu, active && m);
-            const uint32_t p_local = missmask ? (uint32_t)(__ffs(missmask) - 1) : 32u;
+            const uint32_t p_local = missmask ? (uint32_t)(__ffs(missmask) - 1) : csize;
             const bool valid = active && (uint32_t)lane < p_local;
             // candidate colours (and report insertion order) from the first start_sample k-mers
-            uint32_t lim = classic ? 32u : (start_sample > c0 ? min(32u, start_sample - c0) : 0u);
+            uint32_t lim = classic ? csize : (start_sample > c0 ? min(csize, start_sample - c0) : 0u);
             lim = min(lim, min(p_local, n - c0));
             for (uint32_t jj = 0; jj < lim; jj++) {
                 uint32_t y0 = __shfl_sync(0xffffffffu, x0, jj), y1 = __shfl_sync(0xffffffffu, x1, jj);
@@ -323,8 +400,9 @@ readid_vote_narrow_kernel(const uint8_t* __restrict__ bases, const uint8_t* __re
                     uint32_t v = __popc(__ballot_sync(0xffffffffu, (z1 >> b) & 1u));
                     if ((uint32_t)lane == b) cnt1 += v;
                 }
-            nproc += missmask ? p_local + 1 : min(32u, n - c0);
+            nproc += missmask ? p_local + 1 : min(csize, n - c0);
             if (missmask) miss = true;
+            c0 += csize;
         }
         __syncwarp();
         // report in final_report insertion order; the "no hit" key N goes last (inserted at the break)
@@ -518,8 +596,9 @@ int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const ui
     // shared memory budgets
     size_t a_warp = ((tile_smem_bytes(cap) + 7) & ~(size_t)7) + (size_t)tsize * 12 + (size_t)cap * 4 + (MAX_MATES + 1) * 4 + 4;
     size_t a_smem = RA_WARPS * ((a_warp + 15) & ~(size_t)15);
-    const size_t b_thread = small ? (((size_t)(TB + TB / 2) + maxocc + ((maxocc + 31) / 32) * 4 + 3) & ~(size_t)3)
-                                  : (((size_t)(TB + TB / 2) * 2 + (size_t)maxocc * 2 + 3) & ~(size_t)3);
+    const size_t b_esz = small ? 1 : 2;
+    const size_t b_thread = ((((size_t)(TB + TB / 2) + maxocc) * b_esz + 3) & ~(size_t)3) +
+                            4 * ((small ? (maxocc + 31) / 32 : 0) + (TB >= 32 ? TB / 32 : 1) + (TB >= 64 ? TB / 64 : 1));
     size_t b_smem = 32 * b_thread;
     size_t cn_warp = ((tile_smem_bytes(cap) + 15) & ~(size_t)15) + 64 + (MAX_MATES + 1) * 4 + 12;
     size_t cn_smem = RA_WARPS * ((cn_warp + 15) & ~(size_t)15);
