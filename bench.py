@@ -224,6 +224,98 @@ def workload_config(cfg, batch):
                          "and gathers from a 400 MB matrix (126 MB L2)"}
 
 
+# ----------------------------------------------------------------------------- C3 gene search (extra, N=1 only)
+C3 = dict(n_acc=1000, genome_len=3_000_000, n_clades=20, div=0.01, k=21, S=30_000_000, H=2, n_queries=100_000,
+          qlen_lo=1000, qlen_hi=3000)
+
+
+def run_search_extra(torch, dev, ctx, args, quick):
+    """BASELINE.json configs[2]: -g gene search of 100k synthetic 1-3 kb queries against a 1,000-isolate k=21
+    S=30M H=2 index.  Returns a dict for the bench line's `search_c3` key (kernel-level numbers only)."""
+    import colorid_b200 as cb
+    from colorid_b200 import lib as L
+    cfg = dict(C3)
+    if quick:
+        cfg.update(n_acc=64, genome_len=300_000, S=3_000_000, n_queries=5000)
+    g = torch.Generator(device=dev)
+    g.manual_seed(0xC0101D03)
+    A, Lg = cfg["n_acc"], cfg["genome_len"]
+    t0 = time.time()
+    genomes = make_genomes(torch, dev, cfg, 0xC0101D03)                       # [A, Lg] codes
+    lut = torch.tensor(ASCII, device=dev, dtype=torch.uint8)
+    gix = cb.Index(ctx, cfg["S"], cfg["H"], cfg["k"], A)
+    offs = torch.tensor([0, Lg], device=dev, dtype=torch.int64)
+    tb = time.time()
+    for a in range(A):
+        asc = lut[genomes[a].long()].contiguous()
+        torch.cuda.synchronize()
+        gix.build_accession_dev(a, asc.data_ptr(), offs.data_ptr(), 1, Lg)
+    gix.finalize()
+    build_s = time.time() - tb
+    # queries: 80% cut from isolates, 10% with 1-2% substitutions, 10% random
+    nq = cfg["n_queries"]
+    qlen = torch.randint(cfg["qlen_lo"], cfg["qlen_hi"] + 1, (nq,), generator=g, device=dev)
+    qoff = torch.zeros(nq + 1, device=dev, dtype=torch.int64)
+    qoff[1:] = torch.cumsum(qlen, 0)
+    total = int(qoff[-1].item())
+    qi = torch.repeat_interleave(torch.arange(nq, device=dev), qlen)
+    within = torch.arange(total, device=dev) - qoff[qi]
+    iso = torch.randint(0, A, (nq,), generator=g, device=dev)
+    start = (torch.rand(nq, generator=g, device=dev) * (Lg - cfg["qlen_hi"] - 1)).long()
+    codes = genomes.view(-1)[(iso * Lg + start)[qi] + within]
+    kind = torch.rand(nq, generator=g, device=dev)
+    mut_rate = torch.where((kind >= 0.8) & (kind < 0.9), torch.rand(nq, generator=g, device=dev) * 0.01 + 0.01,
+                           torch.zeros(nq, device=dev))
+    mut = torch.rand(total, generator=g, device=dev) < mut_rate[qi]
+    rnd = (kind >= 0.9)[qi]
+    repl = torch.randint(0, 4, (total,), generator=g, device=dev, dtype=torch.uint8)
+    codes = torch.where(mut | rnd, repl, codes)
+    d_bases = lut[codes.long()].contiguous()
+    h_seq_offs = qoff.cpu().numpy().astype(np.uint64)
+    h_query_offs = np.arange(nq + 1, dtype=np.uint64)
+    d_query_offs = torch.from_numpy(h_query_offs.view(np.int64)).to(dev)
+    d_counts = torch.zeros((nq, A), device=dev, dtype=torch.int32)
+    d_nk = torch.zeros(nq, device=dev, dtype=torch.int64)
+    stream = torch.cuda.current_stream()
+    lib = ctx.lib
+    P = lambda a, tp=L.u64p: a.ctypes.data_as(tp)
+
+    def run():
+        L.check(lib.cid_query_counts_dev(gix.h, d_bases.data_ptr(), qoff.data_ptr(), nq, total, d_query_offs.data_ptr(),
+                                         P(h_query_offs), P(h_seq_offs), nq, 0, d_counts.data_ptr(), d_nk.data_ptr(),
+                                         stream.cuda_stream))
+    run()
+    torch.cuda.synchronize()
+    ctx.profile(True)
+    reps = 3
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(reps):
+        run()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / reps
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    lookups = int(d_nk.sum().item())
+    R = 4 * ((A + 31) // 32)
+    peak, peak_src = measured_peak()
+    out = {"workload": "C3 gene search (-g): %d queries of %d-%d bp vs %d-isolate k=%d S=%d H=%d index (BASELINE.json configs[2])"
+                       % (nq, cfg["qlen_lo"], cfg["qlen_hi"], A, cfg["k"], cfg["S"], cfg["H"]),
+           "lookups": lookups, "ms_per_pass": ms, "lookups_per_s": lookups / (ms / 1e3), "unit": "k-mer lookups/s",
+           "build_seconds": build_s, "build_gbp_per_s": A * Lg / build_s / 1e9, "setup_seconds": time.time() - t0,
+           "kernels": {k_: {"ms_per_launch": v[0] / v[1], "launches_per_pass": v[1] / reps} for k_, v in prof.items()}}
+    if "query_counts" in prof:
+        qc_ms = prof["query_counts"][0] / reps            # all query_counts launches of one pass
+        alg = lookups * (cfg["H"] * R + 1) + nq * 4 * A    # SURVEY 8d: H*R + k_in per lookup, + 4N counts per query
+        out["roofline"] = {"bound": "hbm", "kernel": "query_counts", "achieved": alg / (qc_ms / 1e3) / 1e9, "peak": peak,
+                           "unit": "GB/s", "frac": alg / (qc_ms / 1e3) / 1e9 / peak, "traffic": None,
+                           "peak_source": peak_src, "algorithmic_bytes_per_pass": alg, "ms_per_pass": qc_ms}
+    # spot parity on a few queries against the oracle would need the CPU index (1000 x 3 Mbp): covered by tests/ instead
+    gix.close()
+    return out
+
+
 # ----------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
@@ -248,6 +340,9 @@ def run_ours(args):
     K, Wm = args.steps, args.warmup
 
     ctx = cb.Context(local)
+    if args.only_search:
+        print(json.dumps(run_search_extra(torch, dev, ctx, args, args.quick)), flush=True)
+        return
     t0 = time.time()
     genomes = make_genomes(torch, dev, cfg, 0xC0101D02)
     lut = torch.tensor(ASCII, device=dev, dtype=torch.uint8)
@@ -416,6 +511,15 @@ def run_ours(args):
         except Exception as ex:      # the bench line must still print
             cpu = {"value": None, "unit": "read pairs/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
 
+    search_c3 = None
+    if world == 1 and not args.no_search:
+        try:
+            del pool_b, pool_q, h_b, h_q
+            torch.cuda.empty_cache()
+            search_c3 = run_search_extra(torch, dev, ctx, args, args.quick)
+        except Exception as ex:
+            search_c3 = {"error": repr(ex)}
+
     line = {"metric": "read_id read pairs/s", "value": value, "unit": "read pairs/s", "n_gpus": world, "steps": K,
             "warmup": Wm, "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic", "config": workload_config(cfg, batch), "clocks": clocks,
@@ -424,7 +528,7 @@ def run_ours(args):
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "build": {"gbp_per_s": cfg["n_acc"] * cfg["genome_len"] / build_s / 1e9, "seconds": build_s,
                       "note": "index build on device incl. per-accession host sync; not the timed metric"},
-            "report_truncated_reads_last_step": trunc}
+            "report_truncated_reads_last_step": trunc, "search_c3": search_c3}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -438,9 +542,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch-pairs", type=int, default=1_000_000)
     ap.add_argument("--pool-batches", type=int, default=10, help="distinct batches kept in HBM (10 x 1M pairs = C2's 10M)")
-    ap.add_argument("--rep-cap", type=int, default=16)
+    ap.add_argument("--rep-cap", type=int, default=47, help="report entries kept per read (n_acc+1 = never truncated)")
     ap.add_argument("--ref-batch", type=int, default=200_000, help="read pairs per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-search", action="store_true", help="skip the C3 gene-search extra measurement")
+    ap.add_argument("--only-search", action="store_true", help="profiling aid: run only the C3 gene-search measurement")
     ap.add_argument("--quick", action="store_true", help="small genomes / bloom filter (functional check only)")
     args = ap.parse_args()
     if args.impl == "reference":

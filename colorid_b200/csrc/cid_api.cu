@@ -209,6 +209,9 @@ int cid_ctx_create(int device, cid_ctx** out) {
     cudaDeviceProp prop;
     CID_CUDA(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
+    // Row gathers are 8..128-byte random reads: ask L2 to fetch 32-byte sectors instead of 64/128 B.
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+    cudaGetLastError();
     CID_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CID_CUDA(cudaMalloc((void**)&c->d_err, 16));
     CID_CUDA(cudaMemset(c->d_err, 0, 16));
@@ -443,7 +446,7 @@ static int query_front(cid_index* ix, cudaStream_t st, const uint8_t* d_bases, c
     const uint64_t s_lo = h_query_offs[q0], s_hi = h_query_offs[q1];
     const uint64_t nseq = s_hi - s_lo;
     plan_regions(h_seq_offs, h_query_offs + q0, nq, ix->k, qp.gr);
-    plan_units(qp.gr, QUERY_CHUNK, qp.qu);
+    plan_units(qp.gr, QUERY_ITEM_SLOTS, qp.qu);
     // sequence -> group
     std::vector<uint32_t> seq_group(nseq);
     for (uint64_t q = q0; q < q1; q++)

@@ -289,11 +289,11 @@ struct UnitSmem {
     uint64_t* keys;       // [QUERY_CHUNK]
     uint32_t* mult;       // [QUERY_CHUNK]
     uint32_t* rowid;      // [QUERY_CHUNK * H]
-    uint32_t* cnt;        // [32 * 32] per-colour counters of one column block
+    uint32_t* cnt;        // [32 * 32 * 4] per-accession counters of one column block (32 lanes x VEC<=4 words)
     uint32_t* n;          // [4] list length, missing flag
 };
 __host__ __device__ inline size_t unit_smem_bytes(uint32_t H) {
-    return 256 * 4 + (size_t)QUERY_CHUNK * 8 + (size_t)QUERY_CHUNK * 4 + (size_t)QUERY_CHUNK * H * 4 + 1024 * 4 + 16;
+    return 256 * 4 + (size_t)QUERY_CHUNK * 8 + (size_t)QUERY_CHUNK * 4 + (size_t)QUERY_CHUNK * H * 4 + 4096 * 4 + 16;
 }
 __device__ __forceinline__ UnitSmem unit_carve(uint8_t* base, uint32_t H) {
     UnitSmem u;
@@ -301,7 +301,7 @@ __device__ __forceinline__ UnitSmem unit_carve(uint8_t* base, uint32_t H) {
     u.mult = (uint32_t*)(u.keys + QUERY_CHUNK);
     u.rowid = u.mult + QUERY_CHUNK;
     u.cnt = u.rowid + (size_t)QUERY_CHUNK * H;
-    u.lut = u.cnt + 1024;
+    u.lut = u.cnt + 4096;
     u.n = u.lut + 256;
     return u;
 }
@@ -332,11 +332,20 @@ __device__ __forceinline__ uint32_t unit_collect_and_hash(const UnitSmem& u, con
 
 // ================================================================= query_counts  (the row-gather kernel)
 // For every surviving k-mer: AND of its H rows, +1 for every set accession (batch_search_pe.rs:60-74).
-// A lane owns one 32-accession word column; hits are accumulated in bit-sliced (carry-save)
-// counters so the per-k-mer cost is a handful of logic ops instead of one atomic per set bit.
-constexpr int QC_PLANES = 11;   // a lane sees at most QUERY_CHUNK (=1024) k-mers per unit
+// A work item is up to QUERY_ITEM_SLOTS table slots of one query, walked in QUERY_CHUNK pieces
+// (collect -> hash -> gather).  A lane owns VEC consecutive 32-accession words of the row (128-bit
+// loads when VEC == 4: a 128-byte row is one request of 8 lanes, so a warp gathers 4 k-mers at
+// once); hits are accumulated in bit-sliced (carry-save) counters that live in registers for
+// the whole item, so the per-k-mer cost is a few logic ops instead of one atomic per set bit.
+constexpr int QC_PLANES = 11;   // a lane sees at most QUERY_ITEM_SLOTS/2/8 = 1024 k-mers per item (+ unroll slack)
+constexpr int QC_UNR = 4;
 
-template <bool UNIQ>
+template <int VEC> struct RowVec;
+template <> struct RowVec<1> { uint32_t w[1]; __device__ void load(const uint32_t* p) { w[0] = __ldg(p); } };
+template <> struct RowVec<2> { uint32_t w[2]; __device__ void load(const uint32_t* p) { uint2 v = __ldg((const uint2*)p); w[0] = v.x; w[1] = v.y; } };
+template <> struct RowVec<4> { uint32_t w[4]; __device__ void load(const uint32_t* p) { uint4 v = __ldg((const uint4*)p); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; } };
+
+template <int VEC, bool UNIQ, int HT>   // HT: compile-time num_hash (0 = run-time)
 __global__ void __launch_bounds__(256)
 query_counts_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t W, uint32_t N, uint32_t k, uint32_t H,
                     ModS mods, const Slot* __restrict__ table, const uint32_t* __restrict__ unit_group,
@@ -347,72 +356,142 @@ query_counts_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t W, 
     extern __shared__ __align__(16) uint8_t dsm[];
     UnitSmem u = unit_carve(dsm, H);
     const uint32_t g = unit_group[blockIdx.x];
-    const uint32_t n = unit_collect_and_hash(u, table, unit_slot0[blockIdx.x], unit_nslots[blockIdx.x],
-                                             filter ? filter[g] : 0ll, k, H, mods);
-    if (n == 0) return;
+    const uint64_t item_slot0 = unit_slot0[blockIdx.x];
+    const uint32_t item_nslots = unit_nslots[blockIdx.x];
+    const long long filt = filter ? filter[g] : 0ll;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) atomicAdd(&num_kmers[g], (unsigned long long)n);
 
-    const uint32_t lpk = Wp >= 32 ? 32 : Wp;          // lanes per k-mer (Wp is 1,2,4,..: power of two below 32)
-    const uint32_t kpw = 32 / lpk;                    // k-mers per warp pass
-    const uint32_t sub = lane / lpk, colw = lane % lpk;
-    const uint32_t ncb = (Wp + 31) / 32;              // 32-word column blocks
+    const uint32_t vpr = Wp / VEC;                      // vectors per row (Wp is a multiple of VEC)
+    uint32_t lpk = 1;                                   // lanes per k-mer: 1,2,4,..,32 (>= vectors per row)
+    while (lpk < vpr && lpk < 32) lpk <<= 1;
+    const uint32_t kpw = 32 / lpk;                      // k-mers per warp pass
+    const uint32_t sub = lane / lpk, colv = lane % lpk;
+    const uint32_t ncb = (vpr + 31) / 32;               // column blocks of 32 vectors
+    uint32_t total_n = 0;
     for (uint32_t cb = 0; cb < ncb; cb++) {
-        for (int i = tid; i < 1024; i += 256) u.cnt[i] = 0;
-        __syncthreads();
-        const uint32_t col = cb * 32 + colw;
-        const bool colok = col < Wp;
-        uint32_t pl[QC_PLANES];
+        const uint32_t vcol = cb * 32 + colv;
+        const bool colok = vcol < vpr;
+        uint32_t pl[VEC][QC_PLANES];
 #pragma unroll
-        for (int p = 0; p < QC_PLANES; p++) pl[p] = 0;
-        for (uint32_t i0 = warp * kpw; i0 < n; i0 += 8 * kpw) {
-            uint32_t i = i0 + sub;
-            uint32_t x = 0;
-            if (i < n && colok) {
-                x = 0xFFFFFFFFu;
-                for (uint32_t h = 0; h < H; h++) x &= __ldg(rows + (uint64_t)u.rowid[i * H + h] * Wp + col);
+        for (int v = 0; v < VEC; v++)
+#pragma unroll
+            for (int p = 0; p < QC_PLANES; p++) pl[v][p] = 0;
+        uint32_t seen = 0;
+        for (uint32_t c0 = 0; c0 < item_nslots; c0 += QUERY_CHUNK) {
+            __syncthreads();   // previous chunk's lists are dead
+            const uint32_t n = unit_collect_and_hash(u, table, item_slot0 + c0, min((uint32_t)QUERY_CHUNK, item_nslots - c0),
+                                                     filt, k, H, mods);
+            if (cb == 0) total_n += n;
+            // QC_UNR k-mers per warp iteration: all their row loads are issued before any is consumed
+            const uint32_t* colbase = rows + vcol * VEC;
+            const uint32_t hh = HT ? (uint32_t)HT : H;
+            for (uint32_t i0 = warp * kpw + sub; i0 < n + sub; i0 += 8 * kpw * QC_UNR) {
+                uint32_t x[QC_UNR][VEC];
+#pragma unroll
+                for (int un = 0; un < QC_UNR; un++) {
+                    const uint32_t i = i0 + un * 8 * kpw;
+#pragma unroll
+                    for (int v = 0; v < VEC; v++) x[un][v] = 0;
+                    if (i < n && colok) {
+                        const uint32_t* rid = u.rowid + i * hh;
+                        RowVec<VEC> r0;
+                        r0.load(colbase + (uint64_t)rid[0] * Wp);
+#pragma unroll
+                        for (int v = 0; v < VEC; v++) x[un][v] = r0.w[v];
+                        if (HT) {
+#pragma unroll
+                            for (int h = 1; h < (HT ? HT : 1); h++) {
+                                RowVec<VEC> r;
+                                r.load(colbase + (uint64_t)rid[h] * Wp);
+#pragma unroll
+                                for (int v = 0; v < VEC; v++) x[un][v] &= r.w[v];
+                            }
+                        } else {
+                            for (uint32_t h = 1; h < hh; h++) {
+                                RowVec<VEC> r;
+                                r.load(colbase + (uint64_t)rid[h] * Wp);
+#pragma unroll
+                                for (int v = 0; v < VEC; v++) x[un][v] &= r.w[v];
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int un = 0; un < QC_UNR; un++) {
+                    if (UNIQ) {
+                        // exactly one accession hit over the whole row (batch_search_pe.rs:75-82)
+                        const uint32_t i = i0 + un * 8 * kpw;
+                        uint32_t pc = 0;
+#pragma unroll
+                        for (int v = 0; v < VEC; v++) pc += __popc(x[un][v]);
+                        const uint32_t mine = pc;
+                        for (uint32_t o = lpk >> 1; o > 0; o >>= 1) pc += __shfl_xor_sync(0xffffffffu, pc, o);
+                        if (ncb == 1 && pc == 1 && mine == 1) {
+                            uint32_t colour = 0;
+#pragma unroll
+                            for (int v = 0; v < VEC; v++) if (x[un][v]) colour = (vcol * VEC + v) * 32 + (__ffs(x[un][v]) - 1);
+                            uint32_t e = atomicAdd(uniq_n, 1u);
+                            if (e < uniq_cap) {
+                                uniq_list[3 * (uint64_t)e] = g;
+                                uniq_list[3 * (uint64_t)e + 1] = colour;
+                                uniq_list[3 * (uint64_t)e + 2] = u.mult[i];
+                            }
+                        }
+                    }
+                    // carry-save add of x into the bit planes
+#pragma unroll
+                    for (int v = 0; v < VEC; v++) {
+                        uint32_t carry = x[un][v];
+#pragma unroll
+                        for (int p = 0; p < QC_PLANES; p++) {
+                            uint32_t t2 = pl[v][p] & carry;
+                            pl[v][p] ^= carry;
+                            carry = t2;
+                            if (carry == 0) break;
+                        }
+                    }
+                }
+                seen += QC_UNR;
             }
-            if (UNIQ) {
-                // exactly one accession hit over the whole row (batch_search_pe.rs:75-82)
-                uint32_t pc = __popc(x);
-                for (uint32_t o = lpk >> 1; o > 0; o >>= 1) pc += __shfl_xor_sync(0xffffffffu, pc, o);
-                if (ncb == 1 && pc == 1 && x != 0) {
-                    uint32_t e = atomicAdd(uniq_n, 1u);
-                    if (e < uniq_cap) {
-                        uniq_list[3 * (uint64_t)e] = g;
-                        uniq_list[3 * (uint64_t)e + 1] = col * 32 + (__ffs(x) - 1);
-                        uniq_list[3 * (uint64_t)e + 2] = u.mult[i];
+        }
+        // flush: planes -> shared counters of this column block (the 8 warps and 32/lpk sub-groups hold
+        // partial counts of the same columns) -> one global atomic per non-zero accession.
+        __syncthreads();
+        for (int i = tid; i < 1024 * VEC; i += 256) u.cnt[i] = 0;
+        __syncthreads();
+        if (colok && seen) {
+            const int depth = 32 - __clz(seen);          // planes that can be non-zero
+#pragma unroll
+            for (int v = 0; v < VEC; v++) {
+                const uint32_t cbase = (colv * VEC + v) * 32;
+#pragma unroll
+                for (int nb = 0; nb < 8; nb++) {
+                    // four accessions at a time: spread each plane's nibble into four byte lanes
+                    uint32_t lo = 0, hi = 0;
+#pragma unroll
+                    for (int p = 0; p < QC_PLANES; p++) {
+                        if (p >= depth) break;
+                        const uint32_t sp = (((pl[v][p] >> (4 * nb)) & 0xFu) * 0x00204081u) & 0x01010101u;
+                        if (p < 8) lo += sp << p; else hi += sp << (p - 8);
+                    }
+                    if (lo | hi) {
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const uint32_t val = ((lo >> (8 * q)) & 0xFFu) | (((hi >> (8 * q)) & 0xFFu) << 8);
+                            if (val) atomicAdd(&u.cnt[cbase + 4 * nb + q], val);
+                        }
                     }
                 }
             }
-            // carry-save add of x into the bit planes
-            uint32_t carry = x;
-#pragma unroll
-            for (int p = 0; p < QC_PLANES; p++) {
-                uint32_t t2 = pl[p] & carry;
-                pl[p] ^= carry;
-                carry = t2;
-                if (carry == 0) break;
-            }
-        }
-        // flush planes -> shared counters (lanes with the same column in different sub-groups/warps collide)
-        if (colok) {
-#pragma unroll 4
-            for (int b = 0; b < 32; b++) {
-                uint32_t v = 0;
-#pragma unroll
-                for (int p = 0; p < QC_PLANES; p++) v |= ((pl[p] >> b) & 1u) << p;
-                if (v) atomicAdd(&u.cnt[colw * 32 + b], v);
-            }
         }
         __syncthreads();
-        for (int i = tid; i < 1024; i += 256) {
-            uint32_t c = cb * 1024 + i;
-            uint32_t v = u.cnt[i];
-            if (v && c < N) atomicAdd(&counts[(uint64_t)g * N + c], v);
+        for (int i = tid; i < 1024 * VEC; i += 256) {
+            const uint32_t c = cb * 1024 * VEC + i;
+            const uint32_t val = u.cnt[i];
+            if (val && c < N) atomicAdd(&counts[(uint64_t)g * N + c], val);
         }
-        __syncthreads();
     }
+    if (tid == 0 && total_n) atomicAdd(&num_kmers[g], (unsigned long long)total_n);
 }
 
 // Wide-row unique-hit pass (Wp > 32): one warp per k-mer sums popcounts over the whole row.
@@ -425,9 +504,12 @@ query_uniq_wide_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t 
     extern __shared__ __align__(16) uint8_t dsm[];
     UnitSmem u = unit_carve(dsm, H);
     const uint32_t g = unit_group[blockIdx.x];
-    const uint32_t n = unit_collect_and_hash(u, table, unit_slot0[blockIdx.x], unit_nslots[blockIdx.x],
-                                             filter ? filter[g] : 0ll, k, H, mods);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t item_nslots = unit_nslots[blockIdx.x];
+    for (uint32_t c0 = 0; c0 < item_nslots; c0 += QUERY_CHUNK) {
+    __syncthreads();
+    const uint32_t n = unit_collect_and_hash(u, table, unit_slot0[blockIdx.x] + c0, min((uint32_t)QUERY_CHUNK, item_nslots - c0),
+                                             filter ? filter[g] : 0ll, k, H, mods);
     for (uint32_t i = warp; i < n; i += 8) {
         uint32_t pc = 0, where = 0;
         for (uint32_t col = lane; col < Wp; col += 32) {
@@ -446,6 +528,7 @@ query_uniq_wide_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t 
             }
         }
     }
+    }
 }
 
 int launch_query_counts(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, const void* d_table,
@@ -456,23 +539,33 @@ int launch_query_counts(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, con
     size_t smem = unit_smem_bytes(idx->H);
     static bool attr_set = false;
     if (!attr_set) {
-        CID_CUDA(cudaFuncSetAttribute(query_counts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        CID_CUDA(cudaFuncSetAttribute(query_counts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+#define CID_QC_ATTR(VEC, UQ, HT) CID_CUDA(cudaFuncSetAttribute(query_counts_kernel<VEC, UQ, HT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024))
+#define CID_QC_ATTR3(VEC, UQ) CID_QC_ATTR(VEC, UQ, 0); CID_QC_ATTR(VEC, UQ, 2); CID_QC_ATTR(VEC, UQ, 4)
+        CID_QC_ATTR3(1, true); CID_QC_ATTR3(1, false); CID_QC_ATTR3(2, true); CID_QC_ATTR3(2, false);
+        CID_QC_ATTR3(4, true); CID_QC_ATTR3(4, false);
+#undef CID_QC_ATTR3
+#undef CID_QC_ATTR
         CID_CUDA(cudaFuncSetAttribute(query_uniq_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         attr_set = true;
     }
     ModS mods = make_mods(idx->S);
-    const bool inline_uniq = want_uniq && idx->Wp <= 32;
+    const uint32_t vec = idx->Wp >= 128 ? 4 : idx->Wp >= 64 ? 2 : 1;
+    const bool inline_uniq = want_uniq && idx->Wp <= 32 * vec;   // one column block: the warp sees the whole row
     {
     ProfScope ps(ctx, st, KID_QUERY_COUNTS);
-    if (inline_uniq)
-        query_counts_kernel<true><<<(unsigned)nunits, 256, smem, st>>>(
-            idx->rows, idx->Wp, idx->W, idx->N, idx->k, idx->H, mods, (const Slot*)d_table, d_unit_group, d_unit_slot0,
-            d_unit_nslots, (const long long*)d_filter, d_counts, d_num_kmers, d_uniq_list, uniq_cap, d_uniq_n);
-    else
-        query_counts_kernel<false><<<(unsigned)nunits, 256, smem, st>>>(
-            idx->rows, idx->Wp, idx->W, idx->N, idx->k, idx->H, mods, (const Slot*)d_table, d_unit_group, d_unit_slot0,
-            d_unit_nslots, (const long long*)d_filter, d_counts, d_num_kmers, d_uniq_list, uniq_cap, d_uniq_n);
+#define CID_QC_LAUNCH_H(VEC, UQ, HT)                                                                                   \
+    query_counts_kernel<VEC, UQ, HT><<<(unsigned)nunits, 256, smem, st>>>(                                             \
+        idx->rows, idx->Wp, idx->W, idx->N, idx->k, idx->H, mods, (const Slot*)d_table, d_unit_group, d_unit_slot0,    \
+        d_unit_nslots, (const long long*)d_filter, d_counts, d_num_kmers, d_uniq_list, uniq_cap, d_uniq_n)
+#define CID_QC_LAUNCH(VEC, UQ)                                                                                         \
+    do { if (idx->H == 2) CID_QC_LAUNCH_H(VEC, UQ, 2); else if (idx->H == 4) CID_QC_LAUNCH_H(VEC, UQ, 4);              \
+         else CID_QC_LAUNCH_H(VEC, UQ, 0); } while (0)
+    // VEC words per lane: keep a whole warp on one k-mer (coalesced row read, fewest partial counters)
+    if (idx->Wp >= 128) { if (inline_uniq) CID_QC_LAUNCH(4, true); else CID_QC_LAUNCH(4, false); }
+    else if (idx->Wp >= 64) { if (inline_uniq) CID_QC_LAUNCH(2, true); else CID_QC_LAUNCH(2, false); }
+    else { if (inline_uniq) CID_QC_LAUNCH(1, true); else CID_QC_LAUNCH(1, false); }
+#undef CID_QC_LAUNCH
+#undef CID_QC_LAUNCH_H
     }
     ctx->launches++;
     CID_CUDA(cudaGetLastError());
@@ -497,29 +590,45 @@ query_perfect_kernel(const uint32_t* __restrict__ rows, const uint32_t* __restri
     extern __shared__ __align__(16) uint8_t dsm[];
     UnitSmem u = unit_carve(dsm, H);
     const uint32_t g = unit_group[blockIdx.x];
-    const uint32_t n = unit_collect_and_hash(u, table, unit_slot0[blockIdx.x], unit_nslots[blockIdx.x], 0ll, k, H, mods);
-    if (n == 0) return;
     const int tid = threadIdx.x;
-    if (tid == 0) atomicAdd(&num_kmers[g], (unsigned long long)n);
-    // any absent row -> "No perfect hits!" (perfect_search.rs:32-33,38-39)
+    const uint32_t item_nslots = unit_nslots[blockIdx.x];
+    uint32_t total_n = 0;
     bool miss = false;
-    for (uint32_t i = tid; i < n * H; i += 256) {
-        uint32_t r = u.rowid[i];
-        if (!((__ldg(rownz + (r >> 5)) >> (r & 31)) & 1u)) miss = true;
+    // thread owns word columns col = tid%32 (+32..) and the k-mers i = tid/32 (mod 8); at most 16 columns per thread
+    uint32_t acc[16];
+#pragma unroll
+    for (int c = 0; c < 16; c++) acc[c] = 0xFFFFFFFFu;
+    for (uint32_t c0 = 0; c0 < item_nslots; c0 += QUERY_CHUNK) {
+        __syncthreads();
+        const uint32_t n = unit_collect_and_hash(u, table, unit_slot0[blockIdx.x] + c0, min((uint32_t)QUERY_CHUNK, item_nslots - c0),
+                                                 0ll, k, H, mods);
+        total_n += n;
+        // any absent row -> "No perfect hits!" (perfect_search.rs:32-33,38-39)
+        for (uint32_t i = tid; i < n * H; i += 256) {
+            uint32_t r = u.rowid[i];
+            if (!((__ldg(rownz + (r >> 5)) >> (r & 31)) & 1u)) miss = true;
+        }
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            const uint32_t col = (tid % 32) + 32 * c;
+            if (col < W)
+                for (uint32_t i = tid / 32; i < n; i += 8)
+                    for (uint32_t h = 0; h < H; h++) acc[c] &= __ldg(rows + (uint64_t)u.rowid[i * H + h] * Wp + col);
+        }
     }
+    if (tid == 0 && total_n) atomicAdd(&num_kmers[g], (unsigned long long)total_n);
     if (miss) atomicOr(&missing[g], 1u);
-    // AND of every row, column by column: thread owns (column, k-mer residue)
-    for (uint32_t col = tid % 32; col < W; col += 32) {
-        uint32_t acc = 0xFFFFFFFFu;
-        for (uint32_t i = tid / 32; i < n; i += 8)
-            for (uint32_t h = 0; h < H; h++) acc &= __ldg(rows + (uint64_t)u.rowid[i * H + h] * Wp + col);
-        if (acc != 0xFFFFFFFFu) atomicAnd(&and_rows[(uint64_t)g * W + col], acc);
+#pragma unroll
+    for (int c = 0; c < 16; c++) {
+        const uint32_t col = (tid % 32) + 32 * c;
+        if (col < W && acc[c] != 0xFFFFFFFFu) atomicAnd(&and_rows[(uint64_t)g * W + col], acc[c]);
     }
 }
 int launch_query_perfect(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, const void* d_table,
                          const uint32_t* d_unit_group, const uint64_t* d_unit_slot0, const uint32_t* d_unit_nslots,
                          uint64_t nunits, uint32_t* d_and_rows, uint32_t* d_missing, unsigned long long* d_num_kmers) {
     if (nunits == 0) return CID_OK;
+    if (idx->W > 512) { set_error("perfect search: more than 16384 accessions per shard not supported"); return CID_E_UNSUPPORTED; }
     size_t smem = unit_smem_bytes(idx->H);
     static bool attr_set = false;
     if (!attr_set) {

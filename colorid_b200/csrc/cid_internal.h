@@ -138,7 +138,7 @@ struct QueryUnits {            // work list for the gather kernels: (group, firs
     std::vector<uint32_t> nslots;
 };
 void plan_units(const GroupRegions& gr, uint32_t chunk, QueryUnits& qu);
-enum { QUERY_CHUNK = 1024, MAX_HASH = 8 };
+enum { QUERY_CHUNK = 1024, QUERY_ITEM_SLOTS = 16384, MAX_HASH = 8 };
 
 int launch_query_counts(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, const void* d_table,
                         const uint32_t* d_unit_group, const uint64_t* d_unit_slot0, const uint32_t* d_unit_nslots,

@@ -50,8 +50,8 @@ __device__ __forceinline__ bool warp_load_read(Tile& t, int cap, const uint8_t* 
     }
     const uint8_t* src = bases + g.b0;
     for (int i = lane; i < g.len; i += 32) {
-        uint8_t c = __ldg(src + i);
-        if (quals && (uint32_t)__ldg(quals + g.b0 + i) < maxq) c = 'N';
+        uint8_t c = __ldcs(src + i);                      // streamed once: do not displace matrix rows in L2
+        if (quals && (uint32_t)__ldcs(quals + g.b0 + i) < maxq) c = 'N';
         t.ascii[i] = c;
     }
     __syncwarp();
@@ -168,8 +168,7 @@ __device__ __forceinline__ uint32_t hb_window(const uint32_t* bm, uint32_t nb, u
         const uint32_t nw = nb >> 5, w = pos >> 5;
         return __funnelshift_r(bm[w], bm[(w + 1) & (nw - 1)], pos & 31);
     }
-    uint32_t x = bm[0];
-    x *= nb == 4 ? 0x11111111u : nb == 8 ? 0x01010101u : 0x00010001u;     // replicate the nb-bit pattern
+    const uint32_t x = bm[0];                 // tables below 32 buckets keep the pattern replicated (hb_set)
     return __funnelshift_r(x, x, pos);
 }
 __device__ __forceinline__ uint32_t hb_probe(const uint32_t* bm, uint32_t nb, uint32_t pos, uint32_t gw) {
@@ -184,6 +183,10 @@ __device__ __forceinline__ uint32_t hb_probe(const uint32_t* bm, uint32_t nb, ui
         stride += gw;
         pos = (pos + stride) & mask;
     }
+}
+__device__ __forceinline__ void hb_set(uint32_t* bm, uint32_t nb, uint32_t slot) {
+    if (nb >= 32) bm[slot >> 5] |= 1u << (slot & 31);
+    else bm[0] |= (nb == 4 ? 0x11111111u : nb == 8 ? 0x01010101u : 0x00010001u) << slot;
 }
 __device__ __forceinline__ uint32_t hb_cap(uint32_t nb) { return nb == 0 ? 0 : (nb < 8 ? nb - 1 : nb / 8 * 7); }
 
@@ -229,44 +232,56 @@ readid_order_kernel(const uint32_t* __restrict__ entries, const uint32_t* __rest
     uint32_t j = 0;
     uint4 buf = n ? __ldg((const uint4*)row) : make_uint4(0, 0, 0, 0);          // entries j&~3 .. +3
     uint4 nxt = n > 4 ? __ldg((const uint4*)(row + 4)) : make_uint4(0, 0, 0, 0);  // prefetched next group
+    // Each iteration picks at most one item to place (an old bucket during a rehash, otherwise the
+    // next insert call) and then runs ONE shared probe+store, so lanes in different phases do not
+    // serialise two copies of the expensive part.
     while (j < n || s < nb_old) {
+        uint32_t item = 0, hash = 0;
+        bool place = false;
         if (s < nb_old) {
-            // REHASH: move the next full old bucket (resize re-inserts in ascending bucket order)
-            const uint32_t w = bold[s >> 5] >> (s & 31);
-            if (w == 0) { s = (s | 31) + 1; continue; }
-            s += __ffs(w) - 1;
-            const E v = old[s];
-            const uint32_t slot = hb_probe(bcur, nb, hash_of(v), gw);
-            cur[slot] = v;
-            bcur[slot >> 5] |= 1u << (slot & 31);
-            s++;
+            // REHASH: next full old bucket (resize re-inserts in ascending bucket order)
+            const uint32_t w = bold[s >> 5] >> (s & 31);     // old tables below 32 buckets: replicated, harmless
+            if (w == 0) s = (s | 31) + 1;
+            else {
+                s += __ffs(w) - 1;
+                if (s < nb_old) {            // (a replica bit of a small table can point past its end)
+                    item = old[s];
+                    hash = hash_of(item);
+                    place = true;
+                    s++;
+                }
+            }
         } else {
             const uint32_t q = j & 3;
             const uint32_t e = q == 0 ? buf.x : q == 1 ? buf.y : q == 2 ? buf.z : buf.w;
             const bool fresh = ENT_FRESH(e);
             if (growth == 0 && (rbf || fresh)) {
-                // reserve_rehash -> resize(capacity_to_buckets(max(items+1, cap+1))): buckets double
+                // reserve_rehash -> resize(capacity_to_buckets(max(items+1, cap+1))): buckets double;
+                // the same insert call is retried once the rehash has drained
                 old = cur; bold = bcur; nb_old = nb; s = 0;
                 nb = nb == 0 ? 4 : nb * 2;
                 const bool y = in_y(nb);
                 cur = y ? Y : X; bcur = y ? bmY : bmX;
                 for (uint32_t i = 0; i < (nb >= 32 ? nb / 32 : 1u); i++) bcur[i] = 0;
                 growth = hb_cap(nb) - items;
-                continue;                       // the same insert call is retried after the rehash
+            } else {
+                if (fresh) {
+                    hp[j] = (E)e;
+                    if (kSmall) h9[j >> 5] |= ((e >> 8) & 1u) << (j & 31);
+                    item = j; hash = e & 0xFFFFu; place = true;
+                    items++; growth--;
+                }
+                j++;
+                if ((j & 3) == 0) {
+                    buf = nxt;
+                    if (j + 4 < n) nxt = __ldg((const uint4*)(row + j + 4));
+                }
             }
-            if (fresh) {
-                hp[j] = (E)e;
-                if (kSmall) h9[j >> 5] |= ((e >> 8) & 1u) << (j & 31);
-                const uint32_t slot = hb_probe(bcur, nb, e & 0xFFFFu, gw);
-                cur[slot] = (E)j;
-                bcur[slot >> 5] |= 1u << (slot & 31);
-                items++; growth--;
-            }
-            j++;
-            if ((j & 3) == 0) {
-                buf = nxt;
-                if (j + 4 < n) nxt = __ldg((const uint4*)(row + j + 4));
-            }
+        }
+        if (place) {
+            const uint32_t slot = hb_probe(bcur, nb, hash, gw);
+            cur[slot] = (E)item;
+            hb_set(bcur, nb, slot);
         }
     }
     if (!live) return;
@@ -327,7 +342,7 @@ readid_vote_narrow_kernel(const uint8_t* __restrict__ bases, const uint8_t* __re
             HashIn in;
             in.w0 = in.w1 = in.w2 = in.w3 = 0;
             if (active) {
-                uint32_t e = __ldg(ordrow + idx);
+                uint32_t e = __ldcs(ordrow + idx);
                 uint32_t tp = e & 0x3FFu;
                 uint64_t f = codes_window(t.codes, (int)tp, k);
                 uint64_t key = ((e >> 10) & 1u) ? f : revcomp_key(f, k);
