@@ -1,0 +1,81 @@
+"""Multi-GPU glue (one process per GPU, torch.distributed): how units are split across ranks.
+
+Replicated index (configs C1-C4): every rank holds the whole signature matrix; reads / queries are
+independent units dealt in contiguous slices, results concatenated in input order.  No data-path
+collective is needed.
+
+Column-sharded index (C5, or whenever the matrix exceeds one GPU): rank g owns the accessions
+[c_lo, c_hi) (whole 32-accession word columns) of EVERY row.  Every rank processes all k-mers against
+its slice; per-query counts / AND-rows are disjoint column slices, so one all_gather reassembles
+them (NCCL over NVLink on GPUs, gloo in the CPU tests).  Row presence ("is this Bloom row absent?",
+perfect_search.rs:32 / read_id_mt_pe.rs:121) is a property of the WHOLE row, so the per-rank
+row-present bitmaps are OR-reduced once after the build.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def unit_slices(n_units, world):
+    """Contiguous, near-equal slices of [0, n_units) for ranks 0..world-1."""
+    base, rem = divmod(n_units, world)
+    out, lo = [], 0
+    for r in range(world):
+        hi = lo + base + (1 if r < rem else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+def column_shards(n_colours, world):
+    """Accession ranges per rank, aligned to 32-accession words (bit c of a row = word c//32, bit c%32)."""
+    words = (n_colours + 31) // 32
+    out = []
+    for lo, hi in unit_slices(words, world):
+        out.append((min(lo * 32, n_colours), min(hi * 32, n_colours)))
+    return out
+
+
+def gather_counts(local_counts, shards, group=None):
+    """local_counts [nq, n_local] (this rank's accession slice) -> [nq, N] on every rank."""
+    world = dist.get_world_size(group)
+    width = max(hi - lo for lo, hi in shards)
+    nq = local_counts.shape[0]
+    pad = torch.zeros((nq, width), dtype=local_counts.dtype, device=local_counts.device)
+    pad[:, : local_counts.shape[1]] = local_counts
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    return torch.cat([p[:, : hi - lo] for p, (lo, hi) in zip(parts, shards)], dim=1)
+
+
+def gather_and_rows(local_words, shards, group=None):
+    """Perfect search: local AND-rows [nq, W_local] -> [nq, W]; shards are word-aligned so words concatenate."""
+    world = dist.get_world_size(group)
+    wshards = [((lo + 31) // 32, (hi + 31) // 32) for lo, hi in shards]
+    width = max(hi - lo for lo, hi in wshards)
+    nq = local_words.shape[0]
+    pad = torch.zeros((nq, width), dtype=local_words.dtype, device=local_words.device)
+    pad[:, : local_words.shape[1]] = local_words
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    return torch.cat([p[:, : hi - lo] for p, (lo, hi) in zip(parts, wshards)], dim=1)
+
+
+def or_reduce_bitmap(bitmap, group=None):
+    """In-place OR over ranks of a row-present bitmap (int32/int64 tensor)."""
+    dist.all_reduce(bitmap, op=dist.ReduceOp.BOR, group=group)
+    return bitmap
+
+
+def any_reduce_flags(flags, group=None):
+    """Per-query 'some row is absent' flags: OR over ranks (uint8/int32 tensor), in place."""
+    dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=group)
+    return flags
+
+
+def concat_in_order(local_rows, group=None):
+    """Replicated mode: per-rank result arrays (numpy, first axis = this rank's units) -> global order."""
+    world = dist.get_world_size(group)
+    parts = [None] * world
+    dist.all_gather_object(parts, local_rows, group=group)
+    return np.concatenate(parts, axis=0)
