@@ -49,6 +49,9 @@ class Context:
     def __del__(self):
         self.close()
 
+    def set_option(self, name, value):
+        L.check(self.lib.cid_ctx_set_option(self.h, name.encode(), int(value)))
+
     @property
     def launches(self):
         return self.lib.cid_ctx_launch_count(self.h)
@@ -221,6 +224,28 @@ class Index:
                                            C.byref(p), _p(n_set, L.u32p), _p(flags, L.u32p), _p(rep_n, L.u32p),
                                            _p(rep_c, L.u32p), _p(rep_v, L.u32p)))
         return dict(n_set=n_set[:nr], flags=flags[:nr], rep_n=rep_n[:nr], rep_colour=rep_c[:nr], rep_count=rep_v[:nr])
+
+    def read_id_classify(self, reads, quals=None, d=1, start_sample=3, qual_offset=0, group_width=16,
+                         reserve_before_find=True, fp_correct=1e-3, top_cap=8):
+        """parallel_vec end to end: reads in, (kind, hits, n_set, n_top, top) per read out."""
+        flat = [s for r in reads for s in r]
+        bases, offs = pack_seqs(flat)
+        roffs = group_offsets(reads)
+        qarr = None
+        if quals is not None:
+            qarr, _ = pack_seqs([s for r in quals for s in r])
+        nr = len(reads)
+        p = self._params(d, start_sample, qual_offset, group_width, reserve_before_find, None)
+        m = max(nr, 1)
+        kind = np.zeros(m, np.int32)
+        hits, n_set, n_top = np.zeros(m, np.uint32), np.zeros(m, np.uint32), np.zeros(m, np.uint32)
+        top = np.zeros((m, top_cap), np.uint32)
+        n_ref = np.ascontiguousarray(self.n_ref, dtype=np.uint64)
+        L.check(self.lib.cid_read_id_classify(self.h, _p(bases), _p(qarr), _p(offs, L.u64p), len(flat), _p(roffs, L.u64p),
+                                              nr, C.byref(p), _p(n_ref, L.u64p), fp_correct, _p(kind, L.i32p),
+                                              _p(hits, L.u32p), _p(n_set, L.u32p), _p(n_top, L.u32p), _p(top, L.u32p),
+                                              top_cap))
+        return dict(kind=kind[:nr], hits=hits[:nr], n_set=n_set[:nr], n_top=n_top[:nr], top=top[:nr])
 
     def read_kmer_order(self, reads, d=1, group_width=16, reserve_before_find=True, order_cap=512):
         flat = [s for r in reads for s in r]

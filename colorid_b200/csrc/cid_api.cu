@@ -222,6 +222,7 @@ int cid_ctx_create(int device, cid_ctx** out) {
 void cid_ctx_destroy(cid_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    readid_pipe_destroy(c);
     prof_collect(c);
     for (auto e : c->prof_pool) cudaEventDestroy(e);
     for (auto& b : c->scratch) b.release();
@@ -247,6 +248,13 @@ int cid_ctx_profile_read(cid_ctx* c, int kernel, const char** name, double* tota
     return CID_OK;
 }
 uint64_t cid_ctx_launch_count(const cid_ctx* c) { return c ? c->launches : 0; }
+int cid_ctx_set_option(cid_ctx* c, const char* name, int64_t value) {
+    if (!c || !name) { set_error("cid_ctx_set_option: null argument"); return CID_E_INVALID; }
+    if (!strcmp(name, "readid_chunk_reads")) { c->opt_readid_chunk = value > 0 ? (uint64_t)value : 0; return CID_OK; }
+    if (!strcmp(name, "host_threads")) { c->opt_host_threads = value > 0 ? (int)value : 0; return CID_OK; }
+    set_error("cid_ctx_set_option: unknown option '%s'", name);
+    return CID_E_INVALID;
+}
 
 // ------------------------------------------------------------------ index
 int cid_index_create(cid_ctx* ctx, uint64_t bloom_size, uint32_t num_hash, uint32_t k_size, uint32_t n_colors,
@@ -638,121 +646,6 @@ int cid_query_perfect(cid_index* ix, const char* bases, const uint64_t* seq_offs
         }
     }
     return CID_OK;
-}
-
-// ------------------------------------------------------------------ read_id
-static void default_params(cid_readid_params& p, const cid_readid_params* in, uint32_t N) {
-    if (in) p = *in;
-    else { p.downsample = 1; p.start_sample = 3; p.qual_offset = 0; p.group_width = 16; p.reserve_before_find = 1; p.rep_cap = 0; }
-    if (p.downsample == 0) p.downsample = 1;
-    if (p.group_width == 0) p.group_width = 16;
-    if (p.rep_cap == 0) p.rep_cap = N + 1;
-}
-
-int cid_read_id_batch_dev(cid_index* ix, const char* d_bases, const char* d_quals, const uint64_t* d_seq_offs,
-                          uint64_t nseq, uint64_t nbases, const uint64_t* d_read_offs, uint64_t nreads,
-                          uint32_t h_max_read_bases, uint32_t h_max_kmers, const cid_readid_params* p,
-                          uint32_t* d_n_set, uint32_t* d_flags, uint32_t* d_rep_n, uint32_t* d_rep_colour,
-                          uint32_t* d_rep_count, void* stream) {
-    CID_CUDA(cudaSetDevice(ix->ctx->device));
-    cid_readid_params pp;
-    default_params(pp, p, ix->N);
-    return readid_run(ix, (cudaStream_t)stream, (const uint8_t*)d_bases, (const uint8_t*)d_quals, d_seq_offs, nseq, nbases,
-                      d_read_offs, nreads, h_max_read_bases, h_max_kmers, pp, d_n_set, d_flags, d_rep_n, d_rep_colour,
-                      d_rep_count, 0, nullptr, nullptr, nullptr);
-}
-
-// host scan of the read geometry: longest read and most k-mer start positions
-static void read_geometry(const uint64_t* seq_offs, const uint64_t* read_offs, uint64_t nreads, uint32_t k, uint32_t d,
-                          uint32_t* max_bases, uint32_t* max_kmers) {
-    uint64_t mb = 0, mk = 0;
-    for (uint64_t r = 0; r < nreads; r++) {
-        uint64_t b = seq_offs[read_offs[r + 1]] - seq_offs[read_offs[r]], kk = 0;
-        for (uint64_t s = read_offs[r]; s < read_offs[r + 1]; s++) {
-            uint64_t l = seq_offs[s + 1] - seq_offs[s];
-            if (l >= k) kk += (l - k) / d + 1;
-        }
-        mb = std::max(mb, b); mk = std::max(mk, kk);
-    }
-    *max_bases = (uint32_t)std::min<uint64_t>(mb, 0xFFFFFFFFu);
-    *max_kmers = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(mk, 1), 0xFFFFFFFFu);
-}
-
-static int read_id_host(cid_index* ix, const char* bases, const char* quals, const uint64_t* seq_offs, uint64_t nseq,
-                        const uint64_t* read_offs, uint64_t nreads, const cid_readid_params* p, uint32_t* n_set,
-                        uint32_t* flags, uint32_t* rep_n, uint32_t* rep_colour, uint32_t* rep_count, uint32_t order_cap,
-                        uint32_t* order_n, uint8_t* order_seq, uint16_t* order_pos) {
-    cid_ctx* ctx = ix->ctx;
-    cudaStream_t st = ctx->stream;
-    if (!seq_offs || !read_offs) { set_error("read_id: null argument"); return CID_E_INVALID; }
-    CID_CUDA(cudaSetDevice(ctx->device));
-    cid_readid_params pp;
-    default_params(pp, p, ix->N);
-    if (nreads == 0) return CID_OK;
-    const uint64_t nbases = seq_offs[nseq];
-    uint32_t max_bases, max_kmers;
-    read_geometry(seq_offs, read_offs, nreads, ix->k, pp.downsample, &max_bases, &max_kmers);
-    const bool use_q = quals && pp.qual_offset;
-    CID_TRY(ctx->scratch[4].ensure(nbases + 64));
-    CID_TRY(ctx->scratch[5].ensure((nseq + 1) * 8));
-    CID_TRY(ctx->scratch[14].ensure((nreads + 1) * 8));
-    if (use_q) CID_TRY(ctx->scratch[15].ensure(nbases + 64));
-    if (nbases) CID_CUDA(cudaMemcpyAsync(ctx->scratch[4].p, bases, nbases, cudaMemcpyHostToDevice, st));
-    if (use_q && nbases) CID_CUDA(cudaMemcpyAsync(ctx->scratch[15].p, quals, nbases, cudaMemcpyHostToDevice, st));
-    CID_CUDA(cudaMemcpyAsync(ctx->scratch[5].p, seq_offs, (nseq + 1) * 8, cudaMemcpyHostToDevice, st));
-    CID_CUDA(cudaMemcpyAsync(ctx->scratch[14].p, read_offs, (nreads + 1) * 8, cudaMemcpyHostToDevice, st));
-    const bool want_rep = rep_n != nullptr;
-    CID_TRY(ctx->scratch[19].ensure(nreads * 4));
-    CID_TRY(ctx->scratch[20].ensure(nreads * 4));
-    uint32_t* d_n_set = ctx->scratch[19].as<uint32_t>();
-    uint32_t* d_flags = ctx->scratch[20].as<uint32_t>();
-    uint32_t *d_rep_n = nullptr, *d_rc = nullptr, *d_rv = nullptr;
-    if (want_rep) {
-        CID_TRY(ctx->scratch[21].ensure(nreads * 4));
-        CID_TRY(ctx->scratch[22].ensure(nreads * (size_t)pp.rep_cap * 8));
-        d_rep_n = ctx->scratch[21].as<uint32_t>();
-        d_rc = ctx->scratch[22].as<uint32_t>();
-        d_rv = d_rc + nreads * (size_t)pp.rep_cap;
-    }
-    uint32_t* d_on = nullptr; uint8_t* d_os = nullptr; uint16_t* d_op = nullptr;
-    if (order_n) {
-        CID_TRY(ctx->scratch[23].ensure(nreads * 4 + nreads * (size_t)order_cap * 3 + 64));
-        d_on = ctx->scratch[23].as<uint32_t>();
-        d_op = (uint16_t*)(d_on + nreads);
-        d_os = (uint8_t*)(d_op + nreads * (size_t)order_cap);
-    }
-    CID_TRY(readid_run(ix, st, ctx->scratch[4].as<uint8_t>(), use_q ? ctx->scratch[15].as<uint8_t>() : nullptr,
-                       ctx->scratch[5].as<uint64_t>(), nseq, nbases, ctx->scratch[14].as<uint64_t>(), nreads, max_bases,
-                       max_kmers, pp, d_n_set, d_flags, d_rep_n, d_rc, d_rv, order_cap, d_on, d_os, d_op));
-    if (n_set) CID_CUDA(cudaMemcpyAsync(n_set, d_n_set, nreads * 4, cudaMemcpyDeviceToHost, st));
-    if (flags) CID_CUDA(cudaMemcpyAsync(flags, d_flags, nreads * 4, cudaMemcpyDeviceToHost, st));
-    if (want_rep) {
-        CID_CUDA(cudaMemcpyAsync(rep_n, d_rep_n, nreads * 4, cudaMemcpyDeviceToHost, st));
-        CID_CUDA(cudaMemcpyAsync(rep_colour, d_rc, nreads * (size_t)pp.rep_cap * 4, cudaMemcpyDeviceToHost, st));
-        CID_CUDA(cudaMemcpyAsync(rep_count, d_rv, nreads * (size_t)pp.rep_cap * 4, cudaMemcpyDeviceToHost, st));
-    }
-    if (order_n) {
-        CID_CUDA(cudaMemcpyAsync(order_n, d_on, nreads * 4, cudaMemcpyDeviceToHost, st));
-        CID_CUDA(cudaMemcpyAsync(order_pos, d_op, nreads * (size_t)order_cap * 2, cudaMemcpyDeviceToHost, st));
-        CID_CUDA(cudaMemcpyAsync(order_seq, d_os, nreads * (size_t)order_cap, cudaMemcpyDeviceToHost, st));
-    }
-    return check_err_flags(ctx, st);
-}
-
-int cid_read_id_batch(cid_index* ix, const char* bases, const char* quals, const uint64_t* seq_offs, uint64_t nseq,
-                      const uint64_t* read_offs, uint64_t nreads, const cid_readid_params* p, uint32_t* n_set,
-                      uint32_t* flags, uint32_t* rep_n, uint32_t* rep_colour, uint32_t* rep_count) {
-    if (!rep_n || !rep_colour || !rep_count) { set_error("read_id: null report buffers"); return CID_E_INVALID; }
-    return read_id_host(ix, bases, quals, seq_offs, nseq, read_offs, nreads, p, n_set, flags, rep_n, rep_colour, rep_count,
-                        0, nullptr, nullptr, nullptr);
-}
-
-int cid_read_kmer_order(cid_index* ix, const char* bases, const uint64_t* seq_offs, uint64_t nseq,
-                        const uint64_t* read_offs, uint64_t nreads, const cid_readid_params* p, uint32_t order_cap,
-                        uint32_t* order_n, uint8_t* order_seq, uint16_t* order_pos) {
-    if (!order_n || !order_seq || !order_pos || order_cap == 0) { set_error("read_kmer_order: null argument"); return CID_E_INVALID; }
-    return read_id_host(ix, bases, nullptr, seq_offs, nseq, read_offs, nreads, p, nullptr, nullptr, nullptr, nullptr, nullptr,
-                        order_cap, order_n, order_seq, order_pos);
 }
 
 int cid_hash_kmers(cid_index* ix, const char* kmers, uint64_t n, uint64_t* row_ids) {

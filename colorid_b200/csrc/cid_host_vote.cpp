@@ -71,9 +71,10 @@ static inline uint64_t fnv_usize(uint64_t v) {
     return h;
 }
 // entry().or_insert(): the table grows only when a NEW key arrives with no growth left.
-// Returns the positions (into keys[]) in ascending bucket order.
+// Returns the positions (into keys[]) in ascending bucket order.  `hash_of(key)` = FNV-1a of the key.
+template <class HashOf>
 static void usize_map_order(const uint32_t* keys, uint32_t n, uint32_t gw, std::vector<int32_t>& tab,
-                            std::vector<int32_t>& tmp, std::vector<uint32_t>& order) {
+                            std::vector<int32_t>& tmp, std::vector<uint32_t>& order, HashOf hash_of) {
     uint32_t nb = 0, items = 0, growth = 0;
     auto cap_of = [](uint32_t b) { return b == 0 ? 0u : (b < 8 ? b - 1 : b / 8 * 7); };
     auto probe = [&](const std::vector<int32_t>& t, uint32_t buckets, uint64_t hash) -> uint32_t {
@@ -93,16 +94,134 @@ static void usize_map_order(const uint32_t* keys, uint32_t n, uint32_t gw, std::
         if (growth == 0) {
             uint32_t nn = nb == 0 ? 4 : nb * 2;
             tmp.assign(nn, -1);
-            for (uint32_t s = 0; s < nb; s++) if (tab[s] >= 0) tmp[probe(tmp, nn, fnv_usize(keys[tab[s]]))] = tab[s];
+            for (uint32_t s = 0; s < nb; s++) if (tab[s] >= 0) tmp[probe(tmp, nn, hash_of(keys[tab[s]]))] = tab[s];
             tab.swap(tmp);
             nb = nn;
             growth = cap_of(nb) - items;
         }
-        tab[probe(tab, nb, fnv_usize(keys[i]))] = (int32_t)i;
+        tab[probe(tab, nb, hash_of(keys[i]))] = (int32_t)i;
         items++; growth--;
     }
     order.clear();
     for (uint32_t s = 0; s < nb; s++) if (tab[s] >= 0) order.push_back((uint32_t)tab[s]);
+}
+
+// Reads of one library produce the same few key sequences over and over (the members of a clade in
+// ascending colour order, plus the "no hit" key): memoise sequence -> iteration order per thread.
+struct OrderMemo {
+    enum { SIZE = 1 << 10, MAXN = 12 };
+    struct Ent { uint32_t n; uint32_t keys[MAXN]; uint8_t order[MAXN]; };
+    std::vector<Ent> ent;
+    OrderMemo() : ent(SIZE) { for (auto& e : ent) e.n = 0; }
+};
+
+// ---- kmer_poll_plus over a chunk of reads ---------------------------------------------------------
+void vote_params_init(VoteParams& vp, uint64_t bloom_size, uint32_t num_hash, uint32_t n_colors,
+                      const uint64_t* n_ref_by_colour, double fp_correct, uint32_t group_width) {
+    vp.n_colors = n_colors;
+    vp.fp_correct = fp_correct;
+    vp.group_width = (group_width == 8 || group_width == 16) ? group_width : 16;
+    vp.key_hash.resize((size_t)n_colors + 1);
+    for (uint32_t c = 0; c <= n_colors; c++) vp.key_hash[c] = fnv_usize(c);
+    vp.fp.resize(n_colors);      // false_prob_map, read_id_mt_pe.rs:18-38
+    for (uint32_t c = 0; c < n_colors; c++)
+        vp.fp[c] = bloom_false_prob((double)bloom_size, (double)num_hash, (double)n_ref_by_colour[c]);
+}
+
+// Binomial::mass is a pure function of (observations, p_false[colour], hits); reads of one library
+// share a handful of n_set values, so a small per-thread direct-mapped memo removes most of the
+// exp/log work without changing a single result bit.
+struct PmfMemo {
+    enum { SIZE = 1 << 13 };
+    std::vector<uint64_t> key;
+    std::vector<double> val;
+    PmfMemo() : key(SIZE, ~0ull), val(SIZE, 0.0) {}
+    double get(const VoteParams& vp, uint64_t obs, uint32_t colour, uint32_t x) {
+        if (obs >= (1u << 20) || x >= (1u << 20) || colour >= (1u << 24)) return binomial_pmf(obs, vp.fp[colour], x);
+        const uint64_t k = ((uint64_t)colour << 40) | (obs << 20) | x;
+        const uint64_t h = (k * 0x9E3779B97F4A7C15ull) >> (64 - 13);
+        if (key[h] != k) { key[h] = k; val[h] = binomial_pmf(obs, vp.fp[colour], x); }
+        return val[h];
+    }
+};
+
+void classify_chunk(const VoteParams& vp, uint64_t nreads, const uint32_t* n_set, const uint32_t* flags,
+                    const uint32_t* rep_n, const uint32_t* rep_colour, const uint32_t* rep_count, uint32_t rep_cap,
+                    int threads, int32_t* kind, uint32_t* hits, uint32_t* n_top, uint32_t* top, uint32_t top_cap) {
+    const uint32_t n_colors = vp.n_colors;
+    if (threads < 1) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    threads = (int)std::min<uint64_t>((uint64_t)threads, (nreads + 1023) / 1024);
+    std::atomic<uint64_t> next(0);
+    auto work = [&]() {
+        std::vector<int32_t> tab, tmp;
+        std::vector<uint32_t> order;
+        std::vector<std::pair<uint32_t, uint32_t>> cv, sig;
+        PmfMemo memo;
+        OrderMemo omemo;
+        auto hash_of = [&](uint32_t key) -> uint64_t { return key <= n_colors ? vp.key_hash[key] : fnv_usize(key); };
+        for (;;) {
+            uint64_t r0 = next.fetch_add(1024);
+            if (r0 >= nreads) break;
+            uint64_t r1 = std::min(nreads, r0 + 1024);
+            for (uint64_t r = r0; r < r1; r++) {
+                hits[r] = 0; n_top[r] = 0;
+                if (flags[r] & 1u) { kind[r] = CID_CLS_TOO_SHORT; continue; }          // :305-313
+                if (flags[r] & 2u) { kind[r] = CID_CLS_REF_PANIC; continue; }
+                const uint32_t n = rep_n[r];
+                if (n == 0) { kind[r] = CID_CLS_NO_HITS; continue; }                   // report.is_empty(), :332-340
+                const uint32_t* keys = rep_colour + r * (uint64_t)rep_cap;
+                const uint32_t* vals = rep_count + r * (uint64_t)rep_cap;
+                cv.clear();
+                if (n == 1) cv.push_back({keys[0], vals[0]});
+                else {
+                    const uint8_t* ord8 = nullptr;
+                    OrderMemo::Ent* e = nullptr;
+                    if (n <= OrderMemo::MAXN) {
+                        uint64_t h = 0xcbf29ce484222325ULL ^ n;
+                        for (uint32_t i = 0; i < n; i++) h = (h ^ keys[i]) * 0x100000001b3ULL;
+                        e = &omemo.ent[(h ^ (h >> 29)) & (OrderMemo::SIZE - 1)];
+                        if (e->n == n && !memcmp(e->keys, keys, n * 4)) ord8 = e->order;
+                    }
+                    if (ord8) {
+                        for (uint32_t i = 0; i < n; i++) cv.push_back({keys[ord8[i]], vals[ord8[i]]});
+                    } else {
+                        usize_map_order(keys, n, vp.group_width, tab, tmp, order, hash_of);
+                        for (uint32_t i : order) cv.push_back({keys[i], vals[i]});
+                        if (e) { e->n = n; memcpy(e->keys, keys, n * 4); for (uint32_t i = 0; i < n; i++) e->order[i] = (uint8_t)order[i]; }
+                    }
+                    // stable sort by count, descending (read_id_mt_pe.rs:196 sort_by(|a, b| b.1.cmp(a.1)))
+                    for (size_t i = 1; i < cv.size(); i++) {
+                        auto x = cv[i];
+                        size_t j = i;
+                        while (j > 0 && cv[j - 1].second < x.second) { cv[j] = cv[j - 1]; j--; }
+                        cv[j] = x;
+                    }
+                }
+                if (cv[0].first == n_colors && cv.size() == 1) { kind[r] = CID_CLS_NO_HITS; continue; }   // :197-205
+                const uint64_t observations = n_set[r];
+                sig.clear();
+                for (auto& t : cv) {
+                    if (t.first == n_colors) continue;
+                    const double p_false = vp.fp[t.first];
+                    const double critical = (double)observations * p_false;
+                    const double th = (double)t.second;
+                    bool drop = th < critical;
+                    if (!drop && th > critical) drop = memo.get(vp, observations, t.first, t.second) >= vp.fp_correct;
+                    if (!drop) sig.push_back(t);
+                }
+                if (sig.empty()) { kind[r] = CID_CLS_NO_SIGNIFICANT; continue; }
+                uint32_t nt = 0;
+                for (auto& h : sig) if (h.second == sig[0].second) { if (top && nt < top_cap) top[r * (uint64_t)top_cap + nt] = h.first; nt++; }
+                hits[r] = sig[0].second;
+                n_top[r] = nt;
+                kind[r] = nt == 1 ? CID_CLS_ACCEPT : CID_CLS_REJECT_MULTI;
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < threads; t++) th.emplace_back(work);
+    work();
+    for (auto& x : th) x.join();
 }
 
 }  // namespace cid
@@ -125,61 +244,9 @@ int cid_classify_reads(uint64_t bloom_size, uint32_t num_hash, uint32_t n_colors
         set_error("cid_classify_reads: null argument");
         return CID_E_INVALID;
     }
-    if (group_width != 8 && group_width != 16) group_width = 16;
-    std::vector<double> fp(n_colors);      // false_prob_map, read_id_mt_pe.rs:18-38
-    for (uint32_t c = 0; c < n_colors; c++)
-        fp[c] = bloom_false_prob((double)bloom_size, (double)num_hash, (double)n_ref_by_colour[c]);
-    if (threads < 1) threads = (int)std::max(1u, std::thread::hardware_concurrency());
-    std::atomic<uint64_t> next(0);
-    auto work = [&]() {
-        std::vector<int32_t> tab, tmp;
-        std::vector<uint32_t> order;
-        std::vector<std::pair<uint32_t, uint32_t>> cv, sig;
-        for (;;) {
-            uint64_t r0 = next.fetch_add(4096);
-            if (r0 >= nreads) break;
-            uint64_t r1 = std::min(nreads, r0 + 4096);
-            for (uint64_t r = r0; r < r1; r++) {
-                hits[r] = 0; n_top[r] = 0;
-                if (flags[r] & 1u) { kind[r] = CID_CLS_TOO_SHORT; continue; }          // :305-313
-                if (flags[r] & 2u) { kind[r] = CID_CLS_REF_PANIC; continue; }
-                const uint32_t n = rep_n[r];
-                if (n == 0) { kind[r] = CID_CLS_NO_HITS; continue; }                   // report.is_empty(), :332-340
-                const uint32_t* keys = rep_colour + r * (uint64_t)rep_cap;
-                const uint32_t* vals = rep_count + r * (uint64_t)rep_cap;
-                cv.clear();
-                if (n == 1) cv.push_back({keys[0], vals[0]});
-                else {
-                    usize_map_order(keys, n, group_width, tab, tmp, order);
-                    for (uint32_t i : order) cv.push_back({keys[i], vals[i]});
-                    std::stable_sort(cv.begin(), cv.end(), [](const std::pair<uint32_t, uint32_t>& a,
-                                                              const std::pair<uint32_t, uint32_t>& b) { return a.second > b.second; });
-                }
-                if (cv[0].first == n_colors && cv.size() == 1) { kind[r] = CID_CLS_NO_HITS; continue; }   // :197-205
-                const uint64_t observations = n_set[r];
-                sig.clear();
-                for (auto& t : cv) {
-                    if (t.first == n_colors) continue;
-                    const double p_false = fp[t.first];
-                    const double critical = (double)observations * p_false;
-                    const double th = (double)t.second;
-                    bool drop = th < critical;
-                    if (!drop && th > critical) drop = binomial_pmf(observations, p_false, t.second) >= fp_correct;
-                    if (!drop) sig.push_back(t);
-                }
-                if (sig.empty()) { kind[r] = CID_CLS_NO_SIGNIFICANT; continue; }
-                uint32_t nt = 0;
-                for (auto& h : sig) if (h.second == sig[0].second) { if (top && nt < top_cap) top[r * (uint64_t)top_cap + nt] = h.first; nt++; }
-                hits[r] = sig[0].second;
-                n_top[r] = nt;
-                kind[r] = nt == 1 ? CID_CLS_ACCEPT : CID_CLS_REJECT_MULTI;
-            }
-        }
-    };
-    std::vector<std::thread> th;
-    for (int t = 1; t < threads; t++) th.emplace_back(work);
-    work();
-    for (auto& x : th) x.join();
+    VoteParams vp;
+    vote_params_init(vp, bloom_size, num_hash, n_colors, n_ref_by_colour, fp_correct, group_width);
+    classify_chunk(vp, nreads, n_set, flags, rep_n, rep_colour, rep_count, rep_cap, threads, kind, hits, n_top, top, top_cap);
     return CID_OK;
 }
 

@@ -65,6 +65,10 @@ struct cid_ctx {
     std::vector<cudaEvent_t> prof_pool;
     double prof_ms[16] = {0};
     uint64_t prof_n[16] = {0};
+    // read_id host pipeline (cid_readid_pipe.cu): chunked H2D / kernels / D2H / host vote overlap
+    struct cid_readid_pipe* pipe = nullptr;
+    uint64_t opt_readid_chunk = 0;   // reads per pipeline chunk (0 = automatic)
+    int opt_host_threads = 0;        // host threads for the vote (0 = all cores)
 };
 
 struct cid_index {
@@ -151,11 +155,29 @@ int launch_query_perfect(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, co
 int launch_hash_kmers(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, const uint8_t* d_kmers, uint64_t n,
                       uint64_t* d_rows);
 
-// read_id pipeline on device buffers; scratch comes from ctx.
+// read_id kernels on device buffers.  Reads [r_first, r_first + nreads) of the arrays are processed
+// (every per-read array is indexed by the absolute read number, so a caller that stages only a
+// chunk passes pointers biased by the chunk origin).  Per-read scratch (`entries`, `order`, `nocc`)
+// is indexed from 0 and must hold `scr.cap_reads` reads; larger ranges are walked in pieces.
+struct ReadIdScratch { uint32_t* entries; uint16_t* order; uint32_t* nocc; uint64_t cap_reads; };
+void readid_scratch_bytes(const cid_index* idx, uint32_t max_read_bases, uint32_t max_kmers, uint64_t reads,
+                          size_t* entries_bytes, size_t* order_bytes, size_t* nocc_bytes);
 int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const uint8_t* d_quals,
-               const uint64_t* d_seq_offs, uint64_t nseq, uint64_t nbases, const uint64_t* d_read_offs,
-               uint64_t nreads, uint32_t max_read_bases, uint32_t max_kmers, const cid_readid_params& p,
+               const uint64_t* d_seq_offs, const uint64_t* d_read_offs, uint64_t r_first, uint64_t nreads,
+               uint32_t max_read_bases, uint32_t max_kmers, const cid_readid_params& p, const ReadIdScratch& scr,
                uint32_t* d_n_set, uint32_t* d_flags, uint32_t* d_rep_n, uint32_t* d_rep_colour, uint32_t* d_rep_count,
                uint32_t order_cap, uint32_t* d_order_n, uint8_t* d_order_seq, uint16_t* d_order_pos);
+
+// host vote (cid_host_vote.cpp): read_id_mt_pe.rs:187-251 kmer_poll_plus over a chunk of reads
+struct VoteParams { uint32_t n_colors = 0; double fp_correct = 1e-3; uint32_t group_width = 16; std::vector<double> fp; std::vector<uint64_t> key_hash; };
+void vote_params_init(VoteParams& vp, uint64_t bloom_size, uint32_t num_hash, uint32_t n_colors,
+                      const uint64_t* n_ref_by_colour, double fp_correct, uint32_t group_width);
+void classify_chunk(const VoteParams& vp, uint64_t nreads, const uint32_t* n_set, const uint32_t* flags,
+                    const uint32_t* rep_n, const uint32_t* rep_colour, const uint32_t* rep_count, uint32_t rep_cap,
+                    int threads, int32_t* kind, uint32_t* hits, uint32_t* n_top, uint32_t* top, uint32_t top_cap);
+
+// host-pointer read_id pipeline (cid_readid_pipe.cu)
+void default_readid_params(cid_readid_params& p, const cid_readid_params* in, uint32_t N);
+void readid_pipe_destroy(cid_ctx* ctx);
 
 }  // namespace cid

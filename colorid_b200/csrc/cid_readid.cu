@@ -578,35 +578,47 @@ static uint32_t cap_to_buckets(uint32_t cap) {
     return b;
 }
 
+static void readid_dims(const cid_index* idx, uint32_t max_read_bases, uint32_t max_kmers, int* cap, uint32_t* bound,
+                        uint32_t* maxocc) {
+    *cap = (int)((max_read_bases + 31) / 32 * 32 + 32);
+    uint32_t b = max_kmers ? max_kmers : (max_read_bases >= idx->k ? max_read_bases - idx->k + 1 : 1);
+    if (b < 1) b = 1;
+    *bound = b;
+    *maxocc = (b + 3) & ~3u;
+}
+void readid_scratch_bytes(const cid_index* idx, uint32_t max_read_bases, uint32_t max_kmers, uint64_t reads,
+                          size_t* entries_bytes, size_t* order_bytes, size_t* nocc_bytes) {
+    int cap; uint32_t bound, maxocc;
+    readid_dims(idx, max_read_bases, max_kmers, &cap, &bound, &maxocc);
+    *entries_bytes = (size_t)reads * maxocc * 4;
+    *order_bytes = (size_t)reads * maxocc * 2;
+    *nocc_bytes = (size_t)reads * 4;
+}
+
 int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const uint8_t* d_quals,
-               const uint64_t* d_seq_offs, uint64_t nseq, uint64_t nbases, const uint64_t* d_read_offs,
-               uint64_t nreads, uint32_t max_read_bases, uint32_t max_kmers, const cid_readid_params& p,
+               const uint64_t* d_seq_offs, const uint64_t* d_read_offs, uint64_t r_first, uint64_t nreads,
+               uint32_t max_read_bases, uint32_t max_kmers, const cid_readid_params& p, const ReadIdScratch& scr,
                uint32_t* d_n_set, uint32_t* d_flags, uint32_t* d_rep_n, uint32_t* d_rep_colour, uint32_t* d_rep_count,
                uint32_t order_cap, uint32_t* d_order_n, uint8_t* d_order_seq, uint16_t* d_order_pos) {
-    (void)nseq; (void)nbases;
     cid_ctx* ctx = idx->ctx;
     if (nreads == 0) return CID_OK;
     if (idx->k == 0) return CID_E_INVALID;
     if (max_read_bases > 1000) { set_error("read_id: reads longer than 1000 bases (all mates) are not supported yet"); return CID_E_UNSUPPORTED; }
     if (p.downsample == 0 || (p.group_width != 16 && p.group_width != 8)) { set_error("read_id: bad params"); return CID_E_INVALID; }
     if (idx->Wp > 32 * RV_MAXWPL) { set_error("read_id: more than %d accessions per shard not supported", 32 * 32 * RV_MAXWPL); return CID_E_UNSUPPORTED; }
-    const int cap = (int)((max_read_bases + 31) / 32 * 32 + 32);
-    uint32_t bound = max_kmers ? max_kmers : (max_read_bases >= idx->k ? max_read_bases - idx->k + 1 : 1);
-    if (bound < 1) bound = 1;
-    const uint32_t maxocc = (bound + 3) & ~3u;
+    int cap; uint32_t bound, maxocc;
+    readid_dims(idx, max_read_bases, max_kmers, &cap, &bound, &maxocc);
     const uint32_t tsize = (uint32_t)next_pow2(2ull * bound);
     const uint32_t TB = cap_to_buckets(bound + 1);
     const bool small = maxocc <= 255;
     const uint32_t maxq = d_quals && p.qual_offset ? p.qual_offset + 33 : 0;
     const uint8_t* quals = maxq ? d_quals : nullptr;
 
-    const uint64_t sub = std::min<uint64_t>(nreads, 1u << 20);
-    CID_TRY(ctx->scratch[16].ensure(sub * maxocc * 4));
-    CID_TRY(ctx->scratch[17].ensure(sub * maxocc * 2));
-    CID_TRY(ctx->scratch[18].ensure(sub * 4));
-    uint32_t* d_entries = ctx->scratch[16].as<uint32_t>();
-    uint16_t* d_order = ctx->scratch[17].as<uint16_t>();
-    uint32_t* d_nocc = ctx->scratch[18].as<uint32_t>();
+    const uint64_t sub = std::min<uint64_t>(nreads, scr.cap_reads);
+    if (sub == 0) { set_error("read_id: no scratch"); return CID_E_INVALID; }
+    uint32_t* d_entries = scr.entries;
+    uint16_t* d_order = scr.order;
+    uint32_t* d_nocc = scr.nocc;
 
     // shared memory budgets
     size_t a_warp = ((tile_smem_bytes(cap) + 7) & ~(size_t)7) + (size_t)tsize * 12 + (size_t)cap * 4 + (MAX_MATES + 1) * 4 + 4;
@@ -625,8 +637,8 @@ int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const ui
     CID_CUDA(cudaFuncSetAttribute(readid_order_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b_smem));
 
     const ModS mods = make_mods(idx->S);
-    for (uint64_t r0 = 0; r0 < nreads; r0 += sub) {
-        const uint64_t nr = std::min(sub, nreads - r0);
+    for (uint64_t r0 = r_first; r0 < r_first + nreads; r0 += sub) {
+        const uint64_t nr = std::min(sub, r_first + nreads - r0);
         unsigned gridA = (unsigned)std::min<uint64_t>((nr + RA_WARPS - 1) / RA_WARPS, (uint64_t)ctx->sm_count * 32);
         {
         ProfScope ps(ctx, st, KID_READID_KMERIZE);

@@ -1,0 +1,328 @@
+// Host-pointer read_id entry points: read_id_mt_pe.rs:282-363 parallel_vec (+ the streams that feed
+// it, :701-951).  The reference classifies one batch of reads at a time with no overlap between
+// parsing and classification (:762-790).  Here a batch is cut into chunks that flow through a
+// small ring of slots, each with its own CUDA stream and device buffers:
+//
+//     H2D (bases, quals, offsets)  ->  readid_kmerize / readid_order / readid_vote  ->  D2H reports
+//                                                                                   ->  host vote
+//
+// so the PCIe copies of chunk c+1, the kernels of chunk c and the host-side kmer_poll_plus of
+// chunk c-1 run concurrently.  Kernels of neighbouring chunks also overlap on the GPU, which lets
+// the DRAM-access-bound vote kernel hide under the issue-bound kmerize/order kernels.
+#include <algorithm>
+#include <condition_variable>
+#include <cstring>
+#include <deque>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "cid_internal.h"
+
+struct cid_readid_pipe {
+    enum { NS = 3 };
+    struct Slot {
+        cudaStream_t st = nullptr;
+        cudaEvent_t done = nullptr;
+        cid::DevBuf bases, quals, seq_offs, read_offs, entries, order, nocc, n_set, flags, rep_n, rep, ord_out;
+        cid::PinBuf h_n_set, h_flags, h_rep_n, h_rep;
+    } slot[NS];
+    bool ready = false;
+};
+
+namespace cid {
+
+void default_readid_params(cid_readid_params& p, const cid_readid_params* in, uint32_t N) {
+    if (in) p = *in;
+    else { p.downsample = 1; p.start_sample = 3; p.qual_offset = 0; p.group_width = 16; p.reserve_before_find = 1; p.rep_cap = 0; }
+    if (p.downsample == 0) p.downsample = 1;
+    if (p.group_width == 0) p.group_width = 16;
+    if (p.rep_cap == 0) p.rep_cap = N + 1;
+}
+
+void readid_pipe_destroy(cid_ctx* ctx) {
+    cid_readid_pipe* pp = ctx->pipe;
+    if (!pp) return;
+    for (auto& s : pp->slot) {
+        if (s.st) cudaStreamSynchronize(s.st);
+        for (DevBuf* b : {&s.bases, &s.quals, &s.seq_offs, &s.read_offs, &s.entries, &s.order, &s.nocc, &s.n_set, &s.flags,
+                          &s.rep_n, &s.rep, &s.ord_out})
+            b->release();
+        for (PinBuf* b : {&s.h_n_set, &s.h_flags, &s.h_rep_n, &s.h_rep}) b->release();
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.st) cudaStreamDestroy(s.st);
+    }
+    delete pp;
+    ctx->pipe = nullptr;
+}
+
+static int pipe_get(cid_ctx* ctx, cid_readid_pipe** out) {
+    if (!ctx->pipe) ctx->pipe = new cid_readid_pipe();
+    cid_readid_pipe* pp = ctx->pipe;
+    if (!pp->ready) {
+        for (auto& s : pp->slot) {
+            CID_CUDA(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+            CID_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        }
+        pp->ready = true;
+    }
+    *out = pp;
+    return CID_OK;
+}
+
+// host scan of the read geometry: longest read and most k-mer start positions
+static void read_geometry(const uint64_t* seq_offs, const uint64_t* read_offs, uint64_t nreads, uint32_t k, uint32_t d,
+                          uint32_t* max_bases, uint32_t* max_kmers) {
+    uint64_t mb = 0, mk = 0;
+    for (uint64_t r = 0; r < nreads; r++) {
+        uint64_t b = seq_offs[read_offs[r + 1]] - seq_offs[read_offs[r]], kk = 0;
+        for (uint64_t s = read_offs[r]; s < read_offs[r + 1]; s++) {
+            uint64_t l = seq_offs[s + 1] - seq_offs[s];
+            if (l >= k) kk += (l - k) / d + 1;
+        }
+        mb = std::max(mb, b); mk = std::max(mk, kk);
+    }
+    *max_bases = (uint32_t)std::min<uint64_t>(mb, 0xFFFFFFFFu);
+    *max_kmers = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(mk, 1), 0xFFFFFFFFu);
+}
+
+struct HostOut {            // where a chunk's results go (user memory, indexed by absolute read)
+    uint32_t *n_set = nullptr, *flags = nullptr, *rep_n = nullptr, *rep_colour = nullptr, *rep_count = nullptr;
+    uint32_t order_cap = 0;
+    uint32_t* order_n = nullptr; uint8_t* order_seq = nullptr; uint16_t* order_pos = nullptr;
+    // fused host vote
+    const VoteParams* vote = nullptr;
+    int threads = 0;
+    int32_t* kind = nullptr; uint32_t *hits = nullptr, *n_top = nullptr, *top = nullptr; uint32_t top_cap = 0;
+};
+
+struct VoteJob { uint64_t r0, nr; int slot; };
+
+static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals, const uint64_t* seq_offs, uint64_t nseq,
+                            const uint64_t* read_offs, uint64_t nreads, const cid_readid_params* p, const HostOut& out) {
+    cid_ctx* ctx = ix->ctx;
+    if (!seq_offs || !read_offs) { set_error("read_id: null argument"); return CID_E_INVALID; }
+    CID_CUDA(cudaSetDevice(ctx->device));
+    cid_readid_params pp;
+    default_readid_params(pp, p, ix->N);
+    if (nreads == 0) return CID_OK;
+    (void)nseq;
+    uint32_t max_bases, max_kmers;
+    read_geometry(seq_offs, read_offs, nreads, ix->k, pp.downsample, &max_bases, &max_kmers);
+    const bool use_q = quals && pp.qual_offset;
+    const bool want_rep = out.rep_n != nullptr || out.vote != nullptr;
+    const bool fused = out.vote != nullptr;
+    cid_readid_pipe* pipe;
+    CID_TRY(pipe_get(ctx, &pipe));
+    // work queued on the context's own stream (index build / upload) must be visible to the slot streams
+    CID_CUDA(cudaStreamSynchronize(ctx->stream));
+
+    uint64_t chunk = ctx->opt_readid_chunk;
+    if (chunk == 0) chunk = std::min<uint64_t>(131072, std::max<uint64_t>(16384, (nreads + 7) / 8));
+    const uint64_t nchunks = (nreads + chunk - 1) / chunk;
+    const int NS = cid_readid_pipe::NS;
+    const size_t rc = pp.rep_cap;
+
+    // fused vote: a worker thread classifies chunk c while the GPU runs chunks c+1, c+2
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<VoteJob> jobs;
+    bool slot_busy[cid_readid_pipe::NS] = {false, false, false};
+    bool closing = false;
+    int worker_rc = CID_OK;
+    std::thread worker;
+    if (fused) {
+        worker = std::thread([&]() {
+            cudaSetDevice(ctx->device);
+            for (;;) {
+                VoteJob j;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return !jobs.empty() || closing; });
+                    if (jobs.empty()) return;
+                    j = jobs.front();
+                    jobs.pop_front();
+                }
+                auto& s = pipe->slot[j.slot];
+                if (cudaEventSynchronize(s.done) != cudaSuccess) worker_rc = CID_E_CUDA;
+                else {
+                    const uint32_t* hn = s.h_n_set.as<uint32_t>();
+                    classify_chunk(*out.vote, j.nr, hn, s.h_flags.as<uint32_t>(), s.h_rep_n.as<uint32_t>(),
+                                   s.h_rep.as<uint32_t>(), s.h_rep.as<uint32_t>() + j.nr * rc, (uint32_t)rc, out.threads,
+                                   out.kind + j.r0, out.hits + j.r0, out.n_top + j.r0,
+                                   out.top ? out.top + j.r0 * out.top_cap : nullptr, out.top_cap);
+                    if (out.n_set) memcpy(out.n_set + j.r0, hn, j.nr * 4);
+                    if (out.flags) memcpy(out.flags + j.r0, s.h_flags.p, j.nr * 4);
+                }
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    slot_busy[j.slot] = false;
+                }
+                cv.notify_all();
+            }
+        });
+    }
+    auto finish = [&](int rcode) {
+        if (fused) {
+            { std::lock_guard<std::mutex> lk(mu); closing = true; }
+            cv.notify_all();
+            worker.join();
+        }
+        for (auto& s : pipe->slot) cudaStreamSynchronize(s.st);
+        if (rcode == CID_OK && worker_rc != CID_OK) { set_error("read_id: host vote worker failed"); return worker_rc; }
+        return rcode;
+    };
+#define PIPE_TRY(expr) do { int _rc = (expr); if (_rc != CID_OK) return finish(_rc); } while (0)
+#define PIPE_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); return finish(CID_E_CUDA); } } while (0)
+
+    for (uint64_t c = 0; c < nchunks; c++) {
+        const int si = (int)(c % NS);
+        auto& s = pipe->slot[si];
+        const uint64_t r0 = c * chunk, r1 = std::min(nreads, r0 + chunk), nr = r1 - r0;
+        const uint64_t s0 = read_offs[r0], s1 = read_offs[r1];
+        const uint64_t b0 = seq_offs[s0], b1 = seq_offs[s1];
+        if (fused) {          // the slot's pinned staging must have been consumed
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return !slot_busy[si]; });
+        }
+        size_t eb, ob, nb;
+        readid_scratch_bytes(ix, max_bases, max_kmers, nr, &eb, &ob, &nb);
+        PIPE_TRY(s.bases.ensure(b1 - b0 + 64));
+        if (use_q) PIPE_TRY(s.quals.ensure(b1 - b0 + 64));
+        PIPE_TRY(s.seq_offs.ensure((s1 - s0 + 1) * 8));
+        PIPE_TRY(s.read_offs.ensure((nr + 1) * 8));
+        PIPE_TRY(s.entries.ensure(eb));
+        PIPE_TRY(s.order.ensure(ob));
+        PIPE_TRY(s.nocc.ensure(nb));
+        PIPE_TRY(s.n_set.ensure(nr * 4));
+        PIPE_TRY(s.flags.ensure(nr * 4));
+        if (want_rep) { PIPE_TRY(s.rep_n.ensure(nr * 4)); PIPE_TRY(s.rep.ensure(nr * rc * 8)); }
+        if (out.order_n) PIPE_TRY(s.ord_out.ensure(nr * 4 + nr * (size_t)out.order_cap * 3 + 64));
+        if (fused) {
+            PIPE_TRY(s.h_n_set.ensure(nr * 4)); PIPE_TRY(s.h_flags.ensure(nr * 4));
+            PIPE_TRY(s.h_rep_n.ensure(nr * 4)); PIPE_TRY(s.h_rep.ensure(nr * rc * 8));
+        }
+        if (b1 > b0) PIPE_CUDA(cudaMemcpyAsync(s.bases.p, bases + b0, b1 - b0, cudaMemcpyHostToDevice, s.st));
+        if (use_q && b1 > b0) PIPE_CUDA(cudaMemcpyAsync(s.quals.p, quals + b0, b1 - b0, cudaMemcpyHostToDevice, s.st));
+        PIPE_CUDA(cudaMemcpyAsync(s.seq_offs.p, seq_offs + s0, (s1 - s0 + 1) * 8, cudaMemcpyHostToDevice, s.st));
+        PIPE_CUDA(cudaMemcpyAsync(s.read_offs.p, read_offs + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, s.st));
+        // device arrays are indexed by absolute base / sequence / read numbers: bias the chunk buffers
+        const uint8_t* d_bases = s.bases.as<uint8_t>() - b0;
+        const uint8_t* d_quals = use_q ? s.quals.as<uint8_t>() - b0 : nullptr;
+        const uint64_t* d_seq_offs = s.seq_offs.as<uint64_t>() - s0;
+        const uint64_t* d_read_offs = s.read_offs.as<uint64_t>() - r0;
+        uint32_t* d_n_set = s.n_set.as<uint32_t>() - r0;
+        uint32_t* d_flags = s.flags.as<uint32_t>() - r0;
+        uint32_t *d_rep_n = nullptr, *d_rc = nullptr, *d_rv = nullptr;
+        if (want_rep) {
+            d_rep_n = s.rep_n.as<uint32_t>() - r0;
+            d_rc = s.rep.as<uint32_t>() - r0 * rc;
+            d_rv = s.rep.as<uint32_t>() + nr * rc - r0 * rc;
+        }
+        uint32_t* d_on = nullptr; uint8_t* d_os = nullptr; uint16_t* d_op = nullptr;
+        if (out.order_n) {
+            d_on = s.ord_out.as<uint32_t>() - r0;
+            d_op = (uint16_t*)(s.ord_out.as<uint32_t>() + nr) - r0 * (size_t)out.order_cap;
+            d_os = (uint8_t*)((uint16_t*)(s.ord_out.as<uint32_t>() + nr) + nr * (size_t)out.order_cap) - r0 * (size_t)out.order_cap;
+        }
+        ReadIdScratch scr{s.entries.as<uint32_t>(), s.order.as<uint16_t>(), s.nocc.as<uint32_t>(), nr};
+        PIPE_TRY(readid_run(ix, s.st, d_bases, d_quals, d_seq_offs, d_read_offs, r0, nr, max_bases, max_kmers, pp, scr,
+                            d_n_set, d_flags, d_rep_n, d_rc, d_rv, out.order_cap, d_on, d_os, d_op));
+        if (fused) {
+            PIPE_CUDA(cudaMemcpyAsync(s.h_n_set.p, s.n_set.p, nr * 4, cudaMemcpyDeviceToHost, s.st));
+            PIPE_CUDA(cudaMemcpyAsync(s.h_flags.p, s.flags.p, nr * 4, cudaMemcpyDeviceToHost, s.st));
+            PIPE_CUDA(cudaMemcpyAsync(s.h_rep_n.p, s.rep_n.p, nr * 4, cudaMemcpyDeviceToHost, s.st));
+            PIPE_CUDA(cudaMemcpyAsync(s.h_rep.p, s.rep.p, nr * rc * 8, cudaMemcpyDeviceToHost, s.st));
+            PIPE_CUDA(cudaEventRecord(s.done, s.st));
+            { std::lock_guard<std::mutex> lk(mu); slot_busy[si] = true; jobs.push_back(VoteJob{r0, nr, si}); }
+            cv.notify_all();
+        } else {
+            if (out.n_set) PIPE_CUDA(cudaMemcpyAsync(out.n_set + r0, s.n_set.p, nr * 4, cudaMemcpyDeviceToHost, s.st));
+            if (out.flags) PIPE_CUDA(cudaMemcpyAsync(out.flags + r0, s.flags.p, nr * 4, cudaMemcpyDeviceToHost, s.st));
+            if (out.rep_n) {
+                PIPE_CUDA(cudaMemcpyAsync(out.rep_n + r0, s.rep_n.p, nr * 4, cudaMemcpyDeviceToHost, s.st));
+                PIPE_CUDA(cudaMemcpyAsync(out.rep_colour + r0 * rc, s.rep.p, nr * rc * 4, cudaMemcpyDeviceToHost, s.st));
+                PIPE_CUDA(cudaMemcpyAsync(out.rep_count + r0 * rc, s.rep.as<uint32_t>() + nr * rc, nr * rc * 4,
+                                          cudaMemcpyDeviceToHost, s.st));
+            }
+            if (out.order_n) {
+                const size_t oc = out.order_cap;
+                PIPE_CUDA(cudaMemcpyAsync(out.order_n + r0, s.ord_out.p, nr * 4, cudaMemcpyDeviceToHost, s.st));
+                PIPE_CUDA(cudaMemcpyAsync(out.order_pos + r0 * oc, s.ord_out.as<uint32_t>() + nr, nr * oc * 2,
+                                          cudaMemcpyDeviceToHost, s.st));
+                PIPE_CUDA(cudaMemcpyAsync(out.order_seq + r0 * oc, (uint16_t*)(s.ord_out.as<uint32_t>() + nr) + nr * oc,
+                                          nr * oc, cudaMemcpyDeviceToHost, s.st));
+            }
+        }
+    }
+#undef PIPE_TRY
+#undef PIPE_CUDA
+    int rcode = finish(CID_OK);
+    if (rcode != CID_OK) return rcode;
+    return check_err_flags(ctx, ctx->stream);
+}
+
+}  // namespace cid
+
+using namespace cid;
+
+extern "C" {
+
+int cid_read_id_batch_dev(cid_index* ix, const char* d_bases, const char* d_quals, const uint64_t* d_seq_offs,
+                          uint64_t nseq, uint64_t nbases, const uint64_t* d_read_offs, uint64_t nreads,
+                          uint32_t h_max_read_bases, uint32_t h_max_kmers, const cid_readid_params* p,
+                          uint32_t* d_n_set, uint32_t* d_flags, uint32_t* d_rep_n, uint32_t* d_rep_colour,
+                          uint32_t* d_rep_count, void* stream) {
+    (void)nseq; (void)nbases;
+    cid_ctx* ctx = ix->ctx;
+    CID_CUDA(cudaSetDevice(ctx->device));
+    cid_readid_params pp;
+    default_readid_params(pp, p, ix->N);
+    const uint64_t cap = std::min<uint64_t>(std::max<uint64_t>(nreads, 1), 1u << 20);
+    size_t eb, ob, nb;
+    readid_scratch_bytes(ix, h_max_read_bases, h_max_kmers, cap, &eb, &ob, &nb);
+    CID_TRY(ctx->scratch[16].ensure(eb));
+    CID_TRY(ctx->scratch[17].ensure(ob));
+    CID_TRY(ctx->scratch[18].ensure(nb));
+    ReadIdScratch scr{ctx->scratch[16].as<uint32_t>(), ctx->scratch[17].as<uint16_t>(), ctx->scratch[18].as<uint32_t>(), cap};
+    return readid_run(ix, (cudaStream_t)stream, (const uint8_t*)d_bases, (const uint8_t*)d_quals, d_seq_offs, d_read_offs, 0,
+                      nreads, h_max_read_bases, h_max_kmers, pp, scr, d_n_set, d_flags, d_rep_n, d_rep_colour, d_rep_count,
+                      0, nullptr, nullptr, nullptr);
+}
+
+int cid_read_id_batch(cid_index* ix, const char* bases, const char* quals, const uint64_t* seq_offs, uint64_t nseq,
+                      const uint64_t* read_offs, uint64_t nreads, const cid_readid_params* p, uint32_t* n_set,
+                      uint32_t* flags, uint32_t* rep_n, uint32_t* rep_colour, uint32_t* rep_count) {
+    if (!rep_n || !rep_colour || !rep_count) { set_error("read_id: null report buffers"); return CID_E_INVALID; }
+    HostOut o;
+    o.n_set = n_set; o.flags = flags; o.rep_n = rep_n; o.rep_colour = rep_colour; o.rep_count = rep_count;
+    return read_id_pipeline(ix, bases, quals, seq_offs, nseq, read_offs, nreads, p, o);
+}
+
+int cid_read_id_classify(cid_index* ix, const char* bases, const char* quals, const uint64_t* seq_offs, uint64_t nseq,
+                         const uint64_t* read_offs, uint64_t nreads, const cid_readid_params* p,
+                         const uint64_t* n_ref_by_colour, double fp_correct, int32_t* kind, uint32_t* hits,
+                         uint32_t* n_set, uint32_t* n_top, uint32_t* top, uint32_t top_cap) {
+    if (!ix || !n_ref_by_colour || !kind || !hits || !n_set || !n_top) { set_error("read_id_classify: null argument"); return CID_E_INVALID; }
+    cid_readid_params pp;
+    default_readid_params(pp, p, ix->N);
+    pp.rep_cap = ix->N + 1;      // the vote needs the untruncated report
+    VoteParams vp;
+    vote_params_init(vp, ix->S, ix->H, ix->N, n_ref_by_colour, fp_correct, pp.group_width);
+    HostOut o;
+    o.n_set = n_set;
+    o.vote = &vp; o.threads = ix->ctx->opt_host_threads;
+    o.kind = kind; o.hits = hits; o.n_top = n_top; o.top = top; o.top_cap = top ? top_cap : 0;
+    return read_id_pipeline(ix, bases, quals, seq_offs, nseq, read_offs, nreads, &pp, o);
+}
+
+int cid_read_kmer_order(cid_index* ix, const char* bases, const uint64_t* seq_offs, uint64_t nseq,
+                        const uint64_t* read_offs, uint64_t nreads, const cid_readid_params* p, uint32_t order_cap,
+                        uint32_t* order_n, uint8_t* order_seq, uint16_t* order_pos) {
+    if (!order_n || !order_seq || !order_pos || order_cap == 0) { set_error("read_kmer_order: null argument"); return CID_E_INVALID; }
+    HostOut o;
+    o.order_cap = order_cap; o.order_n = order_n; o.order_seq = order_seq; o.order_pos = order_pos;
+    return read_id_pipeline(ix, bases, nullptr, seq_offs, nseq, read_offs, nreads, p, o);
+}
+
+}  // extern "C"

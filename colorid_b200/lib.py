@@ -14,6 +14,7 @@ u16p = C.POINTER(C.c_uint16)
 u32p = C.POINTER(C.c_uint32)
 u64p = C.POINTER(C.c_uint64)
 i64p = C.POINTER(C.c_int64)
+i32p = C.POINTER(C.c_int32)
 vp = C.c_void_p
 
 CID_OK, CID_E_INVALID, CID_E_CUDA, CID_E_NOMEM, CID_E_UNSUPPORTED, CID_E_REF_PANIC, CID_E_CAPACITY = 0, -1, -2, -3, -4, -5, -6
@@ -57,6 +58,9 @@ SIGNATURES = {
                                         C.POINTER(ReadIdParams), vp, vp, vp, vp, vp, vp]),
     "cid_read_kmer_order": (C.c_int, [vp, vp, u64p, C.c_uint64, u64p, C.c_uint64, C.POINTER(ReadIdParams), C.c_uint32,
                                       u32p, u8p, u16p]),
+    "cid_read_id_classify": (C.c_int, [vp, vp, vp, u64p, C.c_uint64, u64p, C.c_uint64, C.POINTER(ReadIdParams), u64p,
+                                       C.c_double, C.POINTER(C.c_int32), u32p, u32p, u32p, u32p, C.c_uint32]),
+    "cid_ctx_set_option": (C.c_int, [vp, C.c_char_p, C.c_int64]),
     "cid_hash_kmers": (C.c_int, [vp, vp, C.c_uint64, u64p]),
     "cid_ctx_profile": (C.c_int, [vp, C.c_int]),
     "cid_ctx_profile_read": (C.c_int, [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double), u64p]),

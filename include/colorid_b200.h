@@ -54,6 +54,10 @@ void cid_ctx_destroy(cid_ctx* ctx);
 int cid_ctx_device(const cid_ctx* ctx);
 /* Counters of kernels launched by this library since ctx creation (for bench `gpu_launches`). */
 uint64_t cid_ctx_launch_count(const cid_ctx* ctx);
+/* Tuning knobs (never change results): "readid_chunk_reads" = reads per pipeline chunk of the
+ * host-pointer read_id entry points (0 = automatic), "host_threads" = host threads used by the
+ * read_id vote (0 = all cores; main.rs:718 rayon pool size `-t`). */
+int cid_ctx_set_option(cid_ctx* ctx, const char* name, int64_t value);
 /* Per-kernel device timing with CUDA events on the launching stream (for bench.py's roofline).
  * cid_ctx_profile(ctx, 1) resets the accumulators and enables timing, (ctx, 0) disables it;
  * cid_ctx_profile_read returns name / total ms / launch count of kernel id 0..N-1
@@ -142,6 +146,15 @@ typedef struct cid_readid_params {
 int cid_read_id_batch(cid_index* idx, const char* bases, const char* quals, const uint64_t* seq_offs, uint64_t nseq,
                       const uint64_t* read_offs, uint64_t nreads, const cid_readid_params* p, uint32_t* n_set,
                       uint32_t* flags, uint32_t* rep_n, uint32_t* rep_colour, uint32_t* rep_count);
+/* The whole of parallel_vec (read_id_mt_pe.rs:282-363) for one batch: reads in, one classification
+ * per read out (the tuple the reference writes to PREFIX_reads.txt, :779-788).  Internally the batch
+ * is cut into chunks whose H2D copy, kernels, D2H copy and host-side kmer_poll_plus overlap; results
+ * are identical to cid_read_id_batch followed by cid_classify_reads.  kind/hits/n_set/n_top are
+ * [nreads]; top (may be NULL) is [nreads*top_cap].  p->rep_cap is ignored (reports are never truncated). */
+int cid_read_id_classify(cid_index* idx, const char* bases, const char* quals, const uint64_t* seq_offs, uint64_t nseq,
+                         const uint64_t* read_offs, uint64_t nreads, const cid_readid_params* p,
+                         const uint64_t* n_ref_by_colour, double fp_correct, int32_t* kind, uint32_t* hits,
+                         uint32_t* n_set, uint32_t* n_top, uint32_t* top, uint32_t top_cap);
 /* Device-resident variant; all pointers are device memory.  h_max_read_bases = longest read (sum
  * of mates, bases) sizes the shared-memory tile; h_max_kmers = largest number of k-mer start
  * positions of any read (0 = derive a bound from h_max_read_bases). */

@@ -212,6 +212,60 @@ def test_read_id_quality_mask_on_device(oracle, ctx):
         assert gd == od
 
 
+def test_read_id_classify_pipeline_equals_oracle(oracle, ctx):
+    """cid_read_id_classify (chunked H2D / kernels / D2H / host vote pipeline) == the oracle's parallel_vec,
+    for one chunk and for many small chunks, and == cid_read_id_batch + cid_classify_reads."""
+    rng = _rng(1234)
+    genomes, oix, gix = _index_pair(oracle, ctx, rng, 46, 31, 2_000_003, 4)
+    gix.n_ref[:] = oix.n_ref
+    reads = synth.reads_from(rng, genomes, 700, read_len=150, insert=330, err=0.004, frac_random=0.25, n_rate=0.002)
+    reads.append([b"ACGT", genomes[0][:150]])
+    reads.append([b"N" * 150, b"N" * 150])
+    reads += synth.reads_from(rng, genomes, 45, read_len=120, insert=300, err=0.0, frac_random=0.0, paired=False)
+    o = oix.read_id_batch(reads)
+    rep = gix.read_id_batch(reads)
+    two_step = cb.api.classify_reads((gix.S, gix.H, gix.N), gix.n_ref, rep)
+    try:
+        for chunk in (0, 64, 97):
+            ctx.set_option("readid_chunk_reads", chunk)
+            g = gix.read_id_classify(reads)
+            for key in ("kind", "hits", "n_set", "n_top"):
+                assert np.array_equal(g[key], o[key]), f"chunk={chunk}: {key} differs from the oracle"
+            for r in range(len(reads)):
+                nt = min(int(o["n_top"][r]), 8)
+                assert g["top"][r, :nt].tolist() == o["top"][r, :nt].tolist(), f"chunk={chunk}: read {r} top differs"
+            for key in ("kind", "hits", "n_top"):
+                assert np.array_equal(g[key], two_step[key])
+            # the chunked raw-report path must equal the single-chunk one
+            rep2 = gix.read_id_batch(reads)
+            for key in ("n_set", "flags", "rep_n"):
+                assert np.array_equal(rep2[key], rep[key])
+            for r in range(len(reads)):
+                n = rep["rep_n"][r]
+                assert np.array_equal(rep2["rep_colour"][r, :n], rep["rep_colour"][r, :n])
+                assert np.array_equal(rep2["rep_count"][r, :n], rep["rep_count"][r, :n])
+    finally:
+        ctx.set_option("readid_chunk_reads", 0)
+
+
+def test_read_id_classify_with_quals(oracle, ctx):
+    rng = _rng(1235)
+    genomes, oix, gix = _index_pair(oracle, ctx, rng, 6, 27, 750_000, 4)
+    gix.n_ref[:] = oix.n_ref
+    reads = synth.reads_from(rng, genomes, 300, read_len=150, insert=320, err=0.002, frac_random=0.1)
+    quals = [[bytes(rng.choice(np.frombuffer(b"#+5?I", dtype=np.uint8), size=len(m), p=[.03, .03, .04, .3, .6]).tolist())
+              for m in r] for r in reads]
+    masked = [[oracle.qual_mask(m, q, 15) for m, q in zip(r, qr)] for r, qr in zip(reads, quals)]
+    o = oix.read_id_batch(masked)
+    try:
+        ctx.set_option("readid_chunk_reads", 70)
+        g = gix.read_id_classify(reads, quals=quals, qual_offset=15)
+    finally:
+        ctx.set_option("readid_chunk_reads", 0)
+    for key in ("kind", "hits", "n_set", "n_top"):
+        assert np.array_equal(g[key], o[key]), key
+
+
 def test_upload_rows_roundtrip(oracle, ctx):
     rng = _rng(77)
     genomes, oix, gix = _index_pair(oracle, ctx, rng, 40, 21, 100_003, 2)
