@@ -100,7 +100,7 @@ int check_err_flags(cid_ctx* ctx, cudaStream_t st);   // syncs the stream
 
 // kernel ids for the profiling hooks (names in cid_api.cu: kKernelNames)
 enum { KID_KMERIZE_INSERT = 0, KID_HISTOGRAM, KID_TO_BLOOM, KID_TRANSPOSE, KID_ROWNZ, KID_QUERY_COUNTS, KID_QUERY_UNIQ_WIDE,
-       KID_QUERY_PERFECT, KID_READID_KMERIZE, KID_READID_ORDER, KID_READID_VOTE, KID_TABLE_CLEAR, KID_OTHER, KID_COUNT };
+       KID_QUERY_PERFECT, KID_READID_KMERIZE, KID_READID_SCHED, KID_READID_ORDER, KID_READID_VOTE, KID_TABLE_CLEAR, KID_OTHER, KID_COUNT };
 struct ProfScope {     // records an event pair around a launch when profiling is enabled
     cid_ctx* ctx; cudaStream_t st; int idx;
     ProfScope(cid_ctx* c, cudaStream_t s, int kernel);

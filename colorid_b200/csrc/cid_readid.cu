@@ -61,31 +61,40 @@ __device__ __forceinline__ bool warp_load_read(Tile& t, int cap, const uint8_t* 
 }
 
 // ================================================================= readid_kmerize
+// COMPACT (reads of <= 255 k-mer positions): only the FIRST occurrence of every distinct k-mer is
+// emitted, split into the three arrays the later kernels want -- hp8/h9w = low 9 bits of FNV-1a
+// (the order kernel's only input), ent16 = tile position | strand << 10 (the vote kernel's).
+// Duplicate HashSet::insert calls matter to hashbrown only through "is there a call after the
+// last fresh one" (bit 31 of nocc), see readid_order_small_kernel.
+template <bool COMPACT>
 __global__ void __launch_bounds__(RA_WARPS * 32)
 readid_kmerize_kernel(const uint8_t* __restrict__ bases, const uint8_t* __restrict__ quals, uint32_t maxq,
                       const uint64_t* __restrict__ seq_offs, const uint64_t* __restrict__ read_offs, uint64_t r0,
                       uint64_t nreads, uint32_t k, uint32_t d, int cap, uint32_t maxocc, uint32_t tsize,
-                      uint32_t* __restrict__ entries, uint32_t* __restrict__ nocc, uint32_t* __restrict__ flags,
-                      uint32_t* __restrict__ err) {
+                      uint32_t* __restrict__ entries, uint8_t* __restrict__ hp8, uint32_t* __restrict__ h9w,
+                      uint16_t* __restrict__ ent16, uint32_t* __restrict__ nocc, uint32_t* __restrict__ nfresh,
+                      uint32_t* __restrict__ flags, uint32_t* __restrict__ err) {
     extern __shared__ __align__(16) uint8_t dsm[];
     __shared__ uint32_t lut[256];
     lut4_init(lut, threadIdx.x, blockDim.x);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t per_warp = ((tile_smem_bytes(cap) + 7) & ~(size_t)7) + (size_t)tsize * 8 + (size_t)tsize * 4 +
-                            (size_t)cap * 4 + (MAX_MATES + 1) * 4 + 4;
+                            (size_t)cap * 4 + (MAX_MATES + 1) * 4 + 4 + 32;
     uint8_t* base = dsm + (size_t)warp * ((per_warp + 15) & ~(size_t)15);
     Tile t = tile_carve(base, cap);
     unsigned long long* tkeys = (unsigned long long*)(base + ((tile_smem_bytes(cap) + 7) & ~(size_t)7));
     uint32_t* tmin = (uint32_t*)(tkeys + tsize);
     uint32_t* pinfo = tmin + tsize;
     uint32_t* moffs = pinfo + cap;
+    uint32_t* h9s = moffs + (MAX_MATES + 1) + 1;      // COMPACT: 9th hash bit of up to 256 fresh k-mers
     const uint32_t tmask = tsize - 1;
+    const uint32_t hwords = (maxocc + 31) / 32;
 
     for (uint64_t rl = (uint64_t)blockIdx.x * RA_WARPS + warp; rl < nreads; rl += (uint64_t)gridDim.x * RA_WARPS) {
         const uint64_t r = r0 + rl;
         const uint64_t s_begin = __ldg(read_offs + r), s_end = __ldg(read_offs + r + 1);
-        uint32_t fl = 0, emitted = 0;
+        uint32_t fl = 0, emitted = 0, nfr = 0;
         ReadGeom g;
         __syncwarp();
         bool ok = s_end > s_begin;
@@ -132,25 +141,46 @@ readid_kmerize_kernel(const uint8_t* __restrict__ bases, const uint8_t* __restri
             __syncwarp();
             // pass 2: emit the insert-call sequence in sequence order (kmer.rs:225-240)
             uint32_t* out = entries + rl * (uint64_t)maxocc;
+            uint32_t last_fresh = 1;
+            if (COMPACT) { if (lane < 8) h9s[lane] = 0; __syncwarp(); }
             for (int tp0 = 0; tp0 < g.len; tp0 += 32) {
                 int tp = tp0 + lane;
                 uint32_t info = tp < g.len ? pinfo[tp] : 0u;
                 bool valid = info >> 31;
-                uint32_t ent = 0;
+                uint32_t ent = 0, f = 0;
+                bool fresh = false;
                 if (valid) {
                     uint32_t s = info & 0xFFFFFu;
-                    bool fresh = tmin[s] == (uint32_t)tp;
-                    uint32_t f = fresh ? (fnv1a_low32_key_lut(lut, tkeys[s], k) & 0xFFFFu) : 0u;
+                    fresh = tmin[s] == (uint32_t)tp;
+                    f = fresh ? (fnv1a_low32_key_lut(lut, tkeys[s], k) & 0xFFFFu) : 0u;
                     ent = f | ((uint32_t)tp << 16) | (((info >> 30) & 1u) << 26) | ((fresh ? 1u : 0u) << 27);
                 }
-                uint32_t bal = __ballot_sync(0xffffffffu, valid);
-                uint32_t rank = __popc(bal & ((1u << lane) - 1));
-                if (valid && emitted + rank < maxocc) out[emitted + rank] = ent;
+                const uint32_t bal = __ballot_sync(0xffffffffu, valid), balf = __ballot_sync(0xffffffffu, fresh);
+                if (COMPACT) {
+                    const uint32_t fi = nfr + __popc(balf & ((1u << lane) - 1));
+                    if (fresh && fi < maxocc) {
+                        hp8[rl * (uint64_t)maxocc + fi] = (uint8_t)f;
+                        ent16[rl * (uint64_t)maxocc + fi] = (uint16_t)((uint32_t)tp | (((info >> 30) & 1u) << 10));
+                        if ((f >> 8) & 1u) atomicOr(&h9s[fi >> 5], 1u << (fi & 31));
+                    }
+                    if (bal) last_fresh = (balf >> (31 - __clz(bal))) & 1u;
+                } else {
+                    const uint32_t rank = __popc(bal & ((1u << lane) - 1));
+                    if (valid && emitted + rank < maxocc) out[emitted + rank] = ent;
+                }
                 emitted += __popc(bal);
+                nfr += __popc(balf);
             }
             if (emitted > maxocc) { if (lane == 0) atomicOr(err, ERRF_LIST_OVERFLOW); emitted = maxocc; }
+            if (COMPACT) {
+                __syncwarp();
+                if ((uint32_t)lane < hwords) h9w[rl * (uint64_t)hwords + lane] = h9s[lane];
+                if (emitted && !last_fresh) emitted |= 0x80000000u;     // a duplicate insert call follows the last fresh one
+            }
+        } else if (COMPACT) {
+            if ((uint32_t)lane < hwords) h9w[rl * (uint64_t)hwords + lane] = 0;
         }
-        if (lane == 0) { nocc[rl] = emitted; flags[r] = fl; }
+        if (lane == 0) { nocc[rl] = emitted; nfresh[rl] = nfr; flags[r] = fl; }
     }
 }
 
@@ -197,12 +227,13 @@ __device__ __forceinline__ uint32_t hb_cap(uint32_t nb) { return nb == 0 ? 0 : (
 // resize at different times.
 template <typename E>
 __global__ void __launch_bounds__(32)
-readid_order_kernel(const uint32_t* __restrict__ entries, const uint32_t* __restrict__ nocc, uint64_t nreads,
-                    uint32_t maxocc, uint32_t TB, uint32_t gw, uint32_t rbf, uint16_t* __restrict__ order,
+readid_order_kernel(const uint32_t* __restrict__ entries, const uint32_t* __restrict__ nocc,
+                    const uint32_t* __restrict__ perm, uint64_t nreads, uint32_t maxocc, uint32_t TB, uint32_t gw, uint32_t rbf, uint16_t* __restrict__ order,
                     uint32_t* __restrict__ n_set_out, uint64_t r0) {
     extern __shared__ __align__(16) uint8_t dsm[];
-    const uint64_t rl = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = rl < nreads;
+    const uint64_t ridx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = ridx < nreads;
+    const uint64_t rl = live ? perm[ridx] : 0;
     // u8 tables (TB <= 512): 9 hash bits as hp (8) + h9 (1); u16 tables: 16 hash bits in hp
     constexpr bool kSmall = sizeof(E) == 1;
     const uint32_t hwords = kSmall ? (maxocc + 31) / 32 : 0;
@@ -292,6 +323,199 @@ readid_order_kernel(const uint32_t* __restrict__ entries, const uint32_t* __rest
     n_set_out[r0 + rl] = c;
 }
 
+// ================================================================= read schedule (counting sort by set size)
+// The 32 reads of a warp walk the same growth ladder only if they hold about the same number of
+// distinct k-mers; quality masking and overlapping mates spread that number widely, so reads are
+// dealt to the order kernel in descending order of their set size (a counting sort: histogram,
+// one-block scan, scatter).  Pure scheduling: results do not depend on the permutation.
+constexpr int SCHED_BINS = 1024;
+__global__ void __launch_bounds__(256)
+sched_hist_kernel(const uint32_t* __restrict__ key, uint64_t n, uint32_t* __restrict__ bins) {
+    __shared__ uint32_t sh[SCHED_BINS];
+    for (int i = threadIdx.x; i < SCHED_BINS; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        atomicAdd(&sh[min(key[i], (uint32_t)SCHED_BINS - 1)], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < SCHED_BINS; i += blockDim.x) if (sh[i]) atomicAdd(&bins[i], sh[i]);
+}
+__global__ void __launch_bounds__(SCHED_BINS)
+sched_scan_kernel(uint32_t* __restrict__ bins) {     // bins[b] <- number of reads with a LARGER key (descending order)
+    __shared__ uint32_t sh[SCHED_BINS];
+    const int t = threadIdx.x;
+    sh[t] = bins[SCHED_BINS - 1 - t];
+    __syncthreads();
+    for (int o = 1; o < SCHED_BINS; o <<= 1) {
+        uint32_t v = t >= o ? sh[t - o] : 0u;
+        __syncthreads();
+        sh[t] += v;
+        __syncthreads();
+    }
+    bins[SCHED_BINS - 1 - t] = t ? sh[t - 1] : 0u;
+}
+__global__ void __launch_bounds__(256)
+sched_scatter_kernel(const uint32_t* __restrict__ key, uint64_t n, uint32_t* __restrict__ cursor, uint32_t* __restrict__ perm) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    perm[atomicAdd(&cursor[min(key[i], (uint32_t)SCHED_BINS - 1)], 1u)] = (uint32_t)i;
+}
+
+// ================================================================= readid_order, small reads (<= 255 k-mer positions)
+// Same emulation as above, re-engineered for throughput (it was 43 % of a read_id step):
+//  * input is the compact list of DISTINCT k-mers (9 hash bits each).  Duplicate insert calls only
+//    matter through hashbrown >= 0.14's reserve-before-find: a duplicate arriving when the table is
+//    exactly full triggers a resize that a fresh key would have triggered anyway -- unless no fresh
+//    key follows, so one flag ("a call follows the last fresh one") carries all of it;
+//  * every per-read array is interleaved across the warp at 4-byte granularity (byte i of lane t
+//    lives at (i/4)*128 + 4t + i%4), so each data-dependent access hits bank == lane: no conflicts;
+//  * shared memory is addressed with explicit 32-bit shared-window addresses;
+//  * the item to place is fetched one step ahead (next full bucket of the old table during a
+//    resize, else the next fresh k-mer) and its hash loads are consumed a step later, so the fetch
+//    chain and the probe chain overlap; the occupancy window loaded by the probe is reused for the
+//    bitmap update;
+//  * reads arrive sorted by set size and are dealt to three instantiations (128/256/512 buckets
+//    at most), so a warp's reads walk the same growth ladder and small sets leave room for more
+//    resident warps;
+//  * output is the index of the distinct k-mer per occupied bucket (u8); the vote kernel looks its
+//    position up in ent16.
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+// byte i / word w of a lane-interleaved array whose lane-0 element 0 sits at shared address `a`
+__device__ __forceinline__ uint32_t il_b(uint32_t a, uint32_t i) { return a + i + (i >> 2) * 124u; }
+__device__ __forceinline__ uint32_t il_w(uint32_t a, uint32_t w) { return a + w * 128u; }
+
+template <int TB> struct OrderSmallLayout {       // words per lane
+    static constexpr int X = TB / 4, Y = TB / 8, HP = TB > 256 ? 64 : TB / 32 * 7, H9 = TB > 256 ? 8 : 0, BX = TB / 32, BY = TB / 64;
+    static constexpr int oX = 0, oY = oX + X, oHP = oY + Y, oH9 = oHP + HP, oBX = oH9 + H9, oBY = oBX + BX, TOTAL = oBY + BY;
+    static constexpr int MAXF = TB > 256 ? 255 : TB / 8 * 7 - 1;      // largest set that never outgrows TB buckets
+};
+
+template <int TB>
+__global__ void __launch_bounds__(32)
+readid_order_small_kernel(const uint8_t* __restrict__ hp8, const uint32_t* __restrict__ h9w,
+                          const uint32_t* __restrict__ nocc, const uint32_t* __restrict__ nfresh,
+                          const uint32_t* __restrict__ perm, uint64_t nreads, uint32_t maxocc, uint32_t gw, uint32_t rbf,
+                          uint8_t* __restrict__ order8, uint32_t* __restrict__ n_set_out, uint64_t r0) {
+    using Lay = OrderSmallLayout<TB>;
+    extern __shared__ __align__(16) uint32_t sm32[];
+    const uint32_t lane = threadIdx.x;
+    const uint64_t idx0 = (uint64_t)blockIdx.x * 32;
+    // reads are sorted by set size (descending): the block's first read decides which instantiation owns it
+    {
+        const uint32_t fmax = nfresh[perm[idx0]];
+        const int cls = fmax <= (uint32_t)OrderSmallLayout<128>::MAXF ? 128 : fmax <= (uint32_t)OrderSmallLayout<256>::MAXF ? 256 : 512;
+        if (cls != TB) return;
+    }
+    const bool live = idx0 + lane < nreads;
+    const uint64_t rl = live ? perm[idx0 + lane] : 0;
+    const uint32_t F = live ? min(nfresh[rl], maxocc) : 0;
+    const bool tail_dup = live && (nocc[rl] >> 31);
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sm32) + lane * 4u;
+    const uint32_t aX = il_w(sbase, Lay::oX), aY = il_w(sbase, Lay::oY), aHP = il_w(sbase, Lay::oHP),
+                   aH9 = il_w(sbase, Lay::oH9), aBX = il_w(sbase, Lay::oBX), aBY = il_w(sbase, Lay::oBY);
+    // stage the hash bits of this lane's read
+    {
+        const uint32_t* src = (const uint32_t*)(hp8 + rl * (uint64_t)maxocc);     // maxocc is a multiple of 4
+        const uint32_t nwords = (F + 3) / 4;
+#pragma unroll 4
+        for (uint32_t w = 0; w < nwords; w++) sts32(il_w(aHP, w), __ldg(src + w));
+        if (TB > 256) {
+            const uint32_t hwords = (maxocc + 31) / 32;
+            for (uint32_t w = 0; w < 8; w++) sts32(il_w(aH9, w), w < hwords ? __ldg(h9w + rl * (uint64_t)hwords + w) : 0u);
+        }
+    }
+    uint32_t nb = 0, growth = 0, f = 0;
+    uint32_t nb_old = 0, s = 0, wcur = 0;          // resize scan: buckets [s, s+32) of the old table left in wcur
+    bool scanning = false, final_done = false;
+    uint32_t aCur = aX, aBcur = aBX, aOld = aX, aBold = aBX;
+    bool p_valid = false;                          // pending placement, fetched in the previous step
+    uint32_t p_item = 0, p_h8 = 0, p_h9 = 0, p_tab = aX, p_bm = aBX, p_nb = 4;
+    for (;;) {
+        // ---- fetch the next item to place ----------------------------------------------------
+        bool f_valid = false, more = true;
+        uint32_t f_item = 0;
+        if (scanning) {
+            if (wcur) {
+                const uint32_t b = __ffs(wcur) - 1;
+                wcur &= wcur - 1;
+                f_item = lds8(il_b(aOld, s + b));
+                f_valid = true;
+            } else {
+                s += 32;
+                if (s < nb_old) {
+                    wcur = lds32(il_w(aBold, s >> 5));
+                    if (nb_old < 32) wcur &= (1u << nb_old) - 1;      // small tables keep their pattern replicated
+                } else scanning = false;
+            }
+        } else if (f < F ? growth == 0 : (rbf && tail_dup && growth == 0 && F > 0 && !final_done)) {
+            // reserve_rehash -> resize: buckets double; the insert call is retried after the old table drained
+            final_done = f >= F;
+            aOld = aCur; aBold = aBcur; nb_old = nb; s = 0;
+            nb = nb == 0 ? 4 : nb * 2;
+            // sizes TB, TB/4, .. live in X, the others in Y
+            const bool y = ((__ffs(TB) - __ffs(nb)) & 1) != 0;
+            aCur = y ? aY : aX; aBcur = y ? aBY : aBX;
+            for (uint32_t i = 0; i < (nb >= 32 ? nb / 32 : 1u); i++) sts32(il_w(aBcur, i), 0u);
+            growth = (nb < 8 ? nb - 1 : nb / 8 * 7) - f;
+            // the pending item below still goes into the old table: its bitmap is read from the next step on
+            if (nb_old) { scanning = true; wcur = 0; s = 0u - 32u; }
+        } else if (f < F) {
+            f_item = f++; growth--;
+            f_valid = true;
+        } else more = false;
+        uint32_t f_h8 = 0, f_h9 = 0;
+        if (f_valid) {                                   // loads only; consumed when the item is placed
+            f_h8 = lds8(il_b(aHP, f_item));
+            if (TB > 256) f_h9 = lds32(il_w(aH9, f_item >> 5));
+        }
+        // ---- place the item fetched one step earlier (into the table that was current then) ----
+        if (p_valid) {
+            uint32_t hash = p_h8;
+            if (TB > 256) hash |= ((p_h9 >> (p_item & 31)) & 1u) << 8;
+            const uint32_t mask = p_nb - 1, nw = p_nb >= 32 ? p_nb >> 5 : 1;
+            const uint32_t width = p_nb < gw ? p_nb : gw, wmask = (1u << width) - 1;
+            uint32_t pos = hash & mask, stride = 0, slot, lo, hi, w0;
+            for (;;) {
+                w0 = pos >> 5;
+                lo = lds32(il_w(p_bm, w0));
+                hi = lds32(il_w(p_bm, (w0 + 1) & (nw - 1)));
+                const uint32_t free_ = ~__funnelshift_r(lo, hi, pos & 31) & wmask;
+                if (free_) { slot = (pos + (uint32_t)__ffs(free_) - 1) & mask; break; }
+                stride += gw;
+                pos = (pos + stride) & mask;
+            }
+            sts8(il_b(p_tab, slot), p_item);
+            if (p_nb >= 32) {
+                const uint32_t ws = slot >> 5;
+                sts32(il_w(p_bm, ws), (ws == w0 ? lo : hi) | (1u << (slot & 31)));
+            } else {
+                sts32(p_bm, lo | ((p_nb == 4 ? 0x11111111u : p_nb == 8 ? 0x01010101u : 0x00010001u) << slot));
+            }
+        }
+        p_valid = f_valid; p_item = f_item; p_h8 = f_h8; p_h9 = f_h9; p_tab = aCur; p_bm = aBcur; p_nb = nb;
+        if (!more && !p_valid) break;
+    }
+    if (!live) return;
+    // occupied buckets in ascending order = HashSet iteration order
+    uint8_t* out = order8 + rl * (uint64_t)maxocc;
+    uint32_t c = 0, pack = 0;
+    for (uint32_t t0 = 0; t0 < nb; t0 += 32) {
+        uint32_t w = lds32(il_w(aBcur, t0 >> 5));
+        if (nb < 32) w &= (1u << nb) - 1;
+        while (w) {
+            const uint32_t t = t0 + __ffs(w) - 1;
+            w &= w - 1;
+            pack |= lds8(il_b(aCur, t)) << (8 * (c & 3));
+            c++;
+            if ((c & 3) == 0) { *(uint32_t*)(out + c - 4) = pack; pack = 0; }
+        }
+    }
+    if (c & 3) *(uint32_t*)(out + (c & ~3u)) = pack;
+    n_set_out[r0 + rl] = c;
+}
+
 // ================================================================= readid_vote (rows of <= 64 accessions)
 template <int WP>
 __global__ void __launch_bounds__(RA_WARPS * 32)
@@ -299,7 +523,8 @@ readid_vote_narrow_kernel(const uint8_t* __restrict__ bases, const uint8_t* __re
                           const uint64_t* __restrict__ seq_offs, const uint64_t* __restrict__ read_offs, uint64_t r0,
                           uint64_t nreads, uint32_t k, uint32_t H, ModS mods, const uint32_t* __restrict__ rows,
                           const uint32_t* __restrict__ rownz, uint32_t N, int cap, uint32_t maxocc,
-                          const uint16_t* __restrict__ order, const uint32_t* __restrict__ n_set,
+                          const uint16_t* __restrict__ order, const uint8_t* __restrict__ order8,
+                          const uint16_t* __restrict__ ent16, const uint32_t* __restrict__ n_set,
                           uint32_t start_sample, uint32_t rep_cap, uint32_t* __restrict__ flags,
                           uint32_t* __restrict__ rep_n, uint32_t* __restrict__ rep_colour,
                           uint32_t* __restrict__ rep_count) {
@@ -323,6 +548,8 @@ readid_vote_narrow_kernel(const uint8_t* __restrict__ bases, const uint8_t* __re
         ReadGeom g;
         warp_load_read(t, cap, bases, quals, maxq, seq_offs, __ldg(read_offs + r), __ldg(read_offs + r + 1), moffs, lane, g);
         const uint16_t* ordrow = order + rl * (uint64_t)maxocc;
+        const uint8_t* ord8row = order8 + rl * (uint64_t)maxocc;
+        const uint16_t* entrow = ent16 + rl * (uint64_t)maxocc;
         uint32_t cand0 = 0, cand1 = 0, cnt0 = 0, cnt1 = 0, nrep = 0, nproc = 0;
         bool miss = false;
         // The first FINE_STEPS steps take only 32/H k-mers with one lane per (k-mer, hash row): most
@@ -342,7 +569,8 @@ readid_vote_narrow_kernel(const uint8_t* __restrict__ bases, const uint8_t* __re
             HashIn in;
             in.w0 = in.w1 = in.w2 = in.w3 = 0;
             if (active) {
-                uint32_t e = __ldcs(ordrow + idx);
+                // k-mer `idx` of the iteration order: tile position + strand
+                uint32_t e = order8 ? (uint32_t)__ldg(entrow + __ldcs(ord8row + idx)) : (uint32_t)__ldcs(ordrow + idx);
                 uint32_t tp = e & 0x3FFu;
                 uint64_t f = codes_window(t.codes, (int)tp, k);
                 uint64_t key = ((e >> 10) & 1u) ? f : revcomp_key(f, k);
@@ -449,7 +677,8 @@ readid_vote_wide_kernel(const uint8_t* __restrict__ bases, const uint8_t* __rest
                         const uint64_t* __restrict__ seq_offs, const uint64_t* __restrict__ read_offs, uint64_t r0,
                         uint64_t nreads, uint32_t k, uint32_t H, ModS mods, const uint32_t* __restrict__ rows,
                         const uint32_t* __restrict__ rownz, uint32_t N, uint32_t Wp, int cap, uint32_t maxocc,
-                        const uint16_t* __restrict__ order, const uint32_t* __restrict__ n_set, uint32_t start_sample,
+                        const uint16_t* __restrict__ order, const uint8_t* __restrict__ order8,
+                        const uint16_t* __restrict__ ent16, const uint32_t* __restrict__ n_set, uint32_t start_sample,
                         uint32_t rep_cap, uint32_t* __restrict__ flags, uint32_t* __restrict__ rep_n,
                         uint32_t* __restrict__ rep_colour, uint32_t* __restrict__ rep_count) {
     extern __shared__ __align__(16) uint8_t dsm[];
@@ -472,6 +701,8 @@ readid_vote_wide_kernel(const uint8_t* __restrict__ bases, const uint8_t* __rest
         ReadGeom g;
         warp_load_read(t, cap, bases, quals, maxq, seq_offs, __ldg(read_offs + r), __ldg(read_offs + r + 1), moffs, lane, g);
         const uint16_t* ordrow = order + rl * (uint64_t)maxocc;
+        const uint8_t* ord8row = order8 + rl * (uint64_t)maxocc;
+        const uint16_t* entrow = ent16 + rl * (uint64_t)maxocc;
         uint32_t* rc = rep_colour + r * (uint64_t)rep_cap;
         uint32_t* rv = rep_count + r * (uint64_t)rep_cap;
         uint32_t cand[RV_MAXWPL], pl[RV_MAXWPL][RV_PLANES];
@@ -480,7 +711,7 @@ readid_vote_wide_kernel(const uint8_t* __restrict__ bases, const uint8_t* __rest
         uint32_t nrep = 0, nproc = 0;
         bool miss = false;
         for (uint32_t j = 0; j < n; j++) {
-            uint32_t e = __ldg(ordrow + j);
+            uint32_t e = order8 ? (uint32_t)__ldg(entrow + __ldg(ord8row + j)) : (uint32_t)__ldg(ordrow + j);
             uint64_t f = codes_window(t.codes, (int)(e & 0x3FFu), k);
             uint64_t key = ((e >> 10) & 1u) ? f : revcomp_key(f, k);
             HashIn in = hashin_from_key(lut, key, k);
@@ -549,7 +780,8 @@ readid_vote_wide_kernel(const uint8_t* __restrict__ bases, const uint8_t* __rest
 }
 
 // ================================================================= order export (parity hook)
-__global__ void order_export_kernel(const uint16_t* __restrict__ order, const uint32_t* __restrict__ n_set,
+__global__ void order_export_kernel(const uint16_t* __restrict__ order, const uint8_t* __restrict__ order8,
+                                    const uint16_t* __restrict__ ent16, const uint32_t* __restrict__ n_set,
                                     const uint64_t* __restrict__ seq_offs, const uint64_t* __restrict__ read_offs,
                                     uint64_t r0, uint64_t nreads, uint32_t maxocc, uint32_t order_cap,
                                     uint32_t* __restrict__ order_n, uint8_t* __restrict__ order_seq,
@@ -562,7 +794,8 @@ __global__ void order_export_kernel(const uint16_t* __restrict__ order, const ui
     uint64_t b0 = seq_offs[s_begin];
     if (threadIdx.x == 0) order_n[r] = n;
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-        uint32_t tp = order[rl * (uint64_t)maxocc + i] & 0x3FFu;
+        uint32_t tp = (order8 ? (uint32_t)ent16[rl * (uint64_t)maxocc + order8[rl * (uint64_t)maxocc + i]]
+                              : (uint32_t)order[rl * (uint64_t)maxocc + i]) & 0x3FFu;
         uint32_t m = 0;
         for (uint64_t s = s_begin + 1; s < s_end; s++) if (seq_offs[s] - b0 <= tp) m = (uint32_t)(s - s_begin);
         order_seq[r * (uint64_t)order_cap + i] = (uint8_t)m;
@@ -590,9 +823,9 @@ void readid_scratch_bytes(const cid_index* idx, uint32_t max_read_bases, uint32_
                           size_t* entries_bytes, size_t* order_bytes, size_t* nocc_bytes) {
     int cap; uint32_t bound, maxocc;
     readid_dims(idx, max_read_bases, max_kmers, &cap, &bound, &maxocc);
-    *entries_bytes = (size_t)reads * maxocc * 4;
+    *entries_bytes = (size_t)reads * (maxocc * 4 + ((maxocc + 31) / 32) * 4);
     *order_bytes = (size_t)reads * maxocc * 2;
-    *nocc_bytes = (size_t)reads * 4;
+    *nocc_bytes = (size_t)reads * 12 + (size_t)SCHED_BINS * 4;    // nocc, nfresh, perm, schedule bins
 }
 
 int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const uint8_t* d_quals,
@@ -617,23 +850,32 @@ int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const ui
     const uint64_t sub = std::min<uint64_t>(nreads, scr.cap_reads);
     if (sub == 0) { set_error("read_id: no scratch"); return CID_E_INVALID; }
     uint32_t* d_entries = scr.entries;
+    // compact layout of the same buffer (small reads): hash bytes | positions | 9th hash bits
+    const uint32_t hwords = (maxocc + 31) / 32;
+    uint8_t* d_hp8 = (uint8_t*)scr.entries;
+    uint16_t* d_ent16 = (uint16_t*)(d_hp8 + sub * maxocc);
+    uint32_t* d_h9w = (uint32_t*)(d_ent16 + sub * maxocc);
     uint16_t* d_order = scr.order;
     uint32_t* d_nocc = scr.nocc;
+    uint32_t* d_nfresh = d_nocc + scr.cap_reads;
+    uint32_t* d_perm = d_nfresh + scr.cap_reads;
+    uint32_t* d_bins = d_perm + scr.cap_reads;
 
     // shared memory budgets
-    size_t a_warp = ((tile_smem_bytes(cap) + 7) & ~(size_t)7) + (size_t)tsize * 12 + (size_t)cap * 4 + (MAX_MATES + 1) * 4 + 4;
+    size_t a_warp = ((tile_smem_bytes(cap) + 7) & ~(size_t)7) + (size_t)tsize * 12 + (size_t)cap * 4 + (MAX_MATES + 1) * 4 + 4 + 32;
     size_t a_smem = RA_WARPS * ((a_warp + 15) & ~(size_t)15);
     const size_t b_esz = small ? 1 : 2;
     const size_t b_thread = ((((size_t)(TB + TB / 2) + maxocc) * b_esz + 3) & ~(size_t)3) +
                             4 * ((small ? (maxocc + 31) / 32 : 0) + (TB >= 32 ? TB / 32 : 1) + (TB >= 64 ? TB / 64 : 1));
     size_t b_smem = 32 * b_thread;
+    if (small) b_smem = 0;      // readid_order_small_kernel<TB> sizes its own shared memory (< 48 KB)
     size_t cn_warp = ((tile_smem_bytes(cap) + 15) & ~(size_t)15) + 64 + (MAX_MATES + 1) * 4 + 12;
     size_t cn_smem = RA_WARPS * ((cn_warp + 15) & ~(size_t)15);
     size_t cw_warp = ((tile_smem_bytes(cap) + 15) & ~(size_t)15) + (MAX_MATES + 1) * 4 + 12;
     size_t cw_smem = RA_WARPS * ((cw_warp + 15) & ~(size_t)15);
     if (a_smem > 200 * 1024 || b_smem > 200 * 1024) { set_error("read_id: read too long for the shared-memory plan"); return CID_E_UNSUPPORTED; }
-    CID_CUDA(cudaFuncSetAttribute(readid_kmerize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a_smem));
-    CID_CUDA(cudaFuncSetAttribute(readid_order_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b_smem));
+    CID_CUDA(cudaFuncSetAttribute(readid_kmerize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a_smem));
+    CID_CUDA(cudaFuncSetAttribute(readid_kmerize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a_smem));
     CID_CUDA(cudaFuncSetAttribute(readid_order_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b_smem));
 
     const ModS mods = make_mods(idx->S);
@@ -642,26 +884,50 @@ int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const ui
         unsigned gridA = (unsigned)std::min<uint64_t>((nr + RA_WARPS - 1) / RA_WARPS, (uint64_t)ctx->sm_count * 32);
         {
         ProfScope ps(ctx, st, KID_READID_KMERIZE);
-        readid_kmerize_kernel<<<gridA, RA_WARPS * 32, a_smem, st>>>(d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr,
-                                                                   idx->k, p.downsample, cap, maxocc, tsize, d_entries,
-                                                                   d_nocc, d_flags, ctx->d_err);
+        if (small)
+            readid_kmerize_kernel<true><<<gridA, RA_WARPS * 32, a_smem, st>>>(d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr,
+                                                                             idx->k, p.downsample, cap, maxocc, tsize, d_entries,
+                                                                             d_hp8, d_h9w, d_ent16, d_nocc, d_nfresh, d_flags, ctx->d_err);
+        else
+            readid_kmerize_kernel<false><<<gridA, RA_WARPS * 32, a_smem, st>>>(d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr,
+                                                                              idx->k, p.downsample, cap, maxocc, tsize, d_entries,
+                                                                              d_hp8, d_h9w, d_ent16, d_nocc, d_nfresh, d_flags, ctx->d_err);
         }
         ctx->launches++;
+        CID_CUDA(cudaGetLastError());
+        // schedule: reads in descending order of their set size (counting sort)
+        {
+            ProfScope ps(ctx, st, KID_READID_SCHED);
+            CID_CUDA(cudaMemsetAsync(d_bins, 0, SCHED_BINS * 4, st));
+            unsigned gridH = (unsigned)std::min<uint64_t>((nr + 255) / 256, (uint64_t)ctx->sm_count * 8);
+            sched_hist_kernel<<<gridH, 256, 0, st>>>(d_nfresh, nr, d_bins);
+            sched_scan_kernel<<<1, SCHED_BINS, 0, st>>>(d_bins);
+            sched_scatter_kernel<<<(unsigned)((nr + 255) / 256), 256, 0, st>>>(d_nfresh, nr, d_bins, d_perm);
+        }
+        ctx->launches += 3;
         CID_CUDA(cudaGetLastError());
         unsigned gridB = (unsigned)((nr + 31) / 32);
         {
         ProfScope ps(ctx, st, KID_READID_ORDER);
-        if (small)
-            readid_order_kernel<uint8_t><<<gridB, 32, b_smem, st>>>(d_entries, d_nocc, nr, maxocc, TB, p.group_width,
-                                                                   p.reserve_before_find, d_order, d_n_set, r0);
+        if (small) {
+            // reads are sorted by set size; every block belongs to exactly one of the three instantiations
+#define CID_ORDER_SMALL(TBV)                                                                                          \
+    readid_order_small_kernel<TBV><<<gridB, 32, OrderSmallLayout<TBV>::TOTAL * 128, st>>>(                            \
+        d_hp8, d_h9w, d_nocc, d_nfresh, d_perm, nr, maxocc, p.group_width, p.reserve_before_find, (uint8_t*)d_order, d_n_set, r0)
+            CID_ORDER_SMALL(512); CID_ORDER_SMALL(256); CID_ORDER_SMALL(128);
+#undef CID_ORDER_SMALL
+            ctx->launches += 2;
+        }
         else
-            readid_order_kernel<uint16_t><<<gridB, 32, b_smem, st>>>(d_entries, d_nocc, nr, maxocc, TB, p.group_width,
+            readid_order_kernel<uint16_t><<<gridB, 32, b_smem, st>>>(d_entries, d_nocc, d_perm, nr, maxocc, TB, p.group_width,
                                                                     p.reserve_before_find, d_order, d_n_set, r0);
         }
         ctx->launches++;
         CID_CUDA(cudaGetLastError());
+        const uint16_t* ord16 = small ? nullptr : d_order;
+        const uint8_t* ord8 = small ? (const uint8_t*)d_order : nullptr;
         if (d_order_n) {
-            order_export_kernel<<<(unsigned)nr, 64, 0, st>>>(d_order, d_n_set, d_seq_offs, d_read_offs, r0, nr, maxocc,
+            order_export_kernel<<<(unsigned)nr, 64, 0, st>>>(ord16, ord8, d_ent16, d_n_set, d_seq_offs, d_read_offs, r0, nr, maxocc,
                                                             order_cap, d_order_n, d_order_seq, d_order_pos);
             ctx->launches++;
             CID_CUDA(cudaGetLastError());
@@ -674,17 +940,17 @@ int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const ui
                 if (idx->Wp == 1)
                     readid_vote_narrow_kernel<1><<<gridA, RA_WARPS * 32, cn_smem, st>>>(
                         d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr, idx->k, idx->H, mods, idx->rows, rownz,
-                        idx->N, cap, maxocc, d_order, d_n_set, p.start_sample, p.rep_cap, d_flags, d_rep_n, d_rep_colour,
+                        idx->N, cap, maxocc, ord16, ord8, d_ent16, d_n_set, p.start_sample, p.rep_cap, d_flags, d_rep_n, d_rep_colour,
                         d_rep_count);
                 else
                     readid_vote_narrow_kernel<2><<<gridA, RA_WARPS * 32, cn_smem, st>>>(
                         d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr, idx->k, idx->H, mods, idx->rows, rownz,
-                        idx->N, cap, maxocc, d_order, d_n_set, p.start_sample, p.rep_cap, d_flags, d_rep_n, d_rep_colour,
+                        idx->N, cap, maxocc, ord16, ord8, d_ent16, d_n_set, p.start_sample, p.rep_cap, d_flags, d_rep_n, d_rep_colour,
                         d_rep_count);
             } else {
                 readid_vote_wide_kernel<<<gridA, RA_WARPS * 32, cw_smem, st>>>(
                     d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr, idx->k, idx->H, mods, idx->rows, rownz, idx->N,
-                    idx->Wp, cap, maxocc, d_order, d_n_set, p.start_sample, p.rep_cap, d_flags, d_rep_n, d_rep_colour,
+                    idx->Wp, cap, maxocc, ord16, ord8, d_ent16, d_n_set, p.start_sample, p.rep_cap, d_flags, d_rep_n, d_rep_colour,
                     d_rep_count);
             }
             ctx->launches++;
