@@ -100,7 +100,7 @@ int check_err_flags(cid_ctx* ctx, cudaStream_t st);   // syncs the stream
 
 // kernel ids for the profiling hooks (names in cid_api.cu: kKernelNames)
 enum { KID_KMERIZE_INSERT = 0, KID_HISTOGRAM, KID_TO_BLOOM, KID_TRANSPOSE, KID_ROWNZ, KID_QUERY_COUNTS, KID_QUERY_UNIQ_WIDE,
-       KID_QUERY_PERFECT, KID_READID_KMERIZE, KID_READID_SCHED, KID_READID_ORDER, KID_READID_VOTE, KID_TABLE_CLEAR, KID_OTHER, KID_COUNT };
+       KID_QUERY_PERFECT, KID_READID_KMERIZE, KID_READID_SCHED, KID_READID_ORDER, KID_READID_VOTE, KID_READID_CLASSIFY, KID_TABLE_CLEAR, KID_OTHER, KID_COUNT };
 struct ProfScope {     // records an event pair around a launch when profiling is enabled
     cid_ctx* ctx; cudaStream_t st; int idx;
     ProfScope(cid_ctx* c, cudaStream_t s, int kernel);
@@ -167,6 +167,13 @@ int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const ui
                uint32_t max_read_bases, uint32_t max_kmers, const cid_readid_params& p, const ReadIdScratch& scr,
                uint32_t* d_n_set, uint32_t* d_flags, uint32_t* d_rep_n, uint32_t* d_rep_colour, uint32_t* d_rep_count,
                uint32_t order_cap, uint32_t* d_order_n, uint8_t* d_order_seq, uint16_t* d_order_pos);
+
+// device side of the vote; reads it cannot decide bit-exactly are appended to `list` for the host vote
+int launch_readid_classify(cid_ctx* ctx, cudaStream_t st, uint64_t r0, uint64_t nreads, uint32_t N, uint32_t rep_cap,
+                           const uint32_t* d_n_set, const uint32_t* d_flags, const uint32_t* d_rep_n,
+                           const uint32_t* d_rep_colour, const uint32_t* d_rep_count, const double* d_fp, double fp_correct,
+                           int32_t* d_kind, uint32_t* d_hits, uint32_t* d_n_top, uint32_t* d_top, uint32_t top_cap,
+                           uint32_t* d_list, uint32_t* d_list_cursor);
 
 // host vote (cid_host_vote.cpp): read_id_mt_pe.rs:187-251 kmer_poll_plus over a chunk of reads
 struct VoteParams { uint32_t n_colors = 0; double fp_correct = 1e-3; uint32_t group_width = 16; std::vector<double> fp; std::vector<uint64_t> key_hash; };

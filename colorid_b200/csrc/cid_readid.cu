@@ -779,6 +779,128 @@ readid_vote_wide_kernel(const uint8_t* __restrict__ bases, const uint8_t* __rest
     }
 }
 
+// ================================================================= readid_classify (device side of kmer_poll_plus)
+// read_id_mt_pe.rs:187-251 on the per-read reports, one thread per read.  Every comparison of the
+// reference is reproduced in f64 (`hits < n*p`, `hits > n*p` are single IEEE multiplies, identical
+// on host and device).  The Binomial pmf goes through device log/exp, which may differ from the
+// host's libm in the last ulps, so a read whose pmf lies within 1e-6 (relative) of the threshold,
+// and any read with a tie at the top (the reference joins the tied names in FnvHashMap iteration
+// order), is NOT decided here: its report is appended to `list` and the host vote
+// (cid_host_vote.cpp, the same code cid_classify_reads runs) classifies it.
+__device__ __forceinline__ double dev_stirling_err(double n) {
+    const double table[16] = {
+        0.0, 0.081061466795327258219670264, 0.041340695955409294093822081, 0.0276779256849983391487892927,
+        0.020790672103765093111522771, 0.0166446911898211921631948653, 0.013876128823070747998745727,
+        0.0118967099458917700950557241, 0.010411265261972096497478567, 0.0092554621827127329177286366,
+        0.008330563433362871256469318, 0.0075736754879518407949720242, 0.006942840107209529865664152,
+        0.0064089941880042070684396310, 0.005951370112758847735624416, 0.0055547335519628013710386899};
+    if (n < 16.0) return table[(int)n];
+    const double n2 = n * n;
+    const double s0 = 1.0 / 12.0, s1 = 1.0 / 360.0, s2 = 1.0 / 1260.0, s3 = 1.0 / 1680.0, s4 = 1.0 / 1188.0;
+    if (n > 500.0) return (s0 - s1 / n2) / n;
+    if (n > 80.0) return (s0 - (s1 - s2 / n2) / n2) / n;
+    if (n > 35.0) return (s0 - (s1 - (s2 - s3 / n2) / n2) / n2) / n;
+    return (s0 - (s1 - (s2 - (s3 - s4 / n2) / n2) / n2) / n2) / n;
+}
+__device__ __forceinline__ double dev_deviance_term(double x, double np) {
+    if (fabs(x - np) < 0.1 * (x + np)) {
+        double v = (x - np) / (x + np);
+        double s = (x - np) * (x - np) / (x + np);
+        double ej = 2.0 * x * v;
+        for (int j = 1; j < 1000; j++) {
+            ej *= v * v;
+            double s1 = s + ej / (double)(2 * j + 1);
+            if (s1 == s) return s1;
+            s = s1;
+        }
+        return s;
+    }
+    return x * log(x / np) + np - x;
+}
+__device__ __forceinline__ double dev_binomial_pmf(double n, double p, double x) {
+    if (p == 0.0) return x == 0.0 ? 1.0 : 0.0;
+    if (p == 1.0) return x == n ? 1.0 : 0.0;
+    const double q = 1.0 - p;
+    if (x == 0.0) return exp(n * log(q));
+    if (x == n) return exp(n * log(p));
+    const double rest = n - x;
+    const double lc = dev_stirling_err(n) - dev_stirling_err(x) - dev_stirling_err(rest) - dev_deviance_term(x, n * p) -
+                      dev_deviance_term(rest, n * q);
+    return exp(lc) * sqrt(n / (2.0 * 3.14159265358979323846 * x * rest));
+}
+
+__global__ void __launch_bounds__(128)
+readid_classify_kernel(uint64_t r0, uint64_t nreads, uint32_t N, uint32_t rep_cap, const uint32_t* __restrict__ n_set,
+                       const uint32_t* __restrict__ flags, const uint32_t* __restrict__ rep_n,
+                       const uint32_t* __restrict__ rep_colour, const uint32_t* __restrict__ rep_count,
+                       const double* __restrict__ fp, double fp_correct, int32_t* __restrict__ kind,
+                       uint32_t* __restrict__ hits, uint32_t* __restrict__ n_top, uint32_t* __restrict__ top,
+                       uint32_t top_cap, uint32_t* __restrict__ list, uint32_t* __restrict__ list_cursor) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nreads) return;
+    const uint64_t r = r0 + i;
+    const uint32_t fl = flags[r], n = rep_n[r];
+    int32_t kd;
+    uint32_t best = 0, nbest = 0, bestc = 0;
+    for (uint32_t t = 0; t < top_cap; t++) top[r * (uint64_t)top_cap + t] = 0;
+    if (fl & 1u) kd = CID_CLS_TOO_SHORT;                     // read_id_mt_pe.rs:305-313
+    else if (fl & 2u) kd = CID_CLS_REF_PANIC;
+    else if (n == 0) kd = CID_CLS_NO_HITS;                   // report.is_empty(), :332-340
+    else {
+        const uint32_t* rc = rep_colour + r * (uint64_t)rep_cap;
+        const uint32_t* rv = rep_count + r * (uint64_t)rep_cap;
+        const double obs = (double)n_set[r];
+        bool uncertain = false, real = false;
+        uint32_t nsig = 0;
+        for (uint32_t e = 0; e < n; e++) {
+            const uint32_t c = rc[e], v = rv[e];
+            if (c >= N) continue;                            // the "no hit" key never votes (:209)
+            real = true;
+            const double p = fp[c];
+            const double critical = __dmul_rn(obs, p), th = (double)v;
+            bool drop = th < critical;                       // not_fp_signicant :168-181
+            if (!drop && th > critical) {
+                const double pmf = dev_binomial_pmf(obs, p, th);
+                if (fabs(pmf - fp_correct) <= 1e-6 * fp_correct || !(pmf == pmf)) uncertain = true;
+                drop = pmf >= fp_correct;
+            }
+            if (!drop) {
+                nsig++;
+                if (v > best) { best = v; nbest = 1; bestc = c; }
+                else if (v == best) nbest++;
+            }
+        }
+        if (!real) kd = CID_CLS_NO_HITS;                     // only the "no hit" key, :197-205
+        else if (uncertain || nbest > 1) {
+            kd = -1;                                         // host decides
+            const uint32_t at = atomicAdd(list_cursor, 2u + 2u * n);
+            list[at] = (uint32_t)i;
+            list[at + 1] = n;
+            for (uint32_t e = 0; e < n; e++) { list[at + 2 + 2 * e] = rc[e]; list[at + 3 + 2 * e] = rv[e]; }
+        } else if (nsig == 0) kd = CID_CLS_NO_SIGNIFICANT;
+        else kd = CID_CLS_ACCEPT;
+    }
+    const bool acc = kd == CID_CLS_ACCEPT;
+    kind[r] = kd;
+    hits[r] = acc ? best : 0u;
+    n_top[r] = acc ? 1u : 0u;
+    if (acc && top_cap) top[r * (uint64_t)top_cap] = bestc;
+}
+int launch_readid_classify(cid_ctx* ctx, cudaStream_t st, uint64_t r0, uint64_t nreads, uint32_t N, uint32_t rep_cap,
+                           const uint32_t* d_n_set, const uint32_t* d_flags, const uint32_t* d_rep_n,
+                           const uint32_t* d_rep_colour, const uint32_t* d_rep_count, const double* d_fp, double fp_correct,
+                           int32_t* d_kind, uint32_t* d_hits, uint32_t* d_n_top, uint32_t* d_top, uint32_t top_cap,
+                           uint32_t* d_list, uint32_t* d_list_cursor) {
+    if (nreads == 0) return CID_OK;
+    ProfScope ps(ctx, st, KID_READID_CLASSIFY);
+    readid_classify_kernel<<<(unsigned)((nreads + 127) / 128), 128, 0, st>>>(r0, nreads, N, rep_cap, d_n_set, d_flags, d_rep_n,
+                                                                           d_rep_colour, d_rep_count, d_fp, fp_correct, d_kind,
+                                                                           d_hits, d_n_top, d_top, top_cap, d_list, d_list_cursor);
+    ctx->launches++;
+    CID_CUDA(cudaGetLastError());
+    return CID_OK;
+}
+
 // ================================================================= order export (parity hook)
 __global__ void order_export_kernel(const uint16_t* __restrict__ order, const uint8_t* __restrict__ order8,
                                     const uint16_t* __restrict__ ent16, const uint32_t* __restrict__ n_set,

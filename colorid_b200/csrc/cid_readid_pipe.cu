@@ -10,7 +10,9 @@
 // chunk c-1 run concurrently.  Kernels of neighbouring chunks also overlap on the GPU, which lets
 // the DRAM-access-bound vote kernel hide under the issue-bound kmerize/order kernels.
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <mutex>
@@ -25,8 +27,10 @@ struct cid_readid_pipe {
         cudaStream_t st = nullptr;
         cudaEvent_t done = nullptr;
         cid::DevBuf bases, quals, seq_offs, read_offs, entries, order, nocc, n_set, flags, rep_n, rep, ord_out;
-        cid::PinBuf h_n_set, h_flags, h_rep_n, h_rep;
+        cid::DevBuf kind, hits, n_top, top, list, cursor;      // fused vote: device classification + undecided list
+        cid::PinBuf h_cursor, h_list;
     } slot[NS];
+    cid::DevBuf fp;            // false_prob per colour (f64), uploaded per call
     bool ready = false;
 };
 
@@ -46,12 +50,13 @@ void readid_pipe_destroy(cid_ctx* ctx) {
     for (auto& s : pp->slot) {
         if (s.st) cudaStreamSynchronize(s.st);
         for (DevBuf* b : {&s.bases, &s.quals, &s.seq_offs, &s.read_offs, &s.entries, &s.order, &s.nocc, &s.n_set, &s.flags,
-                          &s.rep_n, &s.rep, &s.ord_out})
+                          &s.rep_n, &s.rep, &s.ord_out, &s.kind, &s.hits, &s.n_top, &s.top, &s.list, &s.cursor})
             b->release();
-        for (PinBuf* b : {&s.h_n_set, &s.h_flags, &s.h_rep_n, &s.h_rep}) b->release();
+        for (PinBuf* b : {&s.h_cursor, &s.h_list}) b->release();
         if (s.done) cudaEventDestroy(s.done);
         if (s.st) cudaStreamDestroy(s.st);
     }
+    pp->fp.release();
     delete pp;
     ctx->pipe = nullptr;
 }
@@ -98,6 +103,10 @@ struct HostOut {            // where a chunk's results go (user memory, indexed 
 
 struct VoteJob { uint64_t r0, nr; int slot; };
 
+static double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals, const uint64_t* seq_offs, uint64_t nseq,
                             const uint64_t* read_offs, uint64_t nreads, const cid_readid_params* p, const HostOut& out) {
     cid_ctx* ctx = ix->ctx;
@@ -107,8 +116,10 @@ static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals,
     default_readid_params(pp, p, ix->N);
     if (nreads == 0) return CID_OK;
     (void)nseq;
-    uint32_t max_bases, max_kmers;
-    read_geometry(seq_offs, read_offs, nreads, ix->k, pp.downsample, &max_bases, &max_kmers);
+    static const bool trace = getenv("CID_TRACE") != nullptr;     // stage timings on stderr (diagnostics only)
+    const double t_start = now_ms();
+    double t_vote = 0, t_wait = 0, t_evwait = 0;
+    double t_geom = 0;
     const bool use_q = quals && pp.qual_offset;
     const bool want_rep = out.rep_n != nullptr || out.vote != nullptr;
     const bool fused = out.vote != nullptr;
@@ -131,7 +142,12 @@ static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals,
     bool closing = false;
     int worker_rc = CID_OK;
     std::thread worker;
+    std::vector<uint32_t> sub_idx, sub_n_set, sub_flags, sub_rep_n, sub_rc, sub_rv, sub_hits, sub_ntop, sub_top;
+    std::vector<int32_t> sub_kind;
+    uint64_t n_host_voted = 0;
     if (fused) {
+        CID_TRY(pipe->fp.ensure((size_t)ix->N * 8));
+        CID_CUDA(cudaMemcpy(pipe->fp.p, out.vote->fp.data(), (size_t)ix->N * 8, cudaMemcpyHostToDevice));
         worker = std::thread([&]() {
             cudaSetDevice(ctx->device);
             for (;;) {
@@ -144,15 +160,50 @@ static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals,
                     jobs.pop_front();
                 }
                 auto& s = pipe->slot[j.slot];
-                if (cudaEventSynchronize(s.done) != cudaSuccess) worker_rc = CID_E_CUDA;
+                const double t0 = now_ms();
+                const bool evok = cudaEventSynchronize(s.done) == cudaSuccess;
+                const double t1 = now_ms();
+                t_evwait += t1 - t0;
+                if (!evok) worker_rc = CID_E_CUDA;
                 else {
-                    const uint32_t* hn = s.h_n_set.as<uint32_t>();
-                    classify_chunk(*out.vote, j.nr, hn, s.h_flags.as<uint32_t>(), s.h_rep_n.as<uint32_t>(),
-                                   s.h_rep.as<uint32_t>(), s.h_rep.as<uint32_t>() + j.nr * rc, (uint32_t)rc, out.threads,
-                                   out.kind + j.r0, out.hits + j.r0, out.n_top + j.r0,
-                                   out.top ? out.top + j.r0 * out.top_cap : nullptr, out.top_cap);
-                    if (out.n_set) memcpy(out.n_set + j.r0, hn, j.nr * 4);
-                    if (out.flags) memcpy(out.flags + j.r0, s.h_flags.p, j.nr * 4);
+                    // the device decided every read it can decide bit-exactly; the rest come back as
+                    // [read, n, (colour, count) x n] records and go through the host vote
+                    const uint32_t nwords = *s.h_cursor.as<uint32_t>();
+                    if (nwords) {
+                        if (s.h_list.ensure((size_t)nwords * 4) != CID_OK ||
+                            cudaMemcpyAsync(s.h_list.p, s.list.p, (size_t)nwords * 4, cudaMemcpyDeviceToHost, s.st) != cudaSuccess ||
+                            cudaStreamSynchronize(s.st) != cudaSuccess)
+                            worker_rc = CID_E_CUDA;
+                        else {
+                            const uint32_t* L = s.h_list.as<uint32_t>();
+                            sub_idx.clear(); sub_n_set.clear(); sub_rep_n.clear(); sub_rc.clear(); sub_rv.clear();
+                            for (uint32_t at = 0; at + 2 <= nwords;) {
+                                const uint32_t i = L[at], n = L[at + 1];
+                                if (n > rc || at + 2 + 2 * (size_t)n > nwords || i >= j.nr) { worker_rc = CID_E_CAPACITY; break; }
+                                sub_idx.push_back(i);
+                                sub_n_set.push_back(out.n_set[j.r0 + i]);
+                                sub_rep_n.push_back(n);
+                                const size_t base = sub_rc.size();
+                                sub_rc.resize(base + rc, 0); sub_rv.resize(base + rc, 0);
+                                for (uint32_t e = 0; e < n; e++) { sub_rc[base + e] = L[at + 2 + 2 * e]; sub_rv[base + e] = L[at + 3 + 2 * e]; }
+                                at += 2 + 2 * n;
+                            }
+                            const size_t ns = sub_idx.size();
+                            n_host_voted += ns;
+                            sub_flags.assign(ns, 0);
+                            sub_kind.resize(ns); sub_hits.resize(ns); sub_ntop.resize(ns);
+                            sub_top.assign(ns * (size_t)std::max<uint32_t>(out.top_cap, 1), 0);
+                            classify_chunk(*out.vote, ns, sub_n_set.data(), sub_flags.data(), sub_rep_n.data(), sub_rc.data(),
+                                           sub_rv.data(), (uint32_t)rc, out.threads, sub_kind.data(), sub_hits.data(),
+                                           sub_ntop.data(), out.top ? sub_top.data() : nullptr, out.top_cap);
+                            for (size_t q = 0; q < ns; q++) {
+                                const uint64_t r = j.r0 + sub_idx[q];
+                                out.kind[r] = sub_kind[q]; out.hits[r] = sub_hits[q]; out.n_top[r] = sub_ntop[q];
+                                if (out.top) memcpy(out.top + r * out.top_cap, sub_top.data() + q * out.top_cap, (size_t)out.top_cap * 4);
+                            }
+                        }
+                    }
+                    t_vote += now_ms() - t1;
                 }
                 {
                     std::lock_guard<std::mutex> lk(mu);
@@ -182,8 +233,17 @@ static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals,
         const uint64_t s0 = read_offs[r0], s1 = read_offs[r1];
         const uint64_t b0 = seq_offs[s0], b1 = seq_offs[s1];
         if (fused) {          // the slot's pinned staging must have been consumed
+            const double t0 = now_ms();
             std::unique_lock<std::mutex> lk(mu);
             cv.wait(lk, [&] { return !slot_busy[si]; });
+            t_wait += now_ms() - t0;
+        }
+        // longest read / most k-mer positions of THIS chunk size its kernels (scanned while the GPU runs earlier chunks)
+        uint32_t max_bases, max_kmers;
+        {
+            const double t0 = now_ms();
+            read_geometry(seq_offs, read_offs + r0, nr, ix->k, pp.downsample, &max_bases, &max_kmers);
+            t_geom += now_ms() - t0;
         }
         size_t eb, ob, nb;
         readid_scratch_bytes(ix, max_bases, max_kmers, nr, &eb, &ob, &nb);
@@ -199,8 +259,9 @@ static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals,
         if (want_rep) { PIPE_TRY(s.rep_n.ensure(nr * 4)); PIPE_TRY(s.rep.ensure(nr * rc * 8)); }
         if (out.order_n) PIPE_TRY(s.ord_out.ensure(nr * 4 + nr * (size_t)out.order_cap * 3 + 64));
         if (fused) {
-            PIPE_TRY(s.h_n_set.ensure(nr * 4)); PIPE_TRY(s.h_flags.ensure(nr * 4));
-            PIPE_TRY(s.h_rep_n.ensure(nr * 4)); PIPE_TRY(s.h_rep.ensure(nr * rc * 8));
+            PIPE_TRY(s.kind.ensure(nr * 4)); PIPE_TRY(s.hits.ensure(nr * 4)); PIPE_TRY(s.n_top.ensure(nr * 4));
+            PIPE_TRY(s.top.ensure(nr * (size_t)std::max<uint32_t>(out.top_cap, 1) * 4));
+            PIPE_TRY(s.list.ensure(nr * (2 + 2 * rc) * 4)); PIPE_TRY(s.cursor.ensure(16)); PIPE_TRY(s.h_cursor.ensure(16));
         }
         if (b1 > b0) PIPE_CUDA(cudaMemcpyAsync(s.bases.p, bases + b0, b1 - b0, cudaMemcpyHostToDevice, s.st));
         if (use_q && b1 > b0) PIPE_CUDA(cudaMemcpyAsync(s.quals.p, quals + b0, b1 - b0, cudaMemcpyHostToDevice, s.st));
@@ -229,10 +290,20 @@ static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals,
         PIPE_TRY(readid_run(ix, s.st, d_bases, d_quals, d_seq_offs, d_read_offs, r0, nr, max_bases, max_kmers, pp, scr,
                             d_n_set, d_flags, d_rep_n, d_rc, d_rv, out.order_cap, d_on, d_os, d_op));
         if (fused) {
-            PIPE_CUDA(cudaMemcpyAsync(s.h_n_set.p, s.n_set.p, nr * 4, cudaMemcpyDeviceToHost, s.st));
-            PIPE_CUDA(cudaMemcpyAsync(s.h_flags.p, s.flags.p, nr * 4, cudaMemcpyDeviceToHost, s.st));
-            PIPE_CUDA(cudaMemcpyAsync(s.h_rep_n.p, s.rep_n.p, nr * 4, cudaMemcpyDeviceToHost, s.st));
-            PIPE_CUDA(cudaMemcpyAsync(s.h_rep.p, s.rep.p, nr * rc * 8, cudaMemcpyDeviceToHost, s.st));
+            PIPE_CUDA(cudaMemsetAsync(s.cursor.p, 0, 4, s.st));
+            PIPE_TRY(launch_readid_classify(ctx, s.st, r0, nr, ix->N, (uint32_t)rc, d_n_set, d_flags, d_rep_n, d_rc, d_rv,
+                                            pipe->fp.as<double>(), out.vote->fp_correct, s.kind.as<int32_t>() - r0,
+                                            s.hits.as<uint32_t>() - r0, s.n_top.as<uint32_t>() - r0,
+                                            s.top.as<uint32_t>() - r0 * (size_t)out.top_cap, out.top_cap, s.list.as<uint32_t>(),
+                                            s.cursor.as<uint32_t>()));
+            PIPE_CUDA(cudaMemcpyAsync(out.kind + r0, s.kind.p, nr * 4, cudaMemcpyDeviceToHost, s.st));
+            PIPE_CUDA(cudaMemcpyAsync(out.hits + r0, s.hits.p, nr * 4, cudaMemcpyDeviceToHost, s.st));
+            PIPE_CUDA(cudaMemcpyAsync(out.n_top + r0, s.n_top.p, nr * 4, cudaMemcpyDeviceToHost, s.st));
+            PIPE_CUDA(cudaMemcpyAsync(out.n_set + r0, s.n_set.p, nr * 4, cudaMemcpyDeviceToHost, s.st));
+            if (out.flags) PIPE_CUDA(cudaMemcpyAsync(out.flags + r0, s.flags.p, nr * 4, cudaMemcpyDeviceToHost, s.st));
+            if (out.top) PIPE_CUDA(cudaMemcpyAsync(out.top + r0 * (size_t)out.top_cap, s.top.p, nr * (size_t)out.top_cap * 4,
+                                                   cudaMemcpyDeviceToHost, s.st));
+            PIPE_CUDA(cudaMemcpyAsync(s.h_cursor.p, s.cursor.p, 4, cudaMemcpyDeviceToHost, s.st));
             PIPE_CUDA(cudaEventRecord(s.done, s.st));
             { std::lock_guard<std::mutex> lk(mu); slot_busy[si] = true; jobs.push_back(VoteJob{r0, nr, si}); }
             cv.notify_all();
@@ -257,7 +328,13 @@ static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals,
     }
 #undef PIPE_TRY
 #undef PIPE_CUDA
+    const double t_issued = now_ms() - t_start;
     int rcode = finish(CID_OK);
+    if (trace)
+        fprintf(stderr, "[cid trace] read_id: %llu reads, %llu chunks of %llu: geometry %.2f ms, issue loop %.2f ms (slot wait %.2f), "
+                        "host vote busy %.2f ms for %llu undecided reads, vote waiting on GPU %.2f ms, total %.2f ms\n",
+                (unsigned long long)nreads, (unsigned long long)nchunks, (unsigned long long)chunk, t_geom, t_issued, t_wait,
+                t_vote, (unsigned long long)n_host_voted, t_evwait, now_ms() - t_start);
     if (rcode != CID_OK) return rcode;
     return check_err_flags(ctx, ctx->stream);
 }

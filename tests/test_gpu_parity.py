@@ -248,6 +248,30 @@ def test_read_id_classify_pipeline_equals_oracle(oracle, ctx):
         ctx.set_option("readid_chunk_reads", 0)
 
 
+def test_read_id_classify_ties_go_through_host_vote(oracle, ctx):
+    """Identical accessions: every classified read ties at the top, so the device defers all of them to the host
+    vote (names joined in FnvHashMap iteration order)."""
+    rng = _rng(1236)
+    g0, g1 = synth.rand_seq(rng, 6000), synth.rand_seq(rng, 6000)
+    genomes = [g0, g0, g1, g0, g1, synth.mutate(rng, g1, 0.01)]
+    oix, gix = build_both(oracle, ctx, [[g] for g in genomes], 400_009, 3, 25, cb.CID_SEQ_FASTA)
+    gix.n_ref[:] = oix.n_ref
+    reads = synth.reads_from(rng, genomes, 400, read_len=120, insert=300, err=0.002, frac_random=0.1)
+    o = oix.read_id_batch(reads)
+    assert (o["kind"] == oracle.CLS_REJECT_MULTI).sum() > 100
+    try:
+        for chunk in (0, 90):
+            ctx.set_option("readid_chunk_reads", chunk)
+            g = gix.read_id_classify(reads)
+            for key in ("kind", "hits", "n_set", "n_top"):
+                assert np.array_equal(g[key], o[key]), key
+            for r in range(len(reads)):
+                nt = min(int(o["n_top"][r]), 8)
+                assert g["top"][r, :nt].tolist() == o["top"][r, :nt].tolist()
+    finally:
+        ctx.set_option("readid_chunk_reads", 0)
+
+
 def test_read_id_classify_with_quals(oracle, ctx):
     rng = _rng(1235)
     genomes, oix, gix = _index_pair(oracle, ctx, rng, 6, 27, 750_000, 4)
