@@ -172,8 +172,8 @@ int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const ui
 int launch_readid_classify(cid_ctx* ctx, cudaStream_t st, uint64_t r0, uint64_t nreads, uint32_t N, uint32_t rep_cap,
                            const uint32_t* d_n_set, const uint32_t* d_flags, const uint32_t* d_rep_n,
                            const uint32_t* d_rep_colour, const uint32_t* d_rep_count, const double* d_fp, double fp_correct,
-                           int32_t* d_kind, uint32_t* d_hits, uint32_t* d_n_top, uint32_t* d_top, uint32_t top_cap,
-                           uint32_t* d_list, uint32_t* d_list_cursor);
+                           uint32_t group_width, int32_t* d_kind, uint32_t* d_hits, uint32_t* d_n_top, uint32_t* d_top,
+                           uint32_t top_cap, uint32_t* d_list, uint32_t* d_list_cursor);
 
 // host vote (cid_host_vote.cpp): read_id_mt_pe.rs:187-251 kmer_poll_plus over a chunk of reads
 struct VoteParams { uint32_t n_colors = 0; double fp_correct = 1e-3; uint32_t group_width = 16; std::vector<double> fp; std::vector<uint64_t> key_hash; };

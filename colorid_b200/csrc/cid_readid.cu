@@ -829,11 +829,64 @@ __device__ __forceinline__ double dev_binomial_pmf(double n, double p, double x)
     return exp(lc) * sqrt(n / (2.0 * 3.14159265358979323846 * x * rest));
 }
 
+// FnvHashMap<usize,usize> (read_id_mt_pe.rs:195 `report.iter()`) for up to 56 keys: bucket layout
+// after `entry(k).or_insert()` of keys[0..n) in order (the table grows only when a NEW key arrives
+// with no growth left; at most 64 buckets).  Returns, per bucket in ascending order, the key index.
+__device__ __forceinline__ uint32_t dev_probe64(uint64_t occ, uint32_t nb, uint32_t hash, uint32_t gw) {
+    const uint32_t mask = nb - 1;
+    uint32_t pos = hash & mask;
+    const uint32_t width = nb < gw ? nb : gw;
+    const uint64_t wmask = (1ull << width) - 1;
+    for (uint32_t stride = 0;;) {
+        // occupancy bits starting at bucket `pos`, cyclic in the nb-bucket table
+        uint64_t rot = occ >> pos;
+        if (pos) rot |= occ << (nb - pos);
+        const uint64_t free_ = ~rot & wmask;
+        if (free_) return (pos + (uint32_t)__ffsll((long long)free_) - 1) & mask;
+        stride += gw;
+        pos = (pos + stride) & mask;
+    }
+}
+__device__ __forceinline__ uint32_t dev_fnv_usize_low32(uint32_t key) {
+    uint32_t h = 0x84222325u;                  // low half of the FNV offset basis; low 32 bits are closed under h*0x100000001b3
+#pragma unroll
+    for (int b = 0; b < 8; b++) h = (h ^ (b < 4 ? ((key >> (8 * b)) & 0xFFu) : 0u)) * 0x1b3u;
+    return h;
+}
+struct DevMapOrder { uint8_t tab[2][64]; uint32_t nb; int cur; };
+__device__ __forceinline__ void dev_usize_map_order(const uint32_t* __restrict__ keys, uint32_t n, uint32_t gw, DevMapOrder& m) {
+    uint32_t nb = 0, items = 0, growth = 0;
+    uint64_t occ = 0;
+    int cur = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        if (growth == 0) {
+            const uint32_t nn = nb == 0 ? 4 : nb * 2;
+            uint64_t occ2 = 0;
+            for (uint32_t s = 0; s < nb; s++)
+                if ((occ >> s) & 1ull) {
+                    const uint32_t it = m.tab[cur][s];
+                    const uint32_t slot = dev_probe64(occ2, nn, dev_fnv_usize_low32(keys[it]), gw);
+                    m.tab[cur ^ 1][slot] = (uint8_t)it;
+                    occ2 |= 1ull << slot;
+                }
+            occ = occ2; cur ^= 1; nb = nn;
+            growth = (nb < 8 ? nb - 1 : nb / 8 * 7) - items;
+        }
+        const uint32_t slot = dev_probe64(occ, nb, dev_fnv_usize_low32(keys[i]), gw);
+        m.tab[cur][slot] = (uint8_t)i;
+        occ |= 1ull << slot;
+        items++; growth--;
+    }
+    // mark empty buckets
+    for (uint32_t s = 0; s < nb; s++) if (!((occ >> s) & 1ull)) m.tab[cur][s] = 0xFF;
+    m.nb = nb; m.cur = cur;
+}
+
 __global__ void __launch_bounds__(128)
 readid_classify_kernel(uint64_t r0, uint64_t nreads, uint32_t N, uint32_t rep_cap, const uint32_t* __restrict__ n_set,
                        const uint32_t* __restrict__ flags, const uint32_t* __restrict__ rep_n,
                        const uint32_t* __restrict__ rep_colour, const uint32_t* __restrict__ rep_count,
-                       const double* __restrict__ fp, double fp_correct, int32_t* __restrict__ kind,
+                       const double* __restrict__ fp, double fp_correct, uint32_t gw, int32_t* __restrict__ kind,
                        uint32_t* __restrict__ hits, uint32_t* __restrict__ n_top, uint32_t* __restrict__ top,
                        uint32_t top_cap, uint32_t* __restrict__ list, uint32_t* __restrict__ list_cursor) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -852,6 +905,7 @@ readid_classify_kernel(uint64_t r0, uint64_t nreads, uint32_t N, uint32_t rep_ca
         const double obs = (double)n_set[r];
         bool uncertain = false, real = false;
         uint32_t nsig = 0;
+        uint64_t sigmask = 0;                                // significant entries (first 64 of the report)
         for (uint32_t e = 0; e < n; e++) {
             const uint32_t c = rc[e], v = rv[e];
             if (c >= N) continue;                            // the "no hit" key never votes (:209)
@@ -866,12 +920,28 @@ readid_classify_kernel(uint64_t r0, uint64_t nreads, uint32_t N, uint32_t rep_ca
             }
             if (!drop) {
                 nsig++;
+                if (e < 64) sigmask |= 1ull << e;
                 if (v > best) { best = v; nbest = 1; bestc = c; }
                 else if (v == best) nbest++;
             }
         }
         if (!real) kd = CID_CLS_NO_HITS;                     // only the "no hit" key, :197-205
-        else if (uncertain || nbest > 1) {
+        else if (!uncertain && nbest > 1 && n <= 56) {
+            // several accessions share the top count: "reject", names joined in the iteration order of
+            // the report map (:236-249) = ascending bucket of the emulated FnvHashMap<usize,usize>
+            DevMapOrder m;
+            dev_usize_map_order(rc, n, gw, m);
+            uint32_t nt = 0;
+            for (uint32_t sl = 0; sl < m.nb; sl++) {
+                const uint32_t e = m.tab[m.cur][sl];
+                if (e == 0xFFu || !((sigmask >> e) & 1ull) || rv[e] != best) continue;
+                if (nt < top_cap) top[r * (uint64_t)top_cap + nt] = rc[e];
+                nt++;
+            }
+            kd = CID_CLS_REJECT_MULTI;
+            kind[r] = kd; hits[r] = best; n_top[r] = nt;
+            return;
+        } else if (uncertain || nbest > 1) {
             kd = -1;                                         // host decides
             const uint32_t at = atomicAdd(list_cursor, 2u + 2u * n);
             list[at] = (uint32_t)i;
@@ -889,13 +959,13 @@ readid_classify_kernel(uint64_t r0, uint64_t nreads, uint32_t N, uint32_t rep_ca
 int launch_readid_classify(cid_ctx* ctx, cudaStream_t st, uint64_t r0, uint64_t nreads, uint32_t N, uint32_t rep_cap,
                            const uint32_t* d_n_set, const uint32_t* d_flags, const uint32_t* d_rep_n,
                            const uint32_t* d_rep_colour, const uint32_t* d_rep_count, const double* d_fp, double fp_correct,
-                           int32_t* d_kind, uint32_t* d_hits, uint32_t* d_n_top, uint32_t* d_top, uint32_t top_cap,
-                           uint32_t* d_list, uint32_t* d_list_cursor) {
+                           uint32_t group_width, int32_t* d_kind, uint32_t* d_hits, uint32_t* d_n_top, uint32_t* d_top,
+                           uint32_t top_cap, uint32_t* d_list, uint32_t* d_list_cursor) {
     if (nreads == 0) return CID_OK;
     ProfScope ps(ctx, st, KID_READID_CLASSIFY);
     readid_classify_kernel<<<(unsigned)((nreads + 127) / 128), 128, 0, st>>>(r0, nreads, N, rep_cap, d_n_set, d_flags, d_rep_n,
-                                                                           d_rep_colour, d_rep_count, d_fp, fp_correct, d_kind,
-                                                                           d_hits, d_n_top, d_top, top_cap, d_list, d_list_cursor);
+                                                                           d_rep_colour, d_rep_count, d_fp, fp_correct, group_width,
+                                                                           d_kind, d_hits, d_n_top, d_top, top_cap, d_list, d_list_cursor);
     ctx->launches++;
     CID_CUDA(cudaGetLastError());
     return CID_OK;

@@ -28,7 +28,8 @@ struct cid_readid_pipe {
         cudaEvent_t done = nullptr;
         cid::DevBuf bases, quals, seq_offs, read_offs, entries, order, nocc, n_set, flags, rep_n, rep, ord_out;
         cid::DevBuf kind, hits, n_top, top, list, cursor;      // fused vote: device classification + undecided list
-        cid::PinBuf h_cursor, h_list;
+        cid::PinBuf h_cursor, h_list, h_offs;
+        cudaEvent_t offs_done = nullptr;     // the staged offsets have been consumed by their H2D copies
     } slot[NS];
     cid::DevBuf fp;            // false_prob per colour (f64), uploaded per call
     bool ready = false;
@@ -52,7 +53,8 @@ void readid_pipe_destroy(cid_ctx* ctx) {
         for (DevBuf* b : {&s.bases, &s.quals, &s.seq_offs, &s.read_offs, &s.entries, &s.order, &s.nocc, &s.n_set, &s.flags,
                           &s.rep_n, &s.rep, &s.ord_out, &s.kind, &s.hits, &s.n_top, &s.top, &s.list, &s.cursor})
             b->release();
-        for (PinBuf* b : {&s.h_cursor, &s.h_list}) b->release();
+        for (PinBuf* b : {&s.h_cursor, &s.h_list, &s.h_offs}) b->release();
+        if (s.offs_done) cudaEventDestroy(s.offs_done);
         if (s.done) cudaEventDestroy(s.done);
         if (s.st) cudaStreamDestroy(s.st);
     }
@@ -68,6 +70,7 @@ static int pipe_get(cid_ctx* ctx, cid_readid_pipe** out) {
         for (auto& s : pp->slot) {
             CID_CUDA(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
             CID_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+            CID_CUDA(cudaEventCreateWithFlags(&s.offs_done, cudaEventDisableTiming));
         }
         pp->ready = true;
     }
@@ -263,10 +266,21 @@ static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals,
             PIPE_TRY(s.top.ensure(nr * (size_t)std::max<uint32_t>(out.top_cap, 1) * 4));
             PIPE_TRY(s.list.ensure(nr * (2 + 2 * rc) * 4)); PIPE_TRY(s.cursor.ensure(16)); PIPE_TRY(s.h_cursor.ensure(16));
         }
+        // The caller's offset arrays are usually pageable (a pageable cudaMemcpyAsync first drains the
+        // stream, i.e. waits for the big copies queued just before it): stage them in pinned memory.
+        {
+            const size_t nso = s1 - s0 + 1, nro = nr + 1;
+            PIPE_CUDA(cudaEventSynchronize(s.offs_done));          // previous use of this slot's staging
+            PIPE_TRY(s.h_offs.ensure((nso + nro) * 8));
+            uint64_t* ho = s.h_offs.as<uint64_t>();
+            memcpy(ho, seq_offs + s0, nso * 8);
+            memcpy(ho + nso, read_offs + r0, nro * 8);
+            PIPE_CUDA(cudaMemcpyAsync(s.seq_offs.p, ho, nso * 8, cudaMemcpyHostToDevice, s.st));
+            PIPE_CUDA(cudaMemcpyAsync(s.read_offs.p, ho + nso, nro * 8, cudaMemcpyHostToDevice, s.st));
+            PIPE_CUDA(cudaEventRecord(s.offs_done, s.st));
+        }
         if (b1 > b0) PIPE_CUDA(cudaMemcpyAsync(s.bases.p, bases + b0, b1 - b0, cudaMemcpyHostToDevice, s.st));
         if (use_q && b1 > b0) PIPE_CUDA(cudaMemcpyAsync(s.quals.p, quals + b0, b1 - b0, cudaMemcpyHostToDevice, s.st));
-        PIPE_CUDA(cudaMemcpyAsync(s.seq_offs.p, seq_offs + s0, (s1 - s0 + 1) * 8, cudaMemcpyHostToDevice, s.st));
-        PIPE_CUDA(cudaMemcpyAsync(s.read_offs.p, read_offs + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, s.st));
         // device arrays are indexed by absolute base / sequence / read numbers: bias the chunk buffers
         const uint8_t* d_bases = s.bases.as<uint8_t>() - b0;
         const uint8_t* d_quals = use_q ? s.quals.as<uint8_t>() - b0 : nullptr;
@@ -292,7 +306,8 @@ static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals,
         if (fused) {
             PIPE_CUDA(cudaMemsetAsync(s.cursor.p, 0, 4, s.st));
             PIPE_TRY(launch_readid_classify(ctx, s.st, r0, nr, ix->N, (uint32_t)rc, d_n_set, d_flags, d_rep_n, d_rc, d_rv,
-                                            pipe->fp.as<double>(), out.vote->fp_correct, s.kind.as<int32_t>() - r0,
+                                            pipe->fp.as<double>(), out.vote->fp_correct, out.vote->group_width,
+                                            s.kind.as<int32_t>() - r0,
                                             s.hits.as<uint32_t>() - r0, s.n_top.as<uint32_t>() - r0,
                                             s.top.as<uint32_t>() - r0 * (size_t)out.top_cap, out.top_cap, s.list.as<uint32_t>(),
                                             s.cursor.as<uint32_t>()));
