@@ -93,33 +93,84 @@ def make_reads(torch, dev, cfg, genomes, n_pairs, seed):
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region: NVML in-process every 5 ms (the timed
+    region of a default run is ~0.2 s, too short for `nvidia-smi -lms`), nvidia-smi as the fallback."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu):
-        self.gpu, self.rows, self.p = gpu, [], None
+        self.gpu, self.sm, self.mx, self.reasons, self.p, self.th = gpu, [], [], set(), None, None
+        self.run = False
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # torch's device index follows CUDA_VISIBLE_DEVICES; NVML's does not
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = gpu
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if gpu < len(ids) and ids[gpu].isdigit():
+                    phys = int(ids[gpu])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = pynvml
+        except Exception:
+            self.nv = None
+
+    def _poll_nvml(self):
+        nv = self.nv
+        names = ((nv.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"), (nv.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                 (nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"), (nv.nvmlClocksEventReasonSwPowerCap, "sw_power_cap"))
+        try:
+            self.mx.append(int(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        except Exception:
+            pass
+        while self.run:
+            try:
+                self.sm.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                for bit, name in names:
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def _read_smi(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.p.stdout:
+            r = [x.strip() for x in line.split(",")]
+            if r and r[0].isdigit():
+                self.sm.append(int(r[0]))
+            if len(r) > 1 and r[1].isdigit():
+                self.mx.append(int(r[1]))
+            for i, n in enumerate(names):
+                if len(r) > 2 + i and r[2 + i] == "Active":
+                    self.reasons.add(n)
 
     def start(self):
+        self.run = True
+        if self.nv is not None:
+            self.th = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.th.start()
+            return
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+                                       "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read_smi, daemon=True).start()
         except Exception:
             self.p = None
 
-    def _read(self):
-        for line in self.p.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
     def stop(self):
+        self.run = False
+        if self.th:
+            self.th.join(timeout=1.0)
         if self.p:
             self.p.terminate()
-        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
-        return dict(sm_mhz=int(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
-                    samples=len(sm))
+        order = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        return dict(sm_mhz=int(np.median(self.sm)) if self.sm else None, sm_max_mhz=max(self.mx) if self.mx else None,
+                    reasons=[n for n in order if n in self.reasons], samples=len(self.sm),
+                    source="nvml" if self.nv is not None else "nvidia-smi")
 
 
 def measured_peak():
@@ -130,6 +181,18 @@ def measured_peak():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+GATHER_CEILING_G_PER_S = 54.5     # measured: profiles/r1_gather_probe.txt
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
+    same workload (profiles/r1_traffic.json; null when a kernel was not captured)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["bytes_per_launch"]
+    except Exception:
+        return {}
 
 
 def offsets_for(n_pairs, rl):
@@ -391,15 +454,16 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timing ("value") ----
+    # The library runs a batch as chunks alternating over two internal streams (fork/join on the caller's
+    # stream), so kernels of neighbouring chunks overlap; per-kernel event timing would charge each kernel for
+    # the time it shares the GPU, so it is taken in a second, serialised pass over the same K batches below.
     for i in range(Wm):
         step_dev(i)
     barrier()
     launches0 = ctx.launches
-    ctx.profile(True)
     clk = ClockSampler(local)
     clk.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    nproc_sum = 0
     ev0.record(stream)
     for i in range(K):
         step_dev(Wm + i)
@@ -407,9 +471,22 @@ def run_ours(args):
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
     clocks = clk.stop()
+    launches = ctx.launches - launches0
+    # ---- per-kernel pass: same K batches, one stream, CUDA events around every launch (on that stream) ----
+    ctx.set_option("readid_streams", 1)
+    step_dev(0)
+    barrier()
+    ctx.profile(True)
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev2.record(stream)
+    for i in range(K):
+        step_dev(Wm + i)
+    ev3.record(stream)
+    barrier()
+    serial_ms = ev2.elapsed_time(ev3)
     prof = ctx.profile_read()
     ctx.profile(False)
-    launches = ctx.launches - launches0
+    ctx.set_option("readid_streams", 2)
     # algorithmic traffic of the last step (all steps are statistically identical)
     fl = d_flags.cpu().numpy().view(np.uint32)
     nproc_last = int(((fl >> 8) & 0xFFFF).sum())
@@ -458,7 +535,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * batch * e2e_steps / float(t.item())
     h2d = 2 * batch * 2 * rl + seq_offs_np.nbytes + read_offs_np.nbytes
-    d2h = 3 * batch * 4 + 2 * batch * (cfg["n_acc"] + 1) * 4      # per-read reports copied back for the host vote
+    d2h = batch * (4 * 4 + 8 * 4)      # kind, hits, n_set, n_top + top[8] per read; the undecided-read list (<1 % of reads) is extra
 
     if rank != 0:
         if world > 1:
@@ -472,6 +549,7 @@ def run_ours(args):
     alg = {"readid_vote": H * R * nproc_last + read_bytes,        # rows up to and incl. the first miss + the read
            "readid_kmerize": 2 * read_bytes,                       # bases + quals
            "readid_order": 0}
+    traffic = ncu_traffic()
     kern = {}
     for name, (ms, n) in prof.items():
         per = ms / n
@@ -480,13 +558,25 @@ def run_ours(args):
     dom = max(prof, key=lambda k_: prof[k_][0])
     dom_per = prof[dom][0] / prof[dom][1]
     achieved = alg.get(dom, 0) / (dom_per / 1e3) / 1e9
-    sector = (H * 32 * nproc_last + read_bytes) / (kern["readid_vote"]["ms_per_launch"] / 1e3) / 1e9 if "readid_vote" in kern else None
+    vote_ms = kern["readid_vote"]["ms_per_launch"] if "readid_vote" in kern else None
+    gathers = H * nproc_last               # one gather = one 8-byte row read at a random row
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic.get(dom), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg.get(dom),
-                "note": "read_id is issue-bound (XXH3 + FNV + hashbrown-order emulation per k-mer), not HBM-bound: "
-                        "8-byte rows, <=33 algorithmic bytes per lookup",
-                "vote_sector_granular_gbs": sector, "kernels": kern,
+                "measured_in": "second pass over the same K batches with chunk overlap off (one stream), CUDA events "
+                               "around every launch on that stream; serial step %.3f ms vs %.3f ms overlapped"
+                               % (serial_ms / K, dev_ms_max / K),
+                "note": "8-byte rows: a gather moves 8 algorithmic bytes but costs one DRAM access (ncu: ~100 B of DRAM "
+                        "traffic each, 56 B with ld.global.nc.L2::64B at the same rate), so the binding limit is the "
+                        "random-access rate, not bytes; see random_access",
+                "random_access": {"gathers_per_launch": gathers,
+                                  "achieved_g_per_s": gathers / (vote_ms / 1e3) / 1e9 if vote_ms else None,
+                                  "ceiling_g_per_s": GATHER_CEILING_G_PER_S,
+                                  "frac": gathers / (vote_ms / 1e3) / 1e9 / GATHER_CEILING_G_PER_S if vote_ms else None,
+                                  "ceiling_source": "tools/gather_probe.cu on B200: 8-byte __ldg at uniformly random rows of a "
+                                                    "400 MB matrix, 8 loads in flight per thread (profiles/r1_gather_probe.txt)"},
+                "vote_sector_granular_gbs": (H * 32 * nproc_last + read_bytes) / (vote_ms / 1e3) / 1e9 if vote_ms else None,
+                "kernels": kern,
                 "share_of_step": {k_: prof[k_][0] / sum(v[0] for v in prof.values()) for k_ in prof}}
 
     # ---- CPU baseline on a bounded sample (rank 0) ----
@@ -525,7 +615,7 @@ def run_ours(args):
             "warmup": Wm, "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic", "config": workload_config(cfg, batch), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "read pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "includes": "cid_read_id_classify: chunked pipeline of H2D reads+quals+offsets, 3 kernels, D2H reports, host kmer_poll_plus; pinned host buffers"},
+                    "steps": e2e_steps, "includes": "cid_read_id_classify: chunked pipeline of H2D reads+quals+offsets, read_id kernels + device vote, D2H of one classification per read; near-threshold/tied reads re-voted on the host; pinned host buffers"},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "build": {"gbp_per_s": cfg["n_acc"] * cfg["genome_len"] / build_s / 1e9, "seconds": build_s,
                       "note": "index build on device incl. per-accession host sync; not the timed metric"},

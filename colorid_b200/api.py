@@ -199,6 +199,17 @@ class Index:
                                            _p(and_rows, L.u32p), _p(status, L.u8p), _p(n_kmers, L.u64p)))
         return dict(and_rows=and_rows, status=status[:nq], n_kmers=n_kmers[:nq])
 
+    def query_perfect_mf(self, records):
+        """perfect_search.rs:62-120 batch_search_mf (-s -m): one query per FASTA record (list of bytes)."""
+        bases, offs = pack_seqs(list(records))
+        nq = len(records)
+        and_rows = np.zeros((nq, self.W), dtype=np.uint32)
+        status = np.zeros(max(nq, 1), dtype=np.uint8)
+        n_kmers = np.zeros(max(nq, 1), dtype=np.uint64)
+        L.check(self.lib.cid_query_perfect_mf(self.h, _p(bases), _p(offs, L.u64p), nq, _p(and_rows, L.u32p),
+                                              _p(status, L.u8p), _p(n_kmers, L.u64p)))
+        return dict(and_rows=and_rows, status=status[:nq], n_kmers=n_kmers[:nq])
+
     # ---- read_id (read_id_mt_pe.rs:282-363) ----
     def _params(self, d, start_sample, qual_offset, group_width, reserve_before_find, rep_cap):
         return L.ReadIdParams(d, start_sample, qual_offset, group_width, int(reserve_before_find),

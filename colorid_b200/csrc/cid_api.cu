@@ -76,6 +76,10 @@ int check_err_flags(cid_ctx* ctx, cudaStream_t st) {
         set_error("lower-case bases inside k-mers of a raw-case input (FASTQ / read_id) are not supported on the device yet");
         return CID_E_UNSUPPORTED;
     }
+    if (f & ERRF_STRING_NONACGT) {
+        set_error("-s -m query (kmerize_string) with a byte outside ACGTacgt inside a k-mer is not supported on the device");
+        return CID_E_UNSUPPORTED;
+    }
     if (f & ERRF_READ_TOO_LONG) { set_error("a read exceeds the declared maximum read length"); return CID_E_CAPACITY; }
     set_error("internal capacity exceeded (flags 0x%x)", f);
     return CID_E_CAPACITY;
@@ -229,6 +233,8 @@ void cid_ctx_destroy(cid_ctx* c) {
     for (auto& b : c->pinned) b.release();
     if (c->d_err) cudaFree(c->d_err);
     if (c->h_err) cudaFreeHost(c->h_err);
+    for (int i = 0; i < 2; i++) { if (c->aux[i]) cudaStreamDestroy(c->aux[i]); if (c->aux_join[i]) cudaEventDestroy(c->aux_join[i]); }
+    if (c->aux_fork) cudaEventDestroy(c->aux_fork);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -251,6 +257,7 @@ uint64_t cid_ctx_launch_count(const cid_ctx* c) { return c ? c->launches : 0; }
 int cid_ctx_set_option(cid_ctx* c, const char* name, int64_t value) {
     if (!c || !name) { set_error("cid_ctx_set_option: null argument"); return CID_E_INVALID; }
     if (!strcmp(name, "readid_chunk_reads")) { c->opt_readid_chunk = value > 0 ? (uint64_t)value : 0; return CID_OK; }
+    if (!strcmp(name, "readid_streams")) { c->opt_readid_streams = value >= 2 ? 2 : 1; return CID_OK; }
     if (!strcmp(name, "host_threads")) { c->opt_host_threads = value > 0 ? (int)value : 0; return CID_OK; }
     set_error("cid_ctx_set_option: unknown option '%s'", name);
     return CID_E_INVALID;
@@ -606,8 +613,25 @@ int cid_query_counts_dev(cid_index* ix, const char* d_bases, const uint64_t* d_s
     return CID_OK;
 }
 
+static int query_perfect_impl(cid_index* ix, const char* bases, const uint64_t* seq_offs, uint64_t nseq,
+                              const uint64_t* query_offs, uint64_t nq, int seq_mode, uint32_t* and_rows, uint8_t* status,
+                              uint64_t* n_kmers);
+
 int cid_query_perfect(cid_index* ix, const char* bases, const uint64_t* seq_offs, uint64_t nseq,
                       const uint64_t* query_offs, uint64_t nq, uint32_t* and_rows, uint8_t* status, uint64_t* n_kmers) {
+    return query_perfect_impl(ix, bases, seq_offs, nseq, query_offs, nq, CID_SEQ_FASTA, and_rows, status, n_kmers);
+}
+
+int cid_query_perfect_mf(cid_index* ix, const char* bases, const uint64_t* seq_offs, uint64_t nseq, uint32_t* and_rows,
+                         uint8_t* status, uint64_t* n_kmers) {
+    std::vector<uint64_t> qo(nseq + 1);          // one query per record
+    for (uint64_t i = 0; i <= nseq; i++) qo[i] = i;
+    return query_perfect_impl(ix, bases, seq_offs, nseq, qo.data(), nseq, CID_SEQ_STRING, and_rows, status, n_kmers);
+}
+
+static int query_perfect_impl(cid_index* ix, const char* bases, const uint64_t* seq_offs, uint64_t nseq,
+                              const uint64_t* query_offs, uint64_t nq, int seq_mode, uint32_t* and_rows, uint8_t* status,
+                              uint64_t* n_kmers) {
     cid_ctx* ctx = ix->ctx;
     cudaStream_t st = ctx->stream;
     if (!seq_offs || !query_offs || !and_rows || !status || !n_kmers) { set_error("cid_query_perfect: null argument"); return CID_E_INVALID; }
@@ -623,7 +647,7 @@ int cid_query_perfect(cid_index* ix, const char* bases, const uint64_t* seq_offs
         const uint64_t q0 = cuts[b], q1 = cuts[b + 1], bq = q1 - q0;
         QueryPlan qp;
         CID_TRY(query_front(ix, st, ctx->scratch[4].as<uint8_t>(), ctx->scratch[5].as<uint64_t>(), seq_offs, query_offs,
-                            q0, q1, CID_SEQ_FASTA, qp));
+                            q0, q1, seq_mode, qp));
         CID_TRY(check_err_flags(ctx, st));
         CID_TRY(ctx->scratch[10].ensure(bq * W * 4));
         CID_TRY(ctx->scratch[11].ensure(bq * 8));

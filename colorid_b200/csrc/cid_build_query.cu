@@ -87,8 +87,14 @@ kmerize_insert_kernel(const uint8_t* __restrict__ bases, const uint64_t* __restr
 
     for (int p = tid; p < KT; p += KT_THREADS) {
         uint64_t key; bool fwd, low;
-        if (!tile_kmer(t, p, k, key, fwd, low)) continue;
-        if (low && seq_mode != CID_SEQ_FASTA) { atomicOr(err, ERRF_LOWER_RAW); continue; }
+        if (!tile_kmer(t, p, k, key, fwd, low)) {
+            // kmerize_string (kmer.rs:279-293) has no has_no_n test: a window that lies inside one record but
+            // holds a byte outside ACGTacgt is still a k-mer there, and it cannot be packed into 2 bits
+            if (seq_mode == CID_SEQ_STRING && p + (int)k <= t.len && (mask_window(t.start, p, k) & ~1u) == 0u)
+                atomicOr(err, ERRF_STRING_NONACGT);
+            continue;
+        }
+        if (low && seq_mode == CID_SEQ_FASTQ) { atomicOr(err, ERRF_LOWER_RAW); continue; }
         // owner sequence = s0 + #starts <= p
         uint32_t lo = 0, hi = nstarts;
         while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (s_starts[mid] <= (uint32_t)p) lo = mid + 1; else hi = mid; }
@@ -334,19 +340,28 @@ __device__ __forceinline__ uint32_t unit_collect_and_hash(const UnitSmem& u, con
 // For every surviving k-mer: AND of its H rows, +1 for every set accession (batch_search_pe.rs:60-74).
 // A work item is up to QUERY_ITEM_SLOTS table slots of one query, walked in QUERY_CHUNK pieces
 // (collect -> hash -> gather).  A lane owns VEC consecutive 32-accession words of the row (128-bit
-// loads when VEC == 4: a 128-byte row is one request of 8 lanes, so a warp gathers 4 k-mers at
-// once); hits are accumulated in bit-sliced (carry-save) counters that live in registers for
-// the whole item, so the per-k-mer cost is a few logic ops instead of one atomic per set bit.
-constexpr int QC_PLANES = 11;   // a lane sees at most QUERY_ITEM_SLOTS/2/8 = 1024 k-mers per item (+ unroll slack)
-constexpr int QC_UNR = 4;
+// loads when VEC == 4: a 128-byte row is one request of 8 lanes, so a warp gathers 4 k-mers per
+// instruction).  Hits are accumulated in bit-sliced counters that live in registers for the whole
+// item: eight k-mers at a time go through a Harley-Seal carry-save tree (ones/twos/fours planes),
+// and only the weight-8 carry ripples into the upper planes, so counting costs < 4 logic ops per
+// k-mer and word instead of one atomic per set bit.
+constexpr int QC_PLANES = 11;   // a lane sees at most QUERY_ITEM_SLOTS/8 = 2048 k-mers per item; counts < 2^11
+constexpr int QC_TREE = 8;      // k-mers per lane group and carry-save tree step
 
 template <int VEC> struct RowVec;
-template <> struct RowVec<1> { uint32_t w[1]; __device__ void load(const uint32_t* p) { w[0] = __ldg(p); } };
-template <> struct RowVec<2> { uint32_t w[2]; __device__ void load(const uint32_t* p) { uint2 v = __ldg((const uint2*)p); w[0] = v.x; w[1] = v.y; } };
-template <> struct RowVec<4> { uint32_t w[4]; __device__ void load(const uint32_t* p) { uint4 v = __ldg((const uint4*)p); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; } };
+template <> struct RowVec<1> { uint32_t w[1]; __device__ __forceinline__ void load(const uint32_t* p) { w[0] = __ldg(p); } };
+template <> struct RowVec<2> { uint32_t w[2]; __device__ __forceinline__ void load(const uint32_t* p) { uint2 v = __ldg((const uint2*)p); w[0] = v.x; w[1] = v.y; } };
+template <> struct RowVec<4> { uint32_t w[4]; __device__ __forceinline__ void load(const uint32_t* p) { uint4 v = __ldg((const uint4*)p); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; } };
+
+// carry-save adder: (carry, sum) = a + b + c, bitwise
+__device__ __forceinline__ void csa(uint32_t& carry, uint32_t& sum, uint32_t a, uint32_t b, uint32_t c) {
+    const uint32_t u = a ^ b;
+    carry = (a & b) | (u & c);
+    sum = u ^ c;
+}
 
 template <int VEC, bool UNIQ, int HT>   // HT: compile-time num_hash (0 = run-time)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 query_counts_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t W, uint32_t N, uint32_t k, uint32_t H,
                     ModS mods, const Slot* __restrict__ table, const uint32_t* __restrict__ unit_group,
                     const uint64_t* __restrict__ unit_slot0, const uint32_t* __restrict__ unit_nslots,
@@ -362,65 +377,85 @@ query_counts_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t W, 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     const uint32_t vpr = Wp / VEC;                      // vectors per row (Wp is a multiple of VEC)
-    uint32_t lpk = 1;                                   // lanes per k-mer: 1,2,4,..,32 (>= vectors per row)
-    while (lpk < vpr && lpk < 32) lpk <<= 1;
+    // lanes per k-mer: the unique-hit variant reduces over the group with xor-shuffles and needs a power of
+    // two; otherwise any divisor layout works (a 160-byte row takes 10 lanes, 3 k-mers per warp pass)
+    uint32_t lpk = 1;
+    if (UNIQ) { while (lpk < vpr && lpk < 32) lpk <<= 1; }
+    else lpk = vpr < 32 ? vpr : 32;
     const uint32_t kpw = 32 / lpk;                      // k-mers per warp pass
     const uint32_t sub = lane / lpk, colv = lane % lpk;
+    const bool lane_on = sub < kpw;                     // lanes left over by a non-power-of-two layout idle
     const uint32_t ncb = (vpr + 31) / 32;               // column blocks of 32 vectors
+    const uint32_t hh = HT ? (uint32_t)HT : H;
+    const uint32_t stride = 8 * kpw;                    // k-mers per block pass
     uint32_t total_n = 0;
     for (uint32_t cb = 0; cb < ncb; cb++) {
         const uint32_t vcol = cb * 32 + colv;
-        const bool colok = vcol < vpr;
+        const bool colok = lane_on && vcol < vpr;
         uint32_t pl[VEC][QC_PLANES];
 #pragma unroll
         for (int v = 0; v < VEC; v++)
 #pragma unroll
             for (int p = 0; p < QC_PLANES; p++) pl[v][p] = 0;
         uint32_t seen = 0;
+        const uint32_t* colbase = rows + (size_t)vcol * VEC;
         for (uint32_t c0 = 0; c0 < item_nslots; c0 += QUERY_CHUNK) {
             __syncthreads();   // previous chunk's lists are dead
             const uint32_t n = unit_collect_and_hash(u, table, item_slot0 + c0, min((uint32_t)QUERY_CHUNK, item_nslots - c0),
                                                      filt, k, H, mods);
             if (cb == 0) total_n += n;
-            // QC_UNR k-mers per warp iteration: all their row loads are issued before any is consumed
-            const uint32_t* colbase = rows + vcol * VEC;
-            const uint32_t hh = HT ? (uint32_t)HT : H;
-            for (uint32_t i0 = warp * kpw + sub; i0 < n + sub; i0 += 8 * kpw * QC_UNR) {
-                uint32_t x[QC_UNR][VEC];
+            // QC_TREE k-mers per lane group and iteration, in parts of QC_PART k-mers whose row loads (<= 8 per
+            // lane) are all issued before any is consumed
+            constexpr int QC_PART = (HT == 0 || HT > 2) ? 2 : 4;
+            for (uint32_t i0 = warp * kpw + sub; i0 < n + sub; i0 += stride * QC_TREE) {
+                uint32_t x[QC_TREE][VEC];
 #pragma unroll
-                for (int un = 0; un < QC_UNR; un++) {
-                    const uint32_t i = i0 + un * 8 * kpw;
+                for (int half = 0; half < QC_TREE / QC_PART; half++) {
+                    RowVec<VEC> r[QC_PART][HT ? HT : 1];
 #pragma unroll
-                    for (int v = 0; v < VEC; v++) x[un][v] = 0;
-                    if (i < n && colok) {
-                        const uint32_t* rid = u.rowid + i * hh;
-                        RowVec<VEC> r0;
-                        r0.load(colbase + (uint64_t)rid[0] * Wp);
-#pragma unroll
-                        for (int v = 0; v < VEC; v++) x[un][v] = r0.w[v];
+                    for (int un = 0; un < QC_PART; un++) {
+                        const uint32_t i = i0 + (half * QC_PART + un) * stride;
+                        const bool on = i < n && colok;
                         if (HT) {
+                            const uint32_t* rid = u.rowid + (on ? i : 0u) * HT;
 #pragma unroll
-                            for (int h = 1; h < (HT ? HT : 1); h++) {
-                                RowVec<VEC> r;
-                                r.load(colbase + (uint64_t)rid[h] * Wp);
+                            for (int h = 0; h < (HT ? HT : 1); h++) {
+                                if (on) r[un][h].load(colbase + (size_t)rid[h] * Wp);
+                                else {
 #pragma unroll
-                                for (int v = 0; v < VEC; v++) x[un][v] &= r.w[v];
+                                    for (int v = 0; v < VEC; v++) r[un][h].w[v] = 0;
+                                }
                             }
                         } else {
-                            for (uint32_t h = 1; h < hh; h++) {
-                                RowVec<VEC> r;
-                                r.load(colbase + (uint64_t)rid[h] * Wp);
 #pragma unroll
-                                for (int v = 0; v < VEC; v++) x[un][v] &= r.w[v];
+                            for (int v = 0; v < VEC; v++) r[un][0].w[v] = 0;
+                            if (on) {
+                                const uint32_t* rid = u.rowid + i * hh;
+                                r[un][0].load(colbase + (size_t)rid[0] * Wp);
+                                for (uint32_t h = 1; h < hh; h++) {
+                                    RowVec<VEC> t;
+                                    t.load(colbase + (size_t)rid[h] * Wp);
+#pragma unroll
+                                    for (int v = 0; v < VEC; v++) r[un][0].w[v] &= t.w[v];
+                                }
                             }
                         }
                     }
-                }
 #pragma unroll
-                for (int un = 0; un < QC_UNR; un++) {
-                    if (UNIQ) {
+                    for (int un = 0; un < QC_PART; un++)
+#pragma unroll
+                        for (int v = 0; v < VEC; v++) {
+                            uint32_t a = r[un][0].w[v];
+#pragma unroll
+                            for (int h = 1; h < (HT ? HT : 1); h++) a &= r[un][h].w[v];
+                            x[half * QC_PART + un][v] = a;
+                        }
+                }
+                if (UNIQ) {
+#pragma unroll
+                    for (int un = 0; un < QC_TREE; un++) {
                         // exactly one accession hit over the whole row (batch_search_pe.rs:75-82)
-                        const uint32_t i = i0 + un * 8 * kpw;
+                        const uint32_t i = i0 + un * stride;
                         uint32_t pc = 0;
 #pragma unroll
                         for (int v = 0; v < VEC; v++) pc += __popc(x[un][v]);
@@ -438,20 +473,26 @@ query_counts_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t W, 
                             }
                         }
                     }
-                    // carry-save add of x into the bit planes
+                }
+                // Harley-Seal: eight inputs -> ones/twos/fours planes + one weight-8 carry per word
 #pragma unroll
-                    for (int v = 0; v < VEC; v++) {
-                        uint32_t carry = x[un][v];
+                for (int v = 0; v < VEC; v++) {
+                    uint32_t t2a, t2b, t4a, t4b, c8;
+                    csa(t2a, pl[v][0], pl[v][0], x[0][v], x[1][v]);
+                    csa(t2b, pl[v][0], pl[v][0], x[2][v], x[3][v]);
+                    csa(t4a, pl[v][1], pl[v][1], t2a, t2b);
+                    csa(t2a, pl[v][0], pl[v][0], x[4][v], x[5][v]);
+                    csa(t2b, pl[v][0], pl[v][0], x[6][v], x[7][v]);
+                    csa(t4b, pl[v][1], pl[v][1], t2a, t2b);
+                    csa(c8, pl[v][2], pl[v][2], t4a, t4b);
 #pragma unroll
-                        for (int p = 0; p < QC_PLANES; p++) {
-                            uint32_t t2 = pl[v][p] & carry;
-                            pl[v][p] ^= carry;
-                            carry = t2;
-                            if (carry == 0) break;
-                        }
+                    for (int p = 3; p < QC_PLANES; p++) {
+                        const uint32_t t = pl[v][p] & c8;
+                        pl[v][p] ^= c8;
+                        c8 = t;
                     }
                 }
-                seen += QC_UNR;
+                seen += QC_TREE;
             }
         }
         // flush: planes -> shared counters of this column block (the 8 warps and 32/lpk sub-groups hold
@@ -549,7 +590,7 @@ int launch_query_counts(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, con
         attr_set = true;
     }
     ModS mods = make_mods(idx->S);
-    const uint32_t vec = idx->Wp >= 128 ? 4 : idx->Wp >= 64 ? 2 : 1;
+    const uint32_t vec = idx->Wp >= 4 ? 4 : idx->Wp;      // Wp is 1, 2 or a multiple of 4
     const bool inline_uniq = want_uniq && idx->Wp <= 32 * vec;   // one column block: the warp sees the whole row
     {
     ProfScope ps(ctx, st, KID_QUERY_COUNTS);
@@ -560,9 +601,9 @@ int launch_query_counts(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, con
 #define CID_QC_LAUNCH(VEC, UQ)                                                                                         \
     do { if (idx->H == 2) CID_QC_LAUNCH_H(VEC, UQ, 2); else if (idx->H == 4) CID_QC_LAUNCH_H(VEC, UQ, 4);              \
          else CID_QC_LAUNCH_H(VEC, UQ, 0); } while (0)
-    // VEC words per lane: keep a whole warp on one k-mer (coalesced row read, fewest partial counters)
-    if (idx->Wp >= 128) { if (inline_uniq) CID_QC_LAUNCH(4, true); else CID_QC_LAUNCH(4, false); }
-    else if (idx->Wp >= 64) { if (inline_uniq) CID_QC_LAUNCH(2, true); else CID_QC_LAUNCH(2, false); }
+    // VEC words per lane: 128-bit loads whenever a row is 16-byte aligned (several k-mers per warp instruction)
+    if (vec == 4) { if (inline_uniq) CID_QC_LAUNCH(4, true); else CID_QC_LAUNCH(4, false); }
+    else if (vec == 2) { if (inline_uniq) CID_QC_LAUNCH(2, true); else CID_QC_LAUNCH(2, false); }
     else { if (inline_uniq) CID_QC_LAUNCH(1, true); else CID_QC_LAUNCH(1, false); }
 #undef CID_QC_LAUNCH
 #undef CID_QC_LAUNCH_H

@@ -69,6 +69,12 @@ struct cid_ctx {
     struct cid_readid_pipe* pipe = nullptr;
     uint64_t opt_readid_chunk = 0;   // reads per pipeline chunk (0 = automatic)
     int opt_host_threads = 0;        // host threads for the vote (0 = all cores)
+    // device-pointer read_id (cid_read_id_batch_dev): chunks alternate over internal streams forked from /
+    // joined to the caller's stream, so the DRAM-access-bound vote kernel of one chunk runs under the
+    // issue-bound kmerize/order kernels of the next
+    int opt_readid_streams = 2;
+    cudaStream_t aux[2] = {nullptr, nullptr};
+    cudaEvent_t aux_fork = nullptr, aux_join[2] = {nullptr, nullptr};
 };
 
 struct cid_index {
@@ -94,6 +100,7 @@ enum {
     ERRF_STARTS_OVERFLOW = 1u << 1,
     ERRF_LIST_OVERFLOW = 1u << 2,
     ERRF_READ_TOO_LONG = 1u << 3,
+    ERRF_STRING_NONACGT = 1u << 4, // kmerize_string window with a byte outside ACGTacgt (cannot be 2-bit packed)
 };
 
 int check_err_flags(cid_ctx* ctx, cudaStream_t st);   // syncs the stream

@@ -370,16 +370,51 @@ int cid_read_id_batch_dev(cid_index* ix, const char* d_bases, const char* d_qual
     CID_CUDA(cudaSetDevice(ctx->device));
     cid_readid_params pp;
     default_readid_params(pp, p, ix->N);
-    const uint64_t cap = std::min<uint64_t>(std::max<uint64_t>(nreads, 1), 1u << 20);
+    cudaStream_t user = (cudaStream_t)stream;
+    const int nst = (ctx->opt_readid_streams >= 2 && nreads >= 4 * 32768) ? 2 : 1;
+    if (nst == 1) {
+        const uint64_t cap = std::min<uint64_t>(std::max<uint64_t>(nreads, 1), 1u << 20);
+        size_t eb, ob, nb;
+        readid_scratch_bytes(ix, h_max_read_bases, h_max_kmers, cap, &eb, &ob, &nb);
+        CID_TRY(ctx->scratch[16].ensure(eb));
+        CID_TRY(ctx->scratch[17].ensure(ob));
+        CID_TRY(ctx->scratch[18].ensure(nb));
+        ReadIdScratch scr{ctx->scratch[16].as<uint32_t>(), ctx->scratch[17].as<uint16_t>(), ctx->scratch[18].as<uint32_t>(), cap};
+        return readid_run(ix, user, (const uint8_t*)d_bases, (const uint8_t*)d_quals, d_seq_offs, d_read_offs, 0,
+                          nreads, h_max_read_bases, h_max_kmers, pp, scr, d_n_set, d_flags, d_rep_n, d_rep_colour, d_rep_count,
+                          0, nullptr, nullptr, nullptr);
+    }
+    // fork: chunks alternate over two internal streams; join back into the caller's stream
+    for (int i = 0; i < 2; i++) {
+        if (!ctx->aux[i]) CID_CUDA(cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking));
+        if (!ctx->aux_join[i]) CID_CUDA(cudaEventCreateWithFlags(&ctx->aux_join[i], cudaEventDisableTiming));
+    }
+    if (!ctx->aux_fork) CID_CUDA(cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming));
+    const uint64_t chunk = std::min<uint64_t>(131072, std::max<uint64_t>(32768, (nreads + 7) / 8));
     size_t eb, ob, nb;
-    readid_scratch_bytes(ix, h_max_read_bases, h_max_kmers, cap, &eb, &ob, &nb);
-    CID_TRY(ctx->scratch[16].ensure(eb));
-    CID_TRY(ctx->scratch[17].ensure(ob));
-    CID_TRY(ctx->scratch[18].ensure(nb));
-    ReadIdScratch scr{ctx->scratch[16].as<uint32_t>(), ctx->scratch[17].as<uint16_t>(), ctx->scratch[18].as<uint32_t>(), cap};
-    return readid_run(ix, (cudaStream_t)stream, (const uint8_t*)d_bases, (const uint8_t*)d_quals, d_seq_offs, d_read_offs, 0,
-                      nreads, h_max_read_bases, h_max_kmers, pp, scr, d_n_set, d_flags, d_rep_n, d_rep_colour, d_rep_count,
-                      0, nullptr, nullptr, nullptr);
+    readid_scratch_bytes(ix, h_max_read_bases, h_max_kmers, chunk, &eb, &ob, &nb);
+    for (int i = 0; i < 2; i++) {
+        CID_TRY(ctx->scratch[16 + 3 * i].ensure(eb));
+        CID_TRY(ctx->scratch[17 + 3 * i].ensure(ob));
+        CID_TRY(ctx->scratch[18 + 3 * i].ensure(nb));
+    }
+    CID_CUDA(cudaEventRecord(ctx->aux_fork, user));
+    for (int i = 0; i < 2; i++) CID_CUDA(cudaStreamWaitEvent(ctx->aux[i], ctx->aux_fork, 0));
+    int rc = CID_OK;
+    uint64_t c = 0;
+    for (uint64_t r0 = 0; r0 < nreads && rc == CID_OK; r0 += chunk, c++) {
+        const int i = (int)(c & 1);
+        ReadIdScratch scr{ctx->scratch[16 + 3 * i].as<uint32_t>(), ctx->scratch[17 + 3 * i].as<uint16_t>(),
+                          ctx->scratch[18 + 3 * i].as<uint32_t>(), chunk};
+        rc = readid_run(ix, ctx->aux[i], (const uint8_t*)d_bases, (const uint8_t*)d_quals, d_seq_offs, d_read_offs, r0,
+                        std::min(chunk, nreads - r0), h_max_read_bases, h_max_kmers, pp, scr, d_n_set, d_flags, d_rep_n,
+                        d_rep_colour, d_rep_count, 0, nullptr, nullptr, nullptr);
+    }
+    for (int i = 0; i < 2; i++) {       // always join, also after an error, so the caller's stream stays ordered
+        cudaEventRecord(ctx->aux_join[i], ctx->aux[i]);
+        cudaStreamWaitEvent(user, ctx->aux_join[i], 0);
+    }
+    return rc;
 }
 
 int cid_read_id_batch(cid_index* ix, const char* bases, const char* quals, const uint64_t* seq_offs, uint64_t nseq,

@@ -18,7 +18,7 @@ i32p = C.POINTER(C.c_int32)
 vp = C.c_void_p
 
 CID_OK, CID_E_INVALID, CID_E_CUDA, CID_E_NOMEM, CID_E_UNSUPPORTED, CID_E_REF_PANIC, CID_E_CAPACITY = 0, -1, -2, -3, -4, -5, -6
-CID_SEQ_FASTA, CID_SEQ_FASTQ = 0, 1
+CID_SEQ_FASTA, CID_SEQ_FASTQ, CID_SEQ_STRING = 0, 1, 2
 
 
 class ReadIdParams(C.Structure):
@@ -52,6 +52,7 @@ SIGNATURES = {
                                    u64p, u64p, u64p, i64p]),
     "cid_query_counts_dev": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_uint64, vp, u64p, u64p, C.c_uint64, C.c_int, vp, vp, vp]),
     "cid_query_perfect": (C.c_int, [vp, vp, u64p, C.c_uint64, u64p, C.c_uint64, u32p, u8p, u64p]),
+    "cid_query_perfect_mf": (C.c_int, [vp, vp, u64p, C.c_uint64, u32p, u8p, u64p]),
     "cid_read_id_batch": (C.c_int, [vp, vp, vp, u64p, C.c_uint64, u64p, C.c_uint64, C.POINTER(ReadIdParams), u32p, u32p,
                                     u32p, u32p, u32p]),
     "cid_read_id_batch_dev": (C.c_int, [vp, vp, vp, vp, C.c_uint64, C.c_uint64, vp, C.c_uint64, C.c_uint32, C.c_uint32,

@@ -42,7 +42,9 @@ enum {
 /* k-mer extraction semantics (kmer.rs) */
 enum {
     CID_SEQ_FASTA = 0, /* kmerize_vector  kmer.rs:87-125 : has_no_n, compare raw case, then uppercase */
-    CID_SEQ_FASTQ = 1  /* kmers_from_fq_qual / kmers_fq_pe_qual kmer.rs:461-510,581-655 : has_no_n, raw case */
+    CID_SEQ_FASTQ = 1, /* kmers_from_fq_qual / kmers_fq_pe_qual kmer.rs:461-510,581-655 : has_no_n, raw case */
+    CID_SEQ_STRING = 2 /* kmerize_string kmer.rs:271-299 (-s -m): NO has_no_n, compare raw case, then uppercase.
+                          A k-mer holding a byte outside ACGTacgt cannot be packed: CID_E_UNSUPPORTED. */
 };
 
 int cid_version(void);
@@ -122,6 +124,12 @@ int cid_query_counts_dev(cid_index* idx, const char* d_bases, const uint64_t* d_
 int cid_query_perfect(cid_index* idx, const char* bases, const uint64_t* seq_offs, uint64_t nseq,
                       const uint64_t* query_offs, uint64_t nq, uint32_t* and_rows, uint8_t* status,
                       uint64_t* n_kmers);
+
+/* perfect_search.rs:62-120 batch_search_mf (-s -m): one query per FASTA RECORD (sequence s), k-mers by
+ * kmer.rs:271-299 kmerize_string.  status[s]: 0 = AND valid, 1 = "No perfect hits!", 2 = "Warning! no
+ * kmers in query" (record shorter than k, kmer.rs:275-276).  and_rows[nseq*row_words], n_kmers[nseq]. */
+int cid_query_perfect_mf(cid_index* idx, const char* bases, const uint64_t* seq_offs, uint64_t nseq,
+                         uint32_t* and_rows, uint8_t* status, uint64_t* n_kmers);
 
 /* ---- read_id: read_id_mt_pe.rs:282-363 parallel_vec (m == 0) -------------------------------
  * One read = sequences [read_offs[r], read_offs[r+1]) (1 or 2 mates).  If `quals` is non-NULL it

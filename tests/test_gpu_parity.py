@@ -141,6 +141,37 @@ def test_perfect_search(oracle, ctx, N, k, S, H):
     assert (o["status"] == 0).sum() >= 10
 
 
+def test_perfect_search_multifasta_records(oracle, ctx):
+    """-s -m: perfect_search.rs:62-120 batch_search_mf over kmer.rs:271-299 kmerize_string (one query per record)."""
+    rng = _rng(451)
+    N, k, S, H = 70, 21, 300_007, 2
+    genomes, oix, gix = _index_pair(oracle, ctx, rng, N, k, S, H, glen=8000)
+    recs = []
+    for i in range(40):
+        g = genomes[int(rng.integers(0, N))]
+        s = int(rng.integers(0, len(g) - 1500))
+        q = g[s:s + int(rng.integers(k, 1400))]
+        if i % 4 == 3:
+            q = synth.mutate(rng, q, 0.01)
+        if i % 5 == 1:
+            q = q.lower()                      # raw-case compare, then to_uppercase (kmer.rs:280-283)
+        recs.append(q)
+    recs.append(b"ACGTAC")                     # shorter than k -> None -> "Warning! no kmers in query"
+    recs.append(genomes[3][100:100 + k])       # exactly one k-mer
+    recs.append(synth.rand_seq(rng, 700))
+    o = oix.query_perfect(recs, mf=True)
+    g = gix.query_perfect_mf(recs)
+    assert np.array_equal(g["status"], o["status"])
+    assert np.array_equal(g["n_kmers"], o["n_kmers"])
+    assert np.array_equal(g["and_rows"], o["and_rows"])
+    assert (o["status"] == 0).sum() >= 10 and (o["status"] == 2).sum() == 1
+    # kmerize_string has no has_no_n test: an N inside a record is part of its k-mers, which the 2-bit
+    # device path cannot represent -> refused loudly, never silently skipped
+    with pytest.raises(cb.lib.CidError) as ei:
+        gix.query_perfect_mf([genomes[0][:200] + b"N" + genomes[0][201:400]])
+    assert ei.value.code == cb.lib.CID_E_UNSUPPORTED
+
+
 def _readid_compare(oracle, oix, gix, reads, **kw):
     okw = dict(kw)
     o = oix.read_id_batch(reads, order_cap=600, **okw)
