@@ -43,7 +43,7 @@ void PinBuf::release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 
 static const char* kKernelNames[KID_COUNT] = {"kmerize_insert", "region_histogram", "region_to_bloom", "transpose_bitsets",
                                               "rownz", "query_counts", "query_uniq_wide", "query_perfect",
-                                              "readid_kmerize", "readid_sched", "readid_order", "readid_vote", "readid_classify", "table_clear", "other"};
+                                              "readid_kmerize", "readid_sched", "readid_order", "readid_vote", "readid_classify", "table_clear", "other", "query_hash"};
 static cudaEvent_t prof_event(cid_ctx* c) {
     if (!c->prof_pool.empty()) { cudaEvent_t e = c->prof_pool.back(); c->prof_pool.pop_back(); return e; }
     cudaEvent_t e; cudaEventCreate(&e); return e;
@@ -258,6 +258,7 @@ int cid_ctx_set_option(cid_ctx* c, const char* name, int64_t value) {
     if (!c || !name) { set_error("cid_ctx_set_option: null argument"); return CID_E_INVALID; }
     if (!strcmp(name, "readid_chunk_reads")) { c->opt_readid_chunk = value > 0 ? (uint64_t)value : 0; return CID_OK; }
     if (!strcmp(name, "readid_streams")) { c->opt_readid_streams = value >= 2 ? 2 : 1; return CID_OK; }
+    if (!strcmp(name, "query_fused")) { c->opt_query_fused = value != 0; return CID_OK; }
     if (!strcmp(name, "host_threads")) { c->opt_host_threads = value > 0 ? (int)value : 0; return CID_OK; }
     set_error("cid_ctx_set_option: unknown option '%s'", name);
     return CID_E_INVALID;
@@ -561,7 +562,7 @@ int cid_query_counts(cid_index* ix, const char* bases, const uint64_t* seq_offs,
         CID_CUDA(cudaMemsetAsync(ctx->scratch[11].p, 0, bq * 8, st));
         CID_CUDA(cudaMemsetAsync(ctx->scratch[13].p, 0, 16, st));
         CID_TRY(launch_query_counts(ctx, st, ix, qp.d_table, qp.d_unit_group, qp.d_unit_slot0, qp.d_unit_nslots,
-                                    qp.qu.group.size(), ctx->scratch[7].as<int64_t>(), ctx->scratch[10].as<uint32_t>(),
+                                    qp.qu.group.size(), qp.gr.total_slots, ctx->scratch[7].as<int64_t>(), ctx->scratch[10].as<uint32_t>(),
                                     ctx->scratch[11].as<unsigned long long>(), want_uniq, ctx->scratch[12].as<uint32_t>(),
                                     uniq_cap, ctx->scratch[13].as<uint32_t>()));
         CID_CUDA(cudaMemcpyAsync(counts + q0 * N, ctx->scratch[10].p, bq * N * 4, cudaMemcpyDeviceToHost, st));
@@ -607,7 +608,7 @@ int cid_query_counts_dev(cid_index* ix, const char* d_bases, const uint64_t* d_s
         QueryPlan qp;
         CID_TRY(query_front(ix, st, (const uint8_t*)d_bases, d_seq_offs, h_seq_offs, h_query_offs, q0, q1, seq_mode, qp));
         CID_TRY(launch_query_counts(ctx, st, ix, qp.d_table, qp.d_unit_group, qp.d_unit_slot0, qp.d_unit_nslots,
-                                    qp.qu.group.size(), nullptr, d_counts + q0 * N,
+                                    qp.qu.group.size(), qp.gr.total_slots, nullptr, d_counts + q0 * N,
                                     (unsigned long long*)d_num_kmers + q0, false, nullptr, 0, nullptr));
     }
     return CID_OK;

@@ -345,7 +345,7 @@ __device__ __forceinline__ uint32_t unit_collect_and_hash(const UnitSmem& u, con
 // item: eight k-mers at a time go through a Harley-Seal carry-save tree (ones/twos/fours planes),
 // and only the weight-8 carry ripples into the upper planes, so counting costs < 4 logic ops per
 // k-mer and word instead of one atomic per set bit.
-constexpr int QC_PLANES = 11;   // a lane sees at most QUERY_ITEM_SLOTS/8 = 2048 k-mers per item; counts < 2^11
+constexpr int QC_PLANES = 12;   // a lane group sees at most QUERY_ITEM_SLOTS/8 = 2048 k-mers per item; counts <= 2^11
 constexpr int QC_TREE = 8;      // k-mers per lane group and carry-save tree step
 
 template <int VEC> struct RowVec;
@@ -535,6 +535,221 @@ query_counts_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t W, 
     if (tid == 0 && total_n) atomicAdd(&num_kmers[g], (unsigned long long)total_n);
 }
 
+// ================================================================= query_hash + query_gather (streaming row gather)
+// The fast path for 16-byte-aligned rows without unique-hit summaries (-g gene search, the column
+// shards of C5).  query_hash compacts and hashes a work item's k-mers once and leaves their row
+// indices in HBM (H x 4 bytes per k-mer, ~3 % of the row bytes they address); query_gather is then
+// a pure streaming kernel with no block-level phase changes.  Row reads are cp.async (LDGSTS) 16-byte
+// copies into a warp-private ring in shared memory -- every lane copies exactly the bytes it later
+// consumes, so no cross-lane synchronisation is needed -- which keeps 64 KB of row reads in flight
+// per CTA without holding registers, enough to cover DRAM latency at random-row access rates.
+__global__ void __launch_bounds__(256)
+query_hash_kernel(const Slot* __restrict__ table, const uint32_t* __restrict__ unit_group,
+                  const uint64_t* __restrict__ unit_slot0, const uint32_t* __restrict__ unit_nslots,
+                  const long long* __restrict__ filter, uint32_t k, uint32_t H, ModS mods, uint32_t* __restrict__ rid_out,
+                  uint32_t* __restrict__ unit_n, unsigned long long* __restrict__ num_kmers) {
+    __shared__ uint32_t lut[256];
+    __shared__ unsigned long long keys[QUERY_CHUNK];
+    __shared__ uint32_t s_n;
+    const int tid = threadIdx.x;
+    lut4_init(lut, tid, 256);
+    const uint32_t g = unit_group[blockIdx.x];
+    const uint64_t slot0 = unit_slot0[blockIdx.x];
+    const uint32_t nslots = unit_nslots[blockIdx.x];
+    const long long filt = filter ? filter[g] : 0ll;
+    uint32_t total = 0;
+    for (uint32_t c0 = 0; c0 < nslots; c0 += QUERY_CHUNK) {
+        __syncthreads();
+        if (tid == 0) s_n = 0;
+        __syncthreads();
+        const uint32_t cn = min((uint32_t)QUERY_CHUNK, nslots - c0);
+        for (uint32_t s = tid; s < cn; s += 256) {
+            const Slot v = table[slot0 + c0 + s];
+            if (v.key != CID_EMPTY_KEY && (long long)v.count > filt) keys[atomicAdd(&s_n, 1u)] = v.key;
+        }
+        __syncthreads();
+        const uint32_t n = s_n;
+        // survivors so far <= slots scanned so far, so the compact list never leaves the item's slot range
+        for (uint32_t i = tid; i < n; i += 256) {
+            const HashIn in = hashin_from_key(lut, keys[i], k);
+            uint32_t* out = rid_out + (slot0 + total + i) * H;
+            for (uint32_t h = 0; h < H; h++) out[h] = (uint32_t)mod_s(xxh3_kmer(in, k, h), mods);
+        }
+        total += n;
+    }
+    if (tid == 0) {
+        unit_n[blockIdx.x] = total;
+        if (total) atomicAdd(&num_kmers[g], (unsigned long long)total);
+    }
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gptr) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NPEND> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NPEND) : "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+    return v;
+}
+
+constexpr int QG_WARPS = 8;
+constexpr int QG_RING_BYTES = 64 * 1024;            // per CTA
+template <int HT> struct QGCfg {
+    static constexpr int STAGE = HT * 512;          // bytes per warp and stage: 32 lanes x 16 B x HT rows
+    static constexpr int D = QG_RING_BYTES / QG_WARPS / STAGE;   // stages per warp: 8 (H=2), 4 (H=4)
+};
+
+template <int HT>
+__global__ void __launch_bounds__(QG_WARPS * 32, 2)
+query_gather_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t N, const uint32_t* __restrict__ rid,
+                    const uint32_t* __restrict__ unit_group, const uint64_t* __restrict__ unit_slot0,
+                    const uint32_t* __restrict__ unit_n, uint32_t* __restrict__ counts) {
+    using Cfg = QGCfg<HT>;
+    constexpr int D = Cfg::D;
+    static_assert(D >= 2 && 8 % D == 0, "ring depth must divide the tree width");
+    extern __shared__ __align__(16) uint8_t dsm[];
+    uint32_t* cnt = (uint32_t*)(dsm + QG_RING_BYTES);                 // [4096] per-accession counters
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t n = unit_n[blockIdx.x];
+    if (n == 0) return;
+    const uint32_t g = unit_group[blockIdx.x];
+    const uint32_t* myrid = rid + unit_slot0[blockIdx.x] * HT;
+
+    const uint32_t vpr = Wp >> 2;                         // 16-byte vectors per row (<= 32)
+    const uint32_t kpw = 32 / vpr;                        // k-mers per warp step
+    const uint32_t sub = lane / vpr, colv = lane % vpr;
+    const bool lane_on = sub < kpw;
+    const uint32_t IT = 32 / kpw;                         // steps served by one coalesced load of row indices
+    const uint32_t BK = kpw * IT;                         // k-mers per such load (<= 32)
+    // contiguous k-mer range of this warp, a multiple of kpw long
+    const uint32_t per = ((n + QG_WARPS * kpw - 1) / (QG_WARPS * kpw)) * kpw;
+    const uint32_t lo = min(n, warp * per), hi = min(n, lo + per);
+    const uint32_t T = (hi - lo + kpw - 1) / kpw;         // steps of this warp
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(dsm) + warp * (D * Cfg::STAGE) + lane * 16;
+    const uint32_t* colbase = rows + colv * 4;
+
+    uint32_t pl[4][QC_PLANES];
+#pragma unroll
+    for (int v = 0; v < 4; v++)
+#pragma unroll
+        for (int p = 0; p < QC_PLANES; p++) pl[v][p] = 0;
+
+    // row indices of k-mer lo + BK*b + lane (batch b), double-buffered in registers
+    uint32_t cur[HT], nxt[HT];
+    auto load_batch = [&](uint32_t b, uint32_t* dst) {
+        const uint32_t i = lo + b * BK + lane;
+        const bool ok = (uint32_t)lane < BK && i < hi;
+#pragma unroll
+        for (int h = 0; h < HT; h++) dst[h] = 0;
+        if (ok) {
+            if (HT == 2) { const uint2 v = __ldg((const uint2*)(myrid + (size_t)i * 2)); dst[0] = v.x; dst[1] = v.y; }
+            else if (HT == 4) { const uint4 v = __ldg((const uint4*)(myrid + (size_t)i * 4)); dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w; }
+            else {
+#pragma unroll
+                for (int h = 0; h < HT; h++) dst[h] = __ldg(myrid + (size_t)i * HT + h);
+            }
+        }
+    };
+    load_batch(0, cur);
+    load_batch(1, nxt);
+    uint32_t t_issue = 0, it_issue = 0, b_issue = 0;      // next step to issue, its position in its batch, its batch
+    auto issue = [&](int slot) {
+        if (t_issue < T) {
+            if (it_issue == IT) {
+                it_issue = 0; b_issue++;
+#pragma unroll
+                for (int h = 0; h < HT; h++) cur[h] = nxt[h];
+                load_batch(b_issue + 1, nxt);
+            }
+            const uint32_t src = min(kpw * it_issue + sub, 31u);
+            const bool valid = lane_on && lo + kpw * t_issue + sub < hi;
+#pragma unroll
+            for (int h = 0; h < HT; h++) {
+                const uint32_t r = __shfl_sync(0xffffffffu, cur[h], src);
+                if (valid) cp_async16(ring + slot * Cfg::STAGE + h * 512, colbase + (size_t)r * Wp);
+            }
+            t_issue++; it_issue++;
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int s = 0; s < D - 1; s++) issue(s);
+    for (uint32_t t0 = 0; t0 < T; t0 += 8) {
+        uint32_t x[8][4];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            issue((u + D - 1) % D);
+            cp_async_wait<D - 1>();
+            const bool valid = lane_on && lo + kpw * (t0 + u) + sub < hi;
+            uint4 a = make_uint4(0, 0, 0, 0);
+            if (valid) {
+                a = lds128(ring + (u % D) * Cfg::STAGE);
+#pragma unroll
+                for (int h = 1; h < HT; h++) {
+                    const uint4 b = lds128(ring + (u % D) * Cfg::STAGE + h * 512);
+                    a.x &= b.x; a.y &= b.y; a.z &= b.z; a.w &= b.w;
+                }
+            }
+            x[u][0] = a.x; x[u][1] = a.y; x[u][2] = a.z; x[u][3] = a.w;
+        }
+        // Harley-Seal: eight inputs -> ones/twos/fours planes + one weight-8 carry per word
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            uint32_t t2a, t2b, t4a, t4b, c8;
+            csa(t2a, pl[v][0], pl[v][0], x[0][v], x[1][v]);
+            csa(t2b, pl[v][0], pl[v][0], x[2][v], x[3][v]);
+            csa(t4a, pl[v][1], pl[v][1], t2a, t2b);
+            csa(t2a, pl[v][0], pl[v][0], x[4][v], x[5][v]);
+            csa(t2b, pl[v][0], pl[v][0], x[6][v], x[7][v]);
+            csa(t4b, pl[v][1], pl[v][1], t2a, t2b);
+            csa(c8, pl[v][2], pl[v][2], t4a, t4b);
+#pragma unroll
+            for (int p = 3; p < QC_PLANES; p++) {
+                const uint32_t t = pl[v][p] & c8;
+                pl[v][p] ^= c8;
+                c8 = t;
+            }
+        }
+    }
+    cp_async_wait<0>();
+    // flush: planes -> shared counters (warps and sub-groups hold partial counts of the same columns)
+    // -> one global atomic per non-zero accession
+    __syncthreads();
+    for (int i = tid; i < 4096; i += QG_WARPS * 32) cnt[i] = 0;
+    __syncthreads();
+    if (lane_on && T) {
+        const int depth = 32 - __clz(((T + 7) & ~7u));     // planes that can be non-zero
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            const uint32_t cbase = (colv * 4 + v) * 32;
+#pragma unroll
+            for (int nb = 0; nb < 8; nb++) {
+                uint32_t lo8 = 0, hi8 = 0;
+#pragma unroll
+                for (int p = 0; p < QC_PLANES; p++) {
+                    if (p >= depth) break;
+                    const uint32_t sp = (((pl[v][p] >> (4 * nb)) & 0xFu) * 0x00204081u) & 0x01010101u;
+                    if (p < 8) lo8 += sp << p; else hi8 += sp << (p - 8);
+                }
+                if (lo8 | hi8) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const uint32_t val = ((lo8 >> (8 * q)) & 0xFFu) | (((hi8 >> (8 * q)) & 0xFFu) << 8);
+                        if (val) atomicAdd(&cnt[cbase + 4 * nb + q], val);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < 4096; i += QG_WARPS * 32) {
+        const uint32_t val = cnt[i];
+        if (val && (uint32_t)i < N) atomicAdd(&counts[(uint64_t)g * N + i], val);
+    }
+}
+
 // Wide-row unique-hit pass (Wp > 32): one warp per k-mer sums popcounts over the whole row.
 __global__ void __launch_bounds__(256)
 query_uniq_wide_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t k, uint32_t H, ModS mods,
@@ -574,9 +789,44 @@ query_uniq_wide_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t 
 
 int launch_query_counts(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, const void* d_table,
                         const uint32_t* d_unit_group, const uint64_t* d_unit_slot0, const uint32_t* d_unit_nslots,
-                        uint64_t nunits, const int64_t* d_filter, uint32_t* d_counts, unsigned long long* d_num_kmers,
-                        bool want_uniq, uint32_t* d_uniq_list, uint32_t uniq_cap, uint32_t* d_uniq_n) {
+                        uint64_t nunits, uint64_t total_slots, const int64_t* d_filter, uint32_t* d_counts,
+                        unsigned long long* d_num_kmers, bool want_uniq, uint32_t* d_uniq_list, uint32_t uniq_cap,
+                        uint32_t* d_uniq_n) {
     if (nunits == 0) return CID_OK;
+    // streaming path: 16-byte-aligned rows of at most 512 bytes, no unique-hit summaries
+    if (!want_uniq && idx->Wp >= 4 && idx->Wp <= 128 && (idx->H == 2 || idx->H == 4) && !ctx->opt_query_fused) {
+        CID_TRY(ctx->scratch[14].ensure(total_slots * idx->H * 4 + 64));
+        CID_TRY(ctx->scratch[15].ensure(nunits * 4 + 64));
+        uint32_t* d_rid = ctx->scratch[14].as<uint32_t>();
+        uint32_t* d_unit_n = ctx->scratch[15].as<uint32_t>();
+        {
+            ProfScope ps(ctx, st, KID_QUERY_HASH);
+            query_hash_kernel<<<(unsigned)nunits, 256, 0, st>>>((const Slot*)d_table, d_unit_group, d_unit_slot0, d_unit_nslots,
+                                                              (const long long*)d_filter, idx->k, idx->H, make_mods(idx->S),
+                                                              d_rid, d_unit_n, d_num_kmers);
+        }
+        ctx->launches++;
+        CID_CUDA(cudaGetLastError());
+        const size_t gsmem = QG_RING_BYTES + 4096 * 4;
+        static bool gattr = false;
+        if (!gattr) {
+            CID_CUDA(cudaFuncSetAttribute(query_gather_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+            CID_CUDA(cudaFuncSetAttribute(query_gather_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+            gattr = true;
+        }
+        {
+            ProfScope ps(ctx, st, KID_QUERY_COUNTS);
+            if (idx->H == 2)
+                query_gather_kernel<2><<<(unsigned)nunits, QG_WARPS * 32, gsmem, st>>>(idx->rows, idx->Wp, idx->N, d_rid, d_unit_group,
+                                                                                     d_unit_slot0, d_unit_n, d_counts);
+            else
+                query_gather_kernel<4><<<(unsigned)nunits, QG_WARPS * 32, gsmem, st>>>(idx->rows, idx->Wp, idx->N, d_rid, d_unit_group,
+                                                                                     d_unit_slot0, d_unit_n, d_counts);
+        }
+        ctx->launches++;
+        CID_CUDA(cudaGetLastError());
+        return CID_OK;
+    }
     size_t smem = unit_smem_bytes(idx->H);
     static bool attr_set = false;
     if (!attr_set) {

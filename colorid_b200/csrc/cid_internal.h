@@ -71,8 +71,9 @@ struct cid_ctx {
     int opt_host_threads = 0;        // host threads for the vote (0 = all cores)
     // device-pointer read_id (cid_read_id_batch_dev): chunks alternate over internal streams forked from /
     // joined to the caller's stream, so the DRAM-access-bound vote kernel of one chunk runs under the
-    // issue-bound kmerize/order kernels of the next
-    int opt_readid_streams = 2;
+    // issue-bound kmerize/order kernels of the next (measured on B200: no gain, kernels fill the GPU; off by default)
+    int opt_readid_streams = 1;
+    int opt_query_fused = 0;         // 1 = force the fused collect/hash/gather kernel (parity aid)
     cudaStream_t aux[2] = {nullptr, nullptr};
     cudaEvent_t aux_fork = nullptr, aux_join[2] = {nullptr, nullptr};
 };
@@ -107,7 +108,7 @@ int check_err_flags(cid_ctx* ctx, cudaStream_t st);   // syncs the stream
 
 // kernel ids for the profiling hooks (names in cid_api.cu: kKernelNames)
 enum { KID_KMERIZE_INSERT = 0, KID_HISTOGRAM, KID_TO_BLOOM, KID_TRANSPOSE, KID_ROWNZ, KID_QUERY_COUNTS, KID_QUERY_UNIQ_WIDE,
-       KID_QUERY_PERFECT, KID_READID_KMERIZE, KID_READID_SCHED, KID_READID_ORDER, KID_READID_VOTE, KID_READID_CLASSIFY, KID_TABLE_CLEAR, KID_OTHER, KID_COUNT };
+       KID_QUERY_PERFECT, KID_READID_KMERIZE, KID_READID_SCHED, KID_READID_ORDER, KID_READID_VOTE, KID_READID_CLASSIFY, KID_TABLE_CLEAR, KID_OTHER, KID_QUERY_HASH, KID_COUNT };
 struct ProfScope {     // records an event pair around a launch when profiling is enabled
     cid_ctx* ctx; cudaStream_t st; int idx;
     ProfScope(cid_ctx* c, cudaStream_t s, int kernel);
@@ -153,8 +154,9 @@ enum { QUERY_CHUNK = 1024, QUERY_ITEM_SLOTS = 16384, MAX_HASH = 8 };
 
 int launch_query_counts(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, const void* d_table,
                         const uint32_t* d_unit_group, const uint64_t* d_unit_slot0, const uint32_t* d_unit_nslots,
-                        uint64_t nunits, const int64_t* d_filter, uint32_t* d_counts, unsigned long long* d_num_kmers,
-                        bool want_uniq, uint32_t* d_uniq_list, uint32_t uniq_cap, uint32_t* d_uniq_n);
+                        uint64_t nunits, uint64_t total_slots, const int64_t* d_filter, uint32_t* d_counts,
+                        unsigned long long* d_num_kmers, bool want_uniq, uint32_t* d_uniq_list, uint32_t uniq_cap,
+                        uint32_t* d_uniq_n);
 int launch_query_perfect(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, const void* d_table,
                          const uint32_t* d_unit_group, const uint64_t* d_unit_slot0, const uint32_t* d_unit_nslots,
                          uint64_t nunits, uint32_t* d_and_rows, uint32_t* d_missing, unsigned long long* d_num_kmers);

@@ -131,9 +131,20 @@ static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals,
     // work queued on the context's own stream (index build / upload) must be visible to the slot streams
     CID_CUDA(cudaStreamSynchronize(ctx->stream));
 
-    uint64_t chunk = ctx->opt_readid_chunk;
-    if (chunk == 0) chunk = std::min<uint64_t>(131072, std::max<uint64_t>(16384, (nreads + 7) / 8));
-    const uint64_t nchunks = (nreads + chunk - 1) / chunk;
+    // Chunk schedule: a geometric ramp.  Small first chunks start the kernels after a short H2D copy; large
+    // later chunks keep the kernels efficient (the order kernel wants >= 10^5 reads per launch) while their
+    // copies hide behind the kernels of the chunks before them.
+    uint64_t chunk_max = ctx->opt_readid_chunk ? ctx->opt_readid_chunk : 262144;
+    std::vector<uint64_t> cuts{0};
+    for (uint64_t cur = std::min<uint64_t>(32768, chunk_max), at = 0; at < nreads;) {
+        uint64_t size = std::min(cur, nreads - at);
+        if (nreads - at - size < size / 4) size = nreads - at;      // absorb a short tail
+        at += size;
+        cuts.push_back(at);
+        cur = std::min(cur * 2, chunk_max);
+    }
+    const uint64_t nchunks = cuts.size() - 1;
+    const uint64_t chunk = chunk_max;
     const int NS = cid_readid_pipe::NS;
     const size_t rc = pp.rep_cap;
 
@@ -229,10 +240,18 @@ static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals,
 #define PIPE_TRY(expr) do { int _rc = (expr); if (_rc != CID_OK) return finish(_rc); } while (0)
 #define PIPE_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); return finish(CID_E_CUDA); } } while (0)
 
+    // CID_TRACE: per-chunk stage timeline from CUDA events on the slot streams (diagnostics only)
+    std::vector<cudaEvent_t> tev;
+    cudaEvent_t tev0 = nullptr;
+    auto tmark = [&](cudaStream_t stx) {
+        if (!trace) return;
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, stx); tev.push_back(e);
+    };
+    if (trace) { cudaEventCreate(&tev0); cudaEventRecord(tev0, pipe->slot[0].st); }
     for (uint64_t c = 0; c < nchunks; c++) {
         const int si = (int)(c % NS);
         auto& s = pipe->slot[si];
-        const uint64_t r0 = c * chunk, r1 = std::min(nreads, r0 + chunk), nr = r1 - r0;
+        const uint64_t r0 = cuts[c], r1 = cuts[c + 1], nr = r1 - r0;
         const uint64_t s0 = read_offs[r0], s1 = read_offs[r1];
         const uint64_t b0 = seq_offs[s0], b1 = seq_offs[s1];
         if (fused) {          // the slot's pinned staging must have been consumed
@@ -279,8 +298,10 @@ static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals,
             PIPE_CUDA(cudaMemcpyAsync(s.read_offs.p, ho + nso, nro * 8, cudaMemcpyHostToDevice, s.st));
             PIPE_CUDA(cudaEventRecord(s.offs_done, s.st));
         }
+        tmark(s.st);
         if (b1 > b0) PIPE_CUDA(cudaMemcpyAsync(s.bases.p, bases + b0, b1 - b0, cudaMemcpyHostToDevice, s.st));
         if (use_q && b1 > b0) PIPE_CUDA(cudaMemcpyAsync(s.quals.p, quals + b0, b1 - b0, cudaMemcpyHostToDevice, s.st));
+        tmark(s.st);
         // device arrays are indexed by absolute base / sequence / read numbers: bias the chunk buffers
         const uint8_t* d_bases = s.bases.as<uint8_t>() - b0;
         const uint8_t* d_quals = use_q ? s.quals.as<uint8_t>() - b0 : nullptr;
@@ -303,6 +324,7 @@ static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals,
         ReadIdScratch scr{s.entries.as<uint32_t>(), s.order.as<uint16_t>(), s.nocc.as<uint32_t>(), nr};
         PIPE_TRY(readid_run(ix, s.st, d_bases, d_quals, d_seq_offs, d_read_offs, r0, nr, max_bases, max_kmers, pp, scr,
                             d_n_set, d_flags, d_rep_n, d_rc, d_rv, out.order_cap, d_on, d_os, d_op));
+        tmark(s.st);
         if (fused) {
             PIPE_CUDA(cudaMemsetAsync(s.cursor.p, 0, 4, s.st));
             PIPE_TRY(launch_readid_classify(ctx, s.st, r0, nr, ix->N, (uint32_t)rc, d_n_set, d_flags, d_rep_n, d_rc, d_rv,
@@ -320,6 +342,7 @@ static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals,
                                                    cudaMemcpyDeviceToHost, s.st));
             PIPE_CUDA(cudaMemcpyAsync(s.h_cursor.p, s.cursor.p, 4, cudaMemcpyDeviceToHost, s.st));
             PIPE_CUDA(cudaEventRecord(s.done, s.st));
+            tmark(s.st);
             { std::lock_guard<std::mutex> lk(mu); slot_busy[si] = true; jobs.push_back(VoteJob{r0, nr, si}); }
             cv.notify_all();
         } else {
@@ -346,10 +369,21 @@ static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals,
     const double t_issued = now_ms() - t_start;
     int rcode = finish(CID_OK);
     if (trace)
-        fprintf(stderr, "[cid trace] read_id: %llu reads, %llu chunks of %llu: geometry %.2f ms, issue loop %.2f ms (slot wait %.2f), "
+        fprintf(stderr, "[cid trace] read_id: %llu reads, %llu chunks (ramp to %llu): geometry %.2f ms, issue loop %.2f ms (slot wait %.2f), "
                         "host vote busy %.2f ms for %llu undecided reads, vote waiting on GPU %.2f ms, total %.2f ms\n",
                 (unsigned long long)nreads, (unsigned long long)nchunks, (unsigned long long)chunk, t_geom, t_issued, t_wait,
                 t_vote, (unsigned long long)n_host_voted, t_evwait, now_ms() - t_start);
+    if (trace && fused && rcode == CID_OK) {
+        // four marks per chunk: offsets copied | bases+quals copied | kernels done | classify + D2H done
+        for (size_t c = 0; c + 3 < tev.size() && c / 4 < nchunks; c += 4) {
+            float a = 0, b = 0, k2 = 0, d2 = 0;
+            cudaEventElapsedTime(&a, tev0, tev[c]); cudaEventElapsedTime(&b, tev0, tev[c + 1]);
+            cudaEventElapsedTime(&k2, tev0, tev[c + 2]); cudaEventElapsedTime(&d2, tev0, tev[c + 3]);
+            fprintf(stderr, "[cid trace]   chunk %zu: offs@%.2f h2d@%.2f kernels@%.2f out@%.2f ms\n", c / 4, a, b, k2, d2);
+        }
+    }
+    for (auto e : tev) cudaEventDestroy(e);
+    if (tev0) cudaEventDestroy(tev0);
     if (rcode != CID_OK) return rcode;
     return check_err_flags(ctx, ctx->stream);
 }

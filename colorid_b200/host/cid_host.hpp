@@ -1,0 +1,106 @@
+// Host side above the C ABI (include/colorid_b200.h): the callers and data formats either side of the
+// hot path, mirroring the reference's own `pub fn`s (same names, argument meaning, output bytes):
+//
+//   kmer.rs:10-84        read_fasta, read_fasta_mf            -> fastx.cpp
+//   kmer.rs:461-475,581-612, read_id_mt_pe.rs:727-761,870-880  FASTQ(.gz) record iteration -> fastx.cpp
+//   seq.rs:36-56         qual_mask                            -> fastx.cpp
+//   build.rs:15-31       tab_to_map                           -> fastx.cpp
+//   bigsi.rs:19-27,51-69 BigsyMapNew, save_bigsi, read_bigsi  -> bxi.cpp   (bincode 1.x layout)
+//   reports.rs:8-120     generate_report[_gene], mode, read_counts_five_fields -> reports.cpp
+//   build.rs:33-256      build_single / build_multi           -> drivers.cpp
+//   batch_search_pe.rs:9-179, perfect_search.rs:6-120         -> drivers.cpp
+//   read_id_mt_pe.rs:440-951 stream_fasta, per_read_stream_pe/se -> drivers.cpp
+//   main.rs              clap CLI (build / search / read_id / info) -> main.cpp
+//
+// The reference is Rust; this image has no Rust toolchain, so the host side is C++.
+// Everything compute-heavy goes through the C ABI to the GPU; nothing here has a CPU fallback.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace cidh {
+
+struct Error : std::runtime_error { using std::runtime_error::runtime_error; };
+
+// ---- sequences -----------------------------------------------------------------------------------
+// A list of sequences in the ABI's layout: one byte array + offsets[n+1].
+struct SeqBatch {
+    std::string bases;
+    std::vector<uint64_t> offs{0};
+    void add(const std::string& s) { bases += s; offs.push_back(bases.size()); }
+    void add(const char* p, size_t n) { bases.append(p, n); offs.push_back(bases.size()); }
+    uint64_t n() const { return offs.size() - 1; }
+    void clear() { bases.clear(); offs.assign(1, 0); }
+};
+
+// Lines of a plain or gzip file (concatenated members like flate2::MultiGzDecoder); the line
+// terminator ("\n" or "\r\n") is stripped like BufRead::lines() unless keep_eol.
+class LineReader {
+public:
+    explicit LineReader(const std::string& path);
+    ~LineReader();
+    bool next(std::string& line, bool keep_eol = false);
+private:
+    void* gz_;
+    std::vector<char> buf_;
+    size_t pos_ = 0, len_ = 0;
+    bool eof_ = false;
+    bool fill();
+};
+
+std::vector<std::string> read_fasta(const std::string& path);                                      // kmer.rs:10-45
+void read_fasta_mf(const std::string& path, std::vector<std::string>& labels, std::vector<std::string>& seqs);  // kmer.rs:47-84
+std::string qual_mask(const std::string& seq, const std::string& qual, uint8_t max_quality_offset);   // seq.rs:36-56
+// accession -> 1 (FASTA or single-end FASTQ.gz) or 2 (paired FASTQ.gz) file names; a later line with
+// the same accession replaces an earlier one; iteration is in byte-wise sorted order = colour order
+std::map<std::string, std::vector<std::string>> tab_to_map(const std::string& path);                // build.rs:15-31
+// All records of a single-end / paired FASTQ(.gz) as quality-masked sequences (mates are separate
+// sequences); paired input stops at the shorter file (kmer.rs:604,612,649).  Returns records read.
+uint64_t fastq_masked_se(const std::string& path, uint8_t qual_offset, SeqBatch& out);              // kmer.rs:461-475
+uint64_t fastq_masked_pe(const std::string& p1, const std::string& p2, uint8_t qual_offset, SeqBatch& out);   // kmer.rs:581-612
+
+// ---- .bxi ------------------------------------------------------------------------------------------
+struct Bigsi {                                  // bigsi.rs:19-27 BigsyMapNew
+    uint64_t bloom_size = 0, num_hash = 0, k_size = 0;
+    std::map<uint64_t, std::string> colors;     // colour -> accession
+    std::vector<uint64_t> row_ids;              // map keys (non-zero rows)
+    std::vector<uint32_t> words;                // map values: row_words u32 per row (BitVec storage)
+    uint32_t row_words = 0;
+    std::map<std::string, uint64_t> n_ref_kmers;
+    uint32_t n_colors() const { return (uint32_t)colors.size(); }
+};
+void save_bigsi(const std::string& path, const Bigsi& b);   // bigsi.rs:51-57
+Bigsi read_bigsi(const std::string& path);                  // bigsi.rs:59-69 (both variants: same bytes)
+
+// ---- reports ---------------------------------------------------------------------------------------
+// reports.rs:8-48: one line per accession with hits/n_ref > cov (ascending colour; the reference's order
+// is SipHash-random)
+void generate_report(FILE* out, const std::string& query, const Bigsi& ix, const uint32_t* counts, const uint64_t* uniq_n,
+                     const uint64_t* uniq_sum, const uint64_t* uniq_mode, uint64_t num_kmers, double cov);
+// reports.rs:50-62
+void generate_report_gene(FILE* out, const std::string& query, const Bigsi& ix, const uint32_t* counts, uint64_t num_kmers,
+                          double cov);
+// Iteration order of an FnvHashMap<String, _> filled with entry(key).or_insert() in the given order of
+// first appearance (hashbrown, group width 16): reports.rs:98-120 writes PREFIX_counts.txt in it.
+std::vector<size_t> fnv_string_map_order(const std::vector<std::string>& keys_in_insertion_order, uint32_t group_width = 16);
+// reports.rs:98-120 from the (class, accept|reject) column pair of every output line
+void write_counts_five_fields(const std::string& path, const std::vector<std::string>& insertion_keys,
+                              const std::map<std::string, uint64_t>& counts);
+double false_prob(double m, double k, double n);            // read_id_mt_pe.rs:695-698 (for `info`)
+
+// ---- drivers (need a GPU: every one of them goes through the C ABI) -------------------------------
+struct BuildOpts { std::string ref_file, prefix; uint64_t k = 31, bloom = 50000000, hashes = 4, threads = 1; uint8_t quality = 15; int64_t filter = -1; int device = 0; };
+int build(const BuildOpts& o);                              // main.rs:467-553 + build.rs:33-256
+struct SearchOpts { std::string bigsi; std::vector<std::string> files1, files2; int64_t filter = -1; double cov = 0.35;
+                    bool gene_search = false, perfect_search = false, multi_fasta = false; uint8_t quality = 15; int device = 0; };
+int search(const SearchOpts& o);                            // main.rs:555-628
+struct ReadIdOpts { std::string bigsi, prefix; std::vector<std::string> query; uint64_t threads = 0, down_sample = 1, batch = 50000,
+                    bitvector_sample = 3; double correct = 3.0; uint8_t quality = 15; bool high_mem_load = false; int device = 0; };
+int read_id(const ReadIdOpts& o);                           // main.rs:704-866
+int info(const std::string& bigsi);                         // main.rs:630-703
+
+}  // namespace cidh

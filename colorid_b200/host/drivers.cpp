@@ -1,0 +1,423 @@
+// Drivers of the host layer: the reference's build / search / read_id entry points re-expressed over
+// the C ABI (include/colorid_b200.h).  File parsing, quality masking of the build/search inputs and
+// report formatting stay on the host exactly as north_star prescribes; k-mer extraction, Bloom
+// insert, transposition, row gathers and the read vote run on the GPU.  No CPU fallback.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+
+#include "../../include/colorid_b200.h"
+#include "cid_host.hpp"
+
+namespace cidh {
+
+namespace {
+void ck(int rc) { if (rc != CID_OK) throw Error(std::string("colorid_b200: ") + cid_last_error()); }
+bool ends_with(const std::string& s, const char* suf) { size_t n = strlen(suf); return s.size() >= n && !s.compare(s.size() - n, n, suf); }
+struct Timer {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    unsigned long long secs() const { return (unsigned long long)std::chrono::duration_cast<std::chrono::seconds>(std::chrono::steady_clock::now() - t0).count(); }
+};
+struct Gpu {                      // context + device index
+    cid_ctx* ctx = nullptr;
+    cid_index* ix = nullptr;
+    explicit Gpu(int device) { ck(cid_ctx_create(device, &ctx)); }
+    ~Gpu() { if (ix) cid_index_destroy(ix); if (ctx) cid_ctx_destroy(ctx); }
+    void create(uint64_t S, uint64_t H, uint64_t k, uint64_t N) {
+        if (H > 0xFFFFFFFFull || k > 0xFFFFFFFFull || N > 0xFFFFFFFFull) throw Error("index parameters out of range");
+        ck(cid_index_create(ctx, S, (uint32_t)H, (uint32_t)k, (uint32_t)N, &ix));
+    }
+    void upload(const Bigsi& b) {   // main.rs:576 / :796 read_bigsi -> dense device matrix
+        create(b.bloom_size, b.num_hash, b.k_size, b.n_colors());
+        uint64_t c = 0;
+        for (auto& kv : b.colors) if (kv.first != c++) throw Error("index colours are not 0..N-1");
+        ck(cid_index_upload_rows(ix, b.row_ids.data(), b.words.data(), b.row_ids.size()));
+    }
+};
+Bigsi load_index(const std::string& path) {
+    Timer t;
+    Bigsi b = read_bigsi(path);
+    fprintf(stderr, "Index loaded in %llu seconds\n", t.secs());
+    return b;
+}
+}  // namespace
+
+// ------------------------------------------------------------------ build
+int build(const BuildOpts& o) {
+    const auto map = tab_to_map(o.ref_file);
+    if (map.empty()) throw Error("reference file lists no accessions");
+    Gpu g(o.device);
+    g.create(o.bloom, o.hashes, o.k, map.size());
+    Bigsi out;
+    out.bloom_size = o.bloom; out.num_hash = o.hashes; out.k_size = o.k;
+    uint32_t colour = 0;              // colours = rank of the accession in byte-wise sorted order (build.rs:102-113)
+    size_t counter = 1;
+    for (auto& kv : map) {
+        const std::string& acc = kv.first;
+        const auto& files = kv.second;
+        fprintf(stderr, "Adding %s to index (%zu/%zu)\n", acc.c_str(), counter++, map.size());
+        SeqBatch sb;
+        int mode;
+        int64_t cutoff = o.filter;    // -1: FASTQ -> auto_cutoff (build.rs:56-58), FASTA -> keep everything (:86-87)
+        if (files.size() == 2) {
+            fastq_masked_pe(files[0], files[1], o.quality, sb);
+            mode = CID_SEQ_FASTQ;
+        } else if (ends_with(files[0], "gz")) {
+            // build_multi hard-codes quality 15 for single-end reads (build.rs:187); build_single honours -Q (:70)
+            fastq_masked_se(files[0], o.threads == 1 ? o.quality : 15, sb);
+            mode = CID_SEQ_FASTQ;
+        } else {
+            for (auto& s : read_fasta(files[0])) sb.add(s);
+            mode = CID_SEQ_FASTA;
+        }
+        uint64_t nref = 0;
+        int64_t used = 0;
+        ck(cid_build_accession(g.ix, colour, sb.bases.data(), sb.offs.data(), sb.n(), mode, cutoff, &nref, &used));
+        out.colors[colour] = acc;
+        out.n_ref_kmers[acc] = nref;
+        colour++;
+    }
+    ck(cid_build_finalize(g.ix));
+    printf("Saving BIGSI to file.\n");
+    uint64_t nrows = 0;
+    ck(cid_index_count_nonzero_rows(g.ix, &nrows));
+    out.row_words = cid_index_row_words(g.ix);
+    out.row_ids.resize(nrows);
+    out.words.resize(nrows * out.row_words);
+    uint64_t got = 0;
+    ck(cid_index_download_nonzero_rows(g.ix, out.row_ids.data(), out.words.data(), nrows, &got));
+    save_bigsi(o.prefix + ".bxi", out);
+    return 0;
+}
+
+// ------------------------------------------------------------------ search
+namespace {
+void perfect_lines(const Bigsi& b, const std::string& name, const uint32_t* and_row, uint64_t n_kmers) {
+    uint64_t hits = 0;
+    for (uint32_t c = 0; c < b.n_colors(); c++) hits += (and_row[c >> 5] >> (c & 31)) & 1u;
+    fprintf(stderr, "%llu hits\n", (unsigned long long)hits);
+    for (uint32_t c = 0; c < b.n_colors(); c++)
+        if ((and_row[c >> 5] >> (c & 31)) & 1u)
+            printf("%s\t%s\t%llu\t1.00\n", name.c_str(), b.colors.at(c).c_str(), (unsigned long long)n_kmers);
+}
+
+// perfect_search.rs:6-60: one query per FASTA file
+void perfect_batch_search(Gpu& g, const Bigsi& b, const std::vector<std::string>& files) {
+    SeqBatch sb;
+    std::vector<uint64_t> qoffs{0};
+    for (auto& f : files) {
+        fprintf(stderr, "Counting k-mers, this may take a while!\n");
+        for (auto& s : read_fasta(f)) sb.add(s);
+        qoffs.push_back(sb.n());
+    }
+    const uint64_t nq = files.size();
+    const uint32_t W = b.row_words;
+    std::vector<uint32_t> rows(nq * W);
+    std::vector<uint8_t> status(nq);
+    std::vector<uint64_t> nk(nq);
+    ck(cid_query_perfect(g.ix, sb.bases.data(), sb.offs.data(), sb.n(), qoffs.data(), nq, rows.data(), status.data(), nk.data()));
+    for (uint64_t q = 0; q < nq; q++) {
+        fprintf(stderr, "%llu kmers in query\n", (unsigned long long)nk[q]);
+        if (status[q] == 2) fprintf(stderr, "Warning! no kmers in query; maybe your kmer length is larger than your query length?\n");
+        else if (status[q] == 1) fprintf(stderr, "No perfect hits!\n");
+        else perfect_lines(b, files[q], rows.data() + q * W, nk[q]);
+    }
+}
+
+// perfect_search.rs:62-120: one query per FASTA record, labelled by its header
+void perfect_batch_search_mf(Gpu& g, const Bigsi& b, const std::vector<std::string>& files) {
+    for (auto& f : files) {
+        std::vector<std::string> labels, seqs;
+        read_fasta_mf(f, labels, seqs);
+        if (seqs.size() < labels.size()) throw Error("multi-fasta: a header without a sequence (the reference panics: index out of bounds)");
+        SeqBatch sb;
+        for (size_t i = 0; i < labels.size(); i++) sb.add(seqs[i]);
+        const uint64_t nq = labels.size();
+        const uint32_t W = b.row_words;
+        std::vector<uint32_t> rows(nq * W);
+        std::vector<uint8_t> status(nq);
+        std::vector<uint64_t> nk(nq);
+        if (nq) ck(cid_query_perfect_mf(g.ix, sb.bases.data(), sb.offs.data(), nq, rows.data(), status.data(), nk.data()));
+        for (uint64_t q = 0; q < nq; q++) {
+            if (status[q] == 2) {
+                printf("Warning! no kmers in query '%s'; maybe your kmer length is larger than your query length?\n", labels[q].c_str());
+                continue;
+            }
+            fprintf(stderr, "%llu kmers in query\n", (unsigned long long)nk[q]);
+            if (status[q] == 1) fprintf(stderr, "No perfect hits!\n");
+            else perfect_lines(b, labels[q], rows.data() + q * W, nk[q]);
+        }
+    }
+}
+
+// batch_search_pe.rs:9-179: one query per file (pair)
+void batch_search(Gpu& g, const Bigsi& b, const SearchOpts& o) {
+    const uint32_t N = b.n_colors();
+    size_t i = 0;
+    while (i < o.files1.size()) {
+        SeqBatch sb;
+        std::vector<uint64_t> qoffs{0};
+        std::vector<std::string> names;
+        int mode;
+        if (ends_with(o.files1[i], "gz")) {           // FASTQ query: one call per sample
+            const std::string& f1 = o.files1[i];
+            if (o.files2.empty()) {
+                fprintf(stderr, "%s\nCounting k-mers, this may take a while!\n", f1.c_str());
+                fastq_masked_se(f1, o.quality, sb);
+            } else {
+                if (i >= o.files2.size()) throw Error("fewer reverse files than forward files");
+                fprintf(stderr, "Paired end: %s %s\nCounting k-mers, this may take a while!\n", f1.c_str(), o.files2[i].c_str());
+                fastq_masked_pe(f1, o.files2[i], o.quality, sb);
+            }
+            qoffs.push_back(sb.n());
+            names.push_back(f1);
+            mode = CID_SEQ_FASTQ;
+            i++;
+        } else {                                       // a run of FASTA queries goes to the GPU as one batch
+            while (i < o.files1.size() && !ends_with(o.files1[i], "gz")) {
+                fprintf(stderr, "%s\nCounting k-mers, this may take a while!\n", o.files1[i].c_str());
+                for (auto& s : read_fasta(o.files1[i])) sb.add(s);
+                qoffs.push_back(sb.n());
+                names.push_back(o.files1[i]);
+                if (!o.gene_search && o.filter < 0) fprintf(stderr, "no gene search\n");
+                i++;
+            }
+            mode = CID_SEQ_FASTA;
+        }
+        const uint64_t nq = names.size();
+        std::vector<uint32_t> counts(nq * N);
+        std::vector<uint64_t> nk(nq), un, us, um;
+        if (!o.gene_search) { un.resize(nq * N); us.resize(nq * N); um.resize(nq * N); }
+        ck(cid_query_counts(g.ix, sb.bases.data(), sb.offs.data(), sb.n(), qoffs.data(), nq, mode, o.gene_search ? 1 : 0, o.filter,
+                            counts.data(), nk.data(), o.gene_search ? nullptr : un.data(), o.gene_search ? nullptr : us.data(),
+                            o.gene_search ? nullptr : um.data(), nullptr));
+        for (uint64_t q = 0; q < nq; q++) {
+            fprintf(stderr, "%llu k-mers in query\n", (unsigned long long)nk[q]);
+            if (!o.gene_search)
+                generate_report(stdout, names[q], b, counts.data() + q * N, un.data() + q * N, us.data() + q * N, um.data() + q * N,
+                                nk[q], o.cov);
+            else
+                generate_report_gene(stdout, names[q], b, counts.data() + q * N, nk[q], o.cov);
+        }
+    }
+}
+}  // namespace
+
+int search(const SearchOpts& o) {
+    if (ends_with(o.bigsi, ".mxi")) {
+        fprintf(stderr, "Error: An index with minimizers (.mxi) is used, but not available for this function\n");
+        return 0;
+    }
+    fprintf(stderr, "Loading index\n");
+    const Bigsi b = load_index(o.bigsi);
+    Gpu g(o.device);
+    g.upload(b);
+    if (o.perfect_search) {
+        if (o.multi_fasta) perfect_batch_search_mf(g, b, o.files1);
+        else perfect_batch_search(g, b, o.files1);
+    } else {
+        batch_search(g, b, o);
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------ read_id
+namespace {
+struct ReadBatch {
+    std::vector<std::string> ids;
+    std::string bases, quals;
+    std::vector<uint64_t> seq_offs{0}, read_offs{0};
+    bool any_qual = false;
+    void add_mate(const std::string& seq, const std::string* qual, uint8_t off) {
+        if (qual && off) {
+            any_qual = true;
+            if (qual->size() == seq.size()) { bases += seq; quals += *qual; }       // masked on the device
+            else { const std::string m = qual_mask(seq, *qual, off); bases += m; quals.append(m.size(), '~'); }
+        } else {
+            bases += seq;
+            quals.append(seq.size(), '~');
+        }
+        seq_offs.push_back(bases.size());
+    }
+    void end_read(const std::string& id) { ids.push_back(id); read_offs.push_back(seq_offs.size() - 1); }
+    uint64_t n() const { return ids.size(); }
+    void clear() { ids.clear(); bases.clear(); quals.clear(); seq_offs.assign(1, 0); read_offs.assign(1, 0); any_qual = false; }
+};
+
+struct ReadIdRun {
+    Gpu& g; const Bigsi& b; const ReadIdOpts& o;
+    FILE* out;
+    std::vector<uint64_t> n_ref;
+    double fp_correct;
+    uint64_t read_count = 0;
+    std::vector<std::string> count_keys;                 // first-appearance order of the counts-file keys
+    std::map<std::string, uint64_t> counts;
+    ReadIdRun(Gpu& g_, const Bigsi& b_, const ReadIdOpts& o_) : g(g_), b(b_), o(o_) {
+        out = fopen((o.prefix + "_reads.txt").c_str(), "wb");
+        if (!out) throw Error("could not create outfile!");
+        for (auto& kv : b.colors) {
+            auto it = b.n_ref_kmers.find(kv.second);
+            if (it == b.n_ref_kmers.end()) throw Error("index has no k-mer count for accession " + kv.second);
+            n_ref.push_back(it->second);
+        }
+        fp_correct = std::pow(10.0, -o.correct);          // main.rs:711
+        if (o.threads) ck(cid_ctx_set_option(g.ctx, "host_threads", (int64_t)o.threads));
+    }
+    ~ReadIdRun() { if (out) fclose(out); }
+    void tally(const std::string& cls, bool accept) {
+        const std::string key = accept ? cls : "reject";
+        auto it = counts.find(key);
+        if (it == counts.end()) { counts[key] = 1; count_keys.push_back(key); } else it->second++;
+    }
+    // read_id_mt_pe.rs:282-363 parallel_vec for one batch, then the :779-788 output lines in input order
+    void flush(ReadBatch& rb) {
+        const uint64_t n = rb.n();
+        if (n == 0) return;
+        const uint32_t N = b.n_colors();
+        cid_readid_params p;
+        p.downsample = (uint32_t)o.down_sample; p.start_sample = (uint32_t)o.bitvector_sample; p.qual_offset = o.quality;
+        p.group_width = 16; p.reserve_before_find = 1; p.rep_cap = 0;
+        uint32_t top_cap = N < 64 ? N : 64;
+        std::vector<int32_t> kind(n);
+        std::vector<uint32_t> hits(n), n_set(n), n_top(n), top((size_t)n * top_cap);
+        ck(cid_read_id_classify(g.ix, rb.bases.data(), rb.any_qual ? rb.quals.data() : nullptr, rb.seq_offs.data(),
+                                rb.seq_offs.size() - 1, rb.read_offs.data(), n, &p, n_ref.data(), fp_correct, kind.data(),
+                                hits.data(), n_set.data(), n_top.data(), top.data(), top_cap));
+        std::string line;
+        for (uint64_t r = 0; r < n; r++) {
+            std::string cls;
+            const char* verdict = "accept";
+            uint32_t h = 0, ns = n_set[r], nt = 0;
+            switch (kind[r]) {
+                case CID_CLS_TOO_SHORT: cls = "too_short"; ns = 0; break;
+                case CID_CLS_NO_HITS: cls = "no_hits"; break;
+                case CID_CLS_NO_SIGNIFICANT: cls = "no_significant_hits"; verdict = "reject"; break;
+                case CID_CLS_ACCEPT: cls = b.colors.at(top[r * top_cap]); h = hits[r]; nt = 1; break;
+                case CID_CLS_REJECT_MULTI: {
+                    std::vector<uint32_t> all;
+                    const uint32_t* t = top.data() + r * top_cap;
+                    if (n_top[r] > top_cap) {           // more tied accessions than the batch call kept: redo this read alone
+                        all.resize(N);
+                        int32_t k1; uint32_t h1, s1, t1;
+                        const uint64_t s_lo = rb.read_offs[r], s_hi = rb.read_offs[r + 1];
+                        std::vector<uint64_t> so, ro{0, s_hi - s_lo};
+                        for (uint64_t s = s_lo; s <= s_hi; s++) so.push_back(rb.seq_offs[s] - rb.seq_offs[s_lo]);
+                        ck(cid_read_id_classify(g.ix, rb.bases.data() + rb.seq_offs[s_lo],
+                                                rb.any_qual ? rb.quals.data() + rb.seq_offs[s_lo] : nullptr, so.data(), s_hi - s_lo,
+                                                ro.data(), 1, &p, n_ref.data(), fp_correct, &k1, &h1, &s1, &t1, all.data(), N));
+                        t = all.data();
+                    }
+                    for (uint32_t j = 0; j < n_top[r]; j++) { if (j) cls += ','; cls += b.colors.at(t[j]); }
+                    h = hits[r]; nt = n_top[r]; verdict = "reject";
+                    break;
+                }
+                default:
+                    throw Error("read " + rb.ids[r] + ": a later mate is shorter than k-1 (the reference panics in kmerize_vector_skip_n_set)");
+            }
+            line = rb.ids[r]; line += '\t'; line += cls; line += '\t'; line += std::to_string(h); line += '\t';
+            line += std::to_string(ns); line += '\t'; line += verdict; line += '\t'; line += std::to_string(nt); line += '\n';
+            fwrite(line.data(), 1, line.size(), out);
+            tally(cls, verdict[0] == 'a');
+        }
+        read_count += n;
+        rb.clear();
+    }
+    void finish() {
+        fclose(out); out = nullptr;
+        write_counts_five_fields(o.prefix + "_counts.txt", count_keys, counts);   // main.rs:865
+    }
+};
+// The reference flushes every `-c` records (default 50,000; read_id_mt_pe.rs:762); batching never changes
+// the output, so the GPU gets larger batches.
+const uint64_t kGpuBatchReads = 1u << 20;
+const uint64_t kGpuBatchBytes = 600ull << 20;
+}  // namespace
+
+int read_id(const ReadIdOpts& o) {
+    if (o.query.empty()) throw Error("no query files");
+    Timer tload;
+    const Bigsi b = read_bigsi(o.bigsi);
+    fprintf(stderr, "Index loaded in %llu seconds\n", tload.secs());
+    Gpu g(o.device);
+    g.upload(b);
+    ReadIdRun run(g, b, o);
+    ReadBatch rb;
+    Timer t;
+    auto maybe_flush = [&]() { if (rb.n() >= kGpuBatchReads || rb.bases.size() >= kGpuBatchBytes) run.flush(rb); };
+    if (ends_with(o.query[0], ".gz")) {
+        if (o.query.size() > 1) {                       // per_read_stream_pe, read_id_mt_pe.rs:701-832
+            LineReader a(o.query[0]), c(o.query[1]);
+            std::string l1, l2, id, s1, s2;
+            uint64_t line_count = 1;
+            while (a.next(l1)) {
+                const bool have2 = c.next(l2);
+                if (line_count % 4 == 1) id = l1;
+                else if (line_count % 4 == 2) { if (!have2) break; s1 = l1; s2 = l2; }
+                else if (line_count % 4 == 0) {
+                    if (!have2) break;
+                    rb.add_mate(s1, &l1, o.quality);
+                    rb.add_mate(s2, &l2, o.quality);
+                    rb.end_read(id);
+                    maybe_flush();
+                }
+                line_count++;
+            }
+            run.flush(rb);
+            fprintf(stderr, "Classified %llu read pairs in %llu seconds\n", (unsigned long long)run.read_count, t.secs());
+        } else {                                        // per_read_stream_se, :835-951
+            LineReader a(o.query[0]);
+            std::string l, id, s1;
+            uint64_t line_count = 1;
+            while (a.next(l)) {
+                if (line_count % 4 == 1) id = l;
+                else if (line_count % 4 == 2) s1 = l;
+                else if (line_count % 4 == 0) { rb.add_mate(s1, &l, o.quality); rb.end_read(id); maybe_flush(); }
+                line_count++;
+            }
+            run.flush(rb);
+            fprintf(stderr, "Classified %llu reads in %llu seconds\n", (unsigned long long)run.read_count, t.secs());
+        }
+    } else {                                            // stream_fasta, :440-570 (sequence keeps its line feeds)
+        LineReader a(o.query[0]);
+        std::string l, id, sub;
+        uint64_t count = 0;
+        while (a.next(l, /*keep_eol=*/true)) {
+            if (count == 0) id = l.substr(0, l.size() - 1);
+            else if (l.find('>') != std::string::npos) {
+                if (!sub.empty()) {
+                    rb.add_mate(sub, nullptr, 0); rb.end_read(id); maybe_flush();
+                    id = l.substr(0, l.size() - 1);
+                    sub.clear();
+                }
+            } else sub += l;
+            count++;
+        }
+        rb.add_mate(sub, nullptr, 0); rb.end_read(id);
+        run.flush(rb);
+        fprintf(stderr, "Classified %llu reads in %llu seconds\n", (unsigned long long)run.read_count, t.secs());
+    }
+    run.finish();
+    return 0;
+}
+
+// ------------------------------------------------------------------ info
+int info(const std::string& path) {
+    fprintf(stderr, "Loading index\n");
+    const Bigsi b = load_index(path);
+    printf("BIGSI parameters:\nBloomfilter-size: %llu\nNumber of hashes: %llu\nK-mer size: %llu\n", (unsigned long long)b.bloom_size,
+           (unsigned long long)b.num_hash, (unsigned long long)b.k_size);
+    printf("Number of accessions in index: %zu\n", b.colors.size());
+    std::vector<std::string> acc;
+    for (auto& kv : b.colors) acc.push_back(kv.second);
+    std::sort(acc.begin(), acc.end());
+    for (auto& a : acc) {
+        auto it = b.n_ref_kmers.find(a);
+        if (it == b.n_ref_kmers.end()) throw Error("index has no k-mer count for accession " + a);
+        printf("%s %llu %.3f\n", a.c_str(), (unsigned long long)it->second,
+               false_prob((double)b.bloom_size, (double)b.num_hash, (double)it->second));
+    }
+    return 0;
+}
+
+}  // namespace cidh

@@ -1,0 +1,163 @@
+// Sequence file readers of the host layer: FASTA (kmer.rs:10-84), FASTQ(.gz) record iteration
+// (kmer.rs:461-475,581-612), seq.rs:36-56 qual_mask and build.rs:15-31 tab_to_map.
+#include <zlib.h>
+
+#include <cstring>
+#include <fstream>
+#include <sstream>
+
+#include "cid_host.hpp"
+
+namespace cidh {
+
+// ------------------------------------------------------------------ LineReader
+LineReader::LineReader(const std::string& path) : buf_(1 << 20) {
+    gzFile f = gzopen(path.c_str(), "rb");            // transparent for plain files, walks concatenated members
+    if (!f) throw Error("file not found: " + path);
+    gzbuffer(f, 1 << 20);
+    gz_ = f;
+}
+LineReader::~LineReader() { if (gz_) gzclose((gzFile)gz_); }
+bool LineReader::fill() {
+    if (eof_) return false;
+    int n = gzread((gzFile)gz_, buf_.data(), (unsigned)buf_.size());
+    if (n < 0) throw Error("gz read error");
+    pos_ = 0; len_ = (size_t)n;
+    if (n == 0) eof_ = true;
+    return n > 0;
+}
+bool LineReader::next(std::string& line, bool keep_eol) {
+    line.clear();
+    bool any = false;
+    for (;;) {
+        if (pos_ == len_ && !fill()) break;
+        const char* b = buf_.data() + pos_;
+        const char* nl = (const char*)memchr(b, '\n', len_ - pos_);
+        if (nl) {
+            line.append(b, nl - b + (keep_eol ? 1 : 0));
+            pos_ += (size_t)(nl - b) + 1;
+            if (!keep_eol && !line.empty() && line.back() == '\r') line.pop_back();   // BufRead::lines strips CRLF
+            return true;
+        }
+        line.append(b, len_ - pos_);
+        pos_ = len_;
+        any = true;
+    }
+    return any || !line.empty();
+}
+
+// ------------------------------------------------------------------ FASTA
+// str::lines(): split on '\n', a trailing '\r' is dropped, no empty line after a final newline.
+static std::vector<std::string> file_lines(const std::string& path) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) throw Error("file not found: " + path);
+    std::stringstream ss;
+    ss << f.rdbuf();
+    const std::string c = ss.str();
+    std::vector<std::string> lines;
+    size_t at = 0;
+    while (at < c.size()) {
+        size_t nl = c.find('\n', at);
+        size_t end = nl == std::string::npos ? c.size() : nl;
+        size_t e2 = end;
+        if (nl != std::string::npos && e2 > at && c[e2 - 1] == '\r') e2--;
+        lines.emplace_back(c, at, e2 - at);
+        at = nl == std::string::npos ? c.size() : nl + 1;
+    }
+    return lines;
+}
+
+// A record ends at the next line holding a '>' (anywhere in the line) or at the last line of the
+// file; empty records are dropped (kmer.rs:26-42), which is why labels and sequences of
+// read_fasta_mf can fall out of step exactly as in the reference.
+static void fasta_records(const std::string& path, std::vector<std::string>* labels, std::vector<std::string>& seqs) {
+    const std::vector<std::string> lines = file_lines(path);
+    std::string cur;
+    for (size_t i = 0; i < lines.size(); i++) {
+        const std::string& l = lines[i];
+        if (l.find('>') != std::string::npos) {
+            if (labels) labels->push_back(l.substr(1));
+            if (!cur.empty()) seqs.push_back(cur);
+            cur.clear();
+        } else {
+            cur += l;
+            if (i + 1 == lines.size() && !cur.empty()) seqs.push_back(cur);
+        }
+    }
+}
+std::vector<std::string> read_fasta(const std::string& path) {
+    std::vector<std::string> seqs;
+    fasta_records(path, nullptr, seqs);
+    return seqs;
+}
+void read_fasta_mf(const std::string& path, std::vector<std::string>& labels, std::vector<std::string>& seqs) {
+    labels.clear(); seqs.clear();
+    fasta_records(path, &labels, seqs);
+}
+
+// ------------------------------------------------------------------ qual_mask
+// Output has one base per QUALITY character (a longer sequence is truncated; a shorter one makes
+// the reference panic): 'N' where phred+33 < offset+33.  offset 0 returns the sequence untouched.
+std::string qual_mask(const std::string& seq, const std::string& qual, uint8_t off) {
+    if (off == 0) return seq;
+    if (qual.size() > seq.size()) throw Error("ERROR: could not get the next nt in the sequence");
+    const uint8_t maxq = (uint8_t)(off + 33);
+    std::string out(qual.size(), 'N');
+    for (size_t i = 0; i < qual.size(); i++)
+        if ((uint8_t)qual[i] >= maxq) out[i] = seq[i];
+    return out;
+}
+
+// ------------------------------------------------------------------ tab_to_map
+std::map<std::string, std::vector<std::string>> tab_to_map(const std::string& path) {
+    std::map<std::string, std::vector<std::string>> m;
+    LineReader lr(path);
+    std::string l;
+    while (lr.next(l)) {
+        std::vector<std::string> v;
+        size_t at = 0;
+        for (;;) {
+            size_t t = l.find('\t', at);
+            v.emplace_back(l, at, t == std::string::npos ? std::string::npos : t - at);
+            if (t == std::string::npos) break;
+            at = t + 1;
+        }
+        if (v.size() < 2) throw Error("reference file: line without a tab: '" + l + "'");   // v[1] panics in the reference
+        if (v.size() == 2) m[v[0]] = {v[1]};
+        else m[v[0]] = {v[1], v[2]};
+    }
+    return m;
+}
+
+// ------------------------------------------------------------------ FASTQ
+uint64_t fastq_masked_se(const std::string& path, uint8_t qual_offset, SeqBatch& out) {
+    LineReader lr(path);
+    std::string l, seq;
+    uint64_t line_count = 1, n = 0;
+    while (lr.next(l)) {
+        if (line_count % 4 == 2) seq = l;
+        else if (line_count % 4 == 0) { out.add(qual_mask(seq, l, qual_offset)); n++; }
+        line_count++;
+    }
+    return n;
+}
+uint64_t fastq_masked_pe(const std::string& p1, const std::string& p2, uint8_t qual_offset, SeqBatch& out) {
+    LineReader a(p1), b(p2);
+    std::string l1, l2, s1, s2;
+    uint64_t line_count = 1, n = 0;
+    while (a.next(l1)) {
+        const bool have2 = b.next(l2);
+        if (line_count % 4 == 1) { if (!have2) break; }
+        else if (line_count % 4 == 2) { if (!have2) break; s1 = l1; s2 = l2; }
+        else if (line_count % 4 == 0) {
+            if (!have2) break;
+            out.add(qual_mask(s1, l1, qual_offset));
+            out.add(qual_mask(s2, l2, qual_offset));
+            n++;
+        }
+        line_count++;
+    }
+    return n;
+}
+
+}  // namespace cidh

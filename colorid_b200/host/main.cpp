@@ -1,0 +1,153 @@
+// colorid-b200: the reference's command line (main.rs: clap App "colorid" 0.1.4.3) for the subcommands on
+// the BIGSI hot path -- build, search, read_id, info -- with the same flags, defaults and output files,
+// running on the GPU through libcolorid_b200.so.  `batch_id`, `read_filter` and minimizer indexes
+// (-m / .mxi) are outside this path and are refused with a message.
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <set>
+
+#include "cid_host.hpp"
+
+namespace {
+struct Flag { char s; const char* l; bool takes_value; bool multi; };
+struct Parsed {
+    std::map<std::string, std::vector<std::string>> v;
+    bool has(const char* l) const { return v.count(l) != 0; }
+    const std::string& one(const char* l) const { return v.at(l).front(); }
+};
+Parsed parse(int argc, char** argv, int at, const std::vector<Flag>& flags) {
+    Parsed p;
+    auto find = [&](const std::string& a) -> const Flag* {
+        for (auto& f : flags) {
+            if (a.size() == 2 && a[0] == '-' && a[1] == f.s) return &f;
+            if (a.size() > 2 && a[0] == '-' && a[1] == '-' && a.substr(2) == f.l) return &f;
+        }
+        return nullptr;
+    };
+    while (at < argc) {
+        const std::string a = argv[at++];
+        const Flag* f = find(a);
+        if (!f) throw cidh::Error("error: Found argument '" + a + "' which wasn't expected, or isn't valid in this context");
+        auto& dst = p.v[f->l];
+        if (!f->takes_value) { dst.push_back("1"); continue; }
+        if (at >= argc) throw cidh::Error("error: The argument '--" + std::string(f->l) + "' requires a value but none was supplied");
+        dst.push_back(argv[at++]);
+        if (f->multi) while (at < argc && argv[at][0] != '-') dst.push_back(argv[at++]);   // clap min_values(1)
+    }
+    return p;
+}
+void require(const Parsed& p, std::initializer_list<const char*> names) {
+    for (auto n : names) if (!p.has(n)) throw cidh::Error(std::string("error: The following required arguments were not provided:\n    --") + n);
+}
+template <class T> T num(const Parsed& p, const char* l, T dflt) {      // value_t!(..).unwrap_or(default)
+    if (!p.has(l)) return dflt;
+    char* end = nullptr;
+    const std::string& s = p.one(l);
+    if (std::is_floating_point<T>::value) { double d = strtod(s.c_str(), &end); return (*end || s.empty()) ? dflt : (T)d; }
+    long long v = strtoll(s.c_str(), &end, 10);
+    return (*end || s.empty()) ? dflt : (T)v;
+}
+int usage() {
+    fprintf(stderr,
+            "colorid-b200 0.1.4.3 (B200)\nBIGSI based taxonomic ID of sequence data\n\nUSAGE:\n    colorid-b200 <SUBCOMMAND>\n\nSUBCOMMANDS:\n"
+            "    build      builds a bigsi            -b PREFIX -r REFS.tsv -k K -n HASHES -s BLOOM [-t T] [-Q q] [-f cutoff]\n"
+            "    search     does a bigsi search       -b IDX.bxi -q Q... [-r R...] [-f n] [-p cov] [-g] [-s] [-m] [-Q q]\n"
+            "    read_id    id's reads                -b IDX.bxi -q R1.fq.gz [R2.fq.gz] -n PREFIX [-t T] [-c batch] [-d d] [-p e] [-Q q] [-B b] [-H]\n"
+            "    info       dumps index parameters    -b IDX.bxi\n");
+    return 1;
+}
+}  // namespace
+
+int main(int argc, char** argv) {
+    printf("\n ************** initializing logger *****************\n\n");      // main.rs:18
+    if (argc < 2) return usage();
+    const std::string sub = argv[1];
+    int device = 0;
+    if (const char* d = getenv("COLORID_B200_DEVICE")) device = atoi(d);
+    try {
+        if (sub == "build") {
+            Parsed p = parse(argc, argv, 2, {{'b', "bigsi", true, false}, {'r', "refs", true, false}, {'k', "kmer", true, false},
+                                             {'n', "num_hashes", true, false}, {'s', "bloom", true, false}, {'m', "minimizer", false, false},
+                                             {'v', "value", true, false}, {'t', "threads", true, false}, {'Q', "quality", true, false},
+                                             {'f', "filter", true, false}});
+            require(p, {"bigsi", "refs", "kmer", "num_hashes", "bloom"});
+            printf(" Ref_file : %s\n Bigsi file : %s\nK-mer size: %s\nBloom filter parameters: num hashes %s, filter size %s\n",
+                   p.one("refs").c_str(), p.one("bigsi").c_str(), p.one("kmer").c_str(), p.one("num_hashes").c_str(), p.one("bloom").c_str());
+            if (p.has("minimizer")) throw cidh::Error("minimizer indexes (.mxi) are outside the GPU hot path; build without -m");
+            cidh::BuildOpts o;
+            o.ref_file = p.one("refs"); o.prefix = p.one("bigsi");
+            o.k = num<uint64_t>(p, "kmer", 31); o.bloom = num<uint64_t>(p, "bloom", 50000000); o.hashes = num<uint64_t>(p, "num_hashes", 4);
+            o.threads = num<uint64_t>(p, "threads", 1); o.quality = num<uint8_t>(p, "quality", 15); o.filter = num<int64_t>(p, "filter", -1);
+            o.device = device;
+            return cidh::build(o);
+        }
+        if (sub == "search") {
+            Parsed p = parse(argc, argv, 2, {{'b', "bigsi", true, false}, {'q', "query", true, true}, {'r', "reverse", true, true},
+                                             {'f', "filter", true, false}, {'p', "p_shared", true, false}, {'g', "gene_search", false, false},
+                                             {'s', "perfect_search", false, false}, {'m', "multi_fasta", false, false},
+                                             {'Q', "quality", true, false}});
+            require(p, {"bigsi", "query"});
+            cidh::SearchOpts o;
+            o.bigsi = p.one("bigsi"); o.files1 = p.v.at("query");
+            if (p.has("reverse") && p.one("reverse") != "none") o.files2 = p.v.at("reverse");
+            o.filter = num<int64_t>(p, "filter", -1); o.cov = num<double>(p, "p_shared", 0.35);
+            o.gene_search = p.has("gene_search"); o.perfect_search = p.has("perfect_search"); o.multi_fasta = p.has("multi_fasta");
+            o.quality = num<uint8_t>(p, "quality", 15); o.device = device;
+            return cidh::search(o);
+        }
+        if (sub == "read_id") {
+            Parsed p = parse(argc, argv, 2, {{'b', "bigsi", true, false}, {'q', "query", true, true}, {'c', "batch", true, false},
+                                             {'t', "threads", true, false}, {'n', "prefix", true, false}, {'d', "down_sample", true, false},
+                                             {'H', "high_mem_load", false, false}, {'p', "fp_correct", true, false},
+                                             {'Q', "quality", true, false}, {'B', "bitvector_sample", true, false}});
+            require(p, {"bigsi", "query", "prefix"});
+            cidh::ReadIdOpts o;
+            o.bigsi = p.one("bigsi"); o.query = p.v.at("query"); o.prefix = p.one("prefix");
+            o.threads = num<uint64_t>(p, "threads", 0); o.down_sample = num<uint64_t>(p, "down_sample", 1);
+            o.correct = num<double>(p, "fp_correct", 3.0); o.quality = num<uint8_t>(p, "quality", 15);
+            o.batch = num<uint64_t>(p, "batch", 50000); o.high_mem_load = p.has("high_mem_load");
+            o.bitvector_sample = num<uint64_t>(p, "bitvector_sample", 3); o.device = device;
+            if (o.bigsi.size() >= 4 && o.bigsi.compare(o.bigsi.size() - 4, 4, ".mxi") == 0)
+                throw cidh::Error("minimizer indexes (.mxi) are outside the GPU hot path");
+            return cidh::read_id(o);
+        }
+        if (sub == "info") {
+            Parsed p = parse(argc, argv, 2, {{'b', "bigsi", true, false}, {'c', "compressed", true, false}});
+            require(p, {"bigsi"});
+            return cidh::info(p.one("bigsi"));
+        }
+        if (sub == "_host") {
+            // parity hooks for the CPU test-suite (no GPU involved): dump what the host-side readers/writers produce
+            const std::string op = argc > 2 ? argv[2] : "";
+            if (op == "fasta" && argc == 4) {
+                for (auto& r : cidh::read_fasta(argv[3])) printf("%s\n", r.c_str());
+            } else if (op == "fasta_mf" && argc == 4) {
+                std::vector<std::string> l, q;
+                cidh::read_fasta_mf(argv[3], l, q);
+                for (auto& x : l) printf("L\t%s\n", x.c_str());
+                for (auto& x : q) printf("S\t%s\n", x.c_str());
+            } else if (op == "fastq" && (argc == 5 || argc == 6)) {      // Q R1 [R2]
+                cidh::SeqBatch sb;
+                const uint8_t q = (uint8_t)atoi(argv[3]);
+                const uint64_t n = argc == 6 ? cidh::fastq_masked_pe(argv[4], argv[5], q, sb) : cidh::fastq_masked_se(argv[4], q, sb);
+                printf("records\t%llu\n", (unsigned long long)n);
+                for (uint64_t i = 0; i < sb.n(); i++) printf("%.*s\n", (int)(sb.offs[i + 1] - sb.offs[i]), sb.bases.data() + sb.offs[i]);
+            } else if (op == "tab" && argc == 4) {
+                for (auto& kv : cidh::tab_to_map(argv[3])) { printf("%s", kv.first.c_str()); for (auto& f : kv.second) printf("\t%s", f.c_str()); printf("\n"); }
+            } else if (op == "bxi_copy" && argc == 5) {
+                cidh::save_bigsi(argv[4], cidh::read_bigsi(argv[3]));
+            } else if (op == "map_order" && argc >= 4) {
+                std::vector<std::string> keys(argv + 3, argv + argc);
+                for (size_t i : cidh::fnv_string_map_order(keys)) printf("%s\n", keys[i].c_str());
+            } else return usage();
+            return 0;
+        }
+        if (sub == "batch_id" || sub == "read_filter" || sub == "merge")
+            throw cidh::Error("subcommand '" + sub + "' is outside the GPU hot path (DESIGN.md §6); use the reference for it");
+        return usage();
+    } catch (const std::exception& e) {
+        fprintf(stderr, "%s\n", e.what());
+        return 101;                                     // a Rust panic exits with 101
+    }
+}

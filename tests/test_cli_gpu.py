@@ -1,0 +1,280 @@
+"""GPU tests of the host layer end to end: the colorid-b200 CLI (build / search / read_id on files) against the
+oracle's restatement of the reference, byte for byte on the .bxi contents and the output lines (lines whose
+order is hash-random in the reference are compared as sorted lists)."""
+import gzip
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests import bxi_py, synth
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "colorid_b200", "colorid-b200")
+K, S, H = 21, 300_007, 3
+
+
+def run(*args, ok=True):
+    r = subprocess.run([CLI, *map(str, args)], capture_output=True, text=True)
+    if ok:
+        assert r.returncode == 0, r.stderr[-2000:]
+    lines = r.stdout.split("\n")
+    body = lines[3:]
+    if body and body[-1] == "":
+        body = body[:-1]
+    return body, r
+
+
+def wrap_fasta(path, records, width=70):
+    with open(path, "w") as f:
+        for name, seq in records:
+            f.write(f">{name}\n")
+            s = seq.decode()
+            for i in range(0, len(s), width):
+                f.write(s[i:i + width] + "\n")
+
+
+def fastq_bytes(names, seqs, quals):
+    return "".join(f"@{n}\n{s.decode()}\n+\n{q}\n" for n, s, q in zip(names, seqs, quals)).encode()
+
+
+def rand_quals(rng, n, low=0.03):
+    q = np.full(n, 73, np.uint8)
+    q[rng.random(n) < low] = 35
+    return q.tobytes().decode()
+
+
+def read_pairs(rng, genomes, n, tag, **kw):
+    reads = synth.reads_from(rng, genomes, n, **kw)
+    names = [f"{tag}.{i} {i}/1" for i in range(n)]
+    q1 = [rand_quals(rng, len(r[0])) for r in reads]
+    q2 = [rand_quals(rng, len(r[1])) for r in reads]
+    return names, [r[0] for r in reads], [r[1] for r in reads], q1, q2
+
+
+@pytest.fixture(scope="module")
+def world(tmp_path_factory, oracle):
+    """5 FASTA accessions (2 contigs each, one lower-case), one paired-end and one single-end FASTQ.gz accession."""
+    d = tmp_path_factory.mktemp("cli")
+    rng = np.random.default_rng(0xC0101D77)
+    genomes = synth.clade_genomes(rng, 7, 6000, n_clades=3, div=0.02)
+    acc = {}
+    refs = []
+    for i in range(5):
+        g = genomes[i]
+        if i == 2:
+            g = g.lower()
+        name = f"Acc_{chr(ord('E') - i)}"                      # file order differs from sorted (colour) order
+        contigs = [g[:3500], g[3500:]]
+        wrap_fasta(d / f"{name}.fasta", [(f"{name}_c{j}", c) for j, c in enumerate(contigs)])
+        acc[name] = dict(mode=oracle.MODE_FASTA, seqs=contigs)
+        refs.append(f"{name}\t{d}/{name}.fasta")
+    n, s1, s2, q1, q2 = read_pairs(rng, [genomes[5]], 900, "pe", read_len=120, insert=260, err=0.004, frac_random=0.0)
+    (d / "pe_1.fastq.gz").write_bytes(gzip.compress(fastq_bytes(n, s1, q1)))
+    (d / "pe_2.fastq.gz").write_bytes(gzip.compress(fastq_bytes(n, s2, q2)))
+    masked = []
+    for a, b, qa, qb in zip(s1, s2, q1, q2):
+        masked += [oracle.qual_mask(a, qa.encode(), 15), oracle.qual_mask(b, qb.encode(), 15)]
+    acc["Reads_PE"] = dict(mode=oracle.MODE_FASTQ, seqs=masked)
+    refs.append(f"Reads_PE\t{d}/pe_1.fastq.gz\t{d}/pe_2.fastq.gz")
+    n, s1, _, q1, _ = read_pairs(rng, [genomes[6]], 1500, "se", read_len=120, insert=260, err=0.004, frac_random=0.0)
+    (d / "se.fastq.gz").write_bytes(gzip.compress(fastq_bytes(n, s1, q1)))
+    acc["Reads_SE"] = dict(mode=oracle.MODE_FASTQ, seqs=[oracle.qual_mask(a, qa.encode(), 15) for a, qa in zip(s1, q1)])
+    refs.append(f"Reads_SE\t{d}/se.fastq.gz")
+    (d / "refs.tsv").write_text("\n".join(refs) + "\n")
+    names = sorted(acc)                                         # colour = rank in byte-wise sorted order
+    oix = oracle.Index(S, H, K, len(names))
+    for c, name in enumerate(names):
+        oix.build_accession(c, acc[name]["seqs"], acc[name]["mode"], -1)
+    oix.finalize()
+    body, r = run("build", "-b", d / "idx", "-r", d / "refs.tsv", "-k", K, "-n", H, "-s", S)
+    assert body[-1] == "Saving BIGSI to file."
+    return dict(dir=d, genomes=genomes, names=names, oix=oix, rng=rng)
+
+
+def test_build_writes_the_reference_index(world, oracle):
+    got = bxi_py.read_bxi(world["dir"] / "idx.bxi")
+    oix, names = world["oix"], world["names"]
+    assert (got["bloom_size"], got["num_hash"], got["k_size"]) == (S, H, K)
+    assert got["colors"] == dict(enumerate(names))
+    assert got["n_ref"] == {n: int(oix.n_ref[c]) for c, n in enumerate(names)}
+    dense = oix.words()
+    nz = np.flatnonzero(dense.any(axis=1))
+    o = np.argsort(got["row_ids"])
+    assert np.array_equal(got["row_ids"][o], nz.astype(np.uint64))
+    assert np.array_equal(got["words"][o], dense[nz])
+
+
+def _gene_files(world, n=12):
+    d, rng, genomes = world["dir"], world["rng"], world["genomes"]
+    files, seqs = [], []
+    for i in range(n):
+        g = genomes[int(rng.integers(0, 5))]
+        s = int(rng.integers(0, len(g) - 1600))
+        q = g[s:s + int(rng.integers(200, 1500))]
+        if i % 3 == 1:
+            q = synth.mutate(rng, q, 0.03)
+        if i % 5 == 4:
+            q = synth.rand_seq(rng, 600)
+        p = d / f"gene_{i}.fasta"
+        wrap_fasta(p, [(f"gene_{i}", q)])
+        files.append(str(p))
+        seqs.append([q])
+    return files, seqs
+
+
+def test_search_gene_mode(world, oracle):
+    files, seqs = _gene_files(world)
+    o = world["oix"].query_counts(seqs, oracle.MODE_FASTA, True, -1)
+    exp = []
+    for q, f in enumerate(files):
+        nk = int(o["num_kmers"][q])
+        for c, name in enumerate(world["names"]):
+            v = int(o["counts"][q, c])
+            if v and v / nk >= 0.35:
+                exp.append(f"{f}\t{name}\t{nk}\t{v / nk:.3f}")
+    body, _ = run("search", "-b", world["dir"] / "idx.bxi", "-g", "-q", *files)
+    assert len(exp) >= 8
+    assert sorted(body) == sorted(exp)
+
+
+def test_search_default_report_fasta_and_fastq(world, oracle):
+    d, rng, names, oix = world["dir"], world["rng"], world["names"], world["oix"]
+    files, seqs = _gene_files(world, 4)
+
+    def expected(fname, o, q, cov):
+        out = []
+        nk = int(o["num_kmers"][q])
+        for c, name in enumerate(names):
+            v = int(o["counts"][q, c])
+            if not v:
+                continue
+            gc = v / int(oix.n_ref[c])
+            un = int(o["uniq_n"][q, c])
+            mean = int(o["uniq_sum"][q, c]) / un if un else 0.0
+            if gc > cov:
+                out.append(f"{fname}\t{nk}\t{name}\t{gc:.2f}\t{mean:.2f}\t{int(o['uniq_mode'][q, c])}\t{un}")
+        return out
+
+    o = oix.query_counts(seqs, oracle.MODE_FASTA, False, 0)
+    exp = [l for q, f in enumerate(files) for l in expected(f, o, q, 0.01)]
+    body, _ = run("search", "-b", d / "idx.bxi", "-f", 0, "-p", 0.01, "-q", *files)
+    assert len(exp) >= 3 and sorted(body) == sorted(exp)
+    # paired FASTQ sample: quality masking + auto_cutoff on the query (batch_search_pe.rs:24-41)
+    n, s1, s2, q1, q2 = read_pairs(rng, [world["genomes"][1]], 800, "q", read_len=120, insert=260, err=0.004, frac_random=0.02)
+    (d / "q_1.fastq.gz").write_bytes(gzip.compress(fastq_bytes(n, s1, q1)))
+    (d / "q_2.fastq.gz").write_bytes(gzip.compress(fastq_bytes(n, s2, q2)))
+    masked = []
+    for a, b, qa, qb in zip(s1, s2, q1, q2):
+        masked += [oracle.qual_mask(a, qa.encode(), 20), oracle.qual_mask(b, qb.encode(), 20)]
+    o = oix.query_counts([masked], oracle.MODE_FASTQ, False, -1)
+    exp = expected(str(d / "q_1.fastq.gz"), o, 0, 0.35)
+    body, _ = run("search", "-b", d / "idx.bxi", "-Q", 20, "-q", d / "q_1.fastq.gz", "-r", d / "q_2.fastq.gz")
+    assert len(exp) >= 1 and sorted(body) == sorted(exp)
+
+
+def test_search_perfect_and_multifasta(world, oracle):
+    d, rng, names, oix, genomes = world["dir"], world["rng"], world["names"], world["oix"], world["genomes"]
+    files, seqs = [], []
+    for i in range(6):
+        g = genomes[i % 5]
+        s = int(rng.integers(0, 3000))
+        q = g[s:s + 300] if i != 4 else synth.rand_seq(rng, 300)
+        p = d / f"perf_{i}.fasta"
+        wrap_fasta(p, [(f"p{i}", q)])
+        files.append(str(p))
+        seqs.append([q])
+    o = oix.query_perfect(seqs)
+    exp = []
+    for q, f in enumerate(files):
+        if o["status"][q] == 0:
+            for c, name in enumerate(names):
+                if (o["and_rows"][q, c // 32] >> (c % 32)) & 1:
+                    exp.append(f"{f}\t{name}\t{int(o['n_kmers'][q])}\t1.00")
+    body, r = run("search", "-b", d / "idx.bxi", "-s", "-q", *files)
+    assert len(exp) >= 5 and body == exp                      # ascending colour order inside a query, queries in order
+    assert "No perfect hits!" in r.stderr
+    # -s -m: one query per record, labels from the headers; a short record gives the stdout warning
+    recs = [(f"rec{i} note", s[0]) for i, s in enumerate(seqs)] + [("tiny", b"ACGTACGT")]
+    wrap_fasta(d / "multi.fasta", recs)
+    o = oix.query_perfect([s for _, s in recs], mf=True)
+    exp = []
+    for q, (label, _) in enumerate(recs):
+        if o["status"][q] == 2:
+            exp.append(f"Warning! no kmers in query '{label}'; maybe your kmer length is larger than your query length?")
+        elif o["status"][q] == 0:
+            for c, name in enumerate(names):
+                if (o["and_rows"][q, c // 32] >> (c % 32)) & 1:
+                    exp.append(f"{label}\t{name}\t{int(o['n_kmers'][q])}\t1.00")
+    body, _ = run("search", "-b", d / "idx.bxi", "-s", "-m", "-q", d / "multi.fasta")
+    assert body == exp
+
+
+CLS = {0: ("too_short", "accept"), 1: ("no_hits", "accept"), 2: ("no_significant_hits", "reject")}
+
+
+def _expected_read_lines(world, oracle, ids, reads, **kw):
+    oix, names = world["oix"], world["names"]
+    o = oix.read_id_batch(reads, top_cap=len(names), **kw)
+    lines, counts, order = [], {}, []
+    for r, rid in enumerate(ids):
+        kind = int(o["kind"][r])
+        ns = int(o["n_set"][r])
+        if kind in CLS:
+            cls, verdict = CLS[kind]
+            h, nt = 0, 0
+            if kind == 0:
+                ns = 0
+        elif kind == oracle.CLS_ACCEPT:
+            cls, verdict, h, nt = names[int(o["top"][r, 0])], "accept", int(o["hits"][r]), 1
+        else:
+            assert kind == oracle.CLS_REJECT_MULTI
+            nt = int(o["n_top"][r])
+            cls, verdict, h = ",".join(names[int(c)] for c in o["top"][r, :nt]), "reject", int(o["hits"][r])
+        lines.append(f"{rid}\t{cls}\t{h}\t{ns}\t{verdict}\t{nt}")
+        key = cls if verdict == "accept" else "reject"
+        if key not in counts:
+            order.append(key)
+        counts[key] = counts.get(key, 0) + 1
+    it, _ = oracle.hashset_str_order([k.encode() for k in order], 16, True)
+    return lines, [f"{order[i]}\t{counts[order[i]]}" for i in it]
+
+
+def test_read_id_paired_single_and_fasta(world, oracle):
+    d, rng, genomes = world["dir"], world["rng"], world["genomes"]
+    n, s1, s2, q1, q2 = read_pairs(rng, genomes[:5], 3000, "r", read_len=100, insert=180, err=0.006, frac_random=0.2)
+    s1[5], q1[5] = s1[5][:15], q1[5][:15]                      # mate 1 shorter than k -> too_short
+    (d / "r_1.fastq.gz").write_bytes(gzip.compress(fastq_bytes(n, s1, q1)))
+    (d / "r_2.fastq.gz").write_bytes(gzip.compress(fastq_bytes(n, s2, q2)))
+    ids = ["@" + x for x in n]
+    reads = [[oracle.qual_mask(a, qa.encode(), 15), oracle.qual_mask(b, qb.encode(), 15)] for a, b, qa, qb in zip(s1, s2, q1, q2)]
+    exp_lines, exp_counts = _expected_read_lines(world, oracle, ids, reads)
+    run("read_id", "-b", d / "idx.bxi", "-q", d / "r_1.fastq.gz", d / "r_2.fastq.gz", "-n", d / "pe_out")
+    assert (d / "pe_out_reads.txt").read_text().split("\n")[:-1] == exp_lines
+    assert (d / "pe_out_counts.txt").read_text().split("\n")[:-1] == exp_counts
+    classes = {l.split("\t")[1] for l in exp_lines}
+    assert "too_short" in classes and len(classes - CLS_NAMES) >= 3 and len(classes & CLS_NAMES) >= 2
+    # single end, -B 0 (search_index_classic), -d 2, -p 2, -Q 25
+    reads = [[oracle.qual_mask(a, qa.encode(), 25)] for a, qa in zip(s1, q1)]
+    exp_lines, exp_counts = _expected_read_lines(world, oracle, ids, reads, d=2, start_sample=0, fp_correct=10.0 ** -2.0)
+    run("read_id", "-b", d / "idx.bxi", "-q", d / "r_1.fastq.gz", "-n", d / "se_out", "-B", 0, "-d", 2, "-p", 2, "-Q", 25, "-t", 2)
+    assert (d / "se_out_reads.txt").read_text().split("\n")[:-1] == exp_lines
+    assert (d / "se_out_counts.txt").read_text().split("\n")[:-1] == exp_counts
+    # FASTA reads (stream_fasta keeps the line feeds inside the sequence, read_id_mt_pe.rs:477-493)
+    recs = [(f"fa{i}", s1[i] + s2[i]) for i in range(0, 400)]
+    wrap_fasta(d / "reads.fasta", recs, width=60)
+    ids, reads = [], []
+    for name, s in recs:
+        ids.append(">" + name)
+        t = s.decode()
+        reads.append([("".join(t[i:i + 60] + "\n" for i in range(0, len(t), 60))).encode()])
+    exp_lines, exp_counts = _expected_read_lines(world, oracle, ids, reads)
+    run("read_id", "-b", d / "idx.bxi", "-q", d / "reads.fasta", "-n", d / "fa_out")
+    assert (d / "fa_out_reads.txt").read_text().split("\n")[:-1] == exp_lines
+    assert (d / "fa_out_counts.txt").read_text().split("\n")[:-1] == exp_counts
+
+
+CLS_NAMES = {"too_short", "no_hits", "no_significant_hits"}

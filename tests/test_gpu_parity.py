@@ -104,6 +104,40 @@ def test_search_counts_and_unique_hits(oracle, ctx, N, k, S, H):
         assert np.array_equal(g["uniq_mode"], o["uniq_mode"])
 
 
+@pytest.mark.parametrize("N,k,S,H", [(70, 21, 300_007, 2), (300, 21, 200_003, 4), (1000, 21, 100_003, 2),
+                                     (1250, 31, 80_021, 4), (4000, 21, 20_011, 2)])
+def test_gene_search_streaming_gather(oracle, ctx, N, k, S, H):
+    """-g without unique-hit summaries takes query_hash + query_gather (cp.async ring, 1..32 lanes per row):
+    row strides of 4, 12, 32, 40 and 128 words; must equal the oracle and the fused kernel."""
+    rng = _rng(150 + N)
+    genomes, oix, gix = _index_pair(oracle, ctx, rng, N, k, S, H, glen=2500)
+    queries = []
+    for i in range(60):
+        g = genomes[int(rng.integers(0, N))]
+        s = int(rng.integers(0, len(g) - 2100))
+        q = g[s:s + int(rng.integers(k, 2000))]
+        if i % 3 == 1:
+            q = synth.mutate(rng, q, 0.02)
+        if i % 5 == 4:
+            q = synth.rand_seq(rng, 900)
+        queries.append([q] if i % 4 else [q[:len(q) // 2], q[len(q) // 2:]])
+    queries.append([b"ACG"])                                   # zero k-mers
+    queries.append([genomes[1][:k]])                           # exactly one k-mer
+    queries.append([b"".join(genomes[:12])])                   # several work items, > 8K k-mers
+    o = oix.query_counts(queries, oracle.MODE_FASTA, True, 0)
+    g = gix.query_counts(queries, cb.CID_SEQ_FASTA, True, 0, want_uniq=False)
+    assert np.array_equal(g["num_kmers"], o["num_kmers"])
+    assert np.array_equal(g["counts"], o["counts"])
+    ctx.set_option("query_fused", 1)
+    try:
+        f = gix.query_counts(queries, cb.CID_SEQ_FASTA, True, 0, want_uniq=False)
+    finally:
+        ctx.set_option("query_fused", 0)
+    assert np.array_equal(f["num_kmers"], o["num_kmers"])
+    assert np.array_equal(f["counts"], o["counts"])
+    assert int(o["counts"].max()) > 500
+
+
 def test_search_fastq_query_with_filters(oracle, ctx):
     rng = _rng(300)
     genomes, oix, gix = _index_pair(oracle, ctx, rng, 12, 27, 400_009, 4)

@@ -1,0 +1,156 @@
+"""CPU tests of the C++ host layer above the C ABI (colorid_b200/host): FASTA/FASTQ(.gz) readers, qual_mask,
+tab_to_map, the .bxi reader/writer and the counts-file ordering, each against the oracle's restatement of the
+reference (oracle/pyoracle.py) or an independent Python implementation.  No GPU is touched."""
+import gzip
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+from tests import bxi_py, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "colorid_b200", "colorid-b200")
+
+
+def host(*args):
+    r = subprocess.run([CLI, "_host", *map(str, args)], capture_output=True, text=True, check=True)
+    lines = r.stdout.split("\n")
+    assert "initializing logger" in lines[1]
+    return lines[3:-1] if lines[-1] == "" else lines[3:]
+
+
+def cli(*args):
+    return subprocess.run([CLI, *map(str, args)], capture_output=True, text=True)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    if not os.path.exists(CLI):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "colorid_b200", "host")])
+
+
+FASTA_CASES = [
+    ">a desc\nACGT\nTTGA\n>b\nGG\n",                       # plain
+    ">a\nACGT\nTTGA",                                       # no final newline
+    ">a\r\nACGT\r\nTT\r\n>b\r\nCC\r\n",                     # CRLF
+    "ACGT\n>a\nCC\n\nGG\n>b\n>c\nTT\n",                     # sequence before the first header, blank line, empty record
+    ">a\nAC>GT\nTT\n",                                      # '>' inside a sequence line counts as a header (kmer.rs:26)
+    ">a\nACGT\n>tail\n",                                    # header on the last line
+    "",
+]
+
+
+@pytest.mark.parametrize("i", range(len(FASTA_CASES)))
+def test_read_fasta_matches_reference_quirks(tmp_path, i):
+    p = tmp_path / "x.fa"
+    p.write_bytes(FASTA_CASES[i].encode())
+    assert [s.encode() for s in host("fasta", p)] == O.read_fasta(str(p))
+    labels, seqs = O.read_fasta_mf(str(p))
+    got = host("fasta_mf", p)
+    assert [x[2:].encode() for x in got if x.startswith("L\t")] == labels
+    assert [x[2:].encode() for x in got if x.startswith("S\t")] == seqs
+
+
+def _fastq(records):
+    return "".join(f"@{i}\n{s}\n+\n{q}\n" for i, (s, q) in enumerate(records)).encode()
+
+
+def test_fastq_readers_and_qual_mask(tmp_path):
+    rng = np.random.default_rng(5)
+    recs1, recs2 = [], []
+    for i in range(50):
+        n = int(rng.integers(1, 60))
+        s = synth.rand_seq(rng, n).decode()
+        q = "".join(chr(int(x)) for x in rng.integers(33, 75, n))
+        recs1.append((s, q if i % 7 else q[:max(1, n // 2)]))            # a shorter quality string truncates (seq.rs:45)
+        s2 = synth.rand_seq(rng, n).decode()
+        recs2.append((s2, "".join(chr(int(x)) for x in rng.integers(33, 75, n))))
+    p1, p2 = tmp_path / "r1.fq.gz", tmp_path / "r2.fq.gz"
+    # two gzip members in one file: MultiGzDecoder reads through both
+    p1.write_bytes(gzip.compress(_fastq(recs1[:20])) + gzip.compress(_fastq(recs1[20:])))
+    p2.write_bytes(gzip.compress(_fastq(recs2[:40])))                     # the shorter mate file ends the stream
+    for Q in (0, 15, 30):
+        got = host("fastq", Q, p1)
+        assert got[0] == "records\t50"
+        assert [g.encode() for g in got[1:]] == [O.qual_mask(s.encode(), q.encode(), Q) for s, q in recs1]
+        got = host("fastq", Q, p1, p2)
+        assert got[0] == "records\t40"
+        exp = []
+        for (s1, q1), (s2, q2) in zip(recs1[:40], recs2[:40]):
+            exp += [O.qual_mask(s1.encode(), q1.encode(), Q), O.qual_mask(s2.encode(), q2.encode(), Q)]
+        assert [g.encode() for g in got[1:]] == exp
+    plain = tmp_path / "plain.fq"
+    plain.write_bytes(_fastq(recs2[:5]))
+    assert host("fastq", 0, plain)[0] == "records\t5"
+
+
+def test_qual_longer_than_sequence_fails_like_the_reference(tmp_path):
+    p = tmp_path / "bad.fq"
+    p.write_bytes(b"@r\nACG\n+\nIIIII\n")
+    r = cli("_host", "fastq", 15, p)
+    assert r.returncode == 101 and "could not get the next nt" in r.stderr
+
+
+def test_tab_to_map(tmp_path):
+    p = tmp_path / "refs.tsv"
+    p.write_text("b\tb.fa\nA\tr1.gz\tr2.gz\na\ta.fa\nb\tb2.fa\n")
+    # byte-wise sorted accessions (colour order, build.rs:102-113); the later duplicate wins (HashMap::insert)
+    assert host("tab", p) == ["A\tr1.gz\tr2.gz", "a\ta.fa", "b\tb2.fa"]
+
+
+@pytest.mark.parametrize("N", [1, 33, 70])
+def test_bxi_roundtrip(tmp_path, N):
+    rng = np.random.default_rng(N)
+    W = (N + 31) // 32
+    S = 5000
+    row_ids = np.sort(rng.choice(S, size=700, replace=False)).astype(np.uint64)
+    words = rng.integers(0, 2**32, size=(700, W), dtype=np.uint64).astype(np.uint32)
+    if N % 32:
+        words[:, -1] &= np.uint32((1 << (N % 32)) - 1)
+    colors = {c: f"acc_{c:03d}" for c in range(N)}
+    n_ref = {f"acc_{c:03d}": int(rng.integers(1, 10**7)) for c in range(N)}
+    a, b = tmp_path / "a.bxi", tmp_path / "b.bxi"
+    # the reference writes map entries in hash-table order: readers must accept any order
+    bxi_py.write_bxi(a, S, 3, 21, colors, row_ids, words, n_ref, row_order=rng.permutation(700))
+    assert cli("_host", "bxi_copy", a, b).returncode == 0
+    got = bxi_py.read_bxi(b)
+    assert (got["bloom_size"], got["num_hash"], got["k_size"]) == (S, 3, 21)
+    assert got["colors"] == colors and got["n_ref"] == n_ref
+    o = np.argsort(got["row_ids"])
+    assert np.array_equal(got["row_ids"][o], row_ids)
+    assert np.array_equal(got["words"][o], words)
+    # `info` (main.rs:630-703)
+    r = cli("info", "-b", a)
+    lines = r.stdout.split("\n")
+    assert lines[3:8] == ["BIGSI parameters:", f"Bloomfilter-size: {S}", "Number of hashes: 3", "K-mer size: 21",
+                          f"Number of accessions in index: {N}"]
+    for c in range(N):
+        name = colors[c]
+        assert lines[8 + c] == f"{name} {n_ref[name]} {O.false_prob(S, 3, n_ref[name]):.3f}"
+
+
+def test_truncated_bxi_is_rejected(tmp_path):
+    a = tmp_path / "a.bxi"
+    bxi_py.write_bxi(a, 100, 2, 5, {0: "x"}, [3, 7], [[1], [1]], {"x": 4})
+    data = a.read_bytes()
+    a.write_bytes(data[:-5])
+    r = cli("info", "-b", a)
+    assert r.returncode == 101 and "deserialize" in r.stderr
+
+
+def test_counts_file_order_is_fnv_hashmap_order():
+    rng = np.random.default_rng(11)
+    for n in (1, 3, 4, 7, 8, 15, 29, 60):
+        keys = ["reject"] + [f"Genus_species_{int(x)}" for x in rng.choice(10**6, size=n - 1, replace=False)]
+        order, _ = O.hashset_str_order([k.encode() for k in keys], 16, True)
+        assert host("map_order", *keys) == [keys[i] for i in order]
+
+
+def test_cli_flag_errors():
+    r = cli("build", "-b", "x")
+    assert r.returncode == 101 and "required arguments" in r.stderr
+    r = cli("search", "-b", "x.bxi", "-q", "q.fa", "--bogus")
+    assert r.returncode == 101 and "wasn't expected" in r.stderr
