@@ -459,6 +459,7 @@ def run_ours(args):
         step_dev(i)
     barrier()
     launches0 = ctx.launches
+    ctx.read_counter("readid_gather_kmers")          # reset
     ctx.profile(True)
     clk = ClockSampler(local)
     clk.start()
@@ -473,6 +474,7 @@ def run_ours(args):
     prof = ctx.profile_read()
     ctx.profile(False)
     launches = ctx.launches - launches0
+    gather_kmers = ctx.read_counter("readid_gather_kmers") / K      # k-mers per step whose rows the vote kernel read
     # algorithmic traffic of the last step (all steps are statistically identical)
     fl = d_flags.cpu().numpy().view(np.uint32)
     nproc_last = int(((fl >> 8) & 0xFFFF).sum())
@@ -545,14 +547,17 @@ def run_ours(args):
     dom_per = prof[dom][0] / prof[dom][1]
     achieved = alg.get(dom, 0) / (dom_per / 1e3) / 1e9
     vote_ms = kern["readid_vote"]["ms_per_launch"] if "readid_vote" in kern else None
-    gathers = H * nproc_last               # one gather = one 8-byte row read at a random row
+    gathers = H * gather_kmers             # one gather = one 8-byte row read at a random row (device counter)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic.get(dom), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg.get(dom),
                 "measured_in": "the timed region itself: CUDA events around every launch on the launching stream",
                 "note": "8-byte rows: a gather moves 8 algorithmic bytes but costs one DRAM access (ncu: ~100 B of DRAM "
                         "traffic each, 56 B with ld.global.nc.L2::64B at the same rate), so the binding limit is the "
-                        "random-access rate, not bytes; see random_access",
+                        "random-access rate, not bytes; see random_access.  Reads whose candidate set is empty after the "
+                        "first -B k-mers only need the first-miss position, which the L2-resident row-present bitmap "
+                        "answers: those k-mers count in the algorithmic bytes (the reference gathers their rows) but not "
+                        "in gathers_per_launch",
                 "random_access": {"gathers_per_launch": gathers,
                                   "achieved_g_per_s": gathers / (vote_ms / 1e3) / 1e9 if vote_ms else None,
                                   "ceiling_g_per_s": GATHER_CEILING_G_PER_S,

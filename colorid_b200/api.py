@@ -56,6 +56,11 @@ class Context:
     def launches(self):
         return self.lib.cid_ctx_launch_count(self.h)
 
+    def read_counter(self, name):
+        v = C.c_uint64(0)
+        L.check(self.lib.cid_ctx_read_counter(self.h, name.encode(), C.byref(v)))
+        return v.value
+
     def profile(self, enable=True):
         L.check(self.lib.cid_ctx_profile(self.h, int(enable)))
 

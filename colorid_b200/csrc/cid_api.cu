@@ -71,7 +71,7 @@ int check_err_flags(cid_ctx* ctx, cudaStream_t st) {
     CID_CUDA(cudaStreamSynchronize(st));
     uint32_t f = ctx->h_err[0];
     if (!f) return CID_OK;
-    CID_CUDA(cudaMemsetAsync(ctx->d_err, 0, 16, st));
+    CID_CUDA(cudaMemsetAsync(ctx->d_err, 0, 8, st));
     if (f & ERRF_LOWER_RAW) {
         set_error("lower-case bases inside k-mers of a raw-case input (FASTQ / read_id) are not supported on the device yet");
         return CID_E_UNSUPPORTED;
@@ -254,6 +254,17 @@ int cid_ctx_profile_read(cid_ctx* c, int kernel, const char** name, double* tota
     return CID_OK;
 }
 uint64_t cid_ctx_launch_count(const cid_ctx* c) { return c ? c->launches : 0; }
+int cid_ctx_read_counter(cid_ctx* c, const char* name, uint64_t* value) {
+    if (!c || !name || !value) { set_error("cid_ctx_read_counter: null argument"); return CID_E_INVALID; }
+    if (strcmp(name, "readid_gather_kmers")) { set_error("cid_ctx_read_counter: unknown counter '%s'", name); return CID_E_INVALID; }
+    CID_CUDA(cudaSetDevice(c->device));
+    CID_CUDA(cudaDeviceSynchronize());
+    unsigned long long v = 0;
+    CID_CUDA(cudaMemcpy(&v, c->d_err + 2, 8, cudaMemcpyDeviceToHost));
+    CID_CUDA(cudaMemset(c->d_err + 2, 0, 8));
+    *value = v;
+    return CID_OK;
+}
 int cid_ctx_set_option(cid_ctx* c, const char* name, int64_t value) {
     if (!c || !name) { set_error("cid_ctx_set_option: null argument"); return CID_E_INVALID; }
     if (!strcmp(name, "readid_chunk_reads")) { c->opt_readid_chunk = value > 0 ? (uint64_t)value : 0; return CID_OK; }

@@ -522,17 +522,18 @@ __global__ void __launch_bounds__(RA_WARPS * 32)
 readid_vote_narrow_kernel(const uint8_t* __restrict__ bases, const uint8_t* __restrict__ quals, uint32_t maxq,
                           const uint64_t* __restrict__ seq_offs, const uint64_t* __restrict__ read_offs, uint64_t r0,
                           uint64_t nreads, uint32_t k, uint32_t H, ModS mods, const uint32_t* __restrict__ rows,
-                          const uint32_t* __restrict__ rownz, uint32_t N, int cap, uint32_t maxocc,
-                          const uint16_t* __restrict__ order, const uint8_t* __restrict__ order8,
+                          const uint32_t* __restrict__ rownz, const uint32_t* __restrict__ rownz_all, uint32_t N, int cap,
+                          uint32_t maxocc, const uint16_t* __restrict__ order, const uint8_t* __restrict__ order8,
                           const uint16_t* __restrict__ ent16, const uint32_t* __restrict__ n_set,
                           uint32_t start_sample, uint32_t rep_cap, uint32_t* __restrict__ flags,
                           uint32_t* __restrict__ rep_n, uint32_t* __restrict__ rep_colour,
-                          uint32_t* __restrict__ rep_count) {
+                          uint32_t* __restrict__ rep_count, unsigned long long* __restrict__ gather_counter) {
     extern __shared__ __align__(16) uint8_t dsm[];
     __shared__ uint32_t lut[256];
     lut4_init(lut, threadIdx.x, blockDim.x);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t my_gathers = 0;          // k-mers of this warp whose rows were read (diagnostic: bench's random-access rate)
     const size_t per_warp = ((tile_smem_bytes(cap) + 15) & ~(size_t)15) + 64 + (MAX_MATES + 1) * 4 + 12;
     uint8_t* base = dsm + (size_t)warp * ((per_warp + 15) & ~(size_t)15);
     Tile t = tile_carve(base, cap);
@@ -559,9 +560,13 @@ readid_vote_narrow_kernel(const uint8_t* __restrict__ bases, const uint8_t* __re
         const bool can_fine = (H == 1 || H == 2 || H == 4 || H == 8);
         uint32_t fine_left = can_fine ? FINE_STEPS : 0;
         for (uint32_t c0 = 0; c0 < n && !miss;) {
-            const bool fine = fine_left > 0;
+            // Once the candidate set is final (c0 >= start_sample) and EMPTY, no colour can ever be counted
+            // (read_id_mt_pe.rs:155-161): all that is left to learn is where the first absent row is, and the
+            // row-present bitmap (S/8 bytes, L2 resident) answers that without touching the matrix in DRAM.
+            const bool presence_only = !classic && c0 >= start_sample && (cand0 | cand1) == 0u;
+            const bool fine = fine_left > 0 && !presence_only;
             const uint32_t csize = fine ? 32u / H : 32u;
-            if (fine) fine_left--;
+            if (fine_left) fine_left--;
             const uint32_t idx = c0 + lane;
             const bool active = idx < n && (uint32_t)lane < csize;
             uint32_t x0 = 0, x1 = 0;
@@ -605,6 +610,11 @@ readid_vote_narrow_kernel(const uint8_t* __restrict__ bases, const uint8_t* __re
                 uint32_t ca = __shfl_sync(0xffffffffu, a, from), cb2 = __shfl_sync(0xffffffffu, b, from);
                 int cm = __shfl_sync(0xffffffffu, (int)mm, from);
                 if (active) { x0 = ca; x1 = cb2; m = cm != 0; }
+            } else if (active && presence_only) {
+                for (uint32_t h = 0; h < H; h++) {
+                    const uint64_t rid = mod_s(xxh3_kmer(in, k, h), mods);
+                    if (!((__ldg(rownz_all + (rid >> 5)) >> (rid & 31)) & 1u)) { m = true; break; }
+                }
             } else if (active) {
                 x0 = 0xFFFFFFFFu; x1 = WP == 2 ? 0xFFFFFFFFu : 0u;
                 for (uint32_t h = 0; h < H; h++) {
@@ -643,7 +653,9 @@ readid_vote_narrow_kernel(const uint8_t* __restrict__ bases, const uint8_t* __re
                     uint32_t v = __popc(__ballot_sync(0xffffffffu, (z1 >> b) & 1u));
                     if ((uint32_t)lane == b) cnt1 += v;
                 }
-            nproc += missmask ? p_local + 1 : min(csize, n - c0);
+            const uint32_t took = missmask ? p_local + 1 : min(csize, n - c0);
+            nproc += took;
+            if (!presence_only) my_gathers += min(csize, n - c0);
             if (missmask) miss = true;
             c0 += csize;
         }
@@ -665,6 +677,7 @@ readid_vote_narrow_kernel(const uint8_t* __restrict__ bases, const uint8_t* __re
             flags[r] |= (total > rep_cap ? 4u : 0u) | (min(nproc, 0xFFFFu) << 8);
         }
     }
+    if (lane == 0 && my_gathers && gather_counter) atomicAdd(gather_counter, (unsigned long long)my_gathers);
 }
 
 // ================================================================= readid_vote (any row width)
@@ -1131,14 +1144,14 @@ int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const ui
                 if (!idx->rownz_global) rownz = nullptr;   // presence == any word set, already in registers
                 if (idx->Wp == 1)
                     readid_vote_narrow_kernel<1><<<gridA, RA_WARPS * 32, cn_smem, st>>>(
-                        d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr, idx->k, idx->H, mods, idx->rows, rownz,
+                        d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr, idx->k, idx->H, mods, idx->rows, rownz, idx->rownz,
                         idx->N, cap, maxocc, ord16, ord8, d_ent16, d_n_set, p.start_sample, p.rep_cap, d_flags, d_rep_n, d_rep_colour,
-                        d_rep_count);
+                        d_rep_count, (unsigned long long*)(ctx->d_err + 2));
                 else
                     readid_vote_narrow_kernel<2><<<gridA, RA_WARPS * 32, cn_smem, st>>>(
-                        d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr, idx->k, idx->H, mods, idx->rows, rownz,
+                        d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr, idx->k, idx->H, mods, idx->rows, rownz, idx->rownz,
                         idx->N, cap, maxocc, ord16, ord8, d_ent16, d_n_set, p.start_sample, p.rep_cap, d_flags, d_rep_n, d_rep_colour,
-                        d_rep_count);
+                        d_rep_count, (unsigned long long*)(ctx->d_err + 2));
             } else {
                 readid_vote_wide_kernel<<<gridA, RA_WARPS * 32, cw_smem, st>>>(
                     d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr, idx->k, idx->H, mods, idx->rows, rownz, idx->N,

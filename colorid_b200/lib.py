@@ -62,6 +62,7 @@ SIGNATURES = {
     "cid_read_id_classify": (C.c_int, [vp, vp, vp, u64p, C.c_uint64, u64p, C.c_uint64, C.POINTER(ReadIdParams), u64p,
                                        C.c_double, C.POINTER(C.c_int32), u32p, u32p, u32p, u32p, C.c_uint32]),
     "cid_ctx_set_option": (C.c_int, [vp, C.c_char_p, C.c_int64]),
+    "cid_ctx_read_counter": (C.c_int, [vp, C.c_char_p, u64p]),
     "cid_hash_kmers": (C.c_int, [vp, vp, C.c_uint64, u64p]),
     "cid_ctx_profile": (C.c_int, [vp, C.c_int]),
     "cid_ctx_profile_read": (C.c_int, [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double), u64p]),

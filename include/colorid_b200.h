@@ -56,9 +56,14 @@ void cid_ctx_destroy(cid_ctx* ctx);
 int cid_ctx_device(const cid_ctx* ctx);
 /* Counters of kernels launched by this library since ctx creation (for bench `gpu_launches`). */
 uint64_t cid_ctx_launch_count(const cid_ctx* ctx);
+/* Diagnostic device counters, read and reset: "readid_gather_kmers" = k-mers whose matrix rows the read_id
+ * vote kernel actually read (x num_hash = row gathers; bench.py's random-access rate). */
+int cid_ctx_read_counter(cid_ctx* ctx, const char* name, uint64_t* value);
 /* Tuning knobs (never change results): "readid_chunk_reads" = reads per pipeline chunk of the
  * host-pointer read_id entry points (0 = automatic), "host_threads" = host threads used by the
- * read_id vote (0 = all cores; main.rs:718 rayon pool size `-t`). */
+ * read_id vote (0 = all cores; main.rs:718 rayon pool size `-t`), "readid_streams" = 2 forks the chunks of
+ * cid_read_id_batch_dev over two internal streams (default 1), "query_fused" = 1 forces the fused
+ * collect/hash/gather search kernel instead of query_hash + query_gather. */
 int cid_ctx_set_option(cid_ctx* ctx, const char* name, int64_t value);
 /* Per-kernel device timing with CUDA events on the launching stream (for bench.py's roofline).
  * cid_ctx_profile(ctx, 1) resets the accumulators and enables timing, (ctx, 0) disables it;
