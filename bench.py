@@ -379,6 +379,192 @@ def run_search_extra(torch, dev, ctx, args, quick):
     return out
 
 
+
+# ----------------------------------------------------------------------------- C5: column-sharded build + search
+C5 = dict(n_acc=10_000, genome_len=5_000_000, n_clades=100, div=0.01, k=31, S=50_000_000, H=4, n_queries=10_000,
+          qlen_lo=1000, qlen_hi=3000, n_probe=16)
+
+
+def run_c5(args):
+    """BASELINE.json configs[4]: 10,000 synthetic 5 Mbp genomes, k=31 S=50M H=4, the signature matrix column-sharded
+    over the ranks (whole 32-accession word columns per rank), every rank gathering all query k-mers from its slice,
+    per-query counts re-assembled with one NCCL all_gather.  `--c5-acc` scales the accession count (1250 per rank
+    keeps the C5 per-GPU shard shape: 160-byte rows)."""
+    import torch
+    import torch.distributed as dist
+    import colorid_b200 as cb
+    from colorid_b200 import lib as L
+    from colorid_b200 import sharding
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    cfg = dict(C5)
+    if args.c5_acc:
+        cfg["n_acc"] = args.c5_acc
+    if args.quick:
+        cfg.update(genome_len=100_000, S=2_000_003, n_queries=500, n_clades=10)
+    A, Lg, NC = cfg["n_acc"], cfg["genome_len"], cfg["n_clades"]
+    shards = sharding.column_shards(A, world)
+    lo, hi = shards[rank]
+    n_local = hi - lo
+    ctx = cb.Context(local)
+    lut = torch.tensor(ASCII, device=dev, dtype=torch.uint8)
+    g = torch.Generator(device=dev)
+    g.manual_seed(0xC0101D05)
+    roots = torch.randint(0, 4, (NC, Lg), generator=g, device=dev, dtype=torch.uint8)     # identical on every rank
+
+    def acc_codes(a):
+        """accession a = its clade root with `div` substitutions, reproducible on any rank"""
+        ga = torch.Generator(device=dev)
+        ga.manual_seed(0xC5000000 + a)
+        r = roots[a % NC].clone()
+        m = torch.rand(Lg, generator=ga, device=dev) < cfg["div"]
+        r[m] = torch.randint(0, 4, (int(m.sum()),), generator=ga, device=dev, dtype=torch.uint8)
+        return r
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- build: every rank indexes its own accessions (no exchange), then the row-present bitmaps are OR-ed
+    gix = cb.Index(ctx, cfg["S"], cfg["H"], cfg["k"], n_local)
+    offs = torch.tensor([0, Lg], device=dev, dtype=torch.int64)
+    barrier()
+    t0 = time.perf_counter()
+    gen_s = 0.0
+    for a in range(lo, hi):
+        tg = time.perf_counter()
+        asc = lut[acc_codes(a).long()].contiguous()
+        torch.cuda.synchronize()
+        gen_s += time.perf_counter() - tg
+        gix.build_accession_dev(a - lo, asc.data_ptr(), offs.data_ptr(), 1, Lg)
+    gix.finalize()
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0 - gen_s            # synthetic genome generation is not part of the build
+    _, bm_ptr, bm_words = gix.device_ptrs()
+    if world > 1:
+        sharding.or_reduce_bitmap(sharding.device_view(bm_ptr, bm_words, dev))
+        gix.set_rownz_global(True)
+    tb = torch.tensor([build_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+    build_s_max = float(tb.item())
+    log(f"[rank {rank}] shard {lo}..{hi}: built {n_local} accessions in {build_s:.2f}s (+{gen_s:.2f}s generating genomes)")
+
+    # ---- queries (identical on every rank): 70% clade-root slices with 1% substitutions, 20% random, and exact
+    # slices of a few probe accessions spread over the shards (self-query property: count == num_kmers)
+    gq = torch.Generator(device=dev)
+    gq.manual_seed(0xC0101D06)
+    nq = cfg["n_queries"]
+    qlen = torch.randint(cfg["qlen_lo"], cfg["qlen_hi"] + 1, (nq,), generator=gq, device=dev)
+    qoff = torch.zeros(nq + 1, device=dev, dtype=torch.int64)
+    qoff[1:] = torch.cumsum(qlen, 0)
+    total = int(qoff[-1].item())
+    qi = torch.repeat_interleave(torch.arange(nq, device=dev), qlen)
+    within = torch.arange(total, device=dev) - qoff[qi]
+    clade = torch.randint(0, NC, (nq,), generator=gq, device=dev)
+    start = (torch.rand(nq, generator=gq, device=dev) * (Lg - cfg["qlen_hi"] - 1)).long()
+    codes = roots.view(-1)[(clade * Lg + start)[qi] + within]
+    kind = torch.rand(nq, generator=gq, device=dev)
+    mut = (torch.rand(total, generator=gq, device=dev) < 0.01) & (kind < 0.7)[qi]
+    rnd = (kind >= 0.8)[qi]
+    repl = torch.randint(0, 4, (total,), generator=gq, device=dev, dtype=torch.uint8)
+    codes = torch.where(mut | rnd, repl, codes)
+    probes = [int(x) for x in np.linspace(0, A - 1, cfg["n_probe"]).astype(int)]
+    probe_q = []
+    h_qoff = qoff.cpu().numpy()
+    h_start = start.cpu().numpy()
+    exact_q = np.flatnonzero(((kind >= 0.7) & (kind < 0.8)).cpu().numpy())
+    for j, q in enumerate(exact_q[: 4 * len(probes)]):
+        a = probes[j % len(probes)]
+        codes[h_qoff[q]:h_qoff[q + 1]] = acc_codes(a)[h_start[q]:h_start[q] + (h_qoff[q + 1] - h_qoff[q])]
+        probe_q.append((int(q), a))
+    d_bases = lut[codes.long()].contiguous()
+    h_seq_offs = h_qoff.astype(np.uint64)
+    h_query_offs = np.arange(nq + 1, dtype=np.uint64)
+    d_query_offs = torch.from_numpy(h_query_offs.view(np.int64)).to(dev)
+    d_counts = torch.zeros((nq, n_local), device=dev, dtype=torch.int32)
+    d_nk = torch.zeros(nq, device=dev, dtype=torch.int64)
+    stream = torch.cuda.current_stream()
+    lib = ctx.lib
+    P = lambda a, tp=L.u64p: a.ctypes.data_as(tp)
+    gathered = [None]
+
+    def search_pass():
+        L.check(lib.cid_query_counts_dev(gix.h, d_bases.data_ptr(), qoff.data_ptr(), nq, total, d_query_offs.data_ptr(),
+                                         P(h_query_offs), P(h_seq_offs), nq, 0, d_counts.data_ptr(), d_nk.data_ptr(),
+                                         stream.cuda_stream))
+        gathered[0] = sharding.gather_counts(d_counts, shards) if world > 1 else d_counts     # NCCL all_gather
+
+    for _ in range(max(1, args.warmup)):
+        search_pass()
+    barrier()
+    ctx.profile(True)
+    clk = ClockSampler(local)
+    clk.start()
+    K = args.steps
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(K):
+        search_pass()
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1) / K
+    clocks = clk.stop()
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    lookups = int(d_nk.sum().item())
+    # ---- parity at full size: a query cut verbatim from accession a has every one of its k-mers in a's column
+    full = gathered[0]
+    nk_h = d_nk.cpu().numpy()
+    bad = [(q, a) for q, a in probe_q if int(full[q, a].item()) != int(nk_h[q])]
+    assert not bad, f"self-query property violated for {bad[:4]}"
+    assert full.shape == (nq, A)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = measured_peak()
+    Wp = cb.lib.load().cid_index_row_stride(gix.h)
+    R = 4 * Wp
+    kern = {k_: {"ms_per_launch": v[0] / v[1], "launches_per_pass": v[1] / K} for k_, v in prof.items()}
+    qc_ms = prof["query_counts"][0] / K if "query_counts" in prof else None
+    alg = lookups * (cfg["H"] * R + 1) + nq * 4 * n_local
+    roofline = None
+    if qc_ms:
+        roofline = {"bound": "hbm", "kernel": "query_counts", "achieved": alg / (qc_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": alg / (qc_ms / 1e3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_pass": alg, "row_bytes_per_shard": R, "ms_per_pass": qc_ms,
+                    "note": "per rank: every rank gathers all k-mers from its own column slice"}
+    line = {"metric": "search k-mer lookups/s", "value": lookups / (ms_max / 1e3), "unit": "k-mer lookups/s", "n_gpus": world,
+            "steps": K, "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": "C5 column-sharded build + gene search (BASELINE.json configs[4])", "n_accessions": A,
+                       "genome_len": Lg, "k": cfg["k"], "S": cfg["S"], "H": cfg["H"], "accessions_per_rank": n_local,
+                       "row_bytes_per_rank": R, "queries": nq, "collective": "NCCL all_gather of per-query counts (+ one "
+                       "all_gather/OR of the row-present bitmaps after the build)" if world > 1 else "none (single GPU)"},
+            "clocks": clocks, "gpu_launches": int(ctx.launches), "roofline": roofline, "kernels": kern,
+            "build": {"gbp_per_s": A * Lg / build_s_max / 1e9, "seconds": build_s_max,
+                      "note": "all ranks build their accession columns concurrently; max over ranks; synthetic genome "
+                              "generation excluded"},
+            "parity": {"self_query_probes": len(probe_q), "violations": 0}}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ----------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
@@ -628,9 +814,13 @@ def main():
     ap.add_argument("--no-search", action="store_true", help="skip the C3 gene-search extra measurement")
     ap.add_argument("--only-search", action="store_true", help="profiling aid: run only the C3 gene-search measurement")
     ap.add_argument("--quick", action="store_true", help="small genomes / bloom filter (functional check only)")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5"], help="c2 = read_id headline (default); c5 = column-sharded build + search")
+    ap.add_argument("--c5-acc", type=int, default=0, help="total accessions of the c5 workload (default 10,000)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c5":
+        run_c5(args)
     else:
         run_ours(args)
 

@@ -594,15 +594,18 @@ __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
     return v;
 }
 
-constexpr int QG_WARPS = 8;
-constexpr int QG_RING_BYTES = 64 * 1024;            // per CTA
+// 4 warps per work item: the per-thread cost of flushing the bit-sliced counters is fixed, so fewer warps per
+// item amortise it over more gather steps, and 4 CTAs per SM keep three gathering while one flushes.
+constexpr int QG_WARPS = 4;
+constexpr int QG_RING_BYTES = 32 * 1024;            // per CTA (8 KB per warp)
+constexpr int QG_PLANES = 13;                       // a lane group sees <= QUERY_ITEM_SLOTS / QG_WARPS = 4096 k-mers
 template <int HT> struct QGCfg {
     static constexpr int STAGE = HT * 512;          // bytes per warp and stage: 32 lanes x 16 B x HT rows
     static constexpr int D = QG_RING_BYTES / QG_WARPS / STAGE;   // stages per warp: 8 (H=2), 4 (H=4)
 };
 
 template <int HT>
-__global__ void __launch_bounds__(QG_WARPS * 32, 2)
+__global__ void __launch_bounds__(QG_WARPS * 32, 4)
 query_gather_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t N, const uint32_t* __restrict__ rid,
                     const uint32_t* __restrict__ unit_group, const uint64_t* __restrict__ unit_slot0,
                     const uint32_t* __restrict__ unit_n, uint32_t* __restrict__ counts) {
@@ -630,11 +633,11 @@ query_gather_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t N, 
     const uint32_t ring = (uint32_t)__cvta_generic_to_shared(dsm) + warp * (D * Cfg::STAGE) + lane * 16;
     const uint32_t* colbase = rows + colv * 4;
 
-    uint32_t pl[4][QC_PLANES];
+    uint32_t pl[4][QG_PLANES];
 #pragma unroll
     for (int v = 0; v < 4; v++)
 #pragma unroll
-        for (int p = 0; p < QC_PLANES; p++) pl[v][p] = 0;
+        for (int p = 0; p < QG_PLANES; p++) pl[v][p] = 0;
 
     // row indices of k-mer lo + BK*b + lane (batch b), double-buffered in registers
     uint32_t cur[HT], nxt[HT];
@@ -706,7 +709,7 @@ query_gather_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t N, 
             csa(t4b, pl[v][1], pl[v][1], t2a, t2b);
             csa(c8, pl[v][2], pl[v][2], t4a, t4b);
 #pragma unroll
-            for (int p = 3; p < QC_PLANES; p++) {
+            for (int p = 3; p < QG_PLANES; p++) {
                 const uint32_t t = pl[v][p] & c8;
                 pl[v][p] ^= c8;
                 c8 = t;
@@ -717,18 +720,38 @@ query_gather_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t N, 
     // flush: planes -> shared counters (warps and sub-groups hold partial counts of the same columns)
     // -> one global atomic per non-zero accession
     __syncthreads();
-    for (int i = tid; i < 4096; i += QG_WARPS * 32) cnt[i] = 0;
+    const int ncnt = (int)min(4096u, (N + 31) & ~31u);
+    for (int i = tid; i < ncnt; i += QG_WARPS * 32) cnt[i] = 0;
     __syncthreads();
     if (lane_on && T) {
         const int depth = 32 - __clz(((T + 7) & ~7u));     // planes that can be non-zero
 #pragma unroll
         for (int v = 0; v < 4; v++) {
             const uint32_t cbase = (colv * 4 + v) * 32;
+            uint32_t nz = 0;                                 // accessions of this word with a non-zero count
+#pragma unroll
+            for (int p = 0; p < QG_PLANES; p++) nz |= pl[v][p];
+            if (__popc(nz) <= 12) {
+                // sparse (a gene hits a few dozen of a thousand isolates): one shared atomic per non-zero accession
+                while (nz) {
+                    const uint32_t b = __ffs(nz) - 1;
+                    nz &= nz - 1;
+                    uint32_t val = 0;
+#pragma unroll
+                    for (int p = 0; p < QG_PLANES; p++) {
+                        if (p >= depth) break;
+                        val |= ((pl[v][p] >> b) & 1u) << p;
+                    }
+                    atomicAdd(&cnt[cbase + b], val);
+                }
+                continue;
+            }
 #pragma unroll
             for (int nb = 0; nb < 8; nb++) {
+                // dense: four accessions at a time, each plane's nibble spread into four byte lanes
                 uint32_t lo8 = 0, hi8 = 0;
 #pragma unroll
-                for (int p = 0; p < QC_PLANES; p++) {
+                for (int p = 0; p < QG_PLANES; p++) {
                     if (p >= depth) break;
                     const uint32_t sp = (((pl[v][p] >> (4 * nb)) & 0xFu) * 0x00204081u) & 0x01010101u;
                     if (p < 8) lo8 += sp << p; else hi8 += sp << (p - 8);
@@ -744,7 +767,7 @@ query_gather_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t N, 
         }
     }
     __syncthreads();
-    for (int i = tid; i < 4096; i += QG_WARPS * 32) {
+    for (int i = tid; i < ncnt; i += QG_WARPS * 32) {
         const uint32_t val = cnt[i];
         if (val && (uint32_t)i < N) atomicAdd(&counts[(uint64_t)g * N + i], val);
     }

@@ -62,9 +62,30 @@ def gather_and_rows(local_words, shards, group=None):
 
 
 def or_reduce_bitmap(bitmap, group=None):
-    """In-place OR over ranks of a row-present bitmap (int32/int64 tensor)."""
-    dist.all_reduce(bitmap, op=dist.ReduceOp.BOR, group=group)
+    """In-place OR over ranks of a row-present bitmap (int32/int64 tensor).  NCCL has no bitwise reductions,
+    so on GPUs the bitmaps (S/8 bytes each) are all-gathered over NVLink and OR-ed locally."""
+    if dist.get_backend(group) == "nccl":
+        parts = [torch.empty_like(bitmap) for _ in range(dist.get_world_size(group))]
+        dist.all_gather(parts, bitmap, group=group)
+        acc = parts[0]
+        for p in parts[1:]:
+            acc = torch.bitwise_or(acc, p)
+        bitmap.copy_(acc)
+    else:
+        dist.all_reduce(bitmap, op=dist.ReduceOp.BOR, group=group)
     return bitmap
+
+
+class _DevArray:
+    """__cuda_array_interface__ view of a raw device pointer owned by libcolorid_b200 (no copy)."""
+
+    def __init__(self, ptr, n, typestr="<i4"):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 3}
+
+
+def device_view(ptr, n, device, typestr="<i4"):
+    """torch tensor aliasing n elements at device pointer `ptr` (e.g. cid_index_device_ptrs' row-present bitmap)."""
+    return torch.as_tensor(_DevArray(ptr, n, typestr), device=device)
 
 
 def any_reduce_flags(flags, group=None):
