@@ -49,9 +49,25 @@ __device__ __forceinline__ bool warp_load_read(Tile& t, int cap, const uint8_t* 
         if (lane > 0 && lane < g.nm) atomicOr(&t.start[o >> 5], 1u << (o & 31));
     }
     const uint8_t* src = bases + g.b0;
-    for (int i = lane; i < g.len; i += 32) {
-        uint8_t c = __ldcs(src + i);                      // streamed once: do not displace matrix rows in L2
-        if (quals && (uint32_t)__ldcs(quals + g.b0 + i) < maxq) c = 'N';
+    const uint8_t* qsrc = quals ? quals + g.b0 : nullptr;
+    // streamed once (__ldcs): do not displace matrix rows in L2.  Word loads when both streams are 4-byte aligned.
+    int done = 0;
+    if (((uintptr_t)src & 3) == 0 && (!qsrc || (((uintptr_t)qsrc & 3) == 0 && maxq <= 255u))) {
+        const int nw = g.len >> 2;
+        const uint32_t maxq4 = maxq * 0x01010101u;
+        for (int w = lane; w < nw; w += 32) {
+            uint32_t c4 = __ldcs((const uint32_t*)src + w);
+            if (qsrc) {
+                const uint32_t low = __vcmpltu4(__ldcs((const uint32_t*)qsrc + w), maxq4);   // 0xFF where qual < maxq
+                c4 = (c4 & ~low) | (0x4E4E4E4Eu & low);                                      // 'N'
+            }
+            ((uint32_t*)t.ascii)[w] = c4;
+        }
+        done = nw << 2;
+    }
+    for (int i = done + lane; i < g.len; i += 32) {
+        uint8_t c = __ldcs(src + i);
+        if (qsrc && (uint32_t)__ldcs(qsrc + i) < maxq) c = 'N';
         t.ascii[i] = c;
     }
     __syncwarp();
@@ -120,11 +136,14 @@ readid_kmerize_kernel(const uint8_t* __restrict__ bases, const uint8_t* __restri
                 int tp = tp0 + lane;
                 uint32_t info = 0;
                 if (tp < g.len) {
-                    int m = 0;
-                    for (int j = 1; j < g.nm; j++) if ((int)moffs[j] <= tp) m = j;
-                    uint32_t i = (uint32_t)tp - moffs[m];
+                    bool take = true;
+                    if (d != 1) {                       // kmer.rs:229 step_by(d): position inside the mate
+                        int m = 0;
+                        for (int j = 1; j < g.nm; j++) if ((int)moffs[j] <= tp) m = j;
+                        take = ((uint32_t)tp - moffs[m]) % d == 0;
+                    }
                     uint64_t key; bool fwd, low;
-                    if ((d == 1 || i % d == 0) && tile_kmer(t, tp, k, key, fwd, low)) {
+                    if (take && tile_kmer(t, tp, k, key, fwd, low)) {
                         if (low) atomicOr(err, ERRF_LOWER_RAW);
                         uint32_t s = (uint32_t)mix64(key) & tmask;
                         for (;;) {
