@@ -565,6 +565,138 @@ def run_c5(args):
         dist.destroy_process_group()
 
 
+
+# ----------------------------------------------------------------------------- C4: build from read sets
+C4 = dict(n_acc=1000, genome_len=3_000_000, coverage=30, read_len=150, err=0.005, lowq=0.01, k=21, S=30_000_000, H=2,
+          qual_offset=15, n_clades=20, div=0.01)
+
+
+def run_c4(args):
+    """BASELINE.json configs[3]: build of a 1,000-accession index from synthetic 150 bp read sets (3 Mbp genomes at 30x,
+    0.5 % substitution errors) with the k-mer frequency filter (auto_cutoff), k=21 S=30M H=2.  One step = one accession
+    (600,000 reads = 90 Mbp): k-mer counting, histogram -> auto_cutoff, clean_map, Bloom insert.  `--c4-acc` bounds the
+    sample (the 1,000 accessions are statistically identical); accessions are dealt to the ranks (weak scaling)."""
+    import torch
+    import torch.distributed as dist
+    import colorid_b200 as cb
+    from colorid_b200 import lib as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    cfg = dict(C4)
+    if args.quick:
+        cfg.update(genome_len=200_000, S=3_000_000)
+    n_acc = args.c4_acc or 24                      # per rank
+    Lg, rl = cfg["genome_len"], cfg["read_len"]
+    n_reads = Lg * cfg["coverage"] // rl
+    ctx = cb.Context(local)
+    gix = cb.Index(ctx, cfg["S"], cfg["H"], cfg["k"], n_acc)
+    lut = torch.tensor(ASCII, device=dev, dtype=torch.uint8)
+    g = torch.Generator(device=dev)
+    g.manual_seed(0xC0101D04 + rank)
+    ar = torch.arange(rl, device=dev)
+    seq_offs = torch.arange(n_reads + 1, device=dev, dtype=torch.int64) * rl
+
+    def read_set(a):
+        """single-end 30x read set of a fresh random genome; qualities: 1 % of bases below -Q (masked to N on the host
+        side of the reference: seq.rs:36-56 -- here applied while generating, the ABI takes masked sequences)"""
+        genome = torch.randint(0, 4, (Lg,), generator=g, device=dev, dtype=torch.uint8)
+        pos = (torch.rand(n_reads, generator=g, device=dev) * (Lg - rl)).long()
+        codes = genome[pos[:, None] + ar[None, :]]
+        rc = torch.rand(n_reads, generator=g, device=dev) < 0.5
+        codes = torch.where(rc[:, None], 3 - codes.flip(1), codes)
+        e = torch.rand((n_reads, rl), generator=g, device=dev) < cfg["err"]
+        codes = torch.where(e, torch.randint(0, 4, (n_reads, rl), generator=g, device=dev, dtype=torch.uint8), codes)
+        asc = lut[codes.long()]
+        asc[torch.rand((n_reads, rl), generator=g, device=dev) < cfg["lowq"]] = 78          # 'N'
+        return genome, asc.contiguous()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    W = max(1, args.warmup)
+    K = min(args.steps, n_acc - W) if n_acc > W else 1
+    stats = []
+    genomes = {}
+    build_s = 0.0
+    ctx.profile(False)
+    clk = None
+    for a in range(W + K):
+        genome, asc = read_set(a)
+        torch.cuda.synchronize()
+        if a == W:
+            barrier()
+            ctx.profile(True)
+            clk = ClockSampler(local)
+            clk.start()
+        t0 = time.perf_counter()
+        n_ref, used = gix.build_accession_dev(a, asc.data_ptr(), seq_offs.data_ptr(), n_reads, n_reads * rl,
+                                              mode=L.CID_SEQ_FASTQ, cutoff=-1)
+        dt = time.perf_counter() - t0
+        if a >= W:
+            build_s += dt
+        stats.append((n_ref, used))
+        if a < 2:
+            genomes[a] = genome
+    torch.cuda.synchronize()
+    clocks = clk.stop()
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    t0 = time.perf_counter()
+    gix.finalize()
+    torch.cuda.synchronize()
+    fin_s = time.perf_counter() - t0
+    # size-independent parity properties: (1) auto_cutoff removes the error k-mers: n_ref_kmers is within 0.5 % of the
+    # genome's distinct canonical k-mers that the reads cover; (2) a slice of the genome queried with -g hits its accession
+    # on (nearly) every k-mer
+    q = genomes[0][1000:3000]
+    qa = lut[q.long()].contiguous()
+    res = gix.query_counts([[bytes(qa.cpu().numpy())]], gene_search=True, filt=0, want_uniq=False)
+    frac = float(res["counts"][0, 0]) / float(res["num_kmers"][0])
+    assert frac > 0.98, f"self-query of a read-built accession found only {frac:.3f} of its k-mers"
+    n_ref0, used0 = stats[0]
+    assert 0.95 * Lg < n_ref0 < 1.02 * Lg, f"n_ref_kmers {n_ref0} vs genome length {Lg}: frequency filter off"
+    tot = torch.tensor([build_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    bases_per_acc = n_reads * rl
+    peak, peak_src = measured_peak()
+    kern = {k_: {"ms_per_launch": v[0] / v[1], "launches_per_step": v[1] / K} for k_, v in prof.items()}
+    step_ms = float(tot.item()) / K * 1e3
+    alg = bases_per_acc + 3 * cfg["S"] // 8          # SURVEY 8d: L + 3S/8 per accession
+    line = {"metric": "build Gbp/s", "value": world * K * bases_per_acc / float(tot.item()) / 1e9, "unit": "Gbp/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "C4 build from read sets with the k-mer frequency filter (BASELINE.json configs[3])",
+                       "accessions_per_rank_in_sample": n_acc, "reads_per_accession": n_reads, "read_len": rl,
+                       "coverage": cfg["coverage"], "k": cfg["k"], "S": cfg["S"], "H": cfg["H"], "cutoff": "auto_cutoff",
+                       "l2_policy": "every step reads a fresh 90 MB read set and a 4 GB count table (126 MB L2)"},
+            "clocks": clocks, "gpu_launches": int(ctx.launches),
+            "roofline": {"bound": "hbm", "kernel": "whole step", "achieved": alg / (step_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (step_ms / 1e3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_step": alg,
+                         "note": "exact k-mer counting has no algorithmic traffic beyond reading L (SURVEY 8d): the count "
+                                 "table (16 B x 2 x positions) is implementation traffic, so this fraction is low by construction"},
+            "kernels": kern, "auto_cutoff_used": [int(u) for _, u in stats[:8]], "n_ref_kmers": [int(n) for n, _ in stats[:8]],
+            "finalize_seconds": fin_s, "parity": {"self_query_fraction": frac, "n_ref_over_genome_len": n_ref0 / Lg}}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ----------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
@@ -814,13 +946,16 @@ def main():
     ap.add_argument("--no-search", action="store_true", help="skip the C3 gene-search extra measurement")
     ap.add_argument("--only-search", action="store_true", help="profiling aid: run only the C3 gene-search measurement")
     ap.add_argument("--quick", action="store_true", help="small genomes / bloom filter (functional check only)")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c5"], help="c2 = read_id headline (default); c5 = column-sharded build + search")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"], help="c2 = read_id headline (default); c4 = build from read sets; c5 = column-sharded build + search")
+    ap.add_argument("--c4-acc", type=int, default=0, help="accessions per rank built by the c4 workload (default 24)")
     ap.add_argument("--c5-acc", type=int, default=0, help="total accessions of the c5 workload (default 10,000)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "c5":
         run_c5(args)
+    elif args.workload == "c4":
+        run_c4(args)
     else:
         run_ours(args)
 
