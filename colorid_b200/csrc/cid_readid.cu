@@ -110,6 +110,17 @@ readid_kmerize_kernel(const uint8_t* __restrict__ bases, const uint8_t* __restri
     for (uint64_t rl = (uint64_t)blockIdx.x * RA_WARPS + warp; rl < nreads; rl += (uint64_t)gridDim.x * RA_WARPS) {
         const uint64_t r = r0 + rl;
         const uint64_t s_begin = __ldg(read_offs + r), s_end = __ldg(read_offs + r + 1);
+        {   // pull the NEXT read of this warp towards L1 while this one is processed (its bytes are read once, at the top)
+            const uint64_t rn = rl + (uint64_t)gridDim.x * RA_WARPS;
+            if (rn < nreads) {
+                const uint64_t nb0 = __ldg(seq_offs + __ldg(read_offs + r0 + rn)), nb1 = __ldg(seq_offs + __ldg(read_offs + r0 + rn + 1));
+                const uint64_t off = nb0 + (uint64_t)(lane & 15) * 128;
+                if (nb1 > nb0 && off < nb1 + 127) {                       // every 128-byte line the read touches
+                    const uint8_t* pa = (lane < 16 ? bases : quals);
+                    if (pa) asm volatile("prefetch.global.L1 [%0];" ::"l"(pa + min(off, nb1 - 1)));
+                }
+            }
+        }
         uint32_t fl = 0, emitted = 0, nfr = 0;
         ReadGeom g;
         __syncwarp();
