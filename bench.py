@@ -438,6 +438,7 @@ def run_c5(args):
     gix = cb.Index(ctx, cfg["S"], cfg["H"], cfg["k"], n_local)
     offs = torch.tensor([0, Lg], device=dev, dtype=torch.int64)
     barrier()
+    ctx.profile(True)
     t0 = time.perf_counter()
     gen_s = 0.0
     for a in range(lo, hi):
@@ -449,6 +450,8 @@ def run_c5(args):
     gix.finalize()
     torch.cuda.synchronize()
     build_s = time.perf_counter() - t0 - gen_s            # synthetic genome generation is not part of the build
+    build_prof = ctx.profile_read()
+    ctx.profile(False)
     _, bm_ptr, bm_words = gix.device_ptrs()
     if world > 1:
         sharding.or_reduce_bitmap(sharding.device_view(bm_ptr, bm_words, dev))
@@ -558,7 +561,8 @@ def run_c5(args):
             "clocks": clocks, "gpu_launches": int(ctx.launches), "roofline": roofline, "kernels": kern,
             "build": {"gbp_per_s": A * Lg / build_s_max / 1e9, "seconds": build_s_max,
                       "note": "all ranks build their accession columns concurrently; max over ranks; synthetic genome "
-                              "generation excluded"},
+                              "generation excluded",
+                      "kernels_ms_total": {k_: v[0] for k_, v in build_prof.items()}},
             "parity": {"self_query_probes": len(probe_q), "violations": 0}}
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -777,7 +781,7 @@ def run_ours(args):
         step_dev(i)
     barrier()
     launches0 = ctx.launches
-    ctx.read_counter("readid_gather_kmers")          # reset
+    ctx.read_counter("readid_gather_rows")           # reset
     ctx.profile(True)
     clk = ClockSampler(local)
     clk.start()
@@ -792,7 +796,7 @@ def run_ours(args):
     prof = ctx.profile_read()
     ctx.profile(False)
     launches = ctx.launches - launches0
-    gather_kmers = ctx.read_counter("readid_gather_kmers") / K      # k-mers per step whose rows the vote kernel read
+    gather_rows = ctx.read_counter("readid_gather_rows") / K        # matrix rows per step the vote kernel read
     # algorithmic traffic of the last step (all steps are statistically identical)
     fl = d_flags.cpu().numpy().view(np.uint32)
     nproc_last = int(((fl >> 8) & 0xFFFF).sum())
@@ -865,7 +869,7 @@ def run_ours(args):
     dom_per = prof[dom][0] / prof[dom][1]
     achieved = alg.get(dom, 0) / (dom_per / 1e3) / 1e9
     vote_ms = kern["readid_vote"]["ms_per_launch"] if "readid_vote" in kern else None
-    gathers = H * gather_kmers             # one gather = one 8-byte row read at a random row (device counter)
+    gathers = gather_rows                  # one gather = one 8-byte row read at a random row (device counter)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic.get(dom), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg.get(dom),

@@ -256,7 +256,7 @@ int cid_ctx_profile_read(cid_ctx* c, int kernel, const char** name, double* tota
 uint64_t cid_ctx_launch_count(const cid_ctx* c) { return c ? c->launches : 0; }
 int cid_ctx_read_counter(cid_ctx* c, const char* name, uint64_t* value) {
     if (!c || !name || !value) { set_error("cid_ctx_read_counter: null argument"); return CID_E_INVALID; }
-    if (strcmp(name, "readid_gather_kmers")) { set_error("cid_ctx_read_counter: unknown counter '%s'", name); return CID_E_INVALID; }
+    if (strcmp(name, "readid_gather_rows")) { set_error("cid_ctx_read_counter: unknown counter '%s'", name); return CID_E_INVALID; }
     CID_CUDA(cudaSetDevice(c->device));
     CID_CUDA(cudaDeviceSynchronize());
     unsigned long long v = 0;

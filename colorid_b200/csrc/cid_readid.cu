@@ -563,7 +563,7 @@ readid_vote_narrow_kernel(const uint8_t* __restrict__ bases, const uint8_t* __re
     lut4_init(lut, threadIdx.x, blockDim.x);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t my_gathers = 0;          // k-mers of this warp whose rows were read (diagnostic: bench's random-access rate)
+    uint32_t my_gather_rows = 0;      // matrix rows this warp read (diagnostic: bench's random-access rate)
     const size_t per_warp = ((tile_smem_bytes(cap) + 15) & ~(size_t)15) + 64 + (MAX_MATES + 1) * 4 + 12;
     uint8_t* base = dsm + (size_t)warp * ((per_warp + 15) & ~(size_t)15);
     Tile t = tile_carve(base, cap);
@@ -600,7 +600,7 @@ readid_vote_narrow_kernel(const uint8_t* __restrict__ bases, const uint8_t* __re
             const uint32_t idx = c0 + lane;
             const bool active = idx < n && (uint32_t)lane < csize;
             uint32_t x0 = 0, x1 = 0;
-            bool m = false;
+            bool m = false, skipped_rows = false;
             HashIn in;
             in.w0 = in.w1 = in.w2 = in.w3 = 0;
             if (active) {
@@ -646,15 +646,47 @@ readid_vote_narrow_kernel(const uint8_t* __restrict__ bases, const uint8_t* __re
                     if (!((__ldg(rownz_all + (rid >> 5)) >> (rid & 31)) & 1u)) { m = true; break; }
                 }
             } else if (active) {
-                x0 = 0xFFFFFFFFu; x1 = WP == 2 ? 0xFFFFFFFFu : 0u;
-                for (uint32_t h = 0; h < H; h++) {
-                    uint64_t rid = mod_s(xxh3_kmer(in, k, h), mods);
+                // Row 0 first; the other H-1 rows are fetched (all in flight together) only while some candidate
+                // colour can still be counted for this k-mer.  Once the candidate set is final, a k-mer whose
+                // partial AND has lost every candidate bit contributes nothing (read_id_mt_pe.rs:155-161) and only
+                // the PRESENCE of its remaining rows matters, which the L2-resident bitmap answers.
+                const bool cand_final = !classic && c0 >= start_sample;
+                uint32_t rid[MAX_HASH];
+#pragma unroll
+                for (int h = 0; h < MAX_HASH; h++) rid[h] = (uint32_t)h < H ? (uint32_t)mod_s(xxh3_kmer(in, k, h), mods) : 0u;
+                {
                     uint32_t a, b = 0;
-                    if (WP == 2) { uint2 v = __ldg((const uint2*)(rows + rid * 2)); a = v.x; b = v.y; }
-                    else a = __ldg(rows + rid);
-                    bool present = rownz ? ((__ldg(rownz + (rid >> 5)) >> (rid & 31)) & 1u) : ((a | b) != 0u);
+                    if (WP == 2) { uint2 v = __ldg((const uint2*)(rows + (size_t)rid[0] * 2)); a = v.x; b = v.y; }
+                    else a = __ldg(rows + rid[0]);
+                    const bool present = rownz ? ((__ldg(rownz + (rid[0] >> 5)) >> (rid[0] & 31)) & 1u) : ((a | b) != 0u);
                     if (!present) m = true;     // read_id_mt_pe.rs:121-123 `None => break`
-                    x0 &= a; x1 &= b;
+                    x0 = a; x1 = b;
+                }
+                if (cand_final) { x0 &= cand0; x1 &= cand1; }
+                if (!cand_final || (x0 | x1) != 0u) {
+                    uint32_t ra[MAX_HASH], rb[MAX_HASH];
+#pragma unroll
+                    for (int h = 1; h < MAX_HASH; h++) {
+                        ra[h] = 0xFFFFFFFFu; rb[h] = 0xFFFFFFFFu;
+                        if ((uint32_t)h < H) {
+                            if (WP == 2) { uint2 v = __ldg((const uint2*)(rows + (size_t)rid[h] * 2)); ra[h] = v.x; rb[h] = v.y; }
+                            else { ra[h] = __ldg(rows + rid[h]); rb[h] = 0; }
+                        }
+                    }
+#pragma unroll
+                    for (int h = 1; h < MAX_HASH; h++) {
+                        if ((uint32_t)h < H) {
+                            const bool present = rownz ? ((__ldg(rownz + (rid[h] >> 5)) >> (rid[h] & 31)) & 1u) : ((ra[h] | rb[h]) != 0u);
+                            if (!present) m = true;
+                            x0 &= ra[h]; x1 &= rb[h];
+                        }
+                    }
+                    if (WP == 1) x1 = 0;
+                } else {
+#pragma unroll
+                    for (int h = 1; h < MAX_HASH; h++)
+                        if ((uint32_t)h < H && !((__ldg(rownz_all + (rid[h] >> 5)) >> (rid[h] & 31)) & 1u)) m = true;
+                    skipped_rows = true;
                 }
             }
             const uint32_t missmask = __ballot_sync(0xffffffffu, active && m);
@@ -685,7 +717,11 @@ readid_vote_narrow_kernel(const uint8_t* __restrict__ bases, const uint8_t* __re
                 }
             const uint32_t took = missmask ? p_local + 1 : min(csize, n - c0);
             nproc += took;
-            if (!presence_only) my_gathers += min(csize, n - c0);
+            // diagnostic: row reads in units of 1/H k-mer (a k-mer that stopped after row 0 costs one row)
+            if (!presence_only) {
+                const uint32_t act = __popc(__ballot_sync(0xffffffffu, active)), skp = __popc(__ballot_sync(0xffffffffu, skipped_rows));
+                my_gather_rows += (act - skp) * H + skp;
+            }
             if (missmask) miss = true;
             c0 += csize;
         }
@@ -707,7 +743,7 @@ readid_vote_narrow_kernel(const uint8_t* __restrict__ bases, const uint8_t* __re
             flags[r] |= (total > rep_cap ? 4u : 0u) | (min(nproc, 0xFFFFu) << 8);
         }
     }
-    if (lane == 0 && my_gathers && gather_counter) atomicAdd(gather_counter, (unsigned long long)my_gathers);
+    if (lane == 0 && my_gather_rows && gather_counter) atomicAdd(gather_counter, (unsigned long long)my_gather_rows);
 }
 
 // ================================================================= readid_vote (any row width)

@@ -56,8 +56,8 @@ void cid_ctx_destroy(cid_ctx* ctx);
 int cid_ctx_device(const cid_ctx* ctx);
 /* Counters of kernels launched by this library since ctx creation (for bench `gpu_launches`). */
 uint64_t cid_ctx_launch_count(const cid_ctx* ctx);
-/* Diagnostic device counters, read and reset: "readid_gather_kmers" = k-mers whose matrix rows the read_id
- * vote kernel actually read (x num_hash = row gathers; bench.py's random-access rate). */
+/* Diagnostic device counters, read and reset: "readid_gather_rows" = matrix rows the read_id vote kernel
+ * actually read (bench.py's random-access rate). */
 int cid_ctx_read_counter(cid_ctx* ctx, const char* name, uint64_t* value);
 /* Tuning knobs (never change results): "readid_chunk_reads" = reads per pipeline chunk of the
  * host-pointer read_id entry points (0 = automatic), "host_threads" = host threads used by the

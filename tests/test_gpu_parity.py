@@ -371,3 +371,38 @@ def test_lowercase_fastq_is_refused_loudly(ctx):
     with pytest.raises(cb.CidError) as e:
         gix.build_accession(0, [b"acgtacgtacgtacgtacgtacgtacgt"], cb.CID_SEQ_FASTQ, 0)
     assert e.value.code == cb.lib.CID_E_UNSUPPORTED
+
+
+def test_empty_and_degenerate_inputs(oracle, ctx):
+    """Empty batches, empty sequences and queries without k-mers go through every entry point without touching memory
+    they should not (run under compute-sanitizer when changing kernels) and agree with the oracle."""
+    rng = _rng(77)
+    N, k, S, H = 70, 21, 100_003, 2
+    genomes, oix, gix = _index_pair(oracle, ctx, rng, N, k, S, H, glen=3000)
+    # no queries / no reads at all
+    g = gix.query_counts([], cb.CID_SEQ_FASTA, True, 0, want_uniq=False)
+    assert g["counts"].shape == (0, N)
+    assert gix.query_perfect([])["and_rows"].shape[0] == 0
+    assert gix.query_perfect_mf([])["status"].shape[0] == 0
+    assert len(gix.read_id_classify([])["kind"]) == 0
+    assert len(gix.read_id_batch([])["rep_n"]) == 0
+    # queries made only of empty / too-short / all-N sequences, mixed with a real one
+    queries = [[b""], [b"", b"ACGT"], [b"N" * 100], [genomes[3][10:400]], [b"", genomes[4][:k], b""]]
+    o = oix.query_counts(queries, oracle.MODE_FASTA, True, 0)
+    for uq in (True, False):
+        g = gix.query_counts(queries, cb.CID_SEQ_FASTA, True, 0, want_uniq=uq)
+        assert np.array_equal(g["num_kmers"], o["num_kmers"]) and np.array_equal(g["counts"], o["counts"])
+    assert o["num_kmers"].tolist()[:3] == [0, 0, 0] and o["num_kmers"][4] == 1
+    op, gp = oix.query_perfect(queries), gix.query_perfect(queries)
+    assert np.array_equal(gp["status"], op["status"]) and np.array_equal(gp["and_rows"], op["and_rows"])
+    # reads: empty mates, one-base mates, a read whose only k-mer sits at the very end
+    reads = [[genomes[0][:150], b""], [b"A"], [b"N" * 40 + genomes[2][:k]], [genomes[1][:k]]]
+    _readid_compare(oracle, oix, gix, reads)
+    # an accession without any k-mer leaves its column empty and n_ref_kmers == 0
+    gi2 = cb.Index(ctx, S, H, k, 3)
+    oi2 = oracle.Index(S, H, k, 3)
+    for c, seqs in enumerate([[b""], [genomes[0]], [b"ACGTN" * 3]]):
+        assert gi2.build_accession(c, seqs, cb.CID_SEQ_FASTA) == oi2.build_accession(c, seqs, oracle.MODE_FASTA)
+    gi2.finalize()
+    oi2.finalize()
+    assert np.array_equal(gi2.download_dense(), oi2.words())
