@@ -371,8 +371,9 @@ def run_search_extra(torch, dev, ctx, args, quick):
     if "query_counts" in prof:
         qc_ms = prof["query_counts"][0] / reps            # all query_counts launches of one pass
         alg = lookups * (cfg["H"] * R + 1) + nq * 4 * A    # H*R + k_in per lookup, + 4N counts per query
-        out["roofline"] = {"bound": "hbm", "kernel": "query_counts", "achieved": alg / (qc_ms / 1e3) / 1e9, "peak": peak,
+        out["roofline"] = {"bound": "hbm", "kernel": "query_counts (query_gather_kernel)", "achieved": alg / (qc_ms / 1e3) / 1e9, "peak": peak,
                            "unit": "GB/s", "frac": alg / (qc_ms / 1e3) / 1e9 / peak, "traffic": None,
+                           "traffic_captured_launch": ncu_traffic().get("query_counts"),
                            "peak_source": peak_src, "algorithmic_bytes_per_pass": alg, "ms_per_pass": qc_ms}
     # spot parity on a few queries against the oracle would need the CPU index (1000 x 3 Mbp): covered by tests/ instead
     gix.close()

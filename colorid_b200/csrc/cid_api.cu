@@ -80,6 +80,7 @@ int check_err_flags(cid_ctx* ctx, cudaStream_t st) {
         set_error("-s -m query (kmerize_string) with a byte outside ACGTacgt inside a k-mer is not supported on the device");
         return CID_E_UNSUPPORTED;
     }
+    if (f & ERRF_TABLE_FULL) { set_error("k-mer count table overflow"); return CID_E_CAPACITY; }
     if (f & ERRF_READ_TOO_LONG) { set_error("a read exceeds the declared maximum read length"); return CID_E_CAPACITY; }
     set_error("internal capacity exceeded (flags 0x%x)", f);
     return CID_E_CAPACITY;
@@ -174,9 +175,9 @@ static int ensure_bitsets(cid_index* idx) {
 
 // One group worth of count table on scratch[0]; off/mask on scratch[1].
 static int single_region(cid_ctx* ctx, cudaStream_t st, uint64_t nbases, uint32_t k, uint64_t* nslots_out,
-                         uint64_t** d_off, uint64_t** d_mask) {
+                         uint64_t** d_off, uint64_t** d_mask, uint64_t slots_hint = 0) {
     uint64_t npos = nbases >= k ? nbases - k + 1 : 0;
-    uint64_t slots = next_pow2(std::max<uint64_t>(64, 2 * npos));
+    uint64_t slots = slots_hint ? slots_hint : next_pow2(std::max<uint64_t>(64, 2 * npos));
     CID_TRY(ctx->scratch[0].ensure(slots * sizeof(Slot)));
     CID_TRY(ctx->scratch[1].ensure(64));
     uint64_t hv[2] = {0, slots - 1};
@@ -409,9 +410,27 @@ int cid_build_accession_dev(cid_index* ix, uint32_t colour, const char* d_bases,
     CID_CUDA(cudaSetDevice(ctx->device));
     CID_TRY(ensure_bitsets(ix));
     uint64_t nslots; uint64_t *d_off, *d_mask;
-    CID_TRY(single_region(ctx, st, nbases, ix->k, &nslots, &d_off, &d_mask));
-    CID_TRY(launch_kmerize_insert(ctx, st, (const uint8_t*)d_bases, d_seq_offs, nseq, 0, nbases, nullptr, d_off, d_mask,
-                                  ctx->scratch[0].p, ix->k, seq_mode));
+    // Read sets (many short sequences, deep coverage) hold far fewer DISTINCT k-mers than k-mer positions, and the
+    // table is scanned three times after counting (clear, histogram, Bloom insert): size it optimistically for
+    // positions/2 and fall back to the safe 2x-positions table if it ends up more than 60 % full.
+    const uint64_t npos = nbases >= ix->k ? nbases - ix->k + 1 : 0;
+    uint64_t hint = 0;
+    if (seq_mode == CID_SEQ_FASTQ && nseq >= 4096 && npos >= (1ull << 22)) hint = next_pow2(npos / 2);
+    for (;;) {
+        CID_TRY(single_region(ctx, st, nbases, ix->k, &nslots, &d_off, &d_mask, hint));
+        CID_CUDA(cudaMemsetAsync(ctx->d_err + 1, 0, 4, st));
+        CID_TRY(launch_kmerize_insert(ctx, st, (const uint8_t*)d_bases, d_seq_offs, nseq, 0, nbases, nullptr, d_off, d_mask,
+                                      ctx->scratch[0].p, ix->k, seq_mode));
+        CID_CUDA(cudaMemcpyAsync(ctx->h_err, ctx->d_err, 8, cudaMemcpyDeviceToHost, st));
+        CID_CUDA(cudaStreamSynchronize(st));
+        const uint32_t flags = ctx->h_err[0], distinct = ctx->h_err[1];
+        if (hint && ((flags & ERRF_TABLE_FULL) || (uint64_t)distinct * 10 > nslots * 6)) {
+            CID_CUDA(cudaMemsetAsync(ctx->d_err, 0, 8, st));
+            hint = 0;                       // redo with the safe size
+            continue;
+        }
+        break;
+    }
     CID_TRY(check_err_flags(ctx, st));
     int64_t used = cutoff;       // FASTA with -1: keep everything (count > -1)
     if (seq_mode == CID_SEQ_FASTQ && cutoff == -1)

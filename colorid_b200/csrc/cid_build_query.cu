@@ -32,9 +32,10 @@ kmerize_insert_kernel(const uint8_t* __restrict__ bases, const uint64_t* __restr
     __shared__ __align__(16) uint8_t smem[tile_smem_bytes(KT_CAP)];
     __shared__ uint32_t s_starts[KT_MAXSTARTS];
     __shared__ uint64_t s_s0;
-    __shared__ uint32_t s_nstarts;
+    __shared__ uint32_t s_nstarts, s_fresh;
 
     const int tid = threadIdx.x;
+    uint32_t fresh = 0;
     const uint64_t tile_start = base_lo + (uint64_t)blockIdx.x * KT;   // [base_lo, nbases) is the slice of `bases` covered by seq_offs[0..nseq]
     if (tile_start >= nbases) return;
     const int tile_len = (int)min((uint64_t)(KT + k - 1), nbases - tile_start);
@@ -62,6 +63,7 @@ kmerize_insert_kernel(const uint8_t* __restrict__ bases, const uint64_t* __restr
         }
         s_s0 = lo;
         s_nstarts = 0;
+        s_fresh = 0;
     }
     __syncthreads();
     const uint64_t s0 = s_s0;
@@ -100,8 +102,15 @@ kmerize_insert_kernel(const uint8_t* __restrict__ bases, const uint64_t* __restr
         while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (s_starts[mid] <= (uint32_t)p) lo = mid + 1; else hi = mid; }
         uint64_t owner = s0 + lo;
         uint32_t g = seq_group ? __ldg(seq_group + owner) : 0u;
-        table_insert(table + __ldg(region_off + g), __ldg(region_mask + g), key);
+        const int rc = table_insert(table + __ldg(region_off + g), __ldg(region_mask + g), key);
+        if (rc < 0) atomicOr(err, ERRF_TABLE_FULL);
+        fresh += rc > 0;
     }
+    // distinct k-mers inserted by this launch (err[1]): lets the build size count tables optimistically
+    fresh = __reduce_add_sync(0xffffffffu, fresh);
+    if ((tid & 31) == 0 && fresh) atomicAdd(&s_fresh, fresh);
+    __syncthreads();
+    if (tid == 0 && s_fresh) atomicAdd(err + 1, s_fresh);
 }
 
 int launch_kmerize_insert(cid_ctx* ctx, cudaStream_t st, const uint8_t* d_bases, const uint64_t* d_seq_offs,

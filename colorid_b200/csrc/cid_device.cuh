@@ -305,13 +305,17 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {   // murmur3 finalizer: 
     x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
     return x;
 }
-__device__ __forceinline__ void table_insert(Slot* region, uint64_t mask, uint64_t key) {
+// Returns 1 if the key was new, 0 if it was already present, -1 if the region is (nearly) full: the probe
+// sequence is cut after CID_MAX_PROBE slots so an optimistically sized table can never hang a kernel.
+#define CID_MAX_PROBE 2048
+__device__ __forceinline__ int table_insert(Slot* region, uint64_t mask, uint64_t key) {
     uint64_t h = mix64(key) & mask;
-    for (;;) {
+    for (int probes = 0; probes < CID_MAX_PROBE; probes++) {
         unsigned long long prev = atomicCAS(&region[h].key, CID_EMPTY_KEY, (unsigned long long)key);
-        if (prev == CID_EMPTY_KEY || prev == key) { atomicAdd(&region[h].count, 1u); return; }
+        if (prev == CID_EMPTY_KEY || prev == key) { atomicAdd(&region[h].count, 1u); return prev == CID_EMPTY_KEY ? 1 : 0; }
         h = (h + 1) & mask;
     }
+    return -1;
 }
 
 }  // namespace cid

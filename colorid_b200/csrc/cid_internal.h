@@ -101,7 +101,8 @@ enum {
     ERRF_STARTS_OVERFLOW = 1u << 1,
     ERRF_LIST_OVERFLOW = 1u << 2,
     ERRF_READ_TOO_LONG = 1u << 3,
-    ERRF_STRING_NONACGT = 1u << 4, // kmerize_string window with a byte outside ACGTacgt (cannot be 2-bit packed)
+    ERRF_STRING_NONACGT = 1u << 4,
+    ERRF_TABLE_FULL = 1u << 5,     // a count-table region overflowed (only possible with optimistic sizing: caller retries) // kmerize_string window with a byte outside ACGTacgt (cannot be 2-bit packed)
 };
 
 int check_err_flags(cid_ctx* ctx, cudaStream_t st);   // syncs the stream

@@ -52,6 +52,20 @@ private:
     bool fill();
 };
 
+// The same interface with decompression and line splitting on a producer thread (the
+// reference gunzips and parses serially between batches, read_id_mt_pe.rs:727-761).  Blocks of lines travel
+// through a bounded queue, so both mates' files inflate in parallel with each other, with batch assembly and
+// with the GPU call of the previous batch.
+class AsyncLineReader {
+public:
+    explicit AsyncLineReader(const std::string& path, bool keep_eol = false);
+    ~AsyncLineReader();
+    bool next(std::string& line);
+private:
+    struct Impl;
+    Impl* p_;
+};
+
 std::vector<std::string> read_fasta(const std::string& path);                                      // kmer.rs:10-45
 void read_fasta_mf(const std::string& path, std::vector<std::string>& labels, std::vector<std::string>& seqs);  // kmer.rs:47-84
 std::string qual_mask(const std::string& seq, const std::string& qual, uint8_t max_quality_offset);   // seq.rs:36-56

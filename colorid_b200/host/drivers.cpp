@@ -347,7 +347,7 @@ int read_id(const ReadIdOpts& o) {
     auto maybe_flush = [&]() { if (rb.n() >= kGpuBatchReads || rb.bases.size() >= kGpuBatchBytes) run.flush(rb); };
     if (ends_with(o.query[0], ".gz")) {
         if (o.query.size() > 1) {                       // per_read_stream_pe, read_id_mt_pe.rs:701-832
-            LineReader a(o.query[0]), c(o.query[1]);
+            AsyncLineReader a(o.query[0]), c(o.query[1]);
             std::string l1, l2, id, s1, s2;
             uint64_t line_count = 1;
             while (a.next(l1)) {
@@ -366,7 +366,7 @@ int read_id(const ReadIdOpts& o) {
             run.flush(rb);
             fprintf(stderr, "Classified %llu read pairs in %llu seconds\n", (unsigned long long)run.read_count, t.secs());
         } else {                                        // per_read_stream_se, :835-951
-            LineReader a(o.query[0]);
+            AsyncLineReader a(o.query[0]);
             std::string l, id, s1;
             uint64_t line_count = 1;
             while (a.next(l)) {
@@ -379,10 +379,10 @@ int read_id(const ReadIdOpts& o) {
             fprintf(stderr, "Classified %llu reads in %llu seconds\n", (unsigned long long)run.read_count, t.secs());
         }
     } else {                                            // stream_fasta, :440-570 (sequence keeps its line feeds)
-        LineReader a(o.query[0]);
+        AsyncLineReader a(o.query[0], /*keep_eol=*/true);
         std::string l, id, sub;
         uint64_t count = 0;
-        while (a.next(l, /*keep_eol=*/true)) {
+        while (a.next(l)) {
             if (count == 0) id = l.substr(0, l.size() - 1);
             else if (l.find('>') != std::string::npos) {
                 if (!sub.empty()) {

@@ -2,9 +2,14 @@
 // (kmer.rs:461-475,581-612), seq.rs:36-56 qual_mask and build.rs:15-31 tab_to_map.
 #include <zlib.h>
 
+#include <condition_variable>
 #include <cstring>
+#include <deque>
 #include <fstream>
+#include <memory>
+#include <mutex>
 #include <sstream>
+#include <thread>
 
 #include "cid_host.hpp"
 
@@ -44,6 +49,77 @@ bool LineReader::next(std::string& line, bool keep_eol) {
         any = true;
     }
     return any || !line.empty();
+}
+
+// ------------------------------------------------------------------ AsyncLineReader
+struct AsyncLineReader::Impl {
+    struct Block { std::string data; std::vector<uint32_t> end; };       // line i = data[end[i-1] .. end[i])
+    enum { BLOCK_LINES = 1 << 16, DEPTH = 8 };
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<std::unique_ptr<Block>> q;
+    bool done = false, stop = false;
+    std::string error;
+    std::thread th;
+    std::unique_ptr<Block> cur;
+    size_t at = 0;
+    void produce(std::string path, bool keep_eol) {
+        try {
+            LineReader lr(path);
+            std::string l;
+            for (;;) {
+                std::unique_ptr<Block> b(new Block());
+                b->data.reserve(8 << 20);
+                b->end.reserve(BLOCK_LINES);
+                while (b->end.size() < BLOCK_LINES && lr.next(l, keep_eol)) { b->data += l; b->end.push_back((uint32_t)b->data.size()); }
+                const bool last = b->end.size() < BLOCK_LINES;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return q.size() < DEPTH || stop; });
+                    if (stop) return;
+                    if (!b->end.empty()) q.push_back(std::move(b));
+                    if (last) done = true;
+                }
+                cv.notify_all();
+                if (last) return;
+            }
+        } catch (const std::exception& e) {
+            std::lock_guard<std::mutex> lk(mu);
+            error = e.what();
+            done = true;
+            cv.notify_all();
+        }
+    }
+};
+AsyncLineReader::AsyncLineReader(const std::string& path, bool keep_eol) : p_(new Impl()) {
+    { LineReader probe(path); }                      // a missing file fails here, on the caller's thread
+    p_->th = std::thread(&Impl::produce, p_, path, keep_eol);
+}
+AsyncLineReader::~AsyncLineReader() {
+    { std::lock_guard<std::mutex> lk(p_->mu); p_->stop = true; }
+    p_->cv.notify_all();
+    if (p_->th.joinable()) p_->th.join();
+    delete p_;
+}
+bool AsyncLineReader::next(std::string& line) {
+    Impl& s = *p_;
+    if (!s.cur || s.at == s.cur->end.size()) {
+        std::unique_lock<std::mutex> lk(s.mu);
+        s.cv.wait(lk, [&] { return !s.q.empty() || s.done; });
+        if (s.q.empty()) {
+            if (!s.error.empty()) throw Error(s.error);
+            return false;
+        }
+        s.cur = std::move(s.q.front());
+        s.q.pop_front();
+        s.at = 0;
+        lk.unlock();
+        s.cv.notify_all();
+    }
+    const uint32_t lo = s.at ? s.cur->end[s.at - 1] : 0u, hi = s.cur->end[s.at];
+    line.assign(s.cur->data, lo, hi - lo);
+    s.at++;
+    return true;
 }
 
 // ------------------------------------------------------------------ FASTA

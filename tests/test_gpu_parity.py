@@ -72,6 +72,28 @@ def test_build_fastq_autocutoff(oracle, ctx):
         assert np.array_equal(gix.download_dense(), oix.words())
 
 
+def _fast_reads(rng, genome, n, rl):
+    """n single-end reads of length rl as a list of bytes (vectorised: these sets hold > 4M bases)."""
+    g = np.frombuffer(genome, dtype=np.uint8)
+    pos = rng.integers(0, len(g) - rl, size=n)
+    arr = g[pos[:, None] + np.arange(rl)[None, :]].copy()
+    err = rng.random(arr.shape) < 0.004
+    arr[err] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=int(err.sum()))]
+    return [bytes(r) for r in arr]
+
+
+def test_build_fastq_optimistic_count_table(oracle, ctx):
+    """Read sets of >= 4096 sequences / 4M k-mer positions get a count table sized for positions/2 (deep coverage:
+    few distinct k-mers); a low-coverage set overflows it and must fall back to the safe size.  Same bits either way."""
+    rng = _rng(8)
+    k, S, H = 21, 1_000_003, 2
+    deep = _fast_reads(rng, synth.rand_seq(rng, 150_000), 32_000, 150)        # 32x of 150 kb: ~0.7M distinct k-mers
+    shallow = _fast_reads(rng, synth.rand_seq(rng, 6_000_000), 30_000, 150)   # 0.75x of 6 Mb: ~3.9M distinct of 3.9M positions
+    for cutoff in (-1, 0):
+        oix, gix = build_both(oracle, ctx, [deep, shallow], S, H, k, cb.CID_SEQ_FASTQ, cutoff)
+        assert np.array_equal(gix.download_dense(), oix.words())
+
+
 def _index_pair(oracle, ctx, rng, N, k, S, H, glen=8000):
     genomes = synth.clade_genomes(rng, N, glen, n_clades=max(2, N // 8), div=0.01)
     oix, gix = build_both(oracle, ctx, [[g] for g in genomes], S, H, k, cb.CID_SEQ_FASTA)
