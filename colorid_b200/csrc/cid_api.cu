@@ -198,6 +198,14 @@ extern "C" {
 int cid_version(void) { return 100; }
 const char* cid_last_error(void) { return g_err; }
 
+int cid_host_alloc(size_t bytes, void** out) {
+    if (!out) { set_error("cid_host_alloc: null out"); return CID_E_INVALID; }
+    cudaError_t e = cudaHostAlloc(out, std::max<size_t>(bytes, 64), cudaHostAllocPortable);
+    if (e != cudaSuccess) { *out = nullptr; set_error("cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); cudaGetLastError(); return CID_E_NOMEM; }
+    return CID_OK;
+}
+void cid_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 int cid_ctx_create(int device, cid_ctx** out) {
     if (!out) { set_error("cid_ctx_create: null out"); return CID_E_INVALID; }
     int ndev = 0;
@@ -323,23 +331,54 @@ int cid_index_refresh_rownz(cid_index* ix) {
 }
 int cid_index_set_rownz_global(cid_index* ix, int is_global) { ix->rownz_global = is_global != 0; return CID_OK; }
 
+// rows[id] <- words of the i-th uploaded row (any order of ids; the reference writes its map in hash order)
+__global__ void scatter_rows_kernel(const uint64_t* __restrict__ ids, const uint32_t* __restrict__ words, uint64_t n, uint32_t W,
+                                    uint32_t Wp, uint32_t* __restrict__ rows) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * W) return;
+    const uint64_t i = t / W;
+    const uint32_t w = (uint32_t)(t % W);
+    rows[ids[i] * Wp + w] = words[t];
+}
+
 int cid_index_upload_rows(cid_index* ix, const uint64_t* row_ids, const uint32_t* words, uint64_t nrows) {
     cid_ctx* ctx = ix->ctx;
+    cudaStream_t st = ctx->stream;
     CID_CUDA(cudaSetDevice(ctx->device));
-    // scatter on the host into a dense staging image in chunks of rows, then copy (rows are W words each)
-    for (uint64_t i = 0; i < nrows; i++) {
-        if (row_ids[i] >= ix->S) { set_error("row id %llu >= bloom_size", (unsigned long long)row_ids[i]); return CID_E_INVALID; }
+    // chunks of rows staged through two pinned windows (the caller's arrays are pageable), scattered on the device
+    const uint64_t chunk = std::max<uint64_t>(1024, (64ull << 20) / (8 + 4 * (uint64_t)ix->W));   // ~64 MB windows
+    const size_t idb = chunk * 8, wb = chunk * (size_t)ix->W * 4;
+    cudaEvent_t freed[2] = {nullptr, nullptr};
+    for (int b = 0; b < 2; b++) {
+        CID_TRY(ctx->pinned[1 + b].ensure(idb + wb));
+        CID_TRY(ctx->scratch[22 + b].ensure(idb + wb));
+        CID_CUDA(cudaEventCreateWithFlags(&freed[b], cudaEventDisableTiming));
     }
-    // cudaMemcpy2D cannot scatter; group consecutive ids into runs
-    uint64_t i = 0;
-    while (i < nrows) {
-        uint64_t j = i + 1;
-        while (j < nrows && row_ids[j] == row_ids[j - 1] + 1) j++;
-        CID_CUDA(cudaMemcpy2DAsync(ix->rows + row_ids[i] * ix->Wp, (size_t)ix->Wp * 4, words + i * ix->W, (size_t)ix->W * 4,
-                                   (size_t)ix->W * 4, j - i, cudaMemcpyHostToDevice, ctx->stream));
-        i = j;
+    int rc = CID_OK;
+    for (uint64_t r0 = 0, c = 0; r0 < nrows && rc == CID_OK; r0 += chunk, c++) {
+        const int b = (int)(c & 1);
+        const uint64_t n = std::min(chunk, nrows - r0);
+        if (cudaEventSynchronize(freed[b]) != cudaSuccess) { rc = CID_E_CUDA; break; }     // window's previous copy is done
+        for (uint64_t i = r0; i < r0 + n; i++)
+            if (row_ids[i] >= ix->S) { set_error("row id %llu >= bloom_size", (unsigned long long)row_ids[i]); rc = CID_E_INVALID; break; }
+        if (rc != CID_OK) break;
+        char* h = ctx->pinned[1 + b].as<char>();
+        memcpy(h, row_ids + r0, n * 8);
+        memcpy(h + idb, words + r0 * ix->W, n * (size_t)ix->W * 4);
+        char* d = ctx->scratch[22 + b].as<char>();
+        if (cudaMemcpyAsync(d, h, n * 8, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaMemcpyAsync(d + idb, h + idb, n * (size_t)ix->W * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = CID_E_CUDA; break; }
+        cudaEventRecord(freed[b], st);
+        const uint64_t total = n * ix->W;
+        scatter_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const uint64_t*)d, (const uint32_t*)(d + idb), n, ix->W,
+                                                                            ix->Wp, ix->rows);
+        ctx->launches++;
     }
-    CID_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaStreamSynchronize(st);
+    for (int b = 0; b < 2; b++) if (freed[b]) cudaEventDestroy(freed[b]);
+    if (rc == CID_E_CUDA) { set_error("cid_index_upload_rows: CUDA copy failed: %s", cudaGetErrorString(cudaGetLastError())); return rc; }
+    if (rc != CID_OK) return rc;
+    CID_CUDA(cudaGetLastError());
     return cid_index_refresh_rownz(ix);
 }
 

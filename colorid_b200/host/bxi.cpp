@@ -9,6 +9,7 @@
 //
 // Rows stream straight between the file and the flat (row_ids, words) arrays the C ABI takes
 // (cid_index_upload_rows / cid_index_download_nonzero_rows): no per-row heap objects.
+#include <algorithm>
 #include <cstring>
 
 #include "cid_host.hpp"
@@ -64,11 +65,22 @@ void save_bigsi(const std::string& path, const Bigsi& b) {
     const uint32_t W = b.row_words;
     if (W != (nbits + 31) / 32) throw Error("save_bigsi: row width does not match the number of colours");
     w.u64(b.row_ids.size());
-    for (size_t i = 0; i < b.row_ids.size(); i++) {
-        w.u64(b.row_ids[i]);
-        w.u64(W);
-        w.raw(b.words.data() + i * W, (size_t)W * 4);
-        w.u64(nbits);
+    {   // rows in blocks: one record is {u64 row, u64 n_words, n_words x u32, u64 nbits}
+        const size_t rec = 24 + (size_t)W * 4, block = 1 << 16;
+        std::vector<char> out(rec * block);
+        for (size_t i0 = 0; i0 < b.row_ids.size(); i0 += block) {
+            const size_t n = std::min(block, b.row_ids.size() - i0);
+            char* o = out.data();
+            const uint64_t w64 = W;
+            for (size_t i = i0; i < i0 + n; i++, o += rec) {
+                memcpy(o, &b.row_ids[i], 8);
+                memcpy(o + 8, &w64, 8);
+                memcpy(o + 16, b.words.data() + i * W, (size_t)W * 4);
+                memcpy(o + 16 + (size_t)W * 4, &nbits, 8);
+            }
+            w.flush();
+            if (fwrite(out.data(), 1, rec * n, w.f) != rec * n) throw Error("problems preparing serialized data for writing");
+        }
     }
     w.u64(b.n_ref_kmers.size());
     for (auto& kv : b.n_ref_kmers) { w.str(kv.first); w.u64(kv.second); }
@@ -87,13 +99,23 @@ Bigsi read_bigsi(const std::string& path) {
     if (nrows > b.bloom_size) throw Error("can't deserialize");
     b.row_ids.resize(nrows);
     b.words.resize(nrows * b.row_words);
-    for (uint64_t i = 0; i < nrows; i++) {
-        b.row_ids[i] = r.u64();
-        const uint64_t nw = r.u64();
-        if (nw != b.row_words) throw Error("can't deserialize: row width differs from the number of colours");
-        r.raw(b.words.data() + i * b.row_words, (size_t)nw * 4);
-        const uint64_t nbits = r.u64();
-        if (nbits != nc) throw Error("can't deserialize: BitVec length differs from the number of colours");
+    {   // rows in blocks (a per-field fread costs ~10 ns x 4 x 50 M rows)
+        const size_t rec = 24 + (size_t)b.row_words * 4, block = 1 << 16;
+        std::vector<char> in(rec * block);
+        for (uint64_t i0 = 0; i0 < nrows; i0 += block) {
+            const size_t n = (size_t)std::min<uint64_t>(block, nrows - i0);
+            r.raw(in.data(), rec * n);
+            const char* p = in.data();
+            for (uint64_t i = i0; i < i0 + n; i++, p += rec) {
+                uint64_t nw, nbits;
+                memcpy(&b.row_ids[i], p, 8);
+                memcpy(&nw, p + 8, 8);
+                if (nw != b.row_words) throw Error("can't deserialize: row width differs from the number of colours");
+                memcpy(b.words.data() + i * b.row_words, p + 16, (size_t)nw * 4);
+                memcpy(&nbits, p + 16 + (size_t)nw * 4, 8);
+                if (nbits != nc) throw Error("can't deserialize: BitVec length differs from the number of colours");
+            }
+        }
     }
     const uint64_t nr = r.u64();
     for (uint64_t i = 0; i < nr; i++) { std::string a = r.str(); b.n_ref_kmers[a] = r.u64(); }

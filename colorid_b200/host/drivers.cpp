@@ -5,7 +5,10 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <exception>
+#include <thread>
 
 #include "../../include/colorid_b200.h"
 #include "cid_host.hpp"
@@ -19,12 +22,36 @@ struct Timer {
     std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
     unsigned long long secs() const { return (unsigned long long)std::chrono::duration_cast<std::chrono::seconds>(std::chrono::steady_clock::now() - t0).count(); }
 };
+struct Trace {                    // COLORID_B200_TRACE=1: stage timings on stderr (diagnostics only)
+    bool on = getenv("COLORID_B200_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void mark(const char* what) {
+        auto t1 = std::chrono::steady_clock::now();
+        if (on) fprintf(stderr, "[trace] %-28s %8.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 struct Gpu {                      // context + device index
     cid_ctx* ctx = nullptr;
     cid_index* ix = nullptr;
-    explicit Gpu(int device) { ck(cid_ctx_create(device, &ctx)); }
-    ~Gpu() { if (ix) cid_index_destroy(ix); if (ctx) cid_ctx_destroy(ctx); }
+    // creating a CUDA context takes 1.5-2.5 s on a fresh process: do it on a helper thread while the caller
+    // reads its input files, join on first use
+    std::thread starter;
+    int start_rc = CID_OK;
+    std::string start_err;
+    explicit Gpu(int device) {
+        starter = std::thread([this, device] {
+            start_rc = cid_ctx_create(device, &ctx);
+            if (start_rc != CID_OK) start_err = cid_last_error();       // cid_last_error is thread-local
+        });
+    }
+    void ready() {
+        if (starter.joinable()) starter.join();
+        if (start_rc != CID_OK) { int rc = start_rc; start_rc = CID_OK; (void)rc; throw Error("colorid_b200: " + start_err); }
+    }
+    ~Gpu() { if (starter.joinable()) starter.join(); if (ix) cid_index_destroy(ix); if (ctx) cid_ctx_destroy(ctx); }
     void create(uint64_t S, uint64_t H, uint64_t k, uint64_t N) {
+        ready();
         if (H > 0xFFFFFFFFull || k > 0xFFFFFFFFull || N > 0xFFFFFFFFull) throw Error("index parameters out of range");
         ck(cid_index_create(ctx, S, (uint32_t)H, (uint32_t)k, (uint32_t)N, &ix));
     }
@@ -45,10 +72,13 @@ Bigsi load_index(const std::string& path) {
 
 // ------------------------------------------------------------------ build
 int build(const BuildOpts& o) {
+    Trace tr;
+    Gpu g(o.device);
     const auto map = tab_to_map(o.ref_file);
     if (map.empty()) throw Error("reference file lists no accessions");
-    Gpu g(o.device);
     g.create(o.bloom, o.hashes, o.k, map.size());
+    tr.mark("context + index create");
+    double t_read = 0, t_gpu = 0;
     Bigsi out;
     out.bloom_size = o.bloom; out.num_hash = o.hashes; out.k_size = o.k;
     uint32_t colour = 0;              // colours = rank of the accession in byte-wise sorted order (build.rs:102-113)
@@ -59,6 +89,7 @@ int build(const BuildOpts& o) {
         fprintf(stderr, "Adding %s to index (%zu/%zu)\n", acc.c_str(), counter++, map.size());
         SeqBatch sb;
         int mode;
+        const auto ta = std::chrono::steady_clock::now();
         int64_t cutoff = o.filter;    // -1: FASTQ -> auto_cutoff (build.rs:56-58), FASTA -> keep everything (:86-87)
         if (files.size() == 2) {
             fastq_masked_pe(files[0], files[1], o.quality, sb);
@@ -73,12 +104,18 @@ int build(const BuildOpts& o) {
         }
         uint64_t nref = 0;
         int64_t used = 0;
+        const auto tb = std::chrono::steady_clock::now();
         ck(cid_build_accession(g.ix, colour, sb.bases.data(), sb.offs.data(), sb.n(), mode, cutoff, &nref, &used));
+        t_read += std::chrono::duration<double>(tb - ta).count();
+        t_gpu += std::chrono::duration<double>(std::chrono::steady_clock::now() - tb).count();
         out.colors[colour] = acc;
         out.n_ref_kmers[acc] = nref;
         colour++;
     }
+    if (tr.on) fprintf(stderr, "[trace] reading inputs %.3f s, cid_build_accession %.3f s\n", t_read, t_gpu);
+    tr.mark("accessions");
     ck(cid_build_finalize(g.ix));
+    tr.mark("finalize (transpose)");
     printf("Saving BIGSI to file.\n");
     uint64_t nrows = 0;
     ck(cid_index_count_nonzero_rows(g.ix, &nrows));
@@ -87,7 +124,9 @@ int build(const BuildOpts& o) {
     out.words.resize(nrows * out.row_words);
     uint64_t got = 0;
     ck(cid_index_download_nonzero_rows(g.ix, out.row_ids.data(), out.words.data(), nrows, &got));
+    tr.mark("download non-zero rows");
     save_bigsi(o.prefix + ".bxi", out);
+    tr.mark("save_bigsi");
     return 0;
 }
 
@@ -210,47 +249,76 @@ int search(const SearchOpts& o) {
         return 0;
     }
     fprintf(stderr, "Loading index\n");
-    const Bigsi b = load_index(o.bigsi);
+    Trace tr;
     Gpu g(o.device);
+    const Bigsi b = load_index(o.bigsi);
+    tr.mark("read_bigsi");
     g.upload(b);
+    tr.mark("context + index upload");
     if (o.perfect_search) {
         if (o.multi_fasta) perfect_batch_search_mf(g, b, o.files1);
         else perfect_batch_search(g, b, o.files1);
     } else {
         batch_search(g, b, o);
     }
+    tr.mark("queries");
     return 0;
 }
 
 // ------------------------------------------------------------------ read_id
 namespace {
+// The reference flushes every `-c` records (default 50,000; read_id_mt_pe.rs:762); batching never changes
+// the output, so the GPU gets larger batches.
+const uint64_t kGpuBatchReads = 1u << 17;
+const uint64_t kGpuBatchBytes = 96ull << 20;
+
+struct PinnedBytes {               // growable page-locked byte buffer (cid_host_alloc)
+    char* p = nullptr;
+    size_t size = 0, cap = 0;
+    ~PinnedBytes() { cid_host_free(p); }
+    void reserve(size_t want) {
+        if (want <= cap) return;
+        size_t ncap = std::max(want, cap + cap / 2);
+        void* np = nullptr;
+        ck(cid_host_alloc(ncap, &np));
+        if (size) memcpy(np, p, size);
+        cid_host_free(p);
+        p = (char*)np; cap = ncap;
+    }
+    void append(const char* s, size_t n) { reserve(size + n); memcpy(p + size, s, n); size += n; }
+    void fill(char c, size_t n) { reserve(size + n); memset(p + size, c, n); size += n; }
+};
 struct ReadBatch {
     std::vector<std::string> ids;
-    std::string bases, quals;
+    PinnedBytes bases, quals;
     std::vector<uint64_t> seq_offs{0}, read_offs{0};
     bool any_qual = false;
     void add_mate(const std::string& seq, const std::string* qual, uint8_t off) {
+        if (!bases.cap) { bases.reserve(kGpuBatchBytes + (8u << 20)); quals.reserve(kGpuBatchBytes + (8u << 20)); }   // page-locking is slow: once
         if (qual && off) {
             any_qual = true;
-            if (qual->size() == seq.size()) { bases += seq; quals += *qual; }       // masked on the device
-            else { const std::string m = qual_mask(seq, *qual, off); bases += m; quals.append(m.size(), '~'); }
+            if (qual->size() == seq.size()) { bases.append(seq.data(), seq.size()); quals.append(qual->data(), qual->size()); }   // masked on the device
+            else { const std::string m = qual_mask(seq, *qual, off); bases.append(m.data(), m.size()); quals.fill('~', m.size()); }
         } else {
-            bases += seq;
-            quals.append(seq.size(), '~');
+            bases.append(seq.data(), seq.size());
+            quals.fill('~', seq.size());
         }
-        seq_offs.push_back(bases.size());
+        seq_offs.push_back(bases.size);
     }
     void end_read(const std::string& id) { ids.push_back(id); read_offs.push_back(seq_offs.size() - 1); }
     uint64_t n() const { return ids.size(); }
-    void clear() { ids.clear(); bases.clear(); quals.clear(); seq_offs.assign(1, 0); read_offs.assign(1, 0); any_qual = false; }
+    void clear() { ids.clear(); bases.size = 0; quals.size = 0; seq_offs.assign(1, 0); read_offs.assign(1, 0); any_qual = false; }
 };
 
 struct ReadIdRun {
     Gpu& g; const Bigsi& b; const ReadIdOpts& o;
     FILE* out;
     std::vector<uint64_t> n_ref;
+    std::vector<std::string> names;                      // accession by colour
+    std::string outbuf;
     double fp_correct;
     uint64_t read_count = 0;
+    double t_gpu = 0, t_out = 0;
     std::vector<std::string> count_keys;                 // first-appearance order of the counts-file keys
     std::map<std::string, uint64_t> counts;
     ReadIdRun(Gpu& g_, const Bigsi& b_, const ReadIdOpts& o_) : g(g_), b(b_), o(o_) {
@@ -260,8 +328,10 @@ struct ReadIdRun {
             auto it = b.n_ref_kmers.find(kv.second);
             if (it == b.n_ref_kmers.end()) throw Error("index has no k-mer count for accession " + kv.second);
             n_ref.push_back(it->second);
+            names.push_back(kv.second);
         }
         fp_correct = std::pow(10.0, -o.correct);          // main.rs:711
+        g.ready();
         if (o.threads) ck(cid_ctx_set_option(g.ctx, "host_threads", (int64_t)o.threads));
     }
     ~ReadIdRun() { if (out) fclose(out); }
@@ -281,19 +351,25 @@ struct ReadIdRun {
         uint32_t top_cap = N < 64 ? N : 64;
         std::vector<int32_t> kind(n);
         std::vector<uint32_t> hits(n), n_set(n), n_top(n), top((size_t)n * top_cap);
-        ck(cid_read_id_classify(g.ix, rb.bases.data(), rb.any_qual ? rb.quals.data() : nullptr, rb.seq_offs.data(),
+        const auto tg0 = std::chrono::steady_clock::now();
+        ck(cid_read_id_classify(g.ix, rb.bases.p, rb.any_qual ? rb.quals.p : nullptr, rb.seq_offs.data(),
                                 rb.seq_offs.size() - 1, rb.read_offs.data(), n, &p, n_ref.data(), fp_correct, kind.data(),
                                 hits.data(), n_set.data(), n_top.data(), top.data(), top_cap));
-        std::string line;
+        const auto tg1 = std::chrono::steady_clock::now();
+        t_gpu += std::chrono::duration<double>(tg1 - tg0).count();
+        auto put_u = [&](uint32_t v) { char tmp[12]; int k = 0; do { tmp[k++] = (char)('0' + v % 10); v /= 10; } while (v); while (k) outbuf += tmp[--k]; };
+        outbuf.clear();
         for (uint64_t r = 0; r < n; r++) {
-            std::string cls;
-            const char* verdict = "accept";
+            std::string multi;
+            const std::string* cls = nullptr;
+            static const std::string kTooShort = "too_short", kNoHits = "no_hits", kNoSig = "no_significant_hits";
+            bool accept = true;
             uint32_t h = 0, ns = n_set[r], nt = 0;
             switch (kind[r]) {
-                case CID_CLS_TOO_SHORT: cls = "too_short"; ns = 0; break;
-                case CID_CLS_NO_HITS: cls = "no_hits"; break;
-                case CID_CLS_NO_SIGNIFICANT: cls = "no_significant_hits"; verdict = "reject"; break;
-                case CID_CLS_ACCEPT: cls = b.colors.at(top[r * top_cap]); h = hits[r]; nt = 1; break;
+                case CID_CLS_TOO_SHORT: cls = &kTooShort; ns = 0; break;
+                case CID_CLS_NO_HITS: cls = &kNoHits; break;
+                case CID_CLS_NO_SIGNIFICANT: cls = &kNoSig; accept = false; break;
+                case CID_CLS_ACCEPT: cls = &names.at(top[r * top_cap]); h = hits[r]; nt = 1; break;
                 case CID_CLS_REJECT_MULTI: {
                     std::vector<uint32_t> all;
                     const uint32_t* t = top.data() + r * top_cap;
@@ -303,48 +379,69 @@ struct ReadIdRun {
                         const uint64_t s_lo = rb.read_offs[r], s_hi = rb.read_offs[r + 1];
                         std::vector<uint64_t> so, ro{0, s_hi - s_lo};
                         for (uint64_t s = s_lo; s <= s_hi; s++) so.push_back(rb.seq_offs[s] - rb.seq_offs[s_lo]);
-                        ck(cid_read_id_classify(g.ix, rb.bases.data() + rb.seq_offs[s_lo],
-                                                rb.any_qual ? rb.quals.data() + rb.seq_offs[s_lo] : nullptr, so.data(), s_hi - s_lo,
+                        ck(cid_read_id_classify(g.ix, rb.bases.p + rb.seq_offs[s_lo],
+                                                rb.any_qual ? rb.quals.p + rb.seq_offs[s_lo] : nullptr, so.data(), s_hi - s_lo,
                                                 ro.data(), 1, &p, n_ref.data(), fp_correct, &k1, &h1, &s1, &t1, all.data(), N));
                         t = all.data();
                     }
-                    for (uint32_t j = 0; j < n_top[r]; j++) { if (j) cls += ','; cls += b.colors.at(t[j]); }
-                    h = hits[r]; nt = n_top[r]; verdict = "reject";
+                    for (uint32_t j = 0; j < n_top[r]; j++) { if (j) multi += ','; multi += names.at(t[j]); }
+                    cls = &multi; h = hits[r]; nt = n_top[r]; accept = false;
                     break;
                 }
                 default:
                     throw Error("read " + rb.ids[r] + ": a later mate is shorter than k-1 (the reference panics in kmerize_vector_skip_n_set)");
             }
-            line = rb.ids[r]; line += '\t'; line += cls; line += '\t'; line += std::to_string(h); line += '\t';
-            line += std::to_string(ns); line += '\t'; line += verdict; line += '\t'; line += std::to_string(nt); line += '\n';
-            fwrite(line.data(), 1, line.size(), out);
-            tally(cls, verdict[0] == 'a');
+            outbuf += rb.ids[r]; outbuf += '\t'; outbuf += *cls; outbuf += '\t'; put_u(h); outbuf += '\t'; put_u(ns);
+            outbuf += accept ? "\taccept\t" : "\treject\t"; put_u(nt); outbuf += '\n';
+            if (outbuf.size() > (8u << 20)) { fwrite(outbuf.data(), 1, outbuf.size(), out); outbuf.clear(); }
+            tally(*cls, accept);
         }
+        fwrite(outbuf.data(), 1, outbuf.size(), out);
         read_count += n;
         rb.clear();
+        t_out += std::chrono::duration<double>(std::chrono::steady_clock::now() - tg1).count();
     }
     void finish() {
         fclose(out); out = nullptr;
         write_counts_five_fields(o.prefix + "_counts.txt", count_keys, counts);   // main.rs:865
     }
 };
-// The reference flushes every `-c` records (default 50,000; read_id_mt_pe.rs:762); batching never changes
-// the output, so the GPU gets larger batches.
-const uint64_t kGpuBatchReads = 1u << 20;
-const uint64_t kGpuBatchBytes = 600ull << 20;
 }  // namespace
 
 int read_id(const ReadIdOpts& o) {
     if (o.query.empty()) throw Error("no query files");
     Timer tload;
+    Trace tr;
+    Gpu g(o.device);
     const Bigsi b = read_bigsi(o.bigsi);
     fprintf(stderr, "Index loaded in %llu seconds\n", tload.secs());
-    Gpu g(o.device);
+    tr.mark("read_bigsi");
+    g.ready();
+    tr.mark("context create (rest)");
     g.upload(b);
+    tr.mark("index upload");
     ReadIdRun run(g, b, o);
-    ReadBatch rb;
+    // two batches: while the worker thread runs the GPU call and writes the lines of one, the parser fills the other
+    ReadBatch batches[2];
+    int cur = 0;
+    std::thread worker;
+    std::exception_ptr worker_err;
+    auto join_worker = [&]() {
+        if (worker.joinable()) worker.join();
+        if (worker_err) { std::exception_ptr e = worker_err; worker_err = nullptr; std::rethrow_exception(e); }
+    };
+    auto submit = [&]() {
+        join_worker();
+        ReadBatch* full = &batches[cur];
+        worker = std::thread([&run, &worker_err, full] {
+            try { run.flush(*full); } catch (...) { worker_err = std::current_exception(); }
+        });
+        cur ^= 1;
+    };
+    struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{worker};
+#define rb batches[cur]
     Timer t;
-    auto maybe_flush = [&]() { if (rb.n() >= kGpuBatchReads || rb.bases.size() >= kGpuBatchBytes) run.flush(rb); };
+    auto maybe_flush = [&]() { if (rb.n() >= kGpuBatchReads || rb.bases.size >= kGpuBatchBytes) submit(); };
     if (ends_with(o.query[0], ".gz")) {
         if (o.query.size() > 1) {                       // per_read_stream_pe, read_id_mt_pe.rs:701-832
             AsyncLineReader a(o.query[0]), c(o.query[1]);
@@ -363,7 +460,7 @@ int read_id(const ReadIdOpts& o) {
                 }
                 line_count++;
             }
-            run.flush(rb);
+            submit(); join_worker();
             fprintf(stderr, "Classified %llu read pairs in %llu seconds\n", (unsigned long long)run.read_count, t.secs());
         } else {                                        // per_read_stream_se, :835-951
             AsyncLineReader a(o.query[0]);
@@ -375,7 +472,7 @@ int read_id(const ReadIdOpts& o) {
                 else if (line_count % 4 == 0) { rb.add_mate(s1, &l, o.quality); rb.end_read(id); maybe_flush(); }
                 line_count++;
             }
-            run.flush(rb);
+            submit(); join_worker();
             fprintf(stderr, "Classified %llu reads in %llu seconds\n", (unsigned long long)run.read_count, t.secs());
         }
     } else {                                            // stream_fasta, :440-570 (sequence keeps its line feeds)
@@ -394,10 +491,14 @@ int read_id(const ReadIdOpts& o) {
             count++;
         }
         rb.add_mate(sub, nullptr, 0); rb.end_read(id);
-        run.flush(rb);
+        submit(); join_worker();
         fprintf(stderr, "Classified %llu reads in %llu seconds\n", (unsigned long long)run.read_count, t.secs());
     }
+#undef rb
+    tr.mark("parse + classify + write");
+    if (tr.on) fprintf(stderr, "[trace]   of which GPU calls %.3f s, formatting+writing %.3f s\n", run.t_gpu, run.t_out);
     run.finish();
+    tr.mark("counts file");
     return 0;
 }
 

@@ -30,6 +30,8 @@ class ReadIdParams(C.Structure):
 SIGNATURES = {
     "cid_version": (C.c_int, []),
     "cid_last_error": (C.c_char_p, []),
+    "cid_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(vp)]),
+    "cid_host_free": (None, [vp]),
     "cid_ctx_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
     "cid_ctx_destroy": (None, [vp]),
     "cid_ctx_device": (C.c_int, [vp]),

@@ -50,6 +50,11 @@ enum {
 int cid_version(void);
 const char* cid_last_error(void);
 
+/* Page-locked host buffers for callers that fill large batches (reads, queries): copies from them overlap
+ * with kernels; pageable memory works everywhere but serialises the H2D copies. */
+int cid_host_alloc(size_t bytes, void** out);
+void cid_host_free(void* p);
+
 /* ---- context ---------------------------------------------------------------------------- */
 int cid_ctx_create(int device, cid_ctx** out);
 void cid_ctx_destroy(cid_ctx* ctx);

@@ -66,9 +66,10 @@ raw = write_fastq_gz(f"{d}/r_1.fastq.gz", m1, "r") + write_fastq_gz(f"{d}/r_2.fa
 
 def timed(*args):
     t = time.perf_counter()
-    r = subprocess.run([CLI, *args], capture_output=True, text=True)
+    r = subprocess.run([CLI, *args], capture_output=True, text=True, env=dict(os.environ, COLORID_B200_TRACE="1"))
     dt = time.perf_counter() - t
     assert r.returncode == 0, r.stderr[-1000:]
+    print(args[0], "\n".join(l for l in r.stderr.split("\n") if l.startswith("[trace]")), file=sys.stderr)
     return dt, r
 
 
