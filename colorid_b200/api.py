@@ -106,12 +106,14 @@ def classify_reads(index_params, n_ref, rep, fp_correct=1e-3, group_width=16, th
 class Index:
     """Device-resident BIGSI index (bigsi.rs:19-27 BigsyMapNew)."""
 
-    def __init__(self, ctx, bloom_size, num_hash, k, n_colours):
+    def __init__(self, ctx, bloom_size, num_hash, k, n_colours, m=0):
         self.ctx, self.lib = ctx, ctx.lib
-        self.S, self.H, self.k, self.N = bloom_size, num_hash, k, n_colours
+        self.S, self.H, self.k, self.N, self.m = bloom_size, num_hash, k, n_colours, m
         h = L.vp()
         L.check(self.lib.cid_index_create(ctx.h, bloom_size, num_hash, k, n_colours, C.byref(h)))
         self.h = h
+        if m:       # minimizer index (.mxi, bigsi.rs:40-49)
+            L.check(self.lib.cid_index_set_minimizer(h, m))
         self.W = self.lib.cid_index_row_words(h)
         self.n_ref = np.zeros(n_colours, dtype=np.uint64)
 
@@ -129,6 +131,15 @@ class Index:
         n_ref, used = C.c_uint64(0), C.c_int64(0)
         L.check(self.lib.cid_build_accession(self.h, colour, _p(bases), _p(offs, L.u64p), len(seqs), mode, cutoff,
                                              C.byref(n_ref), C.byref(used)))
+        self.n_ref[colour] = n_ref.value
+        return n_ref.value, used.value
+
+    def build_accession_mini(self, colour, seqs, mode=L.CID_SEQ_FASTA, cutoff=-1, variant=L.CID_MINI_OF_KMERS):
+        """build.rs:396-492 build_single_mini (CID_MINI_OF_KMERS) / :258-394 build_multi_mini (CID_MINI_COUNTED)."""
+        bases, offs = pack_seqs(list(seqs))
+        n_ref, used = C.c_uint64(0), C.c_int64(0)
+        L.check(self.lib.cid_build_accession_mini(self.h, colour, _p(bases), _p(offs, L.u64p), len(seqs), mode, cutoff,
+                                                  variant, C.byref(n_ref), C.byref(used)))
         self.n_ref[colour] = n_ref.value
         return n_ref.value, used.value
 

@@ -438,12 +438,20 @@ int cid_index_device_ptrs(cid_index* ix, void** rows, void** rownz_bitmap, uint6
 }
 
 // ------------------------------------------------------------------ build
-int cid_build_accession_dev(cid_index* ix, uint32_t colour, const char* d_bases, const uint64_t* d_seq_offs,
-                            uint64_t nseq, uint64_t nbases, int seq_mode, int64_t cutoff, uint64_t* n_ref_kmers,
-                            int64_t* cutoff_used) {
+// mini_variant: -1 = plain k-mer index; CID_MINI_OF_KMERS / CID_MINI_COUNTED for .mxi indexes
+static int build_accession_impl(cid_index* ix, uint32_t colour, const char* d_bases, const uint64_t* d_seq_offs,
+                                uint64_t nseq, uint64_t nbases, int seq_mode, int64_t cutoff, int mini_variant,
+                                uint64_t* n_ref_kmers, int64_t* cutoff_used) {
     cid_ctx* ctx = ix->ctx;
     cudaStream_t st = ctx->stream;
     if (colour >= ix->N) { set_error("colour %u >= n_colors %u", colour, ix->N); return CID_E_INVALID; }
+    if ((mini_variant >= 0) != (ix->m != 0)) {
+        set_error(ix->m ? "this index holds minimizers: use cid_build_accession_mini" : "cid_build_accession_mini needs cid_index_set_minimizer first");
+        return CID_E_INVALID;
+    }
+    if (mini_variant > CID_MINI_COUNTED) { set_error("bad minimizer build variant %d", mini_variant); return CID_E_INVALID; }
+    const uint32_t count_m = mini_variant == CID_MINI_COUNTED ? ix->m : 0;   // the count table holds minimizers
+    const uint32_t bloom_m = mini_variant == CID_MINI_OF_KMERS ? ix->m : 0;  // ... or k-mers whose minimizer is inserted
     if (seq_mode != CID_SEQ_FASTA && seq_mode != CID_SEQ_FASTQ) { set_error("bad seq_mode"); return CID_E_INVALID; }
     if (cutoff < -1) { set_error("cutoff must be >= -1"); return CID_E_INVALID; }
     CID_CUDA(cudaSetDevice(ctx->device));
@@ -459,7 +467,7 @@ int cid_build_accession_dev(cid_index* ix, uint32_t colour, const char* d_bases,
         CID_TRY(single_region(ctx, st, nbases, ix->k, &nslots, &d_off, &d_mask, hint));
         CID_CUDA(cudaMemsetAsync(ctx->d_err + 1, 0, 4, st));
         CID_TRY(launch_kmerize_insert(ctx, st, (const uint8_t*)d_bases, d_seq_offs, nseq, 0, nbases, nullptr, d_off, d_mask,
-                                      ctx->scratch[0].p, ix->k, seq_mode));
+                                      ctx->scratch[0].p, ix->k, seq_mode, count_m));
         CID_CUDA(cudaMemcpyAsync(ctx->h_err, ctx->d_err, 8, cudaMemcpyDeviceToHost, st));
         CID_CUDA(cudaStreamSynchronize(st));
         const uint32_t flags = ctx->h_err[0], distinct = ctx->h_err[1];
@@ -479,7 +487,8 @@ int cid_build_accession_dev(cid_index* ix, uint32_t colour, const char* d_bases,
     CID_TRY(ctx->scratch[2].ensure(16));
     unsigned long long* d_nref = ctx->scratch[2].as<unsigned long long>();
     CID_CUDA(cudaMemsetAsync(d_nref, 0, 8, st));
-    CID_TRY(launch_region_to_bloom(ctx, st, ctx->scratch[0].p, nslots, used, ix->k, ix->H, ix->S, bitset, d_nref));
+    CID_TRY(launch_region_to_bloom(ctx, st, ctx->scratch[0].p, nslots, used, count_m ? count_m : ix->k, bloom_m, ix->H, ix->S,
+                                   bitset, d_nref));
     unsigned long long nref = 0;
     CID_CUDA(cudaMemcpyAsync(&nref, d_nref, 8, cudaMemcpyDeviceToHost, st));
     CID_CUDA(cudaStreamSynchronize(st));
@@ -488,8 +497,14 @@ int cid_build_accession_dev(cid_index* ix, uint32_t colour, const char* d_bases,
     return CID_OK;
 }
 
-int cid_build_accession(cid_index* ix, uint32_t colour, const char* bases, const uint64_t* seq_offs, uint64_t nseq,
-                        int seq_mode, int64_t cutoff, uint64_t* n_ref_kmers, int64_t* cutoff_used) {
+int cid_build_accession_dev(cid_index* ix, uint32_t colour, const char* d_bases, const uint64_t* d_seq_offs,
+                            uint64_t nseq, uint64_t nbases, int seq_mode, int64_t cutoff, uint64_t* n_ref_kmers,
+                            int64_t* cutoff_used) {
+    return build_accession_impl(ix, colour, d_bases, d_seq_offs, nseq, nbases, seq_mode, cutoff, -1, n_ref_kmers, cutoff_used);
+}
+
+static int build_accession_host(cid_index* ix, uint32_t colour, const char* bases, const uint64_t* seq_offs, uint64_t nseq,
+                                int seq_mode, int64_t cutoff, int mini_variant, uint64_t* n_ref_kmers, int64_t* cutoff_used) {
     cid_ctx* ctx = ix->ctx;
     if (!seq_offs) { set_error("null seq_offs"); return CID_E_INVALID; }
     CID_CUDA(cudaSetDevice(ctx->device));
@@ -498,9 +513,27 @@ int cid_build_accession(cid_index* ix, uint32_t colour, const char* bases, const
     CID_TRY(ctx->scratch[5].ensure((nseq + 1) * 8));
     if (nbases) CID_CUDA(cudaMemcpyAsync(ctx->scratch[4].p, bases, nbases, cudaMemcpyHostToDevice, ctx->stream));
     CID_CUDA(cudaMemcpyAsync(ctx->scratch[5].p, seq_offs, (nseq + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    return cid_build_accession_dev(ix, colour, ctx->scratch[4].as<char>(), ctx->scratch[5].as<uint64_t>(), nseq, nbases,
-                                   seq_mode, cutoff, n_ref_kmers, cutoff_used);
+    return build_accession_impl(ix, colour, ctx->scratch[4].as<char>(), ctx->scratch[5].as<uint64_t>(), nseq, nbases,
+                                seq_mode, cutoff, mini_variant, n_ref_kmers, cutoff_used);
 }
+int cid_build_accession(cid_index* ix, uint32_t colour, const char* bases, const uint64_t* seq_offs, uint64_t nseq,
+                        int seq_mode, int64_t cutoff, uint64_t* n_ref_kmers, int64_t* cutoff_used) {
+    return build_accession_host(ix, colour, bases, seq_offs, nseq, seq_mode, cutoff, -1, n_ref_kmers, cutoff_used);
+}
+int cid_build_accession_mini(cid_index* ix, uint32_t colour, const char* bases, const uint64_t* seq_offs, uint64_t nseq,
+                             int seq_mode, int64_t cutoff, int variant, uint64_t* n_ref_kmers, int64_t* cutoff_used) {
+    if (variant != CID_MINI_OF_KMERS && variant != CID_MINI_COUNTED) { set_error("bad minimizer build variant %d", variant); return CID_E_INVALID; }
+    return build_accession_host(ix, colour, bases, seq_offs, nseq, seq_mode, cutoff, variant, n_ref_kmers, cutoff_used);
+}
+
+int cid_index_set_minimizer(cid_index* ix, uint32_t m_size) {
+    if (!ix) { set_error("cid_index_set_minimizer: null index"); return CID_E_INVALID; }
+    // find_minimizer slices seq[..m] (kmer.rs:974): the reference panics for m > k
+    if (m_size > ix->k) { set_error("minimizer size %u larger than k-mer size %u (the reference panics)", m_size, ix->k); return CID_E_REF_PANIC; }
+    ix->m = m_size;
+    return CID_OK;
+}
+uint32_t cid_index_minimizer(const cid_index* ix) { return ix ? ix->m : 0; }
 
 int cid_build_finalize(cid_index* ix) {
     cid_ctx* ctx = ix->ctx;
@@ -590,6 +623,7 @@ int cid_query_counts(cid_index* ix, const char* bases, const uint64_t* seq_offs,
     cid_ctx* ctx = ix->ctx;
     cudaStream_t st = ctx->stream;
     if (!seq_offs || !query_offs || !counts || !num_kmers) { set_error("cid_query_counts: null argument"); return CID_E_INVALID; }
+    if (ix->m) { set_error("An index with minimizers (.mxi) is used, but not available for this function"); return CID_E_UNSUPPORTED; }   // main.rs:569-573
     if (seq_mode != CID_SEQ_FASTA && seq_mode != CID_SEQ_FASTQ) { set_error("bad seq_mode"); return CID_E_INVALID; }
     CID_CUDA(cudaSetDevice(ctx->device));
     const uint64_t nbases = seq_offs[nseq];
@@ -667,6 +701,7 @@ int cid_query_counts_dev(cid_index* ix, const char* d_bases, const uint64_t* d_s
     (void)nseq; (void)nbases; (void)d_query_offs;
     cid_ctx* ctx = ix->ctx;
     cudaStream_t st = (cudaStream_t)stream;
+    if (ix->m) { set_error("An index with minimizers (.mxi) is used, but not available for this function"); return CID_E_UNSUPPORTED; }   // main.rs:569-573
     CID_CUDA(cudaSetDevice(ctx->device));
     const uint32_t N = ix->N;
     CID_CUDA(cudaMemsetAsync(d_counts, 0, nq * N * 4, st));
@@ -705,6 +740,7 @@ static int query_perfect_impl(cid_index* ix, const char* bases, const uint64_t* 
     cid_ctx* ctx = ix->ctx;
     cudaStream_t st = ctx->stream;
     if (!seq_offs || !query_offs || !and_rows || !status || !n_kmers) { set_error("cid_query_perfect: null argument"); return CID_E_INVALID; }
+    if (ix->m) { set_error("An index with minimizers (.mxi) is used, but not available for this function"); return CID_E_UNSUPPORTED; }   // main.rs:569-573
     CID_CUDA(cudaSetDevice(ctx->device));
     const uint64_t nbases = seq_offs[nseq];
     CID_TRY(ctx->scratch[4].ensure(nbases + 64));
@@ -747,9 +783,10 @@ int cid_hash_kmers(cid_index* ix, const char* kmers, uint64_t n, uint64_t* row_i
     cudaStream_t st = ctx->stream;
     CID_CUDA(cudaSetDevice(ctx->device));
     if (n == 0) return CID_OK;
-    CID_TRY(ctx->scratch[4].ensure(n * ix->k + 64));
+    const uint32_t len = ix->m ? ix->m : ix->k;     // the hashed item of an .mxi index is the minimizer
+    CID_TRY(ctx->scratch[4].ensure(n * len + 64));
     CID_TRY(ctx->scratch[10].ensure(n * ix->H * 8));
-    CID_CUDA(cudaMemcpyAsync(ctx->scratch[4].p, kmers, n * ix->k, cudaMemcpyHostToDevice, st));
+    CID_CUDA(cudaMemcpyAsync(ctx->scratch[4].p, kmers, n * len, cudaMemcpyHostToDevice, st));
     CID_TRY(launch_hash_kmers(ctx, st, ix, ctx->scratch[4].as<uint8_t>(), n, ctx->scratch[10].as<uint64_t>()));
     CID_CUDA(cudaMemcpyAsync(row_ids, ctx->scratch[10].p, n * ix->H * 8, cudaMemcpyDeviceToHost, st));
     CID_CUDA(cudaStreamSynchronize(st));

@@ -24,11 +24,12 @@ constexpr int KT_CAP = KT + 64;       // bytes staged per tile (halo <= 31, roun
 constexpr int KT_THREADS = 256;
 constexpr int KT_MAXSTARTS = KT_CAP + 8;
 
+template <bool MINI>      // MINI: count each k-mer's minimizer of length mini_m instead of the k-mer (build_multi_mini)
 __global__ void __launch_bounds__(KT_THREADS)
 kmerize_insert_kernel(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ seq_offs, uint64_t nseq,
                       uint64_t base_lo, uint64_t nbases, const uint32_t* __restrict__ seq_group, const uint64_t* __restrict__ region_off,
-                      const uint64_t* __restrict__ region_mask, Slot* __restrict__ table, uint32_t k, int seq_mode,
-                      uint32_t* __restrict__ err) {
+                      const uint64_t* __restrict__ region_mask, Slot* __restrict__ table, uint32_t k, uint32_t mini_m,
+                      int seq_mode, uint32_t* __restrict__ err) {
     __shared__ __align__(16) uint8_t smem[tile_smem_bytes(KT_CAP)];
     __shared__ uint32_t s_starts[KT_MAXSTARTS];
     __shared__ uint64_t s_s0;
@@ -97,6 +98,10 @@ kmerize_insert_kernel(const uint8_t* __restrict__ bases, const uint64_t* __restr
             continue;
         }
         if (low && seq_mode == CID_SEQ_FASTQ) { atomicOr(err, ERRF_LOWER_RAW); continue; }
+        if (MINI) {     // build_multi_mini: the counted item is the k-mer's minimizer (kmer.rs:328-361, 694-824)
+            uint32_t mpos; bool mfwd;
+            key = tile_minimizer(t, p, k, mini_m, key, fwd, low, mpos, mfwd);
+        }
         // owner sequence = s0 + #starts <= p
         uint32_t lo = 0, hi = nstarts;
         while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (s_starts[mid] <= (uint32_t)p) lo = mid + 1; else hi = mid; }
@@ -116,13 +121,18 @@ kmerize_insert_kernel(const uint8_t* __restrict__ bases, const uint64_t* __restr
 int launch_kmerize_insert(cid_ctx* ctx, cudaStream_t st, const uint8_t* d_bases, const uint64_t* d_seq_offs,
                           uint64_t nseq, uint64_t base_lo, uint64_t base_hi, const uint32_t* d_seq_group,
                           const uint64_t* d_region_off, const uint64_t* d_region_mask, void* d_table, uint32_t k,
-                          int seq_mode) {
+                          int seq_mode, uint32_t mini_m) {
     if (base_hi <= base_lo || nseq == 0) return CID_OK;
     uint64_t ntiles = (base_hi - base_lo + KT - 1) / KT;
     ProfScope ps(ctx, st, KID_KMERIZE_INSERT);
-    kmerize_insert_kernel<<<(unsigned)ntiles, KT_THREADS, 0, st>>>(d_bases, d_seq_offs, nseq, base_lo, base_hi, d_seq_group,
-                                                                  d_region_off, d_region_mask, (Slot*)d_table, k,
-                                                                  seq_mode, ctx->d_err);
+    if (mini_m)
+        kmerize_insert_kernel<true><<<(unsigned)ntiles, KT_THREADS, 0, st>>>(d_bases, d_seq_offs, nseq, base_lo, base_hi, d_seq_group,
+                                                                            d_region_off, d_region_mask, (Slot*)d_table, k, mini_m,
+                                                                            seq_mode, ctx->d_err);
+    else
+        kmerize_insert_kernel<false><<<(unsigned)ntiles, KT_THREADS, 0, st>>>(d_bases, d_seq_offs, nseq, base_lo, base_hi, d_seq_group,
+                                                                             d_region_off, d_region_mask, (Slot*)d_table, k, 0,
+                                                                             seq_mode, ctx->d_err);
     ctx->launches++;
     CID_CUDA(cudaGetLastError());
     return CID_OK;
@@ -183,8 +193,8 @@ int launch_region_histogram(cid_ctx* ctx, cudaStream_t st, const void* d_region,
 // ================================================================= region_to_bloom
 // clean_map (count > cutoff, kmer.rs:826-837), n_ref_kmers (build.rs:62), BloomFilter::insert.
 __global__ void __launch_bounds__(256)
-region_to_bloom_kernel(const Slot* __restrict__ region, uint64_t nslots, long long cutoff, uint32_t k, uint32_t H,
-                       ModS mods, uint32_t* __restrict__ bitset, unsigned long long* __restrict__ nref) {
+region_to_bloom_kernel(const Slot* __restrict__ region, uint64_t nslots, long long cutoff, uint32_t k, uint32_t mini_m,
+                       uint32_t H, ModS mods, uint32_t* __restrict__ bitset, unsigned long long* __restrict__ nref) {
     __shared__ uint32_t lut[256];
     lut4_init(lut, threadIdx.x, blockDim.x);
     __syncthreads();
@@ -193,9 +203,16 @@ region_to_bloom_kernel(const Slot* __restrict__ region, uint64_t nslots, long lo
         Slot v = region[s];
         if (v.key == CID_EMPTY_KEY || (long long)v.count <= cutoff) continue;
         mine++;
-        HashIn in = hashin_from_key(lut, v.key, k);
+        uint64_t item = v.key;
+        uint32_t len = k;
+        if (mini_m) {   // build_single_mini (build.rs:430-432,445-447,461-463): insert find_minimizer(kmer, m) of every kept k-mer
+            uint32_t which;
+            item = minimizer_packed(v.key, revcomp_key(v.key, k), k, mini_m, which);
+            len = mini_m;
+        }
+        HashIn in = hashin_from_key(lut, item, len);
         for (uint32_t i = 0; i < H; i++) {
-            uint64_t bit = mod_s(xxh3_kmer(in, k, i), mods);
+            uint64_t bit = mod_s(xxh3_kmer(in, len, i), mods);
             atomicOr(&bitset[bit >> 5], 1u << (bit & 31));
         }
     }
@@ -204,11 +221,11 @@ region_to_bloom_kernel(const Slot* __restrict__ region, uint64_t nslots, long lo
     if ((threadIdx.x & 31) == 0 && mine) atomicAdd(nref, (unsigned long long)mine);
 }
 int launch_region_to_bloom(cid_ctx* ctx, cudaStream_t st, const void* d_region, uint64_t nslots, int64_t cutoff,
-                           uint32_t k, uint32_t H, uint64_t S, uint32_t* d_bitset, unsigned long long* d_nref) {
+                           uint32_t k, uint32_t mini_m, uint32_t H, uint64_t S, uint32_t* d_bitset, unsigned long long* d_nref) {
     unsigned grid = (unsigned)std::min<uint64_t>((nslots + 255) / 256, (uint64_t)ctx->sm_count * 16);
     if (grid == 0) grid = 1;
     ProfScope ps(ctx, st, KID_TO_BLOOM);
-    region_to_bloom_kernel<<<grid, 256, 0, st>>>((const Slot*)d_region, nslots, (long long)cutoff, k, H, make_mods(S),
+    region_to_bloom_kernel<<<grid, 256, 0, st>>>((const Slot*)d_region, nslots, (long long)cutoff, k, mini_m, H, make_mods(S),
                                                  d_bitset, d_nref);
     ctx->launches++;
     CID_CUDA(cudaGetLastError());
@@ -985,7 +1002,7 @@ int launch_hash_kmers(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, const
                       uint64_t* d_rows) {
     if (n == 0) return CID_OK;
     ProfScope ps(ctx, st, KID_OTHER);
-    hash_kmers_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_kmers, n, idx->k, idx->H, make_mods(idx->S), d_rows);
+    hash_kmers_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_kmers, n, idx->m ? idx->m : idx->k, idx->H, make_mods(idx->S), d_rows);
     ctx->launches++;
     CID_CUDA(cudaGetLastError());
     return CID_OK;

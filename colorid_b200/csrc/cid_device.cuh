@@ -297,6 +297,60 @@ __device__ __forceinline__ bool tile_kmer(const Tile& t, int i, uint32_t k, uint
     return true;
 }
 
+// ------------------------------------------------------------------ minimizers (.mxi indexes)
+// kmer.rs:971-986 find_minimizer(seq, m) on the canonical k-mer `s` (packed, upper case) and its reverse
+// complement `src`: the smallest of seq[0..m] and, for i in 1..=k-m, seq[i..i+m] and revcomp(seq[i..i+m])
+// -- the reverse complement of the FIRST m-mer is never a candidate.  For upper-case (or all lower-case)
+// bases byte order == numeric order of the 2-bit codes.  `which` = 2*i + (1 if the winner is a reverse
+// complement).  Ties keep the earlier candidate like the reference's strict `<`; tied strings are equal anyway.
+__device__ __forceinline__ uint64_t minimizer_packed(uint64_t s, uint64_t src, uint32_t k, uint32_t m, uint32_t& which) {
+    const uint64_t mm = (1ULL << (2 * m)) - 1;          // m <= 31
+    uint64_t best = (s >> (2 * (k - m))) & mm;
+    uint32_t w = 0;
+    for (uint32_t i = 1; i + m <= k; i++) {
+        const uint64_t f = (s >> (2 * (k - m - i))) & mm;   // seq[i..i+m]
+        const uint64_t r = (src >> (2 * i)) & mm;           // revcomp(seq)[k-(i+m)..k-i]
+        if (f < best) { best = f; w = 2 * i; }
+        if (r < best) { best = r; w = 2 * i + 1; }
+    }
+    which = w;
+    return best;
+}
+// The same on the raw bytes of tile window i, for windows that mix upper and lower case (kmer.rs:328-394 choose
+// the minimizer on the raw-case canonical k-mer and upper-case it afterwards).  Returns the upper-cased codes.
+static __device__ __noinline__ uint64_t minimizer_exact(const Tile& t, int i, uint32_t k, uint32_t m, bool took_fwd, uint32_t& which) {
+    // byte j of the canonical k-mer; byte x of candidate (a, rc): rc ? comp(sb(a+m-1-x)) : sb(a+x)
+    auto sb = [&](uint32_t j) -> uint32_t { return took_fwd ? (uint32_t)t.ascii[i + j] : comp_base(t.ascii[i + k - 1 - j]); };
+    auto cb = [&](uint32_t a, bool rc, uint32_t x) -> uint32_t { return rc ? comp_base(sb(a + m - 1 - x)) : sb(a + x); };
+    uint32_t ba = 0; bool brc = false;
+    for (uint32_t a = 1; a + m <= k; a++) {
+        for (int rc = 0; rc < 2; rc++) {
+            for (uint32_t x = 0; x < m; x++) {
+                const uint32_t c = cb(a, rc != 0, x), b = cb(ba, brc, x);
+                if (c != b) { if (c < b) { ba = a; brc = rc != 0; } break; }
+            }
+        }
+    }
+    uint64_t key = 0;
+    for (uint32_t x = 0; x < m; x++) key = (key << 2) | base_code(cb(ba, brc, x));
+    which = 2 * ba + (brc ? 1u : 0u);
+    return key;
+}
+// Minimizer of the k-mer that tile_kmer() returned for window i (`key`, strand `took_fwd`), plus the forward-read
+// window [mpos, mpos+m) that spells it (mfwd) or its reverse complement (!mfwd).
+__device__ __forceinline__ uint64_t tile_minimizer(const Tile& t, int i, uint32_t k, uint32_t m, uint64_t key, bool took_fwd,
+                                                   bool has_lower, uint32_t& mpos, bool& mfwd) {
+    uint32_t which;
+    uint64_t mk;
+    const uint32_t low = has_lower ? mask_window(t.lower, i, k) : 0u;
+    if (low != 0u && low != (k == 32 ? 0xFFFFFFFFu : ((1u << k) - 1))) mk = minimizer_exact(t, i, k, m, took_fwd, which);
+    else mk = minimizer_packed(key, revcomp_key(key, k), k, m, which);
+    const uint32_t j = which >> 1;
+    mpos = (uint32_t)i + (took_fwd ? j : k - m - j);
+    mfwd = ((which & 1u) == 0u) == took_fwd;
+    return mk;
+}
+
 // ------------------------------------------------------------------ count table (open addressing)
 struct __align__(16) Slot { unsigned long long key; uint32_t count; uint32_t pad; };
 #define CID_EMPTY_KEY 0xFFFFFFFFFFFFFFFFULL

@@ -82,11 +82,11 @@ __device__ __forceinline__ bool warp_load_read(Tile& t, int cap, const uint8_t* 
 // (the order kernel's only input), ent16 = tile position | strand << 10 (the vote kernel's).
 // Duplicate HashSet::insert calls matter to hashbrown only through "is there a call after the
 // last fresh one" (bit 31 of nocc), see readid_order_small_kernel.
-template <bool COMPACT>
-__global__ void __launch_bounds__(RA_WARPS * 32)
+template <bool COMPACT, bool MINI>     // MINI: .mxi index, the set holds minimizers of length mini_m (a separate
+__global__ void __launch_bounds__(RA_WARPS * 32)   // instantiation so the k-mer path keeps its register budget)
 readid_kmerize_kernel(const uint8_t* __restrict__ bases, const uint8_t* __restrict__ quals, uint32_t maxq,
                       const uint64_t* __restrict__ seq_offs, const uint64_t* __restrict__ read_offs, uint64_t r0,
-                      uint64_t nreads, uint32_t k, uint32_t d, int cap, uint32_t maxocc, uint32_t tsize,
+                      uint64_t nreads, uint32_t k, uint32_t mini_m, uint32_t d, int cap, uint32_t maxocc, uint32_t tsize,
                       uint32_t* __restrict__ entries, uint8_t* __restrict__ hp8, uint32_t* __restrict__ h9w,
                       uint16_t* __restrict__ ent16, uint32_t* __restrict__ nocc, uint32_t* __restrict__ nfresh,
                       uint32_t* __restrict__ flags, uint32_t* __restrict__ err) {
@@ -135,8 +135,9 @@ readid_kmerize_kernel(const uint8_t* __restrict__ bases, const uint8_t* __restri
             if (lane == 0) atomicOr(err, ERRF_READ_TOO_LONG);
             fl |= 8u; ok = false;
         }
-        if (ok) {
+        if (ok && !MINI) {
             // kmer.rs:229 `0..l.len()-k+1` wraps for a later mate shorter than k-1 -> slice panic
+            // (minimerize_vector_skip_n_set has a `length_l < k` guard instead, kmer.rs:372: the mate is skipped)
             for (int m = 1; m < g.nm; m++) if (moffs[m + 1] - moffs[m] + 1 < k) { fl |= 2u; ok = false; }
         }
         if (ok) {
@@ -155,7 +156,12 @@ readid_kmerize_kernel(const uint8_t* __restrict__ bases, const uint8_t* __restri
                     }
                     uint64_t key; bool fwd, low;
                     if (take && tile_kmer(t, tp, k, key, fwd, low)) {
-                        if (low) atomicOr(err, ERRF_LOWER_RAW);
+                        uint32_t ipos = (uint32_t)tp;      // window that spells the set's item (k-mer, or its minimizer)
+                        if (MINI) {                        // kmer.rs:363-394: the set holds upper-cased minimizers
+                            bool mfwd;
+                            key = tile_minimizer(t, tp, k, mini_m, key, fwd, low, ipos, mfwd);
+                            fwd = mfwd;
+                        } else if (low) atomicOr(err, ERRF_LOWER_RAW);
                         uint32_t s = (uint32_t)mix64(key) & tmask;
                         for (;;) {
                             unsigned long long prev = atomicCAS(&tkeys[s], CID_EMPTY_KEY, (unsigned long long)key);
@@ -163,7 +169,7 @@ readid_kmerize_kernel(const uint8_t* __restrict__ bases, const uint8_t* __restri
                             s = (s + 1) & tmask;
                         }
                         atomicMin(&tmin[s], (uint32_t)tp);
-                        info = 0x80000000u | (fwd ? 0x40000000u : 0u) | s;
+                        info = 0x80000000u | (fwd ? 0x40000000u : 0u) | (ipos << 16) | s;     // s < tsize <= 2^16
                     }
                 }
                 if (tp < cap) pinfo[tp] = info;
@@ -180,17 +186,17 @@ readid_kmerize_kernel(const uint8_t* __restrict__ bases, const uint8_t* __restri
                 uint32_t ent = 0, f = 0;
                 bool fresh = false;
                 if (valid) {
-                    uint32_t s = info & 0xFFFFFu;
+                    uint32_t s = info & 0xFFFFu;
                     fresh = tmin[s] == (uint32_t)tp;
-                    f = fresh ? (fnv1a_low32_key_lut(lut, tkeys[s], k) & 0xFFFFu) : 0u;
-                    ent = f | ((uint32_t)tp << 16) | (((info >> 30) & 1u) << 26) | ((fresh ? 1u : 0u) << 27);
+                    f = fresh ? (fnv1a_low32_key_lut(lut, tkeys[s], MINI ? mini_m : k) & 0xFFFFu) : 0u;
+                    ent = f | (info & 0x03FF0000u) | (((info >> 30) & 1u) << 26) | ((fresh ? 1u : 0u) << 27);
                 }
                 const uint32_t bal = __ballot_sync(0xffffffffu, valid), balf = __ballot_sync(0xffffffffu, fresh);
                 if (COMPACT) {
                     const uint32_t fi = nfr + __popc(balf & ((1u << lane) - 1));
                     if (fresh && fi < maxocc) {
                         hp8[rl * (uint64_t)maxocc + fi] = (uint8_t)f;
-                        ent16[rl * (uint64_t)maxocc + fi] = (uint16_t)((uint32_t)tp | (((info >> 30) & 1u) << 10));
+                        ent16[rl * (uint64_t)maxocc + fi] = (uint16_t)(((info >> 16) & 0x3FFu) | (((info >> 30) & 1u) << 10));
                         if ((f >> 8) & 1u) atomicOr(&h9s[fi >> 5], 1u << (fi & 31));
                     }
                     if (bal) last_fresh = (balf >> (31 - __clz(bal))) & 1u;
@@ -1054,7 +1060,7 @@ int launch_readid_classify(cid_ctx* ctx, cudaStream_t st, uint64_t r0, uint64_t 
 __global__ void order_export_kernel(const uint16_t* __restrict__ order, const uint8_t* __restrict__ order8,
                                     const uint16_t* __restrict__ ent16, const uint32_t* __restrict__ n_set,
                                     const uint64_t* __restrict__ seq_offs, const uint64_t* __restrict__ read_offs,
-                                    uint64_t r0, uint64_t nreads, uint32_t maxocc, uint32_t order_cap,
+                                    uint64_t r0, uint64_t nreads, uint32_t maxocc, uint32_t order_cap, int mini,
                                     uint32_t* __restrict__ order_n, uint8_t* __restrict__ order_seq,
                                     uint16_t* __restrict__ order_pos) {
     uint64_t rl = blockIdx.x;
@@ -1065,11 +1071,13 @@ __global__ void order_export_kernel(const uint16_t* __restrict__ order, const ui
     uint64_t b0 = seq_offs[s_begin];
     if (threadIdx.x == 0) order_n[r] = n;
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-        uint32_t tp = (order8 ? (uint32_t)ent16[rl * (uint64_t)maxocc + order8[rl * (uint64_t)maxocc + i]]
-                              : (uint32_t)order[rl * (uint64_t)maxocc + i]) & 0x3FFu;
+        const uint32_t e = order8 ? (uint32_t)ent16[rl * (uint64_t)maxocc + order8[rl * (uint64_t)maxocc + i]]
+                                  : (uint32_t)order[rl * (uint64_t)maxocc + i];
+        const uint32_t tp = e & 0x3FFu;
         uint32_t m = 0;
         for (uint64_t s = s_begin + 1; s < s_end; s++) if (seq_offs[s] - b0 <= tp) m = (uint32_t)(s - s_begin);
-        order_seq[r * (uint64_t)order_cap + i] = (uint8_t)m;
+        // minimizer sets: bit 7 = the window spells the minimizer (1) or its reverse complement (0)
+        order_seq[r * (uint64_t)order_cap + i] = (uint8_t)(m | (mini ? ((e >> 10) & 1u) << 7 : 0u));
         order_pos[r * (uint64_t)order_cap + i] = (uint16_t)(tp - (seq_offs[s_begin + m] - b0));
     }
 }
@@ -1145,24 +1153,26 @@ int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const ui
     size_t cw_warp = ((tile_smem_bytes(cap) + 15) & ~(size_t)15) + (MAX_MATES + 1) * 4 + 12;
     size_t cw_smem = RA_WARPS * ((cw_warp + 15) & ~(size_t)15);
     if (a_smem > 200 * 1024 || b_smem > 200 * 1024) { set_error("read_id: read too long for the shared-memory plan"); return CID_E_UNSUPPORTED; }
-    CID_CUDA(cudaFuncSetAttribute(readid_kmerize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a_smem));
-    CID_CUDA(cudaFuncSetAttribute(readid_kmerize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a_smem));
+    CID_CUDA(cudaFuncSetAttribute(readid_kmerize_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a_smem));
+    CID_CUDA(cudaFuncSetAttribute(readid_kmerize_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a_smem));
+    CID_CUDA(cudaFuncSetAttribute(readid_kmerize_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a_smem));
+    CID_CUDA(cudaFuncSetAttribute(readid_kmerize_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a_smem));
     CID_CUDA(cudaFuncSetAttribute(readid_order_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b_smem));
 
     const ModS mods = make_mods(idx->S);
+    const uint32_t kitem = idx->m ? idx->m : idx->k;    // length of the hashed item: k-mer, or minimizer of an .mxi index
     for (uint64_t r0 = r_first; r0 < r_first + nreads; r0 += sub) {
         const uint64_t nr = std::min(sub, r_first + nreads - r0);
         unsigned gridA = (unsigned)std::min<uint64_t>((nr + RA_WARPS - 1) / RA_WARPS, (uint64_t)ctx->sm_count * 32);
         {
         ProfScope ps(ctx, st, KID_READID_KMERIZE);
-        if (small)
-            readid_kmerize_kernel<true><<<gridA, RA_WARPS * 32, a_smem, st>>>(d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr,
-                                                                             idx->k, p.downsample, cap, maxocc, tsize, d_entries,
-                                                                             d_hp8, d_h9w, d_ent16, d_nocc, d_nfresh, d_flags, ctx->d_err);
-        else
-            readid_kmerize_kernel<false><<<gridA, RA_WARPS * 32, a_smem, st>>>(d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr,
-                                                                              idx->k, p.downsample, cap, maxocc, tsize, d_entries,
-                                                                              d_hp8, d_h9w, d_ent16, d_nocc, d_nfresh, d_flags, ctx->d_err);
+#define CID_KMERIZE(C, M)                                                                                              \
+    readid_kmerize_kernel<C, M><<<gridA, RA_WARPS * 32, a_smem, st>>>(d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr, idx->k, \
+                                                                     idx->m, p.downsample, cap, maxocc, tsize, d_entries, d_hp8,   \
+                                                                     d_h9w, d_ent16, d_nocc, d_nfresh, d_flags, ctx->d_err)
+        if (small) { if (idx->m) CID_KMERIZE(true, true); else CID_KMERIZE(true, false); }
+        else { if (idx->m) CID_KMERIZE(false, true); else CID_KMERIZE(false, false); }
+#undef CID_KMERIZE
         }
         ctx->launches++;
         CID_CUDA(cudaGetLastError());
@@ -1199,7 +1209,7 @@ int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const ui
         const uint8_t* ord8 = small ? (const uint8_t*)d_order : nullptr;
         if (d_order_n) {
             order_export_kernel<<<(unsigned)nr, 64, 0, st>>>(ord16, ord8, d_ent16, d_n_set, d_seq_offs, d_read_offs, r0, nr, maxocc,
-                                                            order_cap, d_order_n, d_order_seq, d_order_pos);
+                                                            order_cap, idx->m != 0, d_order_n, d_order_seq, d_order_pos);
             ctx->launches++;
             CID_CUDA(cudaGetLastError());
         }
@@ -1210,17 +1220,17 @@ int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const ui
                 if (!idx->rownz_global) rownz = nullptr;   // presence == any word set, already in registers
                 if (idx->Wp == 1)
                     readid_vote_narrow_kernel<1><<<gridA, RA_WARPS * 32, cn_smem, st>>>(
-                        d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr, idx->k, idx->H, mods, idx->rows, rownz, idx->rownz,
+                        d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr, kitem, idx->H, mods, idx->rows, rownz, idx->rownz,
                         idx->N, cap, maxocc, ord16, ord8, d_ent16, d_n_set, p.start_sample, p.rep_cap, d_flags, d_rep_n, d_rep_colour,
                         d_rep_count, (unsigned long long*)(ctx->d_err + 2));
                 else
                     readid_vote_narrow_kernel<2><<<gridA, RA_WARPS * 32, cn_smem, st>>>(
-                        d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr, idx->k, idx->H, mods, idx->rows, rownz, idx->rownz,
+                        d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr, kitem, idx->H, mods, idx->rows, rownz, idx->rownz,
                         idx->N, cap, maxocc, ord16, ord8, d_ent16, d_n_set, p.start_sample, p.rep_cap, d_flags, d_rep_n, d_rep_colour,
                         d_rep_count, (unsigned long long*)(ctx->d_err + 2));
             } else {
                 readid_vote_wide_kernel<<<gridA, RA_WARPS * 32, cw_smem, st>>>(
-                    d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr, idx->k, idx->H, mods, idx->rows, rownz, idx->N,
+                    d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr, kitem, idx->H, mods, idx->rows, rownz, idx->N,
                     idx->Wp, cap, maxocc, ord16, ord8, d_ent16, d_n_set, p.start_sample, p.rep_cap, d_flags, d_rep_n, d_rep_colour,
                     d_rep_count);
             }

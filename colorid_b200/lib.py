@@ -19,6 +19,7 @@ vp = C.c_void_p
 
 CID_OK, CID_E_INVALID, CID_E_CUDA, CID_E_NOMEM, CID_E_UNSUPPORTED, CID_E_REF_PANIC, CID_E_CAPACITY = 0, -1, -2, -3, -4, -5, -6
 CID_SEQ_FASTA, CID_SEQ_FASTQ, CID_SEQ_STRING = 0, 1, 2
+CID_MINI_OF_KMERS, CID_MINI_COUNTED = 0, 1
 
 
 class ReadIdParams(C.Structure):
@@ -49,6 +50,9 @@ SIGNATURES = {
     "cid_index_set_rownz_global": (C.c_int, [vp, C.c_int]),
     "cid_build_accession": (C.c_int, [vp, C.c_uint32, vp, u64p, C.c_uint64, C.c_int, C.c_int64, u64p, i64p]),
     "cid_build_accession_dev": (C.c_int, [vp, C.c_uint32, vp, vp, C.c_uint64, C.c_uint64, C.c_int, C.c_int64, u64p, i64p]),
+    "cid_index_set_minimizer": (C.c_int, [vp, C.c_uint32]),
+    "cid_index_minimizer": (C.c_uint32, [vp]),
+    "cid_build_accession_mini": (C.c_int, [vp, C.c_uint32, vp, u64p, C.c_uint64, C.c_int, C.c_int64, C.c_int, u64p, i64p]),
     "cid_build_finalize": (C.c_int, [vp]),
     "cid_query_counts": (C.c_int, [vp, vp, u64p, C.c_uint64, u64p, C.c_uint64, C.c_int, C.c_int, C.c_int64, u32p, u64p,
                                    u64p, u64p, u64p, i64p]),

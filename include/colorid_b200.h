@@ -107,6 +107,25 @@ int cid_build_accession(cid_index* idx, uint32_t colour, const char* bases, cons
 int cid_build_accession_dev(cid_index* idx, uint32_t colour, const char* d_bases, const uint64_t* d_seq_offs,
                             uint64_t nseq, uint64_t nbases, int seq_mode, int64_t cutoff, uint64_t* n_ref_kmers,
                             int64_t* cutoff_used);
+/* ---- minimizer indexes (.mxi): bigsi.rs:40-49 BigsyMapMiniNew, `colorid build -m -v M` (main.rs:485-533) -------
+ * cid_index_set_minimizer(idx, M) (1 <= M <= k_size; M > k_size is CID_E_REF_PANIC: find_minimizer slices
+ * seq[..m], kmer.rs:974) turns the index into a minimizer index: the items hashed into the Bloom filters are then
+ * kmer.rs:971-986 find_minimizer(canonical k-mer, M) strings of M bytes instead of the k-mers.  cid_read_id_* then
+ * follow kmer.rs:363-394 minimerize_vector_skip_n_set (read_id_mt_pe.rs:318-322, m != 0): per-mate `len >= k`
+ * guard, lower-case accepted (minimizers are upper-cased), the set holds minimizers; n_set counts them.
+ * cid_query_* return CID_E_UNSUPPORTED with the reference's message (main.rs:569-573).  The two builders of the
+ * reference differ, so both are offered:
+ *   CID_MINI_OF_KMERS  build.rs:396-492 build_single_mini (-t 1): the k-mer count map and cutoff of the plain build,
+ *                      then insert(find_minimizer(kmer, M)) per surviving k-mer; n_ref_kmers = distinct k-mers
+ *                      (the reference records it for FASTA accessions only: the caller drops it for FASTQ).
+ *   CID_MINI_COUNTED   build.rs:258-394 build_multi_mini (-t > 1): a count map of minimizers (one count per k-mer
+ *                      position; kmer.rs:328-361 FASTA, upper-cased after the choice; :694-824 FASTQ), auto_cutoff /
+ *                      clean_map on those counts, insert of the survivors; n_ref_kmers = surviving minimizers. */
+enum { CID_MINI_OF_KMERS = 0, CID_MINI_COUNTED = 1 };
+int cid_index_set_minimizer(cid_index* idx, uint32_t m_size);
+uint32_t cid_index_minimizer(const cid_index* idx);
+int cid_build_accession_mini(cid_index* idx, uint32_t colour, const char* bases, const uint64_t* seq_offs, uint64_t nseq,
+                             int seq_mode, int64_t cutoff, int variant, uint64_t* n_ref_kmers, int64_t* cutoff_used);
 /* Phase 2: transposition of the per-colour bitsets into the row-major matrix (build.rs:116-128). */
 int cid_build_finalize(cid_index* idx);
 
@@ -182,7 +201,9 @@ int cid_read_id_batch_dev(cid_index* idx, const char* d_bases, const char* d_qua
                           uint32_t* d_n_set, uint32_t* d_flags, uint32_t* d_rep_n, uint32_t* d_rep_colour,
                           uint32_t* d_rep_count, void* stream);
 /* Debug/parity hook: the emulated FnvHashSet<String> iteration order of each read's k-mer set as
- * (mate index, position of first occurrence).  order_n[r] entries at [r*order_cap ..]. */
+ * (mate index, position of first occurrence).  order_n[r] entries at [r*order_cap ..].
+ * Minimizer index: the set holds minimizers; order_pos is the start of a window of m_size bases of that mate which
+ * spells the minimizer (bit 7 of order_seq set) or its reverse complement (bit 7 clear). */
 int cid_read_kmer_order(cid_index* idx, const char* bases, const uint64_t* seq_offs, uint64_t nseq,
                         const uint64_t* read_offs, uint64_t nreads, const cid_readid_params* p, uint32_t order_cap,
                         uint32_t* order_n, uint8_t* order_seq, uint16_t* order_pos);
@@ -209,8 +230,8 @@ int cid_classify_reads(uint64_t bloom_size, uint32_t num_hash, uint32_t n_colors
 double cid_false_prob(double bloom_size, double num_hash, double n_ref_kmers);
 double cid_binomial_mass(uint64_t n, double p, uint64_t x);
 
-/* Row indices of canonical k-mers given as ASCII (k bytes each): out[n*num_hash] =
- * xxh3_64(kmer, seed=i) % bloom_size  (simple_bloom.rs:21-24).  Parity hook for the hash. */
+/* Row indices of canonical k-mers given as ASCII (k bytes each; m_size bytes each for a minimizer index):
+ * out[n*num_hash] = xxh3_64(kmer, seed=i) % bloom_size  (simple_bloom.rs:21-24).  Parity hook for the hash. */
 int cid_hash_kmers(cid_index* idx, const char* kmers, uint64_t n, uint64_t* row_ids);
 
 #ifdef __cplusplus

@@ -124,6 +124,40 @@ static bool kmap_add_seq(KMap& m, const std::string& l, size_t k, size_t d, int 
     return for_each_canonical(l, k, d, mode, [&](const std::string& km, size_t, bool) { m[km] += 1; });
 }
 
+// kmer.rs:971-986 find_minimizer: the byte-wise smallest m-mer among seq[0..m] (forward only!), and for
+// i in 1..=len-m both seq[i..i+m] and revcomp(seq)[len-(i+m)..len-i] (= revcomp of seq[i..i+m]).
+// `which` (optional) reports the winner as 2*i + (1 if it came from the reverse complement).
+static std::string find_minimizer(const std::string& seq, size_t m, size_t* which = nullptr) {
+    std::string r = revcomp(seq);
+    size_t L = seq.size();
+    const char* best = seq.data();
+    size_t w = 0;
+    for (size_t i = 1; i + m <= L; i++) {
+        const char* f = seq.data() + i;
+        const char* c = r.data() + (L - (i + m));
+        if (slice_lt(f, best, m)) { best = f; w = 2 * i; }
+        if (slice_lt(c, best, m)) { best = c; w = 2 * i + 1; }
+    }
+    if (which) *which = w;
+    return std::string(best, m);
+}
+
+// Minimizer count maps.  `upper`: kmer.rs:328-361 minimerize_vector_skip_n (FASTA, build_multi_mini) upper-cases the
+// minimizer AFTER it was chosen on the raw-case canonical k-mer; kmer.rs:694-824 kmers_fq_pe_minimizer_qual /
+// kmers_from_fq_minimizer_qual keep the case.  Both: len >= k guard, has_no_n on the forward window, canonical by raw bytes.
+static void minimap_add_seq(KMap& mm, const std::string& l, size_t k, size_t m, size_t d, bool upper) {
+    size_t L = l.size();
+    if (L < k) return;
+    std::string r = revcomp(l);
+    for (size_t i = 0; i + k <= L; i += d) {
+        const char* f = l.data() + i;
+        const char* c = r.data() + (L - (i + k));
+        if (!has_no_n(f, k)) continue;
+        std::string mi = find_minimizer(std::string(slice_lt(f, c, k) ? f : c, k), m);
+        mm[upper ? to_upper_ascii(mi) : mi] += 1;
+    }
+}
+
 // kmer.rs:826-837
 static void clean_map(KMap& m, uint64_t t) {
     for (auto it = m.begin(); it != m.end();) {
@@ -193,6 +227,7 @@ static inline uint64_t bloom_bit(const std::string& kmer, uint64_t seed, uint64_
 
 struct Index {
     uint64_t S; uint32_t H, k, N, W;
+    uint32_t m = 0;                             // bigsi.rs:40-49 BigsyMapMiniNew.m_size (0 = k-mer index)
     std::vector<uint32_t> rows;                 // dense [S][W]; an all-zero row == absent row (build.rs:123-127)
     std::vector<std::vector<uint32_t>> bitsets; // phase-1 per-colour Bloom bitsets (build.rs:63-67)
     bool row_present(uint64_t r) const {
@@ -276,6 +311,38 @@ static bool read_kmer_set(const std::vector<std::string>& seqs, size_t k, size_t
     }
     order = tab.iter_order();
     return ok;
+}
+
+// kmer.rs:363-394 minimerize_vector_skip_n_set (read_id with an .mxi index): len >= k guard per mate, has_no_n,
+// canonical by raw bytes, find_minimizer on the raw-case canonical k-mer, then to_uppercase; set of minimizers.
+// pos/fwd of a key = forward-read window [pos, pos+m) that spells the minimizer (fwd) or its reverse complement.
+static bool read_minimizer_set(const std::vector<std::string>& seqs, size_t k, size_t m, size_t d, HbPolicy pol,
+                               std::vector<ReadKmer>& keys, std::vector<int>& order) {
+    HbTable tab(pol);
+    keys.clear();
+    for (size_t si = 0; si < seqs.size(); si++) {
+        const std::string& l = seqs[si];
+        size_t L = l.size();
+        if (L < k) continue;
+        std::string r = revcomp(l);
+        for (size_t i = 0; i + k <= L; i += d) {
+            const char* f = l.data() + i;
+            const char* c = r.data() + (L - (i + k));
+            if (!has_no_n(f, k)) continue;
+            bool fwd = slice_lt(f, c, k);
+            size_t which = 0;
+            std::string mi = to_upper_ascii(find_minimizer(std::string(fwd ? f : c, k), m, &which));
+            size_t j = which / 2; bool from_rc = which & 1;
+            uint32_t pos = (uint32_t)(i + (fwd ? j : k - m - j));
+            uint8_t mfwd = (uint8_t)((!from_rc) == fwd);
+            uint64_t h = fnv_hash_str(mi);
+            int idx = (int)keys.size();
+            bool fresh = tab.insert(h, idx, [&](int slot_key) { return keys[slot_key].s == mi; });
+            if (fresh) keys.push_back(ReadKmer{mi, (uint32_t)si, pos, mfwd});
+        }
+    }
+    order = tab.iter_order();
+    return true;
 }
 
 struct Report {                        // FnvHashMap<usize,usize> with emulated iteration order
@@ -482,6 +549,59 @@ int orc_build_accession(orc_index* h, uint32_t colour, const char* bases, const 
         }
     return 0;
 }
+// Minimizer indexes (.mxi).  variant 0 = build.rs:396-492 build_single_mini: the k-mer count map and filter of the
+// plain build, then BloomFilter::insert(find_minimizer(kmer, m)) per surviving k-mer; n_ref_kmers = distinct k-mers
+// (the reference records it for FASTA accessions only, :450).  variant 1 = build.rs:258-394 build_multi_mini: a
+// count map of MINIMIZERS (one count per k-mer position), auto_cutoff / clean_map on those counts, Bloom insert
+// of the surviving minimizers, n_ref_kmers = their number (:316,337,352).
+int orc_build_accession_mini(orc_index* h, uint32_t colour, const char* bases, const uint64_t* offs, uint64_t nseq,
+                             int mode, int64_t cutoff, int variant, uint64_t* n_ref_kmers, int64_t* cutoff_used) {
+    Index& ix = h->ix;
+    if (ix.m == 0 || ix.m > ix.k) return -1;          // find_minimizer slices seq[..m]: panics for m > k
+    KMap m;
+    for (uint64_t i = 0; i < nseq; i++) {
+        std::string l(bases + offs[i], offs[i + 1] - offs[i]);
+        if (variant == 0) kmap_add_seq(m, l, ix.k, 1, mode == 0 ? MODE_FASTA : MODE_FASTQ);
+        else minimap_add_seq(m, l, ix.k, ix.m, 1, mode == 0);
+    }
+    int64_t used = -1;
+    if (mode == 0) {
+        if (cutoff != -1) { used = cutoff; clean_map(m, (uint64_t)cutoff); }
+    } else {
+        if (cutoff == -1) { used = auto_cutoff(m); if (used < 0) return -1; }
+        else used = cutoff;
+        clean_map(m, (uint64_t)used);
+    }
+    if (n_ref_kmers) *n_ref_kmers = m.size();
+    if (cutoff_used) *cutoff_used = used;
+    std::vector<uint32_t>& bits = ix.bitsets[colour];
+    bits.assign((ix.S + 31) / 32, 0);
+    for (auto& kv : m) {
+        const std::string item = variant == 0 ? find_minimizer(kv.first, ix.m) : kv.first;
+        for (uint32_t i = 0; i < ix.H; i++) {
+            uint64_t b = bloom_bit(item, i, ix.S);
+            bits[b / 32] |= 1u << (b % 32);
+        }
+    }
+    return 0;
+}
+void orc_index_set_minimizer(orc_index* h, uint32_t m) { h->ix.m = m; }
+// kmer.rs:971-986; out has m bytes.  Returns -1 where the reference panics (m > len).
+int orc_find_minimizer(const char* seq, uint64_t n, uint32_t m, char* out) {
+    if (m > n || m == 0) return -1;
+    std::string r = find_minimizer(std::string(seq, n), m);
+    memcpy(out, r.data(), m);
+    return 0;
+}
+// Minimizer count map of a list of sequences (kmer.rs:328-361 with upper = 1, :694-824 with upper = 0) into an orc_kmap.
+int orc_kmap_add_minimizers(orc_kmap* h, const char* bases, const uint64_t* offs, uint64_t nseq, uint32_t k, uint32_t m,
+                            uint32_t d, int upper) {
+    if (m == 0 || m > k) return -1;
+    for (uint64_t i = 0; i < nseq; i++)
+        minimap_add_seq(h->m, std::string(bases + offs[i], offs[i + 1] - offs[i]), k, m, d, upper != 0);
+    return 0;
+}
+
 // Phase 2 transposition (build.rs:116-128): row i gets bit `colour` iff that accession's bit i is set.
 void orc_build_finalize(orc_index* h, int threads) {
     Index& ix = h->ix;
@@ -620,12 +740,15 @@ int orc_read_id_batch(orc_index* h, const char* bases, const uint64_t* seq_offs,
                 if (rep_n) rep_n[r] = 0;
                 if (order_n) order_n[r] = 0;
                 if (seqs.empty() || seqs[0].size() < ix.k) { cls_kind[r] = CLS_TOO_SHORT; continue; }   // :305-313
-                if (!read_kmer_set(seqs, ix.k, d, pol, keys, order)) { cls_kind[r] = CLS_PANIC; continue; }
+                const bool set_ok = ix.m ? read_minimizer_set(seqs, ix.k, ix.m, d, pol, keys, order)   // :318-322 `if m == 0`
+                                         : read_kmer_set(seqs, ix.k, d, pol, keys, order);
+                if (!set_ok) { cls_kind[r] = CLS_PANIC; continue; }
                 n_set[r] = (uint32_t)keys.size();
                 if (order_n) {
                     order_n[r] = (uint32_t)std::min<size_t>(order.size(), order_cap);
                     for (uint32_t i = 0; i < order_n[r]; i++) {
-                        order_seq[r * (uint64_t)order_cap + i] = (uint8_t)keys[order[i]].seq;
+                        // minimizer mode: bit 7 = the window spells the minimizer itself (1) or its reverse complement (0)
+                        order_seq[r * (uint64_t)order_cap + i] = (uint8_t)(keys[order[i]].seq | (ix.m ? (keys[order[i]].fwd << 7) : 0));
                         order_pos[r * (uint64_t)order_cap + i] = (uint16_t)keys[order[i]].pos;
                     }
                 }

@@ -167,6 +167,24 @@ class KMap:
         return keys[: n * self.k].reshape(n, self.k), counts[:n]
 
 
+def find_minimizer(seq, m):
+    """kmer.rs:971-986 find_minimizer(seq, m) -> bytes (None where the reference panics: m > len(seq))."""
+    out = C.create_string_buffer(max(m, 1))
+    rc = lib().orc_find_minimizer(C.c_char_p(bytes(seq)), C.c_uint64(len(seq)), C.c_uint32(m), out)
+    return None if rc != 0 else out.raw[:m]
+
+
+def minimizer_map(seqs, k, m, d=1, upper=True):
+    """Minimizer count map (kmer.rs:328-361 upper=True / :694-824 upper=False) -> (keys [n, m] uint8, counts)."""
+    km = KMap(m)
+    bases, offs = pack_seqs(list(seqs))
+    rc = lib().orc_kmap_add_minimizers(km.h, _p(bases, C.c_char_p), _p(offs, u64p), C.c_uint64(len(seqs)),
+                                       C.c_uint32(k), C.c_uint32(m), C.c_uint32(d), C.c_int(int(upper)))
+    if rc != 0:
+        raise RuntimeError("reference would panic (m > k)")
+    return km
+
+
 def auto_cutoff_histo(histo):
     cov = np.array(list(histo.keys()), dtype=np.uint64)
     num = np.array(list(histo.values()), dtype=np.uint64)
@@ -176,11 +194,13 @@ def auto_cutoff_histo(histo):
 class Index:
     """Dense BIGSI index model on the CPU (bigsi.rs:19-27 semantics; absent row == zero row)."""
 
-    def __init__(self, bloom_size, num_hash, k, n_colours):
-        self.S, self.H, self.k, self.N = bloom_size, num_hash, k, n_colours
+    def __init__(self, bloom_size, num_hash, k, n_colours, m=0):
+        self.S, self.H, self.k, self.N, self.m = bloom_size, num_hash, k, n_colours, m
         self.W = (n_colours + 31) // 32
         self.h = C.c_void_p(lib().orc_index_new(bloom_size, num_hash, k, n_colours))
         self.n_ref = np.zeros(n_colours, dtype=np.uint64)
+        if m:
+            lib().orc_index_set_minimizer(self.h, C.c_uint32(m))     # .mxi: bigsi.rs:40-49 m_size
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -201,6 +221,19 @@ class Index:
                                        C.byref(used))
         if rc != 0:
             raise RuntimeError("reference would panic (auto_cutoff on a degenerate histogram)")
+        self.n_ref[colour] = n_ref.value
+        return n_ref.value, used.value
+
+    def build_accession_mini(self, colour, seqs, mode, cutoff=-1, variant=0):
+        """variant 0 = build_single_mini (build.rs:396-492), 1 = build_multi_mini (build.rs:258-394)."""
+        bases, offs = pack_seqs(list(seqs))
+        n_ref = C.c_uint64(0)
+        used = C.c_int64(0)
+        rc = lib().orc_build_accession_mini(self.h, C.c_uint32(colour), _p(bases, C.c_char_p), _p(offs, u64p),
+                                            C.c_uint64(len(seqs)), C.c_int(mode), C.c_int64(cutoff), C.c_int(variant),
+                                            C.byref(n_ref), C.byref(used))
+        if rc != 0:
+            raise RuntimeError("reference would panic")
         self.n_ref[colour] = n_ref.value
         return n_ref.value, used.value
 

@@ -170,3 +170,59 @@ def test_fasta_reader_quirks(oracle, tmp_path):
     assert oracle.read_fasta(str(p)) == [b"ACGT"]
     labels, seqs = oracle.read_fasta_mf(str(tmp_path / "x.fa"))
     assert labels == [b"late header"] and seqs == [b"ACGT"]
+
+
+# ---- minimizer (.mxi) path: fixtures from an independent pure-Python restatement (tests/golden/make_golden_minimizer.py)
+MZ = json.load(open(os.path.join(GOLD, "minimizer.json")))
+
+
+def test_find_minimizer_vectors(oracle):
+    for v in MZ["find_minimizer"]:
+        assert oracle.find_minimizer(v["seq"].encode(), v["m"]) == v["min"].encode(), v
+    # kmer.rs:974-985: the reverse complement of the FIRST m-mer is never a candidate
+    assert oracle.find_minimizer(b"TTTTC", 4) == b"GAAA"       # candidates TTTT, TTTC, GAAA (not AAAA)
+    assert oracle.find_minimizer(b"ACGT", 4) == b"ACGT"        # m == k: the k-mer itself
+    assert oracle.find_minimizer(b"ACG", 4) is None            # m > len: the reference panics
+
+
+def test_read_minimizer_sets(oracle):
+    for g in MZ["read_sets"]:
+        ix = oracle.Index(1024, 2, g["k"], 2, m=g["m"])
+        mates = [x.encode() for x in g["mates"]]
+        if len(mates[0]) < g["k"]:
+            continue                                            # parallel_vec: too_short before the set is built
+        res = ix.read_id_batch([mates], d=g["d"], order_cap=512)
+        n = int(res["order_n"][0])
+        assert n == int(res["n_set"][0]) == len(g["set"])
+        got = set()
+        for i in range(n):
+            sq, pos = int(res["order_seq"][0][i]), int(res["order_pos"][0][i])
+            w = mates[sq & 0x7F][pos:pos + g["m"]]
+            got.add((w if sq & 0x80 else oracle.revcomp(w)).upper().decode())
+        assert sorted(got) == g["set"]
+
+
+@needs_reference
+def test_phage_minimizer_index_both_builders(oracle):
+    import hashlib
+    ph = MZ["phage"]
+    P = ph["params"]
+    seqs = [oracle.read_fasta(os.path.join(REFERENCE, "test_data/refs", n + ".fasta")) for n in ph["colours"]]
+    for variant, key in ((0, "single"), (1, "multi")):
+        ix = oracle.Index(P["S"], P["H"], P["k"], 4, m=P["m"])
+        n_ref = [ix.build_accession_mini(c, s, oracle.MODE_FASTA, -1, variant)[0] for c, s in enumerate(seqs)]
+        ix.finalize(threads=2)
+        assert n_ref == ph[key]["n_ref_kmers"]
+        w = ix.words()
+        nz = np.flatnonzero(w.any(axis=1))
+        assert len(nz) == ph[key]["nonzero_rows"]
+        h = hashlib.sha256()
+        for r in nz:
+            h.update(int(r).to_bytes(8, "little") + int(w[r, 0]).to_bytes(4, "little"))
+        assert h.hexdigest() == ph[key]["sha256_rows"]
+    # minimizer counts feed clean_map in build_multi_mini: cutoff 1 drops singletons
+    km = oracle.minimizer_map(seqs[0], P["k"], P["m"])
+    total = len(km)
+    km.clean(1)
+    ix = oracle.Index(P["S"], P["H"], P["k"], 4, m=P["m"])
+    assert ix.build_accession_mini(0, seqs[0], oracle.MODE_FASTA, 1, 1) == (len(km), 1) and 0 < len(km) < total
