@@ -2,7 +2,7 @@
 // in bincode 1.x default configuration: little-endian, fixed-width integers,
 // usize as u64, sequences / maps / strings prefixed with a u64 length, struct fields in declaration order:
 //
-//   u64 bloom_size | u64 num_hash | u64 k_size
+//   u64 bloom_size | u64 num_hash | u64 k_size | [.mxi only: u64 m_size]   (BigsyMapMiniNew, bigsi.rs:40-49,71-89)
 //   u64 n | n x { u64 colour ; u64 len ; bytes }                               colors
 //   u64 n | n x { u64 row ; u64 n_words ; n_words x u32 ; u64 nbits }          map   (BitVec {storage, nbits})
 //   u64 n | n x { u64 len ; bytes ; u64 n_ref_kmers }                          n_ref_kmers
@@ -56,9 +56,10 @@ struct Reader {
 };
 }  // namespace
 
-void save_bigsi(const std::string& path, const Bigsi& b) {
+static void save_impl(const std::string& path, const Bigsi& b, bool mini) {
     Writer w(path);
     w.u64(b.bloom_size); w.u64(b.num_hash); w.u64(b.k_size);
+    if (mini) w.u64(b.m_size);
     w.u64(b.colors.size());
     for (auto& kv : b.colors) { w.u64(kv.first); w.str(kv.second); }
     const uint64_t nbits = b.colors.size();
@@ -87,10 +88,14 @@ void save_bigsi(const std::string& path, const Bigsi& b) {
     w.flush();
 }
 
-Bigsi read_bigsi(const std::string& path) {
+void save_bigsi(const std::string& path, const Bigsi& b) { save_impl(path, b, false); }
+void save_bigsi_mini(const std::string& path, const Bigsi& b) { save_impl(path, b, true); }
+
+static Bigsi read_impl(const std::string& path, bool mini) {
     Reader r(path);
     Bigsi b;
     b.bloom_size = r.u64(); b.num_hash = r.u64(); b.k_size = r.u64();
+    if (mini) { b.m_size = r.u64(); b.mini = true; }
     const uint64_t nc = r.u64();
     if (nc > (1ull << 32)) throw Error("can't deserialize");
     for (uint64_t i = 0; i < nc; i++) { uint64_t c = r.u64(); b.colors[c] = r.str(); }
@@ -121,5 +126,7 @@ Bigsi read_bigsi(const std::string& path) {
     for (uint64_t i = 0; i < nr; i++) { std::string a = r.str(); b.n_ref_kmers[a] = r.u64(); }
     return b;
 }
+Bigsi read_bigsi(const std::string& path) { return read_impl(path, false); }
+Bigsi read_bigsi_mini(const std::string& path) { return read_impl(path, true); }
 
 }  // namespace cidh

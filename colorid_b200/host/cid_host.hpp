@@ -6,8 +6,9 @@
 //   seq.rs:36-56         qual_mask                            -> fastx.cpp
 //   build.rs:15-31       tab_to_map                           -> fastx.cpp
 //   bigsi.rs:19-27,51-69 BigsyMapNew, save_bigsi, read_bigsi  -> bxi.cpp   (bincode 1.x layout)
+//   bigsi.rs:40-49,71-89 BigsyMapMiniNew, save_bigsi_mini, read_bigsi_mini (.mxi) -> bxi.cpp
 //   reports.rs:8-120     generate_report[_gene], mode, read_counts_five_fields -> reports.cpp
-//   build.rs:33-256      build_single / build_multi           -> drivers.cpp
+//   build.rs:33-492      build_single / build_multi [_mini]   -> drivers.cpp
 //   batch_search_pe.rs:9-179, perfect_search.rs:6-120         -> drivers.cpp
 //   read_id_mt_pe.rs:440-951 stream_fasta, per_read_stream_pe/se -> drivers.cpp
 //   main.rs              clap CLI (build / search / read_id / info) -> main.cpp
@@ -78,8 +79,10 @@ uint64_t fastq_masked_se(const std::string& path, uint8_t qual_offset, SeqBatch&
 uint64_t fastq_masked_pe(const std::string& p1, const std::string& p2, uint8_t qual_offset, SeqBatch& out);   // kmer.rs:581-612
 
 // ---- .bxi ------------------------------------------------------------------------------------------
-struct Bigsi {                                  // bigsi.rs:19-27 BigsyMapNew
+struct Bigsi {                                  // bigsi.rs:19-27 BigsyMapNew / :40-49 BigsyMapMiniNew
     uint64_t bloom_size = 0, num_hash = 0, k_size = 0;
+    uint64_t m_size = 0;                        // BigsyMapMiniNew only (.mxi)
+    bool mini = false;
     std::map<uint64_t, std::string> colors;     // colour -> accession
     std::vector<uint64_t> row_ids;              // map keys (non-zero rows)
     std::vector<uint32_t> words;                // map values: row_words u32 per row (BitVec storage)
@@ -89,6 +92,8 @@ struct Bigsi {                                  // bigsi.rs:19-27 BigsyMapNew
 };
 void save_bigsi(const std::string& path, const Bigsi& b);   // bigsi.rs:51-57
 Bigsi read_bigsi(const std::string& path);                  // bigsi.rs:59-69 (both variants: same bytes)
+void save_bigsi_mini(const std::string& path, const Bigsi& b);   // bigsi.rs:71-77 (.mxi: m_size after k_size)
+Bigsi read_bigsi_mini(const std::string& path);             // bigsi.rs:79-89
 
 // ---- reports ---------------------------------------------------------------------------------------
 // reports.rs:8-48: one line per accession with hits/n_ref > cov (ascending colour; the reference's order
@@ -107,7 +112,8 @@ void write_counts_five_fields(const std::string& path, const std::vector<std::st
 double false_prob(double m, double k, double n);            // read_id_mt_pe.rs:695-698 (for `info`)
 
 // ---- drivers (need a GPU: every one of them goes through the C ABI) -------------------------------
-struct BuildOpts { std::string ref_file, prefix; uint64_t k = 31, bloom = 50000000, hashes = 4, threads = 1; uint8_t quality = 15; int64_t filter = -1; int device = 0; };
+struct BuildOpts { std::string ref_file, prefix; uint64_t k = 31, bloom = 50000000, hashes = 4, threads = 1; uint8_t quality = 15; int64_t filter = -1; int device = 0;
+                   bool minimizer = false; uint64_t minimizer_value = 15; };   // -m / -v (main.rs:480-482)
 int build(const BuildOpts& o);                              // main.rs:467-553 + build.rs:33-256
 struct SearchOpts { std::string bigsi; std::vector<std::string> files1, files2; int64_t filter = -1; double cov = 0.35;
                     bool gene_search = false, perfect_search = false, multi_fasta = false; uint8_t quality = 15; int device = 0; };

@@ -57,14 +57,21 @@ struct Gpu {                      // context + device index
     }
     void upload(const Bigsi& b) {   // main.rs:576 / :796 read_bigsi -> dense device matrix
         create(b.bloom_size, b.num_hash, b.k_size, b.n_colors());
+        if (b.mini) {
+            if (b.m_size == 0 || b.m_size > 0xFFFFFFFFull) throw Error("minimizer size out of range");
+            ck(cid_index_set_minimizer(ix, (uint32_t)b.m_size));
+        }
         uint64_t c = 0;
         for (auto& kv : b.colors) if (kv.first != c++) throw Error("index colours are not 0..N-1");
         ck(cid_index_upload_rows(ix, b.row_ids.data(), b.words.data(), b.row_ids.size()));
     }
 };
+Bigsi read_index(const std::string& path) {     // main.rs:633-635,724-728,796-800: the suffix decides the struct
+    return ends_with(path, ".mxi") ? read_bigsi_mini(path) : read_bigsi(path);
+}
 Bigsi load_index(const std::string& path) {
     Timer t;
-    Bigsi b = read_bigsi(path);
+    Bigsi b = read_index(path);
     fprintf(stderr, "Index loaded in %llu seconds\n", t.secs());
     return b;
 }
@@ -77,10 +84,18 @@ int build(const BuildOpts& o) {
     const auto map = tab_to_map(o.ref_file);
     if (map.empty()) throw Error("reference file lists no accessions");
     g.create(o.bloom, o.hashes, o.k, map.size());
+    if (o.minimizer) {            // main.rs:485-533
+        printf("Build with minimizers, minimizer size: %llu\n", (unsigned long long)o.minimizer_value);
+        if (o.minimizer_value == 0 || o.minimizer_value > 0xFFFFFFFFull) throw Error("minimizer size out of range");
+        ck(cid_index_set_minimizer(g.ix, (uint32_t)o.minimizer_value));
+    }
+    // -t 1 -> build_single_mini (minimizers of the filtered k-mers), else build_multi_mini (counted minimizers)
+    const int mini_variant = o.threads == 1 ? CID_MINI_OF_KMERS : CID_MINI_COUNTED;
     tr.mark("context + index create");
     double t_read = 0, t_gpu = 0;
     Bigsi out;
     out.bloom_size = o.bloom; out.num_hash = o.hashes; out.k_size = o.k;
+    out.mini = o.minimizer; out.m_size = o.minimizer ? o.minimizer_value : 0;
     uint32_t colour = 0;              // colours = rank of the accession in byte-wise sorted order (build.rs:102-113)
     size_t counter = 1;
     for (auto& kv : map) {
@@ -95,8 +110,9 @@ int build(const BuildOpts& o) {
             fastq_masked_pe(files[0], files[1], o.quality, sb);
             mode = CID_SEQ_FASTQ;
         } else if (ends_with(files[0], "gz")) {
-            // build_multi hard-codes quality 15 for single-end reads (build.rs:187); build_single honours -Q (:70)
-            fastq_masked_se(files[0], o.threads == 1 ? o.quality : 15, sb);
+            // build_multi hard-codes quality 15 for single-end reads (build.rs:187); build_single (:70) and both
+            // minimizer builders (:322-325, :439) honour -Q
+            fastq_masked_se(files[0], (o.threads == 1 || o.minimizer) ? o.quality : 15, sb);
             mode = CID_SEQ_FASTQ;
         } else {
             for (auto& s : read_fasta(files[0])) sb.add(s);
@@ -105,11 +121,15 @@ int build(const BuildOpts& o) {
         uint64_t nref = 0;
         int64_t used = 0;
         const auto tb = std::chrono::steady_clock::now();
-        ck(cid_build_accession(g.ix, colour, sb.bases.data(), sb.offs.data(), sb.n(), mode, cutoff, &nref, &used));
+        if (o.minimizer)
+            ck(cid_build_accession_mini(g.ix, colour, sb.bases.data(), sb.offs.data(), sb.n(), mode, cutoff, mini_variant, &nref, &used));
+        else
+            ck(cid_build_accession(g.ix, colour, sb.bases.data(), sb.offs.data(), sb.n(), mode, cutoff, &nref, &used));
         t_read += std::chrono::duration<double>(tb - ta).count();
         t_gpu += std::chrono::duration<double>(std::chrono::steady_clock::now() - tb).count();
         out.colors[colour] = acc;
-        out.n_ref_kmers[acc] = nref;
+        // build_single_mini records n_ref_kmers for FASTA accessions only (build.rs:450): FASTQ accessions have no entry
+        if (!(o.minimizer && mini_variant == CID_MINI_OF_KMERS && mode == CID_SEQ_FASTQ)) out.n_ref_kmers[acc] = nref;
         colour++;
     }
     if (tr.on) fprintf(stderr, "[trace] reading inputs %.3f s, cid_build_accession %.3f s\n", t_read, t_gpu);
@@ -125,7 +145,8 @@ int build(const BuildOpts& o) {
     uint64_t got = 0;
     ck(cid_index_download_nonzero_rows(g.ix, out.row_ids.data(), out.words.data(), nrows, &got));
     tr.mark("download non-zero rows");
-    save_bigsi(o.prefix + ".bxi", out);
+    if (o.minimizer) save_bigsi_mini(o.prefix + ".mxi", out);
+    else save_bigsi(o.prefix + ".bxi", out);
     tr.mark("save_bigsi");
     return 0;
 }
@@ -413,7 +434,7 @@ int read_id(const ReadIdOpts& o) {
     Timer tload;
     Trace tr;
     Gpu g(o.device);
-    const Bigsi b = read_bigsi(o.bigsi);
+    const Bigsi b = read_index(o.bigsi);
     fprintf(stderr, "Index loaded in %llu seconds\n", tload.secs());
     tr.mark("read_bigsi");
     g.ready();
@@ -506,8 +527,12 @@ int read_id(const ReadIdOpts& o) {
 int info(const std::string& path) {
     fprintf(stderr, "Loading index\n");
     const Bigsi b = load_index(path);
-    printf("BIGSI parameters:\nBloomfilter-size: %llu\nNumber of hashes: %llu\nK-mer size: %llu\n", (unsigned long long)b.bloom_size,
-           (unsigned long long)b.num_hash, (unsigned long long)b.k_size);
+    if (b.mini)               // main.rs:645-648 (the blank line and the leading space are the reference's)
+        printf("BIGSI parameters:\nBloomfilter-size: %llu\nNumber of hashes: %llu\nK-mer size: %llu\n minimizer size: %llu\n\n",
+               (unsigned long long)b.bloom_size, (unsigned long long)b.num_hash, (unsigned long long)b.k_size, (unsigned long long)b.m_size);
+    else
+        printf("BIGSI parameters:\nBloomfilter-size: %llu\nNumber of hashes: %llu\nK-mer size: %llu\n", (unsigned long long)b.bloom_size,
+               (unsigned long long)b.num_hash, (unsigned long long)b.k_size);
     printf("Number of accessions in index: %zu\n", b.colors.size());
     std::vector<std::string> acc;
     for (auto& kv : b.colors) acc.push_back(kv.second);

@@ -1,7 +1,7 @@
 // colorid-b200: the reference's command line (main.rs: clap App "colorid" 0.1.4.3) for the subcommands on
 // the BIGSI hot path -- build, search, read_id, info -- with the same flags, defaults and output files,
-// running on the GPU through libcolorid_b200.so.  `batch_id`, `read_filter` and minimizer indexes
-// (-m / .mxi) are outside this path and are refused with a message.
+// running on the GPU through libcolorid_b200.so, minimizer indexes (`build -m -v M`, .mxi) included.
+// `batch_id` and `read_filter` are outside this path and are refused with a message.
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -51,10 +51,10 @@ template <class T> T num(const Parsed& p, const char* l, T dflt) {      // value
 int usage() {
     fprintf(stderr,
             "colorid-b200 0.1.4.3 (B200)\nBIGSI based taxonomic ID of sequence data\n\nUSAGE:\n    colorid-b200 <SUBCOMMAND>\n\nSUBCOMMANDS:\n"
-            "    build      builds a bigsi            -b PREFIX -r REFS.tsv -k K -n HASHES -s BLOOM [-t T] [-Q q] [-f cutoff]\n"
+            "    build      builds a bigsi            -b PREFIX -r REFS.tsv -k K -n HASHES -s BLOOM [-t T] [-Q q] [-f cutoff] [-m [-v M]]\n"
             "    search     does a bigsi search       -b IDX.bxi -q Q... [-r R...] [-f n] [-p cov] [-g] [-s] [-m] [-Q q]\n"
-            "    read_id    id's reads                -b IDX.bxi -q R1.fq.gz [R2.fq.gz] -n PREFIX [-t T] [-c batch] [-d d] [-p e] [-Q q] [-B b] [-H]\n"
-            "    info       dumps index parameters    -b IDX.bxi\n");
+            "    read_id    id's reads                -b IDX.bxi|.mxi -q R1.fq.gz [R2.fq.gz] -n PREFIX [-t T] [-c batch] [-d d] [-p e] [-Q q] [-B b] [-H]\n"
+            "    info       dumps index parameters    -b IDX.bxi|.mxi\n");
     return 1;
 }
 }  // namespace
@@ -74,8 +74,9 @@ int main(int argc, char** argv) {
             require(p, {"bigsi", "refs", "kmer", "num_hashes", "bloom"});
             printf(" Ref_file : %s\n Bigsi file : %s\nK-mer size: %s\nBloom filter parameters: num hashes %s, filter size %s\n",
                    p.one("refs").c_str(), p.one("bigsi").c_str(), p.one("kmer").c_str(), p.one("num_hashes").c_str(), p.one("bloom").c_str());
-            if (p.has("minimizer")) throw cidh::Error("minimizer indexes (.mxi) are outside the GPU hot path; build without -m");
             cidh::BuildOpts o;
+            o.minimizer = p.has("minimizer");                              // main.rs:480-482: -v defaults to 15
+            o.minimizer_value = num<uint64_t>(p, "value", 15);
             o.ref_file = p.one("refs"); o.prefix = p.one("bigsi");
             o.k = num<uint64_t>(p, "kmer", 31); o.bloom = num<uint64_t>(p, "bloom", 50000000); o.hashes = num<uint64_t>(p, "num_hashes", 4);
             o.threads = num<uint64_t>(p, "threads", 1); o.quality = num<uint8_t>(p, "quality", 15); o.filter = num<int64_t>(p, "filter", -1);
@@ -108,8 +109,6 @@ int main(int argc, char** argv) {
             o.correct = num<double>(p, "fp_correct", 3.0); o.quality = num<uint8_t>(p, "quality", 15);
             o.batch = num<uint64_t>(p, "batch", 50000); o.high_mem_load = p.has("high_mem_load");
             o.bitvector_sample = num<uint64_t>(p, "bitvector_sample", 3); o.device = device;
-            if (o.bigsi.size() >= 4 && o.bigsi.compare(o.bigsi.size() - 4, 4, ".mxi") == 0)
-                throw cidh::Error("minimizer indexes (.mxi) are outside the GPU hot path");
             return cidh::read_id(o);
         }
         if (sub == "info") {
@@ -137,6 +136,8 @@ int main(int argc, char** argv) {
                 for (auto& kv : cidh::tab_to_map(argv[3])) { printf("%s", kv.first.c_str()); for (auto& f : kv.second) printf("\t%s", f.c_str()); printf("\n"); }
             } else if (op == "bxi_copy" && argc == 5) {
                 cidh::save_bigsi(argv[4], cidh::read_bigsi(argv[3]));
+            } else if (op == "mxi_copy" && argc == 5) {
+                cidh::save_bigsi_mini(argv[4], cidh::read_bigsi_mini(argv[3]));
             } else if (op == "map_order" && argc >= 4) {
                 std::vector<std::string> keys(argv + 3, argv + argc);
                 for (size_t i : cidh::fnv_string_map_order(keys)) printf("%s\n", keys[i].c_str());

@@ -5,13 +5,15 @@ import struct
 import numpy as np
 
 
-def write_bxi(path, bloom_size, num_hash, k_size, colors, row_ids, words, n_ref, row_order=None):
-    """colors: {colour: name}; row_ids: [n]; words: [n, W] uint32; n_ref: {name: count}."""
+def write_bxi(path, bloom_size, num_hash, k_size, colors, row_ids, words, n_ref, row_order=None, m_size=None):
+    """colors: {colour: name}; row_ids: [n]; words: [n, W] uint32; n_ref: {name: count}; m_size: write an .mxi."""
     N = len(colors)
     W = (N + 31) // 32
     words = np.asarray(words, dtype=np.uint32).reshape(len(row_ids), W)
     with open(path, "wb") as f:
         f.write(struct.pack("<QQQ", bloom_size, num_hash, k_size))
+        if m_size is not None:
+            f.write(struct.pack("<Q", m_size))
         f.write(struct.pack("<Q", N))
         for c, name in colors.items():
             b = name.encode()
@@ -26,7 +28,8 @@ def write_bxi(path, bloom_size, num_hash, k_size, colors, row_ids, words, n_ref,
             f.write(struct.pack("<Q", len(b)) + b + struct.pack("<Q", n))
 
 
-def read_bxi(path):
+def read_bxi(path, mini=False):
+    """mini=True: .mxi (bigsi.rs:40-49 BigsyMapMiniNew: m_size follows k_size)."""
     d = open(path, "rb").read()
     at = 0
 
@@ -44,6 +47,8 @@ def read_bxi(path):
         return v
 
     out = dict(bloom_size=u64(), num_hash=u64(), k_size=u64())
+    if mini:
+        out["m_size"] = u64()
     colors = {}
     for _ in range(u64()):
         c = u64()

@@ -18,7 +18,7 @@ def _messy_fasta_accessions(rng, N, glen=6000):
     genomes = synth.clade_genomes(rng, N, glen, n_clades=3, div=0.02)
     accs = []
     for i, g in enumerate(genomes):
-        contigs = [g[:2500], g[2500:2510], g[2510:]]                  # a contig shorter than k is skipped
+        contigs = [g[:2500], g[2500:2510], g[2510:], g[100:900]]      # a contig shorter than k is skipped; a repeat
         if i % 3 == 0:
             contigs[0] = synth.sprinkle(rng, contigs[0], b"NRYn", 0.01)   # has_no_n
         if i % 4 == 1:

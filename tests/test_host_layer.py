@@ -132,6 +132,33 @@ def test_bxi_roundtrip(tmp_path, N):
         assert lines[8 + c] == f"{name} {n_ref[name]} {O.false_prob(S, 3, n_ref[name]):.3f}"
 
 
+def test_mxi_roundtrip_and_info(tmp_path):
+    # bigsi.rs:40-49,71-89: BigsyMapMiniNew = BigsyMapNew with m_size after k_size
+    rng = np.random.default_rng(5)
+    N, S = 40, 3000
+    row_ids = np.sort(rng.choice(S, size=300, replace=False)).astype(np.uint64)
+    words = rng.integers(0, 2**32, size=(300, 2), dtype=np.uint64).astype(np.uint32)
+    words[:, -1] &= np.uint32((1 << (N % 32)) - 1)
+    colors = {c: f"acc_{c:03d}" for c in range(N)}
+    n_ref = {f"acc_{c:03d}": int(rng.integers(1, 10**6)) for c in range(N)}
+    a, b = tmp_path / "a.mxi", tmp_path / "b.mxi"
+    bxi_py.write_bxi(a, S, 4, 31, colors, row_ids, words, n_ref, row_order=rng.permutation(300), m_size=15)
+    assert cli("_host", "mxi_copy", a, b).returncode == 0
+    got = bxi_py.read_bxi(b, mini=True)
+    assert (got["bloom_size"], got["num_hash"], got["k_size"], got["m_size"]) == (S, 4, 31, 15)
+    assert got["colors"] == colors and got["n_ref"] == n_ref
+    o = np.argsort(got["row_ids"])
+    assert np.array_equal(got["row_ids"][o], row_ids) and np.array_equal(got["words"][o], words)
+    lines = cli("info", "-b", a).stdout.split("\n")          # main.rs:633-668: suffix decides the struct
+    assert lines[3:10] == ["BIGSI parameters:", f"Bloomfilter-size: {S}", "Number of hashes: 4", "K-mer size: 31",
+                           " minimizer size: 15", "", f"Number of accessions in index: {N}"]
+    assert lines[10] == f"acc_000 {n_ref['acc_000']} {O.false_prob(S, 4, n_ref['acc_000']):.3f}"
+    # an .mxi read as a .bxi (or the reverse) does not deserialize
+    c = tmp_path / "c.bxi"
+    c.write_bytes(a.read_bytes())
+    assert cli("info", "-b", c).returncode == 101
+
+
 def test_truncated_bxi_is_rejected(tmp_path):
     a = tmp_path / "a.bxi"
     bxi_py.write_bxi(a, 100, 2, 5, {0: "x"}, [3, 7], [[1], [1]], {"x": 4})
