@@ -11,7 +11,9 @@
 //   build.rs:33-492      build_single / build_multi [_mini]   -> drivers.cpp
 //   batch_search_pe.rs:9-179, perfect_search.rs:6-120         -> drivers.cpp
 //   read_id_mt_pe.rs:440-951 stream_fasta, per_read_stream_pe/se -> drivers.cpp
-//   main.rs              clap CLI (build / search / read_id / info) -> main.cpp
+//   read_id_batch.rs:7-181 read_id_batch                      -> drivers.cpp (batch_id)
+//   read_filter.rs:10-191 tab_to_map, read_filter_pe/se       -> fastx.cpp (read_filter)
+//   main.rs              clap CLI (build / search / read_id / batch_id / read_filter / info) -> main.cpp
 //
 // The reference is Rust; this image has no Rust toolchain, so the host side is C++.
 // Everything compute-heavy goes through the C ABI to the GPU; nothing here has a CPU fallback.
@@ -121,6 +123,13 @@ int search(const SearchOpts& o);                            // main.rs:555-628
 struct ReadIdOpts { std::string bigsi, prefix; std::vector<std::string> query; uint64_t threads = 0, down_sample = 1, batch = 50000,
                     bitvector_sample = 3; double correct = 3.0; uint8_t quality = 15; bool high_mem_load = false; int device = 0; };
 int read_id(const ReadIdOpts& o);                           // main.rs:704-866
+struct BatchIdOpts { std::string bigsi, batch_samples, tag; uint64_t threads = 0, down_sample = 1, batch = 50000, bitvector_sample = 3;
+                     double correct = 3.0; uint8_t quality = 15; bool high_mem_load = false; int device = 0; };
+int batch_id(const BatchIdOpts& o);                         // main.rs:869-887 + read_id_batch.rs:7-181
 int info(const std::string& bigsi);                         // main.rs:630-703
+// read_filter.rs:10-191 + main.rs:888-900: keep (or with `exclude` drop) the reads whose PREFIX_reads.txt classification
+// contains `taxon`; writes PREFIX_TAXON_R1.fq.gz / _R2.fq.gz (paired) or PREFIX_TAXON.fq.gz.  Pure file I/O, no GPU.
+struct ReadFilterOpts { std::string classification, taxon, prefix; std::vector<std::string> files; bool exclude = false; };
+int read_filter(const ReadFilterOpts& o);
 
 }  // namespace cidh

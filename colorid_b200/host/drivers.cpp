@@ -429,18 +429,11 @@ struct ReadIdRun {
 };
 }  // namespace
 
-int read_id(const ReadIdOpts& o) {
+namespace {
+// per_read_stream_pe / per_read_stream_se / stream_fasta (read_id_mt_pe.rs:440-951) for one sample, followed by
+// reports::read_counts_five_fields (main.rs:865): o.query in, o.prefix_reads.txt + o.prefix_counts.txt out
+void read_id_sample(Gpu& g, const Bigsi& b, const ReadIdOpts& o, Trace& tr) {
     if (o.query.empty()) throw Error("no query files");
-    Timer tload;
-    Trace tr;
-    Gpu g(o.device);
-    const Bigsi b = read_index(o.bigsi);
-    fprintf(stderr, "Index loaded in %llu seconds\n", tload.secs());
-    tr.mark("read_bigsi");
-    g.ready();
-    tr.mark("context create (rest)");
-    g.upload(b);
-    tr.mark("index upload");
     ReadIdRun run(g, b, o);
     // two batches: while the worker thread runs the GPU call and writes the lines of one, the parser fills the other
     ReadBatch batches[2];
@@ -520,6 +513,45 @@ int read_id(const ReadIdOpts& o) {
     if (tr.on) fprintf(stderr, "[trace]   of which GPU calls %.3f s, formatting+writing %.3f s\n", run.t_gpu, run.t_out);
     run.finish();
     tr.mark("counts file");
+}
+}  // namespace
+
+int read_id(const ReadIdOpts& o) {
+    if (o.query.empty()) throw Error("no query files");
+    Timer tload;
+    Trace tr;
+    Gpu g(o.device);
+    const Bigsi b = read_index(o.bigsi);
+    fprintf(stderr, "Index loaded in %llu seconds\n", tload.secs());
+    tr.mark("read_bigsi");
+    g.ready();
+    tr.mark("context create (rest)");
+    g.upload(b);
+    tr.mark("index upload");
+    read_id_sample(g, b, o, tr);
+    return 0;
+}
+
+// read_id_batch.rs:7-181 read_id_batch: the index is loaded (here: uploaded to the GPU) once, then every sample of
+// the tab-delimited list [sample_name reads1 reads2(optional)] is classified into SAMPLE_TAG_reads.txt / _counts.txt.
+// Samples run in byte-wise sorted order of their names (the reference iterates an FnvHashMap; the files are the same).
+int batch_id(const BatchIdOpts& o) {
+    Timer tload;
+    Trace tr;
+    Gpu g(o.device);
+    const auto batch_map = tab_to_map(o.batch_samples);
+    const Bigsi b = read_index(o.bigsi);
+    fprintf(stderr, "Index loaded in %llu seconds\n", tload.secs());
+    g.upload(b);
+    tr.mark("index load + upload");
+    for (auto& kv : batch_map) {
+        fprintf(stderr, "Classifying %s\n", kv.first.c_str());
+        ReadIdOpts s;
+        s.bigsi = o.bigsi; s.prefix = kv.first + "_" + o.tag; s.query = kv.second;
+        s.threads = o.threads; s.down_sample = o.down_sample; s.batch = o.batch; s.bitvector_sample = o.bitvector_sample;
+        s.correct = o.correct; s.quality = o.quality; s.high_mem_load = o.high_mem_load; s.device = o.device;
+        read_id_sample(g, b, s, tr);
+    }
     return 0;
 }
 

@@ -248,3 +248,72 @@ uint64_t fastq_masked_pe(const std::string& p1, const std::string& p2, uint8_t q
 }
 
 }  // namespace cidh
+
+// ------------------------------------------------------------------ read_filter (read_filter.rs)
+namespace cidh {
+namespace {
+struct GzOut {
+    gzFile f;
+    explicit GzOut(const std::string& path, const char* what) : f(gzopen(path.c_str(), "wb6")) {   // Compression::default() = level 6
+        if (!f) throw Error(what);
+        gzbuffer(f, 1 << 20);
+    }
+    ~GzOut() { if (f) gzclose(f); }
+    void record(const std::string& h, const std::string& s, const std::string& q) {
+        std::string r = h + "\n" + s + "\n+\n" + q + "\n";
+        if (gzwrite(f, r.data(), (unsigned)r.size()) != (int)r.size()) throw Error("could not write reads!");
+    }
+    void finish() { int rc = gzclose(f); f = nullptr; if (rc != Z_OK) throw Error("Could not close new read file"); }
+};
+std::string first_word(const std::string& s) { return s.substr(0, s.find(' ')); }   // header.split(' ')[0]
+}  // namespace
+
+int read_filter(const ReadFilterOpts& o) {
+    // read_filter.rs:10-28 tab_to_map: read id (up to the first blank) of every line whose class CONTAINS the taxon
+    std::map<std::string, std::string> cls;
+    {
+        LineReader lr(o.classification);
+        std::string l;
+        while (lr.next(l)) {
+            const size_t t1 = l.find('\t');
+            if (t1 == std::string::npos) throw Error("classification file: line without a class column (the reference panics)");
+            const size_t t2 = l.find('\t', t1 + 1);
+            const std::string c = l.substr(t1 + 1, t2 == std::string::npos ? std::string::npos : t2 - t1 - 1);
+            if (c.find(o.taxon) != std::string::npos) cls[first_word(l.substr(0, t1))] = c;
+        }
+    }
+    std::string cleaned = o.taxon;
+    for (auto& ch : cleaned) if (ch == ' ') ch = '_';
+    uint64_t kept = 0;
+    if (o.files.size() == 1) {              // read_filter_se, read_filter.rs:139-191
+        LineReader a(o.files[0]);
+        GzOut out(o.prefix + "_" + cleaned + ".fq.gz", "could not create R1!");
+        std::string l, h, s;
+        uint64_t line_count = 1;
+        while (a.next(l)) {
+            if (line_count % 4 == 1) h = l;
+            else if (line_count % 4 == 2) s = l;
+            else if (line_count % 4 == 0 && (cls.count(first_word(h)) != 0) != o.exclude) { out.record(h, s, l); kept++; }
+            line_count++;
+        }
+        out.finish();
+    } else {                                // read_filter_pe, :31-136: stops at the shorter file; the R1 header decides
+        if (o.files.size() < 2) throw Error("no read files");
+        LineReader a(o.files[0]), b(o.files[1]);
+        GzOut o1(o.prefix + "_" + cleaned + "_R1.fq.gz", "could not create R1!"), o2(o.prefix + "_" + cleaned + "_R2.fq.gz", "could not create R2!");
+        std::string l1, l2, h1, h2, s1, s2;
+        uint64_t line_count = 1;
+        while (a.next(l1)) {
+            if (!b.next(l2)) { if (line_count % 4 != 3) break; l2.clear(); }   // the '+' line of mate 2 is never looked at
+            if (line_count % 4 == 1) { h1 = l1; h2 = l2; }
+            else if (line_count % 4 == 2) { s1 = l1; s2 = l2; }
+            else if (line_count % 4 == 0 && (cls.count(first_word(h1)) != 0) != o.exclude) { o1.record(h1, s1, l1); o2.record(h2, s2, l2); kept++; }
+            line_count++;
+        }
+        o1.finish(); o2.finish();
+    }
+    if (o.exclude) fprintf(stderr, "Excluded %llu read pairs  with classification containing '%s' from output files\n", (unsigned long long)kept, o.taxon.c_str());
+    else fprintf(stderr, "Wrote %llu read-pairs with classification containing '%s' to output files\n", (unsigned long long)kept, o.taxon.c_str());
+    return 0;
+}
+}  // namespace cidh

@@ -1,7 +1,7 @@
 // colorid-b200: the reference's command line (main.rs: clap App "colorid" 0.1.4.3) for the subcommands on
 // the BIGSI hot path -- build, search, read_id, info -- with the same flags, defaults and output files,
 // running on the GPU through libcolorid_b200.so, minimizer indexes (`build -m -v M`, .mxi) included.
-// `batch_id` and `read_filter` are outside this path and are refused with a message.
+// `batch_id` (index uploaded once, many samples) and `read_filter` (pure file I/O) complete the read workflow.
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -54,6 +54,8 @@ int usage() {
             "    build      builds a bigsi            -b PREFIX -r REFS.tsv -k K -n HASHES -s BLOOM [-t T] [-Q q] [-f cutoff] [-m [-v M]]\n"
             "    search     does a bigsi search       -b IDX.bxi -q Q... [-r R...] [-f n] [-p cov] [-g] [-s] [-m] [-Q q]\n"
             "    read_id    id's reads                -b IDX.bxi|.mxi -q R1.fq.gz [R2.fq.gz] -n PREFIX [-t T] [-c batch] [-d d] [-p e] [-Q q] [-B b] [-H]\n"
+            "    batch_id   id's reads of many samples -b IDX -q SAMPLES.tsv -T TAG [read_id options]\n"
+            "    read_filter filters reads by class   -c PREFIX_reads.txt -f R1.fq.gz [R2.fq.gz] -t TAXON -p PREFIX [-e]\n"
             "    info       dumps index parameters    -b IDX.bxi|.mxi\n");
     return 1;
 }
@@ -144,8 +146,29 @@ int main(int argc, char** argv) {
             } else return usage();
             return 0;
         }
-        if (sub == "batch_id" || sub == "read_filter" || sub == "merge")
-            throw cidh::Error("subcommand '" + sub + "' is outside the GPU hot path (DESIGN.md §6); use the reference for it");
+        if (sub == "batch_id") {                                   // main.rs:330-416,869-887
+            Parsed p = parse(argc, argv, 2, {{'b', "bigsi", true, false}, {'q', "query", true, true}, {'T', "tag", true, false},
+                                             {'c', "batch", true, false}, {'t', "threads", true, false}, {'d', "down_sample", true, false},
+                                             {'H', "high_mem_load", false, false}, {'p', "fp_correct", true, false},
+                                             {'Q', "quality", true, false}, {'B', "bitvector_sample", true, false}});
+            require(p, {"bigsi", "query", "tag"});
+            cidh::BatchIdOpts o;
+            o.bigsi = p.one("bigsi"); o.batch_samples = p.one("query"); o.tag = p.one("tag");
+            o.threads = num<uint64_t>(p, "threads", 0); o.down_sample = num<uint64_t>(p, "down_sample", 1);
+            o.correct = num<double>(p, "fp_correct", 3.0); o.quality = num<uint8_t>(p, "quality", 15);
+            o.batch = num<uint64_t>(p, "batch", 50000); o.high_mem_load = p.has("high_mem_load");
+            o.bitvector_sample = num<uint64_t>(p, "bitvector_sample", 3); o.device = device;
+            return cidh::batch_id(o);
+        }
+        if (sub == "read_filter") {                                // main.rs:418-465,888-900
+            Parsed p = parse(argc, argv, 2, {{'c', "classification", true, false}, {'f', "files", true, true}, {'t', "taxon", true, false},
+                                             {'p', "prefix", true, false}, {'e', "exclude", false, false}});
+            require(p, {"classification", "files", "taxon", "prefix"});
+            cidh::ReadFilterOpts o;
+            o.classification = p.one("classification"); o.files = p.v.at("files"); o.taxon = p.one("taxon");
+            o.prefix = p.one("prefix"); o.exclude = p.has("exclude");
+            return cidh::read_filter(o);
+        }
         return usage();
     } catch (const std::exception& e) {
         fprintf(stderr, "%s\n", e.what());

@@ -278,3 +278,27 @@ def test_read_id_paired_single_and_fasta(world, oracle):
 
 
 CLS_NAMES = {"too_short", "no_hits", "no_significant_hits"}
+
+
+def test_batch_id_classifies_every_sample_with_one_index_load(world, oracle):
+    # read_id_batch.rs:7-181: SAMPLE_TAG_reads.txt / SAMPLE_TAG_counts.txt per line of the sample list
+    d, rng, genomes = world["dir"], world["rng"], world["genomes"]
+    lines, expect = [], {}
+    for si, paired in enumerate([True, False, True]):
+        n, s1, s2, q1, q2 = read_pairs(rng, genomes[:5], 400 + 50 * si, f"b{si}", read_len=100, insert=180, err=0.006, frac_random=0.2)
+        (d / f"b{si}_1.fastq.gz").write_bytes(gzip.compress(fastq_bytes(n, s1, q1)))
+        (d / f"b{si}_2.fastq.gz").write_bytes(gzip.compress(fastq_bytes(n, s2, q2)))
+        ids = ["@" + x for x in n]
+        if paired:
+            reads = [[oracle.qual_mask(a, qa.encode(), 15), oracle.qual_mask(b, qb.encode(), 15)] for a, b, qa, qb in zip(s1, s2, q1, q2)]
+            lines.append(f"{d}/sample{si}\t{d}/b{si}_1.fastq.gz\t{d}/b{si}_2.fastq.gz")
+        else:
+            reads = [[oracle.qual_mask(a, qa.encode(), 15)] for a, qa in zip(s1, q1)]
+            lines.append(f"{d}/sample{si}\t{d}/b{si}_1.fastq.gz")
+        expect[si] = _expected_read_lines(world, oracle, ids, reads, d=2)
+    (d / "samples.tsv").write_text("\n".join(lines) + "\n")
+    _, r = run("batch_id", "-b", d / "idx.bxi", "-q", d / "samples.tsv", "-T", "run7", "-d", 2)
+    assert [l for l in r.stderr.split("\n") if l.startswith("Classifying")] == [f"Classifying {d}/sample{i}" for i in range(3)]
+    for si, (exp_lines, exp_counts) in expect.items():
+        assert (d / f"sample{si}_run7_reads.txt").read_text().split("\n")[:-1] == exp_lines
+        assert (d / f"sample{si}_run7_counts.txt").read_text().split("\n")[:-1] == exp_counts

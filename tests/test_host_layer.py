@@ -159,6 +159,34 @@ def test_mxi_roundtrip_and_info(tmp_path):
     assert cli("info", "-b", c).returncode == 101
 
 
+def test_read_filter_matches_reference_semantics(tmp_path):
+    # read_filter.rs:10-191: class column CONTAINS the taxon (accept/reject is not looked at); read id = header up to
+    # the first blank; paired input stops at the shorter file; -e inverts
+    rng = np.random.default_rng(3)
+    n = 60
+    hdr = [f"@read.{i} {i}/1" for i in range(n)]
+    cls = [["Listeria_mono", "Listeria_mono,Listeria_innocua", "Salmonella", "no_hits"][int(x)] for x in rng.integers(0, 4, n)]
+    (tmp_path / "x_reads.txt").write_text("".join(f"{h}\t{c}\t5\t120\t{'reject' if ',' in c else 'accept'}\t1\n" for h, c in zip(hdr, cls)))
+    recs1 = [(h, "ACGT" * 5 + str(i % 7) * 0, "I" * 20) for i, h in enumerate(hdr)]
+    recs2 = [(h.replace("/1", "/2"), "TTGCA" * 4, "H" * 20) for h in hdr[:50]]               # mate file is shorter
+    fq = lambda recs: "".join(f"{h}\n{s}\n+\n{q}\n" for h, s, q in recs).encode()
+    (tmp_path / "r1.fq.gz").write_bytes(gzip.compress(fq(recs1)))
+    (tmp_path / "r2.fq.gz").write_bytes(gzip.compress(fq(recs2)))
+    want = [i for i in range(n) if "Listeria_mono" in cls[i]]
+    r = cli("read_filter", "-c", tmp_path / "x_reads.txt", "-f", tmp_path / "r1.fq.gz", tmp_path / "r2.fq.gz", "-t", "Listeria_mono",
+            "-p", tmp_path / "out")
+    assert r.returncode == 0, r.stderr
+    pe = [i for i in want if i < 50]
+    assert gzip.decompress((tmp_path / "out_Listeria_mono_R1.fq.gz").read_bytes()) == fq([recs1[i] for i in pe])
+    assert gzip.decompress((tmp_path / "out_Listeria_mono_R2.fq.gz").read_bytes()) == fq([recs2[i] for i in pe])
+    assert f"Wrote {len(pe)} read-pairs with classification containing 'Listeria_mono' to output files" in r.stderr
+    r = cli("read_filter", "-c", tmp_path / "x_reads.txt", "-f", tmp_path / "r1.fq.gz", "-t", "Listeria_mono", "-p", tmp_path / "ex", "-e")
+    assert r.returncode == 0, r.stderr
+    rest = [i for i in range(n) if i not in want]
+    assert gzip.decompress((tmp_path / "ex_Listeria_mono.fq.gz").read_bytes()) == fq([recs1[i] for i in rest])
+    assert f"Excluded {len(rest)} read pairs  with classification containing 'Listeria_mono' from output files" in r.stderr
+
+
 def test_truncated_bxi_is_rejected(tmp_path):
     a = tmp_path / "a.bxi"
     bxi_py.write_bxi(a, 100, 2, 5, {0: "x"}, [3, 7], [[1], [1]], {"x": 4})
