@@ -726,6 +726,9 @@ def run_ours(args):
     K, Wm = args.steps, args.warmup
 
     ctx = cb.Context(local)
+    for kv in args.opt:
+        name, _, val = kv.partition("=")
+        ctx.set_option(name, int(val))
     if args.only_search:
         print(json.dumps(run_search_extra(torch, dev, ctx, args, args.quick)), flush=True)
         return
@@ -950,6 +953,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-search", action="store_true", help="skip the C3 gene-search extra measurement")
     ap.add_argument("--only-search", action="store_true", help="profiling aid: run only the C3 gene-search measurement")
+    ap.add_argument("--opt", action="append", default=[], help="library tuning option name=value (cid_ctx_set_option), repeatable")
     ap.add_argument("--quick", action="store_true", help="small genomes / bloom filter (functional check only)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"], help="c2 = read_id headline (default); c4 = build from read sets; c5 = column-sharded build + search")
     ap.add_argument("--c4-acc", type=int, default=0, help="accessions per rank built by the c4 workload (default 24)")

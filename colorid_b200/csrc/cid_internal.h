@@ -73,6 +73,8 @@ struct cid_ctx {
     // joined to the caller's stream, so the DRAM-access-bound vote kernel of one chunk runs under the
     // issue-bound kmerize/order kernels of the next (measured on B200: no gain, kernels fill the GPU; off by default)
     int opt_readid_streams = 1;
+    int opt_kmerize_ctas = 0, opt_vote_ctas = 0;   // CTAs per SM of the read_id kmerize / vote grids (0 = fill the GPU);
+                                                   // smaller grids let the two kernels of different chunks share the SMs
     int opt_query_fused = 0;         // 1 = force the fused collect/hash/gather kernel (parity aid)
     cudaStream_t aux[2] = {nullptr, nullptr};
     cudaEvent_t aux_fork = nullptr, aux_join[2] = {nullptr, nullptr};

@@ -1164,10 +1164,12 @@ int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const ui
     for (uint64_t r0 = r_first; r0 < r_first + nreads; r0 += sub) {
         const uint64_t nr = std::min(sub, r_first + nreads - r0);
         unsigned gridA = (unsigned)std::min<uint64_t>((nr + RA_WARPS - 1) / RA_WARPS, (uint64_t)ctx->sm_count * 32);
+        const unsigned gridK = ctx->opt_kmerize_ctas ? std::min<unsigned>(gridA, (unsigned)(ctx->sm_count * ctx->opt_kmerize_ctas)) : gridA;
+        const unsigned gridV = ctx->opt_vote_ctas ? std::min<unsigned>(gridA, (unsigned)(ctx->sm_count * ctx->opt_vote_ctas)) : gridA;
         {
         ProfScope ps(ctx, st, KID_READID_KMERIZE);
 #define CID_KMERIZE(C, M)                                                                                              \
-    readid_kmerize_kernel<C, M><<<gridA, RA_WARPS * 32, a_smem, st>>>(d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr, idx->k, \
+    readid_kmerize_kernel<C, M><<<gridK, RA_WARPS * 32, a_smem, st>>>(d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr, idx->k, \
                                                                      idx->m, p.downsample, cap, maxocc, tsize, d_entries, d_hp8,   \
                                                                      d_h9w, d_ent16, d_nocc, d_nfresh, d_flags, ctx->d_err)
         if (small) { if (idx->m) CID_KMERIZE(true, true); else CID_KMERIZE(true, false); }
@@ -1219,17 +1221,17 @@ int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const ui
             if (idx->Wp <= 2) {
                 if (!idx->rownz_global) rownz = nullptr;   // presence == any word set, already in registers
                 if (idx->Wp == 1)
-                    readid_vote_narrow_kernel<1><<<gridA, RA_WARPS * 32, cn_smem, st>>>(
+                    readid_vote_narrow_kernel<1><<<gridV, RA_WARPS * 32, cn_smem, st>>>(
                         d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr, kitem, idx->H, mods, idx->rows, rownz, idx->rownz,
                         idx->N, cap, maxocc, ord16, ord8, d_ent16, d_n_set, p.start_sample, p.rep_cap, d_flags, d_rep_n, d_rep_colour,
                         d_rep_count, (unsigned long long*)(ctx->d_err + 2));
                 else
-                    readid_vote_narrow_kernel<2><<<gridA, RA_WARPS * 32, cn_smem, st>>>(
+                    readid_vote_narrow_kernel<2><<<gridV, RA_WARPS * 32, cn_smem, st>>>(
                         d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr, kitem, idx->H, mods, idx->rows, rownz, idx->rownz,
                         idx->N, cap, maxocc, ord16, ord8, d_ent16, d_n_set, p.start_sample, p.rep_cap, d_flags, d_rep_n, d_rep_colour,
                         d_rep_count, (unsigned long long*)(ctx->d_err + 2));
             } else {
-                readid_vote_wide_kernel<<<gridA, RA_WARPS * 32, cw_smem, st>>>(
+                readid_vote_wide_kernel<<<gridV, RA_WARPS * 32, cw_smem, st>>>(
                     d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr, kitem, idx->H, mods, idx->rows, rownz, idx->N,
                     idx->Wp, cap, maxocc, ord16, ord8, d_ent16, d_n_set, p.start_sample, p.rep_cap, d_flags, d_rep_n, d_rep_colour,
                     d_rep_count);
