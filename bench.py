@@ -702,6 +702,30 @@ def run_c4(args):
         dist.destroy_process_group()
 
 
+def bind_to_gpu_numa_node(local, world):
+    """N > 1: pin this rank (and the pinned host buffers it first-touches, and the library's host threads) to the CPU
+    cores NVML reports as local to its GPU, so that 8 ranks do not pull their H2D traffic through one socket.  Returns
+    the number of cores kept (0 = left alone)."""
+    if world <= 1:
+        return 0
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[local]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else local
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        allowed = os.sched_getaffinity(0)
+        cores = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1} & allowed
+        if 0 < len(cores) < len(allowed):
+            os.sched_setaffinity(0, cores)
+            return len(cores)
+    except Exception as e:      # affinity is an optimisation only
+        log(f"[numa] affinity not set: {e}")
+    return 0
+
+
 # ----------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
@@ -718,6 +742,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
+    numa_cores = bind_to_gpu_numa_node(local, world)
     cfg = dict(CFG)
     if args.quick:
         cfg.update(genome_len=200_000, S=5_000_000)
@@ -930,7 +955,7 @@ def run_ours(args):
             "warmup": Wm, "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic", "config": workload_config(cfg, batch), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "read pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "includes": "cid_read_id_classify: chunked pipeline of H2D reads+quals+offsets, read_id kernels + device vote, D2H of one classification per read; near-threshold/tied reads re-voted on the host; pinned host buffers"},
+                    "steps": e2e_steps, "host_cores_bound_per_rank": numa_cores or None, "includes": "cid_read_id_classify: chunked pipeline of H2D reads+quals+offsets, read_id kernels + device vote, D2H of one classification per read; near-threshold/tied reads re-voted on the host; pinned host buffers"},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "build": {"gbp_per_s": cfg["n_acc"] * cfg["genome_len"] / build_s / 1e9, "seconds": build_s,
                       "note": "index build on device incl. per-accession host sync; not the timed metric"},

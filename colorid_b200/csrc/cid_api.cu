@@ -43,7 +43,7 @@ void PinBuf::release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 
 static const char* kKernelNames[KID_COUNT] = {"kmerize_insert", "region_histogram", "region_to_bloom", "transpose_bitsets",
                                               "rownz", "query_counts", "query_uniq_wide", "query_perfect",
-                                              "readid_kmerize", "readid_sched", "readid_order", "readid_vote", "readid_classify", "table_clear", "other", "query_hash"};
+                                              "readid_kmerize", "readid_sched", "readid_order", "readid_vote", "readid_classify", "table_clear", "other", "query_hash", "query_front"};
 static cudaEvent_t prof_event(cid_ctx* c) {
     if (!c->prof_pool.empty()) { cudaEvent_t e = c->prof_pool.back(); c->prof_pool.pop_back(); return e; }
     cudaEvent_t e; cudaEventCreate(&e); return e;
@@ -280,6 +280,7 @@ int cid_ctx_set_option(cid_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "readid_streams")) { c->opt_readid_streams = value >= 2 ? 2 : 1; return CID_OK; }
     if (!strcmp(name, "readid_kmerize_ctas")) { c->opt_kmerize_ctas = value > 0 ? (int)value : 0; return CID_OK; }
     if (!strcmp(name, "readid_vote_ctas")) { c->opt_vote_ctas = value > 0 ? (int)value : 0; return CID_OK; }
+    if (!strcmp(name, "query_front")) { c->opt_query_front = value != 0; return CID_OK; }
     if (!strcmp(name, "query_fused")) { c->opt_query_fused = value != 0; return CID_OK; }
     if (!strcmp(name, "host_threads")) { c->opt_host_threads = value > 0 ? (int)value : 0; return CID_OK; }
     set_error("cid_ctx_set_option: unknown option '%s'", name);
@@ -618,6 +619,25 @@ static std::vector<uint64_t> query_batches(const uint64_t* h_seq_offs, const uin
 }
 static const uint64_t kMaxBatchSlots = 1ull << 28;   // 4 GiB of count table per pass
 
+// The shared-memory front end applies when only DISTINCT k-mers matter (every query's filter is 0), no unique-hit
+// summaries are wanted, the streaming gather handles this row shape and every query is small.
+static bool query_front_ok(const cid_index* ix, bool want_uniq, const uint64_t* h_seq_offs, const uint64_t* h_query_offs, uint64_t nq) {
+    return ix->ctx->opt_query_front && !ix->ctx->opt_query_fused && !want_uniq && ix->Wp >= 4 && ix->Wp <= 128 &&
+           (ix->H == 2 || ix->H == 4) && query_front_fits(h_seq_offs, h_query_offs, 0, nq, ix->k);
+}
+// batches of at most 2^28 k-mer positions (row-index lists of <= 4 GiB at H = 4)
+static std::vector<uint64_t> query_front_batches(const uint64_t* h_seq_offs, const uint64_t* h_query_offs, uint64_t nq) {
+    std::vector<uint64_t> cuts{0};
+    uint64_t acc = 0;
+    for (uint64_t q = 0; q < nq; q++) {
+        const uint64_t nb = h_seq_offs[h_query_offs[q + 1]] - h_seq_offs[h_query_offs[q]];
+        if (acc && acc + nb > (1ull << 28)) { cuts.push_back(q); acc = 0; }
+        acc += nb;
+    }
+    cuts.push_back(nq);
+    return cuts;
+}
+
 int cid_query_counts(cid_index* ix, const char* bases, const uint64_t* seq_offs, uint64_t nseq,
                      const uint64_t* query_offs, uint64_t nq, int seq_mode, int gene_search, int64_t filter,
                      uint32_t* counts, uint64_t* num_kmers, uint64_t* uniq_n, uint64_t* uniq_sum, uint64_t* uniq_mode,
@@ -641,6 +661,27 @@ int cid_query_counts(cid_index* ix, const char* bases, const uint64_t* seq_offs,
     if (uniq_sum) memset(uniq_sum, 0, nq * N * 8);
     if (uniq_mode) memset(uniq_mode, 0, nq * N * 8);
 
+    const bool all_distinct = (seq_mode == CID_SEQ_FASTA && gene_search) || filter == 0;
+    if (all_distinct && nq && query_front_ok(ix, want_uniq, seq_offs, query_offs, nq)) {
+        CID_TRY(ctx->scratch[7].ensure((nq + 1) * 8));
+        CID_CUDA(cudaMemcpyAsync(ctx->scratch[7].p, query_offs, (nq + 1) * 8, cudaMemcpyHostToDevice, st));
+        std::vector<uint64_t> fcuts = query_front_batches(seq_offs, query_offs, nq);
+        for (size_t b = 0; b + 1 < fcuts.size(); b++) {
+            const uint64_t q0 = fcuts[b], q1 = fcuts[b + 1], bq = q1 - q0;
+            CID_TRY(ctx->scratch[10].ensure(bq * N * 4));
+            CID_TRY(ctx->scratch[11].ensure(bq * 8));
+            CID_CUDA(cudaMemsetAsync(ctx->scratch[10].p, 0, bq * N * 4, st));
+            CID_CUDA(cudaMemsetAsync(ctx->scratch[11].p, 0, bq * 8, st));
+            CID_TRY(launch_query_front_gather(ctx, st, ix, d_bases, d_seq_offs, ctx->scratch[7].as<uint64_t>(), seq_offs, query_offs,
+                                              q0, q1, seq_mode, ctx->scratch[10].as<uint32_t>(), ctx->scratch[11].as<unsigned long long>()));
+            CID_TRY(check_err_flags(ctx, st));
+            CID_CUDA(cudaMemcpyAsync(counts + q0 * N, ctx->scratch[10].p, bq * N * 4, cudaMemcpyDeviceToHost, st));
+            CID_CUDA(cudaMemcpyAsync(num_kmers + q0, ctx->scratch[11].p, bq * 8, cudaMemcpyDeviceToHost, st));
+            CID_CUDA(cudaStreamSynchronize(st));
+            if (cutoff_used) for (uint64_t q = q0; q < q1; q++) cutoff_used[q] = 0;
+        }
+        return CID_OK;
+    }
     std::vector<uint64_t> cuts = query_batches(seq_offs, query_offs, nq, ix->k, kMaxBatchSlots);
     for (size_t b = 0; b + 1 < cuts.size(); b++) {
         const uint64_t q0 = cuts[b], q1 = cuts[b + 1], bq = q1 - q0;
@@ -700,7 +741,7 @@ int cid_query_counts_dev(cid_index* ix, const char* d_bases, const uint64_t* d_s
                          uint64_t nbases, const uint64_t* d_query_offs, const uint64_t* h_query_offs,
                          const uint64_t* h_seq_offs, uint64_t nq, int seq_mode, uint32_t* d_counts,
                          uint64_t* d_num_kmers, void* stream) {
-    (void)nseq; (void)nbases; (void)d_query_offs;
+    (void)nseq; (void)nbases;
     cid_ctx* ctx = ix->ctx;
     cudaStream_t st = (cudaStream_t)stream;
     if (ix->m) { set_error("An index with minimizers (.mxi) is used, but not available for this function"); return CID_E_UNSUPPORTED; }   // main.rs:569-573
@@ -708,6 +749,14 @@ int cid_query_counts_dev(cid_index* ix, const char* d_bases, const uint64_t* d_s
     const uint32_t N = ix->N;
     CID_CUDA(cudaMemsetAsync(d_counts, 0, nq * N * 4, st));
     CID_CUDA(cudaMemsetAsync(d_num_kmers, 0, nq * 8, st));
+    if (nq && d_query_offs && query_front_ok(ix, false, h_seq_offs, h_query_offs, nq)) {
+        std::vector<uint64_t> fcuts = query_front_batches(h_seq_offs, h_query_offs, nq);
+        for (size_t b = 0; b + 1 < fcuts.size(); b++)
+            CID_TRY(launch_query_front_gather(ctx, st, ix, (const uint8_t*)d_bases, d_seq_offs, d_query_offs, h_seq_offs, h_query_offs,
+                                              fcuts[b], fcuts[b + 1], seq_mode, d_counts + fcuts[b] * N,
+                                              (unsigned long long*)d_num_kmers + fcuts[b]));
+        return CID_OK;
+    }
     std::vector<uint64_t> cuts = query_batches(h_seq_offs, h_query_offs, nq, ix->k, kMaxBatchSlots);
     for (size_t b = 0; b + 1 < cuts.size(); b++) {
         const uint64_t q0 = cuts[b], q1 = cuts[b + 1];

@@ -836,6 +836,173 @@ query_uniq_wide_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t 
     }
 }
 
+// query_gather over prepared row-index lists: unit u = rid[(unit_slot0[u] + i) * H + h], i < unit_n[u] (<= 16384)
+static int launch_query_gather(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, const uint32_t* d_rid,
+                               const uint32_t* d_unit_group, const uint64_t* d_unit_slot0, const uint32_t* d_unit_n,
+                               uint64_t nunits, uint32_t* d_counts) {
+    const size_t gsmem = QG_RING_BYTES + 4096 * 4;
+    static bool gattr = false;
+    if (!gattr) {
+        CID_CUDA(cudaFuncSetAttribute(query_gather_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+        CID_CUDA(cudaFuncSetAttribute(query_gather_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+        gattr = true;
+    }
+    {
+        ProfScope ps(ctx, st, KID_QUERY_COUNTS);
+        if (idx->H == 2)
+            query_gather_kernel<2><<<(unsigned)nunits, QG_WARPS * 32, gsmem, st>>>(idx->rows, idx->Wp, idx->N, d_rid, d_unit_group,
+                                                                                 d_unit_slot0, d_unit_n, d_counts);
+        else
+            query_gather_kernel<4><<<(unsigned)nunits, QG_WARPS * 32, gsmem, st>>>(idx->rows, idx->Wp, idx->N, d_rid, d_unit_group,
+                                                                                 d_unit_slot0, d_unit_n, d_counts);
+    }
+    ctx->launches++;
+    CID_CUDA(cudaGetLastError());
+    return CID_OK;
+}
+
+// ================================================================= query_front (small queries, distinct k-mers only)
+// Gene search (-g: clean_map(0), batch_search_pe.rs:112-113) and any search with filter 0 need the DISTINCT canonical
+// k-mers of a query, not their multiplicities.  For queries of up to QF_MAX_NPOS k-mer positions (genes, plasmids) one CTA
+// owns one query: it dedups in a shared-memory table (64-bit CAS), and the thread that inserts a new k-mer hashes it at
+// once and appends its row indices to the query's list in HBM.  This replaces table_clear + kmerize_insert + query_hash
+// (three passes over a 16-byte-per-slot count table in HBM, ~3 slots per k-mer) by one pass over the bases.
+constexpr int QF_THREADS = 256;
+constexpr uint32_t QF_MAX_NPOS = 8192;              // table of <= 16384 slots (128 KB), list of <= 16384 k-mers per gather unit
+__global__ void __launch_bounds__(QF_THREADS)
+query_front_kernel(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ seq_offs,
+                   const uint64_t* __restrict__ query_offs, const uint32_t* __restrict__ qlist, uint32_t tsize, uint32_t k,
+                   int seq_mode, uint32_t H, ModS mods, const uint64_t* __restrict__ rid_base, uint32_t* __restrict__ rid_out,
+                   uint32_t* __restrict__ unit_n, unsigned long long* __restrict__ num_kmers, uint32_t* __restrict__ err) {
+    extern __shared__ __align__(16) uint8_t dsm[];
+    __shared__ uint32_t lut[256];
+    __shared__ uint32_t s_cnt;
+    unsigned long long* keys = (unsigned long long*)dsm;
+    Tile t = tile_carve(dsm + (size_t)tsize * 8, KT_CAP);
+    const int tid = threadIdx.x;
+    const uint32_t q = qlist[blockIdx.x];
+    const uint32_t tmask = tsize - 1;
+    lut4_init(lut, tid, QF_THREADS);
+    for (uint32_t i = tid; i < tsize; i += QF_THREADS) keys[i] = CID_EMPTY_KEY;
+    for (int i = tid; i < KT_CAP / 32 + 2; i += QF_THREADS) t.start[i] = 0;      // one sequence per tile: no boundaries inside
+    if (tid == 0) s_cnt = 0;
+    const uint64_t base = rid_base[q];
+    const uint64_t s_lo = __ldg(query_offs + q), s_hi = __ldg(query_offs + q + 1);
+    for (uint64_t s = s_lo; s < s_hi; s++) {
+        const uint64_t b0 = __ldg(seq_offs + s), L = __ldg(seq_offs + s + 1) - b0;
+        if (L < k) continue;                                 // kmer.rs:94 / :477 `continue`
+        for (uint64_t t0 = 0; t0 + k <= L; t0 += KT) {
+            const int tile_len = (int)min((uint64_t)(KT + k - 1), L - t0);
+            __syncthreads();                                 // the previous tile is consumed
+            t.len = tile_len;
+            const uint8_t* src = bases + b0 + t0;
+            if ((((uintptr_t)src) & 3) == 0) {
+                const uint32_t* s4 = (const uint32_t*)src;
+                uint32_t* d4 = (uint32_t*)t.ascii;
+                const int n4 = tile_len >> 2;
+                for (int i = tid; i < n4; i += QF_THREADS) d4[i] = __ldg(s4 + i);
+                for (int i = (n4 << 2) + tid; i < tile_len; i += QF_THREADS) t.ascii[i] = __ldg(src + i);
+            } else {
+                for (int i = tid; i < tile_len; i += QF_THREADS) t.ascii[i] = __ldg(src + i);
+            }
+            __syncthreads();
+            tile_pack(t, KT_CAP, tid, QF_THREADS);
+            __syncthreads();
+            for (int p = tid; p < KT; p += QF_THREADS) {
+                uint64_t key; bool fwd, low;
+                if (!tile_kmer(t, p, k, key, fwd, low)) continue;
+                if (low && seq_mode == CID_SEQ_FASTQ) { atomicOr(err, ERRF_LOWER_RAW); continue; }
+                uint32_t h = (uint32_t)mix64(key) & tmask;
+                bool fresh = false;
+                for (;;) {
+                    const unsigned long long prev = atomicCAS(&keys[h], CID_EMPTY_KEY, (unsigned long long)key);
+                    if (prev == CID_EMPTY_KEY) { fresh = true; break; }
+                    if (prev == key) break;
+                    h = (h + 1) & tmask;
+                }
+                if (fresh) {
+                    const uint32_t i = atomicAdd(&s_cnt, 1u);
+                    const HashIn in = hashin_from_key(lut, key, k);
+                    uint32_t* out = rid_out + (base + i) * H;
+                    for (uint32_t hh = 0; hh < H; hh++) out[hh] = (uint32_t)mod_s(xxh3_kmer(in, k, hh), mods);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) { unit_n[q] = s_cnt; num_kmers[q] = s_cnt; }
+}
+
+bool query_front_fits(const uint64_t* h_seq_offs, const uint64_t* h_query_offs, uint64_t q0, uint64_t q1, uint32_t k) {
+    for (uint64_t q = q0; q < q1; q++) {
+        uint64_t npos = 0;
+        for (uint64_t s = h_query_offs[q]; s < h_query_offs[q + 1]; s++) {
+            const uint64_t L = h_seq_offs[s + 1] - h_seq_offs[s];
+            if (L >= k) npos += L - k + 1;
+        }
+        if (npos > QF_MAX_NPOS) return false;
+    }
+    return true;
+}
+
+// Queries [q0, q1) (all within QF_MAX_NPOS): d_counts / d_num_kmers point at query q0.  d_query_offs / d_seq_offs are the
+// caller's whole device arrays (absolute indices).  Synchronises the stream before returning (host staging vectors).
+int launch_query_front_gather(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, const uint8_t* d_bases,
+                              const uint64_t* d_seq_offs, const uint64_t* d_query_offs, const uint64_t* h_seq_offs,
+                              const uint64_t* h_query_offs, uint64_t q0, uint64_t q1, int seq_mode, uint32_t* d_counts,
+                              unsigned long long* d_num_kmers) {
+    const uint64_t bq = q1 - q0;
+    if (bq == 0) return CID_OK;
+    const uint32_t k = idx->k, H = idx->H;
+    std::vector<uint64_t> base(bq);
+    std::vector<uint32_t> group(bq), qlist[4];               // table sizes 2048, 4096, 8192, 16384
+    uint64_t total = 0;
+    for (uint64_t q = 0; q < bq; q++) {
+        uint64_t npos = 0;
+        for (uint64_t s = h_query_offs[q0 + q]; s < h_query_offs[q0 + q + 1]; s++) {
+            const uint64_t L = h_seq_offs[s + 1] - h_seq_offs[s];
+            if (L >= k) npos += L - k + 1;
+        }
+        base[q] = total;
+        total += npos;
+        group[q] = (uint32_t)q;
+        qlist[npos <= 1024 ? 0 : npos <= 2048 ? 1 : npos <= 4096 ? 2 : 3].push_back((uint32_t)q);
+    }
+    CID_TRY(ctx->scratch[14].ensure(total * H * 4 + 64));
+    CID_TRY(ctx->scratch[15].ensure(bq * 4 + 64));
+    CID_TRY(ctx->scratch[6].ensure(bq * 16 + 64));
+    uint32_t* d_rid = ctx->scratch[14].as<uint32_t>();
+    uint32_t* d_unit_n = ctx->scratch[15].as<uint32_t>();
+    uint64_t* d_base = ctx->scratch[6].as<uint64_t>();
+    uint32_t* d_group = (uint32_t*)(d_base + bq);
+    uint32_t* d_qlist = d_group + bq;
+    CID_CUDA(cudaMemcpyAsync(d_base, base.data(), bq * 8, cudaMemcpyHostToDevice, st));
+    CID_CUDA(cudaMemcpyAsync(d_group, group.data(), bq * 4, cudaMemcpyHostToDevice, st));
+    static bool attr = false;
+    if (!attr) {
+        CID_CUDA(cudaFuncSetAttribute(query_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(16384 * 8 + tile_smem_bytes(KT_CAP))));
+        attr = true;
+    }
+    uint64_t at = 0;
+    for (int c = 0; c < 4; c++) {
+        const uint64_t n = qlist[c].size();
+        if (n == 0) continue;
+        CID_CUDA(cudaMemcpyAsync(d_qlist + at, qlist[c].data(), n * 4, cudaMemcpyHostToDevice, st));
+        const uint32_t tsize = 2048u << c;
+        ProfScope ps(ctx, st, KID_QUERY_FRONT);
+        query_front_kernel<<<(unsigned)n, QF_THREADS, (size_t)tsize * 8 + tile_smem_bytes(KT_CAP), st>>>(
+            d_bases, d_seq_offs, d_query_offs + q0, d_qlist + at, tsize, k, seq_mode, H, make_mods(idx->S), d_base, d_rid, d_unit_n,
+            d_num_kmers, ctx->d_err);
+        ctx->launches++;
+        CID_CUDA(cudaGetLastError());
+        at += n;
+    }
+    CID_TRY(launch_query_gather(ctx, st, idx, d_rid, d_group, d_base, d_unit_n, bq, d_counts));
+    CID_CUDA(cudaStreamSynchronize(st));
+    return CID_OK;
+}
+
 int launch_query_counts(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, const void* d_table,
                         const uint32_t* d_unit_group, const uint64_t* d_unit_slot0, const uint32_t* d_unit_nslots,
                         uint64_t nunits, uint64_t total_slots, const int64_t* d_filter, uint32_t* d_counts,
@@ -856,25 +1023,7 @@ int launch_query_counts(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, con
         }
         ctx->launches++;
         CID_CUDA(cudaGetLastError());
-        const size_t gsmem = QG_RING_BYTES + 4096 * 4;
-        static bool gattr = false;
-        if (!gattr) {
-            CID_CUDA(cudaFuncSetAttribute(query_gather_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
-            CID_CUDA(cudaFuncSetAttribute(query_gather_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
-            gattr = true;
-        }
-        {
-            ProfScope ps(ctx, st, KID_QUERY_COUNTS);
-            if (idx->H == 2)
-                query_gather_kernel<2><<<(unsigned)nunits, QG_WARPS * 32, gsmem, st>>>(idx->rows, idx->Wp, idx->N, d_rid, d_unit_group,
-                                                                                     d_unit_slot0, d_unit_n, d_counts);
-            else
-                query_gather_kernel<4><<<(unsigned)nunits, QG_WARPS * 32, gsmem, st>>>(idx->rows, idx->Wp, idx->N, d_rid, d_unit_group,
-                                                                                     d_unit_slot0, d_unit_n, d_counts);
-        }
-        ctx->launches++;
-        CID_CUDA(cudaGetLastError());
-        return CID_OK;
+        return launch_query_gather(ctx, st, idx, d_rid, d_unit_group, d_unit_slot0, d_unit_n, nunits, d_counts);
     }
     size_t smem = unit_smem_bytes(idx->H);
     static bool attr_set = false;

@@ -63,8 +63,8 @@ struct cid_ctx {
     struct ProfRec { int kernel; cudaEvent_t a, b; };
     std::vector<ProfRec> prof_recs;
     std::vector<cudaEvent_t> prof_pool;
-    double prof_ms[16] = {0};
-    uint64_t prof_n[16] = {0};
+    double prof_ms[24] = {0};
+    uint64_t prof_n[24] = {0};
     // read_id host pipeline (cid_readid_pipe.cu): chunked H2D / kernels / D2H / host vote overlap
     struct cid_readid_pipe* pipe = nullptr;
     uint64_t opt_readid_chunk = 0;   // reads per pipeline chunk (0 = automatic)
@@ -75,6 +75,7 @@ struct cid_ctx {
     int opt_readid_streams = 1;
     int opt_kmerize_ctas = 0, opt_vote_ctas = 0;   // CTAs per SM of the read_id kmerize / vote grids (0 = fill the GPU);
                                                    // smaller grids let the two kernels of different chunks share the SMs
+    int opt_query_front = 1;         // 0 = never use the shared-memory dedup front end of small queries (parity aid)
     int opt_query_fused = 0;         // 1 = force the fused collect/hash/gather kernel (parity aid)
     cudaStream_t aux[2] = {nullptr, nullptr};
     cudaEvent_t aux_fork = nullptr, aux_join[2] = {nullptr, nullptr};
@@ -112,7 +113,7 @@ int check_err_flags(cid_ctx* ctx, cudaStream_t st);   // syncs the stream
 
 // kernel ids for the profiling hooks (names in cid_api.cu: kKernelNames)
 enum { KID_KMERIZE_INSERT = 0, KID_HISTOGRAM, KID_TO_BLOOM, KID_TRANSPOSE, KID_ROWNZ, KID_QUERY_COUNTS, KID_QUERY_UNIQ_WIDE,
-       KID_QUERY_PERFECT, KID_READID_KMERIZE, KID_READID_SCHED, KID_READID_ORDER, KID_READID_VOTE, KID_READID_CLASSIFY, KID_TABLE_CLEAR, KID_OTHER, KID_QUERY_HASH, KID_COUNT };
+       KID_QUERY_PERFECT, KID_READID_KMERIZE, KID_READID_SCHED, KID_READID_ORDER, KID_READID_VOTE, KID_READID_CLASSIFY, KID_TABLE_CLEAR, KID_OTHER, KID_QUERY_HASH, KID_QUERY_FRONT, KID_COUNT };
 struct ProfScope {     // records an event pair around a launch when profiling is enabled
     cid_ctx* ctx; cudaStream_t st; int idx;
     ProfScope(cid_ctx* c, cudaStream_t s, int kernel);
@@ -162,6 +163,12 @@ int launch_query_counts(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, con
                         uint64_t nunits, uint64_t total_slots, const int64_t* d_filter, uint32_t* d_counts,
                         unsigned long long* d_num_kmers, bool want_uniq, uint32_t* d_uniq_list, uint32_t uniq_cap,
                         uint32_t* d_uniq_n);
+// small-query fast path (distinct k-mers only): shared-memory dedup + hash, then the streaming gather
+bool query_front_fits(const uint64_t* h_seq_offs, const uint64_t* h_query_offs, uint64_t q0, uint64_t q1, uint32_t k);
+int launch_query_front_gather(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, const uint8_t* d_bases,
+                              const uint64_t* d_seq_offs, const uint64_t* d_query_offs, const uint64_t* h_seq_offs,
+                              const uint64_t* h_query_offs, uint64_t q0, uint64_t q1, int seq_mode, uint32_t* d_counts,
+                              unsigned long long* d_num_kmers);
 int launch_query_perfect(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, const void* d_table,
                          const uint32_t* d_unit_group, const uint64_t* d_unit_slot0, const uint32_t* d_unit_nslots,
                          uint64_t nunits, uint32_t* d_and_rows, uint32_t* d_missing, unsigned long long* d_num_kmers);

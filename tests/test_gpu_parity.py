@@ -160,6 +160,51 @@ def test_gene_search_streaming_gather(oracle, ctx, N, k, S, H):
     assert int(o["counts"].max()) > 500
 
 
+@pytest.mark.parametrize("N,k,S,H", [(70, 21, 300_007, 2), (1000, 21, 100_003, 2), (1250, 31, 80_021, 4), (130, 9, 50_021, 4)])
+def test_gene_search_small_query_front(oracle, ctx, N, k, S, H):
+    """Queries of <= 8192 k-mer positions with filter 0 take query_front (shared-memory dedup + hash, one CTA per query)
+    in front of query_gather; must equal the oracle and the count-table path (option query_front = 0)."""
+    rng = _rng(170 + N)
+    genomes, oix, gix = _index_pair(oracle, ctx, rng, N, k, S, H, glen=2500)
+    queries = []
+    for i in range(90):
+        g = genomes[int(rng.integers(0, N))]
+        s = int(rng.integers(0, 400))
+        q = g[s:s + int(rng.integers(k, 2100))]
+        if i % 3 == 1:
+            q = synth.mutate(rng, q, 0.02)
+        if i % 5 == 4:
+            q = synth.rand_seq(rng, 900)
+        if i % 7 == 3:
+            q = synth.sprinkle(rng, q, b"NnRacgt", 0.02)       # has_no_n, mixed case (raw compare, then upper-case)
+        if i % 11 == 5:
+            q = q.lower()
+        queries.append([q] if i % 4 else [q[:len(q) // 2], q[len(q) // 2:], q[:k - 1], q[5:5 + k]])
+    queries.append([b"ACG"])                                   # zero k-mers
+    queries.append([])                                         # no sequences at all
+    queries.append([genomes[1][:k]])                           # exactly one k-mer
+    queries.append([genomes[2][:1500], genomes[2][:1500], synth.revcomp(genomes[2][:1500])])   # every k-mer three times
+    queries.append([genomes[3][:2400], genomes[4][:2400], genomes[5][:2400], genomes[6][:900]])  # 8,000+ positions: largest table
+    o = oix.query_counts(queries, oracle.MODE_FASTA, True, 0)
+    launches0 = ctx.launches
+    g = gix.query_counts(queries, cb.CID_SEQ_FASTA, True, 0, want_uniq=False)
+    assert ctx.launches - launches0 <= 6                       # <= 4 query_front size classes + 1 gather, no count table
+    assert np.array_equal(g["num_kmers"], o["num_kmers"])
+    assert np.array_equal(g["counts"], o["counts"])
+    ctx.set_option("query_front", 0)
+    try:
+        t = gix.query_counts(queries, cb.CID_SEQ_FASTA, True, 0, want_uniq=False)
+    finally:
+        ctx.set_option("query_front", 1)
+    assert np.array_equal(t["num_kmers"], o["num_kmers"]) and np.array_equal(t["counts"], o["counts"])
+    # FASTQ-mode queries (raw case kept) with -f 0 take the same path
+    fq = [[synth.sprinkle(rng, q[0].upper(), b"N", 0.01)] for q in queries[:30] if q and len(q[0]) >= k]
+    o = oix.query_counts(fq, oracle.MODE_FASTQ, False, 0)
+    g = gix.query_counts(fq, cb.CID_SEQ_FASTQ, False, 0, want_uniq=False)
+    assert np.array_equal(g["num_kmers"], o["num_kmers"]) and np.array_equal(g["counts"], o["counts"])
+    assert int(o["counts"].max()) > 100
+
+
 def test_search_fastq_query_with_filters(oracle, ctx):
     rng = _rng(300)
     genomes, oix, gix = _index_pair(oracle, ctx, rng, 12, 27, 400_009, 4)
