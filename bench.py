@@ -375,7 +375,38 @@ def run_search_extra(torch, dev, ctx, args, quick):
                            "unit": "GB/s", "frac": alg / (qc_ms / 1e3) / 1e9 / peak, "traffic": None,
                            "traffic_captured_launch": ncu_traffic().get("query_counts"),
                            "peak_source": peak_src, "algorithmic_bytes_per_pass": alg, "ms_per_pass": qc_ms}
-    # spot parity on a few queries against the oracle would need the CPU index (1000 x 3 Mbp): covered by tests/ instead
+    # ---- -s -m perfect search of the same queries (perfect_search.rs:62-120) through the host-pointer ABI:
+    # query bases H2D, query_front + streaming AND gather, AND rows + status D2H inside the timed region
+    try:
+        W = (A + 31) // 32
+        h_bases = d_bases.cpu().numpy()
+        and_rows = np.zeros((nq, W), np.uint32)
+        status = np.zeros(nq, np.uint8)
+        nk = np.zeros(nq, np.uint64)
+
+        def run_perfect():
+            L.check(lib.cid_query_perfect_mf(gix.h, h_bases.ctypes.data_as(L.vp), P(h_seq_offs), nq,
+                                             and_rows.ctypes.data_as(L.u32p), status.ctypes.data_as(L.u8p), P(nk)))
+        run_perfect()
+        ctx.profile(True)
+        tp0 = time.time()
+        for _ in range(reps):
+            run_perfect()
+        pms = (time.time() - tp0) / reps * 1e3
+        pprof = ctx.profile_read()
+        ctx.profile(False)
+        # size-independent property: a query cut unmodified from isolate i has every row present and bit i set in its AND
+        exact = (kind < 0.8).cpu().numpy()
+        iso_h = iso.cpu().numpy()
+        bit = (and_rows[np.arange(nq), iso_h // 32] >> (iso_h % 32).astype(np.uint32)) & 1
+        viol = int(((status[exact] != 0) | (bit[exact] != 1)).sum())
+        out["perfect_search"] = {"workload": "-s -m perfect search of the same %d queries (cid_query_perfect_mf, host buffers)" % nq,
+                                 "lookups": int(nk.sum()), "ms_per_pass_wall": pms, "lookups_per_s": int(nk.sum()) / (pms / 1e3),
+                                 "h2d_bytes": int(h_bases.nbytes + h_seq_offs.nbytes), "d2h_bytes": int(and_rows.nbytes + status.nbytes + nk.nbytes),
+                                 "kernels": {k_: {"ms_per_launch": v[0] / v[1], "launches_per_pass": v[1] / reps} for k_, v in pprof.items()},
+                                 "self_query_violations": viol, "queries_with_every_row_present": int((status == 0).sum())}
+    except Exception as ex:
+        out["perfect_search"] = {"error": repr(ex)}
     gix.close()
     return out
 

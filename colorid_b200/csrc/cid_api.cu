@@ -799,22 +799,37 @@ static int query_perfect_impl(cid_index* ix, const char* bases, const uint64_t* 
     if (nbases) CID_CUDA(cudaMemcpyAsync(ctx->scratch[4].p, bases, nbases, cudaMemcpyHostToDevice, st));
     CID_CUDA(cudaMemcpyAsync(ctx->scratch[5].p, seq_offs, (nseq + 1) * 8, cudaMemcpyHostToDevice, st));
     const uint32_t W = ix->W;
-    std::vector<uint64_t> cuts = query_batches(seq_offs, query_offs, nq, ix->k, kMaxBatchSlots);
+    // small queries: shared-memory dedup front end + streaming AND gather (no count table)
+    const bool fast = nq && query_front_ok(ix, false, seq_offs, query_offs, nq);
+    if (fast) {
+        CID_TRY(ctx->scratch[7].ensure((nq + 1) * 8));
+        CID_CUDA(cudaMemcpyAsync(ctx->scratch[7].p, query_offs, (nq + 1) * 8, cudaMemcpyHostToDevice, st));
+    }
+    std::vector<uint64_t> cuts = fast ? query_front_batches(seq_offs, query_offs, nq)
+                                      : query_batches(seq_offs, query_offs, nq, ix->k, kMaxBatchSlots);
     for (size_t b = 0; b + 1 < cuts.size(); b++) {
         const uint64_t q0 = cuts[b], q1 = cuts[b + 1], bq = q1 - q0;
-        QueryPlan qp;
-        CID_TRY(query_front(ix, st, ctx->scratch[4].as<uint8_t>(), ctx->scratch[5].as<uint64_t>(), seq_offs, query_offs,
-                            q0, q1, seq_mode, qp));
-        CID_TRY(check_err_flags(ctx, st));
         CID_TRY(ctx->scratch[10].ensure(bq * W * 4));
         CID_TRY(ctx->scratch[11].ensure(bq * 8));
         CID_TRY(ctx->scratch[13].ensure(bq * 4));
         CID_CUDA(cudaMemsetAsync(ctx->scratch[10].p, 0xFF, bq * W * 4, st));
         CID_CUDA(cudaMemsetAsync(ctx->scratch[11].p, 0, bq * 8, st));
         CID_CUDA(cudaMemsetAsync(ctx->scratch[13].p, 0, bq * 4, st));
-        CID_TRY(launch_query_perfect(ctx, st, ix, qp.d_table, qp.d_unit_group, qp.d_unit_slot0, qp.d_unit_nslots,
-                                     qp.qu.group.size(), ctx->scratch[10].as<uint32_t>(), ctx->scratch[13].as<uint32_t>(),
-                                     ctx->scratch[11].as<unsigned long long>()));
+        if (fast) {
+            CID_TRY(launch_query_front_gather(ctx, st, ix, ctx->scratch[4].as<uint8_t>(), ctx->scratch[5].as<uint64_t>(),
+                                              ctx->scratch[7].as<uint64_t>(), seq_offs, query_offs, q0, q1, seq_mode, nullptr,
+                                              ctx->scratch[11].as<unsigned long long>(), ctx->scratch[10].as<uint32_t>(),
+                                              ctx->scratch[13].as<uint32_t>()));
+            CID_TRY(check_err_flags(ctx, st));
+        } else {
+            QueryPlan qp;
+            CID_TRY(query_front(ix, st, ctx->scratch[4].as<uint8_t>(), ctx->scratch[5].as<uint64_t>(), seq_offs, query_offs,
+                                q0, q1, seq_mode, qp));
+            CID_TRY(check_err_flags(ctx, st));
+            CID_TRY(launch_query_perfect(ctx, st, ix, qp.d_table, qp.d_unit_group, qp.d_unit_slot0, qp.d_unit_nslots,
+                                         qp.qu.group.size(), ctx->scratch[10].as<uint32_t>(), ctx->scratch[13].as<uint32_t>(),
+                                         ctx->scratch[11].as<unsigned long long>()));
+        }
         std::vector<uint32_t> missing(bq);
         CID_CUDA(cudaMemcpyAsync(and_rows + q0 * W, ctx->scratch[10].p, bq * W * 4, cudaMemcpyDeviceToHost, st));
         CID_CUDA(cudaMemcpyAsync(n_kmers + q0, ctx->scratch[11].p, bq * 8, cudaMemcpyDeviceToHost, st));

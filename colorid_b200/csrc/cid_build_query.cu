@@ -630,11 +630,15 @@ template <int HT> struct QGCfg {
     static constexpr int D = QG_RING_BYTES / QG_WARPS / STAGE;   // stages per warp: 8 (H=2), 4 (H=4)
 };
 
-template <int HT>
+// ANDM (perfect search, perfect_search.rs:26-46): instead of counting, every lane ANDs the rows of its column slice; a row
+// index whose row is absent (row-present bitmap, checked where the indices are loaded) raises `missing`; `counts` is then
+// and_rows[group][W] (pre-set to all ones by the caller).
+template <int HT, bool ANDM>
 __global__ void __launch_bounds__(QG_WARPS * 32, 4)
 query_gather_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t N, const uint32_t* __restrict__ rid,
                     const uint32_t* __restrict__ unit_group, const uint64_t* __restrict__ unit_slot0,
-                    const uint32_t* __restrict__ unit_n, uint32_t* __restrict__ counts) {
+                    const uint32_t* __restrict__ unit_n, uint32_t* __restrict__ counts,
+                    const uint32_t* __restrict__ rownz, uint32_t* __restrict__ missing, uint32_t W) {
     using Cfg = QGCfg<HT>;
     constexpr int D = Cfg::D;
     static_assert(D >= 2 && 8 % D == 0, "ring depth must divide the tree width");
@@ -659,11 +663,12 @@ query_gather_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t N, 
     const uint32_t ring = (uint32_t)__cvta_generic_to_shared(dsm) + warp * (D * Cfg::STAGE) + lane * 16;
     const uint32_t* colbase = rows + colv * 4;
 
-    uint32_t pl[4][QG_PLANES];
+    uint32_t pl[4][ANDM ? 1 : QG_PLANES];
 #pragma unroll
     for (int v = 0; v < 4; v++)
 #pragma unroll
-        for (int p = 0; p < QG_PLANES; p++) pl[v][p] = 0;
+        for (int p = 0; p < (ANDM ? 1 : QG_PLANES); p++) pl[v][p] = ANDM ? 0xFFFFFFFFu : 0u;      // ANDM: pl[v][0] is the AND accumulator
+    bool miss = false;
 
     // row indices of k-mer lo + BK*b + lane (batch b), double-buffered in registers
     uint32_t cur[HT], nxt[HT];
@@ -678,6 +683,10 @@ query_gather_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t N, 
             else {
 #pragma unroll
                 for (int h = 0; h < HT; h++) dst[h] = __ldg(myrid + (size_t)i * HT + h);
+            }
+            if (ANDM) {
+#pragma unroll
+                for (int h = 0; h < HT; h++) if (!((__ldg(rownz + (dst[h] >> 5)) >> (dst[h] & 31)) & 1u)) miss = true;
             }
         }
     };
@@ -722,10 +731,11 @@ query_gather_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t N, 
                 }
             }
             x[u][0] = a.x; x[u][1] = a.y; x[u][2] = a.z; x[u][3] = a.w;
+            if (ANDM && valid) { pl[0][0] &= a.x; pl[1][0] &= a.y; pl[2][0] &= a.z; pl[3][0] &= a.w; }
         }
         // Harley-Seal: eight inputs -> ones/twos/fours planes + one weight-8 carry per word
 #pragma unroll
-        for (int v = 0; v < 4; v++) {
+        for (int v = 0; v < (ANDM ? 0 : 4); v++) {
             uint32_t t2a, t2b, t4a, t4b, c8;
             csa(t2a, pl[v][0], pl[v][0], x[0][v], x[1][v]);
             csa(t2b, pl[v][0], pl[v][0], x[2][v], x[3][v]);
@@ -743,13 +753,26 @@ query_gather_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t N, 
         }
     }
     cp_async_wait<0>();
+    if (ANDM) {
+        // AND across the lane groups and warps that hold the same column slice, then into and_rows[g][W]
+        __syncthreads();
+        for (int i = tid; i < (int)Wp; i += QG_WARPS * 32) cnt[i] = 0xFFFFFFFFu;
+        __syncthreads();
+        if (lane_on && T) {
+#pragma unroll
+            for (int v = 0; v < 4; v++) if (pl[v][0] != 0xFFFFFFFFu) atomicAnd(&cnt[colv * 4 + v], pl[v][0]);
+        }
+        if (__syncthreads_or(miss) && tid == 0) atomicOr(&missing[g], 1u);
+        for (int i = tid; i < (int)W; i += QG_WARPS * 32) if (cnt[i] != 0xFFFFFFFFu) atomicAnd(&counts[(uint64_t)g * W + i], cnt[i]);
+        return;
+    }
     // flush: planes -> shared counters (warps and sub-groups hold partial counts of the same columns)
     // -> one global atomic per non-zero accession
     __syncthreads();
     const int ncnt = (int)min(4096u, (N + 31) & ~31u);
     for (int i = tid; i < ncnt; i += QG_WARPS * 32) cnt[i] = 0;
     __syncthreads();
-    if (lane_on && T) {
+    if (!ANDM && lane_on && T) {
         const int depth = 32 - __clz(((T + 7) & ~7u));     // planes that can be non-zero
 #pragma unroll
         for (int v = 0; v < 4; v++) {
@@ -839,22 +862,24 @@ query_uniq_wide_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t 
 // query_gather over prepared row-index lists: unit u = rid[(unit_slot0[u] + i) * H + h], i < unit_n[u] (<= 16384)
 static int launch_query_gather(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, const uint32_t* d_rid,
                                const uint32_t* d_unit_group, const uint64_t* d_unit_slot0, const uint32_t* d_unit_n,
-                               uint64_t nunits, uint32_t* d_counts) {
+                               uint64_t nunits, uint32_t* d_counts, uint32_t* d_and_rows = nullptr, uint32_t* d_missing = nullptr) {
     const size_t gsmem = QG_RING_BYTES + 4096 * 4;
     static bool gattr = false;
     if (!gattr) {
-        CID_CUDA(cudaFuncSetAttribute(query_gather_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
-        CID_CUDA(cudaFuncSetAttribute(query_gather_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+        CID_CUDA(cudaFuncSetAttribute(query_gather_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+        CID_CUDA(cudaFuncSetAttribute(query_gather_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+        CID_CUDA(cudaFuncSetAttribute(query_gather_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+        CID_CUDA(cudaFuncSetAttribute(query_gather_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
         gattr = true;
     }
     {
-        ProfScope ps(ctx, st, KID_QUERY_COUNTS);
-        if (idx->H == 2)
-            query_gather_kernel<2><<<(unsigned)nunits, QG_WARPS * 32, gsmem, st>>>(idx->rows, idx->Wp, idx->N, d_rid, d_unit_group,
-                                                                                 d_unit_slot0, d_unit_n, d_counts);
-        else
-            query_gather_kernel<4><<<(unsigned)nunits, QG_WARPS * 32, gsmem, st>>>(idx->rows, idx->Wp, idx->N, d_rid, d_unit_group,
-                                                                                 d_unit_slot0, d_unit_n, d_counts);
+        ProfScope ps(ctx, st, d_and_rows ? KID_QUERY_PERFECT : KID_QUERY_COUNTS);
+#define CID_QG(HT, AM, OUT)                                                                                             \
+    query_gather_kernel<HT, AM><<<(unsigned)nunits, QG_WARPS * 32, gsmem, st>>>(idx->rows, idx->Wp, idx->N, d_rid, d_unit_group, \
+                                                                               d_unit_slot0, d_unit_n, OUT, idx->rownz, d_missing, idx->W)
+        if (d_and_rows) { if (idx->H == 2) CID_QG(2, true, d_and_rows); else CID_QG(4, true, d_and_rows); }
+        else { if (idx->H == 2) CID_QG(2, false, d_counts); else CID_QG(4, false, d_counts); }
+#undef CID_QG
     }
     ctx->launches++;
     CID_CUDA(cudaGetLastError());
@@ -910,7 +935,11 @@ query_front_kernel(const uint8_t* __restrict__ bases, const uint64_t* __restrict
             __syncthreads();
             for (int p = tid; p < KT; p += QF_THREADS) {
                 uint64_t key; bool fwd, low;
-                if (!tile_kmer(t, p, k, key, fwd, low)) continue;
+                if (!tile_kmer(t, p, k, key, fwd, low)) {
+                    // kmerize_string (kmer.rs:279-293) has no has_no_n test: such a window cannot be packed into 2 bits
+                    if (seq_mode == CID_SEQ_STRING && p + (int)k <= t.len) atomicOr(err, ERRF_STRING_NONACGT);
+                    continue;
+                }
                 if (low && seq_mode == CID_SEQ_FASTQ) { atomicOr(err, ERRF_LOWER_RAW); continue; }
                 uint32_t h = (uint32_t)mix64(key) & tmask;
                 bool fresh = false;
@@ -950,7 +979,7 @@ bool query_front_fits(const uint64_t* h_seq_offs, const uint64_t* h_query_offs, 
 int launch_query_front_gather(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, const uint8_t* d_bases,
                               const uint64_t* d_seq_offs, const uint64_t* d_query_offs, const uint64_t* h_seq_offs,
                               const uint64_t* h_query_offs, uint64_t q0, uint64_t q1, int seq_mode, uint32_t* d_counts,
-                              unsigned long long* d_num_kmers) {
+                              unsigned long long* d_num_kmers, uint32_t* d_and_rows, uint32_t* d_missing) {
     const uint64_t bq = q1 - q0;
     if (bq == 0) return CID_OK;
     const uint32_t k = idx->k, H = idx->H;
@@ -998,7 +1027,7 @@ int launch_query_front_gather(cid_ctx* ctx, cudaStream_t st, const cid_index* id
         CID_CUDA(cudaGetLastError());
         at += n;
     }
-    CID_TRY(launch_query_gather(ctx, st, idx, d_rid, d_group, d_base, d_unit_n, bq, d_counts));
+    CID_TRY(launch_query_gather(ctx, st, idx, d_rid, d_group, d_base, d_unit_n, bq, d_counts, d_and_rows, d_missing));
     CID_CUDA(cudaStreamSynchronize(st));
     return CID_OK;
 }

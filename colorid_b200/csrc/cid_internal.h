@@ -168,7 +168,8 @@ bool query_front_fits(const uint64_t* h_seq_offs, const uint64_t* h_query_offs, 
 int launch_query_front_gather(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, const uint8_t* d_bases,
                               const uint64_t* d_seq_offs, const uint64_t* d_query_offs, const uint64_t* h_seq_offs,
                               const uint64_t* h_query_offs, uint64_t q0, uint64_t q1, int seq_mode, uint32_t* d_counts,
-                              unsigned long long* d_num_kmers);
+                              unsigned long long* d_num_kmers, uint32_t* d_and_rows = nullptr, uint32_t* d_missing = nullptr);
+// d_and_rows != nullptr: perfect search -- AND of all rows into d_and_rows[q][W] (pre-set to ones), absent rows flag d_missing[q]
 int launch_query_perfect(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, const void* d_table,
                          const uint32_t* d_unit_group, const uint64_t* d_unit_slot0, const uint32_t* d_unit_nslots,
                          uint64_t nunits, uint32_t* d_and_rows, uint32_t* d_missing, unsigned long long* d_num_kmers);

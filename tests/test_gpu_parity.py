@@ -220,7 +220,7 @@ def test_search_fastq_query_with_filters(oracle, ctx):
         assert np.array_equal(g["uniq_mode"], o["uniq_mode"])
 
 
-@pytest.mark.parametrize("N,k,S,H", [(4, 27, 750_000, 4), (70, 21, 300_007, 2), (1100, 21, 60_013, 2)])
+@pytest.mark.parametrize("N,k,S,H", [(4, 27, 750_000, 4), (70, 21, 300_007, 2), (1100, 21, 60_013, 2), (1250, 31, 80_021, 4)])
 def test_perfect_search(oracle, ctx, N, k, S, H):
     rng = _rng(400 + N)
     genomes, oix, gix = _index_pair(oracle, ctx, rng, N, k, S, H, glen=3000 if N > 200 else 8000)
@@ -234,11 +234,22 @@ def test_perfect_search(oracle, ctx, N, k, S, H):
         queries.append([q])
     queries.append([b"AC"])
     queries.append([synth.rand_seq(rng, 500)])
+    queries.append([genomes[0][:700], genomes[0][650:1300], b"ACGTACG", genomes[0][:700]])   # several contigs, one too short
     o = oix.query_perfect(queries)
-    g = gix.query_perfect(queries)
-    assert np.array_equal(g["status"], o["status"])
-    assert np.array_equal(g["n_kmers"], o["n_kmers"])
-    assert np.array_equal(g["and_rows"], o["and_rows"])
+    # small queries: query_front + streaming AND gather (rows of >= 4 words, H in {2,4}); else / option off: count table
+    for front in (1, 0):
+        ctx.set_option("query_front", front)
+        try:
+            g = gix.query_perfect(queries)
+        finally:
+            ctx.set_option("query_front", 1)
+        assert np.array_equal(g["status"], o["status"])
+        assert np.array_equal(g["n_kmers"], o["n_kmers"])
+        assert np.array_equal(g["and_rows"], o["and_rows"])
+    # one query beyond 8192 k-mer positions sends the whole call through the count-table path
+    big = queries + [[b"".join(genomes[:4])]]
+    ob, gb = oix.query_perfect(big), gix.query_perfect(big)
+    assert np.array_equal(gb["status"], ob["status"]) and np.array_equal(gb["and_rows"], ob["and_rows"])
     assert (o["status"] == 0).sum() >= 10
 
 
@@ -261,16 +272,21 @@ def test_perfect_search_multifasta_records(oracle, ctx):
     recs.append(genomes[3][100:100 + k])       # exactly one k-mer
     recs.append(synth.rand_seq(rng, 700))
     o = oix.query_perfect(recs, mf=True)
-    g = gix.query_perfect_mf(recs)
-    assert np.array_equal(g["status"], o["status"])
-    assert np.array_equal(g["n_kmers"], o["n_kmers"])
-    assert np.array_equal(g["and_rows"], o["and_rows"])
+    for front in (1, 0):
+        ctx.set_option("query_front", front)
+        try:
+            g = gix.query_perfect_mf(recs)
+            # kmerize_string has no has_no_n test: an N inside a record is part of its k-mers, which the 2-bit
+            # device path cannot represent -> refused loudly, never silently skipped
+            with pytest.raises(cb.lib.CidError) as ei:
+                gix.query_perfect_mf([genomes[0][:200] + b"N" + genomes[0][201:400]])
+            assert ei.value.code == cb.lib.CID_E_UNSUPPORTED
+        finally:
+            ctx.set_option("query_front", 1)
+        assert np.array_equal(g["status"], o["status"])
+        assert np.array_equal(g["n_kmers"], o["n_kmers"])
+        assert np.array_equal(g["and_rows"], o["and_rows"])
     assert (o["status"] == 0).sum() >= 10 and (o["status"] == 2).sum() == 1
-    # kmerize_string has no has_no_n test: an N inside a record is part of its k-mers, which the 2-bit
-    # device path cannot represent -> refused loudly, never silently skipped
-    with pytest.raises(cb.lib.CidError) as ei:
-        gix.query_perfect_mf([genomes[0][:200] + b"N" + genomes[0][201:400]])
-    assert ei.value.code == cb.lib.CID_E_UNSUPPORTED
 
 
 def _readid_compare(oracle, oix, gix, reads, **kw):
