@@ -661,7 +661,10 @@ query_gather_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t N, 
     const uint32_t lo = min(n, warp * per), hi = min(n, lo + per);
     const uint32_t T = (hi - lo + kpw - 1) / kpw;         // steps of this warp
     const uint32_t ring = (uint32_t)__cvta_generic_to_shared(dsm) + warp * (D * Cfg::STAGE) + lane * 16;
-    const uint32_t* colbase = rows + colv * 4;
+    const char* colbase = (const char*)(rows + colv * 4);
+    const uint32_t rowbytes = Wp * 4;
+    // steps in which this lane's k-mer (lo + kpw*t + sub) exists
+    const uint32_t myT = (lane_on && lo + sub < hi) ? (hi - lo - sub + kpw - 1) / kpw : 0u;
 
     uint32_t pl[4][ANDM ? 1 : QG_PLANES];
 #pragma unroll
@@ -702,11 +705,11 @@ query_gather_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t N, 
                 load_batch(b_issue + 1, nxt);
             }
             const uint32_t src = min(kpw * it_issue + sub, 31u);
-            const bool valid = lane_on && lo + kpw * t_issue + sub < hi;
+            const bool valid = t_issue < myT;
 #pragma unroll
             for (int h = 0; h < HT; h++) {
                 const uint32_t r = __shfl_sync(0xffffffffu, cur[h], src);
-                if (valid) cp_async16(ring + slot * Cfg::STAGE + h * 512, colbase + (size_t)r * Wp);
+                if (valid) cp_async16(ring + slot * Cfg::STAGE + h * 512, colbase + (uint64_t)r * rowbytes);
             }
             t_issue++; it_issue++;
         }
@@ -720,7 +723,7 @@ query_gather_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t N, 
         for (int u = 0; u < 8; u++) {
             issue((u + D - 1) % D);
             cp_async_wait<D - 1>();
-            const bool valid = lane_on && lo + kpw * (t0 + u) + sub < hi;
+            const bool valid = t0 + u < myT;
             uint4 a = make_uint4(0, 0, 0, 0);
             if (valid) {
                 a = lds128(ring + (u % D) * Cfg::STAGE);
@@ -766,59 +769,49 @@ query_gather_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t N, 
         for (int i = tid; i < (int)W; i += QG_WARPS * 32) if (cnt[i] != 0xFFFFFFFFu) atomicAnd(&counts[(uint64_t)g * W + i], cnt[i]);
         return;
     }
-    // flush: planes -> shared counters (warps and sub-groups hold partial counts of the same columns)
-    // -> one global atomic per non-zero accession
+    // flush.  The same column word is held by QG_WARPS * kpw lane groups (partial counts over disjoint k-mers).  The
+    // planes go to shared memory (the ring is free now) as 16-byte stores, laid out [plane][partial][column word]; then
+    // ONE thread per column word adds the partials bit-sliced (a full adder per plane: 32 accessions per instruction)
+    // and only the final sums are unpacked, one global atomic per non-zero accession.
     __syncthreads();
-    const int ncnt = (int)min(4096u, (N + 31) & ~31u);
-    for (int i = tid; i < ncnt; i += QG_WARPS * 32) cnt[i] = 0;
-    __syncthreads();
-    if (!ANDM && lane_on && T) {
-        const int depth = 32 - __clz(((T + 7) & ~7u));     // planes that can be non-zero
+    uint32_t* buf = (uint32_t*)dsm;
+    const uint32_t P = QG_WARPS * kpw;
+    const uint32_t Tmax = (per + kpw - 1) / kpw;                       // steps of warp 0, the longest
+    const int depth = min(QG_PLANES, 32 - __clz(((Tmax + 7) & ~7u)));  // planes that can be non-zero in any lane
+    if (lane_on) {
+        const uint32_t pi = warp * kpw + sub;
 #pragma unroll
-        for (int v = 0; v < 4; v++) {
-            const uint32_t cbase = (colv * 4 + v) * 32;
-            uint32_t nz = 0;                                 // accessions of this word with a non-zero count
-#pragma unroll
-            for (int p = 0; p < QG_PLANES; p++) nz |= pl[v][p];
-            if (__popc(nz) <= 12) {
-                // sparse (a gene hits a few dozen of a thousand isolates): one shared atomic per non-zero accession
-                while (nz) {
-                    const uint32_t b = __ffs(nz) - 1;
-                    nz &= nz - 1;
-                    uint32_t val = 0;
-#pragma unroll
-                    for (int p = 0; p < QG_PLANES; p++) {
-                        if (p >= depth) break;
-                        val |= ((pl[v][p] >> b) & 1u) << p;
-                    }
-                    atomicAdd(&cnt[cbase + b], val);
-                }
-                continue;
-            }
-#pragma unroll
-            for (int nb = 0; nb < 8; nb++) {
-                // dense: four accessions at a time, each plane's nibble spread into four byte lanes
-                uint32_t lo8 = 0, hi8 = 0;
-#pragma unroll
-                for (int p = 0; p < QG_PLANES; p++) {
-                    if (p >= depth) break;
-                    const uint32_t sp = (((pl[v][p] >> (4 * nb)) & 0xFu) * 0x00204081u) & 0x01010101u;
-                    if (p < 8) lo8 += sp << p; else hi8 += sp << (p - 8);
-                }
-                if (lo8 | hi8) {
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const uint32_t val = ((lo8 >> (8 * q)) & 0xFFu) | (((hi8 >> (8 * q)) & 0xFFu) << 8);
-                        if (val) atomicAdd(&cnt[cbase + 4 * nb + q], val);
-                    }
-                }
-            }
+        for (int p = 0; p < QG_PLANES; p++) {
+            if (p >= depth) break;
+            *(uint4*)(buf + ((size_t)(p * P + pi) * Wp + colv * 4)) = make_uint4(pl[0][p], pl[1][p], pl[2][p], pl[3][p]);
         }
     }
     __syncthreads();
-    for (int i = tid; i < ncnt; i += QG_WARPS * 32) {
-        const uint32_t val = cnt[i];
-        if (val && (uint32_t)i < N) atomicAdd(&counts[(uint64_t)g * N + i], val);
+    if ((uint32_t)tid < Wp) {
+        constexpr int SP = QG_PLANES + 2;                              // a unit holds <= 16384 k-mers: 15 planes
+        uint32_t acc[SP];
+#pragma unroll
+        for (int p = 0; p < SP; p++) acc[p] = 0;
+        for (uint32_t pi = 0; pi < P; pi++) {
+            uint32_t carry = 0;
+#pragma unroll
+            for (int p = 0; p < SP; p++) {
+                const uint32_t x = p < depth ? buf[(size_t)(p * P + pi) * Wp + tid] : 0u;
+                csa(carry, acc[p], acc[p], x, carry);
+            }
+        }
+        uint32_t nz = 0;
+#pragma unroll
+        for (int p = 0; p < SP; p++) nz |= acc[p];
+        uint32_t* out = counts + (uint64_t)g * N + (uint32_t)tid * 32;
+        while (nz) {
+            const uint32_t bb = __ffs(nz) - 1;
+            nz &= nz - 1;
+            uint32_t val = 0;
+#pragma unroll
+            for (int p = 0; p < SP; p++) val |= ((acc[p] >> bb) & 1u) << p;
+            if ((uint32_t)tid * 32 + bb < N) atomicAdd(out + bb, val);
+        }
     }
 }
 
