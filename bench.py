@@ -379,7 +379,7 @@ def run_search_extra(torch, dev, ctx, args, quick):
     # query bases H2D, query_front + streaming AND gather, AND rows + status D2H inside the timed region
     try:
         W = (A + 31) // 32
-        h_bases = d_bases.cpu().numpy()
+        h_bases = d_bases.cpu().pin_memory().numpy()          # page-locked, as cid_host_alloc would give a caller
         and_rows = np.zeros((nq, W), np.uint32)
         status = np.zeros(nq, np.uint8)
         nk = np.zeros(nq, np.uint64)
@@ -400,7 +400,7 @@ def run_search_extra(torch, dev, ctx, args, quick):
         iso_h = iso.cpu().numpy()
         bit = (and_rows[np.arange(nq), iso_h // 32] >> (iso_h % 32).astype(np.uint32)) & 1
         viol = int(((status[exact] != 0) | (bit[exact] != 1)).sum())
-        out["perfect_search"] = {"workload": "-s -m perfect search of the same %d queries (cid_query_perfect_mf, host buffers)" % nq,
+        out["perfect_search"] = {"workload": "-s -m perfect search of the same %d queries (cid_query_perfect_mf, pinned host buffers)" % nq,
                                  "lookups": int(nk.sum()), "ms_per_pass_wall": pms, "lookups_per_s": int(nk.sum()) / (pms / 1e3),
                                  "h2d_bytes": int(h_bases.nbytes + h_seq_offs.nbytes), "d2h_bytes": int(and_rows.nbytes + status.nbytes + nk.nbytes),
                                  "kernels": {k_: {"ms_per_launch": v[0] / v[1], "launches_per_pass": v[1] / reps} for k_, v in pprof.items()},

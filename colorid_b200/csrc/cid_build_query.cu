@@ -857,7 +857,7 @@ static int launch_query_gather(cid_ctx* ctx, cudaStream_t st, const cid_index* i
                                const uint32_t* d_unit_group, const uint64_t* d_unit_slot0, const uint32_t* d_unit_n,
                                uint64_t nunits, uint32_t* d_counts, uint32_t* d_and_rows = nullptr, uint32_t* d_missing = nullptr) {
     const size_t gsmem = QG_RING_BYTES + 4096 * 4;
-    static bool gattr = false;
+    bool& gattr = ctx->attr_done[0];     // function attributes are per device: remembered per context, not per process
     if (!gattr) {
         CID_CUDA(cudaFuncSetAttribute(query_gather_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
         CID_CUDA(cudaFuncSetAttribute(query_gather_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
@@ -1000,7 +1000,7 @@ int launch_query_front_gather(cid_ctx* ctx, cudaStream_t st, const cid_index* id
     uint32_t* d_qlist = d_group + bq;
     CID_CUDA(cudaMemcpyAsync(d_base, base.data(), bq * 8, cudaMemcpyHostToDevice, st));
     CID_CUDA(cudaMemcpyAsync(d_group, group.data(), bq * 4, cudaMemcpyHostToDevice, st));
-    static bool attr = false;
+    bool& attr = ctx->attr_done[1];
     if (!attr) {
         CID_CUDA(cudaFuncSetAttribute(query_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(16384 * 8 + tile_smem_bytes(KT_CAP))));
@@ -1048,7 +1048,7 @@ int launch_query_counts(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, con
         return launch_query_gather(ctx, st, idx, d_rid, d_unit_group, d_unit_slot0, d_unit_n, nunits, d_counts);
     }
     size_t smem = unit_smem_bytes(idx->H);
-    static bool attr_set = false;
+    bool& attr_set = ctx->attr_done[2];
     if (!attr_set) {
 #define CID_QC_ATTR(VEC, UQ, HT) CID_CUDA(cudaFuncSetAttribute(query_counts_kernel<VEC, UQ, HT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024))
 #define CID_QC_ATTR3(VEC, UQ) CID_QC_ATTR(VEC, UQ, 0); CID_QC_ATTR(VEC, UQ, 2); CID_QC_ATTR(VEC, UQ, 4)
@@ -1141,7 +1141,7 @@ int launch_query_perfect(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, co
     if (nunits == 0) return CID_OK;
     if (idx->W > 512) { set_error("perfect search: more than 16384 accessions per shard not supported"); return CID_E_UNSUPPORTED; }
     size_t smem = unit_smem_bytes(idx->H);
-    static bool attr_set = false;
+    bool& attr_set = ctx->attr_done[3];
     if (!attr_set) {
         CID_CUDA(cudaFuncSetAttribute(query_perfect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         attr_set = true;

@@ -54,6 +54,7 @@ struct cid_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;   // library-owned stream for the host-pointer entry points
     uint64_t launches = 0;
+    bool attr_done[8] = {false};     // cudaFuncSetAttribute (dynamic smem opt-in) already applied on this context's device
     cid::DevBuf scratch[cid::SCRATCH_SLOTS];
     cid::PinBuf pinned[8];
     uint32_t* d_err = nullptr;       // device error/flag words (zeroed before each call)
