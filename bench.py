@@ -372,8 +372,8 @@ def run_search_extra(torch, dev, ctx, args, quick):
         qc_ms = prof["query_counts"][0] / reps            # all query_counts launches of one pass
         alg = lookups * (cfg["H"] * R + 1) + nq * 4 * A    # H*R + k_in per lookup, + 4N counts per query
         out["roofline"] = {"bound": "hbm", "kernel": "query_counts (query_gather_kernel)", "achieved": alg / (qc_ms / 1e3) / 1e9, "peak": peak,
-                           "unit": "GB/s", "frac": alg / (qc_ms / 1e3) / 1e9 / peak, "traffic": None,
-                           "traffic_captured_launch": ncu_traffic().get("query_counts"),
+                           "unit": "GB/s", "frac": alg / (qc_ms / 1e3) / 1e9 / peak,
+                           "traffic": ncu_traffic().get("query_counts"),      # the pass is one query_gather launch
                            "peak_source": peak_src, "algorithmic_bytes_per_pass": alg, "ms_per_pass": qc_ms}
     # ---- -s -m perfect search of the same queries (perfect_search.rs:62-120) through the host-pointer ABI:
     # query bases H2D, query_front + streaming AND gather, AND rows + status D2H inside the timed region
