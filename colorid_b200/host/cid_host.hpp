@@ -124,7 +124,8 @@ struct ReadIdOpts { std::string bigsi, prefix; std::vector<std::string> query; u
                     bitvector_sample = 3; double correct = 3.0; uint8_t quality = 15; bool high_mem_load = false; int device = 0; };
 int read_id(const ReadIdOpts& o);                           // main.rs:704-866
 struct BatchIdOpts { std::string bigsi, batch_samples, tag; uint64_t threads = 0, down_sample = 1, batch = 50000, bitvector_sample = 3;
-                     double correct = 3.0; uint8_t quality = 15; bool high_mem_load = false; int device = 0; };
+                     double correct = 3.0; uint8_t quality = 15; bool high_mem_load = false; int device = 0;
+                     std::vector<int> devices; };          // COLORID_B200_DEVICES=0,1,..: samples dealt to one worker per GPU
 int batch_id(const BatchIdOpts& o);                         // main.rs:869-887 + read_id_batch.rs:7-181
 int info(const std::string& bigsi);                         // main.rs:630-703
 // read_filter.rs:10-191 + main.rs:888-900: keep (or with `exclude` drop) the reads whose PREFIX_reads.txt classification

@@ -3,6 +3,8 @@
 // report formatting stay on the host exactly as north_star prescribes; k-mer extraction, Bloom
 // insert, transposition, row gathers and the read vote run on the GPU.  No CPU fallback.
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
@@ -538,20 +540,41 @@ int read_id(const ReadIdOpts& o) {
 int batch_id(const BatchIdOpts& o) {
     Timer tload;
     Trace tr;
-    Gpu g(o.device);
+    const std::vector<int> devices = o.devices.empty() ? std::vector<int>{o.device} : o.devices;
     const auto batch_map = tab_to_map(o.batch_samples);
     const Bigsi b = read_index(o.bigsi);
     fprintf(stderr, "Index loaded in %llu seconds\n", tload.secs());
-    g.upload(b);
-    tr.mark("index load + upload");
-    for (auto& kv : batch_map) {
-        fprintf(stderr, "Classifying %s\n", kv.first.c_str());
-        ReadIdOpts s;
-        s.bigsi = o.bigsi; s.prefix = kv.first + "_" + o.tag; s.query = kv.second;
-        s.threads = o.threads; s.down_sample = o.down_sample; s.batch = o.batch; s.bitvector_sample = o.bitvector_sample;
-        s.correct = o.correct; s.quality = o.quality; s.high_mem_load = o.high_mem_load; s.device = o.device;
-        read_id_sample(g, b, s, tr);
+    // samples are independent units (replicated index): one worker per GPU, each with its own replica of
+    // the matrix, pulls the next sample; with one device this is the reference's sequential loop
+    std::vector<std::pair<std::string, std::vector<std::string>>> samples(batch_map.begin(), batch_map.end());
+    std::atomic<size_t> next{0};
+    std::mutex log_mu;
+    std::vector<std::exception_ptr> errs(devices.size());
+    auto worker = [&](size_t w) {
+        try {
+            Gpu g(devices[w]);
+            g.upload(b);
+            Trace wtr;
+            for (;;) {
+                const size_t i = next.fetch_add(1);
+                if (i >= samples.size()) break;
+                { std::lock_guard<std::mutex> lk(log_mu); fprintf(stderr, "Classifying %s\n", samples[i].first.c_str()); }
+                ReadIdOpts s;
+                s.bigsi = o.bigsi; s.prefix = samples[i].first + "_" + o.tag; s.query = samples[i].second;
+                s.threads = o.threads; s.down_sample = o.down_sample; s.batch = o.batch; s.bitvector_sample = o.bitvector_sample;
+                s.correct = o.correct; s.quality = o.quality; s.high_mem_load = o.high_mem_load; s.device = devices[w];
+                read_id_sample(g, b, s, wtr);
+            }
+        } catch (...) { errs[w] = std::current_exception(); }
+    };
+    if (devices.size() == 1) worker(0);
+    else {
+        std::vector<std::thread> th;
+        for (size_t w = 0; w < devices.size(); w++) th.emplace_back(worker, w);
+        for (auto& t : th) t.join();
     }
+    for (auto& e : errs) if (e) std::rethrow_exception(e);
+    tr.mark("batch_id");
     return 0;
 }
 

@@ -158,6 +158,8 @@ int main(int argc, char** argv) {
             o.correct = num<double>(p, "fp_correct", 3.0); o.quality = num<uint8_t>(p, "quality", 15);
             o.batch = num<uint64_t>(p, "batch", 50000); o.high_mem_load = p.has("high_mem_load");
             o.bitvector_sample = num<uint64_t>(p, "bitvector_sample", 3); o.device = device;
+            if (const char* ds = getenv("COLORID_B200_DEVICES"))          // e.g. "0,1,2,3": one worker (and index replica) per GPU
+                for (const char* q = ds; *q;) { char* e; long v = strtol(q, &e, 10); if (e == q) break; o.devices.push_back((int)v); q = *e ? e + 1 : e; }
             return cidh::batch_id(o);
         }
         if (sub == "read_filter") {                                // main.rs:418-465,888-900

@@ -302,3 +302,13 @@ def test_batch_id_classifies_every_sample_with_one_index_load(world, oracle):
     for si, (exp_lines, exp_counts) in expect.items():
         assert (d / f"sample{si}_run7_reads.txt").read_text().split("\n")[:-1] == exp_lines
         assert (d / f"sample{si}_run7_counts.txt").read_text().split("\n")[:-1] == exp_counts
+    # samples dealt to one worker per GPU (replicated index): same files whatever the number of devices
+    import torch
+    ndev = torch.cuda.device_count()
+    devs = ",".join(str(i % ndev) for i in range(2))          # two workers (on one GPU if the box has a single one)
+    r = subprocess.run([CLI, "batch_id", "-b", str(d / "idx.bxi"), "-q", str(d / "samples.tsv"), "-T", "multi", "-d", "2"],
+                       capture_output=True, text=True, env=dict(os.environ, COLORID_B200_DEVICES=devs))
+    assert r.returncode == 0, r.stderr[-2000:]
+    for si, (exp_lines, exp_counts) in expect.items():
+        assert (d / f"sample{si}_multi_reads.txt").read_text().split("\n")[:-1] == exp_lines
+        assert (d / f"sample{si}_multi_counts.txt").read_text().split("\n")[:-1] == exp_counts
