@@ -280,6 +280,7 @@ int cid_ctx_set_option(cid_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "readid_streams")) { c->opt_readid_streams = value >= 2 ? 2 : 1; return CID_OK; }
     if (!strcmp(name, "readid_kmerize_ctas")) { c->opt_kmerize_ctas = value > 0 ? (int)value : 0; return CID_OK; }
     if (!strcmp(name, "readid_vote_ctas")) { c->opt_vote_ctas = value > 0 ? (int)value : 0; return CID_OK; }
+    if (!strcmp(name, "build_set")) { c->opt_build_set = value != 0; return CID_OK; }
     if (!strcmp(name, "query_front")) { c->opt_query_front = value != 0; return CID_OK; }
     if (!strcmp(name, "query_fused")) { c->opt_query_fused = value != 0; return CID_OK; }
     if (!strcmp(name, "host_threads")) { c->opt_host_threads = value > 0 ? (int)value : 0; return CID_OK; }
@@ -459,6 +460,36 @@ static int build_accession_impl(cid_index* ix, uint32_t colour, const char* d_ba
     if (cutoff < -1) { set_error("cutoff must be >= -1"); return CID_E_INVALID; }
     CID_CUDA(cudaSetDevice(ctx->device));
     CID_TRY(ensure_bitsets(ix));
+    uint32_t* bitset = ix->bitsets + (uint64_t)colour * ix->bs_words;
+    // No count filter (FASTA without -f: build.rs:86-87; or -f 0): only the SET of k-mers matters.  A key-only table
+    // (8-byte slots, L2-resident for a bacterial genome) replaces the count table and new keys go straight into the bitset.
+    if (ctx->opt_build_set && (cutoff == 0 || (cutoff == -1 && seq_mode == CID_SEQ_FASTA))) {
+        const uint64_t npos0 = nbases >= ix->k ? nbases - ix->k + 1 : 0;
+        uint64_t slots = next_pow2(std::max<uint64_t>(1024, npos0 + npos0 / 2));
+        // read sets repeat every k-mer ~coverage times: start small, grow on overflow
+        if (seq_mode == CID_SEQ_FASTQ && nseq >= 4096) slots = next_pow2(std::max<uint64_t>(1024, npos0 / 4));
+        for (;;) {
+            CID_TRY(ctx->scratch[0].ensure(slots * 8));
+            CID_CUDA(cudaMemsetAsync(ctx->scratch[0].p, 0xFF, slots * 8, st));
+            CID_CUDA(cudaMemsetAsync(bitset, 0, ix->bs_words * 4, st));
+            CID_CUDA(cudaMemsetAsync(ctx->d_err + 1, 0, 4, st));
+            CID_TRY(launch_kmerize_bloom(ctx, st, (const uint8_t*)d_bases, d_seq_offs, nseq, nbases, ctx->scratch[0].p, slots, ix->k,
+                                         seq_mode, count_m, bloom_m, ix->H, ix->S, bitset));
+            CID_CUDA(cudaMemcpyAsync(ctx->h_err, ctx->d_err, 8, cudaMemcpyDeviceToHost, st));
+            CID_CUDA(cudaStreamSynchronize(st));
+            const uint32_t flags = ctx->h_err[0], distinct = ctx->h_err[1];
+            if ((flags & ERRF_TABLE_FULL) || (uint64_t)distinct * 10 > slots * 7) {       // too full to trust the probe limit: redo larger
+                if (slots >= next_pow2(std::max<uint64_t>(1024, 2 * npos0))) { set_error("k-mer set overflow"); return CID_E_CAPACITY; }
+                CID_CUDA(cudaMemsetAsync(ctx->d_err, 0, 8, st));
+                slots *= 2;
+                continue;
+            }
+            CID_TRY(check_err_flags(ctx, st));
+            if (n_ref_kmers) *n_ref_kmers = distinct;
+            if (cutoff_used) *cutoff_used = cutoff;
+            return CID_OK;
+        }
+    }
     uint64_t nslots; uint64_t *d_off, *d_mask;
     // Read sets (many short sequences, deep coverage) hold far fewer DISTINCT k-mers than k-mer positions, and the
     // table is scanned three times after counting (clear, histogram, Bloom insert): size it optimistically for
@@ -485,7 +516,6 @@ static int build_accession_impl(cid_index* ix, uint32_t colour, const char* d_ba
     int64_t used = cutoff;       // FASTA with -1: keep everything (count > -1)
     if (seq_mode == CID_SEQ_FASTQ && cutoff == -1)
         CID_TRY(region_auto_cutoff(ctx, st, ctx->scratch[0].as<Slot>(), nslots, &used));
-    uint32_t* bitset = ix->bitsets + (uint64_t)colour * ix->bs_words;
     CID_CUDA(cudaMemsetAsync(bitset, 0, ix->bs_words * 4, st));
     CID_TRY(ctx->scratch[2].ensure(16));
     unsigned long long* d_nref = ctx->scratch[2].as<unsigned long long>();

@@ -24,13 +24,23 @@ constexpr int KT_CAP = KT + 64;       // bytes staged per tile (halo <= 31, roun
 constexpr int KT_THREADS = 256;
 constexpr int KT_MAXSTARTS = KT_CAP + 8;
 
-template <bool MINI>      // MINI: count each k-mer's minimizer of length mini_m instead of the k-mer (build_multi_mini)
+// SETONLY (builds that keep every k-mer: FASTA without -f, or -f 0): a key-only set instead of the count table, and the
+// thread that inserts a NEW key hashes it into the accession's Bloom bitset at once (simple_bloom.rs:19-26) -- no count
+// table scan, no region_to_bloom launch; err[1] is then n_ref_kmers.
+struct SetSink {
+    unsigned long long* keys; uint64_t mask;     // one set for the whole launch
+    uint32_t* bitset; uint32_t H; ModS mods;
+    uint32_t bloom_m;                            // != 0: insert find_minimizer(k-mer, bloom_m) (build_single_mini)
+};
+template <bool MINI, bool SETONLY>   // MINI: the item is each k-mer's minimizer of length mini_m (build_multi_mini)
 __global__ void __launch_bounds__(KT_THREADS)
 kmerize_insert_kernel(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ seq_offs, uint64_t nseq,
                       uint64_t base_lo, uint64_t nbases, const uint32_t* __restrict__ seq_group, const uint64_t* __restrict__ region_off,
                       const uint64_t* __restrict__ region_mask, Slot* __restrict__ table, uint32_t k, uint32_t mini_m,
-                      int seq_mode, uint32_t* __restrict__ err) {
+                      int seq_mode, uint32_t* __restrict__ err, SetSink sink) {
     __shared__ __align__(16) uint8_t smem[tile_smem_bytes(KT_CAP)];
+    __shared__ uint32_t lut[SETONLY ? 256 : 1];
+    if (SETONLY) lut4_init(lut, threadIdx.x, KT_THREADS);      // made visible by the barriers below
     __shared__ uint32_t s_starts[KT_MAXSTARTS];
     __shared__ uint64_t s_s0;
     __shared__ uint32_t s_nstarts, s_fresh;
@@ -103,11 +113,26 @@ kmerize_insert_kernel(const uint8_t* __restrict__ bases, const uint64_t* __restr
             key = tile_minimizer(t, p, k, mini_m, key, fwd, low, mpos, mfwd);
         }
         // owner sequence = s0 + #starts <= p
-        uint32_t lo = 0, hi = nstarts;
+        uint32_t lo = 0, hi = SETONLY ? 0u : nstarts;
         while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (s_starts[mid] <= (uint32_t)p) lo = mid + 1; else hi = mid; }
-        uint64_t owner = s0 + lo;
-        uint32_t g = seq_group ? __ldg(seq_group + owner) : 0u;
-        const int rc = table_insert(table + __ldg(region_off + g), __ldg(region_mask + g), key);
+        int rc;
+        if (SETONLY) {
+            rc = set_insert(sink.keys, sink.mask, key);
+            if (rc > 0) {
+                uint64_t item = key;
+                uint32_t len = MINI ? mini_m : k;
+                if (sink.bloom_m) { uint32_t which; item = minimizer_packed(key, revcomp_key(key, k), k, sink.bloom_m, which); len = sink.bloom_m; }
+                const HashIn in = hashin_from_key(lut, item, len);
+                for (uint32_t h = 0; h < sink.H; h++) {
+                    const uint64_t bit = mod_s(xxh3_kmer(in, len, h), sink.mods);
+                    atomicOr(&sink.bitset[bit >> 5], 1u << (bit & 31));
+                }
+            }
+        } else {
+            uint64_t owner = s0 + lo;
+            uint32_t g = seq_group ? __ldg(seq_group + owner) : 0u;
+            rc = table_insert(table + __ldg(region_off + g), __ldg(region_mask + g), key);
+        }
         if (rc < 0) atomicOr(err, ERRF_TABLE_FULL);
         fresh += rc > 0;
     }
@@ -125,14 +150,35 @@ int launch_kmerize_insert(cid_ctx* ctx, cudaStream_t st, const uint8_t* d_bases,
     if (base_hi <= base_lo || nseq == 0) return CID_OK;
     uint64_t ntiles = (base_hi - base_lo + KT - 1) / KT;
     ProfScope ps(ctx, st, KID_KMERIZE_INSERT);
+    SetSink none{};
     if (mini_m)
-        kmerize_insert_kernel<true><<<(unsigned)ntiles, KT_THREADS, 0, st>>>(d_bases, d_seq_offs, nseq, base_lo, base_hi, d_seq_group,
-                                                                            d_region_off, d_region_mask, (Slot*)d_table, k, mini_m,
-                                                                            seq_mode, ctx->d_err);
+        kmerize_insert_kernel<true, false><<<(unsigned)ntiles, KT_THREADS, 0, st>>>(d_bases, d_seq_offs, nseq, base_lo, base_hi, d_seq_group,
+                                                                                   d_region_off, d_region_mask, (Slot*)d_table, k, mini_m,
+                                                                                   seq_mode, ctx->d_err, none);
     else
-        kmerize_insert_kernel<false><<<(unsigned)ntiles, KT_THREADS, 0, st>>>(d_bases, d_seq_offs, nseq, base_lo, base_hi, d_seq_group,
-                                                                             d_region_off, d_region_mask, (Slot*)d_table, k, 0,
-                                                                             seq_mode, ctx->d_err);
+        kmerize_insert_kernel<false, false><<<(unsigned)ntiles, KT_THREADS, 0, st>>>(d_bases, d_seq_offs, nseq, base_lo, base_hi, d_seq_group,
+                                                                                    d_region_off, d_region_mask, (Slot*)d_table, k, 0,
+                                                                                    seq_mode, ctx->d_err, none);
+    ctx->launches++;
+    CID_CUDA(cudaGetLastError());
+    return CID_OK;
+}
+
+// Set-only build of one accession: every new canonical k-mer (or minimizer) goes straight into `d_bitset`.
+// count_m != 0: the set holds minimizers (build_multi_mini); bloom_m != 0: the set holds k-mers, their minimizers are inserted.
+int launch_kmerize_bloom(cid_ctx* ctx, cudaStream_t st, const uint8_t* d_bases, const uint64_t* d_seq_offs, uint64_t nseq,
+                         uint64_t nbases, void* d_keys, uint64_t nslots, uint32_t k, int seq_mode, uint32_t count_m, uint32_t bloom_m,
+                         uint32_t H, uint64_t S, uint32_t* d_bitset) {
+    if (nbases == 0 || nseq == 0) return CID_OK;
+    const uint64_t ntiles = (nbases + KT - 1) / KT;
+    SetSink sink{(unsigned long long*)d_keys, nslots - 1, d_bitset, H, make_mods(S), bloom_m};
+    ProfScope ps(ctx, st, KID_KMERIZE_INSERT);
+    if (count_m)
+        kmerize_insert_kernel<true, true><<<(unsigned)ntiles, KT_THREADS, 0, st>>>(d_bases, d_seq_offs, nseq, 0, nbases, nullptr, nullptr, nullptr,
+                                                                                  nullptr, k, count_m, seq_mode, ctx->d_err, sink);
+    else
+        kmerize_insert_kernel<false, true><<<(unsigned)ntiles, KT_THREADS, 0, st>>>(d_bases, d_seq_offs, nseq, 0, nbases, nullptr, nullptr, nullptr,
+                                                                                   nullptr, k, 0, seq_mode, ctx->d_err, sink);
     ctx->launches++;
     CID_CUDA(cudaGetLastError());
     return CID_OK;

@@ -372,4 +372,17 @@ __device__ __forceinline__ int table_insert(Slot* region, uint64_t mask, uint64_
     return -1;
 }
 
+// Key-only variant (8-byte slots) for builds that keep every k-mer (no count filter): the table of a 5-Mbp genome
+// then fits the L2 cache.  Same return values.
+__device__ __forceinline__ int set_insert(unsigned long long* keys, uint64_t mask, uint64_t key) {
+    uint64_t h = mix64(key) & mask;
+    for (int probes = 0; probes < CID_MAX_PROBE; probes++) {
+        const unsigned long long prev = atomicCAS(&keys[h], CID_EMPTY_KEY, (unsigned long long)key);
+        if (prev == CID_EMPTY_KEY) return 1;
+        if (prev == key) return 0;
+        h = (h + 1) & mask;
+    }
+    return -1;
+}
+
 }  // namespace cid

@@ -76,6 +76,7 @@ struct cid_ctx {
     int opt_readid_streams = 1;
     int opt_kmerize_ctas = 0, opt_vote_ctas = 0;   // CTAs per SM of the read_id kmerize / vote grids (0 = fill the GPU);
                                                    // smaller grids let the two kernels of different chunks share the SMs
+    int opt_build_set = 1;           // 0 = always build through the count table (parity aid)
     int opt_query_front = 1;         // 0 = never use the shared-memory dedup front end of small queries (parity aid)
     int opt_query_fused = 0;         // 1 = force the fused collect/hash/gather kernel (parity aid)
     cudaStream_t aux[2] = {nullptr, nullptr};
@@ -143,6 +144,10 @@ int launch_kmerize_insert(cid_ctx* ctx, cudaStream_t st, const uint8_t* d_bases,
                           uint64_t nseq, uint64_t base_lo, uint64_t base_hi, const uint32_t* d_seq_group,
                           const uint64_t* d_region_off, const uint64_t* d_region_mask, void* d_table, uint32_t k,
                           int seq_mode, uint32_t mini_m = 0);   // mini_m != 0: count each k-mer's minimizer instead
+// set-only build (no count filter): new keys are hashed straight into the accession's Bloom bitset; distinct keys in d_err[1]
+int launch_kmerize_bloom(cid_ctx* ctx, cudaStream_t st, const uint8_t* d_bases, const uint64_t* d_seq_offs, uint64_t nseq,
+                         uint64_t nbases, void* d_keys, uint64_t nslots, uint32_t k, int seq_mode, uint32_t count_m, uint32_t bloom_m,
+                         uint32_t H, uint64_t S, uint32_t* d_bitset);
 int launch_region_histogram(cid_ctx* ctx, cudaStream_t st, const void* d_region, uint64_t nslots, uint32_t* d_hist,
                             uint32_t hist_bins, uint32_t* d_overflow, uint32_t overflow_cap, uint32_t* d_overflow_n);
 // k = length of the table's keys; mini_m != 0: insert find_minimizer(key, mini_m) instead of the key itself

@@ -50,8 +50,14 @@ def test_build_fasta_matrix_bit_exact(oracle, ctx, k, S, H, N):
         if i % 11 == 0:
             contigs[2] = synth.sprinkle(rng, contigs[2], b"acgt", 0.3)    # mixed case
         accs.append(contigs)
-    oix, gix = build_both(oracle, ctx, accs, S, H, k, cb.CID_SEQ_FASTA)
+    oix, gix = build_both(oracle, ctx, accs, S, H, k, cb.CID_SEQ_FASTA)      # no filter: key-only set + fused Bloom insert
     assert np.array_equal(gix.download_dense(), oix.words())
+    ctx.set_option("build_set", 0)                                           # the count-table path gives the same bits
+    try:
+        _, gix2 = build_both(oracle, ctx, accs, S, H, k, cb.CID_SEQ_FASTA)
+    finally:
+        ctx.set_option("build_set", 1)
+    assert np.array_equal(gix2.download_dense(), oix.words())
     assert gix.nonzero_rows() == oix.nonzero_rows()
     ids, words = gix.download_nonzero_rows()
     dense = oix.words()
