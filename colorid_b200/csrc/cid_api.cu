@@ -280,6 +280,7 @@ int cid_ctx_set_option(cid_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "readid_streams")) { c->opt_readid_streams = value >= 2 ? 2 : 1; return CID_OK; }
     if (!strcmp(name, "readid_kmerize_ctas")) { c->opt_kmerize_ctas = value > 0 ? (int)value : 0; return CID_OK; }
     if (!strcmp(name, "readid_vote_ctas")) { c->opt_vote_ctas = value > 0 ? (int)value : 0; return CID_OK; }
+    if (!strcmp(name, "readid_serialize")) { c->opt_readid_serialize = value != 0; return CID_OK; }
     if (!strcmp(name, "build_set")) { c->opt_build_set = value != 0; return CID_OK; }
     if (!strcmp(name, "query_front")) { c->opt_query_front = value != 0; return CID_OK; }
     if (!strcmp(name, "query_fused")) { c->opt_query_fused = value != 0; return CID_OK; }
