@@ -632,6 +632,9 @@ def run_c4(args):
     Lg, rl = cfg["genome_len"], cfg["read_len"]
     n_reads = Lg * cfg["coverage"] // rl
     ctx = cb.Context(local)
+    for kv in args.opt:
+        name, _, val = kv.partition("=")
+        ctx.set_option(name, int(val))
     gix = cb.Index(ctx, cfg["S"], cfg["H"], cfg["k"], n_acc)
     lut = torch.tensor(ASCII, device=dev, dtype=torch.uint8)
     g = torch.Generator(device=dev)

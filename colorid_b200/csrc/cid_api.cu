@@ -281,6 +281,7 @@ int cid_ctx_set_option(cid_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "readid_kmerize_ctas")) { c->opt_kmerize_ctas = value > 0 ? (int)value : 0; return CID_OK; }
     if (!strcmp(name, "readid_vote_ctas")) { c->opt_vote_ctas = value > 0 ? (int)value : 0; return CID_OK; }
     if (!strcmp(name, "readid_serialize")) { c->opt_readid_serialize = value != 0; return CID_OK; }
+    if (!strcmp(name, "build_table_div")) { c->opt_build_table_div = value >= 1 ? (int)value : 0; return CID_OK; }
     if (!strcmp(name, "build_set")) { c->opt_build_set = value != 0; return CID_OK; }
     if (!strcmp(name, "query_front")) { c->opt_query_front = value != 0; return CID_OK; }
     if (!strcmp(name, "query_fused")) { c->opt_query_fused = value != 0; return CID_OK; }
@@ -493,11 +494,18 @@ static int build_accession_impl(cid_index* ix, uint32_t colour, const char* d_ba
     }
     uint64_t nslots; uint64_t *d_off, *d_mask;
     // Read sets (many short sequences, deep coverage) hold far fewer DISTINCT k-mers than k-mer positions, and the
-    // table is scanned three times after counting (clear, histogram, Bloom insert): size it optimistically for
-    // positions/2 and fall back to the safe 2x-positions table if it ends up more than 60 % full.
+    // table is scanned three times after counting (clear, histogram, Bloom insert) while its inserts are random DRAM
+    // accesses whose L2 hit rate falls with the table size (36 % at 1 GB): size it optimistically -- for the
+    // distinct/positions ratio the previous read set of this context had (accessions of one build are sequenced alike;
+    // positions/4 for the first one), aiming at 2/3 load -- and double it when it ends up fuller than 80 %.
     const uint64_t npos = nbases >= ix->k ? nbases - ix->k + 1 : 0;
     uint64_t hint = 0;
-    if (seq_mode == CID_SEQ_FASTQ && nseq >= 4096 && npos >= (1ull << 22)) hint = next_pow2(npos / 2);
+    if (seq_mode == CID_SEQ_FASTQ && nseq >= 4096 && npos >= (1ull << 22)) {
+        if (ctx->opt_build_table_div > 0) hint = next_pow2(npos / (uint64_t)ctx->opt_build_table_div);
+        else if (ctx->readset_ratio > 0) hint = next_pow2((uint64_t)(ctx->readset_ratio * (double)npos / 0.68) + 1);
+        else hint = next_pow2(npos / 4);
+        if (hint >= next_pow2(std::max<uint64_t>(64, 2 * npos))) hint = 0;
+    }
     for (;;) {
         CID_TRY(single_region(ctx, st, nbases, ix->k, &nslots, &d_off, &d_mask, hint));
         CID_CUDA(cudaMemsetAsync(ctx->d_err + 1, 0, 4, st));
@@ -506,14 +514,15 @@ static int build_accession_impl(cid_index* ix, uint32_t colour, const char* d_ba
         CID_CUDA(cudaMemcpyAsync(ctx->h_err, ctx->d_err, 8, cudaMemcpyDeviceToHost, st));
         CID_CUDA(cudaStreamSynchronize(st));
         const uint32_t flags = ctx->h_err[0], distinct = ctx->h_err[1];
-        if (hint && ((flags & ERRF_TABLE_FULL) || (uint64_t)distinct * 10 > nslots * 6)) {
+        if (hint && ((flags & ERRF_TABLE_FULL) || (uint64_t)distinct * 10 > nslots * 8)) {        // fuller than 80 %: redo larger
             CID_CUDA(cudaMemsetAsync(ctx->d_err, 0, 8, st));
-            hint = 0;                       // redo with the safe size
+            hint = hint * 2 >= next_pow2(std::max<uint64_t>(64, 2 * npos)) ? 0 : hint * 2;     // 0 = the safe 2x-positions size
             continue;
         }
         break;
     }
     CID_TRY(check_err_flags(ctx, st));
+    if (seq_mode == CID_SEQ_FASTQ && npos) ctx->readset_ratio = (double)ctx->h_err[1] / (double)npos;
     int64_t used = cutoff;       // FASTA with -1: keep everything (count > -1)
     if (seq_mode == CID_SEQ_FASTQ && cutoff == -1)
         CID_TRY(region_auto_cutoff(ctx, st, ctx->scratch[0].as<Slot>(), nslots, &used));

@@ -77,6 +77,8 @@ struct cid_ctx {
     int opt_kmerize_ctas = 0, opt_vote_ctas = 0;   // CTAs per SM of the read_id kmerize / vote grids (0 = fill the GPU);
                                                    // smaller grids let the two kernels of different chunks share the SMs
     int opt_readid_serialize = 0;    // 1 = kernels of consecutive pipeline chunks never overlap (measured: 44.8M vs 46.3M pairs/s e2e, off)
+    int opt_build_table_div = 0;     // read-set builds: first count table = k-mer positions / this (0 = adaptive; grown x4 when > 70 % full)
+    double readset_ratio = 0;        // distinct k-mers / k-mer positions of the last read-set accession built on this context
     int opt_build_set = 1;           // 0 = always build through the count table (parity aid)
     int opt_query_front = 1;         // 0 = never use the shared-memory dedup front end of small queries (parity aid)
     int opt_query_fused = 0;         // 1 = force the fused collect/hash/gather kernel (parity aid)
