@@ -136,14 +136,15 @@ static int table_clear(cid_ctx* ctx, cudaStream_t st, void* d_table, uint64_t ns
 enum { HIST_BINS = 65536, HIST_OVERFLOW_CAP = 1 << 20 };
 
 // Histogram of one region -> auto_cutoff (host arithmetic on a few KB).
-static int region_auto_cutoff(cid_ctx* ctx, cudaStream_t st, const Slot* d_region, uint64_t nslots, int64_t* cutoff) {
+static int region_auto_cutoff(cid_ctx* ctx, cudaStream_t st, const void* d_region, uint64_t nslots, int64_t* cutoff,
+                              bool packed = false) {
     CID_TRY(ctx->scratch[8].ensure((size_t)HIST_BINS * 4 + 16));
     CID_TRY(ctx->scratch[9].ensure((size_t)HIST_OVERFLOW_CAP * 4));
     uint32_t* d_hist = ctx->scratch[8].as<uint32_t>();
     uint32_t* d_ovn = d_hist + HIST_BINS;
     CID_CUDA(cudaMemsetAsync(d_hist, 0, (size_t)HIST_BINS * 4 + 16, st));
     CID_TRY(launch_region_histogram(ctx, st, d_region, nslots, d_hist, HIST_BINS, ctx->scratch[9].as<uint32_t>(),
-                                    HIST_OVERFLOW_CAP, d_ovn));
+                                    HIST_OVERFLOW_CAP, d_ovn, packed));
     std::vector<uint32_t> hh(HIST_BINS + 4);
     CID_CUDA(cudaMemcpyAsync(hh.data(), d_hist, (size_t)HIST_BINS * 4 + 16, cudaMemcpyDeviceToHost, st));
     CID_CUDA(cudaStreamSynchronize(st));
@@ -175,14 +176,17 @@ static int ensure_bitsets(cid_index* idx) {
 
 // One group worth of count table on scratch[0]; off/mask on scratch[1].
 static int single_region(cid_ctx* ctx, cudaStream_t st, uint64_t nbases, uint32_t k, uint64_t* nslots_out,
-                         uint64_t** d_off, uint64_t** d_mask, uint64_t slots_hint = 0) {
+                         uint64_t** d_off, uint64_t** d_mask, uint64_t slots_hint = 0, bool packed = false) {
     uint64_t npos = nbases >= k ? nbases - k + 1 : 0;
     uint64_t slots = slots_hint ? slots_hint : next_pow2(std::max<uint64_t>(64, 2 * npos));
-    CID_TRY(ctx->scratch[0].ensure(slots * sizeof(Slot)));
+    CID_TRY(ctx->scratch[0].ensure(slots * (packed ? 8 : sizeof(Slot))));
     CID_TRY(ctx->scratch[1].ensure(64));
     uint64_t hv[2] = {0, slots - 1};
     CID_CUDA(cudaMemcpyAsync(ctx->scratch[1].p, hv, 16, cudaMemcpyHostToDevice, st));
-    CID_TRY(table_clear(ctx, st, ctx->scratch[0].p, slots));
+    if (packed) {
+        ProfScope ps(ctx, st, KID_TABLE_CLEAR);
+        CID_CUDA(cudaMemsetAsync(ctx->scratch[0].p, 0xFF, slots * 8, st));
+    } else CID_TRY(table_clear(ctx, st, ctx->scratch[0].p, slots));
     *nslots_out = slots;
     *d_off = ctx->scratch[1].as<uint64_t>();
     *d_mask = ctx->scratch[1].as<uint64_t>() + 1;
@@ -282,6 +286,7 @@ int cid_ctx_set_option(cid_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "readid_vote_ctas")) { c->opt_vote_ctas = value > 0 ? (int)value : 0; return CID_OK; }
     if (!strcmp(name, "readid_serialize")) { c->opt_readid_serialize = value != 0; return CID_OK; }
     if (!strcmp(name, "build_table_div")) { c->opt_build_table_div = value >= 1 ? (int)value : 0; return CID_OK; }
+    if (!strcmp(name, "build_packed")) { c->opt_build_packed = value != 0; return CID_OK; }
     if (!strcmp(name, "build_set")) { c->opt_build_set = value != 0; return CID_OK; }
     if (!strcmp(name, "query_front")) { c->opt_query_front = value != 0; return CID_OK; }
     if (!strcmp(name, "query_fused")) { c->opt_query_fused = value != 0; return CID_OK; }
@@ -506,14 +511,22 @@ static int build_accession_impl(cid_index* ix, uint32_t colour, const char* d_ba
         else hint = next_pow2(npos / 4);
         if (hint >= next_pow2(std::max<uint64_t>(64, 2 * npos))) hint = 0;
     }
+    // keys of <= 21 bases (k, or the minimizer length of build_multi_mini) leave room for the count in the same 8-byte
+    // word: half the table, one atomic per insert.  A multiplicity near 2^22 sends the accession back to 16-byte slots.
+    bool packed = ctx->opt_build_packed && (count_m ? count_m : ix->k) <= 21;
     for (;;) {
-        CID_TRY(single_region(ctx, st, nbases, ix->k, &nslots, &d_off, &d_mask, hint));
+        CID_TRY(single_region(ctx, st, nbases, ix->k, &nslots, &d_off, &d_mask, hint, packed));
         CID_CUDA(cudaMemsetAsync(ctx->d_err + 1, 0, 4, st));
         CID_TRY(launch_kmerize_insert(ctx, st, (const uint8_t*)d_bases, d_seq_offs, nseq, 0, nbases, nullptr, d_off, d_mask,
-                                      ctx->scratch[0].p, ix->k, seq_mode, count_m));
+                                      ctx->scratch[0].p, ix->k, seq_mode, count_m, packed ? nslots : 0));
         CID_CUDA(cudaMemcpyAsync(ctx->h_err, ctx->d_err, 8, cudaMemcpyDeviceToHost, st));
         CID_CUDA(cudaStreamSynchronize(st));
         const uint32_t flags = ctx->h_err[0], distinct = ctx->h_err[1];
+        if (flags & ERRF_COUNT_OVERFLOW) {
+            CID_CUDA(cudaMemsetAsync(ctx->d_err, 0, 8, st));
+            packed = false;
+            continue;
+        }
         if (hint && ((flags & ERRF_TABLE_FULL) || (uint64_t)distinct * 10 > nslots * 8)) {        // fuller than 80 %: redo larger
             CID_CUDA(cudaMemsetAsync(ctx->d_err, 0, 8, st));
             hint = hint * 2 >= next_pow2(std::max<uint64_t>(64, 2 * npos)) ? 0 : hint * 2;     // 0 = the safe 2x-positions size
@@ -525,13 +538,13 @@ static int build_accession_impl(cid_index* ix, uint32_t colour, const char* d_ba
     if (seq_mode == CID_SEQ_FASTQ && npos) ctx->readset_ratio = (double)ctx->h_err[1] / (double)npos;
     int64_t used = cutoff;       // FASTA with -1: keep everything (count > -1)
     if (seq_mode == CID_SEQ_FASTQ && cutoff == -1)
-        CID_TRY(region_auto_cutoff(ctx, st, ctx->scratch[0].as<Slot>(), nslots, &used));
+        CID_TRY(region_auto_cutoff(ctx, st, ctx->scratch[0].p, nslots, &used, packed));
     CID_CUDA(cudaMemsetAsync(bitset, 0, ix->bs_words * 4, st));
     CID_TRY(ctx->scratch[2].ensure(16));
     unsigned long long* d_nref = ctx->scratch[2].as<unsigned long long>();
     CID_CUDA(cudaMemsetAsync(d_nref, 0, 8, st));
     CID_TRY(launch_region_to_bloom(ctx, st, ctx->scratch[0].p, nslots, used, count_m ? count_m : ix->k, bloom_m, ix->H, ix->S,
-                                   bitset, d_nref));
+                                   bitset, d_nref, packed));
     unsigned long long nref = 0;
     CID_CUDA(cudaMemcpyAsync(&nref, d_nref, 8, cudaMemcpyDeviceToHost, st));
     CID_CUDA(cudaStreamSynchronize(st));
@@ -732,7 +745,7 @@ int cid_query_counts(cid_index* ix, const char* bases, const uint64_t* seq_offs,
         std::vector<int64_t> filt(bq);
         for (uint64_t q = 0; q < bq; q++) {
             if (seq_mode == CID_SEQ_FASTA && gene_search) filt[q] = 0;
-            else if (filter < 0) CID_TRY(region_auto_cutoff(ctx, st, qp.d_table + qp.gr.off[q], qp.gr.mask[q] + 1, &filt[q]));
+            else if (filter < 0) CID_TRY(region_auto_cutoff(ctx, st, (const void*)(qp.d_table + qp.gr.off[q]), qp.gr.mask[q] + 1, &filt[q]));
             else filt[q] = filter;
             if (cutoff_used) cutoff_used[q0 + q] = filt[q];
         }

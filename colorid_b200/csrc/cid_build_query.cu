@@ -31,6 +31,7 @@ struct SetSink {
     unsigned long long* keys; uint64_t mask;     // one set for the whole launch
     uint32_t* bitset; uint32_t H; ModS mods;
     uint32_t bloom_m;                            // != 0: insert find_minimizer(k-mer, bloom_m) (build_single_mini)
+    uint32_t packed;                             // !SETONLY: `keys` is a packed count table (key << 22 | count) of `mask`+1 words
 };
 template <bool MINI, bool SETONLY>   // MINI: the item is each k-mer's minimizer of length mini_m (build_multi_mini)
 __global__ void __launch_bounds__(KT_THREADS)
@@ -113,7 +114,7 @@ kmerize_insert_kernel(const uint8_t* __restrict__ bases, const uint64_t* __restr
             key = tile_minimizer(t, p, k, mini_m, key, fwd, low, mpos, mfwd);
         }
         // owner sequence = s0 + #starts <= p
-        uint32_t lo = 0, hi = SETONLY ? 0u : nstarts;
+        uint32_t lo = 0, hi = (SETONLY || sink.packed) ? 0u : nstarts;
         while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (s_starts[mid] <= (uint32_t)p) lo = mid + 1; else hi = mid; }
         int rc;
         if (SETONLY) {
@@ -128,6 +129,10 @@ kmerize_insert_kernel(const uint8_t* __restrict__ bases, const uint64_t* __restr
                     atomicOr(&sink.bitset[bit >> 5], 1u << (bit & 31));
                 }
             }
+        } else if (sink.packed) {
+            bool ovf = false;
+            rc = packed_insert(sink.keys, sink.mask, key, ovf);
+            if (ovf) atomicOr(err, ERRF_COUNT_OVERFLOW);
         } else {
             uint64_t owner = s0 + lo;
             uint32_t g = seq_group ? __ldg(seq_group + owner) : 0u;
@@ -146,11 +151,12 @@ kmerize_insert_kernel(const uint8_t* __restrict__ bases, const uint64_t* __restr
 int launch_kmerize_insert(cid_ctx* ctx, cudaStream_t st, const uint8_t* d_bases, const uint64_t* d_seq_offs,
                           uint64_t nseq, uint64_t base_lo, uint64_t base_hi, const uint32_t* d_seq_group,
                           const uint64_t* d_region_off, const uint64_t* d_region_mask, void* d_table, uint32_t k,
-                          int seq_mode, uint32_t mini_m) {
+                          int seq_mode, uint32_t mini_m, uint64_t packed_slots) {
     if (base_hi <= base_lo || nseq == 0) return CID_OK;
     uint64_t ntiles = (base_hi - base_lo + KT - 1) / KT;
     ProfScope ps(ctx, st, KID_KMERIZE_INSERT);
     SetSink none{};
+    if (packed_slots) { none.keys = (unsigned long long*)d_table; none.mask = packed_slots - 1; none.packed = 1; }
     if (mini_m)
         kmerize_insert_kernel<true, false><<<(unsigned)ntiles, KT_THREADS, 0, st>>>(d_bases, d_seq_offs, nseq, base_lo, base_hi, d_seq_group,
                                                                                    d_region_off, d_region_mask, (Slot*)d_table, k, mini_m,
@@ -171,7 +177,7 @@ int launch_kmerize_bloom(cid_ctx* ctx, cudaStream_t st, const uint8_t* d_bases, 
                          uint32_t H, uint64_t S, uint32_t* d_bitset) {
     if (nbases == 0 || nseq == 0) return CID_OK;
     const uint64_t ntiles = (nbases + KT - 1) / KT;
-    SetSink sink{(unsigned long long*)d_keys, nslots - 1, d_bitset, H, make_mods(S), bloom_m};
+    SetSink sink{(unsigned long long*)d_keys, nslots - 1, d_bitset, H, make_mods(S), bloom_m, 0};
     ProfScope ps(ctx, st, KID_KMERIZE_INSERT);
     if (count_m)
         kmerize_insert_kernel<true, true><<<(unsigned)ntiles, KT_THREADS, 0, st>>>(d_bases, d_seq_offs, nseq, 0, nbases, nullptr, nullptr, nullptr,
@@ -203,16 +209,17 @@ void plan_regions(const uint64_t* h_seq_offs, const uint64_t* h_group_offs, uint
 
 // ================================================================= region_histogram
 constexpr int HIST_SMEM_BINS = 1024;
+template <bool PACKED>
 __global__ void __launch_bounds__(256)
-region_histogram_kernel(const Slot* __restrict__ region, uint64_t nslots, uint32_t* __restrict__ hist,
+region_histogram_kernel(const void* __restrict__ region, uint64_t nslots, uint32_t* __restrict__ hist,
                         uint32_t hist_bins, uint32_t* __restrict__ overflow, uint32_t overflow_cap,
                         uint32_t* __restrict__ overflow_n) {
     __shared__ uint32_t sh[HIST_SMEM_BINS];
     for (int i = threadIdx.x; i < HIST_SMEM_BINS; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nslots; s += (uint64_t)gridDim.x * blockDim.x) {
-        Slot v = region[s];
-        if (v.key == CID_EMPTY_KEY) continue;
+        const SlotView v = slot_read<PACKED>(region, s);
+        if (!v.used) continue;
         uint32_t c = v.count;
         if (c < HIST_SMEM_BINS) atomicAdd(&sh[c], 1u);
         else if (c < hist_bins) atomicAdd(&hist[c], 1u);
@@ -225,12 +232,12 @@ region_histogram_kernel(const Slot* __restrict__ region, uint64_t nslots, uint32
     for (int i = threadIdx.x; i < HIST_SMEM_BINS; i += blockDim.x) if (sh[i]) atomicAdd(&hist[i], sh[i]);
 }
 int launch_region_histogram(cid_ctx* ctx, cudaStream_t st, const void* d_region, uint64_t nslots, uint32_t* d_hist,
-                            uint32_t hist_bins, uint32_t* d_overflow, uint32_t overflow_cap, uint32_t* d_overflow_n) {
+                            uint32_t hist_bins, uint32_t* d_overflow, uint32_t overflow_cap, uint32_t* d_overflow_n, bool packed) {
     unsigned grid = (unsigned)std::min<uint64_t>((nslots + 255) / 256, (uint64_t)ctx->sm_count * 16);
     if (grid == 0) grid = 1;
     ProfScope ps(ctx, st, KID_HISTOGRAM);
-    region_histogram_kernel<<<grid, 256, 0, st>>>((const Slot*)d_region, nslots, d_hist, hist_bins, d_overflow,
-                                                  overflow_cap, d_overflow_n);
+    if (packed) region_histogram_kernel<true><<<grid, 256, 0, st>>>(d_region, nslots, d_hist, hist_bins, d_overflow, overflow_cap, d_overflow_n);
+    else region_histogram_kernel<false><<<grid, 256, 0, st>>>(d_region, nslots, d_hist, hist_bins, d_overflow, overflow_cap, d_overflow_n);
     ctx->launches++;
     CID_CUDA(cudaGetLastError());
     return CID_OK;
@@ -238,16 +245,17 @@ int launch_region_histogram(cid_ctx* ctx, cudaStream_t st, const void* d_region,
 
 // ================================================================= region_to_bloom
 // clean_map (count > cutoff, kmer.rs:826-837), n_ref_kmers (build.rs:62), BloomFilter::insert.
+template <bool PACKED>
 __global__ void __launch_bounds__(256)
-region_to_bloom_kernel(const Slot* __restrict__ region, uint64_t nslots, long long cutoff, uint32_t k, uint32_t mini_m,
+region_to_bloom_kernel(const void* __restrict__ region, uint64_t nslots, long long cutoff, uint32_t k, uint32_t mini_m,
                        uint32_t H, ModS mods, uint32_t* __restrict__ bitset, unsigned long long* __restrict__ nref) {
     __shared__ uint32_t lut[256];
     lut4_init(lut, threadIdx.x, blockDim.x);
     __syncthreads();
     uint32_t mine = 0;
     for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nslots; s += (uint64_t)gridDim.x * blockDim.x) {
-        Slot v = region[s];
-        if (v.key == CID_EMPTY_KEY || (long long)v.count <= cutoff) continue;
+        const SlotView v = slot_read<PACKED>(region, s);
+        if (!v.used || (long long)v.count <= cutoff) continue;
         mine++;
         uint64_t item = v.key;
         uint32_t len = k;
@@ -267,12 +275,13 @@ region_to_bloom_kernel(const Slot* __restrict__ region, uint64_t nslots, long lo
     if ((threadIdx.x & 31) == 0 && mine) atomicAdd(nref, (unsigned long long)mine);
 }
 int launch_region_to_bloom(cid_ctx* ctx, cudaStream_t st, const void* d_region, uint64_t nslots, int64_t cutoff,
-                           uint32_t k, uint32_t mini_m, uint32_t H, uint64_t S, uint32_t* d_bitset, unsigned long long* d_nref) {
+                           uint32_t k, uint32_t mini_m, uint32_t H, uint64_t S, uint32_t* d_bitset, unsigned long long* d_nref,
+                           bool packed) {
     unsigned grid = (unsigned)std::min<uint64_t>((nslots + 255) / 256, (uint64_t)ctx->sm_count * 16);
     if (grid == 0) grid = 1;
     ProfScope ps(ctx, st, KID_TO_BLOOM);
-    region_to_bloom_kernel<<<grid, 256, 0, st>>>((const Slot*)d_region, nslots, (long long)cutoff, k, mini_m, H, make_mods(S),
-                                                 d_bitset, d_nref);
+    if (packed) region_to_bloom_kernel<true><<<grid, 256, 0, st>>>(d_region, nslots, (long long)cutoff, k, mini_m, H, make_mods(S), d_bitset, d_nref);
+    else region_to_bloom_kernel<false><<<grid, 256, 0, st>>>(d_region, nslots, (long long)cutoff, k, mini_m, H, make_mods(S), d_bitset, d_nref);
     ctx->launches++;
     CID_CUDA(cudaGetLastError());
     return CID_OK;

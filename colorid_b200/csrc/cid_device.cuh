@@ -372,6 +372,42 @@ __device__ __forceinline__ int table_insert(Slot* region, uint64_t mask, uint64_
     return -1;
 }
 
+// Packed variant for keys of <= 21 bases (42 bits): one 8-byte word holds key << 22 | count, so a read-set build's
+// count table is half as large (more of it stays in L2) and an insert is one load + one atomic.  All ones = empty
+// (never a canonical key: T..T's reverse complement A..A is smaller).  A count within 2^20 of the field's limit raises
+// `overflow` instead of adding (more threads than that cannot be between their load and their add).
+#define CID_PK_BITS 22
+#define CID_PK_CMASK ((1ULL << CID_PK_BITS) - 1)
+__device__ __forceinline__ int packed_insert(unsigned long long* tab, uint64_t mask, uint64_t key, bool& overflow) {
+    uint64_t h = mix64(key) & mask;
+    for (int probes = 0; probes < CID_MAX_PROBE; probes++) {
+        unsigned long long cur = *(volatile unsigned long long*)&tab[h];
+        if (cur == CID_EMPTY_KEY) {
+            cur = atomicCAS(&tab[h], CID_EMPTY_KEY, (unsigned long long)((key << CID_PK_BITS) | 1ULL));
+            if (cur == CID_EMPTY_KEY) return 1;
+        }
+        if ((cur >> CID_PK_BITS) == key) {
+            if ((cur & CID_PK_CMASK) >= CID_PK_CMASK - (1ULL << 20)) overflow = true;
+            else atomicAdd(&tab[h], 1ULL);
+            return 0;
+        }
+        h = (h + 1) & mask;
+    }
+    return -1;
+}
+struct SlotView { uint64_t key; uint32_t count; bool used; };
+template <bool PACKED> __device__ __forceinline__ SlotView slot_read(const void* table, uint64_t i) {
+    SlotView v;
+    if (PACKED) {
+        const unsigned long long w = ((const unsigned long long*)table)[i];
+        v.used = w != CID_EMPTY_KEY; v.key = w >> CID_PK_BITS; v.count = (uint32_t)(w & CID_PK_CMASK);
+    } else {
+        const Slot s = ((const Slot*)table)[i];
+        v.used = s.key != CID_EMPTY_KEY; v.key = s.key; v.count = s.count;
+    }
+    return v;
+}
+
 // Key-only variant (8-byte slots) for builds that keep every k-mer (no count filter): the table of a 5-Mbp genome
 // then fits the L2 cache.  Same return values.
 __device__ __forceinline__ int set_insert(unsigned long long* keys, uint64_t mask, uint64_t key) {

@@ -79,6 +79,7 @@ struct cid_ctx {
     int opt_readid_serialize = 0;    // 1 = kernels of consecutive pipeline chunks never overlap (measured: 44.8M vs 46.3M pairs/s e2e, off)
     int opt_build_table_div = 0;     // read-set builds: first count table = k-mer positions / this (0 = adaptive; grown x4 when > 70 % full)
     double readset_ratio = 0;        // distinct k-mers / k-mer positions of the last read-set accession built on this context
+    int opt_build_packed = 1;        // 0 = never use the packed 8-byte count table (parity aid)
     int opt_build_set = 1;           // 0 = always build through the count table (parity aid)
     int opt_query_front = 1;         // 0 = never use the shared-memory dedup front end of small queries (parity aid)
     int opt_query_fused = 0;         // 1 = force the fused collect/hash/gather kernel (parity aid)
@@ -111,6 +112,7 @@ enum {
     ERRF_LIST_OVERFLOW = 1u << 2,
     ERRF_READ_TOO_LONG = 1u << 3,
     ERRF_STRING_NONACGT = 1u << 4,
+    ERRF_COUNT_OVERFLOW = 1u << 6, // packed count table: a multiplicity near 2^22 (caller redoes the accession with 16-byte slots)
     ERRF_TABLE_FULL = 1u << 5,     // a count-table region overflowed (only possible with optimistic sizing: caller retries) // kmerize_string window with a byte outside ACGTacgt (cannot be 2-bit packed)
 };
 
@@ -146,16 +148,20 @@ void plan_regions(const uint64_t* h_seq_offs, const uint64_t* h_group_offs, uint
 int launch_kmerize_insert(cid_ctx* ctx, cudaStream_t st, const uint8_t* d_bases, const uint64_t* d_seq_offs,
                           uint64_t nseq, uint64_t base_lo, uint64_t base_hi, const uint32_t* d_seq_group,
                           const uint64_t* d_region_off, const uint64_t* d_region_mask, void* d_table, uint32_t k,
-                          int seq_mode, uint32_t mini_m = 0);   // mini_m != 0: count each k-mer's minimizer instead
+                          int seq_mode, uint32_t mini_m = 0, uint64_t packed_slots = 0);
+// mini_m != 0: count each k-mer's minimizer instead; packed_slots != 0: d_table is ONE packed count table (key << 22 | count,
+// keys of <= 21 bases) of that many 8-byte words for the whole launch
 // set-only build (no count filter): new keys are hashed straight into the accession's Bloom bitset; distinct keys in d_err[1]
 int launch_kmerize_bloom(cid_ctx* ctx, cudaStream_t st, const uint8_t* d_bases, const uint64_t* d_seq_offs, uint64_t nseq,
                          uint64_t nbases, void* d_keys, uint64_t nslots, uint32_t k, int seq_mode, uint32_t count_m, uint32_t bloom_m,
                          uint32_t H, uint64_t S, uint32_t* d_bitset);
 int launch_region_histogram(cid_ctx* ctx, cudaStream_t st, const void* d_region, uint64_t nslots, uint32_t* d_hist,
-                            uint32_t hist_bins, uint32_t* d_overflow, uint32_t overflow_cap, uint32_t* d_overflow_n);
+                            uint32_t hist_bins, uint32_t* d_overflow, uint32_t overflow_cap, uint32_t* d_overflow_n,
+                            bool packed = false);
 // k = length of the table's keys; mini_m != 0: insert find_minimizer(key, mini_m) instead of the key itself
 int launch_region_to_bloom(cid_ctx* ctx, cudaStream_t st, const void* d_region, uint64_t nslots, int64_t cutoff,
-                           uint32_t k, uint32_t mini_m, uint32_t H, uint64_t S, uint32_t* d_bitset, unsigned long long* d_nref);
+                           uint32_t k, uint32_t mini_m, uint32_t H, uint64_t S, uint32_t* d_bitset, unsigned long long* d_nref,
+                           bool packed = false);
 int launch_transpose(cid_ctx* ctx, cudaStream_t st, const cid_index* idx);
 int launch_rownz(cid_ctx* ctx, cudaStream_t st, const cid_index* idx);
 

@@ -74,8 +74,30 @@ def test_build_fastq_autocutoff(oracle, ctx):
         reads = synth.reads_from(rng, [g], 1200, read_len=100, insert=200, err=0.01, frac_random=0.0, n_rate=0.002)
         accs.append([m for r in reads for m in r])
     for cutoff in (-1, 0, 2):
-        oix, gix = build_both(oracle, ctx, accs, S, H, k, cb.CID_SEQ_FASTQ, cutoff)
+        oix, gix = build_both(oracle, ctx, accs, S, H, k, cb.CID_SEQ_FASTQ, cutoff)      # k <= 21: packed 8-byte count table
         assert np.array_equal(gix.download_dense(), oix.words())
+    ctx.set_option("build_packed", 0)                                                    # 16-byte slots: same bits
+    try:
+        for cutoff in (-1, 2):
+            oix, gix = build_both(oracle, ctx, accs, S, H, k, cb.CID_SEQ_FASTQ, cutoff)
+            assert np.array_equal(gix.download_dense(), oix.words())
+    finally:
+        ctx.set_option("build_packed", 1)
+
+
+def test_build_packed_count_table_falls_back_on_huge_multiplicity(oracle, ctx):
+    # the packed count table keeps 22 bits of multiplicity next to a 42-bit key: a k-mer seen > 3.1 M times (a poly-A
+    # run) must send the accession through the 16-byte table, with identical results
+    rng = _rng(8)
+    k, S, H = 15, 100_003, 2
+    g = synth.rand_seq(rng, 3000)
+    acc = [b"A" * 3_300_000, g, g, g[:1500]]
+    oix, gix = oracle.Index(S, H, k, 1), cb.Index(ctx, S, H, k, 1)
+    for cutoff in (1, 2, 3_200_000):
+        assert gix.build_accession(0, acc, cb.CID_SEQ_FASTQ, cutoff) == oix.build_accession(0, acc, oracle.MODE_FASTQ, cutoff)
+    oix.finalize()
+    gix.finalize()
+    assert np.array_equal(gix.download_dense(), oix.words()) and gix.nonzero_rows() == H
 
 
 def _fast_reads(rng, genome, n, rl):
