@@ -434,11 +434,12 @@ struct ReadIdRun {
 namespace {
 // per_read_stream_pe / per_read_stream_se / stream_fasta (read_id_mt_pe.rs:440-951) for one sample, followed by
 // reports::read_counts_five_fields (main.rs:865): o.query in, o.prefix_reads.txt + o.prefix_counts.txt out
-void read_id_sample(Gpu& g, const Bigsi& b, const ReadIdOpts& o, Trace& tr) {
+void read_id_sample(Gpu& g, const Bigsi& b, const ReadIdOpts& o, Trace& tr, ReadBatch* batches) {
     if (o.query.empty()) throw Error("no query files");
     ReadIdRun run(g, b, o);
-    // two batches: while the worker thread runs the GPU call and writes the lines of one, the parser fills the other
-    ReadBatch batches[2];
+    // two batches (owned by the caller: their page-locked buffers take ~0.4 s to allocate and are reused across the
+    // samples of batch_id): while the worker thread runs the GPU call and writes the lines of one, the parser fills the other
+    batches[0].clear(); batches[1].clear();
     int cur = 0;
     std::thread worker;
     std::exception_ptr worker_err;
@@ -530,7 +531,8 @@ int read_id(const ReadIdOpts& o) {
     tr.mark("context create (rest)");
     g.upload(b);
     tr.mark("index upload");
-    read_id_sample(g, b, o, tr);
+    ReadBatch batches[2];
+    read_id_sample(g, b, o, tr, batches);
     return 0;
 }
 
@@ -555,6 +557,7 @@ int batch_id(const BatchIdOpts& o) {
             Gpu g(devices[w]);
             g.upload(b);
             Trace wtr;
+            ReadBatch batches[2];
             for (;;) {
                 const size_t i = next.fetch_add(1);
                 if (i >= samples.size()) break;
@@ -563,7 +566,7 @@ int batch_id(const BatchIdOpts& o) {
                 s.bigsi = o.bigsi; s.prefix = samples[i].first + "_" + o.tag; s.query = samples[i].second;
                 s.threads = o.threads; s.down_sample = o.down_sample; s.batch = o.batch; s.bitvector_sample = o.bitvector_sample;
                 s.correct = o.correct; s.quality = o.quality; s.high_mem_load = o.high_mem_load; s.device = devices[w];
-                read_id_sample(g, b, s, wtr);
+                read_id_sample(g, b, s, wtr, batches);
             }
         } catch (...) { errs[w] = std::current_exception(); }
     };

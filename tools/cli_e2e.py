@@ -78,7 +78,20 @@ t_read, r = timed("read_id", "-b", f"{d}/idx.bxi", "-q", f"{d}/r_1.fastq.gz", f"
 n_lines = sum(1 for _ in open(f"{d}/out_reads.txt"))
 t_search, rs = timed("search", "-b", f"{d}/idx.bxi", "-q", f"{d}/r_1.fastq.gz", "-r", f"{d}/r_2.fastq.gz")
 t_info, _ = timed("info", "-b", f"{d}/idx.bxi")
-print(json.dumps({"workload": f"CLI end to end, {n_acc} x {glen} bp FASTA index (k=31 S=50M H=4), {n_pairs} read pairs of 2x{rl} bp as .fastq.gz",
+# batch_id: four samples (the same pair of files under four names), index read and uploaded once
+n_samples = 4
+with open(f"{d}/samples.tsv", "w") as f:
+    for i in range(n_samples):
+        f.write(f"{d}/sample{i}\t{d}/r_1.fastq.gz\t{d}/r_2.fastq.gz\n")
+t_batch, _ = timed("batch_id", "-b", f"{d}/idx.bxi", "-q", f"{d}/samples.tsv", "-T", "b")
+same = all(open(f"{d}/sample{i}_b_reads.txt").read() == open(f"{d}/out_reads.txt").read() for i in range(n_samples))
+# minimizer index of the same references (-m -v 15) and read_id on it
+t_build_mxi, _ = timed("build", "-b", f"{d}/idx", "-r", f"{d}/refs.tsv", "-k", "31", "-n", "4", "-s", "50000000", "-m")
+t_read_mxi, _ = timed("read_id", "-b", f"{d}/idx.mxi", "-q", f"{d}/r_1.fastq.gz", f"{d}/r_2.fastq.gz", "-n", f"{d}/outm")
+print(json.dumps({"batch_id_samples": n_samples, "batch_id_seconds": t_batch, "batch_id_pairs_per_s": n_samples * n_pairs / t_batch,
+                  "batch_id_outputs_equal_read_id": same, "build_mxi_seconds": t_build_mxi, "mxi_bytes": os.path.getsize(f"{d}/idx.mxi"),
+                  "read_id_mxi_seconds": t_read_mxi,
+                  "workload": f"CLI end to end, {n_acc} x {glen} bp FASTA index (k=31 S=50M H=4), {n_pairs} read pairs of 2x{rl} bp as .fastq.gz",
                   "build_seconds": t_build, "build_gbp_per_s": n_acc * glen / t_build / 1e9,
                   "bxi_bytes": os.path.getsize(f"{d}/idx.bxi"), "index_load_seconds_(info)": t_info,
                   "read_id_seconds": t_read, "read_id_pairs_per_s_incl_index_load": n_pairs / t_read,
