@@ -417,6 +417,10 @@ C5 = dict(n_acc=10_000, genome_len=5_000_000, n_clades=100, div=0.01, k=31, S=50
           qlen_lo=1000, qlen_hi=3000, n_probe=16)
 
 
+def lookups_of(d_nk):
+    return int(d_nk.sum().item())
+
+
 def run_c5(args):
     """BASELINE.json configs[4]: 10,000 synthetic 5 Mbp genomes, k=31 S=50M H=4, the signature matrix column-sharded
     over the ranks (whole 32-accession word columns per rank), every rank gathering all query k-mers from its slice,
@@ -561,6 +565,44 @@ def run_c5(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     lookups = int(d_nk.sum().item())
+    # ---- the same pass with the count exchange fused into the gather kernel: every rank adds its column slice into
+    # the full-width result of ALL ranks through NVLink peer memory (CUDA IPC), no collective after the kernel
+    fused = None
+    if world > 1:
+        pc = sharding.PeerCounts(ctx, nq, A, dev)
+
+        def fused_pass():
+            pc.begin_pass()
+            L.check(lib.cid_query_counts_sharded_dev(gix.h, d_bases.data_ptr(), qoff.data_ptr(), nq, total, d_query_offs.data_ptr(),
+                                                     P(h_query_offs), P(h_seq_offs), nq, 0, pc.dest, world, A, lo, d_nk.data_ptr(),
+                                                     stream.cuda_stream))
+            return pc.end_pass()
+
+        def nccl_pass():
+            torch.cuda.synchronize()
+            dist.barrier()
+            search_pass()
+            torch.cuda.synchronize()
+            dist.barrier()
+
+        fused_pass()
+        same = bool(torch.equal(pc.view, gathered[0]))
+        times = {}
+        for name, fn in (("nccl_all_gather", nccl_pass), ("fused_peer_stores", fused_pass)):
+            fn()
+            t0 = time.perf_counter()
+            for _ in range(K):
+                fn()
+            tt = torch.tensor([(time.perf_counter() - t0) / K * 1e3], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            times[name] = float(tt.item())
+        ok = torch.tensor([1 if same and bool(torch.equal(pc.view, gathered[0])) else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        fused = {"ms_per_pass_wall_incl_barriers": times, "lookups_per_s": {k_: lookups_of(d_nk) / (v / 1e3) for k_, v in times.items()},
+                 "identical_to_all_gather_on_every_rank": bool(ok.item()),
+                 "note": "both timed the same way: barrier, pass, stream sync, barrier (wall clock, max over ranks); the fused pass also "
+                         "zeroes its destination and has one more barrier"}
+        pc.close()
     # ---- parity at full size: a query cut verbatim from accession a has every one of its k-mers in a's column
     full = gathered[0]
     nk_h = d_nk.cpu().numpy()
@@ -583,19 +625,27 @@ def run_c5(args):
                     "frac": alg / (qc_ms / 1e3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                     "algorithmic_bytes_per_pass": alg, "row_bytes_per_shard": R, "ms_per_pass": qc_ms,
                     "note": "per rank: every rank gathers all k-mers from its own column slice"}
+    coll = "none (single GPU)"
+    if world > 1:
+        coll = "NCCL all_gather of per-query counts after the kernel (+ one all_gather/OR of the row-present bitmaps after the build)"
+        if fused and fused["identical_to_all_gather_on_every_rank"]:
+            # the product path: the gather kernel stores its column slice into every rank's full-width result over NVLink
+            ms_max = fused["ms_per_pass_wall_incl_barriers"]["fused_peer_stores"]
+            coll = ("count exchange fused into query_gather: 16-byte stores of each rank's column slice into every rank's full-width "
+                    "result through CUDA-IPC peer memory over NVSwitch (cid_query_counts_sharded_dev); ms_per_step is wall clock "
+                    "with the two barriers of a pass; the NCCL all_gather variant is timed alongside (fused_count_exchange)")
     line = {"metric": "search k-mer lookups/s", "value": lookups / (ms_max / 1e3), "unit": "k-mer lookups/s", "n_gpus": world,
             "steps": K, "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": "C5 column-sharded build + gene search (BASELINE.json configs[4])", "n_accessions": A,
                        "genome_len": Lg, "k": cfg["k"], "S": cfg["S"], "H": cfg["H"], "accessions_per_rank": n_local,
-                       "row_bytes_per_rank": R, "queries": nq, "collective": "NCCL all_gather of per-query counts (+ one "
-                       "all_gather/OR of the row-present bitmaps after the build)" if world > 1 else "none (single GPU)"},
+                       "row_bytes_per_rank": R, "queries": nq, "collective": coll},
             "clocks": clocks, "gpu_launches": int(ctx.launches), "roofline": roofline, "kernels": kern,
             "build": {"gbp_per_s": A * Lg / build_s_max / 1e9, "seconds": build_s_max,
                       "note": "all ranks build their accession columns concurrently; max over ranks; synthetic genome "
                               "generation excluded",
                       "kernels_ms_total": {k_: v[0] for k_, v in build_prof.items()}},
-            "parity": {"self_query_probes": len(probe_q), "violations": 0}}
+            "parity": {"self_query_probes": len(probe_q), "violations": 0}, "fused_count_exchange": fused}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -800,26 +800,98 @@ int cid_query_counts_dev(cid_index* ix, const char* d_bases, const uint64_t* d_s
     if (ix->m) { set_error("An index with minimizers (.mxi) is used, but not available for this function"); return CID_E_UNSUPPORTED; }   // main.rs:569-573
     CID_CUDA(cudaSetDevice(ctx->device));
     const uint32_t N = ix->N;
-    CID_CUDA(cudaMemsetAsync(d_counts, 0, nq * N * 4, st));
+    if (d_counts) CID_CUDA(cudaMemsetAsync(d_counts, 0, nq * N * 4, st));
+    else if (!ctx->gather_out) { set_error("cid_query_counts_dev: null counts"); return CID_E_INVALID; }
     CID_CUDA(cudaMemsetAsync(d_num_kmers, 0, nq * 8, st));
+    // column-sharded call: the destination rows of a batch start at its first query
+    const GatherOut* const shared_out = ctx->gather_out;
+    GatherOut batch_out{};
+    auto aim = [&](uint64_t q0) {
+        if (!shared_out) return;
+        batch_out = *shared_out;
+        for (uint32_t d = 0; d < batch_out.n; d++) batch_out.base[d] += q0 * (uint64_t)batch_out.stride;
+        ctx->gather_out = &batch_out;
+    };
+    int rc = CID_OK;
     if (nq && d_query_offs && query_front_ok(ix, false, h_seq_offs, h_query_offs, nq)) {
         std::vector<uint64_t> fcuts = query_front_batches(h_seq_offs, h_query_offs, nq);
-        for (size_t b = 0; b + 1 < fcuts.size(); b++)
-            CID_TRY(launch_query_front_gather(ctx, st, ix, (const uint8_t*)d_bases, d_seq_offs, d_query_offs, h_seq_offs, h_query_offs,
-                                              fcuts[b], fcuts[b + 1], seq_mode, d_counts + fcuts[b] * N,
-                                              (unsigned long long*)d_num_kmers + fcuts[b]));
-        return CID_OK;
+        for (size_t b = 0; b + 1 < fcuts.size() && rc == CID_OK; b++) {
+            aim(fcuts[b]);
+            rc = launch_query_front_gather(ctx, st, ix, (const uint8_t*)d_bases, d_seq_offs, d_query_offs, h_seq_offs, h_query_offs,
+                                           fcuts[b], fcuts[b + 1], seq_mode, d_counts ? d_counts + fcuts[b] * N : nullptr,
+                                           (unsigned long long*)d_num_kmers + fcuts[b]);
+        }
+        ctx->gather_out = shared_out;
+        return rc;
     }
     std::vector<uint64_t> cuts = query_batches(h_seq_offs, h_query_offs, nq, ix->k, kMaxBatchSlots);
-    for (size_t b = 0; b + 1 < cuts.size(); b++) {
+    for (size_t b = 0; b + 1 < cuts.size() && rc == CID_OK; b++) {
         const uint64_t q0 = cuts[b], q1 = cuts[b + 1];
         QueryPlan qp;
-        CID_TRY(query_front(ix, st, (const uint8_t*)d_bases, d_seq_offs, h_seq_offs, h_query_offs, q0, q1, seq_mode, qp));
-        CID_TRY(launch_query_counts(ctx, st, ix, qp.d_table, qp.d_unit_group, qp.d_unit_slot0, qp.d_unit_nslots,
-                                    qp.qu.group.size(), qp.gr.total_slots, nullptr, d_counts + q0 * N,
-                                    (unsigned long long*)d_num_kmers + q0, false, nullptr, 0, nullptr));
+        rc = query_front(ix, st, (const uint8_t*)d_bases, d_seq_offs, h_seq_offs, h_query_offs, q0, q1, seq_mode, qp);
+        if (rc != CID_OK) break;
+        aim(q0);
+        rc = launch_query_counts(ctx, st, ix, qp.d_table, qp.d_unit_group, qp.d_unit_slot0, qp.d_unit_nslots,
+                                 qp.qu.group.size(), qp.gr.total_slots, nullptr, d_counts ? d_counts + q0 * N : nullptr,
+                                 (unsigned long long*)d_num_kmers + q0, false, nullptr, 0, nullptr);
     }
+    ctx->gather_out = shared_out;
+    return rc;
+}
+
+// ---- column-sharded search with the count exchange fused into the gather kernel -----------------------------
+int cid_dev_alloc(cid_ctx* ctx, size_t bytes, void** out) {
+    if (!ctx || !out) { set_error("cid_dev_alloc: null argument"); return CID_E_INVALID; }
+    CID_CUDA(cudaSetDevice(ctx->device));
+    cudaError_t e = cudaMalloc(out, std::max<size_t>(bytes, 256));
+    if (e != cudaSuccess) { *out = nullptr; set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); cudaGetLastError(); return CID_E_NOMEM; }
     return CID_OK;
+}
+void cid_dev_free(cid_ctx* ctx, void* p) { if (ctx && p) { cudaSetDevice(ctx->device); cudaFree(p); } }
+int cid_ipc_export(cid_ctx* ctx, const void* dptr, uint8_t handle[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    if (!ctx || !dptr || !handle) { set_error("cid_ipc_export: null argument"); return CID_E_INVALID; }
+    CID_CUDA(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    CID_CUDA(cudaIpcGetMemHandle(&h, (void*)dptr));
+    memcpy(handle, &h, 64);
+    return CID_OK;
+}
+int cid_ipc_open(cid_ctx* ctx, const uint8_t handle[64], void** out) {
+    if (!ctx || !handle || !out) { set_error("cid_ipc_open: null argument"); return CID_E_INVALID; }
+    CID_CUDA(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CID_CUDA(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return CID_OK;
+}
+int cid_ipc_close(cid_ctx* ctx, void* p) {
+    if (!ctx || !p) return CID_OK;
+    CID_CUDA(cudaSetDevice(ctx->device));
+    CID_CUDA(cudaIpcCloseMemHandle(p));
+    return CID_OK;
+}
+
+int cid_query_counts_sharded_dev(cid_index* ix, const char* d_bases, const uint64_t* d_seq_offs, uint64_t nseq, uint64_t nbases,
+                                 const uint64_t* d_query_offs, const uint64_t* h_query_offs, const uint64_t* h_seq_offs, uint64_t nq,
+                                 int seq_mode, void* const* d_dest_counts, uint32_t n_dest, uint32_t n_total, uint32_t col_offset,
+                                 uint64_t* d_num_kmers, void* stream) {
+    if (!ix || !d_dest_counts || n_dest < 1 || n_dest > 8) { set_error("cid_query_counts_sharded_dev: 1..8 destination buffers"); return CID_E_INVALID; }
+    if ((uint64_t)col_offset + ix->N > n_total) { set_error("cid_query_counts_sharded_dev: shard columns exceed n_total"); return CID_E_INVALID; }
+    if (!(ix->Wp >= 4 && ix->Wp <= 128 && (ix->H == 2 || ix->H == 4)) || ix->ctx->opt_query_fused) {
+        set_error("cid_query_counts_sharded_dev: needs the streaming gather (16-byte aligned rows of <= 512 bytes, num_hash 2 or 4)");
+        return CID_E_UNSUPPORTED;
+    }
+    GatherOut go{};
+    for (uint32_t d = 0; d < n_dest; d++) go.base[d] = (uint32_t*)d_dest_counts[d];
+    go.n = n_dest; go.stride = n_total; go.col0 = col_offset;
+    cid_ctx* ctx = ix->ctx;
+    ctx->gather_out = &go;
+    // the destinations are zeroed by their owners (and a barrier passed) before this call: skip the local memset
+    const int rc = cid_query_counts_dev(ix, d_bases, d_seq_offs, nseq, nbases, d_query_offs, h_query_offs, h_seq_offs, nq, seq_mode,
+                                        nullptr, d_num_kmers, stream);
+    ctx->gather_out = nullptr;
+    return rc;
 }
 
 static int query_perfect_impl(cid_index* ix, const char* bases, const uint64_t* seq_offs, uint64_t nseq,

@@ -693,7 +693,7 @@ __global__ void __launch_bounds__(QG_WARPS * 32, 4)
 query_gather_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t N, const uint32_t* __restrict__ rid,
                     const uint32_t* __restrict__ unit_group, const uint64_t* __restrict__ unit_slot0,
                     const uint32_t* __restrict__ unit_n, uint32_t* __restrict__ counts,
-                    const uint32_t* __restrict__ rownz, uint32_t* __restrict__ missing, uint32_t W) {
+                    const uint32_t* __restrict__ rownz, uint32_t* __restrict__ missing, uint32_t W, GatherOut go) {
     using Cfg = QGCfg<HT>;
     constexpr int D = Cfg::D;
     static_assert(D >= 2 && 8 % D == 0, "ring depth must divide the tree width");
@@ -701,8 +701,14 @@ query_gather_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t N, 
     uint32_t* cnt = (uint32_t*)(dsm + QG_RING_BYTES);                 // [4096] per-accession counters
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t n = unit_n[blockIdx.x];
-    if (n == 0) return;
     const uint32_t g = unit_group[blockIdx.x];
+    if (n == 0) {
+        if (!ANDM && go.dense)                            // a query without k-mers still owns its row slice: zeros
+            for (uint32_t c = tid; c < N; c += QG_WARPS * 32)
+#pragma unroll
+                for (uint32_t d = 0; d < 8; d++) if (d < go.n) go.base[d][(uint64_t)g * go.stride + go.col0 + c] = 0u;
+        return;
+    }
     const uint32_t* myrid = rid + unit_slot0[blockIdx.x] * HT;
 
     const uint32_t vpr = Wp >> 2;                         // 16-byte vectors per row (<= 32)
@@ -858,14 +864,50 @@ query_gather_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t N, 
         uint32_t nz = 0;
 #pragma unroll
         for (int p = 0; p < SP; p++) nz |= acc[p];
-        uint32_t* out = counts + (uint64_t)g * N + (uint32_t)tid * 32;
+        // go.n destinations: the caller's buffer, or in column-sharded mode the same slot [query][col0 + accession] of every
+        // GPU's full-width result (peer memory over NVLink): the count exchange rides on the kernel's own stores
+        const uint64_t off = (uint64_t)g * go.stride + go.col0 + (uint32_t)tid * 32;
+        if (go.dense) {
+            // four counters at a time (nibble spread: each plane's 4 bits into 4 byte lanes), one 16-byte store per destination
+            const bool vec_ok = ((go.stride | go.col0) & 3u) == 0u;
+#pragma unroll
+            for (int nb = 0; nb < 8; nb++) {
+                uint32_t lo8 = 0, hi8 = 0;
+#pragma unroll
+                for (int p = 0; p < SP; p++) {
+                    const uint32_t sp = (((acc[p] >> (4 * nb)) & 0xFu) * 0x00204081u) & 0x01010101u;
+                    if (p < 8) lo8 += sp << p; else hi8 += sp << (p - 8);
+                }
+                uint4 v;
+                v.x = (lo8 & 0xFFu) | ((hi8 & 0xFFu) << 8);
+                v.y = ((lo8 >> 8) & 0xFFu) | (((hi8 >> 8) & 0xFFu) << 8);
+                v.z = ((lo8 >> 16) & 0xFFu) | (((hi8 >> 16) & 0xFFu) << 8);
+                v.w = (lo8 >> 24) | ((hi8 >> 24) << 8);
+                const uint32_t c0 = (uint32_t)tid * 32 + 4 * nb;
+                if (c0 >= N) break;
+                if (vec_ok && c0 + 4 <= N) {
+#pragma unroll
+                    for (uint32_t d = 0; d < 8; d++) if (d < go.n) *(uint4*)(go.base[d] + off + 4 * nb) = v;
+                } else {
+                    const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (uint32_t j = 0; j < 4; j++)
+#pragma unroll
+                        for (uint32_t d = 0; d < 8; d++) if (d < go.n && c0 + j < N) go.base[d][off + 4 * nb + j] = vv[j];
+                }
+            }
+            nz = 0;
+        }
         while (nz) {
             const uint32_t bb = __ffs(nz) - 1;
             nz &= nz - 1;
             uint32_t val = 0;
 #pragma unroll
             for (int p = 0; p < SP; p++) val |= ((acc[p] >> bb) & 1u) << p;
-            if ((uint32_t)tid * 32 + bb < N) atomicAdd(out + bb, val);
+            if ((uint32_t)tid * 32 + bb < N) {
+#pragma unroll
+                for (uint32_t d = 0; d < 8; d++) if (d < go.n) atomicAdd(go.base[d] + off + bb, val);
+            }
         }
     }
 }
@@ -920,11 +962,14 @@ static int launch_query_gather(cid_ctx* ctx, cudaStream_t st, const cid_index* i
         CID_CUDA(cudaFuncSetAttribute(query_gather_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
         gattr = true;
     }
+    GatherOut go{};
+    if (!d_and_rows && ctx->gather_out) go = *ctx->gather_out;
+    else { go.base[0] = d_counts; go.n = 1; go.stride = idx->N; go.col0 = 0; }
     {
         ProfScope ps(ctx, st, d_and_rows ? KID_QUERY_PERFECT : KID_QUERY_COUNTS);
 #define CID_QG(HT, AM, OUT)                                                                                             \
     query_gather_kernel<HT, AM><<<(unsigned)nunits, QG_WARPS * 32, gsmem, st>>>(idx->rows, idx->Wp, idx->N, d_rid, d_unit_group, \
-                                                                               d_unit_slot0, d_unit_n, OUT, idx->rownz, d_missing, idx->W)
+                                                                               d_unit_slot0, d_unit_n, OUT, idx->rownz, d_missing, idx->W, go)
         if (d_and_rows) { if (idx->H == 2) CID_QG(2, true, d_and_rows); else CID_QG(4, true, d_and_rows); }
         else { if (idx->H == 2) CID_QG(2, false, d_counts); else CID_QG(4, false, d_counts); }
 #undef CID_QG
@@ -1075,7 +1120,13 @@ int launch_query_front_gather(cid_ctx* ctx, cudaStream_t st, const cid_index* id
         CID_CUDA(cudaGetLastError());
         at += n;
     }
-    CID_TRY(launch_query_gather(ctx, st, idx, d_rid, d_group, d_base, d_unit_n, bq, d_counts, d_and_rows, d_missing));
+    // one unit per query: a column-sharded destination may be written with plain stores
+    GatherOut dense_out{};
+    const GatherOut* const shared = ctx->gather_out;
+    if (shared && !d_and_rows) { dense_out = *shared; dense_out.dense = 1; ctx->gather_out = &dense_out; }
+    const int grc = launch_query_gather(ctx, st, idx, d_rid, d_group, d_base, d_unit_n, bq, d_counts, d_and_rows, d_missing);
+    ctx->gather_out = shared;
+    CID_TRY(grc);
     CID_CUDA(cudaStreamSynchronize(st));
     return CID_OK;
 }

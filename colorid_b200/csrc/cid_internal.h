@@ -11,6 +11,12 @@
 
 namespace cid {
 
+// Where query_gather adds its per-accession counts: `n` destination buffers (this GPU's own and, in column-sharded
+// mode, the peers' -- NVLink peer memory), rows of `stride` counters, this shard's accessions starting at column `col0`.
+struct GatherOut { uint32_t* base[8]; uint32_t n; uint32_t stride; uint32_t col0; uint32_t dense; };
+// dense: every query is ONE gather unit (query_front path), so each counter is written exactly once: plain 16-byte stores of
+// all counters (zeros included) instead of one atomic per non-zero counter -- what peer memory over NVLink wants
+
 void set_error(const char* fmt, ...);
 
 #define CID_CUDA(expr)                                                                         \
@@ -54,6 +60,7 @@ struct cid_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;   // library-owned stream for the host-pointer entry points
     uint64_t launches = 0;
+    const cid::GatherOut* gather_out = nullptr;   // set for the duration of cid_query_counts_sharded_dev
     bool attr_done[8] = {false};     // cudaFuncSetAttribute (dynamic smem opt-in) already applied on this context's device
     cid::DevBuf scratch[cid::SCRATCH_SLOTS];
     cid::PinBuf pinned[8];

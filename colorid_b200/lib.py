@@ -57,6 +57,13 @@ SIGNATURES = {
     "cid_query_counts": (C.c_int, [vp, vp, u64p, C.c_uint64, u64p, C.c_uint64, C.c_int, C.c_int, C.c_int64, u32p, u64p,
                                    u64p, u64p, u64p, i64p]),
     "cid_query_counts_dev": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_uint64, vp, u64p, u64p, C.c_uint64, C.c_int, vp, vp, vp]),
+    "cid_dev_alloc": (C.c_int, [vp, C.c_size_t, C.POINTER(vp)]),
+    "cid_dev_free": (None, [vp, vp]),
+    "cid_ipc_export": (C.c_int, [vp, vp, u8p]),
+    "cid_ipc_open": (C.c_int, [vp, u8p, C.POINTER(vp)]),
+    "cid_ipc_close": (C.c_int, [vp, vp]),
+    "cid_query_counts_sharded_dev": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_uint64, vp, u64p, u64p, C.c_uint64, C.c_int,
+                                               C.POINTER(vp), C.c_uint32, C.c_uint32, C.c_uint32, vp, vp]),
     "cid_query_perfect": (C.c_int, [vp, vp, u64p, C.c_uint64, u64p, C.c_uint64, u32p, u8p, u64p]),
     "cid_query_perfect_mf": (C.c_int, [vp, vp, u64p, C.c_uint64, u32p, u8p, u64p]),
     "cid_read_id_batch": (C.c_int, [vp, vp, vp, u64p, C.c_uint64, u64p, C.c_uint64, C.POINTER(ReadIdParams), u32p, u32p,

@@ -100,3 +100,56 @@ def concat_in_order(local_rows, group=None):
     parts = [None] * world
     dist.all_gather_object(parts, local_rows, group=group)
     return np.concatenate(parts, axis=0)
+
+
+class PeerCounts:
+    """Full-width [nq, n_total] count buffers, one per rank, each opened on every other rank through CUDA IPC so that
+    cid_query_counts_sharded_dev can add its column slice straight into all of them over NVLink (no collective)."""
+
+    def __init__(self, ctx, nq, n_total, device, group=None):
+        import ctypes as C
+        from . import lib as L
+        self.ctx, self.lib, self.group = ctx, ctx.lib, group
+        self.nq, self.n_total = nq, n_total
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise ValueError("at most 8 destination buffers (one NVSwitch domain)")
+        own = L.vp()
+        L.check(self.lib.cid_dev_alloc(ctx.h, nq * n_total * 4, C.byref(own)))
+        self.own = own.value
+        handle = (C.c_uint8 * 64)()
+        L.check(self.lib.cid_ipc_export(ctx.h, own, handle))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self.ptrs, self._opened = [], []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self.ptrs.append(self.own)
+                continue
+            p = L.vp()
+            L.check(self.lib.cid_ipc_open(ctx.h, (C.c_uint8 * 64).from_buffer_copy(h), C.byref(p)))
+            self.ptrs.append(p.value)
+            self._opened.append(p.value)
+        self.dest = (L.vp * self.world)(*self.ptrs)
+        self.view = device_view(self.own, nq * n_total, device).view(nq, n_total)     # this rank's complete result
+
+    def begin_pass(self):
+        """zero the own buffer; no peer may write before every rank has done so"""
+        self.view.zero_()
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+
+    def end_pass(self):
+        """own stores (local and remote) are complete after the stream sync; the barrier says the same of every peer"""
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        return self.view
+
+    def close(self):
+        for p in self._opened:
+            self.lib.cid_ipc_close(self.ctx.h, p)
+        self._opened = []
+        dist.barrier(group=self.group)          # nobody frees memory a peer still has mapped
+        if self.own:
+            self.lib.cid_dev_free(self.ctx.h, self.own)
+            self.own = None

@@ -146,6 +146,24 @@ int cid_query_counts_dev(cid_index* idx, const char* d_bases, const uint64_t* d_
                          const uint64_t* h_seq_offs, uint64_t nq, int seq_mode, uint32_t* d_counts,
                          uint64_t* d_num_kmers, void* stream);
 
+/* Column-sharded index (GPU g holds the accessions [col_offset, col_offset + n_colors) of every row): every
+ * GPU gathers all k-mers from its slice and the per-query counts are disjoint column slices of the full [nq][n_total]
+ * result.  Instead of a collective after the kernel, the gather kernel itself adds each count into slot
+ * [query][col_offset + accession] of EVERY destination buffer -- the caller's own and its peers' (device memory of the
+ * other GPUs opened with cid_ipc_open: stores travel over NVLink/NVSwitch while the kernel is still gathering).
+ * Protocol per pass: every rank zeroes its own destination, barrier, this call on every rank, stream sync, barrier;
+ * then each rank holds the complete [nq][n_total] counts.  cid_dev_alloc gives cudaMalloc memory (what CUDA IPC needs),
+ * cid_ipc_export / cid_ipc_open move a 64-byte handle between the per-GPU processes.  n_dest <= 8. */
+int cid_dev_alloc(cid_ctx* ctx, size_t bytes, void** dptr);
+void cid_dev_free(cid_ctx* ctx, void* dptr);
+int cid_ipc_export(cid_ctx* ctx, const void* dptr, uint8_t handle[64]);
+int cid_ipc_open(cid_ctx* ctx, const uint8_t handle[64], void** dptr);
+int cid_ipc_close(cid_ctx* ctx, void* dptr);
+int cid_query_counts_sharded_dev(cid_index* idx, const char* d_bases, const uint64_t* d_seq_offs, uint64_t nseq,
+                                 uint64_t nbases, const uint64_t* d_query_offs, const uint64_t* h_query_offs,
+                                 const uint64_t* h_seq_offs, uint64_t nq, int seq_mode, void* const* d_dest_counts,
+                                 uint32_t n_dest, uint32_t n_total, uint32_t col_offset, uint64_t* d_num_kmers, void* stream);
+
 /* ---- perfect search: perfect_search.rs:6-60 batch_search ----------------------------------
  * AND of all num_hash rows of all distinct k-mers of the query (kmerize_vector semantics).
  * and_rows[nq*row_words]; status[q]: 0 = AND valid, 1 = "No perfect hits!" (a row is absent),
