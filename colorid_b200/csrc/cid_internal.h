@@ -76,6 +76,7 @@ struct cid_ctx {
     // read_id host pipeline (cid_readid_pipe.cu): chunked H2D / kernels / D2H / host vote overlap
     struct cid_readid_pipe* pipe = nullptr;
     uint64_t opt_readid_chunk = 0;   // reads per pipeline chunk (0 = automatic)
+    uint64_t opt_readid_chunk0 = 0;  // reads in the first chunk of the ramp (0 = 32768)
     int opt_host_threads = 0;        // host threads for the vote (0 = all cores)
     // device-pointer read_id (cid_read_id_batch_dev): chunks alternate over internal streams forked from /
     // joined to the caller's stream, so the DRAM-access-bound vote kernel of one chunk runs under the

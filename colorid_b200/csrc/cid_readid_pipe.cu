@@ -141,7 +141,7 @@ static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals,
     // 54 GB/s), the kernels consume ~56 K/ms, so a chunk may be at most 1.55x its predecessor.
     uint64_t chunk_max = ctx->opt_readid_chunk ? ctx->opt_readid_chunk : 262144;
     std::vector<uint64_t> cuts{0};
-    for (uint64_t cur = std::min<uint64_t>(32768, chunk_max), at = 0; at < nreads;) {
+    for (uint64_t cur = std::min<uint64_t>(ctx->opt_readid_chunk0 ? ctx->opt_readid_chunk0 : 32768, chunk_max), at = 0; at < nreads;) {
         uint64_t size = std::min(cur, nreads - at);
         if (nreads - at - size < size / 4) size = nreads - at;      // absorb a short tail
         at += size;
