@@ -987,7 +987,38 @@ static int launch_query_gather(cid_ctx* ctx, cudaStream_t st, const cid_index* i
 // (three passes over a 16-byte-per-slot count table in HBM, ~3 slots per k-mer) by one pass over the bases.
 constexpr int QF_THREADS = 256;
 constexpr uint32_t QF_MAX_NPOS = 8192;              // table of <= 16384 slots (128 KB), list of <= 16384 k-mers per gather unit
-__global__ void __launch_bounds__(QF_THREADS)
+// kmerize_string window with a byte outside ACGTacgt (query_front_kernel<true>): builds the canonical upper-cased string;
+// returns true with `key` set when that string is plain ACGT after all (the caller inserts it like any k-mer), else
+// deduplicates it by string comparison in the small `dirty` table (offset of first occurrence + 1 per slot) and, when new,
+// appends its byte-wise XXH3 rows to the query's list.
+constexpr uint32_t QF_DIRTY_SLOTS = 2048;      // distinct non-ACGT k-mers of one record (<= 3/4 of it, else CID_E_UNSUPPORTED)
+__device__ __noinline__ static bool dirty_window(const uint8_t* win, const uint8_t* qbytes, uint32_t off, uint32_t k, uint32_t H, ModS mods,
+                                                 uint32_t* dirty, uint32_t* s_cnt, uint32_t* rid_q, uint32_t* err, uint64_t& key) {
+    uint8_t str[32];
+    if (string_kmer(win, k, str, key)) return true;
+    const HashIn in = hashin_from_bytes(str, k);
+    const uint64_t h0 = xxh3_kmer(in, k, 0);
+    uint32_t slot = (uint32_t)(h0 >> 24) & (QF_DIRTY_SLOTS - 1);
+    for (uint32_t probes = 0;; probes++) {
+        if (probes >= QF_DIRTY_SLOTS * 3 / 4) { atomicOr(err, ERRF_STRING_NONACGT); return false; }
+        const uint32_t prev = atomicCAS(&dirty[slot], 0u, off + 1u);
+        if (prev == 0u) break;
+        uint8_t other[32]; uint64_t okey;
+        string_kmer(qbytes + (prev - 1u), k, other, okey);
+        bool same = true;
+        for (uint32_t j = 0; j < k; j++) same = same && other[j] == str[j];
+        if (same) return false;
+        slot = (slot + 1) & (QF_DIRTY_SLOTS - 1);
+    }
+    const uint32_t i = atomicAdd(s_cnt, 1u);
+    uint32_t* out = rid_q + (size_t)i * H;
+    out[0] = (uint32_t)mod_s(h0, mods);
+    for (uint32_t hh = 1; hh < H; hh++) out[hh] = (uint32_t)mod_s(xxh3_kmer(in, k, hh), mods);
+    return false;
+}
+
+template <bool STRINGM>      // kmerize_string (-s -m): windows with bytes outside ACGTacgt are k-mers too (separate instantiation:
+__global__ void __launch_bounds__(QF_THREADS)    // the byte-string path costs registers the -g / -s paths should not pay)
 query_front_kernel(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ seq_offs,
                    const uint64_t* __restrict__ query_offs, const uint32_t* __restrict__ qlist, uint32_t tsize, uint32_t k,
                    int seq_mode, uint32_t H, ModS mods, const uint64_t* __restrict__ rid_base, uint32_t* __restrict__ rid_out,
@@ -997,15 +1028,19 @@ query_front_kernel(const uint8_t* __restrict__ bases, const uint64_t* __restrict
     __shared__ uint32_t s_cnt;
     unsigned long long* keys = (unsigned long long*)dsm;
     Tile t = tile_carve(dsm + (size_t)tsize * 8, KT_CAP);
+    // kmerize_string only: k-mers holding a byte outside ACGTacgt, deduplicated by (offset of first occurrence + 1)
+    uint32_t* dirty = (uint32_t*)(dsm + (size_t)tsize * 8 + tile_smem_bytes(KT_CAP));
     const int tid = threadIdx.x;
     const uint32_t q = qlist[blockIdx.x];
     const uint32_t tmask = tsize - 1;
     lut4_init(lut, tid, QF_THREADS);
     for (uint32_t i = tid; i < tsize; i += QF_THREADS) keys[i] = CID_EMPTY_KEY;
+    if (STRINGM) for (uint32_t i = tid; i < QF_DIRTY_SLOTS; i += QF_THREADS) dirty[i] = 0u;
     for (int i = tid; i < KT_CAP / 32 + 2; i += QF_THREADS) t.start[i] = 0;      // one sequence per tile: no boundaries inside
     if (tid == 0) s_cnt = 0;
     const uint64_t base = rid_base[q];
     const uint64_t s_lo = __ldg(query_offs + q), s_hi = __ldg(query_offs + q + 1);
+    const uint64_t qbase = __ldg(seq_offs + s_lo);
     for (uint64_t s = s_lo; s < s_hi; s++) {
         const uint64_t b0 = __ldg(seq_offs + s), L = __ldg(seq_offs + s + 1) - b0;
         if (L < k) continue;                                 // kmer.rs:94 / :477 `continue`
@@ -1029,9 +1064,13 @@ query_front_kernel(const uint8_t* __restrict__ bases, const uint64_t* __restrict
             for (int p = tid; p < KT; p += QF_THREADS) {
                 uint64_t key; bool fwd, low;
                 if (!tile_kmer(t, p, k, key, fwd, low)) {
-                    // kmerize_string (kmer.rs:279-293) has no has_no_n test: such a window cannot be packed into 2 bits
-                    if (seq_mode == CID_SEQ_STRING && p + (int)k <= t.len) atomicOr(err, ERRF_STRING_NONACGT);
-                    continue;
+                    if (!STRINGM || p + (int)k > t.len) continue;
+                    // kmerize_string (kmer.rs:279-293) has no has_no_n test: a window with a byte outside ACGTacgt is a k-mer
+                    // too.  Its canonical upper-cased string either turns out to be plain ACGT after all (U -> A in the reverse
+                    // complement) and joins the packed set below, or it is hashed byte-wise and deduplicated by comparing strings.
+                    if (!dirty_window(t.ascii + p, bases + qbase, (uint32_t)(b0 + t0 + p - qbase), k, H, mods, dirty, &s_cnt,
+                                      rid_out + base * H, err, key))
+                        continue;
                 }
                 if (low && seq_mode == CID_SEQ_FASTQ) { atomicOr(err, ERRF_LOWER_RAW); continue; }
                 uint32_t h = (uint32_t)mix64(key) & tmask;
@@ -1102,8 +1141,10 @@ int launch_query_front_gather(cid_ctx* ctx, cudaStream_t st, const cid_index* id
     CID_CUDA(cudaMemcpyAsync(d_group, group.data(), bq * 4, cudaMemcpyHostToDevice, st));
     bool& attr = ctx->attr_done[1];
     if (!attr) {
-        CID_CUDA(cudaFuncSetAttribute(query_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CID_CUDA(cudaFuncSetAttribute(query_front_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(16384 * 8 + tile_smem_bytes(KT_CAP))));
+        CID_CUDA(cudaFuncSetAttribute(query_front_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(16384 * 8 + tile_smem_bytes(KT_CAP) + QF_DIRTY_SLOTS * 4)));
         attr = true;
     }
     uint64_t at = 0;
@@ -1113,9 +1154,15 @@ int launch_query_front_gather(cid_ctx* ctx, cudaStream_t st, const cid_index* id
         CID_CUDA(cudaMemcpyAsync(d_qlist + at, qlist[c].data(), n * 4, cudaMemcpyHostToDevice, st));
         const uint32_t tsize = 2048u << c;
         ProfScope ps(ctx, st, KID_QUERY_FRONT);
-        query_front_kernel<<<(unsigned)n, QF_THREADS, (size_t)tsize * 8 + tile_smem_bytes(KT_CAP), st>>>(
-            d_bases, d_seq_offs, d_query_offs + q0, d_qlist + at, tsize, k, seq_mode, H, make_mods(idx->S), d_base, d_rid, d_unit_n,
-            d_num_kmers, ctx->d_err);
+        const size_t fsmem = (size_t)tsize * 8 + tile_smem_bytes(KT_CAP) + (seq_mode == CID_SEQ_STRING ? QF_DIRTY_SLOTS * 4 : 0);
+        if (seq_mode == CID_SEQ_STRING)
+            query_front_kernel<true><<<(unsigned)n, QF_THREADS, fsmem, st>>>(
+                d_bases, d_seq_offs, d_query_offs + q0, d_qlist + at, tsize, k, seq_mode, H, make_mods(idx->S), d_base, d_rid, d_unit_n,
+                d_num_kmers, ctx->d_err);
+        else
+            query_front_kernel<false><<<(unsigned)n, QF_THREADS, fsmem, st>>>(
+                d_bases, d_seq_offs, d_query_offs + q0, d_qlist + at, tsize, k, seq_mode, H, make_mods(idx->S), d_base, d_rid, d_unit_n,
+                d_num_kmers, ctx->d_err);
         ctx->launches++;
         CID_CUDA(cudaGetLastError());
         at += n;

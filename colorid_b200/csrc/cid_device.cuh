@@ -297,6 +297,51 @@ __device__ __forceinline__ bool tile_kmer(const Tile& t, int i, uint32_t k, uint
     return true;
 }
 
+// ------------------------------------------------------------------ k-mers with bytes outside ACGTacgt (kmerize_string only)
+// kmer.rs:271-299 kmerize_string has no has_no_n test: every window of a record is a k-mer, whatever its bytes.
+// kmer.rs:847-863 switch_base on ANY byte: a<->t c<->g, u->a, n->n (case kept), everything else -> 'N'.
+__device__ __forceinline__ uint32_t switch_base_any(uint32_t c) {
+    switch (c) {
+        case 'a': return 't'; case 'c': return 'g'; case 't': return 'a'; case 'g': return 'c'; case 'u': return 'a'; case 'n': return 'n';
+        case 'A': return 'T'; case 'C': return 'G'; case 'T': return 'A'; case 'G': return 'C'; case 'U': return 'A'; case 'N': return 'N';
+        default: return 'N';
+    }
+}
+// The canonical upper-cased string of the window win[0..k): `fwd < revcomp ? fwd : revcomp` on raw bytes (kmer.rs:280),
+// then to_uppercase (:283).  Returns true when the result is a plain ACGT string (then `key` holds its 2-bit codes).
+__device__ __noinline__ static bool string_kmer(const uint8_t* win, uint32_t k, uint8_t* out, uint64_t& key) {
+    bool took_fwd = false;
+    for (uint32_t j = 0; j < k; j++) {
+        const uint32_t a = win[j], b = switch_base_any(win[k - 1 - j]);
+        if (a != b) { took_fwd = a < b; break; }
+    }
+    bool clean = true;
+    key = 0;
+    for (uint32_t j = 0; j < k; j++) {
+        uint32_t c = took_fwd ? (uint32_t)win[j] : switch_base_any(win[k - 1 - j]);
+        if (c >= 'a' && c <= 'z') c -= 32;
+        out[j] = (uint8_t)c;
+        clean = clean && (c == 'A' || c == 'C' || c == 'G' || c == 'T');
+        key = (key << 2) | base_code(c);
+    }
+    return clean;
+}
+// The words XXH3 reads (see HashIn) straight from k bytes.
+__device__ __forceinline__ uint64_t le_bytes(const uint8_t* p, uint32_t n) {
+    uint64_t v = 0;
+    for (uint32_t i = 0; i < n; i++) v |= (uint64_t)p[i] << (8 * i);
+    return v;
+}
+__device__ __forceinline__ HashIn hashin_from_bytes(const uint8_t* s, uint32_t k) {
+    HashIn in;
+    in.w0 = in.w1 = in.w2 = in.w3 = 0;
+    if (k >= 17) { in.w0 = le_bytes(s, 8); in.w1 = le_bytes(s + 8, 8); in.w2 = le_bytes(s + k - 16, 8); in.w3 = le_bytes(s + k - 8, 8); }
+    else if (k >= 9) { in.w0 = le_bytes(s, 8); in.w1 = le_bytes(s + k - 8, 8); }
+    else if (k >= 4) { in.w0 = le_bytes(s, 4); in.w1 = le_bytes(s + k - 4, 4); }
+    else { in.w0 = s[0]; in.w1 = s[k >> 1]; in.w2 = s[k - 1]; }
+    return in;
+}
+
 // ------------------------------------------------------------------ minimizers (.mxi indexes)
 // kmer.rs:971-986 find_minimizer(seq, m) on the canonical k-mer `s` (packed, upper case) and its reverse
 // complement `src`: the smallest of seq[0..m] and, for i in 1..=k-m, seq[i..i+m] and revcomp(seq[i..i+m])

@@ -304,17 +304,39 @@ def test_perfect_search_multifasta_records(oracle, ctx):
         ctx.set_option("query_front", front)
         try:
             g = gix.query_perfect_mf(recs)
-            # kmerize_string has no has_no_n test: an N inside a record is part of its k-mers, which the 2-bit
-            # device path cannot represent -> refused loudly, never silently skipped
-            with pytest.raises(cb.lib.CidError) as ei:
-                gix.query_perfect_mf([genomes[0][:200] + b"N" + genomes[0][201:400]])
-            assert ei.value.code == cb.lib.CID_E_UNSUPPORTED
         finally:
             ctx.set_option("query_front", 1)
         assert np.array_equal(g["status"], o["status"])
         assert np.array_equal(g["n_kmers"], o["n_kmers"])
         assert np.array_equal(g["and_rows"], o["and_rows"])
     assert (o["status"] == 0).sum() >= 10 and (o["status"] == 2).sum() == 1
+    # kmerize_string has no has_no_n test: windows holding N, IUPAC codes, U/u ... are k-mers too (hashed byte-wise,
+    # upper-cased; U -> A in the reverse complement can even give a plain ACGT string).  Records of <= 8192 positions
+    # take query_front, which handles them; the count-table path cannot represent them and refuses loudly.
+    g0 = genomes[0]
+    dirty = [g0[:200] + b"N" + g0[201:400], g0[:300].replace(b"T", b"U"), g0[100:400].lower().replace(b"t", b"u"),
+             g0[:150] + b"RYKMnn-*" + g0[150:300], b"N" * (k + 5), g0[:k - 1] + b"N", g0[:k] + b"N" + g0[:k], b"U" * 60,
+             synth.sprinkle(rng, g0[:600], b"NnUuRacgt", 0.05), g0[:500]]
+    o = oix.query_perfect(dirty, mf=True)
+    g = gix.query_perfect_mf(dirty)
+    assert np.array_equal(g["n_kmers"], o["n_kmers"]) and np.array_equal(g["status"], o["status"])
+    assert np.array_equal(g["and_rows"], o["and_rows"])
+    assert o["status"][-1] == 0 and (o["status"][:-1] == 1).sum() >= 5          # absent rows: "No perfect hits!"
+    dense_o, dense_g = oracle.Index(101, H, k, N), cb.Index(ctx, 101, H, k, N)   # 101 rows, all present: the AND is computed
+    for c in range(N):
+        assert dense_g.build_accession(c, [genomes[c]]) == dense_o.build_accession(c, [genomes[c]], oracle.MODE_FASTA)
+    dense_o.finalize()
+    dense_g.finalize()
+    o, g = dense_o.query_perfect(dirty, mf=True), dense_g.query_perfect_mf(dirty)
+    assert np.array_equal(g["n_kmers"], o["n_kmers"]) and np.array_equal(g["status"], o["status"])
+    assert np.array_equal(g["and_rows"], o["and_rows"]) and (o["status"] == 0).sum() >= 8
+    ctx.set_option("query_front", 0)
+    try:
+        with pytest.raises(cb.lib.CidError) as ei:
+            gix.query_perfect_mf(dirty[:1])
+        assert ei.value.code == cb.lib.CID_E_UNSUPPORTED
+    finally:
+        ctx.set_option("query_front", 1)
 
 
 def _readid_compare(oracle, oix, gix, reads, **kw):
