@@ -44,7 +44,8 @@ enum {
     CID_SEQ_FASTA = 0, /* kmerize_vector  kmer.rs:87-125 : has_no_n, compare raw case, then uppercase */
     CID_SEQ_FASTQ = 1, /* kmers_from_fq_qual / kmers_fq_pe_qual kmer.rs:461-510,581-655 : has_no_n, raw case */
     CID_SEQ_STRING = 2 /* kmerize_string kmer.rs:271-299 (-s -m): NO has_no_n, compare raw case, then uppercase.
-                          A k-mer holding a byte outside ACGTacgt cannot be packed: CID_E_UNSUPPORTED. */
+                          A window holding a byte outside ACGTacgt (N, IUPAC, U) is a k-mer too: hashed byte-wise
+                          for records of <= 8192 positions; longer records with such bytes: CID_E_UNSUPPORTED. */
 };
 
 int cid_version(void);
