@@ -786,6 +786,140 @@ def run_c4(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------- C1: build from FASTA + FASTQ search
+def run_c1(args):
+    """BASELINE.json configs[0]: build of the 46-genome k=31 S=50M H=4 index from FASTA, then `search` of one paired-end
+    30x FASTQ read set (default 7-column report: auto_cutoff on the query's k-mer counts, per-accession hits and the
+    unique-hit summaries of reports.rs:8-48) through the host-pointer ABI call (`cid_query_counts`, CID_SEQ_FASTQ,
+    filter -1).  Synthetic stand-in for refs/ + SRR548019.fastq.gz, which do not travel to the GPU box.  One step = one
+    search of the whole read set; single GPU (the reference's own CPU-runnable case; under torchrun only rank 0 works)."""
+    import torch
+    import colorid_b200 as cb
+    from colorid_b200 import lib as L
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    cfg = dict(CFG)
+    cfg.update(coverage=30, lowq=0.02)
+    if args.quick:
+        cfg.update(genome_len=200_000, S=5_000_000)
+    ctx = cb.Context(local)
+    for kv in args.opt:
+        name, _, val = kv.partition("=")
+        ctx.set_option(name, int(val))
+    A, Lg, rl = cfg["n_acc"], cfg["genome_len"], cfg["read_len"]
+    genomes = make_genomes(torch, dev, cfg, 0xC0101D01)
+    lut = torch.tensor(ASCII, device=dev, dtype=torch.uint8)
+    gix = cb.Index(ctx, cfg["S"], cfg["H"], cfg["k"], A)
+    offs = torch.tensor([0, Lg], device=dev, dtype=torch.int64)
+    asc = [lut[genomes[a].long()].contiguous() for a in range(A)]
+    torch.cuda.synchronize()
+    tb = time.perf_counter()
+    for a in range(A):
+        gix.build_accession_dev(a, asc[a].data_ptr(), offs.data_ptr(), 1, Lg)
+    gix.finalize()
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - tb
+    del asc
+    # the query: 30x paired-end reads of accession 0 (0.5 % substitutions, 2 % of the bases below -Q -> 'N' by qual_mask,
+    # applied while generating like the c4 workload: the ABI takes masked sequences), no random pairs
+    qcfg = dict(cfg, frac_random=0.0, n_acc=1)
+    n_pairs = Lg * cfg["coverage"] // (2 * rl)
+    W, K = max(1, min(args.warmup, 3)), max(1, min(args.steps, 5))
+    sets = []
+    for i in range(2):                                       # two read sets alternate: 2 x 100 MB of fresh input per step
+        b, q = make_reads(torch, dev, qcfg, genomes[:1], n_pairs, 0xC0101D10 + i)
+        b[q < cfg["qual_offset"] + 33] = 78
+        h = torch.empty(b.shape, dtype=torch.uint8).pin_memory()
+        h.copy_(b)
+        sets.append(h.numpy().reshape(-1))
+        del b, q
+    seq_offs = np.arange(2 * n_pairs + 1, dtype=np.uint64) * np.uint64(rl)
+    query_offs = np.array([0, 2 * n_pairs], dtype=np.uint64)
+    counts = np.zeros((1, A), np.uint32)
+    nk = np.zeros(1, np.uint64)
+    un, us, um = (np.zeros((1, A), np.uint64) for _ in range(3))
+    used = np.zeros(1, np.int64)
+    P = lambda a, tp=L.u64p: a.ctypes.data_as(tp)
+    lib = ctx.lib
+
+    def search(i):
+        L.check(lib.cid_query_counts(gix.h, P(sets[i % 2], L.vp), P(seq_offs), 2 * n_pairs, P(query_offs), 1, L.CID_SEQ_FASTQ, 0, -1,
+                                     P(counts, L.u32p), P(nk), P(un), P(us), P(um), P(used, L.i64p)))
+    for i in range(W):
+        search(i)
+    torch.cuda.synchronize()
+    launches0 = ctx.launches
+    ctx.profile(True)
+    clk = ClockSampler(local)
+    clk.start()
+    t0 = time.perf_counter()
+    for i in range(K):
+        search(W + i)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    clocks = clk.stop()
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    launches = ctx.launches - launches0
+    lookups = int(nk[0])
+    cov0 = float(counts[0, 0]) / float(gix.n_ref[0])
+    # size-independent property: a 30x read set of accession 0 recovers (nearly) all of its k-mers after the filter
+    assert cov0 > 0.97 and int(used[0]) >= 1, (cov0, used)
+    kern_ms = sum(v[0] for v in prof.values()) / K
+    kern = {k_: {"ms_per_launch": v[0] / v[1], "launches_per_step": v[1] / K} for k_, v in prof.items()}
+    peak, peak_src = measured_peak()
+    R = 4 * ((A + 31) // 32)
+    nb = 2 * n_pairs * rl
+    alg = nb + lookups * cfg["H"] * R + 4 * A          # the read set once + H rows per surviving k-mer + counts
+    # CPU: the reference's search is single-threaded (batch_search_pe.rs:9-179); bounded sample = the first `ns` pairs
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            from oracle import pyoracle as O
+            O.lib()
+            oix = oracle_index_from_dense(O, cfg, gix.download_dense(), gix.n_ref.copy())
+            ns = min(n_pairs, 20_000)
+            sub = sets[0][:2 * ns * rl]
+            reads = [bytes(sub[j * rl:(j + 1) * rl]) for j in range(2 * ns)]
+            t0 = time.perf_counter()
+            o = oix.query_counts([reads], O.MODE_FASTQ, False, -1)
+            dt = time.perf_counter() - t0
+            g = gix.query_counts([reads], seq_mode=L.CID_SEQ_FASTQ, gene_search=False, filt=-1)
+            same = all(np.array_equal(g[k_], o[k_]) for k_ in ("counts", "num_kmers", "uniq_n", "uniq_sum", "uniq_mode", "cutoff"))
+            cpu = {"value": 2 * ns * rl / dt / 1e9, "unit": "query Gbp/s", "cores": 1, "kind": "port",
+                   "sample": f"the first {ns} read pairs of the same read set ({2 * ns * rl / 1e6:.0f} Mbp), single thread like the "
+                             "reference's search; C++ restatement of the Rust reference (oracle/)",
+                   "lookups_per_s": float(o["num_kmers"][0]) / dt, "matches_gpu_report": bool(same)}
+        except Exception as ex:
+            cpu = {"value": None, "unit": "query Gbp/s", "cores": 0, "kind": "port", "sample": f"failed: {ex!r}"}
+    line = {"metric": "search query Gbp/s", "value": K * nb / wall / 1e9, "unit": "query Gbp/s", "n_gpus": 1, "steps": K, "warmup": W,
+            "ms_per_step": wall / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic",
+            "config": {"workload": "C1 build from FASTA + search of a 30x paired-end FASTQ read set, default report "
+                                   "(BASELINE.json configs[0], synthetic stand-in)",
+                       "index": f"{A} synthetic genomes x {Lg} bp, k={cfg['k']} S={cfg['S']} H={cfg['H']}",
+                       "read_pairs": n_pairs, "read_len": rl, "filter": "auto_cutoff", "cutoff_used": int(used[0]),
+                       "l2_policy": "two 100 MB read sets alternate; count table and 400 MB matrix exceed the 126 MB L2"},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": K * nb / wall / 1e9, "unit": "query Gbp/s", "h2d_bytes_per_step": int(nb + seq_offs.nbytes),
+                    "d2h_bytes_per_step": int(counts.nbytes + un.nbytes * 3 + 16),
+                    "includes": "cid_query_counts with pinned host reads: H2D, k-mer counting, auto_cutoff, hashing, row gather, "
+                                "unique-hit summaries, D2H (value == e2e: this workload is only measured through the host ABI)"},
+            "lookups": lookups, "lookups_per_s": K * lookups / wall, "kernel_ms_per_step": kern_ms, "kernels": kern,
+            "roofline": {"bound": "hbm", "kernel": "whole step (kernels only)", "achieved": alg / (kern_ms / 1e3) / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": alg / (kern_ms / 1e3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_step": alg,
+                         "note": "exact k-mer counting of the read set dominates and has no algorithmic traffic beyond reading it "
+                                 "(SURVEY 8d): low by construction"},
+            "cpu_baseline": cpu,
+            "build": {"gbp_per_s": A * Lg / build_s / 1e9, "seconds": build_s, "note": "46 FASTA accessions + transposition, device-resident bases"},
+            "parity": {"hits_over_n_ref_kmers_of_source_accession": cov0}}
+    print(json.dumps(line), flush=True)
+
+
 def bind_to_gpu_numa_node(local, world):
     """N > 1: pin this rank (and the pinned host buffers it first-touches, and the library's host threads) to the CPU
     cores NVML reports as local to its GPU, so that 8 ranks do not pull their H2D traffic through one socket.  Returns
@@ -1064,7 +1198,7 @@ def main():
     ap.add_argument("--only-search", action="store_true", help="profiling aid: run only the C3 gene-search measurement")
     ap.add_argument("--opt", action="append", default=[], help="library tuning option name=value (cid_ctx_set_option), repeatable")
     ap.add_argument("--quick", action="store_true", help="small genomes / bloom filter (functional check only)")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"], help="c2 = read_id headline (default); c4 = build from read sets; c5 = column-sharded build + search")
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c4", "c5"], help="c1 = FASTA build + FASTQ search; c2 = read_id headline (default); c4 = build from read sets; c5 = column-sharded build + search")
     ap.add_argument("--c4-acc", type=int, default=0, help="accessions per rank built by the c4 workload (default 24)")
     ap.add_argument("--c5-acc", type=int, default=0, help="total accessions of the c5 workload (default 10,000)")
     args = ap.parse_args()
@@ -1074,6 +1208,8 @@ def main():
         run_c5(args)
     elif args.workload == "c4":
         run_c4(args)
+    elif args.workload == "c1":
+        run_c1(args)
     else:
         run_ours(args)
 

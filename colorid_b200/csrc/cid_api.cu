@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstring>
+#include <chrono>
 #include <map>
 #include <vector>
 
@@ -290,6 +291,7 @@ int cid_ctx_set_option(cid_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "build_packed")) { c->opt_build_packed = value != 0; return CID_OK; }
     if (!strcmp(name, "build_set")) { c->opt_build_set = value != 0; return CID_OK; }
     if (!strcmp(name, "query_front")) { c->opt_query_front = value != 0; return CID_OK; }
+    if (!strcmp(name, "gather_l2_64b")) { c->opt_gather_l2_64b = value < 0 ? -1 : (value != 0); return CID_OK; }
     if (!strcmp(name, "query_fused")) { c->opt_query_fused = value != 0; return CID_OK; }
     if (!strcmp(name, "host_threads")) { c->opt_host_threads = value > 0 ? (int)value : 0; return CID_OK; }
     set_error("cid_ctx_set_option: unknown option '%s'", name);
@@ -737,11 +739,15 @@ int cid_query_counts(cid_index* ix, const char* bases, const uint64_t* seq_offs,
         return CID_OK;
     }
     std::vector<uint64_t> cuts = query_batches(seq_offs, query_offs, nq, ix->k, kMaxBatchSlots);
+    static const bool trace = getenv("CID_TRACE") != nullptr;     // host stage timings on stderr (diagnostics only)
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     for (size_t b = 0; b + 1 < cuts.size(); b++) {
         const uint64_t q0 = cuts[b], q1 = cuts[b + 1], bq = q1 - q0;
         QueryPlan qp;
+        const double t_0 = now();
         CID_TRY(query_front(ix, st, d_bases, d_seq_offs, seq_offs, query_offs, q0, q1, seq_mode, qp));
         CID_TRY(check_err_flags(ctx, st));
+        const double t_front = now();
         // per-query filter (batch_search_pe.rs:34-39 / :112-120)
         std::vector<int64_t> filt(bq);
         for (uint64_t q = 0; q < bq; q++) {
@@ -750,6 +756,7 @@ int cid_query_counts(cid_index* ix, const char* bases, const uint64_t* seq_offs,
             else filt[q] = filter;
             if (cutoff_used) cutoff_used[q0 + q] = filt[q];
         }
+        const double t_cut = now();
         const uint64_t npos_total = qp.gr.total_slots / 2;
         const uint32_t uniq_cap = want_uniq ? (uint32_t)std::min<uint64_t>(npos_total + 1, 0xFFFFFFF0u / 3) : 0;
         CID_TRY(ctx->scratch[7].ensure(bq * 8));
@@ -770,6 +777,7 @@ int cid_query_counts(cid_index* ix, const char* bases, const uint64_t* seq_offs,
         uint32_t nu = 0;
         CID_CUDA(cudaMemcpyAsync(&nu, ctx->scratch[13].p, 4, cudaMemcpyDeviceToHost, st));
         CID_CUDA(cudaStreamSynchronize(st));
+        const double t_counts = now();
         if (want_uniq) {
             if (nu > uniq_cap) { set_error("unique-hit list overflow"); return CID_E_CAPACITY; }
             std::vector<uint32_t> ul((size_t)nu * 3);
@@ -787,6 +795,10 @@ int cid_query_counts(cid_index* ix, const char* bases, const uint64_t* seq_offs,
                 if (uniq_mode) uniq_mode[at] = mode;
             }
         }
+        if (trace)
+            fprintf(stderr, "[cid trace] query_counts batch %zu: %llu queries, H2D + count table + k-mer counting %.2f ms, cutoffs %.2f ms, "
+                            "hash + gather %.2f ms, unique-hit summaries (%u entries) %.2f ms\n", b, (unsigned long long)bq, t_front - t_0,
+                    t_cut - t_front, t_counts - t_cut, nu, now() - t_counts);
     }
     return CID_OK;
 }

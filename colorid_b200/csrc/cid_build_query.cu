@@ -667,6 +667,13 @@ query_hash_kernel(const Slot* __restrict__ table, const uint32_t* __restrict__ u
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gptr) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gptr) : "memory");
 }
+// Same copy with the 64-byte L2 prefetch size.  By default an L2 miss fills the whole 128-byte line from DRAM
+// (profiles/r1_gather_probe.txt: ~100 B of DRAM traffic per 8-byte gather, 56 B with this hint), so a 160-byte row of a C5
+// column shard, which always straddles two lines, costs 256 B of DRAM traffic -- 63 % algorithmic efficiency at 100 % of
+// the DRAM peak.  With 64-byte fills the same row costs three 64-byte atoms (192 B).
+__device__ __forceinline__ void cp_async16_pf64(uint32_t saddr, const void* gptr) {
+    asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" ::"r"(saddr), "l"(gptr) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int NPEND> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NPEND) : "memory"); }
 __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
@@ -693,7 +700,7 @@ __global__ void __launch_bounds__(QG_WARPS * 32, 4)
 query_gather_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t N, const uint32_t* __restrict__ rid,
                     const uint32_t* __restrict__ unit_group, const uint64_t* __restrict__ unit_slot0,
                     const uint32_t* __restrict__ unit_n, uint32_t* __restrict__ counts,
-                    const uint32_t* __restrict__ rownz, uint32_t* __restrict__ missing, uint32_t W, GatherOut go) {
+                    const uint32_t* __restrict__ rownz, uint32_t* __restrict__ missing, uint32_t W, GatherOut go, uint32_t pf64) {
     using Cfg = QGCfg<HT>;
     constexpr int D = Cfg::D;
     static_assert(D >= 2 && 8 % D == 0, "ring depth must divide the tree width");
@@ -770,7 +777,10 @@ query_gather_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t N, 
 #pragma unroll
             for (int h = 0; h < HT; h++) {
                 const uint32_t r = __shfl_sync(0xffffffffu, cur[h], src);
-                if (valid) cp_async16(ring + slot * Cfg::STAGE + h * 512, colbase + (uint64_t)r * rowbytes);
+                if (valid) {
+                    if (pf64) cp_async16_pf64(ring + slot * Cfg::STAGE + h * 512, colbase + (uint64_t)r * rowbytes);
+                    else cp_async16(ring + slot * Cfg::STAGE + h * 512, colbase + (uint64_t)r * rowbytes);
+                }
             }
             t_issue++; it_issue++;
         }
@@ -962,6 +972,8 @@ static int launch_query_gather(cid_ctx* ctx, cudaStream_t st, const cid_index* i
         CID_CUDA(cudaFuncSetAttribute(query_gather_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
         gattr = true;
     }
+    // rows that are not whole 128-byte lines: 64-byte DRAM fills instead of whole-line fills (option gather_l2_64b: -1 = auto)
+    const uint32_t pf64 = ctx->opt_gather_l2_64b < 0 ? ((idx->Wp * 4) % 128 != 0) : (ctx->opt_gather_l2_64b != 0);
     GatherOut go{};
     if (!d_and_rows && ctx->gather_out) go = *ctx->gather_out;
     else { go.base[0] = d_counts; go.n = 1; go.stride = idx->N; go.col0 = 0; }
@@ -969,7 +981,7 @@ static int launch_query_gather(cid_ctx* ctx, cudaStream_t st, const cid_index* i
         ProfScope ps(ctx, st, d_and_rows ? KID_QUERY_PERFECT : KID_QUERY_COUNTS);
 #define CID_QG(HT, AM, OUT)                                                                                             \
     query_gather_kernel<HT, AM><<<(unsigned)nunits, QG_WARPS * 32, gsmem, st>>>(idx->rows, idx->Wp, idx->N, d_rid, d_unit_group, \
-                                                                               d_unit_slot0, d_unit_n, OUT, idx->rownz, d_missing, idx->W, go)
+                                                                               d_unit_slot0, d_unit_n, OUT, idx->rownz, d_missing, idx->W, go, pf64)
         if (d_and_rows) { if (idx->H == 2) CID_QG(2, true, d_and_rows); else CID_QG(4, true, d_and_rows); }
         else { if (idx->H == 2) CID_QG(2, false, d_counts); else CID_QG(4, false, d_counts); }
 #undef CID_QG
