@@ -291,7 +291,7 @@ int cid_ctx_set_option(cid_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "build_packed")) { c->opt_build_packed = value != 0; return CID_OK; }
     if (!strcmp(name, "build_set")) { c->opt_build_set = value != 0; return CID_OK; }
     if (!strcmp(name, "query_front")) { c->opt_query_front = value != 0; return CID_OK; }
-    if (!strcmp(name, "gather_l2_64b")) { c->opt_gather_l2_64b = value < 0 ? -1 : (value != 0); return CID_OK; }
+    if (!strcmp(name, "gather_l2_64b")) { c->opt_gather_l2_64b = value != 0; return CID_OK; }
     if (!strcmp(name, "query_fused")) { c->opt_query_fused = value != 0; return CID_OK; }
     if (!strcmp(name, "host_threads")) { c->opt_host_threads = value > 0 ? (int)value : 0; return CID_OK; }
     set_error("cid_ctx_set_option: unknown option '%s'", name);

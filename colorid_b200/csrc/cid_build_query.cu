@@ -667,10 +667,8 @@ query_hash_kernel(const Slot* __restrict__ table, const uint32_t* __restrict__ u
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gptr) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gptr) : "memory");
 }
-// Same copy with the 64-byte L2 prefetch size.  By default an L2 miss fills the whole 128-byte line from DRAM
-// (profiles/r1_gather_probe.txt: ~100 B of DRAM traffic per 8-byte gather, 56 B with this hint), so a 160-byte row of a C5
-// column shard, which always straddles two lines, costs 256 B of DRAM traffic -- 63 % algorithmic efficiency at 100 % of
-// the DRAM peak.  With 64-byte fills the same row costs three 64-byte atoms (192 B).
+// Same copy with the 64-byte L2 prefetch size (option gather_l2_64b).  Tried for the 160-byte rows of a C5 column shard, which
+// always straddle two 128-byte lines; measured no difference on B200 (profiles/r1_gather_l2_64b.txt), so it is off by default.
 __device__ __forceinline__ void cp_async16_pf64(uint32_t saddr, const void* gptr) {
     asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" ::"r"(saddr), "l"(gptr) : "memory");
 }
@@ -972,8 +970,7 @@ static int launch_query_gather(cid_ctx* ctx, cudaStream_t st, const cid_index* i
         CID_CUDA(cudaFuncSetAttribute(query_gather_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
         gattr = true;
     }
-    // rows that are not whole 128-byte lines: 64-byte DRAM fills instead of whole-line fills (option gather_l2_64b: -1 = auto)
-    const uint32_t pf64 = ctx->opt_gather_l2_64b < 0 ? ((idx->Wp * 4) % 128 != 0) : (ctx->opt_gather_l2_64b != 0);
+    const uint32_t pf64 = ctx->opt_gather_l2_64b != 0;
     GatherOut go{};
     if (!d_and_rows && ctx->gather_out) go = *ctx->gather_out;
     else { go.base[0] = d_counts; go.n = 1; go.stride = idx->N; go.col0 = 0; }

@@ -90,7 +90,7 @@ struct cid_ctx {
     int opt_build_packed = 1;        // 0 = never use the packed 8-byte count table (parity aid)
     int opt_build_set = 1;           // 0 = always build through the count table (parity aid)
     int opt_query_front = 1;         // 0 = never use the shared-memory dedup front end of small queries (parity aid)
-    int opt_gather_l2_64b = -1;      // query_gather row copies with the 64-byte L2 prefetch size: -1 = when rows are not whole 128-byte lines
+    int opt_gather_l2_64b = 0;       // 1 = query_gather row copies with the 64-byte L2 prefetch size (measured: no effect)
     int opt_query_fused = 0;         // 1 = force the fused collect/hash/gather kernel (parity aid)
     cudaStream_t aux[2] = {nullptr, nullptr};
     cudaEvent_t aux_fork = nullptr, aux_join[2] = {nullptr, nullptr};
