@@ -1341,4 +1341,53 @@ int launch_hash_kmers(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, const
     return CID_OK;
 }
 
+// ================================================================= unique-hit summaries (reports.rs:20-26)
+// The fused gather kernel leaves one (query, accession, multiplicity) triple per k-mer that hit exactly one accession.
+// generate_report wants, per (query, accession): their number ("specific"), the mean and the mode of the multiplicities.
+// uniq_hist: one counter per (cell = query * N + accession, multiplicity < MB); triples with larger multiplicities raise
+// *ovf (the caller then falls back to the host summary).  uniq_reduce: one warp per cell -> n, sum, mode (ties towards the
+// smallest multiplicity, like the host path and the oracle).
+__global__ void __launch_bounds__(256)
+uniq_hist_kernel(const uint32_t* __restrict__ list, uint32_t nu, uint32_t N, uint32_t MB, uint32_t* __restrict__ hist,
+                 uint32_t* __restrict__ ovf) {
+    for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < nu; i += gridDim.x * 256) {
+        const uint32_t q = __ldg(list + 3 * (uint64_t)i), c = __ldg(list + 3 * (uint64_t)i + 1), m = __ldg(list + 3 * (uint64_t)i + 2);
+        if (m < MB) atomicAdd(&hist[((uint64_t)q * N + c) * MB + m], 1u);
+        else atomicOr(ovf, 1u);
+    }
+}
+__global__ void __launch_bounds__(256)
+uniq_reduce_kernel(const uint32_t* __restrict__ hist, uint64_t cells, uint32_t MB, unsigned long long* __restrict__ out_n,
+                   unsigned long long* __restrict__ out_sum, unsigned long long* __restrict__ out_mode) {
+    const uint64_t cell = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (cell >= cells) return;
+    unsigned long long n = 0, sum = 0;
+    uint32_t best = 0, mode = 0;
+    for (uint32_t m = lane; m < MB; m += 32) {
+        const uint32_t h = __ldg(hist + cell * MB + m);
+        n += h; sum += (unsigned long long)h * m;
+        if (h > best) { best = h; mode = m; }            // ascending m within a lane: strict > keeps the smallest
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        n += __shfl_xor_sync(0xffffffffu, n, o);
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const uint32_t ob = __shfl_xor_sync(0xffffffffu, best, o), om = __shfl_xor_sync(0xffffffffu, mode, o);
+        if (ob > best || (ob == best && om < mode)) { best = ob; mode = om; }
+    }
+    if (lane == 0) { out_n[cell] = n; out_sum[cell] = sum; out_mode[cell] = n ? mode : 0; }
+}
+int launch_uniq_summaries(cid_ctx* ctx, cudaStream_t st, const uint32_t* d_list, uint32_t nu, uint32_t N, uint64_t cells, uint32_t MB,
+                          uint32_t* d_hist, uint32_t* d_ovf, unsigned long long* d_n, unsigned long long* d_sum,
+                          unsigned long long* d_mode) {
+    ProfScope ps(ctx, st, KID_OTHER);
+    CID_CUDA(cudaMemsetAsync(d_hist, 0, cells * MB * 4, st));
+    CID_CUDA(cudaMemsetAsync(d_ovf, 0, 4, st));
+    if (nu) uniq_hist_kernel<<<std::min<unsigned>((nu + 255) / 256, (unsigned)ctx->sm_count * 8), 256, 0, st>>>(d_list, nu, N, MB, d_hist, d_ovf);
+    uniq_reduce_kernel<<<(unsigned)((cells + 7) / 8), 256, 0, st>>>(d_hist, cells, MB, d_n, d_sum, d_mode);
+    ctx->launches += nu ? 2 : 1;
+    CID_CUDA(cudaGetLastError());
+    return CID_OK;
+}
+
 }  // namespace cid

@@ -91,6 +91,7 @@ struct cid_ctx {
     int opt_build_set = 1;           // 0 = always build through the count table (parity aid)
     int opt_query_front = 1;         // 0 = never use the shared-memory dedup front end of small queries (parity aid)
     int opt_gather_l2_64b = 0;       // 1 = query_gather row copies with the 64-byte L2 prefetch size (measured: no effect)
+    int opt_uniq_device = 1;         // 0 = unique-hit summaries always through the host maps (parity aid)
     int opt_query_fused = 0;         // 1 = force the fused collect/hash/gather kernel (parity aid)
     cudaStream_t aux[2] = {nullptr, nullptr};
     cudaEvent_t aux_fork = nullptr, aux_join[2] = {nullptr, nullptr};
@@ -200,6 +201,11 @@ int launch_query_perfect(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, co
 
 int launch_hash_kmers(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, const uint8_t* d_kmers, uint64_t n,
                       uint64_t* d_rows);
+// unique-hit triples (query, accession, multiplicity) -> per (query, accession) number, sum and mode of the multiplicities
+// (reports.rs:20-26) through a [cells][MB] histogram; *d_ovf != 0 afterwards: a multiplicity >= MB occurred, use the host path
+int launch_uniq_summaries(cid_ctx* ctx, cudaStream_t st, const uint32_t* d_list, uint32_t nu, uint32_t N, uint64_t cells, uint32_t MB,
+                          uint32_t* d_hist, uint32_t* d_ovf, unsigned long long* d_n, unsigned long long* d_sum,
+                          unsigned long long* d_mode);
 
 // read_id kernels on device buffers.  Reads [r_first, r_first + nreads) of the arrays are processed
 // (every per-read array is indexed by the absolute read number, so a caller that stages only a

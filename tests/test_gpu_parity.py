@@ -238,14 +238,23 @@ def test_search_fastq_query_with_filters(oracle, ctx):
     genomes, oix, gix = _index_pair(oracle, ctx, rng, 12, 27, 400_009, 4)
     reads = synth.reads_from(rng, genomes[:2], 1500, read_len=120, insert=250, err=0.01, frac_random=0.05, n_rate=0.001)
     q = [[m for r in reads for m in r]]
-    for filt in (-1, 0, 1, 3):
-        o = oix.query_counts(q, oracle.MODE_FASTQ, False, filt)
-        g = gix.query_counts(q, cb.CID_SEQ_FASTQ, False, filt)
-        assert np.array_equal(g["cutoff"], o["cutoff"])
-        assert np.array_equal(g["num_kmers"], o["num_kmers"])
-        assert np.array_equal(g["counts"], o["counts"])
-        assert np.array_equal(g["uniq_n"], o["uniq_n"]) and np.array_equal(g["uniq_sum"], o["uniq_sum"])
-        assert np.array_equal(g["uniq_mode"], o["uniq_mode"])
+    # a read repeated 1,100 times: unique-hit multiplicities beyond the device histogram's 1,024 bins -> host summary
+    q_rep = [[m for r in reads[:50] for m in r] + [genomes[0][500:620]] * 1100]
+    try:
+        for uniq_device in (1, 0):           # unique-hit summaries (reports.rs:20-26) on the device / through the host maps
+            ctx.set_option("uniq_device", uniq_device)
+            for qq, filters in ((q, (-1, 0, 1, 3)), (q_rep, (0, 2))):
+                for filt in filters:
+                    o = oix.query_counts(qq, oracle.MODE_FASTQ, False, filt)
+                    g = gix.query_counts(qq, cb.CID_SEQ_FASTQ, False, filt)
+                    assert np.array_equal(g["cutoff"], o["cutoff"])
+                    assert np.array_equal(g["num_kmers"], o["num_kmers"])
+                    assert np.array_equal(g["counts"], o["counts"])
+                    assert np.array_equal(g["uniq_n"], o["uniq_n"]) and np.array_equal(g["uniq_sum"], o["uniq_sum"])
+                    assert np.array_equal(g["uniq_mode"], o["uniq_mode"])
+        assert o["uniq_sum"].max() >= 10 * 1100          # the repeated read did hit one accession only
+    finally:
+        ctx.set_option("uniq_device", 1)
 
 
 @pytest.mark.parametrize("N,k,S,H", [(4, 27, 750_000, 4), (70, 21, 300_007, 2), (1100, 21, 60_013, 2), (1250, 31, 80_021, 4)])

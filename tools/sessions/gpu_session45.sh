@@ -8,3 +8,4 @@ for tool in memcheck racecheck synccheck initcheck; do
 done
 timeout 900 $CS --tool memcheck --print-limit 20 --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "perfect or edge or minimizer or sharded or stride" > gpurun_out/s45_memcheck_parity.txt 2>&1
 echo "memcheck parity rc=$?"; tail -5 gpurun_out/s45_memcheck_parity.txt | cut -c1-300
+CID_TRACE=1 timeout 300 python bench.py --workload c1 --no-cpu-baseline > gpurun_out/s45_c1_trace.json 2> gpurun_out/s45_c1_trace.err; grep "cid trace" gpurun_out/s45_c1_trace.err | tail -3
