@@ -138,7 +138,7 @@ enum { HIST_BINS = 65536, HIST_OVERFLOW_CAP = 1 << 20 };
 
 // Histogram of one region -> auto_cutoff (host arithmetic on a few KB).
 static int region_auto_cutoff(cid_ctx* ctx, cudaStream_t st, const void* d_region, uint64_t nslots, int64_t* cutoff,
-                              bool packed = false) {
+                              bool packed = false, uint64_t* survivors = nullptr) {
     CID_TRY(ctx->scratch[8].ensure((size_t)HIST_BINS * 4 + 16));
     CID_TRY(ctx->scratch[9].ensure((size_t)HIST_OVERFLOW_CAP * 4));
     uint32_t* d_hist = ctx->scratch[8].as<uint32_t>();
@@ -162,7 +162,12 @@ static int region_auto_cutoff(cid_ctx* ctx, cudaStream_t st, const void* d_regio
     std::vector<uint64_t> h(max_cov + 2, 0);
     for (uint64_t c = 1; c < std::min<uint64_t>(HIST_BINS, max_cov + 1); c++) h[c] = hh[c];
     for (uint32_t v : ovf) h[v] += 1;
-    return auto_cutoff_dense(h, max_cov, cutoff);
+    CID_TRY(auto_cutoff_dense(h, max_cov, cutoff));
+    if (survivors) {          // clean_map: k-mers with count > cutoff
+        *survivors = 0;
+        for (uint64_t c = (uint64_t)std::max<int64_t>(*cutoff, 0) + 1; c <= max_cov; c++) *survivors += h[c];
+    }
+    return CID_OK;
 }
 
 static int ensure_bitsets(cid_index* idx) {
@@ -292,6 +297,7 @@ int cid_ctx_set_option(cid_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "build_set")) { c->opt_build_set = value != 0; return CID_OK; }
     if (!strcmp(name, "query_front")) { c->opt_query_front = value != 0; return CID_OK; }
     if (!strcmp(name, "gather_l2_64b")) { c->opt_gather_l2_64b = value != 0; return CID_OK; }
+    if (!strcmp(name, "query_compact")) { c->opt_query_compact = value < 0 ? 0 : value > 2 ? 2 : (int)value; return CID_OK; }
     if (!strcmp(name, "uniq_device")) { c->opt_uniq_device = value != 0; return CID_OK; }
     if (!strcmp(name, "query_fused")) { c->opt_query_fused = value != 0; return CID_OK; }
     if (!strcmp(name, "host_threads")) { c->opt_host_threads = value > 0 ? (int)value : 0; return CID_OK; }
@@ -751,11 +757,65 @@ int cid_query_counts(cid_index* ix, const char* bases, const uint64_t* seq_offs,
         const double t_front = now();
         // per-query filter (batch_search_pe.rs:34-39 / :112-120)
         std::vector<int64_t> filt(bq);
+        std::vector<uint64_t> surv(bq, UINT64_MAX);      // k-mers with count > filter, where known
         for (uint64_t q = 0; q < bq; q++) {
             if (seq_mode == CID_SEQ_FASTA && gene_search) filt[q] = 0;
-            else if (filter < 0) CID_TRY(region_auto_cutoff(ctx, st, (const void*)(qp.d_table + qp.gr.off[q]), qp.gr.mask[q] + 1, &filt[q]));
+            else if (filter < 0) CID_TRY(region_auto_cutoff(ctx, st, (const void*)(qp.d_table + qp.gr.off[q]), qp.gr.mask[q] + 1, &filt[q], false, &surv[q]));
             else filt[q] = filter;
             if (cutoff_used) cutoff_used[q0 + q] = filt[q];
+        }
+        // Large, sparse count tables (read-set queries): survivors copied once into a dense slot list, work units over that
+        const void* d_slots = qp.d_table;
+        uint64_t slots_total = qp.gr.total_slots;
+        if (ctx->opt_query_compact && (qp.gr.total_slots >= (1ull << 22) || ctx->opt_query_compact == 2) && bq <= 64) {
+            CID_TRY(ctx->scratch[21].ensure(bq * 8 + 8));
+            unsigned long long* d_surv = ctx->scratch[21].as<unsigned long long>();
+            CID_CUDA(cudaMemsetAsync(d_surv, 0, bq * 8, st));
+            bool counted = false;
+            for (uint64_t q = 0; q < bq; q++)
+                if (surv[q] == UINT64_MAX) {          // no histogram at hand (fixed filter): count pass
+                    CID_TRY(launch_region_compact(ctx, st, qp.d_table + qp.gr.off[q], qp.gr.mask[q] + 1, filt[q], nullptr, d_surv + q, 0));
+                    counted = true;
+                }
+            if (counted) {
+                std::vector<unsigned long long> hs(bq);
+                CID_CUDA(cudaMemcpyAsync(hs.data(), d_surv, bq * 8, cudaMemcpyDeviceToHost, st));
+                CID_CUDA(cudaStreamSynchronize(st));
+                for (uint64_t q = 0; q < bq; q++) if (surv[q] == UINT64_MAX) surv[q] = hs[q];
+                CID_CUDA(cudaMemsetAsync(d_surv, 0, bq * 8, st));
+            }
+            uint64_t dense_total = 0;
+            std::vector<uint64_t> dbase(bq);
+            for (uint64_t q = 0; q < bq; q++) { dbase[q] = dense_total; dense_total += surv[q]; }
+            if (dense_total * 4 <= qp.gr.total_slots || ctx->opt_query_compact == 2) {       // worth it only when the table is mostly empty
+                CID_TRY(ctx->scratch[22].ensure((dense_total + 1) * sizeof(Slot)));
+                Slot* d_dense = ctx->scratch[22].as<Slot>();
+                QueryUnits du;
+                for (uint64_t q = 0; q < bq; q++) {
+                    if (surv[q] == 0) continue;
+                    CID_TRY(launch_region_compact(ctx, st, qp.d_table + qp.gr.off[q], qp.gr.mask[q] + 1, filt[q], d_dense + dbase[q],
+                                                  d_surv + q, surv[q]));
+                    for (uint64_t at = 0; at < surv[q]; at += QUERY_ITEM_SLOTS) {
+                        du.group.push_back((uint32_t)q);
+                        du.slot0.push_back(dbase[q] + at);
+                        du.nslots.push_back((uint32_t)std::min<uint64_t>(QUERY_ITEM_SLOTS, surv[q] - at));
+                    }
+                }
+                const uint64_t nu2 = du.group.size();
+                CID_TRY(ctx->scratch[6].ensure(nu2 * 16 + 64));
+                qp.d_unit_slot0 = ctx->scratch[6].as<uint64_t>();
+                qp.d_unit_group = (uint32_t*)(qp.d_unit_slot0 + nu2);
+                qp.d_unit_nslots = qp.d_unit_group + nu2;
+                if (nu2) {
+                    CID_CUDA(cudaMemcpyAsync(qp.d_unit_slot0, du.slot0.data(), nu2 * 8, cudaMemcpyHostToDevice, st));
+                    CID_CUDA(cudaMemcpyAsync(qp.d_unit_group, du.group.data(), nu2 * 4, cudaMemcpyHostToDevice, st));
+                    CID_CUDA(cudaMemcpyAsync(qp.d_unit_nslots, du.nslots.data(), nu2 * 4, cudaMemcpyHostToDevice, st));
+                    CID_CUDA(cudaStreamSynchronize(st));          // `du` is pageable and dies with this scope
+                }
+                qp.qu = std::move(du);
+                d_slots = d_dense;
+                slots_total = dense_total;
+            }
         }
         const double t_cut = now();
         const uint64_t npos_total = qp.gr.total_slots / 2;
@@ -769,8 +829,8 @@ int cid_query_counts(cid_index* ix, const char* bases, const uint64_t* seq_offs,
         CID_CUDA(cudaMemsetAsync(ctx->scratch[10].p, 0, bq * N * 4, st));
         CID_CUDA(cudaMemsetAsync(ctx->scratch[11].p, 0, bq * 8, st));
         CID_CUDA(cudaMemsetAsync(ctx->scratch[13].p, 0, 16, st));
-        CID_TRY(launch_query_counts(ctx, st, ix, qp.d_table, qp.d_unit_group, qp.d_unit_slot0, qp.d_unit_nslots,
-                                    qp.qu.group.size(), qp.gr.total_slots, ctx->scratch[7].as<int64_t>(), ctx->scratch[10].as<uint32_t>(),
+        CID_TRY(launch_query_counts(ctx, st, ix, d_slots, qp.d_unit_group, qp.d_unit_slot0, qp.d_unit_nslots,
+                                    qp.qu.group.size(), slots_total, ctx->scratch[7].as<int64_t>(), ctx->scratch[10].as<uint32_t>(),
                                     ctx->scratch[11].as<unsigned long long>(), want_uniq, ctx->scratch[12].as<uint32_t>(),
                                     uniq_cap, ctx->scratch[13].as<uint32_t>()));
         CID_CUDA(cudaMemcpyAsync(counts + q0 * N, ctx->scratch[10].p, bq * N * 4, cudaMemcpyDeviceToHost, st));

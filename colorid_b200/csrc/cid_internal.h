@@ -91,6 +91,7 @@ struct cid_ctx {
     int opt_build_set = 1;           // 0 = always build through the count table (parity aid)
     int opt_query_front = 1;         // 0 = never use the shared-memory dedup front end of small queries (parity aid)
     int opt_gather_l2_64b = 0;       // 1 = query_gather row copies with the 64-byte L2 prefetch size (measured: no effect)
+    int opt_query_compact = 1;       // count-table compaction of large queries: 0 = never, 1 = tables of >= 2^22 slots, 2 = always (tests)
     int opt_uniq_device = 1;         // 0 = unique-hit summaries always through the host maps (parity aid)
     int opt_query_fused = 0;         // 1 = force the fused collect/hash/gather kernel (parity aid)
     cudaStream_t aux[2] = {nullptr, nullptr};
@@ -201,6 +202,10 @@ int launch_query_perfect(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, co
 
 int launch_hash_kmers(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, const uint8_t* d_kmers, uint64_t n,
                       uint64_t* d_rows);
+// survivors (count > filt) of one count-table region of 16-byte slots -> dense slot list (d_dense == nullptr: count only);
+// *d_n must be zero before the call
+int launch_region_compact(cid_ctx* ctx, cudaStream_t st, const void* d_region, uint64_t nslots, int64_t filt, void* d_dense,
+                          unsigned long long* d_n, uint64_t cap);
 // unique-hit triples (query, accession, multiplicity) -> per (query, accession) number, sum and mode of the multiplicities
 // (reports.rs:20-26) through a [cells][MB] histogram; *d_ovf != 0 afterwards: a multiplicity >= MB occurred, use the host path
 int launch_uniq_summaries(cid_ctx* ctx, cudaStream_t st, const uint32_t* d_list, uint32_t nu, uint32_t N, uint64_t cells, uint32_t MB,

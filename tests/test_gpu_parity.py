@@ -144,14 +144,19 @@ def test_search_counts_and_unique_hits(oracle, ctx, N, k, S, H):
         queries.append([q] if i % 4 else [q[:len(q) // 2], q[len(q) // 2:], b"ACGT"])
     queries.append([b"ACG"])               # shorter than k: zero k-mers
     queries.append([genomes[0]])           # a whole genome (several work units)
-    for gene in (True, False):
-        o = oix.query_counts(queries, oracle.MODE_FASTA, gene, 0)
-        g = gix.query_counts(queries, cb.CID_SEQ_FASTA, gene, 0)
-        assert np.array_equal(g["num_kmers"], o["num_kmers"])
-        assert np.array_equal(g["counts"], o["counts"])
-        assert np.array_equal(g["uniq_n"], o["uniq_n"])
-        assert np.array_equal(g["uniq_sum"], o["uniq_sum"])
-        assert np.array_equal(g["uniq_mode"], o["uniq_mode"])
+    try:
+        for compact in (1, 2):             # 2: every query's survivors go through the dense slot list (42 regions)
+            ctx.set_option("query_compact", compact)
+            for gene in (True, False):
+                o = oix.query_counts(queries, oracle.MODE_FASTA, gene, 0)
+                g = gix.query_counts(queries, cb.CID_SEQ_FASTA, gene, 0)
+                assert np.array_equal(g["num_kmers"], o["num_kmers"])
+                assert np.array_equal(g["counts"], o["counts"])
+                assert np.array_equal(g["uniq_n"], o["uniq_n"])
+                assert np.array_equal(g["uniq_sum"], o["uniq_sum"])
+                assert np.array_equal(g["uniq_mode"], o["uniq_mode"])
+    finally:
+        ctx.set_option("query_compact", 1)
 
 
 @pytest.mark.parametrize("N,k,S,H", [(70, 21, 300_007, 2), (300, 21, 200_003, 4), (1000, 21, 100_003, 2),
@@ -241,8 +246,11 @@ def test_search_fastq_query_with_filters(oracle, ctx):
     # a read repeated 1,100 times: unique-hit multiplicities beyond the device histogram's 1,024 bins -> host summary
     q_rep = [[m for r in reads[:50] for m in r] + [genomes[0][500:620]] * 1100]
     try:
-        for uniq_device in (1, 0):           # unique-hit summaries (reports.rs:20-26) on the device / through the host maps
+        # unique-hit summaries (reports.rs:20-26) on the device / through the host maps; gather units over the sparse count
+        # table / over the compacted survivor list (forced: these tables are far below the 2^22-slot threshold)
+        for uniq_device, compact in ((1, 1), (0, 1), (1, 2), (0, 2)):
             ctx.set_option("uniq_device", uniq_device)
+            ctx.set_option("query_compact", compact)
             for qq, filters in ((q, (-1, 0, 1, 3)), (q_rep, (0, 2))):
                 for filt in filters:
                     o = oix.query_counts(qq, oracle.MODE_FASTQ, False, filt)
@@ -255,6 +263,7 @@ def test_search_fastq_query_with_filters(oracle, ctx):
         assert o["uniq_sum"].max() >= 10 * 1100          # the repeated read did hit one accession only
     finally:
         ctx.set_option("uniq_device", 1)
+        ctx.set_option("query_compact", 1)
 
 
 @pytest.mark.parametrize("N,k,S,H", [(4, 27, 750_000, 4), (70, 21, 300_007, 2), (1100, 21, 60_013, 2), (1250, 31, 80_021, 4)])
