@@ -297,6 +297,8 @@ int cid_ctx_set_option(cid_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "build_set")) { c->opt_build_set = value != 0; return CID_OK; }
     if (!strcmp(name, "query_front")) { c->opt_query_front = value != 0; return CID_OK; }
     if (!strcmp(name, "gather_l2_64b")) { c->opt_gather_l2_64b = value != 0; return CID_OK; }
+    if (!strcmp(name, "query_table_div")) { c->opt_query_table_div = value > 0 ? (int)value : 0; return CID_OK; }
+    if (!strcmp(name, "query_table_min_slots")) { c->opt_query_table_min = value > 0 ? (uint64_t)value : 0; return CID_OK; }
     if (!strcmp(name, "query_compact")) { c->opt_query_compact = value < 0 ? 0 : value > 2 ? 2 : (int)value; return CID_OK; }
     if (!strcmp(name, "uniq_device")) { c->opt_uniq_device = value != 0; return CID_OK; }
     if (!strcmp(name, "query_fused")) { c->opt_query_fused = value != 0; return CID_OK; }
@@ -621,6 +623,7 @@ struct QueryPlan {
     QueryUnits qu;
     uint32_t* d_unit_group; uint64_t* d_unit_slot0; uint32_t* d_unit_nslots;
     Slot* d_table;
+    uint64_t kmers_bound = 0;      // upper bound on the distinct k-mers in the table
 };
 static int query_front(cid_index* ix, cudaStream_t st, const uint8_t* d_bases, const uint64_t* d_seq_offs,
                        const uint64_t* h_seq_offs, const uint64_t* h_query_offs, uint64_t q0, uint64_t q1, int seq_mode,
@@ -630,36 +633,64 @@ static int query_front(cid_index* ix, cudaStream_t st, const uint8_t* d_bases, c
     const uint64_t s_lo = h_query_offs[q0], s_hi = h_query_offs[q1];
     const uint64_t nseq = s_hi - s_lo;
     plan_regions(h_seq_offs, h_query_offs + q0, nq, ix->k, qp.gr);
-    plan_units(qp.gr, QUERY_ITEM_SLOTS, qp.qu);
+    // A read-set query (one query, many short sequences, deep coverage) holds far fewer DISTINCT k-mers than k-mer positions,
+    // and its table is scanned several times after counting: size it optimistically like the read-set build does (positions/4,
+    // doubled while it ends up fuller than 80 %; the safe 2x-positions size is the last resort).
+    const uint64_t safe_slots = qp.gr.total_slots;
+    uint64_t hint = 0;
+    if (ctx->opt_query_table_div > 0 && nq == 1 && seq_mode == CID_SEQ_FASTQ && safe_slots >= ctx->opt_query_table_min &&
+        (nseq >= 4096 || ctx->opt_query_table_min == 0)) {
+        hint = next_pow2(safe_slots / 2 / (uint64_t)ctx->opt_query_table_div);
+        if (hint >= safe_slots) hint = 0;
+    }
     // sequence -> group
     std::vector<uint32_t> seq_group(nseq);
     for (uint64_t q = q0; q < q1; q++)
         for (uint64_t s = h_query_offs[q]; s < h_query_offs[q + 1]; s++) seq_group[s - s_lo] = (uint32_t)(q - q0);
-    const uint64_t nunits = qp.qu.group.size();
-    CID_TRY(ctx->scratch[0].ensure(qp.gr.total_slots * sizeof(Slot)));
     CID_TRY(ctx->scratch[1].ensure(nq * 16 + 64));
     CID_TRY(ctx->scratch[3].ensure(nseq * 4 + 64));
-    CID_TRY(ctx->scratch[6].ensure(nunits * 16 + 64));
-    uint64_t* d_off = ctx->scratch[1].as<uint64_t>();
-    uint64_t* d_mask = d_off + nq;
-    CID_CUDA(cudaMemcpyAsync(d_off, qp.gr.off.data(), nq * 8, cudaMemcpyHostToDevice, st));
-    CID_CUDA(cudaMemcpyAsync(d_mask, qp.gr.mask.data(), nq * 8, cudaMemcpyHostToDevice, st));
     if (nseq) CID_CUDA(cudaMemcpyAsync(ctx->scratch[3].p, seq_group.data(), nseq * 4, cudaMemcpyHostToDevice, st));
-    qp.d_unit_slot0 = ctx->scratch[6].as<uint64_t>();
-    qp.d_unit_group = (uint32_t*)(qp.d_unit_slot0 + nunits);
-    qp.d_unit_nslots = qp.d_unit_group + nunits;
-    if (nunits) {
-        CID_CUDA(cudaMemcpyAsync(qp.d_unit_slot0, qp.qu.slot0.data(), nunits * 8, cudaMemcpyHostToDevice, st));
-        CID_CUDA(cudaMemcpyAsync(qp.d_unit_group, qp.qu.group.data(), nunits * 4, cudaMemcpyHostToDevice, st));
-        CID_CUDA(cudaMemcpyAsync(qp.d_unit_nslots, qp.qu.nslots.data(), nunits * 4, cudaMemcpyHostToDevice, st));
+    for (;;) {
+        if (hint) { qp.gr.off[0] = 0; qp.gr.mask[0] = hint - 1; qp.gr.total_slots = hint; }
+        else if (qp.gr.total_slots != safe_slots) plan_regions(h_seq_offs, h_query_offs + q0, nq, ix->k, qp.gr);
+        plan_units(qp.gr, QUERY_ITEM_SLOTS, qp.qu);
+        const uint64_t nunits = qp.qu.group.size();
+        CID_TRY(ctx->scratch[0].ensure(qp.gr.total_slots * sizeof(Slot)));
+        CID_TRY(ctx->scratch[6].ensure(nunits * 16 + 64));
+        uint64_t* d_off = ctx->scratch[1].as<uint64_t>();
+        uint64_t* d_mask = d_off + nq;
+        CID_CUDA(cudaMemcpyAsync(d_off, qp.gr.off.data(), nq * 8, cudaMemcpyHostToDevice, st));
+        CID_CUDA(cudaMemcpyAsync(d_mask, qp.gr.mask.data(), nq * 8, cudaMemcpyHostToDevice, st));
+        qp.d_unit_slot0 = ctx->scratch[6].as<uint64_t>();
+        qp.d_unit_group = (uint32_t*)(qp.d_unit_slot0 + nunits);
+        qp.d_unit_nslots = qp.d_unit_group + nunits;
+        if (nunits) {
+            CID_CUDA(cudaMemcpyAsync(qp.d_unit_slot0, qp.qu.slot0.data(), nunits * 8, cudaMemcpyHostToDevice, st));
+            CID_CUDA(cudaMemcpyAsync(qp.d_unit_group, qp.qu.group.data(), nunits * 4, cudaMemcpyHostToDevice, st));
+            CID_CUDA(cudaMemcpyAsync(qp.d_unit_nslots, qp.qu.nslots.data(), nunits * 4, cudaMemcpyHostToDevice, st));
+        }
+        qp.d_table = ctx->scratch[0].as<Slot>();
+        CID_TRY(table_clear(ctx, st, qp.d_table, qp.gr.total_slots));
+        if (hint) CID_CUDA(cudaMemsetAsync(ctx->d_err + 1, 0, 4, st));
+        // the batch's sequences are [s_lo, s_hi): bases [h_seq_offs[s_lo], h_seq_offs[s_hi])
+        const uint64_t b_lo = h_seq_offs[s_lo], b_hi = h_seq_offs[s_hi];
+        // kmerize works on absolute base offsets: pass the offsets slice and the base range it covers
+        CID_TRY(launch_kmerize_insert(ctx, st, d_bases, d_seq_offs + s_lo, nseq, b_lo, b_hi,
+                                            ctx->scratch[3].as<uint32_t>(), d_off, d_mask, qp.d_table, ix->k, seq_mode));
+        qp.kmers_bound = qp.gr.total_slots / 2;       // safe size: 2 slots per k-mer position
+        if (hint) {
+            CID_CUDA(cudaMemcpyAsync(ctx->h_err, ctx->d_err, 8, cudaMemcpyDeviceToHost, st));
+            CID_CUDA(cudaStreamSynchronize(st));
+            const uint32_t flags = ctx->h_err[0], distinct = ctx->h_err[1];
+            if ((flags & ERRF_TABLE_FULL) || (uint64_t)distinct * 10 > hint * 8) {      // fuller than 80 %: redo larger
+                CID_CUDA(cudaMemsetAsync(ctx->d_err, 0, 4, st));        // (other flags come up again in the redo)
+                hint = hint * 2 >= safe_slots ? 0 : hint * 2;
+                continue;
+            }
+            qp.kmers_bound = distinct;
+        }
+        break;
     }
-    qp.d_table = ctx->scratch[0].as<Slot>();
-    CID_TRY(table_clear(ctx, st, qp.d_table, qp.gr.total_slots));
-    // the batch's sequences are [s_lo, s_hi): bases [h_seq_offs[s_lo], h_seq_offs[s_hi])
-    const uint64_t b_lo = h_seq_offs[s_lo], b_hi = h_seq_offs[s_hi];
-    // kmerize works on absolute base offsets: pass the offsets slice and the base range it covers
-    CID_TRY(launch_kmerize_insert(ctx, st, d_bases, d_seq_offs + s_lo, nseq, b_lo, b_hi,
-                                        ctx->scratch[3].as<uint32_t>(), d_off, d_mask, qp.d_table, ix->k, seq_mode));
     // pageable host vectors above must stay alive until the copies complete
     CID_CUDA(cudaStreamSynchronize(st));
     return CID_OK;
@@ -818,7 +849,7 @@ int cid_query_counts(cid_index* ix, const char* bases, const uint64_t* seq_offs,
             }
         }
         const double t_cut = now();
-        const uint64_t npos_total = qp.gr.total_slots / 2;
+        const uint64_t npos_total = qp.kmers_bound;
         const uint32_t uniq_cap = want_uniq ? (uint32_t)std::min<uint64_t>(npos_total + 1, 0xFFFFFFF0u / 3) : 0;
         CID_TRY(ctx->scratch[7].ensure(bq * 8));
         CID_TRY(ctx->scratch[10].ensure(bq * N * 4));

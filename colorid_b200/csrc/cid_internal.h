@@ -91,6 +91,8 @@ struct cid_ctx {
     int opt_build_set = 1;           // 0 = always build through the count table (parity aid)
     int opt_query_front = 1;         // 0 = never use the shared-memory dedup front end of small queries (parity aid)
     int opt_gather_l2_64b = 0;       // 1 = query_gather row copies with the 64-byte L2 prefetch size (measured: no effect)
+    int opt_query_table_div = 4;     // read-set queries: first count table = k-mer positions / this (0 = always the safe 2x-positions table)
+    uint64_t opt_query_table_min = 1ull << 23;   // ... for tables of at least this many slots at the safe size (0 = always: tests)
     int opt_query_compact = 1;       // count-table compaction of large queries: 0 = never, 1 = tables of >= 2^22 slots, 2 = always (tests)
     int opt_uniq_device = 1;         // 0 = unique-hit summaries always through the host maps (parity aid)
     int opt_query_fused = 0;         // 1 = force the fused collect/hash/gather kernel (parity aid)

@@ -248,9 +248,13 @@ def test_search_fastq_query_with_filters(oracle, ctx):
     try:
         # unique-hit summaries (reports.rs:20-26) on the device / through the host maps; gather units over the sparse count
         # table / over the compacted survivor list (forced: these tables are far below the 2^22-slot threshold)
-        for uniq_device, compact in ((1, 1), (0, 1), (1, 2), (0, 2)):
+        # optimistic count table of a read-set query (forced on these small inputs): positions/4, and positions/64, which
+        # overflows and is redone larger
+        for uniq_device, compact, table_div in ((1, 1, 0), (0, 1, 0), (1, 2, 4), (0, 2, 64), (1, 1, 64)):
             ctx.set_option("uniq_device", uniq_device)
             ctx.set_option("query_compact", compact)
+            ctx.set_option("query_table_min_slots", 0 if table_div else 1 << 23)
+            ctx.set_option("query_table_div", table_div if table_div else 4)
             for qq, filters in ((q, (-1, 0, 1, 3)), (q_rep, (0, 2))):
                 for filt in filters:
                     o = oix.query_counts(qq, oracle.MODE_FASTQ, False, filt)
@@ -264,6 +268,8 @@ def test_search_fastq_query_with_filters(oracle, ctx):
     finally:
         ctx.set_option("uniq_device", 1)
         ctx.set_option("query_compact", 1)
+        ctx.set_option("query_table_min_slots", 1 << 23)
+        ctx.set_option("query_table_div", 4)
 
 
 @pytest.mark.parametrize("N,k,S,H", [(4, 27, 750_000, 4), (70, 21, 300_007, 2), (1100, 21, 60_013, 2), (1250, 31, 80_021, 4)])
