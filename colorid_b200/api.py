@@ -103,6 +103,37 @@ def classify_reads(index_params, n_ref, rep, fp_correct=1e-3, group_width=16, th
     return dict(kind=kind[:nr], hits=hits[:nr], n_top=n_top[:nr], top=top[:nr])
 
 
+def merge_shard_reports(shard_reports, shards, n_total, rep_cap=None):
+    """Column-sharded read_id: per-shard reports (dicts from Index.read_id_batch run with the context option
+    readid_report_steps = 1, in shard order) -> the report of the unsharded index (cid_merge_shard_reports).
+    shards = [(c_lo, c_hi)] accession ranges (sharding.column_shards)."""
+    lib = L.load()
+    ns = len(shard_reports)
+    nr = len(shard_reports[0]["n_set"])
+    cap_in = max(r["rep_colour"].shape[1] for r in shard_reports)      # shards of different widths: pad to one row stride
+    cap_out = rep_cap if rep_cap else n_total + 1
+    ncol = np.array([hi - lo for lo, hi in shards], np.uint32)
+    coff = np.array([lo for lo, _ in shards], np.uint32)
+
+    def padded(a):
+        a = np.ascontiguousarray(a, dtype=np.uint32)
+        if a.ndim == 2 and a.shape[1] < cap_in:
+            a = np.ascontiguousarray(np.pad(a, ((0, 0), (0, cap_in - a.shape[1]))))
+        return a
+    keep = [[padded(r[k]) for r in shard_reports] for k in ("rep_n", "rep_colour", "rep_count")]
+    arrs = [(L.u32p * ns)(*[_p(a, L.u32p) for a in ks]) for ks in keep]
+    out_n = np.zeros(max(nr, 1), np.uint32)
+    out_c = np.zeros((max(nr, 1), cap_out), np.uint32)
+    out_v = np.zeros((max(nr, 1), cap_out), np.uint32)
+    flags = np.ascontiguousarray(shard_reports[0]["flags"], dtype=np.uint32).copy()
+    flags &= ~np.uint32(4)                    # truncation is decided again for the merged report
+    if nr == 0:
+        flags = np.zeros(1, np.uint32)
+    L.check(lib.cid_merge_shard_reports(ns, _p(ncol, L.u32p), _p(coff, L.u32p), nr, arrs[0], arrs[1], arrs[2], cap_in, n_total,
+                                        _p(out_n, L.u32p), _p(out_c, L.u32p), _p(out_v, L.u32p), cap_out, _p(flags, L.u32p)))
+    return dict(n_set=shard_reports[0]["n_set"], flags=flags[:nr], rep_n=out_n[:nr], rep_colour=out_c[:nr], rep_count=out_v[:nr])
+
+
 class Index:
     """Device-resident BIGSI index (bigsi.rs:19-27 BigsyMapNew)."""
 

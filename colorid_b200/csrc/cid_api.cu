@@ -291,6 +291,7 @@ int cid_ctx_set_option(cid_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "readid_streams")) { c->opt_readid_streams = value >= 2 ? 2 : 1; return CID_OK; }
     if (!strcmp(name, "readid_kmerize_ctas")) { c->opt_kmerize_ctas = value > 0 ? (int)value : 0; return CID_OK; }
     if (!strcmp(name, "readid_vote_ctas")) { c->opt_vote_ctas = value > 0 ? (int)value : 0; return CID_OK; }
+    if (!strcmp(name, "readid_report_steps")) { c->opt_readid_report_steps = value != 0; return CID_OK; }
     if (!strcmp(name, "readid_serialize")) { c->opt_readid_serialize = value != 0; return CID_OK; }
     if (!strcmp(name, "build_table_div")) { c->opt_build_table_div = value >= 1 ? (int)value : 0; return CID_OK; }
     if (!strcmp(name, "build_packed")) { c->opt_build_packed = value != 0; return CID_OK; }

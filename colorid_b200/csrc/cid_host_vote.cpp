@@ -250,4 +250,53 @@ int cid_classify_reads(uint64_t bloom_size, uint32_t num_hash, uint32_t n_colors
     return CID_OK;
 }
 
+// Column-sharded read_id: every shard classifies the same reads against its accession slice with the option
+// readid_report_steps set, so each report entry is colour | step << 20 (step = index, in set order, of the k-mer whose AND
+// row inserted the colour into final_report, read_id_mt_pe.rs:131-136).  Colours are only ever inserted by ascending k-mer
+// and, within a k-mer, by ascending accession, so sorting the union of the shards' entries by (step, global colour) restores
+// the insertion order of the unsharded run; counts are per colour and need no exchange.  The first-miss position is a
+// property of whole rows (row-present bitmap OR-ed across shards), so every shard reports the "no hit" key or none does.
+int cid_merge_shard_reports(uint32_t n_shards, const uint32_t* shard_n_colors, const uint32_t* shard_col_offset,
+                            uint64_t nreads, const uint32_t* const* rep_n, const uint32_t* const* rep_colour,
+                            const uint32_t* const* rep_count, uint32_t rep_cap_in, uint32_t n_total, uint32_t* out_rep_n,
+                            uint32_t* out_colour, uint32_t* out_count, uint32_t rep_cap_out, uint32_t* out_flags) {
+    if (!n_shards || !shard_n_colors || !shard_col_offset || !rep_n || !rep_colour || !rep_count || !out_rep_n || !out_colour ||
+        !out_count) {
+        set_error("cid_merge_shard_reports: null argument");
+        return CID_E_INVALID;
+    }
+    const uint32_t cmask = (1u << 20) - 1u;
+    struct Ent { uint32_t step, colour, count; };
+    std::vector<Ent> ents;
+    for (uint64_t r = 0; r < nreads; r++) {
+        ents.clear();
+        uint32_t n_miss = 0;
+        for (uint32_t s = 0; s < n_shards; s++) {
+            const uint32_t n = rep_n[s][r];
+            if (n > rep_cap_in) { set_error("cid_merge_shard_reports: rep_n above rep_cap"); return CID_E_INVALID; }
+            for (uint32_t i = 0; i < n; i++) {
+                const uint32_t e = rep_colour[s][r * (uint64_t)rep_cap_in + i], c = e & cmask;
+                if (c == shard_n_colors[s]) { n_miss++; continue; }          // the "no hit" key N of that shard
+                if (c > shard_n_colors[s]) { set_error("cid_merge_shard_reports: colour out of range"); return CID_E_INVALID; }
+                ents.push_back({e >> 20, shard_col_offset[s] + c, rep_count[s][r * (uint64_t)rep_cap_in + i]});
+            }
+        }
+        if (n_miss != 0 && n_miss != n_shards) {
+            set_error("cid_merge_shard_reports: shards disagree on the first absent row of read %llu (row-present bitmaps not merged?)",
+                      (unsigned long long)r);
+            return CID_E_INVALID;
+        }
+        std::sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b) { return a.step != b.step ? a.step < b.step : a.colour < b.colour; });
+        const uint64_t total = ents.size() + (n_miss ? 1 : 0);
+        uint32_t* oc = out_colour + r * (uint64_t)rep_cap_out;
+        uint32_t* ov = out_count + r * (uint64_t)rep_cap_out;
+        uint32_t w = 0;
+        for (const Ent& e : ents) { if (w < rep_cap_out) { oc[w] = e.colour; ov[w] = e.count; w++; } }
+        if (n_miss && w < rep_cap_out) { oc[w] = n_total; ov[w] = 1; w++; }
+        out_rep_n[r] = w;
+        if (out_flags && total > rep_cap_out) out_flags[r] |= 4u;              // truncated, like the kernels' flag bit 2
+    }
+    return CID_OK;
+}
+
 }  // extern "C"

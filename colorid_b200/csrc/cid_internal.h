@@ -84,6 +84,7 @@ struct cid_ctx {
     int opt_readid_streams = 1;
     int opt_kmerize_ctas = 0, opt_vote_ctas = 0;   // CTAs per SM of the read_id kmerize / vote grids (0 = fill the GPU);
                                                    // smaller grids let the two kernels of different chunks share the SMs
+    int opt_readid_report_steps = 0; // 1 = report colours carry their insertion step in bits 20..31 (column-sharded read_id, cid_merge_shard_reports)
     int opt_readid_serialize = 0;    // 1 = kernels of consecutive pipeline chunks never overlap (measured: 44.8M vs 46.3M pairs/s e2e, off)
     int opt_build_table_div = 0;     // read-set builds: first count table = k-mer positions / this (0 = adaptive; grown x4 when > 70 % full)
     double readset_ratio = 0;        // distinct k-mers / k-mer positions of the last read-set accession built on this context

@@ -21,6 +21,10 @@ namespace cid {
 constexpr int RA_WARPS = 4;
 constexpr uint32_t FINE_STEPS = 2;   // fine-grained (lane per hash row) steps at the start of each read's vote
 constexpr int MAX_MATES = 8;
+// option readid_report_steps (column-sharded read_id): a report entry's colour carries, above this bit, the index of the
+// k-mer (in set order) whose AND row first inserted the colour into final_report -- what a merge of per-shard reports
+// needs to restore the reference's insertion order (colours < 2^20 per shard, k-mers < 2^11 per read)
+constexpr uint32_t REP_STEP_SHIFT = 20;
 
 // entry layout (u32): [15:0] fnv low16 | [25:16] tile position | [26] took_fwd | [27] fresh
 #define ENT_TP(e) (((e) >> 16) & 0x3FFu)
@@ -553,8 +557,8 @@ readid_order_small_kernel(const uint8_t* __restrict__ hp8, const uint32_t* __res
 }
 
 // ================================================================= readid_vote (rows of <= 64 accessions)
-template <int WP>
-__global__ void __launch_bounds__(RA_WARPS * 32)
+template <int WP, bool STEPS>      // STEPS: report colours carry their insertion step (column-sharded read_id); a separate
+__global__ void __launch_bounds__(RA_WARPS * 32)      // instantiation so that the replicated-index kernel stays as it was
 readid_vote_narrow_kernel(const uint8_t* __restrict__ bases, const uint8_t* __restrict__ quals, uint32_t maxq,
                           const uint64_t* __restrict__ seq_offs, const uint64_t* __restrict__ read_offs, uint64_t r0,
                           uint64_t nreads, uint32_t k, uint32_t H, ModS mods, const uint32_t* __restrict__ rows,
@@ -570,11 +574,12 @@ readid_vote_narrow_kernel(const uint8_t* __restrict__ bases, const uint8_t* __re
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t my_gather_rows = 0;      // matrix rows this warp read (diagnostic: bench's random-access rate)
-    const size_t per_warp = ((tile_smem_bytes(cap) + 15) & ~(size_t)15) + 64 + (MAX_MATES + 1) * 4 + 12;
+    const size_t per_warp = ((tile_smem_bytes(cap) + 15) & ~(size_t)15) + 64 + 128 + (MAX_MATES + 1) * 4 + 12;
     uint8_t* base = dsm + (size_t)warp * ((per_warp + 15) & ~(size_t)15);
     Tile t = tile_carve(base, cap);
     uint8_t* ord = base + ((tile_smem_bytes(cap) + 15) & ~(size_t)15);
-    uint32_t* moffs = (uint32_t*)(ord + 64);
+    uint16_t* ordstep = (uint16_t*)(ord + 64);      // with_steps: index of the k-mer that inserted the colour (REP_STEP_SHIFT)
+    uint32_t* moffs = (uint32_t*)(ord + 64 + 128);
     const bool classic = start_sample == 0;
 
     for (uint64_t rl = (uint64_t)blockIdx.x * RA_WARPS + warp; rl < nreads; rl += (uint64_t)gridDim.x * RA_WARPS) {
@@ -704,8 +709,8 @@ readid_vote_narrow_kernel(const uint8_t* __restrict__ bases, const uint8_t* __re
             for (uint32_t jj = 0; jj < lim; jj++) {
                 uint32_t y0 = __shfl_sync(0xffffffffu, x0, jj), y1 = __shfl_sync(0xffffffffu, x1, jj);
                 uint32_t nw0 = y0 & ~cand0, nw1 = y1 & ~cand1;
-                while (nw0) { uint32_t b = __ffs(nw0) - 1; nw0 &= nw0 - 1; if (lane == 0 && nrep < 64) ord[nrep] = (uint8_t)b; nrep++; }
-                while (nw1) { uint32_t b = __ffs(nw1) - 1; nw1 &= nw1 - 1; if (lane == 0 && nrep < 64) ord[nrep] = (uint8_t)(32 + b); nrep++; }
+                while (nw0) { uint32_t b = __ffs(nw0) - 1; nw0 &= nw0 - 1; if (lane == 0 && nrep < 64) { ord[nrep] = (uint8_t)b; if (STEPS) ordstep[nrep] = (uint16_t)(c0 + jj); } nrep++; }
+                while (nw1) { uint32_t b = __ffs(nw1) - 1; nw1 &= nw1 - 1; if (lane == 0 && nrep < 64) { ord[nrep] = (uint8_t)(32 + b); if (STEPS) ordstep[nrep] = (uint16_t)(c0 + jj); } nrep++; }
                 cand0 |= y0; cand1 |= y1;
             }
             // per-colour counts over the k-mers before the first miss (colours outside cand never count)
@@ -740,7 +745,7 @@ readid_vote_narrow_kernel(const uint8_t* __restrict__ bases, const uint8_t* __re
             uint32_t i = i0 + lane;
             uint32_t colour = i < nrep ? ord[i] : 0u;
             uint32_t v0 = __shfl_sync(0xffffffffu, cnt0, colour & 31), v1 = __shfl_sync(0xffffffffu, cnt1, colour & 31);
-            if (i < nrep && i < rep_cap) { rc[i] = colour; rv[i] = colour < 32 ? v0 : v1; }
+            if (i < nrep && i < rep_cap) { rc[i] = STEPS ? (colour | ((uint32_t)ordstep[i] << REP_STEP_SHIFT)) : colour; rv[i] = colour < 32 ? v0 : v1; }
         }
         if (lane == 0) {
             if (miss && nrep < rep_cap) { rc[nrep] = N; rv[nrep] = 1; }
@@ -765,7 +770,7 @@ readid_vote_wide_kernel(const uint8_t* __restrict__ bases, const uint8_t* __rest
                         const uint16_t* __restrict__ order, const uint8_t* __restrict__ order8,
                         const uint16_t* __restrict__ ent16, const uint32_t* __restrict__ n_set, uint32_t start_sample,
                         uint32_t rep_cap, uint32_t* __restrict__ flags, uint32_t* __restrict__ rep_n,
-                        uint32_t* __restrict__ rep_colour, uint32_t* __restrict__ rep_count) {
+                        uint32_t* __restrict__ rep_colour, uint32_t* __restrict__ rep_count, uint32_t with_steps) {
     extern __shared__ __align__(16) uint8_t dsm[];
     __shared__ uint32_t lut[256];
     lut4_init(lut, threadIdx.x, blockDim.x);
@@ -825,7 +830,7 @@ readid_vote_wide_kernel(const uint8_t* __restrict__ bases, const uint8_t* __rest
                         uint32_t y = __shfl_sync(0xffffffffu, nw, l);
                         while (y) {
                             uint32_t b = __ffs(y) - 1; y &= y - 1;
-                            if (lane == 0 && nrep < rep_cap) rc[nrep] = (w * 32 + l) * 32 + b;
+                            if (lane == 0 && nrep < rep_cap) rc[nrep] = ((w * 32 + l) * 32 + b) | (with_steps ? (j << REP_STEP_SHIFT) : 0u);
                             nrep++;
                         }
                     }
@@ -845,7 +850,7 @@ readid_vote_wide_kernel(const uint8_t* __restrict__ bases, const uint8_t* __rest
         const uint32_t kept = min(nrep, rep_cap);
         for (uint32_t i = 0; i < kept; i++) {
             uint32_t colour = rc[i];             // written by lane 0 above
-            colour = __shfl_sync(0xffffffffu, colour, 0);
+            colour = __shfl_sync(0xffffffffu, colour, 0) & ((1u << REP_STEP_SHIFT) - 1u);
             uint32_t word = colour >> 5, b = colour & 31, w = word >> 5, owner = word & 31;
             uint32_t v = 0;
 #pragma unroll
@@ -1148,7 +1153,8 @@ int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const ui
                             4 * ((small ? (maxocc + 31) / 32 : 0) + (TB >= 32 ? TB / 32 : 1) + (TB >= 64 ? TB / 64 : 1));
     size_t b_smem = 32 * b_thread;
     if (small) b_smem = 0;      // readid_order_small_kernel<TB> sizes its own shared memory (< 48 KB)
-    size_t cn_warp = ((tile_smem_bytes(cap) + 15) & ~(size_t)15) + 64 + (MAX_MATES + 1) * 4 + 12;
+    size_t cn_warp = ((tile_smem_bytes(cap) + 15) & ~(size_t)15) + 64 + 128 + (MAX_MATES + 1) * 4 + 12;
+    const uint32_t with_steps = ctx->opt_readid_report_steps ? 1u : 0u;
     size_t cn_smem = RA_WARPS * ((cn_warp + 15) & ~(size_t)15);
     size_t cw_warp = ((tile_smem_bytes(cap) + 15) & ~(size_t)15) + (MAX_MATES + 1) * 4 + 12;
     size_t cw_smem = RA_WARPS * ((cw_warp + 15) & ~(size_t)15);
@@ -1220,21 +1226,19 @@ int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const ui
             const uint32_t* rownz = idx->rownz;
             if (idx->Wp <= 2) {
                 if (!idx->rownz_global) rownz = nullptr;   // presence == any word set, already in registers
-                if (idx->Wp == 1)
-                    readid_vote_narrow_kernel<1><<<gridV, RA_WARPS * 32, cn_smem, st>>>(
-                        d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr, kitem, idx->H, mods, idx->rows, rownz, idx->rownz,
-                        idx->N, cap, maxocc, ord16, ord8, d_ent16, d_n_set, p.start_sample, p.rep_cap, d_flags, d_rep_n, d_rep_colour,
-                        d_rep_count, (unsigned long long*)(ctx->d_err + 2));
-                else
-                    readid_vote_narrow_kernel<2><<<gridV, RA_WARPS * 32, cn_smem, st>>>(
-                        d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr, kitem, idx->H, mods, idx->rows, rownz, idx->rownz,
-                        idx->N, cap, maxocc, ord16, ord8, d_ent16, d_n_set, p.start_sample, p.rep_cap, d_flags, d_rep_n, d_rep_colour,
-                        d_rep_count, (unsigned long long*)(ctx->d_err + 2));
+#define CID_VOTE_NARROW(WPV, STV)                                                                                      \
+    readid_vote_narrow_kernel<WPV, STV><<<gridV, RA_WARPS * 32, cn_smem, st>>>(                                        \
+        d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr, kitem, idx->H, mods, idx->rows, rownz, idx->rownz, idx->N, cap,  \
+        maxocc, ord16, ord8, d_ent16, d_n_set, p.start_sample, p.rep_cap, d_flags, d_rep_n, d_rep_colour, d_rep_count,  \
+        (unsigned long long*)(ctx->d_err + 2))
+                if (idx->Wp == 1) { if (with_steps) CID_VOTE_NARROW(1, true); else CID_VOTE_NARROW(1, false); }
+                else { if (with_steps) CID_VOTE_NARROW(2, true); else CID_VOTE_NARROW(2, false); }
+#undef CID_VOTE_NARROW
             } else {
                 readid_vote_wide_kernel<<<gridV, RA_WARPS * 32, cw_smem, st>>>(
                     d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr, kitem, idx->H, mods, idx->rows, rownz, idx->N,
                     idx->Wp, cap, maxocc, ord16, ord8, d_ent16, d_n_set, p.start_sample, p.rep_cap, d_flags, d_rep_n, d_rep_colour,
-                    d_rep_count);
+                    d_rep_count, with_steps);
             }
             ctx->launches++;
             CID_CUDA(cudaGetLastError());

@@ -82,6 +82,8 @@ SIGNATURES = {
     "cid_classify_reads": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, u64p, C.c_double, C.c_uint32, C.c_uint64, u32p,
                                      u32p, u32p, u32p, u32p, C.c_uint32, C.c_int, C.POINTER(C.c_int32), u32p, u32p, u32p,
                                      C.c_uint32]),
+    "cid_merge_shard_reports": (C.c_int, [C.c_uint32, u32p, u32p, C.c_uint64, C.POINTER(u32p), C.POINTER(u32p), C.POINTER(u32p),
+                                          C.c_uint32, C.c_uint32, u32p, u32p, u32p, C.c_uint32, u32p]),
     "cid_false_prob": (C.c_double, [C.c_double, C.c_double, C.c_double]),
     "cid_binomial_mass": (C.c_double, [C.c_uint64, C.c_double, C.c_uint64]),
 }

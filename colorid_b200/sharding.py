@@ -102,6 +102,19 @@ def concat_in_order(local_rows, group=None):
     return np.concatenate(parts, axis=0)
 
 
+def merge_read_reports(local_report, shards, n_total, group=None):
+    """Column-sharded read_id (read_id_mt_pe.rs:104-165 is per-colour once the first absent row is known, and that is a
+    property of whole rows: or_reduce_bitmap + Index.set_rownz_global): every rank classifies ALL reads against its
+    accession slice with the context option readid_report_steps = 1; the sparse per-read reports are all-gathered and
+    merged into the unsharded report on every rank (api.merge_shard_reports), ready for api.classify_reads."""
+    from .api import merge_shard_reports
+    world = dist.get_world_size(group)
+    parts = [None] * world
+    keys = ("n_set", "flags", "rep_n", "rep_colour", "rep_count")
+    dist.all_gather_object(parts, {k: np.ascontiguousarray(local_report[k]) for k in keys}, group=group)
+    return merge_shard_reports(parts, shards, n_total)
+
+
 class PeerCounts:
     """Full-width [nq, n_total] count buffers, one per rank, each opened on every other rank through CUDA IPC so that
     cid_query_counts_sharded_dev can add its column slice straight into all of them over NVLink (no collective)."""

@@ -245,6 +245,16 @@ int cid_classify_reads(uint64_t bloom_size, uint32_t num_hash, uint32_t n_colors
                        const uint32_t* flags, const uint32_t* rep_n, const uint32_t* rep_colour,
                        const uint32_t* rep_count, uint32_t rep_cap, int threads, int32_t* kind, uint32_t* hits,
                        uint32_t* n_top, uint32_t* top, uint32_t top_cap);
+/* Column-sharded read_id (read_id_mt_pe.rs:104-165 search_index is per-colour once the first absent row is known):
+ * each shard runs cid_read_id_batch on the same reads with cid_ctx_set_option(ctx, "readid_report_steps", 1) and the
+ * row-present bitmaps merged (cid_index_set_rownz_global); its rep_colour entries are then colour | step << 20.  This
+ * host call merges the n_shards reports of every read into the report of the unsharded index (global colours
+ * shard_col_offset[s] + colour, the reference's insertion order, the "no hit" key = n_total last), ready for
+ * cid_classify_reads with n_colors = n_total.  n_set and flags are the same on every shard.  out_flags may be NULL. */
+int cid_merge_shard_reports(uint32_t n_shards, const uint32_t* shard_n_colors, const uint32_t* shard_col_offset,
+                            uint64_t nreads, const uint32_t* const* rep_n, const uint32_t* const* rep_colour,
+                            const uint32_t* const* rep_count, uint32_t rep_cap_in, uint32_t n_total, uint32_t* out_rep_n,
+                            uint32_t* out_colour, uint32_t* out_count, uint32_t rep_cap_out, uint32_t* out_flags);
 /* read_id_mt_pe.rs:695-698 false_prob and the Binomial pmf used by :168-181 (parity hooks). */
 double cid_false_prob(double bloom_size, double num_hash, double n_ref_kmers);
 double cid_binomial_mass(uint64_t n, double p, uint64_t x);

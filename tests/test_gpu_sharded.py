@@ -79,6 +79,31 @@ def _worker(rank, world, port, ndev, out_dir):
     parts = [torch.empty_like(both) for _ in range(world)]
     dist.all_gather(parts, both)
     assert all(torch.equal(p, both) for p in parts), "ranks disagree on the exchanged counts"
+    # ---- column-sharded read_id: row-present bitmaps OR-ed across ranks, per-shard reports with insertion steps,
+    # all-gathered and merged on every rank (sharding.merge_read_reports)
+    from colorid_b200.api import classify_reads
+    _, bm_ptr, bm_words = gix.device_ptrs()
+    view = sharding.device_view(bm_ptr, bm_words, dev)
+    bm = view.cpu()
+    sharding.or_reduce_bitmap(bm)
+    view.copy_(bm.to(dev))
+    torch.cuda.synchronize()
+    gix.set_rownz_global(True)
+    ctx.set_option("readid_report_steps", 1)
+    reads = synth.reads_from(rng, genomes, 150, read_len=150, insert=320, err=0.004, frac_random=0.2)
+    merged = sharding.merge_read_reports(gix.read_id_batch(reads), shards, N)
+    n_ref_parts = [None] * world
+    dist.all_gather_object(n_ref_parts, gix.n_ref)
+    cls = classify_reads((S, H, N), np.concatenate(n_ref_parts), merged)
+    if rank == 0:
+        o = whole.read_id_batch(reads, n_ref=np.concatenate(n_ref_parts))
+        same = bool(np.array_equal(merged["n_set"], o["n_set"]) and np.array_equal(cls["kind"], o["kind"]) and
+                    np.array_equal(cls["hits"], o["hits"]) and np.array_equal(cls["n_top"], o["n_top"]))
+        for r in range(len(reads)):
+            gd = dict(zip(merged["rep_colour"][r, :merged["rep_n"][r]].tolist(), merged["rep_count"][r, :merged["rep_n"][r]].tolist()))
+            od = dict(zip(o["rep_colour"][r, :o["rep_n"][r]].tolist(), o["rep_count"][r, :o["rep_n"][r]].tolist()))
+            same = same and gd == od
+        open(os.path.join(out_dir, "ok_readid"), "w").write("1" if same and int(o["rep_n"].max()) >= 2 else "0")
     dist.destroy_process_group()
 
 
@@ -87,3 +112,76 @@ def test_column_sharded_counts_exchanged_through_peer_memory(tmp_path):
     assert ndev >= 1
     mp.spawn(_worker, args=(2, _free_port(), ndev, str(tmp_path)), nprocs=2, join=True)
     assert open(tmp_path / "ok").read() == "1"
+    assert open(tmp_path / "ok_readid").read() == "1", "column-sharded read_id: merged reports / classification differ from the oracle"
+
+
+@pytest.mark.parametrize("N,k,S,H,world", [(100, 21, 200_003, 2, 2), (300, 21, 200_003, 2, 2), (200, 27, 300_007, 4, 3)])
+def test_column_sharded_read_id_merges_to_the_unsharded_report(N, k, S, H, world):
+    """Column-sharded read_id in one process: `world` shard indices (64 + 36 accessions: the narrow-row vote kernel; 160 + 140
+    and 96 + 64 + 40: the wide one) with their row-present bitmaps OR-ed, per-shard reports carrying insertion steps
+    (option readid_report_steps), merged by cid_merge_shard_reports -> the exact report sequence, and classification, of the
+    whole index on the GPU, which test_gpu_parity holds to the oracle."""
+    import colorid_b200 as cb
+    from colorid_b200 import sharding
+    from colorid_b200.api import classify_reads, merge_shard_reports
+    from oracle import pyoracle as O
+    rng = np.random.default_rng(0xC0101D00 + 1300 + N)
+    genomes = synth.clade_genomes(rng, N, 3000, n_clades=max(2, N // 10), div=0.01)
+    reads = synth.reads_from(rng, genomes, 300, read_len=150, insert=320, err=0.004, frac_random=0.2, n_rate=0.002)
+    reads += synth.reads_from(rng, genomes, 40, read_len=100, insert=300, err=0.0, frac_random=0.0, paired=False)
+    reads.append([b"ACGT", genomes[0][:150]])                         # too_short
+    reads.append([b"N" * 150, b"N" * 150])                            # empty set
+    dev = torch.device("cuda:0")
+    ctx = cb.Context(0)
+    sctx = cb.Context(0)
+    sctx.set_option("readid_report_steps", 1)
+    full = cb.Index(ctx, S, H, k, N)
+    for c in range(N):
+        full.build_accession(c, [genomes[c]])
+    full.finalize()
+    shards = sharding.column_shards(N, world)
+    parts, views = [], []
+    for lo, hi in shards:
+        ix = cb.Index(sctx, S, H, k, hi - lo)
+        for c in range(lo, hi):
+            ix.build_accession(c - lo, [genomes[c]])
+        ix.finalize()
+        _, bm_ptr, bm_words = ix.device_ptrs()
+        views.append(sharding.device_view(bm_ptr, bm_words, dev))
+        parts.append(ix)
+    torch.cuda.synchronize()
+    merged_bm = views[0].clone()
+    for v in views[1:]:
+        merged_bm |= v
+    for ix, v in zip(parts, views):                                   # what or_reduce_bitmap does across ranks
+        v.copy_(merged_bm)
+        ix.set_rownz_global(True)
+    torch.cuda.synchronize()
+    n_ref = np.concatenate([ix.n_ref for ix in parts])
+    assert np.array_equal(n_ref, full.n_ref)
+    for kw in (dict(), dict(start_sample=0), dict(start_sample=1), dict(d=2)):
+        want = full.read_id_batch(reads, **kw)
+        got = merge_shard_reports([ix.read_id_batch(reads, **kw) for ix in parts], shards, N)
+        assert np.array_equal(got["n_set"], want["n_set"]) and np.array_equal(got["rep_n"], want["rep_n"])
+        assert np.array_equal(got["flags"] & 7, want["flags"] & 7)
+        for r in range(len(reads)):
+            n = want["rep_n"][r]
+            assert got["rep_colour"][r, :n].tolist() == want["rep_colour"][r, :n].tolist(), (kw, r)
+            assert got["rep_count"][r, :n].tolist() == want["rep_count"][r, :n].tolist(), (kw, r)
+        a, b = classify_reads((S, H, N), n_ref, got), classify_reads((S, H, N), n_ref, want)
+        for key in ("kind", "hits", "n_top", "top"):
+            assert np.array_equal(a[key], b[key])
+    assert int(want["rep_n"].max()) >= 3 and int((want["rep_n"] == 0).sum()) >= 1
+    # the oracle on the whole index agrees with the merged report (as a map; order is checked against the GPU above)
+    whole = O.Index(S, H, k, N)
+    whole.build_many([[g] for g in genomes], O.MODE_FASTA, threads=2)
+    o = whole.read_id_batch(reads)
+    got = merge_shard_reports([ix.read_id_batch(reads) for ix in parts], shards, N)
+    for r in range(len(reads)):
+        gd = dict(zip(got["rep_colour"][r, :got["rep_n"][r]].tolist(), got["rep_count"][r, :got["rep_n"][r]].tolist()))
+        od = dict(zip(o["rep_colour"][r, :o["rep_n"][r]].tolist(), o["rep_count"][r, :o["rep_n"][r]].tolist()))
+        assert gd == od, r
+    for ix in parts + [full]:
+        ix.close()
+    sctx.close()
+    ctx.close()

@@ -1,6 +1,7 @@
 """CPU: the product's host-side vote (cid_classify_reads: kmer_poll_plus, false_prob, Binomial pmf,
 FnvHashMap tie order) against the oracle.  Host logic only: no CUDA call is made."""
 import numpy as np
+import pytest
 
 import colorid_b200.lib as L
 from colorid_b200.api import classify_reads
@@ -70,3 +71,55 @@ def test_classify_reads_equals_oracle_kmer_poll_plus(oracle):
                                                        1e-3, top_cap=16)
         assert (got["kind"][r], got["hits"][r], got["n_top"][r]) == (kind, hits, n_top), r
         assert got["top"][r, :n_top].tolist() == top.tolist(), r
+
+
+def test_merge_shard_reports_restores_insertion_order():
+    """cid_merge_shard_reports (host only): per-shard read_id reports with insertion steps -> the unsharded report."""
+    import colorid_b200 as cb
+    from colorid_b200.api import merge_shard_reports
+    rng = np.random.default_rng(4242)
+    n_total, shards = 300, [(0, 96), (96, 224), (224, 300)]
+    nreads, cap = 200, 40
+    glob_c = np.zeros((nreads, n_total + 1), np.uint32)
+    glob_v = np.zeros((nreads, n_total + 1), np.uint32)
+    glob_n = np.zeros(nreads, np.uint32)
+    reps = [dict(n_set=np.full(nreads, 50, np.uint32), flags=np.zeros(nreads, np.uint32), rep_n=np.zeros(nreads, np.uint32),
+                 rep_colour=np.zeros((nreads, cap), np.uint32), rep_count=np.zeros((nreads, cap), np.uint32)) for _ in shards]
+    for r in range(nreads):
+        ncol = int(rng.integers(0, 25))
+        cols = rng.choice(n_total, size=ncol, replace=False)
+        steps = np.sort(rng.integers(0, 3, size=ncol))                 # colours arrive at k-mers 0..2, ascending within a k-mer
+        seq = sorted(zip(steps.tolist(), cols.tolist()))
+        miss = bool(rng.integers(0, 2))
+        for i, (st, c) in enumerate(seq):
+            glob_c[r, i], glob_v[r, i] = c, int(rng.integers(1, 200))
+        n = len(seq)
+        if miss:
+            glob_c[r, n], glob_v[r, n] = n_total, 1
+            n += 1
+        glob_n[r] = n
+        for s, (lo, hi) in enumerate(shards):
+            k = 0
+            for i, (st, c) in enumerate(seq):
+                if lo <= c < hi:
+                    reps[s]["rep_colour"][r, k] = (c - lo) | (st << 20)
+                    reps[s]["rep_count"][r, k] = glob_v[r, i]
+                    k += 1
+            if miss:
+                reps[s]["rep_colour"][r, k], reps[s]["rep_count"][r, k] = hi - lo, 1
+                k += 1
+            reps[s]["rep_n"][r] = k
+    m = merge_shard_reports(reps, shards, n_total)
+    assert np.array_equal(m["rep_n"], glob_n)
+    for r in range(nreads):
+        n = glob_n[r]
+        assert np.array_equal(m["rep_colour"][r, :n], glob_c[r, :n]) and np.array_equal(m["rep_count"][r, :n], glob_v[r, :n])
+    # shards that disagree on the first absent row (row-present bitmaps not merged) are refused
+    reps[1]["rep_n"][:] = 0
+    r_miss = int(np.argmax(glob_c[np.arange(nreads), np.maximum(glob_n, 1) - 1] == n_total))
+    if glob_n[r_miss] and glob_c[r_miss, glob_n[r_miss] - 1] == n_total:
+        with pytest.raises(cb.CidError):
+            merge_shard_reports(reps, shards, n_total)
+    # a small output capacity truncates and says so
+    m2 = merge_shard_reports([dict(x, rep_n=x["rep_n"].copy()) for x in reps[:1]], shards[:1], 96, rep_cap=2)
+    assert (m2["rep_n"] <= 2).all() and ((m2["flags"] & 4) != 0).sum() == (reps[0]["rep_n"] > 2).sum()
