@@ -233,6 +233,33 @@ class Index:
                                           _p(un, L.u64p), _p(us, L.u64p), _p(um, L.u64p), _p(used, L.i64p)))
         return dict(counts=counts, num_kmers=num_kmers, uniq_n=un, uniq_sum=us, uniq_mode=um, cutoff=used[:nq])
 
+    # ---- column-sharded default report (three calls around one exchange; see include/colorid_b200.h) ----
+    def query_survivors(self, queries, seq_mode=L.CID_SEQ_FASTA, gene_search=False, filt=-1):
+        """-> (device pointer of the dense survivor list, surv[nq], cutoff[nq]); the list is 16 bytes per k-mer."""
+        flat = [s for q in queries for s in q]
+        bases, offs = pack_seqs(flat)
+        qoffs = group_offsets(queries)
+        nq = len(queries)
+        surv = np.zeros(max(nq, 1), dtype=np.uint64)
+        used = np.zeros(max(nq, 1), dtype=np.int64)
+        ptr = L.vp()
+        L.check(self.lib.cid_query_survivors(self.h, _p(bases), _p(offs, L.u64p), len(flat), _p(qoffs, L.u64p), nq, seq_mode,
+                                             int(gene_search), filt, C.byref(ptr), _p(surv, L.u64p), _p(used, L.i64p)))
+        return ptr.value or 0, surv[:nq], used[:nq]
+
+    def slots_counts_dev(self, d_slots, surv, d_counts, d_num_kmers, d_pc, d_col, stream=0):
+        surv = np.ascontiguousarray(surv, dtype=np.uint64)
+        L.check(self.lib.cid_query_slots_counts_dev(self.h, d_slots, _p(surv, L.u64p), len(surv), d_counts, d_num_kmers, d_pc, d_col,
+                                                    stream))
+
+    def slots_uniq_dev(self, d_slots, surv, d_pc_local, d_pc_sum, d_col, stream=0):
+        surv = np.ascontiguousarray(surv, dtype=np.uint64)
+        nq = len(surv)
+        un, us, um = (np.zeros((nq, self.N), dtype=np.uint64) for _ in range(3))
+        L.check(self.lib.cid_query_slots_uniq_dev(self.h, d_slots, _p(surv, L.u64p), nq, d_pc_local, d_pc_sum, d_col,
+                                                  _p(un, L.u64p), _p(us, L.u64p), _p(um, L.u64p), stream))
+        return un, us, um
+
     # ---- perfect search (perfect_search.rs:6-60) ----
     def query_perfect(self, queries):
         flat = [s for q in queries for s in q]

@@ -733,6 +733,109 @@ static std::vector<uint64_t> query_front_batches(const uint64_t* h_seq_offs, con
     return cuts;
 }
 
+// work units -> scratch[6] (synchronous: `qu` may be a temporary)
+static int upload_units(cid_ctx* ctx, cudaStream_t st, const QueryUnits& qu, QueryPlan& qp) {
+    const uint64_t nu = qu.group.size();
+    CID_TRY(ctx->scratch[6].ensure(nu * 16 + 64));
+    qp.d_unit_slot0 = ctx->scratch[6].as<uint64_t>();
+    qp.d_unit_group = (uint32_t*)(qp.d_unit_slot0 + nu);
+    qp.d_unit_nslots = qp.d_unit_group + nu;
+    if (nu) {
+        CID_CUDA(cudaMemcpyAsync(qp.d_unit_slot0, qu.slot0.data(), nu * 8, cudaMemcpyHostToDevice, st));
+        CID_CUDA(cudaMemcpyAsync(qp.d_unit_group, qu.group.data(), nu * 4, cudaMemcpyHostToDevice, st));
+        CID_CUDA(cudaMemcpyAsync(qp.d_unit_nslots, qu.nslots.data(), nu * 4, cudaMemcpyHostToDevice, st));
+        CID_CUDA(cudaStreamSynchronize(st));
+    }
+    return CID_OK;
+}
+
+// Survivors (count > filt[q]) of every query region copied into one dense slot list on scratch[22] (query q at the prefix sum
+// of surv[]), gather work units re-planned over it.  surv[q] == UINT64_MAX: not known yet (counted here).  Unless `force`,
+// nothing changes when the table is less than 3/4 empty.
+static int compact_survivors(cid_ctx* ctx, cudaStream_t st, QueryPlan& qp, const std::vector<int64_t>& filt, std::vector<uint64_t>& surv,
+                             bool force, const void** d_slots, uint64_t* slots_total) {
+    const uint64_t bq = filt.size();
+    CID_TRY(ctx->scratch[21].ensure(bq * 8 + 8));
+    unsigned long long* d_surv = ctx->scratch[21].as<unsigned long long>();
+    CID_CUDA(cudaMemsetAsync(d_surv, 0, bq * 8, st));
+    bool counted = false;
+    for (uint64_t q = 0; q < bq; q++)
+        if (surv[q] == UINT64_MAX) {          // no histogram at hand (fixed filter): count pass
+            CID_TRY(launch_region_compact(ctx, st, qp.d_table + qp.gr.off[q], qp.gr.mask[q] + 1, filt[q], nullptr, d_surv + q, 0));
+            counted = true;
+        }
+    if (counted) {
+        std::vector<unsigned long long> hs(bq);
+        CID_CUDA(cudaMemcpyAsync(hs.data(), d_surv, bq * 8, cudaMemcpyDeviceToHost, st));
+        CID_CUDA(cudaStreamSynchronize(st));
+        for (uint64_t q = 0; q < bq; q++) if (surv[q] == UINT64_MAX) surv[q] = hs[q];
+        CID_CUDA(cudaMemsetAsync(d_surv, 0, bq * 8, st));
+    }
+    uint64_t dense_total = 0;
+    std::vector<uint64_t> dbase(bq);
+    for (uint64_t q = 0; q < bq; q++) { dbase[q] = dense_total; dense_total += surv[q]; }
+    if (!force && dense_total * 4 > qp.gr.total_slots) return CID_OK;       // worth it only when the table is mostly empty
+    CID_TRY(ctx->scratch[22].ensure((dense_total + 1) * sizeof(Slot)));
+    Slot* d_dense = ctx->scratch[22].as<Slot>();
+    QueryUnits du;
+    for (uint64_t q = 0; q < bq; q++) {
+        if (surv[q] == 0) continue;
+        CID_TRY(launch_region_compact(ctx, st, qp.d_table + qp.gr.off[q], qp.gr.mask[q] + 1, filt[q], d_dense + dbase[q], d_surv + q, surv[q]));
+        for (uint64_t at = 0; at < surv[q]; at += QUERY_ITEM_SLOTS) {
+            du.group.push_back((uint32_t)q);
+            du.slot0.push_back(dbase[q] + at);
+            du.nslots.push_back((uint32_t)std::min<uint64_t>(QUERY_ITEM_SLOTS, surv[q] - at));
+        }
+    }
+    CID_TRY(upload_units(ctx, st, du, qp));
+    qp.qu = std::move(du);
+    *d_slots = d_dense;
+    *slots_total = dense_total;
+    return CID_OK;
+}
+
+// reports.rs:20-26 from the unique-hit triples (query in batch, accession, multiplicity) of one batch: per (query, accession)
+// their number ("specific"), the sum (mean = sum / number) and the mode of the multiplicities, written at [(q0 + q) * N + c].
+static int summarize_uniq(cid_ctx* ctx, cudaStream_t st, const uint32_t* d_list, uint32_t nu, uint32_t N, uint64_t bq, uint64_t q0,
+                          uint64_t* uniq_n, uint64_t* uniq_sum, uint64_t* uniq_mode) {
+    // on the device when a [query x accession][multiplicity] histogram fits 64 MB (one FASTQ query: 628k triples took 13 ms
+    // through the host maps below, 2/3 of the whole search)
+    const uint64_t cells = bq * N;
+    const uint32_t MB = cells * 1024 <= (16u << 20) ? 1024u : cells * 256 <= (16u << 20) ? 256u : 0u;
+    if (MB && ctx->opt_uniq_device) {
+        CID_TRY(ctx->scratch[19].ensure(cells * MB * 4 + 16));
+        CID_TRY(ctx->scratch[20].ensure(cells * 24));
+        uint32_t* d_hist = ctx->scratch[19].as<uint32_t>();
+        uint32_t* d_ovf = d_hist + cells * MB;
+        unsigned long long* d_un = ctx->scratch[20].as<unsigned long long>();
+        CID_TRY(launch_uniq_summaries(ctx, st, d_list, nu, N, cells, MB, d_hist, d_ovf, d_un, d_un + cells, d_un + 2 * cells));
+        uint32_t ovf = 0;
+        CID_CUDA(cudaMemcpyAsync(&ovf, d_ovf, 4, cudaMemcpyDeviceToHost, st));
+        CID_CUDA(cudaStreamSynchronize(st));
+        if (!ovf) {
+            if (uniq_n) CID_CUDA(cudaMemcpyAsync(uniq_n + q0 * N, d_un, cells * 8, cudaMemcpyDeviceToHost, st));
+            if (uniq_sum) CID_CUDA(cudaMemcpyAsync(uniq_sum + q0 * N, d_un + cells, cells * 8, cudaMemcpyDeviceToHost, st));
+            if (uniq_mode) CID_CUDA(cudaMemcpyAsync(uniq_mode + q0 * N, d_un + 2 * cells, cells * 8, cudaMemcpyDeviceToHost, st));
+            CID_CUDA(cudaStreamSynchronize(st));
+            return CID_OK;
+        }
+    }
+    std::vector<uint32_t> ul((size_t)nu * 3);
+    if (nu) CID_CUDA(cudaMemcpy(ul.data(), d_list, (size_t)nu * 12, cudaMemcpyDeviceToHost));
+    // Mode ties are broken towards the smallest value (the reference's tie-break is hash-order dependent).
+    std::map<std::pair<uint64_t, uint32_t>, std::map<uint32_t, uint64_t>> freq;
+    for (uint32_t i = 0; i < nu; i++) freq[{q0 + ul[3 * i], ul[3 * i + 1]}][ul[3 * i + 2]] += 1;
+    for (auto& kv : freq) {
+        uint64_t n = 0, sum = 0, mode = 0, best = 0;
+        for (auto& fv : kv.second) { n += fv.second; sum += (uint64_t)fv.first * fv.second; if (fv.second > best) { best = fv.second; mode = fv.first; } }
+        size_t at = kv.first.first * N + kv.first.second;
+        if (uniq_n) uniq_n[at] = n;
+        if (uniq_sum) uniq_sum[at] = sum;
+        if (uniq_mode) uniq_mode[at] = mode;
+    }
+    return CID_OK;
+}
+
 int cid_query_counts(cid_index* ix, const char* bases, const uint64_t* seq_offs, uint64_t nseq,
                      const uint64_t* query_offs, uint64_t nq, int seq_mode, int gene_search, int64_t filter,
                      uint32_t* counts, uint64_t* num_kmers, uint64_t* uniq_n, uint64_t* uniq_sum, uint64_t* uniq_mode,
@@ -799,56 +902,8 @@ int cid_query_counts(cid_index* ix, const char* bases, const uint64_t* seq_offs,
         // Large, sparse count tables (read-set queries): survivors copied once into a dense slot list, work units over that
         const void* d_slots = qp.d_table;
         uint64_t slots_total = qp.gr.total_slots;
-        if (ctx->opt_query_compact && (qp.gr.total_slots >= (1ull << 22) || ctx->opt_query_compact == 2) && bq <= 64) {
-            CID_TRY(ctx->scratch[21].ensure(bq * 8 + 8));
-            unsigned long long* d_surv = ctx->scratch[21].as<unsigned long long>();
-            CID_CUDA(cudaMemsetAsync(d_surv, 0, bq * 8, st));
-            bool counted = false;
-            for (uint64_t q = 0; q < bq; q++)
-                if (surv[q] == UINT64_MAX) {          // no histogram at hand (fixed filter): count pass
-                    CID_TRY(launch_region_compact(ctx, st, qp.d_table + qp.gr.off[q], qp.gr.mask[q] + 1, filt[q], nullptr, d_surv + q, 0));
-                    counted = true;
-                }
-            if (counted) {
-                std::vector<unsigned long long> hs(bq);
-                CID_CUDA(cudaMemcpyAsync(hs.data(), d_surv, bq * 8, cudaMemcpyDeviceToHost, st));
-                CID_CUDA(cudaStreamSynchronize(st));
-                for (uint64_t q = 0; q < bq; q++) if (surv[q] == UINT64_MAX) surv[q] = hs[q];
-                CID_CUDA(cudaMemsetAsync(d_surv, 0, bq * 8, st));
-            }
-            uint64_t dense_total = 0;
-            std::vector<uint64_t> dbase(bq);
-            for (uint64_t q = 0; q < bq; q++) { dbase[q] = dense_total; dense_total += surv[q]; }
-            if (dense_total * 4 <= qp.gr.total_slots || ctx->opt_query_compact == 2) {       // worth it only when the table is mostly empty
-                CID_TRY(ctx->scratch[22].ensure((dense_total + 1) * sizeof(Slot)));
-                Slot* d_dense = ctx->scratch[22].as<Slot>();
-                QueryUnits du;
-                for (uint64_t q = 0; q < bq; q++) {
-                    if (surv[q] == 0) continue;
-                    CID_TRY(launch_region_compact(ctx, st, qp.d_table + qp.gr.off[q], qp.gr.mask[q] + 1, filt[q], d_dense + dbase[q],
-                                                  d_surv + q, surv[q]));
-                    for (uint64_t at = 0; at < surv[q]; at += QUERY_ITEM_SLOTS) {
-                        du.group.push_back((uint32_t)q);
-                        du.slot0.push_back(dbase[q] + at);
-                        du.nslots.push_back((uint32_t)std::min<uint64_t>(QUERY_ITEM_SLOTS, surv[q] - at));
-                    }
-                }
-                const uint64_t nu2 = du.group.size();
-                CID_TRY(ctx->scratch[6].ensure(nu2 * 16 + 64));
-                qp.d_unit_slot0 = ctx->scratch[6].as<uint64_t>();
-                qp.d_unit_group = (uint32_t*)(qp.d_unit_slot0 + nu2);
-                qp.d_unit_nslots = qp.d_unit_group + nu2;
-                if (nu2) {
-                    CID_CUDA(cudaMemcpyAsync(qp.d_unit_slot0, du.slot0.data(), nu2 * 8, cudaMemcpyHostToDevice, st));
-                    CID_CUDA(cudaMemcpyAsync(qp.d_unit_group, du.group.data(), nu2 * 4, cudaMemcpyHostToDevice, st));
-                    CID_CUDA(cudaMemcpyAsync(qp.d_unit_nslots, du.nslots.data(), nu2 * 4, cudaMemcpyHostToDevice, st));
-                    CID_CUDA(cudaStreamSynchronize(st));          // `du` is pageable and dies with this scope
-                }
-                qp.qu = std::move(du);
-                d_slots = d_dense;
-                slots_total = dense_total;
-            }
-        }
+        if (ctx->opt_query_compact && (qp.gr.total_slots >= (1ull << 22) || ctx->opt_query_compact == 2) && bq <= 64)
+            CID_TRY(compact_survivors(ctx, st, qp, filt, surv, ctx->opt_query_compact == 2, &d_slots, &slots_total));
         const double t_cut = now();
         const uint64_t npos_total = qp.kmers_bound;
         const uint32_t uniq_cap = want_uniq ? (uint32_t)std::min<uint64_t>(npos_total + 1, 0xFFFFFFF0u / 3) : 0;
@@ -871,48 +926,9 @@ int cid_query_counts(cid_index* ix, const char* bases, const uint64_t* seq_offs,
         CID_CUDA(cudaMemcpyAsync(&nu, ctx->scratch[13].p, 4, cudaMemcpyDeviceToHost, st));
         CID_CUDA(cudaStreamSynchronize(st));
         const double t_counts = now();
-        bool uniq_done = false;
         if (want_uniq) {
             if (nu > uniq_cap) { set_error("unique-hit list overflow"); return CID_E_CAPACITY; }
-            // summaries on the device when a [query x accession][multiplicity] histogram fits 64 MB (one FASTQ query: 628k
-            // triples took 13 ms through the host maps below, 2/3 of the whole search)
-            const uint64_t cells = bq * N;
-            const uint32_t MB = cells * 1024 <= (16u << 20) ? 1024u : cells * 256 <= (16u << 20) ? 256u : 0u;
-            if (MB && ctx->opt_uniq_device) {
-                CID_TRY(ctx->scratch[19].ensure(cells * MB * 4 + 16));
-                CID_TRY(ctx->scratch[20].ensure(cells * 24));
-                uint32_t* d_hist = ctx->scratch[19].as<uint32_t>();
-                uint32_t* d_ovf = d_hist + cells * MB;
-                unsigned long long* d_un = ctx->scratch[20].as<unsigned long long>();
-                CID_TRY(launch_uniq_summaries(ctx, st, ctx->scratch[12].as<uint32_t>(), nu, N, cells, MB, d_hist, d_ovf, d_un, d_un + cells,
-                                              d_un + 2 * cells));
-                uint32_t ovf = 0;
-                CID_CUDA(cudaMemcpyAsync(&ovf, d_ovf, 4, cudaMemcpyDeviceToHost, st));
-                CID_CUDA(cudaStreamSynchronize(st));
-                if (!ovf) {
-                    if (uniq_n) CID_CUDA(cudaMemcpyAsync(uniq_n + q0 * N, d_un, cells * 8, cudaMemcpyDeviceToHost, st));
-                    if (uniq_sum) CID_CUDA(cudaMemcpyAsync(uniq_sum + q0 * N, d_un + cells, cells * 8, cudaMemcpyDeviceToHost, st));
-                    if (uniq_mode) CID_CUDA(cudaMemcpyAsync(uniq_mode + q0 * N, d_un + 2 * cells, cells * 8, cudaMemcpyDeviceToHost, st));
-                    CID_CUDA(cudaStreamSynchronize(st));
-                    uniq_done = true;
-                }
-            }
-        }
-        if (want_uniq && !uniq_done) {
-            std::vector<uint32_t> ul((size_t)nu * 3);
-            if (nu) CID_CUDA(cudaMemcpy(ul.data(), ctx->scratch[12].p, (size_t)nu * 12, cudaMemcpyDeviceToHost));
-            // reports.rs:20-26: mean = sum/len, modus = mode(values), specific = len.  Mode ties are
-            // broken towards the smallest value (the reference's tie-break is hash-order dependent).
-            std::map<std::pair<uint64_t, uint32_t>, std::map<uint32_t, uint64_t>> freq;
-            for (uint32_t i = 0; i < nu; i++) freq[{q0 + ul[3 * i], ul[3 * i + 1]}][ul[3 * i + 2]] += 1;
-            for (auto& kv : freq) {
-                uint64_t n = 0, s = 0, mode = 0, best = 0;
-                for (auto& fv : kv.second) { n += fv.second; s += (uint64_t)fv.first * fv.second; if (fv.second > best) { best = fv.second; mode = fv.first; } }
-                size_t at = kv.first.first * N + kv.first.second;
-                if (uniq_n) uniq_n[at] = n;
-                if (uniq_sum) uniq_sum[at] = s;
-                if (uniq_mode) uniq_mode[at] = mode;
-            }
+            CID_TRY(summarize_uniq(ctx, st, ctx->scratch[12].as<uint32_t>(), nu, N, bq, q0, uniq_n, uniq_sum, uniq_mode));
         }
         if (trace)
             fprintf(stderr, "[cid trace] query_counts batch %zu: %llu queries, H2D + count table + k-mer counting %.2f ms, cutoffs %.2f ms, "
@@ -920,6 +936,106 @@ int cid_query_counts(cid_index* ix, const char* bases, const uint64_t* seq_offs,
                     t_cut - t_front, t_counts - t_cut, nu, now() - t_counts);
     }
     return CID_OK;
+}
+
+// ---- column-sharded default report: three calls around one cross-shard exchange --------------------------
+int cid_query_survivors(cid_index* ix, const char* bases, const uint64_t* seq_offs, uint64_t nseq, const uint64_t* query_offs,
+                        uint64_t nq, int seq_mode, int gene_search, int64_t filter, void** d_slots, uint64_t* surv,
+                        int64_t* cutoff_used) {
+    cid_ctx* ctx = ix->ctx;
+    cudaStream_t st = ctx->stream;
+    if (!seq_offs || !query_offs || !d_slots || !surv) { set_error("cid_query_survivors: null argument"); return CID_E_INVALID; }
+    if (ix->m) { set_error("An index with minimizers (.mxi) is used, but not available for this function"); return CID_E_UNSUPPORTED; }
+    if (seq_mode != CID_SEQ_FASTA && seq_mode != CID_SEQ_FASTQ) { set_error("bad seq_mode"); return CID_E_INVALID; }
+    CID_CUDA(cudaSetDevice(ctx->device));
+    *d_slots = nullptr;
+    if (nq == 0) return CID_OK;
+    if (query_batches(seq_offs, query_offs, nq, ix->k, kMaxBatchSlots).size() != 2) {
+        set_error("cid_query_survivors: the queries of one call must fit one count-table pass (2^28 slots); split the call");
+        return CID_E_CAPACITY;
+    }
+    const uint64_t nbases = seq_offs[nseq];
+    CID_TRY(ctx->scratch[4].ensure(nbases + 64));
+    CID_TRY(ctx->scratch[5].ensure((nseq + 1) * 8));
+    if (nbases) CID_CUDA(cudaMemcpyAsync(ctx->scratch[4].p, bases, nbases, cudaMemcpyHostToDevice, st));
+    CID_CUDA(cudaMemcpyAsync(ctx->scratch[5].p, seq_offs, (nseq + 1) * 8, cudaMemcpyHostToDevice, st));
+    QueryPlan qp;
+    CID_TRY(query_front(ix, st, ctx->scratch[4].as<uint8_t>(), ctx->scratch[5].as<uint64_t>(), seq_offs, query_offs, 0, nq, seq_mode, qp));
+    CID_TRY(check_err_flags(ctx, st));
+    std::vector<int64_t> filt(nq);
+    std::vector<uint64_t> sv(nq, UINT64_MAX);
+    for (uint64_t q = 0; q < nq; q++) {          // batch_search_pe.rs:34-39 / :112-120
+        if (seq_mode == CID_SEQ_FASTA && gene_search) filt[q] = 0;
+        else if (filter < 0) CID_TRY(region_auto_cutoff(ctx, st, (const void*)(qp.d_table + qp.gr.off[q]), qp.gr.mask[q] + 1, &filt[q], false, &sv[q]));
+        else filt[q] = filter;
+        if (cutoff_used) cutoff_used[q] = filt[q];
+    }
+    const void* dense = nullptr;
+    uint64_t total = 0;
+    CID_TRY(compact_survivors(ctx, st, qp, filt, sv, true, &dense, &total));
+    CID_CUDA(cudaStreamSynchronize(st));
+    for (uint64_t q = 0; q < nq; q++) surv[q] = sv[q];
+    *d_slots = const_cast<void*>(dense);
+    return CID_OK;
+}
+
+int cid_query_slots_counts_dev(cid_index* ix, const void* d_slots, const uint64_t* surv, uint64_t nq, uint32_t* d_counts,
+                               uint64_t* d_num_kmers, uint8_t* d_pc, uint32_t* d_col, void* stream) {
+    cid_ctx* ctx = ix->ctx;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!surv || !d_counts || !d_num_kmers) { set_error("cid_query_slots_counts_dev: null argument"); return CID_E_INVALID; }
+    if (ix->m) { set_error("An index with minimizers (.mxi) is used, but not available for this function"); return CID_E_UNSUPPORTED; }
+    CID_CUDA(cudaSetDevice(ctx->device));
+    const uint32_t N = ix->N;
+    CID_CUDA(cudaMemsetAsync(d_counts, 0, nq * N * 4, st));
+    CID_CUDA(cudaMemsetAsync(d_num_kmers, 0, nq * 8, st));
+    QueryUnits du;
+    uint64_t total = 0;
+    for (uint64_t q = 0; q < nq; q++) {
+        for (uint64_t at = 0; at < surv[q]; at += QUERY_ITEM_SLOTS) {
+            du.group.push_back((uint32_t)q);
+            du.slot0.push_back(total + at);
+            du.nslots.push_back((uint32_t)std::min<uint64_t>(QUERY_ITEM_SLOTS, surv[q] - at));
+        }
+        total += surv[q];
+    }
+    if (total == 0) return CID_OK;
+    if (!d_slots) { set_error("cid_query_slots_counts_dev: null slot list"); return CID_E_INVALID; }
+    QueryPlan qp;
+    CID_TRY(upload_units(ctx, st, du, qp));
+    CID_TRY(launch_query_counts(ctx, st, ix, d_slots, qp.d_unit_group, qp.d_unit_slot0, qp.d_unit_nslots, du.group.size(), total, nullptr,
+                                d_counts, (unsigned long long*)d_num_kmers, false, nullptr, 0, nullptr));
+    if (d_pc && d_col) CID_TRY(launch_slots_popcount(ctx, st, ix, d_slots, total, d_pc, d_col));
+    return check_err_flags(ctx, st);
+}
+
+int cid_query_slots_uniq_dev(cid_index* ix, const void* d_slots, const uint64_t* surv, uint64_t nq, const uint8_t* d_pc_local,
+                             const uint8_t* d_pc_sum, const uint32_t* d_col, uint64_t* uniq_n, uint64_t* uniq_sum,
+                             uint64_t* uniq_mode, void* stream) {
+    cid_ctx* ctx = ix->ctx;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!surv || !d_pc_local || !d_pc_sum || !d_col) { set_error("cid_query_slots_uniq_dev: null argument"); return CID_E_INVALID; }
+    CID_CUDA(cudaSetDevice(ctx->device));
+    const uint32_t N = ix->N;
+    if (uniq_n) memset(uniq_n, 0, nq * N * 8);
+    if (uniq_sum) memset(uniq_sum, 0, nq * N * 8);
+    if (uniq_mode) memset(uniq_mode, 0, nq * N * 8);
+    std::vector<uint64_t> prefix(nq + 1, 0);
+    for (uint64_t q = 0; q < nq; q++) prefix[q + 1] = prefix[q] + surv[q];
+    const uint64_t total = prefix[nq];
+    if (total == 0) return CID_OK;
+    if (total > 0xFFFFFFF0u / 3) { set_error("cid_query_slots_uniq_dev: too many k-mers in one call"); return CID_E_CAPACITY; }
+    CID_TRY(ctx->scratch[7].ensure((nq + 1) * 8));
+    CID_TRY(ctx->scratch[12].ensure((size_t)total * 12 + 16));
+    CID_TRY(ctx->scratch[13].ensure(16));
+    CID_CUDA(cudaMemcpyAsync(ctx->scratch[7].p, prefix.data(), (nq + 1) * 8, cudaMemcpyHostToDevice, st));
+    CID_CUDA(cudaMemsetAsync(ctx->scratch[13].p, 0, 16, st));
+    CID_TRY(launch_uniq_emit(ctx, st, d_slots, ctx->scratch[7].as<uint64_t>(), (uint32_t)nq, total, d_pc_local, d_pc_sum, d_col,
+                             ctx->scratch[12].as<uint32_t>(), (uint32_t)total, ctx->scratch[13].as<uint32_t>()));
+    uint32_t nu = 0;
+    CID_CUDA(cudaMemcpyAsync(&nu, ctx->scratch[13].p, 4, cudaMemcpyDeviceToHost, st));
+    CID_CUDA(cudaStreamSynchronize(st));
+    return summarize_uniq(ctx, st, ctx->scratch[12].as<uint32_t>(), nu, N, nq, 0, uniq_n, uniq_sum, uniq_mode);
 }
 
 int cid_query_counts_dev(cid_index* ix, const char* d_bases, const uint64_t* d_seq_offs, uint64_t nseq,

@@ -1460,4 +1460,79 @@ int launch_region_compact(cid_ctx* ctx, cudaStream_t st, const void* d_region, u
     return CID_OK;
 }
 
+// ================================================================= column-sharded default report
+// "This k-mer hits exactly one accession" (batch_search_pe.rs:75-82) is a statement about the WHOLE row, so a column shard
+// can only say how many of ITS accessions a k-mer hits.  All shards walk the same dense survivor list (one rank's list,
+// broadcast), slots_popcount leaves min(popcount, 2) and the single hit's colour per list index, the per-index bytes are
+// summed across shards (one all-reduce of a byte per k-mer), and uniq_emit keeps the k-mers whose local and global
+// popcounts are both 1 -- in the same (query, accession, multiplicity) triple format the unsharded kernels emit.
+__global__ void __launch_bounds__(256)
+slots_popcount_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t k, uint32_t H, ModS mods,
+                      const Slot* __restrict__ slots, uint64_t n, uint8_t* __restrict__ pc_out, uint32_t* __restrict__ col_out) {
+    __shared__ uint32_t lut[256];
+    lut4_init(lut, threadIdx.x, 256);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (uint64_t i = (uint64_t)blockIdx.x * 8 + warp; i < n; i += (uint64_t)gridDim.x * 8) {
+        const HashIn in = hashin_from_key(lut, slots[i].key, k);
+        uint64_t rid[MAX_HASH];
+        for (uint32_t h = 0; h < H; h++) rid[h] = mod_s(xxh3_kmer(in, k, h), mods);
+        uint32_t pc = 0, where = 0;
+        for (uint32_t c = lane; c < Wp; c += 32) {
+            uint32_t x = 0xFFFFFFFFu;
+            for (uint32_t h = 0; h < H; h++) x &= __ldg(rows + rid[h] * Wp + c);
+            if (x) { pc += __popc(x); where = c * 32 + (__ffs(x) - 1); }
+        }
+        uint32_t tot = pc;
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        const uint32_t owner = __ballot_sync(0xffffffffu, pc == 1);
+        const uint32_t colour = __shfl_sync(0xffffffffu, where, owner ? __ffs(owner) - 1 : 0);
+        if (lane == 0) { pc_out[i] = (uint8_t)min(tot, 2u); col_out[i] = tot == 1 ? colour : 0xFFFFFFFFu; }
+    }
+}
+__global__ void __launch_bounds__(256)
+uniq_emit_kernel(const Slot* __restrict__ slots, const uint64_t* __restrict__ prefix, uint32_t nq, uint64_t n,
+                 const uint8_t* __restrict__ pc_local, const uint8_t* __restrict__ pc_sum, const uint32_t* __restrict__ col,
+                 uint32_t* __restrict__ list, uint32_t cap, uint32_t* __restrict__ n_out) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t stride = (uint64_t)gridDim.x * 256;
+    const uint64_t rounds = (n + stride - 1) / stride;
+    uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    for (uint64_t r = 0; r < rounds; r++, i += stride) {
+        const bool keep = i < n && pc_local[i] == 1 && pc_sum[i] == 1;
+        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+        if (!bal) continue;
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(n_out, (uint32_t)__popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (keep) {
+            uint32_t lo = 0, hi = nq;                   // query of list index i: prefix[q] <= i < prefix[q + 1]
+            while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(prefix + mid) <= i) lo = mid; else hi = mid; }
+            const uint32_t e = base + __popc(bal & ((1u << lane) - 1));
+            if (e < cap) { list[3 * (uint64_t)e] = lo; list[3 * (uint64_t)e + 1] = col[i]; list[3 * (uint64_t)e + 2] = slots[i].count; }
+        }
+    }
+}
+int launch_slots_popcount(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, const void* d_slots, uint64_t n, uint8_t* d_pc,
+                          uint32_t* d_col) {
+    if (n == 0) return CID_OK;
+    ProfScope ps(ctx, st, KID_QUERY_UNIQ_WIDE);
+    const unsigned grid = (unsigned)std::min<uint64_t>((n + 7) / 8, (uint64_t)ctx->sm_count * 32);
+    slots_popcount_kernel<<<grid, 256, 0, st>>>(idx->rows, idx->Wp, idx->k, idx->H, make_mods(idx->S), (const Slot*)d_slots, n, d_pc, d_col);
+    ctx->launches++;
+    CID_CUDA(cudaGetLastError());
+    return CID_OK;
+}
+int launch_uniq_emit(cid_ctx* ctx, cudaStream_t st, const void* d_slots, const uint64_t* d_prefix, uint32_t nq, uint64_t n,
+                     const uint8_t* d_pc_local, const uint8_t* d_pc_sum, const uint32_t* d_col, uint32_t* d_list, uint32_t cap,
+                     uint32_t* d_n) {
+    if (n == 0) return CID_OK;
+    ProfScope ps(ctx, st, KID_OTHER);
+    const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 8);
+    uniq_emit_kernel<<<grid, 256, 0, st>>>((const Slot*)d_slots, d_prefix, nq, n, d_pc_local, d_pc_sum, d_col, d_list, cap, d_n);
+    ctx->launches++;
+    CID_CUDA(cudaGetLastError());
+    return CID_OK;
+}
+
 }  // namespace cid

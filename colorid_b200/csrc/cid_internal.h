@@ -209,6 +209,13 @@ int launch_hash_kmers(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, const
 // *d_n must be zero before the call
 int launch_region_compact(cid_ctx* ctx, cudaStream_t st, const void* d_region, uint64_t nslots, int64_t filt, void* d_dense,
                           unsigned long long* d_n, uint64_t cap);
+// column-sharded default report: per dense-list index min(popcount of the AND row over this shard, 2) and the single hit's colour;
+// then the triples (query, colour, multiplicity) of the k-mers whose local and cross-shard popcounts are both 1
+int launch_slots_popcount(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, const void* d_slots, uint64_t n, uint8_t* d_pc,
+                          uint32_t* d_col);
+int launch_uniq_emit(cid_ctx* ctx, cudaStream_t st, const void* d_slots, const uint64_t* d_prefix, uint32_t nq, uint64_t n,
+                     const uint8_t* d_pc_local, const uint8_t* d_pc_sum, const uint32_t* d_col, uint32_t* d_list, uint32_t cap,
+                     uint32_t* d_n);
 // unique-hit triples (query, accession, multiplicity) -> per (query, accession) number, sum and mode of the multiplicities
 // (reports.rs:20-26) through a [cells][MB] histogram; *d_ovf != 0 afterwards: a multiplicity >= MB occurred, use the host path
 int launch_uniq_summaries(cid_ctx* ctx, cudaStream_t st, const uint32_t* d_list, uint32_t nu, uint32_t N, uint64_t cells, uint32_t MB,

@@ -64,6 +64,10 @@ SIGNATURES = {
     "cid_ipc_close": (C.c_int, [vp, vp]),
     "cid_query_counts_sharded_dev": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_uint64, vp, u64p, u64p, C.c_uint64, C.c_int,
                                                C.POINTER(vp), C.c_uint32, C.c_uint32, C.c_uint32, vp, vp]),
+    "cid_query_survivors": (C.c_int, [vp, vp, u64p, C.c_uint64, u64p, C.c_uint64, C.c_int, C.c_int, C.c_int64, C.POINTER(vp), u64p,
+                                      i64p]),
+    "cid_query_slots_counts_dev": (C.c_int, [vp, vp, u64p, C.c_uint64, vp, vp, vp, vp, vp]),
+    "cid_query_slots_uniq_dev": (C.c_int, [vp, vp, u64p, C.c_uint64, vp, vp, vp, u64p, u64p, u64p, vp]),
     "cid_query_perfect": (C.c_int, [vp, vp, u64p, C.c_uint64, u64p, C.c_uint64, u32p, u8p, u64p]),
     "cid_query_perfect_mf": (C.c_int, [vp, vp, u64p, C.c_uint64, u32p, u8p, u64p]),
     "cid_read_id_batch": (C.c_int, [vp, vp, vp, u64p, C.c_uint64, u64p, C.c_uint64, C.POINTER(ReadIdParams), u32p, u32p,

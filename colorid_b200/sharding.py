@@ -43,8 +43,14 @@ def gather_counts(local_counts, shards, group=None):
     nq = local_counts.shape[0]
     pad = torch.zeros((nq, width), dtype=local_counts.dtype, device=local_counts.device)
     pad[:, : local_counts.shape[1]] = local_counts
-    parts = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(parts, pad, group=group)
+    if pad.is_cuda and dist.get_backend(group) == "gloo":          # gloo has no all_gather of device tensors: stage through the host
+        host = pad.cpu()
+        parts = [torch.empty_like(host) for _ in range(world)]
+        dist.all_gather(parts, host, group=group)
+        parts = [p.to(pad.device) for p in parts]
+    else:
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad, group=group)
     return torch.cat([p[:, : hi - lo] for p, (lo, hi) in zip(parts, shards)], dim=1)
 
 
@@ -100,6 +106,46 @@ def concat_in_order(local_rows, group=None):
     parts = [None] * world
     dist.all_gather_object(parts, local_rows, group=group)
     return np.concatenate(parts, axis=0)
+
+
+def sharded_default_report(gix, queries, shards, device, seq_mode=0, filt=-1, group=None, root=0):
+    """Column-sharded `search` with the default 7-column report (batch_search_pe.rs:9-179, reports.rs:8-48): counts are
+    per-accession and only need gathering, but "this k-mer hits exactly one accession" is about the whole row.  Rank `root`
+    counts the queries' k-mers, applies the filter and broadcasts the dense survivor list, so that a list index means the
+    same k-mer on every rank; every rank gathers its column slice for all of them and leaves one byte per k-mer
+    (min(local popcount, 2)); the bytes are summed across ranks (all_reduce) and each rank summarises the k-mers whose
+    local and global popcounts are both 1 for ITS accessions.  Returns the full-width result on every rank, like
+    api.Index.query_counts on an unsharded index."""
+    rank = dist.get_rank(group)
+    nq = len(queries)
+    meta = [None]
+    d_slots = 0
+    if rank == root:
+        d_slots, surv, cutoff = gix.query_survivors(queries, seq_mode, False, filt)
+        meta = [(surv, cutoff)]
+    dist.broadcast_object_list(meta, src=root, group=group)
+    surv, cutoff = meta[0]
+    total = int(surv.sum())
+    slots = torch.empty(max(total, 1) * 2, dtype=torch.int64, device=device)          # 16 bytes per k-mer
+    if rank == root and total:
+        slots[: total * 2].copy_(device_view(d_slots, total * 2, device, "<i8"))
+    dist.broadcast(slots, src=root, group=group)
+    n_local = gix.N
+    counts = torch.zeros((nq, n_local), dtype=torch.int32, device=device)
+    nk = torch.zeros(max(nq, 1), dtype=torch.int64, device=device)
+    pc = torch.zeros(max(total, 1), dtype=torch.uint8, device=device)
+    col = torch.zeros(max(total, 1), dtype=torch.int32, device=device)
+    stream = torch.cuda.current_stream(device).cuda_stream if device.type == "cuda" else 0
+    gix.slots_counts_dev(slots.data_ptr(), surv, counts.data_ptr(), nk.data_ptr(), pc.data_ptr(), col.data_ptr(), stream)
+    pc_sum = pc.clone()
+    dist.all_reduce(pc_sum, group=group)                      # <= 2 per rank: no overflow of a byte below 128 ranks
+    un, us, um = gix.slots_uniq_dev(slots.data_ptr(), surv, pc.data_ptr(), pc_sum.data_ptr(), col.data_ptr(), stream)
+    out = dict(counts=gather_counts(counts, shards, group).cpu().numpy().astype(np.uint32), num_kmers=nk[:nq].cpu().numpy().astype(np.uint64),
+               cutoff=np.asarray(cutoff))
+    for name, a in (("uniq_n", un), ("uniq_sum", us), ("uniq_mode", um)):
+        t = torch.from_numpy(a.astype(np.int64)).to(device)
+        out[name] = gather_counts(t, shards, group).cpu().numpy().astype(np.uint64)
+    return out
 
 
 def merge_read_reports(local_report, shards, n_total, group=None):

@@ -165,6 +165,27 @@ int cid_query_counts_sharded_dev(cid_index* idx, const char* d_bases, const uint
                                  const uint64_t* h_seq_offs, uint64_t nq, int seq_mode, void* const* d_dest_counts,
                                  uint32_t n_dest, uint32_t n_total, uint32_t col_offset, uint64_t* d_num_kmers, void* stream);
 
+/* Column-sharded DEFAULT report.  "This k-mer hits exactly one accession" (batch_search_pe.rs:75-82, the
+ * unique-hit columns of reports.rs:8-48) is a statement about the whole row, so the shards exchange one byte per k-mer:
+ *   1. cid_query_survivors on ONE shard: k-mer counting, per-query filter (auto_cutoff / fixed / -g), survivors compacted
+ *      into a dense list of 16-byte slots {u64 packed k-mer, u32 count, u32 pad} on the device: query q holds surv[q] slots
+ *      starting at the prefix sum of surv[].  *d_slots stays valid until the next search call on that context.  The list
+ *      (and surv[]) is then copied to every shard (NCCL broadcast), so that list index i means the same k-mer everywhere.
+ *   2. cid_query_slots_counts_dev on every shard: d_counts[nq * n_colors] (hits per accession of this shard: disjoint
+ *      column slices, gathered like cid_query_counts_sharded_dev's), d_num_kmers[nq], and per list index d_pc[i] =
+ *      min(popcount of the AND row over this shard, 2) and d_col[i] = the single accession hit (or 0xFFFFFFFF).
+ *   3. the shards sum their d_pc arrays (one all-reduce of a byte per k-mer) and each calls cid_query_slots_uniq_dev with its
+ *      own d_pc / d_col and the sum: uniq_n / uniq_sum / uniq_mode [nq * n_colors] (host) for ITS accessions, from the
+ *      k-mers whose local and global popcounts are both 1.  All device buffers of 2 and 3 are the caller's. */
+int cid_query_survivors(cid_index* idx, const char* bases, const uint64_t* seq_offs, uint64_t nseq,
+                        const uint64_t* query_offs, uint64_t nq, int seq_mode, int gene_search, int64_t filter,
+                        void** d_slots, uint64_t* surv, int64_t* cutoff_used);
+int cid_query_slots_counts_dev(cid_index* idx, const void* d_slots, const uint64_t* surv, uint64_t nq, uint32_t* d_counts,
+                               uint64_t* d_num_kmers, uint8_t* d_pc, uint32_t* d_col, void* stream);
+int cid_query_slots_uniq_dev(cid_index* idx, const void* d_slots, const uint64_t* surv, uint64_t nq,
+                             const uint8_t* d_pc_local, const uint8_t* d_pc_sum, const uint32_t* d_col, uint64_t* uniq_n,
+                             uint64_t* uniq_sum, uint64_t* uniq_mode, void* stream);
+
 /* ---- perfect search: perfect_search.rs:6-60 batch_search ----------------------------------
  * AND of all num_hash rows of all distinct k-mers of the query (kmerize_vector semantics).
  * and_rows[nq*row_words]; status[q]: 0 = AND valid, 1 = "No perfect hits!" (a row is absent),

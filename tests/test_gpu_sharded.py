@@ -79,6 +79,16 @@ def _worker(rank, world, port, ndev, out_dir):
     parts = [torch.empty_like(both) for _ in range(world)]
     dist.all_gather(parts, both)
     assert all(torch.equal(p, both) for p in parts), "ranks disagree on the exchanged counts"
+    # ---- column-sharded default report: survivors broadcast from rank 0, one byte per k-mer all-reduced
+    fq = synth.reads_from(rng, genomes[:3], 600, read_len=120, insert=250, err=0.01, frac_random=0.05, n_rate=0.001)
+    dq = [[m for r in fq for m in r], [genomes[7][:1200]], [b"ACG"], [genomes[250][100:900], genomes[3][:500]]]
+    reports = [(filt, sharding.sharded_default_report(gix, dq, shards, dev, seq_mode=L.CID_SEQ_FASTQ, filt=filt)) for filt in (-1, 0, 2)]
+    if rank == 0:
+        same = True
+        for filt, got in reports:
+            o = whole.query_counts(dq, O.MODE_FASTQ, False, filt)
+            same = same and all(np.array_equal(got[key], o[key]) for key in ("counts", "num_kmers", "cutoff", "uniq_n", "uniq_sum", "uniq_mode"))
+        open(os.path.join(out_dir, "ok_report"), "w").write("1" if same and int(o["uniq_n"].sum()) > 50 else "0")
     # ---- column-sharded read_id: row-present bitmaps OR-ed across ranks, per-shard reports with insertion steps,
     # all-gathered and merged on every rank (sharding.merge_read_reports)
     from colorid_b200.api import classify_reads
@@ -112,6 +122,7 @@ def test_column_sharded_counts_exchanged_through_peer_memory(tmp_path):
     assert ndev >= 1
     mp.spawn(_worker, args=(2, _free_port(), ndev, str(tmp_path)), nprocs=2, join=True)
     assert open(tmp_path / "ok").read() == "1"
+    assert open(tmp_path / "ok_report").read() == "1", "column-sharded default report differs from the oracle on the whole index"
     assert open(tmp_path / "ok_readid").read() == "1", "column-sharded read_id: merged reports / classification differ from the oracle"
 
 
@@ -184,4 +195,64 @@ def test_column_sharded_read_id_merges_to_the_unsharded_report(N, k, S, H, world
     for ix in parts + [full]:
         ix.close()
     sctx.close()
+    ctx.close()
+
+
+@pytest.mark.parametrize("N,k,S,H,world", [(100, 21, 200_003, 2, 2), (300, 27, 300_007, 4, 3)])
+def test_column_sharded_default_report_one_process(N, k, S, H, world):
+    """The three calls of the column-sharded default report with the exchange done by hand (sum of the per-shard popcount
+    bytes): counts, num_kmers, cutoffs and the unique-hit summaries of every shard, side by side, equal the oracle's on the
+    whole index -- FASTQ read-set query with auto_cutoff and fixed filters, FASTA queries, an empty query."""
+    import colorid_b200 as cb
+    from colorid_b200 import lib as L
+    from colorid_b200 import sharding
+    from oracle import pyoracle as O
+    rng = np.random.default_rng(0xC0101D00 + 1700 + N)
+    genomes = synth.clade_genomes(rng, N, 3000, n_clades=max(2, N // 10), div=0.01)
+    whole = O.Index(S, H, k, N)
+    whole.build_many([[g] for g in genomes], O.MODE_FASTA, threads=2)
+    dev = torch.device("cuda:0")
+    ctx = cb.Context(0)
+    shards = sharding.column_shards(N, world)
+    parts = []
+    for lo, hi in shards:
+        ix = cb.Index(ctx, S, H, k, hi - lo)
+        for c in range(lo, hi):
+            ix.build_accession(c - lo, [genomes[c]])
+        ix.finalize()
+        parts.append(ix)
+    fq = synth.reads_from(rng, genomes[:3], 800, read_len=120, insert=250, err=0.01, frac_random=0.05, n_rate=0.001)
+    cases = [(L.CID_SEQ_FASTQ, O.MODE_FASTQ, [[m for r in fq for m in r], [genomes[N - 1][:900]], [b"ACG"]], (-1, 0, 2)),
+             (L.CID_SEQ_FASTA, O.MODE_FASTA, [[genomes[5]], [genomes[N // 2][100:1500], genomes[1][:700]], [synth.rand_seq(rng, 900)]], (0, 1))]
+    checked = 0
+    for seq_mode, omode, queries, filters in cases:
+        nq = len(queries)
+        for filt in filters:
+            o = whole.query_counts(queries, omode, False, filt)
+            d_slots, surv, cutoff = parts[0].query_survivors(queries, seq_mode, False, filt)
+            total = int(surv.sum())
+            assert np.array_equal(cutoff, o["cutoff"]) and np.array_equal(surv, o["num_kmers"])
+            slots = sharding.device_view(d_slots, max(total, 1) * 2, dev, "<i8").clone() if total else torch.zeros(2, dtype=torch.int64, device=dev)
+            per = []
+            for ix in parts:
+                counts = torch.zeros((nq, ix.N), dtype=torch.int32, device=dev)
+                nk = torch.zeros(nq, dtype=torch.int64, device=dev)
+                pc = torch.zeros(max(total, 1), dtype=torch.uint8, device=dev)
+                col = torch.zeros(max(total, 1), dtype=torch.int32, device=dev)
+                ix.slots_counts_dev(slots.data_ptr(), surv, counts.data_ptr(), nk.data_ptr(), pc.data_ptr(), col.data_ptr())
+                per.append((counts, nk, pc, col))
+            torch.cuda.synchronize()
+            pc_sum = sum(p[2].to(torch.int32) for p in per).to(torch.uint8)
+            un, us, um = zip(*[ix.slots_uniq_dev(slots.data_ptr(), surv, p[2].data_ptr(), pc_sum.data_ptr(), p[3].data_ptr())
+                               for ix, p in zip(parts, per)])
+            assert np.array_equal(np.concatenate([p[0].cpu().numpy() for p in per], axis=1).astype(np.uint32), o["counts"])
+            for p in per:
+                assert np.array_equal(p[1].cpu().numpy().astype(np.uint64), o["num_kmers"])
+            assert np.array_equal(np.concatenate(un, axis=1), o["uniq_n"])
+            assert np.array_equal(np.concatenate(us, axis=1), o["uniq_sum"])
+            assert np.array_equal(np.concatenate(um, axis=1), o["uniq_mode"])
+            checked += int(o["uniq_n"].sum())
+    assert checked > 100
+    for ix in parts:
+        ix.close()
     ctx.close()
