@@ -82,11 +82,13 @@ def _worker(rank, world, port, ndev, out_dir):
     # ---- column-sharded default report: survivors broadcast from rank 0, one byte per k-mer all-reduced
     fq = synth.reads_from(rng, genomes[:3], 600, read_len=120, insert=250, err=0.01, frac_random=0.05, n_rate=0.001)
     dq = [[m for r in fq for m in r], [genomes[7][:1200]], [b"ACG"], [genomes[250][100:900], genomes[3][:500]]]
-    reports = [(filt, sharding.sharded_default_report(gix, dq, shards, dev, seq_mode=L.CID_SEQ_FASTQ, filt=filt)) for filt in (-1, 0, 2)]
+    # (auto_cutoff on a query without k-mers panics in the reference: the empty query only goes with the fixed filters)
+    reports = [(filt, dq[:2] if filt < 0 else dq, sharding.sharded_default_report(gix, dq[:2] if filt < 0 else dq, shards, dev,
+                                                                                   seq_mode=L.CID_SEQ_FASTQ, filt=filt)) for filt in (-1, 0, 2)]
     if rank == 0:
         same = True
-        for filt, got in reports:
-            o = whole.query_counts(dq, O.MODE_FASTQ, False, filt)
+        for filt, qs, got in reports:
+            o = whole.query_counts(qs, O.MODE_FASTQ, False, filt)
             same = same and all(np.array_equal(got[key], o[key]) for key in ("counts", "num_kmers", "cutoff", "uniq_n", "uniq_sum", "uniq_mode"))
         open(os.path.join(out_dir, "ok_report"), "w").write("1" if same and int(o["uniq_n"].sum()) > 50 else "0")
     # ---- column-sharded read_id: row-present bitmaps OR-ed across ranks, per-shard reports with insertion steps,
@@ -222,7 +224,9 @@ def test_column_sharded_default_report_one_process(N, k, S, H, world):
         ix.finalize()
         parts.append(ix)
     fq = synth.reads_from(rng, genomes[:3], 800, read_len=120, insert=250, err=0.01, frac_random=0.05, n_rate=0.001)
-    cases = [(L.CID_SEQ_FASTQ, O.MODE_FASTQ, [[m for r in fq for m in r], [genomes[N - 1][:900]], [b"ACG"]], (-1, 0, 2)),
+    # (auto_cutoff on a query without k-mers panics in the reference: the empty query only goes with the fixed filters)
+    cases = [(L.CID_SEQ_FASTQ, O.MODE_FASTQ, [[m for r in fq for m in r], [genomes[N - 1][:900]]], (-1,)),
+             (L.CID_SEQ_FASTQ, O.MODE_FASTQ, [[m for r in fq for m in r], [genomes[N - 1][:900]], [b"ACG"]], (0, 2)),
              (L.CID_SEQ_FASTA, O.MODE_FASTA, [[genomes[5]], [genomes[N // 2][100:1500], genomes[1][:700]], [synth.rand_seq(rng, 900)]], (0, 1))]
     checked = 0
     for seq_mode, omode, queries, filters in cases:
