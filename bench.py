@@ -603,6 +603,85 @@ def run_c5(args):
                  "note": "both timed the same way: barrier, pass, stream sync, barrier (wall clock, max over ranks); the fused pass also "
                          "zeroes its destination and has one more barrier"}
         pc.close()
+    # ---- column-sharded default report and read_id (--c5-extra): timings + size-independent checks
+    extra = None
+    if world > 1 and args.c5_extra:
+        from colorid_b200.api import classify_reads
+        extra = {}
+        a_src = probes[len(probes) // 2]
+        n_ref_parts = [None] * world
+        dist.all_gather_object(n_ref_parts, gix.n_ref)
+        n_ref_all = np.concatenate(n_ref_parts)
+        rl = CFG["read_len"]
+        qcfg = dict(CFG, genome_len=Lg, n_acc=1, frac_random=0.0, lowq=0.02)
+        n_pairs = Lg * 30 // (2 * rl)
+        b, q = make_reads(torch, dev, qcfg, acc_codes(a_src)[None, :], n_pairs, 0xC0101D51)      # identical on every rank
+        b[q < CFG["qual_offset"] + 33] = 78
+        packed = (b.cpu().numpy().reshape(-1), np.arange(2 * n_pairs + 1, dtype=np.uint64) * np.uint64(rl),
+                  np.array([0, 2 * n_pairs], dtype=np.uint64))
+        del b, q
+        rep = None
+        tms = []
+        for i in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            rep = sharding.sharded_default_report(gix, None, shards, dev, seq_mode=L.CID_SEQ_FASTQ, filt=-1, packed=packed)
+            barrier()
+            tms.append((time.perf_counter() - t0) * 1e3)
+        tt = torch.tensor([min(tms[1:])], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        cov = float(rep["counts"][0, a_src]) / float(n_ref_all[a_src])
+        assert cov > 0.97 and int(rep["uniq_n"][0].sum()) > 0 and int(rep["cutoff"][0]) >= 1, (cov, rep["cutoff"])
+        extra["default_report"] = {"workload": f"30x paired-end read set of accession {a_src} ({2 * n_pairs * rl / 1e6:.0f} Mbp), auto_cutoff, "
+                                               f"7-column report against the {A}-accession column-sharded index",
+                                   "ms_per_query_wall": float(tt.item()), "lookups": int(rep["num_kmers"][0]),
+                                   "hits_over_n_ref_kmers_of_source": cov, "unique_hits_total": int(rep["uniq_n"][0].sum()),
+                                   "cutoff": int(rep["cutoff"][0]),
+                                   "note": "rank 0 counts and filters, broadcasts 16 B per surviving k-mer; every rank gathers its slice, one "
+                                           "byte per k-mer all-reduced; wall clock incl. host packing of results (best of 2 after warm-up)"}
+        # read_id: 100k pairs drawn from four probe accessions spread over the shards
+        src = [probes[1], probes[len(probes) // 3], probes[2 * len(probes) // 3], probes[-2]]
+        rcfg = dict(CFG, genome_len=Lg, n_acc=len(src), frac_random=0.2)
+        nrp = 100_000
+        gen = torch.stack([acc_codes(a) for a in src])
+        rb, rq = make_reads(torch, dev, rcfg, gen, nrp, 0xC0101D52)
+        hb, hq = rb.cpu().numpy(), rq.cpu().numpy()
+        del gen, rb, rq
+        seq_offs_np, read_offs_np = offsets_for(nrp, rl)
+        params = L.ReadIdParams(1, CFG["start_sample"], CFG["qual_offset"], 16, 1, n_local + 1)
+        ctx.set_option("readid_report_steps", 1)
+        cap = n_local + 1
+        o_n_set, o_flags, o_rep_n = (np.zeros(nrp, np.uint32) for _ in range(3))
+        o_rc, o_rv = np.zeros((nrp, cap), np.uint32), np.zeros((nrp, cap), np.uint32)
+        PV = lambda x, tp=L.vp: x.ctypes.data_as(tp)
+        tms, tmerge = [], []
+        for i in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            L.check(lib.cid_read_id_batch(gix.h, PV(hb), PV(hq), PV(seq_offs_np, L.u64p), 2 * nrp, PV(read_offs_np, L.u64p), nrp,
+                                          C.byref(params), PV(o_n_set, L.u32p), PV(o_flags, L.u32p), PV(o_rep_n, L.u32p),
+                                          PV(o_rc, L.u32p), PV(o_rv, L.u32p)))
+            barrier()
+            t1 = time.perf_counter()
+            merged = sharding.merge_read_reports(dict(n_set=o_n_set, flags=o_flags, rep_n=o_rep_n, rep_colour=o_rc, rep_count=o_rv),
+                                                 shards, A)
+            cls = classify_reads((cfg["S"], cfg["H"], A), n_ref_all, merged, fp_correct=CFG["fp_correct"])
+            barrier()
+            tms.append((t1 - t0) * 1e3)
+            tmerge.append((time.perf_counter() - t1) * 1e3)
+        ctx.set_option("readid_report_steps", 0)
+        tt = torch.tensor([min(tms[1:]), min(tmerge[1:])], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        # accepted reads with many hits come from the source accessions (random reads are also "accepted" now and then, on a
+        # handful of Bloom false positives: 2,500 accessions at 33 % bit fill -- the reference's statistics, not checked here)
+        acc = (cls["kind"] == 3) & (cls["hits"] >= 60)
+        top_ok = np.isin(cls["top"][acc, 0], np.array(src))
+        assert acc.sum() > 0.2 * nrp and top_ok.mean() > 0.999, (int(acc.sum()), float(top_ok.mean()))
+        extra["read_id"] = {"workload": f"{nrp} read pairs (80 % from accessions {src}, 20 % random) against the column-sharded index, "
+                                        "every rank classifies all reads against its slice",
+                            "ms_read_id_batch_wall": float(tt[0].item()), "read_pairs_per_s_kernels_and_copies": nrp / (float(tt[0].item()) / 1e3),
+                            "ms_gather_merge_classify_wall": float(tt[1].item()), "accepted_with_60_or_more_hits": int(acc.sum()),
+                            "of_those_with_a_source_accession_on_top": float(top_ok.mean())}
     # ---- parity at full size: a query cut verbatim from accession a has every one of its k-mers in a's column
     full = gathered[0]
     nk_h = d_nk.cpu().numpy()
@@ -645,7 +724,8 @@ def run_c5(args):
                       "note": "all ranks build their accession columns concurrently; max over ranks; synthetic genome "
                               "generation excluded",
                       "kernels_ms_total": {k_: v[0] for k_, v in build_prof.items()}},
-            "parity": {"self_query_probes": len(probe_q), "violations": 0}, "fused_count_exchange": fused}
+            "parity": {"self_query_probes": len(probe_q), "violations": 0}, "fused_count_exchange": fused,
+            "sharded_default_report_and_read_id": extra}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -1201,6 +1281,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c4", "c5"], help="c1 = FASTA build + FASTQ search; c2 = read_id headline (default); c4 = build from read sets; c5 = column-sharded build + search")
     ap.add_argument("--c4-acc", type=int, default=0, help="accessions per rank built by the c4 workload (default 24)")
     ap.add_argument("--c5-acc", type=int, default=0, help="total accessions of the c5 workload (default 10,000)")
+    ap.add_argument("--c5-extra", action="store_true", help="c5, N > 1: also time the column-sharded default report and read_id")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -234,16 +234,21 @@ class Index:
         return dict(counts=counts, num_kmers=num_kmers, uniq_n=un, uniq_sum=us, uniq_mode=um, cutoff=used[:nq])
 
     # ---- column-sharded default report (three calls around one exchange; see include/colorid_b200.h) ----
-    def query_survivors(self, queries, seq_mode=L.CID_SEQ_FASTA, gene_search=False, filt=-1):
-        """-> (device pointer of the dense survivor list, surv[nq], cutoff[nq]); the list is 16 bytes per k-mer."""
-        flat = [s for q in queries for s in q]
-        bases, offs = pack_seqs(flat)
-        qoffs = group_offsets(queries)
-        nq = len(queries)
+    def query_survivors(self, queries, seq_mode=L.CID_SEQ_FASTA, gene_search=False, filt=-1, packed=None):
+        """-> (device pointer of the dense survivor list, surv[nq], cutoff[nq]); the list is 16 bytes per k-mer.
+        packed = (bases u8[], seq_offs u64[nseq + 1], query_offs u64[nq + 1]) replaces `queries` (lists of bytes)."""
+        if packed is not None:
+            bases, offs, qoffs = packed
+            nflat, nq = len(offs) - 1, len(qoffs) - 1
+        else:
+            flat = [s for q in queries for s in q]
+            bases, offs = pack_seqs(flat)
+            qoffs = group_offsets(queries)
+            nflat, nq = len(flat), len(queries)
         surv = np.zeros(max(nq, 1), dtype=np.uint64)
         used = np.zeros(max(nq, 1), dtype=np.int64)
         ptr = L.vp()
-        L.check(self.lib.cid_query_survivors(self.h, _p(bases), _p(offs, L.u64p), len(flat), _p(qoffs, L.u64p), nq, seq_mode,
+        L.check(self.lib.cid_query_survivors(self.h, _p(bases), _p(offs, L.u64p), nflat, _p(qoffs, L.u64p), nq, seq_mode,
                                              int(gene_search), filt, C.byref(ptr), _p(surv, L.u64p), _p(used, L.i64p)))
         return ptr.value or 0, surv[:nq], used[:nq]
 

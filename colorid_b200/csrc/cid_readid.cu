@@ -1151,7 +1151,10 @@ int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const ui
     const size_t b_esz = small ? 1 : 2;
     const size_t b_thread = ((((size_t)(TB + TB / 2) + maxocc) * b_esz + 3) & ~(size_t)3) +
                             4 * ((small ? (maxocc + 31) / 32 : 0) + (TB >= 32 ? TB / 32 : 1) + (TB >= 64 ? TB / 64 : 1));
-    size_t b_smem = 32 * b_thread;
+    // reads per CTA of the general order kernel: 32, fewer when a read's tables are large (1000-base reads: 8.5 KB each)
+    unsigned order_threads = 32;
+    while (order_threads > 1 && order_threads * b_thread > 200 * 1024) order_threads >>= 1;
+    size_t b_smem = order_threads * b_thread;
     if (small) b_smem = 0;      // readid_order_small_kernel<TB> sizes its own shared memory (< 48 KB)
     size_t cn_warp = ((tile_smem_bytes(cap) + 15) & ~(size_t)15) + 64 + 128 + (MAX_MATES + 1) * 4 + 12;
     const uint32_t with_steps = ctx->opt_readid_report_steps ? 1u : 0u;
@@ -1208,7 +1211,7 @@ int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const ui
             ctx->launches += 2;
         }
         else
-            readid_order_kernel<uint16_t><<<gridB, 32, b_smem, st>>>(d_entries, d_nocc, d_perm, nr, maxocc, TB, p.group_width,
+            readid_order_kernel<uint16_t><<<(unsigned)((nr + order_threads - 1) / order_threads), order_threads, b_smem, st>>>(d_entries, d_nocc, d_perm, nr, maxocc, TB, p.group_width,
                                                                     p.reserve_before_find, d_order, d_n_set, r0);
         }
         ctx->launches++;

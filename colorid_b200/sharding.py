@@ -108,7 +108,7 @@ def concat_in_order(local_rows, group=None):
     return np.concatenate(parts, axis=0)
 
 
-def sharded_default_report(gix, queries, shards, device, seq_mode=0, filt=-1, group=None, root=0):
+def sharded_default_report(gix, queries, shards, device, seq_mode=0, filt=-1, group=None, root=0, packed=None):
     """Column-sharded `search` with the default 7-column report (batch_search_pe.rs:9-179, reports.rs:8-48): counts are
     per-accession and only need gathering, but "this k-mer hits exactly one accession" is about the whole row.  Rank `root`
     counts the queries' k-mers, applies the filter and broadcasts the dense survivor list, so that a list index means the
@@ -117,11 +117,11 @@ def sharded_default_report(gix, queries, shards, device, seq_mode=0, filt=-1, gr
     local and global popcounts are both 1 for ITS accessions.  Returns the full-width result on every rank, like
     api.Index.query_counts on an unsharded index."""
     rank = dist.get_rank(group)
-    nq = len(queries)
+    nq = len(packed[2]) - 1 if packed is not None else len(queries)
     meta = [None]
     d_slots = 0
     if rank == root:
-        d_slots, surv, cutoff = gix.query_survivors(queries, seq_mode, False, filt)
+        d_slots, surv, cutoff = gix.query_survivors(queries, seq_mode, False, filt, packed=packed)
         meta = [(surv, cutoff)]
     dist.broadcast_object_list(meta, src=root, group=group)
     surv, cutoff = meta[0]
@@ -155,10 +155,23 @@ def merge_read_reports(local_report, shards, n_total, group=None):
     merged into the unsharded report on every rank (api.merge_shard_reports), ready for api.classify_reads."""
     from .api import merge_shard_reports
     world = dist.get_world_size(group)
+    # only the rep_n[r] used entries of every read travel (a report row has n_local + 1 slots, a read fills a handful)
+    n = np.ascontiguousarray(local_report["rep_n"], dtype=np.uint32)
+    rc, rv = np.asarray(local_report["rep_colour"]), np.asarray(local_report["rep_count"])
+    used = np.arange(rc.shape[1], dtype=np.uint32)[None, :] < n[:, None]
+    mine = dict(n_set=np.ascontiguousarray(local_report["n_set"]), flags=np.ascontiguousarray(local_report["flags"]), rep_n=n,
+                colour=rc[used], count=rv[used])
     parts = [None] * world
-    keys = ("n_set", "flags", "rep_n", "rep_colour", "rep_count")
-    dist.all_gather_object(parts, {k: np.ascontiguousarray(local_report[k]) for k in keys}, group=group)
-    return merge_shard_reports(parts, shards, n_total)
+    dist.all_gather_object(parts, mine, group=group)
+    cap = max(1, max(int(p["rep_n"].max()) if len(p["rep_n"]) else 0 for p in parts))
+    reports = []
+    for p in parts:
+        nr = len(p["rep_n"])
+        sel = np.arange(cap, dtype=np.uint32)[None, :] < p["rep_n"][:, None]
+        c, v = np.zeros((nr, cap), np.uint32), np.zeros((nr, cap), np.uint32)
+        c[sel], v[sel] = p["colour"], p["count"]
+        reports.append(dict(n_set=p["n_set"], flags=p["flags"], rep_n=p["rep_n"], rep_colour=c, rep_count=v))
+    return merge_shard_reports(reports, shards, n_total)
 
 
 class PeerCounts:

@@ -66,13 +66,21 @@ def test_fuzz_build_search_read_id(oracle, ctx, seed):
     # search: gene mode, default report (unique hits), explicit filter; perfect search on both entry points
     queries = [[q] if i % 3 else [q, q[: len(q) // 2]] for i, q in enumerate(_seqs(rng, genomes, 25, 1, min(glen, 300)))]
     queries += [[], [b""], [b"N" * (k + 3)]]
-    for gene, filt, uniq in ((True, 0, False), (False, 0, True), (False, 1, True)):
-        o = oix.query_counts(queries, oracle.MODE_FASTA, gene, filt)
-        g = gix.query_counts(queries, cb.CID_SEQ_FASTA, gene, filt, want_uniq=uniq)
-        assert np.array_equal(g["num_kmers"], o["num_kmers"]) and np.array_equal(g["counts"], o["counts"]), (k, H, N, S, gene, filt)
-        if uniq:
-            for key in ("uniq_n", "uniq_sum", "uniq_mode"):
-                assert np.array_equal(g[key], o[key]), key
+    orng = np.random.default_rng(0xF0230000 + seed)          # path choices (a separate stream: the inputs stay as they were)
+    compact, uniq_device = int(orng.choice([1, 2])), int(orng.choice([0, 1]))
+    ctx.set_option("query_compact", compact)                 # 2: gather units over the compacted survivor list
+    ctx.set_option("uniq_device", uniq_device)               # unique-hit summaries on the device / through the host maps
+    try:
+        for gene, filt, uniq in ((True, 0, False), (False, 0, True), (False, 1, True)):
+            o = oix.query_counts(queries, oracle.MODE_FASTA, gene, filt)
+            g = gix.query_counts(queries, cb.CID_SEQ_FASTA, gene, filt, want_uniq=uniq)
+            assert np.array_equal(g["num_kmers"], o["num_kmers"]) and np.array_equal(g["counts"], o["counts"]), (k, H, N, S, gene, filt, compact)
+            if uniq:
+                for key in ("uniq_n", "uniq_sum", "uniq_mode"):
+                    assert np.array_equal(g[key], o[key]), (key, compact, uniq_device)
+    finally:
+        ctx.set_option("query_compact", 1)
+        ctx.set_option("uniq_device", 1)
     o, g = oix.query_perfect(queries), gix.query_perfect(queries)
     assert np.array_equal(g["status"], o["status"]) and np.array_equal(g["n_kmers"], o["n_kmers"])
     assert np.array_equal(g["and_rows"], o["and_rows"])

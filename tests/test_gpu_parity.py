@@ -410,6 +410,24 @@ def test_read_id_narrow_rows(oracle, ctx, N, k, S, H):
         _readid_compare(oracle, oix, gix, reads, **kw)
 
 
+def test_read_id_reads_up_to_1000_bases(oracle, ctx):
+    """Reads (all mates together) of up to 1,000 bases: the general order kernel with u16 tables of up to 2,048 buckets, fewer
+    reads per CTA as the tables grow; above 1,000 bases the call refuses loudly."""
+    rng = _rng(950)
+    genomes, oix, gix = _index_pair(oracle, ctx, rng, 20, 31, 1_000_003, 4, glen=6000)
+    reads = []
+    for L_ in (300, 520, 700, 901, 990, 1000):
+        reads += synth.reads_from(rng, genomes, 12, read_len=L_, insert=L_ + 50, err=0.002, frac_random=0.2, paired=False)
+    reads += synth.reads_from(rng, genomes, 12, read_len=480, insert=700, err=0.002, frac_random=0.1)       # 2 x 480
+    reads += synth.reads_from(rng, genomes, 20, read_len=150, insert=320, err=0.004, frac_random=0.2)
+    for kw in (dict(d=4), dict(start_sample=0), dict()):
+        o, g = _readid_compare(oracle, oix, gix, reads, **kw)
+    assert int(o["n_set"].max()) > 900
+    with pytest.raises(cb.lib.CidError) as ei:
+        gix.read_id_batch([[genomes[0][:1001]]])
+    assert ei.value.code == cb.lib.CID_E_UNSUPPORTED
+
+
 def test_read_id_wide_rows(oracle, ctx):
     rng = _rng(900)
     genomes, oix, gix = _index_pair(oracle, ctx, rng, 150, 21, 300_007, 2, glen=4000)
