@@ -648,9 +648,9 @@ def run_c5(args):
         hb, hq = rb.cpu().numpy(), rq.cpu().numpy()
         del gen, rb, rq
         seq_offs_np, read_offs_np = offsets_for(nrp, rl)
-        params = L.ReadIdParams(1, CFG["start_sample"], CFG["qual_offset"], 16, 1, n_local + 1)
+        cap = min(n_local + 1, 256)       # report slots per read: ~30 false-positive colours per seeding k-mer at this fill
+        params = L.ReadIdParams(1, CFG["start_sample"], CFG["qual_offset"], 16, 1, cap)
         ctx.set_option("readid_report_steps", 1)
-        cap = n_local + 1
         o_n_set, o_flags, o_rep_n = (np.zeros(nrp, np.uint32) for _ in range(3))
         o_rc, o_rv = np.zeros((nrp, cap), np.uint32), np.zeros((nrp, cap), np.uint32)
         PV = lambda x, tp=L.vp: x.ctypes.data_as(tp)
@@ -664,7 +664,7 @@ def run_c5(args):
             barrier()
             t1 = time.perf_counter()
             merged = sharding.merge_read_reports(dict(n_set=o_n_set, flags=o_flags, rep_n=o_rep_n, rep_colour=o_rc, rep_count=o_rv),
-                                                 shards, A)
+                                                 shards, A, rep_cap=min(A + 1, world * cap))
             cls = classify_reads((cfg["S"], cfg["H"], A), n_ref_all, merged, fp_correct=CFG["fp_correct"])
             barrier()
             tms.append((t1 - t0) * 1e3)
@@ -672,16 +672,21 @@ def run_c5(args):
         ctx.set_option("readid_report_steps", 0)
         tt = torch.tensor([min(tms[1:]), min(tmerge[1:])], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        # accepted reads with many hits come from the source accessions (random reads are also "accepted" now and then, on a
-        # handful of Bloom false positives: 2,500 accessions at 33 % bit fill -- the reference's statistics, not checked here)
+        # Accepted reads with many hits come from a source accession's CLADE.  Not always from the accession itself: when
+        # the first -B k-mers of the set order all carry a sequencing error, the source is not a candidate colour
+        # (read_id_mt_pe.rs:131-136) while a sibling that entered on a Bloom false positive collects the shared k-mers -- the
+        # reference's heuristic at 33 % bit fill, reproduced, a few per cent of the reads.  (Random reads are also "accepted"
+        # now and then on a handful of false positives: hence the hit threshold.)
+        assert int(((merged["flags"] >> 2) & 1).sum()) == 0 and int(((o_flags >> 2) & 1).sum()) == 0, "read reports truncated: raise cap"
         acc = (cls["kind"] == 3) & (cls["hits"] >= 60)
         top_ok = np.isin(cls["top"][acc, 0], np.array(src))
-        assert acc.sum() > 0.2 * nrp and top_ok.mean() > 0.999, (int(acc.sum()), float(top_ok.mean()))
+        clade_ok = np.isin(cls["top"][acc, 0] % NC, np.array([a % NC for a in src]))
+        assert acc.sum() > 0.2 * nrp and clade_ok.mean() > 0.999 and top_ok.mean() > 0.9, (int(acc.sum()), float(top_ok.mean()), float(clade_ok.mean()))
         extra["read_id"] = {"workload": f"{nrp} read pairs (80 % from accessions {src}, 20 % random) against the column-sharded index, "
                                         "every rank classifies all reads against its slice",
                             "ms_read_id_batch_wall": float(tt[0].item()), "read_pairs_per_s_kernels_and_copies": nrp / (float(tt[0].item()) / 1e3),
-                            "ms_gather_merge_classify_wall": float(tt[1].item()), "accepted_with_60_or_more_hits": int(acc.sum()),
-                            "of_those_with_a_source_accession_on_top": float(top_ok.mean())}
+                            "ms_gather_merge_classify_wall": float(tt[1].item()), "report_slots_per_read": cap, "accepted_with_60_or_more_hits": int(acc.sum()),
+                            "of_those_with_a_source_accession_on_top": float(top_ok.mean()), "with_its_clade_on_top": float(clade_ok.mean())}
     # ---- parity at full size: a query cut verbatim from accession a has every one of its k-mers in a's column
     full = gathered[0]
     nk_h = d_nk.cpu().numpy()

@@ -148,7 +148,7 @@ def sharded_default_report(gix, queries, shards, device, seq_mode=0, filt=-1, gr
     return out
 
 
-def merge_read_reports(local_report, shards, n_total, group=None):
+def merge_read_reports(local_report, shards, n_total, group=None, rep_cap=None):
     """Column-sharded read_id (read_id_mt_pe.rs:104-165 is per-colour once the first absent row is known, and that is a
     property of whole rows: or_reduce_bitmap + Index.set_rownz_global): every rank classifies ALL reads against its
     accession slice with the context option readid_report_steps = 1; the sparse per-read reports are all-gathered and
@@ -171,7 +171,7 @@ def merge_read_reports(local_report, shards, n_total, group=None):
         c, v = np.zeros((nr, cap), np.uint32), np.zeros((nr, cap), np.uint32)
         c[sel], v[sel] = p["colour"], p["count"]
         reports.append(dict(n_set=p["n_set"], flags=p["flags"], rep_n=p["rep_n"], rep_colour=c, rep_count=v))
-    return merge_shard_reports(reports, shards, n_total)
+    return merge_shard_reports(reports, shards, n_total, rep_cap=rep_cap)
 
 
 class PeerCounts:
