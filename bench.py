@@ -278,7 +278,8 @@ def run_reference(args):
 
 
 def workload_config(cfg, batch):
-    return {"workload": "C2 read_id: 150bp paired-end reads vs 46-accession k=31 S=50M H=4 index (BASELINE.json configs[1])",
+    return {"workload": ("C2 read_id: 150bp paired-end reads vs 46-accession k=31 S=50M H=4 index (BASELINE.json configs[1])" if cfg["n_acc"] == 46
+                         else f"read_id experiment off the headline config: {cfg['n_acc']} accessions"),
             "index": f"{cfg['n_acc']} synthetic genomes x {cfg['genome_len']} bp in {cfg['n_clades']} clades, "
                      f"k={cfg['k']} S={cfg['S']} H={cfg['H']}, replicated per GPU",
             "read_pairs_per_step_per_gpu": batch, "read_len": cfg["read_len"], "start_sample": cfg["start_sample"],
@@ -1049,6 +1050,8 @@ def run_ours(args):
     cfg = dict(CFG)
     if args.quick:
         cfg.update(genome_len=200_000, S=5_000_000)
+    if args.n_acc:            # experiments off the headline config (e.g. 1,000 accessions: the wide-row vote kernel)
+        cfg.update(n_acc=args.n_acc, n_clades=args.n_clades or max(8, args.n_acc // 5))
     batch = args.batch_pairs
     rl = cfg["read_len"]
     K, Wm = args.steps, args.warmup
@@ -1285,6 +1288,8 @@ def main():
     ap.add_argument("--quick", action="store_true", help="small genomes / bloom filter (functional check only)")
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c4", "c5"], help="c1 = FASTA build + FASTQ search; c2 = read_id headline (default); c4 = build from read sets; c5 = column-sharded build + search")
     ap.add_argument("--c4-acc", type=int, default=0, help="accessions per rank built by the c4 workload (default 24)")
+    ap.add_argument("--n-acc", type=int, default=0, help="c2: accessions of the index (default 46 = the headline config)")
+    ap.add_argument("--n-clades", type=int, default=0, help="c2 with --n-acc: clades (default n_acc / 5)")
     ap.add_argument("--c5-acc", type=int, default=0, help="total accessions of the c5 workload (default 10,000)")
     ap.add_argument("--c5-extra", action="store_true", help="c5, N > 1: also time the column-sharded default report and read_id")
     args = ap.parse_args()

@@ -762,6 +762,7 @@ readid_vote_narrow_kernel(const uint8_t* __restrict__ bases, const uint8_t* __re
 // bit-sliced registers per lane; used when a row has more than 64 accessions.
 constexpr int RV_MAXWPL = 4;       // words per lane: rows up to 128 words (4,096 accessions per shard)
 constexpr int RV_PLANES = 11;      // counts up to 2047 k-mers per read
+template <int WPL>                 // words per lane (1, 2 or 4): 1,024 / 2,048 / 4,096 accessions; sizes the bit-sliced counters
 __global__ void __launch_bounds__(RA_WARPS * 32)
 readid_vote_wide_kernel(const uint8_t* __restrict__ bases, const uint8_t* __restrict__ quals, uint32_t maxq,
                         const uint64_t* __restrict__ seq_offs, const uint64_t* __restrict__ read_offs, uint64_t r0,
@@ -781,7 +782,7 @@ readid_vote_wide_kernel(const uint8_t* __restrict__ bases, const uint8_t* __rest
     Tile t = tile_carve(base, cap);
     uint32_t* moffs = (uint32_t*)(base + ((tile_smem_bytes(cap) + 15) & ~(size_t)15));
     const bool classic = start_sample == 0;
-    const uint32_t wpl = (Wp + 31) / 32;
+    constexpr int U = WPL == 4 ? 2 : 4;      // k-mers whose rows are in flight together (a step of one k-mer is a dependent DRAM round trip)
 
     for (uint64_t rl = (uint64_t)blockIdx.x * RA_WARPS + warp; rl < nreads; rl += (uint64_t)gridDim.x * RA_WARPS) {
         const uint64_t r = r0 + rl;
@@ -795,53 +796,90 @@ readid_vote_wide_kernel(const uint8_t* __restrict__ bases, const uint8_t* __rest
         const uint16_t* entrow = ent16 + rl * (uint64_t)maxocc;
         uint32_t* rc = rep_colour + r * (uint64_t)rep_cap;
         uint32_t* rv = rep_count + r * (uint64_t)rep_cap;
-        uint32_t cand[RV_MAXWPL], pl[RV_MAXWPL][RV_PLANES];
+        uint32_t cand[WPL], pl[WPL][RV_PLANES];
 #pragma unroll
-        for (int w = 0; w < RV_MAXWPL; w++) { cand[w] = 0; for (int p = 0; p < RV_PLANES; p++) pl[w][p] = 0; }
+        for (int w = 0; w < WPL; w++) { cand[w] = 0; for (int p = 0; p < RV_PLANES; p++) pl[w][p] = 0; }
         uint32_t nrep = 0, nproc = 0;
         bool miss = false;
-        for (uint32_t j = 0; j < n; j++) {
-            uint32_t e = order8 ? (uint32_t)__ldg(entrow + __ldg(ord8row + j)) : (uint32_t)__ldg(ordrow + j);
-            uint64_t f = codes_window(t.codes, (int)(e & 0x3FFu), k);
-            uint64_t key = ((e >> 10) & 1u) ? f : revcomp_key(f, k);
-            HashIn in = hashin_from_key(lut, key, k);
-            uint64_t rid[MAX_HASH];
-            bool present = true;
-            for (uint32_t h = 0; h < H; h++) {
-                rid[h] = mod_s(xxh3_kmer(in, k, h), mods);
-                if (!((__ldg(rownz + (rid[h] >> 5)) >> (rid[h] & 31)) & 1u)) present = false;
-            }
-            nproc++;
-            if (!present) { miss = true; break; }
-            const bool seeding = classic || j < start_sample;
+        // 32 k-mers of the set order at a time: lane L hashes k-mer c0 + L (H row indices, row-present bits from the
+        // L2-resident bitmap), a ballot finds the first absent row, and the rows of the k-mers before it are then gathered one
+        // k-mer per step with every lane on its own words.  (Before: all 32 lanes hashed the same k-mer, ~600 redundant
+        // instructions per k-mer, which bound the kernel.)
+        for (uint32_t c0 = 0; c0 < n && !miss; c0 += 32) {
+            const uint32_t idx = c0 + lane;
+            const uint32_t batch = min(32u, n - c0);
+            uint32_t rid_l[MAX_HASH];
+            bool absent = false;
 #pragma unroll
-            for (int w = 0; w < RV_MAXWPL; w++) {
-                if ((uint32_t)w >= wpl) break;
-                uint32_t col = w * 32 + lane;
-                uint32_t x = 0;
-                if (col < Wp) {
-                    x = 0xFFFFFFFFu;
-                    for (uint32_t h = 0; h < H; h++) x &= __ldg(rows + rid[h] * Wp + col);
+            for (int h = 0; h < MAX_HASH; h++) rid_l[h] = 0;
+            if (idx < n) {
+                const uint32_t e = order8 ? (uint32_t)__ldg(entrow + __ldg(ord8row + idx)) : (uint32_t)__ldg(ordrow + idx);
+                const uint64_t f = codes_window(t.codes, (int)(e & 0x3FFu), k);
+                const uint64_t key = ((e >> 10) & 1u) ? f : revcomp_key(f, k);
+                const HashIn in = hashin_from_key(lut, key, k);
+#pragma unroll
+                for (int h = 0; h < MAX_HASH; h++)
+                    if ((uint32_t)h < H) {
+                        rid_l[h] = (uint32_t)mod_s(xxh3_kmer(in, k, h), mods);
+                        if (!((__ldg(rownz + (rid_l[h] >> 5)) >> (rid_l[h] & 31)) & 1u)) absent = true;
+                    }
+            }
+            const uint32_t missmask = __ballot_sync(0xffffffffu, absent);
+            const uint32_t p_local = missmask ? (uint32_t)(__ffs(missmask) - 1) : batch;
+            nproc += missmask ? p_local + 1 : batch;
+            if (missmask) miss = true;
+            for (uint32_t jj0 = 0; jj0 < p_local; jj0 += U) {
+                // the AND rows of U k-mers: all their loads are issued before the first one is consumed
+                uint32_t xs[U][WPL];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const bool on = jj0 + u < p_local;
+                    uint64_t rid[MAX_HASH];
+#pragma unroll
+                    for (int h = 0; h < MAX_HASH; h++)
+                        rid[h] = (uint32_t)h < H ? (uint64_t)__shfl_sync(0xffffffffu, rid_l[h], min(jj0 + u, 31u)) : 0ull;
+#pragma unroll
+                    for (int w = 0; w < WPL; w++) {
+                        const uint32_t col = w * 32 + lane;
+                        uint32_t x = 0;
+                        if (on && col < Wp) {
+                            x = 0xFFFFFFFFu;
+#pragma unroll
+                            for (int h = 0; h < MAX_HASH; h++)            // (static indices: rid[] stays in registers)
+                                if ((uint32_t)h < H) x &= __ldg(rows + rid[h] * Wp + col);
+                        }
+                        xs[u][w] = x;
+                    }
                 }
-                if (seeding) {
-                    // new colours in ascending order across the whole row: lanes take turns per word
-                    uint32_t nw = x & ~cand[w];
-                    for (int l = 0; l < 32; l++) {
-                        uint32_t y = __shfl_sync(0xffffffffu, nw, l);
-                        while (y) {
-                            uint32_t b = __ffs(y) - 1; y &= y - 1;
-                            if (lane == 0 && nrep < rep_cap) rc[nrep] = ((w * 32 + l) * 32 + b) | (with_steps ? (j << REP_STEP_SHIFT) : 0u);
-                            nrep++;
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    if (jj0 + u >= p_local) break;
+                    const uint32_t j = c0 + jj0 + u;
+                    const bool seeding = classic || j < start_sample;
+#pragma unroll
+                    for (int w = 0; w < WPL; w++) {
+                        const uint32_t x = xs[u][w];
+                        if (seeding) {
+                            // new colours in ascending order across the whole row: lanes take turns per word
+                            uint32_t nw = x & ~cand[w];
+                            for (int l = 0; l < 32; l++) {
+                                uint32_t y = __shfl_sync(0xffffffffu, nw, l);
+                                while (y) {
+                                    uint32_t b = __ffs(y) - 1; y &= y - 1;
+                                    if (lane == 0 && nrep < rep_cap) rc[nrep] = ((w * 32 + l) * 32 + b) | (with_steps ? (j << REP_STEP_SHIFT) : 0u);
+                                    nrep++;
+                                }
+                            }
+                            cand[w] |= x;
+                        }
+                        uint32_t carry = x & cand[w];
+#pragma unroll
+                        for (int p = 0; p < RV_PLANES; p++) {
+                            uint32_t t2 = pl[w][p] & carry;
+                            pl[w][p] ^= carry;
+                            carry = t2;
                         }
                     }
-                    cand[w] |= x;
-                }
-                uint32_t carry = x & cand[w];
-#pragma unroll
-                for (int p = 0; p < RV_PLANES; p++) {
-                    uint32_t t2 = pl[w][p] & carry;
-                    pl[w][p] ^= carry;
-                    carry = t2;
                 }
             }
         }
@@ -854,7 +892,7 @@ readid_vote_wide_kernel(const uint8_t* __restrict__ bases, const uint8_t* __rest
             uint32_t word = colour >> 5, b = colour & 31, w = word >> 5, owner = word & 31;
             uint32_t v = 0;
 #pragma unroll
-            for (int ww = 0; ww < RV_MAXWPL; ww++)
+            for (int ww = 0; ww < WPL; ww++)
                 if ((uint32_t)ww == w)
                     for (int p = 0; p < RV_PLANES; p++) v |= ((pl[ww][p] >> b) & 1u) << p;
             v = __shfl_sync(0xffffffffu, v, owner);
@@ -1238,10 +1276,12 @@ int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const ui
                 else { if (with_steps) CID_VOTE_NARROW(2, true); else CID_VOTE_NARROW(2, false); }
 #undef CID_VOTE_NARROW
             } else {
-                readid_vote_wide_kernel<<<gridV, RA_WARPS * 32, cw_smem, st>>>(
-                    d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr, kitem, idx->H, mods, idx->rows, rownz, idx->N,
-                    idx->Wp, cap, maxocc, ord16, ord8, d_ent16, d_n_set, p.start_sample, p.rep_cap, d_flags, d_rep_n, d_rep_colour,
-                    d_rep_count, with_steps);
+#define CID_VOTE_WIDE(WPLV)                                                                                            \
+    readid_vote_wide_kernel<WPLV><<<gridV, RA_WARPS * 32, cw_smem, st>>>(                                              \
+        d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr, kitem, idx->H, mods, idx->rows, rownz, idx->N, idx->Wp, cap, maxocc,  \
+        ord16, ord8, d_ent16, d_n_set, p.start_sample, p.rep_cap, d_flags, d_rep_n, d_rep_colour, d_rep_count, with_steps)
+                if (idx->Wp <= 32) CID_VOTE_WIDE(1); else if (idx->Wp <= 64) CID_VOTE_WIDE(2); else CID_VOTE_WIDE(4);
+#undef CID_VOTE_WIDE
             }
             ctx->launches++;
             CID_CUDA(cudaGetLastError());
