@@ -762,8 +762,14 @@ readid_vote_narrow_kernel(const uint8_t* __restrict__ bases, const uint8_t* __re
 // bit-sliced registers per lane; used when a row has more than 64 accessions.
 constexpr int RV_MAXWPL = 4;       // words per lane: rows up to 128 words (4,096 accessions per shard)
 constexpr int RV_PLANES = 11;      // counts up to 2047 k-mers per read
-template <int WPL>                 // words per lane (1, 2 or 4): 1,024 / 2,048 / 4,096 accessions; sizes the bit-sliced counters
-__global__ void __launch_bounds__(RA_WARPS * 32)
+// carry-save adder: (carry, sum) = a + b + c, bitwise (32 accessions per instruction)
+__device__ __forceinline__ void csa3(uint32_t& carry, uint32_t& sum, uint32_t a, uint32_t b, uint32_t c) {
+    const uint32_t u = a ^ b;
+    carry = (a & b) | (u & c);
+    sum = u ^ c;
+}
+template <int WPL, int HT>         // words per lane (1, 2 or 4): 1,024 / 2,048 / 4,096 accessions; sizes the bit-sliced counters.
+__global__ void __launch_bounds__(RA_WARPS * 32)      // HT: compile-time num_hash (2 or 4; 0 = run-time, predicated up to MAX_HASH)
 readid_vote_wide_kernel(const uint8_t* __restrict__ bases, const uint8_t* __restrict__ quals, uint32_t maxq,
                         const uint64_t* __restrict__ seq_offs, const uint64_t* __restrict__ read_offs, uint64_t r0,
                         uint64_t nreads, uint32_t k, uint32_t H, ModS mods, const uint32_t* __restrict__ rows,
@@ -783,6 +789,7 @@ readid_vote_wide_kernel(const uint8_t* __restrict__ bases, const uint8_t* __rest
     uint32_t* moffs = (uint32_t*)(base + ((tile_smem_bytes(cap) + 15) & ~(size_t)15));
     const bool classic = start_sample == 0;
     constexpr int U = WPL == 4 ? 2 : 4;      // k-mers whose rows are in flight together (a step of one k-mer is a dependent DRAM round trip)
+    constexpr int NH = HT ? HT : MAX_HASH;   // hash slots carried per k-mer
 
     for (uint64_t rl = (uint64_t)blockIdx.x * RA_WARPS + warp; rl < nreads; rl += (uint64_t)gridDim.x * RA_WARPS) {
         const uint64_t r = r0 + rl;
@@ -808,18 +815,18 @@ readid_vote_wide_kernel(const uint8_t* __restrict__ bases, const uint8_t* __rest
         for (uint32_t c0 = 0; c0 < n && !miss; c0 += 32) {
             const uint32_t idx = c0 + lane;
             const uint32_t batch = min(32u, n - c0);
-            uint32_t rid_l[MAX_HASH];
+            uint32_t rid_l[NH];
             bool absent = false;
 #pragma unroll
-            for (int h = 0; h < MAX_HASH; h++) rid_l[h] = 0;
+            for (int h = 0; h < NH; h++) rid_l[h] = 0;
             if (idx < n) {
                 const uint32_t e = order8 ? (uint32_t)__ldg(entrow + __ldg(ord8row + idx)) : (uint32_t)__ldg(ordrow + idx);
                 const uint64_t f = codes_window(t.codes, (int)(e & 0x3FFu), k);
                 const uint64_t key = ((e >> 10) & 1u) ? f : revcomp_key(f, k);
                 const HashIn in = hashin_from_key(lut, key, k);
 #pragma unroll
-                for (int h = 0; h < MAX_HASH; h++)
-                    if ((uint32_t)h < H) {
+                for (int h = 0; h < NH; h++)
+                    if (HT || (uint32_t)h < H) {
                         rid_l[h] = (uint32_t)mod_s(xxh3_kmer(in, k, h), mods);
                         if (!((__ldg(rownz + (rid_l[h] >> 5)) >> (rid_l[h] & 31)) & 1u)) absent = true;
                     }
@@ -834,10 +841,10 @@ readid_vote_wide_kernel(const uint8_t* __restrict__ bases, const uint8_t* __rest
 #pragma unroll
                 for (int u = 0; u < U; u++) {
                     const bool on = jj0 + u < p_local;
-                    uint64_t rid[MAX_HASH];
+                    uint64_t rid[NH];
 #pragma unroll
-                    for (int h = 0; h < MAX_HASH; h++)
-                        rid[h] = (uint32_t)h < H ? (uint64_t)__shfl_sync(0xffffffffu, rid_l[h], min(jj0 + u, 31u)) : 0ull;
+                    for (int h = 0; h < NH; h++)
+                        rid[h] = (HT || (uint32_t)h < H) ? (uint64_t)__shfl_sync(0xffffffffu, rid_l[h], min(jj0 + u, 31u)) : 0ull;
 #pragma unroll
                     for (int w = 0; w < WPL; w++) {
                         const uint32_t col = w * 32 + lane;
@@ -845,11 +852,33 @@ readid_vote_wide_kernel(const uint8_t* __restrict__ bases, const uint8_t* __rest
                         if (on && col < Wp) {
                             x = 0xFFFFFFFFu;
 #pragma unroll
-                            for (int h = 0; h < MAX_HASH; h++)            // (static indices: rid[] stays in registers)
-                                if ((uint32_t)h < H) x &= __ldg(rows + rid[h] * Wp + col);
+                            for (int h = 0; h < NH; h++)                  // (static indices: rid[] stays in registers)
+                                if (HT || (uint32_t)h < H) x &= __ldg(rows + rid[h] * Wp + col);
                         }
                         xs[u][w] = x;
                     }
+                }
+                if (!classic && c0 + jj0 >= start_sample && jj0 + U <= p_local) {
+                    // the candidate set is final and all U k-mers count: one carry-save tree per word instead of U ripple adds
+#pragma unroll
+                    for (int w = 0; w < WPL; w++) {
+                        uint32_t carry;
+                        if (U == 4) {
+                            uint32_t t2a, t2b;
+                            csa3(t2a, pl[w][0], pl[w][0], xs[0][w] & cand[w], xs[1][w] & cand[w]);
+                            csa3(t2b, pl[w][0], pl[w][0], xs[2][w] & cand[w], xs[U - 1][w] & cand[w]);
+                            csa3(carry, pl[w][1], pl[w][1], t2a, t2b);
+                        } else {
+                            csa3(carry, pl[w][0], pl[w][0], xs[0][w] & cand[w], xs[U - 1][w] & cand[w]);
+                        }
+#pragma unroll
+                        for (int p = (U == 4 ? 2 : 1); p < RV_PLANES; p++) {
+                            const uint32_t t2 = pl[w][p] & carry;
+                            pl[w][p] ^= carry;
+                            carry = t2;
+                        }
+                    }
+                    continue;
                 }
 #pragma unroll
                 for (int u = 0; u < U; u++) {
@@ -1276,12 +1305,14 @@ int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const ui
                 else { if (with_steps) CID_VOTE_NARROW(2, true); else CID_VOTE_NARROW(2, false); }
 #undef CID_VOTE_NARROW
             } else {
-#define CID_VOTE_WIDE(WPLV)                                                                                            \
-    readid_vote_wide_kernel<WPLV><<<gridV, RA_WARPS * 32, cw_smem, st>>>(                                              \
+#define CID_VOTE_WIDE_H(WPLV, HTV)                                                                                     \
+    readid_vote_wide_kernel<WPLV, HTV><<<gridV, RA_WARPS * 32, cw_smem, st>>>(                                         \
         d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr, kitem, idx->H, mods, idx->rows, rownz, idx->N, idx->Wp, cap, maxocc,  \
         ord16, ord8, d_ent16, d_n_set, p.start_sample, p.rep_cap, d_flags, d_rep_n, d_rep_colour, d_rep_count, with_steps)
+#define CID_VOTE_WIDE(WPLV) do { if (idx->H == 4) CID_VOTE_WIDE_H(WPLV, 4); else if (idx->H == 2) CID_VOTE_WIDE_H(WPLV, 2); else CID_VOTE_WIDE_H(WPLV, 0); } while (0)
                 if (idx->Wp <= 32) CID_VOTE_WIDE(1); else if (idx->Wp <= 64) CID_VOTE_WIDE(2); else CID_VOTE_WIDE(4);
 #undef CID_VOTE_WIDE
+#undef CID_VOTE_WIDE_H
             }
             ctx->launches++;
             CID_CUDA(cudaGetLastError());
