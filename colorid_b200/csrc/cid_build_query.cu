@@ -1473,21 +1473,36 @@ slots_popcount_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t k
     lut4_init(lut, threadIdx.x, 256);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (uint64_t i = (uint64_t)blockIdx.x * 8 + warp; i < n; i += (uint64_t)gridDim.x * 8) {
-        const HashIn in = hashin_from_key(lut, slots[i].key, k);
-        uint64_t rid[MAX_HASH];
-        for (uint32_t h = 0; h < H; h++) rid[h] = mod_s(xxh3_kmer(in, k, h), mods);
-        uint32_t pc = 0, where = 0;
-        for (uint32_t c = lane; c < Wp; c += 32) {
-            uint32_t x = 0xFFFFFFFFu;
-            for (uint32_t h = 0; h < H; h++) x &= __ldg(rows + rid[h] * Wp + c);
-            if (x) { pc += __popc(x); where = c * 32 + (__ffs(x) - 1); }
+    // a warp takes 32 consecutive list entries: lane L hashes entry L, then the rows of one entry per step are read by all lanes
+    for (uint64_t i0 = ((uint64_t)blockIdx.x * 8 + warp) * 32; i0 < n; i0 += (uint64_t)gridDim.x * 8 * 32) {
+        uint32_t rid_l[MAX_HASH];
+#pragma unroll
+        for (int h = 0; h < MAX_HASH; h++) rid_l[h] = 0;
+        if (i0 + lane < n) {
+            const HashIn in = hashin_from_key(lut, slots[i0 + lane].key, k);
+#pragma unroll
+            for (int h = 0; h < MAX_HASH; h++) if ((uint32_t)h < H) rid_l[h] = (uint32_t)mod_s(xxh3_kmer(in, k, h), mods);
         }
-        uint32_t tot = pc;
-        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-        const uint32_t owner = __ballot_sync(0xffffffffu, pc == 1);
-        const uint32_t colour = __shfl_sync(0xffffffffu, where, owner ? __ffs(owner) - 1 : 0);
-        if (lane == 0) { pc_out[i] = (uint8_t)min(tot, 2u); col_out[i] = tot == 1 ? colour : 0xFFFFFFFFu; }
+        const uint32_t cnt = (uint32_t)min((uint64_t)32, n - i0);
+        uint32_t my_pc = 0, my_col = 0xFFFFFFFFu;
+        for (uint32_t j = 0; j < cnt; j++) {
+            uint64_t rid[MAX_HASH];
+#pragma unroll
+            for (int h = 0; h < MAX_HASH; h++) rid[h] = (uint32_t)h < H ? (uint64_t)__shfl_sync(0xffffffffu, rid_l[h], j) : 0ull;
+            uint32_t pc = 0, where = 0;
+            for (uint32_t c = lane; c < Wp; c += 32) {
+                uint32_t x = 0xFFFFFFFFu;
+#pragma unroll
+                for (int h = 0; h < MAX_HASH; h++) if ((uint32_t)h < H) x &= __ldg(rows + rid[h] * Wp + c);
+                if (x) { pc += __popc(x); where = c * 32 + (__ffs(x) - 1); }
+            }
+            uint32_t tot = pc;
+            for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+            const uint32_t owner = __ballot_sync(0xffffffffu, pc == 1);
+            const uint32_t colour = __shfl_sync(0xffffffffu, where, owner ? __ffs(owner) - 1 : 0);
+            if ((uint32_t)lane == j) { my_pc = min(tot, 2u); my_col = tot == 1 ? colour : 0xFFFFFFFFu; }
+        }
+        if (i0 + lane < n) { pc_out[i0 + lane] = (uint8_t)my_pc; col_out[i0 + lane] = my_col; }       // coalesced
     }
 }
 __global__ void __launch_bounds__(256)
@@ -1517,7 +1532,7 @@ int launch_slots_popcount(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, c
                           uint32_t* d_col) {
     if (n == 0) return CID_OK;
     ProfScope ps(ctx, st, KID_QUERY_UNIQ_WIDE);
-    const unsigned grid = (unsigned)std::min<uint64_t>((n + 7) / 8, (uint64_t)ctx->sm_count * 32);
+    const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 32);
     slots_popcount_kernel<<<grid, 256, 0, st>>>(idx->rows, idx->Wp, idx->k, idx->H, make_mods(idx->S), (const Slot*)d_slots, n, d_pc, d_col);
     ctx->launches++;
     CID_CUDA(cudaGetLastError());
