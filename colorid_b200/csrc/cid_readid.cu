@@ -1229,11 +1229,19 @@ int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const ui
     size_t cw_warp = ((tile_smem_bytes(cap) + 15) & ~(size_t)15) + (MAX_MATES + 1) * 4 + 12;
     size_t cw_smem = RA_WARPS * ((cw_warp + 15) & ~(size_t)15);
     if (a_smem > 200 * 1024 || b_smem > 200 * 1024) { set_error("read_id: read too long for the shared-memory plan"); return CID_E_UNSUPPORTED; }
-    CID_CUDA(cudaFuncSetAttribute(readid_kmerize_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a_smem));
-    CID_CUDA(cudaFuncSetAttribute(readid_kmerize_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a_smem));
-    CID_CUDA(cudaFuncSetAttribute(readid_kmerize_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a_smem));
-    CID_CUDA(cudaFuncSetAttribute(readid_kmerize_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a_smem));
-    CID_CUDA(cudaFuncSetAttribute(readid_order_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b_smem));
+    // The limit is a property of the function on the device, shared by every context (batch_id runs one worker thread and
+    // context per listed device, possibly several on one GPU): always the same constant, never a per-call size, so that one
+    // worker cannot lower it under another's launch.
+    bool& rattr = ctx->attr_done[4];
+    if (!rattr) {
+        const int lim = 200 * 1024;
+        CID_CUDA(cudaFuncSetAttribute(readid_kmerize_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        CID_CUDA(cudaFuncSetAttribute(readid_kmerize_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        CID_CUDA(cudaFuncSetAttribute(readid_kmerize_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        CID_CUDA(cudaFuncSetAttribute(readid_kmerize_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        CID_CUDA(cudaFuncSetAttribute(readid_order_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        rattr = true;
+    }
 
     const ModS mods = make_mods(idx->S);
     const uint32_t kitem = idx->m ? idx->m : idx->k;    // length of the hashed item: k-mer, or minimizer of an .mxi index
