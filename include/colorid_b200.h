@@ -65,11 +65,17 @@ uint64_t cid_ctx_launch_count(const cid_ctx* ctx);
 /* Diagnostic device counters, read and reset: "readid_gather_rows" = matrix rows the read_id vote kernel
  * actually read (bench.py's random-access rate). */
 int cid_ctx_read_counter(cid_ctx* ctx, const char* name, uint64_t* value);
-/* Tuning knobs (never change results): "readid_chunk_reads" = reads per pipeline chunk of the
- * host-pointer read_id entry points (0 = automatic), "host_threads" = host threads used by the
- * read_id vote (0 = all cores; main.rs:718 rayon pool size `-t`), "readid_streams" = 2 forks the chunks of
- * cid_read_id_batch_dev over two internal streams (default 1), "query_fused" = 1 forces the fused
- * collect/hash/gather search kernel instead of query_hash + query_gather. */
+/* Options by name.  None of them changes a result; unknown names return CID_E_INVALID.
+ *   host_threads           host threads of the read_id vote (0 = all cores; main.rs:718 rayon pool size `-t`)
+ *   readid_report_steps    1: read_id report colours carry their insertion step in bits 20..31 (column-sharded read_id:
+ *                          see cid_merge_shard_reports); such reports must be merged before they are classified
+ *   tuning:  readid_chunk_reads / readid_chunk0_reads (reads per pipeline chunk of the host-pointer read_id calls, 0 = automatic),
+ *            readid_streams (2 = chunks of cid_read_id_batch_dev over two internal streams), readid_kmerize_ctas /
+ *            readid_vote_ctas (CTAs per SM, 0 = fill the GPU), readid_serialize, build_table_div / query_table_div (first count
+ *            table of a read set = k-mer positions / this; 0 = adaptive / always the safe size), query_table_min_slots,
+ *            gather_l2_64b
+ *   parity aids (force the slower of two equivalent paths): build_packed, build_set, query_front, query_fused,
+ *            query_compact (0 never / 1 large tables / 2 always), uniq_device */
 int cid_ctx_set_option(cid_ctx* ctx, const char* name, int64_t value);
 /* Per-kernel device timing with CUDA events on the launching stream (for bench.py's roofline).
  * cid_ctx_profile(ctx, 1) resets the accumulators and enables timing, (ctx, 0) disables it;
