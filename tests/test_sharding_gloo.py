@@ -64,6 +64,40 @@ def _worker(rank, world, port, out_dir):
     ok = p_full["status"] == 0
     assert np.array_equal(words[ok], p_full["and_rows"][ok].astype(np.int64))
 
+    # ---- column-sharded read_id, the exchange: every rank holds the entries of ITS colours of each read's report, tagged with
+    # the step at which the colour entered the report; merge_read_reports (sparse all-gather + cid_merge_shard_reports)
+    # must give back the whole report in order on every rank, and the host vote on it the whole index's classification.
+    # (The per-rank compute is synthetic here: the oracle's report of the whole index, its sequence taken as the insertion
+    # order, split by colour range.  The GPU tests run the real kernels per shard.)
+    from colorid_b200.api import classify_reads
+    whole_rep = full.read_id_batch(reads)
+    nr, cap = len(reads), hi - lo + 1
+    mine_rep = dict(n_set=whole_rep["n_set"], flags=np.zeros(nr, np.uint32), rep_n=np.zeros(nr, np.uint32),
+                    rep_colour=np.zeros((nr, cap), np.uint32), rep_count=np.zeros((nr, cap), np.uint32))
+    for r in range(nr):
+        n_loc = 0
+        for i in range(whole_rep["rep_n"][r]):
+            c, v = int(whole_rep["rep_colour"][r, i]), int(whole_rep["rep_count"][r, i])
+            if c == N:                                        # the "no hit" key: every shard reports it (as its own N)
+                mine_rep["rep_colour"][r, n_loc], mine_rep["rep_count"][r, n_loc] = hi - lo, 1
+                n_loc += 1
+            elif lo <= c < hi:
+                mine_rep["rep_colour"][r, n_loc], mine_rep["rep_count"][r, n_loc] = (c - lo) | (i << 20), v
+                n_loc += 1
+        mine_rep["rep_n"][r] = n_loc
+    merged = sharding.merge_read_reports(mine_rep, shards, N)
+    for r in range(nr):
+        n_all = int(whole_rep["rep_n"][r])
+        assert int(merged["rep_n"][r]) == n_all
+        exp_c, exp_v = whole_rep["rep_colour"][r, :n_all].tolist(), whole_rep["rep_count"][r, :n_all].tolist()
+        if N in exp_c:                                        # the merge puts the "no hit" key last, like the kernels
+            j = exp_c.index(N)
+            exp_c, exp_v = exp_c[:j] + exp_c[j + 1:] + [N], exp_v[:j] + exp_v[j + 1:] + [exp_v[j]]
+        assert merged["rep_colour"][r, :n_all].tolist() == exp_c and merged["rep_count"][r, :n_all].tolist() == exp_v
+    cls = classify_reads((S, H, N), full.n_ref, merged)
+    assert np.array_equal(cls["kind"], whole_rep["kind"]) and np.array_equal(cls["hits"], whole_rep["hits"])
+    assert np.array_equal(cls["n_top"], whole_rep["n_top"])
+
     # ---- replicated: reads split across ranks, results concatenated in input order
     sl = sharding.unit_slices(len(reads), world)[rank]
     part = full.read_id_batch(reads[sl[0]:sl[1]])
