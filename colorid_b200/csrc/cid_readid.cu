@@ -812,13 +812,12 @@ readid_vote_wide_kernel(const uint8_t* __restrict__ bases, const uint8_t* __rest
         // L2-resident bitmap), a ballot finds the first absent row, and the rows of the k-mers before it are then gathered one
         // k-mer per step with every lane on its own words.  (Before: all 32 lanes hashed the same k-mer, ~600 redundant
         // instructions per k-mer, which bound the kernel.)
-        for (uint32_t c0 = 0; c0 < n && !miss; c0 += 32) {
-            const uint32_t idx = c0 + lane;
-            const uint32_t batch = min(32u, n - c0);
-            uint32_t rid_l[NH];
-            bool absent = false;
+        // lane L's k-mer of the batch starting at `c`: row indices; the row-present words are only LOADED here (`pres`), they
+        // are looked at after the gather steps of the batch before, so that their latency hides under those
+        auto hash_batch = [&](uint32_t c, uint32_t (&rid_o)[NH], uint32_t (&pres)[NH]) {
 #pragma unroll
-            for (int h = 0; h < NH; h++) rid_l[h] = 0;
+            for (int h = 0; h < NH; h++) { rid_o[h] = 0; pres[h] = 0xFFFFFFFFu; }
+            const uint32_t idx = c + lane;
             if (idx < n) {
                 const uint32_t e = order8 ? (uint32_t)__ldg(entrow + __ldg(ord8row + idx)) : (uint32_t)__ldg(ordrow + idx);
                 const uint64_t f = codes_window(t.codes, (int)(e & 0x3FFu), k);
@@ -827,10 +826,20 @@ readid_vote_wide_kernel(const uint8_t* __restrict__ bases, const uint8_t* __rest
 #pragma unroll
                 for (int h = 0; h < NH; h++)
                     if (HT || (uint32_t)h < H) {
-                        rid_l[h] = (uint32_t)mod_s(xxh3_kmer(in, k, h), mods);
-                        if (!((__ldg(rownz + (rid_l[h] >> 5)) >> (rid_l[h] & 31)) & 1u)) absent = true;
+                        rid_o[h] = (uint32_t)mod_s(xxh3_kmer(in, k, h), mods);
+                        pres[h] = __ldg(rownz + (rid_o[h] >> 5)) >> (rid_o[h] & 31);
                     }
             }
+        };
+        uint32_t rid_l[NH], pres_l[NH];
+        hash_batch(0, rid_l, pres_l);
+        for (uint32_t c0 = 0; c0 < n && !miss; c0 += 32) {
+            const uint32_t batch = min(32u, n - c0);
+            bool absent = false;
+#pragma unroll
+            for (int h = 0; h < NH; h++) if (!(pres_l[h] & 1u)) absent = true;
+            uint32_t rid_n[NH], pres_n[NH];
+            hash_batch(c0 + 32, rid_n, pres_n);           // (a no-op past the end of the set)
             const uint32_t missmask = __ballot_sync(0xffffffffu, absent);
             const uint32_t p_local = missmask ? (uint32_t)(__ffs(missmask) - 1) : batch;
             nproc += missmask ? p_local + 1 : batch;
@@ -911,6 +920,8 @@ readid_vote_wide_kernel(const uint8_t* __restrict__ bases, const uint8_t* __rest
                     }
                 }
             }
+#pragma unroll
+            for (int h = 0; h < NH; h++) { rid_l[h] = rid_n[h]; pres_l[h] = pres_n[h]; }
         }
         __syncwarp();
         // counts for the reported colours
