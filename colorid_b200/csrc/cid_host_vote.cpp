@@ -267,34 +267,60 @@ int cid_merge_shard_reports(uint32_t n_shards, const uint32_t* shard_n_colors, c
     }
     const uint32_t cmask = (1u << 20) - 1u;
     struct Ent { uint32_t step, colour, count; };
-    std::vector<Ent> ents;
-    for (uint64_t r = 0; r < nreads; r++) {
-        ents.clear();
-        uint32_t n_miss = 0;
-        for (uint32_t s = 0; s < n_shards; s++) {
-            const uint32_t n = rep_n[s][r];
-            if (n > rep_cap_in) { set_error("cid_merge_shard_reports: rep_n above rep_cap"); return CID_E_INVALID; }
-            for (uint32_t i = 0; i < n; i++) {
-                const uint32_t e = rep_colour[s][r * (uint64_t)rep_cap_in + i], c = e & cmask;
-                if (c == shard_n_colors[s]) { n_miss++; continue; }          // the "no hit" key N of that shard
-                if (c > shard_n_colors[s]) { set_error("cid_merge_shard_reports: colour out of range"); return CID_E_INVALID; }
-                ents.push_back({e >> 20, shard_col_offset[s] + c, rep_count[s][r * (uint64_t)rep_cap_in + i]});
+    // reads are independent: host threads over contiguous ranges; the first problem found wins (1 = rep_n, 2 = colour, 3 = miss)
+    std::atomic<int> problem{0};
+    std::atomic<unsigned long long> problem_read{0};
+    auto work = [&](uint64_t r_lo, uint64_t r_hi) {
+        std::vector<Ent> ents;
+        for (uint64_t r = r_lo; r < r_hi && !problem.load(std::memory_order_relaxed); r++) {
+            ents.clear();
+            uint32_t n_miss = 0;
+            int bad = 0;
+            for (uint32_t s = 0; s < n_shards && !bad; s++) {
+                const uint32_t n = rep_n[s][r];
+                if (n > rep_cap_in) { bad = 1; break; }
+                for (uint32_t i = 0; i < n; i++) {
+                    const uint32_t e = rep_colour[s][r * (uint64_t)rep_cap_in + i], c = e & cmask;
+                    if (c == shard_n_colors[s]) { n_miss++; continue; }          // the "no hit" key N of that shard
+                    if (c > shard_n_colors[s]) { bad = 2; break; }
+                    ents.push_back({e >> 20, shard_col_offset[s] + c, rep_count[s][r * (uint64_t)rep_cap_in + i]});
+                }
             }
+            if (!bad && n_miss != 0 && n_miss != n_shards) bad = 3;
+            if (bad) {
+                int expected = 0;
+                if (problem.compare_exchange_strong(expected, bad)) problem_read = r;
+                return;
+            }
+            std::sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b) { return a.step != b.step ? a.step < b.step : a.colour < b.colour; });
+            const uint64_t total = ents.size() + (n_miss ? 1 : 0);
+            uint32_t* oc = out_colour + r * (uint64_t)rep_cap_out;
+            uint32_t* ov = out_count + r * (uint64_t)rep_cap_out;
+            uint32_t w = 0;
+            for (const Ent& e : ents) { if (w < rep_cap_out) { oc[w] = e.colour; ov[w] = e.count; w++; } }
+            if (n_miss && w < rep_cap_out) { oc[w] = n_total; ov[w] = 1; w++; }
+            out_rep_n[r] = w;
+            if (out_flags && total > rep_cap_out) out_flags[r] |= 4u;              // truncated, like the kernels' flag bit 2
         }
-        if (n_miss != 0 && n_miss != n_shards) {
+    };
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt == 0) nt = 1;
+    nt = (unsigned)std::min<uint64_t>(nt, std::max<uint64_t>(1, nreads / 2048));
+    if (nt <= 1) work(0, nreads);
+    else {
+        std::vector<std::thread> th;
+        const uint64_t per = (nreads + nt - 1) / nt;
+        for (unsigned t = 0; t < nt; t++) th.emplace_back(work, std::min(nreads, t * per), std::min(nreads, (t + 1) * per));
+        for (auto& x : th) x.join();
+    }
+    switch (problem.load()) {
+        case 1: set_error("cid_merge_shard_reports: rep_n above rep_cap"); return CID_E_INVALID;
+        case 2: set_error("cid_merge_shard_reports: colour out of range"); return CID_E_INVALID;
+        case 3:
             set_error("cid_merge_shard_reports: shards disagree on the first absent row of read %llu (row-present bitmaps not merged?)",
-                      (unsigned long long)r);
+                      problem_read.load());
             return CID_E_INVALID;
-        }
-        std::sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b) { return a.step != b.step ? a.step < b.step : a.colour < b.colour; });
-        const uint64_t total = ents.size() + (n_miss ? 1 : 0);
-        uint32_t* oc = out_colour + r * (uint64_t)rep_cap_out;
-        uint32_t* ov = out_count + r * (uint64_t)rep_cap_out;
-        uint32_t w = 0;
-        for (const Ent& e : ents) { if (w < rep_cap_out) { oc[w] = e.colour; ov[w] = e.count; w++; } }
-        if (n_miss && w < rep_cap_out) { oc[w] = n_total; ov[w] = 1; w++; }
-        out_rep_n[r] = w;
-        if (out_flags && total > rep_cap_out) out_flags[r] |= 4u;              // truncated, like the kernels' flag bit 2
+        default: break;
     }
     return CID_OK;
 }
