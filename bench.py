@@ -618,7 +618,8 @@ def run_c5(args):
         n_pairs = Lg * 30 // (2 * rl)
         b, q = make_reads(torch, dev, qcfg, acc_codes(a_src)[None, :], n_pairs, 0xC0101D51)      # identical on every rank
         b[q < CFG["qual_offset"] + 33] = 78
-        packed = (b.cpu().numpy().reshape(-1), np.arange(2 * n_pairs + 1, dtype=np.uint64) * np.uint64(rl),
+        h_reads = b.cpu().pin_memory()                    # page-locked, as cid_host_alloc would give a caller
+        packed = (h_reads.numpy().reshape(-1), np.arange(2 * n_pairs + 1, dtype=np.uint64) * np.uint64(rl),
                   np.array([0, 2 * n_pairs], dtype=np.uint64))
         del b, q
         rep = None
