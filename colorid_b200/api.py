@@ -345,9 +345,9 @@ class Index:
         p = self._params(d, 3, 0, group_width, reserve_before_find, None)
         on = np.zeros(max(nr, 1), np.uint32)
         osq = np.zeros((max(nr, 1), order_cap), np.uint8)
-        opos = np.zeros((max(nr, 1), order_cap), np.uint16)
-        L.check(self.lib.cid_read_kmer_order(self.h, _p(bases), _p(offs, L.u64p), len(flat), _p(roffs, L.u64p), nr,
-                                             C.byref(p), order_cap, _p(on, L.u32p), _p(osq, L.u8p), _p(opos, L.u16p)))
+        opos = np.zeros((max(nr, 1), order_cap), np.uint32)
+        L.check(self.lib.cid_read_kmer_order32(self.h, _p(bases), _p(offs, L.u64p), len(flat), _p(roffs, L.u64p), nr,
+                                               C.byref(p), order_cap, _p(on, L.u32p), _p(osq, L.u8p), _p(opos, L.u32p)))
         return on[:nr], osq[:nr], opos[:nr]
 
     def hash_kmers(self, kmers):

@@ -44,7 +44,7 @@ void PinBuf::release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 
 static const char* kKernelNames[KID_COUNT] = {"kmerize_insert", "region_histogram", "region_to_bloom", "transpose_bitsets",
                                               "rownz", "query_counts", "query_uniq_wide", "query_perfect",
-                                              "readid_kmerize", "readid_sched", "readid_order", "readid_vote", "readid_classify", "table_clear", "other", "query_hash", "query_front"};
+                                              "readid_kmerize", "readid_sched", "readid_order", "readid_vote", "readid_classify", "table_clear", "other", "query_hash", "query_front", "readid_big"};
 static cudaEvent_t prof_event(cid_ctx* c) {
     if (!c->prof_pool.empty()) { cudaEvent_t e = c->prof_pool.back(); c->prof_pool.pop_back(); return e; }
     cudaEvent_t e; cudaEventCreate(&e); return e;

@@ -51,7 +51,7 @@ struct PinBuf {
     template <class T> T* as() const { return (T*)p; }
 };
 
-enum { SCRATCH_SLOTS = 24 };
+enum { SCRATCH_SLOTS = 28 };
 
 }  // namespace cid
 
@@ -71,8 +71,8 @@ struct cid_ctx {
     struct ProfRec { int kernel; cudaEvent_t a, b; };
     std::vector<ProfRec> prof_recs;
     std::vector<cudaEvent_t> prof_pool;
-    double prof_ms[24] = {0};
-    uint64_t prof_n[24] = {0};
+    double prof_ms[32] = {0};
+    uint64_t prof_n[32] = {0};
     // read_id host pipeline (cid_readid_pipe.cu): chunked H2D / kernels / D2H / host vote overlap
     struct cid_readid_pipe* pipe = nullptr;
     uint64_t opt_readid_chunk = 0;   // reads per pipeline chunk (0 = automatic)
@@ -134,7 +134,7 @@ int check_err_flags(cid_ctx* ctx, cudaStream_t st);   // syncs the stream
 
 // kernel ids for the profiling hooks (names in cid_api.cu: kKernelNames)
 enum { KID_KMERIZE_INSERT = 0, KID_HISTOGRAM, KID_TO_BLOOM, KID_TRANSPOSE, KID_ROWNZ, KID_QUERY_COUNTS, KID_QUERY_UNIQ_WIDE,
-       KID_QUERY_PERFECT, KID_READID_KMERIZE, KID_READID_SCHED, KID_READID_ORDER, KID_READID_VOTE, KID_READID_CLASSIFY, KID_TABLE_CLEAR, KID_OTHER, KID_QUERY_HASH, KID_QUERY_FRONT, KID_COUNT };
+       KID_QUERY_PERFECT, KID_READID_KMERIZE, KID_READID_SCHED, KID_READID_ORDER, KID_READID_VOTE, KID_READID_CLASSIFY, KID_TABLE_CLEAR, KID_OTHER, KID_QUERY_HASH, KID_QUERY_FRONT, KID_READID_BIG, KID_COUNT };
 struct ProfScope {     // records an event pair around a launch when profiling is enabled
     cid_ctx* ctx; cudaStream_t st; int idx;
     ProfScope(cid_ctx* c, cudaStream_t s, int kernel);
@@ -226,14 +226,27 @@ int launch_uniq_summaries(cid_ctx* ctx, cudaStream_t st, const uint32_t* d_list,
 // (every per-read array is indexed by the absolute read number, so a caller that stages only a
 // chunk passes pointers biased by the chunk origin).  Per-read scratch (`entries`, `order`, `nocc`)
 // is indexed from 0 and must hold `scr.cap_reads` reads; larger ranges are walked in pieces.
-struct ReadIdScratch { uint32_t* entries; uint16_t* order; uint32_t* nocc; uint64_t cap_reads; };
+struct ReadIdScratch {
+    uint32_t* entries; uint16_t* order; uint32_t* nocc; uint64_t cap_reads;
+    // general path (cid_readid_big.cu): scratch of big_ctas CTAs sized by readid_big_plan(big_bases, big_kmers)
+    uint8_t* big; uint32_t big_ctas; uint32_t big_bases, big_kmers;
+};
+enum { READID_FAST_BASES = 1000 };     // longest read (all mates) of the warp-per-read kernels
 void readid_scratch_bytes(const cid_index* idx, uint32_t max_read_bases, uint32_t max_kmers, uint64_t reads,
                           size_t* entries_bytes, size_t* order_bytes, size_t* nocc_bytes);
 int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const uint8_t* d_quals,
                const uint64_t* d_seq_offs, const uint64_t* d_read_offs, uint64_t r_first, uint64_t nreads,
                uint32_t max_read_bases, uint32_t max_kmers, const cid_readid_params& p, const ReadIdScratch& scr,
                uint32_t* d_n_set, uint32_t* d_flags, uint32_t* d_rep_n, uint32_t* d_rep_colour, uint32_t* d_rep_count,
-               uint32_t order_cap, uint32_t* d_order_n, uint8_t* d_order_seq, uint16_t* d_order_pos);
+               uint32_t order_cap, uint32_t* d_order_n, uint8_t* d_order_seq, uint32_t* d_order_pos);
+// general path: reads listed in d_list[0 .. *d_list_n) (indices relative to r0), one CTA per read, tables in `d_scratch`
+void readid_big_plan(const cid_index* idx, uint32_t max_bases, uint32_t max_kmers, size_t budget, size_t* bytes, uint32_t* ctas);
+int launch_readid_big(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const uint8_t* d_quals, uint32_t maxq,
+                      const uint64_t* d_seq_offs, const uint64_t* d_read_offs, uint64_t r0, const uint32_t* d_list,
+                      const uint32_t* d_list_n, uint32_t max_bases, uint32_t max_kmers, const cid_readid_params& p,
+                      uint8_t* d_scratch, uint32_t ctas, uint32_t* d_n_set, uint32_t* d_flags, uint32_t* d_rep_n,
+                      uint32_t* d_rep_colour, uint32_t* d_rep_count, uint32_t order_cap, uint32_t* d_order_n,
+                      uint8_t* d_order_seq, uint32_t* d_order_pos);
 
 // device side of the vote; reads it cannot decide bit-exactly are appended to `list` for the host vote
 int launch_readid_classify(cid_ctx* ctx, cudaStream_t st, uint64_t r0, uint64_t nreads, uint32_t N, uint32_t rep_cap,

@@ -93,7 +93,8 @@ readid_kmerize_kernel(const uint8_t* __restrict__ bases, const uint8_t* __restri
                       uint64_t nreads, uint32_t k, uint32_t mini_m, uint32_t d, int cap, uint32_t maxocc, uint32_t tsize,
                       uint32_t* __restrict__ entries, uint8_t* __restrict__ hp8, uint32_t* __restrict__ h9w,
                       uint16_t* __restrict__ ent16, uint32_t* __restrict__ nocc, uint32_t* __restrict__ nfresh,
-                      uint32_t* __restrict__ flags, uint32_t* __restrict__ err) {
+                      uint32_t* __restrict__ flags, uint32_t* __restrict__ err, uint32_t* __restrict__ slow_list,
+                      uint32_t* __restrict__ slow_n) {
     extern __shared__ __align__(16) uint8_t dsm[];
     __shared__ uint32_t lut[256];
     lut4_init(lut, threadIdx.x, blockDim.x);
@@ -135,10 +136,10 @@ readid_kmerize_kernel(const uint8_t* __restrict__ bases, const uint8_t* __restri
             if (l0 < k) ok = false;
         }
         if (!ok) fl |= 1u;
-        if (ok && !warp_load_read(t, cap, bases, quals, maxq, seq_offs, s_begin, s_end, moffs, lane, g)) {
-            if (lane == 0) atomicOr(err, ERRF_READ_TOO_LONG);
-            fl |= 8u; ok = false;
-        }
+        // Reads this kernel cannot hold -- longer than the shared-memory tile, or (below) with a lower-case base inside a
+        // k-mer, which 2-bit keys cannot spell -- go to the general path (cid_readid_big.cu) through a device list.
+        bool slow = false;
+        if (ok && !warp_load_read(t, cap, bases, quals, maxq, seq_offs, s_begin, s_end, moffs, lane, g)) { slow = true; ok = false; }
         if (ok && !MINI) {
             // kmer.rs:229 `0..l.len()-k+1` wraps for a later mate shorter than k-1 -> slice panic
             // (minimerize_vector_skip_n_set has a `length_l < k` guard instead, kmer.rs:372: the mate is skipped)
@@ -148,6 +149,7 @@ readid_kmerize_kernel(const uint8_t* __restrict__ bases, const uint8_t* __restri
             for (uint32_t i = lane; i < tsize; i += 32) { tkeys[i] = CID_EMPTY_KEY; tmin[i] = 0xFFFFFFFFu; }
             __syncwarp();
             // pass 1: every position -> (valid, dedup slot, strand)
+            bool lowseen = false;
             for (int tp0 = 0; tp0 < g.len; tp0 += 32) {
                 int tp = tp0 + lane;
                 uint32_t info = 0;
@@ -165,7 +167,7 @@ readid_kmerize_kernel(const uint8_t* __restrict__ bases, const uint8_t* __restri
                             bool mfwd;
                             key = tile_minimizer(t, tp, k, mini_m, key, fwd, low, ipos, mfwd);
                             fwd = mfwd;
-                        } else if (low) atomicOr(err, ERRF_LOWER_RAW);
+                        } else if (low) lowseen = true;
                         uint32_t s = (uint32_t)mix64(key) & tmask;
                         for (;;) {
                             unsigned long long prev = atomicCAS(&tkeys[s], CID_EMPTY_KEY, (unsigned long long)key);
@@ -179,6 +181,9 @@ readid_kmerize_kernel(const uint8_t* __restrict__ bases, const uint8_t* __restri
                 if (tp < cap) pinfo[tp] = info;
             }
             __syncwarp();
+            if (__any_sync(0xffffffffu, lowseen)) { slow = true; ok = false; }
+        }
+        if (ok) {
             // pass 2: emit the insert-call sequence in sequence order (kmer.rs:225-240)
             uint32_t* out = entries + rl * (uint64_t)maxocc;
             uint32_t last_fresh = 1;
@@ -220,7 +225,10 @@ readid_kmerize_kernel(const uint8_t* __restrict__ bases, const uint8_t* __restri
         } else if (COMPACT) {
             if ((uint32_t)lane < hwords) h9w[rl * (uint64_t)hwords + lane] = 0;
         }
-        if (lane == 0) { nocc[rl] = emitted; nfresh[rl] = nfr; flags[r] = fl; }
+        if (lane == 0) {
+            nocc[rl] = emitted; nfresh[rl] = nfr; flags[r] = fl;
+            if (slow) slow_list[atomicAdd(slow_n, 1u)] = (uint32_t)rl;
+        }
     }
 }
 
@@ -1145,7 +1153,7 @@ __global__ void order_export_kernel(const uint16_t* __restrict__ order, const ui
                                     const uint64_t* __restrict__ seq_offs, const uint64_t* __restrict__ read_offs,
                                     uint64_t r0, uint64_t nreads, uint32_t maxocc, uint32_t order_cap, int mini,
                                     uint32_t* __restrict__ order_n, uint8_t* __restrict__ order_seq,
-                                    uint16_t* __restrict__ order_pos) {
+                                    uint32_t* __restrict__ order_pos) {
     uint64_t rl = blockIdx.x;
     if (rl >= nreads) return;
     uint64_t r = r0 + rl;
@@ -1161,7 +1169,7 @@ __global__ void order_export_kernel(const uint16_t* __restrict__ order, const ui
         for (uint64_t s = s_begin + 1; s < s_end; s++) if (seq_offs[s] - b0 <= tp) m = (uint32_t)(s - s_begin);
         // minimizer sets: bit 7 = the window spells the minimizer (1) or its reverse complement (0)
         order_seq[r * (uint64_t)order_cap + i] = (uint8_t)(m | (mini ? ((e >> 10) & 1u) << 7 : 0u));
-        order_pos[r * (uint64_t)order_cap + i] = (uint16_t)(tp - (seq_offs[s_begin + m] - b0));
+        order_pos[r * (uint64_t)order_cap + i] = (uint32_t)(tp - (seq_offs[s_begin + m] - b0));
     }
 }
 
@@ -1173,10 +1181,14 @@ static uint32_t cap_to_buckets(uint32_t cap) {
     return b;
 }
 
+// Sizes of the warp-per-read kernels: they hold reads of up to READID_FAST_BASES bases (all mates); longer reads (and reads
+// with lower-case k-mers) take the general path of cid_readid_big.cu, so the caller's maxima are clamped here.
 static void readid_dims(const cid_index* idx, uint32_t max_read_bases, uint32_t max_kmers, int* cap, uint32_t* bound,
                         uint32_t* maxocc) {
+    max_read_bases = std::min<uint32_t>(max_read_bases, READID_FAST_BASES);
     *cap = (int)((max_read_bases + 31) / 32 * 32 + 32);
     uint32_t b = max_kmers ? max_kmers : (max_read_bases >= idx->k ? max_read_bases - idx->k + 1 : 1);
+    b = std::min<uint32_t>(b, std::max<uint32_t>(max_read_bases, 1));      // k-mer positions <= bases
     if (b < 1) b = 1;
     *bound = b;
     *maxocc = (b + 3) & ~3u;
@@ -1187,18 +1199,18 @@ void readid_scratch_bytes(const cid_index* idx, uint32_t max_read_bases, uint32_
     readid_dims(idx, max_read_bases, max_kmers, &cap, &bound, &maxocc);
     *entries_bytes = (size_t)reads * (maxocc * 4 + ((maxocc + 31) / 32) * 4);
     *order_bytes = (size_t)reads * maxocc * 2;
-    *nocc_bytes = (size_t)reads * 12 + (size_t)SCHED_BINS * 4;    // nocc, nfresh, perm, schedule bins
+    *nocc_bytes = (size_t)reads * 16 + (size_t)SCHED_BINS * 4 + 16;    // nocc, nfresh, perm, schedule bins, general-path list
 }
 
 int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const uint8_t* d_quals,
                const uint64_t* d_seq_offs, const uint64_t* d_read_offs, uint64_t r_first, uint64_t nreads,
                uint32_t max_read_bases, uint32_t max_kmers, const cid_readid_params& p, const ReadIdScratch& scr,
                uint32_t* d_n_set, uint32_t* d_flags, uint32_t* d_rep_n, uint32_t* d_rep_colour, uint32_t* d_rep_count,
-               uint32_t order_cap, uint32_t* d_order_n, uint8_t* d_order_seq, uint16_t* d_order_pos) {
+               uint32_t order_cap, uint32_t* d_order_n, uint8_t* d_order_seq, uint32_t* d_order_pos) {
     cid_ctx* ctx = idx->ctx;
     if (nreads == 0) return CID_OK;
     if (idx->k == 0) return CID_E_INVALID;
-    if (max_read_bases > 1000) { set_error("read_id: reads longer than 1000 bases (all mates) are not supported yet"); return CID_E_UNSUPPORTED; }
+    if (!scr.big || !scr.big_ctas) { set_error("read_id: no general-path scratch"); return CID_E_INVALID; }
     if (p.downsample == 0 || (p.group_width != 16 && p.group_width != 8)) { set_error("read_id: bad params"); return CID_E_INVALID; }
     if (idx->Wp > 32 * RV_MAXWPL) { set_error("read_id: more than %d accessions per shard not supported", 32 * 32 * RV_MAXWPL); return CID_E_UNSUPPORTED; }
     int cap; uint32_t bound, maxocc;
@@ -1222,6 +1234,8 @@ int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const ui
     uint32_t* d_nfresh = d_nocc + scr.cap_reads;
     uint32_t* d_perm = d_nfresh + scr.cap_reads;
     uint32_t* d_bins = d_perm + scr.cap_reads;
+    uint32_t* d_slow_n = d_bins + SCHED_BINS;
+    uint32_t* d_slow = d_slow_n + 4;
 
     // shared memory budgets
     size_t a_warp = ((tile_smem_bytes(cap) + 7) & ~(size_t)7) + (size_t)tsize * 12 + (size_t)cap * 4 + (MAX_MATES + 1) * 4 + 4 + 32;
@@ -1261,12 +1275,13 @@ int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const ui
         unsigned gridA = (unsigned)std::min<uint64_t>((nr + RA_WARPS - 1) / RA_WARPS, (uint64_t)ctx->sm_count * 32);
         const unsigned gridK = ctx->opt_kmerize_ctas ? std::min<unsigned>(gridA, (unsigned)(ctx->sm_count * ctx->opt_kmerize_ctas)) : gridA;
         const unsigned gridV = ctx->opt_vote_ctas ? std::min<unsigned>(gridA, (unsigned)(ctx->sm_count * ctx->opt_vote_ctas)) : gridA;
+        CID_CUDA(cudaMemsetAsync(d_slow_n, 0, 4, st));
         {
         ProfScope ps(ctx, st, KID_READID_KMERIZE);
 #define CID_KMERIZE(C, M)                                                                                              \
     readid_kmerize_kernel<C, M><<<gridK, RA_WARPS * 32, a_smem, st>>>(d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr, idx->k, \
                                                                      idx->m, p.downsample, cap, maxocc, tsize, d_entries, d_hp8,   \
-                                                                     d_h9w, d_ent16, d_nocc, d_nfresh, d_flags, ctx->d_err)
+                                                                     d_h9w, d_ent16, d_nocc, d_nfresh, d_flags, ctx->d_err, d_slow, d_slow_n)
         if (small) { if (idx->m) CID_KMERIZE(true, true); else CID_KMERIZE(true, false); }
         else { if (idx->m) CID_KMERIZE(false, true); else CID_KMERIZE(false, false); }
 #undef CID_KMERIZE
@@ -1336,6 +1351,10 @@ int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const ui
             ctx->launches++;
             CID_CUDA(cudaGetLastError());
         }
+        // the reads the kernels above handed over (too long for their tiles, lower-case k-mers): general path, CTA per read
+        CID_TRY(launch_readid_big(idx, st, d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, d_slow, d_slow_n, scr.big_bases,
+                                  scr.big_kmers, p, scr.big, scr.big_ctas, d_n_set, d_flags, d_rep_n, d_rep_colour, d_rep_count,
+                                  order_cap, d_order_n, d_order_seq, d_order_pos));
     }
     return CID_OK;
 }

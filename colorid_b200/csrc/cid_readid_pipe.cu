@@ -26,7 +26,7 @@ struct cid_readid_pipe {
     struct Slot {
         cudaStream_t st = nullptr;
         cudaEvent_t done = nullptr;
-        cid::DevBuf bases, quals, seq_offs, read_offs, entries, order, nocc, n_set, flags, rep_n, rep, ord_out;
+        cid::DevBuf bases, quals, seq_offs, read_offs, entries, order, nocc, n_set, flags, rep_n, rep, ord_out, big;
         cid::DevBuf kind, hits, n_top, top, list, cursor;      // fused vote: device classification + undecided list
         cid::PinBuf h_cursor, h_list, h_offs;
         cudaEvent_t offs_done = nullptr;     // the staged offsets have been consumed by their H2D copies
@@ -52,7 +52,7 @@ void readid_pipe_destroy(cid_ctx* ctx) {
     for (auto& s : pp->slot) {
         if (s.st) cudaStreamSynchronize(s.st);
         for (DevBuf* b : {&s.bases, &s.quals, &s.seq_offs, &s.read_offs, &s.entries, &s.order, &s.nocc, &s.n_set, &s.flags,
-                          &s.rep_n, &s.rep, &s.ord_out, &s.kind, &s.hits, &s.n_top, &s.top, &s.list, &s.cursor})
+                          &s.rep_n, &s.rep, &s.ord_out, &s.big, &s.kind, &s.hits, &s.n_top, &s.top, &s.list, &s.cursor})
             b->release();
         for (PinBuf* b : {&s.h_cursor, &s.h_list, &s.h_offs}) b->release();
         if (s.offs_done) cudaEventDestroy(s.offs_done);
@@ -81,10 +81,11 @@ static int pipe_get(cid_ctx* ctx, cid_readid_pipe** out) {
     return CID_OK;
 }
 
-// host scan of the read geometry: longest read and most k-mer start positions
-static void read_geometry(const uint64_t* seq_offs, const uint64_t* read_offs, uint64_t nreads, uint32_t k, uint32_t d,
-                          uint32_t* max_bases, uint32_t* max_kmers) {
-    uint64_t mb = 0, mk = 0;
+// host scan of the read geometry: longest read and most k-mer start positions, over all reads and over the reads the
+// warp-per-read kernels hold (<= READID_FAST_BASES bases; the others take the general path)
+struct Geometry { uint32_t max_bases, max_kmers, fast_bases, fast_kmers; };
+static Geometry read_geometry(const uint64_t* seq_offs, const uint64_t* read_offs, uint64_t nreads, uint32_t k, uint32_t d) {
+    uint64_t mb = 0, mk = 0, fb = 0, fk = 0;
     for (uint64_t r = 0; r < nreads; r++) {
         uint64_t b = seq_offs[read_offs[r + 1]] - seq_offs[read_offs[r]], kk = 0;
         for (uint64_t s = read_offs[r]; s < read_offs[r + 1]; s++) {
@@ -92,15 +93,29 @@ static void read_geometry(const uint64_t* seq_offs, const uint64_t* read_offs, u
             if (l >= k) kk += (l - k) / d + 1;
         }
         mb = std::max(mb, b); mk = std::max(mk, kk);
+        if (b <= READID_FAST_BASES) { fb = std::max(fb, b); fk = std::max(fk, kk); }
     }
-    *max_bases = (uint32_t)std::min<uint64_t>(mb, 0xFFFFFFFFu);
-    *max_kmers = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(mk, 1), 0xFFFFFFFFu);
+    Geometry g;
+    g.max_bases = (uint32_t)std::min<uint64_t>(mb, 0xFFFFFFFFu);
+    g.max_kmers = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(mk, 1), 0xFFFFFFFFu);
+    g.fast_bases = (uint32_t)fb;
+    g.fast_kmers = (uint32_t)std::max<uint64_t>(fk, 1);
+    return g;
+}
+// scratch of the general path for one batch: up to READID_BIG_BUDGET bytes shared by as many CTAs as fit
+static const size_t READID_BIG_BUDGET = 6ull << 30;
+static int big_scratch(cid_index* ix, DevBuf& buf, uint32_t max_bases, uint32_t max_kmers, ReadIdScratch& scr) {
+    size_t bytes; uint32_t ctas;
+    readid_big_plan(ix, max_bases, max_kmers, READID_BIG_BUDGET, &bytes, &ctas);
+    CID_TRY(buf.ensure(bytes));
+    scr.big = buf.as<uint8_t>(); scr.big_ctas = ctas; scr.big_bases = max_bases; scr.big_kmers = max_kmers;
+    return CID_OK;
 }
 
 struct HostOut {            // where a chunk's results go (user memory, indexed by absolute read)
     uint32_t *n_set = nullptr, *flags = nullptr, *rep_n = nullptr, *rep_colour = nullptr, *rep_count = nullptr;
     uint32_t order_cap = 0;
-    uint32_t* order_n = nullptr; uint8_t* order_seq = nullptr; uint16_t* order_pos = nullptr;
+    uint32_t* order_n = nullptr; uint8_t* order_seq = nullptr; uint32_t* order_pos = nullptr;
     // fused host vote
     const VoteParams* vote = nullptr;
     int threads = 0;
@@ -266,12 +281,13 @@ static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals,
             t_wait += now_ms() - t0;
         }
         // longest read / most k-mer positions of THIS chunk size its kernels (scanned while the GPU runs earlier chunks)
-        uint32_t max_bases, max_kmers;
+        Geometry geo;
         {
             const double t0 = now_ms();
-            read_geometry(seq_offs, read_offs + r0, nr, ix->k, pp.downsample, &max_bases, &max_kmers);
+            geo = read_geometry(seq_offs, read_offs + r0, nr, ix->k, pp.downsample);
             t_geom += now_ms() - t0;
         }
+        const uint32_t max_bases = geo.fast_bases, max_kmers = geo.fast_kmers;
         size_t eb, ob, nb;
         readid_scratch_bytes(ix, max_bases, max_kmers, nr, &eb, &ob, &nb);
         PIPE_TRY(s.bases.ensure(b1 - b0 + 64));
@@ -284,7 +300,7 @@ static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals,
         PIPE_TRY(s.n_set.ensure(nr * 4));
         PIPE_TRY(s.flags.ensure(nr * 4));
         if (want_rep) { PIPE_TRY(s.rep_n.ensure(nr * 4)); PIPE_TRY(s.rep.ensure(nr * rc * 8)); }
-        if (out.order_n) PIPE_TRY(s.ord_out.ensure(nr * 4 + nr * (size_t)out.order_cap * 3 + 64));
+        if (out.order_n) PIPE_TRY(s.ord_out.ensure(nr * 4 + nr * (size_t)out.order_cap * 5 + 64));
         if (fused) {
             PIPE_TRY(s.kind.ensure(nr * 4)); PIPE_TRY(s.hits.ensure(nr * 4)); PIPE_TRY(s.n_top.ensure(nr * 4));
             PIPE_TRY(s.top.ensure(nr * (size_t)std::max<uint32_t>(out.top_cap, 1) * 4));
@@ -320,13 +336,14 @@ static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals,
             d_rc = s.rep.as<uint32_t>() - r0 * rc;
             d_rv = s.rep.as<uint32_t>() + nr * rc - r0 * rc;
         }
-        uint32_t* d_on = nullptr; uint8_t* d_os = nullptr; uint16_t* d_op = nullptr;
+        uint32_t* d_on = nullptr; uint8_t* d_os = nullptr; uint32_t* d_op = nullptr;
         if (out.order_n) {
             d_on = s.ord_out.as<uint32_t>() - r0;
-            d_op = (uint16_t*)(s.ord_out.as<uint32_t>() + nr) - r0 * (size_t)out.order_cap;
-            d_os = (uint8_t*)((uint16_t*)(s.ord_out.as<uint32_t>() + nr) + nr * (size_t)out.order_cap) - r0 * (size_t)out.order_cap;
+            d_op = s.ord_out.as<uint32_t>() + nr - r0 * (size_t)out.order_cap;
+            d_os = (uint8_t*)(s.ord_out.as<uint32_t>() + nr + nr * (size_t)out.order_cap) - r0 * (size_t)out.order_cap;
         }
-        ReadIdScratch scr{s.entries.as<uint32_t>(), s.order.as<uint16_t>(), s.nocc.as<uint32_t>(), nr};
+        ReadIdScratch scr{s.entries.as<uint32_t>(), s.order.as<uint16_t>(), s.nocc.as<uint32_t>(), nr, nullptr, 0, 0, 0};
+        PIPE_TRY(big_scratch(ix, s.big, geo.max_bases, geo.max_kmers, scr));
         // Option readid_serialize: this chunk's kernels start only after the previous chunk's have finished (copies still
         // overlap).  Measured on B200: 44.8M pairs/s against 46.3M with free overlap across the slot streams, so it is off.
         if (c > 0 && ctx->opt_readid_serialize) PIPE_CUDA(cudaStreamWaitEvent(s.st, pipe->slot[(c - 1) % NS].kern_done, 0));
@@ -367,9 +384,9 @@ static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals,
             if (out.order_n) {
                 const size_t oc = out.order_cap;
                 PIPE_CUDA(cudaMemcpyAsync(out.order_n + r0, s.ord_out.p, nr * 4, cudaMemcpyDeviceToHost, s.st));
-                PIPE_CUDA(cudaMemcpyAsync(out.order_pos + r0 * oc, s.ord_out.as<uint32_t>() + nr, nr * oc * 2,
+                PIPE_CUDA(cudaMemcpyAsync(out.order_pos + r0 * oc, s.ord_out.as<uint32_t>() + nr, nr * oc * 4,
                                           cudaMemcpyDeviceToHost, s.st));
-                PIPE_CUDA(cudaMemcpyAsync(out.order_seq + r0 * oc, (uint16_t*)(s.ord_out.as<uint32_t>() + nr) + nr * oc,
+                PIPE_CUDA(cudaMemcpyAsync(out.order_seq + r0 * oc, s.ord_out.as<uint32_t>() + nr + nr * oc,
                                           nr * oc, cudaMemcpyDeviceToHost, s.st));
             }
         }
@@ -416,6 +433,7 @@ int cid_read_id_batch_dev(cid_index* ix, const char* d_bases, const char* d_qual
     default_readid_params(pp, p, ix->N);
     cudaStream_t user = (cudaStream_t)stream;
     const int nst = (ctx->opt_readid_streams >= 2 && nreads >= 4 * 32768) ? 2 : 1;
+    const uint32_t big_kmers = h_max_kmers ? h_max_kmers : std::max<uint32_t>(h_max_read_bases, 1);
     if (nst == 1) {
         const uint64_t cap = std::min<uint64_t>(std::max<uint64_t>(nreads, 1), 1u << 20);
         size_t eb, ob, nb;
@@ -423,7 +441,8 @@ int cid_read_id_batch_dev(cid_index* ix, const char* d_bases, const char* d_qual
         CID_TRY(ctx->scratch[16].ensure(eb));
         CID_TRY(ctx->scratch[17].ensure(ob));
         CID_TRY(ctx->scratch[18].ensure(nb));
-        ReadIdScratch scr{ctx->scratch[16].as<uint32_t>(), ctx->scratch[17].as<uint16_t>(), ctx->scratch[18].as<uint32_t>(), cap};
+        ReadIdScratch scr{ctx->scratch[16].as<uint32_t>(), ctx->scratch[17].as<uint16_t>(), ctx->scratch[18].as<uint32_t>(), cap, nullptr, 0, 0, 0};
+        CID_TRY(big_scratch(ix, ctx->scratch[24], h_max_read_bases, big_kmers, scr));
         return readid_run(ix, user, (const uint8_t*)d_bases, (const uint8_t*)d_quals, d_seq_offs, d_read_offs, 0,
                           nreads, h_max_read_bases, h_max_kmers, pp, scr, d_n_set, d_flags, d_rep_n, d_rep_colour, d_rep_count,
                           0, nullptr, nullptr, nullptr);
@@ -449,8 +468,9 @@ int cid_read_id_batch_dev(cid_index* ix, const char* d_bases, const char* d_qual
     for (uint64_t r0 = 0; r0 < nreads && rc == CID_OK; r0 += chunk, c++) {
         const int i = (int)(c & 1);
         ReadIdScratch scr{ctx->scratch[16 + 3 * i].as<uint32_t>(), ctx->scratch[17 + 3 * i].as<uint16_t>(),
-                          ctx->scratch[18 + 3 * i].as<uint32_t>(), chunk};
-        rc = readid_run(ix, ctx->aux[i], (const uint8_t*)d_bases, (const uint8_t*)d_quals, d_seq_offs, d_read_offs, r0,
+                          ctx->scratch[18 + 3 * i].as<uint32_t>(), chunk, nullptr, 0, 0, 0};
+        rc = big_scratch(ix, ctx->scratch[24 + i], h_max_read_bases, big_kmers, scr);
+        if (rc == CID_OK) rc = readid_run(ix, ctx->aux[i], (const uint8_t*)d_bases, (const uint8_t*)d_quals, d_seq_offs, d_read_offs, r0,
                         std::min(chunk, nreads - r0), h_max_read_bases, h_max_kmers, pp, scr, d_n_set, d_flags, d_rep_n,
                         d_rep_colour, d_rep_count, 0, nullptr, nullptr, nullptr);
     }
@@ -487,13 +507,28 @@ int cid_read_id_classify(cid_index* ix, const char* bases, const char* quals, co
     return read_id_pipeline(ix, bases, quals, seq_offs, nseq, read_offs, nreads, &pp, o);
 }
 
-int cid_read_kmer_order(cid_index* ix, const char* bases, const uint64_t* seq_offs, uint64_t nseq,
-                        const uint64_t* read_offs, uint64_t nreads, const cid_readid_params* p, uint32_t order_cap,
-                        uint32_t* order_n, uint8_t* order_seq, uint16_t* order_pos) {
+int cid_read_kmer_order32(cid_index* ix, const char* bases, const uint64_t* seq_offs, uint64_t nseq,
+                          const uint64_t* read_offs, uint64_t nreads, const cid_readid_params* p, uint32_t order_cap,
+                          uint32_t* order_n, uint8_t* order_seq, uint32_t* order_pos) {
     if (!order_n || !order_seq || !order_pos || order_cap == 0) { set_error("read_kmer_order: null argument"); return CID_E_INVALID; }
     HostOut o;
     o.order_cap = order_cap; o.order_n = order_n; o.order_seq = order_seq; o.order_pos = order_pos;
     return read_id_pipeline(ix, bases, nullptr, seq_offs, nseq, read_offs, nreads, p, o);
+}
+
+int cid_read_kmer_order(cid_index* ix, const char* bases, const uint64_t* seq_offs, uint64_t nseq,
+                        const uint64_t* read_offs, uint64_t nreads, const cid_readid_params* p, uint32_t order_cap,
+                        uint32_t* order_n, uint8_t* order_seq, uint16_t* order_pos) {
+    if (!order_pos) { set_error("read_kmer_order: null argument"); return CID_E_INVALID; }
+    std::vector<uint32_t> wide((size_t)nreads * order_cap);
+    CID_TRY(cid_read_kmer_order32(ix, bases, seq_offs, nseq, read_offs, nreads, p, order_cap, order_n, order_seq, wide.data()));
+    for (uint64_t r = 0; r < nreads; r++)
+        for (uint32_t i = 0; i < std::min(order_n[r], order_cap); i++) {
+            const uint32_t v = wide[r * order_cap + i];
+            if (v > 0xFFFFu) { set_error("read_kmer_order: position %u does not fit 16 bits, use cid_read_kmer_order32", v); return CID_E_CAPACITY; }
+            order_pos[r * order_cap + i] = (uint16_t)v;
+        }
+    return CID_OK;
 }
 
 }  // extern "C"

@@ -76,6 +76,8 @@ SIGNATURES = {
                                         C.POINTER(ReadIdParams), vp, vp, vp, vp, vp, vp]),
     "cid_read_kmer_order": (C.c_int, [vp, vp, u64p, C.c_uint64, u64p, C.c_uint64, C.POINTER(ReadIdParams), C.c_uint32,
                                       u32p, u8p, u16p]),
+    "cid_read_kmer_order32": (C.c_int, [vp, vp, u64p, C.c_uint64, u64p, C.c_uint64, C.POINTER(ReadIdParams), C.c_uint32,
+                                        u32p, u8p, u32p]),
     "cid_read_id_classify": (C.c_int, [vp, vp, vp, u64p, C.c_uint64, u64p, C.c_uint64, C.POINTER(ReadIdParams), u64p,
                                        C.c_double, C.POINTER(C.c_int32), u32p, u32p, u32p, u32p, C.c_uint32]),
     "cid_ctx_set_option": (C.c_int, [vp, C.c_char_p, C.c_int64]),

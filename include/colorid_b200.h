@@ -253,6 +253,10 @@ int cid_read_id_batch_dev(cid_index* idx, const char* d_bases, const char* d_qua
 int cid_read_kmer_order(cid_index* idx, const char* bases, const uint64_t* seq_offs, uint64_t nseq,
                         const uint64_t* read_offs, uint64_t nreads, const cid_readid_params* p, uint32_t order_cap,
                         uint32_t* order_n, uint8_t* order_seq, uint16_t* order_pos);
+/* The same with 32-bit positions (reads longer than 65,535 bases: contigs through stream_fasta). */
+int cid_read_kmer_order32(cid_index* idx, const char* bases, const uint64_t* seq_offs, uint64_t nseq,
+                          const uint64_t* read_offs, uint64_t nreads, const cid_readid_params* p, uint32_t order_cap,
+                          uint32_t* order_n, uint8_t* order_seq, uint32_t* order_pos);
 
 /* ---- read_id vote, host side: read_id_mt_pe.rs:187-251 kmer_poll_plus (+ :168-181, :695-698, :18-38)
  * Takes the per-read reports produced by cid_read_id_batch (insertion order) and classifies every

@@ -721,7 +721,7 @@ int orc_read_id_batch(orc_index* h, const char* bases, const uint64_t* seq_offs,
                       uint32_t* n_set, int32_t* cls_kind, uint32_t* hits, uint32_t* n_top,
                       uint32_t* top, uint32_t top_cap,
                       uint32_t* rep_n, uint32_t* rep_colour, uint32_t* rep_count, uint32_t rep_cap,
-                      uint32_t* order_n, uint8_t* order_seq, uint16_t* order_pos, uint32_t order_cap) {
+                      uint32_t* order_n, uint8_t* order_seq, uint32_t* order_pos, uint32_t order_cap) {
     Index& ix = h->ix;
     HbPolicy pol; pol.group_width = group_width; pol.reserve_before_find = reserve_before_find != 0;
     HbPolicy pol_entry; pol_entry.group_width = group_width;
@@ -749,7 +749,7 @@ int orc_read_id_batch(orc_index* h, const char* bases, const uint64_t* seq_offs,
                     for (uint32_t i = 0; i < order_n[r]; i++) {
                         // minimizer mode: bit 7 = the window spells the minimizer itself (1) or its reverse complement (0)
                         order_seq[r * (uint64_t)order_cap + i] = (uint8_t)(keys[order[i]].seq | (ix.m ? (keys[order[i]].fwd << 7) : 0));
-                        order_pos[r * (uint64_t)order_cap + i] = (uint16_t)keys[order[i]].pos;
+                        order_pos[r * (uint64_t)order_cap + i] = (uint32_t)keys[order[i]].pos;
                     }
                 }
                 Report rep(pol_entry);

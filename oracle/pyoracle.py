@@ -314,13 +314,13 @@ class Index:
         rep_v = np.zeros((nr, rep_cap), np.uint32)
         ord_n = np.zeros(nr, np.uint32)
         ord_s = np.zeros((nr, max(order_cap, 1)), np.uint8)
-        ord_p = np.zeros((nr, max(order_cap, 1)), np.uint16)
+        ord_p = np.zeros((nr, max(order_cap, 1)), np.uint32)
         lib().orc_read_id_batch(
             self.h, _p(bases, C.c_char_p), _p(offs, u64p), _p(roffs, u64p), C.c_uint64(nr), C.c_uint32(d),
             C.c_uint32(start_sample), _p(n_ref, u64p), C.c_double(fp_correct), C.c_int(group_width),
             C.c_int(int(reserve_before_find)), C.c_int(threads), _p(n_set, u32p), _p(kind, i32p), _p(hits, u32p),
             _p(n_top, u32p), _p(top, u32p), C.c_uint32(top_cap), _p(rep_n, u32p), _p(rep_c, u32p), _p(rep_v, u32p),
-            C.c_uint32(rep_cap), _p(ord_n, u32p) if order_cap else None, _p(ord_s, u8p), _p(ord_p, u16p),
+            C.c_uint32(rep_cap), _p(ord_n, u32p) if order_cap else None, _p(ord_s, u8p), _p(ord_p, u32p),
             C.c_uint32(order_cap))
         return dict(n_set=n_set, kind=kind, hits=hits, n_top=n_top, top=top, rep_n=rep_n, rep_colour=rep_c,
                     rep_count=rep_v, order_n=ord_n, order_seq=ord_s, order_pos=ord_p)

@@ -363,11 +363,11 @@ def test_perfect_search_multifasta_records(oracle, ctx):
         ctx.set_option("query_front", 1)
 
 
-def _readid_compare(oracle, oix, gix, reads, **kw):
+def _readid_compare(oracle, oix, gix, reads, order_cap=600, **kw):
     okw = dict(kw)
-    o = oix.read_id_batch(reads, order_cap=600, **okw)
+    o = oix.read_id_batch(reads, order_cap=order_cap, **okw)
     on, osq, opos = gix.read_kmer_order(reads, d=kw.get("d", 1), group_width=kw.get("group_width", 16),
-                                        reserve_before_find=kw.get("reserve_before_find", True), order_cap=600)
+                                        reserve_before_find=kw.get("reserve_before_find", True), order_cap=order_cap)
     ok_reads = o["kind"] != oracle.CLS_PANIC
     assert np.array_equal(on[ok_reads], o["order_n"][ok_reads])
     for r in np.flatnonzero(ok_reads):
@@ -412,7 +412,7 @@ def test_read_id_narrow_rows(oracle, ctx, N, k, S, H):
 
 def test_read_id_reads_up_to_1000_bases(oracle, ctx):
     """Reads (all mates together) of up to 1,000 bases: the general order kernel with u16 tables of up to 2,048 buckets, fewer
-    reads per CTA as the tables grow; above 1,000 bases the call refuses loudly."""
+    reads per CTA as the tables grow (longer reads: test_read_id_long_reads)."""
     rng = _rng(950)
     genomes, oix, gix = _index_pair(oracle, ctx, rng, 20, 31, 1_000_003, 4, glen=6000)
     reads = []
@@ -423,9 +423,98 @@ def test_read_id_reads_up_to_1000_bases(oracle, ctx):
     for kw in (dict(d=4), dict(start_sample=0), dict()):
         o, g = _readid_compare(oracle, oix, gix, reads, **kw)
     assert int(o["n_set"].max()) > 900
-    with pytest.raises(cb.lib.CidError) as ei:
-        gix.read_id_batch([[genomes[0][:1001]]])
-    assert ei.value.code == cb.lib.CID_E_UNSUPPORTED
+    assert not (g["flags"] & 16).any()          # none of these took the general path
+
+
+def test_read_id_long_reads(oracle, ctx):
+    """Reads above 1,000 bases (read_id_mt_pe.rs:450-569 stream_fasta hands whole contigs to parallel_vec; long-read FASTQ)
+    go through the CTA-per-read general path: the same k-mer set order (hashbrown tables of up to 65,536 buckets here),
+    reports and flags as the oracle, mixed with short reads in one batch."""
+    rng = _rng(951)
+    genomes, oix, gix = _index_pair(oracle, ctx, rng, 20, 31, 1_000_003, 4, glen=30_000)
+    gix.n_ref[:] = oix.n_ref
+    reads = []
+    for L_ in (1001, 1023, 1500, 2048, 4000, 12_000):
+        reads += synth.reads_from(rng, genomes, 4, read_len=L_, insert=L_ + 50, err=0.002, frac_random=0.25, paired=False)
+    reads += synth.reads_from(rng, genomes, 4, read_len=800, insert=2000, err=0.001, frac_random=0.0)            # 2 x 800
+    reads += synth.reads_from(rng, genomes, 4, read_len=700, insert=900, err=0.0, frac_random=0.0)               # overlapping mates
+    reads += synth.reads_from(rng, genomes, 30, read_len=150, insert=320, err=0.004, frac_random=0.2)            # fast path
+    reads.append([genomes[3]])                                           # a whole accession: no absent row, counts of ~30k
+    reads.append([genomes[5][:9000], synth.revcomp(genomes[5][4000:15_000])])
+    reads.append([synth.sprinkle(rng, genomes[7][:5000], b"NRn", 0.01)])
+    reads.append([genomes[2][:3000] + genomes[2][:3000]])                # every k-mer twice: duplicates at the tail
+    reads.append([b"ACGT", genomes[0][:2000]])                           # too_short
+    reads.append([genomes[0][:2000], b"ACGTAC"])                         # reference panics
+    reads.append([b"N" * 1500])
+    reads.append([synth.rand_seq(rng, 1800)])
+    for kw in (dict(), dict(start_sample=0), dict(d=3, start_sample=1), dict(reserve_before_find=False), dict(group_width=8)):
+        o, g = _readid_compare(oracle, oix, gix, reads, order_cap=31_000, **kw)
+    longish = np.array([sum(len(m) for m in r) > 1000 and len(r[0]) >= 31 for r in reads])      # (too_short never leaves the fast kernel)
+    assert np.array_equal((g["flags"] & 16) != 0, longish)
+    assert int(o["n_set"].max()) > 29_000
+    # the fused pipeline (device vote + host re-vote) on the same batch, one chunk and several
+    oc = oix.read_id_batch(reads)
+    try:
+        for chunk in (0, 9):
+            ctx.set_option("readid_chunk_reads", chunk)
+            gc = gix.read_id_classify(reads)
+            for key in ("kind", "hits", "n_set", "n_top"):
+                assert np.array_equal(gc[key], oc[key]), f"chunk={chunk}: {key}"
+            for r in range(len(reads)):
+                nt = min(int(oc["n_top"][r]), 8)
+                assert gc["top"][r, :nt].tolist() == oc["top"][r, :nt].tolist()
+    finally:
+        ctx.set_option("readid_chunk_reads", 0)
+
+
+def test_read_id_table_exactly_full_at_the_tail(oracle, ctx):
+    """hashbrown >= 0.14 reserves before it looks the key up: a duplicate insert arriving when the table is exactly full
+    resizes it.  Sets of exactly 7/8 * 2^n k-mers followed by a duplicate, on both read_id paths and both growth rules."""
+    rng = _rng(952)
+    k = 21
+    genomes, oix, gix = _index_pair(oracle, ctx, rng, 6, k, 300_007, 3, glen=9000)
+    reads = []
+    for nk in (14, 28, 56, 112, 224, 448, 896, 1792, 3584, 7168):
+        g = genomes[int(rng.integers(0, 6))]
+        first = g[:nk + k - 1]                                       # nk distinct k-mers
+        reads.append([first, first[:k + 3]])                         # + duplicates at the tail
+        reads.append([first])                                        # no tail duplicate
+        reads.append([first + g[nk + k - 1:nk + k + 1]])             # two more fresh k-mers
+    for kw in (dict(), dict(reserve_before_find=False)):
+        _readid_compare(oracle, oix, gix, reads, order_cap=8000, **kw)
+
+
+def test_read_id_lowercase_kmers(oracle, ctx):
+    """kmer.rs:221-243 never upper-cases: a soft-masked (lower-case) k-mer of a read is hashed with its raw bytes, for the set
+    order and for the rows.  Such reads take the general path; upper-case reads of the same batch stay on the fast one."""
+    rng = _rng(953)
+    genomes, oix, gix = _index_pair(oracle, ctx, rng, 12, 27, 500_009, 4, glen=8000)
+    gix.n_ref[:] = oix.n_ref
+    base = synth.reads_from(rng, genomes, 60, read_len=150, insert=320, err=0.002, frac_random=0.1)
+    reads = []
+    for i, r in enumerate(base):
+        if i % 4 == 0: r = [m.lower() for m in r]                                   # all lower case
+        elif i % 4 == 1: r = [r[0][:70] + r[0][70:110].lower() + r[0][110:], r[1]]  # a soft-masked stretch
+        elif i % 4 == 2: r = [synth.sprinkle(rng, m, b"acgtn", 0.02) for m in r]    # scattered lower-case bases
+        reads.append(r)
+    reads.append([genomes[1][:4000].lower()])                                       # long and lower case
+    reads.append([genomes[1][:40] + b"n" + genomes[1][41:150]])                     # 'n' is not a base: no lower-case k-mer
+    def has_lower_kmer(read, k, d):
+        for m in read:
+            for i in range(0, len(m) - k + 1, d):
+                w = m[i:i + k]
+                if all(c in b"ACGTacgt" for c in w) and any(c in b"acgt" for c in w):
+                    return True
+        return False
+    for kw in (dict(), dict(start_sample=0), dict(d=2)):
+        o, g = _readid_compare(oracle, oix, gix, reads, order_cap=4200, **kw)
+        general = np.array([has_lower_kmer(r, 27, kw.get("d", 1)) or sum(len(m) for m in r) > 1000 for r in reads])
+        assert np.array_equal((g["flags"] & 16) != 0, general)
+        assert general.sum() > 30 and not general[-1]
+    oc = oix.read_id_batch(reads)
+    gc = gix.read_id_classify(reads)
+    for key in ("kind", "hits", "n_set", "n_top"):
+        assert np.array_equal(gc[key], oc[key]), key
 
 
 def test_read_id_wide_rows(oracle, ctx):
