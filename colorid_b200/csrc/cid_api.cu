@@ -67,14 +67,17 @@ static void prof_collect(cid_ctx* c) {
     c->prof_recs.clear();
 }
 
-int check_err_flags(cid_ctx* ctx, cudaStream_t st) {
+// lower_raw != nullptr: a raw-case input with lower-case k-mers is not an error for this caller -- it is told so and redoes
+// the work with case-aware count-table slots (ctx->case_aware)
+int check_err_flags(cid_ctx* ctx, cudaStream_t st, bool* lower_raw) {
     CID_CUDA(cudaMemcpyAsync(ctx->h_err, ctx->d_err, 4, cudaMemcpyDeviceToHost, st));
     CID_CUDA(cudaStreamSynchronize(st));
     uint32_t f = ctx->h_err[0];
     if (!f) return CID_OK;
     CID_CUDA(cudaMemsetAsync(ctx->d_err, 0, 8, st));
+    if ((f & ERRF_LOWER_RAW) && lower_raw) { *lower_raw = true; f &= ~(uint32_t)ERRF_LOWER_RAW; if (!f) return CID_OK; }
     if (f & ERRF_LOWER_RAW) {
-        set_error("lower-case bases inside k-mers of a raw-case input (FASTQ / read_id) are not supported on the device yet");
+        set_error("lower-case bases inside k-mers of a raw-case (FASTQ) input are not supported for minimizer indexes");
         return CID_E_UNSUPPORTED;
     }
     if (f & ERRF_STRING_NONACGT) {
@@ -120,7 +123,7 @@ static int auto_cutoff_dense(const std::vector<uint64_t>& h, uint64_t max_cov, i
 
 __global__ void table_clear_kernel(Slot* t, uint64_t n) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        Slot s; s.key = CID_EMPTY_KEY; s.count = 0; s.pad = 0;
+        Slot s; s.key = CID_EMPTY_KEY; s.count = 0; s.pad = CID_CS_UNSET;
         t[i] = s;
     }
 }
@@ -481,6 +484,11 @@ static int build_accession_impl(cid_index* ix, uint32_t colour, const char* d_ba
     CID_CUDA(cudaSetDevice(ctx->device));
     CID_TRY(ensure_bitsets(ix));
     uint32_t* bitset = ix->bitsets + (uint64_t)colour * ix->bs_words;
+    // kmers_from_fq_qual / kmers_fq_pe_qual (kmer.rs:461-510,581-655) keep the case of their k-mers.  The fast tables hold
+    // 2-bit codes only: a pass that meets a lower-case k-mer reports it, and the accession is redone through the 16-byte
+    // count table whose slots carry a case mask (k-mer indexes; minimizer indexes refuse such input).
+    struct CaseGuard { cid_ctx* c; ~CaseGuard() { c->case_aware = false; } } case_guard{ctx};
+    const bool can_case = seq_mode == CID_SEQ_FASTQ && mini_variant < 0;
     // No count filter (FASTA without -f: build.rs:86-87; or -f 0): only the SET of k-mers matters.  A key-only table
     // (8-byte slots, L2-resident for a bacterial genome) replaces the count table and new keys go straight into the bitset.
     if (ctx->opt_build_set && (cutoff == 0 || (cutoff == -1 && seq_mode == CID_SEQ_FASTA))) {
@@ -498,6 +506,11 @@ static int build_accession_impl(cid_index* ix, uint32_t colour, const char* d_ba
             CID_CUDA(cudaMemcpyAsync(ctx->h_err, ctx->d_err, 8, cudaMemcpyDeviceToHost, st));
             CID_CUDA(cudaStreamSynchronize(st));
             const uint32_t flags = ctx->h_err[0], distinct = ctx->h_err[1];
+            if ((flags & ERRF_LOWER_RAW) && can_case) {           // lower-case k-mers: through the case-aware count table
+                CID_CUDA(cudaMemsetAsync(ctx->d_err, 0, 8, st));
+                ctx->case_aware = true;
+                break;
+            }
             if ((flags & ERRF_TABLE_FULL) || (uint64_t)distinct * 10 > slots * 7) {       // too full to trust the probe limit: redo larger
                 if (slots >= next_pow2(std::max<uint64_t>(1024, 2 * npos0))) { set_error("k-mer set overflow"); return CID_E_CAPACITY; }
                 CID_CUDA(cudaMemsetAsync(ctx->d_err, 0, 8, st));
@@ -526,7 +539,7 @@ static int build_accession_impl(cid_index* ix, uint32_t colour, const char* d_ba
     }
     // keys of <= 21 bases (k, or the minimizer length of build_multi_mini) leave room for the count in the same 8-byte
     // word: half the table, one atomic per insert.  A multiplicity near 2^22 sends the accession back to 16-byte slots.
-    bool packed = ctx->opt_build_packed && (count_m ? count_m : ix->k) <= 21;
+    bool packed = ctx->opt_build_packed && (count_m ? count_m : ix->k) <= 21 && !ctx->case_aware;
     for (;;) {
         CID_TRY(single_region(ctx, st, nbases, ix->k, &nslots, &d_off, &d_mask, hint, packed));
         CID_CUDA(cudaMemsetAsync(ctx->d_err + 1, 0, 4, st));
@@ -535,6 +548,12 @@ static int build_accession_impl(cid_index* ix, uint32_t colour, const char* d_ba
         CID_CUDA(cudaMemcpyAsync(ctx->h_err, ctx->d_err, 8, cudaMemcpyDeviceToHost, st));
         CID_CUDA(cudaStreamSynchronize(st));
         const uint32_t flags = ctx->h_err[0], distinct = ctx->h_err[1];
+        if ((flags & ERRF_LOWER_RAW) && can_case && !ctx->case_aware) {
+            CID_CUDA(cudaMemsetAsync(ctx->d_err, 0, 8, st));
+            ctx->case_aware = true;
+            packed = false;
+            continue;
+        }
         if (flags & ERRF_COUNT_OVERFLOW) {
             CID_CUDA(cudaMemsetAsync(ctx->d_err, 0, 8, st));
             packed = false;
@@ -859,12 +878,17 @@ int cid_query_counts(cid_index* ix, const char* bases, const uint64_t* seq_offs,
     if (uniq_sum) memset(uniq_sum, 0, nq * N * 8);
     if (uniq_mode) memset(uniq_mode, 0, nq * N * 8);
 
+    // Raw-case (FASTQ) queries keep the case of their k-mers (kmer.rs:461-510,581-655); the fast tables hold 2-bit codes only.
+    // A pass that meets a lower-case k-mer reports it (`lower`) and the work is redone through the count table with
+    // case-aware slots (ctx->case_aware, reset when this call returns).
+    struct CaseGuard { cid_ctx* c; ~CaseGuard() { c->case_aware = false; } } case_guard{ctx};
+    bool lower = false;
     const bool all_distinct = (seq_mode == CID_SEQ_FASTA && gene_search) || filter == 0;
     if (all_distinct && nq && query_front_ok(ix, want_uniq, seq_offs, query_offs, nq)) {
         CID_TRY(ctx->scratch[7].ensure((nq + 1) * 8));
         CID_CUDA(cudaMemcpyAsync(ctx->scratch[7].p, query_offs, (nq + 1) * 8, cudaMemcpyHostToDevice, st));
         std::vector<uint64_t> fcuts = query_front_batches(seq_offs, query_offs, nq);
-        for (size_t b = 0; b + 1 < fcuts.size(); b++) {
+        for (size_t b = 0; b + 1 < fcuts.size() && !lower; b++) {
             const uint64_t q0 = fcuts[b], q1 = fcuts[b + 1], bq = q1 - q0;
             CID_TRY(ctx->scratch[10].ensure(bq * N * 4));
             CID_TRY(ctx->scratch[11].ensure(bq * 8));
@@ -872,13 +896,15 @@ int cid_query_counts(cid_index* ix, const char* bases, const uint64_t* seq_offs,
             CID_CUDA(cudaMemsetAsync(ctx->scratch[11].p, 0, bq * 8, st));
             CID_TRY(launch_query_front_gather(ctx, st, ix, d_bases, d_seq_offs, ctx->scratch[7].as<uint64_t>(), seq_offs, query_offs,
                                               q0, q1, seq_mode, ctx->scratch[10].as<uint32_t>(), ctx->scratch[11].as<unsigned long long>()));
-            CID_TRY(check_err_flags(ctx, st));
+            CID_TRY(check_err_flags(ctx, st, &lower));
+            if (lower) break;
             CID_CUDA(cudaMemcpyAsync(counts + q0 * N, ctx->scratch[10].p, bq * N * 4, cudaMemcpyDeviceToHost, st));
             CID_CUDA(cudaMemcpyAsync(num_kmers + q0, ctx->scratch[11].p, bq * 8, cudaMemcpyDeviceToHost, st));
             CID_CUDA(cudaStreamSynchronize(st));
             if (cutoff_used) for (uint64_t q = q0; q < q1; q++) cutoff_used[q] = 0;
         }
-        return CID_OK;
+        if (!lower) return CID_OK;
+        ctx->case_aware = true;          // every query again, through the count table
     }
     std::vector<uint64_t> cuts = query_batches(seq_offs, query_offs, nq, ix->k, kMaxBatchSlots);
     static const bool trace = getenv("CID_TRACE") != nullptr;     // host stage timings on stderr (diagnostics only)
@@ -888,7 +914,9 @@ int cid_query_counts(cid_index* ix, const char* bases, const uint64_t* seq_offs,
         QueryPlan qp;
         const double t_0 = now();
         CID_TRY(query_front(ix, st, d_bases, d_seq_offs, seq_offs, query_offs, q0, q1, seq_mode, qp));
-        CID_TRY(check_err_flags(ctx, st));
+        lower = false;
+        CID_TRY(check_err_flags(ctx, st, ctx->case_aware ? nullptr : &lower));
+        if (lower) { ctx->case_aware = true; b--; continue; }        // this batch again, case-aware
         const double t_front = now();
         // per-query filter (batch_search_pe.rs:34-39 / :112-120)
         std::vector<int64_t> filt(bq);
@@ -960,8 +988,14 @@ int cid_query_survivors(cid_index* ix, const char* bases, const uint64_t* seq_of
     if (nbases) CID_CUDA(cudaMemcpyAsync(ctx->scratch[4].p, bases, nbases, cudaMemcpyHostToDevice, st));
     CID_CUDA(cudaMemcpyAsync(ctx->scratch[5].p, seq_offs, (nseq + 1) * 8, cudaMemcpyHostToDevice, st));
     QueryPlan qp;
-    CID_TRY(query_front(ix, st, ctx->scratch[4].as<uint8_t>(), ctx->scratch[5].as<uint64_t>(), seq_offs, query_offs, 0, nq, seq_mode, qp));
-    CID_TRY(check_err_flags(ctx, st));
+    struct CaseGuard { cid_ctx* c; ~CaseGuard() { c->case_aware = false; } } case_guard{ctx};
+    for (;;) {
+        CID_TRY(query_front(ix, st, ctx->scratch[4].as<uint8_t>(), ctx->scratch[5].as<uint64_t>(), seq_offs, query_offs, 0, nq, seq_mode, qp));
+        bool lower = false;
+        CID_TRY(check_err_flags(ctx, st, ctx->case_aware ? nullptr : &lower));
+        if (!lower) break;
+        ctx->case_aware = true;          // lower-case k-mers of a raw-case query: the slots carry their case masks
+    }
     std::vector<int64_t> filt(nq);
     std::vector<uint64_t> sv(nq, UINT64_MAX);
     for (uint64_t q = 0; q < nq; q++) {          // batch_search_pe.rs:34-39 / :112-120

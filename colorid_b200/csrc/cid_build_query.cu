@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(KT_THREADS)
 kmerize_insert_kernel(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ seq_offs, uint64_t nseq,
                       uint64_t base_lo, uint64_t nbases, const uint32_t* __restrict__ seq_group, const uint64_t* __restrict__ region_off,
                       const uint64_t* __restrict__ region_mask, Slot* __restrict__ table, uint32_t k, uint32_t mini_m,
-                      int seq_mode, uint32_t* __restrict__ err, SetSink sink) {
+                      int seq_mode, uint32_t* __restrict__ err, SetSink sink, uint32_t cs_on) {
     __shared__ __align__(16) uint8_t smem[tile_smem_bytes(KT_CAP)];
     __shared__ uint32_t lut[SETONLY ? 256 : 1];
     if (SETONLY) lut4_init(lut, threadIdx.x, KT_THREADS);      // made visible by the barriers below
@@ -108,7 +108,14 @@ kmerize_insert_kernel(const uint8_t* __restrict__ bases, const uint64_t* __restr
                 atomicOr(err, ERRF_STRING_NONACGT);
             continue;
         }
-        if (low && seq_mode == CID_SEQ_FASTQ) { atomicOr(err, ERRF_LOWER_RAW); continue; }
+        uint32_t cs = 0;
+        if (low && seq_mode == CID_SEQ_FASTQ) {
+            // kmer.rs:461-510,581-655 keep the case: the k-mer is (codes, case mask), which only the 16-byte count table of a
+            // case-aware pass can hold; any other pass reports it and the caller redoes the work that way
+            if (!cs_on || MINI || SETONLY || sink.packed) { atomicOr(err, ERRF_LOWER_RAW); continue; }
+            const uint32_t lw = mask_window(t.lower, p, k);
+            cs = fwd ? lw : (__brev(lw) >> (32 - k));
+        }
         if (MINI) {     // build_multi_mini: the counted item is the k-mer's minimizer (kmer.rs:328-361, 694-824)
             uint32_t mpos; bool mfwd;
             key = tile_minimizer(t, p, k, mini_m, key, fwd, low, mpos, mfwd);
@@ -136,7 +143,8 @@ kmerize_insert_kernel(const uint8_t* __restrict__ bases, const uint64_t* __restr
         } else {
             uint64_t owner = s0 + lo;
             uint32_t g = seq_group ? __ldg(seq_group + owner) : 0u;
-            rc = table_insert(table + __ldg(region_off + g), __ldg(region_mask + g), key);
+            rc = cs_on ? table_insert_cs(table + __ldg(region_off + g), __ldg(region_mask + g), key, cs)
+                       : table_insert(table + __ldg(region_off + g), __ldg(region_mask + g), key);
         }
         if (rc < 0) atomicOr(err, ERRF_TABLE_FULL);
         fresh += rc > 0;
@@ -160,11 +168,11 @@ int launch_kmerize_insert(cid_ctx* ctx, cudaStream_t st, const uint8_t* d_bases,
     if (mini_m)
         kmerize_insert_kernel<true, false><<<(unsigned)ntiles, KT_THREADS, 0, st>>>(d_bases, d_seq_offs, nseq, base_lo, base_hi, d_seq_group,
                                                                                    d_region_off, d_region_mask, (Slot*)d_table, k, mini_m,
-                                                                                   seq_mode, ctx->d_err, none);
+                                                                                   seq_mode, ctx->d_err, none, 0u);
     else
         kmerize_insert_kernel<false, false><<<(unsigned)ntiles, KT_THREADS, 0, st>>>(d_bases, d_seq_offs, nseq, base_lo, base_hi, d_seq_group,
                                                                                     d_region_off, d_region_mask, (Slot*)d_table, k, 0,
-                                                                                    seq_mode, ctx->d_err, none);
+                                                                                    seq_mode, ctx->d_err, none, (ctx->case_aware && !packed_slots) ? 1u : 0u);
     ctx->launches++;
     CID_CUDA(cudaGetLastError());
     return CID_OK;
@@ -181,10 +189,10 @@ int launch_kmerize_bloom(cid_ctx* ctx, cudaStream_t st, const uint8_t* d_bases, 
     ProfScope ps(ctx, st, KID_KMERIZE_INSERT);
     if (count_m)
         kmerize_insert_kernel<true, true><<<(unsigned)ntiles, KT_THREADS, 0, st>>>(d_bases, d_seq_offs, nseq, 0, nbases, nullptr, nullptr, nullptr,
-                                                                                  nullptr, k, count_m, seq_mode, ctx->d_err, sink);
+                                                                                  nullptr, k, count_m, seq_mode, ctx->d_err, sink, 0u);
     else
         kmerize_insert_kernel<false, true><<<(unsigned)ntiles, KT_THREADS, 0, st>>>(d_bases, d_seq_offs, nseq, 0, nbases, nullptr, nullptr, nullptr,
-                                                                                   nullptr, k, 0, seq_mode, ctx->d_err, sink);
+                                                                                   nullptr, k, 0, seq_mode, ctx->d_err, sink, 0u);
     ctx->launches++;
     CID_CUDA(cudaGetLastError());
     return CID_OK;
@@ -265,6 +273,7 @@ region_to_bloom_kernel(const void* __restrict__ region, uint64_t nslots, long lo
             len = mini_m;
         }
         HashIn in = hashin_from_key(lut, item, len);
+        if (!mini_m) hashin_apply_case(in, v.cs, len);      // (a minimizer index never runs a case-aware pass)
         for (uint32_t i = 0; i < H; i++) {
             uint64_t bit = mod_s(xxh3_kmer(in, len, i), mods);
             atomicOr(&bitset[bit >> 5], 1u << (bit & 31));
@@ -375,18 +384,20 @@ struct UnitSmem {
     uint32_t* lut;        // [256]
     uint64_t* keys;       // [QUERY_CHUNK]
     uint32_t* mult;       // [QUERY_CHUNK]
+    uint32_t* cs;         // [QUERY_CHUNK] case masks of raw-case k-mers (0 everywhere else)
     uint32_t* rowid;      // [QUERY_CHUNK * H]
     uint32_t* cnt;        // [32 * 32 * 4] per-accession counters of one column block (32 lanes x VEC<=4 words)
     uint32_t* n;          // [4] list length, missing flag
 };
 __host__ __device__ inline size_t unit_smem_bytes(uint32_t H) {
-    return 256 * 4 + (size_t)QUERY_CHUNK * 8 + (size_t)QUERY_CHUNK * 4 + (size_t)QUERY_CHUNK * H * 4 + 4096 * 4 + 16;
+    return 256 * 4 + (size_t)QUERY_CHUNK * 8 + (size_t)QUERY_CHUNK * 8 + (size_t)QUERY_CHUNK * H * 4 + 4096 * 4 + 16;
 }
 __device__ __forceinline__ UnitSmem unit_carve(uint8_t* base, uint32_t H) {
     UnitSmem u;
     u.keys = (uint64_t*)base;
     u.mult = (uint32_t*)(u.keys + QUERY_CHUNK);
-    u.rowid = u.mult + QUERY_CHUNK;
+    u.cs = u.mult + QUERY_CHUNK;
+    u.rowid = u.cs + QUERY_CHUNK;
     u.cnt = u.rowid + (size_t)QUERY_CHUNK * H;
     u.lut = u.cnt + 4096;
     u.n = u.lut + 256;
@@ -405,12 +416,14 @@ __device__ __forceinline__ uint32_t unit_collect_and_hash(const UnitSmem& u, con
             uint32_t i = atomicAdd(&u.n[0], 1u);
             u.keys[i] = v.key;
             u.mult[i] = v.count;
+            u.cs[i] = slot_cs(v.pad);
         }
     }
     __syncthreads();
     const uint32_t n = u.n[0];
     for (uint32_t i = tid; i < n; i += nt) {
         HashIn in = hashin_from_key(u.lut, u.keys[i], k);
+        hashin_apply_case(in, u.cs[i], k);
         for (uint32_t h = 0; h < H; h++) u.rowid[i * H + h] = (uint32_t)mod_s(xxh3_kmer(in, k, h), mods);
     }
     __syncthreads();
@@ -631,6 +644,7 @@ query_hash_kernel(const Slot* __restrict__ table, const uint32_t* __restrict__ u
                   uint32_t* __restrict__ unit_n, unsigned long long* __restrict__ num_kmers) {
     __shared__ uint32_t lut[256];
     __shared__ unsigned long long keys[QUERY_CHUNK];
+    __shared__ uint32_t kcs[QUERY_CHUNK];
     __shared__ uint32_t s_n;
     const int tid = threadIdx.x;
     lut4_init(lut, tid, 256);
@@ -646,13 +660,17 @@ query_hash_kernel(const Slot* __restrict__ table, const uint32_t* __restrict__ u
         const uint32_t cn = min((uint32_t)QUERY_CHUNK, nslots - c0);
         for (uint32_t s = tid; s < cn; s += 256) {
             const Slot v = table[slot0 + c0 + s];
-            if (v.key != CID_EMPTY_KEY && (long long)v.count > filt) keys[atomicAdd(&s_n, 1u)] = v.key;
+            if (v.key != CID_EMPTY_KEY && (long long)v.count > filt) {
+                const uint32_t at = atomicAdd(&s_n, 1u);
+                keys[at] = v.key; kcs[at] = slot_cs(v.pad);
+            }
         }
         __syncthreads();
         const uint32_t n = s_n;
         // survivors so far <= slots scanned so far, so the compact list never leaves the item's slot range
         for (uint32_t i = tid; i < n; i += 256) {
-            const HashIn in = hashin_from_key(lut, keys[i], k);
+            HashIn in = hashin_from_key(lut, keys[i], k);
+            hashin_apply_case(in, kcs[i], k);
             uint32_t* out = rid_out + (slot0 + total + i) * H;
             for (uint32_t h = 0; h < H; h++) out[h] = (uint32_t)mod_s(xxh3_kmer(in, k, h), mods);
         }
@@ -1081,7 +1099,7 @@ query_front_kernel(const uint8_t* __restrict__ bases, const uint64_t* __restrict
                                       rid_out + base * H, err, key))
                         continue;
                 }
-                if (low && seq_mode == CID_SEQ_FASTQ) { atomicOr(err, ERRF_LOWER_RAW); continue; }
+                if (low && seq_mode == CID_SEQ_FASTQ) { atomicOr(err, ERRF_LOWER_RAW); continue; }     // (the caller redoes the call case-aware)
                 uint32_t h = (uint32_t)mix64(key) & tmask;
                 bool fresh = false;
                 for (;;) {
@@ -1479,7 +1497,8 @@ slots_popcount_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t k
 #pragma unroll
         for (int h = 0; h < MAX_HASH; h++) rid_l[h] = 0;
         if (i0 + lane < n) {
-            const HashIn in = hashin_from_key(lut, slots[i0 + lane].key, k);
+            HashIn in = hashin_from_key(lut, slots[i0 + lane].key, k);
+            hashin_apply_case(in, slot_cs(slots[i0 + lane].pad), k);
 #pragma unroll
             for (int h = 0; h < MAX_HASH; h++) if ((uint32_t)h < H) rid_l[h] = (uint32_t)mod_s(xxh3_kmer(in, k, h), mods);
         }

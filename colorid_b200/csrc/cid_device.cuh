@@ -130,6 +130,27 @@ __device__ __forceinline__ HashIn hashin_from_key(const uint32_t* lut, uint64_t 
     return in;
 }
 
+// Raw-case inputs (kmers_from_fq_qual / kmers_fq_pe_qual, kmer.rs:461-510,581-655: no to_uppercase) keep lower-case bases in
+// their k-mers: such a k-mer is the packed codes plus a case mask `cs` (bit j = byte j of the canonical string is lower case).
+// Lower-case ASCII = upper-case | 0x20: spread 8 mask bits over the 8 bytes of a word.
+__device__ __forceinline__ uint64_t case_bytes8(uint32_t bits8) {
+    const uint64_t t = ((uint64_t)(bits8 & 0xFFu) * 0x0101010101010101ULL) & 0x8040201008040201ULL;    // byte i keeps bit i
+    return (((t + 0x7F7F7F7F7F7F7F7FULL) >> 7) & 0x0101010101010101ULL) * 0x20ULL;
+}
+__device__ __forceinline__ void hashin_apply_case(HashIn& in, uint32_t cs, uint32_t k) {
+    if (cs == 0u) return;
+    if (k >= 17) {
+        in.w0 |= case_bytes8(cs); in.w1 |= case_bytes8(cs >> 8);
+        in.w2 |= case_bytes8(cs >> (k - 16)); in.w3 |= case_bytes8(cs >> (k - 8));
+    } else if (k >= 9) {
+        in.w0 |= case_bytes8(cs); in.w1 |= case_bytes8(cs >> (k - 8));
+    } else if (k >= 4) {
+        in.w0 |= case_bytes8(cs & 0xFu) & 0xFFFFFFFFULL; in.w1 |= case_bytes8((cs >> (k - 4)) & 0xFu) & 0xFFFFFFFFULL;
+    } else {
+        in.w0 |= (cs & 1u) << 5; in.w1 |= ((cs >> (k >> 1)) & 1u) << 5; in.w2 |= ((cs >> (k - 1)) & 1u) << 5;
+    }
+}
+
 // Low 32 bits of FNV-1a-64 over the k upper-case ASCII bytes of `key` followed by 0xFF
 // (`impl Hash for str`).  The low 32 bits of h*0x100000001b3 depend only on the low 32 bits of h.
 __device__ __forceinline__ uint32_t fnv1a_low32_key(uint64_t key, uint32_t k) {
@@ -397,8 +418,12 @@ __device__ __forceinline__ uint64_t tile_minimizer(const Tile& t, int i, uint32_
 }
 
 // ------------------------------------------------------------------ count table (open addressing)
+// `pad` is the case mask of a raw-case k-mer (see hashin_apply_case) in tables filled by table_insert_cs, CID_CS_UNSET
+// (what table_clear writes) everywhere else: slot_cs() is what the hashing kernels apply.
 struct __align__(16) Slot { unsigned long long key; uint32_t count; uint32_t pad; };
 #define CID_EMPTY_KEY 0xFFFFFFFFFFFFFFFFULL
+#define CID_CS_UNSET 0xFFFFFFFFu
+__device__ __forceinline__ uint32_t slot_cs(uint32_t pad) { return pad == CID_CS_UNSET ? 0u : pad; }
 
 __device__ __forceinline__ uint64_t mix64(uint64_t x) {   // murmur3 finalizer: slot choice only
     x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
@@ -412,6 +437,22 @@ __device__ __forceinline__ int table_insert(Slot* region, uint64_t mask, uint64_
     for (int probes = 0; probes < CID_MAX_PROBE; probes++) {
         unsigned long long prev = atomicCAS(&region[h].key, CID_EMPTY_KEY, (unsigned long long)key);
         if (prev == CID_EMPTY_KEY || prev == key) { atomicAdd(&region[h].count, 1u); return prev == CID_EMPTY_KEY ? 1 : 0; }
+        h = (h + 1) & mask;
+    }
+    return -1;
+}
+
+// Case-aware variant: the slot of (key, cs).  Two k-mers that differ only in case share their codes, so a slot whose codes
+// match is ours only if its case mask does too; whoever reaches a freshly claimed slot first settles its mask (the claim of
+// the codes and of the mask are two atomics, both idempotent for equal k-mers).  Returns 1 for the call that created the entry.
+__device__ __forceinline__ int table_insert_cs(Slot* region, uint64_t mask, uint64_t key, uint32_t cs) {
+    uint64_t h = mix64(key) & mask;
+    for (int probes = 0; probes < CID_MAX_PROBE; probes++) {
+        const unsigned long long prev = atomicCAS(&region[h].key, CID_EMPTY_KEY, (unsigned long long)key);
+        if (prev == CID_EMPTY_KEY || prev == key) {
+            const uint32_t c = atomicCAS(&region[h].pad, CID_CS_UNSET, cs);
+            if (c == CID_CS_UNSET || c == cs) { atomicAdd(&region[h].count, 1u); return c == CID_CS_UNSET ? 1 : 0; }
+        }
         h = (h + 1) & mask;
     }
     return -1;
@@ -440,15 +481,15 @@ __device__ __forceinline__ int packed_insert(unsigned long long* tab, uint64_t m
     }
     return -1;
 }
-struct SlotView { uint64_t key; uint32_t count; bool used; };
+struct SlotView { uint64_t key; uint32_t count; uint32_t cs; bool used; };
 template <bool PACKED> __device__ __forceinline__ SlotView slot_read(const void* table, uint64_t i) {
     SlotView v;
     if (PACKED) {
         const unsigned long long w = ((const unsigned long long*)table)[i];
-        v.used = w != CID_EMPTY_KEY; v.key = w >> CID_PK_BITS; v.count = (uint32_t)(w & CID_PK_CMASK);
+        v.used = w != CID_EMPTY_KEY; v.key = w >> CID_PK_BITS; v.count = (uint32_t)(w & CID_PK_CMASK); v.cs = 0;
     } else {
         const Slot s = ((const Slot*)table)[i];
-        v.used = s.key != CID_EMPTY_KEY; v.key = s.key; v.count = s.count;
+        v.used = s.key != CID_EMPTY_KEY; v.key = s.key; v.count = s.count; v.cs = slot_cs(s.pad);
     }
     return v;
 }

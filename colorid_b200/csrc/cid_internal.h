@@ -97,6 +97,7 @@ struct cid_ctx {
     int opt_query_compact = 1;       // count-table compaction of large queries: 0 = never, 1 = tables of >= 2^22 slots, 2 = always (tests)
     int opt_uniq_device = 1;         // 0 = unique-hit summaries always through the host maps (parity aid)
     int opt_query_fused = 0;         // 1 = force the fused collect/hash/gather kernel (parity aid)
+    bool case_aware = false;         // set while a raw-case (FASTQ) input with lower-case k-mers is redone: 16-byte count-table slots carry a case mask
     cudaStream_t aux[2] = {nullptr, nullptr};
     cudaEvent_t aux_fork = nullptr, aux_join[2] = {nullptr, nullptr};
 };
@@ -130,7 +131,7 @@ enum {
     ERRF_TABLE_FULL = 1u << 5,     // a count-table region overflowed (only possible with optimistic sizing: caller retries) // kmerize_string window with a byte outside ACGTacgt (cannot be 2-bit packed)
 };
 
-int check_err_flags(cid_ctx* ctx, cudaStream_t st);   // syncs the stream
+int check_err_flags(cid_ctx* ctx, cudaStream_t st, bool* lower_raw = nullptr);   // syncs the stream
 
 // kernel ids for the profiling hooks (names in cid_api.cu: kKernelNames)
 enum { KID_KMERIZE_INSERT = 0, KID_HISTOGRAM, KID_TO_BLOOM, KID_TRANSPOSE, KID_ROWNZ, KID_QUERY_COUNTS, KID_QUERY_UNIQ_WIDE,

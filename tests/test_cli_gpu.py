@@ -280,6 +280,49 @@ def test_read_id_paired_single_and_fasta(world, oracle):
 CLS_NAMES = {"too_short", "no_hits", "no_significant_hits"}
 
 
+def test_read_id_contigs_and_softmasked_reads(world, oracle):
+    """read_id_mt_pe.rs:450-569 stream_fasta on real assemblies: records are whole contigs (single-line and wrapped, one all
+    lower-case like refs/Staphylococcus_aureus_NCTC8532.fasta), far above the 1,000 bases of the warp-per-read kernels; and
+    a FASTQ whose reads carry soft-masked (lower-case) stretches, which kmer.rs:221-243 hashes as they are.  One odd read must
+    never abort the run: every line of PREFIX_reads.txt equals the oracle's."""
+    d, rng, genomes = world["dir"], world["rng"], world["genomes"]
+    recs = [("contig_wrapped", genomes[0][:6000]), ("contig_lower", genomes[1][:5000].lower()),
+            ("contig_mixed", synth.sprinkle(rng, genomes[2][1000:4200], b"acgtN", 0.03)), ("short", genomes[3][:200]),
+            ("random", synth.rand_seq(rng, 2500))]
+    wrap_fasta(d / "contigs.fasta", recs, width=80)
+    ids, reads = [], []
+    for name, s in recs:
+        ids.append(">" + name)
+        t = s.decode()
+        reads.append([("".join(t[i:i + 80] + "\n" for i in range(0, len(t), 80))).encode()])
+    exp_lines, exp_counts = _expected_read_lines(world, oracle, ids, reads)
+    run("read_id", "-b", d / "idx.bxi", "-q", d / "contigs.fasta", "-n", d / "ctg_out")
+    assert (d / "ctg_out_reads.txt").read_text().split("\n")[:-1] == exp_lines
+    assert (d / "ctg_out_counts.txt").read_text().split("\n")[:-1] == exp_counts
+    # single-line records: every k-mer of a contig is valid -> sets of thousands of k-mers, hits in the thousands
+    with open(d / "contigs1.fasta", "wb") as f:
+        for name, s in recs:
+            f.write(b">" + name.encode() + b"\n" + s + b"\n")
+    reads1 = [[s + b"\n"] for _, s in recs]
+    exp_lines, exp_counts = _expected_read_lines(world, oracle, ids, reads1)
+    run("read_id", "-b", d / "idx.bxi", "-q", d / "contigs1.fasta", "-n", d / "ctg1_out", "-B", 0)
+    exp0, expc0 = _expected_read_lines(world, oracle, ids, reads1, start_sample=0)
+    assert (d / "ctg1_out_reads.txt").read_text().split("\n")[:-1] == exp0
+    run("read_id", "-b", d / "idx.bxi", "-q", d / "contigs1.fasta", "-n", d / "ctg1b_out")
+    got = (d / "ctg1b_out_reads.txt").read_text().split("\n")[:-1]
+    assert got == exp_lines and int(got[0].split("\t")[3]) > 5000
+    # soft-masked FASTQ, single end
+    n, s1, s2, q1, q2 = read_pairs(rng, genomes[:5], 500, "m", read_len=120, insert=200, err=0.004, frac_random=0.1)
+    for i in range(0, 500, 3):
+        s1[i] = s1[i][:30] + s1[i][30:75].lower() + s1[i][75:]
+    (d / "m_1.fastq.gz").write_bytes(gzip.compress(fastq_bytes(n, s1, q1)))
+    reads = [[oracle.qual_mask(a, qa.encode(), 15)] for a, qa in zip(s1, q1)]
+    exp_lines, exp_counts = _expected_read_lines(world, oracle, ["@" + x for x in n], reads)
+    run("read_id", "-b", d / "idx.bxi", "-q", d / "m_1.fastq.gz", "-n", d / "m_out")
+    assert (d / "m_out_reads.txt").read_text().split("\n")[:-1] == exp_lines
+    assert (d / "m_out_counts.txt").read_text().split("\n")[:-1] == exp_counts
+
+
 def test_batch_id_classifies_every_sample_with_one_index_load(world, oracle):
     # read_id_batch.rs:7-181: SAMPLE_TAG_reads.txt / SAMPLE_TAG_counts.txt per line of the sample list
     d, rng, genomes = world["dir"], world["rng"], world["genomes"]

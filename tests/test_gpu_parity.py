@@ -630,11 +630,66 @@ def test_upload_rows_roundtrip(oracle, ctx):
     assert np.array_equal(g2.query_counts(q, gene_search=True, filt=0)["counts"], oix.query_counts(q, 0, True, 0)["counts"])
 
 
-def test_lowercase_fastq_is_refused_loudly(ctx):
-    gix = cb.Index(ctx, 10_007, 2, 11, 2)
-    with pytest.raises(cb.CidError) as e:
-        gix.build_accession(0, [b"acgtacgtacgtacgtacgtacgtacgt"], cb.CID_SEQ_FASTQ, 0)
-    assert e.value.code == cb.lib.CID_E_UNSUPPORTED
+def _softmask(rng, reads, frac=0.4):
+    """Lower-case stretches, whole lower-case mates and scattered lower-case bases in a fraction of the reads."""
+    out = []
+    for r in reads:
+        u = rng.random()
+        if u < frac / 3:
+            r = [m.lower() for m in r]
+        elif u < 2 * frac / 3:
+            a = int(rng.integers(0, max(1, len(r[0]) - 40)))
+            r = [r[0][:a] + r[0][a:a + 40].lower() + r[0][a + 40:]] + list(r[1:])
+        elif u < frac:
+            r = [synth.sprinkle(rng, m, b"acgt", 0.03) for m in r]
+        out.append(r)
+    return out
+
+
+@pytest.mark.parametrize("k", [15, 21, 27, 31])
+def test_build_and_search_fastq_lowercase_kmers(oracle, ctx, k):
+    """kmers_from_fq_qual / kmers_fq_pe_qual (kmer.rs:461-510,581-655) never upper-case: a lower-case k-mer of a read set is
+    counted, filtered and hashed with its raw bytes, as a k-mer of its own.  Builds (auto_cutoff, -f 0, -f 2; packed 8-byte
+    table for k <= 21, key-only set, 16-byte slots) and FASTQ searches (shared-memory front end, count table, compacted
+    survivors, unique-hit summaries) all redo such inputs through the case-aware count table."""
+    rng = _rng(40 + k)
+    S, H = 400_009, 3
+    genomes = synth.clade_genomes(rng, 4, 4000, n_clades=2, div=0.03)
+    accs = []
+    for i, g in enumerate(genomes):
+        reads = synth.reads_from(rng, [g], 700, read_len=100, insert=200, err=0.008, frac_random=0.0, n_rate=0.002)
+        if i != 1:
+            reads = _softmask(rng, reads)
+        accs.append([m for r in reads for m in r])
+    for cutoff in (-1, 0, 2):
+        oix, gix = build_both(oracle, ctx, accs, S, H, k, cb.CID_SEQ_FASTQ, cutoff)
+        assert np.array_equal(gix.download_dense(), oix.words()), f"cutoff {cutoff}"
+    # the same read sets as FASTQ queries against the last index (cutoff 2): default report with unique-hit summaries
+    queries = [accs[0], accs[1], accs[2][:300], [accs[3][0].lower()]]
+    for filt in (-1, 0, 1):
+        o = oix.query_counts(queries, oracle.MODE_FASTQ, False, filt)
+        for opts in (dict(), dict(query_compact=2), dict(query_fused=1)):
+            for name, v in opts.items():
+                ctx.set_option(name, v)
+            try:
+                for uq in (True, False):
+                    g = gix.query_counts(queries, cb.CID_SEQ_FASTQ, False, filt, want_uniq=uq)
+                    assert np.array_equal(g["num_kmers"], o["num_kmers"]), (filt, opts, uq)
+                    assert np.array_equal(g["counts"], o["counts"]), (filt, opts, uq)
+                    assert np.array_equal(g["cutoff"], o["cutoff"])
+                    if uq:
+                        for key in ("uniq_n", "uniq_sum", "uniq_mode"):
+                            assert np.array_equal(g[key], o[key]), (filt, opts, key)
+            finally:
+                ctx.set_option("query_compact", 1)
+                ctx.set_option("query_fused", 0)
+    # lower-case reads hit lower-case k-mers of an index built from soft-masked read sets
+    gix.n_ref[:] = oix.n_ref
+    reads = [[accs[0][i], accs[0][i + 1]] for i in range(0, 120, 2)] + [[accs[2][i]] for i in range(0, 60)]
+    o, g = _readid_compare(oracle, oix, gix, reads)
+    assert (g["flags"] & 16).sum() > 10 and int(o["rep_n"].max()) >= 1
+    low_hits = [r for r in range(len(reads)) if (g["flags"][r] & 16) and any(c < 4 for c in o["rep_colour"][r, :o["rep_n"][r]])]
+    assert len(low_hits) > 3, "no lower-case read with a hit: the test does not exercise raw-case row hashing"
 
 
 def test_empty_and_degenerate_inputs(oracle, ctx):
