@@ -351,19 +351,19 @@ def read_fasta(path):
     if lines and lines[-1] == b"":
         lines.pop()                      # str::lines() has no trailing empty item
     lines = [l[:-1] if l.endswith(b"\r") else l for l in lines]
-    vec, sub = [], b""
+    vec, sub = [], []                    # (sub: the pieces of the current contig; joined once, bytes += is quadratic)
     n = len(lines)
     for i, line in enumerate(lines, start=1):
         if b">" in line:
-            if sub:
-                vec.append(sub)
-            sub = b""
+            if any(sub):
+                vec.append(b"".join(sub))
+            sub = []
         elif i == n:
-            sub += line
-            if sub:
-                vec.append(sub)
+            sub.append(line)
+            if any(sub):
+                vec.append(b"".join(sub))
         else:
-            sub += line
+            sub.append(line)
     return vec
 
 
