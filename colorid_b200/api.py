@@ -137,7 +137,7 @@ def merge_shard_reports(shard_reports, shards, n_total, rep_cap=None):
 class Index:
     """Device-resident BIGSI index (bigsi.rs:19-27 BigsyMapNew)."""
 
-    def __init__(self, ctx, bloom_size, num_hash, k, n_colours, m=0):
+    def __init__(self, ctx, bloom_size, num_hash, k, n_colours, m=0, hash_variant=0):
         self.ctx, self.lib = ctx, ctx.lib
         self.S, self.H, self.k, self.N, self.m = bloom_size, num_hash, k, n_colours, m
         h = L.vp()
@@ -145,6 +145,8 @@ class Index:
         self.h = h
         if m:       # minimizer index (.mxi, bigsi.rs:40-49)
             L.check(self.lib.cid_index_set_minimizer(h, m))
+        if hash_variant:   # which draft of XXH3 the rows were / are hashed with (include/colorid_b200.h; 0 = stable)
+            L.check(self.lib.cid_index_set_hash_variant(h, hash_variant))
         self.W = self.lib.cid_index_row_words(h)
         self.n_ref = np.zeros(n_colours, dtype=np.uint64)
 

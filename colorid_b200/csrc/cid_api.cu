@@ -502,7 +502,7 @@ static int build_accession_impl(cid_index* ix, uint32_t colour, const char* d_ba
             CID_CUDA(cudaMemsetAsync(bitset, 0, ix->bs_words * 4, st));
             CID_CUDA(cudaMemsetAsync(ctx->d_err + 1, 0, 4, st));
             CID_TRY(launch_kmerize_bloom(ctx, st, (const uint8_t*)d_bases, d_seq_offs, nseq, nbases, ctx->scratch[0].p, slots, ix->k,
-                                         seq_mode, count_m, bloom_m, ix->H, ix->S, bitset));
+                                         seq_mode, count_m, bloom_m, ix->H, ix->S, ix->hv, bitset));
             CID_CUDA(cudaMemcpyAsync(ctx->h_err, ctx->d_err, 8, cudaMemcpyDeviceToHost, st));
             CID_CUDA(cudaStreamSynchronize(st));
             const uint32_t flags = ctx->h_err[0], distinct = ctx->h_err[1];
@@ -575,7 +575,7 @@ static int build_accession_impl(cid_index* ix, uint32_t colour, const char* d_ba
     CID_TRY(ctx->scratch[2].ensure(16));
     unsigned long long* d_nref = ctx->scratch[2].as<unsigned long long>();
     CID_CUDA(cudaMemsetAsync(d_nref, 0, 8, st));
-    CID_TRY(launch_region_to_bloom(ctx, st, ctx->scratch[0].p, nslots, used, count_m ? count_m : ix->k, bloom_m, ix->H, ix->S,
+    CID_TRY(launch_region_to_bloom(ctx, st, ctx->scratch[0].p, nslots, used, count_m ? count_m : ix->k, bloom_m, ix->H, ix->S, ix->hv,
                                    bitset, d_nref, packed));
     unsigned long long nref = 0;
     CID_CUDA(cudaMemcpyAsync(&nref, d_nref, 8, cudaMemcpyDeviceToHost, st));
@@ -622,6 +622,14 @@ int cid_index_set_minimizer(cid_index* ix, uint32_t m_size) {
     return CID_OK;
 }
 uint32_t cid_index_minimizer(const cid_index* ix) { return ix ? ix->m : 0; }
+
+int cid_index_set_hash_variant(cid_index* ix, uint32_t variant) {
+    if (!ix) { set_error("cid_index_set_hash_variant: null index"); return CID_E_INVALID; }
+    if (variant >= CID_HASH_VARIANTS) { set_error("hash variant %u out of range (0..%d)", variant, CID_HASH_VARIANTS - 1); return CID_E_INVALID; }
+    ix->hv = variant;
+    return CID_OK;
+}
+uint32_t cid_index_hash_variant(const cid_index* ix) { return ix ? ix->hv : 0; }
 
 int cid_build_finalize(cid_index* ix) {
     cid_ctx* ctx = ix->ctx;

@@ -132,7 +132,7 @@ kmerize_insert_kernel(const uint8_t* __restrict__ bases, const uint64_t* __restr
                 if (sink.bloom_m) { uint32_t which; item = minimizer_packed(key, revcomp_key(key, k), k, sink.bloom_m, which); len = sink.bloom_m; }
                 const HashIn in = hashin_from_key(lut, item, len);
                 for (uint32_t h = 0; h < sink.H; h++) {
-                    const uint64_t bit = mod_s(xxh3_kmer(in, len, h), sink.mods);
+                    const uint64_t bit = hash_row(in, len, h, sink.mods);
                     atomicOr(&sink.bitset[bit >> 5], 1u << (bit & 31));
                 }
             }
@@ -182,10 +182,10 @@ int launch_kmerize_insert(cid_ctx* ctx, cudaStream_t st, const uint8_t* d_bases,
 // count_m != 0: the set holds minimizers (build_multi_mini); bloom_m != 0: the set holds k-mers, their minimizers are inserted.
 int launch_kmerize_bloom(cid_ctx* ctx, cudaStream_t st, const uint8_t* d_bases, const uint64_t* d_seq_offs, uint64_t nseq,
                          uint64_t nbases, void* d_keys, uint64_t nslots, uint32_t k, int seq_mode, uint32_t count_m, uint32_t bloom_m,
-                         uint32_t H, uint64_t S, uint32_t* d_bitset) {
+                         uint32_t H, uint64_t S, uint32_t hv, uint32_t* d_bitset) {
     if (nbases == 0 || nseq == 0) return CID_OK;
     const uint64_t ntiles = (nbases + KT - 1) / KT;
-    SetSink sink{(unsigned long long*)d_keys, nslots - 1, d_bitset, H, make_mods(S), bloom_m, 0};
+    SetSink sink{(unsigned long long*)d_keys, nslots - 1, d_bitset, H, make_mods(S, hv), bloom_m, 0};
     ProfScope ps(ctx, st, KID_KMERIZE_INSERT);
     if (count_m)
         kmerize_insert_kernel<true, true><<<(unsigned)ntiles, KT_THREADS, 0, st>>>(d_bases, d_seq_offs, nseq, 0, nbases, nullptr, nullptr, nullptr,
@@ -254,7 +254,7 @@ int launch_region_histogram(cid_ctx* ctx, cudaStream_t st, const void* d_region,
 // ================================================================= region_to_bloom
 // clean_map (count > cutoff, kmer.rs:826-837), n_ref_kmers (build.rs:62), BloomFilter::insert.
 template <bool PACKED>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 region_to_bloom_kernel(const void* __restrict__ region, uint64_t nslots, long long cutoff, uint32_t k, uint32_t mini_m,
                        uint32_t H, ModS mods, uint32_t* __restrict__ bitset, unsigned long long* __restrict__ nref) {
     __shared__ uint32_t lut[256];
@@ -275,7 +275,7 @@ region_to_bloom_kernel(const void* __restrict__ region, uint64_t nslots, long lo
         HashIn in = hashin_from_key(lut, item, len);
         if (!mini_m) hashin_apply_case(in, v.cs, len);      // (a minimizer index never runs a case-aware pass)
         for (uint32_t i = 0; i < H; i++) {
-            uint64_t bit = mod_s(xxh3_kmer(in, len, i), mods);
+            uint64_t bit = hash_row(in, len, i, mods);
             atomicOr(&bitset[bit >> 5], 1u << (bit & 31));
         }
     }
@@ -284,13 +284,13 @@ region_to_bloom_kernel(const void* __restrict__ region, uint64_t nslots, long lo
     if ((threadIdx.x & 31) == 0 && mine) atomicAdd(nref, (unsigned long long)mine);
 }
 int launch_region_to_bloom(cid_ctx* ctx, cudaStream_t st, const void* d_region, uint64_t nslots, int64_t cutoff,
-                           uint32_t k, uint32_t mini_m, uint32_t H, uint64_t S, uint32_t* d_bitset, unsigned long long* d_nref,
+                           uint32_t k, uint32_t mini_m, uint32_t H, uint64_t S, uint32_t hv, uint32_t* d_bitset, unsigned long long* d_nref,
                            bool packed) {
     unsigned grid = (unsigned)std::min<uint64_t>((nslots + 255) / 256, (uint64_t)ctx->sm_count * 16);
     if (grid == 0) grid = 1;
     ProfScope ps(ctx, st, KID_TO_BLOOM);
-    if (packed) region_to_bloom_kernel<true><<<grid, 256, 0, st>>>(d_region, nslots, (long long)cutoff, k, mini_m, H, make_mods(S), d_bitset, d_nref);
-    else region_to_bloom_kernel<false><<<grid, 256, 0, st>>>(d_region, nslots, (long long)cutoff, k, mini_m, H, make_mods(S), d_bitset, d_nref);
+    if (packed) region_to_bloom_kernel<true><<<grid, 256, 0, st>>>(d_region, nslots, (long long)cutoff, k, mini_m, H, make_mods(S, hv), d_bitset, d_nref);
+    else region_to_bloom_kernel<false><<<grid, 256, 0, st>>>(d_region, nslots, (long long)cutoff, k, mini_m, H, make_mods(S, hv), d_bitset, d_nref);
     ctx->launches++;
     CID_CUDA(cudaGetLastError());
     return CID_OK;
@@ -424,7 +424,7 @@ __device__ __forceinline__ uint32_t unit_collect_and_hash(const UnitSmem& u, con
     for (uint32_t i = tid; i < n; i += nt) {
         HashIn in = hashin_from_key(u.lut, u.keys[i], k);
         hashin_apply_case(in, u.cs[i], k);
-        for (uint32_t h = 0; h < H; h++) u.rowid[i * H + h] = (uint32_t)mod_s(xxh3_kmer(in, k, h), mods);
+        for (uint32_t h = 0; h < H; h++) u.rowid[i * H + h] = (uint32_t)hash_row(in, k, h, mods);
     }
     __syncthreads();
     return n;
@@ -672,7 +672,7 @@ query_hash_kernel(const Slot* __restrict__ table, const uint32_t* __restrict__ u
             HashIn in = hashin_from_key(lut, keys[i], k);
             hashin_apply_case(in, kcs[i], k);
             uint32_t* out = rid_out + (slot0 + total + i) * H;
-            for (uint32_t h = 0; h < H; h++) out[h] = (uint32_t)mod_s(xxh3_kmer(in, k, h), mods);
+            for (uint32_t h = 0; h < H; h++) out[h] = (uint32_t)hash_row(in, k, h, mods);
         }
         total += n;
     }
@@ -1024,7 +1024,7 @@ __device__ __noinline__ static bool dirty_window(const uint8_t* win, const uint8
     uint8_t str[32];
     if (string_kmer(win, k, str, key)) return true;
     const HashIn in = hashin_from_bytes(str, k);
-    const uint64_t h0 = xxh3_kmer(in, k, 0);
+    const uint64_t h0 = hash64(in, k, 0, mods);
     uint32_t slot = (uint32_t)(h0 >> 24) & (QF_DIRTY_SLOTS - 1);
     for (uint32_t probes = 0;; probes++) {
         if (probes >= QF_DIRTY_SLOTS * 3 / 4) { atomicOr(err, ERRF_STRING_NONACGT); return false; }
@@ -1040,7 +1040,7 @@ __device__ __noinline__ static bool dirty_window(const uint8_t* win, const uint8
     const uint32_t i = atomicAdd(s_cnt, 1u);
     uint32_t* out = rid_q + (size_t)i * H;
     out[0] = (uint32_t)mod_s(h0, mods);
-    for (uint32_t hh = 1; hh < H; hh++) out[hh] = (uint32_t)mod_s(xxh3_kmer(in, k, hh), mods);
+    for (uint32_t hh = 1; hh < H; hh++) out[hh] = (uint32_t)hash_row(in, k, hh, mods);
     return false;
 }
 
@@ -1112,7 +1112,7 @@ query_front_kernel(const uint8_t* __restrict__ bases, const uint64_t* __restrict
                     const uint32_t i = atomicAdd(&s_cnt, 1u);
                     const HashIn in = hashin_from_key(lut, key, k);
                     uint32_t* out = rid_out + (base + i) * H;
-                    for (uint32_t hh = 0; hh < H; hh++) out[hh] = (uint32_t)mod_s(xxh3_kmer(in, k, hh), mods);
+                    for (uint32_t hh = 0; hh < H; hh++) out[hh] = (uint32_t)hash_row(in, k, hh, mods);
                 }
             }
         }
@@ -1184,11 +1184,11 @@ int launch_query_front_gather(cid_ctx* ctx, cudaStream_t st, const cid_index* id
         const size_t fsmem = (size_t)tsize * 8 + tile_smem_bytes(KT_CAP) + (seq_mode == CID_SEQ_STRING ? QF_DIRTY_SLOTS * 4 : 0);
         if (seq_mode == CID_SEQ_STRING)
             query_front_kernel<true><<<(unsigned)n, QF_THREADS, fsmem, st>>>(
-                d_bases, d_seq_offs, d_query_offs + q0, d_qlist + at, tsize, k, seq_mode, H, make_mods(idx->S), d_base, d_rid, d_unit_n,
+                d_bases, d_seq_offs, d_query_offs + q0, d_qlist + at, tsize, k, seq_mode, H, make_mods(idx->S, idx->hv), d_base, d_rid, d_unit_n,
                 d_num_kmers, ctx->d_err);
         else
             query_front_kernel<false><<<(unsigned)n, QF_THREADS, fsmem, st>>>(
-                d_bases, d_seq_offs, d_query_offs + q0, d_qlist + at, tsize, k, seq_mode, H, make_mods(idx->S), d_base, d_rid, d_unit_n,
+                d_bases, d_seq_offs, d_query_offs + q0, d_qlist + at, tsize, k, seq_mode, H, make_mods(idx->S, idx->hv), d_base, d_rid, d_unit_n,
                 d_num_kmers, ctx->d_err);
         ctx->launches++;
         CID_CUDA(cudaGetLastError());
@@ -1220,7 +1220,7 @@ int launch_query_counts(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, con
         {
             ProfScope ps(ctx, st, KID_QUERY_HASH);
             query_hash_kernel<<<(unsigned)nunits, 256, 0, st>>>((const Slot*)d_table, d_unit_group, d_unit_slot0, d_unit_nslots,
-                                                              (const long long*)d_filter, idx->k, idx->H, make_mods(idx->S),
+                                                              (const long long*)d_filter, idx->k, idx->H, make_mods(idx->S, idx->hv),
                                                               d_rid, d_unit_n, d_num_kmers);
         }
         ctx->launches++;
@@ -1239,7 +1239,7 @@ int launch_query_counts(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, con
         CID_CUDA(cudaFuncSetAttribute(query_uniq_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         attr_set = true;
     }
-    ModS mods = make_mods(idx->S);
+    ModS mods = make_mods(idx->S, idx->hv);
     const uint32_t vec = idx->Wp >= 4 ? 4 : idx->Wp;      // Wp is 1, 2 or a multiple of 4
     const bool inline_uniq = want_uniq && idx->Wp <= 32 * vec;   // one column block: the warp sees the whole row
     {
@@ -1328,7 +1328,7 @@ int launch_query_perfect(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, co
     }
     ProfScope ps(ctx, st, KID_QUERY_PERFECT);
     query_perfect_kernel<<<(unsigned)nunits, 256, smem, st>>>(idx->rows, idx->rownz, idx->Wp, idx->W, idx->k, idx->H,
-                                                             make_mods(idx->S), (const Slot*)d_table, d_unit_group,
+                                                             make_mods(idx->S, idx->hv), (const Slot*)d_table, d_unit_group,
                                                              d_unit_slot0, d_unit_nslots, d_and_rows, d_missing,
                                                              d_num_kmers);
     ctx->launches++;
@@ -1347,13 +1347,13 @@ __global__ void hash_kmers_kernel(const uint8_t* __restrict__ kmers, uint64_t n,
     uint64_t key = 0;
     for (uint32_t j = 0; j < k; j++) key = (key << 2) | base_code(kmers[i * k + j]);
     HashIn in = hashin_from_key(lut, key, k);
-    for (uint32_t h = 0; h < H; h++) out[i * H + h] = mod_s(xxh3_kmer(in, k, h), mods);
+    for (uint32_t h = 0; h < H; h++) out[i * H + h] = hash_row(in, k, h, mods);
 }
 int launch_hash_kmers(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, const uint8_t* d_kmers, uint64_t n,
                       uint64_t* d_rows) {
     if (n == 0) return CID_OK;
     ProfScope ps(ctx, st, KID_OTHER);
-    hash_kmers_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_kmers, n, idx->m ? idx->m : idx->k, idx->H, make_mods(idx->S), d_rows);
+    hash_kmers_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_kmers, n, idx->m ? idx->m : idx->k, idx->H, make_mods(idx->S, idx->hv), d_rows);
     ctx->launches++;
     CID_CUDA(cudaGetLastError());
     return CID_OK;
@@ -1500,7 +1500,7 @@ slots_popcount_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t k
             HashIn in = hashin_from_key(lut, slots[i0 + lane].key, k);
             hashin_apply_case(in, slot_cs(slots[i0 + lane].pad), k);
 #pragma unroll
-            for (int h = 0; h < MAX_HASH; h++) if ((uint32_t)h < H) rid_l[h] = (uint32_t)mod_s(xxh3_kmer(in, k, h), mods);
+            for (int h = 0; h < MAX_HASH; h++) if ((uint32_t)h < H) rid_l[h] = (uint32_t)hash_row(in, k, h, mods);
         }
         const uint32_t cnt = (uint32_t)min((uint64_t)32, n - i0);
         uint32_t my_pc = 0, my_col = 0xFFFFFFFFu;
@@ -1552,7 +1552,7 @@ int launch_slots_popcount(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, c
     if (n == 0) return CID_OK;
     ProfScope ps(ctx, st, KID_QUERY_UNIQ_WIDE);
     const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 32);
-    slots_popcount_kernel<<<grid, 256, 0, st>>>(idx->rows, idx->Wp, idx->k, idx->H, make_mods(idx->S), (const Slot*)d_slots, n, d_pc, d_col);
+    slots_popcount_kernel<<<grid, 256, 0, st>>>(idx->rows, idx->Wp, idx->k, idx->H, make_mods(idx->S, idx->hv), (const Slot*)d_slots, n, d_pc, d_col);
     ctx->launches++;
     CID_CUDA(cudaGetLastError());
     return CID_OK;

@@ -41,7 +41,45 @@ __device__ __forceinline__ uint64_t bswap64(uint64_t x) {
 //   1..3  : w0=in[0]   w1=in[k>>1] w2=in[k-1]
 struct HashIn { uint64_t w0, w1, w2, w3; };
 
-__device__ __forceinline__ uint64_t xxh3_kmer(const HashIn& in, uint32_t k, uint64_t seed) {
+// Hash variants.  The reference pins the third-party crate `xxh3 = "0.1.1"` (Cargo.toml:9), which predates the XXH3 freeze and
+// is not vendored, so which draft of XXH3 a real colorid binary computes is unpinned.  Variant 0 is
+// stable XXH3 (xxHash >= 0.8); the other 31 are the combinations of the five places where the drafts are known to differ,
+// one bit each, so that an index written by a real binary can be matched without touching a kernel (tools/pin_from_bxi.py):
+//   bit 0  final avalanche multiplier PRIME64_3 instead of PRIME_MX1      bit 1  avalanche shift 29 instead of 37
+//   bit 2  128-bit product folded by + instead of ^                       bit 3  seed enters as (len + seed) * PRIME64_1
+//   bit 4  secret read as 32-bit words (kKey[] of the first draft)               instead of secret +/- seed per lane (len >= 17)
+// The variant is resolved on the host into HashCfg (make_mods), which every kernel receives by value: its fields are
+// read by the out-of-line variant path only; variant 0 keeps its immediates.
+#define CID_HASH_VARIANTS 32
+struct HashCfg {
+    uint64_t sec[7];        // secret words at byte offsets 0, 8, .., 48 (32-bit halves byte-swapped for bit 4)
+    uint64_t av_mul;
+    uint32_t av_shift, fold_add, seed_acc, var;
+};
+// h % S for run-time S: see mod_s below
+struct ModS { uint64_t S, M; HashCfg h; };
+__host__ __device__ __forceinline__ ModS make_mods(uint64_t S, uint32_t var = 0) {
+    ModS m; m.S = S;
+    m.M = S <= 1 ? 0 : (uint64_t)((((unsigned __int128)1) << 64) / S);
+    const uint64_t sec[7] = {CID_SEC0, CID_SEC8, CID_SEC16, CID_SEC24, CID_SEC32, CID_SEC40, CID_SEC48};
+    for (int i = 0; i < 7; i++) {
+        uint64_t s = sec[i];
+        if (var & 16u) {     // each 32-bit half byte-swapped: the secret's bytes read as an array of u32 constants
+            auto sw = [](uint32_t x) { return (x >> 24) | ((x >> 8) & 0xFF00u) | ((x << 8) & 0xFF0000u) | (x << 24); };
+            s = ((uint64_t)sw((uint32_t)(s >> 32)) << 32) | sw((uint32_t)s);
+        }
+        m.h.sec[i] = s;
+    }
+    m.h.av_mul = (var & 1u) ? CID_P64_3 : CID_PMX1;
+    m.h.av_shift = (var & 2u) ? 29u : 37u;
+    m.h.fold_add = (var & 4u) ? 1u : 0u;
+    m.h.seed_acc = (var & 8u) ? 1u : 0u;
+    m.h.var = var;
+    return m;
+}
+
+// stable XXH3 (variant 0): every constant an immediate
+__device__ __forceinline__ uint64_t xxh3_kmer_stable(const HashIn& in, uint32_t k, uint64_t seed) {
     if (k >= 17) {
         uint64_t acc = (uint64_t)k * CID_P64_1;
         acc += mul128_fold64(in.w0 ^ (CID_SEC0 + seed), in.w1 ^ (CID_SEC8 - seed));
@@ -70,20 +108,58 @@ __device__ __forceinline__ uint64_t xxh3_kmer(const HashIn& in, uint32_t k, uint
         return h;
     }
 }
+// any variant, from the resolved configuration (rarely run: kept out of line so that the kernels' register budgets are
+// those of the stable path)
+static __device__ __noinline__ uint64_t xxh3_kmer_cfg(uint64_t w0, uint64_t w1, uint64_t w2, uint64_t w3, uint32_t k, uint64_t seed, const HashCfg* cp) {
+    const HashCfg& c = *cp;
+    auto fold = [&](uint64_t a, uint64_t b) { const uint64_t lo = a * b, hi = __umul64hi(a, b); return c.fold_add ? lo + hi : lo ^ hi; };
+    auto aval = [&](uint64_t h) { h ^= h >> c.av_shift; h *= c.av_mul; h ^= h >> 32; return h; };
+    if (k >= 17) {
+        const uint64_t sd = c.seed_acc ? 0ull : seed;
+        uint64_t acc = ((uint64_t)k + (c.seed_acc ? seed : 0ull)) * CID_P64_1;
+        acc += fold(w0 ^ (c.sec[0] + sd), w1 ^ (c.sec[1] - sd));
+        acc += fold(w2 ^ (c.sec[2] + sd), w3 ^ (c.sec[3] - sd));
+        return aval(acc);
+    } else if (k >= 9) {
+        const uint64_t lo = w0 ^ ((c.sec[3] ^ c.sec[4]) + seed);
+        const uint64_t hi = w1 ^ ((c.sec[5] ^ c.sec[6]) - seed);
+        return aval((uint64_t)k + bswap64(lo) + hi + fold(lo, hi));
+    } else if (k >= 4) {
+        const uint32_t s32 = (uint32_t)seed;
+        seed ^= (uint64_t)__byte_perm(s32, 0, 0x0123) << 32;
+        uint64_t h = (w1 + (w0 << 32)) ^ ((c.sec[1] ^ c.sec[2]) - seed);
+        h ^= rotl64(h, 49) ^ rotl64(h, 24);
+        h *= CID_PMX2;
+        h ^= (h >> 35) + k;
+        h *= CID_PMX2;
+        return h ^ (h >> 28);
+    } else {
+        const uint32_t combined = ((uint32_t)w0 << 16) | ((uint32_t)w1 << 24) | (uint32_t)w2 | (k << 8);
+        uint64_t h = (uint64_t)combined ^ ((uint64_t)((uint32_t)c.sec[0] ^ (uint32_t)(c.sec[0] >> 32)) + seed);
+        h ^= h >> 33; h *= CID_P64_2; h ^= h >> 29; h *= CID_P64_3; h ^= h >> 32;
+        return h;
+    }
+}
+__device__ __forceinline__ uint64_t xxh3_kmer(const HashIn& in, uint32_t k, uint64_t seed, const HashCfg& c) {
+    if (c.var == 0u) return xxh3_kmer_stable(in, k, seed);
+    return xxh3_kmer_cfg(in.w0, in.w1, in.w2, in.w3, k, seed, &c);
+}
 
 // h % S for run-time S (2 <= S < 2^63) with M = floor(2^64 / S): q = mulhi(h, M) is floor(h/S) or
 // one less, so a single conditional subtract makes it exact.
-struct ModS { uint64_t S, M; };
-__host__ __device__ __forceinline__ ModS make_mods(uint64_t S) {
-    ModS m; m.S = S;
-    m.M = S <= 1 ? 0 : (uint64_t)((((unsigned __int128)1) << 64) / S);
-    return m;
-}
 __device__ __forceinline__ uint64_t mod_s(uint64_t h, const ModS& m) {
     if (m.S <= 1) return 0;
     uint64_t q = __umul64hi(h, m.M);
     uint64_t r = h - q * m.S;
     return r >= m.S ? r - m.S : r;
+}
+
+// Row index of hash function `seed` (simple_bloom.rs:21-24): xxh3(kmer, seed) % bloom_size, in the index's hash variant.
+__device__ __forceinline__ uint64_t hash64(const HashIn& in, uint32_t k, uint64_t seed, const ModS& m) {
+    return xxh3_kmer(in, k, seed, m.h);
+}
+__device__ __forceinline__ uint64_t hash_row(const HashIn& in, uint32_t k, uint64_t seed, const ModS& m) {
+    return mod_s(hash64(in, k, seed, m), m);
 }
 
 // ------------------------------------------------------------------ 2-bit codes <-> ASCII

@@ -566,7 +566,7 @@ readid_order_small_kernel(const uint8_t* __restrict__ hp8, const uint32_t* __res
 
 // ================================================================= readid_vote (rows of <= 64 accessions)
 template <int WP, bool STEPS>      // STEPS: report colours carry their insertion step (column-sharded read_id); a separate
-__global__ void __launch_bounds__(RA_WARPS * 32)      // instantiation so that the replicated-index kernel stays as it was
+__global__ void __launch_bounds__(RA_WARPS * 32, 9)   // instantiation so that the replicated-index kernel stays as it was
 readid_vote_narrow_kernel(const uint8_t* __restrict__ bases, const uint8_t* __restrict__ quals, uint32_t maxq,
                           const uint64_t* __restrict__ seq_offs, const uint64_t* __restrict__ read_offs, uint64_t r0,
                           uint64_t nreads, uint32_t k, uint32_t H, ModS mods, const uint32_t* __restrict__ rows,
@@ -643,7 +643,7 @@ readid_vote_narrow_kernel(const uint8_t* __restrict__ bases, const uint8_t* __re
                 uint32_t a = 0xFFFFFFFFu, b = WP == 2 ? 0xFFFFFFFFu : 0u;
                 bool mm = false;
                 if (act2) {
-                    uint64_t rid = mod_s(xxh3_kmer(mine, k, h), mods);
+                    uint64_t rid = hash_row(mine, k, h, mods);
                     if (WP == 2) { uint2 v = __ldg((const uint2*)(rows + rid * 2)); a = v.x; b = v.y; }
                     else { a = __ldg(rows + rid); b = 0; }
                     mm = rownz ? !((__ldg(rownz + (rid >> 5)) >> (rid & 31)) & 1u) : ((a | b) == 0u);
@@ -661,7 +661,7 @@ readid_vote_narrow_kernel(const uint8_t* __restrict__ bases, const uint8_t* __re
                 if (active) { x0 = ca; x1 = cb2; m = cm != 0; }
             } else if (active && presence_only) {
                 for (uint32_t h = 0; h < H; h++) {
-                    const uint64_t rid = mod_s(xxh3_kmer(in, k, h), mods);
+                    const uint64_t rid = hash_row(in, k, h, mods);
                     if (!((__ldg(rownz_all + (rid >> 5)) >> (rid & 31)) & 1u)) { m = true; break; }
                 }
             } else if (active) {
@@ -672,7 +672,7 @@ readid_vote_narrow_kernel(const uint8_t* __restrict__ bases, const uint8_t* __re
                 const bool cand_final = !classic && c0 >= start_sample;
                 uint32_t rid[MAX_HASH];
 #pragma unroll
-                for (int h = 0; h < MAX_HASH; h++) rid[h] = (uint32_t)h < H ? (uint32_t)mod_s(xxh3_kmer(in, k, h), mods) : 0u;
+                for (int h = 0; h < MAX_HASH; h++) rid[h] = (uint32_t)h < H ? (uint32_t)hash_row(in, k, h, mods) : 0u;
                 {
                     uint32_t a, b = 0;
                     if (WP == 2) { uint2 v = __ldg((const uint2*)(rows + (size_t)rid[0] * 2)); a = v.x; b = v.y; }
@@ -777,7 +777,7 @@ __device__ __forceinline__ void csa3(uint32_t& carry, uint32_t& sum, uint32_t a,
     sum = u ^ c;
 }
 template <int WPL, int HT>         // words per lane (1, 2 or 4): 1,024 / 2,048 / 4,096 accessions; sizes the bit-sliced counters.
-__global__ void __launch_bounds__(RA_WARPS * 32)      // HT: compile-time num_hash (2 or 4; 0 = run-time, predicated up to MAX_HASH)
+__global__ void __launch_bounds__(RA_WARPS * 32, (WPL == 1 && HT != 0) ? 8 : 1)      // HT: compile-time num_hash (2 or 4; 0 = run-time, predicated up to MAX_HASH)
 readid_vote_wide_kernel(const uint8_t* __restrict__ bases, const uint8_t* __restrict__ quals, uint32_t maxq,
                         const uint64_t* __restrict__ seq_offs, const uint64_t* __restrict__ read_offs, uint64_t r0,
                         uint64_t nreads, uint32_t k, uint32_t H, ModS mods, const uint32_t* __restrict__ rows,
@@ -834,7 +834,7 @@ readid_vote_wide_kernel(const uint8_t* __restrict__ bases, const uint8_t* __rest
 #pragma unroll
                 for (int h = 0; h < NH; h++)
                     if (HT || (uint32_t)h < H) {
-                        rid_o[h] = (uint32_t)mod_s(xxh3_kmer(in, k, h), mods);
+                        rid_o[h] = (uint32_t)hash_row(in, k, h, mods);
                         pres[h] = __ldg(rownz + (rid_o[h] >> 5)) >> (rid_o[h] & 31);
                     }
             }
@@ -1268,7 +1268,7 @@ int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const ui
         rattr = true;
     }
 
-    const ModS mods = make_mods(idx->S);
+    const ModS mods = make_mods(idx->S, idx->hv);
     const uint32_t kitem = idx->m ? idx->m : idx->k;    // length of the hashed item: k-mer, or minimizer of an .mxi index
     for (uint64_t r0 = r_first; r0 < r_first + nreads; r0 += sub) {
         const uint64_t nr = std::min(sub, r_first + nreads - r0);

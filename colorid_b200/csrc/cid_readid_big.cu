@@ -350,7 +350,7 @@ readid_big_kernel(const BigArgs a) {
                         const HashIn in = hashin_from_bytes(str, len_item);
                         bool absent = false;
                         for (uint32_t h = 0; h < H; h++) {
-                            const uint32_t rid = (uint32_t)mod_s(xxh3_kmer(in, len_item, h), a.mods);
+                            const uint32_t rid = (uint32_t)hash_row(in, len_item, h, a.mods);
                             rid_s[tid * H + h] = rid;
                             if (!((a.rownz[rid >> 5] >> (rid & 31)) & 1u)) absent = true;     // read_id_mt_pe.rs:121-128 `None => break`
                         }
@@ -457,7 +457,7 @@ int launch_readid_big(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, c
     a.bases = d_bases; a.quals = maxq ? d_quals : nullptr; a.maxq = maxq;
     a.seq_offs = d_seq_offs; a.read_offs = d_read_offs; a.r0 = r0;
     a.list = d_list; a.list_n = d_list_n;
-    a.k = idx->k; a.mini_m = idx->m; a.d = p.downsample; a.H = idx->H; a.mods = make_mods(idx->S);
+    a.k = idx->k; a.mini_m = idx->m; a.d = p.downsample; a.H = idx->H; a.mods = make_mods(idx->S, idx->hv);
     a.rows = idx->rows; a.rownz = idx->rownz; a.N = idx->N; a.Wp = idx->Wp;
     a.start_sample = p.start_sample; a.rep_cap = p.rep_cap; a.with_steps = ctx->opt_readid_report_steps ? 1u : 0u;
     a.gw = p.group_width; a.rbf = p.reserve_before_find;

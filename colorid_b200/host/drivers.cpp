@@ -56,6 +56,10 @@ struct Gpu {                      // context + device index
         ready();
         if (H > 0xFFFFFFFFull || k > 0xFFFFFFFFull || N > 0xFFFFFFFFull) throw Error("index parameters out of range");
         ck(cid_index_create(ctx, S, (uint32_t)H, (uint32_t)k, (uint32_t)N, &ix));
+        // The reference hashes with the crate `xxh3 = "0.1.1"` (Cargo.toml:9), a pre-freeze XXH3 that is not pinned here:
+        // COLORID_B200_HASH_VARIANT selects the draft an index was / is to be hashed with (include/colorid_b200.h;
+        // default 0 = stable XXH3; tools/pin_from_bxi.py finds the variant that reproduces a given .bxi).
+        if (const char* hv = getenv("COLORID_B200_HASH_VARIANT")) ck(cid_index_set_hash_variant(ix, (uint32_t)strtoul(hv, nullptr, 10)));
     }
     void upload(const Bigsi& b) {   // main.rs:576 / :796 read_bigsi -> dense device matrix
         create(b.bloom_size, b.num_hash, b.k_size, b.n_colors());
@@ -69,6 +73,14 @@ struct Gpu {                      // context + device index
     }
 };
 Bigsi read_index(const std::string& path) {     // main.rs:633-635,724-728,796-800: the suffix decides the struct
+    // A .bxi does not say how its rows were hashed.  Indexes written by this program with the same variant are fine; one
+    // written by a real colorid binary may need another variant -- say so once, unless the user has chosen one.
+    static bool told = false;
+    if (!told && !getenv("COLORID_B200_HASH_VARIANT")) {
+        told = true;
+        fprintf(stderr, "note: rows of %s are read as stable XXH3 (hash variant 0); an index written by the original colorid binary "
+                        "(xxh3 crate 0.1.1) has not been verified against it -- see tools/pin_from_bxi.py / COLORID_B200_HASH_VARIANT\n", path.c_str());
+    }
     return ends_with(path, ".mxi") ? read_bigsi_mini(path) : read_bigsi(path);
 }
 Bigsi load_index(const std::string& path) {

@@ -51,6 +51,8 @@ SIGNATURES = {
     "cid_build_accession": (C.c_int, [vp, C.c_uint32, vp, u64p, C.c_uint64, C.c_int, C.c_int64, u64p, i64p]),
     "cid_build_accession_dev": (C.c_int, [vp, C.c_uint32, vp, vp, C.c_uint64, C.c_uint64, C.c_int, C.c_int64, u64p, i64p]),
     "cid_index_set_minimizer": (C.c_int, [vp, C.c_uint32]),
+    "cid_index_set_hash_variant": (C.c_int, [vp, C.c_uint32]),
+    "cid_index_hash_variant": (C.c_uint32, [vp]),
     "cid_index_minimizer": (C.c_uint32, [vp]),
     "cid_build_accession_mini": (C.c_int, [vp, C.c_uint32, vp, u64p, C.c_uint64, C.c_int, C.c_int64, C.c_int, u64p, i64p]),
     "cid_build_finalize": (C.c_int, [vp]),

@@ -93,6 +93,16 @@ int cid_index_create(cid_ctx* ctx, uint64_t bloom_size, uint32_t num_hash, uint3
 void cid_index_destroy(cid_index* idx);
 uint32_t cid_index_row_words(const cid_index* idx);    /* ceil(n_colors/32) */
 uint32_t cid_index_row_stride(const cid_index* idx);   /* padded words per row on the device */
+/* Hash variant of the index (simple_bloom.rs:21-24 calls the un-vendored crate `xxh3 = "0.1.1"`, Cargo.toml:9, which
+ * predates the XXH3 freeze; which draft a real colorid binary computes is unpinned).  0 = stable XXH3 (xxHash >= 0.8,
+ * the default).  Bits select the places where the drafts differ: 1 = avalanche multiplier PRIME64_3, 2 = avalanche
+ * shift 29, 4 = 128-bit product folded by +, 8 = seed enters as (len + seed) * PRIME64_1 (inputs of 17+ bytes),
+ * 16 = secret read as 32-bit words.  CID_HASH_XXH3_DRAFT_071 / _070 are the combinations recalled for the drafts of
+ * xxHash 0.7.1-0.7.3 / 0.7.0.  Set it before the first build / upload / query; tools/pin_from_bxi.py finds the variant
+ * that reproduces a given .bxi.  Every kernel hashes through it. */
+enum { CID_HASH_XXH3_STABLE = 0, CID_HASH_XXH3_DRAFT_071 = 1, CID_HASH_XXH3_DRAFT_070 = 31 };
+int cid_index_set_hash_variant(cid_index* idx, uint32_t variant);
+uint32_t cid_index_hash_variant(const cid_index* idx);
 /* Rows from a .bxi `map` (bigsi.rs:25): row_ids[n], words[n*row_words]. Replaces read_bigsi's heap map. */
 int cid_index_upload_rows(cid_index* idx, const uint64_t* row_ids, const uint32_t* words, uint64_t nrows);
 int cid_index_count_nonzero_rows(cid_index* idx, uint64_t* nrows);

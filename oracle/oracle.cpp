@@ -219,8 +219,8 @@ struct BitVec {
 };
 
 // simple_bloom.rs:19-26
-static inline uint64_t bloom_bit(const std::string& kmer, uint64_t seed, uint64_t bloom_size) {
-    return xxh3_64_with_seed((const uint8_t*)kmer.data(), kmer.size(), seed) % bloom_size;
+static inline uint64_t bloom_bit(const std::string& kmer, uint64_t seed, uint64_t bloom_size, uint32_t variant) {
+    return xxh3_64_with_seed((const uint8_t*)kmer.data(), kmer.size(), seed, variant) % bloom_size;
 }
 
 // ---------------------------------------------------------------- index model (bigsi.rs:19-27)
@@ -228,6 +228,7 @@ static inline uint64_t bloom_bit(const std::string& kmer, uint64_t seed, uint64_
 struct Index {
     uint64_t S; uint32_t H, k, N, W;
     uint32_t m = 0;                             // bigsi.rs:40-49 BigsyMapMiniNew.m_size (0 = k-mer index)
+    uint32_t hv = 0;                            // hash variant (xxh3_ref.hpp; 0 = stable XXH3)
     std::vector<uint32_t> rows;                 // dense [S][W]; an all-zero row == absent row (build.rs:123-127)
     std::vector<std::vector<uint32_t>> bitsets; // phase-1 per-colour Bloom bitsets (build.rs:63-67)
     bool row_present(uint64_t r) const {
@@ -367,7 +368,7 @@ static void gather_rows(const Index& ix, const std::string& km, std::vector<cons
     (void)zero_is_absent;  // dense model: absent == all-zero (SURVEY §8a note), same in both variants
     slices.clear();
     for (uint32_t i = 0; i < ix.H; i++) {
-        uint64_t bi = bloom_bit(km, i, ix.S);
+        uint64_t bi = bloom_bit(km, i, ix.S, ix.hv);
         if (!ix.row_present(bi)) break;
         slices.push_back(&ix.rows[bi * ix.W]);
     }
@@ -440,6 +441,7 @@ static std::vector<std::string> split_seqs(const char* bases, const uint64_t* of
 extern "C" {
 
 uint64_t orc_xxh3_64(const uint8_t* p, uint64_t len, uint64_t seed) { return xxh3_64_with_seed(p, len, seed); }
+uint64_t orc_xxh3_64_variant(const uint8_t* p, uint64_t len, uint64_t seed, uint32_t variant) { return xxh3_64_with_seed(p, len, seed, variant); }
 uint64_t orc_fnv1a_str(const uint8_t* p, uint64_t len) { return fnv_hash_str(std::string((const char*)p, len)); }
 uint64_t orc_fnv1a_usize(uint64_t v) { return fnv_hash_usize(v); }
 double orc_binomial_mass(uint64_t n, double p, uint64_t x) { return binomial_mass(n, p, x); }
@@ -544,7 +546,7 @@ int orc_build_accession(orc_index* h, uint32_t colour, const char* bases, const 
     bits.assign((ix.S + 31) / 32, 0);
     for (auto& kv : m)
         for (uint32_t i = 0; i < ix.H; i++) {
-            uint64_t b = bloom_bit(kv.first, i, ix.S);
+            uint64_t b = bloom_bit(kv.first, i, ix.S, ix.hv);
             bits[b / 32] |= 1u << (b % 32);
         }
     return 0;
@@ -579,13 +581,14 @@ int orc_build_accession_mini(orc_index* h, uint32_t colour, const char* bases, c
     for (auto& kv : m) {
         const std::string item = variant == 0 ? find_minimizer(kv.first, ix.m) : kv.first;
         for (uint32_t i = 0; i < ix.H; i++) {
-            uint64_t b = bloom_bit(item, i, ix.S);
+            uint64_t b = bloom_bit(item, i, ix.S, ix.hv);
             bits[b / 32] |= 1u << (b % 32);
         }
     }
     return 0;
 }
 void orc_index_set_minimizer(orc_index* h, uint32_t m) { h->ix.m = m; }
+void orc_index_set_hash_variant(orc_index* h, uint32_t v) { h->ix.hv = v; }
 // kmer.rs:971-986; out has m bytes.  Returns -1 where the reference panics (m > len).
 int orc_find_minimizer(const char* seq, uint64_t n, uint32_t m, char* out) {
     if (m > n || m == 0) return -1;
@@ -697,7 +700,7 @@ int orc_query_perfect(orc_index* h, const char* bases, const uint64_t* seq_offs,
         std::vector<uint32_t> acc(ix.W, 0xFFFFFFFFu);
         for (auto& kv : m)
             for (uint32_t i = 0; i < ix.H; i++) {
-                uint64_t bi = bloom_bit(kv.first, i, ix.S);
+                uint64_t bi = bloom_bit(kv.first, i, ix.S, ix.hv);
                 if (!ix.row_present(bi)) { missing = true; break; }
                 for (uint32_t w = 0; w < ix.W; w++) acc[w] &= ix.rows[bi * ix.W + w];
             }

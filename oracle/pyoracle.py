@@ -34,6 +34,8 @@ def lib():
         L = C.CDLL(path)
         L.orc_xxh3_64.restype = C.c_uint64
         L.orc_xxh3_64.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64]
+        L.orc_xxh3_64_variant.restype = C.c_uint64
+        L.orc_xxh3_64_variant.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint32]
         L.orc_fnv1a_str.restype = C.c_uint64
         L.orc_fnv1a_str.argtypes = [C.c_char_p, C.c_uint64]
         L.orc_fnv1a_usize.restype = C.c_uint64
@@ -73,7 +75,10 @@ def pack_seqs(seqs):
     return bases, offs
 
 
-def xxh3_64(b, seed=0):
+def xxh3_64(b, seed=0, variant=0):
+    """variant: see oracle/xxh3_ref.hpp (0 = stable XXH3)."""
+    if variant:
+        return lib().orc_xxh3_64_variant(bytes(b), len(b), seed, variant)
     return lib().orc_xxh3_64(bytes(b), len(b), seed)
 
 
@@ -194,13 +199,16 @@ def auto_cutoff_histo(histo):
 class Index:
     """Dense BIGSI index model on the CPU (bigsi.rs:19-27 semantics; absent row == zero row)."""
 
-    def __init__(self, bloom_size, num_hash, k, n_colours, m=0):
+    def __init__(self, bloom_size, num_hash, k, n_colours, m=0, hash_variant=0):
         self.S, self.H, self.k, self.N, self.m = bloom_size, num_hash, k, n_colours, m
+        self.hash_variant = hash_variant
         self.W = (n_colours + 31) // 32
         self.h = C.c_void_p(lib().orc_index_new(bloom_size, num_hash, k, n_colours))
         self.n_ref = np.zeros(n_colours, dtype=np.uint64)
         if m:
             lib().orc_index_set_minimizer(self.h, C.c_uint32(m))     # .mxi: bigsi.rs:40-49 m_size
+        if hash_variant:
+            lib().orc_index_set_hash_variant(self.h, C.c_uint32(hash_variant))
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -7,7 +7,15 @@
 // The crate is NOT vendored under /root/reference and no reference test asserts a hash
 // value, so hash parity with a real colorid binary is UNPINNED.
 // What is pinned: this restatement == python `xxhash` 3.7.0 (libxxhash 0.8.2) for
-// lengths 0..240 (tests/test_oracle_hash.py).
+// lengths 0..240 (tests/test_oracle_golden.py::test_xxh3_*).
+//
+// `variant` (0 = the stable algorithm above): the crate predates the XXH3 freeze, so the places where the published
+// drafts of XXH3 are known to differ are switchable, one bit each, for inputs of 1..128 bytes (every k-mer / minimizer):
+//   1  final avalanche multiplier PRIME64_3 (0.7.x) instead of PRIME_MX1     2  avalanche shift 29 (0.7.0) instead of 37
+//   4  128-bit product folded by + (0.7.0) instead of ^                      8  seed enters once as (len + seed) * PRIME64_1
+//   16 secret read as 32-bit words (kKey[] of 0.7.0)                            instead of secret +/- seed per lane (17+ bytes)
+// 1 = the 0.7.1-0.7.3 drafts as recalled, 31 = the 0.7.0 draft as recalled.  None of them is pinned either: they exist so
+// that a .bxi written by a real colorid binary can be matched (tools/pin_from_bxi.py).
 #pragma once
 #include <cstdint>
 #include <cstring>
@@ -53,8 +61,71 @@ static inline uint64_t mix16(const uint8_t* in, const uint8_t* sec, uint64_t see
     return mul128_fold64(rd64(in) ^ (rd64(sec) + seed), rd64(in + 8) ^ (rd64(sec + 8) - seed));
 }
 
+struct Xxh3Variant {
+    uint32_t v;
+    uint64_t sec64(const uint8_t* p) const {          // bit 4: the secret's bytes as an array of u32 constants
+        if (!(v & 16u)) return rd64(p);
+        return ((uint64_t)__builtin_bswap32(rd32(p + 4)) << 32) | __builtin_bswap32(rd32(p));
+    }
+    uint64_t fold(uint64_t a, uint64_t b) const {
+        unsigned __int128 p = (unsigned __int128)a * b;
+        return (v & 4u) ? (uint64_t)p + (uint64_t)(p >> 64) : (uint64_t)p ^ (uint64_t)(p >> 64);
+    }
+    uint64_t aval(uint64_t h) const { h ^= h >> ((v & 2u) ? 29 : 37); h *= (v & 1u) ? P64_3 : P_MX1; h ^= h >> 32; return h; }
+    uint64_t mix(const uint8_t* in, const uint8_t* sec, uint64_t seed) const {
+        const uint64_t sd = (v & 8u) ? 0 : seed;
+        return fold(rd64(in) ^ (sec64(sec) + sd), rd64(in + 8) ^ (sec64(sec + 8) - sd));
+    }
+};
+static inline uint64_t xxh3_64_variant(const uint8_t* in, size_t len, uint64_t seed, uint32_t variant) {
+    const Xxh3Variant V{variant};
+    const uint8_t* s = kXxh3Secret;
+    if (len == 0 || len > 128) return 0;           // not produced by any k-mer path
+    if (len <= 3) {
+        uint8_t c1 = in[0], c2 = in[len >> 1], c3 = in[len - 1];
+        uint32_t combined = ((uint32_t)c1 << 16) | ((uint32_t)c2 << 24) | (uint32_t)c3 | ((uint32_t)len << 8);
+        const uint64_t s0 = V.sec64(s);
+        uint64_t bitflip = (uint64_t)((uint32_t)s0 ^ (uint32_t)(s0 >> 32)) + seed;
+        return xxh64_avalanche((uint64_t)combined ^ bitflip);
+    }
+    if (len <= 8) {
+        seed ^= (uint64_t)__builtin_bswap32((uint32_t)seed) << 32;
+        uint32_t in1 = rd32(in), in2 = rd32(in + len - 4);
+        uint64_t bitflip = (V.sec64(s + 8) ^ V.sec64(s + 16)) - seed;
+        uint64_t h = ((uint64_t)in2 + ((uint64_t)in1 << 32)) ^ bitflip;
+        h ^= rotl64(h, 49) ^ rotl64(h, 24);
+        h *= P_MX2;
+        h ^= (h >> 35) + len;
+        h *= P_MX2;
+        return h ^ (h >> 28);
+    }
+    if (len <= 16) {
+        uint64_t bf1 = (V.sec64(s + 24) ^ V.sec64(s + 32)) + seed;
+        uint64_t bf2 = (V.sec64(s + 40) ^ V.sec64(s + 48)) - seed;
+        uint64_t lo = rd64(in) ^ bf1, hi = rd64(in + len - 8) ^ bf2;
+        return V.aval(len + __builtin_bswap64(lo) + hi + V.fold(lo, hi));
+    }
+    uint64_t acc = (variant & 8u) ? (len + seed) * P64_1 : len * P64_1;
+    if (len > 32) {
+        if (len > 64) {
+            if (len > 96) {
+                acc += V.mix(in + 48, s + 96, seed);
+                acc += V.mix(in + len - 64, s + 112, seed);
+            }
+            acc += V.mix(in + 32, s + 64, seed);
+            acc += V.mix(in + len - 48, s + 80, seed);
+        }
+        acc += V.mix(in + 16, s + 32, seed);
+        acc += V.mix(in + len - 32, s + 48, seed);
+    }
+    acc += V.mix(in, s, seed);
+    acc += V.mix(in + len - 16, s + 16, seed);
+    return V.aval(acc);
+}
+
 // Lengths 0..240 (every k the k-mer paths can produce); longer inputs are out of scope.
-static inline uint64_t xxh3_64_with_seed(const uint8_t* in, size_t len, uint64_t seed) {
+static inline uint64_t xxh3_64_with_seed(const uint8_t* in, size_t len, uint64_t seed, uint32_t variant = 0) {
+    if (variant) return xxh3_64_variant(in, len, seed, variant);
     const uint8_t* s = kXxh3Secret;
     if (len == 0) return xxh64_avalanche(seed ^ (rd64(s + 56) ^ rd64(s + 64)));
     if (len <= 3) {

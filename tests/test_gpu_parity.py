@@ -36,6 +36,65 @@ def test_hash_rows_match_oracle(oracle, ctx, k):
     assert np.array_equal(got, exp)
 
 
+@pytest.mark.parametrize("k", [3, 8, 12, 21, 31])
+def test_hash_variants_match_oracle(oracle, ctx, k):
+    """cid_index_set_hash_variant: the 32 combinations of the places where the XXH3 drafts differ (the reference's
+    `xxh3 = "0.1.1"` crate predates the freeze); every variant against the oracle's restatement."""
+    rng = _rng(900 + k)
+    H, S = 4, 999_983
+    kmers = [synth.rand_seq(rng, k) for _ in range(300)]
+    seen = set()
+    for v in range(32):
+        got = cb.Index(ctx, S, H, k, 1, hash_variant=v).hash_kmers(kmers)
+        exp = np.array([[oracle.xxh3_64(km, s, v) % S for s in range(H)] for km in kmers], dtype=np.uint64)
+        assert np.array_equal(got, exp), v
+        seen.add(got.tobytes())
+    if k >= 17:
+        assert len(seen) == 32
+    with pytest.raises(cb.CidError):
+        cb.Index(ctx, S, H, k, 1, hash_variant=32)
+
+
+@pytest.mark.parametrize("variant", [1, 31])
+def test_build_search_read_id_under_a_hash_variant(oracle, ctx, variant):
+    """Every kernel hashes through the index's variant: build (set, count table), the three search front ends, read_id on
+    both paths."""
+    rng = _rng(910 + variant)
+    N, k, S, H = 40, 27, 300_007, 4
+    genomes = synth.clade_genomes(rng, N, 5000, n_clades=5, div=0.01)
+    oix, gix = oracle.Index(S, H, k, N, hash_variant=variant), cb.Index(ctx, S, H, k, N, hash_variant=variant)
+    for c, g in enumerate(genomes):
+        assert gix.build_accession(c, [g]) == oix.build_accession(c, [g], oracle.MODE_FASTA)
+    oix.finalize(); gix.finalize()
+    assert np.array_equal(gix.download_dense(), oix.words())
+    stable = cb.Index(ctx, S, H, k, N)
+    for c, g in enumerate(genomes):
+        stable.build_accession(c, [g])
+    stable.finalize()
+    assert not np.array_equal(stable.download_dense(), oix.words())
+    queries = [[genomes[i][200:1500]] for i in range(0, N, 5)] + [[synth.rand_seq(rng, 700)]]
+    for gene, uq in ((True, False), (False, True)):
+        o = oix.query_counts(queries, oracle.MODE_FASTA, gene, 0)
+        g = gix.query_counts(queries, cb.CID_SEQ_FASTA, gene, 0, want_uniq=uq)
+        assert np.array_equal(g["counts"], o["counts"]) and np.array_equal(g["num_kmers"], o["num_kmers"])
+    op, gp = oix.query_perfect(queries), gix.query_perfect(queries)
+    assert np.array_equal(gp["status"], op["status"]) and np.array_equal(gp["and_rows"], op["and_rows"])
+    reads = synth.reads_from(rng, genomes, 80, read_len=150, insert=320, err=0.003, frac_random=0.2)
+    reads += synth.reads_from(rng, genomes, 4, read_len=1500, insert=1600, err=0.001, frac_random=0.0, paired=False)
+    reads.append([genomes[3][:150].lower()])
+    _readid_compare(oracle, oix, gix, reads, order_cap=1600)
+    # FASTQ read-set build through the count table (auto_cutoff)
+    accs = []
+    for gnm in genomes[:2]:
+        rs = synth.reads_from(rng, [gnm], 600, read_len=100, insert=200, err=0.008, frac_random=0.0)
+        accs.append([m for r in rs for m in r])
+    o2, g2 = oracle.Index(S, H, k, 2, hash_variant=variant), cb.Index(ctx, S, H, k, 2, hash_variant=variant)
+    for c, a in enumerate(accs):
+        assert g2.build_accession(c, a, cb.CID_SEQ_FASTQ, -1) == o2.build_accession(c, a, oracle.MODE_FASTQ, -1)
+    o2.finalize(); g2.finalize()
+    assert np.array_equal(g2.download_dense(), o2.words())
+
+
 @pytest.mark.parametrize("k,S,H,N", [(27, 750_000, 4, 4), (31, 300_007, 4, 46), (21, 200_003, 2, 70), (15, 65_536, 3, 33)])
 def test_build_fasta_matrix_bit_exact(oracle, ctx, k, S, H, N):
     rng = _rng(N)

@@ -104,6 +104,27 @@ def test_phage_self_queries_through_search(phage, oracle):
         assert any(l.split("\t")[1] == n for l in body), body
 
 
+def test_cli_hash_variant_is_found_by_the_pin_tool(phage):
+    """COLORID_B200_HASH_VARIANT selects the XXH3 draft of the CLI; tools/pin_from_bxi.py (numpy only) names it from the .bxi."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("pin_from_bxi", os.path.join(ROOT, "tools", "pin_from_bxi.py"))
+    pin = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(pin)
+    d = phage["dir"]
+    for v in (0, 31):
+        env = dict(os.environ, COLORID_B200_HASH_VARIANT=str(v))
+        r = subprocess.run([CLI, "build", "-s", "750000", "-n", "4", "-k", "27", "-b", str(d / f"hv{v}"), "-r", str(d / "test_data" / "ref_file.txt")],
+                           capture_output=True, text=True, env=env)
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert pin.pin(d / f"hv{v}.bxi", d / "test_data" / "ref_file.txt") == [v]
+        # searching the variant's index needs the variant too: with it the own accession scores 1.000, without it nothing matches
+        f = d / "test_data" / "refs" / "Listeria_phage_B056.fasta"
+        r = subprocess.run([CLI, "search", "-b", str(d / f"hv{v}.bxi"), "-g", "-q", str(f)], capture_output=True, text=True, env=env)
+        assert f"{f}\tListeria_phage_B056\t32634\t1.000" in r.stdout
+    r = subprocess.run([CLI, "search", "-b", str(d / "hv31.bxi"), "-g", "-q", str(f)], capture_output=True, text=True)
+    assert "Listeria_phage_B056\t32634\t1.000" not in r.stdout and "hash variant" in r.stderr
+
+
 # ------------------------------------------------------------------------------------------------ the 16 real genomes
 have_genomes = pytest.mark.skipif(not os.path.isdir(GENOMES), reason="oracle/_ref/refs not staged (run __graft_entry__.build() where /root/reference exists)")
 
