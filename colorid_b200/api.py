@@ -358,3 +358,132 @@ class Index:
         out = np.zeros((len(kmers), self.H), dtype=np.uint64)
         L.check(self.lib.cid_hash_kmers(self.h, _p(arr), len(kmers), _p(out, L.u64p)))
         return out
+
+
+class MultiIndex:
+    """One index over several GPUs of this node (include/colorid_b200.h `cid_mg`): replicated (reads / queries dealt to the
+    GPUs) or column-sharded (every GPU gathers all k-mers from its accession slice).  Same results as `Index`.
+    devices: list of CUDA device ids; an id may repeat (several shards on one GPU)."""
+
+    def __init__(self, devices, mode, bloom_size, num_hash, k, n_colours, m=0, hash_variant=0):
+        self.lib = L.load()
+        self.S, self.H, self.k, self.N, self.m = bloom_size, num_hash, k, n_colours, m
+        self.W = (n_colours + 31) // 32
+        devs = (C.c_int * len(devices))(*devices)
+        h = L.vp()
+        L.check(self.lib.cid_mg_create(devs, len(devices), mode, C.byref(h)))
+        self.h = h
+        L.check(self.lib.cid_mg_index_create(h, bloom_size, num_hash, k, n_colours))
+        if m:
+            L.check(self.lib.cid_mg_index_set_minimizer(h, m))
+        if hash_variant:
+            L.check(self.lib.cid_mg_index_set_hash_variant(h, hash_variant))
+        self.n_ref = np.zeros(n_colours, dtype=np.uint64)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cid_mg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    @property
+    def launches(self):
+        return int(self.lib.cid_mg_launch_count(self.h))
+
+    def set_option(self, name, value):
+        L.check(self.lib.cid_mg_set_option(self.h, name.encode(), int(value)))
+
+    def shard_columns(self):
+        out = []
+        for g in range(self.lib.cid_mg_n_shards(self.h)):
+            a, b = C.c_uint32(0), C.c_uint32(0)
+            L.check(self.lib.cid_mg_shard_columns(self.h, g, C.byref(a), C.byref(b)))
+            out.append((a.value, b.value))
+        return out
+
+    def build_accession(self, colour, seqs, mode=L.CID_SEQ_FASTA, cutoff=-1, mini_variant=-1):
+        bases, offs = pack_seqs(list(seqs))
+        n_ref, used = C.c_uint64(0), C.c_int64(0)
+        L.check(self.lib.cid_mg_build_accession(self.h, colour, _p(bases), _p(offs, L.u64p), len(seqs), mode, cutoff, mini_variant,
+                                                C.byref(n_ref), C.byref(used)))
+        self.n_ref[colour] = n_ref.value
+        return n_ref.value, used.value
+
+    def finalize(self):
+        L.check(self.lib.cid_mg_build_finalize(self.h))
+
+    def upload_rows(self, row_ids, words):
+        row_ids = np.ascontiguousarray(row_ids, dtype=np.uint64)
+        words = np.ascontiguousarray(words, dtype=np.uint32)
+        L.check(self.lib.cid_mg_index_upload_rows(self.h, _p(row_ids, L.u64p), _p(words, L.u32p), len(row_ids)))
+
+    def nonzero_rows(self):
+        n = C.c_uint64(0)
+        L.check(self.lib.cid_mg_index_count_nonzero_rows(self.h, C.byref(n)))
+        return n.value
+
+    def download_nonzero_rows(self):
+        n = self.nonzero_rows()
+        ids = np.zeros(max(n, 1), dtype=np.uint64)
+        words = np.zeros((max(n, 1), self.W), dtype=np.uint32)
+        got = C.c_uint64(0)
+        L.check(self.lib.cid_mg_index_download_nonzero_rows(self.h, _p(ids, L.u64p), _p(words, L.u32p), n, C.byref(got)))
+        return ids[:n], words[:n]
+
+    def query_counts(self, queries, seq_mode=L.CID_SEQ_FASTA, gene_search=False, filt=-1, want_uniq=True):
+        flat = [s for q in queries for s in q]
+        bases, offs = pack_seqs(flat)
+        qoffs = group_offsets(queries)
+        nq = len(queries)
+        counts = np.zeros((nq, self.N), dtype=np.uint32)
+        num_kmers = np.zeros(nq, dtype=np.uint64)
+        un, us, um = ((np.zeros((nq, self.N), dtype=np.uint64) if want_uniq else None) for _ in range(3))
+        used = np.zeros(max(nq, 1), dtype=np.int64)
+        L.check(self.lib.cid_mg_query_counts(self.h, _p(bases), _p(offs, L.u64p), len(flat), _p(qoffs, L.u64p), nq, seq_mode,
+                                             int(gene_search), filt, _p(counts, L.u32p), _p(num_kmers, L.u64p),
+                                             _p(un, L.u64p), _p(us, L.u64p), _p(um, L.u64p), _p(used, L.i64p)))
+        return dict(counts=counts, num_kmers=num_kmers, uniq_n=un, uniq_sum=us, uniq_mode=um, cutoff=used[:nq])
+
+    def query_perfect(self, queries):
+        flat = [s for q in queries for s in q]
+        bases, offs = pack_seqs(flat)
+        qoffs = group_offsets(queries)
+        nq = len(queries)
+        and_rows = np.zeros((nq, self.W), dtype=np.uint32)
+        status = np.zeros(max(nq, 1), dtype=np.uint8)
+        n_kmers = np.zeros(max(nq, 1), dtype=np.uint64)
+        L.check(self.lib.cid_mg_query_perfect(self.h, _p(bases), _p(offs, L.u64p), len(flat), _p(qoffs, L.u64p), nq,
+                                              _p(and_rows, L.u32p), _p(status, L.u8p), _p(n_kmers, L.u64p)))
+        return dict(and_rows=and_rows, status=status[:nq], n_kmers=n_kmers[:nq])
+
+    def query_perfect_mf(self, records):
+        bases, offs = pack_seqs(list(records))
+        nq = len(records)
+        and_rows = np.zeros((nq, self.W), dtype=np.uint32)
+        status = np.zeros(max(nq, 1), dtype=np.uint8)
+        n_kmers = np.zeros(max(nq, 1), dtype=np.uint64)
+        L.check(self.lib.cid_mg_query_perfect_mf(self.h, _p(bases), _p(offs, L.u64p), nq, _p(and_rows, L.u32p),
+                                                 _p(status, L.u8p), _p(n_kmers, L.u64p)))
+        return dict(and_rows=and_rows, status=status[:nq], n_kmers=n_kmers[:nq])
+
+    def read_id_classify(self, reads, quals=None, d=1, start_sample=3, qual_offset=0, group_width=16, reserve_before_find=True,
+                         fp_correct=1e-3, top_cap=8):
+        flat = [s for r in reads for s in r]
+        bases, offs = pack_seqs(flat)
+        roffs = group_offsets(reads)
+        qarr = None
+        if quals is not None:
+            qarr, _ = pack_seqs([s for r in quals for s in r])
+        nr = len(reads)
+        p = L.ReadIdParams(d, start_sample, qual_offset, group_width, int(reserve_before_find), 0)
+        mm = max(nr, 1)
+        kind = np.zeros(mm, np.int32)
+        hits, n_set, n_top = np.zeros(mm, np.uint32), np.zeros(mm, np.uint32), np.zeros(mm, np.uint32)
+        top = np.zeros((mm, top_cap), np.uint32)
+        n_ref = np.ascontiguousarray(self.n_ref, dtype=np.uint64)
+        L.check(self.lib.cid_mg_read_id_classify(self.h, _p(bases), _p(qarr), _p(offs, L.u64p), len(flat), _p(roffs, L.u64p), nr,
+                                                 C.byref(p), _p(n_ref, L.u64p), fp_correct, _p(kind, L.i32p), _p(hits, L.u32p),
+                                                 _p(n_set, L.u32p), _p(n_top, L.u32p), _p(top, L.u32p), top_cap))
+        return dict(kind=kind[:nr], hits=hits[:nr], n_set=n_set[:nr], n_top=n_top[:nr], top=top[:nr])

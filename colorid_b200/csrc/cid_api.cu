@@ -1215,7 +1215,9 @@ static int query_perfect_impl(cid_index* ix, const char* bases, const uint64_t* 
     CID_CUDA(cudaMemcpyAsync(ctx->scratch[5].p, seq_offs, (nseq + 1) * 8, cudaMemcpyHostToDevice, st));
     const uint32_t W = ix->W;
     // small queries: shared-memory dedup front end + streaming AND gather (no count table)
-    const bool fast = nq && query_front_ok(ix, false, seq_offs, query_offs, nq);
+    // (any row shape: rows the streaming gather does not take go through perfect_rids_kernel)
+    const bool fast = nq && ctx->opt_query_front && !ctx->opt_query_fused && ix->Wp * 4ull <= 48 * 1024 &&
+                      query_front_fits(seq_offs, query_offs, 0, nq, ix->k);
     if (fast) {
         CID_TRY(ctx->scratch[7].ensure((nq + 1) * 8));
         CID_CUDA(cudaMemcpyAsync(ctx->scratch[7].p, query_offs, (nq + 1) * 8, cudaMemcpyHostToDevice, st));

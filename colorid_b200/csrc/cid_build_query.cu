@@ -975,6 +975,37 @@ query_uniq_wide_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t 
     }
 }
 
+// Perfect search over prepared row-index lists for the row shapes the streaming gather does not take (rows of 1 or 2 words,
+// rows above 512 bytes, num_hash other than 2 / 4): one CTA per unit, every thread ANDs the rows of its k-mers word by word
+// into a shared accumulator.  Keeps -s -m exact (windows with a byte outside ACGTacgt, hashed by query_front<STRINGM>) on
+// narrow indexes and narrow column shards.
+__global__ void __launch_bounds__(256)
+perfect_rids_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t W, uint32_t H, const uint32_t* __restrict__ rid,
+                    const uint32_t* __restrict__ unit_group, const uint64_t* __restrict__ unit_slot0,
+                    const uint32_t* __restrict__ unit_n, const uint32_t* __restrict__ rownz, uint32_t* __restrict__ and_rows,
+                    uint32_t* __restrict__ missing) {
+    extern __shared__ __align__(16) uint32_t acc[];       // [Wp]
+    const uint32_t n = unit_n[blockIdx.x], g = unit_group[blockIdx.x];
+    if (n == 0) return;
+    for (uint32_t w = threadIdx.x; w < Wp; w += blockDim.x) acc[w] = 0xFFFFFFFFu;
+    __syncthreads();
+    const uint32_t* my = rid + unit_slot0[blockIdx.x] * H;
+    bool miss = false;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        for (uint32_t h = 0; h < H; h++) {
+            const uint32_t r = __ldg(my + (size_t)i * H + h);
+            if (!((__ldg(rownz + (r >> 5)) >> (r & 31)) & 1u)) miss = true;
+        }
+        for (uint32_t w = 0; w < W; w++) {
+            uint32_t x = 0xFFFFFFFFu;
+            for (uint32_t h = 0; h < H; h++) x &= __ldg(rows + (size_t)__ldg(my + (size_t)i * H + h) * Wp + w);
+            if (x != 0xFFFFFFFFu) atomicAnd(&acc[w], x);
+        }
+    }
+    if (__syncthreads_or(miss) && threadIdx.x == 0) atomicOr(&missing[g], 1u);
+    for (uint32_t w = threadIdx.x; w < W; w += blockDim.x) if (acc[w] != 0xFFFFFFFFu) atomicAnd(&and_rows[(uint64_t)g * W + w], acc[w]);
+}
+
 // query_gather over prepared row-index lists: unit u = rid[(unit_slot0[u] + i) * H + h], i < unit_n[u] (<= 16384)
 static int launch_query_gather(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, const uint32_t* d_rid,
                                const uint32_t* d_unit_group, const uint64_t* d_unit_slot0, const uint32_t* d_unit_n,
@@ -1198,7 +1229,14 @@ int launch_query_front_gather(cid_ctx* ctx, cudaStream_t st, const cid_index* id
     GatherOut dense_out{};
     const GatherOut* const shared = ctx->gather_out;
     if (shared && !d_and_rows) { dense_out = *shared; dense_out.dense = 1; ctx->gather_out = &dense_out; }
-    const int grc = launch_query_gather(ctx, st, idx, d_rid, d_group, d_base, d_unit_n, bq, d_counts, d_and_rows, d_missing);
+    int grc;
+    if (d_and_rows && !(idx->Wp >= 4 && idx->Wp <= 128 && (idx->H == 2 || idx->H == 4))) {
+        ProfScope ps(ctx, st, KID_QUERY_PERFECT);
+        perfect_rids_kernel<<<(unsigned)bq, 256, (size_t)idx->Wp * 4, st>>>(idx->rows, idx->Wp, idx->W, idx->H, d_rid, d_group, d_base, d_unit_n,
+                                                                           idx->rownz, d_and_rows, d_missing);
+        ctx->launches++;
+        grc = cudaGetLastError() == cudaSuccess ? CID_OK : CID_E_CUDA;
+    } else grc = launch_query_gather(ctx, st, idx, d_rid, d_group, d_base, d_unit_n, bq, d_counts, d_and_rows, d_missing);
     ctx->gather_out = shared;
     CID_TRY(grc);
     CID_CUDA(cudaStreamSynchronize(st));

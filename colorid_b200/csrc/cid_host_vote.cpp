@@ -137,7 +137,7 @@ struct PmfMemo {
     std::vector<double> val;
     PmfMemo() : key(SIZE, ~0ull), val(SIZE, 0.0) {}
     double get(const VoteParams& vp, uint64_t obs, uint32_t colour, uint32_t x) {
-        if (obs >= (1u << 20) || x >= (1u << 20) || colour >= (1u << 24)) return binomial_pmf(obs, vp.fp[colour], x);
+        if (obs >= (1u << 20) || x >= (1u << 20) || colour >= (1u << 24) - 1) return binomial_pmf(obs, vp.fp[colour], x);   // (the all-ones key is the empty marker)
         const uint64_t k = ((uint64_t)colour << 40) | (obs << 20) | x;
         const uint64_t h = (k * 0x9E3779B97F4A7C15ull) >> (64 - 13);
         if (key[h] != k) { key[h] = k; val[h] = binomial_pmf(obs, vp.fp[colour], x); }
@@ -266,6 +266,8 @@ int cid_merge_shard_reports(uint32_t n_shards, const uint32_t* shard_n_colors, c
         return CID_E_INVALID;
     }
     const uint32_t cmask = (1u << 20) - 1u;
+    for (uint32_t s = 0; s < n_shards; s++)        // colours share a word with the 12-bit insertion step (colour | step << 20)
+        if (shard_n_colors[s] >= cmask) { set_error("cid_merge_shard_reports: shard %u has %u colours, the tagged reports hold < 2^20 - 1", s, shard_n_colors[s]); return CID_E_INVALID; }
     struct Ent { uint32_t step, colour, count; };
     // reads are independent: host threads over contiguous ranges; the first problem found wins (1 = rep_n, 2 = colour, 3 = miss)
     std::atomic<int> problem{0};

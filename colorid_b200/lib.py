@@ -19,6 +19,7 @@ vp = C.c_void_p
 
 CID_OK, CID_E_INVALID, CID_E_CUDA, CID_E_NOMEM, CID_E_UNSUPPORTED, CID_E_REF_PANIC, CID_E_CAPACITY = 0, -1, -2, -3, -4, -5, -6
 CID_SEQ_FASTA, CID_SEQ_FASTQ, CID_SEQ_STRING = 0, 1, 2
+CID_MG_REPLICATED, CID_MG_COLUMNS = 0, 1
 CID_MINI_OF_KMERS, CID_MINI_COUNTED = 0, 1
 
 
@@ -52,6 +53,30 @@ SIGNATURES = {
     "cid_build_accession_dev": (C.c_int, [vp, C.c_uint32, vp, vp, C.c_uint64, C.c_uint64, C.c_int, C.c_int64, u64p, i64p]),
     "cid_index_set_minimizer": (C.c_int, [vp, C.c_uint32]),
     "cid_index_set_hash_variant": (C.c_int, [vp, C.c_uint32]),
+    "cid_mg_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(vp)]),
+    "cid_mg_destroy": (None, [vp]),
+    "cid_mg_n_shards": (C.c_int, [vp]),
+    "cid_mg_mode": (C.c_int, [vp]),
+    "cid_mg_ctx": (vp, [vp, C.c_int]),
+    "cid_mg_index": (vp, [vp, C.c_int]),
+    "cid_mg_shard_columns": (C.c_int, [vp, C.c_int, u32p, u32p]),
+    "cid_mg_shard_of_colour": (C.c_int, [vp, C.c_uint32]),
+    "cid_mg_set_option": (C.c_int, [vp, C.c_char_p, C.c_int64]),
+    "cid_mg_launch_count": (C.c_uint64, [vp]),
+    "cid_mg_index_create": (C.c_int, [vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "cid_mg_index_set_minimizer": (C.c_int, [vp, C.c_uint32]),
+    "cid_mg_index_set_hash_variant": (C.c_int, [vp, C.c_uint32]),
+    "cid_mg_index_upload_rows": (C.c_int, [vp, u64p, u32p, C.c_uint64]),
+    "cid_mg_index_count_nonzero_rows": (C.c_int, [vp, u64p]),
+    "cid_mg_index_download_nonzero_rows": (C.c_int, [vp, u64p, u32p, C.c_uint64, u64p]),
+    "cid_mg_build_accession": (C.c_int, [vp, C.c_uint32, vp, u64p, C.c_uint64, C.c_int, C.c_int64, C.c_int, u64p, C.POINTER(C.c_int64)]),
+    "cid_mg_build_finalize": (C.c_int, [vp]),
+    "cid_mg_query_counts": (C.c_int, [vp, vp, u64p, C.c_uint64, u64p, C.c_uint64, C.c_int, C.c_int, C.c_int64, u32p, u64p, u64p, u64p, u64p,
+                                      C.POINTER(C.c_int64)]),
+    "cid_mg_query_perfect": (C.c_int, [vp, vp, u64p, C.c_uint64, u64p, C.c_uint64, u32p, u8p, u64p]),
+    "cid_mg_query_perfect_mf": (C.c_int, [vp, vp, u64p, C.c_uint64, u32p, u8p, u64p]),
+    "cid_mg_read_id_classify": (C.c_int, [vp, vp, vp, u64p, C.c_uint64, u64p, C.c_uint64, C.POINTER(ReadIdParams), u64p,
+                                          C.c_double, C.POINTER(C.c_int32), u32p, u32p, u32p, u32p, C.c_uint32]),
     "cid_index_hash_variant": (C.c_uint32, [vp]),
     "cid_index_minimizer": (C.c_uint32, [vp]),
     "cid_build_accession_mini": (C.c_int, [vp, C.c_uint32, vp, u64p, C.c_uint64, C.c_int, C.c_int64, C.c_int, u64p, i64p]),

@@ -296,6 +296,55 @@ int cid_merge_shard_reports(uint32_t n_shards, const uint32_t* shard_n_colors, c
                             uint64_t nreads, const uint32_t* const* rep_n, const uint32_t* const* rep_colour,
                             const uint32_t* const* rep_count, uint32_t rep_cap_in, uint32_t n_total, uint32_t* out_rep_n,
                             uint32_t* out_colour, uint32_t* out_count, uint32_t rep_cap_out, uint32_t* out_flags);
+/* ---- multi-GPU: one index over several GPUs of one node (BASELINE north_star) ------------------------------
+ * The reference scales with rayon threads inside one process (main.rs:718, build.rs:146-149); here a cid_mg is a set of GPUs
+ * behind the same host-pointer calls, one host thread per GPU inside the library.
+ *   CID_MG_REPLICATED  every GPU holds the whole matrix (it fits one GPU: C1-C4); reads / queries are dealt to the GPUs in
+ *                      contiguous ranges, no data-path exchange; a build fills column slices on their owner GPUs and copies
+ *                      them into every replica at cid_mg_build_finalize (peer copies);
+ *   CID_MG_COLUMNS     GPU g holds the accessions [col_offset, col_offset + n_colors) of every row (whole 32-accession word
+ *                      columns: C5); every GPU processes ALL k-mers against its slice.  Counts and AND rows are disjoint column
+ *                      slices of the result; the default report exchanges one byte per k-mer (popcounts); read_id merges the
+ *                      shards' sparse reports in insertion order; the row-present bitmaps are OR-ed after build / upload.
+ * Results are identical to the single-GPU entry points of the same name in either mode.  `devices` may list a device more
+ * than once (several shards on one GPU).  A cid_mg is single-owner except cid_mg_build_accession, which may be called from
+ * several host threads at once (accessions of different shards build concurrently). */
+typedef struct cid_mg cid_mg;
+enum { CID_MG_REPLICATED = 0, CID_MG_COLUMNS = 1 };
+int cid_mg_create(const int* devices, int ndev, int shard_mode, cid_mg** out);
+void cid_mg_destroy(cid_mg* mg);
+int cid_mg_n_shards(const cid_mg* mg);
+int cid_mg_mode(const cid_mg* mg);
+cid_ctx* cid_mg_ctx(cid_mg* mg, int shard);                 /* the shard's context / index for the single-GPU calls */
+cid_index* cid_mg_index(cid_mg* mg, int shard);
+int cid_mg_shard_columns(const cid_mg* mg, int shard, uint32_t* col_offset, uint32_t* n_colors);
+int cid_mg_shard_of_colour(const cid_mg* mg, uint32_t colour);
+int cid_mg_set_option(cid_mg* mg, const char* name, int64_t value);      /* cid_ctx_set_option on every shard */
+uint64_t cid_mg_launch_count(const cid_mg* mg);
+int cid_mg_index_create(cid_mg* mg, uint64_t bloom_size, uint32_t num_hash, uint32_t k_size, uint32_t n_colors);
+int cid_mg_index_set_minimizer(cid_mg* mg, uint32_t m_size);
+int cid_mg_index_set_hash_variant(cid_mg* mg, uint32_t variant);
+int cid_mg_index_upload_rows(cid_mg* mg, const uint64_t* row_ids, const uint32_t* words /* nrows * ceil(N/32) */, uint64_t nrows);
+int cid_mg_index_count_nonzero_rows(cid_mg* mg, uint64_t* nrows);
+int cid_mg_index_download_nonzero_rows(cid_mg* mg, uint64_t* row_ids, uint32_t* words, uint64_t cap, uint64_t* nrows);
+/* build.rs:33-256; mini_variant: -1 = k-mer index, else CID_MINI_OF_KMERS / CID_MINI_COUNTED (cid_build_accession_mini) */
+int cid_mg_build_accession(cid_mg* mg, uint32_t colour, const char* bases, const uint64_t* seq_offs, uint64_t nseq, int seq_mode,
+                           int64_t cutoff, int mini_variant, uint64_t* n_ref_kmers, int64_t* cutoff_used);
+int cid_mg_build_finalize(cid_mg* mg);
+/* batch_search_pe.rs:9-179, perfect_search.rs:6-120, read_id_mt_pe.rs:282-363: arguments as cid_query_counts,
+ * cid_query_perfect[_mf] and cid_read_id_classify; all result arrays are full width (n_colors of the whole index) */
+int cid_mg_query_counts(cid_mg* mg, const char* bases, const uint64_t* seq_offs, uint64_t nseq, const uint64_t* query_offs,
+                        uint64_t nq, int seq_mode, int gene_search, int64_t filter, uint32_t* counts, uint64_t* num_kmers,
+                        uint64_t* uniq_n, uint64_t* uniq_sum, uint64_t* uniq_mode, int64_t* cutoff_used);
+int cid_mg_query_perfect(cid_mg* mg, const char* bases, const uint64_t* seq_offs, uint64_t nseq, const uint64_t* query_offs,
+                         uint64_t nq, uint32_t* and_rows, uint8_t* status, uint64_t* n_kmers);
+int cid_mg_query_perfect_mf(cid_mg* mg, const char* bases, const uint64_t* seq_offs, uint64_t nseq, uint32_t* and_rows,
+                            uint8_t* status, uint64_t* n_kmers);
+int cid_mg_read_id_classify(cid_mg* mg, const char* bases, const char* quals, const uint64_t* seq_offs, uint64_t nseq,
+                            const uint64_t* read_offs, uint64_t nreads, const cid_readid_params* p, const uint64_t* n_ref_by_colour,
+                            double fp_correct, int32_t* kind, uint32_t* hits, uint32_t* n_set, uint32_t* n_top, uint32_t* top,
+                            uint32_t top_cap);
+
 /* read_id_mt_pe.rs:695-698 false_prob and the Binomial pmf used by :168-181 (parity hooks). */
 double cid_false_prob(double bloom_size, double num_hash, double n_ref_kmers);
 double cid_binomial_mass(uint64_t n, double p, uint64_t x);

@@ -364,6 +364,31 @@ def test_perfect_search(oracle, ctx, N, k, S, H):
     assert (o["status"] == 0).sum() >= 10
 
 
+@pytest.mark.parametrize("N,H", [(4, 4), (46, 4), (40, 3), (150, 3), (4200, 2)])
+def test_perfect_search_multifasta_non_acgt_on_any_row_shape(oracle, ctx, N, H):
+    """kmerize_string (kmer.rs:271-299) has no has_no_n test: -s -m records with N / IUPAC / U bytes are exact on every row
+    shape -- rows of 1 or 2 words (the C1 index, narrow column shards), num_hash 3, rows above 512 bytes -- through
+    query_front<STRINGM> + perfect_rids_kernel where the streaming gather does not apply."""
+    rng = _rng(460 + N)
+    k, S = 21, 100_003
+    genomes, oix, gix = _index_pair(oracle, ctx, rng, N, k, S, H, glen=1500 if N > 1000 else 4000)
+    recs = []
+    for i in range(24):
+        g = genomes[int(rng.integers(0, N))]
+        q = g[100:100 + int(rng.integers(k, 1200))]
+        if i % 3 == 0:
+            q = synth.sprinkle(rng, q, b"NnRYUu", 0.01)
+        recs.append(q)
+    recs += [b"ACGTN", b"N" * 40, genomes[0][:300]]
+    o = oix.query_perfect(recs, mf=True)
+    g = gix.query_perfect_mf(recs)
+    assert np.array_equal(g["status"], o["status"]) and np.array_equal(g["n_kmers"], o["n_kmers"]) and np.array_equal(g["and_rows"], o["and_rows"])
+    assert (o["status"] == 0).sum() >= 5
+    qs = [[r] for r in recs if b"N" not in r.upper() and b"R" not in r and b"Y" not in r and b"U" not in r.upper()]
+    o2, g2 = oix.query_perfect(qs), gix.query_perfect(qs)
+    assert np.array_equal(g2["status"], o2["status"]) and np.array_equal(g2["and_rows"], o2["and_rows"])
+
+
 def test_perfect_search_multifasta_records(oracle, ctx):
     """-s -m: perfect_search.rs:62-120 batch_search_mf over kmer.rs:271-299 kmerize_string (one query per record)."""
     rng = _rng(451)
