@@ -33,15 +33,29 @@ struct Trace {                    // COLORID_B200_TRACE=1: stage timings on stde
         t0 = t1;
     }
 };
-struct Gpu {                      // context + device index
+// The GPU side of a command: one device (cid_ctx + cid_index), or -- COLORID_B200_DEVICES=0,1,.. -- one index over several
+// GPUs (cid_mg).  COLORID_B200_SHARD=columns|replicated picks the layout; by default the matrix is replicated when it fits
+// one GPU comfortably and column-sharded otherwise (BASELINE north_star).  The same calls either way.
+std::vector<int> env_devices() {
+    std::vector<int> v;
+    if (const char* ds = getenv("COLORID_B200_DEVICES"))
+        for (const char* q = ds; *q;) { char* e; long x = strtol(q, &e, 10); if (e == q) break; v.push_back((int)x); q = *e ? e + 1 : e; }
+    return v;
+}
+struct Gpu {
     cid_ctx* ctx = nullptr;
     cid_index* ix = nullptr;
+    cid_mg* mg = nullptr;             // set instead of ctx/ix when several devices are in use
+    std::vector<int> devs;
     // creating a CUDA context takes 1.5-2.5 s on a fresh process: do it on a helper thread while the caller
     // reads its input files, join on first use
     std::thread starter;
     int start_rc = CID_OK;
     std::string start_err;
-    explicit Gpu(int device) {
+    explicit Gpu(int device, bool multi = false) {
+        if (multi) devs = env_devices();
+        if (devs.size() > 1) return;                      // cid_mg_create once the index shape (hence the layout) is known
+        if (devs.size() == 1) device = devs[0];
         starter = std::thread([this, device] {
             start_rc = cid_ctx_create(device, &ctx);
             if (start_rc != CID_OK) start_err = cid_last_error();       // cid_last_error is thread-local
@@ -51,25 +65,89 @@ struct Gpu {                      // context + device index
         if (starter.joinable()) starter.join();
         if (start_rc != CID_OK) { int rc = start_rc; start_rc = CID_OK; (void)rc; throw Error("colorid_b200: " + start_err); }
     }
-    ~Gpu() { if (starter.joinable()) starter.join(); if (ix) cid_index_destroy(ix); if (ctx) cid_ctx_destroy(ctx); }
+    ~Gpu() {
+        if (starter.joinable()) starter.join();
+        if (mg) cid_mg_destroy(mg);
+        if (ix) cid_index_destroy(ix);
+        if (ctx) cid_ctx_destroy(ctx);
+    }
     void create(uint64_t S, uint64_t H, uint64_t k, uint64_t N) {
-        ready();
         if (H > 0xFFFFFFFFull || k > 0xFFFFFFFFull || N > 0xFFFFFFFFull) throw Error("index parameters out of range");
-        ck(cid_index_create(ctx, S, (uint32_t)H, (uint32_t)k, (uint32_t)N, &ix));
         // The reference hashes with the crate `xxh3 = "0.1.1"` (Cargo.toml:9), a pre-freeze XXH3 that is not pinned here:
         // COLORID_B200_HASH_VARIANT selects the draft an index was / is to be hashed with (include/colorid_b200.h;
         // default 0 = stable XXH3; tools/pin_from_bxi.py finds the variant that reproduces a given .bxi).
-        if (const char* hv = getenv("COLORID_B200_HASH_VARIANT")) ck(cid_index_set_hash_variant(ix, (uint32_t)strtoul(hv, nullptr, 10)));
+        const char* hv = getenv("COLORID_B200_HASH_VARIANT");
+        if (devs.size() > 1) {
+            int mode = -1;
+            if (const char* sm = getenv("COLORID_B200_SHARD")) mode = !strcmp(sm, "columns") ? CID_MG_COLUMNS : !strcmp(sm, "replicated") ? CID_MG_REPLICATED : -1;
+            if (mode < 0) {
+                const uint64_t W = (N + 31) / 32, Wp = W <= 2 ? W : (W + 3) / 4 * 4;
+                mode = S * Wp * 4 > (48ull << 30) ? CID_MG_COLUMNS : CID_MG_REPLICATED;
+            }
+            ck(cid_mg_create(devs.data(), (int)devs.size(), mode, &mg));
+            fprintf(stderr, "%zu GPUs, index %s\n", devs.size(), mode == CID_MG_COLUMNS ? "column-sharded" : "replicated");
+            ck(cid_mg_index_create(mg, S, (uint32_t)H, (uint32_t)k, (uint32_t)N));
+            if (hv) ck(cid_mg_index_set_hash_variant(mg, (uint32_t)strtoul(hv, nullptr, 10)));
+            return;
+        }
+        ready();
+        ck(cid_index_create(ctx, S, (uint32_t)H, (uint32_t)k, (uint32_t)N, &ix));
+        if (hv) ck(cid_index_set_hash_variant(ix, (uint32_t)strtoul(hv, nullptr, 10)));
+    }
+    void set_minimizer(uint32_t m) { ck(mg ? cid_mg_index_set_minimizer(mg, m) : cid_index_set_minimizer(ix, m)); }
+    void set_host_threads(uint64_t t) {
+        if (mg) ck(cid_mg_set_option(mg, "host_threads", (int64_t)t));
+        else { ready(); ck(cid_ctx_set_option(ctx, "host_threads", (int64_t)t)); }
     }
     void upload(const Bigsi& b) {   // main.rs:576 / :796 read_bigsi -> dense device matrix
         create(b.bloom_size, b.num_hash, b.k_size, b.n_colors());
         if (b.mini) {
             if (b.m_size == 0 || b.m_size > 0xFFFFFFFFull) throw Error("minimizer size out of range");
-            ck(cid_index_set_minimizer(ix, (uint32_t)b.m_size));
+            set_minimizer((uint32_t)b.m_size);
         }
         uint64_t c = 0;
         for (auto& kv : b.colors) if (kv.first != c++) throw Error("index colours are not 0..N-1");
-        ck(cid_index_upload_rows(ix, b.row_ids.data(), b.words.data(), b.row_ids.size()));
+        ck(mg ? cid_mg_index_upload_rows(mg, b.row_ids.data(), b.words.data(), b.row_ids.size())
+              : cid_index_upload_rows(ix, b.row_ids.data(), b.words.data(), b.row_ids.size()));
+    }
+    // accessions of different lanes may be built concurrently (one lane per GPU that owns columns)
+    uint32_t lanes() const { return mg ? (uint32_t)cid_mg_n_shards(mg) : 1u; }
+    uint32_t lane_of(uint32_t colour) const { return mg ? (uint32_t)cid_mg_shard_of_colour(mg, colour) : 0u; }
+    void build_accession(uint32_t colour, const SeqBatch& sb, int mode, int64_t cutoff, int mini_variant, uint64_t* nref, int64_t* used) {
+        if (mg) ck(cid_mg_build_accession(mg, colour, sb.bases.data(), sb.offs.data(), sb.n(), mode, cutoff, mini_variant, nref, used));
+        else if (mini_variant >= 0) ck(cid_build_accession_mini(ix, colour, sb.bases.data(), sb.offs.data(), sb.n(), mode, cutoff, mini_variant, nref, used));
+        else ck(cid_build_accession(ix, colour, sb.bases.data(), sb.offs.data(), sb.n(), mode, cutoff, nref, used));
+    }
+    void finalize() { ck(mg ? cid_mg_build_finalize(mg) : cid_build_finalize(ix)); }
+    void nonzero_rows(Bigsi& out) {
+        uint64_t nrows = 0, got = 0;
+        ck(mg ? cid_mg_index_count_nonzero_rows(mg, &nrows) : cid_index_count_nonzero_rows(ix, &nrows));
+        out.row_words = (out.n_colors() + 31) / 32;
+        out.row_ids.resize(nrows);
+        out.words.resize(nrows * out.row_words);
+        ck(mg ? cid_mg_index_download_nonzero_rows(mg, out.row_ids.data(), out.words.data(), nrows, &got)
+              : cid_index_download_nonzero_rows(ix, out.row_ids.data(), out.words.data(), nrows, &got));
+    }
+    void query_counts(const SeqBatch& sb, const std::vector<uint64_t>& qoffs, int mode, bool gene, int64_t filter, uint32_t* counts,
+                      uint64_t* nk, uint64_t* un, uint64_t* us, uint64_t* um) {
+        const uint64_t nq = qoffs.size() - 1;
+        ck(mg ? cid_mg_query_counts(mg, sb.bases.data(), sb.offs.data(), sb.n(), qoffs.data(), nq, mode, gene ? 1 : 0, filter, counts, nk, un, us, um, nullptr)
+              : cid_query_counts(ix, sb.bases.data(), sb.offs.data(), sb.n(), qoffs.data(), nq, mode, gene ? 1 : 0, filter, counts, nk, un, us, um, nullptr));
+    }
+    void query_perfect(const SeqBatch& sb, const std::vector<uint64_t>& qoffs, uint32_t* rows, uint8_t* status, uint64_t* nk) {
+        const uint64_t nq = qoffs.size() - 1;
+        ck(mg ? cid_mg_query_perfect(mg, sb.bases.data(), sb.offs.data(), sb.n(), qoffs.data(), nq, rows, status, nk)
+              : cid_query_perfect(ix, sb.bases.data(), sb.offs.data(), sb.n(), qoffs.data(), nq, rows, status, nk));
+    }
+    void query_perfect_mf(const SeqBatch& sb, uint64_t nq, uint32_t* rows, uint8_t* status, uint64_t* nk) {
+        ck(mg ? cid_mg_query_perfect_mf(mg, sb.bases.data(), sb.offs.data(), nq, rows, status, nk)
+              : cid_query_perfect_mf(ix, sb.bases.data(), sb.offs.data(), nq, rows, status, nk));
+    }
+    void read_id_classify(const char* bases, const char* quals, const uint64_t* seq_offs, uint64_t nseq, const uint64_t* read_offs, uint64_t n,
+                          const cid_readid_params* p, const uint64_t* n_ref, double fp, int32_t* kind, uint32_t* hits, uint32_t* n_set,
+                          uint32_t* n_top, uint32_t* top, uint32_t top_cap) {
+        ck(mg ? cid_mg_read_id_classify(mg, bases, quals, seq_offs, nseq, read_offs, n, p, n_ref, fp, kind, hits, n_set, n_top, top, top_cap)
+              : cid_read_id_classify(ix, bases, quals, seq_offs, nseq, read_offs, n, p, n_ref, fp, kind, hits, n_set, n_top, top, top_cap));
     }
 };
 Bigsi read_index(const std::string& path) {     // main.rs:633-635,724-728,796-800: the suffix decides the struct
@@ -94,70 +172,94 @@ Bigsi load_index(const std::string& path) {
 // ------------------------------------------------------------------ build
 int build(const BuildOpts& o) {
     Trace tr;
-    Gpu g(o.device);
+    Gpu g(o.device, /*multi=*/true);
     const auto map = tab_to_map(o.ref_file);
     if (map.empty()) throw Error("reference file lists no accessions");
     g.create(o.bloom, o.hashes, o.k, map.size());
     if (o.minimizer) {            // main.rs:485-533
         printf("Build with minimizers, minimizer size: %llu\n", (unsigned long long)o.minimizer_value);
         if (o.minimizer_value == 0 || o.minimizer_value > 0xFFFFFFFFull) throw Error("minimizer size out of range");
-        ck(cid_index_set_minimizer(g.ix, (uint32_t)o.minimizer_value));
+        g.set_minimizer((uint32_t)o.minimizer_value);
     }
     // -t 1 -> build_single_mini (minimizers of the filtered k-mers), else build_multi_mini (counted minimizers)
-    const int mini_variant = o.threads == 1 ? CID_MINI_OF_KMERS : CID_MINI_COUNTED;
+    const int mini_variant = !o.minimizer ? -1 : (o.threads == 1 ? CID_MINI_OF_KMERS : CID_MINI_COUNTED);
     tr.mark("context + index create");
-    double t_read = 0, t_gpu = 0;
     Bigsi out;
     out.bloom_size = o.bloom; out.num_hash = o.hashes; out.k_size = o.k;
     out.mini = o.minimizer; out.m_size = o.minimizer ? o.minimizer_value : 0;
-    uint32_t colour = 0;              // colours = rank of the accession in byte-wise sorted order (build.rs:102-113)
-    size_t counter = 1;
-    for (auto& kv : map) {
-        const std::string& acc = kv.first;
-        const auto& files = kv.second;
-        fprintf(stderr, "Adding %s to index (%zu/%zu)\n", acc.c_str(), counter++, map.size());
-        SeqBatch sb;
-        int mode;
-        const auto ta = std::chrono::steady_clock::now();
-        int64_t cutoff = o.filter;    // -1: FASTQ -> auto_cutoff (build.rs:56-58), FASTA -> keep everything (:86-87)
-        if (files.size() == 2) {
-            fastq_masked_pe(files[0], files[1], o.quality, sb);
-            mode = CID_SEQ_FASTQ;
-        } else if (ends_with(files[0], "gz")) {
+    // colours = rank of the accession in byte-wise sorted order (build.rs:102-113)
+    struct Acc { std::string name; std::vector<std::string> files; uint32_t colour; };
+    std::vector<Acc> accs;
+    for (auto& kv : map) accs.push_back(Acc{kv.first, kv.second, (uint32_t)accs.size()});
+    struct AccIn { SeqBatch sb; int mode = CID_SEQ_FASTA; };
+    auto load = [&](const Acc& a) {                   // the reference's readers, on a helper thread
+        AccIn in;
+        if (a.files.size() == 2) {
+            fastq_masked_pe(a.files[0], a.files[1], o.quality, in.sb);
+            in.mode = CID_SEQ_FASTQ;
+        } else if (ends_with(a.files[0], "gz")) {
             // build_multi hard-codes quality 15 for single-end reads (build.rs:187); build_single (:70) and both
             // minimizer builders (:322-325, :439) honour -Q
-            fastq_masked_se(files[0], (o.threads == 1 || o.minimizer) ? o.quality : 15, sb);
-            mode = CID_SEQ_FASTQ;
+            fastq_masked_se(a.files[0], (o.threads == 1 || o.minimizer) ? o.quality : 15, in.sb);
+            in.mode = CID_SEQ_FASTQ;
         } else {
-            for (auto& s : read_fasta(files[0])) sb.add(s);
-            mode = CID_SEQ_FASTA;
+            for (auto& s : read_fasta(a.files[0])) in.sb.add(s);
         }
-        uint64_t nref = 0;
-        int64_t used = 0;
-        const auto tb = std::chrono::steady_clock::now();
-        if (o.minimizer)
-            ck(cid_build_accession_mini(g.ix, colour, sb.bases.data(), sb.offs.data(), sb.n(), mode, cutoff, mini_variant, &nref, &used));
-        else
-            ck(cid_build_accession(g.ix, colour, sb.bases.data(), sb.offs.data(), sb.n(), mode, cutoff, &nref, &used));
-        t_read += std::chrono::duration<double>(tb - ta).count();
-        t_gpu += std::chrono::duration<double>(std::chrono::steady_clock::now() - tb).count();
-        out.colors[colour] = acc;
-        // build_single_mini records n_ref_kmers for FASTA accessions only (build.rs:450): FASTQ accessions have no entry
-        if (!(o.minimizer && mini_variant == CID_MINI_OF_KMERS && mode == CID_SEQ_FASTQ)) out.n_ref_kmers[acc] = nref;
-        colour++;
+        return in;
+    };
+    // One lane per GPU that owns accession columns (one lane on a single GPU).  In each lane the next accession's files are
+    // read and parsed while the GPU builds the current one (the reference reads and builds serially, build.rs:47-99).
+    const uint32_t lanes = g.lanes();
+    std::vector<std::vector<size_t>> todo(lanes);
+    for (size_t i = 0; i < accs.size(); i++) todo[std::min(g.lane_of(accs[i].colour), lanes - 1)].push_back(i);
+    std::mutex out_mu;
+    std::atomic<size_t> counter{1};
+    std::atomic<long long> us_read{0}, us_gpu{0};
+    std::vector<std::exception_ptr> errs(lanes);
+    auto lane = [&](uint32_t l) {
+        try {
+            const auto& list = todo[l];
+            if (list.empty()) return;
+            AccIn next_in;
+            std::exception_ptr next_err;
+            std::thread reader([&] { try { next_in = load(accs[list[0]]); } catch (...) { next_err = std::current_exception(); } });
+            for (size_t j = 0; j < list.size(); j++) {
+                const auto ta = std::chrono::steady_clock::now();
+                reader.join();
+                if (next_err) std::rethrow_exception(next_err);
+                AccIn cur = std::move(next_in);
+                if (j + 1 < list.size())
+                    reader = std::thread([&, j] { try { next_in = load(accs[list[j + 1]]); } catch (...) { next_err = std::current_exception(); } });
+                const Acc& a = accs[list[j]];
+                fprintf(stderr, "Adding %s to index (%zu/%zu)\n", a.name.c_str(), counter.fetch_add(1), accs.size());
+                uint64_t nref = 0;
+                int64_t used = 0;
+                const auto tb = std::chrono::steady_clock::now();
+                // -1: FASTQ -> auto_cutoff (build.rs:56-58), FASTA -> keep everything (:86-87)
+                try { g.build_accession(a.colour, cur.sb, cur.mode, o.filter, mini_variant, &nref, &used); }
+                catch (...) { if (reader.joinable()) reader.join(); throw; }
+                us_read += std::chrono::duration_cast<std::chrono::microseconds>(tb - ta).count();
+                us_gpu += std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - tb).count();
+                std::lock_guard<std::mutex> lk(out_mu);
+                out.colors[a.colour] = a.name;
+                // build_single_mini records n_ref_kmers for FASTA accessions only (build.rs:450): FASTQ accessions have no entry
+                if (!(o.minimizer && mini_variant == CID_MINI_OF_KMERS && cur.mode == CID_SEQ_FASTQ)) out.n_ref_kmers[a.name] = nref;
+            }
+        } catch (...) { errs[l] = std::current_exception(); }
+    };
+    if (lanes == 1) lane(0);
+    else {
+        std::vector<std::thread> th;
+        for (uint32_t l = 0; l < lanes; l++) th.emplace_back(lane, l);
+        for (auto& t : th) t.join();
     }
-    if (tr.on) fprintf(stderr, "[trace] reading inputs %.3f s, cid_build_accession %.3f s\n", t_read, t_gpu);
+    for (auto& e : errs) if (e) std::rethrow_exception(e);
+    if (tr.on) fprintf(stderr, "[trace] waiting for input %.3f s, cid_build_accession %.3f s (summed over %u lanes)\n", us_read / 1e6, us_gpu / 1e6, lanes);
     tr.mark("accessions");
-    ck(cid_build_finalize(g.ix));
+    g.finalize();
     tr.mark("finalize (transpose)");
     printf("Saving BIGSI to file.\n");
-    uint64_t nrows = 0;
-    ck(cid_index_count_nonzero_rows(g.ix, &nrows));
-    out.row_words = cid_index_row_words(g.ix);
-    out.row_ids.resize(nrows);
-    out.words.resize(nrows * out.row_words);
-    uint64_t got = 0;
-    ck(cid_index_download_nonzero_rows(g.ix, out.row_ids.data(), out.words.data(), nrows, &got));
+    g.nonzero_rows(out);
     tr.mark("download non-zero rows");
     if (o.minimizer) save_bigsi_mini(o.prefix + ".mxi", out);
     else save_bigsi(o.prefix + ".bxi", out);
@@ -190,7 +292,7 @@ void perfect_batch_search(Gpu& g, const Bigsi& b, const std::vector<std::string>
     std::vector<uint32_t> rows(nq * W);
     std::vector<uint8_t> status(nq);
     std::vector<uint64_t> nk(nq);
-    ck(cid_query_perfect(g.ix, sb.bases.data(), sb.offs.data(), sb.n(), qoffs.data(), nq, rows.data(), status.data(), nk.data()));
+    g.query_perfect(sb, qoffs, rows.data(), status.data(), nk.data());
     for (uint64_t q = 0; q < nq; q++) {
         fprintf(stderr, "%llu kmers in query\n", (unsigned long long)nk[q]);
         if (status[q] == 2) fprintf(stderr, "Warning! no kmers in query; maybe your kmer length is larger than your query length?\n");
@@ -212,7 +314,7 @@ void perfect_batch_search_mf(Gpu& g, const Bigsi& b, const std::vector<std::stri
         std::vector<uint32_t> rows(nq * W);
         std::vector<uint8_t> status(nq);
         std::vector<uint64_t> nk(nq);
-        if (nq) ck(cid_query_perfect_mf(g.ix, sb.bases.data(), sb.offs.data(), nq, rows.data(), status.data(), nk.data()));
+        if (nq) g.query_perfect_mf(sb, nq, rows.data(), status.data(), nk.data());
         for (uint64_t q = 0; q < nq; q++) {
             if (status[q] == 2) {
                 printf("Warning! no kmers in query '%s'; maybe your kmer length is larger than your query length?\n", labels[q].c_str());
@@ -263,9 +365,8 @@ void batch_search(Gpu& g, const Bigsi& b, const SearchOpts& o) {
         std::vector<uint32_t> counts(nq * N);
         std::vector<uint64_t> nk(nq), un, us, um;
         if (!o.gene_search) { un.resize(nq * N); us.resize(nq * N); um.resize(nq * N); }
-        ck(cid_query_counts(g.ix, sb.bases.data(), sb.offs.data(), sb.n(), qoffs.data(), nq, mode, o.gene_search ? 1 : 0, o.filter,
-                            counts.data(), nk.data(), o.gene_search ? nullptr : un.data(), o.gene_search ? nullptr : us.data(),
-                            o.gene_search ? nullptr : um.data(), nullptr));
+        g.query_counts(sb, qoffs, mode, o.gene_search, o.filter, counts.data(), nk.data(), o.gene_search ? nullptr : un.data(),
+                       o.gene_search ? nullptr : us.data(), o.gene_search ? nullptr : um.data());
         for (uint64_t q = 0; q < nq; q++) {
             fprintf(stderr, "%llu k-mers in query\n", (unsigned long long)nk[q]);
             if (!o.gene_search)
@@ -285,7 +386,7 @@ int search(const SearchOpts& o) {
     }
     fprintf(stderr, "Loading index\n");
     Trace tr;
-    Gpu g(o.device);
+    Gpu g(o.device, /*multi=*/true);
     const Bigsi b = load_index(o.bigsi);
     tr.mark("read_bigsi");
     g.upload(b);
@@ -352,6 +453,7 @@ struct ReadIdRun {
     std::vector<std::string> names;                      // accession by colour
     std::string outbuf;
     double fp_correct;
+    uint64_t threads = 0;                                // -t: host threads of the vote, applied before the first batch
     uint64_t read_count = 0;
     double t_gpu = 0, t_out = 0;
     std::vector<std::string> count_keys;                 // first-appearance order of the counts-file keys
@@ -366,8 +468,7 @@ struct ReadIdRun {
             names.push_back(kv.second);
         }
         fp_correct = std::pow(10.0, -o.correct);          // main.rs:711
-        g.ready();
-        if (o.threads) ck(cid_ctx_set_option(g.ctx, "host_threads", (int64_t)o.threads));
+        if (o.threads) threads = o.threads;
     }
     ~ReadIdRun() { if (out) fclose(out); }
     void tally(const std::string& cls, bool accept) {
@@ -387,9 +488,10 @@ struct ReadIdRun {
         std::vector<int32_t> kind(n);
         std::vector<uint32_t> hits(n), n_set(n), n_top(n), top((size_t)n * top_cap);
         const auto tg0 = std::chrono::steady_clock::now();
-        ck(cid_read_id_classify(g.ix, rb.bases.p, rb.any_qual ? rb.quals.p : nullptr, rb.seq_offs.data(),
-                                rb.seq_offs.size() - 1, rb.read_offs.data(), n, &p, n_ref.data(), fp_correct, kind.data(),
-                                hits.data(), n_set.data(), n_top.data(), top.data(), top_cap));
+        if (threads) { g.set_host_threads(threads); threads = 0; }
+        g.read_id_classify(rb.bases.p, rb.any_qual ? rb.quals.p : nullptr, rb.seq_offs.data(), rb.seq_offs.size() - 1,
+                           rb.read_offs.data(), n, &p, n_ref.data(), fp_correct, kind.data(), hits.data(), n_set.data(), n_top.data(),
+                           top.data(), top_cap);
         const auto tg1 = std::chrono::steady_clock::now();
         t_gpu += std::chrono::duration<double>(tg1 - tg0).count();
         auto put_u = [&](uint32_t v) { char tmp[12]; int k = 0; do { tmp[k++] = (char)('0' + v % 10); v /= 10; } while (v); while (k) outbuf += tmp[--k]; };
@@ -414,9 +516,8 @@ struct ReadIdRun {
                         const uint64_t s_lo = rb.read_offs[r], s_hi = rb.read_offs[r + 1];
                         std::vector<uint64_t> so, ro{0, s_hi - s_lo};
                         for (uint64_t s = s_lo; s <= s_hi; s++) so.push_back(rb.seq_offs[s] - rb.seq_offs[s_lo]);
-                        ck(cid_read_id_classify(g.ix, rb.bases.p + rb.seq_offs[s_lo],
-                                                rb.any_qual ? rb.quals.p + rb.seq_offs[s_lo] : nullptr, so.data(), s_hi - s_lo,
-                                                ro.data(), 1, &p, n_ref.data(), fp_correct, &k1, &h1, &s1, &t1, all.data(), N));
+                        g.read_id_classify(rb.bases.p + rb.seq_offs[s_lo], rb.any_qual ? rb.quals.p + rb.seq_offs[s_lo] : nullptr, so.data(),
+                                           s_hi - s_lo, ro.data(), 1, &p, n_ref.data(), fp_correct, &k1, &h1, &s1, &t1, all.data(), N);
                         t = all.data();
                     }
                     for (uint32_t j = 0; j < n_top[r]; j++) { if (j) multi += ','; multi += names.at(t[j]); }
@@ -535,7 +636,7 @@ int read_id(const ReadIdOpts& o) {
     if (o.query.empty()) throw Error("no query files");
     Timer tload;
     Trace tr;
-    Gpu g(o.device);
+    Gpu g(o.device, /*multi=*/true);
     const Bigsi b = read_index(o.bigsi);
     fprintf(stderr, "Index loaded in %llu seconds\n", tload.secs());
     tr.mark("read_bigsi");

@@ -280,6 +280,41 @@ def test_read_id_paired_single_and_fasta(world, oracle):
 CLS_NAMES = {"too_short", "no_hits", "no_significant_hits"}
 
 
+@pytest.mark.parametrize("shard", ["columns", "replicated"])
+def test_multi_gpu_cli_outputs_equal_the_single_gpu_outputs(world, oracle, shard):
+    """COLORID_B200_DEVICES=.. (one index over several GPUs: cid_mg) with COLORID_B200_SHARD=columns|replicated: `build` writes
+    the same .bxi bytes, `search` (default report, -g, -s, -s -m) the same lines and `read_id` the same files as on one GPU.
+    The device list repeats GPU 0 when the box has a single GPU (several shards on one device: the same host code path)."""
+    import ctypes
+    nd = ctypes.c_int(0)
+    ctypes.CDLL("libcudart.so").cudaGetDeviceCount(ctypes.byref(nd))
+    devs = ",".join(str(g % max(nd.value, 1)) for g in range(3))
+    env = dict(os.environ, COLORID_B200_DEVICES=devs, COLORID_B200_SHARD=shard)
+    d = world["dir"]
+
+    def both(*args, out_files=()):
+        one = subprocess.run([CLI, *map(str, args)], capture_output=True, text=True)
+        keep = {f: open(f, "rb").read() for f in out_files}
+        many = subprocess.run([CLI, *map(str, args)], capture_output=True, text=True, env=env)
+        assert one.returncode == 0 and many.returncode == 0, many.stderr[-2000:]
+        assert "3 GPUs, index " + ("column-sharded" if shard == "columns" else "replicated") in many.stderr
+        assert sorted(one.stdout.split("\n")) == sorted(many.stdout.split("\n"))
+        for f in out_files:
+            assert open(f, "rb").read() == keep[f], f
+    both("build", "-b", d / "mgidx", "-r", d / "refs.tsv", "-k", K, "-n", H, "-s", S, out_files=[str(d / "mgidx.bxi")])
+    assert open(d / "mgidx.bxi", "rb").read() == open(d / "idx.bxi", "rb").read()
+    files, _ = _gene_files(world, n=7)
+    both("search", "-b", d / "idx.bxi", "-g", "-q", *files)
+    both("search", "-b", d / "idx.bxi", "-f", 0, "-p", 0.05, "-q", *files)
+    both("search", "-b", d / "idx.bxi", "-q", d / "pe_1.fastq.gz", "-r", d / "pe_2.fastq.gz")
+    both("search", "-b", d / "idx.bxi", "-s", "-q", *files)
+    n, s1, s2, q1, q2 = read_pairs(world["rng"], world["genomes"][:5], 1200, "mg", read_len=100, insert=180, err=0.006, frac_random=0.2)
+    (d / "mg_1.fastq.gz").write_bytes(gzip.compress(fastq_bytes(n, s1, q1)))
+    (d / "mg_2.fastq.gz").write_bytes(gzip.compress(fastq_bytes(n, s2, q2)))
+    both("read_id", "-b", d / "idx.bxi", "-q", d / "mg_1.fastq.gz", d / "mg_2.fastq.gz", "-n", d / "mg_out",
+         out_files=[str(d / "mg_out_reads.txt"), str(d / "mg_out_counts.txt")])
+
+
 def test_read_id_contigs_and_softmasked_reads(world, oracle):
     """read_id_mt_pe.rs:450-569 stream_fasta on real assemblies: records are whole contigs (single-line and wrapped, one all
     lower-case like refs/Staphylococcus_aureus_NCTC8532.fasta), far above the 1,000 bases of the warp-per-read kernels; and
