@@ -423,6 +423,15 @@ def lookups_of(d_nk):
 
 
 def run_c5(args):
+    import torch.distributed as dist
+    line = c5_measure(args)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    if dist.is_initialized():
+        dist.destroy_process_group()
+
+
+def c5_measure(args, n_acc=0, steps=0, warmup=0):
     """BASELINE.json configs[4]: 10,000 synthetic 5 Mbp genomes, k=31 S=50M H=4, the signature matrix column-sharded
     over the ranks (whole 32-accession word columns per rank), every rank gathering all query k-mers from its slice,
     per-query counts re-assembled with one NCCL all_gather.  `--c5-acc` scales the accession count (1250 per rank
@@ -436,14 +445,14 @@ def run_c5(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
+    if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     cfg = dict(C5)
-    if args.c5_acc:
-        cfg["n_acc"] = args.c5_acc
+    if n_acc or args.c5_acc:
+        cfg["n_acc"] = n_acc or args.c5_acc
     if args.quick:
         cfg.update(genome_len=100_000, S=2_000_003, n_queries=500, n_clades=10)
     A, Lg, NC = cfg["n_acc"], cfg["genome_len"], cfg["n_clades"]
@@ -544,13 +553,13 @@ def run_c5(args):
                                          stream.cuda_stream))
         gathered[0] = sharding.gather_counts(d_counts, shards) if world > 1 else d_counts     # NCCL all_gather
 
-    for _ in range(max(1, args.warmup)):
+    for _ in range(max(1, warmup or args.warmup)):
         search_pass()
     barrier()
     ctx.profile(True)
     clk = ClockSampler(local)
     clk.start()
-    K = args.steps
+    K = steps or args.steps
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for _ in range(K):
@@ -695,10 +704,31 @@ def run_c5(args):
     bad = [(q, a) for q, a in probe_q if int(full[q, a].item()) != int(nk_h[q])]
     assert not bad, f"self-query property violated for {bad[:4]}"
     assert full.shape == (nq, A)
+    # ---- ... and against an UNSHARDED index: the count column of an accession depends on that accession's column alone, so a
+    # one-GPU index over a sample of accessions from every shard must reproduce those columns of the sharded result exactly
+    unsharded = None
+    if rank == 0:
+        sample = sorted({int(x) for lo_, hi_ in shards for x in (lo_, (lo_ + hi_) // 2, hi_ - 1) if hi_ > lo_})
+        uix = cb.Index(ctx, cfg["S"], cfg["H"], cfg["k"], len(sample))
+        for j, a in enumerate(sample):
+            asc = lut[acc_codes(a).long()].contiguous()
+            torch.cuda.synchronize()
+            uix.build_accession_dev(j, asc.data_ptr(), offs.data_ptr(), 1, Lg)
+        uix.finalize()
+        u_counts = torch.zeros((nq, len(sample)), device=dev, dtype=torch.int32)
+        u_nk = torch.zeros(nq, device=dev, dtype=torch.int64)
+        L.check(lib.cid_query_counts_dev(uix.h, d_bases.data_ptr(), qoff.data_ptr(), nq, total, d_query_offs.data_ptr(), P(h_query_offs),
+                                         P(h_seq_offs), nq, 0, u_counts.data_ptr(), u_nk.data_ptr(), stream.cuda_stream))
+        torch.cuda.synchronize()
+        same_cols = bool(torch.equal(u_counts, full[:, torch.tensor(sample, device=dev)].to(torch.int32)))
+        same_nk = bool(torch.equal(u_nk, d_nk))
+        unsharded = {"accessions_sampled": len(sample), "queries": nq, "count_columns_identical": same_cols, "num_kmers_identical": same_nk,
+                     "how": "one-GPU index (rows of 1-2 words: the fused query_counts kernel) built from first / middle / last accession of "
+                            "every shard; its counts must equal those columns of the sharded result"}
+        assert same_cols and same_nk, "sharded counts differ from the unsharded index"
+        uix.close()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
     peak, peak_src = measured_peak()
     Wp = cb.lib.load().cid_index_row_stride(gix.h)
     R = 4 * Wp
@@ -731,11 +761,9 @@ def run_c5(args):
                       "note": "all ranks build their accession columns concurrently; max over ranks; synthetic genome "
                               "generation excluded",
                       "kernels_ms_total": {k_: v[0] for k_, v in build_prof.items()}},
-            "parity": {"self_query_probes": len(probe_q), "violations": 0}, "fused_count_exchange": fused,
+            "parity": {"self_query_probes": len(probe_q), "violations": 0, "matches_unsharded": unsharded}, "fused_count_exchange": fused,
             "sharded_default_report_and_read_id": extra}
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    return line
 
 
 
@@ -1183,6 +1211,21 @@ def run_ours(args):
     h2d = 2 * batch * 2 * rl + seq_offs_np.nbytes + read_offs_np.nbytes
     d2h = batch * (4 * 4 + 8 * 4)      # kind, hits, n_set, n_top + top[8] per read; the undecided-read list (<1 % of reads) is extra
 
+    # ---- N > 1: the column-sharded path (C5 shard shape: 1,250 accessions = 160-byte rows per GPU, A = 1,250 x N accessions:
+    # the full C5 index at N = 8) rides along, so that the driver's scaling run records it: build Gbp/s, lookups/s, the shard
+    # gather's roofline, NCCL all_gather against the fused peer-store exchange, and the comparison with an unsharded index
+    c5 = None
+    if world > 1 and not args.no_c5:
+        try:
+            del pool_b, pool_q
+            torch.cuda.empty_cache()
+            c5 = c5_measure(args, n_acc=(args.c5_acc or 1250 * world), steps=min(K, 5), warmup=min(Wm, 3))
+            if c5 is not None:
+                c5 = {k_: c5[k_] for k_ in ("metric", "value", "unit", "ms_per_step", "scaling", "config", "roofline", "kernels", "build",
+                                            "parity", "fused_count_exchange", "clocks")}
+        except Exception as ex:      # the headline line must still print
+            c5 = {"error": repr(ex)}
+            log(f"[rank {rank}] c5 block failed: {ex!r}")
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -1266,7 +1309,7 @@ def run_ours(args):
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "build": {"gbp_per_s": cfg["n_acc"] * cfg["genome_len"] / build_s / 1e9, "seconds": build_s,
                       "note": "index build on device incl. per-accession host sync; not the timed metric"},
-            "report_truncated_reads_last_step": trunc, "search_c3": search_c3}
+            "report_truncated_reads_last_step": trunc, "search_c3": search_c3, "c5": c5}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -1292,6 +1335,7 @@ def main():
     ap.add_argument("--n-acc", type=int, default=0, help="c2: accessions of the index (default 46 = the headline config)")
     ap.add_argument("--n-clades", type=int, default=0, help="c2 with --n-acc: clades (default n_acc / 5)")
     ap.add_argument("--c5-acc", type=int, default=0, help="total accessions of the c5 workload (default 10,000)")
+    ap.add_argument("--no-c5", action="store_true", help="N > 1: skip the column-sharded C5 block")
     ap.add_argument("--c5-extra", action="store_true", help="c5, N > 1: also time the column-sharded default report and read_id")
     args = ap.parse_args()
     if args.impl == "reference":
