@@ -330,6 +330,11 @@ int cid_index_create(cid_ctx* ctx, uint64_t bloom_size, uint32_t num_hash, uint3
     ix->rownz_words = (ix->S + 31) / 32;
     e = cudaMalloc((void**)&ix->rownz, ix->rownz_words * 4 + 256);
     if (e != cudaSuccess) { set_error("cudaMalloc(rownz) failed"); cudaGetLastError(); cudaFree(ix->rows); delete ix; return CID_E_NOMEM; }
+    {
+        const HashCfg h = make_hashcfg(0);
+        CID_CUDA(cudaMalloc(&ix->d_hcfg, 256));
+        CID_CUDA(cudaMemcpy(ix->d_hcfg, &h, sizeof(h), cudaMemcpyHostToDevice));
+    }
     CID_CUDA(cudaMemsetAsync(ix->rows, 0, bytes, ctx->stream));
     CID_CUDA(cudaMemsetAsync(ix->rownz, 0, ix->rownz_words * 4, ctx->stream));
     CID_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -343,6 +348,7 @@ void cid_index_destroy(cid_index* ix) {
     if (ix->rows) cudaFree(ix->rows);
     if (ix->rownz) cudaFree(ix->rownz);
     if (ix->bitsets) cudaFree(ix->bitsets);
+    if (ix->d_hcfg) cudaFree(ix->d_hcfg);
     delete ix;
 }
 uint32_t cid_index_row_words(const cid_index* ix) { return ix ? ix->W : 0; }
@@ -502,7 +508,7 @@ static int build_accession_impl(cid_index* ix, uint32_t colour, const char* d_ba
             CID_CUDA(cudaMemsetAsync(bitset, 0, ix->bs_words * 4, st));
             CID_CUDA(cudaMemsetAsync(ctx->d_err + 1, 0, 4, st));
             CID_TRY(launch_kmerize_bloom(ctx, st, (const uint8_t*)d_bases, d_seq_offs, nseq, nbases, ctx->scratch[0].p, slots, ix->k,
-                                         seq_mode, count_m, bloom_m, ix->H, ix->S, ix->hv, bitset));
+                                         seq_mode, count_m, bloom_m, ix->H, make_mods(ix->S, ix->hv, (const HashCfg*)ix->d_hcfg), bitset));
             CID_CUDA(cudaMemcpyAsync(ctx->h_err, ctx->d_err, 8, cudaMemcpyDeviceToHost, st));
             CID_CUDA(cudaStreamSynchronize(st));
             const uint32_t flags = ctx->h_err[0], distinct = ctx->h_err[1];
@@ -575,8 +581,8 @@ static int build_accession_impl(cid_index* ix, uint32_t colour, const char* d_ba
     CID_TRY(ctx->scratch[2].ensure(16));
     unsigned long long* d_nref = ctx->scratch[2].as<unsigned long long>();
     CID_CUDA(cudaMemsetAsync(d_nref, 0, 8, st));
-    CID_TRY(launch_region_to_bloom(ctx, st, ctx->scratch[0].p, nslots, used, count_m ? count_m : ix->k, bloom_m, ix->H, ix->S, ix->hv,
-                                   bitset, d_nref, packed));
+    CID_TRY(launch_region_to_bloom(ctx, st, ctx->scratch[0].p, nslots, used, count_m ? count_m : ix->k, bloom_m, ix->H,
+                                   make_mods(ix->S, ix->hv, (const HashCfg*)ix->d_hcfg), bitset, d_nref, packed));
     unsigned long long nref = 0;
     CID_CUDA(cudaMemcpyAsync(&nref, d_nref, 8, cudaMemcpyDeviceToHost, st));
     CID_CUDA(cudaStreamSynchronize(st));
@@ -627,6 +633,9 @@ int cid_index_set_hash_variant(cid_index* ix, uint32_t variant) {
     if (!ix) { set_error("cid_index_set_hash_variant: null index"); return CID_E_INVALID; }
     if (variant >= CID_HASH_VARIANTS) { set_error("hash variant %u out of range (0..%d)", variant, CID_HASH_VARIANTS - 1); return CID_E_INVALID; }
     ix->hv = variant;
+    const HashCfg h = make_hashcfg(variant);
+    CID_CUDA(cudaSetDevice(ix->ctx->device));
+    CID_CUDA(cudaMemcpy(ix->d_hcfg, &h, sizeof(h), cudaMemcpyHostToDevice));
     return CID_OK;
 }
 uint32_t cid_index_hash_variant(const cid_index* ix) { return ix ? ix->hv : 0; }

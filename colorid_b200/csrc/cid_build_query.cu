@@ -182,10 +182,10 @@ int launch_kmerize_insert(cid_ctx* ctx, cudaStream_t st, const uint8_t* d_bases,
 // count_m != 0: the set holds minimizers (build_multi_mini); bloom_m != 0: the set holds k-mers, their minimizers are inserted.
 int launch_kmerize_bloom(cid_ctx* ctx, cudaStream_t st, const uint8_t* d_bases, const uint64_t* d_seq_offs, uint64_t nseq,
                          uint64_t nbases, void* d_keys, uint64_t nslots, uint32_t k, int seq_mode, uint32_t count_m, uint32_t bloom_m,
-                         uint32_t H, uint64_t S, uint32_t hv, uint32_t* d_bitset) {
+                         uint32_t H, const ModS& mods, uint32_t* d_bitset) {
     if (nbases == 0 || nseq == 0) return CID_OK;
     const uint64_t ntiles = (nbases + KT - 1) / KT;
-    SetSink sink{(unsigned long long*)d_keys, nslots - 1, d_bitset, H, make_mods(S, hv), bloom_m, 0};
+    SetSink sink{(unsigned long long*)d_keys, nslots - 1, d_bitset, H, mods, bloom_m, 0};
     ProfScope ps(ctx, st, KID_KMERIZE_INSERT);
     if (count_m)
         kmerize_insert_kernel<true, true><<<(unsigned)ntiles, KT_THREADS, 0, st>>>(d_bases, d_seq_offs, nseq, 0, nbases, nullptr, nullptr, nullptr,
@@ -284,13 +284,13 @@ region_to_bloom_kernel(const void* __restrict__ region, uint64_t nslots, long lo
     if ((threadIdx.x & 31) == 0 && mine) atomicAdd(nref, (unsigned long long)mine);
 }
 int launch_region_to_bloom(cid_ctx* ctx, cudaStream_t st, const void* d_region, uint64_t nslots, int64_t cutoff,
-                           uint32_t k, uint32_t mini_m, uint32_t H, uint64_t S, uint32_t hv, uint32_t* d_bitset, unsigned long long* d_nref,
+                           uint32_t k, uint32_t mini_m, uint32_t H, const ModS& mods, uint32_t* d_bitset, unsigned long long* d_nref,
                            bool packed) {
     unsigned grid = (unsigned)std::min<uint64_t>((nslots + 255) / 256, (uint64_t)ctx->sm_count * 16);
     if (grid == 0) grid = 1;
     ProfScope ps(ctx, st, KID_TO_BLOOM);
-    if (packed) region_to_bloom_kernel<true><<<grid, 256, 0, st>>>(d_region, nslots, (long long)cutoff, k, mini_m, H, make_mods(S, hv), d_bitset, d_nref);
-    else region_to_bloom_kernel<false><<<grid, 256, 0, st>>>(d_region, nslots, (long long)cutoff, k, mini_m, H, make_mods(S, hv), d_bitset, d_nref);
+    if (packed) region_to_bloom_kernel<true><<<grid, 256, 0, st>>>(d_region, nslots, (long long)cutoff, k, mini_m, H, mods, d_bitset, d_nref);
+    else region_to_bloom_kernel<false><<<grid, 256, 0, st>>>(d_region, nslots, (long long)cutoff, k, mini_m, H, mods, d_bitset, d_nref);
     ctx->launches++;
     CID_CUDA(cudaGetLastError());
     return CID_OK;
@@ -1215,11 +1215,11 @@ int launch_query_front_gather(cid_ctx* ctx, cudaStream_t st, const cid_index* id
         const size_t fsmem = (size_t)tsize * 8 + tile_smem_bytes(KT_CAP) + (seq_mode == CID_SEQ_STRING ? QF_DIRTY_SLOTS * 4 : 0);
         if (seq_mode == CID_SEQ_STRING)
             query_front_kernel<true><<<(unsigned)n, QF_THREADS, fsmem, st>>>(
-                d_bases, d_seq_offs, d_query_offs + q0, d_qlist + at, tsize, k, seq_mode, H, make_mods(idx->S, idx->hv), d_base, d_rid, d_unit_n,
+                d_bases, d_seq_offs, d_query_offs + q0, d_qlist + at, tsize, k, seq_mode, H, make_mods(idx->S, idx->hv, (const HashCfg*)idx->d_hcfg), d_base, d_rid, d_unit_n,
                 d_num_kmers, ctx->d_err);
         else
             query_front_kernel<false><<<(unsigned)n, QF_THREADS, fsmem, st>>>(
-                d_bases, d_seq_offs, d_query_offs + q0, d_qlist + at, tsize, k, seq_mode, H, make_mods(idx->S, idx->hv), d_base, d_rid, d_unit_n,
+                d_bases, d_seq_offs, d_query_offs + q0, d_qlist + at, tsize, k, seq_mode, H, make_mods(idx->S, idx->hv, (const HashCfg*)idx->d_hcfg), d_base, d_rid, d_unit_n,
                 d_num_kmers, ctx->d_err);
         ctx->launches++;
         CID_CUDA(cudaGetLastError());
@@ -1258,7 +1258,7 @@ int launch_query_counts(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, con
         {
             ProfScope ps(ctx, st, KID_QUERY_HASH);
             query_hash_kernel<<<(unsigned)nunits, 256, 0, st>>>((const Slot*)d_table, d_unit_group, d_unit_slot0, d_unit_nslots,
-                                                              (const long long*)d_filter, idx->k, idx->H, make_mods(idx->S, idx->hv),
+                                                              (const long long*)d_filter, idx->k, idx->H, make_mods(idx->S, idx->hv, (const HashCfg*)idx->d_hcfg),
                                                               d_rid, d_unit_n, d_num_kmers);
         }
         ctx->launches++;
@@ -1277,7 +1277,7 @@ int launch_query_counts(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, con
         CID_CUDA(cudaFuncSetAttribute(query_uniq_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         attr_set = true;
     }
-    ModS mods = make_mods(idx->S, idx->hv);
+    ModS mods = make_mods(idx->S, idx->hv, (const HashCfg*)idx->d_hcfg);
     const uint32_t vec = idx->Wp >= 4 ? 4 : idx->Wp;      // Wp is 1, 2 or a multiple of 4
     const bool inline_uniq = want_uniq && idx->Wp <= 32 * vec;   // one column block: the warp sees the whole row
     {
@@ -1366,7 +1366,7 @@ int launch_query_perfect(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, co
     }
     ProfScope ps(ctx, st, KID_QUERY_PERFECT);
     query_perfect_kernel<<<(unsigned)nunits, 256, smem, st>>>(idx->rows, idx->rownz, idx->Wp, idx->W, idx->k, idx->H,
-                                                             make_mods(idx->S, idx->hv), (const Slot*)d_table, d_unit_group,
+                                                             make_mods(idx->S, idx->hv, (const HashCfg*)idx->d_hcfg), (const Slot*)d_table, d_unit_group,
                                                              d_unit_slot0, d_unit_nslots, d_and_rows, d_missing,
                                                              d_num_kmers);
     ctx->launches++;
@@ -1391,7 +1391,7 @@ int launch_hash_kmers(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, const
                       uint64_t* d_rows) {
     if (n == 0) return CID_OK;
     ProfScope ps(ctx, st, KID_OTHER);
-    hash_kmers_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_kmers, n, idx->m ? idx->m : idx->k, idx->H, make_mods(idx->S, idx->hv), d_rows);
+    hash_kmers_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_kmers, n, idx->m ? idx->m : idx->k, idx->H, make_mods(idx->S, idx->hv, (const HashCfg*)idx->d_hcfg), d_rows);
     ctx->launches++;
     CID_CUDA(cudaGetLastError());
     return CID_OK;
@@ -1590,7 +1590,7 @@ int launch_slots_popcount(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, c
     if (n == 0) return CID_OK;
     ProfScope ps(ctx, st, KID_QUERY_UNIQ_WIDE);
     const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 32);
-    slots_popcount_kernel<<<grid, 256, 0, st>>>(idx->rows, idx->Wp, idx->k, idx->H, make_mods(idx->S, idx->hv), (const Slot*)d_slots, n, d_pc, d_col);
+    slots_popcount_kernel<<<grid, 256, 0, st>>>(idx->rows, idx->Wp, idx->k, idx->H, make_mods(idx->S, idx->hv, (const HashCfg*)idx->d_hcfg), (const Slot*)d_slots, n, d_pc, d_col);
     ctx->launches++;
     CID_CUDA(cudaGetLastError());
     return CID_OK;

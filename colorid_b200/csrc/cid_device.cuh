@@ -48,19 +48,24 @@ struct HashIn { uint64_t w0, w1, w2, w3; };
 //   bit 0  final avalanche multiplier PRIME64_3 instead of PRIME_MX1      bit 1  avalanche shift 29 instead of 37
 //   bit 2  128-bit product folded by + instead of ^                       bit 3  seed enters as (len + seed) * PRIME64_1
 //   bit 4  secret read as 32-bit words (kKey[] of the first draft)               instead of secret +/- seed per lane (len >= 17)
-// The variant is resolved on the host into HashCfg (make_mods), which every kernel receives by value: its fields are
-// read by the out-of-line variant path only; variant 0 keeps its immediates.
+// The variant is resolved on the host into a HashCfg kept in device memory next to the index; only the out-of-line variant
+// path reads it, variant 0 keeps its immediates.
 #define CID_HASH_VARIANTS 32
 struct HashCfg {
     uint64_t sec[7];        // secret words at byte offsets 0, 8, .., 48 (32-bit halves byte-swapped for bit 4)
     uint64_t av_mul;
     uint32_t av_shift, fold_add, seed_acc, var;
 };
-// h % S for run-time S: see mod_s below
-struct ModS { uint64_t S, M; HashCfg h; };
-__host__ __device__ __forceinline__ ModS make_mods(uint64_t S, uint32_t var = 0) {
-    ModS m; m.S = S;
+// h % S for run-time S: see mod_s below.  `cfg` points to the index's HashCfg in DEVICE memory (only the out-of-line
+// variant path reads it), so a kernel that hashes never needs the address of one of its own parameters.
+struct ModS { uint64_t S, M; uint32_t var; const HashCfg* cfg; };
+__host__ __device__ __forceinline__ ModS make_mods(uint64_t S, uint32_t var = 0, const HashCfg* cfg = nullptr) {
+    ModS m; m.S = S; m.var = var; m.cfg = cfg;
     m.M = S <= 1 ? 0 : (uint64_t)((((unsigned __int128)1) << 64) / S);
+    return m;
+}
+inline HashCfg make_hashcfg(uint32_t var) {
+    HashCfg h;
     const uint64_t sec[7] = {CID_SEC0, CID_SEC8, CID_SEC16, CID_SEC24, CID_SEC32, CID_SEC40, CID_SEC48};
     for (int i = 0; i < 7; i++) {
         uint64_t s = sec[i];
@@ -68,14 +73,14 @@ __host__ __device__ __forceinline__ ModS make_mods(uint64_t S, uint32_t var = 0)
             auto sw = [](uint32_t x) { return (x >> 24) | ((x >> 8) & 0xFF00u) | ((x << 8) & 0xFF0000u) | (x << 24); };
             s = ((uint64_t)sw((uint32_t)(s >> 32)) << 32) | sw((uint32_t)s);
         }
-        m.h.sec[i] = s;
+        h.sec[i] = s;
     }
-    m.h.av_mul = (var & 1u) ? CID_P64_3 : CID_PMX1;
-    m.h.av_shift = (var & 2u) ? 29u : 37u;
-    m.h.fold_add = (var & 4u) ? 1u : 0u;
-    m.h.seed_acc = (var & 8u) ? 1u : 0u;
-    m.h.var = var;
-    return m;
+    h.av_mul = (var & 1u) ? CID_P64_3 : CID_PMX1;
+    h.av_shift = (var & 2u) ? 29u : 37u;
+    h.fold_add = (var & 4u) ? 1u : 0u;
+    h.seed_acc = (var & 8u) ? 1u : 0u;
+    h.var = var;
+    return h;
 }
 
 // stable XXH3 (variant 0): every constant an immediate
@@ -140,9 +145,9 @@ static __device__ __noinline__ uint64_t xxh3_kmer_cfg(uint64_t w0, uint64_t w1, 
         return h;
     }
 }
-__device__ __forceinline__ uint64_t xxh3_kmer(const HashIn& in, uint32_t k, uint64_t seed, const HashCfg& c) {
-    if (c.var == 0u) return xxh3_kmer_stable(in, k, seed);
-    return xxh3_kmer_cfg(in.w0, in.w1, in.w2, in.w3, k, seed, &c);
+__device__ __forceinline__ uint64_t xxh3_kmer(const HashIn& in, uint32_t k, uint64_t seed, const ModS& m) {
+    if (m.var == 0u) return xxh3_kmer_stable(in, k, seed);
+    return xxh3_kmer_cfg(in.w0, in.w1, in.w2, in.w3, k, seed, m.cfg);
 }
 
 // h % S for run-time S (2 <= S < 2^63) with M = floor(2^64 / S): q = mulhi(h, M) is floor(h/S) or
@@ -156,7 +161,7 @@ __device__ __forceinline__ uint64_t mod_s(uint64_t h, const ModS& m) {
 
 // Row index of hash function `seed` (simple_bloom.rs:21-24): xxh3(kmer, seed) % bloom_size, in the index's hash variant.
 __device__ __forceinline__ uint64_t hash64(const HashIn& in, uint32_t k, uint64_t seed, const ModS& m) {
-    return xxh3_kmer(in, k, seed, m.h);
+    return xxh3_kmer(in, k, seed, m);
 }
 __device__ __forceinline__ uint64_t hash_row(const HashIn& in, uint32_t k, uint64_t seed, const ModS& m) {
     return mod_s(hash64(in, k, seed, m), m);

@@ -10,6 +10,7 @@
 #include "../../include/colorid_b200.h"
 
 namespace cid {
+struct ModS;
 
 // Where query_gather adds its per-accession counts: `n` destination buffers (this GPU's own and, in column-sharded
 // mode, the peers' -- NVLink peer memory), rows of `stride` counters, this shard's accessions starting at column `col0`.
@@ -107,6 +108,7 @@ struct cid_index {
     uint64_t S = 0;
     uint32_t H = 0, k = 0, N = 0;
     uint32_t hv = 0;     // hash variant (cid_index_set_hash_variant; 0 = stable XXH3)
+    void* d_hcfg = nullptr;   // cid::HashCfg of the variant, in device memory
     uint32_t m = 0;      // minimizer length of an .mxi index (bigsi.rs:40-49 m_size); 0 = plain k-mer index
     uint32_t W = 0;      // ceil(N/32)
     uint32_t Wp = 0;     // device row stride in words
@@ -170,13 +172,13 @@ int launch_kmerize_insert(cid_ctx* ctx, cudaStream_t st, const uint8_t* d_bases,
 // set-only build (no count filter): new keys are hashed straight into the accession's Bloom bitset; distinct keys in d_err[1]
 int launch_kmerize_bloom(cid_ctx* ctx, cudaStream_t st, const uint8_t* d_bases, const uint64_t* d_seq_offs, uint64_t nseq,
                          uint64_t nbases, void* d_keys, uint64_t nslots, uint32_t k, int seq_mode, uint32_t count_m, uint32_t bloom_m,
-                         uint32_t H, uint64_t S, uint32_t hv, uint32_t* d_bitset);
+                         uint32_t H, const ModS& mods, uint32_t* d_bitset);
 int launch_region_histogram(cid_ctx* ctx, cudaStream_t st, const void* d_region, uint64_t nslots, uint32_t* d_hist,
                             uint32_t hist_bins, uint32_t* d_overflow, uint32_t overflow_cap, uint32_t* d_overflow_n,
                             bool packed = false);
 // k = length of the table's keys; mini_m != 0: insert find_minimizer(key, mini_m) instead of the key itself
 int launch_region_to_bloom(cid_ctx* ctx, cudaStream_t st, const void* d_region, uint64_t nslots, int64_t cutoff,
-                           uint32_t k, uint32_t mini_m, uint32_t H, uint64_t S, uint32_t hv, uint32_t* d_bitset, unsigned long long* d_nref,
+                           uint32_t k, uint32_t mini_m, uint32_t H, const ModS& mods, uint32_t* d_bitset, unsigned long long* d_nref,
                            bool packed = false);
 int launch_transpose(cid_ctx* ctx, cudaStream_t st, const cid_index* idx);
 int launch_rownz(cid_ctx* ctx, cudaStream_t st, const cid_index* idx);

@@ -1268,7 +1268,7 @@ int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const ui
         rattr = true;
     }
 
-    const ModS mods = make_mods(idx->S, idx->hv);
+    const ModS mods = make_mods(idx->S, idx->hv, (const HashCfg*)idx->d_hcfg);
     const uint32_t kitem = idx->m ? idx->m : idx->k;    // length of the hashed item: k-mer, or minimizer of an .mxi index
     for (uint64_t r0 = r_first; r0 < r_first + nreads; r0 += sub) {
         const uint64_t nr = std::min(sub, r_first + nreads - r0);

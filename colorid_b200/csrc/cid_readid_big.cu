@@ -457,7 +457,7 @@ int launch_readid_big(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, c
     a.bases = d_bases; a.quals = maxq ? d_quals : nullptr; a.maxq = maxq;
     a.seq_offs = d_seq_offs; a.read_offs = d_read_offs; a.r0 = r0;
     a.list = d_list; a.list_n = d_list_n;
-    a.k = idx->k; a.mini_m = idx->m; a.d = p.downsample; a.H = idx->H; a.mods = make_mods(idx->S, idx->hv);
+    a.k = idx->k; a.mini_m = idx->m; a.d = p.downsample; a.H = idx->H; a.mods = make_mods(idx->S, idx->hv, (const HashCfg*)idx->d_hcfg);
     a.rows = idx->rows; a.rownz = idx->rownz; a.N = idx->N; a.Wp = idx->Wp;
     a.start_sample = p.start_sample; a.rep_cap = p.rep_cap; a.with_steps = ctx->opt_readid_report_steps ? 1u : 0u;
     a.gw = p.group_width; a.rbf = p.reserve_before_find;
