@@ -5,5 +5,5 @@ include/colorid_b200.h; this package only loads it (ctypes) and offers numpy-fac
 for tests and benchmarks.  There is no CPU fallback.
 """
 from . import lib  # noqa: F401
-from .api import Context, Index, MultiIndex, pack_seqs, group_offsets  # noqa: F401
+from .api import Context, Index, MultiIndex, pack_seqs, group_offsets, pack_reads  # noqa: F401
 from .lib import CID_SEQ_FASTA, CID_SEQ_FASTQ, CID_SEQ_STRING, CID_MINI_OF_KMERS, CID_MINI_COUNTED, CID_MG_REPLICATED, CID_MG_COLUMNS, CidError  # noqa: F401

@@ -339,6 +339,21 @@ class Index:
                                               top_cap))
         return dict(kind=kind[:nr], hits=hits[:nr], n_set=n_set[:nr], n_top=n_top[:nr], top=top[:nr])
 
+    def read_id_classify_packed(self, packed, d=1, start_sample=3, group_width=16, reserve_before_find=True, fp_correct=1e-3, top_cap=8):
+        """cid_read_id_classify_packed on the output of pack_reads()."""
+        nr = len(packed["read_offs"]) - 1
+        p = self._params(d, start_sample, 0, group_width, reserve_before_find, None)
+        m = max(nr, 1)
+        kind = np.zeros(m, np.int32)
+        hits, n_set, n_top = np.zeros(m, np.uint32), np.zeros(m, np.uint32), np.zeros(m, np.uint32)
+        top = np.zeros((m, top_cap), np.uint32)
+        n_ref = np.ascontiguousarray(self.n_ref, dtype=np.uint64)
+        L.check(self.lib.cid_read_id_classify_packed(self.h, _p(packed["words"], L.u32p), _p(packed["word_offs"], L.u64p), packed["flags"],
+                                                     _p(packed["seq_offs"], L.u64p), packed["nseq"], _p(packed["read_offs"], L.u64p), nr,
+                                                     C.byref(p), _p(n_ref, L.u64p), fp_correct, _p(kind, L.i32p), _p(hits, L.u32p),
+                                                     _p(n_set, L.u32p), _p(n_top, L.u32p), _p(top, L.u32p), top_cap))
+        return dict(kind=kind[:nr], hits=hits[:nr], n_set=n_set[:nr], n_top=n_top[:nr], top=top[:nr])
+
     def read_kmer_order(self, reads, d=1, group_width=16, reserve_before_find=True, order_cap=512):
         flat = [s for r in reads for s in r]
         bases, offs = pack_seqs(flat)
@@ -358,6 +373,25 @@ class Index:
         out = np.zeros((len(kmers), self.H), dtype=np.uint64)
         L.check(self.lib.cid_hash_kmers(self.h, _p(arr), len(kmers), _p(out, L.u64p)))
         return out
+
+
+def pack_reads(reads, quals=None, qual_offset=0, threads=0):
+    """cid_pack_reads: lists of mates (bytes) -> dict(words u32[], word_offs u64[n+1], flags, seq_offs, read_offs, nseq)."""
+    lib = L.load()
+    flat = [s for r in reads for s in r]
+    bases, offs = pack_seqs(flat)
+    roffs = group_offsets(reads)
+    qarr = None
+    if quals is not None:
+        qarr, _ = pack_seqs([s for r in quals for s in r])
+    nr = len(reads)
+    cap = int(lib.cid_pack_words_bound(_p(offs, L.u64p), _p(roffs, L.u64p), nr, 1))
+    words = np.zeros(max(cap, 1), dtype=np.uint32)
+    woffs = np.zeros(nr + 1, dtype=np.uint64)
+    flags = C.c_uint32(0)
+    L.check(lib.cid_pack_reads(_p(bases), _p(qarr), _p(offs, L.u64p), len(flat), _p(roffs, L.u64p), nr, qual_offset, threads,
+                               _p(words, L.u32p), cap, _p(woffs, L.u64p), C.byref(flags)))
+    return dict(words=words[:max(int(woffs[nr]), 1)], word_offs=woffs, flags=flags.value, seq_offs=offs, read_offs=roffs, nseq=len(flat))
 
 
 class MultiIndex:

@@ -230,6 +230,9 @@ int launch_uniq_summaries(cid_ctx* ctx, cudaStream_t st, const uint32_t* d_list,
 // (every per-read array is indexed by the absolute read number, so a caller that stages only a
 // chunk passes pointers biased by the chunk origin).  Per-read scratch (`entries`, `order`, `nocc`)
 // is indexed from 0 and must hold `scr.cap_reads` reads; larger ranges are walked in pieces.
+// read source of the read_id kernels: ASCII (+ qualities) or packed planes (cid_pack_reads); see cid_readid.cu
+struct ReadSrc { const uint8_t* bases; const uint8_t* quals; uint32_t maxq; const uint32_t* pk; const uint64_t* pk_offs; uint32_t pk_lower; };
+struct PackedReads { const uint32_t* words; const uint64_t* word_offs; uint32_t lower; };   // device pointers; word_offs indexed by absolute read
 struct ReadIdScratch {
     uint32_t* entries; uint16_t* order; uint32_t* nocc; uint64_t cap_reads;
     // general path (cid_readid_big.cu): scratch of big_ctas CTAs sized by readid_big_plan(big_bases, big_kmers)
@@ -238,14 +241,14 @@ struct ReadIdScratch {
 enum { READID_FAST_BASES = 1000 };     // longest read (all mates) of the warp-per-read kernels
 void readid_scratch_bytes(const cid_index* idx, uint32_t max_read_bases, uint32_t max_kmers, uint64_t reads,
                           size_t* entries_bytes, size_t* order_bytes, size_t* nocc_bytes);
-int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const uint8_t* d_quals,
+int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const uint8_t* d_quals, const PackedReads* d_packed,
                const uint64_t* d_seq_offs, const uint64_t* d_read_offs, uint64_t r_first, uint64_t nreads,
                uint32_t max_read_bases, uint32_t max_kmers, const cid_readid_params& p, const ReadIdScratch& scr,
                uint32_t* d_n_set, uint32_t* d_flags, uint32_t* d_rep_n, uint32_t* d_rep_colour, uint32_t* d_rep_count,
                uint32_t order_cap, uint32_t* d_order_n, uint8_t* d_order_seq, uint32_t* d_order_pos);
 // general path: reads listed in d_list[0 .. *d_list_n) (indices relative to r0), one CTA per read, tables in `d_scratch`
 void readid_big_plan(const cid_index* idx, uint32_t max_bases, uint32_t max_kmers, size_t budget, size_t* bytes, uint32_t* ctas);
-int launch_readid_big(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const uint8_t* d_quals, uint32_t maxq,
+int launch_readid_big(cid_index* idx, cudaStream_t st, const ReadSrc& src,
                       const uint64_t* d_seq_offs, const uint64_t* d_read_offs, uint64_t r0, const uint32_t* d_list,
                       const uint32_t* d_list_n, uint32_t max_bases, uint32_t max_kmers, const cid_readid_params& p,
                       uint8_t* d_scratch, uint32_t ctas, uint32_t* d_n_set, uint32_t* d_flags, uint32_t* d_rep_n,

@@ -33,12 +33,18 @@ constexpr uint32_t REP_STEP_SHIFT = 20;
 
 struct ReadGeom { uint64_t b0; int len; int nm; };
 
+// Where a read's bases come from: ASCII bases (+ qualities for seq.rs:36-56 qual_mask on the device), or the planes a host
+// packer produced (cid_pack_reads: per read 2-bit codes, "not ACGTacgt / masked" bits and optionally lower-case bits, in the
+// tile's own layout, so loading is a copy and the per-kernel mask + pack work disappears along with 3/4 of the H2D bytes).
+
 // Loads one read (all mates, contiguous in `bases`) into a warp-private tile, applying
 // seq.rs:36-56 qual_mask when quals != nullptr.  Returns false if the read does not fit.
-__device__ __forceinline__ bool warp_load_read(Tile& t, int cap, const uint8_t* __restrict__ bases,
-                                               const uint8_t* __restrict__ quals, uint32_t maxq,
+__device__ __forceinline__ bool warp_load_read(Tile& t, int cap, const ReadSrc& src_, uint64_t r,
                                                const uint64_t* __restrict__ seq_offs, uint64_t s_begin, uint64_t s_end,
                                                uint32_t* moffs, int lane, ReadGeom& g) {
+    const uint8_t* __restrict__ bases = src_.bases;
+    const uint8_t* __restrict__ quals = src_.quals;
+    const uint32_t maxq = src_.maxq;
     g.b0 = __ldg(seq_offs + s_begin);
     uint64_t b1 = __ldg(seq_offs + s_end);
     g.nm = (int)(s_end - s_begin);
@@ -51,6 +57,27 @@ __device__ __forceinline__ bool warp_load_read(Tile& t, int cap, const uint8_t* 
         uint32_t o = (uint32_t)(__ldg(seq_offs + s_begin + lane) - g.b0);
         moffs[lane] = o;
         if (lane > 0 && lane < g.nm) atomicOr(&t.start[o >> 5], 1u << (o & 31));
+    }
+    if (src_.pk) {
+        // packed planes: codes | bad | [lower], one copy each (bits past the read's end are "bad" by construction)
+        const uint32_t* __restrict__ pw = src_.pk + __ldg(src_.pk_offs + r);
+        const int ncw = (g.len + 15) >> 4, nbw = (g.len + 31) >> 5;
+        for (int w = lane; w < cap / 16 + 3; w += 32) t.codes[w] = w < ncw ? __ldcs(pw + w) : 0u;
+        for (int w = lane; w < cap / 32 + 2; w += 32) {
+            t.bad[w] = w < nbw ? __ldcs(pw + ncw + w) : 0xFFFFFFFFu;
+            t.lower[w] = (src_.pk_lower && w < nbw) ? __ldcs(pw + ncw + nbw + w) : 0u;
+        }
+        __syncwarp();
+        if (src_.pk_lower) {      // (rare) raw-case consumers read the bytes: spell them from the planes ('N' for any non-base)
+            for (int i = lane; i < g.len; i += 32) {
+                uint32_t c = code_ascii((t.codes[i >> 4] >> (30 - 2 * (i & 15))) & 3u);
+                if ((t.lower[i >> 5] >> (i & 31)) & 1u) c |= 0x20u;
+                if ((t.bad[i >> 5] >> (i & 31)) & 1u) c = 'N';
+                t.ascii[i] = (uint8_t)c;
+            }
+            __syncwarp();
+        }
+        return true;
     }
     const uint8_t* src = bases + g.b0;
     const uint8_t* qsrc = quals ? quals + g.b0 : nullptr;
@@ -88,7 +115,7 @@ __device__ __forceinline__ bool warp_load_read(Tile& t, int cap, const uint8_t* 
 // last fresh one" (bit 31 of nocc), see readid_order_small_kernel.
 template <bool COMPACT, bool MINI>     // MINI: .mxi index, the set holds minimizers of length mini_m (a separate
 __global__ void __launch_bounds__(RA_WARPS * 32)   // instantiation so the k-mer path keeps its register budget)
-readid_kmerize_kernel(const uint8_t* __restrict__ bases, const uint8_t* __restrict__ quals, uint32_t maxq,
+readid_kmerize_kernel(const ReadSrc src,
                       const uint64_t* __restrict__ seq_offs, const uint64_t* __restrict__ read_offs, uint64_t r0,
                       uint64_t nreads, uint32_t k, uint32_t mini_m, uint32_t d, int cap, uint32_t maxocc, uint32_t tsize,
                       uint32_t* __restrict__ entries, uint8_t* __restrict__ hp8, uint32_t* __restrict__ h9w,
@@ -120,8 +147,8 @@ readid_kmerize_kernel(const uint8_t* __restrict__ bases, const uint8_t* __restri
             if (rn < nreads) {
                 const uint64_t nb0 = __ldg(seq_offs + __ldg(read_offs + r0 + rn)), nb1 = __ldg(seq_offs + __ldg(read_offs + r0 + rn + 1));
                 const uint64_t off = nb0 + (uint64_t)(lane & 15) * 128;
-                if (nb1 > nb0 && off < nb1 + 127) {                       // every 128-byte line the read touches
-                    const uint8_t* pa = (lane < 16 ? bases : quals);
+                if (!src.pk && nb1 > nb0 && off < nb1 + 127) {            // every 128-byte line the read touches
+                    const uint8_t* pa = (lane < 16 ? src.bases : src.quals);
                     if (pa) asm volatile("prefetch.global.L1 [%0];" ::"l"(pa + min(off, nb1 - 1)));
                 }
             }
@@ -139,7 +166,7 @@ readid_kmerize_kernel(const uint8_t* __restrict__ bases, const uint8_t* __restri
         // Reads this kernel cannot hold -- longer than the shared-memory tile, or (below) with a lower-case base inside a
         // k-mer, which 2-bit keys cannot spell -- go to the general path (cid_readid_big.cu) through a device list.
         bool slow = false;
-        if (ok && !warp_load_read(t, cap, bases, quals, maxq, seq_offs, s_begin, s_end, moffs, lane, g)) { slow = true; ok = false; }
+        if (ok && !warp_load_read(t, cap, src, r, seq_offs, s_begin, s_end, moffs, lane, g)) { slow = true; ok = false; }
         if (ok && !MINI) {
             // kmer.rs:229 `0..l.len()-k+1` wraps for a later mate shorter than k-1 -> slice panic
             // (minimerize_vector_skip_n_set has a `length_l < k` guard instead, kmer.rs:372: the mate is skipped)
@@ -567,7 +594,7 @@ readid_order_small_kernel(const uint8_t* __restrict__ hp8, const uint32_t* __res
 // ================================================================= readid_vote (rows of <= 64 accessions)
 template <int WP, bool STEPS>      // STEPS: report colours carry their insertion step (column-sharded read_id); a separate
 __global__ void __launch_bounds__(RA_WARPS * 32, 9)   // instantiation so that the replicated-index kernel stays as it was
-readid_vote_narrow_kernel(const uint8_t* __restrict__ bases, const uint8_t* __restrict__ quals, uint32_t maxq,
+readid_vote_narrow_kernel(const ReadSrc src,
                           const uint64_t* __restrict__ seq_offs, const uint64_t* __restrict__ read_offs, uint64_t r0,
                           uint64_t nreads, uint32_t k, uint32_t H, ModS mods, const uint32_t* __restrict__ rows,
                           const uint32_t* __restrict__ rownz, const uint32_t* __restrict__ rownz_all, uint32_t N, int cap,
@@ -596,7 +623,7 @@ readid_vote_narrow_kernel(const uint8_t* __restrict__ bases, const uint8_t* __re
         __syncwarp();
         if (n == 0) { if (lane == 0) rep_n[r] = 0; continue; }
         ReadGeom g;
-        warp_load_read(t, cap, bases, quals, maxq, seq_offs, __ldg(read_offs + r), __ldg(read_offs + r + 1), moffs, lane, g);
+        warp_load_read(t, cap, src, r, seq_offs, __ldg(read_offs + r), __ldg(read_offs + r + 1), moffs, lane, g);
         const uint16_t* ordrow = order + rl * (uint64_t)maxocc;
         const uint8_t* ord8row = order8 + rl * (uint64_t)maxocc;
         const uint16_t* entrow = ent16 + rl * (uint64_t)maxocc;
@@ -778,7 +805,7 @@ __device__ __forceinline__ void csa3(uint32_t& carry, uint32_t& sum, uint32_t a,
 }
 template <int WPL, int HT>         // words per lane (1, 2 or 4): 1,024 / 2,048 / 4,096 accessions; sizes the bit-sliced counters.
 __global__ void __launch_bounds__(RA_WARPS * 32, (WPL == 1 && HT != 0) ? 8 : 1)      // HT: compile-time num_hash (2 or 4; 0 = run-time, predicated up to MAX_HASH)
-readid_vote_wide_kernel(const uint8_t* __restrict__ bases, const uint8_t* __restrict__ quals, uint32_t maxq,
+readid_vote_wide_kernel(const ReadSrc src,
                         const uint64_t* __restrict__ seq_offs, const uint64_t* __restrict__ read_offs, uint64_t r0,
                         uint64_t nreads, uint32_t k, uint32_t H, ModS mods, const uint32_t* __restrict__ rows,
                         const uint32_t* __restrict__ rownz, uint32_t N, uint32_t Wp, int cap, uint32_t maxocc,
@@ -805,7 +832,7 @@ readid_vote_wide_kernel(const uint8_t* __restrict__ bases, const uint8_t* __rest
         __syncwarp();
         if (n == 0) { if (lane == 0) rep_n[r] = 0; continue; }
         ReadGeom g;
-        warp_load_read(t, cap, bases, quals, maxq, seq_offs, __ldg(read_offs + r), __ldg(read_offs + r + 1), moffs, lane, g);
+        warp_load_read(t, cap, src, r, seq_offs, __ldg(read_offs + r), __ldg(read_offs + r + 1), moffs, lane, g);
         const uint16_t* ordrow = order + rl * (uint64_t)maxocc;
         const uint8_t* ord8row = order8 + rl * (uint64_t)maxocc;
         const uint16_t* entrow = ent16 + rl * (uint64_t)maxocc;
@@ -1202,7 +1229,7 @@ void readid_scratch_bytes(const cid_index* idx, uint32_t max_read_bases, uint32_
     *nocc_bytes = (size_t)reads * 16 + (size_t)SCHED_BINS * 4 + 16;    // nocc, nfresh, perm, schedule bins, general-path list
 }
 
-int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const uint8_t* d_quals,
+int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const uint8_t* d_quals, const PackedReads* d_packed,
                const uint64_t* d_seq_offs, const uint64_t* d_read_offs, uint64_t r_first, uint64_t nreads,
                uint32_t max_read_bases, uint32_t max_kmers, const cid_readid_params& p, const ReadIdScratch& scr,
                uint32_t* d_n_set, uint32_t* d_flags, uint32_t* d_rep_n, uint32_t* d_rep_colour, uint32_t* d_rep_count,
@@ -1220,6 +1247,8 @@ int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const ui
     const bool small = maxocc <= 255;
     const uint32_t maxq = d_quals && p.qual_offset ? p.qual_offset + 33 : 0;
     const uint8_t* quals = maxq ? d_quals : nullptr;
+    ReadSrc rsrc{d_bases, quals, maxq, nullptr, nullptr, 0};
+    if (d_packed) { rsrc.pk = d_packed->words; rsrc.pk_offs = d_packed->word_offs; rsrc.pk_lower = d_packed->lower; rsrc.bases = rsrc.quals = nullptr; rsrc.maxq = 0; }
 
     const uint64_t sub = std::min<uint64_t>(nreads, scr.cap_reads);
     if (sub == 0) { set_error("read_id: no scratch"); return CID_E_INVALID; }
@@ -1279,7 +1308,7 @@ int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const ui
         {
         ProfScope ps(ctx, st, KID_READID_KMERIZE);
 #define CID_KMERIZE(C, M)                                                                                              \
-    readid_kmerize_kernel<C, M><<<gridK, RA_WARPS * 32, a_smem, st>>>(d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr, idx->k, \
+    readid_kmerize_kernel<C, M><<<gridK, RA_WARPS * 32, a_smem, st>>>(rsrc, d_seq_offs, d_read_offs, r0, nr, idx->k, \
                                                                      idx->m, p.downsample, cap, maxocc, tsize, d_entries, d_hp8,   \
                                                                      d_h9w, d_ent16, d_nocc, d_nfresh, d_flags, ctx->d_err, d_slow, d_slow_n)
         if (small) { if (idx->m) CID_KMERIZE(true, true); else CID_KMERIZE(true, false); }
@@ -1332,7 +1361,7 @@ int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const ui
                 if (!idx->rownz_global) rownz = nullptr;   // presence == any word set, already in registers
 #define CID_VOTE_NARROW(WPV, STV)                                                                                      \
     readid_vote_narrow_kernel<WPV, STV><<<gridV, RA_WARPS * 32, cn_smem, st>>>(                                        \
-        d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr, kitem, idx->H, mods, idx->rows, rownz, idx->rownz, idx->N, cap,  \
+        rsrc, d_seq_offs, d_read_offs, r0, nr, kitem, idx->H, mods, idx->rows, rownz, idx->rownz, idx->N, cap,  \
         maxocc, ord16, ord8, d_ent16, d_n_set, p.start_sample, p.rep_cap, d_flags, d_rep_n, d_rep_colour, d_rep_count,  \
         (unsigned long long*)(ctx->d_err + 2))
                 if (idx->Wp == 1) { if (with_steps) CID_VOTE_NARROW(1, true); else CID_VOTE_NARROW(1, false); }
@@ -1341,7 +1370,7 @@ int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const ui
             } else {
 #define CID_VOTE_WIDE_H(WPLV, HTV)                                                                                     \
     readid_vote_wide_kernel<WPLV, HTV><<<gridV, RA_WARPS * 32, cw_smem, st>>>(                                         \
-        d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, nr, kitem, idx->H, mods, idx->rows, rownz, idx->N, idx->Wp, cap, maxocc,  \
+        rsrc, d_seq_offs, d_read_offs, r0, nr, kitem, idx->H, mods, idx->rows, rownz, idx->N, idx->Wp, cap, maxocc,  \
         ord16, ord8, d_ent16, d_n_set, p.start_sample, p.rep_cap, d_flags, d_rep_n, d_rep_colour, d_rep_count, with_steps)
 #define CID_VOTE_WIDE(WPLV) do { if (idx->H == 4) CID_VOTE_WIDE_H(WPLV, 4); else if (idx->H == 2) CID_VOTE_WIDE_H(WPLV, 2); else CID_VOTE_WIDE_H(WPLV, 0); } while (0)
                 if (idx->Wp <= 32) CID_VOTE_WIDE(1); else if (idx->Wp <= 64) CID_VOTE_WIDE(2); else CID_VOTE_WIDE(4);
@@ -1352,7 +1381,7 @@ int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const ui
             CID_CUDA(cudaGetLastError());
         }
         // the reads the kernels above handed over (too long for their tiles, lower-case k-mers): general path, CTA per read
-        CID_TRY(launch_readid_big(idx, st, d_bases, quals, maxq, d_seq_offs, d_read_offs, r0, d_slow, d_slow_n, scr.big_bases,
+        CID_TRY(launch_readid_big(idx, st, rsrc, d_seq_offs, d_read_offs, r0, d_slow, d_slow_n, scr.big_bases,
                                   scr.big_kmers, p, scr.big, scr.big_ctas, d_n_set, d_flags, d_rep_n, d_rep_colour, d_rep_count,
                                   order_cap, d_order_n, d_order_seq, d_order_pos));
     }

@@ -73,7 +73,7 @@ static BigLayout big_layout(uint32_t lcap, uint32_t kcap) {
 }
 
 struct BigArgs {
-    const uint8_t* bases; const uint8_t* quals; uint32_t maxq;
+    ReadSrc src;
     const uint64_t* seq_offs; const uint64_t* read_offs; uint64_t r0;
     const uint32_t* list; const uint32_t* list_n;
     uint32_t k, mini_m, d, H; ModS mods;
@@ -178,13 +178,21 @@ readid_big_kernel(const BigArgs a) {
         bool miss = false;
         if (ok) {
             // ---- 1. masked copy -------------------------------------------------------------------------------------
+            const uint32_t* pw = a.src.pk ? a.src.pk + a.src.pk_offs[r] : nullptr;
+            const uint32_t ncw = (L + 15) >> 4, nbw = (L + 31) >> 5;
             for (uint32_t i = tid; i < L + 64; i += BG_THREADS) {
-                uint8_t c = 0;
+                uint32_t c = 0;
                 if (i < L) {
-                    c = a.bases[b0 + i];
-                    if (a.quals && (uint32_t)a.quals[b0 + i] < a.maxq) c = 'N';
+                    if (pw) {        // packed planes: the bytes are spelled back ('N' for any non-base; the case from the lower plane)
+                        c = code_ascii((pw[i >> 4] >> (30 - 2 * (i & 15))) & 3u);
+                        if (a.src.pk_lower && ((pw[ncw + nbw + (i >> 5)] >> (i & 31)) & 1u)) c |= 0x20u;
+                        if ((pw[ncw + (i >> 5)] >> (i & 31)) & 1u) c = 'N';
+                    } else {
+                        c = a.src.bases[b0 + i];
+                        if (a.src.quals && (uint32_t)a.src.quals[b0 + i] < a.src.maxq) c = 'N';
+                    }
                 }
-                seq[i] = c;
+                seq[i] = (uint8_t)c;
             }
             {   // dedup table: key all ones, case unset, first occurrence +inf
                 uint4* t4 = (uint4*)tab;
@@ -444,7 +452,7 @@ void readid_big_plan(const cid_index* idx, uint32_t max_bases, uint32_t max_kmer
     *bytes = L.total * g;
 }
 
-int launch_readid_big(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const uint8_t* d_quals, uint32_t maxq,
+int launch_readid_big(cid_index* idx, cudaStream_t st, const ReadSrc& src,
                       const uint64_t* d_seq_offs, const uint64_t* d_read_offs, uint64_t r0, const uint32_t* d_list,
                       const uint32_t* d_list_n, uint32_t max_bases, uint32_t max_kmers, const cid_readid_params& p,
                       uint8_t* d_scratch, uint32_t ctas, uint32_t* d_n_set, uint32_t* d_flags, uint32_t* d_rep_n,
@@ -454,7 +462,7 @@ int launch_readid_big(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, c
     if (max_bases >= (1u << 23)) { set_error("read_id: reads of 2^23 bases or more are not supported"); return CID_E_UNSUPPORTED; }
     if (d_rep_n && idx->N > BG_MAX_COLOURS) { set_error("read_id: more than %u accessions per shard not supported", BG_MAX_COLOURS); return CID_E_UNSUPPORTED; }
     BigArgs a{};
-    a.bases = d_bases; a.quals = maxq ? d_quals : nullptr; a.maxq = maxq;
+    a.src = src;
     a.seq_offs = d_seq_offs; a.read_offs = d_read_offs; a.r0 = r0;
     a.list = d_list; a.list_n = d_list_n;
     a.k = idx->k; a.mini_m = idx->m; a.d = p.downsample; a.H = idx->H; a.mods = make_mods(idx->S, idx->hv, (const HashCfg*)idx->d_hcfg);

@@ -122,6 +122,7 @@ struct HostOut {            // where a chunk's results go (user memory, indexed 
     int32_t* kind = nullptr; uint32_t *hits = nullptr, *n_top = nullptr, *top = nullptr; uint32_t top_cap = 0;
 };
 
+struct HostPacked { const uint32_t* words; const uint64_t* word_offs; uint32_t lower; };    // cid_pack_reads output (host)
 struct VoteJob { uint64_t r0, nr; int slot; };
 
 static double now_ms() {
@@ -129,7 +130,8 @@ static double now_ms() {
 }
 
 static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals, const uint64_t* seq_offs, uint64_t nseq,
-                            const uint64_t* read_offs, uint64_t nreads, const cid_readid_params* p, const HostOut& out) {
+                            const uint64_t* read_offs, uint64_t nreads, const cid_readid_params* p, const HostOut& out,
+                            const HostPacked* hp = nullptr) {
     cid_ctx* ctx = ix->ctx;
     if (!seq_offs || !read_offs) { set_error("read_id: null argument"); return CID_E_INVALID; }
     CID_CUDA(cudaSetDevice(ctx->device));
@@ -141,7 +143,7 @@ static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals,
     const double t_start = now_ms();
     double t_vote = 0, t_wait = 0, t_evwait = 0;
     double t_geom = 0;
-    const bool use_q = quals && pp.qual_offset;
+    const bool use_q = !hp && quals && pp.qual_offset;
     const bool want_rep = out.rep_n != nullptr || out.vote != nullptr;
     const bool fused = out.vote != nullptr;
     cid_readid_pipe* pipe;
@@ -290,7 +292,9 @@ static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals,
         const uint32_t max_bases = geo.fast_bases, max_kmers = geo.fast_kmers;
         size_t eb, ob, nb;
         readid_scratch_bytes(ix, max_bases, max_kmers, nr, &eb, &ob, &nb);
-        PIPE_TRY(s.bases.ensure(b1 - b0 + 64));
+        const uint64_t w0 = hp ? hp->word_offs[r0] : 0, w1 = hp ? hp->word_offs[r1] : 0;
+        if (hp) { PIPE_TRY(s.bases.ensure((w1 - w0) * 4 + 64)); PIPE_TRY(s.quals.ensure((nr + 1) * 8 + 64)); }
+        else PIPE_TRY(s.bases.ensure(b1 - b0 + 64));
         if (use_q) PIPE_TRY(s.quals.ensure(b1 - b0 + 64));
         PIPE_TRY(s.seq_offs.ensure((s1 - s0 + 1) * 8));
         PIPE_TRY(s.read_offs.ensure((nr + 1) * 8));
@@ -311,19 +315,26 @@ static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals,
         {
             const size_t nso = s1 - s0 + 1, nro = nr + 1;
             PIPE_CUDA(cudaEventSynchronize(s.offs_done));          // previous use of this slot's staging
-            PIPE_TRY(s.h_offs.ensure((nso + nro) * 8));
+            PIPE_TRY(s.h_offs.ensure((nso + nro + (hp ? nro : 0)) * 8));
             uint64_t* ho = s.h_offs.as<uint64_t>();
             memcpy(ho, seq_offs + s0, nso * 8);
             memcpy(ho + nso, read_offs + r0, nro * 8);
             PIPE_CUDA(cudaMemcpyAsync(s.seq_offs.p, ho, nso * 8, cudaMemcpyHostToDevice, s.st));
             PIPE_CUDA(cudaMemcpyAsync(s.read_offs.p, ho + nso, nro * 8, cudaMemcpyHostToDevice, s.st));
+            if (hp) {        // word offset of every read of the chunk (absolute: the device word pointer is biased to match)
+                memcpy(ho + nso + nro, hp->word_offs + r0, nro * 8);
+                PIPE_CUDA(cudaMemcpyAsync(s.quals.p, ho + nso + nro, nro * 8, cudaMemcpyHostToDevice, s.st));
+            }
             PIPE_CUDA(cudaEventRecord(s.offs_done, s.st));
         }
         tmark(s.st);
-        if (b1 > b0) PIPE_CUDA(cudaMemcpyAsync(s.bases.p, bases + b0, b1 - b0, cudaMemcpyHostToDevice, s.st));
+        if (hp) { if (w1 > w0) PIPE_CUDA(cudaMemcpyAsync(s.bases.p, hp->words + w0, (w1 - w0) * 4, cudaMemcpyHostToDevice, s.st)); }
+        else if (b1 > b0) PIPE_CUDA(cudaMemcpyAsync(s.bases.p, bases + b0, b1 - b0, cudaMemcpyHostToDevice, s.st));
         if (use_q && b1 > b0) PIPE_CUDA(cudaMemcpyAsync(s.quals.p, quals + b0, b1 - b0, cudaMemcpyHostToDevice, s.st));
         tmark(s.st);
         // device arrays are indexed by absolute base / sequence / read numbers: bias the chunk buffers
+        PackedReads pk{hp ? s.bases.as<uint32_t>() - w0 : nullptr, hp ? s.quals.as<uint64_t>() - r0 : nullptr, hp ? hp->lower : 0u};
+        const PackedReads* packed_ptr = hp ? &pk : nullptr;
         const uint8_t* d_bases = s.bases.as<uint8_t>() - b0;
         const uint8_t* d_quals = use_q ? s.quals.as<uint8_t>() - b0 : nullptr;
         const uint64_t* d_seq_offs = s.seq_offs.as<uint64_t>() - s0;
@@ -347,7 +358,7 @@ static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals,
         // Option readid_serialize: this chunk's kernels start only after the previous chunk's have finished (copies still
         // overlap).  Measured on B200: 44.8M pairs/s against 46.3M with free overlap across the slot streams, so it is off.
         if (c > 0 && ctx->opt_readid_serialize) PIPE_CUDA(cudaStreamWaitEvent(s.st, pipe->slot[(c - 1) % NS].kern_done, 0));
-        PIPE_TRY(readid_run(ix, s.st, d_bases, d_quals, d_seq_offs, d_read_offs, r0, nr, max_bases, max_kmers, pp, scr,
+        PIPE_TRY(readid_run(ix, s.st, d_bases, d_quals, packed_ptr, d_seq_offs, d_read_offs, r0, nr, max_bases, max_kmers, pp, scr,
                             d_n_set, d_flags, d_rep_n, d_rc, d_rv, out.order_cap, d_on, d_os, d_op));
         tmark(s.st);
         if (fused) {
@@ -421,12 +432,10 @@ using namespace cid;
 
 extern "C" {
 
-int cid_read_id_batch_dev(cid_index* ix, const char* d_bases, const char* d_quals, const uint64_t* d_seq_offs,
-                          uint64_t nseq, uint64_t nbases, const uint64_t* d_read_offs, uint64_t nreads,
-                          uint32_t h_max_read_bases, uint32_t h_max_kmers, const cid_readid_params* p,
-                          uint32_t* d_n_set, uint32_t* d_flags, uint32_t* d_rep_n, uint32_t* d_rep_colour,
-                          uint32_t* d_rep_count, void* stream) {
-    (void)nseq; (void)nbases;
+static int read_id_batch_dev_impl(cid_index* ix, const char* d_bases, const char* d_quals, const PackedReads* pkp_in, const uint64_t* d_seq_offs,
+                                  const uint64_t* d_read_offs, uint64_t nreads, uint32_t h_max_read_bases, uint32_t h_max_kmers,
+                                  const cid_readid_params* p, uint32_t* d_n_set, uint32_t* d_flags, uint32_t* d_rep_n,
+                                  uint32_t* d_rep_colour, uint32_t* d_rep_count, void* stream) {
     cid_ctx* ctx = ix->ctx;
     CID_CUDA(cudaSetDevice(ctx->device));
     cid_readid_params pp;
@@ -434,6 +443,7 @@ int cid_read_id_batch_dev(cid_index* ix, const char* d_bases, const char* d_qual
     cudaStream_t user = (cudaStream_t)stream;
     const int nst = (ctx->opt_readid_streams >= 2 && nreads >= 4 * 32768) ? 2 : 1;
     const uint32_t big_kmers = h_max_kmers ? h_max_kmers : std::max<uint32_t>(h_max_read_bases, 1);
+    const PackedReads* pkp = pkp_in;
     if (nst == 1) {
         const uint64_t cap = std::min<uint64_t>(std::max<uint64_t>(nreads, 1), 1u << 20);
         size_t eb, ob, nb;
@@ -443,7 +453,7 @@ int cid_read_id_batch_dev(cid_index* ix, const char* d_bases, const char* d_qual
         CID_TRY(ctx->scratch[18].ensure(nb));
         ReadIdScratch scr{ctx->scratch[16].as<uint32_t>(), ctx->scratch[17].as<uint16_t>(), ctx->scratch[18].as<uint32_t>(), cap, nullptr, 0, 0, 0};
         CID_TRY(big_scratch(ix, ctx->scratch[24], h_max_read_bases, big_kmers, scr));
-        return readid_run(ix, user, (const uint8_t*)d_bases, (const uint8_t*)d_quals, d_seq_offs, d_read_offs, 0,
+        return readid_run(ix, user, (const uint8_t*)d_bases, (const uint8_t*)d_quals, pkp, d_seq_offs, d_read_offs, 0,
                           nreads, h_max_read_bases, h_max_kmers, pp, scr, d_n_set, d_flags, d_rep_n, d_rep_colour, d_rep_count,
                           0, nullptr, nullptr, nullptr);
     }
@@ -470,7 +480,7 @@ int cid_read_id_batch_dev(cid_index* ix, const char* d_bases, const char* d_qual
         ReadIdScratch scr{ctx->scratch[16 + 3 * i].as<uint32_t>(), ctx->scratch[17 + 3 * i].as<uint16_t>(),
                           ctx->scratch[18 + 3 * i].as<uint32_t>(), chunk, nullptr, 0, 0, 0};
         rc = big_scratch(ix, ctx->scratch[24 + i], h_max_read_bases, big_kmers, scr);
-        if (rc == CID_OK) rc = readid_run(ix, ctx->aux[i], (const uint8_t*)d_bases, (const uint8_t*)d_quals, d_seq_offs, d_read_offs, r0,
+        if (rc == CID_OK) rc = readid_run(ix, ctx->aux[i], (const uint8_t*)d_bases, (const uint8_t*)d_quals, pkp, d_seq_offs, d_read_offs, r0,
                         std::min(chunk, nreads - r0), h_max_read_bases, h_max_kmers, pp, scr, d_n_set, d_flags, d_rep_n,
                         d_rep_colour, d_rep_count, 0, nullptr, nullptr, nullptr);
     }
@@ -479,6 +489,26 @@ int cid_read_id_batch_dev(cid_index* ix, const char* d_bases, const char* d_qual
         cudaStreamWaitEvent(user, ctx->aux_join[i], 0);
     }
     return rc;
+}
+
+int cid_read_id_batch_dev(cid_index* ix, const char* d_bases, const char* d_quals, const uint64_t* d_seq_offs,
+                          uint64_t nseq, uint64_t nbases, const uint64_t* d_read_offs, uint64_t nreads,
+                          uint32_t h_max_read_bases, uint32_t h_max_kmers, const cid_readid_params* p,
+                          uint32_t* d_n_set, uint32_t* d_flags, uint32_t* d_rep_n, uint32_t* d_rep_colour,
+                          uint32_t* d_rep_count, void* stream) {
+    (void)nseq; (void)nbases;
+    return read_id_batch_dev_impl(ix, d_bases, d_quals, nullptr, d_seq_offs, d_read_offs, nreads, h_max_read_bases, h_max_kmers, p, d_n_set,
+                                  d_flags, d_rep_n, d_rep_colour, d_rep_count, stream);
+}
+int cid_read_id_batch_packed_dev(cid_index* ix, const uint32_t* d_words, const uint64_t* d_word_offs, uint32_t pack_flags,
+                                 const uint64_t* d_seq_offs, uint64_t nseq, const uint64_t* d_read_offs, uint64_t nreads,
+                                 uint32_t h_max_read_bases, uint32_t h_max_kmers, const cid_readid_params* p, uint32_t* d_n_set,
+                                 uint32_t* d_flags, uint32_t* d_rep_n, uint32_t* d_rep_colour, uint32_t* d_rep_count, void* stream) {
+    (void)nseq;
+    if (!d_words || !d_word_offs) { set_error("cid_read_id_batch_packed_dev: null argument"); return CID_E_INVALID; }
+    const PackedReads pk{d_words, d_word_offs, pack_flags & CID_PACK_LOWER};
+    return read_id_batch_dev_impl(ix, nullptr, nullptr, &pk, d_seq_offs, d_read_offs, nreads, h_max_read_bases, h_max_kmers, p, d_n_set,
+                                  d_flags, d_rep_n, d_rep_colour, d_rep_count, stream);
 }
 
 int cid_read_id_batch(cid_index* ix, const char* bases, const char* quals, const uint64_t* seq_offs, uint64_t nseq,
@@ -505,6 +535,25 @@ int cid_read_id_classify(cid_index* ix, const char* bases, const char* quals, co
     o.vote = &vp; o.threads = ix->ctx->opt_host_threads;
     o.kind = kind; o.hits = hits; o.n_top = n_top; o.top = top; o.top_cap = top ? top_cap : 0;
     return read_id_pipeline(ix, bases, quals, seq_offs, nseq, read_offs, nreads, &pp, o);
+}
+
+int cid_read_id_classify_packed(cid_index* ix, const uint32_t* words, const uint64_t* word_offs, uint32_t pack_flags,
+                                const uint64_t* seq_offs, uint64_t nseq, const uint64_t* read_offs, uint64_t nreads,
+                                const cid_readid_params* p, const uint64_t* n_ref_by_colour, double fp_correct, int32_t* kind,
+                                uint32_t* hits, uint32_t* n_set, uint32_t* n_top, uint32_t* top, uint32_t top_cap) {
+    if (!ix || !words || !word_offs || !n_ref_by_colour || !kind || !hits || !n_set || !n_top) { set_error("read_id_classify_packed: null argument"); return CID_E_INVALID; }
+    cid_readid_params pp;
+    default_readid_params(pp, p, ix->N);
+    pp.rep_cap = ix->N + 1;
+    pp.qual_offset = 0;          // the packer applied seq.rs:36-56 qual_mask
+    VoteParams vp;
+    vote_params_init(vp, ix->S, ix->H, ix->N, n_ref_by_colour, fp_correct, pp.group_width);
+    HostOut o;
+    o.n_set = n_set;
+    o.vote = &vp; o.threads = ix->ctx->opt_host_threads;
+    o.kind = kind; o.hits = hits; o.n_top = n_top; o.top = top; o.top_cap = top ? top_cap : 0;
+    const HostPacked hp{words, word_offs, pack_flags & CID_PACK_LOWER};
+    return read_id_pipeline(ix, nullptr, nullptr, seq_offs, nseq, read_offs, nreads, &pp, o, &hp);
 }
 
 int cid_read_kmer_order32(cid_index* ix, const char* bases, const uint64_t* seq_offs, uint64_t nseq,

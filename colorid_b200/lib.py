@@ -20,6 +20,7 @@ vp = C.c_void_p
 CID_OK, CID_E_INVALID, CID_E_CUDA, CID_E_NOMEM, CID_E_UNSUPPORTED, CID_E_REF_PANIC, CID_E_CAPACITY = 0, -1, -2, -3, -4, -5, -6
 CID_SEQ_FASTA, CID_SEQ_FASTQ, CID_SEQ_STRING = 0, 1, 2
 CID_MG_REPLICATED, CID_MG_COLUMNS = 0, 1
+CID_PACK_LOWER = 1
 CID_MINI_OF_KMERS, CID_MINI_COUNTED = 0, 1
 
 
@@ -53,6 +54,12 @@ SIGNATURES = {
     "cid_build_accession_dev": (C.c_int, [vp, C.c_uint32, vp, vp, C.c_uint64, C.c_uint64, C.c_int, C.c_int64, u64p, i64p]),
     "cid_index_set_minimizer": (C.c_int, [vp, C.c_uint32]),
     "cid_index_set_hash_variant": (C.c_int, [vp, C.c_uint32]),
+    "cid_pack_words_bound": (C.c_uint64, [u64p, u64p, C.c_uint64, C.c_int]),
+    "cid_pack_reads": (C.c_int, [vp, vp, u64p, C.c_uint64, u64p, C.c_uint64, C.c_uint32, C.c_int, u32p, C.c_uint64, u64p, u32p]),
+    "cid_read_id_classify_packed": (C.c_int, [vp, vp, u64p, C.c_uint32, u64p, C.c_uint64, u64p, C.c_uint64, C.POINTER(ReadIdParams), u64p,
+                                              C.c_double, C.POINTER(C.c_int32), u32p, u32p, u32p, u32p, C.c_uint32]),
+    "cid_read_id_batch_packed_dev": (C.c_int, [vp, vp, vp, C.c_uint32, vp, C.c_uint64, vp, C.c_uint64, C.c_uint32, C.c_uint32,
+                                               C.POINTER(ReadIdParams), vp, vp, vp, vp, vp, vp]),
     "cid_mg_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(vp)]),
     "cid_mg_destroy": (None, [vp]),
     "cid_mg_n_shards": (C.c_int, [vp]),

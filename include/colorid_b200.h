@@ -256,6 +256,31 @@ int cid_read_id_batch_dev(cid_index* idx, const char* d_bases, const char* d_qua
                           uint32_t h_max_read_bases, uint32_t h_max_kmers, const cid_readid_params* p,
                           uint32_t* d_n_set, uint32_t* d_flags, uint32_t* d_rep_n, uint32_t* d_rep_colour,
                           uint32_t* d_rep_count, void* stream);
+/* ---- packed reads ------------------------------------------------------------------------------------------------------
+ * The reference applies seq.rs:36-56 qual_mask on the host while it parses (read_id_mt_pe.rs:733-760).  cid_pack_reads does
+ * the same and emits per read (all mates concatenated, L bases) the planes the kernels work on:
+ *     codes[ceil(L/16)]  2 bits per base (A0 C1 G2 T3), 16 bases per u32, first base in bits 31:30
+ *     bad  [ceil(L/32)]  bit j (LSB first) = base j is not one of ACGTacgt or was masked; bits >= L are set
+ *     lower[ceil(L/32)]  bit j = base j is a lower-case acgt -- present iff *pack_flags & CID_PACK_LOWER (some read has one)
+ * words[word_offs[r] .. word_offs[r+1]) belongs to read r.  3 bits per base instead of the 16 of ASCII + qualities: a quarter
+ * of the host->device bytes, and no masking / packing left for the kernels.  Lossless for read_id (a non-base only has to be
+ * one: kmer.rs:221-243, seq.rs:59-70).  `threads` <= 0: all cores.  cid_pack_words_bound sizes `words`.
+ * cid_read_id_classify_packed / cid_read_id_batch_packed_dev == cid_read_id_classify / cid_read_id_batch_dev on the reads
+ * the planes spell (seq_offs / read_offs as there, in bases; p->qual_offset is ignored: the packer masked). */
+enum { CID_PACK_LOWER = 1 };
+uint64_t cid_pack_words_bound(const uint64_t* seq_offs, const uint64_t* read_offs, uint64_t nreads, int with_lower);
+int cid_pack_reads(const char* bases, const char* quals, const uint64_t* seq_offs, uint64_t nseq, const uint64_t* read_offs,
+                   uint64_t nreads, uint32_t qual_offset, int threads, uint32_t* words, uint64_t words_cap, uint64_t* word_offs,
+                   uint32_t* pack_flags);
+int cid_read_id_classify_packed(cid_index* idx, const uint32_t* words, const uint64_t* word_offs, uint32_t pack_flags,
+                                const uint64_t* seq_offs, uint64_t nseq, const uint64_t* read_offs, uint64_t nreads,
+                                const cid_readid_params* p, const uint64_t* n_ref_by_colour, double fp_correct, int32_t* kind,
+                                uint32_t* hits, uint32_t* n_set, uint32_t* n_top, uint32_t* top, uint32_t top_cap);
+int cid_read_id_batch_packed_dev(cid_index* idx, const uint32_t* d_words, const uint64_t* d_word_offs, uint32_t pack_flags,
+                                 const uint64_t* d_seq_offs, uint64_t nseq, const uint64_t* d_read_offs, uint64_t nreads,
+                                 uint32_t h_max_read_bases, uint32_t h_max_kmers, const cid_readid_params* p, uint32_t* d_n_set,
+                                 uint32_t* d_flags, uint32_t* d_rep_n, uint32_t* d_rep_colour, uint32_t* d_rep_count, void* stream);
+
 /* Debug/parity hook: the emulated FnvHashSet<String> iteration order of each read's k-mer set as
  * (mate index, position of first occurrence).  order_n[r] entries at [r*order_cap ..].
  * Minimizer index: the set holds minimizers; order_pos is the start of a window of m_size bases of that mate which

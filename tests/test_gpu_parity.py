@@ -685,6 +685,43 @@ def test_read_id_classify_ties_go_through_host_vote(oracle, ctx):
         ctx.set_option("readid_chunk_reads", 0)
 
 
+@pytest.mark.parametrize("N,k,S,H", [(46, 31, 2_000_003, 4), (150, 21, 300_007, 2)])
+def test_read_id_packed_input(oracle, ctx, N, k, S, H):
+    """cid_pack_reads + cid_read_id_classify_packed: quality masking and 2-bit packing on the host (where the reference masks:
+    seq.rs:36-56 from read_id_mt_pe.rs:733-760), planes to the device.  Same classifications as the oracle on the masked
+    reads: narrow and wide rows, N / IUPAC bytes, soft-masked reads (lower plane), long reads, too-short and panic reads,
+    one chunk and several."""
+    rng = _rng(1300 + N)
+    genomes, oix, gix = _index_pair(oracle, ctx, rng, N, k, S, H, glen=6000)
+    gix.n_ref[:] = oix.n_ref
+    reads = synth.reads_from(rng, genomes, 500, read_len=150, insert=320, err=0.003, frac_random=0.2, n_rate=0.003)
+    reads += synth.reads_from(rng, genomes, 40, read_len=97, insert=250, err=0.002, frac_random=0.1, paired=False)
+    reads += synth.reads_from(rng, genomes, 5, read_len=2100, insert=2200, err=0.001, frac_random=0.0, paired=False)
+    reads += [[b"ACGT", genomes[0][:150]], [genomes[0][:150], b"ACGTAC"], [b"N" * 150, b"N" * 150], [genomes[1][:k]], [genomes[1][:150], b""]]
+    quals = [[bytes(rng.choice(np.frombuffer(b"#+5?I", dtype=np.uint8), size=len(m), p=[.02, .02, .03, .33, .6]).tolist()) for m in r] for r in reads]
+    for soft in (False, True):
+        rr = list(reads)
+        if soft:
+            rr = _softmask(rng, rr, frac=0.2)
+        masked = [[oracle.qual_mask(m, q, 15) for m, q in zip(r, qr)] for r, qr in zip(rr, quals)]
+        o = oix.read_id_batch(masked)
+        pk = cb.pack_reads(rr, quals, 15)
+        assert bool(pk["flags"] & 1) == soft
+        try:
+            for chunk in (0, 101):
+                ctx.set_option("readid_chunk_reads", chunk)
+                for kw in (dict(), dict(start_sample=0, d=2)):
+                    oo = o if not kw else oix.read_id_batch(masked, **kw)
+                    g = gix.read_id_classify_packed(pk, **kw)
+                    for key in ("kind", "hits", "n_set", "n_top"):
+                        assert np.array_equal(g[key], oo[key]), (soft, chunk, kw, key)
+                    for r in range(len(rr)):
+                        nt = min(int(oo["n_top"][r]), 8)
+                        assert g["top"][r, :nt].tolist() == oo["top"][r, :nt].tolist()
+        finally:
+            ctx.set_option("readid_chunk_reads", 0)
+
+
 def test_read_id_classify_with_quals(oracle, ctx):
     rng = _rng(1235)
     genomes, oix, gix = _index_pair(oracle, ctx, rng, 6, 27, 750_000, 4)
