@@ -13,6 +13,7 @@ index (replicated on every GPU, reads split across GPUs).  One step = one batch 
 `--impl reference` times that CPU restatement alone (the Rust reference cannot be built here).
 """
 import argparse
+import hashlib
 import ctypes as C
 import json
 import os
@@ -89,6 +90,27 @@ def make_reads(torch, dev, cfg, genomes, n_pairs, seed):
         q[torch.rand((n, 2 * rl), generator=g, device=dev) < cfg["lowq"]] = 35
         out_q[s:s + n] = q
     return out_b, out_q
+
+
+def pack_reads_torch(torch, bases, quals, qual_offset):
+    """The planes of cid_pack_reads (include/colorid_b200.h "packed reads") for fixed-length reads, on the device, so that
+    the synthetic pool never crosses PCIe: -> int32 [n, ceil(L/16) + ceil(L/32)] (codes | bad), one row per read (2 mates).
+    Cross-checked against the product's host packer on a sample in run_ours."""
+    n, L = bases.shape
+    a = bases.long()
+    u = a & 0xDF
+    good = ((u == 65) | (u == 67) | (u == 71) | (u == 84)) & (quals.long() >= qual_offset + 33)
+    code = (((a >> 1) ^ (a >> 2)) & 3) * good
+    ncw, nbw = (L + 15) // 16, (L + 31) // 32
+    pad = torch.zeros((n, ncw * 16 - L), device=bases.device, dtype=torch.long)
+    cw = torch.cat([code, pad], 1).view(n, ncw, 16)
+    sh = (30 - 2 * torch.arange(16, device=bases.device)).view(1, 1, 16)
+    codes = (cw << sh).sum(2)
+    badb = torch.cat([(~good).long(), torch.ones((n, nbw * 32 - L), device=bases.device, dtype=torch.long)], 1).view(n, nbw, 32)
+    bad = (badb << torch.arange(32, device=bases.device).view(1, 1, 32)).sum(2)
+    w = torch.cat([codes, bad], 1) & 0xFFFFFFFF
+    w = torch.where(w >= 2 ** 31, w - 2 ** 32, w)
+    return w.to(torch.int32).contiguous()
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -253,7 +275,8 @@ def run_reference(args):
     oix = O.Index(cfg["S"], cfg["H"], cfg["k"], cfg["n_acc"])
     accs = [[lut[genomes[a].numpy()].tobytes()] for a in range(cfg["n_acc"])]
     oix.build_many(accs, O.MODE_FASTA, threads=cores)
-    log(f"[reference] oracle index built on {cores} threads in {time.time() - t0:.1f}s")
+    index_sha = hashlib.sha256(oix.words().tobytes()).hexdigest()
+    log(f"[reference] oracle index built on {cores} threads in {time.time() - t0:.1f}s, sha256 of the matrix {index_sha[:16]}..")
     sample = args.ref_batch
     b, q = make_reads(torch, "cpu", cfg, genomes, sample * (args.steps + args.warmup), 0xC0101D03)
     b, q = b.numpy(), q.numpy()
@@ -271,7 +294,8 @@ def run_reference(args):
             "config": workload_config(cfg, sample),
             "cpu_baseline": {"value": v, "unit": "read pairs/s", "cores": cores, "kind": "port",
                              "sample": f"{sample} read pairs per step; C++ restatement of the Rust reference "
-                                       "(oracle/), read_id parallel over reads like rayon par_iter"},
+                                       "(oracle/), read_id parallel over reads like rayon par_iter",
+                             "index_sha256": index_sha},
             "e2e": {"value": v, "unit": "read pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -1093,7 +1117,9 @@ def run_ours(args):
         print(json.dumps(run_search_extra(torch, dev, ctx, args, args.quick)), flush=True)
         return
     t0 = time.time()
-    genomes = make_genomes(torch, dev, cfg, 0xC0101D02)
+    # (CPU generator: the reference arm builds its index from the very same genomes, so the two arms' index checksums compare)
+    genomes_cpu = make_genomes(torch, "cpu", cfg, 0xC0101D02)
+    genomes = genomes_cpu.to(dev)
     lut = torch.tensor(ASCII, device=dev, dtype=torch.uint8)
     gix = cb.Index(ctx, cfg["S"], cfg["H"], cfg["k"], cfg["n_acc"])
     offs = torch.tensor([0, cfg["genome_len"]], device=dev, dtype=torch.int64)
@@ -1123,9 +1149,26 @@ def run_ours(args):
     lib = ctx.lib
     max_kmers = 2 * (rl - cfg["k"] + 1)
     stream = torch.cuda.current_stream()
+    # The product's read path takes PACKED reads (cid_pack_reads: quality mask + 2-bit codes + "not a base" bits, made by the
+    # host parser -- the reference masks on the host too, seq.rs:36-56): the pool is packed once, on the device
+    packed = not args.ascii_input
+    pool_pk = None
+    if packed:
+        pool_pk = torch.cat([pack_reads_torch(torch, pool_b[s0:s0 + 250_000], pool_q[s0:s0 + 250_000], cfg["qual_offset"])
+                             for s0 in range(0, pool_b.shape[0], 250_000)])
+        wpr = pool_pk.shape[1]                         # words per read pair (19 code + 10 bad words for 2 x 150 bases)
+        woffs_np = np.arange(batch + 1, dtype=np.uint64) * np.uint64(wpr)
+        d_woffs = torch.from_numpy(woffs_np.view(np.int64)).to(dev)
 
     def step_dev(i):
         sl = i % pool_batches
+        if packed:
+            w = pool_pk[sl * batch:(sl + 1) * batch]
+            L.check(lib.cid_read_id_batch_packed_dev(gix.h, w.data_ptr(), d_woffs.data_ptr(), 0, d_seq_offs.data_ptr(), 2 * batch,
+                                                     d_read_offs.data_ptr(), batch, 2 * rl, max_kmers, C.byref(params),
+                                                     d_n_set.data_ptr(), d_flags.data_ptr(), d_rep_n.data_ptr(), d_rc.data_ptr(),
+                                                     d_rv.data_ptr(), stream.cuda_stream))
+            return
         b = pool_b[sl * batch:(sl + 1) * batch]
         q = pool_q[sl * batch:(sl + 1) * batch]
         L.check(lib.cid_read_id_batch_dev(gix.h, b.data_ptr(), q.data_ptr(), d_seq_offs.data_ptr(), 2 * batch,
@@ -1185,31 +1228,71 @@ def run_ours(args):
     n_ref = gix.n_ref.copy()
     P = lambda a, tp=L.vp: a.ctypes.data_as(tp)
 
-    def step_e2e(i):
-        """The call a user makes: host reads + quals in, one classification per read out (parallel_vec)."""
+    h_pk = None
+    if packed:
+        h_pk = torch.empty((e2e_batches * batch, wpr), dtype=torch.int32).pin_memory()
+        h_pk.copy_(pool_pk[:e2e_batches * batch])
+        hpk = h_pk.numpy().view(np.uint32)
+
+    def step_e2e(i, ascii_in=False):
+        """The call a user makes: host reads in, one classification per read out (parallel_vec).  Packed planes by default
+        (what the CLI's parser produces); ascii_in: ASCII bases + qualities, masked and packed on the device."""
         sl = i % e2e_batches
-        b = hb[sl * batch:(sl + 1) * batch]
-        q = hq[sl * batch:(sl + 1) * batch]
-        L.check(lib.cid_read_id_classify(gix.h, P(b), P(q), P(seq_offs_np, L.u64p), 2 * batch, P(read_offs_np, L.u64p),
-                                         batch, C.byref(params), P(n_ref, L.u64p), cfg["fp_correct"], P(o_kind, L.i32p),
-                                         P(o_hits, L.u32p), P(o_n_set, L.u32p), P(o_n_top, L.u32p), P(o_top, L.u32p), 8))
+        if packed and not ascii_in:
+            w = hpk[sl * batch:(sl + 1) * batch]
+            L.check(lib.cid_read_id_classify_packed(gix.h, P(w), P(woffs_np, L.u64p), 0, P(seq_offs_np, L.u64p), 2 * batch,
+                                                    P(read_offs_np, L.u64p), batch, C.byref(params), P(n_ref, L.u64p), cfg["fp_correct"],
+                                                    P(o_kind, L.i32p), P(o_hits, L.u32p), P(o_n_set, L.u32p), P(o_n_top, L.u32p),
+                                                    P(o_top, L.u32p), 8))
+        else:
+            b = hb[sl * batch:(sl + 1) * batch]
+            q = hq[sl * batch:(sl + 1) * batch]
+            L.check(lib.cid_read_id_classify(gix.h, P(b), P(q), P(seq_offs_np, L.u64p), 2 * batch, P(read_offs_np, L.u64p),
+                                             batch, C.byref(params), P(n_ref, L.u64p), cfg["fp_correct"], P(o_kind, L.i32p),
+                                             P(o_hits, L.u32p), P(o_n_set, L.u32p), P(o_n_top, L.u32p), P(o_top, L.u32p), 8))
         return dict(kind=o_kind, hits=o_hits, n_set=o_n_set, n_top=o_n_top, top=o_top)
 
-    for i in range(min(Wm, 2)):
-        cls = step_e2e(i)
-    barrier()
+    def time_e2e(ascii_in):
+        for i in range(min(Wm, 2)):
+            step_e2e(i, ascii_in)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            step_e2e(i, ascii_in)
+        torch.cuda.synchronize()
+        tt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
     e2e_steps = max(1, min(K, 5))
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        cls = step_e2e(i)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * batch * e2e_steps / float(t.item())
-    h2d = 2 * batch * 2 * rl + seq_offs_np.nbytes + read_offs_np.nbytes
+    e2e_s = time_e2e(False)
+    e2e_value = world * batch * e2e_steps / e2e_s
+    h2d_ascii = 2 * batch * 2 * rl + seq_offs_np.nbytes + read_offs_np.nbytes
+    h2d = (batch * wpr * 4 + woffs_np.nbytes + seq_offs_np.nbytes + read_offs_np.nbytes) if packed else h2d_ascii
     d2h = batch * (4 * 4 + 8 * 4)      # kind, hits, n_set, n_top + top[8] per read; the undecided-read list (<1 % of reads) is extra
+    e2e_ascii = None
+    host_pack = None
+    if packed:
+        e2e_ascii_s = time_e2e(True)
+        e2e_ascii = {"value": world * batch * e2e_steps / e2e_ascii_s, "unit": "read pairs/s", "h2d_bytes_per_step": h2d_ascii,
+                     "note": "the same reads through cid_read_id_classify: ASCII bases + qualities over PCIe, masked and packed by the kernels"}
+        # the product's host packer on this rank's cores: what a parser pays to produce the packed input (not in the e2e region:
+        # the reference's parser masks while it parses, before parallel_vec is called, read_id_mt_pe.rs:733-762)
+        pk_words = np.zeros(batch * wpr + 64, np.uint32)
+        pk_offs = np.zeros(batch + 1, np.uint64)
+        pk_flags = C.c_uint32(0)
+        tp = []
+        for i in range(3):
+            t0 = time.perf_counter()
+            L.check(lib.cid_pack_reads(P(hb[:batch]), P(hq[:batch]), P(seq_offs_np, L.u64p), 2 * batch, P(read_offs_np, L.u64p), batch,
+                                       cfg["qual_offset"], 0, P(pk_words, L.u32p), len(pk_words), P(pk_offs, L.u64p), C.byref(pk_flags)))
+            tp.append(time.perf_counter() - t0)
+        same_pack = bool(np.array_equal(pk_words[:batch * wpr], hpk[:batch].reshape(-1)) and np.array_equal(pk_offs, woffs_np))
+        assert same_pack, "device-side packing of the synthetic pool differs from cid_pack_reads"
+        host_pack = {"read_pairs_per_s": batch / min(tp[1:]), "threads": len(numa_cores) if numa_cores else (os.cpu_count() or 1),
+                     "equals_bench_input": same_pack,
+                     "note": "cid_pack_reads (AVX2, host threads of this rank) on one batch of ASCII bases + qualities"}
 
     # ---- N > 1: the column-sharded path (C5 shard shape: 1,250 accessions = 160-byte rows per GPU, A = 1,250 x N accessions:
     # the full C5 index at N = 8) rides along, so that the driver's scaling run records it: build Gbp/s, lookups/s, the shard
@@ -1276,19 +1359,33 @@ def run_ours(args):
             from oracle import pyoracle as O
             O.lib()
             cores = os.cpu_count() or 1
-            oix = oracle_index_from_dense(O, cfg, gix.download_dense(), n_ref)
+            # the oracle builds ITS OWN index from the same genomes (full size: S = 50 M), compared word for word with the GPU's
+            tb0 = time.time()
+            oix = O.Index(cfg["S"], cfg["H"], cfg["k"], cfg["n_acc"])
+            lut_np = np.array(ASCII, dtype=np.uint8)
+            oix.build_many([[lut_np[genomes_cpu[a].numpy()].tobytes()] for a in range(cfg["n_acc"])], O.MODE_FASTA, threads=cores)
+            dense = gix.download_dense()
+            index_same = bool(np.array_equal(oix.words(), dense) and np.array_equal(oix.n_ref, n_ref))
+            index_sha = hashlib.sha256(dense.tobytes()).hexdigest()
+            log(f"[rank 0] oracle index built on {cores} threads in {time.time() - tb0:.1f}s; equals the GPU index: {index_same}")
+            del dense
             ns = min(batch, 2000)
             dt, _ = oracle_read_id(O, oix, cfg, hb[:ns], hq[:ns], cores)
             ns2 = int(min(batch, max(ns, ns / dt * 12.0)))      # ~12 s of CPU work
             dt2, ocls = oracle_read_id(O, oix, cfg, hb[:ns2], hq[:ns2], cores)
             # while we are here: the e2e classifications of these reads must equal the oracle's
             chk = step_e2e(0)
+            ntop = np.minimum(ocls["n_top"].astype(np.int64), 8)
+            colmask = np.arange(8)[None, :] < ntop[:, None]
             same = bool(np.array_equal(chk["kind"][:ns2], ocls["kind"]) and np.array_equal(chk["hits"][:ns2], ocls["hits"])
-                        and np.array_equal(chk["n_top"][:ns2], ocls["n_top"]))
+                        and np.array_equal(chk["n_top"][:ns2], ocls["n_top"]) and np.array_equal(chk["n_set"][:ns2], ocls["n_set"])
+                        and np.array_equal(np.where(colmask, chk["top"][:ns2], 0), np.where(colmask, ocls["top"][:, :8], 0)))
             cpu = {"value": ns2 / dt2, "unit": "read pairs/s", "cores": cores, "kind": "port",
                    "sample": f"{ns2} read pairs of the same workload; C++ restatement of the Rust reference (oracle/), "
                              f"read_id parallel over reads on {cores} threads",
-                   "matches_gpu_classification": same}
+                   "matches_gpu_classification": same,
+                   "checked": "kind, hits, n_set, n_top and the top accession ids of every sampled read",
+                   "index_built_by_oracle_equals_gpu_index": index_same, "index_sha256": index_sha}
         except Exception as ex:      # the bench line must still print
             cpu = {"value": None, "unit": "read pairs/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
 
@@ -1303,9 +1400,15 @@ def run_ours(args):
 
     line = {"metric": "read_id read pairs/s", "value": value, "unit": "read pairs/s", "n_gpus": world, "steps": K,
             "warmup": Wm, "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u32", "data": "synthetic", "config": workload_config(cfg, batch), "clocks": clocks,
+            "dtype": "u32", "data": "synthetic", "config": dict(workload_config(cfg, batch), input="packed reads (cid_pack_reads)" if packed else "ASCII"),
+            "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "read pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "host_cores_bound_per_rank": numa_cores or None, "includes": "cid_read_id_classify: chunked pipeline of H2D reads+quals+offsets, read_id kernels + device vote, D2H of one classification per read; near-threshold/tied reads re-voted on the host; pinned host buffers"},
+                    "steps": e2e_steps, "host_cores_bound_per_rank": numa_cores or None,
+                    "h2d_gbs_per_rank": h2d * e2e_steps / e2e_s / 1e9,
+                    "input": ("packed reads in pinned host memory (cid_pack_reads planes: 2-bit codes + not-a-base bits, quality mask "
+                              "applied by the packer on the host like seq.rs:36-56)" if packed else "ASCII bases + qualities in pinned host memory"),
+                    "includes": ("cid_read_id_classify_packed" if packed else "cid_read_id_classify") + ": chunked pipeline of H2D reads+offsets, read_id kernels + device vote, D2H of one classification per read; near-threshold/tied reads re-voted on the host"},
+            "e2e_ascii": e2e_ascii, "host_pack": host_pack,
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "build": {"gbp_per_s": cfg["n_acc"] * cfg["genome_len"] / build_s / 1e9, "seconds": build_s,
                       "note": "index build on device incl. per-accession host sync; not the timed metric"},
@@ -1335,6 +1438,7 @@ def main():
     ap.add_argument("--n-acc", type=int, default=0, help="c2: accessions of the index (default 46 = the headline config)")
     ap.add_argument("--n-clades", type=int, default=0, help="c2 with --n-acc: clades (default n_acc / 5)")
     ap.add_argument("--c5-acc", type=int, default=0, help="total accessions of the c5 workload (default 10,000)")
+    ap.add_argument("--ascii-input", action="store_true", help="c2: time the ASCII entry points (bases + qualities masked and packed on the device) instead of packed reads")
     ap.add_argument("--no-c5", action="store_true", help="N > 1: skip the column-sharded C5 block")
     ap.add_argument("--c5-extra", action="store_true", help="c5, N > 1: also time the column-sharded default report and read_id")
     args = ap.parse_args()

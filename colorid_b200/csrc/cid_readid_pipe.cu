@@ -10,6 +10,7 @@
 // chunk c-1 run concurrently.  Kernels of neighbouring chunks also overlap on the GPU, which lets
 // the DRAM-access-bound vote kernel hide under the issue-bound kmerize/order kernels.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <cstdlib>
@@ -262,6 +263,40 @@ static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals,
 #define PIPE_TRY(expr) do { int _rc = (expr); if (_rc != CID_OK) return finish(_rc); } while (0)
 #define PIPE_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); return finish(CID_E_CUDA); } } while (0)
 
+    // Host-side preparation of every chunk -- the scan of its read geometry and the copy of its offset arrays into page-locked
+    // staging (pageable cudaMemcpyAsync would drain the stream) -- is ~10 ns per read on one thread: serial, it delays the copy
+    // of a large chunk by milliseconds while the GPU idles.  A few helper threads take the chunks in order; the issue loop
+    // below only waits for "chunk c is prepared".
+    struct Prep { Geometry geo; size_t stage_off = 0; std::atomic<int> ready{0}; };
+    std::vector<Prep> prep(nchunks);
+    size_t stage_words = 0;
+    for (uint64_t c = 0; c < nchunks; c++) {
+        const uint64_t nso = read_offs[cuts[c + 1]] - read_offs[cuts[c]] + 1, nro = cuts[c + 1] - cuts[c] + 1;
+        prep[c].stage_off = stage_words;
+        stage_words += nso + nro + (hp ? nro : 0);
+    }
+    if (ctx->pinned[3].ensure(stage_words * 8 + 64) != CID_OK) return finish(CID_E_NOMEM);
+    uint64_t* const stage = ctx->pinned[3].as<uint64_t>();
+    std::atomic<uint64_t> prep_next{0};
+    auto prep_work = [&]() {
+        for (;;) {
+            const uint64_t c = prep_next.fetch_add(1);
+            if (c >= nchunks) return;
+            const uint64_t r0 = cuts[c], r1 = cuts[c + 1], nr = r1 - r0, s0 = read_offs[r0], s1 = read_offs[r1];
+            prep[c].geo = read_geometry(seq_offs, read_offs + r0, nr, ix->k, pp.downsample);
+            uint64_t* ho = stage + prep[c].stage_off;
+            const size_t nso = s1 - s0 + 1, nro = nr + 1;
+            memcpy(ho, seq_offs + s0, nso * 8);
+            memcpy(ho + nso, read_offs + r0, nro * 8);
+            if (hp) memcpy(ho + nso + nro, hp->word_offs + r0, nro * 8);
+            prep[c].ready.store(1, std::memory_order_release);
+        }
+    };
+    const unsigned n_prep = (unsigned)std::min<uint64_t>(nchunks, std::min(4u, std::max(1u, std::thread::hardware_concurrency())));
+    std::vector<std::thread> prep_threads;
+    for (unsigned i = 0; i < n_prep; i++) prep_threads.emplace_back(prep_work);
+    struct PrepJoin { std::vector<std::thread>& t; ~PrepJoin() { for (auto& x : t) if (x.joinable()) x.join(); } } prep_join{prep_threads};
+
     // CID_TRACE: per-chunk stage timeline from CUDA events on the slot streams (diagnostics only)
     std::vector<cudaEvent_t> tev;
     cudaEvent_t tev0 = nullptr;
@@ -286,7 +321,8 @@ static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals,
         Geometry geo;
         {
             const double t0 = now_ms();
-            geo = read_geometry(seq_offs, read_offs + r0, nr, ix->k, pp.downsample);
+            while (!prep[c].ready.load(std::memory_order_acquire)) std::this_thread::yield();
+            geo = prep[c].geo;
             t_geom += now_ms() - t0;
         }
         const uint32_t max_bases = geo.fast_bases, max_kmers = geo.fast_kmers;
@@ -314,18 +350,11 @@ static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals,
         // stream, i.e. waits for the big copies queued just before it): stage them in pinned memory.
         {
             const size_t nso = s1 - s0 + 1, nro = nr + 1;
-            PIPE_CUDA(cudaEventSynchronize(s.offs_done));          // previous use of this slot's staging
-            PIPE_TRY(s.h_offs.ensure((nso + nro + (hp ? nro : 0)) * 8));
-            uint64_t* ho = s.h_offs.as<uint64_t>();
-            memcpy(ho, seq_offs + s0, nso * 8);
-            memcpy(ho + nso, read_offs + r0, nro * 8);
+            uint64_t* ho = stage + prep[c].stage_off;              // staged by the preparation threads
             PIPE_CUDA(cudaMemcpyAsync(s.seq_offs.p, ho, nso * 8, cudaMemcpyHostToDevice, s.st));
             PIPE_CUDA(cudaMemcpyAsync(s.read_offs.p, ho + nso, nro * 8, cudaMemcpyHostToDevice, s.st));
-            if (hp) {        // word offset of every read of the chunk (absolute: the device word pointer is biased to match)
-                memcpy(ho + nso + nro, hp->word_offs + r0, nro * 8);
-                PIPE_CUDA(cudaMemcpyAsync(s.quals.p, ho + nso + nro, nro * 8, cudaMemcpyHostToDevice, s.st));
-            }
-            PIPE_CUDA(cudaEventRecord(s.offs_done, s.st));
+            // (packed reads: the word offset of every read, absolute -- the device word pointer is biased to match)
+            if (hp) PIPE_CUDA(cudaMemcpyAsync(s.quals.p, ho + nso + nro, nro * 8, cudaMemcpyHostToDevice, s.st));
         }
         tmark(s.st);
         if (hp) { if (w1 > w0) PIPE_CUDA(cudaMemcpyAsync(s.bases.p, hp->words + w0, (w1 - w0) * 4, cudaMemcpyHostToDevice, s.st)); }
