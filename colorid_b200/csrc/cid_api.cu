@@ -753,7 +753,7 @@ static const uint64_t kMaxBatchSlots = 1ull << 28;   // 4 GiB of count table per
 // The shared-memory front end applies when only DISTINCT k-mers matter (every query's filter is 0), no unique-hit
 // summaries are wanted, the streaming gather handles this row shape and every query is small.
 static bool query_front_ok(const cid_index* ix, bool want_uniq, const uint64_t* h_seq_offs, const uint64_t* h_query_offs, uint64_t nq) {
-    return ix->ctx->opt_query_front && !ix->ctx->opt_query_fused && !want_uniq && ix->Wp >= 4 && ix->Wp <= 128 &&
+    return ix->ctx->opt_query_front && !ix->ctx->opt_query_fused && !want_uniq && ix->Wp >= 4 && ix->Wp <= 512 &&
            (ix->H == 2 || ix->H == 4) && query_front_fits(h_seq_offs, h_query_offs, 0, nq, ix->k);
 }
 // batches of at most 2^28 k-mer positions (row-index lists of <= 4 GiB at H = 4)
@@ -1177,8 +1177,8 @@ int cid_query_counts_sharded_dev(cid_index* ix, const char* d_bases, const uint6
                                  uint64_t* d_num_kmers, void* stream) {
     if (!ix || !d_dest_counts || n_dest < 1 || n_dest > 8) { set_error("cid_query_counts_sharded_dev: 1..8 destination buffers"); return CID_E_INVALID; }
     if ((uint64_t)col_offset + ix->N > n_total) { set_error("cid_query_counts_sharded_dev: shard columns exceed n_total"); return CID_E_INVALID; }
-    if (!(ix->Wp >= 4 && ix->Wp <= 128 && (ix->H == 2 || ix->H == 4)) || ix->ctx->opt_query_fused) {
-        set_error("cid_query_counts_sharded_dev: needs the streaming gather (16-byte aligned rows of <= 512 bytes, num_hash 2 or 4)");
+    if (!(ix->Wp >= 4 && ix->Wp <= 512 && (ix->H == 2 || ix->H == 4)) || ix->ctx->opt_query_fused) {
+        set_error("cid_query_counts_sharded_dev: needs the streaming gather (16-byte aligned rows of <= 2 KB, num_hash 2 or 4)");
         return CID_E_UNSUPPORTED;
     }
     GatherOut go{};

@@ -938,6 +938,188 @@ query_gather_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t N, 
     }
 }
 
+// ================================================================= query_gather_tma (rows of 516 bytes .. 2 KB)
+// Wide rows -- an unsharded index of 4,100..16,384 accessions: the full C5 index has 1,264-byte rows and fits one B200 -- are
+// staged by the TMA engine: per k-mer ONE elected lane of a producer warp issues num_hash bulk copies
+// (cp.async.bulk.shared.global, whole rows) into a ring of D stages in shared memory and arms the stage's mbarrier with the
+// byte count; four consumer warps wait on the barrier's phase, AND the rows (every thread owns one 16-byte vector of the row
+// for the whole work item, so its bit-sliced counters never meet another thread's) and release the stage through a second
+// mbarrier.  No thread computes an address per 16 bytes and no register holds a row index on the consumer side; with 32 KB of
+// rows in flight per CTA the row stream runs at HBM speed.  (Rows of <= 512 bytes keep the cp.async ring of query_gather: a
+// bulk copy is a warp-uniform instruction, so several small rows per step would cost MORE instructions than one LDGSTS per
+// lane -- TMA pays where one copy moves a kilobyte.)
+__device__ __forceinline__ void mbar_init(uint32_t a, uint32_t n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(n) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t a, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t a) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+
+constexpr int QT_CONS_WARPS = 4;                       // 128 threads x 16 bytes: rows of up to 2 KB (16,384 accessions)
+constexpr int QT_THREADS = (QT_CONS_WARPS + 1) * 32;   // + the producer warp
+constexpr int QT_PLANES = 15;                          // a work item holds <= QUERY_ITEM_SLOTS = 2^14 k-mers
+constexpr int QT_RING_BYTES = 32 * 1024;
+template <int HT, bool ANDM>
+__global__ void __launch_bounds__(QT_THREADS)
+query_gather_tma_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t N, const uint32_t* __restrict__ rid,
+                        const uint32_t* __restrict__ unit_group, const uint64_t* __restrict__ unit_slot0,
+                        const uint32_t* __restrict__ unit_n, uint32_t* __restrict__ counts, const uint32_t* __restrict__ rownz,
+                        uint32_t* __restrict__ missing, uint32_t W, GatherOut go, uint32_t D) {
+    extern __shared__ __align__(128) uint8_t dsm[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t n = unit_n[blockIdx.x];
+    const uint32_t g = unit_group[blockIdx.x];
+    if (n == 0) {
+        if (!ANDM && go.dense)
+            for (uint32_t c = tid; c < N; c += QT_THREADS)
+#pragma unroll
+                for (uint32_t d = 0; d < 8; d++) if (d < go.n) go.base[d][(uint64_t)g * go.stride + go.col0 + c] = 0u;
+        return;
+    }
+    const uint32_t rowbytes = Wp * 4, stage = HT * rowbytes;
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(dsm);
+    const uint32_t full = ring + QT_RING_BYTES, empty = full + 8 * 8;       // up to 8 stages
+    if (tid == 0) {
+        for (uint32_t s = 0; s < D; s++) { mbar_init(full + 8 * s, 1); mbar_init(empty + 8 * s, QT_CONS_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t* myrid = rid + unit_slot0[blockIdx.x] * HT;
+    if (warp == QT_CONS_WARPS) {
+        // ---- producer warp: row indices 32 k-mers at a time (coalesced), one elected lane issues the bulk copies
+        bool miss = false;
+        for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+            uint32_t r[HT];
+#pragma unroll
+            for (int h = 0; h < HT; h++) r[h] = 0;
+            if (i0 + lane < n) {
+#pragma unroll
+                for (int h = 0; h < HT; h++) r[h] = __ldg(myrid + (size_t)(i0 + lane) * HT + h);
+                if (ANDM) {
+#pragma unroll
+                    for (int h = 0; h < HT; h++) if (!((__ldg(rownz + (r[h] >> 5)) >> (r[h] & 31)) & 1u)) miss = true;
+                }
+            }
+            const uint32_t cnt = min(32u, n - i0);
+            for (uint32_t j = 0; j < cnt; j++) {
+                const uint32_t i = i0 + j, s = i % D, use = i / D;
+                uint32_t rr[HT];
+#pragma unroll
+                for (int h = 0; h < HT; h++) rr[h] = __shfl_sync(0xffffffffu, r[h], j);
+                if (lane == 0) {
+                    if (use) mbar_wait(empty + 8 * s, (use - 1) & 1u);          // the consumers are done with this stage
+                    mbar_expect_tx(full + 8 * s, stage);
+#pragma unroll
+                    for (int h = 0; h < HT; h++) bulk_g2s(ring + s * stage + h * rowbytes, rows + (size_t)rr[h] * Wp, rowbytes, full + 8 * s);
+                }
+            }
+        }
+        if (ANDM && __any_sync(0xffffffffu, miss) && lane == 0) atomicOr(&missing[g], 1u);
+        return;
+    }
+    // ---- consumer warps: thread v owns 16-byte vector v of the row
+    const uint32_t v = (uint32_t)tid, vpr = Wp >> 2;
+    const bool on = v < vpr;
+    uint32_t pl[4][ANDM ? 1 : QT_PLANES];
+#pragma unroll
+    for (int w = 0; w < 4; w++)
+#pragma unroll
+        for (int p = 0; p < (ANDM ? 1 : QT_PLANES); p++) pl[w][p] = ANDM ? 0xFFFFFFFFu : 0u;
+    for (uint32_t i0 = 0; i0 < n; i0 += 8) {
+        uint32_t x[8][4];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const uint32_t i = i0 + u;
+            uint4 a = make_uint4(0, 0, 0, 0);
+            if (i < n) {                                  // (uniform across the CTA)
+                const uint32_t s = i % D;
+                mbar_wait(full + 8 * s, (i / D) & 1u);
+                if (on) {
+                    a = lds128(ring + s * stage + v * 16);
+#pragma unroll
+                    for (int h = 1; h < HT; h++) {
+                        const uint4 b = lds128(ring + s * stage + h * rowbytes + v * 16);
+                        a.x &= b.x; a.y &= b.y; a.z &= b.z; a.w &= b.w;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty + 8 * s);
+                if (ANDM && on) { pl[0][0] &= a.x; pl[1][0] &= a.y; pl[2][0] &= a.z; pl[3][0] &= a.w; }
+            }
+            x[u][0] = a.x; x[u][1] = a.y; x[u][2] = a.z; x[u][3] = a.w;
+        }
+#pragma unroll
+        for (int w = 0; w < (ANDM ? 0 : 4); w++) {
+            uint32_t t2a, t2b, t4a, t4b, c8;
+            csa(t2a, pl[w][0], pl[w][0], x[0][w], x[1][w]);
+            csa(t2b, pl[w][0], pl[w][0], x[2][w], x[3][w]);
+            csa(t4a, pl[w][1], pl[w][1], t2a, t2b);
+            csa(t2a, pl[w][0], pl[w][0], x[4][w], x[5][w]);
+            csa(t2b, pl[w][0], pl[w][0], x[6][w], x[7][w]);
+            csa(t4b, pl[w][1], pl[w][1], t2a, t2b);
+            csa(c8, pl[w][2], pl[w][2], t4a, t4b);
+#pragma unroll
+            for (int p = 3; p < QT_PLANES; p++) {
+                const uint32_t t = pl[w][p] & c8;
+                pl[w][p] ^= c8;
+                c8 = t;
+            }
+        }
+    }
+    if (!on) return;
+    if (ANDM) {
+#pragma unroll
+        for (int w = 0; w < 4; w++)
+            if (v * 4 + w < W && pl[w][0] != 0xFFFFFFFFu) atomicAnd(&counts[(uint64_t)g * W + v * 4 + w], pl[w][0]);
+        return;
+    }
+    // flush: this thread alone holds the counts of its 128 accessions; four at a time (nibble spread), 16-byte stores
+    const bool vec_ok = ((go.stride | go.col0) & 3u) == 0u;
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        const uint32_t cbase = (v * 4 + w) * 32;
+        if (cbase >= N) break;
+        const uint64_t off = (uint64_t)g * go.stride + go.col0 + cbase;
+#pragma unroll
+        for (int nb = 0; nb < 8; nb++) {
+            uint32_t lo8 = 0, hi8 = 0;
+#pragma unroll
+            for (int p = 0; p < QT_PLANES; p++) {
+                const uint32_t sp = (((pl[w][p] >> (4 * nb)) & 0xFu) * 0x00204081u) & 0x01010101u;
+                if (p < 8) lo8 += sp << p; else hi8 += sp << (p - 8);
+            }
+            const uint32_t vv[4] = {(lo8 & 0xFFu) | ((hi8 & 0xFFu) << 8), ((lo8 >> 8) & 0xFFu) | (((hi8 >> 8) & 0xFFu) << 8),
+                                    ((lo8 >> 16) & 0xFFu) | (((hi8 >> 16) & 0xFFu) << 8), (lo8 >> 24) | ((hi8 >> 24) << 8)};
+            const uint32_t c0 = cbase + 4 * nb;
+            if (c0 >= N) break;
+            if (go.dense) {
+                if (vec_ok && c0 + 4 <= N) {
+#pragma unroll
+                    for (uint32_t d = 0; d < 8; d++) if (d < go.n) *(uint4*)(go.base[d] + off + 4 * nb) = make_uint4(vv[0], vv[1], vv[2], vv[3]);
+                } else {
+#pragma unroll
+                    for (uint32_t j = 0; j < 4; j++)
+#pragma unroll
+                        for (uint32_t d = 0; d < 8; d++) if (d < go.n && c0 + j < N) go.base[d][off + 4 * nb + j] = vv[j];
+                }
+            } else {
+#pragma unroll
+                for (uint32_t j = 0; j < 4; j++)
+                    if (vv[j] && c0 + j < N) {
+#pragma unroll
+                        for (uint32_t d = 0; d < 8; d++) if (d < go.n) atomicAdd(go.base[d] + off + 4 * nb + j, vv[j]);
+                    }
+            }
+        }
+    }
+}
+
 // Wide-row unique-hit pass (Wp > 32): one warp per k-mer sums popcounts over the whole row.
 __global__ void __launch_bounds__(256)
 query_uniq_wide_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t k, uint32_t H, ModS mods,
@@ -1023,6 +1205,29 @@ static int launch_query_gather(cid_ctx* ctx, cudaStream_t st, const cid_index* i
     GatherOut go{};
     if (!d_and_rows && ctx->gather_out) go = *ctx->gather_out;
     else { go.base[0] = d_counts; go.n = 1; go.stride = idx->N; go.col0 = 0; }
+    if (idx->Wp > 128) {
+        // rows above 512 bytes: TMA-staged ring (query_gather_tma_kernel)
+        const size_t tsmem = QT_RING_BYTES + 128;
+        bool& tattr = ctx->attr_done[7];
+        if (!tattr) {
+            CID_CUDA(cudaFuncSetAttribute(query_gather_tma_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+            CID_CUDA(cudaFuncSetAttribute(query_gather_tma_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+            CID_CUDA(cudaFuncSetAttribute(query_gather_tma_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+            CID_CUDA(cudaFuncSetAttribute(query_gather_tma_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+            tattr = true;
+        }
+        const uint32_t D = std::min<uint32_t>(8, QT_RING_BYTES / (idx->H * idx->Wp * 4));
+        ProfScope ps(ctx, st, d_and_rows ? KID_QUERY_PERFECT : KID_QUERY_COUNTS);
+#define CID_QT(HT, AM, OUT)                                                                                             \
+    query_gather_tma_kernel<HT, AM><<<(unsigned)nunits, QT_THREADS, tsmem, st>>>(idx->rows, idx->Wp, idx->N, d_rid, d_unit_group, \
+                                                                                d_unit_slot0, d_unit_n, OUT, idx->rownz, d_missing, idx->W, go, D)
+        if (d_and_rows) { if (idx->H == 2) CID_QT(2, true, d_and_rows); else CID_QT(4, true, d_and_rows); }
+        else { if (idx->H == 2) CID_QT(2, false, d_counts); else CID_QT(4, false, d_counts); }
+#undef CID_QT
+        ctx->launches++;
+        CID_CUDA(cudaGetLastError());
+        return CID_OK;
+    }
     {
         ProfScope ps(ctx, st, d_and_rows ? KID_QUERY_PERFECT : KID_QUERY_COUNTS);
 #define CID_QG(HT, AM, OUT)                                                                                             \
@@ -1230,7 +1435,7 @@ int launch_query_front_gather(cid_ctx* ctx, cudaStream_t st, const cid_index* id
     const GatherOut* const shared = ctx->gather_out;
     if (shared && !d_and_rows) { dense_out = *shared; dense_out.dense = 1; ctx->gather_out = &dense_out; }
     int grc;
-    if (d_and_rows && !(idx->Wp >= 4 && idx->Wp <= 128 && (idx->H == 2 || idx->H == 4))) {
+    if (d_and_rows && !(idx->Wp >= 4 && idx->Wp <= 512 && (idx->H == 2 || idx->H == 4))) {
         ProfScope ps(ctx, st, KID_QUERY_PERFECT);
         perfect_rids_kernel<<<(unsigned)bq, 256, (size_t)idx->Wp * 4, st>>>(idx->rows, idx->Wp, idx->W, idx->H, d_rid, d_group, d_base, d_unit_n,
                                                                            idx->rownz, d_and_rows, d_missing);
@@ -1250,7 +1455,7 @@ int launch_query_counts(cid_ctx* ctx, cudaStream_t st, const cid_index* idx, con
                         uint32_t* d_uniq_n) {
     if (nunits == 0) return CID_OK;
     // streaming path: 16-byte-aligned rows of at most 512 bytes, no unique-hit summaries
-    if (!want_uniq && idx->Wp >= 4 && idx->Wp <= 128 && (idx->H == 2 || idx->H == 4) && !ctx->opt_query_fused) {
+    if (!want_uniq && idx->Wp >= 4 && idx->Wp <= 512 && (idx->H == 2 || idx->H == 4) && !ctx->opt_query_fused) {
         CID_TRY(ctx->scratch[14].ensure(total_slots * idx->H * 4 + 64));
         CID_TRY(ctx->scratch[15].ensure(nunits * 4 + 64));
         uint32_t* d_rid = ctx->scratch[14].as<uint32_t>();

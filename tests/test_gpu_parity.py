@@ -364,6 +364,40 @@ def test_perfect_search(oracle, ctx, N, k, S, H):
     assert (o["status"] == 0).sum() >= 10
 
 
+@pytest.mark.parametrize("N,H,k", [(4200, 2, 21), (5000, 4, 31), (16_384, 2, 21)])
+def test_wide_rows_through_the_tma_gather(oracle, ctx, N, H, k):
+    """Rows above 512 bytes (an unsharded index of thousands of accessions: 1,264-byte rows at C5) are staged by TMA bulk
+    copies + mbarriers (query_gather_tma_kernel): -g counts, -s AND rows and -s -m on such an index equal the oracle's."""
+    rng = _rng(470 + N)
+    S = 20_011
+    roots = [synth.rand_seq(rng, 1500) for _ in range(24)]
+    oix, gix = oracle.Index(S, H, k, N), cb.Index(ctx, S, H, k, N)
+    for c in range(N):
+        g = roots[c % 24] if c % 97 else synth.mutate(rng, roots[c % 24], 0.02)
+        assert gix.build_accession(c, [g]) == oix.build_accession(c, [g], oracle.MODE_FASTA)
+    oix.finalize(threads=4); gix.finalize()
+    queries = [[roots[i % 24][50:50 + int(rng.integers(k, 1200))]] for i in range(40)] + [[synth.rand_seq(rng, 400)], [b"ACGT"]]
+    queries.append([roots[0][:600], roots[1][:600]])
+    o = oix.query_counts(queries, oracle.MODE_FASTA, True, 0)
+    for front in (1, 0):                           # shared-memory front end / count table + query_hash, both into the TMA gather
+        ctx.set_option("query_front", front)
+        try:
+            g = gix.query_counts(queries, cb.CID_SEQ_FASTA, True, 0, want_uniq=False)
+            gp = gix.query_perfect(queries)
+        finally:
+            ctx.set_option("query_front", 1)
+        assert np.array_equal(g["counts"], o["counts"]) and np.array_equal(g["num_kmers"], o["num_kmers"]), front
+        op = oix.query_perfect(queries)
+        assert np.array_equal(gp["status"], op["status"]) and np.array_equal(gp["and_rows"], op["and_rows"]), front
+    recs = [q[0] for q in queries] + [roots[2][:100] + b"N" + roots[2][101:500]]
+    om, gm = oix.query_perfect(recs, mf=True), gix.query_perfect_mf(recs)
+    assert np.array_equal(gm["status"], om["status"]) and np.array_equal(gm["and_rows"], om["and_rows"])
+    # a multi-unit query (more than 16,384 distinct k-mers: counts are added with atomics across its work units)
+    big = [[b"".join(roots)]]
+    ob, gb = oix.query_counts(big, oracle.MODE_FASTA, True, 0), gix.query_counts(big, cb.CID_SEQ_FASTA, True, 0, want_uniq=False)
+    assert np.array_equal(gb["counts"], ob["counts"]) and int(ob["num_kmers"][0]) > 16_384
+
+
 @pytest.mark.parametrize("N,H", [(4, 4), (46, 4), (40, 3), (150, 3), (4200, 2)])
 def test_perfect_search_multifasta_non_acgt_on_any_row_shape(oracle, ctx, N, H):
     """kmerize_string (kmer.rs:271-299) has no has_no_n test: -s -m records with N / IUPAC / U bytes are exact on every row
