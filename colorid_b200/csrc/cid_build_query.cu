@@ -297,47 +297,94 @@ int launch_region_to_bloom(cid_ctx* ctx, cudaStream_t st, const void* d_region, 
 }
 
 // ================================================================= transpose_bitsets
-// bitsets[colour][word j] (bit r of word j = Bloom bit 32j+r) -> rows[32j+r][colour/32] bit colour%32.
-// One CTA: 1024 rows x up to 8 word-columns (256 colours): each warp reads 128 B of one colour's
-// bitset (coalesced), 32x32 bit blocks are transposed with ballots, and every row receives up to
-// 32 contiguous bytes.
-constexpr int TR_ROWS = 1024;
-constexpr int TR_WCOLS = 8;
+// bitsets[colour][word j] (bit r of word j = Bloom bit 32j+r) -> rows[32j+r][colour/32] bit colour%32  (build.rs:116-128).
+// One CTA: 256 rows x up to 32 word-columns (1,024 colours).  Loads: 32 contiguous bytes (8 bitset words = 256 rows) per
+// colour, whole sectors, eight passes in flight; 32x32 bit blocks are transposed in registers with a five-step shuffle butterfly
+// (25 instructions per block instead of 32 ballots + selects); the transposed words go through shared memory so that every ROW leaves as one
+// contiguous run -- 128 bytes per row for >= 1,024 colours, the whole row for narrower indexes -- instead of one 4-byte
+// store per lane at a stride of a whole row (r1: 8 % of the HBM copy peak).
+constexpr int TR_ROWS = 256;
+constexpr int TR_WCOLS = 32;
+// lane r holds row r (bit c = column c); returns column `lane` (bit r = row r).  Five butterfly steps; per step a lane swaps
+// the half of its word that belongs to its partner lane^j: the partner's word rotated by +-j (one funnel shift; the bits that
+// wrap around fall where the lane keeps its own) merged under the lane's keep mask (one LOP3).  Masks and rotations depend
+// only on the lane: TrLane is set up once per thread.
+struct TrLane { uint32_t keep[5], rot[5]; };
+__device__ __forceinline__ TrLane transpose32_setup(int lane) {
+    TrLane t;
+#pragma unroll
+    for (int s = 0; s < 5; s++) {
+        const int j = 16 >> s;
+        const uint32_t m = j == 16 ? 0x0000FFFFu : j == 8 ? 0x00FF00FFu : j == 4 ? 0x0F0F0F0Fu : j == 2 ? 0x33333333u : 0x55555555u;
+        t.keep[s] = (lane & j) ? ~m : m;
+        t.rot[s] = (lane & j) ? 32 - j : j;
+    }
+    return t;
+}
+__device__ __forceinline__ uint32_t transpose32(uint32_t x, const TrLane& t) {
+#pragma unroll
+    for (int s = 0; s < 5; s++) {
+        const uint32_t y = __shfl_xor_sync(0xffffffffu, x, 16 >> s);
+        const uint32_t z = __funnelshift_l(y, y, t.rot[s]);
+        x = (x & t.keep[s]) | (z & ~t.keep[s]);
+    }
+    return x;
+}
 __global__ void __launch_bounds__(256)
 transpose_bitsets_kernel(const uint32_t* __restrict__ bitsets, uint64_t bs_words, uint32_t N, uint64_t S,
                          uint32_t* __restrict__ rows, uint32_t Wp, uint32_t W) {
-    __shared__ uint32_t sm[TR_WCOLS][32][33];   // [wcol][colour in group][word in tile]
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    extern __shared__ __align__(16) uint8_t dsm[];
+    uint32_t* sin = (uint32_t*)dsm;                      // [wcol][colour in group][bitset word 0..7], row stride 9: no bank conflicts
+    uint32_t* sout = sin + TR_WCOLS * 32 * 9;            // [row in tile][wcol], row stride 33
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint64_t word0 = (uint64_t)blockIdx.x * (TR_ROWS / 32);       // first bitset word of this row tile
     const uint32_t wc0 = blockIdx.y * TR_WCOLS;
     const uint32_t nwc = min((uint32_t)TR_WCOLS, W - wc0);
-    // load: (wcol, colour) pairs strided over warps
-    for (uint32_t pair = warp; pair < nwc * 32; pair += 8) {
-        uint32_t wc = pair >> 5, c = pair & 31;
-        uint32_t colour = (wc0 + wc) * 32 + c;
-        uint32_t v = 0;
-        if (colour < N && word0 + lane < bs_words) v = __ldg(bitsets + (uint64_t)colour * bs_words + word0 + lane);
-        sm[wc][c][lane] = v;
+    // load: 8 lanes read the 8 words (one 32-byte sector) of one colour, 32 colours per 256-thread pass; the loads of 8 passes
+    // are all in flight before the first one is stored (a pass at a time is a DRAM round trip per pass: 3x slower)
+    const uint32_t j = tid & 7;
+    for (uint32_t p0 = 0; p0 < nwc * 32; p0 += 32 * 8) {
+        uint32_t v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const uint32_t pair = p0 + 32 * u + (tid >> 3), colour = wc0 * 32 + pair;
+            v[u] = 0;
+            if (pair < nwc * 32 && colour < N && word0 + j < bs_words) v[u] = __ldg(bitsets + (uint64_t)colour * bs_words + word0 + j);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const uint32_t pair = p0 + 32 * u + (tid >> 3);
+            if (pair < nwc * 32) sin[pair * 9 + j] = v[u];
+        }
     }
     __syncthreads();
-    // transpose: warp handles (wcol, word j) blocks; lane = colour
-    for (uint32_t blk = warp; blk < nwc * 32; blk += 8) {
-        uint32_t wc = blk >> 5, j = blk & 31;
-        uint32_t x = sm[wc][lane][j];
-        uint32_t mine = 0;
-#pragma unroll
-        for (int r = 0; r < 32; r++) {
-            uint32_t b = __ballot_sync(0xffffffffu, (x >> r) & 1u);
-            if (lane == r) mine = b;
+    // transpose: warp w takes bitset word w of every word-column; lane = colour within the group on input, row on output
+    const TrLane tl = transpose32_setup(lane);
+#pragma unroll 4
+    for (uint32_t wc = 0; wc < nwc; wc++)
+        sout[(warp * 32 + lane) * 33 + wc] = transpose32(sin[(wc * 32 + lane) * 9 + warp], tl);
+    __syncthreads();
+    // store: consecutive threads write consecutive words of a row (and, for narrow indexes, of consecutive rows)
+    const uint64_t row0 = word0 * 32;
+    if (nwc == TR_WCOLS) {
+        for (uint32_t e = tid; e < TR_ROWS * TR_WCOLS; e += 256) {
+            const uint32_t r = e >> 5, w = e & 31;
+            if (row0 + r < S) rows[(row0 + r) * Wp + wc0 + w] = sout[r * 33 + w];
         }
-        uint64_t row = (word0 + j) * 32 + lane;
-        if (row < S) rows[row * Wp + wc0 + wc] = mine;
+    } else {
+        for (uint32_t e = tid; e < TR_ROWS * nwc; e += 256) {
+            const uint32_t r = e / nwc, w = e % nwc;
+            if (row0 + r < S) rows[(row0 + r) * Wp + wc0 + w] = sout[r * 33 + w];
+        }
     }
 }
 int launch_transpose(cid_ctx* ctx, cudaStream_t st, const cid_index* idx) {
     dim3 grid((unsigned)((idx->S + TR_ROWS - 1) / TR_ROWS), (idx->W + TR_WCOLS - 1) / TR_WCOLS);
+    const size_t tsmem = (size_t)(TR_WCOLS * 32 * 9 + TR_ROWS * 33) * 4;
+    bool& tattr = ctx->attr_done[6];
+    if (!tattr) { CID_CUDA(cudaFuncSetAttribute(transpose_bitsets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem)); tattr = true; }
     ProfScope ps(ctx, st, KID_TRANSPOSE);
-    transpose_bitsets_kernel<<<grid, 256, 0, st>>>(idx->bitsets, idx->bs_words, idx->N, idx->S, idx->rows, idx->Wp,
+    transpose_bitsets_kernel<<<grid, 256, tsmem, st>>>(idx->bitsets, idx->bs_words, idx->N, idx->S, idx->rows, idx->Wp,
                                                    idx->W);
     ctx->launches++;
     CID_CUDA(cudaGetLastError());
@@ -971,7 +1018,7 @@ query_gather_tma_kernel(const uint32_t* __restrict__ rows, uint32_t Wp, uint32_t
                         const uint32_t* __restrict__ unit_group, const uint64_t* __restrict__ unit_slot0,
                         const uint32_t* __restrict__ unit_n, uint32_t* __restrict__ counts, const uint32_t* __restrict__ rownz,
                         uint32_t* __restrict__ missing, uint32_t W, GatherOut go, uint32_t D) {
-    extern __shared__ __align__(128) uint8_t dsm[];
+    extern __shared__ __align__(16) uint8_t dsm[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t n = unit_n[blockIdx.x];
     const uint32_t g = unit_group[blockIdx.x];
