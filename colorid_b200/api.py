@@ -126,7 +126,16 @@ def merge_shard_reports(shard_reports, shards, n_total, rep_cap=None):
     out_c = np.zeros((max(nr, 1), cap_out), np.uint32)
     out_v = np.zeros((max(nr, 1), cap_out), np.uint32)
     flags = np.ascontiguousarray(shard_reports[0]["flags"], dtype=np.uint32).copy()
-    flags &= ~np.uint32(4)                    # truncation is decided again for the merged report
+    for r in shard_reports[1:]:
+        # too_short / panic (bits 0, 1) and the set size are properties of the read: identical on every shard
+        if not (np.array_equal(np.asarray(r["flags"]) & 3, flags & 3) and np.array_equal(r["n_set"], shard_reports[0]["n_set"])):
+            raise ValueError("merge_shard_reports: the shards disagree on n_set / flags of a read (different reads or parameters?)")
+    # a shard whose own report was cut at its rep_cap has lost colours: the merged report stays marked truncated (bit 2);
+    # otherwise truncation is decided again for the merged report
+    lost = np.zeros_like(flags)
+    for r in shard_reports:
+        lost |= np.asarray(r["flags"], dtype=np.uint32) & np.uint32(4)
+    flags = (flags & ~np.uint32(4)) | lost
     if nr == 0:
         flags = np.zeros(1, np.uint32)
     L.check(lib.cid_merge_shard_reports(ns, _p(ncol, L.u32p), _p(coff, L.u32p), nr, arrs[0], arrs[1], arrs[2], cap_in, n_total,

@@ -158,6 +158,12 @@ static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals,
     // chunk c+1 must finish within the kernels of chunk c: PCIe delivers ~87 K read pairs/ms (600 B each at
     // 54 GB/s), the kernels consume ~56 K/ms, so a chunk may be at most 1.55x its predecessor.
     uint64_t chunk_max = ctx->opt_readid_chunk ? ctx->opt_readid_chunk : 262144;
+    {   // the per-chunk report (and, fused, the undecided-read list) is dense in the accession count: keep one slot's share of it
+        // below ~1.5 GB so that a wide index shrinks the chunks instead of exhausting device memory (3 slots are in flight)
+        const uint64_t per_read = (uint64_t)pp.rep_cap * 8 + (out.vote ? (2 + 2 * (uint64_t)pp.rep_cap) * 4 : 0);
+        const uint64_t fit = std::max<uint64_t>(1024, (3ull << 29) / std::max<uint64_t>(per_read, 1));
+        chunk_max = std::min(chunk_max, fit);
+    }
     std::vector<uint64_t> cuts{0};
     for (uint64_t cur = std::min<uint64_t>(ctx->opt_readid_chunk0 ? ctx->opt_readid_chunk0 : 32768, chunk_max), at = 0; at < nreads;) {
         uint64_t size = std::min(cur, nreads - at);
