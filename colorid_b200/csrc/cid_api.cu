@@ -44,7 +44,7 @@ void PinBuf::release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 
 static const char* kKernelNames[KID_COUNT] = {"kmerize_insert", "region_histogram", "region_to_bloom", "transpose_bitsets",
                                               "rownz", "query_counts", "query_uniq_wide", "query_perfect",
-                                              "readid_kmerize", "readid_sched", "readid_order", "readid_vote", "readid_classify", "table_clear", "other", "query_hash", "query_front", "readid_big"};
+                                              "readid_kmerize", "readid_sched", "readid_order", "readid_vote", "readid_classify", "table_clear", "other", "query_hash", "query_front", "readid_big", "readid_vp_scan", "readid_vp_gather", "readid_vp_count"};
 static cudaEvent_t prof_event(cid_ctx* c) {
     if (!c->prof_pool.empty()) { cudaEvent_t e = c->prof_pool.back(); c->prof_pool.pop_back(); return e; }
     cudaEvent_t e; cudaEventCreate(&e); return e;
@@ -295,6 +295,10 @@ int cid_ctx_set_option(cid_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "readid_kmerize_ctas")) { c->opt_kmerize_ctas = value > 0 ? (int)value : 0; return CID_OK; }
     if (!strcmp(name, "readid_vote_ctas")) { c->opt_vote_ctas = value > 0 ? (int)value : 0; return CID_OK; }
     if (!strcmp(name, "readid_report_steps")) { c->opt_readid_report_steps = value != 0; return CID_OK; }
+    if (!strcmp(name, "readid_vote_part")) { c->opt_readid_vote_part = value < 0 ? 0 : value > 2 ? 2 : (int)value; return CID_OK; }
+    if (!strcmp(name, "readid_part_ctas")) { c->opt_readid_part_ctas = value > 0 ? (int)value : 0; return CID_OK; }
+    if (!strcmp(name, "readid_part_cap")) { c->opt_readid_part_cap = value > 0 ? (int)((value + 31) & ~31ll) : 0; return CID_OK; }
+    if (!strcmp(name, "readid_part_shift")) { c->opt_readid_part_shift = value > 0 && value < 32 ? (int)value : 0; return CID_OK; }
     if (!strcmp(name, "readid_serialize")) { c->opt_readid_serialize = value != 0; return CID_OK; }
     if (!strcmp(name, "build_table_div")) { c->opt_build_table_div = value >= 1 ? (int)value : 0; return CID_OK; }
     if (!strcmp(name, "build_packed")) { c->opt_build_packed = value != 0; return CID_OK; }

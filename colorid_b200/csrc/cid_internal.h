@@ -62,7 +62,7 @@ struct cid_ctx {
     cudaStream_t stream = nullptr;   // library-owned stream for the host-pointer entry points
     uint64_t launches = 0;
     const cid::GatherOut* gather_out = nullptr;   // set for the duration of cid_query_counts_sharded_dev
-    bool attr_done[8] = {false};     // cudaFuncSetAttribute (dynamic smem opt-in) already applied on this context's device
+    bool attr_done[12] = {false};     // cudaFuncSetAttribute (dynamic smem opt-in) already applied on this context's device
     cid::DevBuf scratch[cid::SCRATCH_SLOTS];
     cid::PinBuf pinned[8];
     uint32_t* d_err = nullptr;       // device error/flag words (zeroed before each call)
@@ -86,6 +86,10 @@ struct cid_ctx {
     int opt_kmerize_ctas = 0, opt_vote_ctas = 0;   // CTAs per SM of the read_id kmerize / vote grids (0 = fill the GPU);
                                                    // smaller grids let the two kernels of different chunks share the SMs
     int opt_readid_report_steps = 0; // 1 = report colours carry their insertion step in bits 20..31 (column-sharded read_id, cid_merge_shard_reports)
+    int opt_readid_vote_part = 1;    // narrow-row vote partitioned by row range (L2-resident gathers): 0 = never, 1 = when the matrix spans >= 3 windows and the chunk is large, 2 = always (tests)
+    int opt_readid_part_ctas = 0;    // CTAs per SM of the partitioned vote's scan kernel (0 = as many as fit)
+    int opt_readid_part_cap = 0;     // tuples per partition bucket (0 = sized from the chunk); tests force the overflow path with a tiny value
+    int opt_readid_part_shift = 0;   // log2 rows per partition (0 = 64 MB windows); tests use small values to get several partitions on small matrices
     int opt_readid_serialize = 0;    // 1 = kernels of consecutive pipeline chunks never overlap (measured: 44.8M vs 46.3M pairs/s e2e, off)
     int opt_build_table_div = 0;     // read-set builds: first count table = k-mer positions / this (0 = adaptive; grown x4 when > 70 % full)
     double readset_ratio = 0;        // distinct k-mers / k-mer positions of the last read-set accession built on this context
@@ -138,7 +142,7 @@ int check_err_flags(cid_ctx* ctx, cudaStream_t st, bool* lower_raw = nullptr);  
 
 // kernel ids for the profiling hooks (names in cid_api.cu: kKernelNames)
 enum { KID_KMERIZE_INSERT = 0, KID_HISTOGRAM, KID_TO_BLOOM, KID_TRANSPOSE, KID_ROWNZ, KID_QUERY_COUNTS, KID_QUERY_UNIQ_WIDE,
-       KID_QUERY_PERFECT, KID_READID_KMERIZE, KID_READID_SCHED, KID_READID_ORDER, KID_READID_VOTE, KID_READID_CLASSIFY, KID_TABLE_CLEAR, KID_OTHER, KID_QUERY_HASH, KID_QUERY_FRONT, KID_READID_BIG, KID_COUNT };
+       KID_QUERY_PERFECT, KID_READID_KMERIZE, KID_READID_SCHED, KID_READID_ORDER, KID_READID_VOTE, KID_READID_CLASSIFY, KID_TABLE_CLEAR, KID_OTHER, KID_QUERY_HASH, KID_QUERY_FRONT, KID_READID_BIG, KID_READID_VP_SCAN, KID_READID_VP_GATHER, KID_READID_VP_COUNT, KID_COUNT };
 struct ProfScope {     // records an event pair around a launch when profiling is enabled
     cid_ctx* ctx; cudaStream_t st; int idx;
     ProfScope(cid_ctx* c, cudaStream_t s, int kernel);
@@ -235,8 +239,9 @@ struct ReadSrc { const uint8_t* bases; const uint8_t* quals; uint32_t maxq; cons
 struct PackedReads { const uint32_t* words; const uint64_t* word_offs; uint32_t lower; };   // device pointers; word_offs indexed by absolute read
 struct ReadIdScratch {
     uint32_t* entries; uint16_t* order; uint32_t* nocc; uint64_t cap_reads;
+    DevBuf* vp = nullptr;      // grown on demand for the partitioned vote (cid_readid_part.cu); nullptr = one-kernel vote only
     // general path (cid_readid_big.cu): scratch of big_ctas CTAs sized by readid_big_plan(big_bases, big_kmers)
-    uint8_t* big; uint32_t big_ctas; uint32_t big_bases, big_kmers;
+    uint8_t* big = nullptr; uint32_t big_ctas = 0; uint32_t big_bases = 0, big_kmers = 0;
 };
 enum { READID_FAST_BASES = 1000 };     // longest read (all mates) of the warp-per-read kernels
 void readid_scratch_bytes(const cid_index* idx, uint32_t max_read_bases, uint32_t max_kmers, uint64_t reads,
@@ -254,6 +259,26 @@ int launch_readid_big(cid_index* idx, cudaStream_t st, const ReadSrc& src,
                       uint8_t* d_scratch, uint32_t ctas, uint32_t* d_n_set, uint32_t* d_flags, uint32_t* d_rep_n,
                       uint32_t* d_rep_colour, uint32_t* d_rep_count, uint32_t order_cap, uint32_t* d_order_n,
                       uint8_t* d_order_seq, uint32_t* d_order_pos);
+
+// partitioned vote of narrow rows (cid_readid_part.cu): row gathers bucketed by row range so that they hit L2
+constexpr int VP_MAXP = 16;        // partitions (row ranges) at most
+constexpr uint32_t VP_MAXB = 15;   // `-B` k-mers read directly at most
+constexpr int VP_MAXCAND = 8;      // candidate colours per read held as one accumulator byte per k-mer
+struct VotePart {                  // device view of one chunk's scratch
+    uint2* tuples; uint32_t cap;   // [P][cap] (row, accumulator slot)
+    uint32_t* cursor;              // [VP_MAXP] tuples per partition, [VP_MAXP] overflow flag
+    uint32_t* direct_n; uint32_t* direct;   // reads left to the one-kernel vote (more than VP_MAXCAND candidates)
+    uint32_t* acc32;               // one byte per k-mer after the first -B, read r at r << ashift
+    uint32_t* info; unsigned long long* candl; uint32_t* initc;
+    uint32_t ashift, pshift, P;
+};
+struct VotePartPlan { uint32_t P, pshift, ashift, cap, ctas_per_sm; size_t o_info, o_initc, o_direct, o_candl, o_acc, o_tuples, bytes; };
+bool votepart_plan(const cid_index* idx, const cid_readid_params& p, int cap_bases, uint32_t maxocc, uint64_t reads, VotePartPlan* out);
+int launch_readid_vote_part(cid_index* idx, cudaStream_t st, const ReadSrc& rsrc, const uint64_t* d_seq_offs,
+                            const uint64_t* d_read_offs, uint64_t r0, uint64_t nr, uint32_t kitem, const ModS& mods, int cap,
+                            uint32_t maxocc, const uint16_t* ord16, const uint8_t* ord8, const uint16_t* d_ent16,
+                            const uint32_t* d_n_set, const cid_readid_params& p, const VotePartPlan& pl, uint8_t* d_scratch,
+                            uint32_t* d_flags, uint32_t* d_rep_n, uint32_t* d_rep_colour, uint32_t* d_rep_count, VotePart* vp_out);
 
 // device side of the vote; reads it cannot decide bit-exactly are appended to `list` for the host vote
 int launch_readid_classify(cid_ctx* ctx, cudaStream_t st, uint64_t r0, uint64_t nreads, uint32_t N, uint32_t rep_cap,

@@ -15,12 +15,11 @@
 
 #include "cid_device.cuh"
 #include "cid_internal.h"
+#include "cid_readid_common.cuh"
 
 namespace cid {
 
-constexpr int RA_WARPS = 4;
 constexpr uint32_t FINE_STEPS = 2;   // fine-grained (lane per hash row) steps at the start of each read's vote
-constexpr int MAX_MATES = 8;
 // option readid_report_steps (column-sharded read_id): a report entry's colour carries, above this bit, the index of the
 // k-mer (in set order) whose AND row first inserted the colour into final_report -- what a merge of per-shard reports
 // needs to restore the reference's insertion order (colours < 2^20 per shard, k-mers < 2^11 per read)
@@ -31,81 +30,6 @@ constexpr uint32_t REP_STEP_SHIFT = 20;
 #define ENT_FWD(e) (((e) >> 26) & 1u)
 #define ENT_FRESH(e) (((e) >> 27) & 1u)
 
-struct ReadGeom { uint64_t b0; int len; int nm; };
-
-// Where a read's bases come from: ASCII bases (+ qualities for seq.rs:36-56 qual_mask on the device), or the planes a host
-// packer produced (cid_pack_reads: per read 2-bit codes, "not ACGTacgt / masked" bits and optionally lower-case bits, in the
-// tile's own layout, so loading is a copy and the per-kernel mask + pack work disappears along with 3/4 of the H2D bytes).
-
-// Loads one read (all mates, contiguous in `bases`) into a warp-private tile, applying
-// seq.rs:36-56 qual_mask when quals != nullptr.  Returns false if the read does not fit.
-__device__ __forceinline__ bool warp_load_read(Tile& t, int cap, const ReadSrc& src_, uint64_t r,
-                                               const uint64_t* __restrict__ seq_offs, uint64_t s_begin, uint64_t s_end,
-                                               uint32_t* moffs, int lane, ReadGeom& g) {
-    const uint8_t* __restrict__ bases = src_.bases;
-    const uint8_t* __restrict__ quals = src_.quals;
-    const uint32_t maxq = src_.maxq;
-    g.b0 = __ldg(seq_offs + s_begin);
-    uint64_t b1 = __ldg(seq_offs + s_end);
-    g.nm = (int)(s_end - s_begin);
-    g.len = (int)min(b1 - g.b0, (uint64_t)0x7fffffff);
-    if (b1 - g.b0 > (uint64_t)cap - 32 || g.nm > MAX_MATES) return false;
-    t.len = g.len;
-    for (int i = lane; i < cap / 32 + 2; i += 32) t.start[i] = 0;
-    __syncwarp();
-    if (lane <= g.nm && lane < MAX_MATES + 1) {
-        uint32_t o = (uint32_t)(__ldg(seq_offs + s_begin + lane) - g.b0);
-        moffs[lane] = o;
-        if (lane > 0 && lane < g.nm) atomicOr(&t.start[o >> 5], 1u << (o & 31));
-    }
-    if (src_.pk) {
-        // packed planes: codes | bad | [lower], one copy each (bits past the read's end are "bad" by construction)
-        const uint32_t* __restrict__ pw = src_.pk + __ldg(src_.pk_offs + r);
-        const int ncw = (g.len + 15) >> 4, nbw = (g.len + 31) >> 5;
-        for (int w = lane; w < cap / 16 + 3; w += 32) t.codes[w] = w < ncw ? __ldcs(pw + w) : 0u;
-        for (int w = lane; w < cap / 32 + 2; w += 32) {
-            t.bad[w] = w < nbw ? __ldcs(pw + ncw + w) : 0xFFFFFFFFu;
-            t.lower[w] = (src_.pk_lower && w < nbw) ? __ldcs(pw + ncw + nbw + w) : 0u;
-        }
-        __syncwarp();
-        if (src_.pk_lower) {      // (rare) raw-case consumers read the bytes: spell them from the planes ('N' for any non-base)
-            for (int i = lane; i < g.len; i += 32) {
-                uint32_t c = code_ascii((t.codes[i >> 4] >> (30 - 2 * (i & 15))) & 3u);
-                if ((t.lower[i >> 5] >> (i & 31)) & 1u) c |= 0x20u;
-                if ((t.bad[i >> 5] >> (i & 31)) & 1u) c = 'N';
-                t.ascii[i] = (uint8_t)c;
-            }
-            __syncwarp();
-        }
-        return true;
-    }
-    const uint8_t* src = bases + g.b0;
-    const uint8_t* qsrc = quals ? quals + g.b0 : nullptr;
-    // streamed once (__ldcs): do not displace matrix rows in L2.  Word loads when both streams are 4-byte aligned.
-    int done = 0;
-    if (((uintptr_t)src & 3) == 0 && (!qsrc || (((uintptr_t)qsrc & 3) == 0 && maxq <= 255u))) {
-        const int nw = g.len >> 2;
-        const uint32_t maxq4 = maxq * 0x01010101u;
-        for (int w = lane; w < nw; w += 32) {
-            uint32_t c4 = __ldcs((const uint32_t*)src + w);
-            if (qsrc) {
-                const uint32_t low = __vcmpltu4(__ldcs((const uint32_t*)qsrc + w), maxq4);   // 0xFF where qual < maxq
-                c4 = (c4 & ~low) | (0x4E4E4E4Eu & low);                                      // 'N'
-            }
-            ((uint32_t*)t.ascii)[w] = c4;
-        }
-        done = nw << 2;
-    }
-    for (int i = done + lane; i < g.len; i += 32) {
-        uint8_t c = __ldcs(src + i);
-        if (qsrc && (uint32_t)__ldcs(qsrc + i) < maxq) c = 'N';
-        t.ascii[i] = c;
-    }
-    __syncwarp();
-    tile_pack(t, cap, lane, 32);
-    __syncwarp();
-    return true;
-}
 
 // ================================================================= readid_kmerize
 // COMPACT (reads of <= 255 k-mer positions): only the FIRST occurrence of every distinct k-mer is
@@ -602,7 +526,11 @@ readid_vote_narrow_kernel(const ReadSrc src,
                           const uint16_t* __restrict__ ent16, const uint32_t* __restrict__ n_set,
                           uint32_t start_sample, uint32_t rep_cap, uint32_t* __restrict__ flags,
                           uint32_t* __restrict__ rep_n, uint32_t* __restrict__ rep_colour,
-                          uint32_t* __restrict__ rep_count, unsigned long long* __restrict__ gather_counter) {
+                          uint32_t* __restrict__ rep_count, unsigned long long* __restrict__ gather_counter,
+                          const uint32_t* __restrict__ sel_list, const uint32_t* __restrict__ sel_n,
+                          const uint32_t* __restrict__ sel_all) {
+    // sel_list != nullptr (after the partitioned vote, cid_readid_part.cu): only the reads it left over -- sel_list[0 .. *sel_n)
+    // -- or, when one of its buckets overflowed (*sel_all != 0), every read of the chunk
     extern __shared__ __align__(16) uint8_t dsm[];
     __shared__ uint32_t lut[256];
     lut4_init(lut, threadIdx.x, blockDim.x);
@@ -616,8 +544,11 @@ readid_vote_narrow_kernel(const ReadSrc src,
     uint16_t* ordstep = (uint16_t*)(ord + 64);      // with_steps: index of the k-mer that inserted the colour (REP_STEP_SHIFT)
     uint32_t* moffs = (uint32_t*)(ord + 64 + 128);
     const bool classic = start_sample == 0;
+    const bool listed = sel_list != nullptr && *sel_all == 0u;
+    const uint64_t nwork = listed ? (uint64_t)*sel_n : nreads;
 
-    for (uint64_t rl = (uint64_t)blockIdx.x * RA_WARPS + warp; rl < nreads; rl += (uint64_t)gridDim.x * RA_WARPS) {
+    for (uint64_t wi = (uint64_t)blockIdx.x * RA_WARPS + warp; wi < nwork; wi += (uint64_t)gridDim.x * RA_WARPS) {
+        const uint64_t rl = listed ? (uint64_t)sel_list[wi] : wi;
         const uint64_t r = r0 + rl;
         const uint32_t n = n_set[r];
         __syncwarp();
@@ -1355,6 +1286,20 @@ int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const ui
             CID_CUDA(cudaGetLastError());
         }
         if (d_rep_n) {
+            // narrow rows in a matrix of several L2-sized windows: scan / per-window gather / count (cid_readid_part.cu);
+            // the one-kernel vote below then only sees the reads that path left over
+            VotePart vpd{};
+            bool parted = false;
+            VotePartPlan vpl;
+            if (scr.vp && votepart_plan(idx, p, cap, maxocc, nr, &vpl) && scr.vp->ensure(vpl.bytes) == CID_OK) {
+                CID_TRY(launch_readid_vote_part(idx, st, rsrc, d_seq_offs, d_read_offs, r0, nr, kitem, mods, cap, maxocc, ord16, ord8,
+                                                d_ent16, d_n_set, p, vpl, scr.vp->as<uint8_t>(), d_flags, d_rep_n, d_rep_colour,
+                                                d_rep_count, &vpd));
+                parted = true;
+            }
+            const uint32_t* sel_list = parted ? vpd.direct : nullptr;
+            const uint32_t* sel_n = parted ? vpd.direct_n : nullptr;
+            const uint32_t* sel_all = parted ? vpd.cursor + VP_MAXP : nullptr;
             ProfScope ps(ctx, st, KID_READID_VOTE);
             const uint32_t* rownz = idx->rownz;
             if (idx->Wp <= 2) {
@@ -1363,7 +1308,7 @@ int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const ui
     readid_vote_narrow_kernel<WPV, STV><<<gridV, RA_WARPS * 32, cn_smem, st>>>(                                        \
         rsrc, d_seq_offs, d_read_offs, r0, nr, kitem, idx->H, mods, idx->rows, rownz, idx->rownz, idx->N, cap,  \
         maxocc, ord16, ord8, d_ent16, d_n_set, p.start_sample, p.rep_cap, d_flags, d_rep_n, d_rep_colour, d_rep_count,  \
-        (unsigned long long*)(ctx->d_err + 2))
+        (unsigned long long*)(ctx->d_err + 2), sel_list, sel_n, sel_all)
                 if (idx->Wp == 1) { if (with_steps) CID_VOTE_NARROW(1, true); else CID_VOTE_NARROW(1, false); }
                 else { if (with_steps) CID_VOTE_NARROW(2, true); else CID_VOTE_NARROW(2, false); }
 #undef CID_VOTE_NARROW

@@ -27,7 +27,7 @@ struct cid_readid_pipe {
     struct Slot {
         cudaStream_t st = nullptr;
         cudaEvent_t done = nullptr;
-        cid::DevBuf bases, quals, seq_offs, read_offs, entries, order, nocc, n_set, flags, rep_n, rep, ord_out, big;
+        cid::DevBuf bases, quals, seq_offs, read_offs, entries, order, nocc, n_set, flags, rep_n, rep, ord_out, big, vp;
         cid::DevBuf kind, hits, n_top, top, list, cursor;      // fused vote: device classification + undecided list
         cid::PinBuf h_cursor, h_list, h_offs;
         cudaEvent_t offs_done = nullptr;     // the staged offsets have been consumed by their H2D copies
@@ -53,7 +53,7 @@ void readid_pipe_destroy(cid_ctx* ctx) {
     for (auto& s : pp->slot) {
         if (s.st) cudaStreamSynchronize(s.st);
         for (DevBuf* b : {&s.bases, &s.quals, &s.seq_offs, &s.read_offs, &s.entries, &s.order, &s.nocc, &s.n_set, &s.flags,
-                          &s.rep_n, &s.rep, &s.ord_out, &s.big, &s.kind, &s.hits, &s.n_top, &s.top, &s.list, &s.cursor})
+                          &s.rep_n, &s.rep, &s.ord_out, &s.big, &s.vp, &s.kind, &s.hits, &s.n_top, &s.top, &s.list, &s.cursor})
             b->release();
         for (PinBuf* b : {&s.h_cursor, &s.h_list, &s.h_offs}) b->release();
         if (s.offs_done) cudaEventDestroy(s.offs_done);
@@ -388,7 +388,7 @@ static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals,
             d_op = s.ord_out.as<uint32_t>() + nr - r0 * (size_t)out.order_cap;
             d_os = (uint8_t*)(s.ord_out.as<uint32_t>() + nr + nr * (size_t)out.order_cap) - r0 * (size_t)out.order_cap;
         }
-        ReadIdScratch scr{s.entries.as<uint32_t>(), s.order.as<uint16_t>(), s.nocc.as<uint32_t>(), nr, nullptr, 0, 0, 0};
+        ReadIdScratch scr{s.entries.as<uint32_t>(), s.order.as<uint16_t>(), s.nocc.as<uint32_t>(), nr, &s.vp};
         PIPE_TRY(big_scratch(ix, s.big, geo.max_bases, geo.max_kmers, scr));
         // Option readid_serialize: this chunk's kernels start only after the previous chunk's have finished (copies still
         // overlap).  Measured on B200: 44.8M pairs/s against 46.3M with free overlap across the slot streams, so it is off.
@@ -486,7 +486,7 @@ static int read_id_batch_dev_impl(cid_index* ix, const char* d_bases, const char
         CID_TRY(ctx->scratch[16].ensure(eb));
         CID_TRY(ctx->scratch[17].ensure(ob));
         CID_TRY(ctx->scratch[18].ensure(nb));
-        ReadIdScratch scr{ctx->scratch[16].as<uint32_t>(), ctx->scratch[17].as<uint16_t>(), ctx->scratch[18].as<uint32_t>(), cap, nullptr, 0, 0, 0};
+        ReadIdScratch scr{ctx->scratch[16].as<uint32_t>(), ctx->scratch[17].as<uint16_t>(), ctx->scratch[18].as<uint32_t>(), cap, &ctx->scratch[26]};
         CID_TRY(big_scratch(ix, ctx->scratch[24], h_max_read_bases, big_kmers, scr));
         return readid_run(ix, user, (const uint8_t*)d_bases, (const uint8_t*)d_quals, pkp, d_seq_offs, d_read_offs, 0,
                           nreads, h_max_read_bases, h_max_kmers, pp, scr, d_n_set, d_flags, d_rep_n, d_rep_colour, d_rep_count,
@@ -513,7 +513,7 @@ static int read_id_batch_dev_impl(cid_index* ix, const char* d_bases, const char
     for (uint64_t r0 = 0; r0 < nreads && rc == CID_OK; r0 += chunk, c++) {
         const int i = (int)(c & 1);
         ReadIdScratch scr{ctx->scratch[16 + 3 * i].as<uint32_t>(), ctx->scratch[17 + 3 * i].as<uint16_t>(),
-                          ctx->scratch[18 + 3 * i].as<uint32_t>(), chunk, nullptr, 0, 0, 0};
+                          ctx->scratch[18 + 3 * i].as<uint32_t>(), chunk, &ctx->scratch[26 + i]};
         rc = big_scratch(ix, ctx->scratch[24 + i], h_max_read_bases, big_kmers, scr);
         if (rc == CID_OK) rc = readid_run(ix, ctx->aux[i], (const uint8_t*)d_bases, (const uint8_t*)d_quals, pkp, d_seq_offs, d_read_offs, r0,
                         std::min(chunk, nreads - r0), h_max_read_bases, h_max_kmers, pp, scr, d_n_set, d_flags, d_rep_n,

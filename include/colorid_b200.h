@@ -75,7 +75,10 @@ int cid_ctx_read_counter(cid_ctx* ctx, const char* name, uint64_t* value);
  *            table of a read set = k-mer positions / this; 0 = adaptive / always the safe size), query_table_min_slots,
  *            gather_l2_64b
  *   parity aids (force the slower of two equivalent paths): build_packed, build_set, query_front, query_fused,
- *            query_compact (0 never / 1 large tables / 2 always), uniq_device */
+ *            query_compact (0 never / 1 large tables / 2 always), uniq_device,
+ *            readid_vote_part (narrow-row read_id vote partitioned by row range so that its gathers hit L2: 0 never / 1 when the
+ *            matrix spans >= 3 windows of 64 MB and the chunk has >= 16,384 reads / 2 always), readid_part_shift (log2 rows per
+ *            window, 0 = 64 MB), readid_part_cap (tuples per window bucket, 0 = sized from the chunk) */
 int cid_ctx_set_option(cid_ctx* ctx, const char* name, int64_t value);
 /* Per-kernel device timing with CUDA events on the launching stream (for bench.py's roofline).
  * cid_ctx_profile(ctx, 1) resets the accumulators and enables timing, (ctx, 0) disables it;

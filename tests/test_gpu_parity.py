@@ -880,3 +880,93 @@ def test_empty_and_degenerate_inputs(oracle, ctx):
     gi2.finalize()
     oi2.finalize()
     assert np.array_equal(gi2.download_dense(), oi2.words())
+
+
+def _reports_equal(a, b):
+    for key in ("n_set", "flags", "rep_n"):
+        assert np.array_equal(a[key], b[key]), key
+    for r in range(len(a["rep_n"])):
+        n = a["rep_n"][r]
+        assert np.array_equal(a["rep_colour"][r, :n], b["rep_colour"][r, :n]), f"read {r}: report order"
+        assert np.array_equal(a["rep_count"][r, :n], b["rep_count"][r, :n]), f"read {r}: report counts"
+
+
+@pytest.mark.parametrize("N,k,S,H,clades", [(46, 31, 2_000_003, 4, 6), (64, 21, 300_007, 2, 3), (20, 27, 750_000, 3, 10), (30, 31, 1_000_003, 4, 2)])
+def test_read_id_partitioned_vote(oracle, ctx, N, k, S, H, clades):
+    """cid_readid_part.cu (scan / per-window gather / count) against the oracle and, entry by entry (insertion order, flags),
+    against the one-kernel vote: reads with 0, 1..8 and more than 8 candidate colours (clades of up to 21 near-identical
+    genomes), misses at every position, sets shorter than -B, -B 1/3/7/15, -d 3, 4- and 8-byte rows, run-time num_hash."""
+    rng = _rng(9100 + N)
+    genomes = synth.clade_genomes(rng, N, 8000, n_clades=clades, div=0.004)
+    oix, gix = build_both(oracle, ctx, [[g] for g in genomes], S, H, k, cb.CID_SEQ_FASTA)
+    reads = synth.reads_from(rng, genomes, 500, read_len=150, insert=320, err=0.003, frac_random=0.2, n_rate=0.002)
+    reads += synth.reads_from(rng, genomes, 100, read_len=150, insert=200, err=0.0, frac_random=0.0)
+    reads += synth.reads_from(rng, genomes, 60, read_len=100, insert=300, err=0.02, frac_random=0.0, paired=False)
+    reads.append([b"ACGT", genomes[0][:150]])
+    reads.append([genomes[0][:k + 1]])                                 # two k-mers: fewer than -B
+    reads.append([genomes[0][:k]])
+    reads.append([b"N" * 150, b"N" * 150])
+    reads.append([genomes[1][:150], genomes[1][:150]])
+    for kw in (dict(), dict(start_sample=1), dict(start_sample=7), dict(start_sample=15), dict(d=3), dict(start_sample=0)):
+        res = {}
+        for part in (0, 2):
+            ctx.set_option("readid_vote_part", part)
+            ctx.set_option("readid_part_shift", 14)                    # 16,384-row windows (the plan widens them until P <= 16)
+            try:
+                if part == 2:
+                    _readid_compare(oracle, oix, gix, reads, **kw)
+                res[part] = gix.read_id_batch(reads, d=kw.get("d", 1), start_sample=kw.get("start_sample", 3))
+            finally:
+                ctx.set_option("readid_vote_part", 1)
+                ctx.set_option("readid_part_shift", 0)
+        _reports_equal(res[0], res[2])
+        if kw.get("start_sample", 3) == 3 and clades <= 3:
+            # the clades are wide enough for reads with more than 8 candidates (left to the one-kernel vote)
+            assert (res[2]["rep_n"] > 9).sum() > 10
+    # a bucket that overflows: the whole chunk is redone by the one-kernel vote, same reports
+    ctx.set_option("readid_vote_part", 2)
+    ctx.set_option("readid_part_shift", 14)
+    ctx.set_option("readid_part_cap", 64)
+    try:
+        over = gix.read_id_batch(reads)
+    finally:
+        ctx.set_option("readid_vote_part", 1)
+        ctx.set_option("readid_part_shift", 0)
+        ctx.set_option("readid_part_cap", 0)
+    ctx.set_option("readid_vote_part", 0)
+    try:
+        base = gix.read_id_batch(reads)
+    finally:
+        ctx.set_option("readid_vote_part", 1)
+    _reports_equal(base, over)
+
+
+def test_read_id_partitioned_vote_classify_and_packed(oracle, ctx):
+    """The same path under cid_read_id_classify (ASCII + qualities masked on the device) and cid_read_id_classify_packed (planes
+    from the host packer), several pipeline chunks in flight: classifications and top accessions against the oracle."""
+    rng = _rng(9200)
+    N, k, S, H = 46, 31, 2_000_003, 4
+    genomes, oix, gix = _index_pair(oracle, ctx, rng, N, k, S, H)
+    gix.n_ref[:] = oix.n_ref
+    reads = synth.reads_from(rng, genomes, 3000, read_len=150, insert=320, err=0.004, frac_random=0.2, n_rate=0.002)
+    quals = [[bytes(rng.choice(np.frombuffer(b"#+5?I", dtype=np.uint8), size=len(m), p=[.01, .01, .02, .36, .6]).tolist())
+              for m in r] for r in reads]
+    masked = [[oracle.qual_mask(m, q, 15) for m, q in zip(r, qr)] for r, qr in zip(reads, quals)]
+    o = oix.read_id_batch(masked)
+    pk = cb.pack_reads(reads, quals, 15)
+    ctx.set_option("readid_vote_part", 2)
+    ctx.set_option("readid_part_shift", 15)
+    ctx.set_option("readid_chunk_reads", 700)
+    try:
+        g = gix.read_id_classify(reads, quals=quals, qual_offset=15)
+        gp = gix.read_id_classify_packed(pk)
+    finally:
+        ctx.set_option("readid_vote_part", 1)
+        ctx.set_option("readid_part_shift", 0)
+        ctx.set_option("readid_chunk_reads", 0)
+    for res in (g, gp):
+        for key in ("kind", "hits", "n_set", "n_top"):
+            assert np.array_equal(res[key], o[key]), key
+        for r in range(len(reads)):
+            nt = min(int(o["n_top"][r]), 8)
+            assert res["top"][r, :nt].tolist() == o["top"][r, :nt].tolist()
