@@ -265,14 +265,15 @@ constexpr int VP_MAXP = 16;        // partitions (row ranges) at most
 constexpr uint32_t VP_MAXB = 15;   // `-B` k-mers read directly at most
 constexpr int VP_MAXCAND = 8;      // candidate colours per read held as one accumulator byte per k-mer
 struct VotePart {                  // device view of one chunk's scratch
-    uint2* tuples; uint32_t cap;   // [P][cap] (row, accumulator slot)
-    uint32_t* cursor;              // [VP_MAXP] tuples per partition, [VP_MAXP] overflow flag
+    uint2* tuples; uint32_t cap;   // [P][cap] (row, accumulator slot): per-warp blocks interleaved, cap_warp tuples per warp at most
+    uint32_t cap_warp; uint32_t* ntup;   // [P][W] tuples each warp of the scan pushed
+    uint32_t* cursor;              // [VP_MAXP] longest per-warp total of each partition, [VP_MAXP] overflow flag
     uint32_t* direct_n; uint32_t* direct;   // reads left to the one-kernel vote (more than VP_MAXCAND candidates)
     uint32_t* acc32;               // one byte per k-mer after the first -B, read r at r << ashift
     uint32_t* info; unsigned long long* candl; uint32_t* initc;
     uint32_t ashift, pshift, P;
 };
-struct VotePartPlan { uint32_t P, pshift, ashift, cap, ctas_per_sm; size_t o_info, o_initc, o_direct, o_candl, o_acc, o_tuples, bytes; };
+struct VotePartPlan { uint32_t P, pshift, ashift, cap, cap_warp, grid, ctas_per_sm; size_t o_ntup; size_t o_info, o_initc, o_direct, o_candl, o_acc, o_tuples, bytes; };
 bool votepart_plan(const cid_index* idx, const cid_readid_params& p, int cap_bases, uint32_t maxocc, uint64_t reads, VotePartPlan* out);
 int launch_readid_vote_part(cid_index* idx, cudaStream_t st, const ReadSrc& rsrc, const uint64_t* d_seq_offs,
                             const uint64_t* d_read_offs, uint64_t r0, uint64_t nr, uint32_t kitem, const ModS& mods, int cap,

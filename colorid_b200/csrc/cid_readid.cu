@@ -52,7 +52,7 @@ readid_kmerize_kernel(const ReadSrc src,
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t per_warp = ((tile_smem_bytes(cap) + 7) & ~(size_t)7) + (size_t)tsize * 8 + (size_t)tsize * 4 +
-                            (size_t)cap * 4 + (MAX_MATES + 1) * 4 + 4 + 32;
+                            (size_t)cap * 4 + (MAX_MATES + 1) * 4 + 4 + 32 + (COMPACT ? 512 : 0);
     uint8_t* base = dsm + (size_t)warp * ((per_warp + 15) & ~(size_t)15);
     Tile t = tile_carve(base, cap);
     unsigned long long* tkeys = (unsigned long long*)(base + ((tile_smem_bytes(cap) + 7) & ~(size_t)7));
@@ -60,6 +60,7 @@ readid_kmerize_kernel(const ReadSrc src,
     uint32_t* pinfo = tmin + tsize;
     uint32_t* moffs = pinfo + cap;
     uint32_t* h9s = moffs + (MAX_MATES + 1) + 1;      // COMPACT: 9th hash bit of up to 256 fresh k-mers
+    uint16_t* fslot = (uint16_t*)(h9s + 8);           // COMPACT: dedup-table slot of the i-th distinct k-mer
     const uint32_t tmask = tsize - 1;
     const uint32_t hwords = (maxocc + 31) / 32;
 
@@ -148,16 +149,15 @@ readid_kmerize_kernel(const ReadSrc src,
                 if (valid) {
                     uint32_t s = info & 0xFFFFu;
                     fresh = tmin[s] == (uint32_t)tp;
-                    f = fresh ? (fnv1a_low32_key_lut(lut, tkeys[s], MINI ? mini_m : k) & 0xFFFFu) : 0u;
+                    f = (!COMPACT && fresh) ? (fnv1a_low32_key_lut(lut, tkeys[s], MINI ? mini_m : k) & 0xFFFFu) : 0u;
                     ent = f | (info & 0x03FF0000u) | (((info >> 30) & 1u) << 26) | ((fresh ? 1u : 0u) << 27);
                 }
                 const uint32_t bal = __ballot_sync(0xffffffffu, valid), balf = __ballot_sync(0xffffffffu, fresh);
                 if (COMPACT) {
                     const uint32_t fi = nfr + __popc(balf & ((1u << lane) - 1));
                     if (fresh && fi < maxocc) {
-                        hp8[rl * (uint64_t)maxocc + fi] = (uint8_t)f;
                         ent16[rl * (uint64_t)maxocc + fi] = (uint16_t)(((info >> 16) & 0x3FFu) | (((info >> 30) & 1u) << 10));
-                        if ((f >> 8) & 1u) atomicOr(&h9s[fi >> 5], 1u << (fi & 31));
+                        fslot[fi] = (uint16_t)(info & 0xFFFFu);
                     }
                     if (bal) last_fresh = (balf >> (31 - __clz(bal))) & 1u;
                 } else {
@@ -166,6 +166,20 @@ readid_kmerize_kernel(const ReadSrc src,
                 }
                 emitted += __popc(bal);
                 nfr += __popc(balf);
+            }
+            if (COMPACT) {
+                // FNV-1a of the distinct k-mers, 32 at a time with every lane busy (in the loop over the read's positions only
+                // the lanes of FIRST occurrences hashed: about a third of them, at the full cost of the 31-step chain per step)
+                __syncwarp();
+                const uint32_t nfd = min(nfr, maxocc);
+                for (uint32_t f0 = 0; f0 < nfd; f0 += 32) {
+                    const uint32_t fi = f0 + lane;
+                    const bool act = fi < nfd;
+                    const uint32_t f = act ? (fnv1a_low32_key_lut(lut, (uint64_t)tkeys[fslot[fi]], MINI ? mini_m : k) & 0xFFFFu) : 0u;
+                    if (act) hp8[rl * (uint64_t)maxocc + fi] = (uint8_t)f;
+                    const uint32_t b9 = __ballot_sync(0xffffffffu, (f >> 8) & 1u);
+                    if (lane == 0) h9s[f0 >> 5] = b9;
+                }
             }
             if (emitted > maxocc) { if (lane == 0) atomicOr(err, ERRF_LIST_OVERFLOW); emitted = maxocc; }
             if (COMPACT) {
@@ -1198,7 +1212,7 @@ int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const ui
     uint32_t* d_slow = d_slow_n + 4;
 
     // shared memory budgets
-    size_t a_warp = ((tile_smem_bytes(cap) + 7) & ~(size_t)7) + (size_t)tsize * 12 + (size_t)cap * 4 + (MAX_MATES + 1) * 4 + 4 + 32;
+    size_t a_warp = ((tile_smem_bytes(cap) + 7) & ~(size_t)7) + (size_t)tsize * 12 + (size_t)cap * 4 + (MAX_MATES + 1) * 4 + 4 + 32 + 512;
     size_t a_smem = RA_WARPS * ((a_warp + 15) & ~(size_t)15);
     const size_t b_esz = small ? 1 : 2;
     const size_t b_thread = ((((size_t)(TB + TB / 2) + maxocc) * b_esz + 3) & ~(size_t)3) +

@@ -28,7 +28,7 @@
 
 namespace cid {
 
-constexpr int VP_BLK = 128;                 // tuples of bucket space reserved per atomic
+constexpr int VP_BLK_LOG2 = 7, VP_BLK = 1 << VP_BLK_LOG2;   // tuples per block of a warp's share of a bucket
 constexpr uint32_t VP_NULL = 0xFFFFFFFFu;   // slot of a padding tuple
 enum { VPM_NONE = 0, VPM_PART = 1, VPM_DIRECT = 2 };
 // info word per read: [11:0] k-mers walked (incl. the one that missed) | [23:12] accumulator bytes | [24] miss | [28:25] candidates | [30:29] mode
@@ -82,40 +82,32 @@ readid_vp_scan_kernel(const ReadSrc src, const uint64_t* __restrict__ seq_offs, 
     unsigned long long my_rows = 0;
     constexpr int NH = HT ? HT : MAX_HASH;
 
-    // Bucket space: lane p owns partition p's cursor state -- the block being filled (rbase, rused) and the next one (rnext),
-    // VP_BLK tuples each, reserved with one atomic long before its base is needed.  (A first version staged tuples in
-    // shared-memory rings and reserved 32 tuples per flush: the scan then waited on the six cursor words for 35 % of its
-    // stall samples -- same-address atomics of different warps complete one per ~6 cycles.)
-    uint32_t rbase = 0, rnext = 0, rused = 0;
-    if ((uint32_t)lane < vp.P) { rbase = atomicAdd(vp.cursor + lane, (uint32_t)VP_BLK); rnext = atomicAdd(vp.cursor + lane, (uint32_t)VP_BLK); }
+    // Bucket space needs no atomics: block i of warp w in partition p's bucket is block i * W + w (W warps in the grid), so a
+    // warp's position in a bucket is a function of how many tuples it has pushed there (lane p counts partition p's).  The
+    // gather kernel gets the per-warp totals and skips what was not written.  (Reserving blocks with atomicAdd -- 32 tuples
+    // per atomic, then 128 with the next block requested ahead -- left the scan waiting on the cursor words for 35 % of its
+    // stall samples: ptxas parks the returned base in a temporary and copies it at once.)
+    const uint32_t W = gridDim.x * RA_WARPS, wid = blockIdx.x * RA_WARPS + warp;
+    uint32_t tot = 0;                            // lane p: tuples this warp pushed into partition p
     const uint32_t pb0 = (lane & 1) ? 0xFFFFFFFFu : 0u, pb1 = (lane & 2) ? 0xFFFFFFFFu : 0u, pb2 = (lane & 4) ? 0xFFFFFFFFu : 0u,
                    pb3 = (lane & 8) ? 0xFFFFFFFFu : 0u;
-    // one tuple per lane (or none) straight into its partition's block: the lanes of a partition take consecutive slots
+    // one tuple per lane (or none) straight into its partition's bucket: the lanes of a partition take consecutive slots
     auto emit = [&](bool v, uint32_t rid, uint32_t slot) {
         const uint32_t part = rid >> vp.pshift;                       // < P <= 16
         const uint32_t bv = __ballot_sync(0xffffffffu, v);
         const uint32_t b0 = __ballot_sync(0xffffffffu, part & 1u), b1 = __ballot_sync(0xffffffffu, part & 2u),
                        b2 = __ballot_sync(0xffffffffu, part & 4u), b3 = __ballot_sync(0xffffffffu, part & 8u);
-        // lanes that push into MY tuple's partition / into the partition this lane owns
+        // lanes that push into MY tuple's partition / into the partition this lane counts
         const uint32_t same = bv & ~(b0 ^ ((part & 1u) ? 0xFFFFFFFFu : 0u)) & ~(b1 ^ ((part & 2u) ? 0xFFFFFFFFu : 0u)) &
                               ~(b2 ^ ((part & 4u) ? 0xFFFFFFFFu : 0u)) & ~(b3 ^ ((part & 8u) ? 0xFFFFFFFFu : 0u));
         const uint32_t mine = lane < VP_MAXP ? (bv & ~(b0 ^ pb0) & ~(b1 ^ pb1) & ~(b2 ^ pb2) & ~(b3 ^ pb3)) : 0u;
-        const uint32_t pos = __shfl_sync(0xffffffffu, rused, part) + __popc(same & lt);
-        uint32_t at = __shfl_sync(0xffffffffu, rbase, part) + pos;
-        if (__any_sync(0xffffffffu, v && pos >= (uint32_t)VP_BLK)) {    // (rnext may still be in flight: only touched when needed)
-            const uint32_t nx = __shfl_sync(0xffffffffu, rnext, part);
-            if (pos >= (uint32_t)VP_BLK) at = nx + (pos - (uint32_t)VP_BLK);
-        }
+        const uint32_t pos = __shfl_sync(0xffffffffu, tot, part) + __popc(same & lt);
         if (v) {
-            if (at < vp.cap) vp.tuples[(size_t)part * vp.cap + at] = make_uint2(rid, slot);
-            else vp.cursor[VP_MAXP] = 1u;        // bucket full: every read of the chunk is redone by the one-kernel vote
+            const uint32_t at = ((pos >> VP_BLK_LOG2) * W + wid) * (uint32_t)VP_BLK + (pos & (uint32_t)(VP_BLK - 1));
+            if (pos < vp.cap_warp) vp.tuples[(size_t)part * vp.cap + at] = make_uint2(rid, slot);
+            else vp.cursor[VP_MAXP] = 1u;        // bucket share used up: every read of the chunk is redone by the one-kernel vote
         }
-        rused += __popc(mine);
-        if (rused >= (uint32_t)VP_BLK) {         // (only lanes < P ever count anything)
-            rused -= (uint32_t)VP_BLK;
-            rbase = rnext;
-            rnext = atomicAdd(vp.cursor + lane, (uint32_t)VP_BLK);
-        }
+        tot += __popc(mine);
     };
 
     for (uint64_t rl = (uint64_t)blockIdx.x * RA_WARPS + warp; rl < nreads; rl += (uint64_t)gridDim.x * RA_WARPS) {
@@ -262,31 +254,35 @@ readid_vp_scan_kernel(const ReadSrc src, const uint64_t* __restrict__ seq_offs, 
             vp.initc[rl] = initc;
         }
     }
-    // the unused rest of the two blocks every partition has in hand: padding tuples (the gather kernel skips them)
-    for (uint32_t p = 0; p < vp.P; p++) {
-        const uint32_t b = __shfl_sync(0xffffffffu, rbase, p), u = __shfl_sync(0xffffffffu, rused, p), nx = __shfl_sync(0xffffffffu, rnext, p);
-        for (uint32_t i = u + lane; i < 2u * VP_BLK; i += 32) {
-            const uint32_t at = i < (uint32_t)VP_BLK ? b + i : nx + (i - (uint32_t)VP_BLK);
-            if (at < vp.cap) vp.tuples[(size_t)p * vp.cap + at] = make_uint2(0u, VP_NULL);
-        }
+    // per-warp totals (what the gather kernel may read) and the longest one (how far it has to look)
+    if ((uint32_t)lane < vp.P) {
+        const uint32_t t2 = min(tot, vp.cap_warp);
+        vp.ntup[(size_t)lane * W + wid] = t2;
+        if (t2) atomicMax(vp.cursor + lane, t2);
     }
     if (lane == 0 && my_rows && gather_counter) atomicAdd(gather_counter, my_rows);
 }
 
 // One partition's bucket: row from the L2-resident window -> one bit per candidate colour -> AND into the accumulator byte.
+// The bucket is W interleaved per-warp block sequences (see the scan kernel): block b belongs to warp b % W and is its
+// (b / W)-th; ntup[w] says how many tuples that warp wrote, maxtup the largest of them.
 template <int WP>
 __global__ void __launch_bounds__(256)
-readid_vp_gather_kernel(const uint32_t* __restrict__ rows, const uint2* __restrict__ tuples, const uint32_t* __restrict__ cursor,
-                        uint32_t cap, const unsigned long long* __restrict__ candl, uint32_t* __restrict__ acc32, uint32_t ashift) {
-    const uint32_t n = min(*cursor, cap);
+readid_vp_gather_kernel(const uint32_t* __restrict__ rows, const uint2* __restrict__ tuples, const uint32_t* __restrict__ ntup,
+                        const uint32_t* __restrict__ maxtup, uint32_t W, uint64_t Wmagic, const unsigned long long* __restrict__ candl,
+                        uint32_t* __restrict__ acc32, uint32_t ashift) {
     constexpr int ILP = 8;
-    for (uint64_t base = (uint64_t)blockIdx.x * 256 * ILP; base < n; base += (uint64_t)gridDim.x * 256 * ILP) {
+    const uint64_t ntot = (uint64_t)((*maxtup + VP_BLK - 1) >> VP_BLK_LOG2) * W * VP_BLK;      // < 2^32 (the plan caps the bucket)
+    for (uint64_t base = (uint64_t)blockIdx.x * 256 * ILP; base < ntot; base += (uint64_t)gridDim.x * 256 * ILP) {
         uint2 tp[ILP], v[ILP];
         unsigned long long cl[ILP];
 #pragma unroll
         for (int u = 0; u < ILP; u++) {
-            const uint64_t i = base + (uint64_t)u * 256 + threadIdx.x;
-            tp[u] = i < n ? __ldcs(tuples + i) : make_uint2(0u, VP_NULL);       // streamed once: do not displace the window
+            const uint64_t t = base + (uint64_t)u * 256 + threadIdx.x;
+            const uint32_t blk = (uint32_t)(t >> VP_BLK_LOG2);
+            const uint32_t i = (uint32_t)(((uint64_t)blk * Wmagic) >> 40), w = blk - i * W;      // blk / W, blk % W (exact: see the launcher)
+            const bool ok = t < ntot && (i << VP_BLK_LOG2) + ((uint32_t)t & (uint32_t)(VP_BLK - 1)) < __ldg(ntup + w);
+            tp[u] = ok ? __ldcs(tuples + t) : make_uint2(0u, VP_NULL);          // streamed once: do not displace the window
         }
 #pragma unroll
         for (int u = 0; u < ILP; u++) {
@@ -369,15 +365,19 @@ bool votepart_plan(const cid_index* idx, const cid_readid_params& p, int cap_bas
     uint32_t ashift = 2;
     while ((1u << ashift) < maxocc) ashift++;
     if ((reads << ashift) >= 0xFFFFFFFFull) return false;
-    const uint64_t worst = reads * (uint64_t)maxocc * idx->H;
-    uint64_t cap = ((worst / P + worst / (4 * P) + 8192) + 31) & ~31ull;             // 25 % slack over a uniform split
-    // the scan kernel runs as resident CTAs of 4 warps, each warp leaves at most 2 VP_BLK padding tuples per partition
+    // the scan kernel runs as resident CTAs of 4 warps striding over the reads; warp w owns every W-th block of each bucket
     const size_t smem = RA_WARPS * (((tile_smem_bytes(cap_bases) + 15) & ~(size_t)15) + 64 + 768);
     pl.ctas_per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (smem + 1024)));
     if (ctx->opt_readid_part_ctas) pl.ctas_per_sm = std::min<uint32_t>(pl.ctas_per_sm, (uint32_t)ctx->opt_readid_part_ctas);
-    cap += (uint64_t)ctx->sm_count * pl.ctas_per_sm * RA_WARPS * (2 * VP_BLK);
-    if (ctx->opt_readid_part_cap) cap = (uint64_t)ctx->opt_readid_part_cap;
-    if (cap >= 0xFFFFFF00ull) return false;
+    pl.grid = (uint32_t)std::min<uint64_t>((reads + RA_WARPS - 1) / RA_WARPS, (uint64_t)ctx->sm_count * pl.ctas_per_sm);
+    const uint64_t W = (uint64_t)pl.grid * RA_WARPS;
+    // a warp's share of a bucket: its reads' worst case split evenly over the partitions, 30 % slack, two blocks on top
+    const uint64_t per_warp = ((reads + W - 1) / W) * (uint64_t)maxocc * idx->H / P;
+    uint64_t cap_warp = (((per_warp + per_warp * 3 / 10) >> VP_BLK_LOG2) + 3) << VP_BLK_LOG2;
+    if (ctx->opt_readid_part_cap) cap_warp = (uint64_t)ctx->opt_readid_part_cap;
+    const uint64_t cap = W * (((cap_warp + VP_BLK - 1) >> VP_BLK_LOG2) << VP_BLK_LOG2);
+    if (cap >= 0xFFFFFF00ull || W >= 8192) return false;
+    pl.cap_warp = (uint32_t)cap_warp;
     pl.P = P; pl.pshift = pshift; pl.ashift = ashift; pl.cap = (uint32_t)cap;
     size_t o = 256;                                       // cursors, overflow flag, direct-list length
     pl.o_info = o; o += (reads * 4 + 255) & ~(size_t)255;
@@ -385,6 +385,7 @@ bool votepart_plan(const cid_index* idx, const cid_readid_params& p, int cap_bas
     pl.o_direct = o; o += (reads * 4 + 255) & ~(size_t)255;
     pl.o_candl = o; o += (reads * 8 + 255) & ~(size_t)255;
     pl.o_acc = o; o += ((size_t)reads << ashift) + 256;
+    pl.o_ntup = o; o += (size_t)VP_MAXP * W * 4 + 256;
     pl.o_tuples = o; o += (size_t)P * cap * 8;
     pl.bytes = o;
     if (!forced && pl.bytes > (24ull << 30)) return false;
@@ -407,7 +408,8 @@ int launch_readid_vote_part(cid_index* idx, cudaStream_t st, const ReadSrc& rsrc
     vp.candl = (unsigned long long*)(d_scratch + pl.o_candl);
     vp.acc32 = (uint32_t*)(d_scratch + pl.o_acc);
     vp.tuples = (uint2*)(d_scratch + pl.o_tuples);
-    vp.cap = pl.cap; vp.ashift = pl.ashift; vp.pshift = pl.pshift; vp.P = pl.P;
+    vp.ntup = (uint32_t*)(d_scratch + pl.o_ntup);
+    vp.cap = pl.cap; vp.cap_warp = pl.cap_warp; vp.ashift = pl.ashift; vp.pshift = pl.pshift; vp.P = pl.P;
     *vp_out = vp;
     CID_CUDA(cudaMemsetAsync(d_scratch, 0, 256, st));
     const size_t tile_b = (tile_smem_bytes(cap) + 15) & ~(size_t)15;
@@ -424,8 +426,7 @@ int launch_readid_vote_part(cid_index* idx, cudaStream_t st, const ReadSrc& rsrc
         CID_CUDA(cudaFuncSetAttribute(readid_vp_scan_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
         attr = true;
     }
-    // resident CTAs only (the kernel strides over the reads): every warp pads its last block per partition
-    const unsigned gridA = (unsigned)std::min<uint64_t>((nr + RA_WARPS - 1) / RA_WARPS, (uint64_t)ctx->sm_count * pl.ctas_per_sm);
+    const unsigned gridA = pl.grid;              // (the buckets are laid out for exactly this many warps)
     {
         ProfScope ps(ctx, st, KID_READID_VP_SCAN);
 #define CID_VP_SCAN(WPV, HTV)                                                                                          \
@@ -440,11 +441,14 @@ int launch_readid_vote_part(cid_index* idx, cudaStream_t st, const ReadSrc& rsrc
     {
         ProfScope ps(ctx, st, KID_READID_VP_GATHER);
         const unsigned gridG = (unsigned)ctx->sm_count * 8;
+        const uint32_t W = pl.grid * RA_WARPS;
+        // blk / W as (blk * Wmagic) >> 40 with Wmagic = floor(2^40 / W) + 1: exact for blk < 2^26 and W < 2^13
+        const uint64_t Wmagic = (1ull << 40) / W + 1;
         for (uint32_t q = 0; q < pl.P; q++) {
             if (idx->Wp == 1)
-                readid_vp_gather_kernel<1><<<gridG, 256, 0, st>>>(idx->rows, vp.tuples + (size_t)q * vp.cap, vp.cursor + q, vp.cap, vp.candl, vp.acc32, vp.ashift);
+                readid_vp_gather_kernel<1><<<gridG, 256, 0, st>>>(idx->rows, vp.tuples + (size_t)q * vp.cap, vp.ntup + (size_t)q * W, vp.cursor + q, W, Wmagic, vp.candl, vp.acc32, vp.ashift);
             else
-                readid_vp_gather_kernel<2><<<gridG, 256, 0, st>>>(idx->rows, vp.tuples + (size_t)q * vp.cap, vp.cursor + q, vp.cap, vp.candl, vp.acc32, vp.ashift);
+                readid_vp_gather_kernel<2><<<gridG, 256, 0, st>>>(idx->rows, vp.tuples + (size_t)q * vp.cap, vp.ntup + (size_t)q * W, vp.cursor + q, W, Wmagic, vp.candl, vp.acc32, vp.ashift);
         }
     }
     ctx->launches += pl.P;
