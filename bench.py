@@ -211,10 +211,13 @@ GATHER_CEILING_G_PER_S = 54.5     # measured: profiles/r1_gather_probe.txt
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
     same workload (profiles/r1_traffic.json; null when a kernel was not captured)."""
-    try:
-        return json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["bytes_per_launch"]
-    except Exception:
-        return {}
+    out = {}
+    for name in ("r1_traffic.json", "r2_traffic.json"):       # (round 2 adds the kernels of the partitioned vote)
+        try:
+            out.update(json.load(open(os.path.join(ROOT, "profiles", name)))["bytes_per_launch"])
+        except Exception:
+            pass
+    return out
 
 
 def offsets_for(n_pairs, rl):
@@ -1327,27 +1330,53 @@ def run_ours(args):
         per = ms / n
         kern[name] = {"ms_per_launch": per, "launches_per_step": n / K, "algorithmic_bytes_per_launch": alg.get(name),
                       "gbs": (alg[name] / (per / 1e3) / 1e9) if alg.get(name) else None}
-    dom = max(prof, key=lambda k_: prof[k_][0])
-    dom_per = prof[dom][0] / prof[dom][1]
-    achieved = alg.get(dom, 0) / (dom_per / 1e3) / 1e9
-    vote_ms = kern["readid_vote"]["ms_per_launch"] if "readid_vote" in kern else None
+    # The vote of narrow rows is a STAGE of kernels when the matrix spans several L2-sized windows (cid_readid_part.cu):
+    # scan (hash, first miss, one (row, slot) tuple per gather, bucketed by row window) -> one gather launch per window (rows
+    # read from the L2-resident window) -> count -> the one-kernel vote on the reads left over.  The stage does the work the
+    # reference's search_index does per read, so the roofline line is quoted on the stage: its algorithmic bytes over the
+    # summed duration of its launches in one step.
+    VOTE_PARTS = ("readid_vp_scan", "readid_vp_gather", "readid_vp_count", "readid_vote")
+    parted = "readid_vp_scan" in prof
+    vote_ms = sum(prof[k_][0] for k_ in VOTE_PARTS if k_ in prof) / K if any(k_ in prof for k_ in VOTE_PARTS) else None
+    if parted:
+        kern["readid_vote"]["algorithmic_bytes_per_launch"] = None
+        kern["readid_vote"]["gbs"] = None
+        kern["readid_vote"]["note"] = "leftover reads only (more than 8 candidate colours)"
+        dom, dom_ms, dom_traffic = "readid vote stage (readid_vp_scan + readid_vp_gather per window + readid_vp_count + readid_vote)", vote_ms, \
+            sum(traffic.get(k_, 0) * kern[k_]["launches_per_step"] for k_ in VOTE_PARTS if k_ in kern and traffic.get(k_)) or None
+        achieved = alg["readid_vote"] / (vote_ms / 1e3) / 1e9
+        dom_alg = alg["readid_vote"]
+    else:
+        dom = max(prof, key=lambda k_: prof[k_][0])
+        dom_ms = prof[dom][0] / prof[dom][1]
+        achieved = alg.get(dom, 0) / (dom_ms / 1e3) / 1e9
+        dom_traffic, dom_alg = traffic.get(dom), alg.get(dom)
     gathers = gather_rows                  # one gather = one 8-byte row read at a random row (device counter)
+    gather_ms = prof["readid_vp_gather"][0] / K if parted else None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic.get(dom), "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg.get(dom),
+                "frac": achieved / peak, "traffic": dom_traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": dom_alg, "ms_per_step": dom_ms,
                 "measured_in": "the timed region itself: CUDA events around every launch on the launching stream",
-                "note": "8-byte rows: a gather moves 8 algorithmic bytes but costs one DRAM access (ncu: ~100 B of DRAM "
-                        "traffic each, 56 B with ld.global.nc.L2::64B at the same rate), so the binding limit is the "
-                        "random-access rate, not bytes; see random_access.  Reads whose candidate set is empty after the "
-                        "first -B k-mers only need the first-miss position, which the L2-resident row-present bitmap "
-                        "answers: those k-mers count in the algorithmic bytes (the reference gathers their rows) but not "
-                        "in gathers_per_launch",
+                "note": "8-byte rows: a gather moves 8 algorithmic bytes but costs one memory access, so bytes are the wrong "
+                        "yardstick for this shape (SURVEY 8d, R < 32) and the access RATE is reported next to them.  Read "
+                        "straight from the 400 MB matrix the rows come at the DRAM random-access rate (54.5 G/s, "
+                        "profiles/r1_gather_probe.txt; the one-kernel vote of round 1 ran at 82 % of it); bucketed by row "
+                        "window they come from L2 (275 G/s for a 64 MB window, profiles/r2_l2_window_probe.txt) and the "
+                        "stage is bound by the instructions of its scan kernel (XXH3 x num_hash per k-mer), not by memory.  "
+                        "Reads whose candidate set is empty after the first -B k-mers only need the first-miss position, "
+                        "which the L2-resident row-present bitmap answers: those k-mers count in the algorithmic bytes "
+                        "(the reference gathers their rows) but not in gathers_per_launch",
                 "random_access": {"gathers_per_launch": gathers,
                                   "achieved_g_per_s": gathers / (vote_ms / 1e3) / 1e9 if vote_ms else None,
                                   "ceiling_g_per_s": GATHER_CEILING_G_PER_S,
                                   "frac": gathers / (vote_ms / 1e3) / 1e9 / GATHER_CEILING_G_PER_S if vote_ms else None,
                                   "ceiling_source": "tools/gather_probe.cu on B200: 8-byte __ldg at uniformly random rows of a "
                                                     "400 MB matrix, 8 loads in flight per thread (profiles/r1_gather_probe.txt)"},
+                "window_gather": ({"tuples_per_step": gathers, "ms_per_step": gather_ms,
+                                   "g_tuples_per_s": gathers / (gather_ms / 1e3) / 1e9,
+                                   "l2_window_ceiling_g_per_s": 275.0,
+                                   "source": "readid_vp_gather launches only; ceiling: tools/l2_window_probe.cu (profiles/r2_l2_window_probe.txt)"}
+                                  if parted and gather_ms else None),
                 "vote_sector_granular_gbs": (H * 32 * nproc_last + read_bytes) / (vote_ms / 1e3) / 1e9 if vote_ms else None,
                 "kernels": kern,
                 "share_of_step": {k_: prof[k_][0] / sum(v[0] for v in prof.values()) for k_ in prof}}

@@ -1316,10 +1316,11 @@ int readid_run(cid_index* idx, cudaStream_t st, const uint8_t* d_bases, const ui
             const uint32_t* sel_all = parted ? vpd.cursor + VP_MAXP : nullptr;
             ProfScope ps(ctx, st, KID_READID_VOTE);
             const uint32_t* rownz = idx->rownz;
+            const unsigned gridN = gridV;      // (a smaller grid for the leftover reads of the partitioned vote measured no faster)
             if (idx->Wp <= 2) {
                 if (!idx->rownz_global) rownz = nullptr;   // presence == any word set, already in registers
 #define CID_VOTE_NARROW(WPV, STV)                                                                                      \
-    readid_vote_narrow_kernel<WPV, STV><<<gridV, RA_WARPS * 32, cn_smem, st>>>(                                        \
+    readid_vote_narrow_kernel<WPV, STV><<<gridN, RA_WARPS * 32, cn_smem, st>>>(                                        \
         rsrc, d_seq_offs, d_read_offs, r0, nr, kitem, idx->H, mods, idx->rows, rownz, idx->rownz, idx->N, cap,  \
         maxocc, ord16, ord8, d_ent16, d_n_set, p.start_sample, p.rep_cap, d_flags, d_rep_n, d_rep_colour, d_rep_count,  \
         (unsigned long long*)(ctx->d_err + 2), sel_list, sel_n, sel_all)

@@ -164,13 +164,14 @@ static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals,
         const uint64_t fit = std::max<uint64_t>(1024, (3ull << 29) / std::max<uint64_t>(per_read, 1));
         chunk_max = std::min(chunk_max, fit);
     }
+    const uint64_t growth_pct = ctx->opt_readid_chunk_growth ? (uint64_t)ctx->opt_readid_chunk_growth : 150;
     std::vector<uint64_t> cuts{0};
     for (uint64_t cur = std::min<uint64_t>(ctx->opt_readid_chunk0 ? ctx->opt_readid_chunk0 : 32768, chunk_max), at = 0; at < nreads;) {
         uint64_t size = std::min(cur, nreads - at);
         if (nreads - at - size < size / 4) size = nreads - at;      // absorb a short tail
         at += size;
         cuts.push_back(at);
-        cur = std::min(cur + cur / 2, chunk_max);
+        cur = std::min(cur * growth_pct / 100, chunk_max);
     }
     const uint64_t nchunks = cuts.size() - 1;
     const uint64_t chunk = chunk_max;
