@@ -26,6 +26,8 @@ struct cid_readid_pipe {
     enum { NS = 3 };
     struct Slot {
         cudaStream_t st = nullptr;
+        cudaStream_t cst = nullptr;          // the chunk's input copies run on their own stream (see the issue loop)
+        cudaEvent_t h2d_done = nullptr;
         cudaEvent_t done = nullptr;
         cid::DevBuf bases, quals, seq_offs, read_offs, entries, order, nocc, n_set, flags, rep_n, rep, ord_out, big, vp;
         cid::DevBuf kind, hits, n_top, top, list, cursor;      // fused vote: device classification + undecided list
@@ -51,6 +53,7 @@ void readid_pipe_destroy(cid_ctx* ctx) {
     cid_readid_pipe* pp = ctx->pipe;
     if (!pp) return;
     for (auto& s : pp->slot) {
+        if (s.cst) cudaStreamSynchronize(s.cst);
         if (s.st) cudaStreamSynchronize(s.st);
         for (DevBuf* b : {&s.bases, &s.quals, &s.seq_offs, &s.read_offs, &s.entries, &s.order, &s.nocc, &s.n_set, &s.flags,
                           &s.rep_n, &s.rep, &s.ord_out, &s.big, &s.vp, &s.kind, &s.hits, &s.n_top, &s.top, &s.list, &s.cursor})
@@ -60,6 +63,8 @@ void readid_pipe_destroy(cid_ctx* ctx) {
         if (s.kern_done) cudaEventDestroy(s.kern_done);
         if (s.done) cudaEventDestroy(s.done);
         if (s.st) cudaStreamDestroy(s.st);
+        if (s.cst) cudaStreamDestroy(s.cst);
+        if (s.h2d_done) cudaEventDestroy(s.h2d_done);
     }
     pp->fp.release();
     delete pp;
@@ -72,6 +77,8 @@ static int pipe_get(cid_ctx* ctx, cid_readid_pipe** out) {
     if (!pp->ready) {
         for (auto& s : pp->slot) {
             CID_CUDA(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+            CID_CUDA(cudaStreamCreateWithFlags(&s.cst, cudaStreamNonBlocking));
+            CID_CUDA(cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
             CID_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
             CID_CUDA(cudaEventCreateWithFlags(&s.offs_done, cudaEventDisableTiming));
             CID_CUDA(cudaEventCreateWithFlags(&s.kern_done, cudaEventDisableTiming));
@@ -157,16 +164,20 @@ static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals,
     // copies hide behind the kernels of the chunks before them.  The growth factor is 1.5 because the copy of
     // chunk c+1 must finish within the kernels of chunk c: PCIe delivers ~87 K read pairs/ms (600 B each at
     // 54 GB/s), the kernels consume ~56 K/ms, so a chunk may be at most 1.55x its predecessor.
-    uint64_t chunk_max = ctx->opt_readid_chunk ? ctx->opt_readid_chunk : 262144;
+    // Packed reads are 4x fewer bytes per read than ASCII bases + qualities: PCIe then delivers ~370 K read pairs/ms, six times
+    // what the kernels consume, so the ramp can be steep (65,536 -> x4 -> up to 2^20 reads: three chunks per million pairs
+    // instead of seven; the kernels are 8 % faster on a 672 K chunk than on seven chunks of 33 K .. 319 K: 46.9 -> 48.7 M pairs/s).
+    const bool steep = hp != nullptr;
+    uint64_t chunk_max = ctx->opt_readid_chunk ? ctx->opt_readid_chunk : (steep ? 1048576 : 262144);
     {   // the per-chunk report (and, fused, the undecided-read list) is dense in the accession count: keep one slot's share of it
         // below ~1.5 GB so that a wide index shrinks the chunks instead of exhausting device memory (3 slots are in flight)
         const uint64_t per_read = (uint64_t)pp.rep_cap * 8 + (out.vote ? (2 + 2 * (uint64_t)pp.rep_cap) * 4 : 0);
         const uint64_t fit = std::max<uint64_t>(1024, (3ull << 29) / std::max<uint64_t>(per_read, 1));
         chunk_max = std::min(chunk_max, fit);
     }
-    const uint64_t growth_pct = ctx->opt_readid_chunk_growth ? (uint64_t)ctx->opt_readid_chunk_growth : 150;
+    const uint64_t growth_pct = ctx->opt_readid_chunk_growth ? (uint64_t)ctx->opt_readid_chunk_growth : (steep ? 400 : 150);
     std::vector<uint64_t> cuts{0};
-    for (uint64_t cur = std::min<uint64_t>(ctx->opt_readid_chunk0 ? ctx->opt_readid_chunk0 : 32768, chunk_max), at = 0; at < nreads;) {
+    for (uint64_t cur = std::min<uint64_t>(ctx->opt_readid_chunk0 ? ctx->opt_readid_chunk0 : (steep ? 65536 : 32768), chunk_max), at = 0; at < nreads;) {
         uint64_t size = std::min(cur, nreads - at);
         if (nreads - at - size < size / 4) size = nreads - at;      // absorb a short tail
         at += size;
@@ -263,7 +274,7 @@ static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals,
             cv.notify_all();
             worker.join();
         }
-        for (auto& s : pipe->slot) cudaStreamSynchronize(s.st);
+        for (auto& s : pipe->slot) { cudaStreamSynchronize(s.cst); cudaStreamSynchronize(s.st); }
         if (rcode == CID_OK && worker_rc != CID_OK) { set_error("read_id: host vote worker failed"); return worker_rc; }
         return rcode;
     };
@@ -355,19 +366,26 @@ static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals,
         }
         // The caller's offset arrays are usually pageable (a pageable cudaMemcpyAsync first drains the
         // stream, i.e. waits for the big copies queued just before it): stage them in pinned memory.
+        // The input copies go to a stream of their own and the kernels wait for them through an event.  Enqueued on the stream
+        // that also carries the chunk's kernels, the copy of the reads ran 4-5x slower than alone (116 MB: 10.8 ms against
+        // 2.1 ms, the GPU otherwise idle: CID_TRACE timelines of round 2) -- whatever the driver does with a copy that has
+        // dependent launches queued behind it, a copy-only stream does not see it.
+        if (c >= (uint64_t)NS) PIPE_CUDA(cudaStreamWaitEvent(s.cst, s.kern_done, 0));      // the slot's buffers are free again
         {
             const size_t nso = s1 - s0 + 1, nro = nr + 1;
             uint64_t* ho = stage + prep[c].stage_off;              // staged by the preparation threads
-            PIPE_CUDA(cudaMemcpyAsync(s.seq_offs.p, ho, nso * 8, cudaMemcpyHostToDevice, s.st));
-            PIPE_CUDA(cudaMemcpyAsync(s.read_offs.p, ho + nso, nro * 8, cudaMemcpyHostToDevice, s.st));
+            PIPE_CUDA(cudaMemcpyAsync(s.seq_offs.p, ho, nso * 8, cudaMemcpyHostToDevice, s.cst));
+            PIPE_CUDA(cudaMemcpyAsync(s.read_offs.p, ho + nso, nro * 8, cudaMemcpyHostToDevice, s.cst));
             // (packed reads: the word offset of every read, absolute -- the device word pointer is biased to match)
-            if (hp) PIPE_CUDA(cudaMemcpyAsync(s.quals.p, ho + nso + nro, nro * 8, cudaMemcpyHostToDevice, s.st));
+            if (hp) PIPE_CUDA(cudaMemcpyAsync(s.quals.p, ho + nso + nro, nro * 8, cudaMemcpyHostToDevice, s.cst));
         }
-        tmark(s.st);
-        if (hp) { if (w1 > w0) PIPE_CUDA(cudaMemcpyAsync(s.bases.p, hp->words + w0, (w1 - w0) * 4, cudaMemcpyHostToDevice, s.st)); }
-        else if (b1 > b0) PIPE_CUDA(cudaMemcpyAsync(s.bases.p, bases + b0, b1 - b0, cudaMemcpyHostToDevice, s.st));
-        if (use_q && b1 > b0) PIPE_CUDA(cudaMemcpyAsync(s.quals.p, quals + b0, b1 - b0, cudaMemcpyHostToDevice, s.st));
-        tmark(s.st);
+        tmark(s.cst);
+        if (hp) { if (w1 > w0) PIPE_CUDA(cudaMemcpyAsync(s.bases.p, hp->words + w0, (w1 - w0) * 4, cudaMemcpyHostToDevice, s.cst)); }
+        else if (b1 > b0) PIPE_CUDA(cudaMemcpyAsync(s.bases.p, bases + b0, b1 - b0, cudaMemcpyHostToDevice, s.cst));
+        if (use_q && b1 > b0) PIPE_CUDA(cudaMemcpyAsync(s.quals.p, quals + b0, b1 - b0, cudaMemcpyHostToDevice, s.cst));
+        tmark(s.cst);
+        PIPE_CUDA(cudaEventRecord(s.h2d_done, s.cst));
+        PIPE_CUDA(cudaStreamWaitEvent(s.st, s.h2d_done, 0));
         // device arrays are indexed by absolute base / sequence / read numbers: bias the chunk buffers
         PackedReads pk{hp ? s.bases.as<uint32_t>() - w0 : nullptr, hp ? s.quals.as<uint64_t>() - r0 : nullptr, hp ? hp->lower : 0u};
         const PackedReads* packed_ptr = hp ? &pk : nullptr;
