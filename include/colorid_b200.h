@@ -69,7 +69,10 @@ int cid_ctx_read_counter(cid_ctx* ctx, const char* name, uint64_t* value);
  *   host_threads           host threads of the read_id vote (0 = all cores; main.rs:718 rayon pool size `-t`)
  *   readid_report_steps    1: read_id report colours carry their insertion step in bits 20..31 (column-sharded read_id:
  *                          see cid_merge_shard_reports); such reports must be merged before they are classified
- *   tuning:  readid_chunk_reads / readid_chunk0_reads (reads per pipeline chunk of the host-pointer read_id calls, 0 = automatic),
+ *   tuning:  readid_chunk_reads / readid_chunk0_reads / readid_chunk_growth_pct (largest and first pipeline chunk of the
+ *            host-pointer read_id calls and the size of a chunk relative to its predecessor in percent; 0 = automatic:
+ *            32,768 -> x1.5 -> 262,144 reads for ASCII input, 65,536 -> x4 -> 2^20 for packed reads), readid_part_ctas (CTAs
+ *            per SM of the partitioned vote's scan kernel),
  *            readid_streams (2 = chunks of cid_read_id_batch_dev over two internal streams), readid_kmerize_ctas /
  *            readid_vote_ctas (CTAs per SM, 0 = fill the GPU), readid_serialize, build_table_div / query_table_div (first count
  *            table of a read set = k-mer positions / this; 0 = adaptive / always the safe size), query_table_min_slots,
