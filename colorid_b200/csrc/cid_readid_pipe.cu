@@ -285,7 +285,10 @@ static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals,
     // staging (pageable cudaMemcpyAsync would drain the stream) -- is ~10 ns per read on one thread: serial, it delays the copy
     // of a large chunk by milliseconds while the GPU idles.  A few helper threads take the chunks in order; the issue loop
     // below only waits for "chunk c is prepared".
-    struct Prep { Geometry geo; size_t stage_off = 0; std::atomic<int> ready{0}; };
+    // (A chunk is cut into PREP_PARTS pieces, so that the first chunk -- nothing runs before it is prepared -- and the large
+    // chunks of the steep ramp are scanned by all helpers at once: 0.45 -> 0.12 ms for 65,536 reads.)
+    enum { PREP_PARTS = 4 };
+    struct Prep { Geometry geo[PREP_PARTS]; size_t stage_off = 0; std::atomic<int> ready{0}; };
     std::vector<Prep> prep(nchunks);
     size_t stage_words = 0;
     for (uint64_t c = 0; c < nchunks; c++) {
@@ -298,19 +301,23 @@ static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals,
     std::atomic<uint64_t> prep_next{0};
     auto prep_work = [&]() {
         for (;;) {
-            const uint64_t c = prep_next.fetch_add(1);
+            const uint64_t task = prep_next.fetch_add(1), c = task / PREP_PARTS, part = task % PREP_PARTS;
             if (c >= nchunks) return;
             const uint64_t r0 = cuts[c], r1 = cuts[c + 1], nr = r1 - r0, s0 = read_offs[r0], s1 = read_offs[r1];
-            prep[c].geo = read_geometry(seq_offs, read_offs + r0, nr, ix->k, pp.downsample);
+            // reads [pa, pb) of the chunk: their geometry, and their share of the offset arrays (the +1 end entries go with the last part)
+            const uint64_t pa = nr * part / PREP_PARTS, pb = nr * (part + 1) / PREP_PARTS;
+            const bool last = part == PREP_PARTS - 1;
+            prep[c].geo[part] = read_geometry(seq_offs, read_offs + r0 + pa, pb - pa, ix->k, pp.downsample);
             uint64_t* ho = stage + prep[c].stage_off;
             const size_t nso = s1 - s0 + 1, nro = nr + 1;
-            memcpy(ho, seq_offs + s0, nso * 8);
-            memcpy(ho + nso, read_offs + r0, nro * 8);
-            if (hp) memcpy(ho + nso + nro, hp->word_offs + r0, nro * 8);
-            prep[c].ready.store(1, std::memory_order_release);
+            const uint64_t sa = read_offs[r0 + pa], sb = read_offs[r0 + pb];
+            memcpy(ho + (sa - s0), seq_offs + sa, (sb - sa + (last ? 1 : 0)) * 8);
+            memcpy(ho + nso + pa, read_offs + r0 + pa, (pb - pa + (last ? 1 : 0)) * 8);
+            if (hp) memcpy(ho + nso + nro + pa, hp->word_offs + r0 + pa, (pb - pa + (last ? 1 : 0)) * 8);
+            prep[c].ready.fetch_add(1, std::memory_order_release);
         }
     };
-    const unsigned n_prep = (unsigned)std::min<uint64_t>(nchunks, std::min(4u, std::max(1u, std::thread::hardware_concurrency())));
+    const unsigned n_prep = (unsigned)std::min<uint64_t>(nchunks * PREP_PARTS, std::min(4u, std::max(1u, std::thread::hardware_concurrency())));
     std::vector<std::thread> prep_threads;
     for (unsigned i = 0; i < n_prep; i++) prep_threads.emplace_back(prep_work);
     struct PrepJoin { std::vector<std::thread>& t; ~PrepJoin() { for (auto& x : t) if (x.joinable()) x.join(); } } prep_join{prep_threads};
@@ -339,8 +346,13 @@ static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals,
         Geometry geo;
         {
             const double t0 = now_ms();
-            while (!prep[c].ready.load(std::memory_order_acquire)) std::this_thread::yield();
-            geo = prep[c].geo;
+            while (prep[c].ready.load(std::memory_order_acquire) < PREP_PARTS) std::this_thread::yield();
+            geo = prep[c].geo[0];
+            for (int q = 1; q < PREP_PARTS; q++) {
+                const Geometry& g2 = prep[c].geo[q];
+                geo.max_bases = std::max(geo.max_bases, g2.max_bases); geo.max_kmers = std::max(geo.max_kmers, g2.max_kmers);
+                geo.fast_bases = std::max(geo.fast_bases, g2.fast_bases); geo.fast_kmers = std::max(geo.fast_kmers, g2.fast_kmers);
+            }
             t_geom += now_ms() - t0;
         }
         const uint32_t max_bases = geo.fast_bases, max_kmers = geo.fast_kmers;

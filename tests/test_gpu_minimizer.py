@@ -102,6 +102,16 @@ def test_read_id_over_minimizer_sets(oracle, ctx, N, k, m, S, H):
     for kw in (dict(), dict(start_sample=0), dict(d=3), dict(group_width=8)):
         o, g = _readid_compare(oracle, oix, gix, reads, **kw)
         assert (o["kind"] != oracle.CLS_PANIC).all()
+    if N <= 64:
+        # the vote partitioned by row window (cid_readid_part.cu) on minimizer sets: items of m bases (XXH3's 9..16-byte path)
+        ctx.set_option("readid_vote_part", 2)
+        ctx.set_option("readid_part_shift", 13)
+        try:
+            for kw in (dict(), dict(d=3)):
+                _readid_compare(oracle, oix, gix, reads, **kw)
+        finally:
+            ctx.set_option("readid_vote_part", 1)
+            ctx.set_option("readid_part_shift", 0)
     # the set really holds minimizers: far fewer items than k-mers
     assert 0 < int(o["n_set"].max()) < 2 * (150 - k + 1) // 2
 
