@@ -970,3 +970,29 @@ def test_read_id_partitioned_vote_classify_and_packed(oracle, ctx):
         for r in range(len(reads)):
             nt = min(int(o["n_top"][r]), 8)
             assert res["top"][r, :nt].tolist() == o["top"][r, :nt].tolist()
+
+
+def test_read_id_partitioned_vote_long_sets(oracle, ctx):
+    """The partitioned vote on reads of 2 x 250 and 2 x 480 bases: more than 255 distinct k-mers per read, i.e. the general
+    order kernel (16-bit entries, no compact arrays) feeds the scan kernel; plus a few reads beyond the fast path (general
+    CTA-per-read path in the same batch)."""
+    rng = _rng(9300)
+    N, k, S, H = 40, 31, 1_500_007, 4
+    genomes = synth.clade_genomes(rng, N, 9000, n_clades=5, div=0.005)
+    oix, gix = build_both(oracle, ctx, [[g] for g in genomes], S, H, k, cb.CID_SEQ_FASTA)
+    reads = synth.reads_from(rng, genomes, 200, read_len=250, insert=520, err=0.003, frac_random=0.2, n_rate=0.002)
+    reads += synth.reads_from(rng, genomes, 60, read_len=480, insert=1000, err=0.002, frac_random=0.1)
+    reads += synth.reads_from(rng, genomes, 4, read_len=1500, insert=3200, err=0.001, frac_random=0.0, paired=False)
+    res = {}
+    for part in (0, 2):
+        ctx.set_option("readid_vote_part", part)
+        ctx.set_option("readid_part_shift", 15)
+        try:
+            if part == 2:
+                _readid_compare(oracle, oix, gix, reads, order_cap=3200)
+            res[part] = gix.read_id_batch(reads)
+        finally:
+            ctx.set_option("readid_vote_part", 1)
+            ctx.set_option("readid_part_shift", 0)
+    _reports_equal(res[0], res[2])
+    assert int(res[2]["n_set"].max()) > 255
