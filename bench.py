@@ -1116,6 +1116,7 @@ def run_ours(args):
     K, Wm = args.steps, args.warmup
 
     ctx = cb.Context(local)
+    ctx.set_option("host_ranks", world)          # the ranks of one node share its host memory system (read_id chunk schedule)
     for kv in args.opt:
         name, _, val = kv.partition("=")
         ctx.set_option(name, int(val))

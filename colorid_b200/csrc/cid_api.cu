@@ -290,6 +290,7 @@ int cid_ctx_read_counter(cid_ctx* c, const char* name, uint64_t* value) {
 int cid_ctx_set_option(cid_ctx* c, const char* name, int64_t value) {
     if (!c || !name) { set_error("cid_ctx_set_option: null argument"); return CID_E_INVALID; }
     if (!strcmp(name, "readid_chunk0_reads")) { c->opt_readid_chunk0 = value > 0 ? (uint64_t)value : 0; return CID_OK; }
+    if (!strcmp(name, "host_ranks")) { c->opt_host_ranks = value > 1 ? (int)value : 1; return CID_OK; }
     if (!strcmp(name, "readid_chunk_growth_pct")) { c->opt_readid_chunk_growth = value > 100 ? (int)value : 0; return CID_OK; }
     if (!strcmp(name, "readid_chunk_reads")) { c->opt_readid_chunk = value > 0 ? (uint64_t)value : 0; return CID_OK; }
     if (!strcmp(name, "readid_streams")) { c->opt_readid_streams = value >= 2 ? 2 : 1; return CID_OK; }

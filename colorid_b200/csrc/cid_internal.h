@@ -77,6 +77,7 @@ struct cid_ctx {
     // read_id host pipeline (cid_readid_pipe.cu): chunked H2D / kernels / D2H / host vote overlap
     struct cid_readid_pipe* pipe = nullptr;
     uint64_t opt_readid_chunk = 0;   // reads per pipeline chunk (0 = automatic)
+    int opt_host_ranks = 1;          // ranks (processes or cid_mg shards) that share this host's memory system with this context
     int opt_readid_chunk_growth = 0; // size of a pipeline chunk relative to its predecessor, in percent (0 = automatic)
     uint64_t opt_readid_chunk0 = 0;  // reads in the first chunk of the ramp (0 = 32768)
     int opt_host_threads = 0;        // host threads for the vote (0 = all cores)

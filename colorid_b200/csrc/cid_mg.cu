@@ -142,6 +142,7 @@ int cid_mg_create(const int* devices, int ndev, int shard_mode, cid_mg** out) {
     mg->slice.assign(ndev, nullptr);
     const int rc = parallel(mg->n, [&](uint32_t g) { return cid_ctx_create(mg->dev[g], &mg->ctx[g]); });
     if (rc != CID_OK) { cid_mg_destroy(mg); return rc; }
+    for (int g = 0; g < ndev; g++) mg->ctx[g]->opt_host_ranks = ndev;      // the shards' pipelines share this host's memory system
     // peer access between distinct devices: the column copies of a replicated build and the fused count exchange
     for (int a = 0; a < ndev; a++)
         for (int b = 0; b < ndev; b++) {

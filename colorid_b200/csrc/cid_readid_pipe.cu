@@ -164,10 +164,13 @@ static int read_id_pipeline(cid_index* ix, const char* bases, const char* quals,
     // copies hide behind the kernels of the chunks before them.  The growth factor is 1.5 because the copy of
     // chunk c+1 must finish within the kernels of chunk c: PCIe delivers ~87 K read pairs/ms (600 B each at
     // 54 GB/s), the kernels consume ~56 K/ms, so a chunk may be at most 1.55x its predecessor.
-    // Packed reads are 4x fewer bytes per read than ASCII bases + qualities: PCIe then delivers ~370 K read pairs/ms, six times
-    // what the kernels consume, so the ramp can be steep (65,536 -> x4 -> up to 2^20 reads: three chunks per million pairs
-    // instead of seven; the kernels are 8 % faster on a 672 K chunk than on seven chunks of 33 K .. 319 K: 46.9 -> 48.7 M pairs/s).
-    const bool steep = hp != nullptr;
+    // Packed reads are 4x fewer bytes per read than ASCII bases + qualities: one rank alone gets 55 GB/s over PCIe, ~370 K read
+    // pairs/ms, six times what the kernels consume, so the ramp can be steep (65,536 -> x4 -> up to 2^20 reads: three chunks
+    // per million pairs instead of seven; the kernels are 8 % faster on a 672 K chunk than on seven chunks of 33 K .. 319 K:
+    // 46.9 -> 49.4 M pairs/s).  Eight ranks of one node share the host's memory system and get ~16 GB/s each: the steep ramp
+    // then starves the GPUs (328 M pairs/s on 8 GPUs against 345 M with x1.5), so it is only taken when the caller has not
+    // said that more than two ranks share the host (option host_ranks; cid_mg sets it to its number of GPUs).
+    const bool steep = hp != nullptr && ctx->opt_host_ranks <= 2;
     uint64_t chunk_max = ctx->opt_readid_chunk ? ctx->opt_readid_chunk : (steep ? 1048576 : 262144);
     {   // the per-chunk report (and, fused, the undecided-read list) is dense in the accession count: keep one slot's share of it
         // below ~1.5 GB so that a wide index shrinks the chunks instead of exhausting device memory (3 slots are in flight)

@@ -67,6 +67,8 @@ uint64_t cid_ctx_launch_count(const cid_ctx* ctx);
 int cid_ctx_read_counter(cid_ctx* ctx, const char* name, uint64_t* value);
 /* Options by name.  None of them changes a result; unknown names return CID_E_INVALID.
  *   host_threads           host threads of the read_id vote (0 = all cores; main.rs:718 rayon pool size `-t`)
+ *   host_ranks             how many ranks (processes, or shards of a cid_mg) share this host with the context (default 1): the
+ *                          read_id pipeline sizes its chunks for the host -> device rate a rank can expect
  *   readid_report_steps    1: read_id report colours carry their insertion step in bits 20..31 (column-sharded read_id:
  *                          see cid_merge_shard_reports); such reports must be merged before they are classified
  *   tuning:  readid_chunk_reads / readid_chunk0_reads / readid_chunk_growth_pct (largest and first pipeline chunk of the
