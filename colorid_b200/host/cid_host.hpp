@@ -42,13 +42,30 @@ struct SeqBatch {
 
 // Lines of a plain or gzip file (concatenated members like flate2::MultiGzDecoder); the line
 // terminator ("\n" or "\r\n") is stripped like BufRead::lines() unless keep_eol.
+// A gzip file mapped into memory and decoded by the host layer's own inflater (fast_inflate.hpp).
+class MappedGz {
+public:
+    explicit MappedGz(const std::string& path);      // throws if the file cannot be mapped or is not gzip
+    ~MappedGz();
+    size_t read(char* dst, size_t cap);
+    static bool eligible(const std::string& path);    // regular file that starts with the gzip magic
+private:
+    class GzInflater* inf_ = nullptr;
+    void* map_ = nullptr;
+    size_t len_ = 0;
+};
+
 class LineReader {
 public:
     explicit LineReader(const std::string& path);
     ~LineReader();
     bool next(std::string& line, bool keep_eol = false);
+    // Up to max_lines lines at once: their raw bytes (EOLs included) are appended to `data`, line i of the call is
+    // data[begin[i], end[i]) (EOL -- "\n" or "\r\n" -- excluded unless keep_eol).  Returns the number of lines added.
+    size_t next_lines(std::string& data, std::vector<uint32_t>& begin, std::vector<uint32_t>& end, size_t max_lines, bool keep_eol = false);
 private:
-    void* gz_;
+    void* gz_ = nullptr;                 // zlib gzFile: plain files, pipes, COLORID_B200_ZLIB=1
+    MappedGz* fast_ = nullptr;           // regular gzip files: the host layer's own decoder over the mapped file
     std::vector<char> buf_;
     size_t pos_ = 0, len_ = 0;
     bool eof_ = false;

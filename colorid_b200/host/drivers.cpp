@@ -425,7 +425,8 @@ struct PinnedBytes {               // growable page-locked byte buffer (cid_host
     void fill(char c, size_t n) { reserve(size + n); memset(p + size, c, n); size += n; }
 };
 struct ReadBatch {
-    std::vector<std::string> ids;
+    std::string id_data;                       // read ids back to back (no string per read on the parsing thread)
+    std::vector<uint32_t> id_off{0};
     PinnedBytes bases, quals;
     std::vector<uint64_t> seq_offs{0}, read_offs{0};
     bool any_qual = false;
@@ -441,9 +442,10 @@ struct ReadBatch {
         }
         seq_offs.push_back(bases.size);
     }
-    void end_read(const std::string& id) { ids.push_back(id); read_offs.push_back(seq_offs.size() - 1); }
-    uint64_t n() const { return ids.size(); }
-    void clear() { ids.clear(); bases.size = 0; quals.size = 0; seq_offs.assign(1, 0); read_offs.assign(1, 0); any_qual = false; }
+    void end_read(const std::string& id) { id_data += id; id_off.push_back((uint32_t)id_data.size()); read_offs.push_back(seq_offs.size() - 1); }
+    uint64_t n() const { return id_off.size() - 1; }
+    std::string id(uint64_t r) const { return id_data.substr(id_off[r], id_off[r + 1] - id_off[r]); }
+    void clear() { id_data.clear(); id_off.assign(1, 0); bases.size = 0; quals.size = 0; seq_offs.assign(1, 0); read_offs.assign(1, 0); any_qual = false; }
 };
 
 struct ReadIdRun {
@@ -525,9 +527,9 @@ struct ReadIdRun {
                     break;
                 }
                 default:
-                    throw Error("read " + rb.ids[r] + ": a later mate is shorter than k-1 (the reference panics in kmerize_vector_skip_n_set)");
+                    throw Error("read " + rb.id(r) + ": a later mate is shorter than k-1 (the reference panics in kmerize_vector_skip_n_set)");
             }
-            outbuf += rb.ids[r]; outbuf += '\t'; outbuf += *cls; outbuf += '\t'; put_u(h); outbuf += '\t'; put_u(ns);
+            outbuf.append(rb.id_data, rb.id_off[r], rb.id_off[r + 1] - rb.id_off[r]); outbuf += '\t'; outbuf += *cls; outbuf += '\t'; put_u(h); outbuf += '\t'; put_u(ns);
             outbuf += accept ? "\taccept\t" : "\treject\t"; put_u(nt); outbuf += '\n';
             if (outbuf.size() > (8u << 20)) { fwrite(outbuf.data(), 1, outbuf.size(), out); outbuf.clear(); }
             tally(*cls, accept);
@@ -579,8 +581,8 @@ void read_id_sample(Gpu& g, const Bigsi& b, const ReadIdOpts& o, Trace& tr, Read
             uint64_t line_count = 1;
             while (a.next(l1)) {
                 const bool have2 = c.next(l2);
-                if (line_count % 4 == 1) id = l1;
-                else if (line_count % 4 == 2) { if (!have2) break; s1 = l1; s2 = l2; }
+                if (line_count % 4 == 1) id.swap(l1);
+                else if (line_count % 4 == 2) { if (!have2) break; s1.swap(l1); s2.swap(l2); }
                 else if (line_count % 4 == 0) {
                     if (!have2) break;
                     rb.add_mate(s1, &l1, o.quality);
@@ -597,8 +599,8 @@ void read_id_sample(Gpu& g, const Bigsi& b, const ReadIdOpts& o, Trace& tr, Read
             std::string l, id, s1;
             uint64_t line_count = 1;
             while (a.next(l)) {
-                if (line_count % 4 == 1) id = l;
-                else if (line_count % 4 == 2) s1 = l;
+                if (line_count % 4 == 1) id.swap(l);
+                else if (line_count % 4 == 2) s1.swap(l);
                 else if (line_count % 4 == 0) { rb.add_mate(s1, &l, o.quality); rb.end_read(id); maybe_flush(); }
                 line_count++;
             }

@@ -1,5 +1,9 @@
 // Sequence file readers of the host layer: FASTA (kmer.rs:10-84), FASTQ(.gz) record iteration
 // (kmer.rs:461-475,581-612), seq.rs:36-56 qual_mask and build.rs:15-31 tab_to_map.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <condition_variable>
@@ -12,22 +16,63 @@
 #include <thread>
 
 #include "cid_host.hpp"
+#include "fast_inflate.hpp"
 
 namespace cidh {
 
 // ------------------------------------------------------------------ LineReader
+bool MappedGz::eligible(const std::string& path) {
+    const int fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) return false;
+    struct stat st;
+    unsigned char magic[2] = {0, 0};
+    const bool ok = fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size >= 18 && pread(fd, magic, 2, 0) == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+    close(fd);
+    return ok;
+}
+MappedGz::MappedGz(const std::string& path) {
+    const int fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) throw Error("file not found: " + path);
+    struct stat st;
+    if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode) || st.st_size == 0) { close(fd); throw Error("cannot map " + path); }
+    void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) throw Error("cannot map " + path);
+    madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+    map_ = m; len_ = (size_t)st.st_size;
+    inf_ = new GzInflater((const uint8_t*)m, len_, path);
+}
+MappedGz::~MappedGz() {
+    delete inf_;
+    if (map_) munmap(map_, len_);
+}
+size_t MappedGz::read(char* dst, size_t cap) { return inf_->read((uint8_t*)dst, cap); }
+
 LineReader::LineReader(const std::string& path) : buf_(1 << 20) {
-    gzFile f = gzopen(path.c_str(), "rb");            // transparent for plain files, walks concatenated members
+    // A regular file that starts with the gzip magic is mapped and decoded by the host layer's own inflater (every member's
+    // CRC checked); anything else -- plain text, pipes, or COLORID_B200_ZLIB=1 -- goes through zlib's gzread (transparent
+    // for plain files, walks concatenated members).
+    const char* force = getenv("COLORID_B200_ZLIB");
+    if (!(force && *force && *force != '0') && MappedGz::eligible(path)) { fast_ = new MappedGz(path); return; }
+    gzFile f = gzopen(path.c_str(), "rb");
     if (!f) throw Error("file not found: " + path);
     gzbuffer(f, 1 << 20);
     gz_ = f;
 }
-LineReader::~LineReader() { if (gz_) gzclose((gzFile)gz_); }
+LineReader::~LineReader() {
+    if (gz_) gzclose((gzFile)gz_);
+    delete fast_;
+}
 bool LineReader::fill() {
     if (eof_) return false;
-    int n = gzread((gzFile)gz_, buf_.data(), (unsigned)buf_.size());
-    if (n < 0) throw Error("gz read error");
-    pos_ = 0; len_ = (size_t)n;
+    size_t n;
+    if (fast_) n = fast_->read(buf_.data(), buf_.size());
+    else {
+        const int r = gzread((gzFile)gz_, buf_.data(), (unsigned)buf_.size());
+        if (r < 0) throw Error("gz read error");
+        n = (size_t)r;
+    }
+    pos_ = 0; len_ = n;
     if (n == 0) eof_ = true;
     return n > 0;
 }
@@ -51,9 +96,43 @@ bool LineReader::next(std::string& line, bool keep_eol) {
     return any || !line.empty();
 }
 
+size_t LineReader::next_lines(std::string& data, std::vector<uint32_t>& begin, std::vector<uint32_t>& end, size_t max_lines, bool keep_eol) {
+    size_t added = 0;
+    size_t line_start = data.size();            // where the line being assembled began (it may span refills of the buffer)
+    while (added < max_lines) {
+        if (pos_ == len_ && !fill()) {
+            if (data.size() > line_start) { begin.push_back((uint32_t)line_start); end.push_back((uint32_t)data.size()); added++; }   // last line without EOL
+            break;
+        }
+        const char* const b = buf_.data() + pos_;
+        const char* const e = buf_.data() + len_;
+        const size_t d0 = data.size();
+        const char* s = b;
+        while (added < max_lines) {
+            const char* nl = (const char*)memchr(s, '\n', (size_t)(e - s));
+            if (!nl) break;
+            const size_t lend = d0 + (size_t)(nl - b);       // where this '\n' lands in `data`
+            size_t le = keep_eol ? lend + 1 : lend;
+            if (!keep_eol && lend > line_start) {
+                const char prev = nl > b ? nl[-1] : data[d0 - 1];
+                if (prev == '\r') le--;                      // BufRead::lines strips CRLF
+            }
+            begin.push_back((uint32_t)line_start);
+            end.push_back((uint32_t)le);
+            line_start = lend + 1;
+            added++;
+            s = nl + 1;
+        }
+        if (added == max_lines) { data.append(b, (size_t)(s - b)); pos_ += (size_t)(s - b); break; }
+        data.append(b, (size_t)(e - b));                      // whole lines and the start of the next one
+        pos_ = len_;
+    }
+    return added;
+}
+
 // ------------------------------------------------------------------ AsyncLineReader
 struct AsyncLineReader::Impl {
-    struct Block { std::string data; std::vector<uint32_t> end; };       // line i = data[end[i-1] .. end[i])
+    struct Block { std::string data; std::vector<uint32_t> begin, end; };       // line i = data[begin[i] .. end[i])
     enum { BLOCK_LINES = 1 << 16, DEPTH = 8 };
     std::mutex mu;
     std::condition_variable cv;
@@ -66,12 +145,12 @@ struct AsyncLineReader::Impl {
     void produce(std::string path, bool keep_eol) {
         try {
             LineReader lr(path);
-            std::string l;
             for (;;) {
                 std::unique_ptr<Block> b(new Block());
-                b->data.reserve(8 << 20);
+                b->data.reserve(10 << 20);
+                b->begin.reserve(BLOCK_LINES);
                 b->end.reserve(BLOCK_LINES);
-                while (b->end.size() < BLOCK_LINES && lr.next(l, keep_eol)) { b->data += l; b->end.push_back((uint32_t)b->data.size()); }
+                lr.next_lines(b->data, b->begin, b->end, BLOCK_LINES, keep_eol);     // whole lines, split with memchr: no per-line strings here
                 const bool last = b->end.size() < BLOCK_LINES;
                 {
                     std::unique_lock<std::mutex> lk(mu);
@@ -116,7 +195,7 @@ bool AsyncLineReader::next(std::string& line) {
         lk.unlock();
         s.cv.notify_all();
     }
-    const uint32_t lo = s.at ? s.cur->end[s.at - 1] : 0u, hi = s.cur->end[s.at];
+    const uint32_t lo = s.cur->begin[s.at], hi = s.cur->end[s.at];
     line.assign(s.cur->data, lo, hi - lo);
     s.at++;
     return true;

@@ -7,6 +7,8 @@
 #include <map>
 #include <set>
 
+#include <zlib.h>
+
 #include "cid_host.hpp"
 
 namespace {
@@ -134,6 +136,25 @@ int main(int argc, char** argv) {
                 const uint64_t n = argc == 6 ? cidh::fastq_masked_pe(argv[4], argv[5], q, sb) : cidh::fastq_masked_se(argv[4], q, sb);
                 printf("records\t%llu\n", (unsigned long long)n);
                 for (uint64_t i = 0; i < sb.n(); i++) printf("%.*s\n", (int)(sb.offs[i + 1] - sb.offs[i]), sb.bases.data() + sb.offs[i]);
+            } else if (op == "lines" && argc == 4) {            // raw lines of a (gz) file, EOLs kept: the decoder's parity hook
+                cidh::LineReader lr(argv[3]);
+                std::string l;
+                unsigned long long n = 0, bytes = 0;
+                unsigned long crc = crc32(0L, Z_NULL, 0);
+                while (lr.next(l, true)) { n++; bytes += l.size(); crc = crc32(crc, (const Bytef*)l.data(), (uInt)l.size()); }
+                printf("lines\t%llu\nbytes\t%llu\ncrc32\t%08lx\n", n, bytes, crc);
+            } else if (op == "gunzip" && argc == 4) {           // decode only (timing aid): bytes out
+                unsigned long long bytes = 0;
+                std::vector<char> buf(1 << 20);
+                if (getenv("COLORID_B200_ZLIB")) {
+                    gzFile f = gzopen(argv[3], "rb"); gzbuffer(f, 1 << 20);
+                    for (int n; (n = gzread(f, buf.data(), (unsigned)buf.size())) > 0;) bytes += (unsigned long long)n;
+                    gzclose(f);
+                } else {
+                    cidh::MappedGz mg(argv[3]);
+                    for (size_t n; (n = mg.read(buf.data(), buf.size())) > 0;) bytes += n;
+                }
+                printf("bytes\t%llu\n", bytes);
             } else if (op == "tab" && argc == 4) {
                 for (auto& kv : cidh::tab_to_map(argv[3])) { printf("%s", kv.first.c_str()); for (auto& f : kv.second) printf("\t%s", f.c_str()); printf("\n"); }
             } else if (op == "bxi_copy" && argc == 5) {

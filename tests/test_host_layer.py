@@ -209,3 +209,74 @@ def test_cli_flag_errors():
     assert r.returncode == 101 and "required arguments" in r.stderr
     r = cli("search", "-b", "x.bxi", "-q", "q.fa", "--bogus")
     assert r.returncode == 101 and "wasn't expected" in r.stderr
+
+
+# ----------------------------------------------------------------------------- the host layer's own gzip decoder
+def _lines_report(path, zlib_only=False):
+    env = dict(os.environ)
+    if zlib_only:
+        env["COLORID_B200_ZLIB"] = "1"
+    r = subprocess.run([CLI, "_host", "lines", str(path)], capture_output=True, text=True, env=env)
+    if r.returncode != 0:
+        return r.returncode, r.stderr
+    d = dict(l.split("\t") for l in r.stdout.split("\n") if l.count("\t") == 1 and l.split("\t")[0] in ("lines", "bytes", "crc32"))
+    return 0, (int(d["lines"]), int(d["bytes"]), int(d["crc32"], 16))
+
+
+def _fastq_blob(rng, n, rl=150):
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    seq = lut[rng.integers(0, 4, (n, rl))]
+    q = np.full((n, rl), 73, np.uint8)
+    q[rng.random((n, rl)) < 0.05] = 50
+    ids = np.frombuffer(b"".join(b"@read%07d/1\n" % i for i in range(n)), dtype=np.uint8).reshape(n, -1)
+    nl = np.full((n, 1), 10, np.uint8)
+    plus = np.tile(np.frombuffer(b"+\n", dtype=np.uint8), (n, 1))
+    return np.concatenate([ids, seq, nl, plus, q, nl], axis=1).tobytes()
+
+
+def test_gzip_decoder_equals_zlib(tmp_path):
+    """fast_inflate.cpp (the mapped-file gzip decoder behind LineReader) against zlib on every block type and framing:
+    dynamic / fixed / stored blocks, Huffman-only streams, long runs (distance 1), periods 2..7, tiny blocks, several members
+    (an empty one among them), trailing garbage; and through COLORID_B200_ZLIB=1 the gzread path gives the same lines."""
+    import zlib
+    rng = np.random.default_rng(0xC0101D05)
+    fq = _fastq_blob(rng, 6000)
+    rb = rng.integers(0, 256, 200_000, dtype=np.uint8).tobytes()
+
+    def z(data, level=6, strategy=zlib.Z_DEFAULT_STRATEGY, memlevel=8):
+        co = zlib.compressobj(level, zlib.DEFLATED, 31, memlevel, strategy)
+        return co.compress(data) + co.flush()
+
+    periodic = b"".join((bytes([65 + i]) * 1 + b"CG"[:p - 1]) * 400 + b"\n" for i, p in enumerate([2, 3, 4, 5, 6, 7, 2, 3]))
+    cases = {
+        "l1": (z(fq, 1), fq), "l6": (z(fq, 6), fq), "l9": (z(fq[:400_000], 9), fq[:400_000]),
+        "stored": (z(rb, 0), rb), "incompressible": (z(rb, 6), rb),
+        "fixed": (z(fq[:300_000], 6, zlib.Z_FIXED), fq[:300_000]), "huffman_only": (z(fq[:300_000], 6, zlib.Z_HUFFMAN_ONLY), fq[:300_000]),
+        "runs": (z(b"I" * 3_000_000 + b"\n" + b"\0" * 70_000, 9), b"I" * 3_000_000 + b"\n" + b"\0" * 70_000),
+        "periods": (z(periodic, 9), periodic), "tiny_blocks": (z(fq, 1, memlevel=1), fq),
+        "members": (z(fq[:50_000], 6) + z(b"", 6) + z(fq[50_000:90_000], 1) + z(b"no newline at the end", 9), fq[:90_000] + b"no newline at the end"),
+        "garbage_after": (z(b"hello\nworld\n", 6) + b"\0\0\0\0 not gzip", b"hello\nworld\n"),
+        "big": (z(fq * 9, 1), fq * 9),            # several 4 MB output chunks: history carried across them
+    }
+    for name, (gz, data) in cases.items():
+        p = tmp_path / f"{name}.gz"
+        p.write_bytes(gz)
+        want = (data.count(b"\n") + (1 if data and not data.endswith(b"\n") else 0), len(data), zlib.crc32(data) & 0xFFFFFFFF)
+        assert _lines_report(p) == (0, want), name
+        assert _lines_report(p, zlib_only=True) == (0, want), name
+
+
+def test_gzip_decoder_fails_loudly_on_damage(tmp_path):
+    """A flipped byte in the middle, a truncated file and a wrong CRC in the trailer all end in an error, never in wrong data."""
+    import zlib
+    rng = np.random.default_rng(0xC0101D06)
+    co = zlib.compressobj(6, zlib.DEFLATED, 31)
+    gz = co.compress(_fastq_blob(rng, 3000)) + co.flush()
+    damaged = {"flip": bytearray(gz), "trunc": bytearray(gz[:len(gz) // 2]), "crc": bytearray(gz)}
+    damaged["flip"][len(gz) // 2] ^= 0x55
+    damaged["crc"][-6] ^= 1
+    for name, blob in damaged.items():
+        p = tmp_path / f"{name}.gz"
+        p.write_bytes(bytes(blob))
+        rc, msg = _lines_report(p)
+        assert rc != 0 and "gzip stream" in msg, (name, rc, msg)
