@@ -23,6 +23,7 @@
 #include <map>
 #include <stdexcept>
 #include <string>
+#include <string_view>
 #include <vector>
 
 namespace cidh {
@@ -81,6 +82,9 @@ public:
     explicit AsyncLineReader(const std::string& path, bool keep_eol = false);
     ~AsyncLineReader();
     bool next(std::string& line);
+    // The next line as a view into the reader's current block: valid until the call that crosses into the next block, i.e. --
+    // blocks hold a multiple of four lines -- for the four lines of a FASTQ record at least.
+    bool next_view(std::string_view& line);
 private:
     struct Impl;
     Impl* p_;

@@ -430,19 +430,19 @@ struct ReadBatch {
     PinnedBytes bases, quals;
     std::vector<uint64_t> seq_offs{0}, read_offs{0};
     bool any_qual = false;
-    void add_mate(const std::string& seq, const std::string* qual, uint8_t off) {
+    void add_mate(std::string_view seq, const std::string_view* qual, uint8_t off) {
         if (!bases.cap) { bases.reserve(kGpuBatchBytes + (8u << 20)); quals.reserve(kGpuBatchBytes + (8u << 20)); }   // page-locking is slow: once
         if (qual && off) {
             any_qual = true;
             if (qual->size() == seq.size()) { bases.append(seq.data(), seq.size()); quals.append(qual->data(), qual->size()); }   // masked on the device
-            else { const std::string m = qual_mask(seq, *qual, off); bases.append(m.data(), m.size()); quals.fill('~', m.size()); }
+            else { const std::string m = qual_mask(std::string(seq), std::string(*qual), off); bases.append(m.data(), m.size()); quals.fill('~', m.size()); }
         } else {
             bases.append(seq.data(), seq.size());
             quals.fill('~', seq.size());
         }
         seq_offs.push_back(bases.size);
     }
-    void end_read(const std::string& id) { id_data += id; id_off.push_back((uint32_t)id_data.size()); read_offs.push_back(seq_offs.size() - 1); }
+    void end_read(std::string_view id) { id_data.append(id.data(), id.size()); id_off.push_back((uint32_t)id_data.size()); read_offs.push_back(seq_offs.size() - 1); }
     uint64_t n() const { return id_off.size() - 1; }
     std::string id(uint64_t r) const { return id_data.substr(id_off[r], id_off[r + 1] - id_off[r]); }
     void clear() { id_data.clear(); id_off.assign(1, 0); bases.size = 0; quals.size = 0; seq_offs.assign(1, 0); read_offs.assign(1, 0); any_qual = false; }
@@ -577,12 +577,12 @@ void read_id_sample(Gpu& g, const Bigsi& b, const ReadIdOpts& o, Trace& tr, Read
     if (ends_with(o.query[0], ".gz")) {
         if (o.query.size() > 1) {                       // per_read_stream_pe, read_id_mt_pe.rs:701-832
             AsyncLineReader a(o.query[0]), c(o.query[1]);
-            std::string l1, l2, id, s1, s2;
+            std::string_view l1, l2, id, s1, s2;       // views into the readers' blocks: a record's four lines share a block
             uint64_t line_count = 1;
-            while (a.next(l1)) {
-                const bool have2 = c.next(l2);
-                if (line_count % 4 == 1) id.swap(l1);
-                else if (line_count % 4 == 2) { if (!have2) break; s1.swap(l1); s2.swap(l2); }
+            while (a.next_view(l1)) {
+                const bool have2 = c.next_view(l2);
+                if (line_count % 4 == 1) id = l1;
+                else if (line_count % 4 == 2) { if (!have2) break; s1 = l1; s2 = l2; }
                 else if (line_count % 4 == 0) {
                     if (!have2) break;
                     rb.add_mate(s1, &l1, o.quality);
@@ -596,11 +596,11 @@ void read_id_sample(Gpu& g, const Bigsi& b, const ReadIdOpts& o, Trace& tr, Read
             fprintf(stderr, "Classified %llu read pairs in %llu seconds\n", (unsigned long long)run.read_count, t.secs());
         } else {                                        // per_read_stream_se, :835-951
             AsyncLineReader a(o.query[0]);
-            std::string l, id, s1;
+            std::string_view l, id, s1;
             uint64_t line_count = 1;
-            while (a.next(l)) {
-                if (line_count % 4 == 1) id.swap(l);
-                else if (line_count % 4 == 2) s1.swap(l);
+            while (a.next_view(l)) {
+                if (line_count % 4 == 1) id = l;
+                else if (line_count % 4 == 2) s1 = l;
                 else if (line_count % 4 == 0) { rb.add_mate(s1, &l, o.quality); rb.end_read(id); maybe_flush(); }
                 line_count++;
             }

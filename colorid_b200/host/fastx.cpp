@@ -180,7 +180,7 @@ AsyncLineReader::~AsyncLineReader() {
     if (p_->th.joinable()) p_->th.join();
     delete p_;
 }
-bool AsyncLineReader::next(std::string& line) {
+bool AsyncLineReader::next_view(std::string_view& line) {
     Impl& s = *p_;
     if (!s.cur || s.at == s.cur->end.size()) {
         std::unique_lock<std::mutex> lk(s.mu);
@@ -196,8 +196,14 @@ bool AsyncLineReader::next(std::string& line) {
         s.cv.notify_all();
     }
     const uint32_t lo = s.cur->begin[s.at], hi = s.cur->end[s.at];
-    line.assign(s.cur->data, lo, hi - lo);
+    line = std::string_view(s.cur->data.data() + lo, hi - lo);
     s.at++;
+    return true;
+}
+bool AsyncLineReader::next(std::string& line) {
+    std::string_view v;
+    if (!next_view(v)) return false;
+    line.assign(v.data(), v.size());
     return true;
 }
 
