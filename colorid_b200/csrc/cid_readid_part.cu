@@ -45,13 +45,22 @@ static __device__ __noinline__ void hash_rows_ool(uint64_t w0, uint64_t w1, uint
 #pragma unroll
     for (int h = 0; h < NH; h++) if (HT || (uint32_t)h < H) out[h] = (uint32_t)hash_row(in, k, h, mods);
 }
+// (stable XXH3 and a bloom size above 1 -- every real index: the checks of the variant and of the degenerate modulus are
+// made once per k-mer here instead of once per hash)
+__device__ __forceinline__ uint32_t row_stable(const HashIn& in, uint32_t k, uint64_t seed, const ModS& m) {
+    const uint64_t h = xxh3_kmer_stable(in, k, seed);
+    const uint64_t r = h - __umul64hi(h, m.M) * m.S;
+    return (uint32_t)(r >= m.S ? r - m.S : r);
+}
 static __device__ __noinline__ uint4 hash_rows_4(uint64_t w0, uint64_t w1, uint64_t w2, uint64_t w3, uint32_t k, const ModS mods) {
     HashIn in; in.w0 = w0; in.w1 = w1; in.w2 = w2; in.w3 = w3;
+    if (mods.var == 0u && mods.S > 1) return make_uint4(row_stable(in, k, 0, mods), row_stable(in, k, 1, mods), row_stable(in, k, 2, mods), row_stable(in, k, 3, mods));
     return make_uint4((uint32_t)hash_row(in, k, 0, mods), (uint32_t)hash_row(in, k, 1, mods), (uint32_t)hash_row(in, k, 2, mods),
                       (uint32_t)hash_row(in, k, 3, mods));
 }
 static __device__ __noinline__ uint2 hash_rows_2(uint64_t w0, uint64_t w1, uint64_t w2, uint64_t w3, uint32_t k, const ModS mods) {
     HashIn in; in.w0 = w0; in.w1 = w1; in.w2 = w2; in.w3 = w3;
+    if (mods.var == 0u && mods.S > 1) return make_uint2(row_stable(in, k, 0, mods), row_stable(in, k, 1, mods));
     return make_uint2((uint32_t)hash_row(in, k, 0, mods), (uint32_t)hash_row(in, k, 1, mods));
 }
 template <int HT, int NH>
