@@ -20,7 +20,7 @@
 //   count   (warp per read)  per candidate: count over the accumulator bytes + the first -B k-mers -> the read's report,
 //                            in the layout and insertion order the one-kernel vote writes.
 // Reports are bit-identical to readid_vote_narrow_kernel's (tests/test_gpu_parity.py::test_read_id_partitioned_vote*).
-// Measured (B200, C2, one million read pairs): scan 5.46 + six gathers 2.46 + count 0.28 ms against 8.9 ms for the one-kernel vote,
+// Measured (B200, C2, one million read pairs): scan 5.29 + six gathers 2.17 + count 0.28 ms against 8.9 ms for the one-kernel vote,
 // 15.2 instead of 43.9 GB of DRAM traffic; the stage is bound by the scan's instructions (profiles/r2_readid_part_history.txt).
 #include <algorithm>
 
