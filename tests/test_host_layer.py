@@ -258,6 +258,17 @@ def test_gzip_decoder_equals_zlib(tmp_path):
         "garbage_after": (z(b"hello\nworld\n", 6) + b"\0\0\0\0 not gzip", b"hello\nworld\n"),
         "big": (z(fq * 9, 1), fq * 9),            # several 4 MB output chunks: history carried across them
     }
+    # empty stored blocks in mid-stream (Z_SYNC_FLUSH / Z_FULL_FLUSH: pigz, bgzip-like writers) and a header with every
+    # optional field (FEXTRA as BGZF writes it, FNAME, FCOMMENT, FHCRC)
+    co = zlib.compressobj(6, zlib.DEFLATED, 31)
+    parts = [co.compress(fq[:100_000]), co.flush(zlib.Z_SYNC_FLUSH), co.compress(fq[100_000:250_000]), co.flush(zlib.Z_FULL_FLUSH),
+             co.compress(fq[250_000:300_000]), co.flush()]
+    cases["sync_flushes"] = (b"".join(parts), fq[:300_000])
+    raw = zlib.compressobj(6, zlib.DEFLATED, -15)
+    body = raw.compress(fq[:120_000]) + raw.flush()
+    hdr = bytes([0x1f, 0x8b, 8, 0x02 | 0x04 | 0x08 | 0x10, 0, 0, 0, 0, 0, 3]) + (6).to_bytes(2, "little") + b"BC\x02\x00\x00\x00" + b"name.fq\0" + b"a comment\0"
+    hdr += (zlib.crc32(hdr) & 0xFFFF).to_bytes(2, "little")
+    cases["all_header_fields"] = (hdr + body + (zlib.crc32(fq[:120_000]) & 0xFFFFFFFF).to_bytes(4, "little") + (120_000).to_bytes(4, "little"), fq[:120_000])
     for name, (gz, data) in cases.items():
         p = tmp_path / f"{name}.gz"
         p.write_bytes(gz)
@@ -280,3 +291,44 @@ def test_gzip_decoder_fails_loudly_on_damage(tmp_path):
         p.write_bytes(bytes(blob))
         rc, msg = _lines_report(p)
         assert rc != 0 and "gzip stream" in msg, (name, rc, msg)
+
+
+def test_gzip_decoder_fuzz_against_zlib(tmp_path):
+    """Seeded differential fuzzing of the decoder: texts of mixed entropy (random bytes, small alphabets, repeats, runs),
+    every compression level / strategy / window size / memory level zlib offers, members concatenated at random."""
+    import zlib
+    rng = np.random.default_rng(0xC0101D07)
+
+    def blob():
+        parts = []
+        for _ in range(int(rng.integers(1, 6))):
+            kind = int(rng.integers(0, 5))
+            n = int(rng.integers(1, 60_000))
+            if kind == 0:
+                parts.append(rng.integers(0, 256, n, dtype=np.uint8).tobytes())
+            elif kind == 1:
+                parts.append(np.frombuffer(b"ACGT\n", dtype=np.uint8)[rng.integers(0, 5, n)].tobytes())
+            elif kind == 2:
+                unit = rng.integers(33, 80, int(rng.integers(1, 40)), dtype=np.uint8).tobytes()
+                parts.append(unit * (n // len(unit) + 1))
+            elif kind == 3:
+                parts.append(bytes([int(rng.integers(0, 256))]) * n)
+            else:
+                parts.append(_fastq_blob(rng, max(1, n // 330)))
+        return b"".join(parts)
+
+    for it in range(40):
+        members, data = [], b""
+        for _ in range(int(rng.integers(1, 4))):
+            d = blob() if rng.random() > 0.1 else b""
+            co = zlib.compressobj(int(rng.integers(0, 10)), zlib.DEFLATED, 16 + int(rng.integers(9, 16)), int(rng.integers(1, 10)),
+                                  int(rng.choice([zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED])))
+            cut = int(rng.integers(0, len(d) + 1))
+            members.append(co.compress(d[:cut]) + (co.flush(zlib.Z_SYNC_FLUSH) if rng.random() < 0.5 else b"") + co.compress(d[cut:]) + co.flush())
+            data += d
+        p = tmp_path / f"f{it}.gz"
+        p.write_bytes(b"".join(members))
+        if len(p.read_bytes()) < 18:
+            continue
+        want = (data.count(b"\n") + (1 if data and not data.endswith(b"\n") else 0), len(data), zlib.crc32(data) & 0xFFFFFFFF)
+        assert _lines_report(p) == (0, want), it
