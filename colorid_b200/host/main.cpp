@@ -143,6 +143,21 @@ int main(int argc, char** argv) {
                 unsigned long crc = crc32(0L, Z_NULL, 0);
                 while (lr.next(l, true)) { n++; bytes += l.size(); crc = crc32(crc, (const Bytef*)l.data(), (uInt)l.size()); }
                 printf("lines\t%llu\nbytes\t%llu\ncrc32\t%08lx\n", n, bytes, crc);
+            } else if (op == "alines" && (argc == 4 || argc == 5)) {   // the same through AsyncLineReader (block-wise splitting); argv[4] = keep EOLs
+                const bool keep = argc == 5 && atoi(argv[4]) != 0;
+                cidh::AsyncLineReader lr(argv[3], keep);
+                std::string_view v;
+                unsigned long long n = 0, bytes = 0;
+                unsigned long crc = crc32(0L, Z_NULL, 0);
+                while (lr.next_view(v)) { n++; bytes += v.size(); crc = crc32(crc, (const Bytef*)v.data(), (uInt)v.size()); if (!keep) crc = crc32(crc, (const Bytef*)"\n", 1); }
+                printf("lines\t%llu\nbytes\t%llu\ncrc32\t%08lx\n", n, bytes, crc);
+            } else if (op == "lines1" && argc == 4) {            // LineReader::next without EOLs, one '\n' folded in per line
+                cidh::LineReader lr(argv[3]);
+                std::string l;
+                unsigned long long n = 0, bytes = 0;
+                unsigned long crc = crc32(0L, Z_NULL, 0);
+                while (lr.next(l, false)) { n++; bytes += l.size(); crc = crc32(crc, (const Bytef*)l.data(), (uInt)l.size()); crc = crc32(crc, (const Bytef*)"\n", 1); }
+                printf("lines\t%llu\nbytes\t%llu\ncrc32\t%08lx\n", n, bytes, crc);
             } else if (op == "gunzip" && argc == 4) {           // decode only (timing aid): bytes out
                 unsigned long long bytes = 0;
                 std::vector<char> buf(1 << 20);

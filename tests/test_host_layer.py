@@ -332,3 +332,31 @@ def test_gzip_decoder_fuzz_against_zlib(tmp_path):
             continue
         want = (data.count(b"\n") + (1 if data and not data.endswith(b"\n") else 0), len(data), zlib.crc32(data) & 0xFFFFFFFF)
         assert _lines_report(p) == (0, want), it
+
+
+def test_block_line_splitter_equals_line_reader(tmp_path):
+    """AsyncLineReader splits whole blocks with memchr (LineReader::next_lines) where LineReader::next walks line by line:
+    same lines on CRLF files, blank lines, a last line without newline, lines longer than the 1 MB read buffer, lone CRs,
+    more than one block of 65,536 lines -- with the EOLs stripped (BufRead::lines) and kept (stream_fasta)."""
+    import zlib
+    rng = np.random.default_rng(0xC0101D08)
+    texts = {
+        "crlf": b"".join(b"line %d\r\n" % i for i in range(1000)),
+        "mixed": b"a\n\r\nb\r\n\n\nc\rd\ne\r",                       # blank lines, CR inside a line, a last line ending in CR
+        "no_final_newline": b"x\ny\nzzz",
+        "empty": b"",
+        "only_newlines": b"\n" * 70_000,
+        "long_lines": b"".join(bytes([65 + i % 26]) * n + b"\n" for i, n in enumerate([3_000_000, 1, 1_048_576, 1_048_575, 0, 2_500_000])),
+        "many_blocks": b"".join(b"%d\n" % i for i in range(200_000)),
+        "fastq": _fastq_blob(rng, 40_000),
+    }
+    for name, data in texts.items():
+        for gz in (False, True):
+            p = tmp_path / (name + (".gz" if gz else ".txt"))
+            p.write_bytes(zlib.compress(data, 6, 31) if gz else data)
+            for op_a, op_b in ((("alines", p, 1), ("lines", p)), (("alines", p, 0), ("lines1", p))):
+                ra = subprocess.run([CLI, "_host", *map(str, op_a)], capture_output=True, text=True)
+                rb = subprocess.run([CLI, "_host", *map(str, op_b)], capture_output=True, text=True)
+                assert ra.returncode == 0 and rb.returncode == 0, (name, gz, ra.stderr, rb.stderr)
+                pick = lambda out: [l for l in out.split("\n") if l.split("\t")[0] in ("lines", "bytes", "crc32")]
+                assert pick(ra.stdout) == pick(rb.stdout) and len(pick(ra.stdout)) == 3, (name, gz, op_a[0], op_a[-1])
