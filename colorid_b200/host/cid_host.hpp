@@ -51,7 +51,8 @@ public:
     size_t read(char* dst, size_t cap);
     static bool eligible(const std::string& path);    // regular file that starts with the gzip magic
 private:
-    class GzInflater* inf_ = nullptr;
+    class GzInflater* inf_ = nullptr;    // one of the two
+    class GzParallel* par_ = nullptr;
     void* map_ = nullptr;
     size_t len_ = 0;
 };

@@ -12,10 +12,10 @@
 namespace cidh {
 
 namespace {
-// table entry: value << 16 | flags << 12 | extra bits << 8 | code bits to consume
+// table entry (fast_inflate.hpp): value << 16 | flags << 12 | extra bits << 8 | code bits to consume
 // F_LIT2: two literals in one first-level entry (value = first | second << 8, code bits = both codes): decoding literals is a
 // chain of dependent table lookups (load latency per symbol), and FASTQ text is almost all literals with 2..6-bit codes
-enum : uint32_t { F_LIT = 1u << 12, F_BASE = 2u << 12, F_EOB = 4u << 12, F_SUB = 8u << 12, F_LIT2 = 1u << 7 };
+enum : uint32_t { F_LIT = GzInflater::F_LIT, F_BASE = GzInflater::F_BASE, F_EOB = GzInflater::F_EOB, F_SUB = GzInflater::F_SUB, F_LIT2 = GzInflater::F_LIT2 };
 const uint16_t kLenBase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
 const uint8_t kLenExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
 const uint16_t kDistBase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
@@ -80,8 +80,9 @@ static uint32_t crc32_clmul(const unsigned char* buf, size_t len, uint32_t crc) 
     x1 = _mm_xor_si128(x1, x2);
     return (uint32_t)_mm_extract_epi32(x1, 1);
 }
+}  // namespace
 // zlib-compatible: running crc in, running crc out
-static uint32_t crc32_fast(uint32_t crc, const unsigned char* p, size_t n) {
+uint32_t GzInflater::crc32_fast(uint32_t crc, const unsigned char* p, size_t n) {
     if (n >= 64 && __builtin_cpu_supports("pclmul") && __builtin_cpu_supports("sse4.1")) {
         const size_t m = n & ~(size_t)15;
         crc = ~crc32_clmul(p, m, ~crc);
@@ -89,7 +90,6 @@ static uint32_t crc32_fast(uint32_t crc, const unsigned char* p, size_t n) {
     }
     return n ? (uint32_t)crc32(crc, p, (uInt)n) : crc;
 }
-}  // namespace
 
 GzInflater::GzInflater(const uint8_t* data, size_t n, const std::string& what)
     : base_(data), in_(data), end_(data + n), what_(what), obuf_((size_t)HIST + CHUNK + SLACK) {}
@@ -131,34 +131,59 @@ void GzInflater::byte_align() {
     bitcnt_ = 0;
 }
 
-void GzInflater::parse_header() {
+size_t GzInflater::header_size(const uint8_t* p, const uint8_t* end, const char** why) {
     // RFC 1952: ID1 ID2 CM FLG MTIME(4) XFL OS [FEXTRA] [FNAME] [FCOMMENT] [FHCRC]
-    if (end_ - in_ < 10) fail("truncated header");
-    if (in_[0] != 0x1f || in_[1] != 0x8b) fail("not a gzip member");
-    if (in_[2] != 8) fail("unknown compression method");
-    const unsigned flg = in_[3];
-    if (flg & 0xE0) fail("reserved header flags set");
-    in_ += 10;
+    const uint8_t* in = p;
+    auto bad = [&](const char* w) -> size_t { *why = w; return 0; };
+    if (end - in < 10) return bad("truncated header");
+    if (in[0] != 0x1f || in[1] != 0x8b) return bad("not a gzip member");
+    if (in[2] != 8) return bad("unknown compression method");
+    const unsigned flg = in[3];
+    if (flg & 0xE0) return bad("reserved header flags set");
+    in += 10;
     if (flg & 4) {
-        if (end_ - in_ < 2) fail("truncated header");
-        const size_t xlen = in_[0] | ((size_t)in_[1] << 8);
-        in_ += 2;
-        if ((size_t)(end_ - in_) < xlen) fail("truncated header");
-        in_ += xlen;
+        if (end - in < 2) return bad("truncated header");
+        const size_t xlen = in[0] | ((size_t)in[1] << 8);
+        in += 2;
+        if ((size_t)(end - in) < xlen) return bad("truncated header");
+        in += xlen;
     }
     for (unsigned f = 8; f <= 16; f <<= 1)      // FNAME, FCOMMENT: zero-terminated
         if (flg & f) {
-            const uint8_t* z = (const uint8_t*)memchr(in_, 0, (size_t)(end_ - in_));
-            if (!z) fail("truncated header");
-            in_ = z + 1;
+            const uint8_t* z = (const uint8_t*)memchr(in, 0, (size_t)(end - in));
+            if (!z) return bad("truncated header");
+            in = z + 1;
         }
     if (flg & 2) {
-        if (end_ - in_ < 2) fail("truncated header");
-        in_ += 2;
+        if (end - in < 2) return bad("truncated header");
+        in += 2;
     }
+    return (size_t)(in - p);
+}
+
+void GzInflater::parse_header() {
+    const char* why = nullptr;
+    const size_t h = header_size(in_, end_, &why);
+    if (!h) fail(why);
+    in_ += h;
     crc_ = (uint32_t)crc32(0L, Z_NULL, 0);
     crc_from_ = out_;
     member_start_ = (int64_t)out_;
+    last_block_ = false;
+    st_ = ST_BLOCK;
+}
+
+void GzInflater::resume(uint64_t bitpos, bool at_header, const uint8_t* win, size_t nwin, uint32_t crc, uint64_t member_len) {
+    in_ = base_ + (bitpos >> 3);
+    bitbuf_ = 0; bitcnt_ = 0; fed_zero_bytes_ = 0;
+    out_ = taken_ = crc_from_ = HIST;
+    if (at_header) { st_ = ST_MEMBER; return; }
+    refill();
+    bits((unsigned)(bitpos & 7));
+    if (nwin > (size_t)HIST) { win += nwin - HIST; nwin = HIST; }
+    memcpy(obuf_.data() + HIST - nwin, win, nwin);
+    crc_ = crc;
+    member_start_ = (int64_t)HIST - (int64_t)member_len;
     last_block_ = false;
     st_ = ST_BLOCK;
 }
@@ -259,16 +284,18 @@ void GzInflater::build_table(const uint8_t* lens, unsigned n, unsigned tbits, bo
     ok = true;
 }
 
-void GzInflater::build_fixed() {
-    uint8_t lens[288];
+void GzInflater::fixed_lengths(uint8_t lens[288], uint8_t dl[32]) {
     for (unsigned i = 0; i < 144; i++) lens[i] = 8;
     for (unsigned i = 144; i < 256; i++) lens[i] = 9;
     for (unsigned i = 256; i < 280; i++) lens[i] = 7;
     for (unsigned i = 280; i < 288; i++) lens[i] = 8;
+    for (unsigned i = 0; i < 32; i++) dl[i] = 5;
+}
+void GzInflater::build_fixed() {
+    uint8_t lens[288], dl[32];
+    fixed_lengths(lens, dl);
     bool ok = false;
     build_table(lens, 288, LBITS, false, lt_, ok);
-    uint8_t dl[32];
-    for (unsigned i = 0; i < 32; i++) dl[i] = 5;
     build_table(dl, 32, DBITS, true, dt_, ok);
 }
 

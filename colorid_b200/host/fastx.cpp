@@ -40,13 +40,27 @@ MappedGz::MappedGz(const std::string& path) {
     if (m == MAP_FAILED) throw Error("cannot map " + path);
     madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
     map_ = m; len_ = (size_t)st.st_size;
-    inf_ = new GzInflater((const uint8_t*)m, len_, path);
+    // Large files are decoded by several threads (GzParallel): COLORID_B200_GZ_THREADS (default: a quarter of the cores, at
+    // most 6; 1 = the sequential decoder), COLORID_B200_GZ_SPAN = compressed bytes per thread and round (default 2 MiB).
+    GzParallel::Config cfg;
+    const unsigned hw = std::thread::hardware_concurrency();
+    cfg.threads = std::min(6u, std::max(1u, hw / 4));
+    if (const char* e = getenv("COLORID_B200_GZ_THREADS")) { const long v = atol(e); if (v >= 1 && v <= 64) cfg.threads = (unsigned)v; }
+    if (const char* e = getenv("COLORID_B200_GZ_SPAN")) { const long long v = atoll(e); if (v >= 4096) cfg.span = (size_t)v; }
+    try {
+        if (cfg.threads >= 2 && len_ >= 4 * cfg.span) par_ = new GzParallel((const uint8_t*)m, len_, path, cfg);
+        else inf_ = new GzInflater((const uint8_t*)m, len_, path);
+    } catch (...) {
+        munmap(m, len_);
+        throw;
+    }
 }
 MappedGz::~MappedGz() {
+    delete par_;
     delete inf_;
     if (map_) munmap(map_, len_);
 }
-size_t MappedGz::read(char* dst, size_t cap) { return inf_->read((uint8_t*)dst, cap); }
+size_t MappedGz::read(char* dst, size_t cap) { return par_ ? par_->read((uint8_t*)dst, cap) : inf_->read((uint8_t*)dst, cap); }
 
 LineReader::LineReader(const std::string& path) : buf_(1 << 20) {
     // A regular file that starts with the gzip magic is mapped and decoded by the host layer's own inflater (every member's
@@ -137,6 +151,7 @@ struct AsyncLineReader::Impl {
     std::mutex mu;
     std::condition_variable cv;
     std::deque<std::unique_ptr<Block>> q;
+    std::vector<std::unique_ptr<Block>> spare;          // consumed blocks go back to the producer: a fresh 10 MB string per block is page faults
     bool done = false, stop = false;
     std::string error;
     std::thread th;
@@ -146,10 +161,18 @@ struct AsyncLineReader::Impl {
         try {
             LineReader lr(path);
             for (;;) {
-                std::unique_ptr<Block> b(new Block());
-                b->data.reserve(10 << 20);
-                b->begin.reserve(BLOCK_LINES);
-                b->end.reserve(BLOCK_LINES);
+                std::unique_ptr<Block> b;
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    if (!spare.empty()) { b = std::move(spare.back()); spare.pop_back(); }
+                }
+                if (b) { b->data.clear(); b->begin.clear(); b->end.clear(); }
+                else {
+                    b.reset(new Block());
+                    b->data.reserve(10 << 20);
+                    b->begin.reserve(BLOCK_LINES);
+                    b->end.reserve(BLOCK_LINES);
+                }
                 lr.next_lines(b->data, b->begin, b->end, BLOCK_LINES, keep_eol);     // whole lines, split with memchr: no per-line strings here
                 const bool last = b->end.size() < BLOCK_LINES;
                 {
@@ -189,6 +212,7 @@ bool AsyncLineReader::next_view(std::string_view& line) {
             if (!s.error.empty()) throw Error(s.error);
             return false;
         }
+        if (s.cur) s.spare.push_back(std::move(s.cur));
         s.cur = std::move(s.q.front());
         s.q.pop_front();
         s.at = 0;

@@ -151,6 +151,12 @@ int main(int argc, char** argv) {
                 unsigned long crc = crc32(0L, Z_NULL, 0);
                 while (lr.next_view(v)) { n++; bytes += v.size(); crc = crc32(crc, (const Bytef*)v.data(), (uInt)v.size()); if (!keep) crc = crc32(crc, (const Bytef*)"\n", 1); }
                 printf("lines\t%llu\nbytes\t%llu\ncrc32\t%08lx\n", n, bytes, crc);
+            } else if (op == "acount" && argc == 4) {            // AsyncLineReader as the drivers use it, lines only counted (timing aid)
+                cidh::AsyncLineReader lr(argv[3]);
+                std::string_view v;
+                unsigned long long n = 0, bytes = 0;
+                while (lr.next_view(v)) { n++; bytes += v.size(); }
+                printf("lines\t%llu\nbytes\t%llu\n", n, bytes);
             } else if (op == "lines1" && argc == 4) {            // LineReader::next without EOLs, one '\n' folded in per line
                 cidh::LineReader lr(argv[3]);
                 std::string l;

@@ -212,10 +212,14 @@ def test_cli_flag_errors():
 
 
 # ----------------------------------------------------------------------------- the host layer's own gzip decoder
-def _lines_report(path, zlib_only=False):
+def _lines_report(path, zlib_only=False, gz_threads=None, gz_span=None):
     env = dict(os.environ)
     if zlib_only:
         env["COLORID_B200_ZLIB"] = "1"
+    if gz_threads is not None:
+        env["COLORID_B200_GZ_THREADS"] = str(gz_threads)
+    if gz_span is not None:
+        env["COLORID_B200_GZ_SPAN"] = str(gz_span)
     r = subprocess.run([CLI, "_host", "lines", str(path)], capture_output=True, text=True, env=env)
     if r.returncode != 0:
         return r.returncode, r.stderr
@@ -332,6 +336,70 @@ def test_gzip_decoder_fuzz_against_zlib(tmp_path):
             continue
         want = (data.count(b"\n") + (1 if data and not data.endswith(b"\n") else 0), len(data), zlib.crc32(data) & 0xFFFFFFFF)
         assert _lines_report(p) == (0, want), it
+        assert _lines_report(p, gz_threads=3, gz_span=4096) == (0, want), ("parallel", it)      # (files of 16 KB and more)
+
+
+def _gz(data, level=6, strategy=None, memlevel=8):
+    import zlib
+    co = zlib.compressobj(level, zlib.DEFLATED, 31, memlevel, zlib.Z_DEFAULT_STRATEGY if strategy is None else strategy)
+    return co.compress(data) + co.flush()
+
+
+def test_parallel_gzip_decoder_equals_zlib(tmp_path):
+    """par_inflate.cpp (one gzip stream on several threads: block headers found by search and confirmed by the span before,
+    unknown window bytes carried as 16-bit markers) against zlib.  Spans of 4 KB .. 64 KB make small files take every path:
+    chains of 2 .. 5 spans (tiny blocks), spans without a block header (blocks larger than a span, stored and fixed blocks),
+    a member younger than one window when its second span is resolved, members ending inside a round, runs of small members
+    (handed to the sequential decoder), a block that inflates beyond the span buffers (handed over mid-stream), bytes after
+    the last member.  COLORID_B200_GZ_THREADS=1 is the sequential decoder on the same files."""
+    import zlib
+    rng = np.random.default_rng(0xC0101D08)
+    fq = _fastq_blob(rng, 12000)
+    rb = rng.integers(0, 256, 600_000, dtype=np.uint8).tobytes()
+    runs = b"I" * 30_000_000 + b"\n" + fq[:200_000] + b"\0" * 7_000_000
+    mixed = fq[:700_000] + rb + fq[700_000:] + b"A" * 500_000 + rb[:1000]
+    cases = {
+        "l1": (_gz(fq, 1), fq), "l6": (_gz(fq, 6), fq), "l9": (_gz(fq, 9), fq),
+        "stored": (_gz(rb, 0), rb), "incompressible": (_gz(rb, 6), rb),
+        "fixed": (_gz(fq, 6, zlib.Z_FIXED), fq), "huffman_only": (_gz(fq, 6, zlib.Z_HUFFMAN_ONLY), fq),
+        "runs": (_gz(runs, 9), runs), "tiny_blocks": (_gz(fq, 1, memlevel=1), fq),
+        "members_big": (_gz(fq, 6) + _gz(fq[:1_000_000], 1) + _gz(b"", 6) + _gz(fq[5:], 9), fq + fq[:1_000_000] + fq[5:]),
+        "members_small": (b"".join(_gz(fq[i:i + 20_000], 6) for i in range(0, len(fq), 20_000)), fq),
+        "mixed": (_gz(mixed, 6), mixed), "garbage_after": (_gz(fq, 6) + b"\0\0\0 trailing", fq),
+    }
+    for name, (gz, data) in cases.items():
+        p = tmp_path / f"{name}.gz"
+        p.write_bytes(gz)
+        want = (data.count(b"\n") + (1 if data and not data.endswith(b"\n") else 0), len(data), zlib.crc32(data) & 0xFFFFFFFF)
+        for threads, span in ((2, 4096), (3, 16384), (5, 65536), (1, None)):
+            assert _lines_report(p, gz_threads=threads, gz_span=span) == (0, want), (name, threads, span)
+
+
+def test_parallel_gzip_decoder_fails_loudly_on_damage(tmp_path):
+    """Single flipped bits anywhere in a stream, truncation and a wrong trailer: an error, never different data -- a span that
+    started on a false block header is dropped by the chain check, real damage is reported by the sequential decoder that
+    takes over at the last verified block."""
+    rng = np.random.default_rng(0xC0101D09)
+    gz = _gz(_fastq_blob(rng, 12000), 1, memlevel=2)
+    for trial in range(24):
+        b = bytearray(gz)
+        pos = int(rng.integers(20, len(b) - 8))
+        b[pos] ^= 1 << int(rng.integers(0, 8))
+        p = tmp_path / "flip.gz"
+        p.write_bytes(bytes(b))
+        rc, msg = _lines_report(p, gz_threads=3, gz_span=16384)
+        assert rc != 0 and "gzip stream" in msg, (trial, pos, rc, msg)
+    for cut in (len(gz) // 3, len(gz) * 2 // 3, len(gz) - 9, len(gz) - 4):
+        p = tmp_path / "trunc.gz"
+        p.write_bytes(gz[:cut])
+        rc, msg = _lines_report(p, gz_threads=3, gz_span=16384)
+        assert rc != 0 and "gzip stream" in msg, (cut, rc, msg)
+    b = bytearray(gz)
+    b[-6] ^= 1
+    p = tmp_path / "crc.gz"
+    p.write_bytes(bytes(b))
+    rc, msg = _lines_report(p, gz_threads=3, gz_span=16384)
+    assert rc != 0 and "CRC mismatch" in msg, (rc, msg)
 
 
 def test_block_line_splitter_equals_line_reader(tmp_path):
