@@ -86,9 +86,15 @@ public:
     // The next line as a view into the reader's current block: valid until the call that crosses into the next block, i.e. --
     // blocks hold a multiple of four lines -- for the four lines of a FASTQ record at least.
     bool next_view(std::string_view& line);
+    // The unread lines of the current block at once: line i is data[begin[i], end[i]) for at <= i < n.  false at the end of the
+    // file.  skip_lines(k) marks k of them as read (k <= n - at).
+    struct LineBlock { const char* data; const uint32_t* begin; const uint32_t* end; size_t n; };
+    bool peek_block(LineBlock& b, size_t& at);
+    void skip_lines(size_t k);
 private:
     struct Impl;
     Impl* p_;
+    bool load();
 };
 
 std::vector<std::string> read_fasta(const std::string& path);                                      // kmer.rs:10-45
@@ -99,6 +105,7 @@ std::string qual_mask(const std::string& seq, const std::string& qual, uint8_t m
 std::map<std::string, std::vector<std::string>> tab_to_map(const std::string& path);                // build.rs:15-31
 // All records of a single-end / paired FASTQ(.gz) as quality-masked sequences (mates are separate
 // sequences); paired input stops at the shorter file (kmer.rs:604,612,649).  Returns records read.
+int fastq_parse_digest(const std::vector<std::string>& files, uint8_t quality);                     // `_host fastq_parse` (tests, timing)
 uint64_t fastq_masked_se(const std::string& path, uint8_t qual_offset, SeqBatch& out);              // kmer.rs:461-475
 uint64_t fastq_masked_pe(const std::string& p1, const std::string& p2, uint8_t qual_offset, SeqBatch& out);   // kmer.rs:581-612
 

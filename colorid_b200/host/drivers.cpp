@@ -11,6 +11,7 @@
 #include <cstring>
 #include <exception>
 #include <thread>
+#include <zlib.h>      // crc32 of the `_host fastq_parse` digest
 
 #include "../../include/colorid_b200.h"
 #include "cid_host.hpp"
@@ -411,14 +412,17 @@ const uint64_t kGpuBatchBytes = 96ull << 20;
 struct PinnedBytes {               // growable page-locked byte buffer (cid_host_alloc)
     char* p = nullptr;
     size_t size = 0, cap = 0;
-    ~PinnedBytes() { cid_host_free(p); }
+    bool pageable = false;         // plain memory: `_host fastq_parse`, which runs without a GPU
+    ~PinnedBytes() { release(p); }
+    void release(char* q) { if (pageable) free(q); else cid_host_free(q); }
     void reserve(size_t want) {
         if (want <= cap) return;
         size_t ncap = std::max(want, cap + cap / 2);
         void* np = nullptr;
-        ck(cid_host_alloc(ncap, &np));
+        if (pageable) { np = malloc(ncap); if (!np) throw Error("out of memory"); }
+        else ck(cid_host_alloc(ncap, &np));
         if (size) memcpy(np, p, size);
-        cid_host_free(p);
+        release(p);
         p = (char*)np; cap = ncap;
     }
     void append(const char* s, size_t n) { reserve(size + n); memcpy(p + size, s, n); size += n; }
@@ -448,18 +452,127 @@ struct ReadBatch {
     void clear() { id_data.clear(); id_off.assign(1, 0); bases.size = 0; quals.size = 0; seq_offs.assign(1, 0); read_offs.assign(1, 0); any_qual = false; }
 };
 
+// The record loop of per_read_stream_pe / per_read_stream_se (read_id_mt_pe.rs:701-832, :835-951) over one or two readers:
+// line 1 of a record is the id (of file 1), line 2 the sequences, line 4 the qualities; paired input stops where file 2 does.
+// Whole stretches of records are taken from the readers' line blocks at once: the lengths are in the line tables, so this
+// thread lays out the offsets and the ids, and the bases and qualities -- 600 MB per million pairs, what bounded read_id of
+// .fastq.gz once the inflating was parallel -- are copied by kCopyThreads threads.  A record whose quality line is not as long
+// as its sequence (qual_mask on the host), the last lines of a file and COLORID_B200_PARSE_SLOW=1 go line by line.
+const size_t kCopyThreads = 4;
+// stretches / batches of fewer records than this stay on one thread; COLORID_B200_PAR_MIN overrides it (the tests set 1 so
+// that small inputs take the threaded paths)
+size_t par_min(size_t dflt) {
+    static const long v = [] { const char* e = getenv("COLORID_B200_PAR_MIN"); return e && *e ? atol(e) : -1L; }();
+    return v >= 0 ? (size_t)v : dflt;
+}
+size_t take_records(const AsyncLineReader::LineBlock* b, const size_t* at, int nfiles, size_t nrec, uint8_t quality, ReadBatch& rb) {
+    if (rb.n() >= kGpuBatchReads) return 0;
+    nrec = std::min<size_t>(nrec, kGpuBatchReads - rb.n());
+    const bool use_q = quality != 0;
+    const size_t seq0 = rb.seq_offs.size() - 1;           // index of the first new sequence
+    size_t bytes = rb.bases.size, k = 0;
+    for (; k < nrec; k++) {
+        if (bytes >= kGpuBatchBytes) break;                // the batch is full (flushed by the caller)
+        size_t ls[2];
+        bool same = true;
+        for (int f = 0; f < nfiles; f++) {
+            const size_t i = at[f] + 4 * k;
+            ls[f] = b[f].end[i + 1] - b[f].begin[i + 1];
+            if (use_q && (size_t)(b[f].end[i + 3] - b[f].begin[i + 3]) != ls[f]) same = false;
+        }
+        if (!same) break;
+        for (int f = 0; f < nfiles; f++) { bytes += ls[f]; rb.seq_offs.push_back(bytes); }
+        const size_t i0 = at[0] + 4 * k;
+        rb.id_data.append(b[0].data + b[0].begin[i0], b[0].end[i0] - b[0].begin[i0]);
+        rb.id_off.push_back((uint32_t)rb.id_data.size());
+        rb.read_offs.push_back(rb.seq_offs.size() - 1);
+    }
+    if (k == 0) return 0;
+    if (!rb.bases.cap) { rb.bases.reserve(kGpuBatchBytes + (8u << 20)); rb.quals.reserve(kGpuBatchBytes + (8u << 20)); }
+    rb.bases.reserve(bytes); rb.quals.reserve(bytes);
+    if (use_q) rb.any_qual = true;
+    char* const bases = rb.bases.p;
+    char* const quals = rb.quals.p;
+    const uint64_t* const so = rb.seq_offs.data();
+    auto copy = [&](size_t r0, size_t r1) {
+        for (size_t r = r0; r < r1; r++)
+            for (int f = 0; f < nfiles; f++) {
+                const size_t m = seq0 + r * (size_t)nfiles + (size_t)f, d = so[m], n = so[m + 1] - d, i = at[f] + 4 * r;
+                memcpy(bases + d, b[f].data + b[f].begin[i + 1], n);
+                if (use_q) memcpy(quals + d, b[f].data + b[f].begin[i + 3], n);
+                else memset(quals + d, '~', n);
+            }
+    };
+    const size_t nt = k >= par_min(4096) ? kCopyThreads : 1;
+    std::vector<std::thread> th;
+    size_t spawned = 0;
+    try {
+        for (size_t t = 1; t < nt; t++) { th.emplace_back(copy, k * t / nt, k * (t + 1) / nt); spawned = t; }
+    } catch (...) {}                                          // no more threads to be had: their shares are copied here
+    copy(0, k / nt);
+    if (spawned + 1 < nt) copy(k * (spawned + 1) / nt, k);
+    for (auto& t : th) t.join();
+    rb.bases.size = rb.quals.size = bytes;
+    return k;
+}
+
+template <class Cur, class Flush>
+void parse_fastq_records(AsyncLineReader** rd, int nfiles, uint8_t quality, Cur&& cur_batch, Flush&& maybe_flush) {
+    static const bool fast = [] { const char* e = getenv("COLORID_B200_PARSE_SLOW"); return !(e && *e && *e != '0'); }();
+    std::string_view l[2], id, s[2];
+    uint64_t line_count = 1;
+    unsigned slow_lines = 0;                 // lines still to be taken one by one (a record the block path declined)
+    for (;;) {
+        if (fast && line_count % 4 == 1 && !slow_lines) {
+            AsyncLineReader::LineBlock b[2];
+            size_t at[2], nrec = SIZE_MAX;
+            bool ok = true;
+            for (int f = 0; f < nfiles && ok; f++) {
+                ok = rd[f]->peek_block(b[f], at[f]);
+                if (ok) nrec = std::min(nrec, (b[f].n - at[f]) / 4);
+            }
+            if (ok && nrec > 0) {
+                const size_t done = take_records(b, at, nfiles, nrec, quality, cur_batch());
+                if (done) {
+                    for (int f = 0; f < nfiles; f++) rd[f]->skip_lines(4 * done);
+                    line_count += 4 * done;
+                    maybe_flush();
+                    continue;
+                }
+            }
+            slow_lines = 4;                  // the end of a file, fewer than four lines left in a block, or a record for qual_mask
+        }
+        if (!rd[0]->next_view(l[0])) break;
+        const bool have2 = nfiles < 2 || rd[1]->next_view(l[1]);
+        if (line_count % 4 == 1) id = l[0];
+        else if (line_count % 4 == 2) { if (!have2) break; s[0] = l[0]; s[1] = l[1]; }
+        else if (line_count % 4 == 0) {
+            if (!have2) break;
+            ReadBatch& rb = cur_batch();
+            for (int f = 0; f < nfiles; f++) rb.add_mate(s[f], &l[f], quality);
+            rb.end_read(id);
+            maybe_flush();
+        }
+        line_count++;
+        if (slow_lines) slow_lines--;
+    }
+}
+
 struct ReadIdRun {
     Gpu& g; const Bigsi& b; const ReadIdOpts& o;
     FILE* out;
     std::vector<uint64_t> n_ref;
     std::vector<std::string> names;                      // accession by colour
-    std::string outbuf;
+    enum { kFormatThreads = 4 };
+    std::vector<std::string> outbufs;
     double fp_correct;
     uint64_t threads = 0;                                // -t: host threads of the vote, applied before the first batch
     uint64_t read_count = 0;
     double t_gpu = 0, t_out = 0;
     std::vector<std::string> count_keys;                 // first-appearance order of the counts-file keys
-    std::map<std::string, uint64_t> counts;
+    std::vector<uint64_t> slot_counts;                   // by position in count_keys
+    int slot_too_short = -1, slot_no_hits = -1, slot_reject = -1;
+    std::vector<int> slot_color;                         // by colour; -1 = not seen yet
     ReadIdRun(Gpu& g_, const Bigsi& b_, const ReadIdOpts& o_) : g(g_), b(b_), o(o_) {
         out = fopen((o.prefix + "_reads.txt").c_str(), "wb");
         if (!out) throw Error("could not create outfile!");
@@ -469,14 +582,19 @@ struct ReadIdRun {
             n_ref.push_back(it->second);
             names.push_back(kv.second);
         }
+        slot_color.assign(names.size(), -1);
         fp_correct = std::pow(10.0, -o.correct);          // main.rs:711
         if (o.threads) threads = o.threads;
     }
     ~ReadIdRun() { if (out) fclose(out); }
-    void tally(const std::string& cls, bool accept) {
-        const std::string key = accept ? cls : "reject";
-        auto it = counts.find(key);
-        if (it == counts.end()) { counts[key] = 1; count_keys.push_back(key); } else it->second++;
+    // one more read under `key` (an accession, too_short, no_hits or reject); `slot` caches where that key is counted
+    void count_slot(int& slot, const std::string& key) {
+        if (slot < 0) {
+            const auto it = std::find(count_keys.begin(), count_keys.end(), key);      // (an accession may be called "reject")
+            if (it == count_keys.end()) { count_keys.push_back(key); slot_counts.push_back(0); slot = (int)count_keys.size() - 1; }
+            else slot = (int)(it - count_keys.begin());
+        }
+        slot_counts[(size_t)slot]++;
     }
     // read_id_mt_pe.rs:282-363 parallel_vec for one batch, then the :779-788 output lines in input order
     void flush(ReadBatch& rb) {
@@ -496,51 +614,87 @@ struct ReadIdRun {
                            top.data(), top_cap);
         const auto tg1 = std::chrono::steady_clock::now();
         t_gpu += std::chrono::duration<double>(tg1 - tg0).count();
-        auto put_u = [&](uint32_t v) { char tmp[12]; int k = 0; do { tmp[k++] = (char)('0' + v % 10); v /= 10; } while (v); while (k) outbuf += tmp[--k]; };
-        outbuf.clear();
+        // ---- tally (first appearance fixes the order of the counts file: one pass in read order, no strings) and the rare
+        // read with more tied accessions than the batch call kept, which is classified again on its own
+        std::map<uint64_t, std::string> wide_multi;
         for (uint64_t r = 0; r < n; r++) {
-            std::string multi;
-            const std::string* cls = nullptr;
-            static const std::string kTooShort = "too_short", kNoHits = "no_hits", kNoSig = "no_significant_hits";
-            bool accept = true;
-            uint32_t h = 0, ns = n_set[r], nt = 0;
             switch (kind[r]) {
-                case CID_CLS_TOO_SHORT: cls = &kTooShort; ns = 0; break;
-                case CID_CLS_NO_HITS: cls = &kNoHits; break;
-                case CID_CLS_NO_SIGNIFICANT: cls = &kNoSig; accept = false; break;
-                case CID_CLS_ACCEPT: cls = &names.at(top[r * top_cap]); h = hits[r]; nt = 1; break;
-                case CID_CLS_REJECT_MULTI: {
-                    std::vector<uint32_t> all;
-                    const uint32_t* t = top.data() + r * top_cap;
-                    if (n_top[r] > top_cap) {           // more tied accessions than the batch call kept: redo this read alone
-                        all.resize(N);
+                case CID_CLS_TOO_SHORT: count_slot(slot_too_short, "too_short"); break;
+                case CID_CLS_NO_HITS: count_slot(slot_no_hits, "no_hits"); break;
+                case CID_CLS_NO_SIGNIFICANT: count_slot(slot_reject, "reject"); break;
+                case CID_CLS_ACCEPT: { const uint32_t c = top[r * top_cap]; count_slot(slot_color.at(c), names[c]); break; }
+                case CID_CLS_REJECT_MULTI:
+                    count_slot(slot_reject, "reject");
+                    if (n_top[r] > top_cap) {
+                        std::vector<uint32_t> all(N);
                         int32_t k1; uint32_t h1, s1, t1;
                         const uint64_t s_lo = rb.read_offs[r], s_hi = rb.read_offs[r + 1];
                         std::vector<uint64_t> so, ro{0, s_hi - s_lo};
-                        for (uint64_t s = s_lo; s <= s_hi; s++) so.push_back(rb.seq_offs[s] - rb.seq_offs[s_lo]);
+                        for (uint64_t q = s_lo; q <= s_hi; q++) so.push_back(rb.seq_offs[q] - rb.seq_offs[s_lo]);
                         g.read_id_classify(rb.bases.p + rb.seq_offs[s_lo], rb.any_qual ? rb.quals.p + rb.seq_offs[s_lo] : nullptr, so.data(),
                                            s_hi - s_lo, ro.data(), 1, &p, n_ref.data(), fp_correct, &k1, &h1, &s1, &t1, all.data(), N);
-                        t = all.data();
+                        std::string& multi = wide_multi[r];
+                        for (uint32_t j = 0; j < n_top[r]; j++) { if (j) multi += ','; multi += names.at(all[j]); }
                     }
-                    for (uint32_t j = 0; j < n_top[r]; j++) { if (j) multi += ','; multi += names.at(t[j]); }
-                    cls = &multi; h = hits[r]; nt = n_top[r]; accept = false;
                     break;
-                }
                 default:
                     throw Error("read " + rb.id(r) + ": a later mate is shorter than k-1 (the reference panics in kmerize_vector_skip_n_set)");
             }
-            outbuf.append(rb.id_data, rb.id_off[r], rb.id_off[r + 1] - rb.id_off[r]); outbuf += '\t'; outbuf += *cls; outbuf += '\t'; put_u(h); outbuf += '\t'; put_u(ns);
-            outbuf += accept ? "\taccept\t" : "\treject\t"; put_u(nt); outbuf += '\n';
-            if (outbuf.size() > (8u << 20)) { fwrite(outbuf.data(), 1, outbuf.size(), out); outbuf.clear(); }
-            tally(*cls, accept);
         }
-        fwrite(outbuf.data(), 1, outbuf.size(), out);
+        // ---- the read_id_mt_pe.rs:779-788 lines, formatted in kFormatThreads stretches of reads and written in input order
+        auto format = [&](uint64_t r0, uint64_t r1, std::string& ob) {
+            auto put_u = [&](uint32_t v) { char tmp[12]; int k = 0; do { tmp[k++] = (char)('0' + v % 10); v /= 10; } while (v); while (k) ob += tmp[--k]; };
+            ob.clear();
+            ob.reserve((size_t)(r1 - r0) * 48);
+            std::string multi;
+            for (uint64_t r = r0; r < r1; r++) {
+                const std::string* cls = nullptr;
+                static const std::string kTooShort = "too_short", kNoHits = "no_hits", kNoSig = "no_significant_hits";
+                bool accept = true;
+                uint32_t h = 0, ns = n_set[r], nt = 0;
+                switch (kind[r]) {
+                    case CID_CLS_TOO_SHORT: cls = &kTooShort; ns = 0; break;
+                    case CID_CLS_NO_HITS: cls = &kNoHits; break;
+                    case CID_CLS_NO_SIGNIFICANT: cls = &kNoSig; accept = false; break;
+                    case CID_CLS_ACCEPT: cls = &names[top[r * top_cap]]; h = hits[r]; nt = 1; break;
+                    default: {                               // CID_CLS_REJECT_MULTI (anything else was refused above)
+                        const auto w = wide_multi.find(r);
+                        if (w != wide_multi.end()) cls = &w->second;
+                        else {
+                            const uint32_t* t = top.data() + r * top_cap;
+                            multi.clear();
+                            for (uint32_t j = 0; j < n_top[r]; j++) { if (j) multi += ','; multi += names[t[j]]; }
+                            cls = &multi;
+                        }
+                        h = hits[r]; nt = n_top[r]; accept = false;
+                        break;
+                    }
+                }
+                ob.append(rb.id_data, rb.id_off[r], rb.id_off[r + 1] - rb.id_off[r]); ob += '\t'; ob += *cls; ob += '\t'; put_u(h); ob += '\t'; put_u(ns);
+                ob += accept ? "\taccept\t" : "\treject\t"; put_u(nt); ob += '\n';
+            }
+        };
+        const size_t nt_fmt = n >= par_min(8192) ? (size_t)kFormatThreads : 1;
+        outbufs.resize(kFormatThreads);
+        {
+            std::vector<std::thread> th;
+            size_t spawned = 0;
+            try {
+                for (size_t t = 1; t < nt_fmt; t++) { th.emplace_back(format, n * t / nt_fmt, n * (t + 1) / nt_fmt, std::ref(outbufs[t])); spawned = t; }
+            } catch (...) {}
+            format(0, n / nt_fmt, outbufs[0]);
+            for (auto& t : th) t.join();
+            for (size_t t = spawned + 1; t < nt_fmt; t++) format(n * t / nt_fmt, n * (t + 1) / nt_fmt, outbufs[t]);      // (threads that could not be started)
+        }
+        for (size_t t = 0; t < nt_fmt; t++) fwrite(outbufs[t].data(), 1, outbufs[t].size(), out);
         read_count += n;
         rb.clear();
         t_out += std::chrono::duration<double>(std::chrono::steady_clock::now() - tg1).count();
     }
     void finish() {
         fclose(out); out = nullptr;
+        std::map<std::string, uint64_t> counts;
+        for (size_t i = 0; i < count_keys.size(); i++) counts[count_keys[i]] = slot_counts[i];
         write_counts_five_fields(o.prefix + "_counts.txt", count_keys, counts);   // main.rs:865
     }
 };
@@ -575,35 +729,17 @@ void read_id_sample(Gpu& g, const Bigsi& b, const ReadIdOpts& o, Trace& tr, Read
     Timer t;
     auto maybe_flush = [&]() { if (rb.n() >= kGpuBatchReads || rb.bases.size >= kGpuBatchBytes) submit(); };
     if (ends_with(o.query[0], ".gz")) {
+        auto cur_batch = [&]() -> ReadBatch& { return batches[cur]; };
         if (o.query.size() > 1) {                       // per_read_stream_pe, read_id_mt_pe.rs:701-832
             AsyncLineReader a(o.query[0]), c(o.query[1]);
-            std::string_view l1, l2, id, s1, s2;       // views into the readers' blocks: a record's four lines share a block
-            uint64_t line_count = 1;
-            while (a.next_view(l1)) {
-                const bool have2 = c.next_view(l2);
-                if (line_count % 4 == 1) id = l1;
-                else if (line_count % 4 == 2) { if (!have2) break; s1 = l1; s2 = l2; }
-                else if (line_count % 4 == 0) {
-                    if (!have2) break;
-                    rb.add_mate(s1, &l1, o.quality);
-                    rb.add_mate(s2, &l2, o.quality);
-                    rb.end_read(id);
-                    maybe_flush();
-                }
-                line_count++;
-            }
+            AsyncLineReader* rd[2] = {&a, &c};
+            parse_fastq_records(rd, 2, o.quality, cur_batch, maybe_flush);
             submit(); join_worker();
             fprintf(stderr, "Classified %llu read pairs in %llu seconds\n", (unsigned long long)run.read_count, t.secs());
         } else {                                        // per_read_stream_se, :835-951
             AsyncLineReader a(o.query[0]);
-            std::string_view l, id, s1;
-            uint64_t line_count = 1;
-            while (a.next_view(l)) {
-                if (line_count % 4 == 1) id = l;
-                else if (line_count % 4 == 2) s1 = l;
-                else if (line_count % 4 == 0) { rb.add_mate(s1, &l, o.quality); rb.end_read(id); maybe_flush(); }
-                line_count++;
-            }
+            AsyncLineReader* rd[2] = {&a, nullptr};
+            parse_fastq_records(rd, 1, o.quality, cur_batch, maybe_flush);
             submit(); join_worker();
             fprintf(stderr, "Classified %llu reads in %llu seconds\n", (unsigned long long)run.read_count, t.secs());
         }
@@ -633,6 +769,38 @@ void read_id_sample(Gpu& g, const Bigsi& b, const ReadIdOpts& o, Trace& tr, Read
     tr.mark("counts file");
 }
 }  // namespace
+
+// `_host fastq_parse`: the record loop of read_id over one or two FASTQ(.gz) files, every batch digested instead of classified
+// (no GPU needed): what the tests compare between the block-wise and the line-by-line path.
+int fastq_parse_digest(const std::vector<std::string>& files, uint8_t quality) {
+    if (files.empty() || files.size() > 2) throw Error("one or two files");
+    ReadBatch rb;
+    rb.bases.pageable = rb.quals.pageable = true;
+    uint64_t n_batches = 0, n_reads = 0;
+    unsigned long crc = crc32(0L, Z_NULL, 0);
+    const bool timing_only = getenv("COLORID_B200_PARSE_NODIGEST") != nullptr;          // (zlib's crc32 is slower than the loop it checks)
+    auto fold = [&](const void* p, size_t n) { if (!timing_only) crc = crc32(crc, (const Bytef*)p, (uInt)n); };
+    auto digest = [&]() {
+        if (!rb.n()) return;
+        n_batches++; n_reads += rb.n();
+        const uint64_t n = rb.n();
+        fold(&n, 8); fold(rb.bases.p, rb.bases.size);
+        const unsigned char q = rb.any_qual ? 1 : 0;
+        fold(&q, 1);
+        if (rb.any_qual) fold(rb.quals.p, rb.quals.size);
+        fold(rb.seq_offs.data(), rb.seq_offs.size() * 8); fold(rb.read_offs.data(), rb.read_offs.size() * 8);
+        fold(rb.id_data.data(), rb.id_data.size()); fold(rb.id_off.data(), rb.id_off.size() * 4);
+        rb.clear();
+    };
+    auto cur_batch = [&]() -> ReadBatch& { return rb; };
+    auto maybe_flush = [&]() { if (rb.n() >= kGpuBatchReads || rb.bases.size >= kGpuBatchBytes) digest(); };
+    std::unique_ptr<AsyncLineReader> a(new AsyncLineReader(files[0])), c(files.size() > 1 ? new AsyncLineReader(files[1]) : nullptr);
+    AsyncLineReader* rd[2] = {a.get(), c.get()};
+    parse_fastq_records(rd, (int)files.size(), quality, cur_batch, maybe_flush);
+    digest();
+    printf("reads\t%llu\nbatches\t%llu\ncrc32\t%08lx\n", (unsigned long long)n_reads, (unsigned long long)n_batches, crc);
+    return 0;
+}
 
 int read_id(const ReadIdOpts& o) {
     if (o.query.empty()) throw Error("no query files");

@@ -40,11 +40,11 @@ MappedGz::MappedGz(const std::string& path) {
     if (m == MAP_FAILED) throw Error("cannot map " + path);
     madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
     map_ = m; len_ = (size_t)st.st_size;
-    // Large files are decoded by several threads (GzParallel): COLORID_B200_GZ_THREADS (default: a quarter of the cores, at
+    // Large files are decoded by several threads (GzParallel): COLORID_B200_GZ_THREADS (default: 3/8 of the cores, at
     // most 6; 1 = the sequential decoder), COLORID_B200_GZ_SPAN = compressed bytes per thread and round (default 2 MiB).
     GzParallel::Config cfg;
     const unsigned hw = std::thread::hardware_concurrency();
-    cfg.threads = std::min(6u, std::max(1u, hw / 4));
+    cfg.threads = std::min(6u, std::max(1u, hw * 3 / 8));
     if (const char* e = getenv("COLORID_B200_GZ_THREADS")) { const long v = atol(e); if (v >= 1 && v <= 64) cfg.threads = (unsigned)v; }
     if (const char* e = getenv("COLORID_B200_GZ_SPAN")) { const long long v = atoll(e); if (v >= 4096) cfg.span = (size_t)v; }
     try {
@@ -203,7 +203,8 @@ AsyncLineReader::~AsyncLineReader() {
     if (p_->th.joinable()) p_->th.join();
     delete p_;
 }
-bool AsyncLineReader::next_view(std::string_view& line) {
+// makes the current block one with unread lines; false at the end of the file
+bool AsyncLineReader::load() {
     Impl& s = *p_;
     if (!s.cur || s.at == s.cur->end.size()) {
         std::unique_lock<std::mutex> lk(s.mu);
@@ -219,11 +220,24 @@ bool AsyncLineReader::next_view(std::string_view& line) {
         lk.unlock();
         s.cv.notify_all();
     }
+    return true;
+}
+bool AsyncLineReader::next_view(std::string_view& line) {
+    if (!load()) return false;
+    Impl& s = *p_;
     const uint32_t lo = s.cur->begin[s.at], hi = s.cur->end[s.at];
     line = std::string_view(s.cur->data.data() + lo, hi - lo);
     s.at++;
     return true;
 }
+bool AsyncLineReader::peek_block(LineBlock& b, size_t& at) {
+    if (!load()) return false;
+    Impl& s = *p_;
+    b.data = s.cur->data.data(); b.begin = s.cur->begin.data(); b.end = s.cur->end.data(); b.n = s.cur->end.size();
+    at = s.at;
+    return true;
+}
+void AsyncLineReader::skip_lines(size_t k) { p_->at += k; }
 bool AsyncLineReader::next(std::string& line) {
     std::string_view v;
     if (!next_view(v)) return false;

@@ -151,6 +151,8 @@ int main(int argc, char** argv) {
                 unsigned long crc = crc32(0L, Z_NULL, 0);
                 while (lr.next_view(v)) { n++; bytes += v.size(); crc = crc32(crc, (const Bytef*)v.data(), (uInt)v.size()); if (!keep) crc = crc32(crc, (const Bytef*)"\n", 1); }
                 printf("lines\t%llu\nbytes\t%llu\ncrc32\t%08lx\n", n, bytes, crc);
+            } else if (op == "fastq_parse" && (argc == 5 || argc == 6)) {      // <quality offset> <file1> [file2]: read_id's record loop, batches digested
+                return cidh::fastq_parse_digest(std::vector<std::string>(argv + 4, argv + argc), (uint8_t)atoi(argv[3]));
             } else if (op == "acount" && argc == 4) {            // AsyncLineReader as the drivers use it, lines only counted (timing aid)
                 cidh::AsyncLineReader lr(argv[3]);
                 std::string_view v;

@@ -17,8 +17,8 @@ CLI = os.path.join(ROOT, "colorid_b200", "colorid-b200")
 K, S, H = 21, 300_007, 3
 
 
-def run(*args, ok=True):
-    r = subprocess.run([CLI, *map(str, args)], capture_output=True, text=True)
+def run(*args, ok=True, env=None):
+    r = subprocess.run([CLI, *map(str, args)], capture_output=True, text=True, env=None if env is None else dict(os.environ, **env))
     if ok:
         assert r.returncode == 0, r.stderr[-2000:]
     lines = r.stdout.split("\n")
@@ -257,6 +257,13 @@ def test_read_id_paired_single_and_fasta(world, oracle):
     assert (d / "pe_out_counts.txt").read_text().split("\n")[:-1] == exp_counts
     classes = {l.split("\t")[1] for l in exp_lines}
     assert "too_short" in classes and len(classes - CLS_NAMES) >= 3 and len(classes & CLS_NAMES) >= 2
+    # the host layer's threaded paths on this small input (several inflating threads per file, bases copied and report lines
+    # formatted by four threads each), and the line-by-line record loop with the sequential decoder
+    for name, env in (("par", {"COLORID_B200_PAR_MIN": "1", "COLORID_B200_GZ_THREADS": "3", "COLORID_B200_GZ_SPAN": "8192"}),
+                      ("seq", {"COLORID_B200_PARSE_SLOW": "1", "COLORID_B200_GZ_THREADS": "1"})):
+        run("read_id", "-b", d / "idx.bxi", "-q", d / "r_1.fastq.gz", d / "r_2.fastq.gz", "-n", d / f"pe_{name}", env=env)
+        assert (d / f"pe_{name}_reads.txt").read_text().split("\n")[:-1] == exp_lines, name
+        assert (d / f"pe_{name}_counts.txt").read_text().split("\n")[:-1] == exp_counts, name
     # single end, -B 0 (search_index_classic), -d 2, -p 2, -Q 25
     reads = [[oracle.qual_mask(a, qa.encode(), 25)] for a, qa in zip(s1, q1)]
     exp_lines, exp_counts = _expected_read_lines(world, oracle, ids, reads, d=2, start_sample=0, fp_correct=10.0 ** -2.0)

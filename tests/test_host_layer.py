@@ -402,6 +402,84 @@ def test_parallel_gzip_decoder_fails_loudly_on_damage(tmp_path):
     assert rc != 0 and "CRC mismatch" in msg, (rc, msg)
 
 
+def _parse_digest(files, quality, slow, **env_extra):
+    env = dict(os.environ, **{k: str(v) for k, v in env_extra.items()})
+    env["COLORID_B200_PARSE_SLOW"] = "1" if slow else "0"
+    r = subprocess.run([CLI, "_host", "fastq_parse", str(quality)] + [str(f) for f in files], capture_output=True, text=True, env=env)
+    if r.returncode != 0:
+        return r.returncode, r.stderr.strip().split("\n")[-1]
+    d = dict(l.split("\t") for l in r.stdout.split("\n") if l.count("\t") == 1 and l.split("\t")[0] in ("reads", "batches", "crc32"))
+    return 0, (int(d["reads"]), int(d["batches"]), d["crc32"])
+
+
+def test_read_id_record_loop_blockwise_equals_linewise(tmp_path):
+    """read_id's FASTQ record loop (drivers.cpp parse_fastq_records) takes whole stretches of records out of the readers' line
+    blocks and copies bases and qualities on several threads; COLORID_B200_PARSE_SLOW=1 is the line-by-line loop of
+    per_read_stream_pe / _se (read_id_mt_pe.rs:701-951).  `_host fastq_parse` digests every batch either way (bases,
+    qualities, offsets, ids, batch boundaries): equal on paired and single files, quality masking on and off, several line
+    blocks, a second file that ends early (at a record boundary and inside a record), a shorter first file, records whose
+    quality line is shorter than the sequence (qual_mask on the host), CRLF files, reads long enough to fill a batch by
+    bytes, and .gz input through the multi-threaded decoder."""
+    import zlib
+    rng = np.random.default_rng(0xC0101D0A)
+
+    def fastq(n, rl, tag, crlf=False, short_qual_every=0):
+        lut = np.frombuffer(b"ACGTN", dtype=np.uint8)
+        out = []
+        for i in range(n):
+            L = int(rl if isinstance(rl, int) else rng.integers(rl[0], rl[1]))
+            seq = lut[rng.integers(0, 5, L)].tobytes()
+            q = rng.integers(35, 74, L, dtype=np.uint8).tobytes()
+            if short_qual_every and i % short_qual_every == short_qual_every - 1:
+                q = q[: max(1, L - 7)]
+            out.append(b"@%s%07d\n" % (tag, i) + seq + b"\n+\n" + q + b"\n")
+        blob = b"".join(out)
+        return blob.replace(b"\n", b"\r\n") if crlf else blob
+
+    n = 40_000                                   # 2.4 line blocks of 65,536 lines
+    r1, r2 = fastq(n, (30, 200), b"a"), fastq(n, (30, 200), b"b")
+    cases = {}
+
+    def put(name, files, quality=15, **env):
+        paths = []
+        for j, blob in enumerate(files):
+            p = tmp_path / f"{name}_{j}.fastq"
+            p.write_bytes(blob)
+            paths.append(p)
+        cases[name] = (paths, quality, env)
+
+    put("pe", [r1, r2])
+    put("pe_q0", [r1, r2], quality=0)
+    put("se", [r1])
+    lines2 = r2.split(b"\n")
+    for cut in (4 * 17_000, 4 * 17_000 + 1, 4 * 17_000 + 2, 4 * 17_000 + 3, 4 * 16_384, 4 * 16_384 + 2):
+        put(f"pe_short2_{cut}", [r1, b"\n".join(lines2[:cut]) + b"\n"])
+    put("pe_short1", [b"\n".join(r1.split(b"\n")[: 4 * 20_001 + 2]) + b"\n", r2])
+    put("pe_qual_mask", [fastq(n, (30, 200), b"a", short_qual_every=1000), fastq(n, (30, 200), b"b", short_qual_every=777)])
+    put("pe_crlf", [fastq(20_000, 100, b"a", crlf=True), fastq(20_000, 100, b"b", crlf=True)])
+    put("se_no_final_newline", [r1[:-1]])
+    put("empty", [b"", b""])
+    for name, (paths, quality, env) in cases.items():
+        fast, slow = _parse_digest(paths, quality, False, **env), _parse_digest(paths, quality, True, **env)
+        assert fast[0] == 0 and fast == slow, (name, fast, slow)
+        assert _parse_digest(paths, quality, False, COLORID_B200_PAR_MIN=1, **env) == slow, (name, "copy threads on every stretch")
+    assert _parse_digest(cases["pe"][0], 15, False)[1][0] == n and _parse_digest(cases["pe_short2_%d" % (4 * 17_000 + 2)][0], 15, False)[1][0] == 17_000
+    # batches that fill up by bytes (96 MB of bases): 2 x 1,900 reads of 30 kb
+    big = [fastq(1900, 30_000, t) for t in (b"a", b"b")]
+    put("pe_long", big)
+    fast, slow = _parse_digest(cases["pe_long"][0], 15, False), _parse_digest(cases["pe_long"][0], 15, True)
+    assert fast[0] == 0 and fast == slow and fast[1][1] == 2, (fast, slow)
+    # .gz through the multi-threaded decoder
+    gz = []
+    for j, blob in enumerate((r1, r2)):
+        p = tmp_path / f"pe_{j}.fastq.gz"
+        p.write_bytes(_gz(blob, 1, memlevel=2))
+        gz.append(p)
+    want = _parse_digest(cases["pe"][0], 15, True)
+    for threads in (1, 3):
+        assert _parse_digest(gz, 15, False, COLORID_B200_GZ_THREADS=threads, COLORID_B200_GZ_SPAN=65536) == want, threads
+
+
 def test_block_line_splitter_equals_line_reader(tmp_path):
     """AsyncLineReader splits whole blocks with memchr (LineReader::next_lines) where LineReader::next walks line by line:
     same lines on CRLF files, blank lines, a last line without newline, lines longer than the 1 MB read buffer, lone CRs,

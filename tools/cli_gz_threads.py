@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""CLI `batch_id` on .fastq.gz pairs against the number of inflating threads per file (COLORID_B200_GZ_THREADS), and the bare
+"""CLI `batch_id` on .fastq.gz pairs against the number of inflating threads per file (COLORID_B200_GZ_THREADS; 0 = default), and the bare
 decoder (`_host gunzip`) beside it.  Same synthetic data as tools/cli_e2e.py (46 x 3.3 Mbp index, 2 x 150 bp pairs, gzip -1).
 Prints one JSON line; the CLI's [trace] lines go to stderr.  Profiling aid, not the bench contract."""
 import hashlib, json, os, re, subprocess, sys, tempfile, time
@@ -71,7 +71,7 @@ out = {"workload": f"CLI batch_id, {n_samples} samples of {n_pairs} read pairs (
        "generate_seconds": t_gen, "build_seconds": t_build, "batch_id": {}, "gunzip_mb_per_s": {}}
 digests = set()
 for T in threads:
-    env = {"COLORID_B200_GZ_THREADS": str(T)}
+    env = {"COLORID_B200_GZ_THREADS": str(T)} if T else {}            # 0 = the CLI's default
     dt, r = cli(env, "batch_id", "-b", f"{d}/idx.bxi", "-q", f"{d}/samples.tsv", "-T", "b")
     per = [float(m.group(1)) for m in re.finditer(r"\[trace\] parse \+ classify \+ write\s+([0-9.]+) s", r.stderr)]
     print(f"== COLORID_B200_GZ_THREADS={T}\n" + "\n".join(l for l in r.stderr.split("\n") if l.startswith("[trace]")), file=sys.stderr)
@@ -84,7 +84,7 @@ for T in threads:
     out["batch_id"][str(T)] = {"seconds": dt, "per_sample_seconds": per, "steady_pairs_per_s": n_pairs / steady if steady else None}
     sys.stderr.flush()
 out["outputs_identical_across_thread_counts"] = len(digests) == 1
-for T in sorted(set(threads + [2, 8])):
+for T in sorted(set(t for t in threads if t) | {2, 8}):
     best = None
     for _ in range(2):
         t = time.perf_counter()
