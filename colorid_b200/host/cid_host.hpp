@@ -18,6 +18,7 @@
 // The reference is Rust; this image has no Rust toolchain, so the host side is C++.
 // Everything compute-heavy goes through the C ABI to the GPU; nothing here has a CPU fallback.
 #pragma once
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <map>
@@ -53,6 +54,7 @@ public:
 private:
     class GzInflater* inf_ = nullptr;    // one of the two
     class GzParallel* par_ = nullptr;
+    static std::atomic<int> live_;       // MappedGz objects alive: they share the cores
     void* map_ = nullptr;
     size_t len_ = 0;
 };

@@ -6,6 +6,7 @@
 #include <unistd.h>
 #include <zlib.h>
 
+#include <atomic>
 #include <condition_variable>
 #include <cstring>
 #include <deque>
@@ -30,7 +31,9 @@ bool MappedGz::eligible(const std::string& path) {
     close(fd);
     return ok;
 }
+std::atomic<int> MappedGz::live_{0};
 MappedGz::MappedGz(const std::string& path) {
+    struct Live { bool keep = false; Live() { live_++; } ~Live() { if (!keep) live_--; } } live;
     const int fd = open(path.c_str(), O_RDONLY);
     if (fd < 0) throw Error("file not found: " + path);
     struct stat st;
@@ -40,11 +43,14 @@ MappedGz::MappedGz(const std::string& path) {
     if (m == MAP_FAILED) throw Error("cannot map " + path);
     madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
     map_ = m; len_ = (size_t)st.st_size;
-    // Large files are decoded by several threads (GzParallel): COLORID_B200_GZ_THREADS (default: 3/8 of the cores, at
-    // most 6; 1 = the sequential decoder), COLORID_B200_GZ_SPAN = compressed bytes per thread and round (default 2 MiB).
+    // Large files are decoded by several threads (GzParallel): COLORID_B200_GZ_THREADS (default: 3/4 of the cores shared by the open
+    // files, at most 6 each; 1 = the sequential decoder), COLORID_B200_GZ_SPAN = compressed bytes per thread and round (default 2 MiB).
     GzParallel::Config cfg;
     const unsigned hw = std::thread::hardware_concurrency();
-    cfg.threads = std::min(6u, std::max(1u, hw * 3 / 8));
+    // 3/4 of the cores are shared by the gzip files open at this moment (two per paired sample; `batch_id` on several GPUs has
+    // several samples open), at most 6 threads each
+    const unsigned open_now = (unsigned)std::max(1, live_.load());
+    cfg.threads = std::min(6u, std::max(1u, hw * 3 / 4 / open_now));
     if (const char* e = getenv("COLORID_B200_GZ_THREADS")) { const long v = atol(e); if (v >= 1 && v <= 64) cfg.threads = (unsigned)v; }
     if (const char* e = getenv("COLORID_B200_GZ_SPAN")) { const long long v = atoll(e); if (v >= 4096) cfg.span = (size_t)v; }
     try {
@@ -54,11 +60,13 @@ MappedGz::MappedGz(const std::string& path) {
         munmap(m, len_);
         throw;
     }
+    live.keep = true;
 }
 MappedGz::~MappedGz() {
     delete par_;
     delete inf_;
     if (map_) munmap(map_, len_);
+    live_--;
 }
 size_t MappedGz::read(char* dst, size_t cap) { return par_ ? par_->read((uint8_t*)dst, cap) : inf_->read((uint8_t*)dst, cap); }
 
@@ -194,7 +202,11 @@ struct AsyncLineReader::Impl {
     }
 };
 AsyncLineReader::AsyncLineReader(const std::string& path, bool keep_eol) : p_(new Impl()) {
-    { LineReader probe(path); }                      // a missing file fails here, on the caller's thread
+    {                                                // a missing file fails here, on the caller's thread
+        const int fd = open(path.c_str(), O_RDONLY);
+        if (fd < 0) throw Error("file not found: " + path);
+        close(fd);
+    }
     p_->th = std::thread(&Impl::produce, p_, path, keep_eol);
 }
 AsyncLineReader::~AsyncLineReader() {

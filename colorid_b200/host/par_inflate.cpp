@@ -327,6 +327,7 @@ struct GzParallel::Impl {
     const uint8_t* base; size_t n;
     std::string what;
     unsigned T; size_t span;
+    size_t work_span;                        // span of the next round: `span`, less where the data inflates by more than 8x
     size_t soft_cap, hard_cap;               // output symbols of one span: stop at the next block / give up
 
     // coordinator state: the stream is verified up to here
@@ -360,6 +361,7 @@ struct GzParallel::Impl {
         : base(d), n(len), what(w), T(cfg.threads < 1 ? 1 : cfg.threads), span(cfg.span < 4096 ? 4096 : cfg.span), sync(T) {
         sets[0] = std::vector<Span>(T);
         sets[1] = std::vector<Span>(T);
+        work_span = span;
         soft_cap = span * 16;
         hard_cap = span * 48;
     }
@@ -592,17 +594,17 @@ struct GzParallel::Impl {
                 }
                 const uint64_t pos_byte = pos_bit >> 3;
                 const size_t remaining = n - (size_t)pos_byte;
-                if (T < 2 || remaining < span || small_members >= 4) {
+                if (T < 2 || remaining < work_span || small_members >= 4) {
                     if (!job_flush()) return;
                     sequential();
                     break;
                 }
                 // ---- lay out the round
                 spans = sets[round & 1].data();
-                size_t sp = span;
+                size_t sp = work_span;
                 n_spans = (int)T;
-                if (remaining < (size_t)T * span) {
-                    n_spans = (int)std::max<size_t>(1, std::min<size_t>(T, remaining / (span / 2)));
+                if (remaining < (size_t)T * sp) {
+                    n_spans = (int)std::max<size_t>(1, std::min<size_t>(T, remaining / (sp / 2)));
                     sp = (remaining + n_spans - 1) / n_spans;
                 }
                 for (int j = 0; j < n_spans; j++) {
@@ -673,6 +675,14 @@ struct GzParallel::Impl {
                 job.chain = chain;
                 job.nextk.store(0);
                 job.active = true;
+                {
+                    // data that inflates by more than 8x gets shorter spans, so that a span's output stays around 8 x `span` symbols
+                    // and below the cap at which a span stops early (which would leave the spans after it unused)
+                    const uint64_t used_bits = chain.back()->end_bit - pos_bit;
+                    const double ratio = used_bits ? (double)total * 8.0 / (double)used_bits : 1.0;
+                    const size_t lo = std::max<size_t>(4096, span / 32);
+                    work_span = ratio > 8.0 ? std::max(lo, (size_t)((double)span * 8.0 / ratio)) : span;
+                }
                 const Span& last = *chain.back();
                 const End how = last.end;
                 const uint64_t end_bit = last.end_bit;
