@@ -461,6 +461,16 @@ struct GzParallel::Impl {
         }
     }
 
+    // a round's thread: its share of the round before, then its span.  Nothing may leave a thread as an exception (out of
+    // memory while growing a buffer, say): the span then counts as given up and the stream continues from the one before it.
+    std::atomic<bool> thread_failed{false};
+    void round_thread(int idx) noexcept {
+        try { job_work(); } catch (...) { thread_failed.store(true); }
+        try { run_span(idx); } catch (...) {
+            spans[idx].end = idx ? E_NOSYNC : E_GIVE_UP;
+            if (idx) { int64_t e = -1; sync[idx].compare_exchange_strong(e, -2); }
+        }
+    }
     void run_span(int idx) {
         Span& s = spans[idx];
         s.end = E_NONE; s.next = -1; s.out = WIN; s.n_cand = 0;
@@ -624,14 +634,14 @@ struct GzParallel::Impl {
                     std::vector<std::thread> th;
                     int started = 1;
                     try {
-                        for (int j = 1; j < n_spans; j++) { th.emplace_back([this, j] { job_work(); run_span(j); }); started = j + 1; }
+                        for (int j = 1; j < n_spans; j++) { th.emplace_back([this, j] { round_thread(j); }); started = j + 1; }
                     } catch (...) {
                         for (int j = started; j < n_spans; j++) { spans[j].end = E_NOSYNC; sync[j].store(-2); }
                     }
-                    job_work();
-                    run_span(0);
+                    round_thread(0);
                     for (auto& t : th) t.join();
                 }
+                if (thread_failed.load()) fail("internal error while resolving a round");
                 if (!job_finish()) return;
                 if (abort.load()) return;
                 // ---- the chain of spans that are the stream
