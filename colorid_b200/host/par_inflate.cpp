@@ -725,7 +725,7 @@ struct GzParallel::Impl {
             put(std::move(e));
         } catch (const std::exception& ex) {
             // what was decoded before the damage is still delivered, as the sequential decoder would
-            try { job_flush(); } catch (...) {}
+            if (!thread_failed.load()) { try { job_flush(); } catch (...) {} }
             Item e;
             e.eof = true;
             e.error = ex.what();
