@@ -342,22 +342,24 @@ std::map<std::string, std::vector<std::string>> tab_to_map(const std::string& pa
 
 // ------------------------------------------------------------------ FASTQ
 // seq.rs:36-56 applied while appending to the batch (no per-record strings)
-static void add_masked(SeqBatch& out, const std::string& seq, const std::string& qual, uint8_t off) {
-    if (off == 0) { out.add(seq); return; }
+static void add_masked(SeqBatch& out, std::string_view seq, std::string_view qual, uint8_t off) {
+    if (off == 0) { out.add(seq.data(), seq.size()); return; }
     if (qual.size() > seq.size()) throw Error("ERROR: could not get the next nt in the sequence");
     const uint8_t maxq = (uint8_t)(off + 33);
     const size_t at = out.bases.size(), n = qual.size();
-    out.bases.append(seq, 0, n);
+    out.bases.append(seq.data(), n);
     char* p = &out.bases[at];
-    for (size_t i = 0; i < n; i++) if ((uint8_t)qual[i] < maxq) p[i] = 'N';
+    const char* q = qual.data();
+    for (size_t i = 0; i < n; i++) p[i] = (uint8_t)q[i] < maxq ? 'N' : p[i];       // (a select, not a branch: vectorised)
     out.offs.push_back(out.bases.size());
 }
+// (the lines are views into the readers' blocks: the four lines of a record share a block)
 uint64_t fastq_masked_se(const std::string& path, uint8_t qual_offset, SeqBatch& out) {
     AsyncLineReader lr(path);
-    std::string l, seq;
+    std::string_view l, seq;
     uint64_t line_count = 1, n = 0;
-    while (lr.next(l)) {
-        if (line_count % 4 == 2) seq.swap(l);
+    while (lr.next_view(l)) {
+        if (line_count % 4 == 2) seq = l;
         else if (line_count % 4 == 0) { add_masked(out, seq, l, qual_offset); n++; }
         line_count++;
     }
@@ -365,12 +367,12 @@ uint64_t fastq_masked_se(const std::string& path, uint8_t qual_offset, SeqBatch&
 }
 uint64_t fastq_masked_pe(const std::string& p1, const std::string& p2, uint8_t qual_offset, SeqBatch& out) {
     AsyncLineReader a(p1), b(p2);           // both files inflate on their own threads
-    std::string l1, l2, s1, s2;
+    std::string_view l1, l2, s1, s2;
     uint64_t line_count = 1, n = 0;
-    while (a.next(l1)) {
-        const bool have2 = b.next(l2);
+    while (a.next_view(l1)) {
+        const bool have2 = b.next_view(l2);
         if (line_count % 4 == 1) { if (!have2) break; }
-        else if (line_count % 4 == 2) { if (!have2) break; s1.swap(l1); s2.swap(l2); }
+        else if (line_count % 4 == 2) { if (!have2) break; s1 = l1; s2 = l2; }
         else if (line_count % 4 == 0) {
             if (!have2) break;
             add_masked(out, s1, l1, qual_offset);
